@@ -1,0 +1,82 @@
+/*
+ * xaac_b200.h — C-ABI of libxaac_b200.so: B200-native (sm_100a) kernels for the decode-side DSP hot path
+ * of ittiam-systems/libxaac.  Plain C, plain pointers and sizes; no CUDA or torch types in the signatures
+ * (streams travel as void*).  Host code that stays C — the reference's own bitstream parser — binds to
+ * exactly these entry points (see INTEGRATION.md for the function-selector / --wrap stubs).
+ *
+ * Conventions (mirroring the reference, decoder/ixheaacd_error_standards.h:24-26):
+ *   return 0 on success; a value with bit 31 set (XAAC_B200_FATAL) is fatal (CUDA failure, bad argument).
+ *   The library never falls back to a CPU path: without a CUDA device every call fails loudly.
+ *   The caller owns every buffer.  "_dev" entry points take device pointers and are asynchronous on the
+ *   given stream; "_host" entry points take host pointers, copy in, run, copy out and synchronise.
+ *
+ * Unit of work for the IMDCT stage: one frame x one core channel ("unit"), 1024 spectral lines.
+ */
+#ifndef XAAC_B200_H
+#define XAAC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XAAC_B200_OK 0
+#define XAAC_B200_FATAL ((int32_t)0x80000000)
+#define XAAC_B200_ERR_CUDA ((int32_t)0x80000001)
+#define XAAC_B200_ERR_ARG ((int32_t)0x80000002)
+#define XAAC_B200_ERR_NO_ROM ((int32_t)0x80000003)
+
+/* window_sequence codes, decoder/ixheaacd_cnst.h:100-103 */
+#define XAAC_ONLY_LONG_SEQUENCE 0
+#define XAAC_LONG_START_SEQUENCE 1
+#define XAAC_EIGHT_SHORT_SEQUENCE 2
+#define XAAC_LONG_STOP_SEQUENCE 3
+
+typedef struct xaac_b200_ctx xaac_b200_ctx;
+
+/* ---- context --------------------------------------------------------------------------------------- */
+int32_t xaac_b200_create(xaac_b200_ctx **ctx, int32_t device);
+void xaac_b200_destroy(xaac_b200_ctx *ctx);
+const char *xaac_b200_last_error(const xaac_b200_ctx *ctx);
+int32_t xaac_b200_num_sms(const xaac_b200_ctx *ctx);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches evidence) */
+int64_t xaac_b200_launch_count(const xaac_b200_ctx *ctx);
+int32_t xaac_b200_sync(xaac_b200_ctx *ctx);
+
+/* ---- ROM tables ------------------------------------------------------------------------------------
+ * The reference hands its const tables to every hot function as pointer arguments
+ * (ia_aac_dec_imdct_tables_struct *, decoder/ixheaacd_aac_rom.h:112-168).  The drop-in does
+ * the same once per context: `tables` points at the host's ia_aac_dec_imdct_tables_struct (only the leading
+ * XAAC_B200_IMDCT_ROM_BYTES are read: cosine_array_2048_256, dig_rev_table8_long/short, fft_twiddle,
+ * only_long_window_sine/kbd, only_short_window_sine/kbd). */
+#define XAAC_B200_IMDCT_ROM_BYTES 7500
+int32_t xaac_b200_set_imdct_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes);
+
+/* ---- AAC IMDCT + window/overlap-add (batched) -------------------------------------------------------
+ * Replaces ixheaacd_imdct_process (decoder/ixheaacd_lpfuncs.c:347-802) for 1024-sample frames, i.e. the
+ * selector leaves ixheaacd_calc_max_spectral_line / pretwiddle_compute / imdct_using_fft / post_twiddle /
+ * post_twid_overlap_add / over_lap_add1 / over_lap_add2 / spec_to_overlapbuf / overlap_buf_out /
+ * overlap_out_copy / neg_shift_spec (decoder/ixheaacd_function_selector.h:61-223) fused into one kernel.
+ *
+ *   spec        [n_units][1024] WORD32 spectral coefficients (ptr_spec_coeff); not modified
+ *   overlap     [n_units][512]  WORD32 ia_aac_dec_overlap_info.ptr_overlap_buf, updated in place
+ *   wstate      [n_units][2]    {window_shape, window_sequence} saved from the previous frame
+ *                               (ia_aac_dec_overlap_info), updated in place
+ *   ics         [n_units][2]    {window_sequence, window_shape} of this frame (ia_ics_info_struct)
+ *   out         WORD32 time samples. ch_fac == 1: [n_units][1024]. ch_fac > 1: units u, u+1, .. u+ch_fac-1
+ *               are the channels of one frame, written interleaved with stride ch_fac like the reference's
+ *               time buffer.
+ *   qshift_adj  [n_units] ia_ics_info_struct.qshift_adj as set by the stage (2, 1)
+ */
+int32_t xaac_b200_imdct_process_dev(xaac_b200_ctx *ctx, const int32_t *d_spec, int32_t *d_overlap,
+                                    uint8_t *d_wstate, const uint8_t *d_ics, int32_t *d_out,
+                                    int8_t *d_qshift_adj, int64_t n_units, int32_t ch_fac, void *stream);
+int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, const int32_t *spec, int32_t *overlap,
+                                     uint8_t *wstate, const uint8_t *ics, int32_t *out, int8_t *qshift_adj,
+                                     int64_t n_units, int32_t ch_fac);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XAAC_B200_H */

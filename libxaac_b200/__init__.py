@@ -1,0 +1,25 @@
+"""libxaac_b200 — B200-native (sm_100a) kernels for the decode-side DSP hot path of libxaac.
+
+Host-side mirror of the reference's stage interface over the C-ABI in include/xaac_b200.h.
+PyTorch is used only for device memory and streams.
+"""
+from ._lib import XaacB200Error, load, LIB_PATH  # noqa: F401
+from .context import Context  # noqa: F401
+from .imdct import (  # noqa: F401
+    ONLY_LONG_SEQUENCE,
+    LONG_START_SEQUENCE,
+    EIGHT_SHORT_SEQUENCE,
+    LONG_STOP_SEQUENCE,
+    ImdctBatch,
+    imdct_process,
+    imdct_process_host,
+)
+
+__all__ = [
+    "Context",
+    "ImdctBatch",
+    "imdct_process",
+    "imdct_process_host",
+    "XaacB200Error",
+    "load",
+]

@@ -1,0 +1,59 @@
+"""ctypes binding of libxaac_b200.so (C-ABI declared in include/xaac_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or no device is usable, importing the
+product API raises.  The CPU oracle under oracle/ is test infrastructure and is never touched from here.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxaac_b200.so")
+ROM_DIR = os.path.join(_HERE, "rom")
+
+FATAL = -0x80000000
+
+_c = ctypes
+_vp, _i32, _i64, _sz = _c.c_void_p, _c.c_int32, _c.c_int64, _c.c_size_t
+
+# name -> (restype, argtypes); kept in sync with include/xaac_b200.h (tests/test_abi.py checks both ways)
+SIGNATURES = {
+    "xaac_b200_create": (_i32, [_c.POINTER(_vp), _i32]),
+    "xaac_b200_destroy": (None, [_vp]),
+    "xaac_b200_last_error": (_c.c_char_p, [_vp]),
+    "xaac_b200_num_sms": (_i32, [_vp]),
+    "xaac_b200_launch_count": (_i64, [_vp]),
+    "xaac_b200_sync": (_i32, [_vp]),
+    "xaac_b200_set_imdct_rom": (_i32, [_vp, _vp, _sz]),
+    "xaac_b200_imdct_process_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "xaac_b200_imdct_process_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32]),
+}
+
+_lib = None
+
+
+class XaacB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XaacB200Error(
+            f"{LIB_PATH} not found: build it with `make lib` (or __graft_entry__.build()). "
+            "libxaac_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def rom_blob(name):
+    with open(os.path.join(ROM_DIR, name), "rb") as f:
+        return f.read()

@@ -1,0 +1,56 @@
+"""Context: one per process/GPU. Owns the device copy of the ROM tables and the host-API staging."""
+import ctypes
+
+from . import _lib
+
+
+class Context:
+    def __init__(self, device=0, imdct_rom=None):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        rc = self._lib.xaac_b200_create(ctypes.byref(self._h), int(device))
+        if rc != 0:
+            self._h = ctypes.c_void_p()
+            raise _lib.XaacB200Error(
+                f"xaac_b200_create(device={device}) failed with 0x{rc & 0xffffffff:08x}: "
+                "a CUDA device is required (no CPU fallback)"
+            )
+        self.device = int(device)
+        self.set_imdct_rom(imdct_rom if imdct_rom is not None else _lib.rom_blob("imdct_rom.bin"))
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    @property
+    def handle(self):
+        return self._h
+
+    def check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.xaac_b200_last_error(self._h)
+            raise _lib.XaacB200Error(f"{what} failed (0x{rc & 0xffffffff:08x}): {msg.decode() if msg else ''}")
+
+    def set_imdct_rom(self, blob):
+        """blob: bytes of the host's ia_aac_dec_imdct_tables_struct (>= 7500 leading bytes)."""
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        self.check(self._lib.xaac_b200_set_imdct_rom(self._h, buf, len(blob)), "xaac_b200_set_imdct_rom")
+
+    @property
+    def num_sms(self):
+        return self._lib.xaac_b200_num_sms(self._h)
+
+    @property
+    def launch_count(self):
+        return self._lib.xaac_b200_launch_count(self._h)
+
+    def sync(self):
+        self.check(self._lib.xaac_b200_sync(self._h), "xaac_b200_sync")
+
+    def close(self):
+        if self._h:
+            self._lib.xaac_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,36 @@
+// kernels.h — internal launch interface between the C-ABI (xaac_b200_api.cu) and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace xb {
+
+// Byte offsets inside the IMDCT ROM blob: the leading 7500 bytes of the reference's
+// ia_aac_dec_imdct_tables_struct (decoder/ixheaacd_aac_rom.h:112-121), which the host passes in
+// exactly as the reference passes `ptr_aac_tables->pstr_imdct_tables` to its own kernels.
+constexpr int kRomCos = 0;             // WORD16 cosine_array_2048_256[514]
+constexpr int kRomDigRevLong = 1028;   // WORD8  dig_rev_table8_long[64]   (octal digit swap; implied by the kernel)
+constexpr int kRomDigRevShort = 1092;  // WORD8  dig_rev_table8_short[8]   (identity)
+constexpr int kRomFftTw = 1100;        // WORD32 fft_twiddle[448]
+constexpr int kRomWinLongSine = 2892;  // WORD16[1024]
+constexpr int kRomWinLongKbd = 4940;   // WORD16[1024]
+constexpr int kRomWinShortSine = 6988; // WORD16[128]
+constexpr int kRomWinShortKbd = 7244;  // WORD16[128]
+constexpr int kRomImdctBytes = 7500;
+
+struct ImdctArgs {
+  const int32_t *spec;   // [n_units][1024] spectral coefficients (read-only; the reference destroys them)
+  int32_t *overlap;      // [n_units][512]  overlap state, in/out
+  uint8_t *wstate;       // [n_units][2]    {window_shape, window_sequence} of the previous frame, in/out
+  const uint8_t *ics;    // [n_units][2]    {window_sequence, window_shape} of this frame
+  int32_t *out;          // WORD32 time samples, 1024 per unit (layout: see ch_fac)
+  int8_t *qshift_adj;    // [n_units]       ia_ics_info_struct.qshift_adj produced by the stage
+  const uint8_t *rom;    // device copy of the IMDCT ROM blob
+  long long n_units;
+  int ch_fac;
+};
+
+size_t imdct_smem_bytes();
+cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
+
+}  // namespace xb

@@ -1,0 +1,189 @@
+// xaac_b200_api.cu — the C-ABI (include/xaac_b200.h) over the sm_100a kernels.
+// No CPU fallback exists anywhere in this library: every entry point needs a CUDA device and reports
+// XAAC_B200_ERR_CUDA otherwise.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <cuda_runtime.h>
+#include "../../include/xaac_b200.h"
+#include "kernels.h"
+
+struct xaac_b200_ctx {
+  int device = 0;
+  int num_sms = 0;
+  long long launches = 0;
+  uint8_t *d_rom_imdct = nullptr;
+  bool have_imdct_rom = false;
+  char err[256] = {0};
+  // staging for the *_host entry points: kPipe chunks in flight, one stream each
+  static constexpr int kPipe = 3;
+  cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
+  void *stage[kPipe] = {nullptr, nullptr, nullptr};
+  size_t stage_bytes = 0;
+};
+
+namespace {
+
+int32_t fail(xaac_b200_ctx *ctx, cudaError_t e, const char *what) {
+  if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+  return XAAC_B200_ERR_CUDA;
+}
+int32_t bad_arg(xaac_b200_ctx *ctx, const char *what) {
+  if (ctx) snprintf(ctx->err, sizeof(ctx->err), "bad argument: %s", what);
+  return XAAC_B200_ERR_ARG;
+}
+#define CK(call, what)                              \
+  do {                                              \
+    cudaError_t e__ = (call);                       \
+    if (e__ != cudaSuccess) return fail(ctx, e__, what); \
+  } while (0)
+
+int32_t ensure_stage(xaac_b200_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->stage_bytes) return XAAC_B200_OK;
+  for (int i = 0; i < xaac_b200_ctx::kPipe; i++) {
+    if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    ctx->stage[i] = nullptr;
+  }
+  ctx->stage_bytes = 0;
+  for (int i = 0; i < xaac_b200_ctx::kPipe; i++) CK(cudaMalloc(&ctx->stage[i], bytes), "cudaMalloc(stage)");
+  ctx->stage_bytes = bytes;
+  return XAAC_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t xaac_b200_create(xaac_b200_ctx **out, int32_t device) {
+  if (!out) return XAAC_B200_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    fprintf(stderr, "xaac_b200_create: no usable CUDA device %d (%s); this library has no CPU fallback\n", device,
+            e == cudaSuccess ? "device index out of range" : cudaGetErrorString(e));
+    return XAAC_B200_ERR_CUDA;
+  }
+  xaac_b200_ctx *ctx = new (std::nothrow) xaac_b200_ctx();
+  if (!ctx) return XAAC_B200_FATAL;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+      cudaMalloc((void **)&ctx->d_rom_imdct, xb::kRomImdctBytes + 64) != cudaSuccess) {
+    delete ctx;
+    return XAAC_B200_ERR_CUDA;
+  }
+  for (int i = 0; i < xaac_b200_ctx::kPipe; i++) {
+    if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess) {
+      xaac_b200_destroy(ctx);
+      return XAAC_B200_ERR_CUDA;
+    }
+  }
+  *out = ctx;
+  return XAAC_B200_OK;
+}
+
+void xaac_b200_destroy(xaac_b200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < xaac_b200_ctx::kPipe; i++) {
+    if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+    if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+  }
+  if (ctx->d_rom_imdct) cudaFree(ctx->d_rom_imdct);
+  delete ctx;
+}
+
+const char *xaac_b200_last_error(const xaac_b200_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+int32_t xaac_b200_num_sms(const xaac_b200_ctx *ctx) { return ctx ? ctx->num_sms : 0; }
+int64_t xaac_b200_launch_count(const xaac_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t xaac_b200_sync(xaac_b200_ctx *ctx) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_set_imdct_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
+  if (!ctx || !tables) return bad_arg(ctx, "null");
+  if (bytes < (size_t)xb::kRomImdctBytes) return bad_arg(ctx, "IMDCT ROM blob shorter than 7500 bytes");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaMemcpy(ctx->d_rom_imdct, tables, xb::kRomImdctBytes, cudaMemcpyHostToDevice), "cudaMemcpy(rom)");
+  ctx->have_imdct_rom = true;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_imdct_process_dev(xaac_b200_ctx *ctx, const int32_t *d_spec, int32_t *d_overlap,
+                                    uint8_t *d_wstate, const uint8_t *d_ics, int32_t *d_out,
+                                    int8_t *d_qshift_adj, int64_t n_units, int32_t ch_fac, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->have_imdct_rom) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_imdct_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0 || ch_fac < 1) return bad_arg(ctx, "n_units/ch_fac");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_spec || !d_overlap || !d_wstate || !d_ics || !d_out || !d_qshift_adj) return bad_arg(ctx, "null buffer");
+  if (ch_fac > 1 && (n_units % ch_fac) != 0) return bad_arg(ctx, "n_units must be a multiple of ch_fac");
+  xb::ImdctArgs a;
+  a.spec = d_spec;
+  a.overlap = d_overlap;
+  a.wstate = d_wstate;
+  a.ics = d_ics;
+  a.out = d_out;
+  a.qshift_adj = d_qshift_adj;
+  a.rom = ctx->d_rom_imdct;
+  a.n_units = n_units;
+  a.ch_fac = ch_fac;
+  CK(xb::launch_imdct(a, ctx->num_sms, (cudaStream_t)stream), "launch imdct_ola_kernel");
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+// Host-buffer entry point: chunks the batch and runs H2D / kernel / D2H of successive chunks on kPipe
+// streams so PCIe and the SMs overlap. Pinned host memory makes the copies truly asynchronous.
+int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, const int32_t *spec, int32_t *overlap, uint8_t *wstate,
+                                     const uint8_t *ics, int32_t *out, int8_t *qshift_adj, int64_t n_units,
+                                     int32_t ch_fac) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (n_units < 0 || ch_fac < 1) return bad_arg(ctx, "n_units/ch_fac");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!spec || !overlap || !wstate || !ics || !out || !qshift_adj) return bad_arg(ctx, "null buffer");
+  if (ch_fac > 1 && (n_units % ch_fac) != 0) return bad_arg(ctx, "n_units must be a multiple of ch_fac");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int64_t chunk = 8192;
+  if (chunk > n_units) chunk = n_units;
+  if (ch_fac > 1) chunk = ((chunk + ch_fac - 1) / ch_fac) * ch_fac;
+  // per-unit staging layout: spec 4096 | out 4096 | overlap 2048 | wstate 2 | ics 2 | qadj 1 (+pad)
+  const size_t per_unit = 4096 + 4096 + 2048 + 16;
+  int32_t rc = ensure_stage(ctx, per_unit * (size_t)chunk);
+  if (rc != XAAC_B200_OK) return rc;
+  int slot = 0;
+  for (int64_t u0 = 0; u0 < n_units; u0 += chunk, slot = (slot + 1) % xaac_b200_ctx::kPipe) {
+    int64_t n = (n_units - u0 < chunk) ? (n_units - u0) : chunk;
+    cudaStream_t st = ctx->streams[slot];
+    uint8_t *base = (uint8_t *)ctx->stage[slot];
+    int32_t *d_spec = (int32_t *)base;
+    int32_t *d_out = (int32_t *)(base + 4096 * (size_t)chunk);
+    int32_t *d_ovl = (int32_t *)(base + 8192 * (size_t)chunk);
+    uint8_t *d_ws = base + 10240 * (size_t)chunk;
+    uint8_t *d_ics = d_ws + 4 * (size_t)chunk;
+    int8_t *d_qa = (int8_t *)(d_ws + 8 * (size_t)chunk);
+    CK(cudaMemcpyAsync(d_spec, spec + u0 * 1024, (size_t)n * 4096, cudaMemcpyHostToDevice, st), "H2D spec");
+    CK(cudaMemcpyAsync(d_ovl, overlap + u0 * 512, (size_t)n * 2048, cudaMemcpyHostToDevice, st), "H2D overlap");
+    CK(cudaMemcpyAsync(d_ws, wstate + u0 * 2, (size_t)n * 2, cudaMemcpyHostToDevice, st), "H2D wstate");
+    CK(cudaMemcpyAsync(d_ics, ics + u0 * 2, (size_t)n * 2, cudaMemcpyHostToDevice, st), "H2D ics");
+    rc = xaac_b200_imdct_process_dev(ctx, d_spec, d_ovl, d_ws, d_ics, d_out, d_qa, n, ch_fac, st);
+    if (rc != XAAC_B200_OK) return rc;
+    CK(cudaMemcpyAsync(out + u0 * 1024, d_out, (size_t)n * 4096, cudaMemcpyDeviceToHost, st), "D2H out");
+    CK(cudaMemcpyAsync(overlap + u0 * 512, d_ovl, (size_t)n * 2048, cudaMemcpyDeviceToHost, st), "D2H overlap");
+    CK(cudaMemcpyAsync(wstate + u0 * 2, d_ws, (size_t)n * 2, cudaMemcpyDeviceToHost, st), "D2H wstate");
+    CK(cudaMemcpyAsync(qshift_adj + u0, d_qa, (size_t)n, cudaMemcpyDeviceToHost, st), "D2H qshift_adj");
+  }
+  for (int i = 0; i < xaac_b200_ctx::kPipe; i++) CK(cudaStreamSynchronize(ctx->streams[i]), "stream sync");
+  return XAAC_B200_OK;
+}
+
+}  // extern "C"

@@ -9,63 +9,7 @@
  *
  * Every function states which reference function it drives (file:line in /root/reference).
  */
-#include <string.h>
-#include <stdlib.h>
-#include <stdint.h>
-#include "ixheaacd_sbr_common.h"
-#include "ixheaac_type_def.h"
-#include "ixheaac_constants.h"
-#include "ixheaac_basic_ops32.h"
-#include "ixheaac_basic_ops16.h"
-#include "ixheaac_basic_ops40.h"
-#include "ixheaac_basic_ops.h"
-#include "ixheaacd_bitbuffer.h"
-#include "ixheaac_basic_op.h"
-#include "ixheaacd_intrinsics.h"
-#include "ixheaacd_defines.h"
-#include "ixheaacd_aac_rom.h"
-#include "ixheaacd_definitions.h"
-#include "ixheaacd_error_codes.h"
-#include "ixheaacd_pulsedata.h"
-#include "ixheaacd_pns.h"
-#include "ixheaacd_drc_data_struct.h"
-#include "ixheaacd_lt_predict.h"
-#include "ixheaacd_cnst.h"
-#include "ixheaacd_ec_defines.h"
-#include "ixheaacd_ec_struct_def.h"
-#include "ixheaacd_channelinfo.h"
-#include "ixheaacd_drc_dec.h"
-#include "ixheaacd_sbrdecoder.h"
-#include "ixheaacd_block.h"
-#include "ixheaacd_channel.h"
-#include "ixheaacd_sbr_payload.h"
-#include "ixheaacd_common_rom.h"
-#include "ixheaacd_sbrdecsettings.h"
-#include "ixheaacd_sbr_scale.h"
-#include "ixheaacd_env_extr_part.h"
-#include "ixheaacd_sbr_rom.h"
-#include "ixheaacd_lpp_tran.h"
-#include "ixheaacd_hybrid.h"
-#include "ixheaacd_ps_dec.h"
-#include "ixheaacd_env_extr.h"
-#include "ixheaacd_adts.h"
-#include "ixheaacd_audioobjtypes.h"
-#include "ixheaacd_memory_standards.h"
-#include "ixheaacd_latmdemux.h"
-#include "ixheaacd_qmf_dec.h"
-#include "ixheaacd_aacdec.h"
-#include "ixheaacd_mps_polyphase.h"
-#include "ixheaacd_config.h"
-#include "ixheaacd_mps_macro_def.h"
-#include "ixheaacd_mps_struct_def.h"
-#include "ixheaacd_mps_res_rom.h"
-#include "ixheaacd_mps_aac_struct.h"
-#include "ixheaacd_mps_dec.h"
-#include "ixheaacd_struct_def.h"
-#include "ixheaacd_tns.h"
-#include "ixheaacd_aac_imdct.h"
-#include "ixheaacd_multichannel.h"
-#include "ixheaacd_function_selector.h"
+#include "ref_headers.h"
 
 /* ------------------------------------------------------------------------------------------------
  * ROM access: lets tools/extract_rom.py and the tests read the reference's const tables.

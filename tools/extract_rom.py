@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Extract the ISO/IEC 14496-3 constant tables the hot path consumes from the compiled reference.
+
+The reference passes its ROM tables to every hot function as pointer arguments; a drop-in
+deployment does the same through xaac_b200_set_*_rom().  For standalone use (tests, bench, GPU box — where
+/root/reference does not exist) the same bytes are kept as small binary blobs under libxaac_b200/rom/.
+This script regenerates them from oracle/_ref/libxaac_ref.so (built by `make ref`); it is the only producer
+of those blobs.  Run:  python tools/extract_rom.py
+"""
+import ctypes
+import hashlib
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libxaac_ref.so")
+OUT = os.path.join(ROOT, "libxaac_b200", "rom")
+
+
+def dump(lib, getter, nbytes, name):
+    fn = getattr(lib, getter)
+    fn.restype = ctypes.c_void_p
+    total = ctypes.c_int(0)
+    p = fn(ctypes.byref(total))
+    assert total.value >= nbytes, (getter, total.value, nbytes)
+    data = ctypes.string_at(p, nbytes)
+    path = os.path.join(OUT, name)
+    with open(path, "wb") as f:
+        f.write(data)
+    print(f"{name}: {nbytes} bytes sha256={hashlib.sha256(data).hexdigest()[:16]}")
+
+
+def main():
+    lib = ctypes.CDLL(REF)
+    os.makedirs(OUT, exist_ok=True)
+    # leading part of ia_aac_dec_imdct_tables_struct (decoder/ixheaacd_aac_rom.h:112-121)
+    dump(lib, "ref_rom_imdct_tables", 7500, "imdct_rom.bin")
+    for getter, n, name in EXTRA:
+        dump(lib, getter, n, name)
+
+
+EXTRA = []
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED compiled reference.
+
+Pipeline (all binaries come from `make ref`, i.e. gcc on the sources where they lie in /root/reference):
+  synthetic WAV (numpy)  ->  oracle/_ref/xaacenc (reference encoder)  ->  bitstream
+  bitstream              ->  oracle/_ref/xaacdec_tap (reference decoder + ld --wrap stage taps, oracle/ref_taps.c)
+                         ->  per-call records (inputs, state-before, outputs, state-after)
+  records                ->  tests/golden/*.npz (a small, window-sequence-balanced selection)
+
+The reference ships no golden vectors for this path; these fixtures are what pins the oracle and
+the CUDA kernels on the GPU box, where /root/reference does not exist.  Run: python tools/make_golden.py
+"""
+import os
+import subprocess
+import sys
+import tempfile
+import wave
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def synth(fs, seconds, channels, seed):
+    """Tonal + noise + click bursts + silence + full-scale segment: exercises long, start/stop and short blocks."""
+    rng = np.random.default_rng(seed)
+    n = int(fs * seconds)
+    t = np.arange(n) / fs
+    x = 0.35 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 3520 * t + 1.0)
+    x += 0.05 * rng.standard_normal(n)
+    # castanet-like clicks every ~0.37 s force block switching
+    for k in range(int(seconds / 0.37)):
+        p = int((0.2 + 0.37 * k) * fs)
+        ln = min(300, n - p)
+        if ln > 0:
+            x[p:p + ln] += 0.9 * rng.standard_normal(ln) * np.exp(-np.arange(ln) / 40.0)
+    x[int(0.45 * n):int(0.5 * n)] = 0.0  # silence
+    seg = slice(int(0.8 * n), int(0.85 * n))
+    x[seg] = np.sign(np.sin(2 * np.pi * 1000 * t[seg]))  # full-scale square
+    x = np.clip(x, -1.0, 1.0)
+    chans = [x]
+    if channels == 2:
+        y = np.roll(x, 37) * 0.8 + 0.1 * np.sin(2 * np.pi * 997 * t)
+        chans.append(np.clip(y, -1, 1))
+    pcm = (np.stack(chans, axis=1) * 32767.0).astype(np.int16)
+    return pcm
+
+
+def write_wav(path, pcm, fs):
+    with wave.open(path, "wb") as w:
+        w.setnchannels(pcm.shape[1])
+        w.setsampwidth(2)
+        w.setframerate(fs)
+        w.writeframes(pcm.tobytes())
+
+
+def run(cmd, env=None):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout.decode(errors="replace")[-2000:])
+        raise RuntimeError("command failed: " + " ".join(cmd))
+    return r.stdout.decode(errors="replace")
+
+
+def encode(wav, out, aot, br, extra=()):
+    run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{out}", f"-aot:{aot}", "-adts:1", f"-br:{br}", *extra])
+
+
+def decode_tap(bitstream, wav_out, tapfile, dec_args=(), tap_max=100000):
+    env = dict(os.environ, XAAC_TAP_FILE=tapfile, XAAC_TAP_MAX=str(tap_max))
+    run([os.path.join(REFDIR, "xaacdec_tap"), f"-ifile:{bitstream}", f"-ofile:{wav_out}", *dec_args], env=env)
+
+
+def read_imdct_records(path):
+    recs = []
+    rec_words = 9 + 1024 + 512 + 1024 + 512
+    raw = np.fromfile(path, dtype=np.int32)
+    assert raw.size % rec_words == 0, (raw.size, rec_words)
+    raw = raw.reshape(-1, rec_words)
+    for r in raw:
+        assert r[0] == 0x31444D49
+        recs.append(dict(hdr=r[1:9].copy(), spec=r[9:1033].copy(), ovl_in=r[1033:1545].copy(),
+                         out=r[1545:2569].copy(), ovl_out=r[2569:3081].copy()))
+    return recs
+
+
+def select_balanced(recs, per_class):
+    """keep up to per_class records for every (prev_seq, win_seq) transition that occurs."""
+    buckets = {}
+    for i, r in enumerate(recs):
+        key = (int(r["hdr"][4]), int(r["hdr"][5]))
+        buckets.setdefault(key, []).append(i)
+    keep = []
+    for key, idx in sorted(buckets.items()):
+        step = max(1, len(idx) // per_class)
+        keep += idx[::step][:per_class]
+    return sorted(keep), {k: len(v) for k, v in buckets.items()}
+
+
+def make_imdct_golden(tmp):
+    out = {}
+    all_recs = []
+    for fs, ch, seed, br in ((48000, 1, 11, 64000), (44100, 2, 12, 128000)):
+        wav = os.path.join(tmp, f"in_{fs}_{ch}.wav")
+        write_wav(wav, synth(fs, 6.0, ch, seed), fs)
+        aac = os.path.join(tmp, f"lc_{fs}_{ch}.aac")
+        encode(wav, aac, 2, br)
+        tap = os.path.join(tmp, f"lc_{fs}_{ch}.tap")
+        decode_tap(aac, os.path.join(tmp, "o.wav"), tap, ["-peak_limiter_off:1"])
+        recs = read_imdct_records(tap)
+        print(f"AAC-LC {fs} Hz {ch}ch: {len(recs)} imdct_process calls tapped")
+        all_recs += recs
+    keep, hist = select_balanced(all_recs, 6)
+    print("transition histogram (prev_seq, win_seq):", hist)
+    sel = [all_recs[i] for i in keep]
+    # config 1 of BASELINE.json ("AAC-LC mono 48 kHz long-block: 1024-pt IMDCT + sine-window OLA, 1 frame on the
+    # reference CPU path").  The reference encoder always signals KBD for long blocks, so the sine-window case is
+    # produced by re-running the compiled reference stage (ref_imdct_process -> ixheaacd_imdct_process) on a tapped
+    # mono 48 kHz long->long frame's own spectrum and overlap with window_shape forced to sine.
+    import ctypes
+    ref = ctypes.CDLL(os.path.join(REFDIR, "libxaac_ref.so"))
+    src = next(r for r in all_recs if r["hdr"][2] == 1 and r["hdr"][4] == 0 and r["hdr"][5] == 0
+               and np.abs(r["spec"].astype(np.int64)).max() > 1 << 20)
+    spec = src["spec"].copy()
+    ovl = src["ovl_in"].copy()
+    o = np.zeros(1024, np.int32)
+    ps, pq = ctypes.c_int32(0), ctypes.c_int32(0)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    adj = ref.ref_imdct_process(P(spec), P(ovl), ctypes.byref(ps), ctypes.byref(pq), 0, 0, P(o), 1)
+    first = dict(hdr=np.array([1024, 2, 1, 0, 0, 0, 0, adj], np.int32), spec=src["spec"].copy(),
+                 ovl_in=src["ovl_in"].copy(), out=o, ovl_out=ovl)
+    sel = [first] + sel
+    # hdr columns: frame_length, aot, ch_fac, prev_shape, prev_seq, win_seq, win_shape, qshift_adj
+    out["hdr"] = np.stack([r["hdr"] for r in sel]).astype(np.int32)
+    for k in ("spec", "ovl_in", "out", "ovl_out"):
+        out[k] = np.stack([r[k] for r in sel]).astype(np.int32)
+    path = os.path.join(GOLD, "imdct_tapped.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(sel)} records, {os.path.getsize(path)} bytes")
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        make_imdct_golden(tmp)
+
+
+if __name__ == "__main__":
+    main()
