@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the libxaac decode-side DSP hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's own generic-C path on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic pre-parsed frames (one frame for every stream
+of the batch, state carried from step to step like consecutive frames of a stream).  One JSON line is printed by
+rank 0.  `value` is device-resident throughput, `e2e` goes through the host-buffer C-ABI call with pinned host
+buffers (H2D + kernel + D2H inside the timed region).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMDCT_BYTES_PER_UNIT = 12288  # 4096 spec in + 2048 overlap in + 2048 overlap out + 4096 WORD32 out
+WORKLOADS = {
+    # name -> (BASELINE.json config index, stereo frames per GPU, description)
+    "aac_lc_stereo_imdct_ola": (1, 65536, "AAC-LC stereo 44.1 kHz batch=65536 frames, IMDCT+OLA only"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic pre-parsed batch: per-unit magnitude 2^12..2^27, corner units, window-sequence walk
+# ---------------------------------------------------------------------------------------------------------
+def sequence_walk(n_units, n_steps, seed):
+    """ics[step][unit] = (window_sequence, window_shape): legal AAC block-switching walk with ~90 % long->long,
+    4 % start, 4 % stop, 2 % short in the stationary mix; both channels of a frame share the sequence."""
+    rng = np.random.default_rng(seed)
+    n_frames = n_units // 2
+    prev = np.zeros(n_frames, np.uint8)
+    out = np.zeros((n_steps, n_units, 2), np.uint8)
+    for s in range(n_steps):
+        r = rng.random(n_frames)
+        nxt = np.zeros(n_frames, np.uint8)
+        longish = (prev == 0) | (prev == 3)
+        nxt[longish & (r < 0.045)] = 1                 # long -> start
+        shortish = ~longish
+        nxt[shortish] = np.where(r[shortish] < 0.33, 2, 3)  # start/short -> short | stop
+        shape = (rng.random(n_frames) < 0.9).astype(np.uint8)  # the reference encoder signals KBD for most frames
+        out[s, 0::2, 0] = nxt
+        out[s, 1::2, 0] = nxt
+        out[s, 0::2, 1] = shape
+        out[s, 1::2, 1] = shape
+        prev = nxt
+    return out
+
+
+def make_spec_torch(n_units, seed, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    s = torch.randint(12, 28, (n_units, 1), generator=g, device=device, dtype=torch.int32)
+    spec = torch.empty((n_units, 1024), dtype=torch.int32, device=device)
+    chunk = 16384
+    for i in range(0, n_units, chunk):
+        r = torch.randint(-(2 ** 31), 2 ** 31 - 1, (min(chunk, n_units - i), 1024), generator=g, device=device,
+                          dtype=torch.int64).to(torch.int32)
+        spec[i:i + chunk] = r >> (31 - s[i:i + chunk])
+    # corner units: silence, alternating full scale, impulse, DC
+    spec[0] = 0
+    spec[1] = torch.where(torch.arange(1024, device=device) % 2 == 0, 2 ** 31 - 1, -(2 ** 31)).to(torch.int32)
+    spec[2] = 0
+    spec[2, 17] = 2 ** 31 - 1
+    spec[3] = 1 << 20
+    return spec
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own generic-C stage (oracle/_ref) or, if that was not built, our C port (oracle/)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_arm(n_units, threads, seed, reps=1):
+    """Time ixheaacd_imdct_process on `n_units` units spread over `threads` host threads (one private state per
+    unit; the 1024-sample path touches no global scratch). Returns (units_per_s, kind)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    rng = np.random.default_rng(seed)
+    s = rng.integers(12, 28, size=(n_units, 1))
+    spec0 = ((rng.random((n_units, 1024)) * 2 - 1) * (2.0 ** s)).astype(np.int64).astype(np.int32)
+    walk = sequence_walk(n_units, reps + 1, seed)
+    P = oracle_util.P
+    if ref is not None:
+        kind, lib = "reference", ref.lib
+        fn = lib.ref_imdct_process_batch
+    else:
+        kind = "port"
+        orc = oracle_util.Oracle()
+        lib, rom = orc.lib, orc.rom
+        fn = lib.xo_imdct_process_batch
+    ovl = np.zeros((n_units, 512), np.int32)
+    pshape = np.zeros(n_units, np.int32)
+    pseq = np.zeros(n_units, np.int32)
+    out = np.zeros((n_units, 1024), np.int32)
+    adj = np.zeros(n_units, np.int32)
+    bounds = np.linspace(0, n_units, threads + 1).astype(int)
+
+    def work(t, step, spec):
+        a, b = bounds[t], bounds[t + 1]
+        if b <= a:
+            return
+        ws = np.ascontiguousarray(walk[step, a:b, 0], np.int32)
+        wh = np.ascontiguousarray(walk[step, a:b, 1], np.int32)
+        args = [P(spec[a:b]), P(ovl[a:b]), P(pshape[a:b]), P(pseq[a:b]), P(ws), P(wh), P(out[a:b]), P(adj[a:b]),
+                int(b - a)]
+        if kind == "port":
+            args = [P(rom)] + args
+        fn(*args)
+
+    def one_pass(step):
+        spec = spec0.copy()  # the reference destroys its input spectrum
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t, step, spec)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    one_pass(0)  # warm-up (page faults, caches)
+    dt = sum(one_pass(1 + r) for r in range(reps))
+    return n_units * reps / dt, kind
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = host_threads()
+    cfg_idx, frames, desc = WORKLOADS[args.workload]
+    sample_units = min(2 * frames, 4096 * cores)
+    sample_units -= sample_units % 2
+    t0 = time.perf_counter()
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_arm(sample_units, cores, 0xAAC0 + cfg_idx, reps=1)
+    ups, kind = cpu_arm(sample_units, cores, 0xAAC0 + cfg_idx, reps=max(1, args.steps))
+    fps = ups / 2.0
+    line = {
+        "impl": "reference", "metric": "decoded_stereo_frames_per_sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (sample_units / 2) / fps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload, "baseline_config": desc, "stage": "ixheaacd_imdct_process",
+                   "step": f"bounded sample: {sample_units // 2} stereo frames per step on host cores"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample_units} units (frame x channel) x {max(1, args.steps)} passes, "
+                                   f"{cores} threads, private state per unit"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="aac_lc_stereo_imdct_ola", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="stereo frames per GPU (default: the config's batch)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps for the host-buffer arm (default min(steps,5))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import libxaac_b200 as xb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg_idx, frames, desc = WORKLOADS[args.workload]
+    if args.frames:
+        frames = args.frames
+    n_units = 2 * frames  # stereo: two core channels per frame; each rank owns its own streams (weak scaling)
+    K, W = args.steps, args.warmup
+    seed = 0xAAC0 + cfg_idx + 1000 * rank
+
+    ctx = xb.Context(local_rank)
+    spec = make_spec_torch(n_units, seed, dev)
+    walk = torch.from_numpy(sequence_walk(n_units, W + K, seed)).to(dev)
+    state = xb.ImdctBatch(n_units, device=dev)
+    out = torch.empty((n_units, 1024), dtype=torch.int32, device=dev)
+    adj = torch.empty((n_units,), dtype=torch.int8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident arm --------------------------------------------------------------------------
+    for s in range(W):
+        xb.imdct_process(ctx, state, spec, walk[s], out, adj, stream=stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record(stream)
+    for s in range(K):
+        xb.imdct_process(ctx, state, spec, walk[W + s], out, adj, stream=stream)
+        ev[s + 1].record(stream)
+    barrier()
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    total_ms = ev[0].elapsed_time(ev[K])
+    gpu_launches = ctx.launch_count - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * frames * K / (total_ms_max * 1e-3)
+    kernel_ms = float(np.mean(step_ms))  # one kernel launch per step: step time == launch duration
+
+    # ---- end-to-end arm: host buffers through the C-ABI ---------------------------------------------------
+    Ke = args.e2e_steps or min(K, 5)
+    h_spec = torch.empty((n_units, 1024), dtype=torch.int32).pin_memory()
+    h_spec.copy_(spec)
+    h_out = torch.empty((n_units, 1024), dtype=torch.int32).pin_memory()
+    h_adj = torch.empty((n_units,), dtype=torch.int8).pin_memory()
+    h_walk = walk.cpu().pin_memory()
+    hstate = xb.ImdctHostState(ctx, n_units)
+    xb.imdct_process_host(ctx, hstate, h_spec, h_walk[0], h_out, h_adj)  # warm-up (staging allocation)
+    xb.imdct_process_host(ctx, hstate, h_spec, h_walk[1], h_out, h_adj)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        xb.imdct_process_host(ctx, hstate, h_spec, h_walk[(2 + s) % (W + K)], h_out, h_adj)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * frames * Ke / float(te.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = IMDCT_BYTES_PER_UNIT * n_units / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": "decoded_stereo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.workload, "baseline_config": desc, "stereo_frames_per_gpu": frames,
+                       "units_per_gpu": n_units, "stage": "IMDCT + window/OLA (fixed-point WORD32, bit-exact)",
+                       "window_sequence_mix": "walk: ~90% long, 4% start, 4% stop, 2% short",
+                       "l2_policy": "per-step working set 1.25 GiB >> 126 MB L2 (no flush needed)",
+                       "realtime_x_per_stream": value / world / frames * frames / 43.066 / frames},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_units * (4096 + 2),
+                    "d2h_bytes_per_step": n_units * (4096 + 1), "steps": Ke,
+                    "timer": "host wall clock around the synchronous xaac_b200_imdct_process_host call"},
+            "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "hbm", "kernel": "imdct_ola_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_unit": IMDCT_BYTES_PER_UNIT, "units_per_launch": n_units,
+                         "launch_ms": kernel_ms},
+        }
+        line["config"]["realtime_x_per_stream"] = (value / world) / frames / 43.066 if frames else None
+        if not args.no_cpu_baseline and world == 1:
+            cores = host_threads()
+            ups1, kind = cpu_arm(8192, 1, 0xAAC0 + cfg_idx, reps=1)
+            upsN, kind = cpu_arm(4096 * cores, cores, 0xAAC0 + cfg_idx, reps=2)
+            line["cpu_baseline"] = {"value": upsN / 2.0, "unit": "frames/s", "cores": cores, "kind": kind,
+                                    "value_1core": ups1 / 2.0,
+                                    "sample": f"{4096 * cores} units x 2 passes on {cores} threads "
+                                              f"(1-core figure: 8192 units), ixheaacd_imdct_process per unit"}
+        print(json.dumps(line), flush=True)
+    hstate.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -72,9 +72,24 @@ int32_t xaac_b200_set_imdct_rom(xaac_b200_ctx *ctx, const void *tables, size_t b
 int32_t xaac_b200_imdct_process_dev(xaac_b200_ctx *ctx, const int32_t *d_spec, int32_t *d_overlap,
                                     uint8_t *d_wstate, const uint8_t *d_ics, int32_t *d_out,
                                     int8_t *d_qshift_adj, int64_t n_units, int32_t ch_fac, void *stream);
-int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, const int32_t *spec, int32_t *overlap,
-                                     uint8_t *wstate, const uint8_t *ics, int32_t *out, int8_t *qshift_adj,
-                                     int64_t n_units, int32_t ch_fac);
+
+/* Device-resident per-unit state of the stage (what ia_aac_dec_overlap_info carries from frame to frame:
+ * ptr_overlap_buf[512], window_shape, window_sequence; decoder/ixheaacd_channelinfo.h:88-93).  A stream's state
+ * stays in HBM between frames; upload/download are the checkpoint/resume path. A new state is the decoder's
+ * reset state: zero overlap, sine window, ONLY_LONG_SEQUENCE. */
+typedef struct xaac_b200_imdct_state xaac_b200_imdct_state;
+int32_t xaac_b200_imdct_state_create(xaac_b200_ctx *ctx, int64_t n_units, xaac_b200_imdct_state **state);
+void xaac_b200_imdct_state_destroy(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state);
+int32_t xaac_b200_imdct_state_upload(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, const int32_t *overlap,
+                                     const uint8_t *wstate);
+int32_t xaac_b200_imdct_state_download(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, int32_t *overlap,
+                                       uint8_t *wstate);
+
+/* Host-buffer entry point: one frame for every unit of `state`.  spec/ics are read from host memory, out and
+ * qshift_adj are written to host memory; the batch is chunked and copies overlap with the kernel on internal
+ * streams (pinned host memory recommended).  Returns after everything has completed. */
+int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, const int32_t *spec,
+                                     const uint8_t *ics, int32_t *out, int8_t *qshift_adj, int32_t ch_fac);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ from .imdct import (  # noqa: F401
     EIGHT_SHORT_SEQUENCE,
     LONG_STOP_SEQUENCE,
     ImdctBatch,
+    ImdctHostState,
     imdct_process,
     imdct_process_host,
 )
@@ -18,6 +19,7 @@ from .imdct import (  # noqa: F401
 __all__ = [
     "Context",
     "ImdctBatch",
+    "ImdctHostState",
     "imdct_process",
     "imdct_process_host",
     "XaacB200Error",

@@ -25,7 +25,11 @@ SIGNATURES = {
     "xaac_b200_sync": (_i32, [_vp]),
     "xaac_b200_set_imdct_rom": (_i32, [_vp, _vp, _sz]),
     "xaac_b200_imdct_process_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "xaac_b200_imdct_process_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32]),
+    "xaac_b200_imdct_state_create": (_i32, [_vp, _i64, _c.POINTER(_vp)]),
+    "xaac_b200_imdct_state_destroy": (None, [_vp, _vp]),
+    "xaac_b200_imdct_state_upload": (_i32, [_vp, _vp, _vp, _vp]),
+    "xaac_b200_imdct_state_download": (_i32, [_vp, _vp, _vp, _vp]),
+    "xaac_b200_imdct_process_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32]),
 }
 
 _lib = None

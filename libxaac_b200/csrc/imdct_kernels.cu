@@ -251,16 +251,19 @@ imdct_ola_kernel(ImdctArgs p) {
   const unsigned full = 0xffffffffu;
 
   {  // block-shared ROM: cos/sin pairs and FFT twiddles
-    const i32 *cs_g = reinterpret_cast<const i32 *>(p.rom + kRomCos);
-    const i32 *tw_g = reinterpret_cast<const i32 *>(p.rom + kRomFftTw);
+    const i32 *cs_g = reinterpret_cast<const i32 *>(p.rom + kDevCos);
+    const i32 *tw_g = reinterpret_cast<const i32 *>(p.rom + kDevFftTw);
     for (int i = threadIdx.x; i < 257; i += blockDim.x) sm.cs[i] = cs_g[i];
     for (int i = threadIdx.x; i < 448; i += blockDim.x) sm.tw[i] = tw_g[i];
   }
   __syncthreads();
-  const i16 *win_long[2] = {reinterpret_cast<const i16 *>(p.rom + kRomWinLongSine),
-                            reinterpret_cast<const i16 *>(p.rom + kRomWinLongKbd)};
-  const i16 *win_short[2] = {reinterpret_cast<const i16 *>(p.rom + kRomWinShortSine),
-                             reinterpret_cast<const i16 *>(p.rom + kRomWinShortKbd)};
+  // window tables stay in global memory (L1/L2 resident, read-only path); shape 0 = sine, 1 = KBD
+  auto win_long = [&](int shape) {
+    return reinterpret_cast<const i16 *>(p.rom + kDevWinLongSine + shape * (kDevWinLongKbd - kDevWinLongSine));
+  };
+  auto win_short = [&](int shape) {
+    return reinterpret_cast<const i16 *>(p.rom + kDevWinShortSine + shape * (kDevWinShortKbd - kDevWinShortSine));
+  };
 
   int2 *X = sm.w[warp].X;
   int2 *Y = sm.w[warp].Y;
@@ -373,7 +376,7 @@ imdct_ola_kernel(ImdctArgs p) {
       const i32 adj_hi = 50 << 16;
       if (win_seq == kSeqOnlyLong && prev_longish) {
         // ---- fused post-twiddle + window + OLA (aac_imdct.c:506-832) ----
-        const i16 *win = win_long[prev_shape];
+        const i16 *win = win_long(prev_shape);
         const int2 *win4 = reinterpret_cast<const int2 *>(win);
         int2 *ovl2 = reinterpret_cast<int2 *>(ovl_g);
 #pragma unroll 4
@@ -435,8 +438,8 @@ imdct_ola_kernel(ImdctArgs p) {
         __syncwarp();
         for (int i = lane; i < 512; i += 32) P[i] = ovl_g[i];
         __syncwarp();
-        const i16 *wl = win_long[prev_shape];
-        const i16 *wsp = win_short[prev_shape];
+        const i16 *wl = win_long(prev_shape);
+        const i16 *wsp = win_short(prev_shape);
         const int s1 = 64, s7 = 448, s8 = 512, s9 = 576, s14 = 896;
         if (win_seq == kSeqOnlyLong) {  // previous was start/short (lpfuncs.c:489-521)
           process_win_seq(T, P, out_g, wl, wsp, q_shift, ch_fac, 1, lane);
@@ -545,9 +548,9 @@ imdct_ola_kernel(ImdctArgs p) {
       __syncwarp();
       for (int i = lane; i < 512; i += 32) P[i] = ovl_g[i];
       __syncwarp();
-      const i16 *sw = win_short[win_shape];
-      const i16 *wsp = win_short[prev_shape];
-      const i16 *wl = win_long[prev_shape];
+      const i16 *sw = win_short(win_shape);
+      const i16 *wsp = win_short(prev_shape);
+      const i16 *wl = win_long(prev_shape);
       const int s1 = 64, s2 = 128, s6 = 384, s7 = 448, s8 = 512, s9 = 576, s10 = 640, s14 = 896, s15 = 960;
       if (!prev_longish) {
         for (int i = lane; i < s7; i += 32) out_g[ch_fac * i] = shl32_sat(sext16(P[i]), 15);

@@ -18,6 +18,16 @@ constexpr int kRomWinShortSine = 6988; // WORD16[128]
 constexpr int kRomWinShortKbd = 7244;  // WORD16[128]
 constexpr int kRomImdctBytes = 7500;
 
+// Device-side layout of the same tables (re-packed by xaac_b200_set_imdct_rom so that every table is 16-byte
+// aligned for vector loads; the digit-reverse tables are not needed on the device).
+constexpr int kDevCos = 0;              // 1028 B -> padded to 1040
+constexpr int kDevFftTw = 1040;         // 1792 B
+constexpr int kDevWinLongSine = 2832;   // 2048 B
+constexpr int kDevWinLongKbd = 4880;    // 2048 B
+constexpr int kDevWinShortSine = 6928;  // 256 B
+constexpr int kDevWinShortKbd = 7184;   // 256 B
+constexpr int kDevImdctBytes = 7440;
+
 struct ImdctArgs {
   const int32_t *spec;   // [n_units][1024] spectral coefficients (read-only; the reference destroys them)
   int32_t *overlap;      // [n_units][512]  overlap state, in/out
@@ -25,7 +35,7 @@ struct ImdctArgs {
   const uint8_t *ics;    // [n_units][2]    {window_sequence, window_shape} of this frame
   int32_t *out;          // WORD32 time samples, 1024 per unit (layout: see ch_fac)
   int8_t *qshift_adj;    // [n_units]       ia_ics_info_struct.qshift_adj produced by the stage
-  const uint8_t *rom;    // device copy of the IMDCT ROM blob
+  const uint8_t *rom;    // device copy of the IMDCT tables in the kDev* layout
   long long n_units;
   int ch_fac;
 };

@@ -23,6 +23,12 @@ struct xaac_b200_ctx {
   size_t stage_bytes = 0;
 };
 
+struct xaac_b200_imdct_state {
+  int64_t n_units = 0;
+  int32_t *d_overlap = nullptr;  // [n][512]
+  uint8_t *d_wstate = nullptr;   // [n][2] {window_shape, window_sequence}
+};
+
 namespace {
 
 int32_t fail(xaac_b200_ctx *ctx, cudaError_t e, const char *what) {
@@ -110,7 +116,17 @@ int32_t xaac_b200_set_imdct_rom(xaac_b200_ctx *ctx, const void *tables, size_t b
   if (!ctx || !tables) return bad_arg(ctx, "null");
   if (bytes < (size_t)xb::kRomImdctBytes) return bad_arg(ctx, "IMDCT ROM blob shorter than 7500 bytes");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-  CK(cudaMemcpy(ctx->d_rom_imdct, tables, xb::kRomImdctBytes, cudaMemcpyHostToDevice), "cudaMemcpy(rom)");
+  // re-pack into the aligned device layout (kernels.h kDev*)
+  uint8_t packed[xb::kDevImdctBytes];
+  memset(packed, 0, sizeof(packed));
+  const uint8_t *src = (const uint8_t *)tables;
+  memcpy(packed + xb::kDevCos, src + xb::kRomCos, 1028);
+  memcpy(packed + xb::kDevFftTw, src + xb::kRomFftTw, 1792);
+  memcpy(packed + xb::kDevWinLongSine, src + xb::kRomWinLongSine, 2048);
+  memcpy(packed + xb::kDevWinLongKbd, src + xb::kRomWinLongKbd, 2048);
+  memcpy(packed + xb::kDevWinShortSine, src + xb::kRomWinShortSine, 256);
+  memcpy(packed + xb::kDevWinShortKbd, src + xb::kRomWinShortKbd, 256);
+  CK(cudaMemcpy(ctx->d_rom_imdct, packed, sizeof(packed), cudaMemcpyHostToDevice), "cudaMemcpy(rom)");
   ctx->have_imdct_rom = true;
   return XAAC_B200_OK;
 }
@@ -142,22 +158,69 @@ int32_t xaac_b200_imdct_process_dev(xaac_b200_ctx *ctx, const int32_t *d_spec, i
   return XAAC_B200_OK;
 }
 
+int32_t xaac_b200_imdct_state_create(xaac_b200_ctx *ctx, int64_t n_units, xaac_b200_imdct_state **out) {
+  if (!ctx || !out || n_units < 0) return bad_arg(ctx, "state_create");
+  *out = nullptr;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  xaac_b200_imdct_state *st = new (std::nothrow) xaac_b200_imdct_state();
+  if (!st) return XAAC_B200_FATAL;
+  st->n_units = n_units;
+  size_t n = (size_t)(n_units > 0 ? n_units : 1);
+  cudaError_t e = cudaMalloc((void **)&st->d_overlap, n * 2048);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_wstate, n * 2);
+  if (e == cudaSuccess) e = cudaMemset(st->d_overlap, 0, n * 2048);
+  if (e == cudaSuccess) e = cudaMemset(st->d_wstate, 0, n * 2);
+  if (e != cudaSuccess) {
+    xaac_b200_imdct_state_destroy(ctx, st);
+    return fail(ctx, e, "imdct_state_create");
+  }
+  *out = st;
+  return XAAC_B200_OK;
+}
+
+void xaac_b200_imdct_state_destroy(xaac_b200_ctx *ctx, xaac_b200_imdct_state *st) {
+  if (!st) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (st->d_overlap) cudaFree(st->d_overlap);
+  if (st->d_wstate) cudaFree(st->d_wstate);
+  delete st;
+}
+
+int32_t xaac_b200_imdct_state_upload(xaac_b200_ctx *ctx, xaac_b200_imdct_state *st, const int32_t *overlap,
+                                     const uint8_t *wstate) {
+  if (!ctx || !st || !overlap || !wstate) return bad_arg(ctx, "state_upload");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaMemcpy(st->d_overlap, overlap, (size_t)st->n_units * 2048, cudaMemcpyHostToDevice), "H2D overlap");
+  CK(cudaMemcpy(st->d_wstate, wstate, (size_t)st->n_units * 2, cudaMemcpyHostToDevice), "H2D wstate");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_imdct_state_download(xaac_b200_ctx *ctx, xaac_b200_imdct_state *st, int32_t *overlap,
+                                       uint8_t *wstate) {
+  if (!ctx || !st || !overlap || !wstate) return bad_arg(ctx, "state_download");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaMemcpy(overlap, st->d_overlap, (size_t)st->n_units * 2048, cudaMemcpyDeviceToHost), "D2H overlap");
+  CK(cudaMemcpy(wstate, st->d_wstate, (size_t)st->n_units * 2, cudaMemcpyDeviceToHost), "D2H wstate");
+  return XAAC_B200_OK;
+}
+
 // Host-buffer entry point: chunks the batch and runs H2D / kernel / D2H of successive chunks on kPipe
 // streams so PCIe and the SMs overlap. Pinned host memory makes the copies truly asynchronous.
-int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, const int32_t *spec, int32_t *overlap, uint8_t *wstate,
-                                     const uint8_t *ics, int32_t *out, int8_t *qshift_adj, int64_t n_units,
-                                     int32_t ch_fac) {
-  if (!ctx) return XAAC_B200_ERR_ARG;
-  if (n_units < 0 || ch_fac < 1) return bad_arg(ctx, "n_units/ch_fac");
+// The overlap/window state never leaves HBM.
+int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, const int32_t *spec,
+                                     const uint8_t *ics, int32_t *out, int8_t *qshift_adj, int32_t ch_fac) {
+  if (!ctx || !state) return XAAC_B200_ERR_ARG;
+  const int64_t n_units = state->n_units;
+  if (ch_fac < 1) return bad_arg(ctx, "ch_fac");
   if (n_units == 0) return XAAC_B200_OK;
-  if (!spec || !overlap || !wstate || !ics || !out || !qshift_adj) return bad_arg(ctx, "null buffer");
+  if (!spec || !ics || !out || !qshift_adj) return bad_arg(ctx, "null buffer");
   if (ch_fac > 1 && (n_units % ch_fac) != 0) return bad_arg(ctx, "n_units must be a multiple of ch_fac");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   int64_t chunk = 8192;
   if (chunk > n_units) chunk = n_units;
   if (ch_fac > 1) chunk = ((chunk + ch_fac - 1) / ch_fac) * ch_fac;
-  // per-unit staging layout: spec 4096 | out 4096 | overlap 2048 | wstate 2 | ics 2 | qadj 1 (+pad)
-  const size_t per_unit = 4096 + 4096 + 2048 + 16;
+  // per-unit staging layout: spec 4096 | out 4096 | ics 2 | qadj 1 (+pad)
+  const size_t per_unit = 4096 + 4096 + 16;
   int32_t rc = ensure_stage(ctx, per_unit * (size_t)chunk);
   if (rc != XAAC_B200_OK) return rc;
   int slot = 0;
@@ -167,19 +230,14 @@ int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, const int32_t *spec, in
     uint8_t *base = (uint8_t *)ctx->stage[slot];
     int32_t *d_spec = (int32_t *)base;
     int32_t *d_out = (int32_t *)(base + 4096 * (size_t)chunk);
-    int32_t *d_ovl = (int32_t *)(base + 8192 * (size_t)chunk);
-    uint8_t *d_ws = base + 10240 * (size_t)chunk;
-    uint8_t *d_ics = d_ws + 4 * (size_t)chunk;
-    int8_t *d_qa = (int8_t *)(d_ws + 8 * (size_t)chunk);
+    uint8_t *d_ics = base + 8192 * (size_t)chunk;
+    int8_t *d_qa = (int8_t *)(d_ics + 4 * (size_t)chunk);
     CK(cudaMemcpyAsync(d_spec, spec + u0 * 1024, (size_t)n * 4096, cudaMemcpyHostToDevice, st), "H2D spec");
-    CK(cudaMemcpyAsync(d_ovl, overlap + u0 * 512, (size_t)n * 2048, cudaMemcpyHostToDevice, st), "H2D overlap");
-    CK(cudaMemcpyAsync(d_ws, wstate + u0 * 2, (size_t)n * 2, cudaMemcpyHostToDevice, st), "H2D wstate");
     CK(cudaMemcpyAsync(d_ics, ics + u0 * 2, (size_t)n * 2, cudaMemcpyHostToDevice, st), "H2D ics");
-    rc = xaac_b200_imdct_process_dev(ctx, d_spec, d_ovl, d_ws, d_ics, d_out, d_qa, n, ch_fac, st);
+    rc = xaac_b200_imdct_process_dev(ctx, d_spec, state->d_overlap + u0 * 512, state->d_wstate + u0 * 2, d_ics,
+                                     d_out, d_qa, n, ch_fac, st);
     if (rc != XAAC_B200_OK) return rc;
     CK(cudaMemcpyAsync(out + u0 * 1024, d_out, (size_t)n * 4096, cudaMemcpyDeviceToHost, st), "D2H out");
-    CK(cudaMemcpyAsync(overlap + u0 * 512, d_ovl, (size_t)n * 2048, cudaMemcpyDeviceToHost, st), "D2H overlap");
-    CK(cudaMemcpyAsync(wstate + u0 * 2, d_ws, (size_t)n * 2, cudaMemcpyDeviceToHost, st), "D2H wstate");
     CK(cudaMemcpyAsync(qshift_adj + u0, d_qa, (size_t)n, cudaMemcpyDeviceToHost, st), "D2H qshift_adj");
   }
   for (int i = 0; i < xaac_b200_ctx::kPipe; i++) CK(cudaStreamSynchronize(ctx->streams[i]), "stream sync");

@@ -63,19 +63,52 @@ def imdct_process(ctx, state, spec_coeff, ics, out_samples=None, qshift_adj=None
     return out_samples, qshift_adj
 
 
-def imdct_process_host(ctx, spec_coeff, overlap, wstate, ics, out_samples, qshift_adj, ch_fac=1):
+class ImdctHostState:
+    """Library-owned device-resident state for the host-buffer entry point (xaac_b200_imdct_state_*)."""
+
+    def __init__(self, ctx, n_units):
+        self.ctx = ctx
+        self.n = int(n_units)
+        self._h = ctypes.c_void_p()
+        ctx.check(ctx._lib.xaac_b200_imdct_state_create(ctx.handle, self.n, ctypes.byref(self._h)),
+                  "xaac_b200_imdct_state_create")
+
+    def upload(self, overlap, wstate):
+        _chk(overlap, torch.int32, (self.n, 512), "overlap", "cpu")
+        _chk(wstate, torch.uint8, (self.n, 2), "wstate", "cpu")
+        self.ctx.check(self.ctx._lib.xaac_b200_imdct_state_upload(self.ctx.handle, self._h, _ptr(overlap), _ptr(wstate)),
+                       "xaac_b200_imdct_state_upload")
+
+    def download(self):
+        overlap = torch.empty((self.n, 512), dtype=torch.int32)
+        wstate = torch.empty((self.n, 2), dtype=torch.uint8)
+        self.ctx.check(self.ctx._lib.xaac_b200_imdct_state_download(self.ctx.handle, self._h, _ptr(overlap), _ptr(wstate)),
+                       "xaac_b200_imdct_state_download")
+        return overlap, wstate
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.xaac_b200_imdct_state_destroy(self.ctx.handle, self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def imdct_process_host(ctx, state, spec_coeff, ics, out_samples, qshift_adj, ch_fac=1):
     """Same stage through the host-buffer C-ABI entry point (copies + kernel + copies, synchronous).
-    All tensors are CPU tensors (pinned memory makes the copies overlap with the kernel)."""
-    n = spec_coeff.shape[0]
+    spec_coeff/ics/out_samples/qshift_adj are CPU tensors (pinned memory lets copies overlap the kernel);
+    `state` is an ImdctHostState that stays in HBM."""
+    n = state.n
     _chk(spec_coeff, torch.int32, (n, 1024), "spec_coeff", "cpu")
-    _chk(overlap, torch.int32, (n, 512), "overlap", "cpu")
-    _chk(wstate, torch.uint8, (n, 2), "wstate", "cpu")
     _chk(ics, torch.uint8, (n, 2), "ics", "cpu")
     _chk(qshift_adj, torch.int8, (n,), "qshift_adj", "cpu")
     if out_samples.numel() != n * 1024 or out_samples.dtype != torch.int32 or not out_samples.is_contiguous():
         raise ValueError("out_samples: expected contiguous int32 with n*1024 elements")
     rc = ctx._lib.xaac_b200_imdct_process_host(
-        ctx.handle, _ptr(spec_coeff), _ptr(overlap), _ptr(wstate), _ptr(ics), _ptr(out_samples), _ptr(qshift_adj),
-        n, int(ch_fac))
+        ctx.handle, state._h, _ptr(spec_coeff), _ptr(ics), _ptr(out_samples), _ptr(qshift_adj), int(ch_fac))
     ctx.check(rc, "xaac_b200_imdct_process_host")
     return out_samples, qshift_adj

@@ -124,18 +124,27 @@ def test_stream_state_carry(ctx, oracle):
 
 
 def test_host_entry_point(ctx, oracle):
-    """xaac_b200_imdct_process_host: host buffers in, host buffers out (chunked, pipelined copies)."""
+    """xaac_b200_imdct_process_host: host buffers in, host buffers out (chunked, pipelined copies), state resident
+    in HBM across two consecutive frames, then downloaded (checkpoint path)."""
     import torch
     import libxaac_b200 as xb
     n = 20000  # > 2 chunks of 8192
     spec, ovl, wstate, ics = oracle_util.synth_units(n, 77)
     t = lambda a: torch.from_numpy(a.copy()).pin_memory()
-    h_spec, h_ovl, h_ws, h_ics = t(spec), t(ovl), t(wstate), t(ics)
+    st = xb.ImdctHostState(ctx, n)
+    st.upload(torch.from_numpy(ovl), torch.from_numpy(wstate))
     h_out = torch.empty((n, 1024), dtype=torch.int32).pin_memory()
     h_adj = torch.empty((n,), dtype=torch.int8).pin_memory()
-    xb.imdct_process_host(ctx, h_spec, h_ovl, h_ws, h_ics, h_out, h_adj)
+    xb.imdct_process_host(ctx, st, t(spec), t(ics), h_out, h_adj)
     e = oracle.imdct_batch(spec, ovl, wstate, ics)
-    assert_same((h_out.numpy(), h_ovl.numpy(), h_ws.numpy(), h_adj.numpy()), e, "host api")
+    d_ovl, d_ws = st.download()
+    assert_same((h_out.numpy(), d_ovl.numpy(), d_ws.numpy(), h_adj.numpy()), e, "host api frame 0")
+    spec2, _, _, ics2 = oracle_util.synth_units(n, 78)
+    xb.imdct_process_host(ctx, st, t(spec2), t(ics2), h_out, h_adj)
+    e2 = oracle.imdct_batch(spec2, e[1], e[2], ics2)
+    d_ovl, d_ws = st.download()
+    assert_same((h_out.numpy(), d_ovl.numpy(), d_ws.numpy(), h_adj.numpy()), e2, "host api frame 1")
+    st.close()
 
 
 def test_empty_batch_and_bad_args(ctx):
@@ -146,7 +155,7 @@ def test_empty_batch_and_bad_args(ctx):
                                 torch.empty((0, 2), dtype=torch.uint8, device="cuda"))
     assert out.numel() == 0
     st = xb.ImdctBatch(3)
-    with pytest.raises(xb.XaacB200Error):  # 3 units cannot be interleaved as stereo
+    with pytest.raises((xb.XaacB200Error, ValueError)):  # 3 units cannot be interleaved as stereo
         xb.imdct_process(ctx, st, torch.zeros((3, 1024), dtype=torch.int32, device="cuda"),
                          torch.zeros((3, 2), dtype=torch.uint8, device="cuda"), ch_fac=2)
     with pytest.raises(ValueError):
