@@ -52,11 +52,15 @@ struct C8 {
   i32 r[8], i[8];
 };
 
-// Radix-8 butterfly core, aac_imdct.c:876-999 (a = 0) and :1213-1375 (a = 1: legs 1,2,4,6 arrive
+// Radix-8 butterfly core, aac_imdct.c:876-999 (k1 = 1) and :1213-1375 (k1 = 2: legs 1,2,4,6 arrive
 // doubled after the twiddle multiply, legs 3,5,7 do not). Results are left in storage order.
-XB_DEV void bfly8(C8 &x, const int a) {
+// k1 is a multiplier rather than a shift count so that a run-time value costs one IMAD (fma pipe), not SHF+IADD.
+XB_DEV void bfly8(C8 &x, const i32 k1) {
   i32 t;
+  const i32 k2 = k1 * 2;
 #define SH(v, s) lsl((v), (s))
+#define M1(v) ((i32)((u32)(v) * (u32)k1))
+#define M2(v) ((i32)((u32)(v) * (u32)k2))
   x.r[0] = wadd(x.r[0], x.r[4]); x.i[0] = wadd(x.i[0], x.i[4]);
   x.r[4] = wsub(x.r[0], SH(x.r[4], 1)); x.i[4] = wsub(x.i[0], SH(x.i[4], 1));
   x.r[2] = wadd(x.r[2], x.r[6]); x.i[2] = wadd(x.i[2], x.i[6]);
@@ -67,16 +71,16 @@ XB_DEV void bfly8(C8 &x, const int a) {
   t = x.r[6];
   x.r[6] = wsub(x.r[4], SH(x.i[6], 1)); x.i[6] = wadd(x.i[4], SH(t, 1));
 
-  x.r[1] = wadd(x.r[1], SH(x.r[5], a)); x.i[1] = wadd(x.i[1], SH(x.i[5], a));
-  x.r[5] = wsub(x.r[1], SH(x.r[5], a + 1)); x.i[5] = wsub(x.i[1], SH(x.i[5], a + 1));
+  x.r[1] = wadd(x.r[1], M1(x.r[5])); x.i[1] = wadd(x.i[1], M1(x.i[5]));
+  x.r[5] = wsub(x.r[1], M2(x.r[5])); x.i[5] = wsub(x.i[1], M2(x.i[5]));
   x.r[3] = wadd(x.r[3], x.r[7]); x.i[3] = wadd(x.i[3], x.i[7]);
   x.r[7] = wsub(x.r[3], SH(x.r[7], 1)); x.i[7] = wsub(x.i[3], SH(x.i[7], 1));
-  x.r[1] = wadd(x.r[1], SH(x.r[3], a)); x.i[1] = wadd(x.i[1], SH(x.i[3], a));
-  x.r[3] = wsub(x.r[1], SH(x.r[3], a + 1)); x.i[3] = wsub(x.i[1], SH(x.i[3], a + 1));
+  x.r[1] = wadd(x.r[1], M1(x.r[3])); x.i[1] = wadd(x.i[1], M1(x.i[3]));
+  x.r[3] = wsub(x.r[1], M2(x.r[3])); x.i[3] = wsub(x.i[1], M2(x.i[3]));
   x.r[5] = wadd(x.r[5], x.i[5]); x.i[5] = wsub(x.r[5], SH(x.i[5], 1));
   x.r[7] = wadd(x.r[7], x.i[7]); x.i[7] = wsub(x.r[7], SH(x.i[7], 1));
-  x.i[7] = wsub(x.r[5], SH(x.i[7], a)); x.r[5] = wsub(x.i[7], SH(x.r[5], 1));
-  x.i[5] = wsub(SH(x.r[7], a), x.i[5]); x.r[7] = wsub(x.i[5], SH(x.r[7], a + 1));
+  x.i[7] = wsub(x.r[5], M1(x.i[7])); x.r[5] = wsub(x.i[7], SH(x.r[5], 1));
+  x.i[5] = wsub(M1(x.r[7]), x.i[5]); x.r[7] = wsub(x.i[5], M2(x.r[7]));
   x.i[7] = SH(x.i[7], 1); x.r[5] = SH(x.r[5], 1); x.i[5] = SH(x.i[5], 1); x.r[7] = SH(x.r[7], 1);
 
   x.r[0] = wadd(x.r[0], x.r[1]); x.i[0] = wadd(x.i[0], x.i[1]);
@@ -99,6 +103,8 @@ XB_DEV void bfly8(C8 &x, const int a) {
   x.r[6] = t;   x.i[6] = i3;
   x.r[7] = wneg(n6r); x.i[7] = wneg(n6i);
 #undef SH
+#undef M1
+#undef M2
 }
 
 // aac_imdct.c:1179-1185 (doubled) / :1256-1260 (plain)
@@ -144,7 +150,7 @@ XB_DEV void post_bin(int2 y, i32 C, i32 S, i32 adj_hi, i32 &outr, i32 &outi) {
 // ---- the rare-path helpers below work on T (post-twiddled block, smem) and P (overlap copy, smem) ----
 
 // block.c:1193-1218
-XB_DEV void ola1(const i32 *coef, const i32 *prev, i32 *out, const i16 *w, int q_shift, int size, int ch_fac,
+__device__ __noinline__ void ola1(const i32 *coef, const i32 *prev, i32 *out, const i16 *w, int q_shift, int size, int ch_fac,
                  int lane) {
   for (int i = lane; i < size; i += 32) {
     i32 w1 = w[2 * size - 2 * i - 1], w2 = w[2 * size - 2 * i - 2];
@@ -157,7 +163,7 @@ XB_DEV void ola1(const i32 *coef, const i32 *prev, i32 *out, const i16 *w, int q
 }
 
 // block.c:1220-1240 (ch_fac == 1 at every call site). prev/out may alias different parts of P.
-XB_DEV void ola2(const i32 *coef, const i32 *prev, i32 *out, const i16 *w, int q_shift, int size, int lane) {
+__device__ __noinline__ void ola2(const i32 *coef, const i32 *prev, i32 *out, const i16 *w, int q_shift, int size, int lane) {
   for (int i = lane; i < size; i += 32) {
     i32 a = sub_sat(mul32x16(coef[size + i], w[2 * i]), mul32x16(prev[size - 1 - i], w[2 * i + 1]));
     i32 b = sub_sat(mul32x16(neg_sat(coef[2 * size - 1 - i]), w[2 * size - 2 * i - 1]),
@@ -168,7 +174,7 @@ XB_DEV void ola2(const i32 *coef, const i32 *prev, i32 *out, const i16 *w, int q
 }
 
 // lpfuncs.c:94-178
-XB_DEV void process_win_seq(const i32 *coef, const i32 *prev, i32 *out, const i16 *wl, const i16 *ws, int q_shift,
+__device__ __noinline__ void process_win_seq(const i32 *coef, const i32 *prev, i32 *out, const i16 *wl, const i16 *ws, int q_shift,
                             int ch_fac, int flag, int lane) {
   const int s1 = 64, s7 = 448, s8 = 512, s9 = 576, s14 = 896, s15 = 960;
   const i16 *w_sh, *w_lg;
@@ -206,7 +212,7 @@ XB_DEV void process_win_seq(const i32 *coef, const i32 *prev, i32 *out, const i1
 }
 
 // lpfuncs.c:218-284 incl. the four long_short_win_process calls (:180-216)
-XB_DEV void long_short_win_seq(const i32 *cur, i32 *prev, i32 *out, const i16 *sw, const i16 *swp, const i16 *lwp,
+__device__ __noinline__ void long_short_win_seq(const i32 *cur, i32 *prev, i32 *out, const i16 *sw, const i16 *swp, const i16 *lwp,
                                int q_shift, int ch_fac, int lane) {
   const int s1 = 64, s2 = 128, s3 = 192, s6 = 384, s7 = 448, s8 = 512, s9 = 576, s10 = 640, s16 = 1024;
   for (int i = lane; i < s7; i += 32) out[ch_fac * i] = mul32x16_fullsat(prev[s8 - 1 - i], neg16(lwp[2 * i + 1]));
@@ -242,7 +248,7 @@ XB_DEV void long_short_win_seq(const i32 *cur, i32 *prev, i32 *out, const i16 *s
   }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
 imdct_ola_kernel(ImdctArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BlockSmem &sm = *reinterpret_cast<BlockSmem *>(smem_raw);
@@ -314,9 +320,12 @@ imdct_ola_kernel(ImdctArgs p) {
       }
       __syncwarp();
       // ---- radix-8 stage 1 (aac_imdct.c:856-1000): digit-reversed gather == stride-64 read ----
-#pragma unroll
+      // The two butterflies of a lane are a rolled loop on purpose: the unrolled body overflowed the 32 KB
+      // instruction cache (ncu: stall_no_instruction dominant, profiles/r1_imdct_a.md).
+      // Output slot of leg p: swz(64*(b&7) + 8*(b>>3) + p) == s1base ^ p  (p < 8 only touches the low 3 bits).
+#pragma unroll 1
       for (int t = 0; t < 2; t++) {
-        int b = lane + 32 * t;
+        const int b = lane + 32 * t;
         C8 x;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -324,51 +333,51 @@ imdct_ola_kernel(ImdctArgs p) {
           x.r[q] = e.x;
           x.i[q] = e.y;
         }
-        bfly8(x, 0);
-        int g8 = ((b & 7) << 6) | ((b >> 3) << 3);
+        bfly8(x, 1);
+        const int kk = b & 7;
+        const int s1base = (kk << 6) | ((b >> 4) << 4) | ((((b >> 3) ^ kk) & 1) << 3) | kk;
 #pragma unroll
-        for (int q = 0; q < 8; q++) stY<true>(Y, g8 + q, x.r[q], x.i[q]);
+        for (int q = 0; q < 8; q++) Y[s1base ^ q] = make_int2(x.r[q], x.i[q]);
       }
       __syncwarp();
       // ---- stage 2 (del = 8): 56 twiddled columns + 8 plain ones (aac_imdct.c:1007-1384) ----
-#pragma unroll
+      // column m, block k: element q sits at swz(m + 64k + 8q) == (s2base ^ ((q&1)<<3)) + 16*(q>>1)
+#pragma unroll 1
       for (int t = 0; t < 2; t++) {
-        int k = lane & 7;
-        int m = (t == 0) ? 1 + (lane >> 3) : (lane < 24 ? 5 + (lane >> 3) : 0);
-        int base = m + 64 * k;
+        const int k = lane & 7;
+        const int m = (t == 0) ? 1 + (lane >> 3) : (lane < 24 ? 5 + (lane >> 3) : 0);
+        const int s2base = (k << 6) | ((k & 1) << 3) | ((m ^ k) & 7);
+        int2 *Ye = Y + s2base;
+        int2 *Yo = Y + (s2base ^ 8);
         C8 x;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          int2 e = ldY<true>(Y, base + 8 * q);
+          int2 e = ((q & 1) ? Yo : Ye)[16 * (q >> 1)];
           x.r[q] = e.x;
           x.i[q] = e.y;
         }
-        if (t == 0) {
-          tw_all(x, sm.tw, 8 * m);
-          bfly8(x, 1);
-        } else {
-          if (m != 0) tw_all(x, sm.tw, 8 * m);
-          bfly8(x, m != 0 ? 1 : 0);
-        }
+        if (m != 0) tw_all(x, sm.tw, 8 * m);
+        bfly8(x, m != 0 ? 2 : 1);
 #pragma unroll
-        for (int q = 0; q < 8; q++) stY<true>(Y, base + 8 * q, x.r[q], x.i[q]);
+        for (int q = 0; q < 8; q++) ((q & 1) ? Yo : Ye)[16 * (q >> 1)] = make_int2(x.r[q], x.i[q]);
       }
       __syncwarp();
       // ---- stage 3 (del = 64), all columns twiddled incl. column 0 (aac_imdct.c:1386-1621) ----
-#pragma unroll
+      // element q of column m sits at swz(m + 64q) == 64q + (m ^ c_q), c_q = (q&7) | ((q&1)<<3)
+#pragma unroll 1
       for (int t = 0; t < 2; t++) {
-        int m = lane + 32 * t;
+        const int m = lane + 32 * t;
         C8 x;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          int2 e = ldY<true>(Y, m + 64 * q);
+          int2 e = Y[64 * q + (m ^ ((q & 7) | ((q & 1) << 3)))];
           x.r[q] = e.x;
           x.i[q] = e.y;
         }
         tw_all(x, sm.tw, m);
-        bfly8(x, 1);
+        bfly8(x, 2);
 #pragma unroll
-        for (int q = 0; q < 8; q++) stY<true>(Y, m + 64 * q, x.r[q], x.i[q]);
+        for (int q = 0; q < 8; q++) Y[64 * q + (m ^ ((q & 7) | ((q & 1) << 3)))] = make_int2(x.r[q], x.i[q]);
       }
       __syncwarp();
       q_shift = (31 + expo + 2) - 26;  // lpfuncs.c:423 with imdct_scale = expo + 2
@@ -379,7 +388,7 @@ imdct_ola_kernel(ImdctArgs p) {
         const i16 *win = win_long(prev_shape);
         const int2 *win4 = reinterpret_cast<const int2 *>(win);
         int2 *ovl2 = reinterpret_cast<int2 *>(ovl_g);
-#pragma unroll 4
+#pragma unroll 2
         for (int j = 0; j < 8; j++) {
           int c = lane + 32 * j, c2 = 511 - c;
           i32 C, S, r1, i1, r2, i2;
@@ -498,7 +507,7 @@ imdct_ola_kernel(ImdctArgs p) {
       }
       __syncwarp();
       // 64-point FFT per window: stage 1 (identity digit reversal) then the final twiddled stage
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < 2; t++) {
         int j = lane + 32 * t;
         int wofs = (j >> 3) << 6, g = j & 7;
@@ -509,12 +518,12 @@ imdct_ola_kernel(ImdctArgs p) {
           x.r[q] = e.x;
           x.i[q] = e.y;
         }
-        bfly8(x, 0);
+        bfly8(x, 1);
 #pragma unroll
         for (int q = 0; q < 8; q++) stY<false>(Y, wofs + 8 * g + q, x.r[q], x.i[q]);
       }
       __syncwarp();
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < 2; t++) {
         int j = lane + 32 * t;
         int wofs = (j >> 3) << 6, m = j & 7;
@@ -526,7 +535,7 @@ imdct_ola_kernel(ImdctArgs p) {
           x.i[q] = e.y;
         }
         tw_all(x, sm.tw, 8 * m);
-        bfly8(x, 1);
+        bfly8(x, 2);
 #pragma unroll
         for (int q = 0; q < 8; q++) stY<false>(Y, wofs + m + 8 * q, x.r[q], x.i[q]);
       }
