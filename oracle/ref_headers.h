@@ -8,6 +8,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <stdint.h>
+#include <stddef.h>
 #include "ixheaacd_sbr_common.h"
 #include "ixheaac_type_def.h"
 #include "ixheaac_constants.h"

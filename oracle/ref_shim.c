@@ -77,3 +77,116 @@ int ref_inverse_transform(int32_t *spec, int32_t *scratch, int32_t expo, int32_t
 void ref_post_twiddle(int32_t *out, int32_t *spec, int32_t npoints) {
   (*ixheaacd_post_twiddle)(out, spec, (ia_aac_dec_imdct_tables_struct *)&ixheaacd_imdct_tables, npoints);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Fixed-point SBR QMF banks.
+ * ---------------------------------------------------------------------------------------------- */
+const void *ref_rom_qmf_tables(int *bytes) {
+  if (bytes) *bytes = (int)sizeof(ixheaacd_aac_qmf_dec_tables);
+  return &ixheaacd_aac_qmf_dec_tables;
+}
+/* offsets of the members our QMF ROM blob relies on (checked by tests against the product's constants) */
+int ref_rom_qmf_offsets(int *o) {
+  int n = 0;
+#define OFF(m) o[n++] = (int)offsetof(ia_qmf_dec_tables_struct, m)
+  OFF(w_32); OFF(w_16); OFF(dig_rev_table2_32); OFF(dig_rev_table4_16); OFF(sbr_sin_cos_twiddle_l64);
+  OFF(sbr_alt_sin_twiddle_l64); OFF(sbr_cos_sin_twiddle_ds_l32); OFF(sbr_sin_cos_twiddle_l32);
+  OFF(sbr_alt_sin_twiddle_l32); OFF(sbr_t_cos_sin_l32); OFF(post_fft_tbl); OFF(dct23_tw); OFF(qmf_c);
+  OFF(dig_rev_table2_128);
+#undef OFF
+  return n;
+}
+
+/* ixheaacd_cos_sin_mod (decoder/generic/ixheaacd_qmf_dec_generic.c:259): no_channels = 64 (synthesis, M = 32)
+ * or 32 (analysis, M = 16); subband[128] in place. */
+void ref_cos_sin_mod(int32_t *subband, int32_t no_channels) {
+  ia_sbr_qmf_filter_bank_struct bank;
+  ia_qmf_dec_tables_struct *t = (ia_qmf_dec_tables_struct *)&ixheaacd_aac_qmf_dec_tables;
+  memset(&bank, 0, sizeof(bank));
+  bank.no_channels = no_channels;
+  if (no_channels == 64) {
+    bank.cos_twiddle = t->sbr_sin_cos_twiddle_l64;
+    bank.alt_sin_twiddle = t->sbr_alt_sin_twiddle_l64;
+    ixheaacd_cos_sin_mod(subband, &bank, t->w_32, t->dig_rev_table2_32);
+  } else {
+    bank.cos_twiddle = t->sbr_sin_cos_twiddle_l32;
+    bank.alt_sin_twiddle = t->sbr_alt_sin_twiddle_l32;
+    ixheaacd_cos_sin_mod(subband, &bank, t->w_16, t->dig_rev_table4_16);
+  }
+}
+
+/* ixheaacd_cplx_synt_qmffilt (decoder/ixheaacd_qmf_dec.c:811), HQ (complex) 64-band, no PS, no DRC, AAC-LC/HE-AAC
+ * object type — exactly how ixheaacd_sbr_dec calls it at sbr_dec.c:1273 for a non-PS HQ channel.
+ *   matrix        [32][128] : per slot re[64] | im[64]  (modified in place: block shifts + modulation)
+ *   filter_states [1280] WORD16, in/out;  *drc_offset in/out (0..1152 step 128);  *filter_pos in/out (0..576 step 64)
+ *   sf[4] = {ov_lb_scale, lb_scale, hb_scale, st_syn_scale}
+ *   time_out      2048 WORD16 at stride ch_fac */
+void ref_synt_qmffilt_hq(int32_t *matrix, int16_t *filter_states, int32_t *drc_offset, int32_t *filter_pos,
+                         const int32_t *sf, int32_t lsb, int32_t usb, int32_t split, int16_t *time_out,
+                         int32_t ch_fac) {
+  ia_sbr_qmf_filter_bank_struct bank;
+  ia_sbr_scale_fact_struct s;
+  ia_sbr_tables_struct tabs;
+  static WORD32 dump[MAX_ENV_COLS][128];
+  WORD32 *re[MAX_ENV_COLS], *im[MAX_ENV_COLS], *ore[MAX_ENV_COLS], *oim[MAX_ENV_COLS];
+  ia_qmf_dec_tables_struct *t = (ia_qmf_dec_tables_struct *)&ixheaacd_aac_qmf_dec_tables;
+  memset(&bank, 0, sizeof(bank));
+  memset(&s, 0, sizeof(s));
+  memset(&tabs, 0, sizeof(tabs));
+  tabs.qmf_dec_tables_ptr = t;
+  for (int i = 0; i < 32; i++) {
+    re[i] = matrix + 128 * i;
+    im[i] = re[i] + 64;
+    ore[i] = dump[i];
+    oim[i] = dump[i] + 64;
+  }
+  bank.no_channels = 64;
+  bank.num_time_slots = 32;
+  bank.lsb = (WORD16)lsb;
+  bank.usb = (WORD16)usb;
+  bank.filter_states = filter_states;
+  bank.ixheaacd_drc_offset = (WORD16)*drc_offset;
+  bank.p_filter = t->qmf_c;
+  bank.filter_pos_syn = (WORD16 *)t->qmf_c + *filter_pos;
+  s.ov_lb_scale = (WORD16)sf[0];
+  s.lb_scale = (WORD16)sf[1];
+  s.hb_scale = (WORD16)sf[2];
+  s.st_syn_scale = (WORD16)sf[3];
+  ixheaacd_cplx_synt_qmffilt(re, im, split, ore, oim, &s, time_out, &bank, NULL, 0, 0, &tabs, NULL, ch_fac, 0,
+                             NULL, AOT_SBR);
+  *drc_offset = bank.ixheaacd_drc_offset;
+  *filter_pos = (int32_t)(bank.filter_pos_syn - (WORD16 *)t->qmf_c);
+}
+
+/* ixheaacd_cplx_anal_qmffilt (decoder/generic/ixheaacd_qmf_dec_generic.c:590), HQ 32-band, as called from
+ * ixheaacd_sbr_dec (sbr_dec.c:1025).
+ *   time_in   1024 WORD16 at stride ch_fac
+ *   states    [320] WORD16 in/out; *pos in/out (offset of core_samples_buffer, 0..288 step 32);
+ *   *filter_pos in/out (offset into qmf_c)
+ *   matrix    [32][128]: real[i][0..31] at matrix[128 i], imag at +64 (only the first 32 of each written)
+ *   returns lb_scale set by the stage */
+int ref_anal_qmffilt_hq(const int16_t *time_in, int32_t ch_fac, int16_t *states, int32_t *pos, int32_t *filter_pos,
+                        int32_t usb, int32_t *matrix) {
+  ia_sbr_qmf_filter_bank_struct bank;
+  ia_sbr_scale_fact_struct s;
+  WORD32 *re[MAX_ENV_COLS], *im[MAX_ENV_COLS];
+  ia_qmf_dec_tables_struct *t = (ia_qmf_dec_tables_struct *)&ixheaacd_aac_qmf_dec_tables;
+  memset(&bank, 0, sizeof(bank));
+  memset(&s, 0, sizeof(s));
+  for (int i = 0; i < 32; i++) {
+    re[i] = matrix + 128 * i;
+    im[i] = re[i] + 64;
+  }
+  bank.no_channels = 32;
+  bank.num_time_slots = 32;
+  bank.lsb = 0;
+  bank.usb = (WORD16)usb;
+  bank.anal_filter_states = states;
+  bank.core_samples_buffer = states + *pos;
+  bank.analy_win_coeff = t->qmf_c;
+  bank.filter_pos = (WORD16 *)t->qmf_c + *filter_pos;
+  ixheaacd_cplx_anal_qmffilt(time_in, &s, re, im, &bank, t, ch_fac, 0, AOT_SBR);
+  *pos = (int32_t)(bank.core_samples_buffer - states);
+  *filter_pos = (int32_t)(bank.filter_pos - (WORD16 *)t->qmf_c);
+  return s.lb_scale;
+}

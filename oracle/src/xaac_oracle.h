@@ -30,4 +30,33 @@ int xo_imdct_process(const uint8_t *rom, int32_t *spec, int32_t *ovl, int32_t *p
 void xo_imdct_process_batch(const uint8_t *rom, int32_t *spec, int32_t *ovl, int32_t *prev_shape,
                             int32_t *prev_seq, const int32_t *win_seq, const int32_t *win_shape, int32_t *out,
                             int32_t *qshift_adj, int n);
+
+/* ---- fixed-point SBR QMF banks ------------------------------------------------------------------------
+ * QMF ROM blob = the leading 3464 bytes of ia_qmf_dec_tables_struct (decoder/ixheaacd_sbr_rom.h:71-95). */
+#define XO_QROM_W32 0              /* WORD16[60]  radix-4 twiddles, 32-point */
+#define XO_QROM_W16 120            /* WORD16[24]  radix-4 twiddles, 16-point */
+#define XO_QROM_DIGREV2_32 168     /* WORD32[4] */
+#define XO_QROM_DIGREV4_16 184     /* WORD32[2] */
+#define XO_QROM_SINCOS_L64 192     /* WORD16[64] */
+#define XO_QROM_ALTSIN_L64 320     /* WORD16[32] */
+#define XO_QROM_COSSIN_DS_L32 384  /* WORD16[64] */
+#define XO_QROM_SINCOS_L32 512     /* WORD16[32] */
+#define XO_QROM_ALTSIN_L32 576     /* WORD16[16] */
+#define XO_QROM_TCOSSIN_L32 608    /* WORD16[64] */
+#define XO_QROM_POST_FFT 736       /* WORD16[18] */
+#define XO_QROM_DCT23_TW 772       /* WORD16[66] */
+#define XO_QROM_QMF_C 904          /* WORD16[1280] */
+#define XO_QROM_BYTES 3464
+
+void xo_cos_sin_mod(const uint8_t *qrom, int32_t *subband, int no_channels);
+void xo_synt_qmffilt_hq(const uint8_t *qrom, int32_t *matrix, int16_t *filter_states, int32_t *drc_offset,
+                        int32_t *filter_pos, const int32_t *sf, int lsb, int usb, int split, int16_t *time_out,
+                        int ch_fac);
+int xo_anal_qmffilt_hq(const uint8_t *qrom, const int16_t *time_in, int ch_fac, int16_t *states, int32_t *pos,
+                       int32_t *filter_pos, int usb, int32_t *matrix);
+void xo_synt_qmffilt_hq_batch(const uint8_t *qrom, int32_t *matrix, int16_t *filter_states, int32_t *drc_offset,
+                              int32_t *filter_pos, const int32_t *sf, const int32_t *lsb, const int32_t *usb,
+                              int16_t *time_out, int n);
+void xo_anal_qmffilt_hq_batch(const uint8_t *qrom, const int16_t *time_in, int16_t *states, int32_t *pos,
+                              int32_t *filter_pos, const int32_t *usb, int32_t *matrix, int n);
 #endif
