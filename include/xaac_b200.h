@@ -91,6 +91,43 @@ int32_t xaac_b200_imdct_state_download(xaac_b200_ctx *ctx, xaac_b200_imdct_state
 int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, const int32_t *spec,
                                      const uint8_t *ics, int32_t *out, int8_t *qshift_adj, int32_t ch_fac);
 
+/* ---- fixed-point SBR QMF banks ----------------------------------------------------------------------
+ * ROM: `tables` points at the host's ia_qmf_dec_tables_struct (decoder/ixheaacd_sbr_rom.h:71-123), i.e. what the
+ * reference passes around as sbr_tables_ptr->qmf_dec_tables_ptr; only the leading XAAC_B200_QMF_ROM_BYTES are read
+ * (w_32, w_16, dig_rev tables, sbr_*_twiddle_*, post_fft_tbl, dct23_tw, qmf_c). */
+#define XAAC_B200_QMF_ROM_BYTES 3464
+int32_t xaac_b200_set_qmf_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes);
+
+/* Complex ("HQ") 64-band QMF synthesis, batched.  Replaces ixheaacd_cplx_synt_qmffilt
+ * (decoder/ixheaacd_qmf_dec.c:811-1129) as ixheaacd_sbr_dec calls it for a non-PS, non-low-power channel
+ * (decoder/ixheaacd_sbr_dec.c:1273), together with the link-time leaves ixheaacd_inv_emodulation / cos_sin_mod /
+ * radix4bfly / postradixcompute2 / shiftrountine_with_rnd / sbr_qmfsyn64_winadd
+ * (decoder/generic/ixheaacd_qmf_dec_generic.c) and the selector leaf ixheaacd_adjust_scale.
+ * Unit = one frame of one output channel.
+ *   matrix         [n_units][32][128] WORD32: per time slot re[64] | im[64] (the reference's qmf_real[i]/qmf_imag[i]
+ *                  rows, slot stride 128 words); read-only
+ *   filter_states  [n_units][1280] WORD16 (ia_sbr_qmf_filter_bank_struct.filter_states), in/out
+ *   pos            [n_units][2] WORD16 {ixheaacd_drc_offset, filter_pos_syn - p_filter}, in/out
+ *   params         [n_units][8] WORD16 {ov_lb_scale, lb_scale, hb_scale, st_syn_scale (ia_sbr_scale_fact_struct),
+ *                  lsb, usb (filter bank), split (= op_delay, 6), 0}
+ *   pcm            PCM16, 2048 samples per unit; ch_fac as for the IMDCT stage
+ */
+int32_t xaac_b200_qmf_synth_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_matrix, int16_t *d_filter_states,
+                                   int16_t *d_pos, const int16_t *d_params, int16_t *d_pcm, int64_t n_units,
+                                   int32_t ch_fac, void *stream);
+
+/* Device-resident synthesis-bank state for the host-buffer entry point (reset state: zero filter states,
+ * offsets 0 — decoder/ixheaacd_sbrdec_initfuncs.c:1154-1213). */
+typedef struct xaac_b200_qmf_synth_state xaac_b200_qmf_synth_state;
+int32_t xaac_b200_qmf_synth_state_create(xaac_b200_ctx *ctx, int64_t n_units, xaac_b200_qmf_synth_state **state);
+void xaac_b200_qmf_synth_state_destroy(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *state);
+int32_t xaac_b200_qmf_synth_state_upload(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *state,
+                                         const int16_t *filter_states, const int16_t *pos);
+int32_t xaac_b200_qmf_synth_state_download(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *state,
+                                           int16_t *filter_states, int16_t *pos);
+int32_t xaac_b200_qmf_synth_hq_host(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *state, const int32_t *matrix,
+                                    const int16_t *params, int16_t *pcm, int32_t ch_fac);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,8 +15,20 @@ from .imdct import (  # noqa: F401
     imdct_process,
     imdct_process_host,
 )
+from .qmf import (  # noqa: F401
+    QmfSynthBatch,
+    QmfSynthHostState,
+    cplx_synt_qmffilt,
+    cplx_synt_qmffilt_host,
+    synth_params,
+)
 
 __all__ = [
+    "QmfSynthBatch",
+    "QmfSynthHostState",
+    "cplx_synt_qmffilt",
+    "cplx_synt_qmffilt_host",
+    "synth_params",
     "Context",
     "ImdctBatch",
     "ImdctHostState",

@@ -30,6 +30,13 @@ SIGNATURES = {
     "xaac_b200_imdct_state_upload": (_i32, [_vp, _vp, _vp, _vp]),
     "xaac_b200_imdct_state_download": (_i32, [_vp, _vp, _vp, _vp]),
     "xaac_b200_imdct_process_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "xaac_b200_set_qmf_rom": (_i32, [_vp, _vp, _sz]),
+    "xaac_b200_qmf_synth_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "xaac_b200_qmf_synth_state_create": (_i32, [_vp, _i64, _c.POINTER(_vp)]),
+    "xaac_b200_qmf_synth_state_destroy": (None, [_vp, _vp]),
+    "xaac_b200_qmf_synth_state_upload": (_i32, [_vp, _vp, _vp, _vp]),
+    "xaac_b200_qmf_synth_state_download": (_i32, [_vp, _vp, _vp, _vp]),
+    "xaac_b200_qmf_synth_hq_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32]),
 }
 
 _lib = None

@@ -5,7 +5,7 @@ from . import _lib
 
 
 class Context:
-    def __init__(self, device=0, imdct_rom=None):
+    def __init__(self, device=0, imdct_rom=None, qmf_rom=None):
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         rc = self._lib.xaac_b200_create(ctypes.byref(self._h), int(device))
@@ -17,6 +17,7 @@ class Context:
             )
         self.device = int(device)
         self.set_imdct_rom(imdct_rom if imdct_rom is not None else _lib.rom_blob("imdct_rom.bin"))
+        self.set_qmf_rom(qmf_rom if qmf_rom is not None else _lib.rom_blob("qmf_rom.bin"))
 
     # -- plumbing ---------------------------------------------------------------------------------
     @property
@@ -32,6 +33,11 @@ class Context:
         """blob: bytes of the host's ia_aac_dec_imdct_tables_struct (>= 7500 leading bytes)."""
         buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
         self.check(self._lib.xaac_b200_set_imdct_rom(self._h, buf, len(blob)), "xaac_b200_set_imdct_rom")
+
+    def set_qmf_rom(self, blob):
+        """blob: bytes of the host's ia_qmf_dec_tables_struct (>= 3464 leading bytes)."""
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        self.check(self._lib.xaac_b200_set_qmf_rom(self._h, buf, len(blob)), "xaac_b200_set_qmf_rom")
 
     @property
     def num_sms(self):

@@ -40,6 +40,36 @@ struct ImdctArgs {
   int ch_fac;
 };
 
+// ---- fixed-point SBR QMF banks -------------------------------------------------------------------------
+// Byte offsets inside the QMF ROM blob: the leading 3464 bytes of the reference's ia_qmf_dec_tables_struct
+// (decoder/ixheaacd_sbr_rom.h:71-95), handed over by the host like `sbr_tables_ptr->qmf_dec_tables_ptr`.
+constexpr int kQRomW32 = 0;             // WORD16 w_32[60]
+constexpr int kQRomW16 = 120;           // WORD16 w_16[24]
+constexpr int kQRomDigRev2_32 = 168;    // WORD32[4]
+constexpr int kQRomDigRev4_16 = 184;    // WORD32[2]
+constexpr int kQRomSinCosL64 = 192;     // WORD16 sbr_sin_cos_twiddle_l64[64]
+constexpr int kQRomAltSinL64 = 320;     // WORD16 sbr_alt_sin_twiddle_l64[32]
+constexpr int kQRomSinCosL32 = 512;     // WORD16 sbr_sin_cos_twiddle_l32[32]
+constexpr int kQRomAltSinL32 = 576;     // WORD16 sbr_alt_sin_twiddle_l32[16]
+constexpr int kQRomTCosSinL32 = 608;    // WORD16 sbr_t_cos_sin_l32[64]
+constexpr int kQRomQmfC = 904;          // WORD16 qmf_c[1280]
+constexpr int kQRomBytes = 3464;
+
+struct QmfSynthArgs {
+  const int32_t *matrix;   // [n_units][32][128] per slot re[64] | im[64]  (read-only here)
+  int16_t *states;         // [n_units][1280]   ia_sbr_qmf_filter_bank_struct.filter_states, in/out
+  int16_t *pos;            // [n_units][2]      {ixheaacd_drc_offset, filter_pos_syn - qmf_c}, in/out
+  const int16_t *params;   // [n_units][8]      {ov_lb_scale, lb_scale, hb_scale, st_syn_scale, lsb, usb, split, 0}
+  int16_t *pcm;            // PCM16, 2048 per unit (ch_fac interleave as for the IMDCT stage)
+  const uint8_t *rom;      // device image built by qmf_synth_build_tables()
+  long long n_units;
+  int ch_fac;
+};
+
+size_t qmf_synth_table_bytes();
+bool qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out);
+cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

@@ -15,12 +15,20 @@ struct xaac_b200_ctx {
   long long launches = 0;
   uint8_t *d_rom_imdct = nullptr;
   bool have_imdct_rom = false;
+  uint8_t *d_rom_qmf_syn = nullptr;  // table image of qmf_synth_hq_kernel
+  bool have_qmf_rom = false;
   char err[256] = {0};
   // staging for the *_host entry points: kPipe chunks in flight, one stream each
   static constexpr int kPipe = 3;
   cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
   void *stage[kPipe] = {nullptr, nullptr, nullptr};
   size_t stage_bytes = 0;
+};
+
+struct xaac_b200_qmf_synth_state {
+  int64_t n_units = 0;
+  int16_t *d_states = nullptr;  // [n][1280]
+  int16_t *d_pos = nullptr;     // [n][2]
 };
 
 struct xaac_b200_imdct_state {
@@ -98,6 +106,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
     if (ctx->stage[i]) cudaFree(ctx->stage[i]);
   }
   if (ctx->d_rom_imdct) cudaFree(ctx->d_rom_imdct);
+  if (ctx->d_rom_qmf_syn) cudaFree(ctx->d_rom_qmf_syn);
   delete ctx;
 }
 
@@ -239,6 +248,141 @@ int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *
     if (rc != XAAC_B200_OK) return rc;
     CK(cudaMemcpyAsync(out + u0 * 1024, d_out, (size_t)n * 4096, cudaMemcpyDeviceToHost, st), "D2H out");
     CK(cudaMemcpyAsync(qshift_adj + u0, d_qa, (size_t)n, cudaMemcpyDeviceToHost, st), "D2H qshift_adj");
+  }
+  for (int i = 0; i < xaac_b200_ctx::kPipe; i++) CK(cudaStreamSynchronize(ctx->streams[i]), "stream sync");
+  return XAAC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// QMF banks
+// ---------------------------------------------------------------------------------------------------------
+int32_t xaac_b200_set_qmf_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
+  if (!ctx || !tables) return bad_arg(ctx, "null");
+  if (bytes < (size_t)xb::kQRomBytes) return bad_arg(ctx, "QMF ROM blob shorter than 3464 bytes");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  size_t n = xb::qmf_synth_table_bytes();
+  uint8_t *img = (uint8_t *)calloc(1, n + 64);
+  if (!img) return XAAC_B200_FATAL;
+  if (!xb::qmf_synth_build_tables((const uint8_t *)tables, img)) {
+    free(img);
+    return bad_arg(ctx, "QMF tables: unexpected digit-reverse table or prototype filter exceeds the no-saturation bound");
+  }
+  if (!ctx->d_rom_qmf_syn) {
+    cudaError_t e = cudaMalloc((void **)&ctx->d_rom_qmf_syn, n);
+    if (e != cudaSuccess) {
+      free(img);
+      return fail(ctx, e, "cudaMalloc(qmf rom)");
+    }
+  }
+  cudaError_t e = cudaMemcpy(ctx->d_rom_qmf_syn, img, n, cudaMemcpyHostToDevice);
+  free(img);
+  if (e != cudaSuccess) return fail(ctx, e, "cudaMemcpy(qmf rom)");
+  ctx->have_qmf_rom = true;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_qmf_synth_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_matrix, int16_t *d_filter_states,
+                                   int16_t *d_pos, const int16_t *d_params, int16_t *d_pcm, int64_t n_units,
+                                   int32_t ch_fac, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->have_qmf_rom) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_qmf_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0 || ch_fac < 1) return bad_arg(ctx, "n_units/ch_fac");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_matrix || !d_filter_states || !d_pos || !d_params || !d_pcm) return bad_arg(ctx, "null buffer");
+  if (ch_fac > 1 && (n_units % ch_fac) != 0) return bad_arg(ctx, "n_units must be a multiple of ch_fac");
+  xb::QmfSynthArgs a;
+  a.matrix = d_matrix;
+  a.states = d_filter_states;
+  a.pos = d_pos;
+  a.params = d_params;
+  a.pcm = d_pcm;
+  a.rom = ctx->d_rom_qmf_syn;
+  a.n_units = n_units;
+  a.ch_fac = ch_fac;
+  CK(xb::launch_qmf_synth_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch qmf_synth_hq_kernel");
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_qmf_synth_state_create(xaac_b200_ctx *ctx, int64_t n_units, xaac_b200_qmf_synth_state **out) {
+  if (!ctx || !out || n_units < 0) return bad_arg(ctx, "state_create");
+  *out = nullptr;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  xaac_b200_qmf_synth_state *st = new (std::nothrow) xaac_b200_qmf_synth_state();
+  if (!st) return XAAC_B200_FATAL;
+  st->n_units = n_units;
+  size_t n = (size_t)(n_units > 0 ? n_units : 1);
+  cudaError_t e = cudaMalloc((void **)&st->d_states, n * 2560);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_pos, n * 4);
+  if (e == cudaSuccess) e = cudaMemset(st->d_states, 0, n * 2560);
+  if (e == cudaSuccess) e = cudaMemset(st->d_pos, 0, n * 4);
+  if (e != cudaSuccess) {
+    xaac_b200_qmf_synth_state_destroy(ctx, st);
+    return fail(ctx, e, "qmf_synth_state_create");
+  }
+  *out = st;
+  return XAAC_B200_OK;
+}
+
+void xaac_b200_qmf_synth_state_destroy(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *st) {
+  if (!st) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (st->d_states) cudaFree(st->d_states);
+  if (st->d_pos) cudaFree(st->d_pos);
+  delete st;
+}
+
+int32_t xaac_b200_qmf_synth_state_upload(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *st,
+                                         const int16_t *filter_states, const int16_t *pos) {
+  if (!ctx || !st || !filter_states || !pos) return bad_arg(ctx, "state_upload");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaMemcpy(st->d_states, filter_states, (size_t)st->n_units * 2560, cudaMemcpyHostToDevice), "H2D states");
+  CK(cudaMemcpy(st->d_pos, pos, (size_t)st->n_units * 4, cudaMemcpyHostToDevice), "H2D pos");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_qmf_synth_state_download(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *st,
+                                           int16_t *filter_states, int16_t *pos) {
+  if (!ctx || !st || !filter_states || !pos) return bad_arg(ctx, "state_download");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaMemcpy(filter_states, st->d_states, (size_t)st->n_units * 2560, cudaMemcpyDeviceToHost), "D2H states");
+  CK(cudaMemcpy(pos, st->d_pos, (size_t)st->n_units * 4, cudaMemcpyDeviceToHost), "D2H pos");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_qmf_synth_hq_host(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *state, const int32_t *matrix,
+                                    const int16_t *params, int16_t *pcm, int32_t ch_fac) {
+  if (!ctx || !state) return XAAC_B200_ERR_ARG;
+  const int64_t n_units = state->n_units;
+  if (ch_fac < 1) return bad_arg(ctx, "ch_fac");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!matrix || !params || !pcm) return bad_arg(ctx, "null buffer");
+  if (ch_fac > 1 && (n_units % ch_fac) != 0) return bad_arg(ctx, "n_units must be a multiple of ch_fac");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int64_t chunk = 4096;
+  if (chunk > n_units) chunk = n_units;
+  if (ch_fac > 1) chunk = ((chunk + ch_fac - 1) / ch_fac) * ch_fac;
+  // per-unit staging layout: matrix 16384 | pcm 4096 | params 16
+  const size_t per_unit = 16384 + 4096 + 16;
+  int32_t rc = ensure_stage(ctx, per_unit * (size_t)chunk);
+  if (rc != XAAC_B200_OK) return rc;
+  int slot = 0;
+  for (int64_t u0 = 0; u0 < n_units; u0 += chunk, slot = (slot + 1) % xaac_b200_ctx::kPipe) {
+    int64_t n = (n_units - u0 < chunk) ? (n_units - u0) : chunk;
+    cudaStream_t st = ctx->streams[slot];
+    uint8_t *base = (uint8_t *)ctx->stage[slot];
+    int32_t *d_mat = (int32_t *)base;
+    int16_t *d_pcm = (int16_t *)(base + 16384 * (size_t)chunk);
+    int16_t *d_prm = (int16_t *)(base + 20480 * (size_t)chunk);
+    CK(cudaMemcpyAsync(d_mat, matrix + u0 * 4096, (size_t)n * 16384, cudaMemcpyHostToDevice, st), "H2D matrix");
+    CK(cudaMemcpyAsync(d_prm, params + u0 * 8, (size_t)n * 16, cudaMemcpyHostToDevice, st), "H2D params");
+    rc = xaac_b200_qmf_synth_hq_dev(ctx, d_mat, state->d_states + u0 * 1280, state->d_pos + u0 * 2, d_prm, d_pcm, n,
+                                    ch_fac, st);
+    if (rc != XAAC_B200_OK) return rc;
+    CK(cudaMemcpyAsync(pcm + u0 * 2048, d_pcm, (size_t)n * 4096, cudaMemcpyDeviceToHost, st), "D2H pcm");
   }
   for (int i = 0; i < xaac_b200_ctx::kPipe; i++) CK(cudaStreamSynchronize(ctx->streams[i]), "stream sync");
   return XAAC_B200_OK;

@@ -61,6 +61,48 @@ class Oracle:
         return out, ov, np.stack([ps, pq], 1).astype(np.uint8), adj.astype(np.int8)
 
 
+    # ---- QMF banks -------------------------------------------------------------------------------------
+    @property
+    def qrom(self):
+        if not hasattr(self, "_qrom"):
+            self._qrom = rom("qmf_rom.bin")
+        return self._qrom
+
+    def cos_sin_mod(self, subband, no_channels):
+        sb = np.ascontiguousarray(subband, np.int32).copy()
+        self.lib.xo_cos_sin_mod(P(self.qrom), P(sb), int(no_channels))
+        return sb
+
+    def synth_batch(self, matrix, filter_states, pos, params):
+        """matrix [n,32,128] i32, filter_states [n,1280] i16, pos [n,2] i16, params [n,8] i16.
+        Returns (pcm [n,2048] i16, filter_states', pos')."""
+        n = matrix.shape[0]
+        m = np.ascontiguousarray(matrix, np.int32).copy()
+        fs = np.ascontiguousarray(filter_states, np.int16).copy()
+        off = np.ascontiguousarray(pos[:, 0], np.int32).copy()
+        fp = np.ascontiguousarray(pos[:, 1], np.int32).copy()
+        sf = np.ascontiguousarray(params[:, 0:4], np.int32).copy()
+        lsb = np.ascontiguousarray(params[:, 4], np.int32).copy()
+        usb = np.ascontiguousarray(params[:, 5], np.int32).copy()
+        assert (params[:, 6] == 6).all()
+        pcm = np.zeros((n, 2048), np.int16)
+        self.lib.xo_synt_qmffilt_hq_batch(P(self.qrom), P(m), P(fs), P(off), P(fp), P(sf), P(lsb), P(usb), P(pcm), n)
+        return pcm, fs, np.stack([off, fp], 1).astype(np.int16)
+
+    def anal_batch(self, time_in, states, pos, usb):
+        """time_in [n,1024] i16, states [n,320] i16, pos [n,2] i16 {core_samples offset, filter_pos}, usb [n].
+        Returns (matrix [n,32,128] i32, states', pos')."""
+        n = time_in.shape[0]
+        t = np.ascontiguousarray(time_in, np.int16)
+        st = np.ascontiguousarray(states, np.int16).copy()
+        po = np.ascontiguousarray(pos[:, 0], np.int32).copy()
+        fp = np.ascontiguousarray(pos[:, 1], np.int32).copy()
+        ub = np.ascontiguousarray(usb, np.int32).copy()
+        m = np.zeros((n, 32, 128), np.int32)
+        self.lib.xo_anal_qmffilt_hq_batch(P(self.qrom), P(t), P(st), P(po), P(fp), P(ub), P(m), n)
+        return m, st, np.stack([po, fp], 1).astype(np.int16)
+
+
 class Ref:
     """The unmodified reference, compiled from /root/reference by oracle/Makefile (target ref)."""
 
@@ -79,6 +121,37 @@ class Ref:
         total = ctypes.c_int(0)
         p = fn(ctypes.byref(total))
         return np.frombuffer(ctypes.string_at(p, nbytes), dtype=np.uint8).copy()
+
+    def rom_qmf(self, nbytes=3464):
+        fn = self.lib.ref_rom_qmf_tables
+        fn.restype = ctypes.c_void_p
+        total = ctypes.c_int(0)
+        p = fn(ctypes.byref(total))
+        return np.frombuffer(ctypes.string_at(p, nbytes), dtype=np.uint8).copy()
+
+    def cos_sin_mod(self, subband, no_channels):
+        sb = np.ascontiguousarray(subband, np.int32).copy()
+        self.lib.ref_cos_sin_mod(P(sb), int(no_channels))
+        return sb
+
+    def synth(self, matrix, filter_states, pos, params, ch_fac=1):
+        """single unit through ixheaacd_cplx_synt_qmffilt"""
+        m = np.ascontiguousarray(matrix, np.int32).copy()
+        fs = np.ascontiguousarray(filter_states, np.int16).copy()
+        off, fp = ctypes.c_int32(int(pos[0])), ctypes.c_int32(int(pos[1]))
+        sf = np.ascontiguousarray(params[0:4], np.int32).copy()
+        pcm = np.zeros(2048 * ch_fac, np.int16)
+        self.lib.ref_synt_qmffilt_hq(P(m), P(fs), ctypes.byref(off), ctypes.byref(fp), P(sf), int(params[4]),
+                                     int(params[5]), int(params[6]), P(pcm), int(ch_fac))
+        return pcm[::ch_fac].copy(), fs, np.array([off.value, fp.value], np.int16)
+
+    def anal(self, time_in, states, pos, usb, ch_fac=1):
+        st = np.ascontiguousarray(states, np.int16).copy()
+        po, fp = ctypes.c_int32(int(pos[0])), ctypes.c_int32(int(pos[1]))
+        m = np.zeros((32, 128), np.int32)
+        t = np.ascontiguousarray(time_in, np.int16)
+        lb = self.lib.ref_anal_qmffilt_hq(P(t), int(ch_fac), P(st), ctypes.byref(po), ctypes.byref(fp), int(usb), P(m))
+        return m, st, np.array([po.value, fp.value], np.int16), lb
 
     def imdct_process(self, spec, ovl, prev_shape, prev_seq, win_seq, win_shape, ch_fac=1):
         sp = np.ascontiguousarray(spec, np.int32).copy()
@@ -118,3 +191,35 @@ def synth_units(n, seed, seq_mix=True):
         ics[:, 0] = rng.integers(0, 4, n)
         ics[:, 1] = rng.integers(0, 2, n)
     return spec, ovl, wstate, ics
+
+
+def synth_qmf_units(n, seed):
+    """Synthetic synthesis-bank inputs: QMF matrices with per-unit magnitude, random filter state,
+    ring/coefficient offsets in every phase, scale factors spanning left and right block shifts, lsb/usb spread.
+    Returns matrix [n,32,128] i32, filter_states [n,1280] i16, pos [n,2] i16, params [n,8] i16."""
+    rng = np.random.default_rng(seed)
+    s = rng.integers(8, 30, size=(n, 1, 1))
+    matrix = ((rng.random((n, 32, 128)) * 2 - 1) * (2.0 ** s)).astype(np.int64).astype(np.int32)
+    fs = rng.integers(-32768, 32768, (n, 1280)).astype(np.int16)
+    pos = np.stack([rng.integers(0, 10, n) * 128, rng.integers(0, 10, n) * 64], 1).astype(np.int16)
+    params = np.zeros((n, 8), np.int16)
+    params[:, 0] = rng.integers(-16, 8, n)   # ov_lb_scale
+    params[:, 1] = rng.integers(-16, 8, n)   # lb_scale
+    params[:, 2] = rng.integers(-16, 8, n)   # hb_scale
+    params[:, 3] = -6                        # st_syn_scale (reference constant)
+    lsb = rng.integers(0, 41, n)
+    params[:, 4] = lsb
+    params[:, 5] = np.minimum(64, lsb + rng.integers(0, 33, n))
+    params[:, 6] = 6
+    if n >= 8:
+        matrix[0] = 0
+        fs[0] = 0
+        matrix[1] = rng.integers(-2 ** 31, 2 ** 31, (32, 128), dtype=np.int64).astype(np.int32)  # saturating everywhere
+        params[1, 0:3] = (-20, -20, -20)
+        matrix[2] = 2 ** 31 - 1
+        matrix[3] = -(2 ** 31)
+        params[4, 0:3] = (31, 31, 31)       # extreme right shifts
+        params[5, 0] = params[5, 1]         # ov_lb_shift == lb_shift branch
+        params[6, 4:6] = (0, 0)             # no bands scaled
+        params[7, 4:6] = (64, 64)           # everything low band
+    return matrix, fs, pos, params

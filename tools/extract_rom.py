@@ -38,7 +38,8 @@ def main():
         dump(lib, getter, n, name)
 
 
-EXTRA = []
+# leading part of ia_qmf_dec_tables_struct up to and including qmf_c (decoder/ixheaacd_sbr_rom.h:71-95)
+EXTRA = [("ref_rom_qmf_tables", 3464, "qmf_rom.bin")]
 
 if __name__ == "__main__":
     main()
