@@ -24,9 +24,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 IMDCT_BYTES_PER_UNIT = 12288  # 4096 spec in + 2048 overlap in + 2048 overlap out + 4096 WORD32 out
+SYNTH_BYTES_PER_UNIT = 25600  # 16384 matrix + 2560 state in + 2560 state out + 4096 PCM16 out
 WORKLOADS = {
     # name -> (BASELINE.json config index, stereo frames per GPU, description)
     "aac_lc_stereo_imdct_ola": (1, 65536, "AAC-LC stereo 44.1 kHz batch=65536 frames, IMDCT+OLA only"),
+    "qmf_synth_hq": (3, 65536, "stand-alone fixed-point HQ 64-band QMF synthesis stage of the HE-AAC chain, "
+                               "batch=65536 stereo frames (131072 output channels)"),
 }
 
 
@@ -81,6 +84,73 @@ def make_spec_torch(n_units, seed, device):
     spec[2, 17] = 2 ** 31 - 1
     spec[3] = 1 << 20
     return spec
+
+
+def make_synth_inputs_torch(n_units, seed, device):
+    """QMF matrices [n,32,128] with per-unit magnitude 2^14..2^26 and typical HE-AAC scale factors."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    s = torch.randint(14, 27, (n_units, 1, 1), generator=g, device=device, dtype=torch.int32)
+    matrix = torch.empty((n_units, 32, 128), dtype=torch.int32, device=device)
+    chunk = 8192
+    for i in range(0, n_units, chunk):
+        r = torch.randint(-(2 ** 31), 2 ** 31 - 1, (min(chunk, n_units - i), 32, 128), generator=g, device=device,
+                          dtype=torch.int64).to(torch.int32)
+        matrix[i:i + chunk] = r >> (31 - s[i:i + chunk])
+    params = torch.zeros((n_units, 8), dtype=torch.int16, device=device)
+    params[:, 0] = torch.randint(-10, -3, (n_units,), generator=g, device=device)  # ov_lb_scale
+    params[:, 1] = torch.randint(-10, -3, (n_units,), generator=g, device=device)  # lb_scale
+    params[:, 2] = torch.randint(-12, -4, (n_units,), generator=g, device=device)  # hb_scale
+    params[:, 3] = -6
+    lsb = torch.randint(16, 33, (n_units,), generator=g, device=device)
+    params[:, 4] = lsb
+    params[:, 5] = torch.clamp(lsb + torch.randint(8, 33, (n_units,), generator=g, device=device), max=64)
+    params[:, 6] = 6
+    matrix[0] = 0
+    matrix[1] = 2 ** 31 - 1
+    return matrix, params
+
+
+def cpu_arm_synth(n_units, threads, seed, reps=1):
+    """Time ixheaacd_cplx_synt_qmffilt (HQ) per unit on host threads. Returns (units_per_s, kind)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    matrix0, fs, pos, params = oracle_util.synth_qmf_units(n_units, seed)
+    params[:, 0:3] = np.clip(params[:, 0:3], -12, -3)
+    P = oracle_util.P
+    pcm = np.zeros((n_units, 2048), np.int16)
+    bounds = np.linspace(0, n_units, threads + 1).astype(int)
+    sf = np.ascontiguousarray(params[:, 0:4], np.int32)
+    off = np.ascontiguousarray(pos[:, 0], np.int32)
+    fp = np.ascontiguousarray(pos[:, 1], np.int32)
+    lsb = np.ascontiguousarray(params[:, 4], np.int32)
+    usb = np.ascontiguousarray(params[:, 5], np.int32)
+    if ref is not None:
+        kind, fn, pre = "reference", ref.lib.ref_synt_qmffilt_hq_batch, []
+    else:
+        orc = oracle_util.Oracle()
+        kind, fn, pre = "port", orc.lib.xo_synt_qmffilt_hq_batch, [P(orc.qrom)]
+
+    def work(t, matrix):
+        a, b = bounds[t], bounds[t + 1]
+        if b > a:
+            fn(*pre, P(matrix[a:b]), P(fs[a:b]), P(off[a:b]), P(fp[a:b]), P(sf[a:b]), P(lsb[a:b]), P(usb[a:b]),
+               P(pcm[a:b]), int(b - a))
+
+    def one_pass():
+        matrix = matrix0.copy()  # the reference modifies the matrix in place
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t, matrix)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    one_pass()
+    dt = sum(one_pass() for _ in range(reps))
+    return n_units * reps / dt, kind
 
 
 class ClockSampler:
@@ -198,32 +268,102 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+STAGES = {
+    "aac_lc_stereo_imdct_ola": dict(kernel="imdct_ola_kernel", bytes_per_unit=IMDCT_BYTES_PER_UNIT,
+                                    stage="IMDCT + window/OLA (fixed-point WORD32, bit-exact)",
+                                    ref_stage="ixheaacd_imdct_process", cpu=cpu_arm, cpu_units_per_core=4096,
+                                    realtime_fps=43.066, h2d=4096 + 2, d2h=4096 + 1),
+    "qmf_synth_hq": dict(kernel="qmf_synth_hq_kernel", bytes_per_unit=SYNTH_BYTES_PER_UNIT,
+                         stage="complex 64-band QMF synthesis (fixed-point, bit-exact)",
+                         ref_stage="ixheaacd_cplx_synt_qmffilt", cpu=cpu_arm_synth, cpu_units_per_core=1024,
+                         realtime_fps=21.533, h2d=16384 + 16, d2h=4096),
+}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = host_threads()
     cfg_idx, frames, desc = WORKLOADS[args.workload]
-    sample_units = min(2 * frames, 4096 * cores)
+    stg = STAGES[args.workload]
+    sample_units = min(2 * frames, stg["cpu_units_per_core"] * cores)
     sample_units -= sample_units % 2
     t0 = time.perf_counter()
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_arm(sample_units, cores, 0xAAC0 + cfg_idx, reps=1)
-    ups, kind = cpu_arm(sample_units, cores, 0xAAC0 + cfg_idx, reps=max(1, args.steps))
+    ups, kind = stg["cpu"](sample_units, cores, 0xAAC0 + cfg_idx, reps=max(1, args.steps))
     fps = ups / 2.0
     line = {
         "impl": "reference", "metric": "decoded_stereo_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (sample_units / 2) / fps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload, "baseline_config": desc, "stage": "ixheaacd_imdct_process",
+        "config": {"workload": args.workload, "baseline_config": desc, "stage": stg["ref_stage"],
                    "step": f"bounded sample: {sample_units // 2} stereo frames per step on host cores"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample_units} units (frame x channel) x {max(1, args.steps)} passes, "
-                                   f"{cores} threads, private state per unit"},
+                         "sample": f"{sample_units} units (frame x channel) x {max(1, args.steps)} passes "
+                                   f"(+1 warm-up), {cores} threads, private state per unit"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line), flush=True)
+
+
+class ImdctWork:
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        self.spec = make_spec_torch(n_units, seed, dev)
+        self.walk = torch.from_numpy(sequence_walk(n_units, steps_total, seed)).to(dev)
+        self.state = xb.ImdctBatch(n_units, device=dev)
+        self.out = torch.empty((n_units, 1024), dtype=torch.int32, device=dev)
+        self.adj = torch.empty((n_units,), dtype=torch.int8, device=dev)
+        self.nw = steps_total
+
+    def step(self, i, stream):
+        self.xb.imdct_process(self.ctx, self.state, self.spec, self.walk[i % self.nw], self.out, self.adj, stream=stream)
+
+    def host_setup(self):
+        import torch
+        self.h_spec = torch.empty((self.n, 1024), dtype=torch.int32).pin_memory()
+        self.h_spec.copy_(self.spec)
+        self.h_out = torch.empty((self.n, 1024), dtype=torch.int32).pin_memory()
+        self.h_adj = torch.empty((self.n,), dtype=torch.int8).pin_memory()
+        self.h_walk = self.walk.cpu().pin_memory()
+        self.hstate = self.xb.ImdctHostState(self.ctx, self.n)
+
+    def host_step(self, i):
+        self.xb.imdct_process_host(self.ctx, self.hstate, self.h_spec, self.h_walk[i % self.nw], self.h_out, self.h_adj)
+
+    def host_close(self):
+        self.hstate.close()
+
+
+class SynthWork:
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        self.matrix, self.params = make_synth_inputs_torch(n_units, seed, dev)
+        self.state = xb.QmfSynthBatch(n_units, device=dev)
+        self.pcm = torch.empty((n_units, 2048), dtype=torch.int16, device=dev)
+
+    def step(self, i, stream):
+        self.xb.cplx_synt_qmffilt(self.ctx, self.state, self.matrix, self.params, self.pcm, stream=stream)
+
+    def host_setup(self):
+        import torch
+        self.h_matrix = torch.empty((self.n, 32, 128), dtype=torch.int32).pin_memory()
+        self.h_matrix.copy_(self.matrix)
+        self.h_params = self.params.cpu().pin_memory()
+        self.h_pcm = torch.empty((self.n, 2048), dtype=torch.int16).pin_memory()
+        self.hstate = self.xb.QmfSynthHostState(self.ctx, self.n)
+
+    def host_step(self, i):
+        self.xb.cplx_synt_qmffilt_host(self.ctx, self.hstate, self.h_matrix, self.h_params, self.h_pcm)
+
+    def host_close(self):
+        self.hstate.close()
+
+
+WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork}
 
 
 def main():
@@ -236,6 +376,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="stereo frames per GPU (default: the config's batch)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps for the host-buffer arm (default min(steps,5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-stages", action="store_true", help="skip the short extra per-stage roofline runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -259,18 +400,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cfg_idx, frames, desc = WORKLOADS[args.workload]
+    stg = STAGES[args.workload]
     if args.frames:
         frames = args.frames
-    n_units = 2 * frames  # stereo: two core channels per frame; each rank owns its own streams (weak scaling)
+    n_units = 2 * frames  # stereo: two channels per frame; each rank owns its own streams (weak scaling)
     K, W = args.steps, args.warmup
     seed = 0xAAC0 + cfg_idx + 1000 * rank
-
     ctx = xb.Context(local_rank)
-    spec = make_spec_torch(n_units, seed, dev)
-    walk = torch.from_numpy(sequence_walk(n_units, W + K, seed)).to(dev)
-    state = xb.ImdctBatch(n_units, device=dev)
-    out = torch.empty((n_units, 1024), dtype=torch.int32, device=dev)
-    adj = torch.empty((n_units,), dtype=torch.int8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -278,24 +414,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def timed(work, k, w, first=0):
+        """w warm-up + k timed steps on the launching stream; returns (per-step ms list, total ms, launches)."""
+        for s_ in range(w):
+            work.step(first + s_, stream)
+        barrier()
+        l0 = ctx.launch_count
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+        barrier()
+        ev[0].record(stream)
+        for s_ in range(k):
+            work.step(first + w + s_, stream)
+            ev[s_ + 1].record(stream)
+        barrier()
+        return [ev[i].elapsed_time(ev[i + 1]) for i in range(k)], ev[0].elapsed_time(ev[k]), ctx.launch_count - l0
+
     # ---- device-resident arm --------------------------------------------------------------------------
-    for s in range(W):
-        xb.imdct_process(ctx, state, spec, walk[s], out, adj, stream=stream)
-    barrier()
+    work = WORK[args.workload](xb, ctx, n_units, W + K, seed, dev)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = ctx.launch_count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-    barrier()
-    ev[0].record(stream)
-    for s in range(K):
-        xb.imdct_process(ctx, state, spec, walk[W + s], out, adj, stream=stream)
-        ev[s + 1].record(stream)
-    barrier()
-    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
-    total_ms = ev[0].elapsed_time(ev[K])
-    gpu_launches = ctx.launch_count - launches0
+    step_ms, total_ms, gpu_launches = timed(work, K, W)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -305,18 +444,13 @@ def main():
 
     # ---- end-to-end arm: host buffers through the C-ABI ---------------------------------------------------
     Ke = args.e2e_steps or min(K, 5)
-    h_spec = torch.empty((n_units, 1024), dtype=torch.int32).pin_memory()
-    h_spec.copy_(spec)
-    h_out = torch.empty((n_units, 1024), dtype=torch.int32).pin_memory()
-    h_adj = torch.empty((n_units,), dtype=torch.int8).pin_memory()
-    h_walk = walk.cpu().pin_memory()
-    hstate = xb.ImdctHostState(ctx, n_units)
-    xb.imdct_process_host(ctx, hstate, h_spec, h_walk[0], h_out, h_adj)  # warm-up (staging allocation)
-    xb.imdct_process_host(ctx, hstate, h_spec, h_walk[1], h_out, h_adj)
+    work.host_setup()
+    work.host_step(0)  # warm-up (staging allocation)
+    work.host_step(1)
     barrier()
     t0 = time.perf_counter()
-    for s in range(Ke):
-        xb.imdct_process_host(ctx, hstate, h_spec, h_walk[(2 + s) % (W + K)], h_out, h_adj)
+    for s_ in range(Ke):
+        work.host_step(2 + s_)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -324,40 +458,59 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * frames * Ke / float(te.item())
     clocks = sampler.stop() if rank == 0 else None
+    work.host_close()
+    del work
+    torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = peaks()
-        achieved = IMDCT_BYTES_PER_UNIT * n_units / (kernel_ms * 1e-3) / 1e9
+        achieved = stg["bytes_per_unit"] * n_units / (kernel_ms * 1e-3) / 1e9
         line = {
             "metric": "decoded_stereo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": args.workload, "baseline_config": desc, "stereo_frames_per_gpu": frames,
-                       "units_per_gpu": n_units, "stage": "IMDCT + window/OLA (fixed-point WORD32, bit-exact)",
-                       "window_sequence_mix": "walk: ~90% long, 4% start, 4% stop, 2% short",
-                       "l2_policy": "per-step working set 1.25 GiB >> 126 MB L2 (no flush needed)",
-                       "realtime_x_per_stream": value / world / frames * frames / 43.066 / frames},
+                       "units_per_gpu": n_units, "stage": stg["stage"],
+                       "l2_policy": "per-step working set > 1 GiB >> 126 MB L2 (no flush needed)",
+                       "realtime_x_per_stream": (value / world) / frames / stg["realtime_fps"]},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_units * (4096 + 2),
-                    "d2h_bytes_per_step": n_units * (4096 + 1), "steps": Ke,
-                    "timer": "host wall clock around the synchronous xaac_b200_imdct_process_host call"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_units * stg["h2d"],
+                    "d2h_bytes_per_step": n_units * stg["d2h"], "steps": Ke,
+                    "timer": "host wall clock around the synchronous host-buffer C-ABI call"},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "kernel": "imdct_ola_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": stg["kernel"], "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_unit": IMDCT_BYTES_PER_UNIT, "units_per_launch": n_units,
+                         "bytes_per_unit": stg["bytes_per_unit"], "units_per_launch": n_units,
                          "launch_ms": kernel_ms},
         }
-        line["config"]["realtime_x_per_stream"] = (value / world) / frames / 43.066 if frames else None
+        if args.workload == "aac_lc_stereo_imdct_ola":
+            line["config"]["window_sequence_mix"] = "walk: ~90% long, 4% start, 4% stop, 2% short"
+        # short extra runs of the other stage kernels so every hot kernel has a live roofline number
+        if not args.no_extra_stages and world == 1:
+            extra = {}
+            for name in WORK:
+                if name == args.workload:
+                    continue
+                w2 = WORK[name](xb, ctx, n_units, 8, seed, dev)
+                ms, _, _ = timed(w2, 5, 3)
+                ach = STAGES[name]["bytes_per_unit"] * n_units / (float(np.mean(ms)) * 1e-3) / 1e9
+                extra[name] = {"kernel": STAGES[name]["kernel"], "launch_ms": float(np.mean(ms)),
+                               "units_per_launch": n_units, "bytes_per_unit": STAGES[name]["bytes_per_unit"],
+                               "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                               "stereo_frames_per_sec": frames / (float(np.mean(ms)) * 1e-3)}
+                del w2
+                torch.cuda.empty_cache()
+            line["stage_rooflines"] = extra
         if not args.no_cpu_baseline and world == 1:
             cores = host_threads()
-            ups1, kind = cpu_arm(8192, 1, 0xAAC0 + cfg_idx, reps=1)
-            upsN, kind = cpu_arm(4096 * cores, cores, 0xAAC0 + cfg_idx, reps=2)
+            ups1, kind = stg["cpu"](stg["cpu_units_per_core"], 1, 0xAAC0 + cfg_idx, reps=1)
+            upsN, kind = stg["cpu"](stg["cpu_units_per_core"] * cores, cores, 0xAAC0 + cfg_idx, reps=2)
             line["cpu_baseline"] = {"value": upsN / 2.0, "unit": "frames/s", "cores": cores, "kind": kind,
                                     "value_1core": ups1 / 2.0,
-                                    "sample": f"{4096 * cores} units x 2 passes on {cores} threads "
-                                              f"(1-core figure: 8192 units), ixheaacd_imdct_process per unit"}
+                                    "sample": f"{stg['cpu_units_per_core'] * cores} units x 2 passes on {cores} threads "
+                                              f"(1-core figure: {stg['cpu_units_per_core']} units), "
+                                              f"{stg['ref_stage']} per unit"}
         print(json.dumps(line), flush=True)
-    hstate.close()
     if world > 1:
         dist.destroy_process_group()
 

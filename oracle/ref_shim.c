@@ -127,7 +127,7 @@ void ref_synt_qmffilt_hq(int32_t *matrix, int16_t *filter_states, int32_t *drc_o
   ia_sbr_qmf_filter_bank_struct bank;
   ia_sbr_scale_fact_struct s;
   ia_sbr_tables_struct tabs;
-  static WORD32 dump[MAX_ENV_COLS][128];
+  WORD32 dump[32][128]; /* qmf_real_out / qmf_imag_out sink (thread-private) */
   WORD32 *re[MAX_ENV_COLS], *im[MAX_ENV_COLS], *ore[MAX_ENV_COLS], *oim[MAX_ENV_COLS];
   ia_qmf_dec_tables_struct *t = (ia_qmf_dec_tables_struct *)&ixheaacd_aac_qmf_dec_tables;
   memset(&bank, 0, sizeof(bank));
@@ -189,4 +189,13 @@ int ref_anal_qmffilt_hq(const int16_t *time_in, int32_t ch_fac, int16_t *states,
   *pos = (int32_t)(bank.core_samples_buffer - states);
   *filter_pos = (int32_t)(bank.filter_pos - (WORD16 *)t->qmf_c);
   return s.lb_scale;
+}
+
+/* batch driver for the CPU baseline: n units, unit-major, private state per unit */
+void ref_synt_qmffilt_hq_batch(int32_t *matrix, int16_t *filter_states, int32_t *drc_offset, int32_t *filter_pos,
+                               const int32_t *sf, const int32_t *lsb, const int32_t *usb, int16_t *time_out,
+                               int32_t n) {
+  for (int32_t u = 0; u < n; u++)
+    ref_synt_qmffilt_hq(matrix + (size_t)u * 4096, filter_states + (size_t)u * 1280, drc_offset + u, filter_pos + u,
+                        sf + 4 * u, lsb[u], usb[u], 6, time_out + (size_t)u * 2048, 1);
 }
