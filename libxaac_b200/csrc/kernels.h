@@ -64,10 +64,11 @@ struct QmfSynthArgs {
   const uint8_t *rom;      // device image built by qmf_synth_build_tables()
   long long n_units;
   int ch_fac;
+  int fast_bits;           // inputs below 2^fast_bits cannot saturate any add of the modulation
 };
 
 size_t qmf_synth_table_bytes();
-bool qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out);
+int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out);  // returns fast_bits (>0) or -1
 cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStream_t stream);
 
 size_t imdct_smem_bytes();

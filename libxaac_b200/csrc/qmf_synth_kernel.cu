@@ -56,23 +56,132 @@ struct SynBlockSmem {
 // (stride 2 inside groups of 8) and the pre-twiddle scatter conflict-free for 64-bit accesses.
 XB_DEV int tsw(int e) { return e ^ (((e >> 3) & 3) << 1); }
 
+// Saturating adds have no single-instruction form on sm_100 (add.sat.s32 lowers to IADD3 + 2 PLOP3 + 2 SEL), and the
+// modulation is made of them.  Every slot pair is therefore classified first: if all its block-shifted inputs are
+// below 2^fast_bits (a bound derived from the installed tables under which no add of the reference can saturate,
+// see qmf_synth_build_tables), the pair runs with plain wrapping adds — bit-identical by construction; otherwise it
+// runs the exact saturating code.  Real decoder data always takes the first path.
+template <bool SAT> XB_DEV i32 A_(i32 a, i32 b) { return SAT ? add_sat(a, b) : wadd(a, b); }
+template <bool SAT> XB_DEV i32 S_(i32 a, i32 b) { return SAT ? sub_sat(a, b) : wsub(a, b); }
+template <bool SAT> XB_DEV i32 N_(i32 a) { return SAT ? neg_sat(a) : wneg(a); }
+
 // one radix-4 butterfly, generic:1766-1822. e[m] = leg m (re,im); tw = 3 x (si<<16, co<<16)
+template <bool SAT>
 XB_DEV void radix4(int2 &e0, int2 &e1, int2 &e2, int2 &e3, const int2 t1, const int2 t2, const int2 t3) {
-  i32 xh0 = add_sat(e0.x, e2.x), xl0 = sub_sat(e0.x, e2.x);
-  i32 xh20 = add_sat(e1.x, e3.x), xl20 = sub_sat(e1.x, e3.x);
-  i32 xh1 = add_sat(e0.y, e2.y), xl1 = sub_sat(e0.y, e2.y);
-  i32 xh21 = add_sat(e1.y, e3.y), xl21 = sub_sat(e1.y, e3.y);
-  i32 xt0 = sub_sat(xh0, xh20), yt0 = sub_sat(xh1, xh21);
-  i32 xt1 = add_sat(xl0, xl21), xt2 = sub_sat(xl0, xl21);
-  i32 yt2 = add_sat(xl1, xl20), yt1 = sub_sat(xl1, xl20);
-  e0.x = add_sat(xh0, xh20);
-  e0.y = add_sat(xh1, xh21);
+  i32 xh0 = A_<SAT>(e0.x, e2.x), xl0 = S_<SAT>(e0.x, e2.x);
+  i32 xh20 = A_<SAT>(e1.x, e3.x), xl20 = S_<SAT>(e1.x, e3.x);
+  i32 xh1 = A_<SAT>(e0.y, e2.y), xl1 = S_<SAT>(e0.y, e2.y);
+  i32 xh21 = A_<SAT>(e1.y, e3.y), xl21 = S_<SAT>(e1.y, e3.y);
+  i32 xt0 = S_<SAT>(xh0, xh20), yt0 = S_<SAT>(xh1, xh21);
+  i32 xt1 = A_<SAT>(xl0, xl21), xt2 = S_<SAT>(xl0, xl21);
+  i32 yt2 = A_<SAT>(xl1, xl20), yt1 = S_<SAT>(xl1, xl20);
+  e0.x = A_<SAT>(xh0, xh20);
+  e0.y = A_<SAT>(xh1, xh21);
   e3.x = lsl(wadd(__mulhi(yt2, t3.x), __mulhi(xt2, t3.y)), 1);
   e3.y = lsl(wsub(__mulhi(yt2, t3.y), __mulhi(xt2, t3.x)), 1);
   e2.x = lsl(wadd(__mulhi(yt0, t2.x), __mulhi(xt0, t2.y)), 1);
   e2.y = lsl(wsub(__mulhi(yt0, t2.y), __mulhi(xt0, t2.x)), 1);
   e1.x = lsl(wadd(__mulhi(yt1, t1.x), __mulhi(xt1, t1.y)), 1);
   e1.y = lsl(wsub(__mulhi(yt1, t1.y), __mulhi(xt1, t1.x)), 1);
+}
+
+struct SynLane {       // per-lane constants of the modulation stages
+  int s1base, s2base;  // FFT leg bases (leg m at base ^ swizzle handled via idx arrays below)
+  int s1idx[4], s2idx[4];
+  int pf_a, pf_b, pb_a, pb_b;  // radix-2 sources of the front / back complex of this lane
+  i32 pf_sgn, pb_sgn;          // +1 / -1
+  int pre_e;                   // pre-twiddle scatter slot
+  int r16;
+};
+
+// Modulation of one slot pair: block-shifted inputs v[8] (a,b,c,d per slot; odd lanes hold them swapped, which turns
+// the reference's alternating front/back pre-twiddle steps into one branch-free formula) -> fo[8] folded state samples
+// (value << 16) of the slot this lane serves (lanes 0-15: first slot, 16-31: second).
+template <bool SAT>
+XB_DEV void modulate_pair(const i32 *v, int2 *T, const SynBlockSmem &sm, const SynLane &L, int lane, i32 clamp_lo,
+                          i32 clamp_hi, i32 fold_mul, i32 *fo) {
+  const int2 ptw = sm.pre_tw[lane];
+  // ---- pre-twiddle (generic:290-367) ----
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    i32 a = v[4 * s + 0], b = v[4 * s + 1], c = v[4 * s + 2], d = v[4 * s + 3];
+    int2 o1, o2;
+    o1.x = A_<SAT>(__mulhi(a, ptw.y), __mulhi(b, ptw.x));
+    o1.y = S_<SAT>(__mulhi(b, ptw.y), __mulhi(a, ptw.x));
+    o2.x = S_<SAT>(__mulhi(d, ptw.x), __mulhi(c, ptw.y));
+    o2.y = A_<SAT>(__mulhi(c, ptw.x), __mulhi(d, ptw.y));
+    T[s * kTSlot + L.pre_e] = o1;
+    T[s * kTSlot + kTHalf + L.pre_e] = o2;
+  }
+  __syncwarp();
+  {  // ---- radix-4 stage 1 (span 8) ----
+    const int i1 = L.r16 & 7;
+    int2 e0 = T[L.s1idx[0]], e1 = T[L.s1idx[1]], e2 = T[L.s1idx[2]], e3 = T[L.s1idx[3]];
+    radix4<SAT>(e0, e1, e2, e3, sm.w1[3 * i1], sm.w1[3 * i1 + 1], sm.w1[3 * i1 + 2]);
+    T[L.s1idx[0]] = e0; T[L.s1idx[1]] = e1; T[L.s1idx[2]] = e2; T[L.s1idx[3]] = e3;
+  }
+  __syncwarp();
+  {  // ---- radix-4 stage 2 (4 groups, span 2) ----
+    const int i2 = L.r16 & 1;
+    int2 e0 = T[L.s2idx[0]], e1 = T[L.s2idx[1]], e2 = T[L.s2idx[2]], e3 = T[L.s2idx[3]];
+    radix4<SAT>(e0, e1, e2, e3, sm.w2[3 * i2], sm.w2[3 * i2 + 1], sm.w2[3 * i2 + 2]);
+    T[L.s2idx[0]] = e0; T[L.s2idx[1]] = e1; T[L.s2idx[2]] = e2; T[L.s2idx[3]] = e3;
+  }
+  __syncwarp();
+  // ---- radix-2 + digit reversal (generic:1934) + post-twiddle (generic:388-465) + fold (generic:1638) ----
+  const int2 alt_b = sm.alt_tw[L.r16];
+  const int2 alt_f = sm.alt_tw[L.r16 > 0 ? L.r16 - 1 : 0];
+  i32 G1[4], G2[4];  // [0]=G[2u] [1]=G[2u+1] [2]=G[62-2u] [3]=G[63-2u]
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    int2 fa = T[L.pf_a + h * kTHalf], fb = T[L.pf_b + h * kTHalf];
+    int2 ba = T[L.pb_a + h * kTHalf], bb = T[L.pb_b + h * kTHalf];
+    i32 Ff_r, Ff_i, Fb_r, Fb_i;
+    if (SAT) {
+      Ff_r = L.pf_sgn < 0 ? sub_sat(fa.x, fb.x) : add_sat(fa.x, fb.x);
+      Ff_i = L.pf_sgn < 0 ? sub_sat(fa.y, fb.y) : add_sat(fa.y, fb.y);
+      Fb_r = L.pb_sgn < 0 ? sub_sat(ba.x, bb.x) : add_sat(ba.x, bb.x);
+      Fb_i = L.pb_sgn < 0 ? sub_sat(ba.y, bb.y) : add_sat(ba.y, bb.y);
+    } else {
+      Ff_r = (i32)((u32)fb.x * (u32)L.pf_sgn + (u32)fa.x);
+      Ff_i = (i32)((u32)fb.y * (u32)L.pf_sgn + (u32)fa.y);
+      Fb_r = (i32)((u32)bb.x * (u32)L.pb_sgn + (u32)ba.x);
+      Fb_i = (i32)((u32)bb.y * (u32)L.pb_sgn + (u32)ba.y);
+    }
+    i32 *G = h ? G2 : G1;
+    // front pair: words (2u, 2u+1) = (fim, fre) with alt[u-1]; u == 0 is the special first pair
+    i32 fim = Ff_r, fre = Ff_i;
+    i32 t_add = A_<SAT>(__mulhi(fre, alt_f.x), __mulhi(fim, alt_f.y));
+    i32 t_sub = h ? S_<SAT>(__mulhi(fre, alt_f.y), __mulhi(fim, alt_f.x))
+                  : S_<SAT>(__mulhi(fim, alt_f.x), __mulhi(fre, alt_f.y));
+    if (L.r16 == 0) {
+      G[0] = h ? (Ff_i >> 1) : (Ff_r >> 1);
+      G[3] = h ? N_<SAT>(Ff_r >> 1) : N_<SAT>(Ff_i >> 1);
+    } else {
+      G[0] = h ? t_sub : t_add;
+      G[3] = h ? N_<SAT>(t_add) : t_sub;
+    }
+    // back pair: words (62-2u, 63-2u) = (im, re) with alt[u]
+    i32 im = Fb_r, re = Fb_i;
+    i32 b_add = A_<SAT>(__mulhi(re, alt_b.y), __mulhi(im, alt_b.x));
+    i32 b_sub = h ? S_<SAT>(__mulhi(re, alt_b.x), __mulhi(im, alt_b.y))
+                  : S_<SAT>(__mulhi(im, alt_b.y), __mulhi(re, alt_b.x));
+    G[2] = h ? b_sub : b_add;
+    G[1] = h ? N_<SAT>(b_add) : b_sub;
+  }
+  auto R = [&](i32 x) {
+    x = max(clamp_lo, min(clamp_hi, x));
+    return (i32)(((u32)x * (u32)fold_mul + 0x8000u) & 0xffff0000u);
+  };
+  // j = 2u: r1=G1[0] i1=G2[0] r2=G1[3] i2=G2[3];  j = 2u+1: r1=G1[1] i1=G2[1] r2=G1[2] i2=G2[2]
+  fo[0] = R(S_<SAT>(G2[0], G1[0]));  // st[2u]
+  fo[1] = R(S_<SAT>(G2[1], G1[1]));  // st[2u+1]
+  fo[2] = R(S_<SAT>(G2[2], G1[2]));  // st[62-2u]
+  fo[3] = R(S_<SAT>(G2[3], G1[3]));  // st[63-2u]
+  fo[4] = R(A_<SAT>(G2[3], G1[3]));  // st[64+2u]
+  fo[5] = R(A_<SAT>(G2[2], G1[2]));  // st[65+2u]
+  fo[6] = R(A_<SAT>(G2[1], G1[1]));  // st[126-2u]
+  fo[7] = R(A_<SAT>(G2[0], G1[0]));  // st[127-2u]
 }
 
 __global__ void __launch_bounds__(kSynWarps * 32, 2)
@@ -92,31 +201,30 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
   int2 *T = sm.w[warp].T;
   const int warps_total = gridDim.x * kSynWarps;
 
-  // lane roles
-  const int fs_slot = lane >> 4;  // which slot of the pair this lane serves in the FFT/post stages
-  const int r16 = lane & 15;
-  // stage 1: half h1, position i1 -> legs at i1 + 8m
-  const int h1 = r16 >> 3, i1 = r16 & 7;
-  int s1idx[4];
+  // lane roles in the FFT / post stages: lanes 0-15 serve the first slot of a pair, 16-31 the second
+  SynLane L;
+  const int fs_slot = lane >> 4;
+  L.r16 = lane & 15;
+  {
+    const int h1 = L.r16 >> 3, i1 = L.r16 & 7, g2 = (L.r16 >> 1) & 3, i2 = L.r16 & 1;
 #pragma unroll
-  for (int m = 0; m < 4; m++) s1idx[m] = fs_slot * kTSlot + h1 * kTHalf + tsw(i1 + 8 * m);
-  // stage 2: half h2, group g2, position i2 -> legs at 8 g2 + i2 + 2m
-  const int g2 = (r16 >> 1) & 3, i2 = r16 & 1;
-  int s2idx[4];
-#pragma unroll
-  for (int m = 0; m < 4; m++) s2idx[m] = fs_slot * kTSlot + h1 * kTHalf + tsw(8 * g2 + i2 + 2 * m);
-  // post: pair index u = r16: front complex u, back complex 31-u of each half
-  const i32 pm_f = sm.postmap[r16], pm_b = sm.postmap[31 - r16];
-  const int pf_a = fs_slot * kTSlot + tsw(pm_f & 255), pf_b = fs_slot * kTSlot + tsw((pm_f & 255) + 1);
-  const int pb_a = fs_slot * kTSlot + tsw(pm_b & 255), pb_b = fs_slot * kTSlot + tsw((pm_b & 255) + 1);
-  const bool pf_neg = (pm_f >> 8) & 1, pb_neg = (pm_b >> 8) & 1;
-  const int2 alt_b = sm.alt_tw[r16];
-  const int2 alt_f = sm.alt_tw[r16 > 0 ? r16 - 1 : 0];
-  const int2 ptw = sm.pre_tw[lane];
-  const int2 w1a = sm.w1[3 * i1], w1b = sm.w1[3 * i1 + 1], w1c = sm.w1[3 * i1 + 2];
-  const int2 w2a = sm.w2[3 * i2], w2b = sm.w2[3 * i2 + 1], w2c = sm.w2[3 * i2 + 2];
-  // pre-twiddle scatter slot of lane n (even n -> complex n/2, odd n -> complex 31-(n-1)/2)
-  const int pre_e = tsw((lane & 1) ? 31 - (lane >> 1) : (lane >> 1));
+    for (int m = 0; m < 4; m++) {
+      L.s1idx[m] = fs_slot * kTSlot + h1 * kTHalf + tsw(i1 + 8 * m);          // legs at i1 + 8m
+      L.s2idx[m] = fs_slot * kTSlot + h1 * kTHalf + tsw(8 * g2 + i2 + 2 * m);  // legs at 8 g2 + i2 + 2m
+    }
+    const i32 pm_f = sm.postmap[L.r16], pm_b = sm.postmap[31 - L.r16];
+    L.pf_a = fs_slot * kTSlot + tsw(pm_f & 255);
+    L.pf_b = fs_slot * kTSlot + tsw((pm_f & 255) + 1);
+    L.pb_a = fs_slot * kTSlot + tsw(pm_b & 255);
+    L.pb_b = fs_slot * kTSlot + tsw((pm_b & 255) + 1);
+    L.pf_sgn = ((pm_f >> 8) & 1) ? -1 : 1;
+    L.pb_sgn = ((pm_b >> 8) & 1) ? -1 : 1;
+    // pre-twiddle: step n = lane; even n -> complex n/2, odd n -> complex 31-(n-1)/2
+    L.pre_e = tsw((lane & 1) ? 31 - (lane >> 1) : (lane >> 1));
+  }
+  // band read first / second by this lane (odd lanes swapped, see modulate_pair)
+  const int bandA = (lane & 1) ? 63 - lane : lane;
+  const int bandB = 63 - bandA;
 
   for (long long u = (long long)blockIdx.x * kSynWarps + warp; u < p.n_units; u += warps_total) {
     const i32 *mat = p.matrix + u * 4096;
@@ -128,7 +236,7 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
     int ov_lb_shift = (st_syn - ov_lb_scale) - 8, lb_shift = (st_syn - lb_scale) - 8;
     int hb_shift = (st_syn - hb_scale) - 8;
     const int out_shift = -(st_syn - 3) + 1;
-    // per-lane block shift of band `lane` (A) and band 63-lane (B): value * mul >> shr
+    // per-lane block shift of its two bands: value * mul >> shr   (env_calc.c:1099-1157)
     auto enc = [](int sh, i32 &mul, int &shr) {
       sh = max(-31, min(31, sh));
       mul = sh > 0 ? (i32)(1u << sh) : 1;
@@ -136,165 +244,86 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
     };
     i32 mulA_ov, mulA_lb, mulB_ov, mulB_lb;
     int shrA_ov, shrA_lb, shrB_ov, shrB_lb;
-    {
-      const int ka = lane, kb = 63 - lane;
-      int a_ov = ka < lsb ? ov_lb_shift : (ka < usb ? hb_shift : 0);
-      int a_lb = ka < lsb ? lb_shift : (ka < usb ? hb_shift : 0);
-      int b_ov = kb < lsb ? ov_lb_shift : (kb < usb ? hb_shift : 0);
-      int b_lb = kb < lsb ? lb_shift : (kb < usb ? hb_shift : 0);
-      enc(a_ov, mulA_ov, shrA_ov);
-      enc(a_lb, mulA_lb, shrA_lb);
-      enc(b_ov, mulB_ov, shrB_ov);
-      enc(b_lb, mulB_lb, shrB_lb);
-    }
+    enc(bandA < lsb ? ov_lb_shift : (bandA < usb ? hb_shift : 0), mulA_ov, shrA_ov);
+    enc(bandA < lsb ? lb_shift : (bandA < usb ? hb_shift : 0), mulA_lb, shrA_lb);
+    enc(bandB < lsb ? ov_lb_shift : (bandB < usb ? hb_shift : 0), mulB_ov, shrB_ov);
+    enc(bandB < lsb ? lb_shift : (bandB < usb ? hb_shift : 0), mulB_lb, shrB_lb);
     // fold: round16(shl32_sat(x, out_shift)) kept as value<<16 == ((clamp(x) << s) + 0x8000) & 0xffff0000
     const i32 clamp_lo = (i32)0x80000000 >> out_shift;
     const i32 clamp_hi = (i32)(0x7fff7fffu >> out_shift);
     const i32 fold_mul = (i32)(1u << out_shift);
 
-    // ---- filter state: HBM (reference layout, WORD16[1280]) -> smem (tap-major, <<16) ----
+    // ---- filter state: HBM (reference layout, WORD16[1280]) -> smem (tap-major, <<16); lane = output pair ----
     {
-      const int4 *src = reinterpret_cast<const int4 *>(p.states + u * 1280);
+      const i32 *src = reinterpret_cast<const i32 *>(p.states + u * 1280);
+      i32 wv[20];
 #pragma unroll
-      for (int t = 0; t < 5; t++) {
-        int i4 = lane + 32 * t;
-        int4 v = __ldg(src + i4);
-        int e = 8 * i4;                 // first of 8 consecutive samples: same block, same half
-        int B = e >> 7, s = e & 127, h = s >> 6, kp = (s & 63) >> 1;
-        int base = kp * kStStride + ((h ^ (B & 1)) * 20) + 2 * B;
-        i32 wv[4] = {v.x, v.y, v.z, v.w};
+      for (int t = 0; t < 20; t++) wv[t] = __ldg(src + 32 * t + lane);  // t = 2B + h: samples 128B + 64h + 2 lane (+1)
 #pragma unroll
-        for (int wi = 0; wi < 4; wi++)
-          *reinterpret_cast<int2 *>(st + base + wi * kStStride) =
-              make_int2((i32)((u32)wv[wi] << 16), (i32)((u32)wv[wi] & 0xffff0000u));
+      for (int t = 0; t < 20; t++) {
+        const int B = t >> 1, h = t & 1;
+        *reinterpret_cast<int2 *>(st + lane * kStStride + ((h ^ (B & 1)) * 20) + 2 * B) =
+            make_int2((i32)((u32)wv[t] << 16), (i32)((u32)wv[t] & 0xffff0000u));
       }
     }
     __syncwarp();
 
-    // register prefetch of the first slot pair: s1[n], s1[63-n], s2[n], s2[63-n] for two slots
+    // register prefetch of the first slot pair
     i32 nx[8];
 #pragma unroll
     for (int s = 0; s < 2; s++) {
       const i32 *m = mat + 128 * s;
-      nx[4 * s + 0] = __ldg(m + lane);
-      nx[4 * s + 1] = __ldg(m + 63 - lane);
-      nx[4 * s + 2] = __ldg(m + 64 + lane);
-      nx[4 * s + 3] = __ldg(m + 127 - lane);
+      nx[4 * s + 0] = __ldg(m + bandA);
+      nx[4 * s + 1] = __ldg(m + bandB);
+      nx[4 * s + 2] = __ldg(m + 64 + bandA);
+      nx[4 * s + 3] = __ldg(m + 64 + bandB);
     }
     int16_t *pcm = p.pcm + ((p.ch_fac == 1) ? u * 2048 : (u / p.ch_fac) * (2048LL * p.ch_fac) + (u % p.ch_fac));
 
 #pragma unroll 1
     for (int pr = 0; pr < 16; pr++) {
-      i32 cur[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) cur[j] = nx[j];
-      if (pr < 15) {
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-          const i32 *m = mat + 128 * (2 * pr + 2 + s);
-          nx[4 * s + 0] = __ldg(m + lane);
-          nx[4 * s + 1] = __ldg(m + 63 - lane);
-          nx[4 * s + 2] = __ldg(m + 64 + lane);
-          nx[4 * s + 3] = __ldg(m + 127 - lane);
-        }
-      }
-      // ---- block shift (env_calc.c:1099) + pre-twiddle (generic:290-367), lane = step n, both slots ----
+      // ---- block shift (env_calc.c:1099) of the pair's inputs + magnitude classification ----
+      i32 v[8];
+      u32 mag = 0;
 #pragma unroll
       for (int s = 0; s < 2; s++) {
         const bool ov = (2 * pr + s) < split;
         const i32 mA = ov ? mulA_ov : mulA_lb, mB = ov ? mulB_ov : mulB_lb;
         const int rA = ov ? shrA_ov : shrA_lb, rB = ov ? shrB_ov : shrB_lb;
-        i32 a = (i32)((u32)cur[4 * s + 0] * (u32)mA) >> rA;  // s1[n]
-        i32 b = (i32)((u32)cur[4 * s + 1] * (u32)mB) >> rB;  // s1[63-n]
-        i32 c = (i32)((u32)cur[4 * s + 2] * (u32)mA) >> rA;  // s2[n]
-        i32 d = (i32)((u32)cur[4 * s + 3] * (u32)mB) >> rB;  // s2[63-n]
-        int2 o1, o2;
-        if (!(lane & 1)) {
-          o1.x = add_sat(__mulhi(a, ptw.y), __mulhi(b, ptw.x));
-          o1.y = sub_sat(__mulhi(b, ptw.y), __mulhi(a, ptw.x));
-          o2.x = sub_sat(__mulhi(d, ptw.x), __mulhi(c, ptw.y));
-          o2.y = add_sat(__mulhi(c, ptw.x), __mulhi(d, ptw.y));
-        } else {
-          o1.y = sub_sat(__mulhi(a, ptw.y), __mulhi(b, ptw.x));
-          o1.x = add_sat(__mulhi(b, ptw.y), __mulhi(a, ptw.x));
-          o2.y = add_sat(__mulhi(d, ptw.x), __mulhi(c, ptw.y));
-          o2.x = sub_sat(__mulhi(c, ptw.x), __mulhi(d, ptw.y));
-        }
-        T[s * kTSlot + pre_e] = o1;
-        T[s * kTSlot + kTHalf + pre_e] = o2;
+        v[4 * s + 0] = (i32)((u32)nx[4 * s + 0] * (u32)mA) >> rA;
+        v[4 * s + 1] = (i32)((u32)nx[4 * s + 1] * (u32)mB) >> rB;
+        v[4 * s + 2] = (i32)((u32)nx[4 * s + 2] * (u32)mA) >> rA;
+        v[4 * s + 3] = (i32)((u32)nx[4 * s + 3] * (u32)mB) >> rB;
       }
-      __syncwarp();
-      // ---- radix-4 stage 1 (span 8) ----
-      {
-        int2 e0 = T[s1idx[0]], e1 = T[s1idx[1]], e2 = T[s1idx[2]], e3 = T[s1idx[3]];
-        radix4(e0, e1, e2, e3, w1a, w1b, w1c);
-        T[s1idx[0]] = e0; T[s1idx[1]] = e1; T[s1idx[2]] = e2; T[s1idx[3]] = e3;
-      }
-      __syncwarp();
-      // ---- radix-4 stage 2 (4 groups, span 2) ----
-      {
-        int2 e0 = T[s2idx[0]], e1 = T[s2idx[1]], e2 = T[s2idx[2]], e3 = T[s2idx[3]];
-        radix4(e0, e1, e2, e3, w2a, w2b, w2c);
-        T[s2idx[0]] = e0; T[s2idx[1]] = e1; T[s2idx[2]] = e2; T[s2idx[3]] = e3;
-      }
-      __syncwarp();
-      // ---- radix-2 + digit reversal (generic:1934) + post-twiddle (generic:388-465) + fold (generic:1638) ----
-      i32 fo[8];
-      {
-        i32 G1[4], G2[4];  // [0]=G[2u] [1]=G[2u+1] [2]=G[62-2u] [3]=G[63-2u]
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          int2 fa = T[pf_a + h * kTHalf], fb = T[pf_b + h * kTHalf];
-          int2 ba = T[pb_a + h * kTHalf], bb = T[pb_b + h * kTHalf];
-          i32 Ff_r = pf_neg ? sub_sat(fa.x, fb.x) : add_sat(fa.x, fb.x);
-          i32 Ff_i = pf_neg ? sub_sat(fa.y, fb.y) : add_sat(fa.y, fb.y);
-          i32 Fb_r = pb_neg ? sub_sat(ba.x, bb.x) : add_sat(ba.x, bb.x);
-          i32 Fb_i = pb_neg ? sub_sat(ba.y, bb.y) : add_sat(ba.y, bb.y);
-          i32 *G = h ? G2 : G1;
-          // front pair: words (2u, 2u+1) = (fim, fre) with alt[u-1]; u == 0 is the special first pair
-          i32 fim = Ff_r, fre = Ff_i;
-          i32 t_add = add_sat(__mulhi(fre, alt_f.x), __mulhi(fim, alt_f.y));
-          i32 t_sub = h ? sub_sat(__mulhi(fre, alt_f.y), __mulhi(fim, alt_f.x))
-                        : sub_sat(__mulhi(fim, alt_f.x), __mulhi(fre, alt_f.y));
-          if (r16 == 0) {
-            G[0] = h ? (Ff_i >> 1) : (Ff_r >> 1);
-            G[3] = h ? neg_sat(Ff_r >> 1) : neg_sat(Ff_i >> 1);
-          } else {
-            G[0] = h ? t_sub : t_add;
-            G[3] = h ? neg_sat(t_add) : t_sub;
-          }
-          // back pair: words (62-2u, 63-2u) = (im, re) with alt[u]
-          i32 im = Fb_r, re = Fb_i;
-          i32 b_add = add_sat(__mulhi(re, alt_b.y), __mulhi(im, alt_b.x));
-          i32 b_sub = h ? sub_sat(__mulhi(re, alt_b.x), __mulhi(im, alt_b.y))
-                        : sub_sat(__mulhi(im, alt_b.y), __mulhi(re, alt_b.x));
-          G[2] = h ? b_sub : b_add;
-          G[1] = h ? neg_sat(b_add) : b_sub;
+      for (int j = 0; j < 8; j++) mag |= (u32)(v[j] ^ (v[j] >> 31));
+      if (pr < 15) {
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const i32 *m = mat + 128 * (2 * pr + 2 + s);
+          nx[4 * s + 0] = __ldg(m + bandA);
+          nx[4 * s + 1] = __ldg(m + bandB);
+          nx[4 * s + 2] = __ldg(m + 64 + bandA);
+          nx[4 * s + 3] = __ldg(m + 64 + bandB);
         }
-        auto R = [&](i32 x) {
-          x = max(clamp_lo, min(clamp_hi, x));
-          return (i32)(((u32)x * (u32)fold_mul + 0x8000u) & 0xffff0000u);
-        };
-        // j = 2u: r1=G1[0] i1=G2[0] r2=G1[3] i2=G2[3];  j = 2u+1: r1=G1[1] i1=G2[1] r2=G1[2] i2=G2[2]
-        fo[0] = R(sub_sat(G2[0], G1[0]));  // st[2u]
-        fo[1] = R(sub_sat(G2[1], G1[1]));  // st[2u+1]
-        fo[2] = R(sub_sat(G2[2], G1[2]));  // st[62-2u]
-        fo[3] = R(sub_sat(G2[3], G1[3]));  // st[63-2u]
-        fo[4] = R(add_sat(G2[3], G1[3]));  // st[64+2u]
-        fo[5] = R(add_sat(G2[2], G1[2]));  // st[65+2u]
-        fo[6] = R(add_sat(G2[1], G1[1]));  // st[126-2u]
-        fo[7] = R(add_sat(G2[0], G1[0]));  // st[127-2u]
       }
+      mag = __reduce_or_sync(0xffffffffu, mag);
+      i32 fo[8];
+      if ((mag >> p.fast_bits) == 0)
+        modulate_pair<false>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, fo);
+      else
+        modulate_pair<true>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, fo);
+
       // ---- per slot: commit the fold into the ring, then the 10-tap window (generic:1508) ----
 #pragma unroll
       for (int s = 0; s < 2; s++) {
         const int Bw = off >> 7;
         if (fs_slot == s) {
           const int c0 = (Bw & 1) * 20 + 2 * Bw, c1 = ((Bw & 1) ^ 1) * 20 + 2 * Bw;
-          *reinterpret_cast<int2 *>(st + r16 * kStStride + c0) = make_int2(fo[0], fo[1]);
-          *reinterpret_cast<int2 *>(st + (31 - r16) * kStStride + c0) = make_int2(fo[2], fo[3]);
-          *reinterpret_cast<int2 *>(st + r16 * kStStride + c1) = make_int2(fo[4], fo[5]);
-          *reinterpret_cast<int2 *>(st + (31 - r16) * kStStride + c1) = make_int2(fo[6], fo[7]);
+          *reinterpret_cast<int2 *>(st + L.r16 * kStStride + c0) = make_int2(fo[0], fo[1]);
+          *reinterpret_cast<int2 *>(st + (31 - L.r16) * kStStride + c0) = make_int2(fo[2], fo[3]);
+          *reinterpret_cast<int2 *>(st + L.r16 * kStStride + c1) = make_int2(fo[4], fo[5]);
+          *reinterpret_cast<int2 *>(st + (31 - L.r16) * kStStride + c1) = make_int2(fo[6], fo[7]);
         }
         __syncwarp();
         const int slot = 2 * pr + s;
@@ -310,7 +339,9 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
           acc0 += __mulhi(x.z, cb.x);
           acc1 += __mulhi(x.w, cb.y);
         }
-        i32 o0 = shl32_sat(acc0, 1) >> 16, o1 = shl32_sat(acc1, 1) >> 16;
+        // shl32_sat(acc, 1) >> 16  ==  clamp(acc, -2^30, 2^30-1) >> 15
+        i32 o0 = max(-0x40000000, min(0x3fffffff, acc0)) >> 15;
+        i32 o1 = max(-0x40000000, min(0x3fffffff, acc1)) >> 15;
         if (p.ch_fac == 1) {
           *reinterpret_cast<i32 *>(pcm + 64 * slot + 2 * lane) = (o0 & 0xffff) | (i32)((u32)o1 << 16);
         } else {
@@ -327,20 +358,12 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
 
     // ---- filter state back to HBM in the reference layout ----
     {
-      int4 *dst = reinterpret_cast<int4 *>(p.states + u * 1280);
+      i32 *dst = reinterpret_cast<i32 *>(p.states + u * 1280);
 #pragma unroll
-      for (int t = 0; t < 5; t++) {
-        int i4 = lane + 32 * t;
-        int e = 8 * i4;
-        int B = e >> 7, s = e & 127, h = s >> 6, kp = (s & 63) >> 1;
-        int base = kp * kStStride + ((h ^ (B & 1)) * 20) + 2 * B;
-        i32 wv[4];
-#pragma unroll
-        for (int wi = 0; wi < 4; wi++) {
-          int2 x = *reinterpret_cast<const int2 *>(st + base + wi * kStStride);
-          wv[wi] = (i32)(((u32)x.x >> 16) | ((u32)x.y & 0xffff0000u));
-        }
-        dst[i4] = make_int4(wv[0], wv[1], wv[2], wv[3]);
+      for (int t = 0; t < 20; t++) {
+        const int B = t >> 1, h = t & 1;
+        int2 x = *reinterpret_cast<const int2 *>(st + lane * kStStride + ((h ^ (B & 1)) * 20) + 2 * B);
+        dst[32 * t + lane] = (i32)(((u32)x.x >> 16) | ((u32)x.y & 0xffff0000u));
       }
       if (lane == 0) {
         p.pos[2 * u] = (int16_t)off;
@@ -355,7 +378,7 @@ size_t qmf_synth_table_bytes() { return offsetof(SynBlockSmem, w); }
 
 // Host-side construction of the block-shared table image from the reference-layout QMF ROM blob
 // (leading bytes of ia_qmf_dec_tables_struct). Returns false if the prototype violates the no-saturation bound.
-bool qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
+int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
   SynBlockSmem *t = reinterpret_cast<SynBlockSmem *>(out);  // only the leading table part is written
   const int16_t *w32 = reinterpret_cast<const int16_t *>(qrom + kQRomW32);
   const int32_t *dr = reinterpret_cast<const int32_t *>(qrom + kQRomDigRev2_32);
@@ -378,22 +401,52 @@ bool qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
     for (int half = 0; half < 2; half++) {
       int cb = (blk >> 1) * 16 + (blk & 1) * 4 + 8 * half;
       int op = ((dr[blk] >> 2) >> 1) + half;
-      if (op < 0 || op + 20 >= 32) return false;
+      if (op < 0 || op + 20 >= 32) return -1;
       t->postmap[op] = cb;
       t->postmap[op + 16] = cb | 256;
       t->postmap[op + 4] = cb + 2;
       t->postmap[op + 20] = (cb + 2) | 256;
     }
   for (int i = 0; i < 32; i++)
-    if (t->postmap[i] < 0) return false;
+    if (t->postmap[i] < 0) return -1;
   // no-saturation bound of the window-add accumulation (see file header)
   for (int fpos = 0; fpos < 640; fpos += 64)
     for (int k = 0; k < 64; k++) {
       long long s = 0;
       for (int B = 0; B < 10; B++) s += c[fpos + 64 * B + k] < 0 ? -(long long)c[fpos + 64 * B + k] : c[fpos + 64 * B + k];
-      if (s * 32768 + 0x4000 >= 0x7fffffffLL) return false;
+      if (s * 32768 + 0x4000 >= 0x7fffffffLL) return -1;
     }
-  return true;
+  // Largest k such that inputs bounded by 2^k cannot make any add of the modulation saturate.
+  // |mul32x16(x, w)| <= |x||w|/65536 + 1.  S_* = max(|sin| + |cos|) over each twiddle table.
+  auto smax = [](const int16_t *tab, int pairs) {
+    long long m = 0;
+    for (int i = 0; i < pairs; i++) {
+      long long a = tab[2 * i] < 0 ? -(long long)tab[2 * i] : tab[2 * i];
+      long long b = tab[2 * i + 1] < 0 ? -(long long)tab[2 * i + 1] : tab[2 * i + 1];
+      if (a + b > m) m = a + b;
+    }
+    return (double)m;
+  };
+  const double S_pre = smax(sc, 32), S_w = smax(w32, 30), S_alt = smax(al, 16);
+  int fast_bits = 0;
+  for (int k = 30; k >= 1; k--) {
+    double A = (double)(1ULL << k);
+    double B = A * S_pre / 65536.0 + 2.0;                              // pre-twiddle
+    for (int stage = 0; stage < 2; stage++) {                          // two radix-4 stages
+      double sum4 = 4.0 * B;
+      double tw = 2.0 * (sum4 * S_w / 65536.0 + 2.0);
+      B = sum4 > tw ? sum4 : tw;
+    }
+    double F = 2.0 * B;                                                // radix-2
+    double G = F * S_alt / 65536.0 + 2.0;                              // post-twiddle
+    if (F / 2.0 + 1.0 > G) G = F / 2.0 + 1.0;
+    double fold = 2.0 * G;                                             // fold add/sub
+    if (fold * 1.0001 + 16.0 < 2147483647.0) {
+      fast_bits = k;
+      break;
+    }
+  }
+  return fast_bits;
 }
 
 cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStream_t stream) {

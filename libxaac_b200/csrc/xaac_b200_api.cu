@@ -17,6 +17,7 @@ struct xaac_b200_ctx {
   bool have_imdct_rom = false;
   uint8_t *d_rom_qmf_syn = nullptr;  // table image of qmf_synth_hq_kernel
   bool have_qmf_rom = false;
+  int qmf_fast_bits = 0;
   char err[256] = {0};
   // staging for the *_host entry points: kPipe chunks in flight, one stream each
   static constexpr int kPipe = 3;
@@ -263,7 +264,8 @@ int32_t xaac_b200_set_qmf_rom(xaac_b200_ctx *ctx, const void *tables, size_t byt
   size_t n = xb::qmf_synth_table_bytes();
   uint8_t *img = (uint8_t *)calloc(1, n + 64);
   if (!img) return XAAC_B200_FATAL;
-  if (!xb::qmf_synth_build_tables((const uint8_t *)tables, img)) {
+  int fast_bits = xb::qmf_synth_build_tables((const uint8_t *)tables, img);
+  if (fast_bits <= 0) {
     free(img);
     return bad_arg(ctx, "QMF tables: unexpected digit-reverse table or prototype filter exceeds the no-saturation bound");
   }
@@ -278,6 +280,7 @@ int32_t xaac_b200_set_qmf_rom(xaac_b200_ctx *ctx, const void *tables, size_t byt
   free(img);
   if (e != cudaSuccess) return fail(ctx, e, "cudaMemcpy(qmf rom)");
   ctx->have_qmf_rom = true;
+  ctx->qmf_fast_bits = fast_bits;
   return XAAC_B200_OK;
 }
 
@@ -300,6 +303,7 @@ int32_t xaac_b200_qmf_synth_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_matrix, 
   a.params = d_params;
   a.pcm = d_pcm;
   a.rom = ctx->d_rom_qmf_syn;
+  a.fast_bits = ctx->qmf_fast_bits;
   a.n_units = n_units;
   a.ch_fac = ch_fac;
   CK(xb::launch_qmf_synth_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch qmf_synth_hq_kernel");
