@@ -65,6 +65,7 @@ struct QmfSynthArgs {
   long long n_units;
   int ch_fac;
   int fast_bits;           // inputs below 2^fast_bits cannot saturate any add of the modulation
+  int zero;                // always 0; an operand the compiler cannot fold (see add3 in qmf_synth_kernel.cu)
 };
 
 size_t qmf_synth_table_bytes();

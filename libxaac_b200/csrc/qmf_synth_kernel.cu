@@ -15,7 +15,7 @@
 //   HBM matrix[32][128] WORD32 --LDG.32 coalesced, register double-buffered one slot pair ahead-->
 //     block shift -> pre-twiddle -> smem T (two slots at a time so that the 2 x 16 radix-4 butterflies of a stage
 //     fill all 32 lanes) -> radix-4, radix-4 -> radix-2 + post-twiddle + fold fused in registers
-//     -> filter state (smem, tap-major transposed, stored as value<<16 so a tap is one IMAD.HI)
+//     -> filter state (smem, tap-major transposed, one sign-extended sample per word so a tap is one IMAD)
 //     -> window-add -> PCM16 pairs, STG.32 coalesced.
 //   HBM filter_states[1280] WORD16 is read once and written once per unit in the reference's own layout.
 // Algorithmic HBM bytes per unit: 16384 + 2560 + 2560 + 4096 = 25600.
@@ -38,12 +38,12 @@ constexpr int kTHalf = 40;             // int2 per FFT half (32 used; +8 keeps t
 constexpr int kTSlot = 2 * kTHalf;
 
 struct SynWarpSmem {
-  i32 st[kStWords];      // filter state: [pair k'][class][block B][elem], each sample << 16
+  i32 st[kStWords];      // filter state: [pair k'][class][block B][elem], sign-extended WORD16 samples
   int2 T[2 * kTSlot];    // FFT workspace for two slots
 };
 
 struct SynBlockSmem {
-  i32 coef[32 * kCoStride];  // qmf_c[2k'+elem+64q] << 16
+  i32 coef[32 * kCoStride];  // qmf_c[2k'+elem+64q], sign-extended
   int2 pre_tw[32];           // (wim<<16, wre<<16)  sbr_sin_cos_twiddle_l64
   int2 alt_tw[16];           // (wim<<16, wre<<16)  sbr_alt_sin_twiddle_l64
   int2 w1[24];               // radix-4 stage 1: position i -> (si,co) x 3, each << 16
@@ -65,9 +65,14 @@ template <bool SAT> XB_DEV i32 A_(i32 a, i32 b) { return SAT ? add_sat(a, b) : w
 template <bool SAT> XB_DEV i32 S_(i32 a, i32 b) { return SAT ? sub_sat(a, b) : wsub(a, b); }
 template <bool SAT> XB_DEV i32 N_(i32 a) { return SAT ? neg_sat(a) : wneg(a); }
 
+// Wrapping a+b / a-b as a 3-input add with a run-time zero: keeps the add on the ALU pipe (IADD3) instead of
+// letting ptxas fold it into IMAD.HI's 64-bit addend, which costs extra register-pair moves on the (busier) FMA pipe.
+XB_DEV i32 add3(i32 a, i32 b, i32 z) { return (i32)((u32)a + (u32)b + (u32)z); }
+XB_DEV i32 sub3(i32 a, i32 b, i32 z) { return (i32)((u32)a - (u32)b + (u32)z); }
+
 // one radix-4 butterfly, generic:1766-1822. e[m] = leg m (re,im); tw = 3 x (si<<16, co<<16)
 template <bool SAT>
-XB_DEV void radix4(int2 &e0, int2 &e1, int2 &e2, int2 &e3, const int2 t1, const int2 t2, const int2 t3) {
+XB_DEV void radix4(int2 &e0, int2 &e1, int2 &e2, int2 &e3, const int2 t1, const int2 t2, const int2 t3, const i32 z) {
   i32 xh0 = A_<SAT>(e0.x, e2.x), xl0 = S_<SAT>(e0.x, e2.x);
   i32 xh20 = A_<SAT>(e1.x, e3.x), xl20 = S_<SAT>(e1.x, e3.x);
   i32 xh1 = A_<SAT>(e0.y, e2.y), xl1 = S_<SAT>(e0.y, e2.y);
@@ -77,13 +82,17 @@ XB_DEV void radix4(int2 &e0, int2 &e1, int2 &e2, int2 &e3, const int2 t1, const 
   i32 yt2 = A_<SAT>(xl1, xl20), yt1 = S_<SAT>(xl1, xl20);
   e0.x = A_<SAT>(xh0, xh20);
   e0.y = A_<SAT>(xh1, xh21);
-  e3.x = lsl(wadd(__mulhi(yt2, t3.x), __mulhi(xt2, t3.y)), 1);
-  e3.y = lsl(wsub(__mulhi(yt2, t3.y), __mulhi(xt2, t3.x)), 1);
-  e2.x = lsl(wadd(__mulhi(yt0, t2.x), __mulhi(xt0, t2.y)), 1);
-  e2.y = lsl(wsub(__mulhi(yt0, t2.y), __mulhi(xt0, t2.x)), 1);
-  e1.x = lsl(wadd(__mulhi(yt1, t1.x), __mulhi(xt1, t1.y)), 1);
-  e1.y = lsl(wsub(__mulhi(yt1, t1.y), __mulhi(xt1, t1.x)), 1);
+  e3.x = lsl(add3(__mulhi(yt2, t3.x), __mulhi(xt2, t3.y), z), 1);
+  e3.y = lsl(sub3(__mulhi(yt2, t3.y), __mulhi(xt2, t3.x), z), 1);
+  e2.x = lsl(add3(__mulhi(yt0, t2.x), __mulhi(xt0, t2.y), z), 1);
+  e2.y = lsl(sub3(__mulhi(yt0, t2.y), __mulhi(xt0, t2.x), z), 1);
+  e1.x = lsl(add3(__mulhi(yt1, t1.x), __mulhi(xt1, t1.y), z), 1);
+  e1.y = lsl(sub3(__mulhi(yt1, t1.y), __mulhi(xt1, t1.x), z), 1);
 }
+
+// rotation helpers for the (possibly saturating) pre/post twiddles
+template <bool SAT> XB_DEV i32 RA_(i32 a, i32 b, i32 z) { return SAT ? add_sat(a, b) : add3(a, b, z); }
+template <bool SAT> XB_DEV i32 RS_(i32 a, i32 b, i32 z) { return SAT ? sub_sat(a, b) : sub3(a, b, z); }
 
 struct SynLane {       // per-lane constants of the modulation stages
   int s1base, s2base;  // FFT leg bases (leg m at base ^ swizzle handled via idx arrays below)
@@ -96,20 +105,20 @@ struct SynLane {       // per-lane constants of the modulation stages
 
 // Modulation of one slot pair: block-shifted inputs v[8] (a,b,c,d per slot; odd lanes hold them swapped, which turns
 // the reference's alternating front/back pre-twiddle steps into one branch-free formula) -> fo[8] folded state samples
-// (value << 16) of the slot this lane serves (lanes 0-15: first slot, 16-31: second).
+// (sign-extended WORD16 values) of the slot this lane serves (lanes 0-15: first slot, 16-31: second).
 template <bool SAT>
 XB_DEV void modulate_pair(const i32 *v, int2 *T, const SynBlockSmem &sm, const SynLane &L, int lane, i32 clamp_lo,
-                          i32 clamp_hi, i32 fold_mul, i32 *fo) {
+                          i32 clamp_hi, i32 fold_mul, i32 z, i32 *fo) {
   const int2 ptw = sm.pre_tw[lane];
   // ---- pre-twiddle (generic:290-367) ----
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     i32 a = v[4 * s + 0], b = v[4 * s + 1], c = v[4 * s + 2], d = v[4 * s + 3];
     int2 o1, o2;
-    o1.x = A_<SAT>(__mulhi(a, ptw.y), __mulhi(b, ptw.x));
-    o1.y = S_<SAT>(__mulhi(b, ptw.y), __mulhi(a, ptw.x));
-    o2.x = S_<SAT>(__mulhi(d, ptw.x), __mulhi(c, ptw.y));
-    o2.y = A_<SAT>(__mulhi(c, ptw.x), __mulhi(d, ptw.y));
+    o1.x = RA_<SAT>(__mulhi(a, ptw.y), __mulhi(b, ptw.x), z);
+    o1.y = RS_<SAT>(__mulhi(b, ptw.y), __mulhi(a, ptw.x), z);
+    o2.x = RS_<SAT>(__mulhi(d, ptw.x), __mulhi(c, ptw.y), z);
+    o2.y = RA_<SAT>(__mulhi(c, ptw.x), __mulhi(d, ptw.y), z);
     T[s * kTSlot + L.pre_e] = o1;
     T[s * kTSlot + kTHalf + L.pre_e] = o2;
   }
@@ -117,14 +126,14 @@ XB_DEV void modulate_pair(const i32 *v, int2 *T, const SynBlockSmem &sm, const S
   {  // ---- radix-4 stage 1 (span 8) ----
     const int i1 = L.r16 & 7;
     int2 e0 = T[L.s1idx[0]], e1 = T[L.s1idx[1]], e2 = T[L.s1idx[2]], e3 = T[L.s1idx[3]];
-    radix4<SAT>(e0, e1, e2, e3, sm.w1[3 * i1], sm.w1[3 * i1 + 1], sm.w1[3 * i1 + 2]);
+    radix4<SAT>(e0, e1, e2, e3, sm.w1[3 * i1], sm.w1[3 * i1 + 1], sm.w1[3 * i1 + 2], z);
     T[L.s1idx[0]] = e0; T[L.s1idx[1]] = e1; T[L.s1idx[2]] = e2; T[L.s1idx[3]] = e3;
   }
   __syncwarp();
   {  // ---- radix-4 stage 2 (4 groups, span 2) ----
     const int i2 = L.r16 & 1;
     int2 e0 = T[L.s2idx[0]], e1 = T[L.s2idx[1]], e2 = T[L.s2idx[2]], e3 = T[L.s2idx[3]];
-    radix4<SAT>(e0, e1, e2, e3, sm.w2[3 * i2], sm.w2[3 * i2 + 1], sm.w2[3 * i2 + 2]);
+    radix4<SAT>(e0, e1, e2, e3, sm.w2[3 * i2], sm.w2[3 * i2 + 1], sm.w2[3 * i2 + 2], z);
     T[L.s2idx[0]] = e0; T[L.s2idx[1]] = e1; T[L.s2idx[2]] = e2; T[L.s2idx[3]] = e3;
   }
   __syncwarp();
@@ -151,9 +160,9 @@ XB_DEV void modulate_pair(const i32 *v, int2 *T, const SynBlockSmem &sm, const S
     i32 *G = h ? G2 : G1;
     // front pair: words (2u, 2u+1) = (fim, fre) with alt[u-1]; u == 0 is the special first pair
     i32 fim = Ff_r, fre = Ff_i;
-    i32 t_add = A_<SAT>(__mulhi(fre, alt_f.x), __mulhi(fim, alt_f.y));
-    i32 t_sub = h ? S_<SAT>(__mulhi(fre, alt_f.y), __mulhi(fim, alt_f.x))
-                  : S_<SAT>(__mulhi(fim, alt_f.x), __mulhi(fre, alt_f.y));
+    i32 t_add = RA_<SAT>(__mulhi(fre, alt_f.x), __mulhi(fim, alt_f.y), z);
+    i32 t_sub = h ? RS_<SAT>(__mulhi(fre, alt_f.y), __mulhi(fim, alt_f.x), z)
+                  : RS_<SAT>(__mulhi(fim, alt_f.x), __mulhi(fre, alt_f.y), z);
     if (L.r16 == 0) {
       G[0] = h ? (Ff_i >> 1) : (Ff_r >> 1);
       G[3] = h ? N_<SAT>(Ff_r >> 1) : N_<SAT>(Ff_i >> 1);
@@ -163,15 +172,15 @@ XB_DEV void modulate_pair(const i32 *v, int2 *T, const SynBlockSmem &sm, const S
     }
     // back pair: words (62-2u, 63-2u) = (im, re) with alt[u]
     i32 im = Fb_r, re = Fb_i;
-    i32 b_add = A_<SAT>(__mulhi(re, alt_b.y), __mulhi(im, alt_b.x));
-    i32 b_sub = h ? S_<SAT>(__mulhi(re, alt_b.x), __mulhi(im, alt_b.y))
-                  : S_<SAT>(__mulhi(im, alt_b.y), __mulhi(re, alt_b.x));
+    i32 b_add = RA_<SAT>(__mulhi(re, alt_b.y), __mulhi(im, alt_b.x), z);
+    i32 b_sub = h ? RS_<SAT>(__mulhi(re, alt_b.x), __mulhi(im, alt_b.y), z)
+                  : RS_<SAT>(__mulhi(im, alt_b.y), __mulhi(re, alt_b.x), z);
     G[2] = h ? b_sub : b_add;
     G[1] = h ? N_<SAT>(b_add) : b_sub;
   }
   auto R = [&](i32 x) {
     x = max(clamp_lo, min(clamp_hi, x));
-    return (i32)(((u32)x * (u32)fold_mul + 0x8000u) & 0xffff0000u);
+    return (i32)((u32)x * (u32)fold_mul + 0x8000u) >> 16;
   };
   // j = 2u: r1=G1[0] i1=G2[0] r2=G1[3] i2=G2[3];  j = 2u+1: r1=G1[1] i1=G2[1] r2=G1[2] i2=G2[2]
   fo[0] = R(S_<SAT>(G2[0], G1[0]));  // st[2u]
@@ -248,7 +257,7 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
     enc(bandA < lsb ? lb_shift : (bandA < usb ? hb_shift : 0), mulA_lb, shrA_lb);
     enc(bandB < lsb ? ov_lb_shift : (bandB < usb ? hb_shift : 0), mulB_ov, shrB_ov);
     enc(bandB < lsb ? lb_shift : (bandB < usb ? hb_shift : 0), mulB_lb, shrB_lb);
-    // fold: round16(shl32_sat(x, out_shift)) kept as value<<16 == ((clamp(x) << s) + 0x8000) & 0xffff0000
+    // fold: round16(shl32_sat(x, out_shift)) == ((clamp(x) << s) + 0x8000) >> 16 with the clamp bounds below
     const i32 clamp_lo = (i32)0x80000000 >> out_shift;
     const i32 clamp_hi = (i32)(0x7fff7fffu >> out_shift);
     const i32 fold_mul = (i32)(1u << out_shift);
@@ -263,7 +272,7 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
       for (int t = 0; t < 20; t++) {
         const int B = t >> 1, h = t & 1;
         *reinterpret_cast<int2 *>(st + lane * kStStride + ((h ^ (B & 1)) * 20) + 2 * B) =
-            make_int2((i32)((u32)wv[t] << 16), (i32)((u32)wv[t] & 0xffff0000u));
+            make_int2((i32)(int16_t)wv[t], wv[t] >> 16);
       }
     }
     __syncwarp();
@@ -310,9 +319,9 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
       mag = __reduce_or_sync(0xffffffffu, mag);
       i32 fo[8];
       if ((mag >> p.fast_bits) == 0)
-        modulate_pair<false>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, fo);
+        modulate_pair<false>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, p.zero, fo);
       else
-        modulate_pair<true>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, fo);
+        modulate_pair<true>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, 0, fo);
 
       // ---- per slot: commit the fold into the ring, then the 10-tap window (generic:1508) ----
 #pragma unroll
@@ -334,10 +343,10 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
         for (int q = 0; q < 5; q++) {
           int4 x = sv[q];
           int2 ca = cv[2 * q], cb = cv[2 * q + 1];
-          acc0 += __mulhi(x.x, ca.x);
-          acc1 += __mulhi(x.y, ca.y);
-          acc0 += __mulhi(x.z, cb.x);
-          acc1 += __mulhi(x.w, cb.y);
+          acc0 += x.x * ca.x;
+          acc1 += x.y * ca.y;
+          acc0 += x.z * cb.x;
+          acc1 += x.w * cb.y;
         }
         // shl32_sat(acc, 1) >> 16  ==  clamp(acc, -2^30, 2^30-1) >> 15
         i32 o0 = max(-0x40000000, min(0x3fffffff, acc0)) >> 15;
@@ -363,7 +372,7 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
       for (int t = 0; t < 20; t++) {
         const int B = t >> 1, h = t & 1;
         int2 x = *reinterpret_cast<const int2 *>(st + lane * kStStride + ((h ^ (B & 1)) * 20) + 2 * B);
-        dst[32 * t + lane] = (i32)(((u32)x.x >> 16) | ((u32)x.y & 0xffff0000u));
+        dst[32 * t + lane] = (i32)(((u32)x.x & 0xffffu) | ((u32)x.y << 16));
       }
       if (lane == 0) {
         p.pos[2 * u] = (int16_t)off;
@@ -388,7 +397,7 @@ int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
   auto hi = [](int16_t v) { return (int32_t)((uint32_t)(uint16_t)v << 16); };
   for (int k = 0; k < 32; k++)
     for (int q = 0; q < 19; q++)
-      for (int e = 0; e < 2; e++) t->coef[k * kCoStride + 2 * q + e] = hi(c[2 * k + e + 64 * q]);
+      for (int e = 0; e < 2; e++) t->coef[k * kCoStride + 2 * q + e] = (int32_t)c[2 * k + e + 64 * q];
   for (int n = 0; n < 32; n++) t->pre_tw[n] = make_int2(hi(sc[2 * n]), hi(sc[2 * n + 1]));
   for (int n = 0; n < 16; n++) t->alt_tw[n] = make_int2(hi(al[2 * n]), hi(al[2 * n + 1]));
   for (int i = 0; i < 8; i++)

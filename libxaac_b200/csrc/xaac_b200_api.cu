@@ -304,6 +304,7 @@ int32_t xaac_b200_qmf_synth_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_matrix, 
   a.pcm = d_pcm;
   a.rom = ctx->d_rom_qmf_syn;
   a.fast_bits = ctx->qmf_fast_bits;
+  a.zero = 0;
   a.n_units = n_units;
   a.ch_fac = ch_fac;
   CK(xb::launch_qmf_synth_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch qmf_synth_hq_kernel");
