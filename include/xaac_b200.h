@@ -128,6 +128,23 @@ int32_t xaac_b200_qmf_synth_state_download(xaac_b200_ctx *ctx, xaac_b200_qmf_syn
 int32_t xaac_b200_qmf_synth_hq_host(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *state, const int32_t *matrix,
                                     const int16_t *params, int16_t *pcm, int32_t ch_fac);
 
+/* Complex ("HQ") 32-band QMF analysis, batched.  Replaces ixheaacd_cplx_anal_qmffilt
+ * (decoder/generic/ixheaacd_qmf_dec_generic.c:590-741; prototype decoder/ixheaacd_qmf_dec.h:74-80) as
+ * ixheaacd_sbr_dec calls it with low_pow_flag = 0 (decoder/ixheaacd_sbr_dec.c:1025), together with the link-time
+ * leaves ixheaacd_sbr_qmfanal32_winadd, ixheaacd_fwd_modulation, ixheaacd_cos_sin_mod, ixheaacd_radix4bfly,
+ * ixheaacd_postradixcompute4.  The stage sets lb_scale = -8 (generic:635); callers use that constant.
+ * Unit = one frame of one core channel.
+ *   pcm     PCM16 core samples, 1024 per unit; ch_fac as for the IMDCT stage (time_sample_buf stride)
+ *   states  [n_units][320] WORD16 anal_filter_states, in/out
+ *   pos     [n_units][2] WORD16 {core_samples_buffer - anal_filter_states, filter_pos - analy_win_coeff}, in/out
+ *   usb     [n_units] WORD16 qmf_bank->usb
+ *   matrix  [n_units][32][128] WORD32: qmf_real[i][0..31] at row offset 0, qmf_imag[i][0..31] at row offset 64;
+ *           the other 64 words of each row are left untouched (the reference does not write them either)
+ */
+int32_t xaac_b200_qmf_anal_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_pcm, int16_t *d_states, int16_t *d_pos,
+                                  const int16_t *d_usb, int32_t *d_matrix, int64_t n_units, int32_t ch_fac,
+                                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

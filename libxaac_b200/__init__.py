@@ -16,14 +16,18 @@ from .imdct import (  # noqa: F401
     imdct_process_host,
 )
 from .qmf import (  # noqa: F401
+    QmfAnalBatch,
     QmfSynthBatch,
     QmfSynthHostState,
+    cplx_anal_qmffilt,
     cplx_synt_qmffilt,
     cplx_synt_qmffilt_host,
     synth_params,
 )
 
 __all__ = [
+    "QmfAnalBatch",
+    "cplx_anal_qmffilt",
     "QmfSynthBatch",
     "QmfSynthHostState",
     "cplx_synt_qmffilt",

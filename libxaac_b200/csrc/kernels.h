@@ -72,6 +72,22 @@ size_t qmf_synth_table_bytes();
 int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out);  // returns fast_bits (>0) or -1
 cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStream_t stream);
 
+struct QmfAnalArgs {
+  const int16_t *pcm;      // core-coder time samples, 1024 per unit (ch_fac interleave as for the IMDCT output)
+  int16_t *states;         // [n_units][320]  ia_sbr_qmf_filter_bank_struct.anal_filter_states, in/out
+  int16_t *pos;            // [n_units][2]    {core_samples_buffer - anal_filter_states, filter_pos - qmf_c}, in/out
+  const int16_t *usb;      // [n_units]       qmf_bank->usb (bands rotated by t_cos)
+  int32_t *matrix;         // [n_units][32][128]: re at +0..31, im at +64..95 of each slot row
+  const uint8_t *rom;      // device image built by qmf_anal_build_tables()
+  long long n_units;
+  int ch_fac;
+  int exact;               // 1: use saturating adds in the modulation (only if the table bound check failed)
+};
+
+size_t qmf_anal_table_bytes();
+int qmf_anal_build_tables(const uint8_t *qrom, uint8_t *out);  // 0: wrapping path exact, 1: need saturating, -1: bad
+cudaError_t launch_qmf_anal_hq(const QmfAnalArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

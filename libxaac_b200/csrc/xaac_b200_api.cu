@@ -18,6 +18,8 @@ struct xaac_b200_ctx {
   uint8_t *d_rom_qmf_syn = nullptr;  // table image of qmf_synth_hq_kernel
   bool have_qmf_rom = false;
   int qmf_fast_bits = 0;
+  uint8_t *d_rom_qmf_ana = nullptr;  // table image of qmf_anal_hq_kernel
+  int qmf_anal_exact = 0;
   char err[256] = {0};
   // staging for the *_host entry points: kPipe chunks in flight, one stream each
   static constexpr int kPipe = 3;
@@ -108,6 +110,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   }
   if (ctx->d_rom_imdct) cudaFree(ctx->d_rom_imdct);
   if (ctx->d_rom_qmf_syn) cudaFree(ctx->d_rom_qmf_syn);
+  if (ctx->d_rom_qmf_ana) cudaFree(ctx->d_rom_qmf_ana);
   delete ctx;
 }
 
@@ -279,6 +282,27 @@ int32_t xaac_b200_set_qmf_rom(xaac_b200_ctx *ctx, const void *tables, size_t byt
   cudaError_t e = cudaMemcpy(ctx->d_rom_qmf_syn, img, n, cudaMemcpyHostToDevice);
   free(img);
   if (e != cudaSuccess) return fail(ctx, e, "cudaMemcpy(qmf rom)");
+  {  // analysis bank tables
+    size_t na = xb::qmf_anal_table_bytes();
+    uint8_t *ia = (uint8_t *)calloc(1, na + 64);
+    if (!ia) return XAAC_B200_FATAL;
+    int ex = xb::qmf_anal_build_tables((const uint8_t *)tables, ia);
+    if (ex < 0) {
+      free(ia);
+      return bad_arg(ctx, "QMF tables: unexpected dig_rev_table4_16");
+    }
+    if (!ctx->d_rom_qmf_ana) {
+      cudaError_t e2 = cudaMalloc((void **)&ctx->d_rom_qmf_ana, na);
+      if (e2 != cudaSuccess) {
+        free(ia);
+        return fail(ctx, e2, "cudaMalloc(qmf anal rom)");
+      }
+    }
+    cudaError_t e2 = cudaMemcpy(ctx->d_rom_qmf_ana, ia, na, cudaMemcpyHostToDevice);
+    free(ia);
+    if (e2 != cudaSuccess) return fail(ctx, e2, "cudaMemcpy(qmf anal rom)");
+    ctx->qmf_anal_exact = ex;
+  }
   ctx->have_qmf_rom = true;
   ctx->qmf_fast_bits = fast_bits;
   return XAAC_B200_OK;
@@ -390,6 +414,33 @@ int32_t xaac_b200_qmf_synth_hq_host(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_stat
     CK(cudaMemcpyAsync(pcm + u0 * 2048, d_pcm, (size_t)n * 4096, cudaMemcpyDeviceToHost, st), "D2H pcm");
   }
   for (int i = 0; i < xaac_b200_ctx::kPipe; i++) CK(cudaStreamSynchronize(ctx->streams[i]), "stream sync");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_qmf_anal_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_pcm, int16_t *d_states, int16_t *d_pos,
+                                  const int16_t *d_usb, int32_t *d_matrix, int64_t n_units, int32_t ch_fac,
+                                  void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->have_qmf_rom) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_qmf_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0 || ch_fac < 1) return bad_arg(ctx, "n_units/ch_fac");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_pcm || !d_states || !d_pos || !d_usb || !d_matrix) return bad_arg(ctx, "null buffer");
+  if (ch_fac > 1 && (n_units % ch_fac) != 0) return bad_arg(ctx, "n_units must be a multiple of ch_fac");
+  xb::QmfAnalArgs a;
+  a.pcm = d_pcm;
+  a.states = d_states;
+  a.pos = d_pos;
+  a.usb = d_usb;
+  a.matrix = d_matrix;
+  a.rom = ctx->d_rom_qmf_ana;
+  a.n_units = n_units;
+  a.ch_fac = ch_fac;
+  a.exact = ctx->qmf_anal_exact;
+  CK(xb::launch_qmf_anal_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch qmf_anal_hq_kernel");
+  ctx->launches++;
   return XAAC_B200_OK;
 }
 

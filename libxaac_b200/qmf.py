@@ -106,3 +106,36 @@ def cplx_synt_qmffilt_host(ctx, state, matrix, params, time_out, ch_fac=1):
                                              int(ch_fac))
     ctx.check(rc, "xaac_b200_qmf_synth_hq_host")
     return time_out
+
+
+class QmfAnalBatch:
+    """Persistent analysis-bank state of a batch of core channels (device tensors): the 320-sample WORD16 ring
+    (anal_filter_states) and {core_samples_buffer offset, filter_pos offset}."""
+
+    def __init__(self, n_units, device="cuda:0"):
+        self.n = int(n_units)
+        self.states = torch.zeros((self.n, 320), dtype=torch.int16, device=device)
+        self.pos = torch.zeros((self.n, 2), dtype=torch.int16, device=device)
+
+
+ANAL_LB_SCALE_HQ = -8  # sbr_scale_factor->lb_scale set by the stage, generic/ixheaacd_qmf_dec_generic.c:635
+
+
+def cplx_anal_qmffilt(ctx, state, time_in, usb, matrix=None, ch_fac=1, stream=None):
+    """Batched drop-in for ixheaacd_cplx_anal_qmffilt (HQ, 32 bands). time_in: int16 [n,1024] (ch_fac=1) or
+    [n/ch_fac,1024,ch_fac]; usb: int16 [n]; matrix: int32 [n,32,128] (rows: re at 0..31, im at 64..95)."""
+    n = state.n
+    if time_in.numel() != n * 1024 or time_in.dtype != torch.int16 or not time_in.is_contiguous():
+        raise ValueError("time_in: expected contiguous int16 with n*1024 elements")
+    _chk(usb, torch.int16, (n,), "usb", "cuda")
+    if n % ch_fac:
+        raise ValueError("n_units must be a multiple of ch_fac")
+    if matrix is None:
+        matrix = torch.zeros((n, 32, 128), dtype=torch.int32, device=time_in.device)
+    _chk(matrix, torch.int32, (n, 32, 128), "matrix", "cuda")
+    if stream is None:
+        stream = torch.cuda.current_stream(time_in.device)
+    rc = ctx._lib.xaac_b200_qmf_anal_hq_dev(ctx.handle, _ptr(time_in), _ptr(state.states), _ptr(state.pos), _ptr(usb),
+                                           _ptr(matrix), n, int(ch_fac), ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_qmf_anal_hq_dev")
+    return matrix
