@@ -145,6 +145,38 @@ int32_t xaac_b200_qmf_anal_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_pcm, int1
                                   const int16_t *d_usb, int32_t *d_matrix, int64_t n_units, int32_t ch_fac,
                                   void *stream);
 
+/* ---- fixed-point complex ("HQ") SBR HF generator, batched --------------------------------------------
+ * Replaces ixheaacd_hf_generator (decoder/ixheaacd_lpp_tran.c:956-1258; prototype decoder/ixheaacd_lpp_tran.h:72-80) as
+ * ixheaacd_sbr_dec calls it (decoder/ixheaacd_sbr_dec.c:1169), with its leaves ixheaacd_invfilt_level_emphasis,
+ * ixheaacd_filterstep3 and the selector leaves ixheaacd_covariance_matrix_calc_2 and ixheaacd_fix_div.
+ * Unit = one frame of one SBR channel.
+ *   lpc      [n_units][2][128] WORD32: hf_generator->lpc_filt_states_real[i] (64) | _imag[i] (64); read-only
+ *   matrix   [n_units][38][128] WORD32: qmf_real[i] (64) | qmf_imag[i] (64) for the 6 overlap + 32 current slots;
+ *            bands >= max_qmf_subband are generated in place
+ *   params   [n_units][80] WORD16, XAAC_HF_* offsets below: ia_transposer_settings_struct
+ *            (decoder/ixheaacd_lpp_tran.h:50-57) followed by the scalar arguments of the reference call
+ *   bw_prev  [n_units][6] WORD32 hf_generator->bw_array_prev, in/out
+ *   hb_scale [n_units] WORD16 sbr_scale_factor->hb_scale produced by the stage */
+#define XAAC_HF_NUM_PATCHES 0
+#define XAAC_HF_START_PATCH 1
+#define XAAC_HF_STOP_PATCH 2
+#define XAAC_HF_NUM_COLUMNS 3
+#define XAAC_HF_BW_BORDERS 4       /* [10] */
+#define XAAC_HF_PATCH 14           /* [6][6] src_start, src_end, guard_start, dst_start, dst_end, num_bands */
+#define XAAC_HF_FACTOR 50          /* time_step */
+#define XAAC_HF_NUM_IF_BANDS 51
+#define XAAC_HF_START_IDX 52       /* border_vec[0] */
+#define XAAC_HF_STOP_IDX 53        /* border_vec[num_env] - num_time_slots */
+#define XAAC_HF_INVF 54            /* [10] sbr_invf_mode */
+#define XAAC_HF_INVF_PREV 64       /* [10] sbr_invf_mode_prev */
+#define XAAC_HF_OV_LB_SCALE 74
+#define XAAC_HF_LB_SCALE 75
+#define XAAC_HF_MAX_QMF_SUBBAND 76
+#define XAAC_HF_PARAM_WORDS 80
+int32_t xaac_b200_hf_generator_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_lpc, int32_t *d_matrix,
+                                      const int16_t *d_params, int32_t *d_bw_prev, int16_t *d_hb_scale,
+                                      int64_t n_units, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,8 +24,10 @@ from .qmf import (  # noqa: F401
     cplx_synt_qmffilt_host,
     synth_params,
 )
+from .sbr import hf_generator  # noqa: F401
 
 __all__ = [
+    "hf_generator",
     "QmfAnalBatch",
     "cplx_anal_qmffilt",
     "QmfSynthBatch",

@@ -38,6 +38,7 @@ SIGNATURES = {
     "xaac_b200_qmf_synth_state_download": (_i32, [_vp, _vp, _vp, _vp]),
     "xaac_b200_qmf_synth_hq_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32]),
     "xaac_b200_qmf_anal_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "xaac_b200_hf_generator_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -88,6 +88,16 @@ size_t qmf_anal_table_bytes();
 int qmf_anal_build_tables(const uint8_t *qrom, uint8_t *out);  // 0: wrapping path exact, 1: need saturating, -1: bad
 cudaError_t launch_qmf_anal_hq(const QmfAnalArgs &args, int num_sms, cudaStream_t stream);
 
+struct HfGenArgs {
+  const int32_t *lpc;      // [n_units][2][128]  lpc_filt_states_{real,imag}[i] as re[64] | im[64] rows (read-only)
+  int32_t *matrix;         // [n_units][38][128] QMF rows (6 overlap + 32 current); high band written in place
+  const int16_t *params;   // [n_units][80]      transposer settings + scalar arguments (include/xaac_b200.h)
+  int32_t *bw_prev;        // [n_units][6]       ia_sbr_hf_generator_struct.bw_array_prev, in/out
+  int16_t *hb_scale;       // [n_units]          sbr_scale_factor->hb_scale set by the stage
+  long long n_units;
+};
+cudaError_t launch_hf_generator_hq(const HfGenArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

@@ -444,4 +444,24 @@ int32_t xaac_b200_qmf_anal_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_pcm, int1
   return XAAC_B200_OK;
 }
 
+int32_t xaac_b200_hf_generator_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_lpc, int32_t *d_matrix,
+                                      const int16_t *d_params, int32_t *d_bw_prev, int16_t *d_hb_scale,
+                                      int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_lpc || !d_matrix || !d_params || !d_bw_prev || !d_hb_scale) return bad_arg(ctx, "null buffer");
+  xb::HfGenArgs a;
+  a.lpc = d_lpc;
+  a.matrix = d_matrix;
+  a.params = d_params;
+  a.bw_prev = d_bw_prev;
+  a.hb_scale = d_hb_scale;
+  a.n_units = n_units;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(xb::launch_hf_generator_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch hf_generator_hq_kernel");
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
 }  // extern "C"

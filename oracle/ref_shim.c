@@ -199,3 +199,66 @@ void ref_synt_qmffilt_hq_batch(int32_t *matrix, int16_t *filter_states, int32_t 
     ref_synt_qmffilt_hq(matrix + (size_t)u * 4096, filter_states + (size_t)u * 1280, drc_offset + u, filter_pos + u,
                         sf + 4 * u, lsb[u], usb[u], 6, time_out + (size_t)u * 2048, 1);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * HQ HF generator: ixheaacd_hf_generator (decoder/ixheaacd_lpp_tran.c:956-1258) as ixheaacd_sbr_dec calls it at
+ * sbr_dec.c:1169.
+ *   lpc      [2][128]  lpc_filt_states_{real,imag}[i] as re[64] | im[64] rows (read-only here)
+ *   matrix   [38][128] QMF rows (6 overlap + 32 current), high band written in place
+ *   prm      [80] WORD16, layout XO_HF_* in oracle/src/xaac_oracle.h
+ *   bw_prev  [6] WORD32 bw_array_prev, in/out
+ *   returns hb_scale
+ * ---------------------------------------------------------------------------------------------- */
+int ref_hf_generator_hq(const int32_t *lpc, int32_t *matrix, const int16_t *prm, int32_t *bw_prev) {
+  ia_sbr_hf_generator_struct hf;
+  ia_transposer_settings_struct set;
+  ia_sbr_scale_fact_struct sf;
+  WORD32 *re[40], *im[40];
+  WORD32 invf[MAX_NUM_NOISE_VALUES], invf_prev[MAX_NUM_NOISE_VALUES];
+  static __thread WORD32 scratch[40 * 128];
+  static __thread WORD32 lpc_r[2][64], lpc_i[2][64];
+  memset(&hf, 0, sizeof(hf));
+  memset(&set, 0, sizeof(set));
+  memset(&sf, 0, sizeof(sf));
+  set.num_patches = prm[0];
+  set.start_patch = prm[1];
+  set.stop_patch = prm[2];
+  set.num_columns = prm[3];
+  for (int i = 0; i < MAX_NUM_NOISE_VALUES; i++) set.bw_borders[i] = prm[4 + i];
+  for (int p = 0; p < MAX_NUM_PATCHES; p++) {
+    const int16_t *q = prm + 14 + 6 * p;
+    set.str_patch_param[p].src_start_band = q[0];
+    set.str_patch_param[p].src_end_band = q[1];
+    set.str_patch_param[p].guard_start_band = q[2];
+    set.str_patch_param[p].dst_start_band = q[3];
+    set.str_patch_param[p].dst_end_band = q[4];
+    set.str_patch_param[p].num_bands_in_patch = q[5];
+  }
+  for (int i = 0; i < MAX_NUM_NOISE_VALUES; i++) {
+    invf[i] = prm[54 + i];
+    invf_prev[i] = prm[64 + i];
+  }
+  sf.ov_lb_scale = prm[74];
+  sf.lb_scale = prm[75];
+  hf.pstr_settings = &set;
+  for (int i = 0; i < MAX_NUM_PATCHES; i++) hf.bw_array_prev[i] = bw_prev[i];
+  for (int i = 0; i < 2; i++) {
+    memcpy(lpc_r[i], lpc + 128 * i, 64 * sizeof(WORD32));
+    memcpy(lpc_i[i], lpc + 128 * i + 64, 64 * sizeof(WORD32));
+    hf.lpc_filt_states_real[i] = lpc_r[i];
+    hf.lpc_filt_states_imag[i] = lpc_i[i];
+  }
+  memset(scratch, 0, 2 * 128 * sizeof(WORD32));
+  memcpy(scratch + 256, matrix, 38 * 128 * sizeof(WORD32));
+  for (int i = 0; i < 38; i++) {
+    re[i] = scratch + 256 + 128 * i;
+    im[i] = re[i] + 64;
+  }
+  /* factor (time_step), first_slot_offset, last_slot_offset are pre-multiplied by the caller of this shim:
+   * prm[52] = start_idx argument (border_vec[0]), prm[53] = stop_idx argument (border_vec[num_env] - num_time_slots) */
+  ixheaacd_hf_generator(&hf, &sf, re, im, prm[50], prm[52], prm[53], prm[51], prm[76], invf, invf_prev, scratch,
+                        AOT_SBR);
+  memcpy(matrix, scratch + 256, 38 * 128 * sizeof(WORD32));
+  for (int i = 0; i < MAX_NUM_PATCHES; i++) bw_prev[i] = hf.bw_array_prev[i];
+  return sf.hb_scale;
+}

@@ -24,6 +24,12 @@ static FILE *tap_fp(void) {
   }
   return fp;
 }
+/* XAAC_TAP_STAGES: comma-separated subset of {imd,hfg,env,sbr,ps}; default = all */
+static int tap_on(const char *stage) {
+  const char *p = getenv("XAAC_TAP_STAGES");
+  if (!p || !*p) return 1;
+  return strstr(p, stage) != NULL;
+}
 static int tap_limit(void) {
   static int lim = -1;
   if (lim < 0) {
@@ -45,7 +51,7 @@ VOID __wrap_ixheaacd_imdct_process(ia_aac_dec_overlap_info *ovl, WORD32 *spec, i
                                    WORD slot) {
   static int count = 0;
   FILE *fp = tap_fp();
-  int rec = fp && ics->frame_length == 1024 && count < tap_limit();
+  int rec = fp && tap_on("imd") && ics->frame_length == 1024 && count < tap_limit();
   int32_t hdr[9];
   int32_t spec_in[1024], ovl_in[512];
   if (rec) {
@@ -71,6 +77,60 @@ VOID __wrap_ixheaacd_imdct_process(ia_aac_dec_overlap_info *ovl, WORD32 *spec, i
     fwrite(ovl_in, 4, 512, fp);
     fwrite(o, 4, 1024, fp);
     fwrite(ovl->ptr_overlap_buf, 4, 512, fp);
+    fflush(fp);
+    count++;
+  }
+}
+
+/* ---- ixheaacd_hf_generator (decoder/ixheaacd_lpp_tran.c:956), HQ path --------------------------------------
+ * record: int32 magic 'HFG1', int16 prm[80] (layout XO_HF_*), int32 bw_prev_in[6], int32 lpc[2][128],
+ *         int32 matrix_in[38][128], int32 matrix_out[38][128], int32 bw_prev_out[6], int32 hb_scale */
+VOID __real_ixheaacd_hf_generator(ia_sbr_hf_generator_struct *, ia_sbr_scale_fact_struct *, WORD32 **, WORD32 **,
+                                  WORD32, WORD32, WORD32, WORD32, WORD32, WORD32 *, WORD32 *, WORD32 *, WORD);
+
+VOID __wrap_ixheaacd_hf_generator(ia_sbr_hf_generator_struct *hf, ia_sbr_scale_fact_struct *sf, WORD32 **re,
+                                  WORD32 **im, WORD32 factor, WORD32 start_idx, WORD32 stop_idx, WORD32 num_if_bands,
+                                  WORD32 max_qmf_subband, WORD32 *invf, WORD32 *invf_prev, WORD32 *sub_sig_x,
+                                  WORD aot) {
+  static int count = 0;
+  FILE *fp = tap_fp();
+  ia_transposer_settings_struct *set = hf->pstr_settings;
+  int rec = fp && tap_on("hfg") && count < tap_limit() && set->num_columns == 32;
+  int16_t prm[80];
+  int32_t bw_in[6], lpc[2][128];
+  static int32_t m_in[38][128];
+  if (rec) {
+    memset(prm, 0, sizeof(prm));
+    prm[0] = set->num_patches; prm[1] = set->start_patch; prm[2] = set->stop_patch; prm[3] = set->num_columns;
+    for (int i = 0; i < MAX_NUM_NOISE_VALUES; i++) prm[4 + i] = set->bw_borders[i];
+    for (int p = 0; p < MAX_NUM_PATCHES; p++) {
+      int16_t *q = prm + 14 + 6 * p;
+      q[0] = set->str_patch_param[p].src_start_band; q[1] = set->str_patch_param[p].src_end_band;
+      q[2] = set->str_patch_param[p].guard_start_band; q[3] = set->str_patch_param[p].dst_start_band;
+      q[4] = set->str_patch_param[p].dst_end_band; q[5] = set->str_patch_param[p].num_bands_in_patch;
+    }
+    prm[50] = (int16_t)factor; prm[51] = (int16_t)num_if_bands; prm[52] = (int16_t)start_idx; prm[53] = (int16_t)stop_idx;
+    for (int i = 0; i < MAX_NUM_NOISE_VALUES; i++) { prm[54 + i] = (int16_t)invf[i]; prm[64 + i] = (int16_t)invf_prev[i]; }
+    prm[74] = sf->ov_lb_scale; prm[75] = sf->lb_scale; prm[76] = (int16_t)max_qmf_subband;
+    for (int i = 0; i < 6; i++) bw_in[i] = hf->bw_array_prev[i];
+    for (int i = 0; i < 2; i++) {
+      memcpy(lpc[i], hf->lpc_filt_states_real[i], 64 * 4);
+      memcpy(lpc[i] + 64, hf->lpc_filt_states_imag[i], 64 * 4);
+    }
+    for (int i = 0; i < 38; i++) { memcpy(m_in[i], re[i], 64 * 4); memcpy(m_in[i] + 64, im[i], 64 * 4); }
+  }
+  __real_ixheaacd_hf_generator(hf, sf, re, im, factor, start_idx, stop_idx, num_if_bands, max_qmf_subband, invf,
+                               invf_prev, sub_sig_x, aot);
+  if (rec) {
+    int32_t magic = 0x31474648, hb = sf->hb_scale;
+    fwrite(&magic, 4, 1, fp);
+    fwrite(prm, 2, 80, fp);
+    fwrite(bw_in, 4, 6, fp);
+    fwrite(lpc, 4, 256, fp);
+    fwrite(m_in, 4, 38 * 128, fp);
+    for (int i = 0; i < 38; i++) { fwrite(re[i], 4, 64, fp); fwrite(im[i], 4, 64, fp); }
+    fwrite(hf->bw_array_prev, 4, 6, fp);
+    fwrite(&hb, 4, 1, fp);
     fflush(fp);
     count++;
   }

@@ -59,4 +59,28 @@ void xo_synt_qmffilt_hq_batch(const uint8_t *qrom, int32_t *matrix, int16_t *fil
                               int16_t *time_out, int n);
 void xo_anal_qmffilt_hq_batch(const uint8_t *qrom, const int16_t *time_in, int16_t *states, int32_t *pos,
                               int32_t *filter_pos, const int32_t *usb, int32_t *matrix, int n);
+
+/* ---- fixed-point HQ HF generator --------------------------------------------------------------------------
+ * Per-unit parameter record (WORD16[80]) — the fields of ia_transposer_settings_struct
+ * (decoder/ixheaacd_lpp_tran.h:50-57) and the scalar arguments of ixheaacd_hf_generator (lpp_tran.c:956-962). */
+#define XO_HF_NUM_PATCHES 0
+#define XO_HF_START_PATCH 1
+#define XO_HF_STOP_PATCH 2
+#define XO_HF_NUM_COLUMNS 3
+#define XO_HF_BW_BORDERS 4      /* [10] */
+#define XO_HF_PATCH 14          /* [6][6]: src_start, src_end, guard_start, dst_start, dst_end, num_bands */
+#define XO_HF_FACTOR 50         /* time_step */
+#define XO_HF_NUM_IF_BANDS 51
+#define XO_HF_START_IDX 52      /* border_vec[0] */
+#define XO_HF_STOP_IDX 53       /* border_vec[num_env] - num_time_slots */
+#define XO_HF_INVF 54           /* [10] sbr_invf_mode */
+#define XO_HF_INVF_PREV 64      /* [10] */
+#define XO_HF_OV_LB_SCALE 74
+#define XO_HF_LB_SCALE 75
+#define XO_HF_MAX_QMF_SUBBAND 76
+#define XO_HF_PRM_WORDS 80
+
+int xo_hf_generator_hq(const int32_t *lpc, int32_t *matrix, const int16_t *prm, int32_t *bw_prev);
+void xo_hf_generator_hq_batch(const int32_t *lpc, int32_t *matrix, const int16_t *prm, int32_t *bw_prev,
+                              int32_t *hb_scale, int n);
 #endif

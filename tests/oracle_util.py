@@ -103,6 +103,20 @@ class Oracle:
         return m, st, np.stack([po, fp], 1).astype(np.int16)
 
 
+    # ---- HF generator ------------------------------------------------------------------------------------
+    def hfgen_batch(self, lpc, matrix, prm, bw_prev):
+        """lpc [n,2,128] i32, matrix [n,38,128] i32, prm [n,80] i16, bw_prev [n,6] i32.
+        Returns (matrix', bw_prev', hb_scale [n] i16)."""
+        n = matrix.shape[0]
+        l = np.ascontiguousarray(lpc, np.int32)
+        m = np.ascontiguousarray(matrix, np.int32).copy()
+        pr = np.ascontiguousarray(prm, np.int16)
+        bw = np.ascontiguousarray(bw_prev, np.int32).copy()
+        hb = np.zeros(n, np.int32)
+        self.lib.xo_hf_generator_hq_batch(P(l), P(m), P(pr), P(bw), P(hb), n)
+        return m, bw, hb.astype(np.int16)
+
+
 class Ref:
     """The unmodified reference, compiled from /root/reference by oracle/Makefile (target ref)."""
 
@@ -121,6 +135,13 @@ class Ref:
         total = ctypes.c_int(0)
         p = fn(ctypes.byref(total))
         return np.frombuffer(ctypes.string_at(p, nbytes), dtype=np.uint8).copy()
+
+    def hfgen(self, lpc, matrix, prm, bw_prev):
+        m = np.ascontiguousarray(matrix, np.int32).copy()
+        bw = np.ascontiguousarray(bw_prev, np.int32).copy()
+        hb = self.lib.ref_hf_generator_hq(P(np.ascontiguousarray(lpc, np.int32)), P(m),
+                                          P(np.ascontiguousarray(prm, np.int16)), P(bw))
+        return m, bw, hb
 
     def rom_qmf(self, nbytes=3464):
         fn = self.lib.ref_rom_qmf_tables
@@ -223,3 +244,29 @@ def synth_qmf_units(n, seed):
         params[6, 4:6] = (0, 0)             # no bands scaled
         params[7, 4:6] = (64, 64)           # everything low band
     return matrix, fs, pos, params
+
+
+def synth_hfgen_units(n, seed, golden_prm):
+    """HF-generator inputs: parameter rows drawn from the tapped real ones (transposer settings are table-driven) with
+    randomised inverse-filter modes, envelope borders and start band; random QMF matrices / LPC states with per-unit
+    magnitude. Returns lpc [n,2,128], matrix [n,38,128], prm [n,80], bw_prev [n,6]."""
+    rng = np.random.default_rng(seed)
+    prm = golden_prm[rng.integers(0, len(golden_prm), n)].copy()
+    prm[:, 54:64] = rng.integers(0, 4, (n, 10))
+    prm[:, 64:74] = rng.integers(0, 4, (n, 10))
+    prm[:, 52] = rng.integers(0, 3, n)
+    prm[:, 53] = rng.integers(-1, 3, n)
+    prm[:, 76] = prm[:, 76] + rng.integers(-3, 6, n)
+    prm[:, 74] = rng.integers(-4, 24, n)
+    prm[:, 75] = rng.integers(-4, 24, n)
+    s = rng.integers(8, 31, size=(n, 1, 1))
+    matrix = ((rng.random((n, 38, 128)) * 2 - 1) * (2.0 ** s)).astype(np.int64).astype(np.int32)
+    lpc = ((rng.random((n, 2, 128)) * 2 - 1) * (2.0 ** s)).astype(np.int64).astype(np.int32)
+    bw_prev = rng.integers(0, 0x7f800000, (n, 6)).astype(np.int32)
+    if n >= 4:
+        matrix[0] = 0
+        lpc[0] = 0
+        matrix[1] = rng.integers(-2 ** 31, 2 ** 31, (38, 128), dtype=np.int64).astype(np.int32)
+        matrix[2, :, :] = 1 << 29
+        bw_prev[3] = 0
+    return lpc, matrix, prm, bw_prev

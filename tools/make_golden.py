@@ -68,8 +68,8 @@ def encode(wav, out, aot, br, extra=()):
     run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{out}", f"-aot:{aot}", "-adts:1", f"-br:{br}", *extra])
 
 
-def decode_tap(bitstream, wav_out, tapfile, dec_args=(), tap_max=100000):
-    env = dict(os.environ, XAAC_TAP_FILE=tapfile, XAAC_TAP_MAX=str(tap_max))
+def decode_tap(bitstream, wav_out, tapfile, dec_args=(), tap_max=100000, stages="imd"):
+    env = dict(os.environ, XAAC_TAP_FILE=tapfile, XAAC_TAP_MAX=str(tap_max), XAAC_TAP_STAGES=stages)
     run([os.path.join(REFDIR, "xaacdec_tap"), f"-ifile:{bitstream}", f"-ofile:{wav_out}", *dec_args], env=env)
 
 
@@ -141,10 +141,64 @@ def make_imdct_golden(tmp):
     print(f"wrote {path}: {len(sel)} records, {os.path.getsize(path)} bytes")
 
 
+HFG_REC_BYTES = 4 + 160 + 24 + 1024 + 2 * 38 * 128 * 4 + 24 + 4
+
+
+def read_hfg_records(path):
+    """records written by __wrap_ixheaacd_hf_generator (oracle/ref_taps.c)"""
+    raw = np.fromfile(path, dtype=np.uint8)
+    assert raw.size % HFG_REC_BYTES == 0, (raw.size, HFG_REC_BYTES)
+    out = []
+    for r in raw.reshape(-1, HFG_REC_BYTES):
+        assert r[0:4].view(np.int32)[0] == 0x31474648
+        o = 188 + 1024
+        out.append(dict(prm=r[4:164].view(np.int16).copy(), bw_in=r[164:188].view(np.int32).copy(),
+                        lpc=r[188:o].view(np.int32).copy().reshape(2, 128),
+                        m_in=r[o:o + 19456].view(np.int32).copy().reshape(38, 128),
+                        m_out=r[o + 19456:o + 38912].view(np.int32).copy().reshape(38, 128),
+                        bw_out=r[o + 38912:o + 38936].view(np.int32).copy(),
+                        hb=int(r[o + 38936:o + 38940].view(np.int32)[0])))
+    return out
+
+
+def make_hfgen_golden(tmp):
+    """HE-AACv2 (mono + PS, 44.1 kHz, 32 kb/s) and HE-AACv1 mono (48 kHz) streams decoded with -esbr:0 take the complex
+    HQ SBR path (decoder/ixheaacd_sbrdecoder.c:408-419); every ixheaacd_hf_generator call is tapped."""
+    recs = []
+    for fs, ch, aot, br, seed in ((44100, 2, 29, 32000, 13), (48000, 1, 5, 32000, 14)):
+        wav = os.path.join(tmp, f"in_{fs}_{ch}_{aot}.wav")
+        write_wav(wav, synth(fs, 5.0, ch, seed), fs)
+        aac = os.path.join(tmp, f"he_{aot}.aac")
+        encode(wav, aac, aot, br)
+        tap = os.path.join(tmp, f"he_{aot}.tap")
+        decode_tap(aac, os.path.join(tmp, "o.wav"), tap, ["-esbr:0"], stages="hfg")
+        r = read_hfg_records(tap) if os.path.exists(tap) and os.path.getsize(tap) else []
+        print(f"aot {aot} {fs} Hz {ch}ch: {len(r)} hf_generator calls tapped")
+        recs += r
+    # keep a spread: first frames (start-up state), every ~9th afterwards, all distinct parameter rows
+    keep, seen = [], set()
+    for i, r in enumerate(recs):
+        key = r["prm"].tobytes()
+        if i < 4 or i % 9 == 0 or key not in seen:
+            keep.append(i)
+        seen.add(key)
+    keep = keep[:36]
+    sel = [recs[i] for i in keep]
+    out = {k: np.stack([r[k] for r in sel]) for k in ("prm", "bw_in", "lpc", "m_in", "m_out", "bw_out")}
+    out["hb"] = np.array([r["hb"] for r in sel], np.int32)
+    path = os.path.join(GOLD, "hfgen_tapped.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(sel)} records, {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ["imdct", "hfgen"]
     with tempfile.TemporaryDirectory() as tmp:
-        make_imdct_golden(tmp)
+        if "imdct" in which:
+            make_imdct_golden(tmp)
+        if "hfgen" in which:
+            make_hfgen_golden(tmp)
 
 
 if __name__ == "__main__":
