@@ -262,3 +262,60 @@ int ref_hf_generator_hq(const int32_t *lpc, int32_t *matrix, const int16_t *prm,
   for (int i = 0; i < MAX_NUM_PATCHES; i++) bw_prev[i] = hf.bw_array_prev[i];
   return sf.hb_scale;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * HQ envelope adjuster: ixheaacd_calc_sbrenvelope (decoder/ixheaacd_env_calc.c:692-1015) as ixheaacd_sbr_dec calls
+ * it at sbr_dec.c:1195 with low_pow_flag = 0.  Record layouts: XO_ENV_* in oracle/src/xaac_oracle.h.
+ *   prm [656] WORD16 side info; sf [8] WORD16 scale factors in/out; state [232] WORD16 in/out;
+ *   matrix [38][128] in/out.  Returns the reference's error code.
+ * ---------------------------------------------------------------------------------------------- */
+#include "ref_pack.h"
+const void *ref_rom_env_tables(int *bytes) {
+  if (bytes) *bytes = (int)sizeof(ixheaacd_aac_dec_env_calc_tables);
+  return &ixheaacd_aac_dec_env_calc_tables;
+}
+const void *ref_rom_misc_tables(int *bytes) {
+  if (bytes) *bytes = (int)sizeof(ixheaacd_str_fft_n_transcendent_tables);
+  return &ixheaacd_str_fft_n_transcendent_tables;
+}
+int ref_rom_env_offsets(int *o) {
+  int n = 0;
+  o[n++] = (int)offsetof(ia_env_calc_tables_struct, sbr_lim_gains_m);
+  o[n++] = (int)offsetof(ia_env_calc_tables_struct, sbr_smooth_filter);
+  o[n++] = (int)offsetof(ia_env_calc_tables_struct, sbr_inv_int_table);
+  o[n++] = (int)offsetof(ia_env_calc_tables_struct, sbr_rand_ph);
+  o[n++] = (int)sizeof(ia_env_calc_tables_struct);
+  o[n++] = (int)offsetof(ixheaacd_misc_tables, inv_table);
+  o[n++] = (int)offsetof(ixheaacd_misc_tables, sqrt_table);
+  o[n++] = (int)offsetof(ixheaacd_misc_tables, dummy);
+  return n;
+}
+
+int ref_calc_sbrenvelope_hq(const int16_t *prm, int16_t *sf, int16_t *state, int32_t *matrix) {
+  static __thread struct { ia_sbr_frame_info_data_struct f; WORD16 extra[512]; } __attribute__((aligned(8))) fd;
+  ia_sbr_header_data_struct h;
+  ia_freq_band_data_struct fb;
+  ia_sbr_prev_frame_data_struct pv;
+  ia_sbr_scale_fact_struct s;
+  ia_sbr_calc_env_struct ce;
+  ia_sbr_tables_struct tabs;
+  WORD16 filt_me[2 * MAX_FREQ_COEFFS], filt_noise[MAX_FREQ_COEFFS], deg[64];
+  WORD32 *re[MAX_ENV_COLS], *im[MAX_ENV_COLS];
+  memset(&fd, 0, sizeof(fd)); memset(&h, 0, sizeof(h)); memset(&fb, 0, sizeof(fb)); memset(&pv, 0, sizeof(pv));
+  memset(&s, 0, sizeof(s)); memset(&ce, 0, sizeof(ce)); memset(&tabs, 0, sizeof(tabs)); memset(deg, 0, sizeof(deg));
+  unpack_env_prm(prm, &h, &fb, &fd.f, &pv);
+  unpack_sf(sf, &s);
+  ce.filt_buf_me = filt_me;
+  ce.filt_buf_noise_m = filt_noise;
+  unpack_env_state(state, &ce);
+  tabs.env_calc_tables_ptr = (ia_env_calc_tables_struct *)&ixheaacd_aac_dec_env_calc_tables;
+  tabs.qmf_dec_tables_ptr = (ia_qmf_dec_tables_struct *)&ixheaacd_aac_qmf_dec_tables;
+  tabs.sbr_rand_ph = tabs.env_calc_tables_ptr->sbr_rand_ph;
+  for (int i = 0; i < 38; i++) { re[i] = matrix + 128 * i; im[i] = re[i] + 64; }
+  IA_ERRORCODE err = ixheaacd_calc_sbrenvelope(&s, &ce, &h, &fd.f, &pv, re, im, deg, 0, &tabs,
+                                               (ixheaacd_misc_tables *)&ixheaacd_str_fft_n_transcendent_tables, matrix,
+                                               AOT_SBR);
+  pack_sf(sf, &s);
+  pack_env_state(state, &ce);
+  return (int)err;
+}

@@ -135,3 +135,47 @@ VOID __wrap_ixheaacd_hf_generator(ia_sbr_hf_generator_struct *hf, ia_sbr_scale_f
     count++;
   }
 }
+
+/* ---- ixheaacd_calc_sbrenvelope (decoder/ixheaacd_env_calc.c:692), HQ path ------------------------------------
+ * record: int32 magic 'ENV1', int16 prm[656] (XO_ENV_*), int16 sf_in[8], int16 st_in[232], int32 m_in[38][128],
+ *         int32 m_out[38][128], int16 sf_out[8], int16 st_out[232], int32 err */
+#include "ref_pack.h"
+IA_ERRORCODE __real_ixheaacd_calc_sbrenvelope(ia_sbr_scale_fact_struct *, ia_sbr_calc_env_struct *,
+                                              ia_sbr_header_data_struct *, ia_sbr_frame_info_data_struct *,
+                                              ia_sbr_prev_frame_data_struct *, WORD32 **, WORD32 **, WORD16 *, FLAG,
+                                              ia_sbr_tables_struct *, ixheaacd_misc_tables *, WORD32 *, WORD32);
+
+IA_ERRORCODE __wrap_ixheaacd_calc_sbrenvelope(ia_sbr_scale_fact_struct *sf, ia_sbr_calc_env_struct *ce,
+                                              ia_sbr_header_data_struct *h, ia_sbr_frame_info_data_struct *f,
+                                              ia_sbr_prev_frame_data_struct *pv, WORD32 **re, WORD32 **im,
+                                              WORD16 *deg, FLAG low_pow, ia_sbr_tables_struct *t,
+                                              ixheaacd_misc_tables *ct, WORD32 *qmf, WORD32 aot) {
+  static int count = 0;
+  FILE *fp = tap_fp();
+  int rec = fp && tap_on("env") && count < tap_limit() && !low_pow && h->num_time_slots == 16;
+  static int16_t prm[XO_ENV_PRM_WORDS], sfr[8], st[XO_ENV_ST_WORDS];
+  if (rec) {
+    int32_t magic = 0x31564e45;
+    pack_env_prm(prm, h, f, pv);
+    pack_sf(sfr, sf);
+    pack_env_state(st, ce);
+    fwrite(&magic, 4, 1, fp);
+    fwrite(prm, 2, XO_ENV_PRM_WORDS, fp);
+    fwrite(sfr, 2, 8, fp);
+    fwrite(st, 2, XO_ENV_ST_WORDS, fp);
+    for (int i = 0; i < 38; i++) { fwrite(re[i], 4, 64, fp); fwrite(im[i], 4, 64, fp); }
+  }
+  IA_ERRORCODE err = __real_ixheaacd_calc_sbrenvelope(sf, ce, h, f, pv, re, im, deg, low_pow, t, ct, qmf, aot);
+  if (rec) {
+    int32_t e = (int32_t)err;
+    for (int i = 0; i < 38; i++) { fwrite(re[i], 4, 64, fp); fwrite(im[i], 4, 64, fp); }
+    pack_sf(sfr, sf);
+    pack_env_state(st, ce);
+    fwrite(sfr, 2, 8, fp);
+    fwrite(st, 2, XO_ENV_ST_WORDS, fp);
+    fwrite(&e, 4, 1, fp);
+    fflush(fp);
+    count++;
+  }
+  return err;
+}

@@ -83,4 +83,73 @@ void xo_anal_qmffilt_hq_batch(const uint8_t *qrom, const int16_t *time_in, int16
 int xo_hf_generator_hq(const int32_t *lpc, int32_t *matrix, const int16_t *prm, int32_t *bw_prev);
 void xo_hf_generator_hq_batch(const int32_t *lpc, int32_t *matrix, const int16_t *prm, int32_t *bw_prev,
                               int32_t *hb_scale, int n);
+
+/* ---- fixed-point HQ envelope adjuster ---------------------------------------------------------------------
+ * ROMs: env_rom = the host's ia_env_calc_tables_struct (decoder/ixheaacd_sbr_rom.h:59-68, 2404 bytes);
+ *       misc_rom = the leading 2470 bytes of ixheaacd_misc_tables (decoder/ixheaacd_common_rom.h:27-44). */
+#define XO_EROM_LIM_GAINS 0   /* WORD16[8]  */
+#define XO_EROM_SMOOTH 24     /* WORD16[4]  */
+#define XO_EROM_INV_INT 32    /* WORD16[49] */
+#define XO_EROM_RAND_PH 132   /* WORD32[512+56] */
+#define XO_EROM_BYTES 2404
+#define XO_MROM_INV_TABLE 1444  /* WORD16[256] */
+#define XO_MROM_SQRT_TABLE 1956 /* WORD16[257] */
+#define XO_MROM_BYTES 2470
+/* ia_sbr_scale_fact_struct (decoder/ixheaacd_sbr_scale.h:23-31) as WORD16[8] */
+#define XO_SF_LB 0
+#define XO_SF_ST_LB 1
+#define XO_SF_OV_LB 2
+#define XO_SF_HB 3
+#define XO_SF_OV_HB 4
+#define XO_SF_ST_SYN 5
+#define XO_SF_PS 6
+/* per-frame SBR side-info record (WORD16[XO_ENV_PRM_WORDS]): the fields of ia_sbr_header_data_struct,
+ * ia_freq_band_data_struct (decoder/ixheaacd_env_extr_part.h:33-100), ia_frame_info_struct and
+ * ia_sbr_frame_info_data_struct (decoder/ixheaacd_env_extr.h:54-120) the fixed-point SBR stage reads */
+#define XO_ENV_NUM_TIME_SLOTS 0
+#define XO_ENV_TIME_STEP 1
+#define XO_ENV_CHANNEL_MODE 2
+#define XO_ENV_LIMITER_GAINS 3
+#define XO_ENV_INTERPOL_FREQ 4
+#define XO_ENV_SMOOTHING_MODE 5
+#define XO_ENV_NUM_SF_LO 6
+#define XO_ENV_NUM_SF_HI 7
+#define XO_ENV_NUM_NF_BANDS 8
+#define XO_ENV_SUB_BAND_START 9
+#define XO_ENV_SUB_BAND_END 10
+#define XO_ENV_NUM_LF_BANDS 11
+#define XO_ENV_NUM_ENV 12
+#define XO_ENV_TRANSIENT_ENV 13
+#define XO_ENV_MAX_QMF_SUBBAND 14
+#define XO_ENV_MAX_QMF_SUBBAND_PREV 15
+#define XO_ENV_BORDER_VEC 16       /* [9]  */
+#define XO_ENV_FREQ_RES 25         /* [8]  */
+#define XO_ENV_NOISE_BORDER_VEC 33 /* [3]  */
+#define XO_ENV_LIM_TBL 36          /* [13] */
+#define XO_ENV_FREQ_LO 49          /* [29] */
+#define XO_ENV_FREQ_HI 78          /* [57] */
+#define XO_ENV_FREQ_NOISE 135      /* [6]  */
+#define XO_ENV_NOISE_FLOOR 141     /* [10] */
+#define XO_ENV_ADD_HARMONICS 151   /* [56] */
+#define XO_ENV_SF_ARR 207          /* [448] int_env_sf_arr */
+#define XO_ENV_PRM_WORDS 656
+/* ia_sbr_calc_env_struct (decoder/ixheaacd_env_calc.h:24-33) as WORD16[XO_ENV_ST_WORDS]:
+ * filt_buf_me[112], filt_buf_noise_m[56], filt_buf_noise_e, start_up, ph_index, tansient_env_prev, harm_index,
+ * harm_flags_prev[56] */
+#define XO_ENV_ST_FILT_ME 0
+#define XO_ENV_ST_FILT_NOISE 112
+#define XO_ENV_ST_NOISE_E 168
+#define XO_ENV_ST_START_UP 169
+#define XO_ENV_ST_PH_INDEX 170
+#define XO_ENV_ST_TRANS_PREV 171
+#define XO_ENV_ST_HARM_INDEX 172
+#define XO_ENV_ST_HARM_PREV 173
+#define XO_ENV_ST_WORDS 232
+
+int xo_expsubbandsamples_hq(const int32_t *matrix, int b0, int b1, int s0, int s1);
+void xo_adjust_scale_hq(int32_t *matrix, int b0, int b1, int s0, int s1, int shift);
+int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, const int16_t *prm, int16_t *sf,
+                           int16_t *state, int32_t *matrix);
+void xo_calc_sbrenvelope_hq_batch(const uint8_t *env_rom, const uint8_t *misc_rom, const int16_t *prm, int16_t *sf,
+                                  int16_t *state, int32_t *matrix, int32_t *err, int n);
 #endif

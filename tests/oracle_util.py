@@ -117,6 +117,28 @@ class Oracle:
         return m, bw, hb.astype(np.int16)
 
 
+    # ---- envelope adjuster -------------------------------------------------------------------------------
+    @property
+    def erom(self):
+        if not hasattr(self, "_erom"):
+            self._erom = rom("env_rom.bin")
+            self._mrom = rom("misc_rom.bin")
+        return self._erom
+
+    def envcalc_batch(self, prm, sf, state, matrix):
+        """prm [n,656] i16, sf [n,8] i16, state [n,232] i16, matrix [n,38,128] i32.
+        Returns (matrix', sf', state', err [n] i32)."""
+        n = matrix.shape[0]
+        m = np.ascontiguousarray(matrix, np.int32).copy()
+        s = np.ascontiguousarray(sf, np.int16).copy()
+        st = np.ascontiguousarray(state, np.int16).copy()
+        err = np.zeros(n, np.int32)
+        er = self.erom
+        self.lib.xo_calc_sbrenvelope_hq_batch(P(er), P(self._mrom), P(np.ascontiguousarray(prm, np.int16)), P(s), P(st),
+                                              P(m), P(err), n)
+        return m, s, st, err
+
+
 class Ref:
     """The unmodified reference, compiled from /root/reference by oracle/Makefile (target ref)."""
 
@@ -142,6 +164,21 @@ class Ref:
         hb = self.lib.ref_hf_generator_hq(P(np.ascontiguousarray(lpc, np.int32)), P(m),
                                           P(np.ascontiguousarray(prm, np.int16)), P(bw))
         return m, bw, hb
+
+    def envcalc(self, prm, sf, state, matrix):
+        m = np.ascontiguousarray(matrix, np.int32).copy()
+        s = np.ascontiguousarray(sf, np.int16).copy()
+        st = np.ascontiguousarray(state, np.int16).copy()
+        err = self.lib.ref_calc_sbrenvelope_hq(P(np.ascontiguousarray(prm, np.int16)), P(s), P(st), P(m))
+        return m, s, st, err
+
+    def rom_blob(self, getter, nbytes):
+        fn = getattr(self.lib, getter)
+        fn.restype = ctypes.c_void_p
+        total = ctypes.c_int(0)
+        p = fn(ctypes.byref(total))
+        assert total.value >= nbytes
+        return np.frombuffer(ctypes.string_at(p, nbytes), dtype=np.uint8).copy()
 
     def rom_qmf(self, nbytes=3464):
         fn = self.lib.ref_rom_qmf_tables
@@ -270,3 +307,52 @@ def synth_hfgen_units(n, seed, golden_prm):
         matrix[2, :, :] = 1 << 29
         bw_prev[3] = 0
     return lpc, matrix, prm, bw_prev
+
+
+def synth_env_units(n, seed, golden):
+    """Envelope-adjuster inputs: side-info rows and states drawn from the tapped real ones (frequency tables, grids and
+    envelope data obey many invariants) with randomised limiter gains / interpolation / smoothing / channel mode /
+    harmonics / transient position / envelope exponents / scale factors / adjuster state; random QMF matrices with
+    per-unit magnitude.  Returns prm [n,656] i16, sf [n,8] i16, state [n,232] i16, matrix [n,38,128] i32."""
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, len(golden["prm"]), n)
+    prm = golden["prm"][idx].copy()
+    sf = golden["sf_in"][idx].copy()
+    st = golden["st_in"][idx].copy()
+    s = rng.integers(6, 31, size=(n, 1, 1))
+    matrix = ((rng.random((n, 38, 128)) * 2 - 1) * (2.0 ** s)).astype(np.int64).astype(np.int32)
+    for u in range(n):
+        if u % 7 == 0:
+            matrix[u] = golden["m_in"][idx[u]]
+        prm[u, 3] = rng.integers(0, 4)
+        prm[u, 4] = rng.integers(0, 2)
+        prm[u, 5] = rng.integers(0, 2)
+        prm[u, 2] = rng.choice([1, 3])
+        nhi = prm[u, 7]
+        if u % 3 == 0:
+            prm[u, 151:151 + nhi] = rng.random(nhi) < 0.3
+        if u % 5 == 0:
+            prm[u, 13] = rng.integers(-1, prm[u, 12] + 1)
+        if u % 2 == 0:
+            v = prm[u, 207:207 + 448].astype(np.int32)
+            v = (v & 0xFFC0) | np.clip((v & 0x3F) + rng.integers(-6, 7, 448), 0, 63)
+            prm[u, 207:207 + 448] = v.astype(np.uint16).view(np.int16)
+        sf[u, 3] = rng.integers(-4, 20)
+        sf[u, 4] = rng.integers(-4, 20)
+        sf[u, 0] = rng.integers(-4, 20)
+        if u % 4 == 0:
+            st[u, 0:112:2] = rng.integers(0, 32767, 56)
+            st[u, 1:112:2] = rng.integers(-10, 20, 56)
+            st[u, 112:168] = rng.integers(0, 32767, 56)
+            st[u, 168] = rng.integers(-5, 25)
+            st[u, 169] = rng.integers(0, 2)
+            st[u, 170] = rng.integers(0, 512)
+            st[u, 171] = rng.integers(-1, 1)
+            st[u, 172] = rng.integers(0, 4)
+            st[u, 173:229] = rng.integers(0, 2, 56)
+    if n >= 4:
+        matrix[0] = 0
+        matrix[1] = rng.integers(-2 ** 31, 2 ** 31, (38, 128), dtype=np.int64).astype(np.int32)
+        matrix[2] = 2 ** 31 - 1
+        matrix[3] = -(2 ** 31)
+    return prm, sf, st, matrix

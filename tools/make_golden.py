@@ -191,14 +191,73 @@ def make_hfgen_golden(tmp):
     print(f"wrote {path}: {len(sel)} records, {os.path.getsize(path)} bytes")
 
 
+ENV_REC_BYTES = 4 + 656 * 2 + 16 + 464 + 2 * 38 * 128 * 4 + 16 + 464 + 4
+
+
+def read_env_records(path):
+    """records written by __wrap_ixheaacd_calc_sbrenvelope (oracle/ref_taps.c)"""
+    raw = np.fromfile(path, dtype=np.uint8)
+    assert raw.size % ENV_REC_BYTES == 0, (raw.size, ENV_REC_BYTES)
+    out = []
+    for r in raw.reshape(-1, ENV_REC_BYTES):
+        assert r[0:4].view(np.int32)[0] == 0x31564E45
+        o = 4
+        d = {}
+        for name, nbytes, dt, shape in (("prm", 1312, np.int16, (656,)), ("sf_in", 16, np.int16, (8,)),
+                                        ("st_in", 464, np.int16, (232,)), ("m_in", 19456, np.int32, (38, 128)),
+                                        ("m_out", 19456, np.int32, (38, 128)), ("sf_out", 16, np.int16, (8,)),
+                                        ("st_out", 464, np.int16, (232,)), ("err", 4, np.int32, (1,))):
+            d[name] = r[o:o + nbytes].view(dt).copy().reshape(shape)
+            o += nbytes
+        out.append(d)
+    return out
+
+
+def he_streams(tmp, stages, reader):
+    """HE-AACv2 (mono + PS, 44.1 kHz, 32 kb/s) and HE-AACv1 mono (48 kHz) decoded with -esbr:0: both take the complex
+    HQ SBR path (decoder/ixheaacd_sbrdecoder.c:408-419)."""
+    recs = []
+    for fs, ch, aot, br, seed in ((44100, 2, 29, 32000, 13), (48000, 1, 5, 32000, 14)):
+        wav = os.path.join(tmp, f"in_{fs}_{ch}_{aot}.wav")
+        write_wav(wav, synth(fs, 5.0, ch, seed), fs)
+        aac = os.path.join(tmp, f"he_{aot}.aac")
+        encode(wav, aac, aot, br)
+        tap = os.path.join(tmp, f"he_{aot}_{stages}.tap")
+        decode_tap(aac, os.path.join(tmp, "o.wav"), tap, ["-esbr:0"], stages=stages)
+        r = reader(tap) if os.path.exists(tap) and os.path.getsize(tap) else []
+        print(f"aot {aot} {fs} Hz {ch}ch: {len(r)} {stages} calls tapped")
+        recs += r
+    return recs
+
+
+def make_envcalc_golden(tmp):
+    """every ixheaacd_calc_sbrenvelope call of the two HQ streams is tapped; keep the start-up frames, every frame
+    with a transient / more than one envelope / added harmonics, and a thin spread of the rest."""
+    recs = he_streams(tmp, "env", read_env_records)
+    keep = []
+    for i, r in enumerate(recs):
+        p = r["prm"]
+        special = p[12] > 1 or p[13] >= 0 or p[151:207].any() or r["st_in"][169] != 0
+        if special or i % 12 == 0:
+            keep.append(i)
+    keep = keep[:40]
+    sel = [recs[i] for i in keep]
+    out = {k: np.stack([r[k] for r in sel]) for k in sel[0]}
+    path = os.path.join(GOLD, "envcalc_tapped.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(sel)} of {len(recs)} records, {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
         if "hfgen" in which:
             make_hfgen_golden(tmp)
+        if "envcalc" in which:
+            make_envcalc_golden(tmp)
 
 
 if __name__ == "__main__":
