@@ -177,6 +177,76 @@ int32_t xaac_b200_hf_generator_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_lpc, 
                                       const int16_t *d_params, int32_t *d_bw_prev, int16_t *d_hb_scale,
                                       int64_t n_units, void *stream);
 
+/* ---- fixed-point complex ("HQ") SBR envelope adjuster, batched -----------------------------------------
+ * ROM: `env_tables` points at the host's ia_env_calc_tables_struct (decoder/ixheaacd_sbr_rom.h:59-68; what the
+ * reference reaches as ptr_sbr_tables->env_calc_tables_ptr / ->sbr_rand_ph), `misc_tables` at the host's
+ * ixheaacd_misc_tables (decoder/ixheaacd_common_rom.h:27-44; pstr_common_tables) of which the leading
+ * XAAC_B200_MISC_ROM_BYTES (through inv_table and sqrt_table) are read. */
+#define XAAC_B200_ENV_ROM_BYTES 2404
+#define XAAC_B200_MISC_ROM_BYTES 2470
+int32_t xaac_b200_set_env_rom(xaac_b200_ctx *ctx, const void *env_tables, size_t env_bytes, const void *misc_tables,
+                              size_t misc_bytes);
+
+/* ia_sbr_scale_fact_struct (decoder/ixheaacd_sbr_scale.h:23-31) as WORD16[8] */
+#define XAAC_SF_LB 0
+#define XAAC_SF_ST_LB 1
+#define XAAC_SF_OV_LB 2
+#define XAAC_SF_HB 3
+#define XAAC_SF_OV_HB 4
+#define XAAC_SF_ST_SYN 5
+#define XAAC_SF_PS 6
+/* Per-frame SBR side-info record, WORD16[XAAC_ENV_PARAM_WORDS]: the fields of ia_sbr_header_data_struct,
+ * ia_freq_band_data_struct (decoder/ixheaacd_env_extr_part.h:33-100), ia_frame_info_struct and
+ * ia_sbr_frame_info_data_struct / ia_sbr_prev_frame_data_struct (decoder/ixheaacd_env_extr.h:44-120) the stage reads. */
+#define XAAC_ENV_NUM_TIME_SLOTS 0
+#define XAAC_ENV_TIME_STEP 1
+#define XAAC_ENV_CHANNEL_MODE 2        /* 1 SBR_MONO, 2 SBR_STEREO, 3 PS_STEREO */
+#define XAAC_ENV_LIMITER_GAINS 3
+#define XAAC_ENV_INTERPOL_FREQ 4
+#define XAAC_ENV_SMOOTHING_MODE 5
+#define XAAC_ENV_NUM_SF_LO 6
+#define XAAC_ENV_NUM_SF_HI 7
+#define XAAC_ENV_NUM_NF_BANDS 8
+#define XAAC_ENV_SUB_BAND_START 9
+#define XAAC_ENV_SUB_BAND_END 10
+#define XAAC_ENV_NUM_LF_BANDS 11
+#define XAAC_ENV_NUM_ENV 12
+#define XAAC_ENV_TRANSIENT_ENV 13
+#define XAAC_ENV_MAX_QMF_SUBBAND 14      /* frame_data->max_qmf_subband_aac */
+#define XAAC_ENV_MAX_QMF_SUBBAND_PREV 15 /* frame_data_prev->max_qmf_subband_aac */
+#define XAAC_ENV_BORDER_VEC 16           /* [9]  */
+#define XAAC_ENV_FREQ_RES 25             /* [8]  */
+#define XAAC_ENV_NOISE_BORDER_VEC 33     /* [3]  */
+#define XAAC_ENV_LIM_TBL 36              /* [13] freq_band_tbl_lim */
+#define XAAC_ENV_FREQ_LO 49              /* [29] freq_band_tbl_lo */
+#define XAAC_ENV_FREQ_HI 78              /* [57] freq_band_tbl_hi */
+#define XAAC_ENV_FREQ_NOISE 135          /* [6]  freq_band_tbl_noise */
+#define XAAC_ENV_NOISE_FLOOR 141         /* [10] int_noise_floor */
+#define XAAC_ENV_ADD_HARMONICS 151       /* [56] add_harmonics */
+#define XAAC_ENV_SF_ARR 207              /* [448] int_env_sf_arr */
+#define XAAC_ENV_PARAM_WORDS 656
+/* ia_sbr_calc_env_struct (decoder/ixheaacd_env_calc.h:24-33) as WORD16[XAAC_ENV_STATE_WORDS] */
+#define XAAC_ENV_ST_FILT_ME 0        /* [112] filt_buf_me (mantissa, exponent pairs) */
+#define XAAC_ENV_ST_FILT_NOISE 112   /* [56]  filt_buf_noise_m */
+#define XAAC_ENV_ST_NOISE_E 168
+#define XAAC_ENV_ST_START_UP 169
+#define XAAC_ENV_ST_PH_INDEX 170
+#define XAAC_ENV_ST_TRANS_PREV 171
+#define XAAC_ENV_ST_HARM_INDEX 172
+#define XAAC_ENV_ST_HARM_PREV 173    /* [56]  harm_flags_prev */
+#define XAAC_ENV_STATE_WORDS 232
+/* Replaces ixheaacd_calc_sbrenvelope (decoder/ixheaacd_env_calc.c:692-1015; prototype decoder/ixheaacd_env_calc.h:35-45)
+ * as ixheaacd_sbr_dec calls it with low_pow_flag = 0 (decoder/ixheaacd_sbr_dec.c:1195), with ixheaacd_adj_timeslot
+ * (decoder/ixheaacd_env_dec.c:845) and the selector leaves ixheaacd_enery_calc_per_subband, ixheaacd_conv_ergtoamplitude,
+ * ixheaacd_ixheaacd_expsubbandsamples, ixheaacd_adjust_scale.  Unit = one frame of one SBR channel.
+ *   params  [n_units][656] WORD16 side info (read-only)
+ *   sf      [n_units][8]   WORD16 scale factors; reads lb/hb/ov_hb, writes hb_scale and ov_hb_scale
+ *   state   [n_units][232] WORD16 adjuster state, in/out
+ *   matrix  [n_units][38][128] WORD32 QMF rows (re[64] | im[64]); bands >= max_qmf_subband adjusted in place
+ *   err     [n_units] WORD32 or NULL: the reference's per-call return value (0 or 0x80000000) */
+int32_t xaac_b200_calc_sbrenvelope_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_params, int16_t *d_sf, int16_t *d_state,
+                                          int32_t *d_matrix, int32_t *d_err, int64_t n_units, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

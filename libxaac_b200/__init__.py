@@ -24,10 +24,11 @@ from .qmf import (  # noqa: F401
     cplx_synt_qmffilt_host,
     synth_params,
 )
-from .sbr import hf_generator  # noqa: F401
+from .sbr import calc_sbrenvelope, hf_generator  # noqa: F401
 
 __all__ = [
     "hf_generator",
+    "calc_sbrenvelope",
     "QmfAnalBatch",
     "cplx_anal_qmffilt",
     "QmfSynthBatch",

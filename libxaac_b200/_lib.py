@@ -39,6 +39,8 @@ SIGNATURES = {
     "xaac_b200_qmf_synth_hq_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32]),
     "xaac_b200_qmf_anal_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "xaac_b200_hf_generator_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "xaac_b200_set_env_rom": (_i32, [_vp, _vp, _sz, _vp, _sz]),
+    "xaac_b200_calc_sbrenvelope_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -5,7 +5,7 @@ from . import _lib
 
 
 class Context:
-    def __init__(self, device=0, imdct_rom=None, qmf_rom=None):
+    def __init__(self, device=0, imdct_rom=None, qmf_rom=None, env_rom=None, misc_rom=None):
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         rc = self._lib.xaac_b200_create(ctypes.byref(self._h), int(device))
@@ -18,6 +18,8 @@ class Context:
         self.device = int(device)
         self.set_imdct_rom(imdct_rom if imdct_rom is not None else _lib.rom_blob("imdct_rom.bin"))
         self.set_qmf_rom(qmf_rom if qmf_rom is not None else _lib.rom_blob("qmf_rom.bin"))
+        self.set_env_rom(env_rom if env_rom is not None else _lib.rom_blob("env_rom.bin"),
+                         misc_rom if misc_rom is not None else _lib.rom_blob("misc_rom.bin"))
 
     # -- plumbing ---------------------------------------------------------------------------------
     @property
@@ -38,6 +40,14 @@ class Context:
         """blob: bytes of the host's ia_qmf_dec_tables_struct (>= 3464 leading bytes)."""
         buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
         self.check(self._lib.xaac_b200_set_qmf_rom(self._h, buf, len(blob)), "xaac_b200_set_qmf_rom")
+
+    def set_env_rom(self, env_blob, misc_blob):
+        """env_blob: bytes of the host's ia_env_calc_tables_struct (2404); misc_blob: leading >= 2470 bytes of the
+        host's ixheaacd_misc_tables."""
+        e = (ctypes.c_char * len(env_blob)).from_buffer_copy(env_blob)
+        m = (ctypes.c_char * len(misc_blob)).from_buffer_copy(misc_blob)
+        self.check(self._lib.xaac_b200_set_env_rom(self._h, e, len(env_blob), m, len(misc_blob)),
+                   "xaac_b200_set_env_rom")
 
     @property
     def num_sms(self):

@@ -98,6 +98,42 @@ struct HfGenArgs {
 };
 cudaError_t launch_hf_generator_hq(const HfGenArgs &args, int num_sms, cudaStream_t stream);
 
+// ---- fixed-point HQ envelope adjuster ----------------------------------------------------------------------
+// env ROM = the host's ia_env_calc_tables_struct (decoder/ixheaacd_sbr_rom.h:59-68); misc ROM = the leading part of
+// ixheaacd_misc_tables up to sqrt_table (decoder/ixheaacd_common_rom.h:27-37).
+constexpr int kERomLimGains = 0;      // WORD16[8]
+constexpr int kERomSmooth = 24;       // WORD16[4]
+constexpr int kERomInvInt = 32;       // WORD16[49]
+constexpr int kERomRandPh = 132;      // WORD32[512 + 56]
+constexpr int kERomBytes = 2404;
+constexpr int kMRomInvTable = 1444;   // WORD16[256]
+constexpr int kMRomSqrtTable = 1956;  // WORD16[257]
+constexpr int kMRomBytes = 2470;
+// ia_sbr_scale_fact_struct as WORD16[8] (include/xaac_b200.h XAAC_SF_*)
+constexpr int kSfLb = 0, kSfStLb = 1, kSfOvLb = 2, kSfHb = 3, kSfOvHb = 4, kSfStSyn = 5, kSfPs = 6;
+// per-frame SBR side-info record (include/xaac_b200.h XAAC_ENV_*)
+constexpr int kEnvNumTimeSlots = 0, kEnvTimeStep = 1, kEnvChannelMode = 2, kEnvLimiterGains = 3, kEnvInterpolFreq = 4,
+              kEnvSmoothingMode = 5, kEnvNumSfLo = 6, kEnvNumSfHi = 7, kEnvNumNfBands = 8, kEnvSubBandStart = 9,
+              kEnvSubBandEnd = 10, kEnvNumLfBands = 11, kEnvNumEnv = 12, kEnvTransientEnv = 13, kEnvMaxQmfSubband = 14,
+              kEnvMaxQmfSubbandPrev = 15, kEnvBorderVec = 16, kEnvFreqRes = 25, kEnvNoiseBorderVec = 33,
+              kEnvLimTbl = 36, kEnvFreqLo = 49, kEnvFreqHi = 78, kEnvFreqNoise = 135, kEnvNoiseFloor = 141,
+              kEnvAddHarmonics = 151, kEnvSfArr = 207, kEnvPrmWords = 656;
+// ia_sbr_calc_env_struct as WORD16[232] (include/xaac_b200.h XAAC_ENV_ST_*)
+constexpr int kEnvStFiltMe = 0, kEnvStFiltNoise = 112, kEnvStNoiseE = 168, kEnvStStartUp = 169, kEnvStPhIndex = 170,
+              kEnvStTransPrev = 171, kEnvStHarmIndex = 172, kEnvStHarmPrev = 173, kEnvStWords = 232;
+
+struct EnvCalcArgs {
+  const int16_t *params;   // [n_units][656]      side info (read-only)
+  int16_t *sf;             // [n_units][8]        ia_sbr_scale_fact_struct, hb_scale / ov_hb_scale updated
+  int16_t *state;          // [n_units][232]      ia_sbr_calc_env_struct, in/out
+  int32_t *matrix;         // [n_units][38][128]  QMF rows; high band adjusted in place
+  int32_t *err;            // [n_units] or null   0 / 0x80000000 like the reference's return value
+  const uint8_t *env_rom;  // device copy of ia_env_calc_tables_struct
+  const uint8_t *misc_rom; // device copy of the leading part of ixheaacd_misc_tables
+  long long n_units;
+};
+cudaError_t launch_calc_sbrenvelope_hq(const EnvCalcArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

@@ -20,6 +20,9 @@ struct xaac_b200_ctx {
   int qmf_fast_bits = 0;
   uint8_t *d_rom_qmf_ana = nullptr;  // table image of qmf_anal_hq_kernel
   int qmf_anal_exact = 0;
+  uint8_t *d_rom_env = nullptr;   // ia_env_calc_tables_struct
+  uint8_t *d_rom_misc = nullptr;  // leading part of ixheaacd_misc_tables
+  bool have_env_rom = false;
   char err[256] = {0};
   // staging for the *_host entry points: kPipe chunks in flight, one stream each
   static constexpr int kPipe = 3;
@@ -111,6 +114,8 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   if (ctx->d_rom_imdct) cudaFree(ctx->d_rom_imdct);
   if (ctx->d_rom_qmf_syn) cudaFree(ctx->d_rom_qmf_syn);
   if (ctx->d_rom_qmf_ana) cudaFree(ctx->d_rom_qmf_ana);
+  if (ctx->d_rom_env) cudaFree(ctx->d_rom_env);
+  if (ctx->d_rom_misc) cudaFree(ctx->d_rom_misc);
   delete ctx;
 }
 
@@ -460,6 +465,45 @@ int32_t xaac_b200_hf_generator_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_lpc, 
   a.n_units = n_units;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   CK(xb::launch_hf_generator_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch hf_generator_hq_kernel");
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_set_env_rom(xaac_b200_ctx *ctx, const void *env_tables, size_t env_bytes, const void *misc_tables,
+                              size_t misc_bytes) {
+  if (!ctx || !env_tables || !misc_tables) return bad_arg(ctx, "null");
+  if (env_bytes < (size_t)xb::kERomBytes) return bad_arg(ctx, "env ROM blob shorter than 2404 bytes");
+  if (misc_bytes < (size_t)xb::kMRomBytes) return bad_arg(ctx, "misc ROM blob shorter than 2470 bytes");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (!ctx->d_rom_env) CK(cudaMalloc((void **)&ctx->d_rom_env, xb::kERomBytes + 60), "cudaMalloc(env rom)");
+  if (!ctx->d_rom_misc) CK(cudaMalloc((void **)&ctx->d_rom_misc, xb::kMRomBytes + 58), "cudaMalloc(misc rom)");
+  CK(cudaMemcpy(ctx->d_rom_env, env_tables, xb::kERomBytes, cudaMemcpyHostToDevice), "H2D env rom");
+  CK(cudaMemcpy(ctx->d_rom_misc, misc_tables, xb::kMRomBytes, cudaMemcpyHostToDevice), "H2D misc rom");
+  ctx->have_env_rom = true;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_calc_sbrenvelope_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_params, int16_t *d_sf, int16_t *d_state,
+                                          int32_t *d_matrix, int32_t *d_err, int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->have_env_rom) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_env_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_params || !d_sf || !d_state || !d_matrix) return bad_arg(ctx, "null buffer");
+  xb::EnvCalcArgs a;
+  a.params = d_params;
+  a.sf = d_sf;
+  a.state = d_state;
+  a.matrix = d_matrix;
+  a.err = d_err;
+  a.env_rom = ctx->d_rom_env;
+  a.misc_rom = ctx->d_rom_misc;
+  a.n_units = n_units;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(xb::launch_calc_sbrenvelope_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch calc_sbrenvelope_hq_kernel");
   ctx->launches++;
   return XAAC_B200_OK;
 }

@@ -3,6 +3,10 @@
 hf_generator  <- ixheaacd_hf_generator(ia_sbr_hf_generator_struct*, ia_sbr_scale_fact_struct*, WORD32 **qmf_real,
                  WORD32 **qmf_imag, time_step, first_slot_offset, last_slot_offset, num_if_bands,
                  max_qmf_subband_aac, sbr_invf_mode, sbr_invf_mode_prev, ...)   (decoder/ixheaacd_lpp_tran.c:956)
+
+calc_sbrenvelope <- ixheaacd_calc_sbrenvelope(ia_sbr_scale_fact_struct*, ia_sbr_calc_env_struct*, header, frame data,
+                 prev frame data, WORD32 **anal_buf_real, WORD32 **anal_buf_imag, degree_alias, low_pow_flag = 0, ...)
+                 (decoder/ixheaacd_env_calc.c:692)
 """
 import ctypes
 
@@ -11,6 +15,8 @@ import torch
 from .imdct import _chk, _ptr
 
 HF_PARAM_WORDS = 80
+ENV_PARAM_WORDS = 656
+ENV_STATE_WORDS = 232
 
 
 def hf_generator(ctx, lpc, matrix, params, bw_prev, hb_scale=None, stream=None):
@@ -29,3 +35,22 @@ def hf_generator(ctx, lpc, matrix, params, bw_prev, hb_scale=None, stream=None):
                                                _ptr(hb_scale), n, ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_hf_generator_hq_dev")
     return hb_scale
+
+
+def calc_sbrenvelope(ctx, params, sf, state, matrix, err=None, stream=None):
+    """Batched drop-in for ixheaacd_calc_sbrenvelope (HQ). params int16 [n,656] (XAAC_ENV_* layout); sf int16 [n,8]
+    (in place: hb_scale, ov_hb_scale); state int16 [n,232] (in place); matrix int32 [n,38,128] (in place).
+    Returns err int32 [n] (0 or 0x80000000 per unit, the reference's return value)."""
+    n = matrix.shape[0]
+    _chk(params, torch.int16, (n, ENV_PARAM_WORDS), "params", "cuda")
+    _chk(sf, torch.int16, (n, 8), "sf", "cuda")
+    _chk(state, torch.int16, (n, ENV_STATE_WORDS), "state", "cuda")
+    _chk(matrix, torch.int32, (n, 38, 128), "matrix", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=matrix.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(matrix.device)
+    rc = ctx._lib.xaac_b200_calc_sbrenvelope_hq_dev(ctx.handle, _ptr(params), _ptr(sf), _ptr(state), _ptr(matrix),
+                                                   _ptr(err), n, ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_calc_sbrenvelope_hq_dev")
+    return err

@@ -248,10 +248,15 @@ static void noise_limiting(const i16 *prm, int skip, const me_t *orig, const me_
   }
 }
 
+/* The reference shifts promoted WORD16 values by run-time counts that may exceed 31 here (`x >> diff`).  That is
+ * undefined in ISO C; the reference build this oracle is pinned to (gcc, x86-64) executes SAR/SHL, which use the count
+ * modulo 32.  The oracle states that behaviour explicitly. */
+#define X86_SHIFT(c) ((c) & 31)
+
 /* decoder/ixheaacd_env_calc.c:1080-1097 */
 static void noise_rescale(i16 *p, int diff, int n, int stride) {
-  if (diff > 0) for (int k = 0; k < n; k++) p[k * stride] = (i16)(p[k * stride] >> diff);
-  else if (diff < 0) for (int k = 0; k < n; k++) p[k * stride] = (i16)((i32)p[k * stride] << -diff);
+  if (diff > 0) for (int k = 0; k < n; k++) p[k * stride] = (i16)(p[k * stride] >> X86_SHIFT(diff));
+  else if (diff < 0) for (int k = 0; k < n; k++) p[k * stride] = (i16)((u32)(i32)p[k * stride] << X86_SHIFT(-diff));
 }
 
 /* per-stream envelope-adjuster state record (WORD16[XO_ENV_ST_WORDS]) = ia_sbr_calc_env_struct
@@ -430,7 +435,7 @@ int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, cons
         i32 fe = fme[2 * k + 1], fm = fme[2 * k], diff = gain[k].e - fe;
         if (diff >= 0) {
           fme[2 * k + 1] = gain[k].e;
-          fme[2 * k] = (i16)(fme[2 * k] >> diff);
+          fme[2 * k] = (i16)(fme[2 * k] >> X86_SHIFT(diff));
         } else {
           int reserve = ox_norm32(fm) - 16;
           if (diff + reserve >= 0) {
@@ -440,7 +445,7 @@ int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, cons
             fme[2 * k] = (i16)((u32)fm << reserve);
             fme[2 * k + 1] = (i16)(fe - reserve);
             int shift = -(reserve + diff);
-            gain[k].m = (i16)(gain[k].m >> shift);
+            gain[k].m = (i16)(gain[k].m >> X86_SHIFT(shift));
             gain[k].e = (i16)(gain[k].e + shift);
           }
         }
