@@ -319,3 +319,72 @@ int ref_calc_sbrenvelope_hq(const int16_t *prm, int16_t *sf, int16_t *state, int
   pack_env_state(state, &ce);
   return (int)err;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole fixed-point HQ SBR stage: ixheaacd_sbr_dec (decoder/ixheaacd_sbr_dec.c:662) with low_pow_flag = 0, driven
+ * from the flat records of the C-ABI (XO_SIDE_*, XO_SBR_ST_*, XO_PS_ST_* in oracle/src/xaac_oracle.h).
+ *   side [1232] WORD16; st [3920] WORD16 in/out; ps [3888] WORD16 in/out or NULL (mono SBR);
+ *   time_in 1024 WORD16; out_l / out_r 2048 WORD16 each (out_r only with PS).  Returns the stage's return value.
+ * ---------------------------------------------------------------------------------------------- */
+const void *ref_rom_ps_tables(int *bytes) {
+  if (bytes) *bytes = (int)sizeof(ixheaacd_aac_dec_ps_tables);
+  return &ixheaacd_aac_dec_ps_tables;
+}
+int ref_rom_ps_offsets(int *o) {
+  int n = 0;
+#define OFF(m) o[n++] = (int)offsetof(ia_ps_tables_struct, m)
+  OFF(decay_scale_factor); OFF(hyb_resol); OFF(rev_link_decay_ser); OFF(rev_link_delay_ser); OFF(borders_group);
+  OFF(group_shift); OFF(group_to_bin); OFF(hybrid_to_bin); OFF(delay_to_bin); OFF(frac_delay_phase_fac_qmf_re_im);
+  OFF(frac_delay_phase_fac_qmf_sub_re_im); OFF(frac_delay_phase_fac_qmf_ser_re_im);
+  OFF(frac_delay_phase_fac_qmf_sub_ser_re_im); OFF(scale_factors); OFF(scale_factors_fine); OFF(alpha_values);
+  OFF(p2_6); OFF(p8_13); OFF(huff_iid_dt);
+#undef OFF
+  return n;
+}
+
+int ref_sbr_dec_hq(const int16_t *side, int16_t *st, int16_t *ps, const int16_t *time_in, int16_t *out_l,
+                   int16_t *out_r) {
+  static __thread ref_sbr_ctx c;
+  static __thread WORD16 tbuf[2 * 2048];
+  const int use_ps = ps != NULL && side[XO_SIDE_PS];
+  const int ch_fac = use_ps ? 2 : 1;
+  unpack_sbr_ctx(&c, side, st, ps);
+  memset(tbuf, 0, sizeof(tbuf));
+  for (int i = 0; i < 1024; i++) tbuf[ch_fac * i] = time_in[i];
+  WORD32 ret = ixheaacd_sbr_dec(&c.d, tbuf, &c.h, &c.fd.f, &c.pv, ps ? &c.ps : NULL, ps ? &c.bank_r : NULL,
+                                ps ? &c.sf_r : NULL, side[XO_SIDE_APPLY], 0, c.work, &c.tabs,
+                                (ixheaacd_misc_tables *)&ixheaacd_str_fft_n_transcendent_tables, ch_fac, NULL, 0, NULL,
+                                AOT_SBR, 0, NULL, 0, 0);
+  pack_sbr_state(st, &c.d, &c.pv);
+  if (ps) pack_ps_state(ps, &c.ps, &c.bank_r, &c.sf_r);
+  for (int i = 0; i < 2048; i++) out_l[i] = tbuf[ch_fac * i];
+  if (out_r) for (int i = 0; i < 2048; i++) out_r[i] = use_ps ? tbuf[2 * i + 1] : 0;
+  return (int)ret;
+}
+
+/* Per-slot PS work exactly as the left ixheaacd_cplx_synt_qmffilt call does it (decoder/ixheaacd_qmf_dec.c:1003-1030):
+ * ixheaacd_init_rot_env at the PS envelope borders + ixheaacd_apply_ps (+ ixheaacd_shiftrountine) for the 32 slots of a
+ * frame.  m [38][128] in/out (left), right [32][128] out; lb_scale / ps_scale enter through sf[8]. */
+VOID ixheaacd_apply_ps(ia_ps_dec_struct *, WORD32 **, WORD32 **, WORD32 *, WORD32 *, ia_sbr_scale_fact_struct *, WORD16,
+                       ia_sbr_tables_struct *, WORD);
+VOID ixheaacd_init_rot_env(ia_ps_dec_struct *, WORD16, WORD16, ia_sbr_tables_struct *, const WORD16 *);
+VOID ixheaacd_shiftrountine(WORD32 *, WORD32 *, WORD32, WORD32);
+void ref_ps_apply_frame(const int16_t *side, const int16_t *st, int16_t *ps, const int16_t *sf, int32_t *m,
+                        int32_t *right, int usb, int common_shift) {
+  static __thread ref_sbr_ctx c;
+  ia_sbr_scale_fact_struct s;
+  WORD32 *re[40], *im[40];
+  unpack_sbr_ctx(&c, side, st, ps);
+  unpack_sf(sf, &s);
+  for (int i = 0; i < 38; i++) { re[i] = m + 128 * i; im[i] = re[i] + 64; }
+  int env = 0;
+  for (int i = 0; i < 32; i++) {
+    if (i == c.ps.border_position[env]) {
+      ixheaacd_init_rot_env(&c.ps, (WORD16)env, (WORD16)usb, &c.tabs, ixheaacd_str_fft_n_transcendent_tables.trig_data);
+      env++;
+    }
+    ixheaacd_apply_ps(&c.ps, &re[i], &im[i], right + 128 * i, right + 128 * i + 64, &s, (WORD16)i, &c.tabs, 32);
+    if (common_shift) ixheaacd_shiftrountine(re[i], im[i], 64, common_shift);
+  }
+  pack_ps_state(ps, &c.ps, &c.bank_r, &c.sf_r);
+}

@@ -179,3 +179,58 @@ IA_ERRORCODE __wrap_ixheaacd_calc_sbrenvelope(ia_sbr_scale_fact_struct *sf, ia_s
   }
   return err;
 }
+
+/* ---- ixheaacd_sbr_dec (decoder/ixheaacd_sbr_dec.c:662), fixed-point HQ path, whole stage ------------------------
+ * record: int32 magic 'SBR1', int32 hdr[7] = {apply_processing, ch_fac, aot, ps_present, ret, 0, 0},
+ *   int16 side[XO_SIDE_WORDS], st_in[XO_SBR_ST_WORDS], ps_in[XO_PS_ST_WORDS], time_in[1024],
+ *   st_out[XO_SBR_ST_WORDS], ps_out[XO_PS_ST_WORDS], out_l[2048], out_r[2048] */
+WORD32 __real_ixheaacd_sbr_dec(ia_sbr_dec_struct *, WORD16 *, ia_sbr_header_data_struct *, ia_sbr_frame_info_data_struct *,
+                               ia_sbr_prev_frame_data_struct *, ia_ps_dec_struct *, ia_sbr_qmf_filter_bank_struct *,
+                               ia_sbr_scale_fact_struct *, FLAG, FLAG, WORD32 *, ia_sbr_tables_struct *,
+                               ixheaacd_misc_tables *, WORD, ia_pvc_data_struct *, FLAG, WORD32[][64], WORD32, WORD32,
+                               VOID *, WORD32, WORD32);
+
+WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *d, WORD16 *time, ia_sbr_header_data_struct *h,
+                               ia_sbr_frame_info_data_struct *f, ia_sbr_prev_frame_data_struct *pv, ia_ps_dec_struct *ps,
+                               ia_sbr_qmf_filter_bank_struct *bank_r, ia_sbr_scale_fact_struct *sf_r, FLAG apply,
+                               FLAG low_pow, WORD32 *work, ia_sbr_tables_struct *t, ixheaacd_misc_tables *ct, WORD ch_fac,
+                               ia_pvc_data_struct *pvc, FLAG drc_on, WORD32 drc[][64], WORD32 aot, WORD32 ldmps,
+                               VOID *self, WORD32 mps, WORD32 ec) {
+  static int count = 0;
+  FILE *fp = tap_fp();
+  int rec = fp && tap_on("sbr") && count < tap_limit() && !low_pow && !h->enh_sbr && h->num_time_slots == 16 &&
+            aot != AOT_ER_AAC_ELD && aot != AOT_ER_AAC_LD && !ldmps && !drc_on;
+  static int16_t side[XO_SIDE_WORDS], st[XO_SBR_ST_WORDS], pst[XO_PS_ST_WORDS], tin[1024], out[2048];
+  int ps_present = 0;
+  if (rec) {
+    int32_t magic = 0x31524253;
+    ps_present = (ps != NULL && bank_r != NULL && sf_r != NULL);
+    pack_side(side, d, h, f, pv, ps_present ? ps : NULL, apply);
+    pack_sbr_state(st, d, pv);
+    memset(pst, 0, sizeof(pst));
+    if (ps_present) pack_ps_state(pst, ps, bank_r, sf_r);
+    for (int i = 0; i < 1024; i++) tin[i] = time[ch_fac * i];
+    fwrite(&magic, 4, 1, fp);
+  }
+  WORD32 ret = __real_ixheaacd_sbr_dec(d, time, h, f, pv, ps, bank_r, sf_r, apply, low_pow, work, t, ct, ch_fac, pvc,
+                                       drc_on, drc, aot, ldmps, self, mps, ec);
+  if (rec) {
+    int32_t hdr[7] = {apply, ch_fac, aot, ps_present, ret, 0, 0};
+    fwrite(hdr, 4, 7, fp);
+    fwrite(side, 2, XO_SIDE_WORDS, fp);
+    fwrite(st, 2, XO_SBR_ST_WORDS, fp);
+    fwrite(pst, 2, XO_PS_ST_WORDS, fp);
+    fwrite(tin, 2, 1024, fp);
+    pack_sbr_state(st, d, pv);
+    if (ps_present) pack_ps_state(pst, ps, bank_r, sf_r);
+    fwrite(st, 2, XO_SBR_ST_WORDS, fp);
+    fwrite(pst, 2, XO_PS_ST_WORDS, fp);
+    for (int i = 0; i < 2048; i++) out[i] = time[ch_fac * i];
+    fwrite(out, 2, 2048, fp);
+    for (int i = 0; i < 2048; i++) out[i] = (ch_fac > 1) ? time[ch_fac * i + 1] : 0;
+    fwrite(out, 2, 2048, fp);
+    fflush(fp);
+    count++;
+  }
+  return ret;
+}

@@ -152,4 +152,93 @@ int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, cons
                            int16_t *state, int32_t *matrix);
 void xo_calc_sbrenvelope_hq_batch(const uint8_t *env_rom, const uint8_t *misc_rom, const int16_t *prm, int16_t *sf,
                                   int16_t *state, int32_t *matrix, int32_t *err, int n);
+
+/* ---- whole fixed-point HQ SBR stage (ixheaacd_sbr_dec) and parametric stereo -------------------------------
+ * Per-channel SBR state blob, WORD16[XO_SBR_ST_WORDS] (32-bit members at even offsets, little endian):
+ * what ia_sbr_dec_struct carries from frame to frame on this path (SURVEY.md §8a "State per stream"). */
+#define XO_SBR_ST_ANAL_STATES 0   /* [320]  str_codec_qmf_bank.anal_filter_states */
+#define XO_SBR_ST_ANAL_POS 320    /* [2]    {core_samples_buffer - anal_filter_states, filter_pos - qmf_c} */
+#define XO_SBR_ST_SYN_POS 322     /* [2]    {ixheaacd_drc_offset, filter_pos_syn - qmf_c} */
+#define XO_SBR_ST_SF 324          /* [8]    str_sbr_scale_fact (XO_SF_*) */
+#define XO_SBR_ST_MISC 332        /* [16]   XO_SBR_MISC_* */
+#define XO_SBR_ST_ENV 348         /* [232]  str_sbr_calc_env (XO_ENV_ST_*) */
+#define XO_SBR_ST_SYN_STATES 580  /* [1280] str_synthesis_qmf_bank.filter_states */
+#define XO_SBR_ST_BW_PREV 1860    /* WORD32[6]      str_hf_generator.bw_array_prev */
+#define XO_SBR_ST_LPC 1872        /* WORD32[2][128] lpc_filt_states_real[i] | _imag[i] */
+#define XO_SBR_ST_OV 2384         /* WORD32[6][128] ptr_sbr_overlap_buf: re[64] | im[64] per overlap slot */
+#define XO_SBR_ST_WORDS 3920
+#define XO_SBR_MISC_MAX_QMF_PREV 0  /* prev_frame_data.max_qmf_subband_aac */
+#define XO_SBR_MISC_END_POS_PREV 1  /* prev_frame_data.end_position */
+#define XO_SBR_MISC_INVF_PREV 2     /* [10] prev_frame_data.sbr_invf_mode */
+#define XO_SBR_MISC_CODEC_USB 12    /* str_codec_qmf_bank.usb */
+#define XO_SBR_MISC_SYN_LSB 13      /* str_synthesis_qmf_bank.lsb */
+#define XO_SBR_MISC_SYN_USB 14      /* str_synthesis_qmf_bank.usb */
+/* Per-frame side-info record for the whole stage, WORD16[XO_SIDE_WORDS] */
+#define XO_SIDE_ENV 0        /* [656] XO_ENV_* (MAX_QMF_SUBBAND_PREV is taken from the state) */
+#define XO_SIDE_HF 656       /* [80]  XO_HF_*: transposer settings, NUM_IF_BANDS, INVF; the rest is derived */
+#define XO_SIDE_APPLY 736    /* apply_processing (sync_state == SBR_ACTIVE) */
+#define XO_SIDE_PS 737       /* 0: no PS; 1: PS active (channel_mode == PS_STEREO), rotation as the reference's own
+                                x86-64 gcc build executes it; 2: PS active, rotation as the C source is written
+                                (see apply_rot in oracle/src/ps.c) */
+#define XO_SIDE_PS_PRM 744   /* [488] XO_PS_PRM_* */
+#define XO_SIDE_WORDS 1232
+#define XO_PS_PRM_IID_QUANT 0
+#define XO_PS_PRM_NUM_ENV 1
+#define XO_PS_PRM_BORDER 2   /* [7]     border_position */
+#define XO_PS_PRM_IID 9      /* [7][34] iid_par_table */
+#define XO_PS_PRM_ICC 247    /* [7][34] icc_par_table */
+#define XO_PS_PRM_WORDS 488
+/* PS state blob, WORD16[XO_PS_ST_WORDS]: ia_ps_dec_struct delay lines, mixing matrices, transient detector,
+ * hybrid delay lines (decoder/ixheaacd_ps_dec.h:97-141) + the right-channel synthesis bank */
+#define XO_PS_ST_AP 0             /* [2][64]    delay_buf_qmf_ap_re_im */
+#define XO_PS_ST_LD 128           /* [14][24]   delay_buf_qmf_ld_re_im */
+#define XO_PS_ST_SD 464           /* [64]       delay_buf_qmf_sd_re_im */
+#define XO_PS_ST_SER 528          /* [5][3][64] delay_buf_qmf_ser_re_im */
+#define XO_PS_ST_SUB 1488         /* [2][32]    delay_buf_qmf_sub_re_im */
+#define XO_PS_ST_SUB_SER 1552     /* [5][3][32] delay_buf_qmf_sub_ser_re_im */
+#define XO_PS_ST_HVEC 2032        /* [6][48]    h11_h12_vec, h21_h22_vec, H11_H12, H21_H22, delta_h11_h12, delta_h21_h22 */
+#define XO_PS_ST_IDX 2320         /* [12]       XO_PS_IDX_* */
+#define XO_PS_ST_PEAK 2332        /* WORD32[3][20] peak_decay_diff, energy_prev, peak_decay_diff_prev */
+#define XO_PS_ST_HYB 2452         /* WORD32[3][2][12] str_hybrid.ptr_qmf_buf_re[b] | _im[b] */
+#define XO_PS_ST_SYN_STATES_R 2596 /* [1280]    right synthesis bank filter_states */
+#define XO_PS_ST_SYN_POS_R 3876   /* [2] */
+#define XO_PS_ST_SF_R 3878        /* [8]        right channel's str_sbr_scale_fact */
+#define XO_PS_ST_WORDS 3888
+#define XO_PS_IDX_SER 0           /* [3] delay_buf_idx_ser */
+#define XO_PS_IDX_DELAY 3
+#define XO_PS_IDX_DELAY_LONG 4
+#define XO_PS_IDX_SCALE 5         /* delay_buffer_scale */
+#define XO_PS_IDX_USB 6
+#define XO_PS_IDX_LSB_R 8         /* right synthesis bank lsb / usb */
+#define XO_PS_IDX_USB_R 9
+/* PS ROM = leading 1230 bytes of ia_ps_tables_struct (decoder/ixheaacd_sbr_rom.h:177-203); WORD16 offsets */
+#define XO_PSROM_DECAY_SF 0
+#define XO_PSROM_HYB_RESOL 72
+#define XO_PSROM_REV_DECAY 75
+#define XO_PSROM_REV_DELAY 78
+#define XO_PSROM_BORDERS_GROUP 81
+#define XO_PSROM_GROUP_SHIFT 104
+#define XO_PSROM_GROUP_TO_BIN 110
+#define XO_PSROM_HYB_TO_BIN 132
+#define XO_PSROM_DELAY_TO_BIN 142
+#define XO_PSROM_FRAC_QMF 174
+#define XO_PSROM_FRAC_SUB 222
+#define XO_PSROM_FRAC_QMF_SER 254
+#define XO_PSROM_FRAC_SUB_SER 446
+#define XO_PSROM_SCALE 542
+#define XO_PSROM_SCALE_FINE 557
+#define XO_PSROM_ALPHA 588
+#define XO_PSROM_P2_6 596
+#define XO_PSROM_P8_13 602
+#define XO_PSROM_BYTES 1230
+
+void xo_ps_apply_frame(const uint8_t *env_rom, const uint8_t *misc_rom, const uint8_t *ps_rom, const int16_t *ps_prm,
+                       int16_t *ps, int32_t *m, int32_t *right, int usb, int shiftdelay_late, int common_shift,
+                       int as_built);
+void xo_ps_synth_pair(const uint8_t *qrom, const uint8_t *env_rom, const uint8_t *misc_rom, const uint8_t *ps_rom,
+                      const int16_t *ps_prm, int16_t *st, int16_t *ps, int32_t *m, int16_t *out_l, int16_t *out_r,
+                      int ch_out, int as_built);
+int xo_sbr_dec_hq(const uint8_t *qrom, const uint8_t *env_rom, const uint8_t *misc_rom, const uint8_t *ps_rom,
+                  const int16_t *side, int16_t *st, int16_t *ps_st, const int16_t *time_in, int ch_in,
+                  int16_t *time_out, int16_t *time_out_r, int ch_out, int32_t *scratch);
 #endif

@@ -139,17 +139,70 @@ class Oracle:
         return m, s, st, err
 
 
+    # ---- whole SBR stage / PS ------------------------------------------------------------------------------
+    @property
+    def psrom(self):
+        if not hasattr(self, "_psrom"):
+            self._psrom = rom("ps_rom.bin")
+        return self._psrom
+
+    def sbr_dec(self, side, st, ps, time_in):
+        """single unit: side [1232] i16, st [3920] i16, ps [3888] i16, time_in [1024] i16.
+        Returns (st', ps', out_l [2048], out_r [2048], err)."""
+        s = np.ascontiguousarray(st, np.int16).copy()
+        p = np.ascontiguousarray(ps, np.int16).copy()
+        ol = np.zeros(2048, np.int16)
+        orr = np.zeros(2048, np.int16)
+        scratch = np.zeros(40 * 128, np.int32)
+        self.erom
+        err = self.lib.xo_sbr_dec_hq(P(self.qrom), P(self._erom), P(self._mrom), P(self.psrom),
+                                     P(np.ascontiguousarray(side, np.int16)), P(s), P(p),
+                                     P(np.ascontiguousarray(time_in, np.int16)), 1, P(ol), P(orr), 1, P(scratch))
+        return s, p, ol, orr, err
+
+    def sbr_dec_batch(self, side, st, ps, time_in):
+        outs = [self.sbr_dec(side[u], st[u], ps[u], time_in[u]) for u in range(len(side))]
+        return tuple(np.stack([o[k] for o in outs]) for k in range(4)) + (np.array([o[4] for o in outs], np.int32),)
+
+    def ps_apply_frame(self, ps_prm, ps, m, usb, shiftdelay_late, common_shift, as_built):
+        p = np.ascontiguousarray(ps, np.int16).copy()
+        mm = np.ascontiguousarray(m, np.int32).copy()
+        right = np.zeros((32, 128), np.int32)
+        self.erom
+        self.lib.xo_ps_apply_frame(P(self._erom), P(self._mrom), P(self.psrom), P(np.ascontiguousarray(ps_prm, np.int16)),
+                                   P(p), P(mm), P(right), int(usb), int(shiftdelay_late), int(common_shift), int(as_built))
+        return mm, right, p
+
+
 class Ref:
     """The unmodified reference, compiled from /root/reference by oracle/Makefile (target ref)."""
 
-    def __init__(self):
-        self.lib = ctypes.CDLL(REF_SO)
+    def __init__(self, path=REF_SO):
+        self.lib = ctypes.CDLL(path)
 
     @staticmethod
-    def try_load():
-        if not os.path.exists(REF_SO):
+    def try_load(path=REF_SO):
+        if not os.path.exists(path):
             return None
-        return Ref()
+        return Ref(path)
+
+    def sbr_dec(self, side, st, ps, time_in):
+        """ixheaacd_sbr_dec driven from the flat records; ps may be None (no PS instance)."""
+        s = np.ascontiguousarray(st, np.int16).copy()
+        p = None if ps is None else np.ascontiguousarray(ps, np.int16).copy()
+        ol = np.zeros(2048, np.int16)
+        orr = np.zeros(2048, np.int16)
+        err = self.lib.ref_sbr_dec_hq(P(np.ascontiguousarray(side, np.int16)), P(s), None if p is None else P(p),
+                                      P(np.ascontiguousarray(time_in, np.int16)), P(ol), P(orr))
+        return s, p, ol, orr, err
+
+    def ps_apply_frame(self, side, st, ps, sf, m, usb, common_shift):
+        p = np.ascontiguousarray(ps, np.int16).copy()
+        mm = np.ascontiguousarray(m, np.int32).copy()
+        right = np.zeros((32, 128), np.int32)
+        self.lib.ref_ps_apply_frame(P(np.ascontiguousarray(side, np.int16)), P(np.ascontiguousarray(st, np.int16)), P(p),
+                                    P(np.ascontiguousarray(sf, np.int16)), P(mm), P(right), int(usb), int(common_shift))
+        return mm, right, p
 
     def rom_imdct(self, nbytes=7500):
         fn = self.lib.ref_rom_imdct_tables
@@ -356,3 +409,46 @@ def synth_env_units(n, seed, golden):
         matrix[2] = 2 ** 31 - 1
         matrix[3] = -(2 ** 31)
     return prm, sf, st, matrix
+
+
+REF_NSA_SO = os.path.join(ROOT, "oracle", "_ref", "libxaac_ref_nsa.so")
+PS_ST_DSP_WORDS = 2596  # PS state words before the right synthesis bank
+
+
+def synth_sbr_units(n, seed, golden):
+    """Whole-stage inputs: side info and state drawn from tapped real frames (their invariants intact), core PCM replaced
+    by scaled noise / tones per unit, analysis / synthesis / overlap / LPC state perturbed.  Every third unit has
+    apply_processing = 0 (upsampling only); PS units alternate between the two rotation modes.
+    Returns side [n,1232], st [n,3920], ps [n,3888], tin [n,1024] (all int16)."""
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, len(golden["side"]), n)
+    side = golden["side"][idx].copy()
+    st = golden["st_in"][idx].copy()
+    ps = golden["ps_in"][idx].copy()
+    tin = np.zeros((n, 1024), np.int16)
+    for u in range(n):
+        amp = 2.0 ** rng.integers(2, 16)
+        kind = u % 4
+        if kind == 0:
+            x = golden["tin"][idx[u]].astype(np.float64)
+        elif kind == 1:
+            x = rng.standard_normal(1024) * amp / 3
+        elif kind == 2:
+            x = amp * np.sin(2 * np.pi * rng.uniform(0.001, 0.49) * np.arange(1024) + rng.uniform(0, 6))
+        else:
+            x = rng.integers(-32768, 32768, 1024).astype(np.float64)
+        tin[u] = np.clip(x, -32768, 32767).astype(np.int16)
+        if u % 3 == 2 and not side[u, 737]:
+            side[u, 736] = 0
+        if side[u, 737] and u % 2:
+            side[u, 737] = 2
+        if u % 5 == 1:
+            st[u, 0:320] = rng.integers(-20000, 20000, 320)
+            st[u, 580:1860] = rng.integers(-20000, 20000, 1280)
+            sc = rng.integers(10, 30)
+            ov = ((rng.random(768) * 2 - 1) * 2.0 ** sc).astype(np.int64).astype(np.int32)
+            ov[384:] = 0
+            st[u, 2384:3920] = ov.view(np.int16)
+            st[u, 326] = rng.integers(-6, 16)      # ov_lb_scale
+            st[u, 328] = rng.integers(0, 20)       # ov_hb_scale
+    return side, st, ps, tin

@@ -42,7 +42,9 @@ def main():
 # ia_env_calc_tables_struct (decoder/ixheaacd_sbr_rom.h:59-68) and the leading part of ixheaacd_misc_tables up to and
 # including sqrt_table (decoder/ixheaacd_common_rom.h:27-37)
 EXTRA = [("ref_rom_qmf_tables", 3464, "qmf_rom.bin"), ("ref_rom_env_tables", 2404, "env_rom.bin"),
-         ("ref_rom_misc_tables", 2470, "misc_rom.bin")]
+         ("ref_rom_misc_tables", 2470, "misc_rom.bin"),
+         # leading part of ia_ps_tables_struct through p8_13 (decoder/ixheaacd_sbr_rom.h:177-203)
+         ("ref_rom_ps_tables", 1230, "ps_rom.bin")]
 
 if __name__ == "__main__":
     main()

@@ -248,9 +248,45 @@ def make_envcalc_golden(tmp):
     print(f"wrote {path}: {len(sel)} of {len(recs)} records, {os.path.getsize(path)} bytes")
 
 
+SBR_SIDE, SBR_ST, SBR_PS = 1232, 3920, 3888
+SBR_REC_BYTES = 4 + 28 + 2 * (SBR_SIDE + SBR_ST + SBR_PS + 1024 + SBR_ST + SBR_PS + 2048 + 2048)
+
+
+def read_sbr_records(path):
+    """records written by __wrap_ixheaacd_sbr_dec (oracle/ref_taps.c)"""
+    raw = np.fromfile(path, dtype=np.uint8)
+    assert raw.size % SBR_REC_BYTES == 0, (raw.size, SBR_REC_BYTES)
+    out = []
+    for r in raw.reshape(-1, SBR_REC_BYTES):
+        assert r[0:4].view(np.int32)[0] == 0x31524253
+        d = {"hdr": r[4:32].view(np.int32).copy()}
+        o = 32
+        for name, n in (("side", SBR_SIDE), ("st_in", SBR_ST), ("ps_in", SBR_PS), ("tin", 1024), ("st_out", SBR_ST),
+                        ("ps_out", SBR_PS), ("out_l", 2048), ("out_r", 2048)):
+            d[name] = r[o:o + 2 * n].view(np.int16).copy()
+            o += 2 * n
+        out.append(d)
+    return out
+
+
+def make_sbrdec_golden(tmp):
+    """whole-stage ixheaacd_sbr_dec records: a run of 12 CONSECUTIVE frames from the start of each stream (so the tests
+    can also carry the state from frame to frame) plus a spread of later frames."""
+    recs = he_streams(tmp, "sbr", read_sbr_records)
+    n_ps = sum(1 for r in recs if r["side"][737])
+    keep = list(range(0, 12)) + list(range(20, n_ps, 16)) + list(range(n_ps, n_ps + 12)) + \
+        list(range(n_ps + 20, len(recs), 18))
+    sel = [recs[i] for i in keep]
+    out = {k: np.stack([r[k] for r in sel]) for k in sel[0]}
+    out["index"] = np.array(keep, np.int32)
+    path = os.path.join(GOLD, "sbrdec_tapped.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(sel)} of {len(recs)} records ({n_ps} with PS), {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
@@ -258,6 +294,8 @@ def main():
             make_hfgen_golden(tmp)
         if "envcalc" in which:
             make_envcalc_golden(tmp)
+        if "sbrdec" in which:
+            make_sbrdec_golden(tmp)
 
 
 if __name__ == "__main__":
