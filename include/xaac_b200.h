@@ -247,6 +247,88 @@ int32_t xaac_b200_set_env_rom(xaac_b200_ctx *ctx, const void *env_tables, size_t
 int32_t xaac_b200_calc_sbrenvelope_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_params, int16_t *d_sf, int16_t *d_state,
                                           int32_t *d_matrix, int32_t *d_err, int64_t n_units, void *stream);
 
+/* ---- whole fixed-point HQ SBR stage, batched ------------------------------------------------------------
+ * Replaces ixheaacd_sbr_dec (decoder/ixheaacd_sbr_dec.c:662-1310, fixed-point branch, low_pow_flag = 0, 1024-sample
+ * core frames, non-ELD/LD object types, no DRC/MPS) as ixheaacd_applysbr calls it (decoder/ixheaacd_sbrdecoder.c:877):
+ * overlap hand-over + ixheaacd_rescale_x_overlap, ixheaacd_cplx_anal_qmffilt, the ixheaacd_expsubbandsamples /
+ * ixheaacd_adjust_scale bookkeeping, ixheaacd_hf_generator, ixheaacd_calc_sbrenvelope, LPC / overlap state update,
+ * [ixheaacd_init_ps_scale + per-slot ixheaacd_init_rot_env / ixheaacd_apply_ps] and ixheaacd_cplx_synt_qmffilt (x2 with PS).
+ * Unit = one frame of one SBR channel (with PS: one mono core channel in, stereo out).
+ *
+ * ROM: in addition to the QMF / envelope ROMs, `ps_tables` points at the host's ia_ps_tables_struct
+ * (decoder/ixheaacd_sbr_rom.h:177-238; sbr_tables_ptr->ps_tables_ptr), leading XAAC_B200_PS_ROM_BYTES read. */
+#define XAAC_B200_PS_ROM_BYTES 1230
+int32_t xaac_b200_set_ps_rom(xaac_b200_ctx *ctx, const void *ps_tables, size_t bytes);
+
+/* Per-frame side-info record of the stage, WORD16[XAAC_SIDE_WORDS] */
+#define XAAC_SIDE_ENV 0        /* [656] XAAC_ENV_* (MAX_QMF_SUBBAND_PREV is taken from the state) */
+#define XAAC_SIDE_HF 656       /* [80]  XAAC_HF_*: transposer settings, NUM_IF_BANDS and INVF are read, the rest is derived */
+#define XAAC_SIDE_APPLY 736    /* apply_processing argument (sync_state == SBR_ACTIVE) */
+#define XAAC_SIDE_PS 737       /* 0 no PS this frame; 1 PS, stereo rotation exactly as the reference's own x86-64 gcc build
+                                  executes ixheaacd_apply_rot_dec (its type-punned H11_H12 copy is read back as zero, so QMF
+                                  bands 3..usb-1 of both outputs are 0 - bit-exact with that build); 2 PS, rotation as the C
+                                  source is written (bit-exact with the same file built with -fno-strict-aliasing) */
+#define XAAC_SIDE_PS_PRM 744   /* [488] XAAC_PS_PRM_*: ia_ps_dec_struct.iid_quant, num_env, border_position[7],
+                                  iid_par_table[7][34], icc_par_table[7][34] after ixheaacd_decode_ps_data */
+#define XAAC_SIDE_WORDS 1232
+#define XAAC_PS_PRM_IID_QUANT 0
+#define XAAC_PS_PRM_NUM_ENV 1
+#define XAAC_PS_PRM_BORDER 2
+#define XAAC_PS_PRM_IID 9
+#define XAAC_PS_PRM_ICC 247
+/* Channel state as a host blob, WORD16[XAAC_SBR_ST_WORDS] per unit (32-bit members at even offsets): what
+ * ia_sbr_dec_struct / ia_sbr_prev_frame_data_struct carry from frame to frame on this path */
+#define XAAC_SBR_ST_ANAL_STATES 0   /* [320]  str_codec_qmf_bank.anal_filter_states */
+#define XAAC_SBR_ST_ANAL_POS 320    /* [2]    {core_samples_buffer - anal_filter_states, filter_pos - qmf_c} */
+#define XAAC_SBR_ST_SYN_POS 322     /* [2]    {ixheaacd_drc_offset, filter_pos_syn - qmf_c} */
+#define XAAC_SBR_ST_SF 324          /* [8]    str_sbr_scale_fact (XAAC_SF_*) */
+#define XAAC_SBR_ST_MISC 332        /* [16]   0 prev max_qmf_subband_aac, 1 prev end_position, 2..11 prev sbr_invf_mode,
+                                              12 codec bank usb, 13 synthesis bank lsb, 14 synthesis bank usb */
+#define XAAC_SBR_ST_ENV 348         /* [232]  str_sbr_calc_env (XAAC_ENV_ST_*) */
+#define XAAC_SBR_ST_SYN_STATES 580  /* [1280] str_synthesis_qmf_bank.filter_states */
+#define XAAC_SBR_ST_BW_PREV 1860    /* WORD32[6]      str_hf_generator.bw_array_prev */
+#define XAAC_SBR_ST_LPC 1872        /* WORD32[2][128] lpc_filt_states_real[i] (64, 32 used) | _imag[i] */
+#define XAAC_SBR_ST_OV 2384         /* WORD32[6][128] ptr_sbr_overlap_buf */
+#define XAAC_SBR_ST_WORDS 3920
+/* PS state as a host blob, WORD16[XAAC_PS_ST_WORDS] per unit: ia_ps_dec_struct (decoder/ixheaacd_ps_dec.h:97-141)
+ * and the right channel's synthesis bank + scale factors */
+#define XAAC_PS_ST_AP 0
+#define XAAC_PS_ST_LD 128
+#define XAAC_PS_ST_SD 464
+#define XAAC_PS_ST_SER 528
+#define XAAC_PS_ST_SUB 1488
+#define XAAC_PS_ST_SUB_SER 1552
+#define XAAC_PS_ST_HVEC 2032
+#define XAAC_PS_ST_IDX 2320         /* [12] delay_buf_idx_ser[3], delay_buf_idx, delay_buf_idx_long, delay_buffer_scale,
+                                            usb, -, right bank lsb, right bank usb */
+#define XAAC_PS_ST_PEAK 2332        /* WORD32[3][20] */
+#define XAAC_PS_ST_HYB 2452         /* WORD32[3][2][12] */
+#define XAAC_PS_ST_SYN_STATES_R 2596
+#define XAAC_PS_ST_SYN_POS_R 3876
+#define XAAC_PS_ST_SF_R 3878
+#define XAAC_PS_ST_WORDS 3888
+
+/* Device-resident state of n_units channels (structure of arrays in HBM) plus the stage's scratch QMF matrices.
+ * upload / download move host blobs (checkpoint / resume, or hand-over from / to the CPU reference at a frame
+ * boundary); either blob pointer may be NULL.  A new state is all-zero; upload the decoder's reset state
+ * (decoder/ixheaacd_sbrdec_initfuncs.c:599-1213) before the first frame. */
+typedef struct xaac_b200_sbr_state xaac_b200_sbr_state;
+int32_t xaac_b200_sbr_state_create(xaac_b200_ctx *ctx, int64_t n_units, int32_t with_ps, xaac_b200_sbr_state **state);
+void xaac_b200_sbr_state_destroy(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state);
+int32_t xaac_b200_sbr_state_upload(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, const int16_t *st_blob,
+                                   const int16_t *ps_blob);
+int32_t xaac_b200_sbr_state_download(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, int16_t *st_blob,
+                                     int16_t *ps_blob);
+/* One frame for every unit of `state` (asynchronous on `stream`):
+ *   d_side     [n][1232] WORD16 side info
+ *   d_time_in  [n][1024] PCM16 core-coder output (after ixheaacd_allocate_sbr_scr's WORD32 -> WORD16 conversion)
+ *   d_time_out state without PS: [n][2048] PCM16; state with PS: [n][2048][2] interleaved L/R like the reference's
+ *              stereo time buffer (R is written only for units whose frame runs PS)
+ *   d_err      [n] WORD32 or NULL: the stage's return value per unit (0 / 0x80000000); a unit that fails keeps neither a
+ *              valid output nor a defined state, as in the reference, which aborts the frame */
+int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, const int16_t *d_side,
+                                 const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

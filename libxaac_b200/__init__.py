@@ -24,11 +24,13 @@ from .qmf import (  # noqa: F401
     cplx_synt_qmffilt_host,
     synth_params,
 )
-from .sbr import calc_sbrenvelope, hf_generator  # noqa: F401
+from .sbr import SbrState, calc_sbrenvelope, hf_generator, sbr_dec  # noqa: F401
 
 __all__ = [
     "hf_generator",
     "calc_sbrenvelope",
+    "SbrState",
+    "sbr_dec",
     "QmfAnalBatch",
     "cplx_anal_qmffilt",
     "QmfSynthBatch",

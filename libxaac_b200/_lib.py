@@ -41,6 +41,12 @@ SIGNATURES = {
     "xaac_b200_hf_generator_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "xaac_b200_set_env_rom": (_i32, [_vp, _vp, _sz, _vp, _sz]),
     "xaac_b200_calc_sbrenvelope_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "xaac_b200_set_ps_rom": (_i32, [_vp, _vp, _sz]),
+    "xaac_b200_sbr_state_create": (_i32, [_vp, _i64, _i32, _c.POINTER(_vp)]),
+    "xaac_b200_sbr_state_destroy": (None, [_vp, _vp]),
+    "xaac_b200_sbr_state_upload": (_i32, [_vp, _vp, _vp, _vp]),
+    "xaac_b200_sbr_state_download": (_i32, [_vp, _vp, _vp, _vp]),
+    "xaac_b200_sbr_dec_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

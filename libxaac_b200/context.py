@@ -5,7 +5,7 @@ from . import _lib
 
 
 class Context:
-    def __init__(self, device=0, imdct_rom=None, qmf_rom=None, env_rom=None, misc_rom=None):
+    def __init__(self, device=0, imdct_rom=None, qmf_rom=None, env_rom=None, misc_rom=None, ps_rom=None):
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         rc = self._lib.xaac_b200_create(ctypes.byref(self._h), int(device))
@@ -20,6 +20,7 @@ class Context:
         self.set_qmf_rom(qmf_rom if qmf_rom is not None else _lib.rom_blob("qmf_rom.bin"))
         self.set_env_rom(env_rom if env_rom is not None else _lib.rom_blob("env_rom.bin"),
                          misc_rom if misc_rom is not None else _lib.rom_blob("misc_rom.bin"))
+        self.set_ps_rom(ps_rom if ps_rom is not None else _lib.rom_blob("ps_rom.bin"))
 
     # -- plumbing ---------------------------------------------------------------------------------
     @property
@@ -48,6 +49,11 @@ class Context:
         m = (ctypes.c_char * len(misc_blob)).from_buffer_copy(misc_blob)
         self.check(self._lib.xaac_b200_set_env_rom(self._h, e, len(env_blob), m, len(misc_blob)),
                    "xaac_b200_set_env_rom")
+
+    def set_ps_rom(self, blob):
+        """blob: leading >= 1230 bytes of the host's ia_ps_tables_struct."""
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        self.check(self._lib.xaac_b200_set_ps_rom(self._h, buf, len(blob)), "xaac_b200_set_ps_rom")
 
     @property
     def num_sms(self):

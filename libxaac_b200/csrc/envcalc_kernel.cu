@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include "fixmath.cuh"
 #include "kernels.h"
+#include "sbr_common.cuh"
 
 namespace xb {
 
@@ -150,35 +151,6 @@ XB_DEV void subbandgain(i32 ref_m, i32 noise_m, i32 est_m, i32 est_e, i32 noise_
   }
 }
 
-// headroom of [slot range] x [band range] (env_calc.c:1159-1207), warp-cooperative
-XB_DEV int warp_headroom(const i32 *mat, int b0, int b1, int s0, int s1, int lane) {
-  i32 mx = 1;
-  const int nb = b1 - b0;
-  if (nb > 0) {
-    const int total = (s1 - s0) * nb;
-    for (int i = lane; i < total; i += 32) {
-      const int l = s0 + i / nb, k = b0 + i % nb;
-      mx |= abs_nrm(mat[128 * l + k]) | abs_nrm(mat[128 * l + 64 + k]);
-    }
-  }
-  mx = __reduce_or_sync(0xffffffffu, (unsigned)mx);
-  return pnorm32(mx);
-}
-
-// env_calc.c:1099-1157 (complex), warp-cooperative
-XB_DEV void warp_adjust_scale(i32 *mat, int b0, int b1, int s0, int s1, int shift, int lane) {
-  if (shift == 0 || b1 <= b0) return;
-  shift = max(-31, min(31, shift));
-  const int nb = b1 - b0, total = (s1 - s0) * nb;
-  for (int i = lane; i < total; i += 32) {
-    const int l = s0 + i / nb, k = b0 + i % nb;
-    i32 *pr = mat + 128 * l + k, *pi = pr + 64;
-    const i32 a = *pr, b = *pi;
-    *pr = shift > 0 ? lsl(a, shift) : (a >> -shift);
-    *pi = shift > 0 ? lsl(b, shift) : (b >> -shift);
-  }
-}
-
 __global__ void __launch_bounds__(kEnvWarps * 32)
 calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
   __shared__ EnvRomS rom;
@@ -201,8 +173,12 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
 
   for (long long u = (long long)blockIdx.x * kEnvWarps + warp; u < p.n_units; u += warps_total) {
     __syncwarp();
+    if (p.gate && p.gate[u * p.gate_stride] == 0) {
+      if (lane == 0 && p.err) p.err[u] = 0;
+      continue;
+    }
     {
-      const i32 *src = reinterpret_cast<const i32 *>(p.params + u * kEnvPrmWords);
+      const i32 *src = reinterpret_cast<const i32 *>(p.params + u * p.prm_stride);
       for (int i = lane; i < kEnvPrmWords / 2; i += 32) reinterpret_cast<i32 *>(w.prm)[i] = __ldg(src + i);
       const i32 *ss = reinterpret_cast<const i32 *>(p.state + u * kEnvStWords);
       for (int i = lane; i < kEnvStWords / 2; i += 32) reinterpret_cast<i32 *>(w.st)[i] = ss[i];
@@ -218,7 +194,8 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
     const int16_t *border = prm + kEnvBorderVec, *freq_res = prm + kEnvFreqRes, *nborder = prm + kEnvNoiseBorderVec;
     const int num_nf = prm[kEnvNumNfBands];
     const int sb_start = prm[kEnvSubBandStart], sb_end = prm[kEnvSubBandEnd];
-    const int max_qmf = prm[kEnvMaxQmfSubband], max_qmf_prev = prm[kEnvMaxQmfSubbandPrev];
+    const int max_qmf = prm[kEnvMaxQmfSubband];
+    const int max_qmf_prev = p.max_qmf_prev ? p.max_qmf_prev[u * 16] : prm[kEnvMaxQmfSubbandPrev];
     const int num_sub_bands = sb_end - sb_start, skip = max_qmf - sb_start, bands = num_sub_bands - skip;
     const int16_t *fnoise = prm + kEnvFreqNoise;
     const int16_t *sf_arr = prm + kEnvSfArr;

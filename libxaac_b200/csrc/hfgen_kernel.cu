@@ -58,6 +58,7 @@ hf_generator_hq_kernel(HfGenArgs p) {
   const i32 nbw0 = 0x00000000, nbw06 = 0x4ccccccd, nbw075 = 0x60000000, nbw09 = 0x73333333, nbw098 = 0x7d70a3d7;
 
   for (long long u = (long long)blockIdx.x * kHfWarps + warp; u < p.n_units; u += warps_total) {
+    if (p.gate && p.gate[u * p.gate_stride] == 0) continue;
     int16_t *prm = s_prm[warp];
     {
       const i32 *src = reinterpret_cast<const i32 *>(p.params + u * 80);
@@ -101,7 +102,7 @@ hf_generator_hq_kernel(HfGenArgs p) {
     }
     if (lane == 0) {
       int cs = prm[74] < prm[75] ? prm[74] : prm[75];
-      p.hb_scale[u] = (int16_t)(cs - 2);  // lpp_tran.c:1257, LPC_SCALE_FACTOR = 2
+      p.hb_scale[u * p.hb_stride] = (int16_t)(cs - 2);  // lpp_tran.c:1257, LPC_SCALE_FACTOR = 2
     }
 
     for (int lb0 = start_patch; lb0 < stop_patch; lb0 += 32) {

@@ -66,6 +66,9 @@ struct QmfSynthArgs {
   int ch_fac;
   int fast_bits;           // inputs below 2^fast_bits cannot saturate any add of the modulation
   int zero;                // always 0; an operand the compiler cannot fold (see add3 in qmf_synth_kernel.cu)
+  long long mat_stride = 4096;      // words between the matrices of consecutive units (4864 inside the SBR stage)
+  long long pcm_unit_stride = 0;    // != 0: unit u writes at pcm + u * pcm_unit_stride with sample stride ch_fac
+  const int16_t *gate = nullptr;    // optional: unit u is skipped when gate[u] == 0
 };
 
 size_t qmf_synth_table_bytes();
@@ -82,6 +85,8 @@ struct QmfAnalArgs {
   long long n_units;
   int ch_fac;
   int exact;               // 1: use saturating adds in the modulation (only if the table bound check failed)
+  long long mat_stride = 4096;      // words between the matrices of consecutive units
+  long long pcm_unit_stride = 0;    // != 0: unit u reads at pcm + u * pcm_unit_stride with sample stride ch_fac
 };
 
 size_t qmf_anal_table_bytes();
@@ -95,6 +100,9 @@ struct HfGenArgs {
   int32_t *bw_prev;        // [n_units][6]       ia_sbr_hf_generator_struct.bw_array_prev, in/out
   int16_t *hb_scale;       // [n_units]          sbr_scale_factor->hb_scale set by the stage
   long long n_units;
+  int hb_stride = 1;                 // hb_scale[u * hb_stride]
+  const int16_t *gate = nullptr;     // optional: unit u is skipped when gate[u * gate_stride] == 0
+  long long gate_stride = 0;
 };
 cudaError_t launch_hf_generator_hq(const HfGenArgs &args, int num_sms, cudaStream_t stream);
 
@@ -131,8 +139,72 @@ struct EnvCalcArgs {
   const uint8_t *env_rom;  // device copy of ia_env_calc_tables_struct
   const uint8_t *misc_rom; // device copy of the leading part of ixheaacd_misc_tables
   long long n_units;
+  long long prm_stride = kEnvPrmWords;  // words between the side-info records of consecutive units
+  const int16_t *gate = nullptr;        // optional: unit u is skipped when gate[u * gate_stride] == 0
+  long long gate_stride = 0;
+  const int16_t *max_qmf_prev = nullptr;  // optional override of params[kEnvMaxQmfSubbandPrev]: max_qmf_prev[u * 16]
 };
 cudaError_t launch_calc_sbrenvelope_hq(const EnvCalcArgs &args, int num_sms, cudaStream_t stream);
+
+// ---- whole fixed-point HQ SBR stage (ixheaacd_sbr_dec) -------------------------------------------------------
+// HF generator argument record (include/xaac_b200.h XAAC_HF_*)
+constexpr int kHfFactor = 50, kHfNumIfBands = 51, kHfStartIdx = 52, kHfStopIdx = 53, kHfInvf = 54, kHfInvfPrev = 64,
+              kHfOvLbScale = 74, kHfLbScale = 75, kHfMaxQmfSubband = 76;
+// per-frame side-info record of the stage (include/xaac_b200.h XAAC_SIDE_*)
+constexpr int kSideEnv = 0, kSideHf = 656, kSideApply = 736, kSidePs = 737, kSidePsPrm = 744, kSideWords = 1232;
+constexpr int kPsPrmIidQuant = 0, kPsPrmNumEnv = 1, kPsPrmBorder = 2, kPsPrmIid = 9, kPsPrmIcc = 247;
+// misc words of the channel state (XAAC_SBR_MISC_*)
+constexpr int kMiscMaxQmfPrev = 0, kMiscEndPosPrev = 1, kMiscInvfPrev = 2, kMiscCodecUsb = 12, kMiscSynLsb = 13,
+              kMiscSynUsb = 14;
+constexpr int kSbrMatWords = 38 * 128;  // scratch QMF matrix of one unit: 6 overlap + 32 current slots, re[64] | im[64]
+// host blob layout of the channel state (XAAC_SBR_ST_*), WORD16 offsets
+constexpr int kSbrStAnalStates = 0, kSbrStAnalPos = 320, kSbrStSynPos = 322, kSbrStSf = 324, kSbrStMisc = 332,
+              kSbrStEnv = 348, kSbrStSynStates = 580, kSbrStBwPrev = 1860, kSbrStLpc = 1872, kSbrStOv = 2384,
+              kSbrStWords = 3920;
+// PS state blob (XAAC_PS_ST_*), WORD16 offsets; the first kPsDspWords live in one device array
+constexpr int kPsStAp = 0, kPsStLd = 128, kPsStSd = 464, kPsStSer = 528, kPsStSub = 1488, kPsStSubSer = 1552,
+              kPsStHvec = 2032, kPsStIdx = 2320, kPsStPeak = 2332, kPsStHyb = 2452, kPsDspWords = 2596,
+              kPsStSynStatesR = 2596, kPsStSynPosR = 3876, kPsStSfR = 3878, kPsStWords = 3888;
+constexpr int kPsIdxSer = 0, kPsIdxDelay = 3, kPsIdxDelayLong = 4, kPsIdxScale = 5, kPsIdxUsb = 6, kPsIdxLsbR = 8,
+              kPsIdxUsbR = 9;
+// PS ROM = leading 1230 bytes of ia_ps_tables_struct (decoder/ixheaacd_sbr_rom.h:177-203), WORD16 offsets
+constexpr int kPsRomDecaySf = 0, kPsRomHybResol = 72, kPsRomRevDecay = 75, kPsRomRevDelay = 78, kPsRomBordersGroup = 81,
+              kPsRomGroupShift = 104, kPsRomGroupToBin = 110, kPsRomHybToBin = 132, kPsRomDelayToBin = 142,
+              kPsRomFracQmf = 174, kPsRomFracSub = 222, kPsRomFracQmfSer = 254, kPsRomFracSubSer = 446, kPsRomScale = 542,
+              kPsRomScaleFine = 557, kPsRomAlpha = 588, kPsRomP2_6 = 596, kPsRomP8_13 = 602, kPsRomBytes = 1230;
+
+struct SbrStageArgs {
+  const int16_t *side;   // [n][1232] side info
+  int32_t *matrix;       // [n][38][128] scratch QMF matrix
+  int32_t *ov;           // [n][768]  overlap slots (state)
+  int32_t *lpc;          // [n][256]  LPC state rows (state)
+  int16_t *sf;           // [n][8]    scale factors (state)
+  int16_t *misc;         // [n][16]   misc state words
+  int16_t *usb;          // [n]       scratch: analysis bank usb for the analysis kernel
+  int16_t *hf_prm;       // [n][80]   scratch: HF generator argument records
+  int16_t *synp;         // [n][8]    scratch: synthesis kernel parameter rows
+  const int32_t *err;    // [n]       per-unit return value of the envelope adjuster
+  long long n_units;
+};
+cudaError_t launch_sbr_pre(const SbrStageArgs &a, int num_sms, cudaStream_t s);
+cudaError_t launch_sbr_scale(const SbrStageArgs &a, int num_sms, cudaStream_t s);
+cudaError_t launch_sbr_post(const SbrStageArgs &a, int num_sms, cudaStream_t s);
+
+struct PsArgs {
+  const int16_t *side;     // [n][1232]
+  int32_t *matrix;         // [n][38][128] left matrix, rows 0..31 rewritten in the synthesis scale
+  int32_t *right;          // [n][32][128] right matrix (out)
+  int16_t *ps_state;       // [n][2596]    PS state, in/out
+  int16_t *sf;             // [n][8]       left scale factors (ps_scale written)
+  int16_t *sf_r;           // [n][8]       right channel's scale factors
+  int16_t *synp;           // [n][8]       in: {ov_lb, lb, hb, st_syn, lsb, usb, 6, 0}; out: left synthesis parameters
+  int16_t *synp_r;         // [n][8]       out: right synthesis parameters
+  int16_t *ps_done;        // [n]          out: 1 when the unit ran PS
+  const int32_t *err;
+  const uint8_t *ps_rom, *env_rom, *misc_rom;
+  long long n_units;
+};
+cudaError_t launch_ps_frame(const PsArgs &args, int num_sms, cudaStream_t stream);
 
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);

@@ -53,8 +53,9 @@ __device__ __forceinline__ void anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm
   auto SUB = [](i32 a, i32 b) { return SAT ? sub_sat(a, b) : wsub(a, b); };
   auto NEG = [](i32 a) { return SAT ? neg_sat(a) : wneg(a); };
   const unsigned full = 0xffffffffu;
-  const int16_t *pcm = p.pcm + ((p.ch_fac == 1) ? u * 1024 : (u / p.ch_fac) * (1024LL * p.ch_fac) + (u % p.ch_fac));
-  i32 *mat = p.matrix + u * 4096;
+  const int16_t *pcm = p.pcm + (p.pcm_unit_stride ? u * p.pcm_unit_stride
+                                                     : ((p.ch_fac == 1) ? u * 1024 : (u / p.ch_fac) * (1024LL * p.ch_fac) + (u % p.ch_fac)));
+  i32 *mat = p.matrix + u * p.mat_stride;
   int pos = p.pos[2 * u], f1 = p.pos[2 * u + 1], f2 = f1 + 64;
   const int usb = p.usb[u];
   {  // ring: HBM -> smem (same layout)

@@ -236,7 +236,8 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
   const int bandB = 63 - bandA;
 
   for (long long u = (long long)blockIdx.x * kSynWarps + warp; u < p.n_units; u += warps_total) {
-    const i32 *mat = p.matrix + u * 4096;
+    if (p.gate && p.gate[u] == 0) continue;
+    const i32 *mat = p.matrix + u * p.mat_stride;
     const int16_t *prm = p.params + u * 8;
     const int ov_lb_scale = prm[0], lb_scale = prm[1], hb_scale = prm[2], st_syn = prm[3];
     const int lsb = prm[4], usb = prm[5], split = prm[6];
@@ -287,7 +288,8 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
       nx[4 * s + 2] = __ldg(m + 64 + bandA);
       nx[4 * s + 3] = __ldg(m + 64 + bandB);
     }
-    int16_t *pcm = p.pcm + ((p.ch_fac == 1) ? u * 2048 : (u / p.ch_fac) * (2048LL * p.ch_fac) + (u % p.ch_fac));
+    int16_t *pcm = p.pcm + (p.pcm_unit_stride ? u * p.pcm_unit_stride
+                                               : ((p.ch_fac == 1) ? u * 2048 : (u / p.ch_fac) * (2048LL * p.ch_fac) + (u % p.ch_fac)));
 
 #pragma unroll 1
     for (int pr = 0; pr < 16; pr++) {

@@ -23,6 +23,8 @@ struct xaac_b200_ctx {
   uint8_t *d_rom_env = nullptr;   // ia_env_calc_tables_struct
   uint8_t *d_rom_misc = nullptr;  // leading part of ixheaacd_misc_tables
   bool have_env_rom = false;
+  uint8_t *d_rom_ps = nullptr;    // leading part of ia_ps_tables_struct
+  bool have_ps_rom = false;
   char err[256] = {0};
   // staging for the *_host entry points: kPipe chunks in flight, one stream each
   static constexpr int kPipe = 3;
@@ -43,7 +45,28 @@ struct xaac_b200_imdct_state {
   uint8_t *d_wstate = nullptr;   // [n][2] {window_shape, window_sequence}
 };
 
+// Device-resident state of the whole SBR stage, structure of arrays (one array per member of the host blob).
+struct xaac_b200_sbr_state {
+  int64_t n_units = 0;
+  bool with_ps = false;
+  // channel state (host blob XAAC_SBR_ST_*)
+  int16_t *anal_states = nullptr, *anal_pos = nullptr, *syn_pos = nullptr, *sf = nullptr, *misc = nullptr, *env = nullptr,
+          *syn_states = nullptr;
+  int32_t *bw_prev = nullptr, *lpc = nullptr, *ov = nullptr;
+  // PS state (host blob XAAC_PS_ST_*)
+  int16_t *ps = nullptr, *syn_states_r = nullptr, *syn_pos_r = nullptr, *sf_r = nullptr;
+  // scratch
+  int32_t *matrix = nullptr, *right = nullptr, *err = nullptr;
+  int16_t *usb = nullptr, *hf_prm = nullptr, *synp = nullptr, *synp_r = nullptr, *ps_done = nullptr;
+};
+
 namespace {
+
+struct BlobPart {
+  void **dev;
+  size_t bytes;   // per unit
+  size_t offset;  // byte offset inside the host blob
+};
 
 int32_t fail(xaac_b200_ctx *ctx, cudaError_t e, const char *what) {
   if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
@@ -116,6 +139,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   if (ctx->d_rom_qmf_ana) cudaFree(ctx->d_rom_qmf_ana);
   if (ctx->d_rom_env) cudaFree(ctx->d_rom_env);
   if (ctx->d_rom_misc) cudaFree(ctx->d_rom_misc);
+  if (ctx->d_rom_ps) cudaFree(ctx->d_rom_ps);
   delete ctx;
 }
 
@@ -505,6 +529,186 @@ int32_t xaac_b200_calc_sbrenvelope_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_p
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   CK(xb::launch_calc_sbrenvelope_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch calc_sbrenvelope_hq_kernel");
   ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_set_ps_rom(xaac_b200_ctx *ctx, const void *ps_tables, size_t bytes) {
+  if (!ctx || !ps_tables) return bad_arg(ctx, "null");
+  if (bytes < (size_t)xb::kPsRomBytes) return bad_arg(ctx, "PS ROM blob shorter than 1230 bytes");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (!ctx->d_rom_ps) CK(cudaMalloc((void **)&ctx->d_rom_ps, xb::kPsRomBytes + 50), "cudaMalloc(ps rom)");
+  CK(cudaMemcpy(ctx->d_rom_ps, ps_tables, xb::kPsRomBytes, cudaMemcpyHostToDevice), "H2D ps rom");
+  ctx->have_ps_rom = true;
+  return XAAC_B200_OK;
+}
+
+static void sbr_state_parts(xaac_b200_sbr_state *s, BlobPart *st, int *n_st, BlobPart *ps, int *n_ps) {
+  int i = 0;
+  st[i++] = {(void **)&s->anal_states, 640, 2 * (size_t)xb::kSbrStAnalStates};
+  st[i++] = {(void **)&s->anal_pos, 4, 2 * (size_t)xb::kSbrStAnalPos};
+  st[i++] = {(void **)&s->syn_pos, 4, 2 * (size_t)xb::kSbrStSynPos};
+  st[i++] = {(void **)&s->sf, 16, 2 * (size_t)xb::kSbrStSf};
+  st[i++] = {(void **)&s->misc, 32, 2 * (size_t)xb::kSbrStMisc};
+  st[i++] = {(void **)&s->env, 464, 2 * (size_t)xb::kSbrStEnv};
+  st[i++] = {(void **)&s->syn_states, 2560, 2 * (size_t)xb::kSbrStSynStates};
+  st[i++] = {(void **)&s->bw_prev, 24, 2 * (size_t)xb::kSbrStBwPrev};
+  st[i++] = {(void **)&s->lpc, 1024, 2 * (size_t)xb::kSbrStLpc};
+  st[i++] = {(void **)&s->ov, 3072, 2 * (size_t)xb::kSbrStOv};
+  *n_st = i;
+  i = 0;
+  ps[i++] = {(void **)&s->ps, 2 * (size_t)xb::kPsDspWords, 0};
+  ps[i++] = {(void **)&s->syn_states_r, 2560, 2 * (size_t)xb::kPsStSynStatesR};
+  ps[i++] = {(void **)&s->syn_pos_r, 4, 2 * (size_t)xb::kPsStSynPosR};
+  ps[i++] = {(void **)&s->sf_r, 16, 2 * (size_t)xb::kPsStSfR};
+  *n_ps = i;
+}
+
+void xaac_b200_sbr_state_destroy(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s) {
+  if (!s) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  BlobPart st[16], ps[8];
+  int n_st, n_ps;
+  sbr_state_parts(s, st, &n_st, ps, &n_ps);
+  for (int i = 0; i < n_st; i++) if (*st[i].dev) cudaFree(*st[i].dev);
+  for (int i = 0; i < n_ps; i++) if (*ps[i].dev) cudaFree(*ps[i].dev);
+  void *scr[] = {s->matrix, s->right, s->err, s->usb, s->hf_prm, s->synp, s->synp_r, s->ps_done};
+  for (void *q : scr) if (q) cudaFree(q);
+  delete s;
+}
+
+int32_t xaac_b200_sbr_state_create(xaac_b200_ctx *ctx, int64_t n_units, int32_t with_ps, xaac_b200_sbr_state **out) {
+  if (!ctx || !out || n_units <= 0) return bad_arg(ctx, "sbr_state_create");
+  *out = nullptr;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  xaac_b200_sbr_state *s = new (std::nothrow) xaac_b200_sbr_state();
+  if (!s) return XAAC_B200_FATAL;
+  s->n_units = n_units;
+  s->with_ps = with_ps != 0;
+  BlobPart st[16], ps[8];
+  int n_st, n_ps;
+  sbr_state_parts(s, st, &n_st, ps, &n_ps);
+  bool ok = true;
+  auto alloc0 = [&](void **q, size_t bytes) {
+    if (!ok) return;
+    if (cudaMalloc(q, bytes) != cudaSuccess || cudaMemset(*q, 0, bytes) != cudaSuccess) ok = false;
+  };
+  for (int i = 0; i < n_st; i++) alloc0(st[i].dev, st[i].bytes * (size_t)n_units);
+  if (s->with_ps)
+    for (int i = 0; i < n_ps; i++) alloc0(ps[i].dev, ps[i].bytes * (size_t)n_units);
+  alloc0((void **)&s->matrix, (size_t)n_units * xb::kSbrMatWords * 4);
+  alloc0((void **)&s->err, (size_t)n_units * 4);
+  alloc0((void **)&s->usb, (size_t)n_units * 2);
+  alloc0((void **)&s->hf_prm, (size_t)n_units * 160);
+  alloc0((void **)&s->synp, (size_t)n_units * 16);
+  if (s->with_ps) {
+    alloc0((void **)&s->right, (size_t)n_units * 4096 * 4);
+    alloc0((void **)&s->synp_r, (size_t)n_units * 16);
+    alloc0((void **)&s->ps_done, (size_t)n_units * 2);
+  }
+  if (!ok) {
+    cudaError_t e = cudaGetLastError();
+    xaac_b200_sbr_state_destroy(ctx, s);
+    return fail(ctx, e, "cudaMalloc(sbr state)");
+  }
+  *out = s;
+  return XAAC_B200_OK;
+}
+
+static int32_t sbr_state_copy(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, int16_t *st_blob, int16_t *ps_blob, bool up) {
+  if (!ctx || !s) return XAAC_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  BlobPart st[16], ps[8];
+  int n_st, n_ps;
+  sbr_state_parts(s, st, &n_st, ps, &n_ps);
+  auto run = [&](BlobPart *parts, int n, int16_t *blob, size_t pitch) -> cudaError_t {
+    for (int i = 0; i < n; i++) {
+      uint8_t *h = (uint8_t *)blob + parts[i].offset;
+      cudaError_t e = up ? cudaMemcpy2D(*parts[i].dev, parts[i].bytes, h, pitch, parts[i].bytes, (size_t)s->n_units,
+                                        cudaMemcpyHostToDevice)
+                         : cudaMemcpy2D(h, pitch, *parts[i].dev, parts[i].bytes, parts[i].bytes, (size_t)s->n_units,
+                                        cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  if (st_blob) CK(run(st, n_st, st_blob, 2 * (size_t)xb::kSbrStWords), "sbr state copy");
+  if (ps_blob) {
+    if (!s->with_ps) return bad_arg(ctx, "state was created without PS");
+    CK(run(ps, n_ps, ps_blob, 2 * (size_t)xb::kPsStWords), "ps state copy");
+  }
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_sbr_state_upload(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *st_blob,
+                                   const int16_t *ps_blob) {
+  return sbr_state_copy(ctx, s, (int16_t *)st_blob, (int16_t *)ps_blob, true);
+}
+int32_t xaac_b200_sbr_state_download(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, int16_t *st_blob, int16_t *ps_blob) {
+  return sbr_state_copy(ctx, s, st_blob, ps_blob, false);
+}
+
+int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side,
+                                 const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, void *stream) {
+  if (!ctx || !s) return XAAC_B200_ERR_ARG;
+  if (!ctx->have_qmf_rom || !ctx->have_env_rom || (s->with_ps && !ctx->have_ps_rom)) {
+    snprintf(ctx->err, sizeof(ctx->err), "set_qmf_rom / set_env_rom / set_ps_rom have not all been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (!d_side || !d_time_in || !d_time_out) return bad_arg(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = s->n_units;
+  int32_t *err = d_err ? d_err : s->err;
+  xb::SbrStageArgs g;
+  g.side = d_side; g.matrix = s->matrix; g.ov = s->ov; g.lpc = s->lpc; g.sf = s->sf; g.misc = s->misc; g.usb = s->usb;
+  g.hf_prm = s->hf_prm; g.synp = s->synp; g.err = err; g.n_units = n;
+  CK(xb::launch_sbr_pre(g, ctx->num_sms, st), "launch sbr_pre_kernel");
+  {
+    xb::QmfAnalArgs a;
+    a.pcm = d_time_in; a.states = s->anal_states; a.pos = s->anal_pos; a.usb = s->usb;
+    a.matrix = s->matrix + 6 * 128; a.rom = ctx->d_rom_qmf_ana; a.n_units = n; a.ch_fac = 1;
+    a.exact = ctx->qmf_anal_exact; a.mat_stride = xb::kSbrMatWords;
+    CK(xb::launch_qmf_anal_hq(a, ctx->num_sms, st), "launch qmf_anal_hq_kernel");
+  }
+  CK(xb::launch_sbr_scale(g, ctx->num_sms, st), "launch sbr_scale_kernel");
+  {
+    xb::HfGenArgs a;
+    a.lpc = s->lpc; a.matrix = s->matrix; a.params = s->hf_prm; a.bw_prev = s->bw_prev; a.hb_scale = s->sf + xb::kSfHb;
+    a.hb_stride = 8; a.n_units = n; a.gate = d_side + xb::kSideApply; a.gate_stride = xb::kSideWords;
+    CK(xb::launch_hf_generator_hq(a, ctx->num_sms, st), "launch hf_generator_hq_kernel");
+  }
+  {
+    xb::EnvCalcArgs a;
+    a.params = d_side; a.prm_stride = xb::kSideWords; a.sf = s->sf; a.state = s->env; a.matrix = s->matrix; a.err = err;
+    a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n;
+    a.gate = d_side + xb::kSideApply; a.gate_stride = xb::kSideWords; a.max_qmf_prev = s->misc;
+    CK(xb::launch_calc_sbrenvelope_hq(a, ctx->num_sms, st), "launch calc_sbrenvelope_hq_kernel");
+  }
+  CK(xb::launch_sbr_post(g, ctx->num_sms, st), "launch sbr_post_kernel");
+  ctx->launches += 6;
+  xb::QmfSynthArgs y;
+  y.matrix = s->matrix; y.states = s->syn_states; y.pos = s->syn_pos; y.params = s->synp; y.pcm = d_time_out;
+  y.rom = ctx->d_rom_qmf_syn; y.n_units = n; y.fast_bits = ctx->qmf_fast_bits; y.zero = 0;
+  y.mat_stride = xb::kSbrMatWords;
+  if (s->with_ps) {
+    xb::PsArgs a;
+    a.side = d_side; a.matrix = s->matrix; a.right = s->right; a.ps_state = s->ps; a.sf = s->sf; a.sf_r = s->sf_r;
+    a.synp = s->synp; a.synp_r = s->synp_r; a.ps_done = s->ps_done; a.err = err; a.ps_rom = ctx->d_rom_ps;
+    a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n;
+    CK(xb::launch_ps_frame(a, ctx->num_sms, st), "launch ps_frame_kernel");
+    y.ch_fac = 2;
+    y.pcm_unit_stride = 4096;
+    CK(xb::launch_qmf_synth_hq(y, ctx->num_sms, st), "launch qmf_synth_hq_kernel (left)");
+    xb::QmfSynthArgs r = y;
+    r.matrix = s->right; r.mat_stride = 4096; r.states = s->syn_states_r; r.pos = s->syn_pos_r; r.params = s->synp_r;
+    r.pcm = d_time_out + 1; r.gate = s->ps_done;
+    CK(xb::launch_qmf_synth_hq(r, ctx->num_sms, st), "launch qmf_synth_hq_kernel (right)");
+    ctx->launches += 3;
+  } else {
+    y.ch_fac = 1;
+    CK(xb::launch_qmf_synth_hq(y, ctx->num_sms, st), "launch qmf_synth_hq_kernel");
+    ctx->launches += 1;
+  }
   return XAAC_B200_OK;
 }
 

@@ -17,6 +17,9 @@ from .imdct import _chk, _ptr
 HF_PARAM_WORDS = 80
 ENV_PARAM_WORDS = 656
 ENV_STATE_WORDS = 232
+SIDE_WORDS = 1232
+SBR_STATE_WORDS = 3920
+PS_STATE_WORDS = 3888
 
 
 def hf_generator(ctx, lpc, matrix, params, bw_prev, hb_scale=None, stream=None):
@@ -54,3 +57,69 @@ def calc_sbrenvelope(ctx, params, sf, state, matrix, err=None, stream=None):
                                                    _ptr(err), n, ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_calc_sbrenvelope_hq_dev")
     return err
+
+
+class SbrState:
+    """Device-resident state of n SBR channels for sbr_dec (what ia_sbr_dec_struct / ia_ps_dec_struct carry between
+    frames).  upload / download move host blobs: numpy int16 [n, 3920] (channel) and [n, 3888] (PS)."""
+
+    def __init__(self, ctx, n_units, with_ps=False):
+        self.ctx, self.n_units, self.with_ps = ctx, int(n_units), bool(with_ps)
+        self._h = ctypes.c_void_p()
+        ctx.check(ctx._lib.xaac_b200_sbr_state_create(ctx.handle, self.n_units, int(self.with_ps), ctypes.byref(self._h)),
+                  "xaac_b200_sbr_state_create")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def upload(self, st_blob=None, ps_blob=None):
+        import numpy as np
+        a = None if st_blob is None else np.ascontiguousarray(st_blob, np.int16)
+        b = None if ps_blob is None else np.ascontiguousarray(ps_blob, np.int16)
+        assert a is None or a.shape == (self.n_units, SBR_STATE_WORDS)
+        assert b is None or b.shape == (self.n_units, PS_STATE_WORDS)
+        rc = self.ctx._lib.xaac_b200_sbr_state_upload(self.ctx.handle, self._h,
+                                                      None if a is None else a.ctypes.data_as(ctypes.c_void_p),
+                                                      None if b is None else b.ctypes.data_as(ctypes.c_void_p))
+        self.ctx.check(rc, "xaac_b200_sbr_state_upload")
+
+    def download(self):
+        import numpy as np
+        a = np.zeros((self.n_units, SBR_STATE_WORDS), np.int16)
+        b = np.zeros((self.n_units, PS_STATE_WORDS), np.int16) if self.with_ps else None
+        rc = self.ctx._lib.xaac_b200_sbr_state_download(self.ctx.handle, self._h, a.ctypes.data_as(ctypes.c_void_p),
+                                                        None if b is None else b.ctypes.data_as(ctypes.c_void_p))
+        self.ctx.check(rc, "xaac_b200_sbr_state_download")
+        return a, b
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.xaac_b200_sbr_state_destroy(self.ctx.handle, self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sbr_dec(ctx, state, side, time_in, time_out=None, err=None, stream=None):
+    """Batched drop-in for ixheaacd_sbr_dec (fixed-point HQ path).  side int16 [n,1232]; time_in int16 [n,1024];
+    returns (time_out, err): time_out int16 [n,2048] or, for a PS state, [n,2048,2] (interleaved L/R); err int32 [n]."""
+    n = state.n_units
+    _chk(side, torch.int16, (n, SIDE_WORDS), "side", "cuda")
+    _chk(time_in, torch.int16, (n, 1024), "time_in", "cuda")
+    shape = (n, 2048, 2) if state.with_ps else (n, 2048)
+    if time_out is None:
+        time_out = torch.zeros(shape, dtype=torch.int16, device=side.device)
+    _chk(time_out, torch.int16, shape, "time_out", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=side.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(side.device)
+    rc = ctx._lib.xaac_b200_sbr_dec_hq_dev(ctx.handle, state.handle, _ptr(side), _ptr(time_in), _ptr(time_out), _ptr(err),
+                                          ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_sbr_dec_hq_dev")
+    return time_out, err
