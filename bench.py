@@ -25,8 +25,23 @@ sys.path.insert(0, ROOT)
 
 IMDCT_BYTES_PER_UNIT = 12288  # 4096 spec in + 2048 overlap in + 2048 overlap out + 4096 WORD32 out
 SYNTH_BYTES_PER_UNIT = 25600  # 16384 matrix + 2560 state in + 2560 state out + 4096 PCM16 out
+# algorithmic HBM bytes per unit and launch of every kernel of the HE-AACv2 chain
+CHAIN_KERNEL_BYTES = {
+    "imdct_ola_kernel": 12288,            # 4096 spec + 2048 + 2048 overlap + 4096 WORD32 out
+    "pcm16_from_imdct_kernel": 6144,      # 4096 in + 2048 out
+    "sbr_pre_kernel": 6144,               # 3072 overlap slots in + 3072 matrix rows out
+    "qmf_anal_hq_kernel": 11520,          # 2048 PCM16 + 2 x 640 state + 8192 matrix
+    "sbr_scale_kernel": 29184,            # 38 x 32 bands x 8 B read + written, 32 x 64 x 4 B cleared, 2 KB LPC rows r/w
+    "hf_generator_hq_kernel": 13824,      # hfgen_kernel.cu header
+    "calc_sbrenvelope_hq_kernel": 19760,  # envcalc_kernel.cu header
+    "sbr_post_kernel": 4672,              # 1536 overlap out + LPC rows 2 x 1024 + parameters
+    "ps_frame_kernel": 60928,             # ps_kernel.cu header
+    "qmf_synth_hq_kernel": SYNTH_BYTES_PER_UNIT,
+}
 WORKLOADS = {
     # name -> (BASELINE.json config index, stereo frames per GPU, description)
+    "heaacv2_chain": (3, 131072, "HE-AACv2 (SBR+PS) stereo 44.1 kHz batch=131072: full IMDCT->QMF->SBR->PS "
+                                 "hybrid/decorrelate chain (fixed-point path of the reference, -esbr:0)"),
     "aac_lc_stereo_imdct_ola": (1, 65536, "AAC-LC stereo 44.1 kHz batch=65536 frames, IMDCT+OLA only"),
     "qmf_synth_hq": (3, 65536, "stand-alone fixed-point HQ 64-band QMF synthesis stage of the HE-AAC chain, "
                                "batch=65536 stereo frames (131072 output channels)"),
@@ -261,6 +276,64 @@ def cpu_arm(n_units, threads, seed, reps=1):
     return n_units * reps / dt, kind
 
 
+def load_chain_golden():
+    """HE-AACv2 side info / state tapped from a real decode of the reference (tests/golden/sbrdec_tapped.npz, made by
+    tools/make_golden.py): records 1..11 are consecutive frames of one 44.1 kHz mono+PS stream."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sbrdec_tapped.npz"))
+    assert g["side"][1:12, 737].all()
+    return g["side"][1:12].copy(), g["st_in"][1].copy(), g["ps_in"][1].copy()
+
+
+def chain_inputs_np(n_units, seed):
+    rng = np.random.default_rng(seed)
+    s = rng.integers(12, 22, size=(n_units, 1))
+    spec = ((rng.random((n_units, 1024)) * 2 - 1) * (2.0 ** s)).astype(np.int64).astype(np.int32)
+    return spec
+
+
+def cpu_arm_chain(n_units, threads, seed, reps=1):
+    """Time the reference's own chain per stream-frame on host threads: ixheaacd_imdct_process -> WORD32->WORD16
+    hand-over -> ixheaacd_sbr_dec (HQ + PS, 2 x ixheaacd_cplx_synt_qmffilt), persistent reference structs per stream.
+    Returns (stream_frames_per_s * 2, kind): the factor 2 keeps the caller's units/2 = frames convention."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    if ref is None:
+        raise SystemExit("bench.py: the HE-AACv2 chain CPU baseline needs oracle/_ref/libxaac_ref.so (make ref)")
+    side_frames, st0, ps0 = load_chain_golden()
+    P = oracle_util.P
+    side0 = np.ascontiguousarray(np.tile(side_frames[0], (n_units, 1)))
+    st = np.ascontiguousarray(np.tile(st0, (n_units, 1)))
+    ps = np.ascontiguousarray(np.tile(ps0, (n_units, 1)))
+    ref.lib.ref_chain_create.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(ref.lib.ref_chain_create(n_units, P(side0), P(st), P(ps)))
+    spec0 = chain_inputs_np(n_units, seed)
+    walk = sequence_walk(n_units + (n_units & 1), reps + 1, seed)[:, :n_units]
+    out = np.zeros((n_units, 2048, 2), np.int16)
+    bounds = np.linspace(0, n_units, threads + 1).astype(int)
+    sides = [np.ascontiguousarray(side_frames[(np.arange(n_units) + f) % 11]) for f in range(11)]
+
+    def work(t, spec, ics, side):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            ref.lib.ref_chain_step(h, a, b, P(spec), P(ics), P(side), P(out))
+
+    def one_pass(step):
+        spec = spec0.copy()
+        ics = np.ascontiguousarray(walk[step])
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t, spec, ics, sides[step % 11])) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    one_pass(0)
+    dt = sum(one_pass(1 + r) for r in range(reps))
+    ref.lib.ref_chain_destroy(h)
+    return 2.0 * n_units * reps / dt, "reference"
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -269,6 +342,11 @@ def host_threads():
 
 
 STAGES = {
+    "heaacv2_chain": dict(kernel=None, bytes_per_unit=None, units_per_frame=1,
+                          stage="IMDCT+OLA -> PCM16 hand-over -> QMF analysis -> HF generation -> envelope adjustment -> "
+                                "PS hybrid/decorrelation/rotation -> 2 x QMF synthesis (fixed-point, bit-exact)",
+                          ref_stage="ixheaacd_imdct_process + ixheaacd_sbr_dec (HQ, PS)", cpu=cpu_arm_chain,
+                          cpu_units_per_core=128, cpu_reps=12, realtime_fps=21.533, h2d=4096 + 2 + 2464, d2h=8192),
     "aac_lc_stereo_imdct_ola": dict(kernel="imdct_ola_kernel", bytes_per_unit=IMDCT_BYTES_PER_UNIT,
                                     stage="IMDCT + window/OLA (fixed-point WORD32, bit-exact)",
                                     ref_stage="ixheaacd_imdct_process", cpu=cpu_arm, cpu_units_per_core=4096,
@@ -290,6 +368,10 @@ def run_reference_arm(args, rank, world):
     sample_units -= sample_units % 2
     t0 = time.perf_counter()
     ups, kind = stg["cpu"](sample_units, cores, 0xAAC0 + cfg_idx, reps=max(1, args.steps))
+    unit_name = "units (frame x channel)"
+    if stg.get("units_per_frame", 2) == 1:
+        sample_units *= 2  # the chain's CPU arm counts stream-frames and returns 2 x frames/s
+        unit_name = "half stream-frames (i.e. %d stream-frames)" % (sample_units // 2)
     fps = ups / 2.0
     line = {
         "impl": "reference", "metric": "decoded_stereo_frames_per_sec", "value": fps, "unit": "frames/s",
@@ -299,7 +381,7 @@ def run_reference_arm(args, rank, world):
         "config": {"workload": args.workload, "baseline_config": desc, "stage": stg["ref_stage"],
                    "step": f"bounded sample: {sample_units // 2} stereo frames per step on host cores"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample_units} units (frame x channel) x {max(1, args.steps)} passes "
+                         "sample": f"{sample_units} {unit_name} x {max(1, args.steps)} passes "
                                    f"(+1 warm-up), {cores} threads, private state per unit"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
@@ -363,7 +445,63 @@ class SynthWork:
         self.hstate.close()
 
 
-WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork}
+class ChainWork:
+    """HE-AACv2 stream-frames: mono core IMDCT -> PCM16 -> SBR stage with PS -> stereo PCM16.  Side info / initial state
+    are tiled from a tapped real stream (11 consecutive frames, unit u runs them with phase u mod 11); the core
+    spectra are seeded noise with per-unit magnitude and a block-switching walk."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        side_frames, st0, ps0 = load_chain_golden()
+        self.spec = torch.from_numpy(chain_inputs_np(n_units, seed)).to(dev)
+        walk = sequence_walk(n_units + (n_units & 1), steps_total, seed)[:, :n_units]
+        self.walk = torch.from_numpy(np.ascontiguousarray(walk)).to(dev)
+        self.nw = steps_total
+        sf = torch.from_numpy(side_frames).to(dev)
+        phase = torch.arange(n_units, device=dev)
+        self.side = [sf[(phase + f) % 11].contiguous() for f in range(11)]
+        self.imdct_state = xb.ImdctBatch(n_units, device=dev)
+        self.state = xb.SbrState(ctx, n_units, with_ps=True)
+        self.st0, self.ps0 = st0, ps0
+        self.state.upload(np.tile(st0, (n_units, 1)), np.tile(ps0, (n_units, 1)))
+        self.w32 = torch.empty((n_units, 1024), dtype=torch.int32, device=dev)
+        self.adj = torch.empty((n_units,), dtype=torch.int8, device=dev)
+        self.p16 = torch.empty((n_units, 1024), dtype=torch.int16, device=dev)
+        self.pcm = torch.empty((n_units, 2048, 2), dtype=torch.int16, device=dev)
+        self.err = torch.zeros((n_units,), dtype=torch.int32, device=dev)
+
+    def step(self, i, stream):
+        xb, ctx = self.xb, self.ctx
+        xb.imdct_process(ctx, self.imdct_state, self.spec, self.walk[i % self.nw], self.w32, self.adj, stream=stream)
+        xb.imdct_out_to_pcm16(ctx, self.w32, self.adj, 0, self.p16, stream=stream)
+        xb.sbr_dec(ctx, self.state, self.side[i % 11], self.p16, self.pcm, self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0, "the SBR stage reported an error for some unit"
+
+    def host_setup(self):
+        import torch
+        self.h_spec = torch.empty((self.n, 1024), dtype=torch.int32).pin_memory()
+        self.h_spec.copy_(self.spec)
+        self.h_walk = self.walk.cpu().pin_memory()
+        self.h_side = [x.cpu().pin_memory() for x in self.side]
+        self.h_pcm = torch.empty((self.n, 2048, 2), dtype=torch.int16).pin_memory()
+        self.h_imdct = self.xb.ImdctHostState(self.ctx, self.n)
+        self.h_state = self.xb.SbrState(self.ctx, self.n, with_ps=True)
+        self.h_state.upload(np.tile(self.st0, (self.n, 1)), np.tile(self.ps0, (self.n, 1)))
+
+    def host_step(self, i):
+        self.xb.heaac_frame_host(self.ctx, self.h_imdct, self.h_state, self.h_spec, self.h_walk[i % self.nw],
+                                 self.h_side[i % 11], self.h_pcm)
+
+    def host_close(self):
+        self.h_imdct.close()
+        self.h_state.close()
+        self.state.close()
+
+
+WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv2_chain": ChainWork}
 
 
 def main():
@@ -372,7 +510,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="aac_lc_stereo_imdct_ola", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="heaacv2_chain", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="stereo frames per GPU (default: the config's batch)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps for the host-buffer arm (default min(steps,5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -403,7 +541,8 @@ def main():
     stg = STAGES[args.workload]
     if args.frames:
         frames = args.frames
-    n_units = 2 * frames  # stereo: two channels per frame; each rank owns its own streams (weak scaling)
+    upf = stg.get("units_per_frame", 2)
+    n_units = upf * frames  # units (frame x core channel) per rank; each rank owns its own streams (weak scaling)
     K, W = args.steps, args.warmup
     seed = 0xAAC0 + cfg_idx + 1000 * rank
     ctx = xb.Context(local_rank)
@@ -440,7 +579,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = world * frames * K / (total_ms_max * 1e-3)
-    kernel_ms = float(np.mean(step_ms))  # one kernel launch per step: step time == launch duration
+    kernel_ms = float(np.mean(step_ms))  # single-kernel workloads: one launch per step, step time == launch duration
+    if hasattr(work, "check"):
+        work.check()
+    kernel_table = None
+    if stg["kernel"] is None:
+        # multi-kernel step: a second pass of K steps with every launch bracketed by CUDA events on the launching
+        # stream (xaac_b200_kernel_timing) attributes the step time to the kernels
+        ctx.kernel_timing(True)
+        for s_ in range(K):
+            work.step(W + K + s_, stream)
+        kt = ctx.kernel_times()
+        ctx.kernel_timing(False)
+        tot = sum(v[0] for v in kt.values())
+        kernel_table = {}
+        for name, (ms, cnt) in kt.items():
+            per = ms / cnt
+            b = CHAIN_KERNEL_BYTES.get(name)
+            kernel_table[name] = {"launch_ms": per, "launches_per_step": cnt / K, "share_of_step": ms / tot,
+                                  "bytes_per_unit": b, "units_per_launch": n_units,
+                                  "achieved": None if b is None else b * n_units / (per * 1e-3) / 1e9}
 
     # ---- end-to-end arm: host buffers through the C-ABI ---------------------------------------------------
     Ke = args.e2e_steps or min(K, 5)
@@ -464,6 +622,11 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
+        if kernel_table is not None:
+            # the BASELINE metric kernel is the QMF synthesis; it is also the largest share of the chain
+            top = "qmf_synth_hq_kernel"
+            stg = dict(stg, kernel=top, bytes_per_unit=CHAIN_KERNEL_BYTES[top])
+            kernel_ms = kernel_table[top]["launch_ms"]
         achieved = stg["bytes_per_unit"] * n_units / (kernel_ms * 1e-3) / 1e9
         line = {
             "metric": "decoded_stereo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -483,6 +646,13 @@ def main():
                          "bytes_per_unit": stg["bytes_per_unit"], "units_per_launch": n_units,
                          "launch_ms": kernel_ms},
         }
+        if kernel_table is not None:
+            for v in kernel_table.values():
+                v["peak"] = peak
+                v["frac"] = None if v["achieved"] is None else v["achieved"] / peak
+            line["kernels"] = kernel_table
+            line["roofline"]["note"] = ("per-launch duration from CUDA events around every launch of a second pass of "
+                                        "the same steps; two launches per step (left, right)")
         if args.workload == "aac_lc_stereo_imdct_ola":
             line["config"]["window_sequence_mix"] = "walk: ~90% long, 4% start, 4% stop, 2% short"
         # short extra runs of the other stage kernels so every hot kernel has a live roofline number
@@ -491,23 +661,27 @@ def main():
             for name in WORK:
                 if name == args.workload:
                     continue
-                w2 = WORK[name](xb, ctx, n_units, 8, seed, dev)
+                if name == "heaacv2_chain":
+                    continue
+                w2 = WORK[name](xb, ctx, 131072, 8, seed, dev)
                 ms, _, _ = timed(w2, 5, 3)
-                ach = STAGES[name]["bytes_per_unit"] * n_units / (float(np.mean(ms)) * 1e-3) / 1e9
+                ach = STAGES[name]["bytes_per_unit"] * 131072 / (float(np.mean(ms)) * 1e-3) / 1e9
                 extra[name] = {"kernel": STAGES[name]["kernel"], "launch_ms": float(np.mean(ms)),
-                               "units_per_launch": n_units, "bytes_per_unit": STAGES[name]["bytes_per_unit"],
+                               "units_per_launch": 131072, "bytes_per_unit": STAGES[name]["bytes_per_unit"],
                                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                               "stereo_frames_per_sec": frames / (float(np.mean(ms)) * 1e-3)}
+                               "stereo_frames_per_sec": 65536 / (float(np.mean(ms)) * 1e-3)}
                 del w2
                 torch.cuda.empty_cache()
             line["stage_rooflines"] = extra
         if not args.no_cpu_baseline and world == 1:
             cores = host_threads()
-            ups1, kind = stg["cpu"](stg["cpu_units_per_core"], 1, 0xAAC0 + cfg_idx, reps=1)
-            upsN, kind = stg["cpu"](stg["cpu_units_per_core"] * cores, cores, 0xAAC0 + cfg_idx, reps=2)
+            stg = STAGES[args.workload]
+            creps = stg.get("cpu_reps", 2)
+            ups1, kind = stg["cpu"](stg["cpu_units_per_core"], 1, 0xAAC0 + cfg_idx, reps=max(1, creps // 4))
+            upsN, kind = stg["cpu"](stg["cpu_units_per_core"] * cores, cores, 0xAAC0 + cfg_idx, reps=creps)
             line["cpu_baseline"] = {"value": upsN / 2.0, "unit": "frames/s", "cores": cores, "kind": kind,
                                     "value_1core": ups1 / 2.0,
-                                    "sample": f"{stg['cpu_units_per_core'] * cores} units x 2 passes on {cores} threads "
+                                    "sample": f"{stg['cpu_units_per_core'] * cores} units x {creps} passes on {cores} threads "
                                               f"(1-core figure: {stg['cpu_units_per_core']} units), "
                                               f"{stg['ref_stage']} per unit"}
         print(json.dumps(line), flush=True)

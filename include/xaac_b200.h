@@ -43,6 +43,12 @@ int32_t xaac_b200_num_sms(const xaac_b200_ctx *ctx);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches evidence) */
 int64_t xaac_b200_launch_count(const xaac_b200_ctx *ctx);
 int32_t xaac_b200_sync(xaac_b200_ctx *ctx);
+/* Profiling hook (the counterpart of the reference testbench's ARM_PROFILE_HW MCPS printout,
+ * test/decoder/ixheaacd_main.c:2198-2229): when enabled, every kernel launch is bracketed by CUDA events on its own
+ * stream.  xaac_b200_kernel_times synchronises and writes "kernel:total_ms:launches;" records into buf.
+ * Enabling / disabling clears the records. */
+int32_t xaac_b200_kernel_timing(xaac_b200_ctx *ctx, int32_t enable);
+int32_t xaac_b200_kernel_times(xaac_b200_ctx *ctx, char *buf, size_t buf_bytes);
 
 /* ---- ROM tables ------------------------------------------------------------------------------------
  * The reference hands its const tables to every hot function as pointer arguments
@@ -328,6 +334,24 @@ int32_t xaac_b200_sbr_state_download(xaac_b200_ctx *ctx, xaac_b200_sbr_state *st
  *              valid output nor a defined state, as in the reference, which aborts the frame */
 int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, const int16_t *d_side,
                                  const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, void *stream);
+
+/* Host-buffer entry point for a whole HE-AAC (v1 mono / v2) frame per unit: IMDCT + window/OLA of the core channel
+ * (xaac_b200_imdct_process_dev), the WORD32 -> PCM16 hand-over (xaac_b200_imdct_out_to_pcm16_dev, mode 0) and the SBR
+ * stage, chunked and pipelined over internal streams (H2D, kernels, D2H overlap).  Both states stay resident in HBM.
+ *   spec [n][1024] WORD32, ics [n][2], side [n][1232] WORD16 (host, pinned recommended)
+ *   pcm  [n][2048] PCM16, or [n][2048][2] for a PS state; err [n] WORD32 or NULL */
+int32_t xaac_b200_heaac_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *imdct_state, xaac_b200_sbr_state *sbr_state,
+                                   const int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *pcm,
+                                   int32_t *err);
+
+/* ---- stage glue: WORD32 IMDCT output -> PCM16 ---------------------------------------------
+ * mode 0 replaces the conversion loop of ixheaacd_allocate_sbr_scr (decoder/ixheaacd_api.c:337-370):
+ *        round16(shl32_sat(x, qshift_adj)), the core-coder -> SBR hand-over;
+ * mode 1 replaces ixheaacd_scale_adjust (decoder/ixheaacd_peak_limiter.c:324-333) + the round16 loop of
+ *        ixheaacd_dec_execute (decoder/ixheaacd_api.c:3676-3681): the AAC-LC output stage with -peak_limiter_off:1.
+ *   d_in [n_units][1024] WORD32, d_qshift_adj [n_units] (as written by xaac_b200_imdct_process_dev), d_out [n_units][1024] */
+int32_t xaac_b200_imdct_out_to_pcm16_dev(xaac_b200_ctx *ctx, const int32_t *d_in, const int8_t *d_qshift_adj,
+                                         int16_t *d_out, int64_t n_units, int32_t mode, void *stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ from .imdct import (  # noqa: F401
     ImdctHostState,
     imdct_process,
     imdct_process_host,
+    imdct_out_to_pcm16,
 )
 from .qmf import (  # noqa: F401
     QmfAnalBatch,
@@ -24,13 +25,14 @@ from .qmf import (  # noqa: F401
     cplx_synt_qmffilt_host,
     synth_params,
 )
-from .sbr import SbrState, calc_sbrenvelope, hf_generator, sbr_dec  # noqa: F401
+from .sbr import SbrState, calc_sbrenvelope, heaac_frame_host, hf_generator, sbr_dec  # noqa: F401
 
 __all__ = [
     "hf_generator",
     "calc_sbrenvelope",
     "SbrState",
     "sbr_dec",
+    "heaac_frame_host",
     "QmfAnalBatch",
     "cplx_anal_qmffilt",
     "QmfSynthBatch",
@@ -43,6 +45,7 @@ __all__ = [
     "ImdctHostState",
     "imdct_process",
     "imdct_process_host",
+    "imdct_out_to_pcm16",
     "XaacB200Error",
     "load",
 ]

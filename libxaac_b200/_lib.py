@@ -23,6 +23,8 @@ SIGNATURES = {
     "xaac_b200_num_sms": (_i32, [_vp]),
     "xaac_b200_launch_count": (_i64, [_vp]),
     "xaac_b200_sync": (_i32, [_vp]),
+    "xaac_b200_kernel_timing": (_i32, [_vp, _i32]),
+    "xaac_b200_kernel_times": (_i32, [_vp, _vp, _sz]),
     "xaac_b200_set_imdct_rom": (_i32, [_vp, _vp, _sz]),
     "xaac_b200_imdct_process_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "xaac_b200_imdct_state_create": (_i32, [_vp, _i64, _c.POINTER(_vp)]),
@@ -47,6 +49,8 @@ SIGNATURES = {
     "xaac_b200_sbr_state_upload": (_i32, [_vp, _vp, _vp, _vp]),
     "xaac_b200_sbr_state_download": (_i32, [_vp, _vp, _vp, _vp]),
     "xaac_b200_sbr_dec_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "xaac_b200_heaac_frame_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "xaac_b200_imdct_out_to_pcm16_dev": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
 }
 
 _lib = None

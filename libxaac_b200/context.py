@@ -63,6 +63,21 @@ class Context:
     def launch_count(self):
         return self._lib.xaac_b200_launch_count(self._h)
 
+    def kernel_timing(self, enable):
+        """bracket every kernel launch with CUDA events (profiling hook); clears previous records"""
+        self.check(self._lib.xaac_b200_kernel_timing(self._h, int(bool(enable))), "xaac_b200_kernel_timing")
+
+    def kernel_times(self):
+        """{kernel name: (total ms, launches)} since kernel_timing(True)"""
+        buf = ctypes.create_string_buffer(8192)
+        self.check(self._lib.xaac_b200_kernel_times(self._h, buf, len(buf)), "xaac_b200_kernel_times")
+        out = {}
+        for rec in buf.value.decode().split(";"):
+            if rec:
+                name, ms, cnt = rec.split(":")
+                out[name] = (float(ms), int(cnt))
+        return out
+
     def sync(self):
         self.check(self._lib.xaac_b200_sync(self._h), "xaac_b200_sync")
 

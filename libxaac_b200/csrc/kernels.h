@@ -189,6 +189,8 @@ struct SbrStageArgs {
 cudaError_t launch_sbr_pre(const SbrStageArgs &a, int num_sms, cudaStream_t s);
 cudaError_t launch_sbr_scale(const SbrStageArgs &a, int num_sms, cudaStream_t s);
 cudaError_t launch_sbr_post(const SbrStageArgs &a, int num_sms, cudaStream_t s);
+cudaError_t launch_pcm16_from_imdct(const int32_t *in, const int8_t *qshift_adj, int16_t *out, long long n_units, int mode,
+                                    int num_sms, cudaStream_t s);
 
 struct PsArgs {
   const int16_t *side;     // [n][1232]

@@ -26,6 +26,12 @@ struct xaac_b200_ctx {
   uint8_t *d_rom_ps = nullptr;    // leading part of ia_ps_tables_struct
   bool have_ps_rom = false;
   char err[256] = {0};
+  // optional per-kernel timing (CUDA events on the launching stream around every kernel)
+  static constexpr int kMaxTicks = 8192;
+  bool timing = false;
+  int n_ticks = 0;
+  const char *tick_name[kMaxTicks];
+  cudaEvent_t tick_ev[kMaxTicks][2];
   // staging for the *_host entry points: kPipe chunks in flight, one stream each
   static constexpr int kPipe = 3;
   cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
@@ -68,6 +74,20 @@ struct BlobPart {
   size_t offset;  // byte offset inside the host blob
 };
 
+void tick(xaac_b200_ctx *ctx, cudaStream_t st, const char *name, bool start) {
+  if (!ctx->timing || ctx->n_ticks >= xaac_b200_ctx::kMaxTicks) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  if (start) {
+    ctx->tick_name[ctx->n_ticks] = name;
+    ctx->tick_ev[ctx->n_ticks][0] = ev;
+  } else {
+    ctx->tick_ev[ctx->n_ticks][1] = ev;
+    ctx->n_ticks++;
+  }
+}
+
 int32_t fail(xaac_b200_ctx *ctx, cudaError_t e, const char *what) {
   if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
   return XAAC_B200_ERR_CUDA;
@@ -76,6 +96,14 @@ int32_t bad_arg(xaac_b200_ctx *ctx, const char *what) {
   if (ctx) snprintf(ctx->err, sizeof(ctx->err), "bad argument: %s", what);
   return XAAC_B200_ERR_ARG;
 }
+// kernel launch with optional per-kernel CUDA-event timing (xaac_b200_kernel_timing)
+#define LAUNCH(name, strm, call)                                   \
+  do {                                                             \
+    tick(ctx, (cudaStream_t)(strm), name, true);                   \
+    cudaError_t e__ = (call);                                      \
+    if (e__ != cudaSuccess) return fail(ctx, e__, "launch " name); \
+    tick(ctx, (cudaStream_t)(strm), name, false);                  \
+  } while (0)
 #define CK(call, what)                              \
   do {                                              \
     cudaError_t e__ = (call);                       \
@@ -195,7 +223,7 @@ int32_t xaac_b200_imdct_process_dev(xaac_b200_ctx *ctx, const int32_t *d_spec, i
   a.rom = ctx->d_rom_imdct;
   a.n_units = n_units;
   a.ch_fac = ch_fac;
-  CK(xb::launch_imdct(a, ctx->num_sms, (cudaStream_t)stream), "launch imdct_ola_kernel");
+  LAUNCH("imdct_ola_kernel", stream, xb::launch_imdct(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }
@@ -360,7 +388,7 @@ int32_t xaac_b200_qmf_synth_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_matrix, 
   a.zero = 0;
   a.n_units = n_units;
   a.ch_fac = ch_fac;
-  CK(xb::launch_qmf_synth_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch qmf_synth_hq_kernel");
+  LAUNCH("qmf_synth_hq_kernel", stream, xb::launch_qmf_synth_hq(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }
@@ -468,7 +496,7 @@ int32_t xaac_b200_qmf_anal_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_pcm, int1
   a.n_units = n_units;
   a.ch_fac = ch_fac;
   a.exact = ctx->qmf_anal_exact;
-  CK(xb::launch_qmf_anal_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch qmf_anal_hq_kernel");
+  LAUNCH("qmf_anal_hq_kernel", stream, xb::launch_qmf_anal_hq(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }
@@ -488,7 +516,7 @@ int32_t xaac_b200_hf_generator_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_lpc, 
   a.hb_scale = d_hb_scale;
   a.n_units = n_units;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-  CK(xb::launch_hf_generator_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch hf_generator_hq_kernel");
+  LAUNCH("hf_generator_hq_kernel", stream, xb::launch_hf_generator_hq(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }
@@ -527,7 +555,7 @@ int32_t xaac_b200_calc_sbrenvelope_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_p
   a.misc_rom = ctx->d_rom_misc;
   a.n_units = n_units;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-  CK(xb::launch_calc_sbrenvelope_hq(a, ctx->num_sms, (cudaStream_t)stream), "launch calc_sbrenvelope_hq_kernel");
+  LAUNCH("calc_sbrenvelope_hq_kernel", stream, xb::launch_calc_sbrenvelope_hq(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }
@@ -647,67 +675,183 @@ int32_t xaac_b200_sbr_state_download(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s,
   return sbr_state_copy(ctx, s, st_blob, ps_blob, false);
 }
 
-int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side,
-                                 const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, void *stream) {
+extern "C" int32_t xaac_b200_imdct_out_to_pcm16_dev(xaac_b200_ctx *, const int32_t *, const int8_t *, int16_t *, int64_t,
+                                                    int32_t, void *);
+// One frame for units [u0, u0 + n) of the state; d_side / d_time_in / d_time_out / d_err point at the chunk's first unit.
+static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long long u0, long long n, const int16_t *d_side,
+                             const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, cudaStream_t st) {
+  int32_t *err = d_err ? d_err : s->err + u0;
+  xb::SbrStageArgs g;
+  g.side = d_side; g.matrix = s->matrix + u0 * xb::kSbrMatWords; g.ov = s->ov + u0 * 768; g.lpc = s->lpc + u0 * 256;
+  g.sf = s->sf + u0 * 8; g.misc = s->misc + u0 * 16; g.usb = s->usb + u0; g.hf_prm = s->hf_prm + u0 * 80;
+  g.synp = s->synp + u0 * 8; g.err = err; g.n_units = n;
+  LAUNCH("sbr_pre_kernel", st, xb::launch_sbr_pre(g, ctx->num_sms, st));
+  {
+    xb::QmfAnalArgs a;
+    a.pcm = d_time_in; a.states = s->anal_states + u0 * 320; a.pos = s->anal_pos + u0 * 2; a.usb = g.usb;
+    a.matrix = g.matrix + 6 * 128; a.rom = ctx->d_rom_qmf_ana; a.n_units = n; a.ch_fac = 1;
+    a.exact = ctx->qmf_anal_exact; a.mat_stride = xb::kSbrMatWords;
+    LAUNCH("qmf_anal_hq_kernel", st, xb::launch_qmf_anal_hq(a, ctx->num_sms, st));
+  }
+  LAUNCH("sbr_scale_kernel", st, xb::launch_sbr_scale(g, ctx->num_sms, st));
+  {
+    xb::HfGenArgs a;
+    a.lpc = g.lpc; a.matrix = g.matrix; a.params = g.hf_prm; a.bw_prev = s->bw_prev + u0 * 6;
+    a.hb_scale = g.sf + xb::kSfHb; a.hb_stride = 8; a.n_units = n;
+    a.gate = d_side + xb::kSideApply; a.gate_stride = xb::kSideWords;
+    LAUNCH("hf_generator_hq_kernel", st, xb::launch_hf_generator_hq(a, ctx->num_sms, st));
+  }
+  {
+    xb::EnvCalcArgs a;
+    a.params = d_side; a.prm_stride = xb::kSideWords; a.sf = g.sf; a.state = s->env + u0 * xb::kEnvStWords;
+    a.matrix = g.matrix; a.err = err; a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n;
+    a.gate = d_side + xb::kSideApply; a.gate_stride = xb::kSideWords; a.max_qmf_prev = g.misc;
+    LAUNCH("calc_sbrenvelope_hq_kernel", st, xb::launch_calc_sbrenvelope_hq(a, ctx->num_sms, st));
+  }
+  LAUNCH("sbr_post_kernel", st, xb::launch_sbr_post(g, ctx->num_sms, st));
+  ctx->launches += 6;
+  xb::QmfSynthArgs y;
+  y.matrix = g.matrix; y.states = s->syn_states + u0 * 1280; y.pos = s->syn_pos + u0 * 2; y.params = g.synp;
+  y.pcm = d_time_out; y.rom = ctx->d_rom_qmf_syn; y.n_units = n; y.fast_bits = ctx->qmf_fast_bits; y.zero = 0;
+  y.mat_stride = xb::kSbrMatWords;
+  if (s->with_ps) {
+    xb::PsArgs a;
+    a.side = d_side; a.matrix = g.matrix; a.right = s->right + u0 * 4096; a.ps_state = s->ps + u0 * xb::kPsDspWords;
+    a.sf = g.sf; a.sf_r = s->sf_r + u0 * 8; a.synp = g.synp; a.synp_r = s->synp_r + u0 * 8; a.ps_done = s->ps_done + u0;
+    a.err = err; a.ps_rom = ctx->d_rom_ps; a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n;
+    LAUNCH("ps_frame_kernel", st, xb::launch_ps_frame(a, ctx->num_sms, st));
+    y.ch_fac = 2;
+    y.pcm_unit_stride = 4096;
+    LAUNCH("qmf_synth_hq_kernel", st, xb::launch_qmf_synth_hq(y, ctx->num_sms, st));
+    xb::QmfSynthArgs r = y;
+    r.matrix = a.right; r.mat_stride = 4096; r.states = s->syn_states_r + u0 * 1280; r.pos = s->syn_pos_r + u0 * 2;
+    r.params = a.synp_r; r.pcm = d_time_out + 1; r.gate = a.ps_done;
+    LAUNCH("qmf_synth_hq_kernel", st, xb::launch_qmf_synth_hq(r, ctx->num_sms, st));
+    ctx->launches += 3;
+  } else {
+    y.ch_fac = 1;
+    LAUNCH("qmf_synth_hq_kernel", st, xb::launch_qmf_synth_hq(y, ctx->num_sms, st));
+    ctx->launches += 1;
+  }
+  return XAAC_B200_OK;
+}
+
+static int32_t sbr_check(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s) {
   if (!ctx || !s) return XAAC_B200_ERR_ARG;
   if (!ctx->have_qmf_rom || !ctx->have_env_rom || (s->with_ps && !ctx->have_ps_rom)) {
     snprintf(ctx->err, sizeof(ctx->err), "set_qmf_rom / set_env_rom / set_ps_rom have not all been called");
     return XAAC_B200_ERR_NO_ROM;
   }
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side,
+                                 const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, void *stream) {
+  int32_t rc = sbr_check(ctx, s);
+  if (rc != XAAC_B200_OK) return rc;
   if (!d_side || !d_time_in || !d_time_out) return bad_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long n = s->n_units;
-  int32_t *err = d_err ? d_err : s->err;
-  xb::SbrStageArgs g;
-  g.side = d_side; g.matrix = s->matrix; g.ov = s->ov; g.lpc = s->lpc; g.sf = s->sf; g.misc = s->misc; g.usb = s->usb;
-  g.hf_prm = s->hf_prm; g.synp = s->synp; g.err = err; g.n_units = n;
-  CK(xb::launch_sbr_pre(g, ctx->num_sms, st), "launch sbr_pre_kernel");
-  {
-    xb::QmfAnalArgs a;
-    a.pcm = d_time_in; a.states = s->anal_states; a.pos = s->anal_pos; a.usb = s->usb;
-    a.matrix = s->matrix + 6 * 128; a.rom = ctx->d_rom_qmf_ana; a.n_units = n; a.ch_fac = 1;
-    a.exact = ctx->qmf_anal_exact; a.mat_stride = xb::kSbrMatWords;
-    CK(xb::launch_qmf_anal_hq(a, ctx->num_sms, st), "launch qmf_anal_hq_kernel");
+  return sbr_dec_range(ctx, s, 0, s->n_units, d_side, d_time_in, d_time_out, d_err, (cudaStream_t)stream);
+}
+
+// HE-AAC frame from host buffers: IMDCT (mono or one core channel per unit) -> WORD32->PCM16 hand-over -> SBR stage.
+int32_t xaac_b200_heaac_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *ist, xaac_b200_sbr_state *s,
+                                   const int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *pcm,
+                                   int32_t *err) {
+  int32_t rc = sbr_check(ctx, s);
+  if (rc != XAAC_B200_OK) return rc;
+  if (!ist || !ctx->have_imdct_rom) return bad_arg(ctx, "IMDCT state / ROM missing");
+  if (ist->n_units != s->n_units) return bad_arg(ctx, "IMDCT and SBR states must have the same number of units");
+  if (!spec || !ics || !side || !pcm) return bad_arg(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  const int64_t n_units = s->n_units;
+  int64_t chunk = 4096;
+  if (chunk > n_units) chunk = n_units;
+  const size_t out_words = s->with_ps ? 4096 : 2048;
+  // per-unit staging: spec 4096 | WORD32 out 4096 | side 2464 | pcm16 in 2048 | pcm out 2*out_words | err 4 | ics 2 | adj 1 (+1)
+  const size_t o_spec = 0, o_w32 = 4096, o_side = 8192, o_p16 = 8192 + 2464, o_pcm = o_p16 + 2048,
+               o_err = o_pcm + 2 * out_words, o_ics = o_err + 4, o_adj = o_ics + 2, per_unit = o_adj + 2;
+  rc = ensure_stage(ctx, per_unit * (size_t)chunk);
+  if (rc != XAAC_B200_OK) return rc;
+  int slot = 0;
+  for (int64_t u0 = 0; u0 < n_units; u0 += chunk, slot = (slot + 1) % xaac_b200_ctx::kPipe) {
+    const int64_t n = (n_units - u0 < chunk) ? (n_units - u0) : chunk;
+    cudaStream_t st = ctx->streams[slot];
+    uint8_t *base = (uint8_t *)ctx->stage[slot];
+    int32_t *d_spec = (int32_t *)(base + o_spec * chunk), *d_w32 = (int32_t *)(base + o_w32 * chunk);
+    int16_t *d_side = (int16_t *)(base + o_side * chunk), *d_p16 = (int16_t *)(base + o_p16 * chunk);
+    int16_t *d_pcm = (int16_t *)(base + o_pcm * chunk);
+    int32_t *d_err = (int32_t *)(base + o_err * chunk);
+    uint8_t *d_ics = base + o_ics * chunk;
+    int8_t *d_adj = (int8_t *)(base + o_adj * chunk);
+    CK(cudaMemcpyAsync(d_spec, spec + u0 * 1024, (size_t)n * 4096, cudaMemcpyHostToDevice, st), "H2D spec");
+    CK(cudaMemcpyAsync(d_ics, ics + u0 * 2, (size_t)n * 2, cudaMemcpyHostToDevice, st), "H2D ics");
+    CK(cudaMemcpyAsync(d_side, side + u0 * xb::kSideWords, (size_t)n * xb::kSideWords * 2, cudaMemcpyHostToDevice, st),
+       "H2D side");
+    rc = xaac_b200_imdct_process_dev(ctx, d_spec, ist->d_overlap + u0 * 512, ist->d_wstate + u0 * 2, d_ics, d_w32, d_adj, n,
+                                     1, st);
+    if (rc != XAAC_B200_OK) return rc;
+    rc = xaac_b200_imdct_out_to_pcm16_dev(ctx, d_w32, d_adj, d_p16, n, 0, st);
+    if (rc != XAAC_B200_OK) return rc;
+    rc = sbr_dec_range(ctx, s, u0, n, d_side, d_p16, d_pcm, d_err, st);
+    if (rc != XAAC_B200_OK) return rc;
+    CK(cudaMemcpyAsync(pcm + u0 * out_words, d_pcm, (size_t)n * out_words * 2, cudaMemcpyDeviceToHost, st), "D2H pcm");
+    if (err) CK(cudaMemcpyAsync(err + u0, d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H err");
   }
-  CK(xb::launch_sbr_scale(g, ctx->num_sms, st), "launch sbr_scale_kernel");
-  {
-    xb::HfGenArgs a;
-    a.lpc = s->lpc; a.matrix = s->matrix; a.params = s->hf_prm; a.bw_prev = s->bw_prev; a.hb_scale = s->sf + xb::kSfHb;
-    a.hb_stride = 8; a.n_units = n; a.gate = d_side + xb::kSideApply; a.gate_stride = xb::kSideWords;
-    CK(xb::launch_hf_generator_hq(a, ctx->num_sms, st), "launch hf_generator_hq_kernel");
+  for (int i = 0; i < xaac_b200_ctx::kPipe; i++) CK(cudaStreamSynchronize(ctx->streams[i]), "stream sync");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_imdct_out_to_pcm16_dev(xaac_b200_ctx *ctx, const int32_t *d_in, const int8_t *d_qshift_adj,
+                                         int16_t *d_out, int64_t n_units, int32_t mode, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (n_units < 0 || (mode != 0 && mode != 1)) return bad_arg(ctx, "n_units/mode");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_in || !d_qshift_adj || !d_out) return bad_arg(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  LAUNCH("pcm16_from_imdct_kernel", stream, xb::launch_pcm16_from_imdct(d_in, d_qshift_adj, d_out, n_units, mode, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_kernel_timing(xaac_b200_ctx *ctx, int32_t enable) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  for (int i = 0; i < ctx->n_ticks; i++) {
+    cudaEventDestroy(ctx->tick_ev[i][0]);
+    cudaEventDestroy(ctx->tick_ev[i][1]);
   }
-  {
-    xb::EnvCalcArgs a;
-    a.params = d_side; a.prm_stride = xb::kSideWords; a.sf = s->sf; a.state = s->env; a.matrix = s->matrix; a.err = err;
-    a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n;
-    a.gate = d_side + xb::kSideApply; a.gate_stride = xb::kSideWords; a.max_qmf_prev = s->misc;
-    CK(xb::launch_calc_sbrenvelope_hq(a, ctx->num_sms, st), "launch calc_sbrenvelope_hq_kernel");
+  ctx->n_ticks = 0;
+  ctx->timing = enable != 0;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_kernel_times(xaac_b200_ctx *ctx, char *buf, size_t buf_bytes) {
+  if (!ctx || !buf || buf_bytes < 2) return XAAC_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  const char *names[64];
+  double ms[64];
+  int cnt[64], n = 0;
+  for (int i = 0; i < ctx->n_ticks; i++) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->tick_ev[i][0], ctx->tick_ev[i][1]) != cudaSuccess) continue;
+    int k = 0;
+    while (k < n && strcmp(names[k], ctx->tick_name[i]) != 0) k++;
+    if (k == n) {
+      if (n == 64) continue;
+      names[n] = ctx->tick_name[i]; ms[n] = 0; cnt[n] = 0; n++;
+    }
+    ms[k] += t;
+    cnt[k]++;
   }
-  CK(xb::launch_sbr_post(g, ctx->num_sms, st), "launch sbr_post_kernel");
-  ctx->launches += 6;
-  xb::QmfSynthArgs y;
-  y.matrix = s->matrix; y.states = s->syn_states; y.pos = s->syn_pos; y.params = s->synp; y.pcm = d_time_out;
-  y.rom = ctx->d_rom_qmf_syn; y.n_units = n; y.fast_bits = ctx->qmf_fast_bits; y.zero = 0;
-  y.mat_stride = xb::kSbrMatWords;
-  if (s->with_ps) {
-    xb::PsArgs a;
-    a.side = d_side; a.matrix = s->matrix; a.right = s->right; a.ps_state = s->ps; a.sf = s->sf; a.sf_r = s->sf_r;
-    a.synp = s->synp; a.synp_r = s->synp_r; a.ps_done = s->ps_done; a.err = err; a.ps_rom = ctx->d_rom_ps;
-    a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n;
-    CK(xb::launch_ps_frame(a, ctx->num_sms, st), "launch ps_frame_kernel");
-    y.ch_fac = 2;
-    y.pcm_unit_stride = 4096;
-    CK(xb::launch_qmf_synth_hq(y, ctx->num_sms, st), "launch qmf_synth_hq_kernel (left)");
-    xb::QmfSynthArgs r = y;
-    r.matrix = s->right; r.mat_stride = 4096; r.states = s->syn_states_r; r.pos = s->syn_pos_r; r.params = s->synp_r;
-    r.pcm = d_time_out + 1; r.gate = s->ps_done;
-    CK(xb::launch_qmf_synth_hq(r, ctx->num_sms, st), "launch qmf_synth_hq_kernel (right)");
-    ctx->launches += 3;
-  } else {
-    y.ch_fac = 1;
-    CK(xb::launch_qmf_synth_hq(y, ctx->num_sms, st), "launch qmf_synth_hq_kernel");
-    ctx->launches += 1;
+  size_t o = 0;
+  buf[0] = 0;
+  for (int k = 0; k < n; k++) {
+    int w = snprintf(buf + o, buf_bytes - o, "%s:%.6f:%d;", names[k], ms[k], cnt[k]);
+    if (w < 0 || (size_t)w >= buf_bytes - o) break;
+    o += (size_t)w;
   }
   return XAAC_B200_OK;
 }

@@ -112,3 +112,19 @@ def imdct_process_host(ctx, state, spec_coeff, ics, out_samples, qshift_adj, ch_
         ctx.handle, state._h, _ptr(spec_coeff), _ptr(ics), _ptr(out_samples), _ptr(qshift_adj), int(ch_fac))
     ctx.check(rc, "xaac_b200_imdct_process_host")
     return out_samples, qshift_adj
+
+
+def imdct_out_to_pcm16(ctx, samples, qshift_adj, mode=0, out=None, stream=None):
+    """WORD32 IMDCT output [n,1024] -> PCM16 [n,1024].  mode 0: SBR hand-over of ixheaacd_allocate_sbr_scr
+    (decoder/ixheaacd_api.c:337-370); mode 1: AAC-LC output (ixheaacd_scale_adjust + round16, api.c:3676-3681)."""
+    n = samples.shape[0]
+    _chk(samples, torch.int32, (n, 1024), "samples", "cuda")
+    _chk(qshift_adj, torch.int8, (n,), "qshift_adj", "cuda")
+    if out is None:
+        out = torch.empty((n, 1024), dtype=torch.int16, device=samples.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(samples.device)
+    rc = ctx._lib.xaac_b200_imdct_out_to_pcm16_dev(ctx.handle, _ptr(samples), _ptr(qshift_adj), _ptr(out), n, int(mode),
+                                                  ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_imdct_out_to_pcm16_dev")
+    return out

@@ -123,3 +123,18 @@ def sbr_dec(ctx, state, side, time_in, time_out=None, err=None, stream=None):
                                           ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_sbr_dec_hq_dev")
     return time_out, err
+
+
+def heaac_frame_host(ctx, imdct_state, sbr_state, spec_coeff, ics, side, pcm, err=None):
+    """One HE-AAC frame per unit from host buffers (IMDCT + hand-over + SBR stage, chunked / pipelined inside the
+    library; both states stay in HBM).  spec_coeff int32 [n,1024], ics uint8 [n,2], side int16 [n,1232] and pcm int16
+    [n,2048] / [n,2048,2] are CPU tensors (pinned recommended); imdct_state is an ImdctHostState."""
+    n = sbr_state.n_units
+    _chk(spec_coeff, torch.int32, (n, 1024), "spec_coeff", "cpu")
+    _chk(ics, torch.uint8, (n, 2), "ics", "cpu")
+    _chk(side, torch.int16, (n, SIDE_WORDS), "side", "cpu")
+    _chk(pcm, torch.int16, (n, 2048, 2) if sbr_state.with_ps else (n, 2048), "pcm", "cpu")
+    rc = ctx._lib.xaac_b200_heaac_frame_host(ctx.handle, imdct_state._h, sbr_state.handle, _ptr(spec_coeff), _ptr(ics),
+                                            _ptr(side), _ptr(pcm), None if err is None else _ptr(err))
+    ctx.check(rc, "xaac_b200_heaac_frame_host")
+    return pcm

@@ -388,3 +388,64 @@ void ref_ps_apply_frame(const int16_t *side, const int16_t *st, int16_t *ps, con
   }
   pack_ps_state(ps, &c.ps, &c.bank_r, &c.sf_r);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * CPU baseline for the HE-AAC chain (bench.py): n persistent decoder channels, each with its own reference structs,
+ * stepped one frame at a time through the UNMODIFIED reference stages exactly as ixheaacd_dec_execute chains them:
+ * ixheaacd_imdct_process -> the WORD32->WORD16 loop of ixheaacd_allocate_sbr_scr -> ixheaacd_sbr_dec.
+ * Only the per-frame side info is refreshed between steps (the state lives in the reference's own structs).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  ref_sbr_ctx c;
+  WORD32 overlap[512];
+  int32_t prev_shape, prev_seq;
+} ref_chain_unit;
+typedef struct { int n; ref_chain_unit *u; } ref_chain;
+
+void *ref_chain_create(int n, const int16_t *side, const int16_t *st, const int16_t *ps) {
+  ref_chain *h = (ref_chain *)calloc(1, sizeof(ref_chain));
+  h->n = n;
+  h->u = (ref_chain_unit *)calloc((size_t)n, sizeof(ref_chain_unit));
+  if (!h->u) { free(h); return NULL; }
+  for (int i = 0; i < n; i++)
+    unpack_sbr_ctx(&h->u[i].c, side + (size_t)i * XO_SIDE_WORDS, st + (size_t)i * XO_SBR_ST_WORDS,
+                   ps ? ps + (size_t)i * XO_PS_ST_WORDS : NULL);
+  return h;
+}
+void ref_chain_destroy(void *hv) {
+  ref_chain *h = (ref_chain *)hv;
+  if (h) { free(h->u); free(h); }
+}
+/* units [a, b): spec [n][1024] (destroyed), ics [n][2] {window_sequence, window_shape}, side [n][1232],
+ * out [n][2048][2] (stereo) */
+void ref_chain_step(void *hv, int a, int b, int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *out) {
+  ref_chain *h = (ref_chain *)hv;
+  WORD32 tbuf32[1024];
+  WORD16 tbuf[2 * 2048];
+  for (int i = a; i < b; i++) {
+    ref_chain_unit *u = &h->u[i];
+    const int16_t *sd = side + (size_t)i * XO_SIDE_WORDS;
+    int adj = ref_imdct_process(spec + (size_t)i * 1024, u->overlap, &u->prev_shape, &u->prev_seq, ics[2 * i],
+                                ics[2 * i + 1], tbuf32, 1);
+    const int use_ps = sd[XO_SIDE_PS] != 0;
+    const int ch_fac = use_ps ? 2 : 1;
+    for (int k = 0; k < 1024; k++) tbuf[ch_fac * k] = ixheaac_round16(ixheaac_shl32_sat(tbuf32[k], adj));
+    /* refresh the per-frame side info in the persistent structs */
+    ia_freq_band_data_struct *fb = &u->c.fb;
+    ia_sbr_prev_frame_data_struct pv_keep = u->c.pv;
+    unpack_env_prm(sd + XO_SIDE_ENV, &u->c.h, fb, &u->c.fd.f, &u->c.pv);
+    u->c.pv = pv_keep; /* previous-frame data is state, maintained by ixheaacd_sbr_dec itself */
+    const int16_t *hf = sd + XO_SIDE_HF;
+    unpack_hf_settings(hf, &u->c.set);
+    fb->num_if_bands = hf[XO_HF_NUM_IF_BANDS];
+    for (int k = 0; k < MAX_NUM_NOISE_VALUES; k++) u->c.fd.f.sbr_invf_mode[k] = hf[XO_HF_INVF + k];
+    if (use_ps) unpack_side_ps(sd, &u->c.ps);
+    ixheaacd_sbr_dec(&u->c.d, tbuf, &u->c.h, &u->c.fd.f, &u->c.pv, &u->c.ps, &u->c.bank_r, &u->c.sf_r, sd[XO_SIDE_APPLY], 0,
+                     u->c.work, &u->c.tabs, (ixheaacd_misc_tables *)&ixheaacd_str_fft_n_transcendent_tables, ch_fac, NULL,
+                     0, NULL, AOT_SBR, 0, NULL, 0, 0);
+    int16_t *o = out + (size_t)i * 4096;
+    if (use_ps) memcpy(o, tbuf, 4096 * sizeof(int16_t));
+    else for (int k = 0; k < 2048; k++) { o[2 * k] = tbuf[k]; o[2 * k + 1] = tbuf[k]; }
+  }
+}
+int ref_chain_unit_bytes(void) { return (int)sizeof(ref_chain_unit); }

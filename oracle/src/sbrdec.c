@@ -145,3 +145,17 @@ int xo_sbr_dec_hq(const uint8_t *qrom, const uint8_t *env_rom, const uint8_t *mi
   sf[XO_SF_OV_LB] = (i16)save_lb_scale; /* :1308 */
   return 0;
 }
+
+/* Stage glue.  mode 0: the SBR hand-over of ixheaacd_allocate_sbr_scr (decoder/ixheaacd_api.c:337-370),
+ * round16(shl32_sat(x, qshift_adj)); mode 1: the AAC-LC output stage with the peak limiter off — ixheaacd_scale_adjust
+ * (decoder/ixheaacd_peak_limiter.c:324-333, wrapping x * (1 << qshift_adj)) followed by round16
+ * (decoder/ixheaacd_api.c:3676-3681). */
+void xo_imdct_out_to_pcm16(const i32 *in, const int8_t *qshift_adj, i16 *out, int n_units, int mode) {
+  for (int u = 0; u < n_units; u++)
+    for (int i = 0; i < 1024; i++) {
+      i32 x = in[(size_t)u * 1024 + i];
+      int q = qshift_adj[u];
+      x = mode ? (i32)((u32)x * (u32)(1 << q)) : ox_shl32_sat(x, q);
+      out[(size_t)u * 1024 + i] = ox_round16(x);
+    }
+}

@@ -241,4 +241,5 @@ void xo_ps_synth_pair(const uint8_t *qrom, const uint8_t *env_rom, const uint8_t
 int xo_sbr_dec_hq(const uint8_t *qrom, const uint8_t *env_rom, const uint8_t *misc_rom, const uint8_t *ps_rom,
                   const int16_t *side, int16_t *st, int16_t *ps_st, const int16_t *time_in, int ch_in,
                   int16_t *time_out, int16_t *time_out_r, int ch_out, int32_t *scratch);
+void xo_imdct_out_to_pcm16(const int32_t *in, const int8_t *qshift_adj, int16_t *out, int n_units, int mode);
 #endif
