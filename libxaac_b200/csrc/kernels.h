@@ -205,6 +205,7 @@ struct PsArgs {
   const int32_t *err;
   const uint8_t *ps_rom, *env_rom, *misc_rom;
   long long n_units;
+  int rot_nosat = 0;       // 1: no fractional-delay phase factor of the ROM is -32768 (checked by xaac_b200_set_ps_rom)
 };
 cudaError_t launch_ps_frame(const PsArgs &args, int num_sms, cudaStream_t stream);
 

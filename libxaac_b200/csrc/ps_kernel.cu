@@ -30,8 +30,9 @@ constexpr int kPsWarps = 4;
 
 struct PsWarpS {
   int16_t st[kPsDspWords];  // PS state, blob layout (kernels.h kPsSt*)
-  i32 rowL[128], rowR[128]; // the slot being processed: re[64] | im[64]
   i32 hyb[64];              // left_re[16] | left_im[16] | right_re[16] | right_im[16]
+  i32 xs[3][2][44];         // hybrid filter input history: 12 delayed + 32 new samples of QMF bands 0..2 (re, im)
+  i32 hybL[32][21];         // hybrid analysis of all 32 slots: [slot][re 0..9 | im 10..19] (odd row stride: no conflicts)
   int16_t tr[24];           // transient ratio per bin (+ tr[20] = 0)
 };
 
@@ -135,20 +136,13 @@ XB_DEV void filt_2_ch(const i32 *q, i32 *h, const int16_t *p2_6) {
   h[1] = sub_sat(cum0, cum1);
 }
 
-// ps_dec.c:212-234
-XB_DEV i32 divide16_pos(i32 op1, i32 op2) {
+// ps_dec.c:212-234, low 16 bits of the result.  The reference runs a 16-step restoring division on the normalised
+// high halves U = (op1 << n) >> 16, V = (op2 << n) >> 16; for 0 <= op1 < op2 (the only way it is called, :574-579) the
+// quotient bits land in the low half as floor(U * 2^15 / V) (first bit has weight 2^15), which is one 32-bit division.
+XB_DEV i32 divide16_pos_lo(i32 op1, i32 op2) {
   const int nrm = norm32(op2);
-  u32 u = (u32)op1 << nrm, v = (u32)op2 << nrm;
-  u &= 0xffff0000u;
-  v &= 0xffff0000u;
-  if (u != 0) {
-#pragma unroll 1
-    for (int k = 16; k > 0; k--) {
-      if (u >= v) u = ((u - v) << 1) + 1;
-      else u <<= 1;
-    }
-  }
-  return (i32)u;
+  const u32 U = ((u32)op1 << nrm) >> 16, V = ((u32)op2 << nrm) >> 16;
+  return (i32)(((U << 15) / V) & 0xffffu);
 }
 
 // ps_dec.c:677-712
@@ -265,9 +259,87 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
     int16_t *h11v = hv, *h21v = hv + 48, *H11 = hv + 96, *H21 = hv + 144, *d11 = hv + 192, *d21 = hv + 240;
     __syncwarp();
 
+    // ---- hybrid analysis of all 32 slots (hybrid.c:214-285): a 13-tap FIR over time, so the slots are independent:
+    //      lane = slot.  x[t], t = -12..31: 12 delayed samples from the state, then QMF rows 6..37 of bands 0..2 in
+    //      the scale the reference sees them in (pre-shifted rows < 32, ixheaacd_apply_ps' shiftdelay for slots >= 26)
+    for (int i = lane; i < 3 * 2 * 44; i += 32) {
+      const int b = i / 88, c = (i / 44) & 1, j = i % 44;
+      i32 v;
+      if (j < 12) {
+        v = hybq[24 * b + 12 * c + j];
+      } else {
+        const int t = j - 12, l6 = t + 6;
+        v = mat[128 * l6 + 64 * c + b];
+        if (l6 < 32) v = blockshift(v, pre(b, l6));
+        const int sd = t < 26 ? 0 : shiftdelay_late;
+        v = sd < 0 ? shl32(v, -sd) : shr32(v, sd);
+      }
+      w.xs[b][c][j] = v;
+    }
+    __syncwarp();
+    {
+      const int s_ = lane;
+      i32 wre[13], wim[13], hr[6], hi[6];
+#pragma unroll
+      for (int j = 0; j < 13; j++) { wre[j] = w.xs[0][0][s_ + j]; wim[j] = w.xs[0][1][s_ + j]; }
+      filt_8_ch(wre, wim, hr, hi, rom + kPsRomP8_13);
+#pragma unroll
+      for (int q = 0; q < 6; q++) { w.hybL[s_][q] = hr[q]; w.hybL[s_][10 + q] = hi[q]; }
+#pragma unroll
+      for (int b = 1; b < 3; b++) {
+#pragma unroll
+        for (int j = 0; j < 13; j++) { wre[j] = w.xs[b][0][s_ + j]; wim[j] = w.xs[b][1][s_ + j]; }
+        filt_2_ch(wre, hr, rom + kPsRomP2_6);
+        filt_2_ch(wim, hi, rom + kPsRomP2_6);
+        w.hybL[s_][4 + 2 * b] = hr[0]; w.hybL[s_][5 + 2 * b] = hr[1];
+        w.hybL[s_][14 + 2 * b] = hi[0]; w.hybL[s_][15 + 2 * b] = hi[1];
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < 72; i += 32) hybq[i] = w.xs[i / 24][(i / 12) & 1][32 + i % 12];
+    __syncwarp();
+
+    // ---- per-lane constants of the slot loop ----
+    // all-pass decorrelators: lanes 0..9 hybrid sub-subbands, lanes 10..29 QMF bands 3..22
+    const bool ap_act = lane < 30, hy = lane < 10;
+    const int sb = hy ? lane : (ap_act ? lane - 7 : 3);
+    int16_t *ap_dl = hy ? st + kPsStSub + 2 * sb : st + kPsStAp + 2 * sb;
+    const int ap_dl_stride = hy ? 32 : 64;
+    int16_t *ap_q = hy ? st + kPsStSubSer + 2 * sb : st + kPsStSer + 2 * sb;
+    const int ap_q_stride = hy ? 96 : 192, ap_m_stride = hy ? 32 : 64;
+    const int16_t *ff = rom + (hy ? kPsRomFracSub : kPsRomFracQmf) + 2 * sb;
+    const i32 f0r = ff[0], f0i = ff[1];
+    i32 fmr[3], fmi[3], dec[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const int16_t *f = rom + (hy ? kPsRomFracSubSer + 32 * m : kPsRomFracQmfSer + 64 * m) + 2 * sb;
+      fmr[m] = f[0];
+      fmi[m] = f[1];
+      dec[m] = hy ? rom[kPsRomRevDecay + m] : rom[kPsRomDecaySf + 3 * sb + m];
+    }
+    const int trbin = hy ? rom[kPsRomHybToBin + sb] : rom[kPsRomDelayToBin + sb];
+    const int rd0 = rom[kPsRomRevDelay], rd1 = rom[kPsRomRevDelay + 1], rd2 = rom[kPsRomRevDelay + 2];
+    const bool nosat = p.rot_nosat != 0;  // no fractional-delay factor is -32768: the 16x16 rotations cannot saturate
+    auto rotr = [&](i32 r, i32 i, i32 fr, i32 fi) { return sext16((nosat ? r * fr - i * fi : sub_sat(r * fr, i * fi)) >> 15); };
+    auto roti = [&](i32 r, i32 i, i32 fr, i32 fi) { return sext16((nosat ? r * fi + i * fr : add_sat(r * fi, i * fr)) >> 15); };
+    // mixing matrices: lane g < 22 keeps h11/h12/h21/h22 of stereo group g (previous envelope target, interpolated
+    // value, per-slot increment) in registers for the whole frame
+    const int gi = lane < 22 ? lane : 0;
+    i32 hv11 = h11v[2 * gi], hv12 = h11v[2 * gi + 1], hv21 = h21v[2 * gi], hv22 = h21v[2 * gi + 1];
+    i32 H11r = H11[2 * gi], H12r = H11[2 * gi + 1], H21r = H21[2 * gi], H22r = H21[2 * gi + 1];
+    i32 D11r = d11[2 * gi], D12r = d11[2 * gi + 1], D21r = d21[2 * gi], D22r = d21[2 * gi + 1];
+    const int b20 = borders[20], b21 = borders[21], b22 = borders[22];
+    // power terms of the wide parameter bins 14..19 = stereo groups 16..21 (ps_dec.c:535-556): group of band k
+    int gshA = -1, gshB = -1, grpA = -1, grpB = -1;
+    for (int g = 16; g < 22; g++) {
+      if (lane >= borders[g] && lane < borders[g + 1]) { grpA = g - 16; gshA = rom[kPsRomGroupShift + g - 16]; }
+      if (lane + 32 >= borders[g] && lane + 32 < borders[g + 1]) { grpB = g - 16; gshB = rom[kPsRomGroupShift + g - 16]; }
+    }
+    const int shA_ov = pre(lane, 0), shA_lb = pre(lane, 6), shB_ov = pre(lane + 32, 0), shB_lb = pre(lane + 32, 6);
+
 #pragma unroll 1
     for (int slot = 0; slot < 32; slot++) {
-      // ---- ixheaacd_init_rot_env at PS envelope borders ----
+      // ---- ixheaacd_init_rot_env at PS envelope borders (ps_dec.c:714-854): lane = stereo group ----
       if (env < 7 && slot == prm[kPsPrmBorder + env]) {
         if (env == 0) {
           const int usb_prev = ps_usb;
@@ -304,71 +376,58 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
           const i32 ipa = mul32x16(rescale, bpa), ima = mul32x16(rescale, bma);
           const i32 h11 = m16_shl(cos512(ipa, trig), c2), h12 = m16_shl(cos512(ima, trig), c1);
           const i32 h21 = m16_shl(sin512(ipa, trig), c2), h22 = m16_shl(sin512(ima, trig), c1);
-          d11[2 * g] = (int16_t)m16_shl(inv_len, sext16(h11 - h11v[2 * g]));
-          d11[2 * g + 1] = (int16_t)m16_shl(inv_len, sext16(h12 - h11v[2 * g + 1]));
-          d21[2 * g] = (int16_t)m16_shl(inv_len, sext16(h21 - h21v[2 * g]));
-          d21[2 * g + 1] = (int16_t)m16_shl(inv_len, sext16(h22 - h21v[2 * g + 1]));
-          H11[2 * g] = h11v[2 * g]; H11[2 * g + 1] = h11v[2 * g + 1];
-          H21[2 * g] = h21v[2 * g]; H21[2 * g + 1] = h21v[2 * g + 1];
-          h11v[2 * g] = (int16_t)h11; h11v[2 * g + 1] = (int16_t)h12;
-          h21v[2 * g] = (int16_t)h21; h21v[2 * g + 1] = (int16_t)h22;
+          D11r = m16_shl(inv_len, sext16(h11 - hv11));
+          D12r = m16_shl(inv_len, sext16(h12 - hv12));
+          D21r = m16_shl(inv_len, sext16(h21 - hv21));
+          D22r = m16_shl(inv_len, sext16(h22 - hv22));
+          H11r = hv11; H12r = hv12; H21r = hv21; H22r = hv22;
+          hv11 = h11; hv12 = h12; hv21 = h21; hv22 = h22;
         }
         env++;
         __syncwarp();
       }
 
-      // ---- load the left row (pre-shifted) ----
+      // ---- left row (pre-shifted), this slot's hybrid sub-subbands ----
+      i32 lAr, lAi, lBr, lBi;  // bands lane and lane + 32 of the left input
       {
         const i32 *row = mat + 128 * slot;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int k = lane + 32 * h, sh = pre(k, slot);
-          w.rowL[k] = blockshift(row[k], sh);
-          w.rowL[64 + k] = blockshift(row[64 + k], sh);
-        }
+        const int sA = slot < 6 ? shA_ov : shA_lb, sB = slot < 6 ? shB_ov : shB_lb;
+        lAr = blockshift(row[lane], sA);
+        lAi = blockshift(row[64 + lane], sA);
+        lBr = blockshift(row[32 + lane], sB);
+        lBi = blockshift(row[96 + lane], sB);
       }
-      // ---- hybrid analysis of slot + 6 (hybrid.c:214-285): lane b < 3 owns QMF band b ----
-      if (lane < 3) {
-        const int band = lane, l6 = slot + 6;
-        i32 wre[13], wim[13];
-        i32 *bre = hybq + 24 * band, *bim = bre + 12;
-#pragma unroll
-        for (int j = 0; j < 12; j++) { wre[j] = bre[j]; wim[j] = bim[j]; }
-        i32 tr_ = mat[128 * l6 + band], ti_ = mat[128 * l6 + 64 + band];
-        if (l6 < 32) { const int sh = pre(band, l6); tr_ = blockshift(tr_, sh); ti_ = blockshift(ti_, sh); }
-        const int sd = slot < 26 ? 0 : shiftdelay_late;
-        if (sd < 0) { tr_ = shl32(tr_, -sd); ti_ = shl32(ti_, -sd); }
-        else { tr_ = shr32(tr_, sd); ti_ = shr32(ti_, sd); }
-        wre[12] = tr_;
-        wim[12] = ti_;
-#pragma unroll
-        for (int j = 0; j < 12; j++) { bre[j] = wre[j + 1]; bim[j] = wim[j + 1]; }
-        if (band == 0) {
-          filt_8_ch(wre, wim, w.hyb, w.hyb + 16, rom + kPsRomP8_13);
-        } else {
-          const int off = 6 + 2 * (band - 1);
-          filt_2_ch(wre, w.hyb + off, rom + kPsRomP2_6);
-          filt_2_ch(wim, w.hyb + 16 + off, rom + kPsRomP2_6);
-        }
+      if (lane < 10) {
+        w.hyb[lane] = w.hybL[slot][lane];
+        w.hyb[16 + lane] = w.hybL[slot][10 + lane];
       }
-      __syncwarp();
       const i32 *lre = w.hyb, *lim = w.hyb + 16;
       i32 *rre = w.hyb + 32, *rim = w.hyb + 48;
 
-      // ---- power per bin and transient ratio (ps_dec.c:482-590): lane = bin ----
+      // ---- power per parameter bin (ps_dec.c:482-556).  All terms are >= 0, so the reference's running add32_sat
+      //      equals min(MAX_32, exact sum); the exact group sums stay below 2^32 after the group shifts ----
+      const u32 tA = min((u32)pw(lAr) + (u32)pw(lAi), 0x7fffffffu), tB = min((u32)pw(lBr) + (u32)pw(lBi), 0x7fffffffu);
+      u32 gsum[6];
+#pragma unroll
+      for (int g = 0; g < 6; g++) {
+        const u32 v = ((grpA == g && lane < ps_usb) ? (tA >> gshA) : 0u) + ((grpB == g && lane + 32 < ps_usb) ? (tB >> gshB) : 0u);
+        gsum[g] = __reduce_add_sync(full, v);
+      }
+      __syncwarp();
+      // bins 8..13 are QMF bands 3..8: fetch from the owning lane
+      const u32 tq = __shfl_sync(full, tA, (lane >= 8 && lane < 14) ? lane - 5 : 0);
       if (lane < 20) {
         const int bin = lane;
         i32 pwr;
         if (bin == 0) pwr = add_sat(add_sat(add_sat(pw(lre[0]), pw(lim[0])), pw(lre[5])), pw(lim[5]));
         else if (bin == 1) pwr = add_sat(add_sat(add_sat(pw(lre[4]), pw(lim[4])), pw(lre[1])), pw(lim[1]));
-        else if (bin < 8) { const int sb = borders[bin + 2]; pwr = add_sat(pw(lre[sb]), pw(lim[sb])); }
-        else if (bin < 14) { const int sb = bin - 5; pwr = add_sat(pw(w.rowL[sb]), pw(w.rowL[64 + sb])); }
+        else if (bin < 8) { const int s_ = borders[bin + 2]; pwr = add_sat(pw(lre[s_]), pw(lim[s_])); }
+        else if (bin < 14) pwr = (i32)tq;
         else {
-          const int gr = bin + 2;
-          const int mxs = min(ps_usb, (int)borders[gr + 1]), gs = rom[kPsRomGroupShift + gr - 16];
-          pwr = 0;
-          for (int sb = borders[gr]; sb < mxs; sb++)
-            pwr = add_sat(pwr, add_sat(pw(w.rowL[sb]), pw(w.rowL[64 + sb])) >> gs);
+          u32 v = gsum[0];
+#pragma unroll
+          for (int g = 1; g < 6; g++) if (bin - 14 == g) v = gsum[g];
+          pwr = (i32)min(v, 0x7fffffffu);
         }
         i32 pv = shl32(pwr, 1);
         if (pv < 0) pv = 0;
@@ -380,140 +439,159 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
         const i32 nrg = add_sat(lsl(mul32x16(peak[20 + bin], 0x6000), 1), pv >> 2);
         peak[20 + bin] = nrg;
         pd = add_sat(pd, pd >> 1);
-        w.tr[bin] = pd <= nrg ? (int16_t)0x7fff : (int16_t)divide16_pos(nrg, pd);
+        w.tr[bin] = pd <= nrg ? (int16_t)0x7fff : (int16_t)divide16_pos_lo(nrg, pd);
       } else if (lane == 20) {
         w.tr[20] = 0;
       }
       __syncwarp();
 
-      // ---- all-pass decorrelators: lanes 0..9 hybrid sub-subbands, lanes 10..29 QMF bands 3..22 ----
-      if (lane < 30) {
-        const bool hy = lane < 10;
-        const int sb = hy ? lane : lane - 7;
-        int16_t *dl = hy ? st + kPsStSub + 32 * d_idx + 2 * sb : st + kPsStAp + 64 * d_idx + 2 * sb;
-        const int16_t *fac = rom + (hy ? kPsRomFracSub : kPsRomFracQmf) + 2 * sb;
+      // ---- all-pass decorrelators (ps_dec.c:236-448) ----
+      i32 apr = 0, api = 0;  // decorrelated signal of QMF band sb (lanes 10..29)
+      const i32 qin_r = __shfl_sync(full, lAr, sb), qin_i = __shfl_sync(full, lAi, sb);  // left input of QMF band sb
+      if (ap_act) {
+        int16_t *dl = ap_dl + ap_dl_stride * d_idx;
         const i32 r0 = dl[0], i0 = dl[1];
-        i32 rin = rot_re(r0, i0, fac), iin = rot_im(r0, i0, fac);
-        const i32 inr = hy ? lre[sb] : w.rowL[sb], ini = hy ? lim[sb] : w.rowL[64 + sb];
+        i32 rin = rotr(r0, i0, f0r, f0i), iin = roti(r0, i0, f0r, f0i);
+        const i32 inr = hy ? lre[sb] : qin_r, ini = hy ? lim[sb] : qin_i;
         dl[0] = (int16_t)round16(inr);
         dl[1] = (int16_t)round16(ini);
 #pragma unroll
         for (int m = 0; m < 3; m++) {
           const int di = m == 0 ? d_ser0 : (m == 1 ? d_ser1 : d_ser2);
-          int16_t *q = hy ? st + kPsStSubSer + 96 * di + 32 * m + 2 * sb : st + kPsStSer + 192 * di + 64 * m + 2 * sb;
-          const int16_t *f = rom + (hy ? kPsRomFracSubSer + 32 * m : kPsRomFracQmfSer + 64 * m) + 2 * sb;
-          const i32 decay = hy ? rom[kPsRomRevDecay + m] : rom[kPsRomDecaySf + 3 * sb + m];
+          int16_t *q = ap_q + ap_q_stride * di + ap_m_stride * m;
           const i32 q0 = q[0], q1 = q[1];
-          i32 rt = rot_re(q0, q1, f), it = rot_im(q0, q1, f);
-          rt = sext16(rt - m16_shl(rin, decay));
-          it = sext16(it - m16_shl(iin, decay));
-          q[0] = (int16_t)(rin + m16_shl(rt, decay));
-          q[1] = (int16_t)(iin + m16_shl(it, decay));
+          i32 rt = rotr(q0, q1, fmr[m], fmi[m]), it = roti(q0, q1, fmr[m], fmi[m]);
+          rt = sext16(rt - m16_shl(rin, dec[m]));
+          it = sext16(it - m16_shl(iin, dec[m]));
+          q[0] = (int16_t)(rin + m16_shl(rt, dec[m]));
+          q[1] = (int16_t)(iin + m16_shl(it, dec[m]));
           rin = rt;
           iin = it;
         }
-        const i32 t = w.tr[hy ? rom[kPsRomHybToBin + sb] : rom[kPsRomDelayToBin + sb]];
-        const i32 outr = shl32(rin * t, 1), outi = shl32(iin * t, 1);
-        if (hy) { rre[sb] = outr; rim[sb] = outi; }
-        else { w.rowR[sb] = outr; w.rowR[64 + sb] = outi; }
+        const i32 t = w.tr[trbin];
+        apr = shl32(rin * t, 1);
+        api = shl32(iin * t, 1);
+        if (hy) { rre[sb] = apr; rim[sb] = api; }
       }
-      __syncwarp();
-      // ---- plain delays (ps_dec.c:596-645) and clearing above usb ----
+      // right input of bands lane / lane + 32 before the rotation: all-pass output (bands 3..22, from lane band + 7),
+      // plain delays (ps_dec.c:596-645) or zero at and above usb
+      i32 rAr = __shfl_sync(full, apr, min(lane + 7, 29)), rAi = __shfl_sync(full, api, min(lane + 7, 29));
+      i32 rBr = 0, rBi = 0;
       {
-        const int b20 = borders[20], b21 = borders[21], b22 = borders[22];
         const int us = sext16(ps_usb);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int k = lane + 32 * h;
-          if (k >= b20 && k < min(us, b21)) {
-            int16_t *d = st + kPsStLd + 24 * d_long + 2 * (k - b20);
-            const i32 r = d[0], i = d[1], t = w.tr[18];
-            d[0] = (int16_t)round16(w.rowL[k]);
-            d[1] = (int16_t)round16(w.rowL[64 + k]);
-            w.rowR[k] = shl32(r * t, 1);
-            w.rowR[64 + k] = shl32(i * t, 1);
-          } else if (k >= b21 && k < min(us, b22)) {
-            int16_t *d = st + kPsStSd + 2 * (k - b21);
-            const i32 r = d[0], i = d[1], t = w.tr[19];
-            d[0] = (int16_t)round16(w.rowL[k]);
-            d[1] = (int16_t)round16(w.rowL[64 + k]);
-            w.rowR[k] = shl32(r * t, 1);
-            w.rowR[64 + k] = shl32(i * t, 1);
-          }
-          if (k >= ps_usb) { w.rowR[k] = 0; w.rowR[64 + k] = 0; }
+        if (lane < 3 || lane >= 23) { rAr = 0; rAi = 0; }
+        if (lane >= b20 && lane < min(us, b21)) {
+          int16_t *d = st + kPsStLd + 24 * d_long + 2 * (lane - b20);
+          const i32 r = d[0], i = d[1], t = w.tr[18];
+          d[0] = (int16_t)round16(lAr);
+          d[1] = (int16_t)round16(lAi);
+          rAr = shl32(r * t, 1);
+          rAi = shl32(i * t, 1);
         }
+        const int kB = lane + 32;
+        if (kB >= b20 && kB < min(us, b21)) {
+          int16_t *d = st + kPsStLd + 24 * d_long + 2 * (kB - b20);
+          const i32 r = d[0], i = d[1], t = w.tr[18];
+          d[0] = (int16_t)round16(lBr);
+          d[1] = (int16_t)round16(lBi);
+          rBr = shl32(r * t, 1);
+          rBi = shl32(i * t, 1);
+        } else if (kB >= b21 && kB < min(us, b22)) {
+          int16_t *d = st + kPsStSd + 2 * (kB - b21);
+          const i32 r = d[0], i = d[1], t = w.tr[19];
+          d[0] = (int16_t)round16(lBr);
+          d[1] = (int16_t)round16(lBi);
+          rBr = shl32(r * t, 1);
+          rBi = shl32(i * t, 1);
+        }
+        if (lane >= ps_usb) { rAr = 0; rAi = 0; }
+        if (kB >= ps_usb) { rBr = 0; rBi = 0; }
       }
       d_long = sext16(d_long + 1);
       if (d_long >= 14) d_long = 0;
       d_idx = d_idx + 1 >= 2 ? 0 : d_idx + 1;
-      d_ser0 = d_ser0 + 1 >= rom[kPsRomRevDelay] ? 0 : d_ser0 + 1;
-      d_ser1 = d_ser1 + 1 >= rom[kPsRomRevDelay + 1] ? 0 : d_ser1 + 1;
-      d_ser2 = d_ser2 + 1 >= rom[kPsRomRevDelay + 2] ? 0 : d_ser2 + 1;
+      d_ser0 = d_ser0 + 1 >= rd0 ? 0 : d_ser0 + 1;
+      d_ser1 = d_ser1 + 1 >= rd1 ? 0 : d_ser1 + 1;
+      d_ser2 = d_ser2 + 1 >= rd2 ? 0 : d_ser2 + 1;
+
       // ---- rotation (ps_dec.c:856-991) ----
-      for (int j = lane; j < 44; j += 32) {
-        H11[j] = (int16_t)(H11[j] + d11[j]);
-        H21[j] = (int16_t)(H21[j] + d21[j]);
-      }
+      H11r = sext16(H11r + D11r); H12r = sext16(H12r + D12r); H21r = sext16(H21r + D21r); H22r = sext16(H22r + D22r);
       __syncwarp();
-      if (lane < 10) {
-        const int s = lane;
-        const i32 a = add_sat(mul32x16(lre[s], H11[2 * s]), mul32x16(rre[s], H21[2 * s]));
-        const i32 b = add_sat(mul32x16(lim[s], H11[2 * s]), mul32x16(rim[s], H21[2 * s]));
-        const i32 c = add_sat(mul32x16(lre[s], H11[2 * s + 1]), mul32x16(rre[s], H21[2 * s + 1]));
-        const i32 d = add_sat(mul32x16(lim[s], H11[2 * s + 1]), mul32x16(rim[s], H21[2 * s + 1]));
-        w.hyb[s] = shl32(a, 2);
-        w.hyb[16 + s] = shl32(b, 2);
-        w.hyb[32 + s] = shl32(c, 2);
-        w.hyb[48 + s] = shl32(d, 2);
+      if (lane < 10) {  // hybrid sub-subband s = stereo group s
+        const int s_ = lane;
+        const i32 a = add_sat(mul32x16(lre[s_], H11r), mul32x16(rre[s_], H21r));
+        const i32 b = add_sat(mul32x16(lim[s_], H11r), mul32x16(rim[s_], H21r));
+        const i32 c = add_sat(mul32x16(lre[s_], H12r), mul32x16(rre[s_], H22r));
+        const i32 d = add_sat(mul32x16(lim[s_], H12r), mul32x16(rim[s_], H22r));
+        w.hyb[s_] = shl32(a, 2);
+        w.hyb[16 + s_] = shl32(b, 2);
+        w.hyb[32 + s_] = shl32(c, 2);
+        w.hyb[48 + s_] = shl32(d, 2);
       }
-      // QMF bands 3..usb-1
+      // QMF bands 3..usb-1.  as_built: the reference's x86-64 gcc build reads its type-punned coefficient copy as
+      // zero (see apply_rot in oracle/src/ps.c), so both outputs are 0 there.
+      i32 oLAr = lAr, oLAi = lAi, oLBr = lBr, oLBi = lBi, oRAr = rAr, oRAi = rAi, oRBr = rBr, oRBi = rBi;
+      if (as_built) {
+        if (lane >= 3 && lane < ps_usb) { oLAr = oLAi = oRAr = oRAi = 0; }
+        if (lane + 32 < ps_usb) { oLBr = oLBi = oRBr = oRBi = 0; }
+      } else {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int k = lane + 32 * h;
-        if (k >= 3 && k < ps_usb) {
-          i32 h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-          if (!as_built) {  // see apply_rot in oracle/src/ps.c: the reference's x86-64 gcc build reads these as zero
-            int g = 10;
-            while (g < 21 && k >= borders[g + 1]) g++;
-            if (k >= borders[g] && k < min(ps_usb, (int)borders[g + 1])) {
-              h0 = H11[2 * g]; h1 = H11[2 * g + 1]; h2 = H21[2 * g]; h3 = H21[2 * g + 1];
-            }
+        for (int h = 0; h < 2; h++) {
+          const int k = lane + 32 * h;
+          int g = 10;
+          while (g < 21 && k >= borders[g + 1]) g++;
+          const i32 h0 = __shfl_sync(full, H11r, g), h1 = __shfl_sync(full, H12r, g);
+          const i32 h2 = __shfl_sync(full, H21r, g), h3 = __shfl_sync(full, H22r, g);
+          if (k >= 3 && k < ps_usb) {
+            const i32 lr = h ? lBr : lAr, li = h ? lBi : lAi, rr = h ? rBr : rAr, ri = h ? rBi : rAi;
+            const i32 a = shl32(add_sat(mul32x16(lr, h0), mul32x16(rr, h2)), 2);
+            const i32 b = shl32(add_sat(mul32x16(li, h0), mul32x16(ri, h2)), 2);
+            const i32 c = shl32(add_sat(mul32x16(lr, h1), mul32x16(rr, h3)), 2);
+            const i32 d = shl32(add_sat(mul32x16(li, h1), mul32x16(ri, h3)), 2);
+            if (h) { oLBr = a; oLBi = b; oRBr = c; oRBi = d; }
+            else { oLAr = a; oLAi = b; oRAr = c; oRAi = d; }
           }
-          const i32 lr = w.rowL[k], li = w.rowL[64 + k], rr = w.rowR[k], ri = w.rowR[64 + k];
-          w.rowL[k] = shl32(add_sat(mul32x16(lr, h0), mul32x16(rr, h2)), 2);
-          w.rowL[64 + k] = shl32(add_sat(mul32x16(li, h0), mul32x16(ri, h2)), 2);
-          w.rowR[k] = shl32(add_sat(mul32x16(lr, h1), mul32x16(rr, h3)), 2);
-          w.rowR[64 + k] = shl32(add_sat(mul32x16(li, h1), mul32x16(ri, h3)), 2);
         }
       }
       __syncwarp();
-      if (lane < 3) {  // fold the hybrid sub-subbands back into QMF bands 0..2 (resolutions 8->6, 2, 2)
-        const int s = lane, o = s == 0 ? 0 : 6 + 2 * (s - 1), cnt = s == 0 ? 6 : 2;
-        i32 a = w.hyb[o], b = w.hyb[16 + o], c = w.hyb[32 + o], d = w.hyb[48 + o];
-        for (int q = 1; q < cnt; q++) {
-          a = add_sat(a, w.hyb[o + q]);
-          b = add_sat(b, w.hyb[16 + o + q]);
-          c = add_sat(c, w.hyb[32 + o + q]);
-          d = add_sat(d, w.hyb[48 + o + q]);
-        }
-        w.rowL[s] = a; w.rowL[64 + s] = b; w.rowR[s] = c; w.rowR[64 + s] = d;
+      // fold the hybrid sub-subbands back into QMF bands 0..2 (resolutions 8 -> 6, 2, 2): lane = 4 * band + component
+      i32 fold = 0;
+      if (lane < 12) {
+        const int s_ = lane >> 2, c = lane & 3, o = s_ == 0 ? 0 : 6 + 2 * (s_ - 1), cnt = s_ == 0 ? 6 : 2;
+        fold = w.hyb[16 * c + o];
+        for (int q = 1; q < cnt; q++) fold = add_sat(fold, w.hyb[16 * c + o + q]);
       }
-      __syncwarp();
+      {
+        const int src = 4 * min(lane, 2);
+        const i32 f0 = __shfl_sync(full, fold, src), f1 = __shfl_sync(full, fold, src + 1);
+        const i32 f2 = __shfl_sync(full, fold, src + 2), f3 = __shfl_sync(full, fold, src + 3);
+        if (lane < 3) { oLAr = f0; oLAi = f1; oRAr = f2; oRAi = f3; }
+      }
       // ---- ixheaacd_shiftrountine on the left row, store both rows ----
       {
+        auto cs = [&](i32 v) {
+          if (common_shift < 0) return v >> min(-common_shift, 31);
+          if (common_shift > 0) return shl32_sat(v, min(common_shift, 31));
+          return v;
+        };
         i32 *lrow = mat + 128 * slot, *rrow = right + 128 * slot;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int k = lane + 32 * q;
-          i32 v = w.rowL[k];
-          if (common_shift < 0) v = v >> min(-common_shift, 31);
-          else if (common_shift > 0) v = shl32_sat(v, min(common_shift, 31));
-          lrow[k] = v;
-          rrow[k] = w.rowR[k];
-        }
+        lrow[lane] = cs(oLAr);
+        lrow[32 + lane] = cs(oLBr);
+        lrow[64 + lane] = cs(oLAi);
+        lrow[96 + lane] = cs(oLBi);
+        rrow[lane] = oRAr;
+        rrow[32 + lane] = oRBr;
+        rrow[64 + lane] = oRAi;
+        rrow[96 + lane] = oRBi;
       }
       __syncwarp();
     }
+    if (lane < 22) {  // mixing-matrix state back to shared memory
+      h11v[2 * lane] = (int16_t)hv11; h11v[2 * lane + 1] = (int16_t)hv12; h21v[2 * lane] = (int16_t)hv21; h21v[2 * lane + 1] = (int16_t)hv22;
+      H11[2 * lane] = (int16_t)H11r; H11[2 * lane + 1] = (int16_t)H12r; H21[2 * lane] = (int16_t)H21r; H21[2 * lane + 1] = (int16_t)H22r;
+      d11[2 * lane] = (int16_t)D11r; d11[2 * lane + 1] = (int16_t)D12r; d21[2 * lane] = (int16_t)D21r; d21[2 * lane + 1] = (int16_t)D22r;
+    }
+    __syncwarp();
 
     if (lane == 0) {
       p.ps_done[u] = 1;

@@ -25,6 +25,7 @@ struct xaac_b200_ctx {
   bool have_env_rom = false;
   uint8_t *d_rom_ps = nullptr;    // leading part of ia_ps_tables_struct
   bool have_ps_rom = false;
+  int ps_rot_nosat = 0;           // no fractional-delay phase factor equals -32768 (16x16 rotations cannot saturate)
   char err[256] = {0};
   // optional per-kernel timing (CUDA events on the launching stream around every kernel)
   static constexpr int kMaxTicks = 8192;
@@ -566,6 +567,13 @@ int32_t xaac_b200_set_ps_rom(xaac_b200_ctx *ctx, const void *ps_tables, size_t b
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (!ctx->d_rom_ps) CK(cudaMalloc((void **)&ctx->d_rom_ps, xb::kPsRomBytes + 50), "cudaMalloc(ps rom)");
   CK(cudaMemcpy(ctx->d_rom_ps, ps_tables, xb::kPsRomBytes, cudaMemcpyHostToDevice), "H2D ps rom");
+  {
+    const int16_t *t = (const int16_t *)ps_tables;
+    int ok = 1;
+    for (int i = xb::kPsRomFracQmf; i < xb::kPsRomScale; i++)
+      if (t[i] == -32768) ok = 0;
+    ctx->ps_rot_nosat = ok;
+  }
   ctx->have_ps_rom = true;
   return XAAC_B200_OK;
 }
@@ -718,7 +726,7 @@ static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long lo
     xb::PsArgs a;
     a.side = d_side; a.matrix = g.matrix; a.right = s->right + u0 * 4096; a.ps_state = s->ps + u0 * xb::kPsDspWords;
     a.sf = g.sf; a.sf_r = s->sf_r + u0 * 8; a.synp = g.synp; a.synp_r = s->synp_r + u0 * 8; a.ps_done = s->ps_done + u0;
-    a.err = err; a.ps_rom = ctx->d_rom_ps; a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n;
+    a.err = err; a.ps_rom = ctx->d_rom_ps; a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n; a.rot_nosat = ctx->ps_rot_nosat;
     LAUNCH("ps_frame_kernel", st, xb::launch_ps_frame(a, ctx->num_sms, st));
     y.ch_fac = 2;
     y.pcm_unit_stride = 4096;

@@ -164,6 +164,13 @@ class Oracle:
         outs = [self.sbr_dec(side[u], st[u], ps[u], time_in[u]) for u in range(len(side))]
         return tuple(np.stack([o[k] for o in outs]) for k in range(4)) + (np.array([o[4] for o in outs], np.int32),)
 
+    def imdct_out_to_pcm16(self, samples, qshift_adj, mode):
+        x = np.ascontiguousarray(samples, np.int32)
+        q = np.ascontiguousarray(qshift_adj, np.int8)
+        out = np.zeros(x.shape, np.int16)
+        self.lib.xo_imdct_out_to_pcm16(P(x), P(q), P(out), int(x.shape[0]), int(mode))
+        return out
+
     def ps_apply_frame(self, ps_prm, ps, m, usb, shiftdelay_late, common_shift, as_built):
         p = np.ascontiguousarray(ps, np.int16).copy()
         mm = np.ascontiguousarray(m, np.int32).copy()

@@ -1,0 +1,85 @@
+"""GPU parity tests for the stage glue and the host-buffer HE-AAC frame entry point (IMDCT -> PCM16 hand-over -> SBR
+stage with PS), against the chained CPU oracles."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_util
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "sbrdec_tapped.npz")
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_imdct_out_to_pcm16(ctx, oracle, mode):
+    import torch
+    import libxaac_b200 as xb
+    rng = np.random.default_rng(3 + mode)
+    n = 257
+    s = rng.integers(8, 32, (n, 1))
+    x = ((rng.random((n, 1024)) * 2 - 1) * 2.0 ** s).astype(np.int64).clip(-2 ** 31, 2 ** 31 - 1).astype(np.int32)
+    x[0, :4] = (2 ** 31 - 1, -2 ** 31, 0x7FFF8000, -1)
+    q = rng.integers(1, 3, n).astype(np.int8)
+    got = xb.imdct_out_to_pcm16(ctx, torch.from_numpy(x).cuda(), torch.from_numpy(q).cuda(), mode).cpu().numpy()
+    assert np.array_equal(got, oracle.imdct_out_to_pcm16(x, q, mode))
+
+
+def test_heaac_frame_host_matches_chained_oracles(ctx, oracle):
+    """3 consecutive frames for 300 streams (chunked inside the library when n > 4096 is not needed here; the chunk path
+    is covered by n = 5000 below with a cheaper check)"""
+    import torch
+    import libxaac_b200 as xb
+    g = np.load(GOLD)
+    n, frames = 300, 3
+    base = 1
+    rng = np.random.default_rng(21)
+    ist = xb.ImdctHostState(ctx, n)
+    sst = xb.SbrState(ctx, n, with_ps=True)
+    st = np.tile(g["st_in"][base], (n, 1))
+    ps = np.tile(g["ps_in"][base], (n, 1))
+    sst.upload(st, ps)
+    ovl = np.zeros((n, 512), np.int32)
+    wstate = np.zeros((n, 2), np.uint8)
+    for f in range(frames):
+        s = rng.integers(10, 22, (n, 1))
+        spec = ((rng.random((n, 1024)) * 2 - 1) * 2.0 ** s).astype(np.int64).astype(np.int32)
+        ics = np.zeros((n, 2), np.uint8)
+        ics[:, 1] = rng.integers(0, 2, n)
+        side = np.ascontiguousarray(g["side"][base + (np.arange(n) + f) % 11])
+        pcm = torch.zeros((n, 2048, 2), dtype=torch.int16)
+        err = torch.zeros((n,), dtype=torch.int32)
+        xb.heaac_frame_host(ctx, ist, sst, torch.from_numpy(spec), torch.from_numpy(ics), torch.from_numpy(side), pcm, err)
+        out32, ovl, wstate, adj = oracle.imdct_batch(spec, ovl, wstate, ics)
+        p16 = oracle.imdct_out_to_pcm16(out32, adj, 0)
+        st, ps, ol, orr, eerr = oracle.sbr_dec_batch(side, st, ps, p16)
+        assert np.array_equal(err.numpy(), eerr)
+        assert np.array_equal(pcm.numpy()[:, :, 0], ol), f"frame {f}: left PCM"
+        assert np.array_equal(pcm.numpy()[:, :, 1], orr), f"frame {f}: right PCM"
+    st2, ps2 = sst.download()
+    assert np.array_equal(st2, st) and np.array_equal(ps2, ps)
+    ist.close()
+    sst.close()
+
+
+def test_heaac_frame_host_chunked_is_unit_independent(ctx):
+    """n = 5000 > one 4096-unit chunk: identical streams must produce identical PCM in every chunk"""
+    import torch
+    import libxaac_b200 as xb
+    g = np.load(GOLD)
+    n = 5000
+    ist = xb.ImdctHostState(ctx, n)
+    sst = xb.SbrState(ctx, n, with_ps=True)
+    sst.upload(np.tile(g["st_in"][1], (n, 1)), np.tile(g["ps_in"][1], (n, 1)))
+    rng = np.random.default_rng(4)
+    spec1 = ((rng.random(1024) * 2 - 1) * 2.0 ** 18).astype(np.int64).astype(np.int32)
+    spec = torch.from_numpy(np.tile(spec1, (n, 1)))
+    ics = torch.zeros((n, 2), dtype=torch.uint8)
+    side = torch.from_numpy(np.tile(g["side"][1], (n, 1)))
+    pcm = torch.zeros((n, 2048, 2), dtype=torch.int16)
+    xb.heaac_frame_host(ctx, ist, sst, spec, ics, side, pcm)
+    p = pcm.numpy()
+    assert np.abs(p[0].astype(np.int32)).max() > 0
+    assert (p == p[0]).all()
+    ist.close()
+    sst.close()
