@@ -48,6 +48,14 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic():
+    """per-unit DRAM bytes of each kernel measured by ncu (profiles/r1_traffic.json); bench.py does not run ncu"""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    return {k: v for k, v in json.load(open(p)).items() if isinstance(v, dict)}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -642,7 +650,9 @@ def main():
                     "timer": "host wall clock around the synchronous host-buffer C-ABI call"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "kernel": stg["kernel"], "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (ncu_traffic().get(stg["kernel"], {}).get("bytes_per_unit", 0) * n_units) or None,
+                         "traffic_source": ncu_traffic().get(stg["kernel"], {}).get("source"), "peak_source": peak_src,
                          "bytes_per_unit": stg["bytes_per_unit"], "units_per_launch": n_units,
                          "launch_ms": kernel_ms},
         }

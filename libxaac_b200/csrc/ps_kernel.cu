@@ -419,9 +419,12 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       if (lane < 20) {
         const int bin = lane;
         i32 pwr;
-        if (bin == 0) pwr = add_sat(add_sat(add_sat(pw(lre[0]), pw(lim[0])), pw(lre[5])), pw(lim[5]));
-        else if (bin == 1) pwr = add_sat(add_sat(add_sat(pw(lre[4]), pw(lim[4])), pw(lre[1])), pw(lim[1]));
-        else if (bin < 8) { const int s_ = borders[bin + 2]; pwr = add_sat(pw(lre[s_]), pw(lim[s_])); }
+        if (bin < 8) {  // hybrid sub-subbands: bins 0 / 1 pair (0, 5) / (4, 1), bins 2..7 one sub-subband each
+          const int s1 = bin == 0 ? 0 : (bin == 1 ? 4 : (int)borders[bin + 2]), s2 = bin == 0 ? 5 : 1;
+          pwr = add_sat(pw(lre[s1]), pw(lim[s1]));
+          const i32 p2 = add_sat(add_sat(pwr, pw(lre[s2])), pw(lim[s2]));
+          if (bin < 2) pwr = p2;
+        }
         else if (bin < 14) pwr = (i32)tq;
         else {
           u32 v = gsum[0];
