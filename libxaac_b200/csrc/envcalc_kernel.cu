@@ -160,10 +160,15 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
   {
     const int16_t *e = reinterpret_cast<const int16_t *>(p.env_rom);
     const int16_t *m = reinterpret_cast<const int16_t *>(p.misc_rom);
+#pragma unroll 1
     for (int i = threadIdx.x; i < 8; i += blockDim.x) rom.lim_gains[i] = e[i];
+#pragma unroll 1
     for (int i = threadIdx.x; i < 4; i += blockDim.x) rom.smooth[i] = e[kERomSmooth / 2 + i];
+#pragma unroll 1
     for (int i = threadIdx.x; i < 49; i += blockDim.x) rom.inv_int[i] = e[kERomInvInt / 2 + i];
+#pragma unroll 1
     for (int i = threadIdx.x; i < 256; i += blockDim.x) rom.inv_table[i] = m[kMRomInvTable / 2 + i];
+#pragma unroll 1
     for (int i = threadIdx.x; i < 257; i += blockDim.x) rom.sqrt_table[i] = m[kMRomSqrtTable / 2 + i];
   }
   __syncthreads();
@@ -179,10 +184,14 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
     }
     {
       const i32 *src = reinterpret_cast<const i32 *>(p.params + u * p.prm_stride);
+#pragma unroll 1
       for (int i = lane; i < kEnvPrmWords / 2; i += 32) reinterpret_cast<i32 *>(w.prm)[i] = __ldg(src + i);
       const i32 *ss = reinterpret_cast<const i32 *>(p.state + u * kEnvStWords);
+#pragma unroll 1
       for (int i = lane; i < kEnvStWords / 2; i += 32) reinterpret_cast<i32 *>(w.st)[i] = ss[i];
+#pragma unroll 1
       for (int i = lane; i < 2 * kMaxB; i += 32) w.est[i] = w.gain[i] = w.noise[i] = w.sine[i] = w.orig[i] = 0;
+#pragma unroll 1
       for (int i = lane; i < kMaxB; i += 32) w.sine_mapped[i] = 8;
     }
     __syncwarp();
@@ -207,6 +216,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
     {  // ixheaacd_map_sineflags: distinct scale-factor bands hit distinct centre bands
       const int nhi = prm[kEnvNumSfHi];
       const int16_t *fhi = prm + kEnvFreqHi;
+#pragma unroll 1
       for (int i = lane; i < nhi; i += 32) {
         const int pidx = nhi - 1 - i;
         const int old = st[kEnvStHarmPrev + pidx];
@@ -222,15 +232,18 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
     {  // env_calc.c:772-791
       const int first = (max_qmf_prev > max_qmf ? max_qmf_prev : max_qmf) - sb_start;
       int mx = 0;
+#pragma unroll 1
       for (int i = first + lane; i < num_sub_bands; i += 32) mx = max(mx, (int)filt_noise[i]);
       mx = __reduce_max_sync(full, mx);
       adj_e = (st[kEnvStNoiseE] - norm32(mx)) - 16;
     }
     {  // :793-841
       int off = 0;
+#pragma unroll 1
       for (int i = 0; i < num_env; i++) {
         const int n = prm[kEnvNumSfLo + freq_res[i]];
         int mx = 0;
+#pragma unroll 1
         for (int j = lane; j < n; j += 32) mx = max(mx, sf_arr[off + j] & 0x3f);
         mx = __reduce_max_sync(full, mx);
         off += n;
@@ -242,6 +255,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
     __syncwarp();
 
     int err = 0, m_off = 0, nf_idx = 0;
+#pragma unroll 1
     for (int env = 0; env < num_env; env++) {
       const int start = 2 * border[env], end = 2 * border[env + 1], fr = freq_res[env];
       if (start >= 38 || end > 38 || nf_idx >= 2) { err = 1; break; }
@@ -255,9 +269,11 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
       // ---- energy estimation ----
       if (prm[kEnvInterpolFreq]) {
         const i32 inv_width = rom.inv_int[(end - start) >> 0];
+#pragma unroll 1
         for (int c = lane; c < sb_end - max_qmf; c += 32) {
           const int k = max_qmf + c;
           i32 max_val = 1;
+#pragma unroll 1
           for (int l = start; l < end; l++) {
             max_val = max(max_val, abs_nrm(mat[128 * l + k]));
             max_val = max(max_val, abs_nrm(mat[128 * l + 64 + k]));
@@ -265,6 +281,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
           const int pre = pnorm32(max_val) - 4;
           int shift = 16 - pre;
           i32 accu = 0;
+#pragma unroll 1
           for (int l = start; l < end; l++) {
             const i32 a = mat[128 * l + k], b = mat[128 * l + 64 + k];
             const i32 ta = sext16(shift > 0 ? (a >> shift) : lsl(a, -shift));
@@ -284,10 +301,12 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
       } else {
         // per scale-factor band (env_calc.c:1298-1380); lanes own bands, a band's sfb partners are summed in order
         int first_li = -1;
+#pragma unroll 1
         for (int j = 0; j < num_sfb; j++)
           if (ftab[j] >= max_qmf) { first_li = ftab[j]; break; }
         const int top = ftab[num_sfb];
         const i32 inv_width = rom.inv_int[end - start];
+#pragma unroll 1
         for (int k0 = (first_li < 0 ? top : first_li); k0 < top; k0 += 32) {
           const int k = k0 + lane;
           const bool act = k < top;
@@ -298,6 +317,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
             while (ftab[j + 1] <= k) j++;
             li = ftab[j];
             ui = ftab[j + 1];
+#pragma unroll 1
             for (int l = start; l < end; l++) orv |= abs_nrm(mat[128 * l + k]) | abs_nrm(mat[128 * l + 64 + k]);
             w.line[k - first_li] = orv;
           }
@@ -305,6 +325,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
           int pre = 0;
           if (act) {
             i32 mx = 1;
+#pragma unroll 1
             for (int kk = li; kk < ui; kk++) mx |= w.line[kk - first_li];
             pre = pnorm32(mx) - 4;
           }
@@ -312,6 +333,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
           if (act) {
             const int s = min(16 - pre, 31);
             i32 line = 0;
+#pragma unroll 1
             for (int l = start; l < end; l++) {
               const i32 ta = sext16(shr32_dir(mat[128 * l + k], s));
               line = add_sat(line, ta * ta);
@@ -323,6 +345,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
           __syncwarp();
           if (act) {
             i32 accumulate = 0;
+#pragma unroll 1
             for (int kk = li; kk < ui; kk++) accumulate = add_sat(accumulate, w.line[kk - first_li]);
             const int shift = pnorm32(accumulate);
             i32 sum_m = sext16(shr32_dir_sat_limit(accumulate, 16 - shift));
@@ -344,6 +367,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
       // ---- gains per band (env_calc.c:616-688) ----
       {
         const int f0 = ftab[0], top = ftab[num_sfb];
+#pragma unroll 1
         for (int c = lane; c < top - max(max_qmf, f0); c += 32) {
           const int k = max(max_qmf, f0) + c;  // c indexes bands k >= max_qmf in walk order
           int j = 0;
@@ -352,8 +376,10 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
           const i32 v = sf_arr[m_off + j];
           const i32 ref_e = sext16((v & 0x3f) - 16), ref_m = sext16(v & 0xffc0);
           bool present = false;
+#pragma unroll 1
           for (int kk = li; kk < ui; kk++) present |= (env >= w.sine_mapped[kk - f0]);
           int nb = 0, ui_noise = fnoise[1];
+#pragma unroll 1
           for (int kk = f0; kk <= k; kk++)
             if (kk >= ui_noise) {
               nb++;
@@ -374,10 +400,12 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
       {
         const int16_t *lim = prm + kEnvLimTbl;
         const i32 lg_m = rom.lim_gains[2 * prm[kEnvLimiterGains]], lg_e = rom.lim_gains[2 * prm[kEnvLimiterGains] + 1];
+#pragma unroll 1
         for (int c = lane; c < prm[kEnvNumLfBands]; c += 32) {
           const int b0 = lim[c] > skip ? lim[c] - skip : 0, b1 = lim[c + 1] > skip ? lim[c + 1] - skip : 0;
           if (b0 >= b1) continue;
           i32 om = 0, oe = 0, em = 0, ee = 0;
+#pragma unroll 1
           for (int k = b0; k < b1; k++) {
             acc_add(om, oe, w.orig[2 * k], w.orig[2 * k + 1]);
             acc_add(em, ee, w.est[2 * k], w.est[2 * k + 1]);
@@ -395,6 +423,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
           mg_e = sext16(mg_e - nv);
           mg_m = sext16(lsl(mt, nv) >> 16);
           if (mg_e >= 34) { mg_m = 0x3000; mg_e = 34; }
+#pragma unroll 1
           for (int k = b0; k < b1; k++) {
             const i32 gm = w.gain[2 * k], ge = w.gain[2 * k + 1];
             if (ge > mg_e || (ge == mg_e && gm > mg_m)) {
@@ -407,6 +436,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
             }
           }
           i32 am = 0, ae = 0;
+#pragma unroll 1
           for (int k = b0; k < b1; k++) {
             acc_add(am, ae, ((i32)w.gain[2 * k] * w.est[2 * k]) >> 15, w.gain[2 * k + 1] + w.est[2 * k + 1]);
             if (w.sine[2 * k] != 0) acc_add(am, ae, w.sine[2 * k], w.sine[2 * k + 1]);
@@ -418,6 +448,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
           i32 bg_e = sext16(mant_div(sum_m, sext16(am), bg_m, rom));
           bg_e = sext16(bg_e + (sum_e - sext16(ae)) + 1);
           if (bg_e > 2 || (bg_e == 2 && bg_m > 0x5061)) { bg_m = 0x5061; bg_e = 2; }
+#pragma unroll 1
           for (int k = b0; k < b1; k++) {
             w.gain[2 * k] = (int16_t)mult16_shl_(w.gain[2 * k], bg_m);
             w.sine[2 * k] = (int16_t)mult16_shl_(w.sine[2 * k], bg_m);
@@ -434,6 +465,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
       int noise_e = sext16(start < 32 ? adj_e : final_e);
       const bool start_up = st[kEnvStStartUp] != 0;
       __syncwarp();
+#pragma unroll 1
       for (int k = lane; k < bands; k += 32) {
         mant_exp_sqrt(&w.sine[2 * k], rom);
         mant_exp_sqrt(&w.gain[2 * k], rom);
@@ -475,6 +507,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
       // ---- time-slot adjustment (env_calc.c:518-609, env_dec.c:845-923) ----
       int ph_index = st[kEnvStPhIndex], harm = st[kEnvStHarmIndex];
       int filt_noise_e = st[kEnvStNoiseE];
+#pragma unroll 1
       for (int l = start; l < end; l++) {
         int scale_change;
         if (l < 32) scale_change = adj_e - input_e;
@@ -498,6 +531,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
         const i32 direct = sat16(0x7fff - ratio);
         const int sc = sext16(sext16(scale_change) - 1);
         const int nfe = sext16(noise_e - 16);
+#pragma unroll 1
         for (int k = lane; k < bands; k += 32) {
           i32 g = w.gain[2 * k], nz = w.noise[2 * k];
           if (ratio) {
@@ -539,6 +573,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
         harm = (harm + 1) & 3;
         __syncwarp();
       }
+#pragma unroll 1
       for (int k = lane; k < bands; k += 32) {  // env_calc.c:1060-1078
         fme[2 * k] = w.gain[2 * k];
         fno[k] = w.noise[2 * k];
@@ -573,6 +608,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
     __syncwarp();
     {
       i32 *ds = reinterpret_cast<i32 *>(p.state + u * kEnvStWords);
+#pragma unroll 1
       for (int i = lane; i < kEnvStWords / 2; i += 32) ds[i] = reinterpret_cast<const i32 *>(w.st)[i];
       if (lane == 0 && p.err) p.err[u] = err ? (i32)0x80000000 : 0;
     }

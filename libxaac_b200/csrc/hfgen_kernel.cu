@@ -122,9 +122,15 @@ hf_generator_hq_kernel(HfGenArgs p) {
           p12 = A;
           p12i = B;
         }
-#pragma unroll 2
+        // rows are prefetched four ahead (register ring): each iteration's two loads are a coalesced 128-byte request per
+        // component, and the arithmetic of row m overlaps the latency of rows m+1..m+4
+        i32 pr[4], pi[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { pr[q] = mat[128 * q + lb]; pi[q] = mat[128 * q + 64 + lb]; }
+#pragma unroll 4
         for (int m = 0; m < L; m++) {
-          i32 r0 = mat[128 * m + lb] >> 3, i0 = mat[128 * m + 64 + lb] >> 3;
+          const i32 r0 = pr[m & 3] >> 3, i0 = pi[m & 3] >> 3;
+          if (m + 4 < L) { pr[m & 3] = mat[128 * (m + 4) + lb]; pi[m & 3] = mat[128 * (m + 4) + 64 + lb]; }
           i32 A = wadd(hm(r0, r1), hm(i0, i1)), B = wsub(hm(i0, r1), hm(r0, i1));
           p01 = wadd(p01, A);
           p01i = wadd(p01i, B);
@@ -195,8 +201,16 @@ hf_generator_hq_kernel(HfGenArgs p) {
         auto rowr = [&](int t) { return t < 2 ? lpc[128 * t + lb] : mat[128 * (t - 2) + lb]; };
         auto rowi = [&](int t) { return t < 2 ? lpc[128 * t + 64 + lb] : mat[128 * (t - 2) + 64 + lb]; };
         i32 p2r = rowr(start_idx), p2i = rowi(start_idx), p1r = rowr(start_idx + 1), p1i = rowi(start_idx + 1);
+        // the source column is prefetched two slots ahead (these reads hit L2: the covariance pass has just streamed them)
+        i32 nr0 = start_idx < stop_idx ? mat[128 * start_idx + lb] : 0, ni0 = start_idx < stop_idx ? mat[128 * start_idx + 64 + lb] : 0;
+        i32 nr1 = start_idx + 1 < stop_idx ? mat[128 * (start_idx + 1) + lb] : 0;
+        i32 ni1 = start_idx + 1 < stop_idx ? mat[128 * (start_idx + 1) + 64 + lb] : 0;
+#pragma unroll 2
         for (int t = start_idx; t < stop_idx; t++) {
-          const i32 cr = mat[128 * t + lb], ci = mat[128 * t + 64 + lb];  // scratch row t + 2
+          const i32 cr = nr0, ci = ni0;  // scratch row t + 2
+          nr0 = nr1;
+          ni0 = ni1;
+          if (t + 2 < stop_idx) { nr1 = mat[128 * (t + 2) + lb]; ni1 = mat[128 * (t + 2) + 64 + lb]; }
           i32 outr, outi;
           if (bw > 0) {
             i32 acc = wsub(wadd(wsub(mul32x16(p1r, a0r), mul32x16(p1i, a0i)), mul32x16(p2r, a1r)), mul32x16(p2i, a1i));

@@ -83,3 +83,43 @@ def test_heaac_frame_host_chunked_is_unit_independent(ctx):
     assert (p == p[0]).all()
     ist.close()
     sst.close()
+
+
+def test_full_batch_tiling_property(ctx, oracle):
+    """BASELINE configs[3] size (131072 stream-frames): 64 distinct units tiled 2048x through the device path.  Tile 0 is
+    checked bit-exactly against the oracle, every other tile must equal tile 0 (units are independent and the kernels
+    are deterministic) — two consecutive frames, so the carried state is covered too."""
+    import torch
+    import libxaac_b200 as xb
+    g = np.load(GOLD)
+    base_n, tiles = 64, 2048
+    n = base_n * tiles
+    rng = np.random.default_rng(8)
+    st = np.tile(g["st_in"][1], (base_n, 1))
+    ps = np.tile(g["ps_in"][1], (base_n, 1))
+    state = xb.SbrState(ctx, n, with_ps=True)
+    state.upload(np.tile(st, (tiles, 1)), np.tile(ps, (tiles, 1)))
+    imdct_state = xb.ImdctBatch(n)
+    ovl = np.zeros((base_n, 512), np.int32)
+    wstate = np.zeros((base_n, 2), np.uint8)
+    for f in range(2):
+        s = rng.integers(10, 22, (base_n, 1))
+        spec = ((rng.random((base_n, 1024)) * 2 - 1) * 2.0 ** s).astype(np.int64).astype(np.int32)
+        ics = np.zeros((base_n, 2), np.uint8)
+        ics[:, 1] = rng.integers(0, 2, base_n)
+        side = np.ascontiguousarray(g["side"][1 + (np.arange(base_n) + f) % 11])
+        d_spec = torch.from_numpy(spec).cuda().repeat(tiles, 1)
+        d_ics = torch.from_numpy(ics).cuda().repeat(tiles, 1)
+        d_side = torch.from_numpy(side).cuda().repeat(tiles, 1)
+        w32, adj = xb.imdct_process(ctx, imdct_state, d_spec, d_ics)
+        p16 = xb.imdct_out_to_pcm16(ctx, w32, adj, 0)
+        out, err = xb.sbr_dec(ctx, state, d_side, p16)
+        torch.cuda.synchronize()
+        assert int(err.abs().max().item()) == 0
+        o = out.view(tiles, base_n, 2048, 2)
+        assert bool((o == o[0:1]).all().item()), f"frame {f}: tiles differ"
+        out32, ovl, wstate, eadj = oracle.imdct_batch(spec, ovl, wstate, ics)
+        st, ps, ol, orr, _ = oracle.sbr_dec_batch(side, st, ps, oracle.imdct_out_to_pcm16(out32, eadj, 0))
+        got = o[0].cpu().numpy()
+        assert np.array_equal(got[:, :, 0], ol) and np.array_equal(got[:, :, 1], orr), f"frame {f}: tile 0 vs oracle"
+    state.close()
