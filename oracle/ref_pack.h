@@ -166,7 +166,8 @@ static void unpack_side_ps(const int16_t *side, ia_ps_dec_struct *ps) {
   memcpy(ps->icc_par_table, pp + XO_PS_PRM_ICC, 238 * sizeof(int16_t));
 }
 
-static void pack_sbr_state(int16_t *st, const ia_sbr_dec_struct *d, const ia_sbr_prev_frame_data_struct *pv) {
+static void pack_sbr_state_lp(int16_t *st, const ia_sbr_dec_struct *d, const ia_sbr_prev_frame_data_struct *pv,
+                              int low_pow) {
   const ia_sbr_qmf_filter_bank_struct *a = &d->str_codec_qmf_bank, *s = &d->str_synthesis_qmf_bank;
   memset(st, 0, XO_SBR_ST_WORDS * sizeof(int16_t));
   memcpy(st + XO_SBR_ST_ANAL_STATES, a->anal_filter_states, 320 * sizeof(int16_t));
@@ -189,9 +190,14 @@ static void pack_sbr_state(int16_t *st, const ia_sbr_dec_struct *d, const ia_sbr
   for (int i = 0; i < 2; i++) {
     /* the reference allocates NO_ANALYSIS_CHANNELS (32) words per LPC state row (sbrdec_initfuncs.c:946-968) */
     memcpy(lpc + 128 * i, d->str_hf_generator.lpc_filt_states_real[i], 32 * sizeof(int32_t));
-    memcpy(lpc + 128 * i + 64, d->str_hf_generator.lpc_filt_states_imag[i], 32 * sizeof(int32_t));
+    if (!low_pow && d->str_hf_generator.lpc_filt_states_imag[i])
+      memcpy(lpc + 128 * i + 64, d->str_hf_generator.lpc_filt_states_imag[i], 32 * sizeof(int32_t));
   }
-  memcpy(st + XO_SBR_ST_OV, d->ptr_sbr_overlap_buf, 6 * 128 * sizeof(int32_t));
+  /* low power: 6 real slots of 64 words (raw, in the reference's own order); HQ: 6 x (re[64] | im[64]) */
+  memcpy(st + XO_SBR_ST_OV, d->ptr_sbr_overlap_buf, (low_pow ? 6 * 64 : 6 * 128) * sizeof(int32_t));
+}
+static void pack_sbr_state(int16_t *st, const ia_sbr_dec_struct *d, const ia_sbr_prev_frame_data_struct *pv) {
+  pack_sbr_state_lp(st, d, pv, 0);
 }
 
 static void pack_ps_state(int16_t *p, const ia_ps_dec_struct *ps, const ia_sbr_qmf_filter_bank_struct *bank_r,
@@ -240,13 +246,18 @@ typedef struct {
   WORD16 anal_states[320], syn_states[1280], syn_states_r[1280];
   WORD16 filt_me[2 * MAX_FREQ_COEFFS], filt_noise[MAX_FREQ_COEFFS];
   WORD32 lpc_r[2][64], lpc_i[2][64], ov[6 * 128];
+  WORD32 lpc_lp[2][32]; /* low power: the reference walks from row 0 to row 1 with a stride of 32 words */
   WORD16 ps_ap[2][64], ps_ld[14][24], ps_sd[64], ps_ser[5][3][64];
   WORD32 ps_hyb_io[64], ps_work[32], ps_temp[16], ps_qbuf[3][2][12], ps_peak[60];
   WORD32 qmf_out[32][128];
   WORD32 work[64 * 128];
 } ref_sbr_ctx;
 
+static void unpack_sbr_ctx_lp(ref_sbr_ctx *c, const int16_t *side, const int16_t *st, const int16_t *p, int low_pow);
 static void unpack_sbr_ctx(ref_sbr_ctx *c, const int16_t *side, const int16_t *st, const int16_t *p) {
+  unpack_sbr_ctx_lp(c, side, st, p, 0);
+}
+static void unpack_sbr_ctx_lp(ref_sbr_ctx *c, const int16_t *side, const int16_t *st, const int16_t *p, int low_pow) {
   memset(c, 0, sizeof(*c));
   ia_qmf_dec_tables_struct *qt = (ia_qmf_dec_tables_struct *)&ixheaacd_aac_qmf_dec_tables;
   c->tabs.env_calc_tables_ptr = (ia_env_calc_tables_struct *)&ixheaacd_aac_dec_env_calc_tables;
@@ -288,6 +299,10 @@ static void unpack_sbr_ctx(ref_sbr_ctx *c, const int16_t *side, const int16_t *s
     memcpy(c->lpc_r[i], lpc + 128 * i, 256); memcpy(c->lpc_i[i], lpc + 128 * i + 64, 256);
     d->str_hf_generator.lpc_filt_states_real[i] = c->lpc_r[i];
     d->str_hf_generator.lpc_filt_states_imag[i] = c->lpc_i[i];
+    if (low_pow) {
+      memcpy(c->lpc_lp[i], lpc + 128 * i, 128);
+      d->str_hf_generator.lpc_filt_states_real[i] = c->lpc_lp[i];
+    }
   }
   memcpy(c->ov, st + XO_SBR_ST_OV, sizeof(c->ov));
   d->ptr_sbr_overlap_buf = c->ov;

@@ -449,3 +449,21 @@ void ref_chain_step(void *hv, int a, int b, int32_t *spec, const uint8_t *ics, c
   }
 }
 int ref_chain_unit_bytes(void) { return (int)sizeof(ref_chain_unit); }
+
+
+/* ixheaacd_sbr_dec with low_pow_flag = 1 (real-valued SBR, what the reference runs for stereo HE-AACv1), driven from
+ * the flat records.  st [3920] in/out (overlap: 6 real slots of 64 words; LPC rows: 32 real words), time_in 1024,
+ * out 2048. */
+int ref_sbr_dec_lp(const int16_t *side, int16_t *st, const int16_t *time_in, int16_t *out) {
+  static __thread ref_sbr_ctx c;
+  static __thread WORD16 tbuf[2048];
+  unpack_sbr_ctx_lp(&c, side, st, NULL, 1);
+  memset(tbuf, 0, sizeof(tbuf));
+  memcpy(tbuf, time_in, 1024 * sizeof(WORD16));
+  WORD32 ret = ixheaacd_sbr_dec(&c.d, tbuf, &c.h, &c.fd.f, &c.pv, NULL, NULL, NULL, side[XO_SIDE_APPLY], 1, c.work, &c.tabs,
+                                (ixheaacd_misc_tables *)&ixheaacd_str_fft_n_transcendent_tables, 1, NULL, 0, NULL, AOT_SBR,
+                                0, NULL, 0, 0);
+  pack_sbr_state_lp(st, &c.d, &c.pv, 1);
+  memcpy(out, tbuf, 2048 * sizeof(int16_t));
+  return (int)ret;
+}

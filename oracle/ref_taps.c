@@ -198,7 +198,7 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *d, WORD16 *time, ia_sbr_header
                                VOID *self, WORD32 mps, WORD32 ec) {
   static int count = 0;
   FILE *fp = tap_fp();
-  int rec = fp && tap_on("sbr") && count < tap_limit() && !low_pow && !h->enh_sbr && h->num_time_slots == 16 &&
+  int rec = fp && tap_on(low_pow ? "slp" : "sbr") && count < tap_limit() && !h->enh_sbr && h->num_time_slots == 16 &&
             aot != AOT_ER_AAC_ELD && aot != AOT_ER_AAC_LD && !ldmps && !drc_on;
   static int16_t side[XO_SIDE_WORDS], st[XO_SBR_ST_WORDS], pst[XO_PS_ST_WORDS], tin[1024], out[2048];
   int ps_present = 0;
@@ -206,7 +206,7 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *d, WORD16 *time, ia_sbr_header
     int32_t magic = 0x31524253;
     ps_present = (ps != NULL && bank_r != NULL && sf_r != NULL);
     pack_side(side, d, h, f, pv, ps_present ? ps : NULL, apply);
-    pack_sbr_state(st, d, pv);
+    pack_sbr_state_lp(st, d, pv, low_pow);
     memset(pst, 0, sizeof(pst));
     if (ps_present) pack_ps_state(pst, ps, bank_r, sf_r);
     for (int i = 0; i < 1024; i++) tin[i] = time[ch_fac * i];
@@ -215,13 +215,13 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *d, WORD16 *time, ia_sbr_header
   WORD32 ret = __real_ixheaacd_sbr_dec(d, time, h, f, pv, ps, bank_r, sf_r, apply, low_pow, work, t, ct, ch_fac, pvc,
                                        drc_on, drc, aot, ldmps, self, mps, ec);
   if (rec) {
-    int32_t hdr[7] = {apply, ch_fac, aot, ps_present, ret, 0, 0};
+    int32_t hdr[7] = {apply, ch_fac, aot, ps_present, ret, low_pow, 0};
     fwrite(hdr, 4, 7, fp);
     fwrite(side, 2, XO_SIDE_WORDS, fp);
     fwrite(st, 2, XO_SBR_ST_WORDS, fp);
     fwrite(pst, 2, XO_PS_ST_WORDS, fp);
     fwrite(tin, 2, 1024, fp);
-    pack_sbr_state(st, d, pv);
+    pack_sbr_state_lp(st, d, pv, low_pow);
     if (ps_present) pack_ps_state(pst, ps, bank_r, sf_r);
     fwrite(st, 2, XO_SBR_ST_WORDS, fp);
     fwrite(pst, 2, XO_PS_ST_WORDS, fp);

@@ -26,6 +26,11 @@ typedef struct {
   const i16 *inv_table, *sqrt_table;
 } env_rom_t;
 
+/* The reference shifts promoted WORD16 values by run-time counts that may exceed 31 here (`x >> diff`).  That is
+ * undefined in ISO C; the reference build this oracle is pinned to (gcc, x86-64) executes SAR/SHL, which use the count
+ * modulo 32.  The oracle states that behaviour explicitly. */
+#define X86_SHIFT(c) ((c) & 31)
+
 typedef struct { i16 m, e; } me_t;
 
 /* decoder/ixheaacd_basic_funcs.c:66-99 */
@@ -248,10 +253,7 @@ static void noise_limiting(const i16 *prm, int skip, const me_t *orig, const me_
   }
 }
 
-/* The reference shifts promoted WORD16 values by run-time counts that may exceed 31 here (`x >> diff`).  That is
- * undefined in ISO C; the reference build this oracle is pinned to (gcc, x86-64) executes SAR/SHL, which use the count
- * modulo 32.  The oracle states that behaviour explicitly. */
-#define X86_SHIFT(c) ((c) & 31)
+
 
 /* decoder/ixheaacd_env_calc.c:1080-1097 */
 static void noise_rescale(i16 *p, int diff, int n, int stride) {
@@ -312,10 +314,13 @@ static void adj_timeslot(i32 *re, i32 *im, i16 *filt_me, i16 *filt_noise, const 
   st->harm_index = (i16)((harm + 1) & 3);
 }
 
-/* decoder/ixheaacd_env_calc.c:692-1015 for low_pow_flag == 0, non-ELD/LD object types, 1024-sample core frames
- * (num_time_slots 16, max_cols 32).  Returns 0 or 0x80000000 (IA_FATAL_ERROR) like the reference. */
-int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, const i16 *prm, i16 *sf, i16 *state,
-                           i32 *matrix) {
+#include "envcalc_lp.inc"
+
+/* decoder/ixheaacd_env_calc.c:692-1015 for non-ELD/LD object types, 1024-sample core frames (num_time_slots 16,
+ * max_cols 32).  low_pow = 0: complex matrix, 128 words per slot; low_pow = 1: real matrix, 64 words per slot, `deg` =
+ * degree_alias[64] from the low-power HF generator.  Returns 0 or 0x80000000 (IA_FATAL_ERROR) like the reference. */
+static int calc_sbrenvelope(const uint8_t *env_rom, const uint8_t *misc_rom, const i16 *prm, i16 *sf, i16 *state,
+                            i32 *matrix, int low_pow, const i16 *deg) {
   env_rom_t rom;
   rom.lim_gains = (const i16 *)(env_rom + XO_EROM_LIM_GAINS);
   rom.smooth_filter = (const i16 *)(env_rom + XO_EROM_SMOOTH);
@@ -337,7 +342,8 @@ int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, cons
   const int num_sub_bands = sb_end - sb_start, skip = max_qmf - sb_start, bands = num_sub_bands - skip;
   const i16 *noise_floor = prm + XO_ENV_NOISE_FLOOR;
   const i16 *sf_arr = prm + XO_ENV_SF_ARR;
-  int8_t sine_mapped[MAXB];
+  int8_t sine_mapped[MAXB], alias_red[64 + MAXB];
+  memset(alias_red, 0, sizeof(alias_red));
   me_t est[MAXB], gain[MAXB], noise[MAXB], sine[MAXB], orig[MAXB];
   memset(est, 0, sizeof(est)); memset(gain, 0, sizeof(gain)); memset(noise, 0, sizeof(noise));
   memset(sine, 0, sizeof(sine)); memset(orig, 0, sizeof(orig));
@@ -381,12 +387,15 @@ int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, cons
     int noise_absc = (i == trans_env || i == st->trans_prev);
     int smooth_len = noise_absc ? 0 : ((1 - prm[XO_ENV_SMOOTHING_MODE]) << 2);
     int input_e = 15 - sf[XO_SF_HB];
-    if (prm[XO_ENV_INTERPOL_FREQ]) energy_per_subband(matrix, start, end, max_qmf, sb_end, input_e, est, &rom);
+    if (low_pow) {
+      if (prm[XO_ENV_INTERPOL_FREQ]) energy_per_subband_lp(matrix, start, end, max_qmf, sb_end, input_e, est, &rom);
+      else energy_per_sfb_lp(matrix, num_sf[fr], ftab[fr], start, end, max_qmf, input_e, est, &rom);
+    } else if (prm[XO_ENV_INTERPOL_FREQ]) energy_per_subband(matrix, start, end, max_qmf, sb_end, input_e, est, &rom);
     else energy_per_sfb(matrix, num_sf[fr], ftab[fr], start, end, max_qmf, input_e, est, &rom);
     if (ftab[fr][0] < sb_start) return (int)0x80000000;
 
     { /* decoder/ixheaacd_env_calc.c:616-688 */
-      int ui_noise = fnoise[1], nb = 0, c = 0, sm = 0;
+      int ui_noise = fnoise[1], nb = 0, c = 0, sm = 0, ar = ftab[fr][0] - sb_start;
       i16 nm = (i16)(noise_floor[0] & MASK_M), ne = (i16)((noise_floor[0] & MASK_E) - NOISE_EXP_OFFSET);
       for (int j = 0; j < num_sf[fr]; j++) {
         int li = ftab[fr][j], ui = ftab[fr][j + 1];
@@ -395,6 +404,7 @@ int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, cons
         int present = 0;
         for (int k = li; k < ui; k++) if (i >= sine_mapped[sm++]) present = 1;
         for (int k = li; k < ui; k++) {
+          alias_red[ar++] = (int8_t)!present;
           if (k >= ui_noise) {
             nb++;
             ui_noise = fnoise[nb + 1];
@@ -414,8 +424,10 @@ int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, cons
     m += num_sf[fr];
     noise_limiting(prm, skip, orig, est, gain, noise, sine, rom.lim_gains + 2 * prm[XO_ENV_LIMITER_GAINS], noise_absc,
                    &rom);
+    if (low_pow) alias_reduction(deg + sb_start, gain, est, alias_red, num_sub_bands, &rom);
     i16 noise_e = (i16)(start < 32 ? adj_e : final_e);
-    for (int k = 0; k < bands; k++) { /* :450-477 */
+    if (low_pow) conv_erg_to_amplitude_lp(bands, noise_e, sine, gain, noise, &rom);
+    else for (int k = 0; k < bands; k++) { /* :450-477 */
       mant_exp_sqrt(&sine[k], &rom);
       mant_exp_sqrt(&gain[k], &rom);
       mant_exp_sqrt(&noise[k], &rom);
@@ -464,6 +476,23 @@ int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, cons
       }
       noise_rescale(st->filt_noise, st->filt_noise_e - noise_e, num_sub_bands, 1);
       st->filt_noise_e = noise_e;
+      if (low_pow) { /* :556-584 */
+        int index = st->ph_index, harm = st->harm_index, finv = max_qmf & 1;
+        i32 *re = matrix + 64 * l + max_qmf;
+        const i32 *rnd = rom.rand_ph + index + 1;
+        st->ph_index = (i16)((index + num_sub_bands) & 511);
+        st->harm_index = (i16)((harm + 1) & 3);
+        if (!(harm & 1)) {
+          harm_idx_zerotwo_lp(re, gain, scale_change, sine, rnd, noise, num_sub_bands, noise_absc, harm);
+        } else {
+          int nz = (noise_e - 16) - (i16)(15 - sf[XO_SF_LB]);
+          finv = !finv;
+          finv = (finv << 1) - 1;
+          if (harm == 3) finv = -finv;
+          harm_idx_onethree_lp(re, gain, scale_change, sine, rnd, noise, num_sub_bands, noise_absc, finv, nz, max_qmf);
+        }
+        continue;
+      }
       i16 ratio = (l - start) < smooth_len ? rom.smooth_filter[l - start] : 0;
       adj_timeslot(matrix + 128 * l + max_qmf, matrix + 128 * l + 64 + max_qmf, fme, fno, gain, noise, sine,
                    (i16)(noise_e - 16), st, max_qmf, bands, (i16)scale_change, ratio, noise_absc, &rom);
@@ -474,19 +503,30 @@ int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, cons
   { /* :956-1007 */
     int first_start = border[0] * 2, ov_reserve = 0, reserve = 0;
     if (prm[XO_ENV_CHANNEL_MODE] == 3) {
-      ov_reserve = xo_expsubbandsamples_hq(matrix, max_qmf, sb_end, 0, first_start);
-      reserve = xo_expsubbandsamples_hq(matrix, max_qmf, sb_end, first_start, 32);
+      ov_reserve = low_pow ? xo_expsubbandsamples_lp(matrix, max_qmf, sb_end, 0, first_start)
+                           : xo_expsubbandsamples_hq(matrix, max_qmf, sb_end, 0, first_start);
+      reserve = low_pow ? xo_expsubbandsamples_lp(matrix, max_qmf, sb_end, first_start, 32)
+                        : xo_expsubbandsamples_hq(matrix, max_qmf, sb_end, first_start, 32);
     }
     int ov_adj_e = 15 - sf[XO_SF_OV_HB];
     int output_e = (ov_adj_e - ov_reserve) > (adj_e - reserve) ? (ov_adj_e - ov_reserve) : (adj_e - reserve);
-    xo_adjust_scale_hq(matrix, max_qmf, sb_end, 0, first_start, ov_adj_e - output_e);
-    xo_adjust_scale_hq(matrix, max_qmf, sb_end, first_start, prm[XO_ENV_NUM_TIME_SLOTS] * prm[XO_ENV_TIME_STEP],
-                       adj_e - output_e);
+    void (*adj)(i32 *, int, int, int, int, int) = low_pow ? xo_adjust_scale_lp : xo_adjust_scale_hq;
+    adj(matrix, max_qmf, sb_end, 0, first_start, ov_adj_e - output_e);
+    adj(matrix, max_qmf, sb_end, first_start, prm[XO_ENV_NUM_TIME_SLOTS] * prm[XO_ENV_TIME_STEP], adj_e - output_e);
     sf[XO_SF_HB] = (i16)(15 - output_e);
     sf[XO_SF_OV_HB] = (i16)(15 - final_e);
   }
   st->trans_prev = (trans_env == num_env) ? 0 : -1;
   return 0;
+}
+
+int xo_calc_sbrenvelope_hq(const uint8_t *env_rom, const uint8_t *misc_rom, const i16 *prm, i16 *sf, i16 *state,
+                           i32 *matrix) {
+  return calc_sbrenvelope(env_rom, misc_rom, prm, sf, state, matrix, 0, 0);
+}
+int xo_calc_sbrenvelope_lp(const uint8_t *env_rom, const uint8_t *misc_rom, const i16 *prm, i16 *sf, i16 *state,
+                           i32 *matrix, const i16 *degree_alias) {
+  return calc_sbrenvelope(env_rom, misc_rom, prm, sf, state, matrix, 1, degree_alias);
 }
 
 void xo_calc_sbrenvelope_hq_batch(const uint8_t *env_rom, const uint8_t *misc_rom, const i16 *prm, i16 *sf, i16 *state,

@@ -286,3 +286,232 @@ void xo_anal_qmffilt_hq_batch(const uint8_t *qrom, const i16 *time_in, i16 *stat
     xo_anal_qmffilt_hq(qrom, time_in + (size_t)u * 1024, 1, states + (size_t)u * 320, pos + u, filter_pos + u, usb[u],
                        matrix + (size_t)u * 4096);
 }
+
+/* =====================================================================================================
+ * Low-power (real-valued) SBR filterbanks: what the reference runs for stereo HE-AACv1 in its fixed-point path
+ * (low_pow_flag = 1, decoder/ixheaacd_sbrdecoder.c:408-419).
+ * ===================================================================================================== */
+
+/* generic:63-239 — DCT-III of one slot: in[64] (window-add output, destroyed) -> out[0..31]; out needs 32 words */
+static void dct3_32(const uint8_t *qrom, i32 *in, i32 *out) {
+  const i16 *tw = T16(XO_QROM_DCT23_TW) + 4, *post = T16(XO_QROM_POST_FFT);
+  int f = 49, r = 47, o = 0;
+  i32 t0, t1, t2, t3, u0, u1, u2, u3, v4, v5;
+  i16 re, im;
+  out[o++] = in[48] >> 7;
+  out[o++] = 0;
+  for (int n = 1; n < 16; n++) {
+    t0 = in[f++];
+    t1 = in[r--];
+    t0 = ox_add_sat(ox_shr32(t0, 7), ox_shr32(t1, 7));
+    t2 = in[f - 33];
+    t3 = in[r - 31];
+    t1 = ox_sub_sat(ox_shr32(t2, 7), ox_shr32(t3, 7));
+    re = tw[0];
+    im = tw[1];
+    tw += 4;
+    out[o++] = ox_add(ox_mul32x16(t0, re), ox_mul32x16(t1, im));
+    out[o++] = ox_add(ox_sub(0, ox_mul32x16(t1, re)), ox_mul32x16(t0, im));
+  }
+  re = tw[0];
+  im = tw[1];
+  t1 = in[r--];
+  t0 = in[r - 31];
+  t1 = ox_sub_sat(ox_shr32(t1, 7), ox_shr32(t0, 7));
+  t0 = t1;
+  u2 = ox_add(ox_mul32x16(t0, re), ox_mul32x16(t1, im));
+  u3 = ox_add(ox_sub(0, ox_mul32x16(t1, re)), ox_mul32x16(t0, im));
+  int pf = 0, pr = 31;
+  u0 = out[0];
+  u1 = out[1];
+  t0 = ox_sub(ox_sub(0, u1), u3);
+  t1 = ox_sub(u0, u2);
+  u0 = ox_add(ox_add(u0, u2), t0);
+  u1 = ox_add(ox_sub(u1, u3), t1);
+  out[pf++] = u0 >> 1;
+  out[pf++] = u1 >> 1;
+  const i16 *tf = post + 2, *tr = post + 14;
+  for (int n = 1; n <= 8; n++) {
+    const int last = n == 8;
+    u0 = out[pf];
+    u1 = out[pf + 1];
+    u3 = out[pr];
+    u2 = out[pr - 1];
+    re = last ? (i16)(-*tr) : *tr;
+    tr -= 2;
+    im = *tf;
+    tf += 2;
+    t0 = ox_sub(u0, u2);
+    t1 = ox_add(u0, u2);
+    t2 = ox_add(u1, u3);
+    t3 = ox_sub(u1, u3);
+    if (!last) {
+      v4 = ox_add(ox_mul32x16(t0, re), ox_mul32x16(t2, im));
+      v5 = ox_add(ox_sub(0, ox_mul32x16(t2, re)), ox_mul32x16(t0, im));
+    } else {
+      v4 = ox_sub(ox_mul32x16(t0, re), ox_mul32x16(t2, im));
+      v5 = ox_add(ox_mul32x16(t2, re), ox_mul32x16(t0, im));
+    }
+    t1 >>= 1;
+    t3 >>= 1;
+    if (!last) {
+      out[pf++] = ox_sub(t1, v4);
+      out[pf++] = ox_add(t3, v5);
+      out[pr--] = ox_add(ox_sub(0, t3), v5);
+      out[pr--] = ox_add(t1, v4);
+    } else {
+      out[pf++] = ox_add(t1, v4);
+      out[pf++] = ox_add(t3, v5);
+    }
+  }
+  radix4_stage(T16(XO_QROM_W16), out, 1, 4);
+  post_radix4_16(in, out, T32(XO_QROM_DIGREV4_16));
+  out[0] = in[0];
+  out[2] = in[1];
+  int po = 2, p1 = 18;
+  pf = 1;
+  pr = 30;
+  for (int k = 7; k != 0; k--) {
+    i32 a = in[po++], b = in[po++];
+    out[pf] = b; pf += 2;
+    out[pf] = a; pf += 2;
+    a = in[p1++];
+    b = in[p1++];
+    out[pr] = b; pr -= 2;
+    out[pr] = a; pr -= 2;
+  }
+  {
+    i32 a = in[po++], b = in[po++];
+    out[pf] = b; pf += 2;
+    out[pf] = a;
+  }
+}
+
+void xo_dct3_32(const uint8_t *qrom, i32 *in, i32 *out) { dct3_32(qrom, in, out); }
+
+/* decoder/generic/ixheaacd_qmf_dec_generic.c:590-741 with low_pow_flag = 1: real 32-band analysis of 1024 core samples
+ * into matrix[32][64] (bands 0..31 of each 64-word row written).  Returns lb_scale (-10, :631). */
+int xo_anal_qmffilt_lp(const uint8_t *qrom, const i16 *time_in, int ch_fac, i16 *states, i32 *pos_io, i32 *fpos_io,
+                       i32 *matrix) {
+  const i16 *qmf_c = T16(XO_QROM_QMF_C);
+  int pos = *pos_io;
+  int f1 = *fpos_io, f2 = f1 + 64;
+  for (int i = 0; i < 32; i++) {
+    i32 buf[128];
+    for (int k = 0; k < 32; k++) states[pos + 31 - k] = time_in[ch_fac * (32 * i + k)];
+    const i16 *fp1 = states + ((i & 1) ? 32 : 0), *fp2 = states + ((i & 1) ? 0 : 32);
+    for (int n = 0; n < 32; n++) {
+      i32 a = ox_mult16x16(fp1[n], qmf_c[f1 + 2 * n]);
+      i32 b = ox_mult16x16(fp2[n], qmf_c[f2 + 2 * n]);
+      for (int j = 1; j < 5; j++) {
+        a = ox_add_sat(a, ox_mult16x16(fp1[n + 64 * j], qmf_c[f1 + 2 * (n + 64 * j)]));
+        b = ox_add_sat(b, ox_mult16x16(fp2[n + 64 * j], qmf_c[f2 + 2 * (n + 64 * j)]));
+      }
+      buf[n] = a;
+      buf[n + 32] = b;
+    }
+    pos -= 32;
+    if (pos < 0) pos = 288;
+    {
+      int n1 = f2 + 64, n2 = f1 + 64;
+      f1 = n1;
+      f2 = n2;
+      if (f2 > 640) { f1 = 0; f2 = 64; }
+    }
+    dct3_32(qrom, buf, matrix + 64 * i);
+  }
+  *pos_io = pos;
+  *fpos_io = f1;
+  return -10;
+}
+
+/* decoder/ixheaacd_qmf_dec.c:72-211 + generic:241-257 — DCT-II of one slot straight into 128 WORD16 state samples.
+ * x[64] is destroyed; fs points at the slot's state block (generic:851-867: dct2_64(.., filter_states + 32), [96] = 0) */
+static void inv_modulation_lp(const uint8_t *qrom, i32 *x, i16 *fs) {
+  i32 X[64];
+  for (int n = 0; n < 32; n++) { X[n] = x[2 * n]; X[63 - n] = x[2 * n + 1]; } /* pretwdct2 */
+  radix4_stage(T16(XO_QROM_W32), X, 1, 8);
+  radix4_stage(T16(XO_QROM_W32) + 48, X, 4, 2);
+  post_radix2_32(x, X, T32(XO_QROM_DIGREV2_32));
+  { /* fftposttw, qmf_dec.c:107-159 */
+    const i16 *tf = T16(XO_QROM_POST_FFT) + 1, *tr = T16(XO_QROM_POST_FFT) + 15;
+    int pf = 0, pr = 63;
+    x[0] = ox_shl1(x[0]);
+    x[1] = ox_shl1(x[1]);
+    pf = 2;
+    for (int k = 1; k <= 16; k++) {
+      i32 t0 = x[pf], t1 = x[pf + 1], t3 = x[pr], t2 = x[pr - 1];
+      i32 in2 = ox_sub_sat(t3, t1), in1 = ox_add_sat(t3, t1);
+      t1 = ox_sub_sat(t0, t2);
+      t3 = ox_add_sat(t0, t2);
+      i16 re = *tf++, im = *tr--;
+      i32 v1 = ox_shl1(ox_sub(ox_mul32x16(in1, re), ox_mul32x16(t1, im)));
+      i32 v2 = ox_shl1(ox_add(ox_mul32x16(t1, re), ox_mul32x16(in1, im)));
+      x[pf++] = ox_add_sat(t3, v1);
+      x[pf++] = ox_add_sat(in2, v2);
+      x[pr--] = ox_sub_sat(v2, in2);
+      x[pr--] = ox_sub_sat(t3, v1);
+    }
+  }
+  { /* posttwdct2, qmf_dec.c:161-211: out_fwd = fs + 32 */
+    i16 *of = fs + 32, *orv = fs + 32 + 63, *or2 = fs + 31, *of2 = fs + 32 + 65;
+    const i16 *tw = T16(XO_QROM_DCT23_TW) + 2;
+    int p = 0;
+    i32 ore = x[p++], oim = x[p++];
+    i64 s = ((i64)ore + (i64)oim) >> 1;
+    i32 ore1 = s >= OX_MAX32 ? OX_MAX32 : (s <= OX_MIN32 ? OX_MIN32 : (i32)s);
+    *of++ = ox_round16(ox_shl32(ore1, 4));
+    i32 last = ox_sub_sat(ore, oim);
+    for (int k = 30; k >= 0; k--) {
+      i32 ire = x[p++], iim = x[p++];
+      i16 re = *tw++, im = *tw++;
+      ore = ox_sub_sat(ox_mul32x16(ire, re), ox_mul32x16(iim, im));
+      oim = ox_add_sat(ox_mul32x16(iim, re), ox_mul32x16(ire, im));
+      i16 r1 = ox_round16(ox_shl32(ore, 4)), i1 = ox_round16(ox_shl32(oim, 4)), i2 = ox_neg16(i1);
+      *of++ = r1;
+      *or2-- = r1;
+      *orv-- = i1;
+      *of2++ = i2;
+    }
+    i16 r1 = ox_round16(ox_shl32(ox_mul32x16(last, *tw), 4));
+    *of++ = r1;
+    *or2-- = r1;
+  }
+  fs[96] = 0;
+}
+
+/* decoder/ixheaacd_qmf_dec.c:811-1129 with low_pow_flag = 1: real 64-band synthesis.  matrix [32][64] in place. */
+void xo_synt_qmffilt_lp(const uint8_t *qrom, i32 *matrix, i16 *fs, i32 *drc_offset, i32 *filter_pos, const i32 *sf,
+                        int lsb, int usb, int split, i16 *time_out, int ch_fac) {
+  const i16 *qmf_c = T16(XO_QROM_QMF_C);
+  const int shifts[3] = {(sf[3] - sf[0]) - 4, (sf[3] - sf[1]) - 4, (sf[3] - sf[2]) - 4}; /* ov_lb, lb, hb: :905-907 */
+  for (int l = 0; l < 32; l++)
+    for (int k = 0; k < usb; k++) {
+      int sh = k < lsb ? ((shifts[0] == shifts[1] || l >= split) ? shifts[1] : shifts[0]) : shifts[2];
+      if (k < lsb && shifts[0] == shifts[1]) sh = shifts[0];
+      if (sh > 31) sh = 31;
+      if (sh < -31) sh = -31;
+      i32 *p = matrix + 64 * l + k;
+      if (sh > 0) *p = ox_lsl(*p, sh);
+      else if (sh < 0) *p = *p >> -sh;
+    }
+  int off = *drc_offset, fpos = *filter_pos;
+  for (int i = 0; i < 32; i++) {
+    inv_modulation_lp(qrom, matrix + 64 * i, fs + off);
+    const i16 *fp1 = fs + ((i & 1) ? 64 : 0), *fp2 = fs + ((i & 1) ? 0 : 64);
+    const i16 *c = qmf_c + fpos;
+    i16 *out = time_out + ch_fac * 64 * i;
+    for (int k = 0; k < 64; k++) { /* generic:1508-1542 with shift = 2 */
+      i32 acc = 0x8000 >> 2;
+      for (int j = 0; j < 5; j++) acc = ox_add_sat(acc, ox_mult16x16(fp1[256 * j + k], c[k + 128 * j]));
+      for (int j = 0; j < 5; j++) acc = ox_add_sat(acc, ox_mult16x16(fp2[128 + 256 * j + k], c[k + 64 + 128 * j]));
+      out[ch_fac * k] = (i16)(ox_shl32_sat(acc, 2) >> 16);
+    }
+    off -= 128;
+    if (off < 0) off += 1280;
+    fpos += 64;
+    if (fpos == 640) fpos = 0;
+  }
+  *drc_offset = off;
+  *filter_pos = fpos;
+}

@@ -242,4 +242,20 @@ int xo_sbr_dec_hq(const uint8_t *qrom, const uint8_t *env_rom, const uint8_t *mi
                   const int16_t *side, int16_t *st, int16_t *ps_st, const int16_t *time_in, int ch_in,
                   int16_t *time_out, int16_t *time_out_r, int ch_out, int32_t *scratch);
 void xo_imdct_out_to_pcm16(const int32_t *in, const int8_t *qshift_adj, int16_t *out, int n_units, int mode);
+
+/* ---- low-power (real-valued) SBR path: matrices are [slot][64] real ------------------------------------------ */
+void xo_dct3_32(const uint8_t *qrom, int32_t *in, int32_t *out);
+int xo_anal_qmffilt_lp(const uint8_t *qrom, const int16_t *time_in, int ch_fac, int16_t *states, int32_t *pos,
+                       int32_t *filter_pos, int32_t *matrix);
+void xo_synt_qmffilt_lp(const uint8_t *qrom, int32_t *matrix, int16_t *filter_states, int32_t *drc_offset,
+                        int32_t *filter_pos, const int32_t *sf, int lsb, int usb, int split, int16_t *time_out,
+                        int ch_fac);
+int xo_expsubbandsamples_lp(const int32_t *matrix, int b0, int b1, int s0, int s1);
+void xo_adjust_scale_lp(int32_t *matrix, int b0, int b1, int s0, int s1, int shift);
+int xo_calc_sbrenvelope_lp(const uint8_t *env_rom, const uint8_t *misc_rom, const int16_t *prm, int16_t *sf,
+                           int16_t *state, int32_t *matrix, const int16_t *degree_alias);
+void xo_low_pow_hf_generator(const int32_t *lpc, int32_t *scratch, const int16_t *prm, int32_t *bw_prev,
+                             int16_t *degree_alias, int norm_max);
+int xo_sbr_dec_lp(const uint8_t *qrom, const uint8_t *env_rom, const uint8_t *misc_rom, const int16_t *side,
+                  int16_t *st, const int16_t *time_in, int ch_in, int16_t *time_out, int ch_out, int32_t *scratch);
 #endif

@@ -164,6 +164,16 @@ class Oracle:
         outs = [self.sbr_dec(side[u], st[u], ps[u], time_in[u]) for u in range(len(side))]
         return tuple(np.stack([o[k] for o in outs]) for k in range(4)) + (np.array([o[4] for o in outs], np.int32),)
 
+    def sbr_dec_lp(self, side, st, time_in):
+        """low-power stage, single unit. Returns (st', out [2048], err)."""
+        s = np.ascontiguousarray(st, np.int16).copy()
+        out = np.zeros(2048, np.int16)
+        scratch = np.zeros(40 * 64, np.int32)
+        self.erom
+        err = self.lib.xo_sbr_dec_lp(P(self.qrom), P(self._erom), P(self._mrom), P(np.ascontiguousarray(side, np.int16)),
+                                     P(s), P(np.ascontiguousarray(time_in, np.int16)), 1, P(out), 1, P(scratch))
+        return s, out, err
+
     def imdct_out_to_pcm16(self, samples, qshift_adj, mode):
         x = np.ascontiguousarray(samples, np.int32)
         q = np.ascontiguousarray(qshift_adj, np.int8)
@@ -202,6 +212,13 @@ class Ref:
         err = self.lib.ref_sbr_dec_hq(P(np.ascontiguousarray(side, np.int16)), P(s), None if p is None else P(p),
                                       P(np.ascontiguousarray(time_in, np.int16)), P(ol), P(orr))
         return s, p, ol, orr, err
+
+    def sbr_dec_lp(self, side, st, time_in):
+        s = np.ascontiguousarray(st, np.int16).copy()
+        out = np.zeros(2048, np.int16)
+        err = self.lib.ref_sbr_dec_lp(P(np.ascontiguousarray(side, np.int16)), P(s),
+                                      P(np.ascontiguousarray(time_in, np.int16)), P(out))
+        return s, out, err
 
     def ps_apply_frame(self, side, st, ps, sf, m, usb, common_shift):
         p = np.ascontiguousarray(ps, np.int16).copy()
@@ -459,3 +476,41 @@ def synth_sbr_units(n, seed, golden):
             st[u, 326] = rng.integers(-6, 16)      # ov_lb_scale
             st[u, 328] = rng.integers(0, 20)       # ov_hb_scale
     return side, st, ps, tin
+
+
+def synth_sbr_lp_units(n, seed, golden):
+    """Low-power whole-stage inputs: side info / state from tapped HE-AACv1 stereo frames, core PCM and state perturbed
+    like synth_sbr_units.  Returns side [n,1232], st [n,3920], tin [n,1024]."""
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, len(golden["side"]), n)
+    side = golden["side"][idx].copy()
+    st = golden["st_in"][idx].copy()
+    tin = np.zeros((n, 1024), np.int16)
+    for u in range(n):
+        amp = 2.0 ** rng.integers(2, 16)
+        kind = u % 4
+        if kind == 0:
+            x = golden["tin"][idx[u]].astype(np.float64)
+        elif kind == 1:
+            x = rng.standard_normal(1024) * amp / 3
+        elif kind == 2:
+            x = amp * np.sin(2 * np.pi * rng.uniform(0.001, 0.49) * np.arange(1024) + rng.uniform(0, 6))
+        else:
+            x = rng.integers(-32768, 32768, 1024).astype(np.float64)
+        tin[u] = np.clip(x, -32768, 32767).astype(np.int16)
+        if u % 3 == 2:
+            side[u, 736] = 0
+        if u % 5 == 1:
+            st[u, 0:320] = rng.integers(-20000, 20000, 320)
+            st[u, 580:1860] = rng.integers(-20000, 20000, 1280)
+            ov = np.zeros(768, np.int32)
+            ov[:384] = ((rng.random(384) * 2 - 1) * 2.0 ** rng.integers(10, 30)).astype(np.int64).astype(np.int32)
+            st[u, 2384:3920] = ov.view(np.int16)
+            st[u, 326] = rng.integers(-6, 16)
+            st[u, 328] = rng.integers(0, 20)
+        if u % 4 == 1:
+            nhi = side[u, 7]
+            side[u, 151:151 + nhi] = rng.random(nhi) < 0.3
+            side[u, 3] = rng.integers(0, 4)
+            side[u, 4] = rng.integers(0, 2)
+    return side, st, tin

@@ -284,9 +284,30 @@ def make_sbrdec_golden(tmp):
     print(f"wrote {path}: {len(sel)} of {len(recs)} records ({n_ps} with PS), {os.path.getsize(path)} bytes")
 
 
+def make_sbrdec_lp_golden(tmp):
+    """whole-stage records of the low-power (real-valued) path: HE-AACv1 STEREO 48 kHz decoded with -esbr:0 (two
+    ixheaacd_sbr_dec calls per frame, one per channel; records alternate between the channels)."""
+    fs, ch, aot, br, seed = 48000, 2, 5, 64000, 15
+    wav = os.path.join(tmp, "in_v1st.wav")
+    write_wav(wav, synth(fs, 5.0, ch, seed), fs)
+    aac = os.path.join(tmp, "he_v1st.aac")
+    encode(wav, aac, aot, br)
+    tap = os.path.join(tmp, "he_v1st.tap")
+    decode_tap(aac, os.path.join(tmp, "o.wav"), tap, ["-esbr:0"], stages="slp")
+    recs = read_sbr_records(tap)
+    assert all(r["hdr"][5] == 1 for r in recs)
+    keep = list(range(0, 26)) + list(range(30, len(recs), 14))
+    sel = [recs[i] for i in keep]
+    out = {k: np.stack([r[k] for r in sel]) for k in ("hdr", "side", "st_in", "tin", "st_out", "out_l")}
+    out["index"] = np.array(keep, np.int32)
+    path = os.path.join(GOLD, "sbrdec_lp_tapped.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(sel)} of {len(recs)} records, {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
@@ -296,6 +317,8 @@ def main():
             make_envcalc_golden(tmp)
         if "sbrdec" in which:
             make_sbrdec_golden(tmp)
+        if "sbrdec_lp" in which:
+            make_sbrdec_lp_golden(tmp)
 
 
 if __name__ == "__main__":
