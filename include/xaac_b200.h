@@ -319,6 +319,9 @@ int32_t xaac_b200_set_ps_rom(xaac_b200_ctx *ctx, const void *ps_tables, size_t b
  * boundary); either blob pointer may be NULL.  A new state is all-zero; upload the decoder's reset state
  * (decoder/ixheaacd_sbrdec_initfuncs.c:599-1213) before the first frame. */
 typedef struct xaac_b200_sbr_state xaac_b200_sbr_state;
+/* with_ps: 0 = one HQ channel per unit, 1 = HQ channel + parametric stereo (second synthesis bank),
+ * XAAC_B200_SBR_STATE_LP = low-power channel (xaac_b200_sbr_dec_lp_dev only; no stage scratch is allocated) */
+#define XAAC_B200_SBR_STATE_LP 2
 int32_t xaac_b200_sbr_state_create(xaac_b200_ctx *ctx, int64_t n_units, int32_t with_ps, xaac_b200_sbr_state **state);
 void xaac_b200_sbr_state_destroy(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state);
 int32_t xaac_b200_sbr_state_upload(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, const int16_t *st_blob,
@@ -334,6 +337,25 @@ int32_t xaac_b200_sbr_state_download(xaac_b200_ctx *ctx, xaac_b200_sbr_state *st
  *              valid output nor a defined state, as in the reference, which aborts the frame */
 int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, const int16_t *d_side,
                                  const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, void *stream);
+
+/* ---- low-power (real-valued) SBR stage: ixheaacd_sbr_dec with low_pow_flag = 1 --------------------------------
+ * The path the reference runs for stereo HE-AACv1 in its fixed-point mode (decoder/ixheaacd_sbrdecoder.c:408-419:
+ * low_pow_flag = 1 unless the stream is mono / PS): 32-band real analysis (ixheaacd_cplx_anal_qmffilt with
+ * ixheaacd_dct3_32, decoder/generic/ixheaacd_qmf_dec_generic.c:63-239, 590-741), ixheaacd_low_pow_hf_generator
+ * (decoder/ixheaacd_lpp_tran.c:843-954), ixheaacd_calc_sbrenvelope with the low-power leaves and alias reduction
+ * (decoder/ixheaacd_env_calc.c:78-227, 692-1015, 1564-1757) and the real 64-band synthesis (ixheaacd_cplx_synt_qmffilt
+ * with ixheaacd_inv_modulation_lp / ixheaacd_dct2_64, decoder/ixheaacd_qmf_dec.c:72-211, 811-1129).
+ * ONE fused kernel: the unit's QMF matrix never leaves shared memory.  Same side-info record and state blob as the HQ
+ * stage (the overlap slots hold 6 real rows of 64 words, the LPC rows 32 real words each); the state must have been
+ * created with XAAC_B200_SBR_STATE_LP or with_ps = 0.
+ *   d_side     [n][1232] WORD16 side info (PS part ignored)
+ *   d_time_in  [n][1024] PCM16 core-coder output of the unit's channel
+ *   d_time_out [n / out_ch][2048][out_ch] PCM16: unit u is channel u % out_ch of frame u / out_ch (out_ch = 2 gives the
+ *              reference's interleaved stereo time buffer)
+ *   d_err      [n] WORD32 or NULL (0 / 0x80000000) */
+int32_t xaac_b200_sbr_dec_lp_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, const int16_t *d_side,
+                                 const int16_t *d_time_in, int16_t *d_time_out, int32_t out_ch, int32_t *d_err,
+                                 void *stream);
 
 /* Host-buffer entry point for a whole HE-AAC (v1 mono / v2) frame per unit: IMDCT + window/OLA of the core channel
  * (xaac_b200_imdct_process_dev), the WORD32 -> PCM16 hand-over (xaac_b200_imdct_out_to_pcm16_dev, mode 0) and the SBR

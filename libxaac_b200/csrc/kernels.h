@@ -209,6 +209,26 @@ struct PsArgs {
 };
 cudaError_t launch_ps_frame(const PsArgs &args, int num_sms, cudaStream_t stream);
 
+// ---- whole fixed-point LOW-POWER SBR stage (ixheaacd_sbr_dec, low_pow_flag = 1), one fused kernel ----------------
+struct SbrLpArgs {
+  const int16_t *side;       // [n][1232] side info (XAAC_SIDE_*; the PS part is ignored)
+  const int16_t *time_in;    // core-coder PCM16: unit u reads 1024 samples at time_in + u * in_unit_stride, stride in_ch
+  int16_t *time_out;         // PCM16 out: unit u writes 2048 samples at time_out + (u / out_ch) * 2048 * out_ch + u % out_ch,
+                             // sample stride out_ch (out_ch = 2: L/R interleaved stereo frames)
+  int16_t *anal_states, *anal_pos, *syn_pos, *sf, *misc, *env, *syn_states;  // channel state, structure of arrays
+  int32_t *bw_prev, *lpc, *ov;
+  int32_t *err;              // [n] or null: 0 / 0x80000000
+  const uint8_t *lp_rom;     // device image built by sbr_lp_build_tables()
+  const uint8_t *env_rom, *misc_rom;
+  long long n_units;
+  long long in_unit_stride = 1024;
+  int in_ch = 1;
+  int out_ch = 1;
+};
+size_t sbr_lp_table_bytes();
+int sbr_lp_build_tables(const uint8_t *qrom, uint8_t *out);  // 0 ok, -1 tables unsupported
+cudaError_t launch_sbr_dec_lp(const SbrLpArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

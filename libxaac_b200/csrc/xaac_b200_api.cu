@@ -20,6 +20,7 @@ struct xaac_b200_ctx {
   int qmf_fast_bits = 0;
   uint8_t *d_rom_qmf_ana = nullptr;  // table image of qmf_anal_hq_kernel
   int qmf_anal_exact = 0;
+  uint8_t *d_rom_lp = nullptr;       // table image of sbr_dec_lp_kernel (null: tables unsupported by the LP kernel)
   uint8_t *d_rom_env = nullptr;   // ia_env_calc_tables_struct
   uint8_t *d_rom_misc = nullptr;  // leading part of ixheaacd_misc_tables
   bool have_env_rom = false;
@@ -56,6 +57,7 @@ struct xaac_b200_imdct_state {
 struct xaac_b200_sbr_state {
   int64_t n_units = 0;
   bool with_ps = false;
+  bool lp_only = false;  // created for the low-power stage: no stage scratch
   // channel state (host blob XAAC_SBR_ST_*)
   int16_t *anal_states = nullptr, *anal_pos = nullptr, *syn_pos = nullptr, *sf = nullptr, *misc = nullptr, *env = nullptr,
           *syn_states = nullptr;
@@ -166,6 +168,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   if (ctx->d_rom_imdct) cudaFree(ctx->d_rom_imdct);
   if (ctx->d_rom_qmf_syn) cudaFree(ctx->d_rom_qmf_syn);
   if (ctx->d_rom_qmf_ana) cudaFree(ctx->d_rom_qmf_ana);
+  if (ctx->d_rom_lp) cudaFree(ctx->d_rom_lp);
   if (ctx->d_rom_env) cudaFree(ctx->d_rom_env);
   if (ctx->d_rom_misc) cudaFree(ctx->d_rom_misc);
   if (ctx->d_rom_ps) cudaFree(ctx->d_rom_ps);
@@ -360,6 +363,21 @@ int32_t xaac_b200_set_qmf_rom(xaac_b200_ctx *ctx, const void *tables, size_t byt
     free(ia);
     if (e2 != cudaSuccess) return fail(ctx, e2, "cudaMemcpy(qmf anal rom)");
     ctx->qmf_anal_exact = ex;
+  }
+  {  // low-power stage tables (dct3_32 / dct2_64 twiddles, prototype)
+    size_t nl = xb::sbr_lp_table_bytes();
+    uint8_t *il = (uint8_t *)calloc(1, nl + 64);
+    if (!il) return XAAC_B200_FATAL;
+    if (xb::sbr_lp_build_tables((const uint8_t *)tables, il) == 0) {
+      cudaError_t e3 = ctx->d_rom_lp ? cudaSuccess : cudaMalloc((void **)&ctx->d_rom_lp, nl);
+      if (e3 == cudaSuccess) e3 = cudaMemcpy(ctx->d_rom_lp, il, nl, cudaMemcpyHostToDevice);
+      free(il);
+      if (e3 != cudaSuccess) return fail(ctx, e3, "cudaMemcpy(lp rom)");
+    } else {
+      free(il);
+      if (ctx->d_rom_lp) cudaFree(ctx->d_rom_lp);
+      ctx->d_rom_lp = nullptr;
+    }
   }
   ctx->have_qmf_rom = true;
   ctx->qmf_fast_bits = fast_bits;
@@ -619,7 +637,8 @@ int32_t xaac_b200_sbr_state_create(xaac_b200_ctx *ctx, int64_t n_units, int32_t 
   xaac_b200_sbr_state *s = new (std::nothrow) xaac_b200_sbr_state();
   if (!s) return XAAC_B200_FATAL;
   s->n_units = n_units;
-  s->with_ps = with_ps != 0;
+  s->lp_only = with_ps == XAAC_B200_SBR_STATE_LP;
+  s->with_ps = with_ps != 0 && !s->lp_only;
   BlobPart st[16], ps[8];
   int n_st, n_ps;
   sbr_state_parts(s, st, &n_st, ps, &n_ps);
@@ -631,11 +650,13 @@ int32_t xaac_b200_sbr_state_create(xaac_b200_ctx *ctx, int64_t n_units, int32_t 
   for (int i = 0; i < n_st; i++) alloc0(st[i].dev, st[i].bytes * (size_t)n_units);
   if (s->with_ps)
     for (int i = 0; i < n_ps; i++) alloc0(ps[i].dev, ps[i].bytes * (size_t)n_units);
-  alloc0((void **)&s->matrix, (size_t)n_units * xb::kSbrMatWords * 4);
   alloc0((void **)&s->err, (size_t)n_units * 4);
-  alloc0((void **)&s->usb, (size_t)n_units * 2);
-  alloc0((void **)&s->hf_prm, (size_t)n_units * 160);
-  alloc0((void **)&s->synp, (size_t)n_units * 16);
+  if (!s->lp_only) {
+    alloc0((void **)&s->matrix, (size_t)n_units * xb::kSbrMatWords * 4);
+    alloc0((void **)&s->usb, (size_t)n_units * 2);
+    alloc0((void **)&s->hf_prm, (size_t)n_units * 160);
+    alloc0((void **)&s->synp, (size_t)n_units * 16);
+  }
   if (s->with_ps) {
     alloc0((void **)&s->right, (size_t)n_units * 4096 * 4);
     alloc0((void **)&s->synp_r, (size_t)n_units * 16);
@@ -746,6 +767,7 @@ static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long lo
 
 static int32_t sbr_check(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s) {
   if (!ctx || !s) return XAAC_B200_ERR_ARG;
+  if (s->lp_only) return bad_arg(ctx, "state was created for the low-power stage (XAAC_B200_SBR_STATE_LP)");
   if (!ctx->have_qmf_rom || !ctx->have_env_rom || (s->with_ps && !ctx->have_ps_rom)) {
     snprintf(ctx->err, sizeof(ctx->err), "set_qmf_rom / set_env_rom / set_ps_rom have not all been called");
     return XAAC_B200_ERR_NO_ROM;
@@ -760,6 +782,38 @@ int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, con
   if (!d_side || !d_time_in || !d_time_out) return bad_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   return sbr_dec_range(ctx, s, 0, s->n_units, d_side, d_time_in, d_time_out, d_err, (cudaStream_t)stream);
+}
+
+// One low-power frame for units [u0, u0 + n) of the state.
+static int32_t sbr_dec_lp_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long long u0, long long n, const int16_t *d_side,
+                                const int16_t *d_time_in, int16_t *d_time_out, int32_t out_ch, int32_t *d_err,
+                                cudaStream_t st) {
+  xb::SbrLpArgs a;
+  a.side = d_side; a.time_in = d_time_in; a.time_out = d_time_out;
+  a.anal_states = s->anal_states + u0 * 320; a.anal_pos = s->anal_pos + u0 * 2; a.syn_pos = s->syn_pos + u0 * 2;
+  a.sf = s->sf + u0 * 8; a.misc = s->misc + u0 * 16; a.env = s->env + u0 * xb::kEnvStWords;
+  a.syn_states = s->syn_states + u0 * 1280; a.bw_prev = s->bw_prev + u0 * 6; a.lpc = s->lpc + u0 * 256; a.ov = s->ov + u0 * 768;
+  a.err = d_err ? d_err : s->err + u0;
+  a.lp_rom = ctx->d_rom_lp; a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc;
+  a.n_units = n; a.out_ch = out_ch;
+  LAUNCH("sbr_dec_lp_kernel", st, xb::launch_sbr_dec_lp(a, ctx->num_sms, st));
+  ctx->launches += 1;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_sbr_dec_lp_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side,
+                                 const int16_t *d_time_in, int16_t *d_time_out, int32_t out_ch, int32_t *d_err,
+                                 void *stream) {
+  if (!ctx || !s) return XAAC_B200_ERR_ARG;
+  if (!ctx->have_qmf_rom || !ctx->have_env_rom) {
+    snprintf(ctx->err, sizeof(ctx->err), "set_qmf_rom / set_env_rom have not both been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (!ctx->d_rom_lp) return bad_arg(ctx, "the installed QMF tables are not supported by the low-power kernel");
+  if (!d_side || !d_time_in || !d_time_out) return bad_arg(ctx, "null buffer");
+  if (out_ch < 1 || (s->n_units % out_ch) != 0) return bad_arg(ctx, "out_ch must divide the number of units");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return sbr_dec_lp_range(ctx, s, 0, s->n_units, d_side, d_time_in, d_time_out, out_ch, d_err, (cudaStream_t)stream);
 }
 
 // HE-AAC frame from host buffers: IMDCT (mono or one core channel per unit) -> WORD32->PCM16 hand-over -> SBR stage.

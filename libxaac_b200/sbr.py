@@ -63,10 +63,13 @@ class SbrState:
     """Device-resident state of n SBR channels for sbr_dec (what ia_sbr_dec_struct / ia_ps_dec_struct carry between
     frames).  upload / download move host blobs: numpy int16 [n, 3920] (channel) and [n, 3888] (PS)."""
 
-    def __init__(self, ctx, n_units, with_ps=False):
-        self.ctx, self.n_units, self.with_ps = ctx, int(n_units), bool(with_ps)
+    def __init__(self, ctx, n_units, with_ps=False, low_power=False):
+        """low_power=True: state for sbr_dec_lp only (XAAC_B200_SBR_STATE_LP: no stage scratch in HBM)"""
+        self.ctx, self.n_units, self.with_ps = ctx, int(n_units), bool(with_ps) and not low_power
+        self.low_power = bool(low_power)
         self._h = ctypes.c_void_p()
-        ctx.check(ctx._lib.xaac_b200_sbr_state_create(ctx.handle, self.n_units, int(self.with_ps), ctypes.byref(self._h)),
+        mode = 2 if self.low_power else int(self.with_ps)
+        ctx.check(ctx._lib.xaac_b200_sbr_state_create(ctx.handle, self.n_units, mode, ctypes.byref(self._h)),
                   "xaac_b200_sbr_state_create")
 
     @property
@@ -122,6 +125,28 @@ def sbr_dec(ctx, state, side, time_in, time_out=None, err=None, stream=None):
     rc = ctx._lib.xaac_b200_sbr_dec_hq_dev(ctx.handle, state.handle, _ptr(side), _ptr(time_in), _ptr(time_out), _ptr(err),
                                           ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_sbr_dec_hq_dev")
+    return time_out, err
+
+
+def sbr_dec_lp(ctx, state, side, time_in, time_out=None, out_ch=1, err=None, stream=None):
+    """Batched drop-in for ixheaacd_sbr_dec with low_pow_flag = 1 (the fixed-point path of stereo HE-AACv1,
+    decoder/ixheaacd_sbr_dec.c:662; one fused kernel).  side int16 [n,1232]; time_in int16 [n,1024]; returns
+    (time_out, err): time_out int16 [n // out_ch, 2048, out_ch] (unit u = channel u % out_ch of frame u // out_ch), or
+    [n, 2048] for out_ch = 1; err int32 [n]."""
+    n = state.n_units
+    _chk(side, torch.int16, (n, SIDE_WORDS), "side", "cuda")
+    _chk(time_in, torch.int16, (n, 1024), "time_in", "cuda")
+    shape = (n, 2048) if out_ch == 1 else (n // out_ch, 2048, out_ch)
+    if time_out is None:
+        time_out = torch.zeros(shape, dtype=torch.int16, device=side.device)
+    _chk(time_out, torch.int16, shape, "time_out", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=side.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(side.device)
+    rc = ctx._lib.xaac_b200_sbr_dec_lp_dev(ctx.handle, state.handle, _ptr(side), _ptr(time_in), _ptr(time_out), int(out_ch),
+                                          _ptr(err), ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_sbr_dec_lp_dev")
     return time_out, err
 
 
