@@ -37,12 +37,17 @@ CHAIN_KERNEL_BYTES = {
     "sbr_post_kernel": 4672,              # 1536 overlap out + LPC rows 2 x 1024 + parameters
     "ps_frame_kernel": 60928,             # ps_kernel.cu header
     "qmf_synth_hq_kernel": SYNTH_BYTES_PER_UNIT,
+    # fused low-power stage (sbr_lp_kernel.cu): 2048 PCM16 in + 4096 PCM16 out + 2 x 5536 channel state (analysis ring 644,
+    # synthesis ring 2564, envelope state 464, overlap rows 1536, LPC rows 256, scale factors / misc / bw 72) + 1480 side info
+    "sbr_dec_lp_kernel": 18696,
 }
 WORKLOADS = {
     # name -> (BASELINE.json config index, stereo frames per GPU, description)
     "heaacv2_chain": (3, 131072, "HE-AACv2 (SBR+PS) stereo 44.1 kHz batch=131072: full IMDCT->QMF->SBR->PS "
                                  "hybrid/decorrelate chain (fixed-point path of the reference, -esbr:0)"),
     "aac_lc_stereo_imdct_ola": (1, 65536, "AAC-LC stereo 44.1 kHz batch=65536 frames, IMDCT+OLA only"),
+    "heaacv1_stereo_chain": (2, 65536, "HE-AACv1 stereo 48 kHz batch=65536: IMDCT + 64-band QMF analysis/synthesis + LPP "
+                                       "HF-gen + env_calc (fixed-point path of the reference, -esbr:0: low-power SBR)"),
     "qmf_synth_hq": (3, 65536, "stand-alone fixed-point HQ 64-band QMF synthesis stage of the HE-AAC chain, "
                                "batch=65536 stereo frames (131072 output channels)"),
 }
@@ -342,6 +347,62 @@ def cpu_arm_chain(n_units, threads, seed, reps=1):
     return 2.0 * n_units * reps / dt, "reference"
 
 
+def load_chain_lp_golden():
+    """HE-AACv1 stereo side info / state tapped from a real decode of the reference (tests/golden/sbrdec_lp_tapped.npz):
+    records 2..25 are 12 consecutive frames of the two channels (even records L, odd records R)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sbrdec_lp_tapped.npz"))
+    side = np.stack([g["side"][2:26:2], g["side"][3:26:2]], axis=1)  # [frame 12][ch 2][1232]
+    st0 = np.stack([g["st_in"][2], g["st_in"][3]])                   # [ch 2][3920]
+    return side.copy(), st0.copy()
+
+
+def chain_lp_side(side_frames, n_units, f):
+    """side info of frame f for n_units channel units (unit u = channel u & 1 of stream u >> 1, phase (u >> 1) mod 12)"""
+    u = np.arange(n_units)
+    return np.ascontiguousarray(side_frames[((u >> 1) + f) % 12, u & 1])
+
+
+def cpu_arm_chain_lp(n_units, threads, seed, reps=1):
+    """Time the reference's own stereo HE-AACv1 chain per channel unit on host threads: ixheaacd_imdct_process ->
+    WORD32->WORD16 hand-over -> ixheaacd_sbr_dec (low_pow_flag = 1).  Returns (units_per_s, kind)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    if ref is None:
+        raise SystemExit("bench.py: the HE-AACv1 chain CPU baseline needs oracle/_ref/libxaac_ref.so (make ref)")
+    n_units -= n_units & 1
+    side_frames, st0 = load_chain_lp_golden()
+    P = oracle_util.P
+    st = np.ascontiguousarray(np.tile(st0, (n_units // 2, 1)))
+    ref.lib.ref_chain_lp_create.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(ref.lib.ref_chain_lp_create(n_units, P(chain_lp_side(side_frames, n_units, 0)), P(st)))
+    spec0 = chain_inputs_np(n_units, seed)
+    walk = sequence_walk(n_units, reps + 1, seed)
+    out = np.zeros((n_units // 2, 2048, 2), np.int16)
+    bounds = (np.linspace(0, n_units // 2, threads + 1).astype(int)) * 2
+    sides = [chain_lp_side(side_frames, n_units, f) for f in range(12)]
+
+    def work(t, spec, ics, side):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            ref.lib.ref_chain_lp_step(h, a, b, P(spec), P(ics), P(side), P(out))
+
+    def one_pass(step):
+        spec = spec0.copy()
+        ics = np.ascontiguousarray(walk[step])
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t, spec, ics, sides[step % 12])) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    one_pass(0)
+    dt = sum(one_pass(1 + r) for r in range(reps))
+    ref.lib.ref_chain_destroy(h)
+    return n_units * reps / dt, "reference"
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -355,6 +416,12 @@ STAGES = {
                                 "PS hybrid/decorrelation/rotation -> 2 x QMF synthesis (fixed-point, bit-exact)",
                           ref_stage="ixheaacd_imdct_process + ixheaacd_sbr_dec (HQ, PS)", cpu=cpu_arm_chain,
                           cpu_units_per_core=128, cpu_reps=12, realtime_fps=21.533, h2d=4096 + 2 + 2464, d2h=8192),
+    "heaacv1_stereo_chain": dict(kernel=None, top_kernel="sbr_dec_lp_kernel", bytes_per_unit=None,
+                                 stage="per channel: IMDCT+OLA -> PCM16 hand-over -> fused low-power SBR stage (real QMF "
+                                       "analysis, LP HF generation, envelope adjustment + alias reduction, real QMF "
+                                       "synthesis; fixed-point, bit-exact)",
+                                 ref_stage="ixheaacd_imdct_process + ixheaacd_sbr_dec (low power)", cpu=cpu_arm_chain_lp,
+                                 cpu_units_per_core=256, cpu_reps=12, realtime_fps=23.4375, h2d=4096 + 2 + 2464, d2h=4096),
     "aac_lc_stereo_imdct_ola": dict(kernel="imdct_ola_kernel", bytes_per_unit=IMDCT_BYTES_PER_UNIT,
                                     stage="IMDCT + window/OLA (fixed-point WORD32, bit-exact)",
                                     ref_stage="ixheaacd_imdct_process", cpu=cpu_arm, cpu_units_per_core=4096,
@@ -509,7 +576,61 @@ class ChainWork:
         self.state.close()
 
 
-WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv2_chain": ChainWork}
+class ChainLpWork:
+    """Stereo HE-AACv1 frames on the reference's fixed-point low-power path: unit = one core channel (units 2k / 2k+1 =
+    L / R of stream k): IMDCT -> PCM16 -> fused LP SBR stage -> interleaved stereo PCM16.  Side info / initial state are
+    tiled from a tapped real stream (12 consecutive frames, stream k runs them with phase k mod 12)."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        side_frames, st0 = load_chain_lp_golden()
+        self.spec = torch.from_numpy(chain_inputs_np(n_units, seed)).to(dev)
+        self.walk = torch.from_numpy(sequence_walk(n_units, steps_total, seed)).to(dev)
+        self.nw = steps_total
+        self.side = [torch.from_numpy(chain_lp_side(side_frames, n_units, f)).to(dev) for f in range(12)]
+        self.imdct_state = xb.ImdctBatch(n_units, device=dev)
+        self.state = xb.SbrState(ctx, n_units, low_power=True)
+        self.st0 = st0
+        self.state.upload(np.tile(st0, (n_units // 2, 1)), None)
+        self.w32 = torch.empty((n_units, 1024), dtype=torch.int32, device=dev)
+        self.adj = torch.empty((n_units,), dtype=torch.int8, device=dev)
+        self.p16 = torch.empty((n_units, 1024), dtype=torch.int16, device=dev)
+        self.pcm = torch.empty((n_units // 2, 2048, 2), dtype=torch.int16, device=dev)
+        self.err = torch.zeros((n_units,), dtype=torch.int32, device=dev)
+
+    def step(self, i, stream):
+        xb, ctx = self.xb, self.ctx
+        xb.imdct_process(ctx, self.imdct_state, self.spec, self.walk[i % self.nw], self.w32, self.adj, stream=stream)
+        xb.imdct_out_to_pcm16(ctx, self.w32, self.adj, 0, self.p16, stream=stream)
+        xb.sbr_dec_lp(ctx, self.state, self.side[i % 12], self.p16, self.pcm, 2, self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0, "the LP SBR stage reported an error for some unit"
+
+    def host_setup(self):
+        import torch
+        self.h_spec = torch.empty((self.n, 1024), dtype=torch.int32).pin_memory()
+        self.h_spec.copy_(self.spec)
+        self.h_walk = self.walk.cpu().pin_memory()
+        self.h_side = [x.cpu().pin_memory() for x in self.side]
+        self.h_pcm = torch.empty((self.n // 2, 2048, 2), dtype=torch.int16).pin_memory()
+        self.h_imdct = self.xb.ImdctHostState(self.ctx, self.n)
+        self.h_state = self.xb.SbrState(self.ctx, self.n, low_power=True)
+        self.h_state.upload(np.tile(self.st0, (self.n // 2, 1)), None)
+
+    def host_step(self, i):
+        self.xb.heaac_lp_frame_host(self.ctx, self.h_imdct, self.h_state, self.h_spec, self.h_walk[i % self.nw],
+                                    self.h_side[i % 12], self.h_pcm, 2)
+
+    def host_close(self):
+        self.h_imdct.close()
+        self.h_state.close()
+        self.state.close()
+
+
+WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv2_chain": ChainWork,
+        "heaacv1_stereo_chain": ChainLpWork}
 
 
 def main():
@@ -632,7 +753,7 @@ def main():
         peak, peak_src = peaks()
         if kernel_table is not None:
             # the BASELINE metric kernel is the QMF synthesis; it is also the largest share of the chain
-            top = "qmf_synth_hq_kernel"
+            top = stg.get("top_kernel", "qmf_synth_hq_kernel")
             stg = dict(stg, kernel=top, bytes_per_unit=CHAIN_KERNEL_BYTES[top])
             kernel_ms = kernel_table[top]["launch_ms"]
         achieved = stg["bytes_per_unit"] * n_units / (kernel_ms * 1e-3) / 1e9
@@ -662,7 +783,8 @@ def main():
                 v["frac"] = None if v["achieved"] is None else v["achieved"] / peak
             line["kernels"] = kernel_table
             line["roofline"]["note"] = ("per-launch duration from CUDA events around every launch of a second pass of "
-                                        "the same steps; two launches per step (left, right)")
+                                        "the same steps" + ("; two launches per step (left, right)"
+                                                            if top == "qmf_synth_hq_kernel" else ""))
         if args.workload == "aac_lc_stereo_imdct_ola":
             line["config"]["window_sequence_mix"] = "walk: ~90% long, 4% start, 4% stop, 2% short"
         # short extra runs of the other stage kernels so every hot kernel has a live roofline number
@@ -671,7 +793,7 @@ def main():
             for name in WORK:
                 if name == args.workload:
                     continue
-                if name == "heaacv2_chain":
+                if STAGES[name]["kernel"] is None:
                     continue
                 w2 = WORK[name](xb, ctx, 131072, 8, seed, dev)
                 ms, _, _ = timed(w2, 5, 3)

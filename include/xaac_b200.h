@@ -366,6 +366,12 @@ int32_t xaac_b200_heaac_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *im
                                    const int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *pcm,
                                    int32_t *err);
 
+/* The same for stereo HE-AACv1 streams on the low-power path: unit = one core channel (units 2k / 2k+1 = L / R of stream
+ * k with out_ch = 2), `sbr_state` created with XAAC_B200_SBR_STATE_LP.  pcm [n / out_ch][2048][out_ch] PCM16. */
+int32_t xaac_b200_heaac_lp_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *imdct_state,
+                                      xaac_b200_sbr_state *sbr_state, const int32_t *spec, const uint8_t *ics,
+                                      const int16_t *side, int16_t *pcm, int32_t out_ch, int32_t *err);
+
 /* ---- stage glue: WORD32 IMDCT output -> PCM16 ---------------------------------------------
  * mode 0 replaces the conversion loop of ixheaacd_allocate_sbr_scr (decoder/ixheaacd_api.c:337-370):
  *        round16(shl32_sat(x, qshift_adj)), the core-coder -> SBR hand-over;

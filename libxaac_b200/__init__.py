@@ -25,7 +25,7 @@ from .qmf import (  # noqa: F401
     cplx_synt_qmffilt_host,
     synth_params,
 )
-from .sbr import SbrState, calc_sbrenvelope, heaac_frame_host, hf_generator, sbr_dec, sbr_dec_lp  # noqa: F401
+from .sbr import SbrState, calc_sbrenvelope, heaac_frame_host, heaac_lp_frame_host, hf_generator, sbr_dec, sbr_dec_lp  # noqa: F401
 
 __all__ = [
     "hf_generator",
@@ -34,6 +34,7 @@ __all__ = [
     "sbr_dec",
     "sbr_dec_lp",
     "heaac_frame_host",
+    "heaac_lp_frame_host",
     "QmfAnalBatch",
     "cplx_anal_qmffilt",
     "QmfSynthBatch",

@@ -51,6 +51,7 @@ SIGNATURES = {
     "xaac_b200_sbr_dec_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xaac_b200_sbr_dec_lp_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "xaac_b200_heaac_frame_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "xaac_b200_heaac_lp_frame_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "xaac_b200_imdct_out_to_pcm16_dev": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
 }
 

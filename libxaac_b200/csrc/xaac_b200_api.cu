@@ -864,6 +864,57 @@ int32_t xaac_b200_heaac_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *is
   return XAAC_B200_OK;
 }
 
+// Stereo HE-AACv1 (low-power SBR) frames from host buffers: unit = one channel; IMDCT -> hand-over -> fused LP stage.
+int32_t xaac_b200_heaac_lp_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *ist, xaac_b200_sbr_state *s,
+                                      const int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *pcm,
+                                      int32_t out_ch, int32_t *err) {
+  if (!ctx || !s) return XAAC_B200_ERR_ARG;
+  if (!ctx->have_qmf_rom || !ctx->have_env_rom || !ctx->d_rom_lp) {
+    snprintf(ctx->err, sizeof(ctx->err), "set_qmf_rom / set_env_rom have not both been called (or tables unsupported)");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (!ist || !ctx->have_imdct_rom) return bad_arg(ctx, "IMDCT state / ROM missing");
+  if (ist->n_units != s->n_units) return bad_arg(ctx, "IMDCT and SBR states must have the same number of units");
+  if (!spec || !ics || !side || !pcm) return bad_arg(ctx, "null buffer");
+  if (out_ch < 1 || out_ch > 8 || (s->n_units % out_ch) != 0) return bad_arg(ctx, "out_ch must divide the number of units");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  const int64_t n_units = s->n_units;
+  int64_t chunk = 4096;  // multiple of every out_ch <= 8
+  if (chunk > n_units) chunk = n_units;
+  // per-unit staging: spec 4096 | WORD32 out 4096 | side 2464 | pcm16 in 2048 | pcm out 4096 | err 4 | ics 2 | adj 1 (+1)
+  const size_t o_spec = 0, o_w32 = 4096, o_side = 8192, o_p16 = 8192 + 2464, o_pcm = o_p16 + 2048, o_err = o_pcm + 4096,
+               o_ics = o_err + 4, o_adj = o_ics + 2, per_unit = o_adj + 2;
+  int32_t rc = ensure_stage(ctx, per_unit * (size_t)chunk);
+  if (rc != XAAC_B200_OK) return rc;
+  int slot = 0;
+  for (int64_t u0 = 0; u0 < n_units; u0 += chunk, slot = (slot + 1) % xaac_b200_ctx::kPipe) {
+    const int64_t n = (n_units - u0 < chunk) ? (n_units - u0) : chunk;
+    cudaStream_t st = ctx->streams[slot];
+    uint8_t *base = (uint8_t *)ctx->stage[slot];
+    int32_t *d_spec = (int32_t *)(base + o_spec * chunk), *d_w32 = (int32_t *)(base + o_w32 * chunk);
+    int16_t *d_side = (int16_t *)(base + o_side * chunk), *d_p16 = (int16_t *)(base + o_p16 * chunk);
+    int16_t *d_pcm = (int16_t *)(base + o_pcm * chunk);
+    int32_t *d_err = (int32_t *)(base + o_err * chunk);
+    uint8_t *d_ics = base + o_ics * chunk;
+    int8_t *d_adj = (int8_t *)(base + o_adj * chunk);
+    CK(cudaMemcpyAsync(d_spec, spec + u0 * 1024, (size_t)n * 4096, cudaMemcpyHostToDevice, st), "H2D spec");
+    CK(cudaMemcpyAsync(d_ics, ics + u0 * 2, (size_t)n * 2, cudaMemcpyHostToDevice, st), "H2D ics");
+    CK(cudaMemcpyAsync(d_side, side + u0 * xb::kSideWords, (size_t)n * xb::kSideWords * 2, cudaMemcpyHostToDevice, st),
+       "H2D side");
+    rc = xaac_b200_imdct_process_dev(ctx, d_spec, ist->d_overlap + u0 * 512, ist->d_wstate + u0 * 2, d_ics, d_w32, d_adj, n,
+                                     1, st);
+    if (rc != XAAC_B200_OK) return rc;
+    rc = xaac_b200_imdct_out_to_pcm16_dev(ctx, d_w32, d_adj, d_p16, n, 0, st);
+    if (rc != XAAC_B200_OK) return rc;
+    rc = sbr_dec_lp_range(ctx, s, u0, n, d_side, d_p16, d_pcm, out_ch, d_err, st);
+    if (rc != XAAC_B200_OK) return rc;
+    CK(cudaMemcpyAsync(pcm + u0 * 2048, d_pcm, (size_t)n * 4096, cudaMemcpyDeviceToHost, st), "D2H pcm");
+    if (err) CK(cudaMemcpyAsync(err + u0, d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H err");
+  }
+  for (int i = 0; i < xaac_b200_ctx::kPipe; i++) CK(cudaStreamSynchronize(ctx->streams[i]), "stream sync");
+  return XAAC_B200_OK;
+}
+
 int32_t xaac_b200_imdct_out_to_pcm16_dev(xaac_b200_ctx *ctx, const int32_t *d_in, const int8_t *d_qshift_adj,
                                          int16_t *d_out, int64_t n_units, int32_t mode, void *stream) {
   if (!ctx) return XAAC_B200_ERR_ARG;

@@ -163,3 +163,18 @@ def heaac_frame_host(ctx, imdct_state, sbr_state, spec_coeff, ics, side, pcm, er
                                             _ptr(side), _ptr(pcm), None if err is None else _ptr(err))
     ctx.check(rc, "xaac_b200_heaac_frame_host")
     return pcm
+
+
+def heaac_lp_frame_host(ctx, imdct_state, sbr_state, spec_coeff, ics, side, pcm, out_ch=2, err=None):
+    """One stereo HE-AACv1 frame per `out_ch` units from host buffers (IMDCT + hand-over + fused low-power SBR stage).
+    spec_coeff int32 [n,1024], ics uint8 [n,2], side int16 [n,1232], pcm int16 [n // out_ch, 2048, out_ch] (CPU tensors,
+    pinned recommended); sbr_state created with low_power=True."""
+    n = sbr_state.n_units
+    _chk(spec_coeff, torch.int32, (n, 1024), "spec_coeff", "cpu")
+    _chk(ics, torch.uint8, (n, 2), "ics", "cpu")
+    _chk(side, torch.int16, (n, SIDE_WORDS), "side", "cpu")
+    _chk(pcm, torch.int16, (n // out_ch, 2048, out_ch), "pcm", "cpu")
+    rc = ctx._lib.xaac_b200_heaac_lp_frame_host(ctx.handle, imdct_state._h, sbr_state.handle, _ptr(spec_coeff), _ptr(ics),
+                                               _ptr(side), _ptr(pcm), int(out_ch), None if err is None else _ptr(err))
+    ctx.check(rc, "xaac_b200_heaac_lp_frame_host")
+    return pcm

@@ -467,3 +467,43 @@ int ref_sbr_dec_lp(const int16_t *side, int16_t *st, const int16_t *time_in, int
   memcpy(out, tbuf, 2048 * sizeof(int16_t));
   return (int)ret;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * CPU baseline for the stereo HE-AACv1 chain (bench.py, BASELINE configs[2]): n persistent decoder CHANNELS (units
+ * 2k / 2k+1 = L / R of stream k) stepped through the UNMODIFIED reference stages ixheaacd_imdct_process -> WORD32->WORD16
+ * hand-over -> ixheaacd_sbr_dec with low_pow_flag = 1.  out [n / 2][2048][2] interleaved like the reference's buffer.
+ * ---------------------------------------------------------------------------------------------- */
+void *ref_chain_lp_create(int n, const int16_t *side, const int16_t *st) {
+  ref_chain *h = (ref_chain *)calloc(1, sizeof(ref_chain));
+  h->n = n;
+  h->u = (ref_chain_unit *)calloc((size_t)n, sizeof(ref_chain_unit));
+  if (!h->u) { free(h); return NULL; }
+  for (int i = 0; i < n; i++)
+    unpack_sbr_ctx_lp(&h->u[i].c, side + (size_t)i * XO_SIDE_WORDS, st + (size_t)i * XO_SBR_ST_WORDS, NULL, 1);
+  return h;
+}
+void ref_chain_lp_step(void *hv, int a, int b, int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *out) {
+  ref_chain *h = (ref_chain *)hv;
+  WORD32 tbuf32[1024];
+  WORD16 tbuf[2048];
+  for (int i = a; i < b; i++) {
+    ref_chain_unit *u = &h->u[i];
+    const int16_t *sd = side + (size_t)i * XO_SIDE_WORDS;
+    int adj = ref_imdct_process(spec + (size_t)i * 1024, u->overlap, &u->prev_shape, &u->prev_seq, ics[2 * i],
+                                ics[2 * i + 1], tbuf32, 1);
+    for (int k = 0; k < 1024; k++) tbuf[k] = ixheaac_round16(ixheaac_shl32_sat(tbuf32[k], adj));
+    ia_freq_band_data_struct *fb = &u->c.fb;
+    ia_sbr_prev_frame_data_struct pv_keep = u->c.pv;
+    unpack_env_prm(sd + XO_SIDE_ENV, &u->c.h, fb, &u->c.fd.f, &u->c.pv);
+    u->c.pv = pv_keep;
+    const int16_t *hf = sd + XO_SIDE_HF;
+    unpack_hf_settings(hf, &u->c.set);
+    fb->num_if_bands = hf[XO_HF_NUM_IF_BANDS];
+    for (int k = 0; k < MAX_NUM_NOISE_VALUES; k++) u->c.fd.f.sbr_invf_mode[k] = hf[XO_HF_INVF + k];
+    ixheaacd_sbr_dec(&u->c.d, tbuf, &u->c.h, &u->c.fd.f, &u->c.pv, NULL, NULL, NULL, sd[XO_SIDE_APPLY], 1, u->c.work,
+                     &u->c.tabs, (ixheaacd_misc_tables *)&ixheaacd_str_fft_n_transcendent_tables, 1, NULL, 0, NULL, AOT_SBR,
+                     0, NULL, 0, 0);
+    int16_t *o = out + (size_t)(i >> 1) * 4096 + (i & 1);
+    for (int k = 0; k < 2048; k++) o[2 * k] = tbuf[k];
+  }
+}

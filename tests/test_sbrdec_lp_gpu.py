@@ -98,3 +98,89 @@ def test_stereo_streams_state_resident(ctx, oracle):
             if u < 2:
                 assert np.array_equal(o, g["out_l"][2 + (u % 2) + 2 * f])
         assert np.array_equal(st2[u], s), f"unit {u}: final state differs at {np.argwhere(st2[u] != s).ravel()[:10]}"
+
+
+def test_heaac_lp_frame_host_matches_chained_oracles(ctx, oracle):
+    """stereo HE-AACv1 streams through the host-buffer entry point (IMDCT -> PCM16 hand-over -> fused LP stage), 3 frames,
+    n = 4400 channel units (> one 4096-unit chunk), against the chained CPU oracles; block-switching walk included"""
+    import torch
+    import libxaac_b200 as xb
+    g = np.load(GOLD)
+    n, frames = 4400, 3
+    rng = np.random.default_rng(33)
+    ist = xb.ImdctHostState(ctx, n)
+    sst = xb.SbrState(ctx, n, low_power=True)
+    u = np.arange(n)
+    st = np.ascontiguousarray(g["st_in"][2 + (u & 1)])
+    sst.upload(st, None)
+    ovl = np.zeros((n, 512), np.int32)
+    wstate = np.zeros((n, 2), np.uint8)
+    check = np.concatenate([np.arange(0, 40), np.arange(4090, 4130), np.arange(n - 20, n)])
+    for f in range(frames):
+        s = rng.integers(10, 22, (n, 1))
+        spec = ((rng.random((n, 1024)) * 2 - 1) * 2.0 ** s).astype(np.int64).astype(np.int32)
+        ics = np.zeros((n, 2), np.uint8)
+        ics[:, 1] = rng.integers(0, 2, n)
+        if f == 1:
+            ics[::7, 0] = 1  # long -> start
+        if f == 2:
+            ics[::7, 0] = 3  # start -> stop
+        side = np.ascontiguousarray(g["side"][2 + (u & 1) + 2 * (((u >> 1) + f) % 12)])
+        pcm = torch.zeros((n // 2, 2048, 2), dtype=torch.int16)
+        err = torch.zeros((n,), dtype=torch.int32)
+        xb.heaac_lp_frame_host(ctx, ist, sst, torch.from_numpy(spec), torch.from_numpy(ics), torch.from_numpy(side), pcm, 2,
+                               err)
+        out32, ovl, wstate, adj = oracle.imdct_batch(spec, ovl, wstate, ics)
+        p16 = oracle.imdct_out_to_pcm16(out32, adj, 0)
+        assert int(np.abs(err.numpy()).max()) == 0
+        got = pcm.numpy()
+        for k in check:
+            st[k], o, e = oracle.sbr_dec_lp(side[k], st[k], p16[k])
+            assert e == 0
+            assert np.array_equal(got[k // 2, :, k % 2], o), f"frame {f} unit {k}: PCM"
+    st2, _ = sst.download()
+    for k in check:
+        assert np.array_equal(st2[k], st[k]), f"unit {k}: final state"
+    ist.close()
+    sst.close()
+
+
+def test_full_batch_tiling_property(ctx, oracle):
+    """BASELINE configs[2] size (65536 stereo frames = 131072 channel units): 64 distinct units tiled 2048x through the
+    device path; tile 0 bit-exact against the oracle, every other tile equal to tile 0; two consecutive frames."""
+    import torch
+    import libxaac_b200 as xb
+    g = np.load(GOLD)
+    base_n, tiles = 64, 2048
+    n = base_n * tiles
+    rng = np.random.default_rng(9)
+    u = np.arange(base_n)
+    st = np.ascontiguousarray(g["st_in"][2 + (u & 1)])
+    state = xb.SbrState(ctx, n, low_power=True)
+    state.upload(np.tile(st, (tiles, 1)), None)
+    imdct_state = xb.ImdctBatch(n)
+    ovl = np.zeros((base_n, 512), np.int32)
+    wstate = np.zeros((base_n, 2), np.uint8)
+    for f in range(2):
+        s = rng.integers(10, 22, (base_n, 1))
+        spec = ((rng.random((base_n, 1024)) * 2 - 1) * 2.0 ** s).astype(np.int64).astype(np.int32)
+        ics = np.zeros((base_n, 2), np.uint8)
+        ics[:, 1] = rng.integers(0, 2, base_n)
+        side = np.ascontiguousarray(g["side"][2 + (u & 1) + 2 * (((u >> 1) + f) % 12)])
+        d_spec = torch.from_numpy(spec).cuda().repeat(tiles, 1)
+        d_ics = torch.from_numpy(ics).cuda().repeat(tiles, 1)
+        d_side = torch.from_numpy(side).cuda().repeat(tiles, 1)
+        w32, adj = xb.imdct_process(ctx, imdct_state, d_spec, d_ics)
+        p16 = xb.imdct_out_to_pcm16(ctx, w32, adj, 0)
+        out, err = xb.sbr_dec_lp(ctx, state, d_side, p16, out_ch=2)
+        torch.cuda.synchronize()
+        assert int(err.abs().max().item()) == 0
+        o = out.view(tiles, base_n // 2, 2048, 2)
+        assert bool((o == o[0:1]).all().item()), f"frame {f}: tiles differ"
+        out32, ovl, wstate, eadj = oracle.imdct_batch(spec, ovl, wstate, ics)
+        e16 = oracle.imdct_out_to_pcm16(out32, eadj, 0)
+        got = o[0].cpu().numpy()
+        for k in range(base_n):
+            st[k], eo, ee = oracle.sbr_dec_lp(side[k], st[k], e16[k])
+            assert ee == 0 and np.array_equal(got[k // 2, :, k % 2], eo), f"frame {f} unit {k}: tile 0 vs oracle"
+    state.close()
