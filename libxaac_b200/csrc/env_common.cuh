@@ -61,14 +61,16 @@ XB_DEV void mant_exp_sqrt(int16_t *v, const EnvRomS &r) {
   }
 }
 
+// the (mantissa, exponent) running sum the reference open-codes in avggain_calc / noiselimiting (env_calc.c:1493-1527,
+// 326-336): the operand with the smaller exponent is shifted down (ixheaac_shr32: count & 0xff, >= 31 gives the sign) and
+// added.  Branch-free, because the lanes of a warp walk different limiter bands here.
 XB_DEV void acc_add(i32 &am, i32 &ae, i32 m, i32 e) {
   const i32 d = e - ae;
-  if (d >= 0) {
-    am = m + shr32(am, d);
-    ae = e;
-  } else {
-    am = shr32(m, -d) + am;
-  }
+  const bool ge = d >= 0;
+  const int s = min((ge ? d : -d) & 0xff, 31);
+  const i32 big = ge ? m : am, small = ge ? am : m;
+  am = big + (small >> s);
+  ae = ge ? e : ae;
 }
 
 // env_calc.c:1382-1452

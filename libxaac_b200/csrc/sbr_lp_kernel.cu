@@ -42,6 +42,8 @@ struct LpTab {  // block-shared tables (image built on the host by sbr_lp_build_
   i32 post[18];   // post_fft_tbl << 16
   i32 w16[24];    // w_16 << 16
   i32 w32[60];    // w_32 << 16
+  i32 periodic;   // 1: qmf_c[i] == qmf_c[i + 640] (the time-invariant window forms below need it)
+  i32 pad;
 };
 
 struct LpWarpS {
@@ -57,6 +59,7 @@ struct LpWarpS {
   int8_t sine_mapped[64];
   int8_t alias_red[128];
   int16_t sf[8], misc[16];
+  int16_t limv[4 * 13];  // per limiter band: {max gain m, e | boost m, e, energy sum m, e}
 };
 
 struct LpBlockS {
@@ -514,14 +517,15 @@ XB_DEV int lp_envelope(LpWarpS &w, const EnvRomS &rom, const i32 *rand_ph, int l
     m_off += num_sfb;
     __syncwarp();
 
-    // ---- noise limiter: one lane per limiter band (env_calc.c:229-421) ----
+    // ---- noise limiter (env_calc.c:229-421).  The (mantissa, exponent) sums round, so their order is part of the
+    // contract: lane = limiter band for the two accumulations, lane = band for everything that is per band ----
     {
       const int16_t *lim = prm + kEnvLimTbl;
+      const int nlf = min((int)prm[kEnvNumLfBands], 12);
       const i32 lg_m = rom.lim_gains[2 * prm[kEnvLimiterGains]], lg_e = rom.lim_gains[2 * prm[kEnvLimiterGains] + 1];
 #pragma unroll 1
-      for (int c = lane; c < prm[kEnvNumLfBands]; c += 32) {
+      for (int c = lane; c < nlf; c += 32) {
         const int b0 = lim[c] > skip ? lim[c] - skip : 0, b1 = lim[c + 1] > skip ? lim[c + 1] - skip : 0;
-        if (b0 >= b1) continue;
         i32 om = 0, oe = 0, em = 0, ee = 0;
 #pragma unroll 1
         for (int k = b0; k < b1; k++) {
@@ -541,8 +545,25 @@ XB_DEV int lp_envelope(LpWarpS &w, const EnvRomS &rom, const i32 *rand_ph, int l
         mg_e = sext16(mg_e - nv);
         mg_m = sext16(lsl(mt, nv) >> 16);
         if (mg_e >= 34) { mg_m = 0x3000; mg_e = 34; }
+        w.limv[4 * c] = (int16_t)mg_m;
+        w.limv[4 * c + 1] = (int16_t)mg_e;
+        w.limv[4 * c + 2] = (int16_t)sum_m;
+        w.limv[4 * c + 3] = (int16_t)sum_e;
+      }
+      __syncwarp();
+      int myc[2] = {-1, -1};
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int k = lane + 32 * h;
+        if (k < bands) {
 #pragma unroll 1
-        for (int k = b0; k < b1; k++) {
+          for (int cc = 0; cc < nlf; cc++) {
+            const int b0 = lim[cc] > skip ? lim[cc] - skip : 0, b1 = lim[cc + 1] > skip ? lim[cc + 1] - skip : 0;
+            if (k >= b0 && k < b1) { myc[h] = cc; break; }
+          }
+        }
+        if (myc[h] >= 0) {
+          const i32 mg_m = w.limv[4 * myc[h]], mg_e = w.limv[4 * myc[h] + 1];
           const i32 gm = w.gain[2 * k], ge = w.gain[2 * k + 1];
           if (ge > mg_e || (ge == mg_e && gm > mg_m)) {
             i32 na_m;
@@ -553,21 +574,36 @@ XB_DEV int lp_envelope(LpWarpS &w, const EnvRomS &rom, const i32 *rand_ph, int l
             w.gain[2 * k + 1] = (int16_t)mg_e;
           }
         }
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int c = lane; c < nlf; c += 32) {
+        const int b0 = lim[c] > skip ? lim[c] - skip : 0, b1 = lim[c + 1] > skip ? lim[c + 1] - skip : 0;
+        if (b0 >= b1) continue;
+        const i32 sum_m = w.limv[4 * c + 2], sum_e = w.limv[4 * c + 3];
         i32 am = 0, ae = 0;
 #pragma unroll 1
         for (int k = b0; k < b1; k++) {
           acc_add(am, ae, ((i32)w.gain[2 * k] * w.est[2 * k]) >> 15, w.gain[2 * k + 1] + w.est[2 * k + 1]);
-          if (w.sine[2 * k] != 0) acc_add(am, ae, w.sine[2 * k], w.sine[2 * k + 1]);
-          else if (!noise_absc) acc_add(am, ae, w.noise[2 * k], w.noise[2 * k + 1]);
+          const i32 sm = w.sine[2 * k];
+          const bool use_s = sm != 0;
+          if (use_s || !noise_absc) acc_add(am, ae, use_s ? sm : (i32)w.noise[2 * k], use_s ? (i32)w.sine[2 * k + 1] : (i32)w.noise[2 * k + 1]);
         }
-        nv = 16 - norm32(am);
+        int nv = 16 - norm32(am);
         if (nv > 0) { am >>= nv; ae += nv; }
         i32 bg_m;
         i32 bg_e = sext16(mant_div(sum_m, sext16(am), bg_m, rom));
         bg_e = sext16(bg_e + (sum_e - sext16(ae)) + 1);
         if (bg_e > 2 || (bg_e == 2 && bg_m > 0x5061)) { bg_m = 0x5061; bg_e = 2; }
-#pragma unroll 1
-        for (int k = b0; k < b1; k++) {
+        w.limv[4 * c] = (int16_t)bg_m;
+        w.limv[4 * c + 1] = (int16_t)bg_e;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int k = lane + 32 * h;
+        if (myc[h] >= 0) {
+          const i32 bg_m = w.limv[4 * myc[h]], bg_e = w.limv[4 * myc[h] + 1];
           w.gain[2 * k] = (int16_t)mult16_shl_(w.gain[2 * k], bg_m);
           w.sine[2 * k] = (int16_t)mult16_shl_(w.sine[2 * k], bg_m);
           w.noise[2 * k] = (int16_t)mult16_shl_(w.noise[2 * k], bg_m);
@@ -584,28 +620,45 @@ XB_DEV int lp_envelope(LpWarpS &w, const EnvRomS &rom, const i32 *rand_ph, int l
       const int16_t *deg = w.deg + sb_start;
       const int nsb = num_sub_bands;
       int ngrp = 0;
-      if (lane == 0) {
-        int grouping = 0, i = 0;
+      {  // the grouping walk of env_calc.c:92-123 on two ballot masks, executed redundantly by every lane
+        unsigned long long cond = 0, ared = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int k = lane + 32 * h;
+          const bool r = k < nsb && w.alias_red[k] != 0;
+          const bool c = r && k < nsb - 1 && deg[k + 1] != 0;
+          cond |= (unsigned long long)__ballot_sync(full, c) << (32 * h);
+          ared |= (unsigned long long)__ballot_sync(full, r) << (32 * h);
+        }
+        int grouping = 0, i = 0, last = 0;
 #pragma unroll 1
         for (int k = 0; k < nsb - 1; k++) {
-          if (deg[k + 1] != 0 && w.alias_red[k]) {
+          const bool c = (cond >> k) & 1;
+          int fv = -1;
+          if (c) {
             if (!grouping) {
-              w.fvec[i++] = (int16_t)k;
+              fv = k;
               grouping = 1;
-            } else if (w.fvec[i - 1] + 3 == k) {
-              w.fvec[i++] = (int16_t)(k + 1);
+            } else if (last + 3 == k) {
+              fv = k + 1;
               grouping = 0;
             }
           } else if (grouping) {
             grouping = 0;
-            w.fvec[i] = (int16_t)(w.alias_red[k] ? k + 1 : k);
+            fv = ((ared >> k) & 1) ? k + 1 : k;
+          }
+          if (fv >= 0) {
+            if (lane == 0) w.fvec[i] = (int16_t)fv;
+            last = fv;
             i++;
           }
         }
-        if (grouping) w.fvec[i++] = (int16_t)nsb;
+        if (grouping) {
+          if (lane == 0) w.fvec[i] = (int16_t)nsb;
+          i++;
+        }
         ngrp = i >> 1;
       }
-      ngrp = __shfl_sync(full, ngrp, 0);
       __syncwarp();
 #pragma unroll 1
       for (int g = lane; g < ngrp; g += 32) {
@@ -720,6 +773,30 @@ XB_DEV int lp_envelope(LpWarpS &w, const EnvRomS &rom, const i32 *rand_ph, int l
     int ph_index = st[kEnvStPhIndex], harm = st[kEnvStHarmIndex];
     int filt_noise_e = st[kEnvStNoiseE];
     const int nsb = num_sub_bands;
+    const int n1 = nsb - 1;
+    // everything that depends only on the band is hoisted out of the slot loop: lane owns bands lane and lane + 32
+    i32 h_gm[2], h_ge[2], h_sm[2], h_nz[2], h_add[2];
+    bool h_act[2], h_tone[2];
+    {
+      int tone_carry = 0;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int k = lane + 32 * h;
+        h_act[h] = k < nsb;
+        h_gm[h] = h_act[h] ? (i32)w.gain[2 * k] : 0;
+        h_ge[h] = h_act[h] ? (i32)w.gain[2 * k + 1] : 0;
+        h_sm[h] = h_act[h] ? (i32)w.sine[2 * k] : 0;
+        h_nz[h] = h_act[h] ? (i32)w.noise[2 * k] : 0;
+        const unsigned bal = __ballot_sync(full, h_act[h] && h_sm[h] != 0);
+        h_tone[h] = (tone_carry + __popc(bal & (0xffffffffu >> (31 - lane)))) <= 16;
+        tone_carry += __popc(bal);
+        h_add[h] = 0;
+        if (k >= 1 && k < n1) h_add[h] = mul32x16(kLpFactor, sext16((i32)w.sine[2 * (k - 1)] - (i32)w.sine[2 * (k + 1)]));
+        else if (k == n1 && k >= 1) h_add[h] = mul32x16(kLpFactor, (i32)w.sine[2 * (k - 1)]);  // tms of the last band
+        else if (k == 0) h_add[h] = mul32x16(kLpFactor, nsb > 1 ? (i32)w.sine[2] : 0);        // tm2 of the first band
+      }
+    }
+    const int finv_base = (max_qmf & 1) ? -1 : 1;  // finv = !finv; finv = (finv << 1) - 1
 #pragma unroll 1
     for (int l = start; l < end; l++) {
       int scale_change;
@@ -731,6 +808,8 @@ XB_DEV int lp_envelope(LpWarpS &w, const EnvRomS &rom, const i32 *rand_ph, int l
           noise_e = sext16(final_e);
           if (diff > 0) for (int k = lane; k < bands; k += 32) w.noise[2 * k] = (int16_t)(w.noise[2 * k] >> (diff & 31));
           else if (diff < 0) for (int k = lane; k < bands; k += 32) w.noise[2 * k] = (int16_t)lsl((i32)w.noise[2 * k], (-diff) & 31);
+#pragma unroll
+          for (int h = 0; h < 2; h++) h_nz[h] = h_act[h] ? (i32)w.noise[2 * (lane + 32 * h)] : 0;
         }
       }
       {
@@ -739,82 +818,58 @@ XB_DEV int lp_envelope(LpWarpS &w, const EnvRomS &rom, const i32 *rand_ph, int l
         else if (diff < 0) for (int k = lane; k < num_sub_bands; k += 32) filt_noise[k] = (int16_t)lsl((i32)filt_noise[k], (-diff) & 31);
         filt_noise_e = noise_e;
       }
-      __syncwarp();
       const int sc = scale_change - 1;
       i32 *re = mat + LS * l + max_qmf;
       const i32 *rnd = rand_ph + ph_index + 1;
-      if (!(harm & 1)) {  // ixheaacd_harm_idx_zerotwolp_dec
-#pragma unroll 1
-        for (int k = lane; k < nsb; k += 32) {
-          const i32 s = gain_shift(mul32x16(re[k], w.gain[2 * k]), w.gain[2 * k + 1] - sc);
-          const i32 sl = lsl((i32)w.sine[2 * k], 16);
-          i32 o;
-          if (!noise_absc && sl == 0) o = mac_noise(s, __ldg(rnd + k), w.noise[2 * k]);
-          else if (harm == 0) o = add_sat(s, sl);
-          else o = sub_sat(s, sl);
-          re[k] = o;
-        }
-      } else {  // ixheaacd_harm_idx_onethreelp
-        int finv0 = (max_qmf & 1) ? -1 : 1;  // finv = !finv; finv = (finv << 1) - 1
-        if (harm == 3) finv0 = -finv0;
-        const int nz = (noise_e - 16) - sext16(15 - sf_lb_in);
-        const int n1 = nsb - 1;
-        int tone_carry = 0;
-#pragma unroll 1
-        for (int k0 = 0; k0 < nsb; k0 += 32) {
-          const int k = k0 + lane;
-          const bool act = k < nsb;
-          const i32 sk = act ? (i32)w.sine[2 * k] : 0;
-          const unsigned bal = __ballot_sync(full, act && sk != 0);
-          const int tone = tone_carry + __popc(bal & (0xffffffffu >> (31 - lane)));
-          tone_carry += __popc(bal);
-          if (!act) continue;
-          i32 s = gain_shift(mul32x16(re[k], w.gain[2 * k]), w.gain[2 * k + 1] - sc);
-          if (sk == 0 && !noise_absc) s = mac_noise(s, __ldg(rnd + k), w.noise[2 * k]);
-          if (k == 0) {
-            const i32 sl_next = nsb > 1 ? (i32)w.sine[2] : 0;
-            const i32 tm2 = mul32x16(kLpFactor, sl_next);
-            i32 tm = mul32x16(kLpFactor, sk);
-            const int tmp = sext16(nz);
-            if (tmp > 0) tm = shl32(tm, tmp);
-            else tm = shr32(tm, -tmp);
-            if (finv0 < 0) {
-              if (max_qmf > 0) re[-1] = add_sat(re[-1], tm);
-              s = sub_sat(s, tm2);
-            } else {
-              if (max_qmf > 0) re[-1] = sub_sat(re[-1], tm);
-              s = add_sat(s, tm2);
-            }
-            re[0] = s;
-          } else if (k < n1) {
-            if (tone <= 16) {
-              const i32 add_sine = mul32x16(kLpFactor, sext16((i32)w.sine[2 * (k - 1)] - (i32)w.sine[2 * (k + 1)]));
-              const bool neg = ((k - 1) & 1) ? (finv0 > 0) : (finv0 < 0);
-              s = add_sat(s, neg ? wneg(add_sine) : add_sine);
-            }
-            re[k] = s;
-          } else {  // k == n1 >= 1
-            const bool plus = ((n1 - 1) & 1) ? (finv0 < 0) : (finv0 > 0);
-            const i32 tms = mul32x16(kLpFactor, (i32)w.sine[2 * (k - 1)]);
-            if (tone <= 16) {
-              const i32 tm2 = mul32x16(kLpFactor, sk);
-              if (plus) {
-                re[k] = add_sat(s, tms);
-                if (k + max_qmf < 62) re[k + 1] = sub_sat(re[k + 1], tm2);
-              } else {
-                re[k] = sub_sat(s, tms);
-                if (k + max_qmf < 62) re[k + 1] = add_sat(re[k + 1], tm2);
-              }
-            } else {
-              re[k] = s;
-            }
+      const bool odd = (harm & 1) != 0;
+      const int finv0 = (harm == 3) ? -finv_base : finv_base;
+      const int nz = sext16((noise_e - 16) - sext16(15 - sf_lb_in));
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if (!h_act[h]) continue;
+        const int k = lane + 32 * h;
+        i32 s = gain_shift(mul32x16(re[k], h_gm[h]), h_ge[h] - sc);
+        const i32 sk = h_sm[h];
+        const bool noisy = sk == 0 && !noise_absc;
+        if (noisy) s = mac_noise(s, __ldg(rnd + k), h_nz[h]);
+        if (!odd) {  // ixheaacd_harm_idx_zerotwolp_dec (env_calc.c:1564-1615)
+          if (!noisy) {
+            const i32 sl = lsl(sk, 16);
+            s = harm == 0 ? add_sat(s, sl) : sub_sat(s, sl);
+          }
+        } else if (k == 0) {  // ixheaacd_harm_idx_onethreelp (env_calc.c:1617-1757): first band
+          i32 tm = mul32x16(kLpFactor, sk);
+          if (nz > 0) tm = shl32(tm, nz);
+          else tm = shr32(tm, -nz);
+          if (finv0 < 0) {
+            if (max_qmf > 0) re[-1] = add_sat(re[-1], tm);
+            s = sub_sat(s, h_add[h]);
+          } else {
+            if (max_qmf > 0) re[-1] = sub_sat(re[-1], tm);
+            s = add_sat(s, h_add[h]);
+          }
+        } else if (k < n1) {  // middle bands: finv alternates from band 1 on
+          if (h_tone[h]) {
+            const bool neg = ((k - 1) & 1) ? (finv0 > 0) : (finv0 < 0);
+            s = add_sat(s, neg ? wneg(h_add[h]) : h_add[h]);
+          }
+        } else if (h_tone[h]) {  // last band (k == n1 >= 1)
+          const bool plus = ((n1 - 1) & 1) ? (finv0 < 0) : (finv0 > 0);
+          const i32 tm2 = mul32x16(kLpFactor, sk);
+          if (plus) {
+            s = add_sat(s, h_add[h]);
+            if (k + max_qmf < 62) re[k + 1] = sub_sat(re[k + 1], tm2);
+          } else {
+            s = sub_sat(s, h_add[h]);
+            if (k + max_qmf < 62) re[k + 1] = add_sat(re[k + 1], tm2);
           }
         }
+        re[k] = s;
       }
       ph_index = (ph_index + nsb) & 511;
       harm = (harm + 1) & 3;
-      __syncwarp();
     }
+    __syncwarp();
 #pragma unroll 1
     for (int k = lane; k < bands; k += 32) {  // env_calc.c:1060-1078
       fme[2 * k] = w.gain[2 * k];
@@ -1130,33 +1185,89 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
     {
       const int16_t *pcm = p.time_in + u * p.in_unit_stride;
       int pos = p.anal_pos[2 * u], f1 = p.anal_pos[2 * u + 1], f2 = f1 + 64;
-      i32 nxt = pcm[(long long)p.in_ch * lane];
+      // The reference keeps its 320-sample ring position and its coefficient phase in lock step (pos / 32 + filter_pos / 64
+      // = 0 mod 10, both even, from reset on); then the window is the time-invariant FIR
+      //   a[n] = sum_m x[t0 + 31 - n - 64 m] c[128 m + 2 n],  b[n] = sum_m x[t0 - 1 - n - 64 m] c[64 + 128 m + 2 n]
+      // on the plain time history.  Any other (position, phase) pair runs the literal ring emulation below.
+      const int P0 = pos >> 5, F0 = f1 >> 6;
+      const bool lock = tab.periodic && (pos & 63) == 0 && (f1 & 127) == 0 && pos >= 0 && pos <= 256 && f1 >= 0 &&
+                        f1 <= 512 && ((P0 + F0) % 10 == 0);
+      if (lock) {
+        int16_t *T = reinterpret_cast<int16_t *>(w.y);  // T[j] = sample at time j - 288 relative to the frame start
 #pragma unroll 1
-      for (int slot = 0; slot < 32; slot++) {
-        w.ring[pos + 31 - lane] = (int16_t)nxt;
-        if (slot < 31) nxt = pcm[(long long)p.in_ch * (32 * (slot + 1) + lane)];
-        __syncwarp();
-        const int16_t *fp1 = w.ring + ((slot & 1) ? 32 : 0), *fp2 = w.ring + ((slot & 1) ? 0 : 32);
-        i32 a = 0, b = 0;
+        for (int j = lane; j < 288; j += 32) {
+          int q = P0 + 9 - (j >> 5);
+          if (q >= 10) q -= 10;
+          T[j] = w.ring[32 * q + 31 - (j & 31)];
+        }
+        if (p.in_ch == 1 && ((reinterpret_cast<uintptr_t>(pcm) & 3) == 0)) {
+          const i32 *src = reinterpret_cast<const i32 *>(pcm);
+          i32 *dst = reinterpret_cast<i32 *>(T + 288);
+#pragma unroll 4
+          for (int j = lane; j < 512; j += 32) dst[j] = __ldg(src + j);
+        } else {
+#pragma unroll 4
+          for (int j = lane; j < 1024; j += 32) T[288 + j] = pcm[(long long)p.in_ch * j];
+        }
+        i32 ca[5], cb[5];
 #pragma unroll
-        for (int j = 0; j < 5; j++) {
-          a += (i32)fp1[lane + 64 * j] * (i32)tab.qmf_c[f1 + 2 * (lane + 64 * j)];
-          b += (i32)fp2[lane + 64 * j] * (i32)tab.qmf_c[f2 + 2 * (lane + 64 * j)];
+        for (int mm = 0; mm < 5; mm++) {
+          ca[mm] = tab.qmf_c[128 * mm + 2 * lane];
+          cb[mm] = tab.qmf_c[64 + 128 * mm + 2 * lane];
         }
         __syncwarp();
-        pos -= 32;
-        if (pos < 0) pos = 288;
-        {
-          const int n1 = f2 + 64, n2 = f1 + 64;
-          f1 = n1;
-          f2 = n2;
-          if (f2 > 640) {
-            f1 = 0;
-            f2 = 64;
+        const int16_t *ta = T + 288 + 31 - lane, *tb = T + 288 - 1 - lane;
+#pragma unroll 2
+        for (int slot = 0; slot < 32; slot++) {
+          i32 a = 0, b = 0;
+#pragma unroll
+          for (int mm = 0; mm < 5; mm++) {
+            a += (i32)ta[32 * slot - 64 * mm] * ca[mm];
+            b += (i32)tb[32 * slot - 64 * mm] * cb[mm];
           }
+          m[LS * (6 + slot) + lane] = a;
+          m[LS * (6 + slot) + 32 + lane] = b;
         }
-        m[LS * (6 + slot) + lane] = a;
-        m[LS * (6 + slot) + 32 + lane] = b;
+        // ring after 32 slots: block q holds the latest slot i <= 31 with i = P0 - q (mod 10), newest sample first
+#pragma unroll 1
+        for (int pp = lane; pp < 320; pp += 32) {
+          const int q = pp >> 5;
+          int d = (31 - (P0 - q)) % 10;
+          if (d < 0) d += 10;
+          w.ring[pp] = T[288 + 32 * (31 - d) + 31 - (pp & 31)];
+        }
+        const int Pf = (P0 + 8) % 10;
+        pos = 32 * Pf;
+        f1 = 64 * ((10 - Pf) % 10);
+      } else {
+        i32 nxt = pcm[(long long)p.in_ch * lane];
+#pragma unroll 1
+        for (int slot = 0; slot < 32; slot++) {
+          w.ring[pos + 31 - lane] = (int16_t)nxt;
+          if (slot < 31) nxt = pcm[(long long)p.in_ch * (32 * (slot + 1) + lane)];
+          __syncwarp();
+          const int16_t *fp1 = w.ring + ((slot & 1) ? 32 : 0), *fp2 = w.ring + ((slot & 1) ? 0 : 32);
+          i32 a = 0, b = 0;
+#pragma unroll
+          for (int j = 0; j < 5; j++) {
+            a += (i32)fp1[lane + 64 * j] * (i32)tab.qmf_c[f1 + 2 * (lane + 64 * j)];
+            b += (i32)fp2[lane + 64 * j] * (i32)tab.qmf_c[f2 + 2 * (lane + 64 * j)];
+          }
+          __syncwarp();
+          pos -= 32;
+          if (pos < 0) pos = 288;
+          {
+            const int n1 = f2 + 64, n2 = f1 + 64;
+            f1 = n1;
+            f2 = n2;
+            if (f2 > 640) {
+              f1 = 0;
+              f2 = 64;
+            }
+          }
+          m[LS * (6 + slot) + lane] = a;
+          m[LS * (6 + slot) + 32 + lane] = b;
+        }
       }
       __syncwarp();
       // DCT-III of the 32 slots, lane = slot
@@ -1295,22 +1406,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
       // 10-tap window (generic:1508-1542, shift = 2): lane -> outputs 2*lane, 2*lane+1 of every slot
       {
         int16_t *out = p.time_out + (u / p.out_ch) * (2048LL * p.out_ch) + (u % p.out_ch);
-        int fpos = fpos0;
-#pragma unroll 1
-        for (int i = 0; i < 32; i++) {
-          i32 acc0 = 0x8000 >> 2, acc1 = 0x8000 >> 2;
-          int ab = (i - b0) % 10;  // age of ring block 0 at this slot
-          if (ab < 0) ab += 10;
-#pragma unroll
-          for (int b = 0; b < 10; b++) {
-            int a = ab + b;
-            if (a >= 10) a -= 10;
-            const int idx = ((i + b) & 1) * 32;  // word offset of the 64-sample phase inside the block
-            const i32 hv = w.y[LS * (9 + i - a) + idx + lane];
-            const i32 cv = *reinterpret_cast<const i32 *>(tab.qmf_c + fpos + 64 * b + 2 * lane);
-            acc0 += sext16(hv) * sext16(cv);
-            acc1 += (hv >> 16) * (cv >> 16);
-          }
+        auto store = [&](int i, i32 acc0, i32 acc1) {
           const i32 o0 = shl32_sat(acc0, 2) >> 16, o1 = shl32_sat(acc1, 2) >> 16;
           if (p.out_ch == 1) {
             *reinterpret_cast<i32 *>(out + 64 * i + 2 * lane) = (o0 & 0xffff) | (i32)((u32)o1 << 16);
@@ -1318,8 +1414,53 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
             out[(long long)p.out_ch * (64 * i + 2 * lane)] = (int16_t)o0;
             out[(long long)p.out_ch * (64 * i + 2 * lane + 1)] = (int16_t)o1;
           }
-          fpos += 64;
-          if (fpos == 640) fpos = 0;
+        };
+        // Ring offset and coefficient phase are in lock step in the reference (drc_offset / 128 + filter_pos_syn / 64 = 0
+        // mod 10, both even): the window is then the time-invariant FIR over the last 10 slots' state blocks,
+        //   out_i[k] = sum_a block_{i-a}[64 (a & 1) + k] c[64 a + k]; any other pair runs the literal form below.
+        const int f0s = fpos0 >> 6;
+        const bool lock = tab.periodic && (off0 & 255) == 0 && (fpos0 & 127) == 0 && ((b0 + f0s) % 10 == 0);
+        if (lock) {
+          i32 clo[10], chi[10];
+#pragma unroll
+          for (int a = 0; a < 10; a++) {
+            const i32 cv = *reinterpret_cast<const i32 *>(tab.qmf_c + 64 * a + 2 * lane);
+            clo[a] = sext16(cv);
+            chi[a] = cv >> 16;
+          }
+          const i32 *hp = w.y + LS * 9 + lane;
+#pragma unroll 2
+          for (int i = 0; i < 32; i++) {
+            i32 acc0 = 0x8000 >> 2, acc1 = 0x8000 >> 2;
+#pragma unroll
+            for (int a = 0; a < 10; a++) {
+              const i32 hv = hp[LS * (i - a) + 32 * (a & 1)];
+              acc0 += sext16(hv) * clo[a];
+              acc1 += (hv >> 16) * chi[a];
+            }
+            store(i, acc0, acc1);
+          }
+        } else {
+          int fpos = fpos0;
+#pragma unroll 1
+          for (int i = 0; i < 32; i++) {
+            i32 acc0 = 0x8000 >> 2, acc1 = 0x8000 >> 2;
+            int ab = (i - b0) % 10;  // age of ring block 0 at this slot
+            if (ab < 0) ab += 10;
+#pragma unroll 1
+            for (int b = 0; b < 10; b++) {
+              int a = ab + b;
+              if (a >= 10) a -= 10;
+              const int idx = ((i + b) & 1) * 32;  // word offset of the 64-sample phase inside the block
+              const i32 hv = w.y[LS * (9 + i - a) + idx + lane];
+              const i32 cv = *reinterpret_cast<const i32 *>(tab.qmf_c + fpos + 64 * b + 2 * lane);
+              acc0 += sext16(hv) * sext16(cv);
+              acc1 += (hv >> 16) * (cv >> 16);
+            }
+            store(i, acc0, acc1);
+            fpos += 64;
+            if (fpos == 640) fpos = 0;
+          }
         }
       }
       // ring after 32 slots: block b holds slot 31 - a, a = (b - b0 + 31) mod 10
@@ -1368,6 +1509,10 @@ int sbr_lp_build_tables(const uint8_t *qrom, uint8_t *out) {
   for (int i = 0; i < 18; i++) t->post[i] = hi(pf[i]);
   for (int i = 0; i < 24; i++) t->w16[i] = hi(w16[i]);
   for (int i = 0; i < 60; i++) t->w32[i] = hi(w32[i]);
+  t->periodic = 1;
+  for (int i = 0; i < 640; i++)
+    if (c[i] != c[i + 640]) t->periodic = 0;
+  t->pad = 0;
   for (int fpos = 0; fpos < 640; fpos += 64)
     for (int k = 0; k < 64; k++) {
       long long s = 0;

@@ -184,3 +184,22 @@ def test_full_batch_tiling_property(ctx, oracle):
             st[k], eo, ee = oracle.sbr_dec_lp(side[k], st[k], e16[k])
             assert ee == 0 and np.array_equal(got[k // 2, :, k % 2], eo), f"frame {f} unit {k}: tile 0 vs oracle"
     state.close()
+
+
+def test_non_lockstep_ring_positions(ctx, oracle):
+    """The reference keeps ring position and coefficient phase of both banks in lock step; the kernel's time-invariant
+    window forms rely on that and fall back to the literal ring emulation otherwise.  Drive every (position, phase)
+    combination the reference functions accept and compare with the oracle."""
+    g = np.load(GOLD)
+    n = 400
+    side, st, tin = oracle_util.synth_sbr_lp_units(n, 17, g)
+    rng = np.random.default_rng(17)
+    st[:, 320] = 32 * rng.integers(0, 10, n)
+    st[:, 321] = 64 * rng.integers(0, 10, n)
+    st[:, 322] = 128 * rng.integers(0, 10, n)
+    st[:, 323] = 64 * rng.integers(0, 10, n)
+    outs, st2 = run_gpu(ctx, side, st, tin)
+    out, err = outs[0]
+    for u in range(n):
+        es, eo, ee = oracle.sbr_dec_lp(side[u], st[u], tin[u])
+        check(u, st2[u], out[u], err[u], es, eo, ee, "non-lockstep")
