@@ -33,7 +33,7 @@
 
 namespace xb {
 
-constexpr int kLpWarps = 8;
+constexpr int kLpWarps = 12;
 constexpr int LS = 65;  // word stride of a matrix row in shared memory (odd: column walks are conflict-free)
 
 struct LpTab {  // block-shared tables (image built on the host by sbr_lp_build_tables)
@@ -47,13 +47,17 @@ struct LpTab {  // block-shared tables (image built on the host by sbr_lp_build_
 };
 
 struct LpWarpS {
-  i32 x[40 * LS];  // rows 0,1: LPC state rows; rows 2..39: QMF matrix rows 0..37
-  i32 y[41 * LS];  // analysis: DCT temporaries; synthesis: history of 9 old + 32 new blocks of 128 WORD16 state samples
+  // envelope work arrays; during the analysis window the 791 words est .. pre hold the unit's time history instead
+  int16_t est[2 * kMaxB], gain[2 * kMaxB], noise[2 * kMaxB], sine[2 * kMaxB], orig[2 * kMaxB];
+  i32 line[kMaxB];
+  // pre | x are contiguous rows of LS words.  x rows 0,1: LPC state rows; x rows 2..39: QMF matrix rows 0..37.
+  // During the synthesis the 9 rows before matrix row 0 (pre + the dead LPC rows) hold the 9 old blocks of the state
+  // ring and matrix row s itself receives the 128 WORD16 state samples of slot s: rows of `pre` = window history.
+  i32 pre[7 * LS];
+  i32 x[40 * LS];
   int16_t side[740];  // XAAC_SIDE_ENV [656] | XAAC_SIDE_HF [80] | apply
   int16_t st[kEnvStWords];
   int16_t ring[320];
-  int16_t est[2 * kMaxB], gain[2 * kMaxB], noise[2 * kMaxB], sine[2 * kMaxB], orig[2 * kMaxB];
-  i32 line[kMaxB];
   int16_t deg[64];
   int16_t fvec[64];
   int8_t sine_mapped[64];
@@ -61,6 +65,8 @@ struct LpWarpS {
   int16_t sf[8], misc[16];
   int16_t limv[4 * 13];  // per limiter band: {max gain m, e | boost m, e, energy sum m, e}
 };
+static_assert(offsetof(LpWarpS, pre) == 4 * 336 && offsetof(LpWarpS, x) == offsetof(LpWarpS, pre) + 4 * 7 * LS,
+              "est..pre..x must be contiguous");
 
 struct LpBlockS {
   LpTab tab;
@@ -142,35 +148,37 @@ XB_DEV void radix4_lane(const i32 *w, i32 *x, int groups, int span) {
   }
 }
 
-// generic:63-239 — DCT-III of one slot.  in: the slot's row (64 window-add outputs, destroyed; result in in[0..31]);
-// out: 32-word temporary.  dig_rev_table4_16 = {0, 16} (checked at ROM install).
-XB_DEV void dct3_32_lane(const LpTab &t, i32 *in, i32 *out) {
-  out[0] = in[48] >> 7;
-  out[1] = 0;
-#pragma unroll 1
+// generic:63-239 — DCT-III of one slot, in place in the slot's 64-word row: in = row[0..63] (window-add outputs), result
+// in row[0..31].  The two twiddle passes run in registers (static indices), the 16-point FFT in place in shared memory.
+// dig_rev_table4_16 = {0, 16} (checked at ROM install).
+XB_DEV void dct3_32_lane(const LpTab &t, i32 *row) {
+  i32 o[32];
+  o[0] = row[48] >> 7;
+  o[1] = 0;
+#pragma unroll
   for (int n = 1; n < 16; n++) {
-    const i32 t0 = add_sat(in[48 + n] >> 7, in[48 - n] >> 7);
-    const i32 t1 = sub_sat(in[16 + n] >> 7, in[16 - n] >> 7);
+    const i32 t0 = add_sat(row[48 + n] >> 7, row[48 - n] >> 7);
+    const i32 t1 = sub_sat(row[16 + n] >> 7, row[16 - n] >> 7);
     const i32 re = t.dct23[4 * n], im = t.dct23[4 * n + 1];
-    out[2 * n] = wadd(__mulhi(t0, re), __mulhi(t1, im));
-    out[2 * n + 1] = wadd(wneg(__mulhi(t1, re)), __mulhi(t0, im));
+    o[2 * n] = wadd(__mulhi(t0, re), __mulhi(t1, im));
+    o[2 * n + 1] = wadd(wneg(__mulhi(t1, re)), __mulhi(t0, im));
   }
   {
     const i32 re = t.dct23[64], im = t.dct23[65];
-    const i32 t1 = sub_sat(in[32] >> 7, in[0] >> 7), t0 = t1;
+    const i32 t1 = sub_sat(row[32] >> 7, row[0] >> 7), t0 = t1;
     const i32 u2 = wadd(__mulhi(t0, re), __mulhi(t1, im));
     const i32 u3 = wadd(wneg(__mulhi(t1, re)), __mulhi(t0, im));
-    i32 u0 = out[0], u1 = out[1];
+    i32 u0 = o[0], u1 = o[1];
     const i32 a = wsub(wneg(u1), u3), b = wsub(u0, u2);
     u0 = wadd(wadd(u0, u2), a);
     u1 = wadd(wsub(u1, u3), b);
-    out[0] = u0 >> 1;
-    out[1] = u1 >> 1;
+    o[0] = u0 >> 1;
+    o[1] = u1 >> 1;
   }
-#pragma unroll 1
+#pragma unroll
   for (int n = 1; n <= 8; n++) {
     const bool last = n == 8;
-    const i32 u0 = out[2 * n], u1 = out[2 * n + 1], u3 = out[33 - 2 * n], u2 = out[32 - 2 * n];
+    const i32 u0 = o[2 * n], u1 = o[2 * n + 1], u3 = o[33 - 2 * n], u2 = o[32 - 2 * n];
     i32 re = t.post[16 - 2 * n];
     if (last) re = (i32)((u32)(-(re >> 16)) << 16);  // (WORD16)(-*tr), wrapping
     const i32 im = t.post[2 * n];
@@ -179,82 +187,89 @@ XB_DEV void dct3_32_lane(const LpTab &t, i32 *in, i32 *out) {
     if (!last) {
       const i32 v4 = wadd(__mulhi(t0, re), __mulhi(t2, im));
       const i32 v5 = wadd(wneg(__mulhi(t2, re)), __mulhi(t0, im));
-      out[2 * n] = wsub(t1, v4);
-      out[2 * n + 1] = wadd(t3, v5);
-      out[33 - 2 * n] = wadd(wneg(t3), v5);
-      out[32 - 2 * n] = wadd(t1, v4);
+      o[2 * n] = wsub(t1, v4);
+      o[2 * n + 1] = wadd(t3, v5);
+      o[33 - 2 * n] = wadd(wneg(t3), v5);
+      o[32 - 2 * n] = wadd(t1, v4);
     } else {
       const i32 v4 = wsub(__mulhi(t0, re), __mulhi(t2, im));
       const i32 v5 = wadd(__mulhi(t2, re), __mulhi(t0, im));
-      out[16] = wadd(t1, v4);
-      out[17] = wadd(t3, v5);
+      o[16] = wadd(t1, v4);
+      o[17] = wadd(t3, v5);
     }
   }
-  radix4_lane(t.w16, out, 1, 4);
-  // generic:1831-1932 — final radix-4 (no twiddles) with digit-reversed scatter: out -> in[0..31]
+#pragma unroll
+  for (int i = 0; i < 32; i++) row[i] = o[i];
+  radix4_lane(t.w16, row, 1, 4);
+  // generic:1831-1932 — final radix-4 (no twiddles) with digit-reversed scatter: row[0..31] -> row[32..63]
+  i32 *in = row + 32;
 #pragma unroll 1
   for (int k = 0; k < 2; k++) {
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
-      const i32 *c = out + 16 * k + 8 * half;
-      const int o = 4 * k + 2 * half;
+      const i32 *c = row + 16 * k + 8 * half;
+      const int q = 4 * k + 2 * half;
       const i32 xh0 = add_sat(c[0], c[4]), xh1 = add_sat(c[1], c[5]);
       const i32 xl0 = sub_sat(c[0], c[4]), xl1 = sub_sat(c[1], c[5]);
       const i32 zh0 = add_sat(c[2], c[6]), zh1 = add_sat(c[3], c[7]);
       const i32 zl0 = sub_sat(c[2], c[6]), zl1 = sub_sat(c[3], c[7]);
-      in[o] = add_sat(xh0, zh0);
-      in[o + 1] = add_sat(xh1, zh1);
-      in[8 + o] = add_sat(xl0, zl1);
-      in[8 + o + 1] = sub_sat(xl1, zl0);
-      in[16 + o] = sub_sat(xh0, zh0);
-      in[16 + o + 1] = sub_sat(xh1, zh1);
-      in[24 + o] = sub_sat(xl0, zl1);
-      in[24 + o + 1] = add_sat(xl1, zl0);
+      in[q] = add_sat(xh0, zh0);
+      in[q + 1] = add_sat(xh1, zh1);
+      in[8 + q] = add_sat(xl0, zl1);
+      in[8 + q + 1] = sub_sat(xl1, zl0);
+      in[16 + q] = sub_sat(xh0, zh0);
+      in[16 + q + 1] = sub_sat(xh1, zh1);
+      in[24 + q] = sub_sat(xl0, zl1);
+      in[24 + q + 1] = add_sat(xl1, zl0);
     }
   }
-  // generic:216-238 — output permutation in[0..31] -> out[0..31], then back into the row
-  out[0] = in[0];
-  out[2] = in[1];
+  // generic:216-238 — output permutation row[32..63] -> row[0..31]
+  row[0] = in[0];
+  row[2] = in[1];
 #pragma unroll 1
   for (int q = 0; q < 7; q++) {
-    out[1 + 4 * q] = in[3 + 2 * q];
-    out[3 + 4 * q] = in[2 + 2 * q];
-    out[30 - 4 * q] = in[19 + 2 * q];
-    out[28 - 4 * q] = in[18 + 2 * q];
+    row[1 + 4 * q] = in[3 + 2 * q];
+    row[3 + 4 * q] = in[2 + 2 * q];
+    row[30 - 4 * q] = in[19 + 2 * q];
+    row[28 - 4 * q] = in[18 + 2 * q];
   }
-  out[29] = in[17];
-  out[31] = in[16];
-#pragma unroll 1
-  for (int i = 0; i < 32; i++) in[i] = out[i];
+  row[29] = in[17];
+  row[31] = in[16];
 }
 
-// qmf_dec.c:72-211 + generic:241-257 — DCT-II of one slot: x = the slot's row (64 words, destroyed); X = 64-word row of
-// the history buffer that receives the slot's 128 WORD16 state samples (fs[0..127]).  dig_rev_table2_32 = {0,64,16,80}.
-XB_DEV void dct2_64_lane(const LpTab &t, i32 *x, i32 *X) {
-#pragma unroll 1
+// qmf_dec.c:72-211 + generic:241-257 — DCT-II of one slot, in place: the slot's 64-word row is replaced by its 128 WORD16
+// state samples fs[0..127].  The three passes that permute (pretwdct2, the digit-reversed radix-2 stage, the final
+// scatter) go through registers with static indices; the FFT stages and twiddle passes run in place in shared memory.
+// dig_rev_table2_32 = {0, 64, 16, 80} (checked at ROM install).
+XB_DEV void dct2_64_lane(const LpTab &t, i32 *x) {
+  i32 v[64];
+#pragma unroll
   for (int n = 0; n < 32; n++) {  // pretwdct2
-    X[n] = x[2 * n];
-    X[63 - n] = x[2 * n + 1];
+    v[n] = x[2 * n];
+    v[63 - n] = x[2 * n + 1];
   }
-  radix4_lane(t.w32, X, 1, 8);
-  radix4_lane(t.w32 + 48, X, 4, 2);
-  // generic:1934-2015 — final radix-2 with digit-reversed scatter X -> x
-#pragma unroll 1
+#pragma unroll
+  for (int i = 0; i < 64; i++) x[i] = v[i];
+  radix4_lane(t.w32, x, 1, 8);
+  radix4_lane(t.w32 + 48, x, 4, 2);
+  // generic:1934-2015 — final radix-2 with digit-reversed scatter
+#pragma unroll
+  for (int i = 0; i < 64; i++) v[i] = x[i];
+#pragma unroll
   for (int blk = 0; blk < 4; blk++) {
     const int h2 = (blk & 1) * 16 + (blk >> 1) * 4;  // dig_rev_table2_32[blk] >> 2
-#pragma unroll 1
+#pragma unroll
     for (int half = 0; half < 2; half++) {
-      const i32 *c = X + (blk >> 1) * 32 + (blk & 1) * 8 + 16 * half;
-      const int o = h2 + 2 * half;
-      const i32 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5], c6 = c[6], c7 = c[7];
-      x[o] = add_sat(c0, c2);
-      x[o + 1] = add_sat(c1, c3);
-      x[32 + o] = sub_sat(c0, c2);
-      x[32 + o + 1] = sub_sat(c1, c3);
-      x[8 + o] = add_sat(c4, c6);
-      x[8 + o + 1] = add_sat(c5, c7);
-      x[40 + o] = sub_sat(c4, c6);
-      x[40 + o + 1] = sub_sat(c5, c7);
+      const int c = (blk >> 1) * 32 + (blk & 1) * 8 + 16 * half;
+      const int q = h2 + 2 * half;
+      x[q] = add_sat(v[c], v[c + 2]);
+      x[q + 1] = add_sat(v[c + 1], v[c + 3]);
+      x[32 + q] = sub_sat(v[c], v[c + 2]);
+      x[32 + q + 1] = sub_sat(v[c + 1], v[c + 3]);
+      x[8 + q] = add_sat(v[c + 4], v[c + 6]);
+      x[8 + q + 1] = add_sat(v[c + 5], v[c + 7]);
+      x[40 + q] = sub_sat(v[c + 4], v[c + 6]);
+      x[40 + q + 1] = sub_sat(v[c + 5], v[c + 7]);
     }
   }
   // fftposttw, qmf_dec.c:107-159
@@ -273,18 +288,14 @@ XB_DEV void dct2_64_lane(const LpTab &t, i32 *x, i32 *X) {
     x[65 - 2 * k] = sub_sat(v2, in2);
     x[64 - 2 * k] = sub_sat(t3, v1);
   }
-  // posttwdct2, qmf_dec.c:161-211 -> fs[0..127] (out_fwd = fs + 32), fs[96] = 0 (generic:255)
-  int16_t *fs = reinterpret_cast<int16_t *>(X);
+  // posttwdct2, qmf_dec.c:161-211, pass 1 in place: x[0] = fs[32], x[1] = fs[0] = fs[64], x[2+2q] = r1_q, x[3+2q] = i1_q
   {
     const i32 ore = x[0], oim = x[1];
     const long long s = ((long long)ore + (long long)oim) >> 1;
     const i32 ore1 = s >= 0x7fffffffLL ? 0x7fffffff : (s <= -0x80000000LL ? (i32)0x80000000 : (i32)s);
-    fs[32] = (int16_t)round16(shl32(ore1, 4));
     const i32 last = sub_sat(ore, oim);
-    const i32 r1 = round16(shl32(__mulhi(last, t.dct23[64]), 4));
-    fs[64] = (int16_t)r1;
-    fs[0] = (int16_t)r1;
-    fs[96] = 0;
+    x[0] = round16(shl32(ore1, 4));
+    x[1] = round16(shl32(__mulhi(last, t.dct23[64]), 4));
   }
 #pragma unroll 1
   for (int q = 0; q < 31; q++) {
@@ -292,12 +303,23 @@ XB_DEV void dct2_64_lane(const LpTab &t, i32 *x, i32 *X) {
     const i32 re = t.dct23[2 + 2 * q], im = t.dct23[3 + 2 * q];
     const i32 ore = sub_sat(__mulhi(ire, re), __mulhi(iim, im));
     const i32 oim = add_sat(__mulhi(iim, re), __mulhi(ire, im));
-    const i32 r1 = round16(shl32(ore, 4)), i1 = round16(shl32(oim, 4));
-    fs[33 + q] = (int16_t)r1;
-    fs[31 - q] = (int16_t)r1;
-    fs[95 - q] = (int16_t)i1;
-    fs[97 + q] = (int16_t)neg16(i1);
+    x[2 + 2 * q] = round16(shl32(ore, 4));
+    x[3 + 2 * q] = round16(shl32(oim, 4));
   }
+  // pass 2: scatter to fs[33+q] = fs[31-q] = r1_q, fs[95-q] = i1_q, fs[97+q] = -i1_q (saturating), fs[96] = 0 (generic:255)
+#pragma unroll
+  for (int i = 0; i < 64; i++) v[i] = x[i];
+  auto FS = [&](int pidx) -> i32 {
+    if (pidx == 0 || pidx == 64) return v[1];
+    if (pidx < 32) return v[2 + 2 * (31 - pidx)];
+    if (pidx == 32) return v[0];
+    if (pidx < 64) return v[2 + 2 * (pidx - 33)];
+    if (pidx < 96) return v[3 + 2 * (95 - pidx)];
+    if (pidx == 96) return 0;
+    return neg16(v[3 + 2 * (pidx - 97)]);
+  };
+#pragma unroll
+  for (int j = 0; j < 64; j++) x[j] = (FS(2 * j) & 0xffff) | (i32)((u32)FS(2 * j + 1) << 16);
 }
 
 XB_DEV i32 mac_noise(i32 sig, i32 rnd, i32 nz) {  // ixheaac_mac16x16in32_shl_sat(sig, extract16h(rnd), nz)
@@ -1193,7 +1215,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
       const bool lock = tab.periodic && (pos & 63) == 0 && (f1 & 127) == 0 && pos >= 0 && pos <= 256 && f1 >= 0 &&
                         f1 <= 512 && ((P0 + F0) % 10 == 0);
       if (lock) {
-        int16_t *T = reinterpret_cast<int16_t *>(w.y);  // T[j] = sample at time j - 288 relative to the frame start
+        int16_t *T = w.est;  // 1312 samples over est .. pre; T[j] = sample at time j - 288 relative to the frame start
 #pragma unroll 1
         for (int j = lane; j < 288; j += 32) {
           int q = P0 + 9 - (j >> 5);
@@ -1271,7 +1293,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
       }
       __syncwarp();
       // DCT-III of the 32 slots, lane = slot
-      dct3_32_lane(tab, m + LS * (6 + lane), w.y + LS * lane);
+      dct3_32_lane(tab, m + LS * (6 + lane));
       __syncwarp();
       if (lane == 0) {
         w.sf[kSfStLb] = 0;
@@ -1387,7 +1409,8 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
           }
         }
       }
-      // history: 9 blocks of the old ring, rows 0..8 (row 9 + s holds slot s)
+      // history: 9 blocks of the old ring in the 9 rows before matrix row 0 (row 9 + s = matrix row s holds slot s)
+      i32 *hist = w.pre;
       const int b0 = off0 >> 7;
       {
         const i32 *ss = reinterpret_cast<const i32 *>(p.syn_states + u * 1280);
@@ -1396,12 +1419,12 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
           const int b = i >> 6;
           int a0 = b - b0;
           if (a0 < 0) a0 += 10;
-          if (a0 != 0) w.y[LS * (9 - a0) + (i & 63)] = ss[i];
+          if (a0 != 0) hist[LS * (9 - a0) + (i & 63)] = ss[i];
         }
       }
       __syncwarp();
       // DCT-II of the 32 slots, lane = slot: matrix row -> 128 WORD16 state samples in history row 9 + slot
-      dct2_64_lane(tab, m + LS * lane, w.y + LS * (9 + lane));
+      dct2_64_lane(tab, m + LS * lane);
       __syncwarp();
       // 10-tap window (generic:1508-1542, shift = 2): lane -> outputs 2*lane, 2*lane+1 of every slot
       {
@@ -1428,7 +1451,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
             clo[a] = sext16(cv);
             chi[a] = cv >> 16;
           }
-          const i32 *hp = w.y + LS * 9 + lane;
+          const i32 *hp = hist + LS * 9 + lane;
 #pragma unroll 2
           for (int i = 0; i < 32; i++) {
             i32 acc0 = 0x8000 >> 2, acc1 = 0x8000 >> 2;
@@ -1452,7 +1475,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
               int a = ab + b;
               if (a >= 10) a -= 10;
               const int idx = ((i + b) & 1) * 32;  // word offset of the 64-sample phase inside the block
-              const i32 hv = w.y[LS * (9 + i - a) + idx + lane];
+              const i32 hv = hist[LS * (9 + i - a) + idx + lane];
               const i32 cv = *reinterpret_cast<const i32 *>(tab.qmf_c + fpos + 64 * b + 2 * lane);
               acc0 += sext16(hv) * sext16(cv);
               acc1 += (hv >> 16) * (cv >> 16);
@@ -1471,7 +1494,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
           const int b = i >> 6;
           int a = (b - b0 + 31) % 10;
           if (a < 0) a += 10;
-          sd[i] = w.y[LS * (40 - a) + (i & 63)];
+          sd[i] = hist[LS * (40 - a) + (i & 63)];
         }
         if (lane == 0) {
           int off = (off0 - 128 * 32) % 1280;
