@@ -34,6 +34,10 @@
 namespace xb {
 
 constexpr int kLpWarps = 12;
+#ifndef LP_GROUP
+#define LP_GROUP 4
+#endif
+constexpr int kLpGroup = LP_GROUP;  // warps per phase-barrier group
 constexpr int LS = 65;  // word stride of a matrix row in shared memory (odd: column walks are conflict-free)
 
 struct LpTab {  // block-shared tables (image built on the host by sbr_lp_build_tables)
@@ -1128,8 +1132,37 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
   const long long warps_total = (long long)gridDim.x * kLpWarps;
 
 #pragma unroll 1
-  for (long long u = (long long)blockIdx.x * kLpWarps + warp; u < p.n_units; u += warps_total) {
+  for (long long u0 = (long long)blockIdx.x * kLpWarps; u0 < p.n_units; u0 += warps_total) {
+    const long long u = u0 + warp;
+    // The warps of a block walk the phases of the stage together (block barrier between phases) so that they execute
+    // the same few KB of this 120 KB kernel at the same time: without it the instruction cache thrashes
+    // (profiles/r1_lp.md).  Only the last, partially filled iteration of a block runs unsynchronised.
+    // Barrier groups of kLpGroup warps (named barriers) rather than the whole block: the groups drift apart, so one
+    // group's global loads overlap another group's arithmetic.
+    const int grp = warp / kLpGroup;
+    const bool sync_ok = u0 + (grp + 1) * kLpGroup <= p.n_units;
+#define LP_PHASE_SYNC()                                                                        \
+  do {                                                                                         \
+    if (sync_ok) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kLpGroup * 32) : "memory"); \
+  } while (0)
+    if (u >= p.n_units) continue;
     __syncwarp();
+    {  // pull the next unit of this warp into L2 while this one is processed (its loads then cost an L2 hit, not DRAM)
+      const long long un = u + warps_total;
+      if (un < p.n_units) {
+        auto pf = [&](const void *base, int bytes) {
+          const char *q = reinterpret_cast<const char *>(base);
+          for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
+        };
+        pf(p.side + un * kSideWords, 1480);
+        pf(p.time_in + un * p.in_unit_stride, p.in_ch == 1 ? 2048 : 0);
+        pf(p.syn_states + un * 1280, 2560);
+        pf(p.ov + un * 768, 1536);
+        pf(p.anal_states + un * 320, 640);
+        pf(p.env + un * kEnvStWords, 464);
+        pf(p.lpc + un * 256, 640);
+      }
+    }
     // ---------------- load ----------------
     {
       const i32 *src = reinterpret_cast<const i32 *>(p.side + u * kSideWords);
@@ -1203,6 +1236,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
       __syncwarp();
     }
 
+    LP_PHASE_SYNC();
     // ---------------- analysis: 5-tap window per slot (generic:528-588), lanes = outputs ----------------
     {
       const int16_t *pcm = p.time_in + u * p.in_unit_stride;
@@ -1292,6 +1326,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
         }
       }
       __syncwarp();
+      LP_PHASE_SYNC();
       // DCT-III of the 32 slots, lane = slot
       dct3_32_lane(tab, m + LS * (6 + lane));
       __syncwarp();
@@ -1310,6 +1345,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
     }
     __syncwarp();
 
+    LP_PHASE_SYNC();
     // ---------------- block floating point (sbr_dec.c:1050-1127, real) ----------------
     int save_lb_scale, max_samp_val;
     {
@@ -1362,6 +1398,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
     }
     __syncwarp();
 
+    LP_PHASE_SYNC();
     // ---------------- state that does not depend on the synthesis ----------------
     {
       i32 *lpc = p.lpc + u * 256;
@@ -1391,6 +1428,8 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
       err = 2;  // ring positions the reference can never produce
       if (lane == 0 && p.err) p.err[u] = (i32)0x80000000;
     }
+    i32 *const hist = w.pre;  // 9 old ring blocks in the 9 rows before matrix row 0; row 9 + s = matrix row s holds slot s
+    const int b0 = off0 >> 7;
     if (!err) {
       const int st_syn = w.sf[kSfStSyn];
       const int sh_ov = max(-31, min(31, (st_syn - w.sf[kSfOvLb]) - 4));
@@ -1409,9 +1448,6 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
           }
         }
       }
-      // history: 9 blocks of the old ring in the 9 rows before matrix row 0 (row 9 + s = matrix row s holds slot s)
-      i32 *hist = w.pre;
-      const int b0 = off0 >> 7;
       {
         const i32 *ss = reinterpret_cast<const i32 *>(p.syn_states + u * 1280);
 #pragma unroll 1
@@ -1422,10 +1458,14 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
           if (a0 != 0) hist[LS * (9 - a0) + (i & 63)] = ss[i];
         }
       }
-      __syncwarp();
-      // DCT-II of the 32 slots, lane = slot: matrix row -> 128 WORD16 state samples in history row 9 + slot
-      dct2_64_lane(tab, m + LS * lane);
-      __syncwarp();
+    }
+    __syncwarp();
+    LP_PHASE_SYNC();
+    // DCT-II of the 32 slots, lane = slot: matrix row -> 128 WORD16 state samples in history row 9 + slot
+    if (!err) dct2_64_lane(tab, m + LS * lane);
+    __syncwarp();
+    LP_PHASE_SYNC();
+    if (!err) {
       // 10-tap window (generic:1508-1542, shift = 2): lane -> outputs 2*lane, 2*lane+1 of every slot
       {
         int16_t *out = p.time_out + (u / p.out_ch) * (2048LL * p.out_ch) + (u % p.out_ch);
