@@ -258,4 +258,23 @@ void xo_low_pow_hf_generator(const int32_t *lpc, int32_t *scratch, const int16_t
                              int16_t *degree_alias, int norm_max);
 int xo_sbr_dec_lp(const uint8_t *qrom, const uint8_t *env_rom, const uint8_t *misc_rom, const int16_t *side,
                   int16_t *st, const int16_t *time_in, int ch_in, int16_t *time_out, int ch_out, int32_t *scratch);
+
+/* ---- USAC frequency-domain core transform (usac_fd.c) ------------------------------------------------------------
+ * ROM blob (XO_UROM_BYTES): the reference's const tables of the path, concatenated by ref_rom_usac_tables(). */
+#define XO_UROM_FFT_TW 0          /* WORD32[514]  ixheaacd_twiddle_table_fft_32x32 */
+#define XO_UROM_COS512 2056       /* WORD32[512]  ixheaacd_pre_post_twid_cos_512 */
+#define XO_UROM_SIN512 4104       /* WORD32[512]  ixheaacd_pre_post_twid_sin_512 */
+#define XO_UROM_COS64 6152        /* WORD32[64]   ixheaacd_pre_post_twid_cos_64 */
+#define XO_UROM_SIN64 6408        /* WORD32[64]   ixheaacd_pre_post_twid_sin_64 */
+#define XO_UROM_SINE1024 6664     /* WORD32[1024] ixheaacd_sine_win_1024 */
+#define XO_UROM_KBD1024 10760     /* WORD32[1024] ixheaacd_kbd_win1024 */
+#define XO_UROM_SINE128 14856     /* WORD32[128]  ixheaacd_sine_win_128 */
+#define XO_UROM_KBD128 15368      /* WORD32[128]  ixheaacd_kbd_win128 */
+#define XO_UROM_BYTES 15880
+int xo_usac_complex_fft(const uint8_t *urom, int32_t *xr, int32_t *xi, int npoints, int preshift);
+int xo_usac_fd_frm_dec(const uint8_t *urom, int32_t *coef, int32_t *ov, int win_seq, int win_shape, int win_shape_prev,
+                       int32_t *out);
+void xo_usac_fd_frm_dec_batch(const uint8_t *urom, int32_t *coef, int32_t *ov, const int32_t *win_seq,
+                              const int32_t *win_shape, const int32_t *win_shape_prev, int32_t *out, int32_t *err, int n);
+
 #endif

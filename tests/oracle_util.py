@@ -174,6 +174,31 @@ class Oracle:
                                      P(s), P(np.ascontiguousarray(time_in, np.int16)), 1, P(out), 1, P(scratch))
         return s, out, err
 
+    # ---- USAC frequency-domain core transform ------------------------------------------------------------------
+    @property
+    def urom(self):
+        if not hasattr(self, "_urom"):
+            self._urom = rom("usac_rom.bin")
+        return self._urom
+
+    def usac_complex_fft(self, xr, xi, preshift):
+        a = np.ascontiguousarray(xr, np.int32).copy()
+        b = np.ascontiguousarray(xi, np.int32).copy()
+        ps = self.lib.xo_usac_complex_fft(P(self.urom), P(a), P(b), len(a), int(preshift))
+        return a, b, ps
+
+    def usac_fd_batch(self, coef, ov, win_seq, win_shape, win_shape_prev):
+        """coef [n,1024], ov [n,1024], sequences / shapes [n].  Returns (out [n,1024], ov', err [n])."""
+        n = coef.shape[0]
+        c = np.ascontiguousarray(coef, np.int32).copy()
+        o = np.ascontiguousarray(ov, np.int32).copy()
+        out = np.zeros((n, 1024), np.int32)
+        err = np.zeros(n, np.int32)
+        self.lib.xo_usac_fd_frm_dec_batch(P(self.urom), P(c), P(o), P(np.ascontiguousarray(win_seq, np.int32)),
+                                          P(np.ascontiguousarray(win_shape, np.int32)),
+                                          P(np.ascontiguousarray(win_shape_prev, np.int32)), P(out), P(err), n)
+        return out, o, err
+
     def imdct_out_to_pcm16(self, samples, qshift_adj, mode):
         x = np.ascontiguousarray(samples, np.int32)
         q = np.ascontiguousarray(qshift_adj, np.int8)
@@ -227,6 +252,23 @@ class Ref:
         self.lib.ref_ps_apply_frame(P(np.ascontiguousarray(side, np.int16)), P(np.ascontiguousarray(st, np.int16)), P(p),
                                     P(np.ascontiguousarray(sf, np.int16)), P(mm), P(right), int(usb), int(common_shift))
         return mm, right, p
+
+    def usac_complex_fft(self, xr, xi, preshift):
+        a = np.ascontiguousarray(xr, np.int32).copy()
+        b = np.ascontiguousarray(xi, np.int32).copy()
+        ps = self.lib.ref_usac_complex_fft(P(a), P(b), len(a), int(preshift))
+        return a, b, ps
+
+    def usac_fd_batch(self, coef, ov, win_seq, win_shape, win_shape_prev):
+        n = coef.shape[0]
+        c = np.ascontiguousarray(coef, np.int32).copy()
+        o = np.ascontiguousarray(ov, np.int32).copy()
+        out = np.zeros((n, 1024), np.int32)
+        err = np.zeros(n, np.int32)
+        self.lib.ref_usac_fd_frm_dec_batch(P(c), P(o), P(np.ascontiguousarray(win_seq, np.int32)),
+                                           P(np.ascontiguousarray(win_shape, np.int32)),
+                                           P(np.ascontiguousarray(win_shape_prev, np.int32)), P(out), P(err), n)
+        return out, o, err
 
     def rom_imdct(self, nbytes=7500):
         fn = self.lib.ref_rom_imdct_tables
@@ -514,3 +556,38 @@ def synth_sbr_lp_units(n, seed, golden):
             side[u, 3] = rng.integers(0, 4)
             side[u, 4] = rng.integers(0, 2)
     return side, st, tin
+
+
+def usac_seq_walk(n_units, n_frames, seed):
+    """legal USAC FD window-sequence walk per unit: seq [frames, n] (0 ONLY_LONG, 1 LONG_START, 2 EIGHT_SHORT,
+    3 LONG_STOP, 4 STOP_START), shape [frames, n] (0 sine, 1 KBD)"""
+    rng = np.random.default_rng(seed)
+    seq = np.zeros((n_frames, n_units), np.int32)
+    shape = rng.integers(0, 2, (n_frames, n_units)).astype(np.int32)
+    prev = np.zeros(n_units, np.int32)
+    for f in range(n_frames):
+        r = rng.random(n_units)
+        nxt = np.zeros(n_units, np.int32)
+        longish = (prev == 0) | (prev == 3)          # after ONLY_LONG / LONG_STOP: long or start
+        nxt[longish] = np.where(r[longish] < 0.3, 1, 0)
+        startish = (prev == 1) | (prev == 2) | (prev == 4)  # after a start-type / short frame: short, stop or stop-start
+        nxt[startish] = np.where(r[startish] < 0.4, 2, np.where(r[startish] < 0.8, 3, 4))
+        seq[f] = nxt
+        prev = nxt
+    return seq, shape
+
+
+def synth_usac_units(n, seed):
+    """dequantised USAC spectra [n,1024] with per-unit magnitude 2^4 .. 2^30 plus corner units, overlap [n,1024]"""
+    rng = np.random.default_rng(seed)
+    s = rng.integers(4, 31, (n, 1))
+    coef = ((rng.random((n, 1024)) * 2 - 1) * 2.0 ** s).astype(np.int64).clip(-2 ** 31, 2 ** 31 - 1).astype(np.int32)
+    ov = ((rng.random((n, 1024)) * 2 - 1) * 2.0 ** rng.integers(0, 29, (n, 1))).astype(np.int64).astype(np.int32)
+    if n > 4:
+        coef[0] = 0
+        coef[1] = np.where(np.arange(1024) % 2 == 0, 2 ** 31 - 1, -2 ** 31)
+        coef[2] = 0
+        coef[2, 5] = 2 ** 31 - 1
+        coef[3] = 1 << 20
+        ov[0] = 0
+    return coef, ov

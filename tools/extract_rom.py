@@ -44,7 +44,10 @@ def main():
 EXTRA = [("ref_rom_qmf_tables", 3464, "qmf_rom.bin"), ("ref_rom_env_tables", 2404, "env_rom.bin"),
          ("ref_rom_misc_tables", 2470, "misc_rom.bin"),
          # leading part of ia_ps_tables_struct through p8_13 (decoder/ixheaacd_sbr_rom.h:177-203)
-         ("ref_rom_ps_tables", 1230, "ps_rom.bin")]
+         ("ref_rom_ps_tables", 1230, "ps_rom.bin"),
+         # USAC frequency-domain core transform: FFT twiddles, pre / post twiddles (512, 64), sine / KBD windows (1024, 128)
+         # concatenated by ref_rom_usac_tables (oracle/ref_shim_usac.c; layout XAAC_UROM_* in include/xaac_b200.h)
+         ("ref_rom_usac_tables", 15880, "usac_rom.bin")]
 
 if __name__ == "__main__":
     main()
