@@ -381,6 +381,36 @@ int32_t xaac_b200_heaac_lp_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state 
 int32_t xaac_b200_imdct_out_to_pcm16_dev(xaac_b200_ctx *ctx, const int32_t *d_in, const int8_t *d_qshift_adj,
                                          int16_t *d_out, int64_t n_units, int32_t mode, void *stream);
 
+/* ---- USAC frequency-domain core transform -------------------------------------------------------
+ * Batched drop-in for ixheaacd_fd_frm_dec(ia_usac_data_struct *, WORD32 i_ch) (decoder/ixheaacd_imdct.c:596; called from
+ * ixheaacd_core_coder_data, decoder/ixheaacd_ext_ch_ele.c:991) for pure frequency-domain streams: previous frame FD
+ * (td_frame_prev = 0), no FAC data, frame ok, ccfl = 1024.  Covers ixheaacd_fd_imdct_long / _short, ixheaacd_acelp_imdct,
+ * the saturating FFT ixheaacd_complex_fft_p2_dec (decoder/ixheaacd_fft.c:1412; selector entry ixheaacd_complex_fft_p2,
+ * also ixheaacd_calc_pre_twid / ixheaacd_calc_post_twid) and the windowing leaves of decoder/ixheaacd_basic_ops.c.
+ * LPD / FAC transitions stay on the host (they need the ACELP state).
+ * ROM blob (XAAC_UROM_BYTES): the reference's tables, concatenated in this order — in a drop-in deployment the host
+ * memcpy's them from its own const arrays:
+ *   ixheaacd_twiddle_table_fft_32x32[514], ixheaacd_pre_post_twid_cos_512[512], _sin_512[512], _cos_64[64], _sin_64[64],
+ *   ixheaacd_sine_win_1024[1024], ixheaacd_kbd_win1024[1024], ixheaacd_sine_win_128[128], ixheaacd_kbd_win128[128] (WORD32). */
+#define XAAC_UROM_FFT_TW 0
+#define XAAC_UROM_COS512 2056
+#define XAAC_UROM_SIN512 4104
+#define XAAC_UROM_COS64 6152
+#define XAAC_UROM_SIN64 6408
+#define XAAC_UROM_SINE1024 6664
+#define XAAC_UROM_KBD1024 10760
+#define XAAC_UROM_SINE128 14856
+#define XAAC_UROM_KBD128 15368
+#define XAAC_UROM_BYTES 15880
+int32_t xaac_b200_set_usac_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes);
+/*   d_coef    [n][1024] WORD32 usac_data->coef_fix[ch] (read-only here; the reference uses it as workspace)
+ *   d_overlap [n][1024] WORD32 usac_data->overlap_data_ptr[ch], in/out
+ *   d_wstate  [n] uint8 usac_data->window_shape_prev[ch], in/out (set to this frame's shape, ext_ch_ele.c:968)
+ *   d_ics     [n][2] uint8 {window_sequence (0 ONLY_LONG, 1 LONG_START, 2 EIGHT_SHORT, 3 LONG_STOP, 4 STOP_START), window_shape}
+ *   d_out     [n][1024] WORD32 usac_data->output_data_ptr[ch] (Q15; the reference then scales by 2^-15 to float) */
+int32_t xaac_b200_usac_fd_frm_dec_dev(xaac_b200_ctx *ctx, const int32_t *d_coef, int32_t *d_overlap, uint8_t *d_wstate,
+                                      const uint8_t *d_ics, int32_t *d_out, int64_t n_units, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

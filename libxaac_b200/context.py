@@ -5,7 +5,7 @@ from . import _lib
 
 
 class Context:
-    def __init__(self, device=0, imdct_rom=None, qmf_rom=None, env_rom=None, misc_rom=None, ps_rom=None):
+    def __init__(self, device=0, imdct_rom=None, qmf_rom=None, env_rom=None, misc_rom=None, ps_rom=None, usac_rom=None):
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         rc = self._lib.xaac_b200_create(ctypes.byref(self._h), int(device))
@@ -21,6 +21,7 @@ class Context:
         self.set_env_rom(env_rom if env_rom is not None else _lib.rom_blob("env_rom.bin"),
                          misc_rom if misc_rom is not None else _lib.rom_blob("misc_rom.bin"))
         self.set_ps_rom(ps_rom if ps_rom is not None else _lib.rom_blob("ps_rom.bin"))
+        self.set_usac_rom(usac_rom if usac_rom is not None else _lib.rom_blob("usac_rom.bin"))
 
     # -- plumbing ---------------------------------------------------------------------------------
     @property
@@ -54,6 +55,11 @@ class Context:
         """blob: leading >= 1230 bytes of the host's ia_ps_tables_struct."""
         buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
         self.check(self._lib.xaac_b200_set_ps_rom(self._h, buf, len(blob)), "xaac_b200_set_ps_rom")
+
+    def set_usac_rom(self, blob):
+        """blob: the host's USAC FD tables concatenated in the XAAC_UROM_* order (15880 bytes)."""
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        self.check(self._lib.xaac_b200_set_usac_rom(self._h, buf, len(blob)), "xaac_b200_set_usac_rom")
 
     @property
     def num_sms(self):

@@ -229,6 +229,31 @@ size_t sbr_lp_table_bytes();
 int sbr_lp_build_tables(const uint8_t *qrom, uint8_t *out);  // 0 ok, -1 tables unsupported
 cudaError_t launch_sbr_dec_lp(const SbrLpArgs &args, int num_sms, cudaStream_t stream);
 
+// ---- USAC frequency-domain core transform (ixheaacd_fd_frm_dec) ------------------------------------------------------
+// ROM blob = the reference's const tables of the path in this order (include/xaac_b200.h XAAC_UROM_*)
+constexpr int kURomFftTw = 0;        // WORD32[514]  ixheaacd_twiddle_table_fft_32x32
+constexpr int kURomCos512 = 2056;    // WORD32[512]  ixheaacd_pre_post_twid_cos_512
+constexpr int kURomSin512 = 4104;    // WORD32[512]  ixheaacd_pre_post_twid_sin_512
+constexpr int kURomCos64 = 6152;     // WORD32[64]   ixheaacd_pre_post_twid_cos_64
+constexpr int kURomSin64 = 6408;     // WORD32[64]   ixheaacd_pre_post_twid_sin_64
+constexpr int kURomSine1024 = 6664;  // WORD32[1024] ixheaacd_sine_win_1024
+constexpr int kURomKbd1024 = 10760;  // WORD32[1024] ixheaacd_kbd_win1024
+constexpr int kURomSine128 = 14856;  // WORD32[128]  ixheaacd_sine_win_128
+constexpr int kURomKbd128 = 15368;   // WORD32[128]  ixheaacd_kbd_win128
+constexpr int kURomBytes = 15880;
+struct UsacFdArgs {
+  const int32_t *coef;   // [n][1024] dequantised spectrum usac_data->coef_fix[ch] (read-only here; the reference destroys it)
+  int32_t *overlap;      // [n][1024] usac_data->overlap_data_ptr[ch], in/out
+  uint8_t *wstate;       // [n]       usac_data->window_shape_prev[ch], in/out
+  const uint8_t *ics;    // [n][2]    {window_sequence, window_shape} of this frame
+  int32_t *out;          // [n][1024] usac_data->output_data_ptr[ch] (WORD32, Q15)
+  const uint8_t *rom;    // device copy of the ROM blob
+  long long n_units;
+};
+size_t usac_fd_smem_bytes();
+int usac_fd_check_tables(const uint8_t *urom);
+cudaError_t launch_usac_fd(const UsacFdArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

@@ -25,6 +25,7 @@ struct xaac_b200_ctx {
   uint8_t *d_rom_misc = nullptr;  // leading part of ixheaacd_misc_tables
   bool have_env_rom = false;
   uint8_t *d_rom_ps = nullptr;    // leading part of ia_ps_tables_struct
+  uint8_t *d_rom_usac = nullptr;  // USAC FD tables (XAAC_UROM_*)
   bool have_ps_rom = false;
   int ps_rot_nosat = 0;           // no fractional-delay phase factor equals -32768 (16x16 rotations cannot saturate)
   char err[256] = {0};
@@ -172,6 +173,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   if (ctx->d_rom_env) cudaFree(ctx->d_rom_env);
   if (ctx->d_rom_misc) cudaFree(ctx->d_rom_misc);
   if (ctx->d_rom_ps) cudaFree(ctx->d_rom_ps);
+  if (ctx->d_rom_usac) cudaFree(ctx->d_rom_usac);
   delete ctx;
 }
 
@@ -923,6 +925,35 @@ int32_t xaac_b200_imdct_out_to_pcm16_dev(xaac_b200_ctx *ctx, const int32_t *d_in
   if (!d_in || !d_qshift_adj || !d_out) return bad_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   LAUNCH("pcm16_from_imdct_kernel", stream, xb::launch_pcm16_from_imdct(d_in, d_qshift_adj, d_out, n_units, mode, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_set_usac_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
+  if (!ctx || !tables) return bad_arg(ctx, "null");
+  if (bytes < (size_t)xb::kURomBytes) return bad_arg(ctx, "USAC ROM blob shorter than 15880 bytes");
+  if (xb::usac_fd_check_tables((const uint8_t *)tables) != 0) return bad_arg(ctx, "USAC tables");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (!ctx->d_rom_usac) CK(cudaMalloc((void **)&ctx->d_rom_usac, xb::kURomBytes + 56), "cudaMalloc(usac rom)");
+  CK(cudaMemcpy(ctx->d_rom_usac, tables, xb::kURomBytes, cudaMemcpyHostToDevice), "H2D usac rom");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_usac_fd_frm_dec_dev(xaac_b200_ctx *ctx, const int32_t *d_coef, int32_t *d_overlap, uint8_t *d_wstate,
+                                      const uint8_t *d_ics, int32_t *d_out, int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->d_rom_usac) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_usac_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_coef || !d_overlap || !d_wstate || !d_ics || !d_out) return bad_arg(ctx, "null buffer");
+  xb::UsacFdArgs a;
+  a.coef = d_coef; a.overlap = d_overlap; a.wstate = d_wstate; a.ics = d_ics; a.out = d_out; a.rom = ctx->d_rom_usac;
+  a.n_units = n_units;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  LAUNCH("usac_fd_kernel", stream, xb::launch_usac_fd(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }
