@@ -41,6 +41,7 @@ CHAIN_KERNEL_BYTES = {
     # synthesis ring 2564, envelope state 464, overlap rows 1536, LPC rows 256, scale factors / misc / bw 72) + 1480 side info
     "sbr_dec_lp_kernel": 18696,
 }
+USAC_FD_BYTES_PER_UNIT = 16384  # 4096 coefficients + 4096 overlap in + 4096 overlap out + 4096 WORD32 out
 WORKLOADS = {
     # name -> (BASELINE.json config index, stereo frames per GPU, description)
     "heaacv2_chain": (3, 131072, "HE-AACv2 (SBR+PS) stereo 44.1 kHz batch=131072: full IMDCT->QMF->SBR->PS "
@@ -48,6 +49,9 @@ WORKLOADS = {
     "aac_lc_stereo_imdct_ola": (1, 65536, "AAC-LC stereo 44.1 kHz batch=65536 frames, IMDCT+OLA only"),
     "heaacv1_stereo_chain": (2, 65536, "HE-AACv1 stereo 48 kHz batch=65536: IMDCT + 64-band QMF analysis/synthesis + LPP "
                                        "HF-gen + env_calc (fixed-point path of the reference, -esbr:0: low-power SBR)"),
+    "usac_fd_imdct": (4, 131072, "xHE-AAC/USAC stereo 32 kHz batch=131072: the fixed-point FD core transform of the chain "
+                                 "(ixheaacd_fd_frm_dec: IMDCT 1024/128 + windowing + overlap); the float eSBR stage is not "
+                                 "built yet"),
     "qmf_synth_hq": (3, 65536, "stand-alone fixed-point HQ 64-band QMF synthesis stage of the HE-AAC chain, "
                                "batch=65536 stereo frames (131072 output channels)"),
 }
@@ -403,6 +407,73 @@ def cpu_arm_chain_lp(n_units, threads, seed, reps=1):
     return n_units * reps / dt, "reference"
 
 
+def usac_walk(n_units, n_steps, seed):
+    """ics[step][unit] = (window_sequence, window_shape) of a legal USAC FD walk, both channels of a frame alike:
+    ~85 % ONLY_LONG, the rest start / short / stop / stop-start runs"""
+    rng = np.random.default_rng(seed)
+    nf = n_units // 2
+    prev = np.zeros(nf, np.uint8)
+    out = np.zeros((n_steps, n_units, 2), np.uint8)
+    for s_ in range(n_steps):
+        r = rng.random(nf)
+        nxt = np.zeros(nf, np.uint8)
+        longish = (prev == 0) | (prev == 3)
+        nxt[longish & (r < 0.05)] = 1
+        st = ~longish
+        nxt[st] = np.where(r[st] < 0.35, 2, np.where(r[st] < 0.85, 3, 4))
+        shape = (rng.random(nf) < 0.5).astype(np.uint8)
+        out[s_, 0::2, 0] = nxt
+        out[s_, 1::2, 0] = nxt
+        out[s_, 0::2, 1] = shape
+        out[s_, 1::2, 1] = shape
+        prev = nxt
+    return out
+
+
+def cpu_arm_usac(n_units, threads, seed, reps=1):
+    """Time ixheaacd_fd_frm_dec per unit on host threads (unmodified reference through oracle/_ref, or the C port)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    P = oracle_util.P
+    rng = np.random.default_rng(seed)
+    s = rng.integers(12, 28, size=(n_units, 1))
+    coef0 = ((rng.random((n_units, 1024)) * 2 - 1) * (2.0 ** s)).astype(np.int64).astype(np.int32)
+    walk = usac_walk(n_units, reps + 1, seed)
+    ov = np.zeros((n_units, 1024), np.int32)
+    out = np.zeros((n_units, 1024), np.int32)
+    err = np.zeros(n_units, np.int32)
+    prev = np.zeros(n_units, np.int32)
+    bounds = np.linspace(0, n_units, threads + 1).astype(int)
+    if ref is not None:
+        kind, fn, pre = "reference", ref.lib.ref_usac_fd_frm_dec_batch, []
+    else:
+        orc = oracle_util.Oracle()
+        kind, fn, pre = "port", orc.lib.xo_usac_fd_frm_dec_batch, [P(orc.urom)]
+
+    def work(t, coef, seq, shape):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            fn(*pre, P(coef[a:b]), P(ov[a:b]), P(seq[a:b]), P(shape[a:b]), P(prev[a:b]), P(out[a:b]), P(err[a:b]), b - a)
+
+    def one_pass(step):
+        coef = coef0.copy()
+        seq = np.ascontiguousarray(walk[step, :, 0], np.int32)
+        shape = np.ascontiguousarray(walk[step, :, 1], np.int32)
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t, coef, seq, shape)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        dt = time.perf_counter() - t0
+        prev[:] = shape
+        return dt
+
+    one_pass(0)
+    dt = sum(one_pass(1 + r) for r in range(reps))
+    return n_units * reps / dt, kind
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -426,6 +497,11 @@ STAGES = {
                                     stage="IMDCT + window/OLA (fixed-point WORD32, bit-exact)",
                                     ref_stage="ixheaacd_imdct_process", cpu=cpu_arm, cpu_units_per_core=4096,
                                     realtime_fps=43.066, h2d=4096 + 2, d2h=4096 + 1),
+    "usac_fd_imdct": dict(kernel="usac_fd_kernel", bytes_per_unit=USAC_FD_BYTES_PER_UNIT,
+                          stage="USAC FD core transform: IMDCT 1024 / 8 x 128 (saturating radix-4 FFT) + windowing + overlap "
+                                "(fixed-point WORD32, bit-exact)",
+                          ref_stage="ixheaacd_fd_frm_dec", cpu=cpu_arm_usac, cpu_units_per_core=2048, realtime_fps=31.25,
+                          h2d=4096 + 2, d2h=4096),
     "qmf_synth_hq": dict(kernel="qmf_synth_hq_kernel", bytes_per_unit=SYNTH_BYTES_PER_UNIT,
                          stage="complex 64-band QMF synthesis (fixed-point, bit-exact)",
                          ref_stage="ixheaacd_cplx_synt_qmffilt", cpu=cpu_arm_synth, cpu_units_per_core=1024,
@@ -576,6 +652,42 @@ class ChainWork:
         self.state.close()
 
 
+class UsacFdWork:
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        self.coef = make_spec_torch(n_units, seed, dev)
+        self.walk = torch.from_numpy(usac_walk(n_units, steps_total, seed)).to(dev)
+        self.state = xb.UsacFdBatch(n_units, device=dev)
+        self.out = torch.empty((n_units, 1024), dtype=torch.int32, device=dev)
+        self.nw = steps_total
+
+    def step(self, i, stream):
+        self.xb.usac_fd_frm_dec(self.ctx, self.state, self.coef, self.walk[i % self.nw], self.out, stream=stream)
+
+    def host_setup(self):
+        """no dedicated host-buffer entry point for this stage yet: the end-to-end arm copies through pinned buffers
+        around the device call (H2D coefficients + ics, D2H output inside the timed region)"""
+        import torch
+        self.h_coef = torch.empty((self.n, 1024), dtype=torch.int32).pin_memory()
+        self.h_coef.copy_(self.coef)
+        self.h_out = torch.empty((self.n, 1024), dtype=torch.int32).pin_memory()
+        self.h_walk = self.walk.cpu().pin_memory()
+        self.d_coef = torch.empty_like(self.coef)
+        self.d_ics = torch.empty((self.n, 2), dtype=torch.uint8, device=self.coef.device)
+
+    def host_step(self, i):
+        import torch
+        self.d_coef.copy_(self.h_coef, non_blocking=True)
+        self.d_ics.copy_(self.h_walk[i % self.nw], non_blocking=True)
+        self.xb.usac_fd_frm_dec(self.ctx, self.state, self.d_coef, self.d_ics, self.out)
+        self.h_out.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
+
+
 class ChainLpWork:
     """Stereo HE-AACv1 frames on the reference's fixed-point low-power path: unit = one core channel (units 2k / 2k+1 =
     L / R of stream k): IMDCT -> PCM16 -> fused LP SBR stage -> interleaved stereo PCM16.  Side info / initial state are
@@ -630,7 +742,7 @@ class ChainLpWork:
 
 
 WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv2_chain": ChainWork,
-        "heaacv1_stereo_chain": ChainLpWork}
+        "heaacv1_stereo_chain": ChainLpWork, "usac_fd_imdct": UsacFdWork}
 
 
 def main():
