@@ -188,6 +188,15 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
     const bool as_built = mode != 2;
     const int16_t *prm = side + kSidePsPrm;
     int16_t *st = w.st;
+    {  // pull this warp's next unit towards L2 while this one is processed
+      const long long un = u + warps_total;
+      if (un < p.n_units) {
+        const char *q0 = reinterpret_cast<const char *>(p.ps_state + un * kPsDspWords);
+        for (int o = lane * 128; o < kPsDspWords * 2; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + o));
+        const char *q1 = reinterpret_cast<const char *>(p.side + un * kSideWords);
+        for (int o = lane * 128; o < kSideWords * 2; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + o));
+      }
+    }
     __syncwarp();
     {
       const i32 *src = reinterpret_cast<const i32 *>(p.ps_state + u * kPsDspWords);
@@ -337,6 +346,8 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
     }
     const int shA_ov = pre(lane, 0), shA_lb = pre(lane, 6), shB_ov = pre(lane + 32, 0), shB_lb = pre(lane + 32, 6);
 
+    // the left row of the next slot is fetched one slot ahead (its latency was the top stall of the slot loop)
+    i32 nAr = mat[lane], nAi = mat[64 + lane], nBr = mat[32 + lane], nBi = mat[96 + lane];
 #pragma unroll 1
     for (int slot = 0; slot < 32; slot++) {
       // ---- ixheaacd_init_rot_env at PS envelope borders (ps_dec.c:714-854): lane = stereo group ----
@@ -390,12 +401,15 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       // ---- left row (pre-shifted), this slot's hybrid sub-subbands ----
       i32 lAr, lAi, lBr, lBi;  // bands lane and lane + 32 of the left input
       {
-        const i32 *row = mat + 128 * slot;
         const int sA = slot < 6 ? shA_ov : shA_lb, sB = slot < 6 ? shB_ov : shB_lb;
-        lAr = blockshift(row[lane], sA);
-        lAi = blockshift(row[64 + lane], sA);
-        lBr = blockshift(row[32 + lane], sB);
-        lBi = blockshift(row[96 + lane], sB);
+        lAr = blockshift(nAr, sA);
+        lAi = blockshift(nAi, sA);
+        lBr = blockshift(nBr, sB);
+        lBi = blockshift(nBi, sB);
+        if (slot < 31) {
+          const i32 *row = mat + 128 * (slot + 1);
+          nAr = row[lane]; nAi = row[64 + lane]; nBr = row[32 + lane]; nBi = row[96 + lane];
+        }
       }
       if (lane < 10) {
         w.hyb[lane] = w.hybL[slot][lane];
