@@ -144,7 +144,7 @@ def make_synth_inputs_torch(n_units, seed, device):
     return matrix, params
 
 
-def cpu_arm_synth(n_units, threads, seed, reps=1):
+def cpu_arm_synth(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time ixheaacd_cplx_synt_qmffilt (HQ) per unit on host threads. Returns (units_per_s, kind)."""
     from tests import oracle_util
     ref = oracle_util.Ref.try_load()
@@ -181,8 +181,11 @@ def cpu_arm_synth(n_units, threads, seed, reps=1):
         return time.perf_counter() - t0
 
     one_pass()
-    dt = sum(one_pass() for _ in range(reps))
-    return n_units * reps / dt, kind
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass()
+        done += 1
+    return n_units * done / dt, kind
 
 
 class ClockSampler:
@@ -241,7 +244,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own generic-C stage (oracle/_ref) or, if that was not built, our C port (oracle/)
 # ---------------------------------------------------------------------------------------------------------
-def cpu_arm(n_units, threads, seed, reps=1):
+def cpu_arm(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time ixheaacd_imdct_process on `n_units` units spread over `threads` host threads (one private state per
     unit; the 1024-sample path touches no global scratch). Returns (units_per_s, kind)."""
     from tests import oracle_util
@@ -289,8 +292,11 @@ def cpu_arm(n_units, threads, seed, reps=1):
         return time.perf_counter() - t0
 
     one_pass(0)  # warm-up (page faults, caches)
-    dt = sum(one_pass(1 + r) for r in range(reps))
-    return n_units * reps / dt, kind
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass(1 + done % reps)
+        done += 1
+    return n_units * done / dt, kind
 
 
 def load_chain_golden():
@@ -308,7 +314,7 @@ def chain_inputs_np(n_units, seed):
     return spec
 
 
-def cpu_arm_chain(n_units, threads, seed, reps=1):
+def cpu_arm_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time the reference's own chain per stream-frame on host threads: ixheaacd_imdct_process -> WORD32->WORD16
     hand-over -> ixheaacd_sbr_dec (HQ + PS, 2 x ixheaacd_cplx_synt_qmffilt), persistent reference structs per stream.
     Returns (stream_frames_per_s * 2, kind): the factor 2 keeps the caller's units/2 = frames convention."""
@@ -346,9 +352,12 @@ def cpu_arm_chain(n_units, threads, seed, reps=1):
         return time.perf_counter() - t0
 
     one_pass(0)
-    dt = sum(one_pass(1 + r) for r in range(reps))
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass(1 + done % reps)
+        done += 1
     ref.lib.ref_chain_destroy(h)
-    return 2.0 * n_units * reps / dt, "reference"
+    return 2.0 * n_units * done / dt, "reference"
 
 
 def load_chain_lp_golden():
@@ -366,7 +375,7 @@ def chain_lp_side(side_frames, n_units, f):
     return np.ascontiguousarray(side_frames[((u >> 1) + f) % 12, u & 1])
 
 
-def cpu_arm_chain_lp(n_units, threads, seed, reps=1):
+def cpu_arm_chain_lp(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time the reference's own stereo HE-AACv1 chain per channel unit on host threads: ixheaacd_imdct_process ->
     WORD32->WORD16 hand-over -> ixheaacd_sbr_dec (low_pow_flag = 1).  Returns (units_per_s, kind)."""
     from tests import oracle_util
@@ -402,9 +411,12 @@ def cpu_arm_chain_lp(n_units, threads, seed, reps=1):
         return time.perf_counter() - t0
 
     one_pass(0)
-    dt = sum(one_pass(1 + r) for r in range(reps))
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass(1 + done % reps)
+        done += 1
     ref.lib.ref_chain_destroy(h)
-    return n_units * reps / dt, "reference"
+    return n_units * done / dt, "reference"
 
 
 def usac_walk(n_units, n_steps, seed):
@@ -430,7 +442,7 @@ def usac_walk(n_units, n_steps, seed):
     return out
 
 
-def cpu_arm_usac(n_units, threads, seed, reps=1):
+def cpu_arm_usac(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time ixheaacd_fd_frm_dec per unit on host threads (unmodified reference through oracle/_ref, or the C port)."""
     from tests import oracle_util
     ref = oracle_util.Ref.try_load()
@@ -470,8 +482,11 @@ def cpu_arm_usac(n_units, threads, seed, reps=1):
         return dt
 
     one_pass(0)
-    dt = sum(one_pass(1 + r) for r in range(reps))
-    return n_units * reps / dt, kind
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass(1 + done % reps)
+        done += 1
+    return n_units * done / dt, kind
 
 
 def host_threads():
@@ -518,7 +533,7 @@ def run_reference_arm(args, rank, world):
     sample_units = min(2 * frames, stg["cpu_units_per_core"] * cores)
     sample_units -= sample_units % 2
     t0 = time.perf_counter()
-    ups, kind = stg["cpu"](sample_units, cores, 0xAAC0 + cfg_idx, reps=max(1, args.steps))
+    ups, kind = stg["cpu"](sample_units, cores, 0xAAC0 + cfg_idx, reps=max(1, args.steps), min_seconds=10.0)
     unit_name = "units (frame x channel)"
     if stg.get("units_per_frame", 2) == 1:
         sample_units *= 2  # the chain's CPU arm counts stream-frames and returns 2 x frames/s
@@ -532,8 +547,8 @@ def run_reference_arm(args, rank, world):
         "config": {"workload": args.workload, "baseline_config": desc, "stage": stg["ref_stage"],
                    "step": f"bounded sample: {sample_units // 2} stereo frames per step on host cores"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample_units} {unit_name} x {max(1, args.steps)} passes "
-                                   f"(+1 warm-up), {cores} threads, private state per unit"},
+                         "sample": f"{sample_units} {unit_name} per pass, at least {max(1, args.steps)} passes and 10 s "
+                                   f"of timed CPU work (+1 warm-up pass), {cores} threads, private state per unit"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
@@ -922,10 +937,11 @@ def main():
             stg = STAGES[args.workload]
             creps = stg.get("cpu_reps", 2)
             ups1, kind = stg["cpu"](stg["cpu_units_per_core"], 1, 0xAAC0 + cfg_idx, reps=max(1, creps // 4))
-            upsN, kind = stg["cpu"](stg["cpu_units_per_core"] * cores, cores, 0xAAC0 + cfg_idx, reps=creps)
+            upsN, kind = stg["cpu"](stg["cpu_units_per_core"] * cores, cores, 0xAAC0 + cfg_idx, reps=creps, min_seconds=10.0)
             line["cpu_baseline"] = {"value": upsN / 2.0, "unit": "frames/s", "cores": cores, "kind": kind,
                                     "value_1core": ups1 / 2.0,
-                                    "sample": f"{stg['cpu_units_per_core'] * cores} units x {creps} passes on {cores} threads "
+                                    "sample": f"{stg['cpu_units_per_core'] * cores} units per pass, >= {creps} passes and >= 10 s of "
+                                              f"timed CPU work on {cores} threads "
                                               f"(1-core figure: {stg['cpu_units_per_core']} units), "
                                               f"{stg['ref_stage']} per unit"}
         print(json.dumps(line), flush=True)
