@@ -69,3 +69,13 @@ def test_streams_state_resident(ctx, oracle):
         prev = shape[f]
         assert np.array_equal(out.cpu().numpy(), eo), f"frame {f}"
     assert np.array_equal(st.overlap.cpu().numpy(), ov)
+
+
+def test_golden_tapped_real_decode(ctx):
+    """records tapped from the reference decoding a real xHE-AAC stream (tests/golden/usac_fd_tapped.npz)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "usac_fd_tapped.npz"))
+    h = g["hdr"]
+    out, ov, ws = run_gpu(ctx, g["coef"], g["ov_in"], h[:, 1], h[:, 2], h[:, 3])
+    assert np.array_equal(out, g["out"]) and np.array_equal(ov, g["ov_out"])
+    assert np.array_equal(ws, h[:, 2].astype(np.uint8))

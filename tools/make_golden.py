@@ -305,9 +305,49 @@ def make_sbrdec_lp_golden(tmp):
     print(f"wrote {path}: {len(sel)} of {len(recs)} records, {os.path.getsize(path)} bytes")
 
 
+def make_usac_fd_golden(tmp):
+    """USAC (xHE-AAC, aot 42, ccfl 1024) stereo 32 kHz: every ixheaacd_fd_frm_dec call of a real decode is tapped
+    (oracle/ref_taps_usac.c).  Records of pure FD frames (previous frame FD, no FAC data, no concealment) are kept:
+    a window-sequence-balanced selection plus a run of consecutive frames of both channels."""
+    fs, ch, br, seed = 32000, 2, 64000, 16
+    wav = os.path.join(tmp, "in_usac.wav")
+    write_wav(wav, synth(fs, 8.0, ch, seed), fs)
+    mp4 = os.path.join(tmp, "usac.mp4")
+    run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{mp4}", "-aot:42", f"-br:{br}", "-ccfl_idx:3"])
+    meta = os.path.join(tmp, "usac.txt")
+    tap = os.path.join(tmp, "usac.tap")
+    decode_tap(mp4, os.path.join(tmp, "o.wav"), tap, [f"-imeta:{meta}", "-mp4:1"], stages="ufd")
+    rec_words = 9 + 4 * 1024
+    raw = np.fromfile(tap + ".ufd", dtype=np.int32)
+    assert raw.size and raw.size % rec_words == 0, (raw.size, rec_words)
+    raw = raw.reshape(-1, rec_words)
+    assert (raw[:, 0] == 0x31444655).all()
+    hdr = raw[:, 1:9]
+    fd = (hdr[:, 4] == 0) & (hdr[:, 5] == 0) & (hdr[:, 6] == 0) & (hdr[:, 7] == 0)
+    print(f"USAC {fs} Hz {ch}ch: {len(raw)} fd_frm_dec calls tapped, {int(fd.sum())} pure FD; "
+          f"window sequences: {np.bincount(hdr[:, 1], minlength=5).tolist()}")
+    idx = np.nonzero(fd)[0]
+    keep = set()
+    for seq in range(5):
+        cand = idx[hdr[idx, 1] == seq]
+        keep.update(cand[:: max(1, len(cand) // 8)][:8].tolist())
+    # a run of 24 consecutive calls (12 frames x 2 channels) that are all pure FD, for the state-carry test
+    run0 = next((i for i in range(40, len(raw) - 24) if fd[i:i + 24].all()), None)
+    if run0 is not None:
+        keep.update(range(run0, run0 + 24))
+    keep = sorted(keep)
+    sel = raw[keep]
+    out = dict(hdr=sel[:, 1:9].copy(), coef=sel[:, 9:1033].copy(), ov_in=sel[:, 1033:2057].copy(),
+               out=sel[:, 2057:3081].copy(), ov_out=sel[:, 3081:4105].copy(), index=np.array(keep, np.int32),
+               run_start=np.array([-1 if run0 is None else keep.index(run0)], np.int32))
+    path = os.path.join(GOLD, "usac_fd_tapped.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(keep)} records, {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
@@ -317,6 +357,8 @@ def main():
             make_envcalc_golden(tmp)
         if "sbrdec" in which:
             make_sbrdec_golden(tmp)
+        if "usac_fd" in which:
+            make_usac_fd_golden(tmp)
         if "sbrdec_lp" in which:
             make_sbrdec_lp_golden(tmp)
 
