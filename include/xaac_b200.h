@@ -381,6 +381,37 @@ int32_t xaac_b200_heaac_lp_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state 
 int32_t xaac_b200_imdct_out_to_pcm16_dev(xaac_b200_ctx *ctx, const int32_t *d_in, const int8_t *d_qshift_adj,
                                          int16_t *d_out, int64_t n_units, int32_t mode, void *stream);
 
+/* ---- AAC-LC output stage: peak limiter + round16 (SURVEY.md 8a-F "LC output") -----------------------------------------
+ * Batched drop-in for ixheaacd_peak_limiter_process(ia_peak_limiter_struct *, VOID *samples, UWORD32 frame_len,
+ * UWORD8 *qshift_adj) (decoder/ixheaacd_peak_limiter.c:177-307) followed by the round16 loop of ixheaacd_dec_execute
+ * (decoder/ixheaacd_api.c:3676-3681): what the reference runs on the WORD32 IMDCT output of an AAC-LC stream with its
+ * default flags (-peak_limiter_off:0).  Unit = one stream (1 or 2 channels, 1024 samples per channel).
+ * Per-stream state: ia_peak_limiter_struct (decoder/ixheaacd_peak_limiter_struct_def.h:29-48) as 32-bit words: */
+#define XAAC_PL_ATTACK_CONST 0   /* float  attack_constant */
+#define XAAC_PL_RELEASE_CONST 1  /* float  release_constant */
+#define XAAC_PL_GAIN_MOD 2       /* float  gain_modified */
+#define XAAC_PL_MIN_GAIN 3       /* float  min_gain (written by the stage) */
+#define XAAC_PL_PSG 4            /* double pre_smoothed_gain */
+#define XAAC_PL_ATTACK 6         /* attack_time_samples (<= 512) */
+#define XAAC_PL_DELAY_IDX 7      /* delayed_input_index */
+#define XAAC_PL_MAX_IDX 8        /* max_idx */
+#define XAAC_PL_CIR 9            /* cir_buf_pnt */
+#define XAAC_PL_LIMITER_ON 10
+#define XAAC_PL_NUM_CH 11
+#define XAAC_PL_MAX_BUF 12       /* float[512]    max_buf */
+#define XAAC_PL_DELAYED 524      /* float[512][2] delayed_input */
+#define XAAC_PL_STATE_WORDS 1548
+/* host-side: the state ixheaacd_peak_limiter_init produces (decoder/ixheaacd_peak_limiter.c:45-75) */
+int32_t xaac_b200_peak_limiter_state_init(int32_t *state, int32_t num_channels, int32_t sample_rate);
+/*   d_state      [n][1548] in/out
+ *   d_samples    [n][1024][ch] WORD32, interleaved like the reference's time_data (e.g. xaac_b200_imdct_process_dev, ch_fac = ch)
+ *   d_qshift_adj [n][ch] (as written by xaac_b200_imdct_process_dev)
+ *   d_out32      [n][1024][ch] limited WORD32 samples, or NULL;  d_pcm16 [n][1024][ch] PCM16, or NULL (one of them required)
+ *   d_err        [n] or NULL: 0 / 0x80000000 (state not supported: more than 2 channels, attack > 512, limiter off) */
+int32_t xaac_b200_peak_limiter_dev(xaac_b200_ctx *ctx, int32_t *d_state, const int32_t *d_samples,
+                                   const int8_t *d_qshift_adj, int32_t *d_out32, int16_t *d_pcm16, int32_t *d_err,
+                                   int64_t n_units, int32_t num_channels, void *stream);
+
 /* ---- USAC frequency-domain core transform -------------------------------------------------------
  * Batched drop-in for ixheaacd_fd_frm_dec(ia_usac_data_struct *, WORD32 i_ch) (decoder/ixheaacd_imdct.c:596; called from
  * ixheaacd_core_coder_data, decoder/ixheaacd_ext_ch_ele.c:991) for pure frequency-domain streams: previous frame FD

@@ -25,6 +25,7 @@ from .qmf import (  # noqa: F401
     cplx_synt_qmffilt_host,
     synth_params,
 )
+from .output import PeakLimiterBatch, peak_limiter_process, peak_limiter_reset_state  # noqa: F401
 from .usac import STOP_START_SEQUENCE, UsacFdBatch, usac_fd_frm_dec  # noqa: F401
 from .sbr import SbrState, calc_sbrenvelope, heaac_frame_host, heaac_lp_frame_host, hf_generator, sbr_dec, sbr_dec_lp  # noqa: F401
 
@@ -34,6 +35,9 @@ __all__ = [
     "SbrState",
     "sbr_dec",
     "sbr_dec_lp",
+    "PeakLimiterBatch",
+    "peak_limiter_process",
+    "peak_limiter_reset_state",
     "UsacFdBatch",
     "usac_fd_frm_dec",
     "heaac_frame_host",

@@ -52,6 +52,8 @@ SIGNATURES = {
     "xaac_b200_sbr_dec_lp_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "xaac_b200_heaac_frame_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xaac_b200_heaac_lp_frame_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "xaac_b200_peak_limiter_state_init": (_i32, [_vp, _i32, _i32]),
+    "xaac_b200_peak_limiter_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "xaac_b200_set_usac_rom": (_i32, [_vp, _vp, _sz]),
     "xaac_b200_usac_fd_frm_dec_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "xaac_b200_imdct_out_to_pcm16_dev": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),

@@ -254,6 +254,23 @@ size_t usac_fd_smem_bytes();
 int usac_fd_check_tables(const uint8_t *urom);
 cudaError_t launch_usac_fd(const UsacFdArgs &args, int num_sms, cudaStream_t stream);
 
+// ---- AAC-LC output stage: peak limiter + round16 -----------------------------------------------------------------------
+// per-stream state record = ia_peak_limiter_struct as 32-bit words (include/xaac_b200.h XAAC_PL_*)
+constexpr int kPlAttackConst = 0, kPlReleaseConst = 1, kPlGainMod = 2, kPlMinGain = 3, kPlPsg = 4, kPlAttack = 6,
+              kPlDelayIdx = 7, kPlMaxIdx = 8, kPlCir = 9, kPlLimiterOn = 10, kPlNumCh = 11, kPlMaxBuf = 12,
+              kPlMaxAttack = 512, kPlDelayed = 524, kPlWords = 1548;
+struct PeakLimArgs {
+  int32_t *state;            // [n][1548] in/out
+  const int32_t *samples;    // [n][1024][ch] WORD32 time samples (interleaved like the reference's time_data), read-only
+  const int8_t *qshift_adj;  // [n][ch]
+  int32_t *out32;            // [n][1024][ch] limited WORD32 samples or null
+  int16_t *pcm16;            // [n][1024][ch] round16 of them or null
+  int32_t *err;              // [n] or null
+  long long n_units;
+  int ch;
+};
+cudaError_t launch_peak_limiter(const PeakLimArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

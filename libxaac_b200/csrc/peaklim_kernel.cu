@@ -1,0 +1,195 @@
+// peaklim_kernel.cu — the AAC-LC output stage for sm_100a (B200): peak limiter + round16.
+//
+// One warp owns one stream (all channels of one 1024-sample frame; the limiter couples the channels through the common
+// gain).  Replaces, bit-exactly,
+//   ixheaacd_peak_limiter_process      decoder/ixheaacd_peak_limiter.c:177-307   (WORD32 variant, PEAK_LIM_THR_FIX)
+//   the round16 loop of ixheaacd_dec_execute   decoder/ixheaacd_api.c:3676-3681
+// for ia_peak_limiter_struct states produced by ixheaacd_peak_limiter_init (:45-75) with 1 or 2 channels.
+//
+// The reference's per-sample loop is split into phases that do not feed back into each other: (1) scaled samples and
+// their channel maximum, lanes = samples; (2) the sliding maximum over the attack window with the reference's own
+// (max_idx, cir_buf_pnt) bookkeeping — a uniform serial walk, the occasional window rescan is a warp argmax; (3) raw
+// gains, lanes = samples; (4) the attack / release recursion — serial by nature, and skipped when the limiter is at
+// rest and no sample of the frame exceeds the threshold (every real frame that does not clip); (5) delayed, limited
+// output, lanes = samples.  All float / double arithmetic uses the round-to-nearest intrinsics in the reference's
+// operation order (the reference build is x86-64 SSE2 without FMA), so results are bit-identical.
+// Algorithmic HBM bytes per stream (stereo): 8192 (WORD32 in) + 4096 (PCM16 out) + 2 x ~3 KB state.
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "fixmath.cuh"
+#include "kernels.h"
+
+namespace xb {
+
+constexpr int kPlWarps = 8;
+
+struct PlWarpS {
+  float T[1024];   // channel maximum per sample
+  float G[1024];   // window maximum, then raw gain, then smoothed gain per sample
+  float mb[kPlMaxAttack];  // max_buf at frame start
+};
+
+__global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PlWarpS *ws = reinterpret_cast<PlWarpS *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  PlWarpS &w = ws[warp];
+  const long long warps_total = (long long)gridDim.x * kPlWarps;
+  const float thr = 2147483648.0f;  // (float)PEAK_LIM_THR_FIX
+
+  for (long long u = (long long)blockIdx.x * kPlWarps + warp; u < p.n_units; u += warps_total) {
+    __syncwarp();
+    i32 *st = p.state + u * kPlWords;
+    const int ch = st[kPlNumCh], A = st[kPlAttack];
+    if (ch != p.ch || A < 1 || A > kPlMaxAttack || !st[kPlLimiterOn]) {
+      if (lane == 0 && p.err) p.err[u] = (i32)0x80000000;
+      continue;
+    }
+    const i32 *in = p.samples + u * 1024 * ch;
+    float *mbg = reinterpret_cast<float *>(st + kPlMaxBuf), *dlg = reinterpret_cast<float *>(st + kPlDelayed);
+    const float ac = __int_as_float(st[kPlAttackConst]), rc = __int_as_float(st[kPlReleaseConst]);
+    float gm = __int_as_float(st[kPlGainMod]);
+    double psg = __hiloint2double(st[kPlPsg + 1], st[kPlPsg]);
+    int cir = st[kPlCir], max_idx = st[kPlMaxIdx];
+    const int cir0 = cir, di0 = st[kPlDelayIdx];
+    const float gt0 = (float)(1 << p.qshift_adj[u * ch]), gt1 = ch > 1 ? (float)(1 << p.qshift_adj[u * ch + 1]) : 0.f;
+    for (int j = lane; j < A; j += 32) w.mb[j] = mbg[j];
+    // ---- phase 1 (peak_limiter.c:201-206): t[i] = max_j |samples[i][j] * gain_t[j]| ----
+#pragma unroll 4
+    for (int i = lane; i < 1024; i += 32) {
+      float m;
+      if (ch == 2) {
+        const int2 s = *reinterpret_cast<const int2 *>(in + 2 * i);
+        m = fmaxf(fabsf(__fmul_rn(__int2float_rn(s.x), gt0)), fabsf(__fmul_rn(__int2float_rn(s.y), gt1)));
+      } else {
+        m = fabsf(__fmul_rn(__int2float_rn(in[i]), gt0));
+      }
+      w.T[i] = m;
+    }
+    __syncwarp();
+    // ---- phase 2 (:207-222): window maximum with the reference's index bookkeeping; uniform over the warp ----
+    float cur_max = w.mb[max_idx];
+#pragma unroll 1
+    for (int i = 0; i < 1024; i++) {
+      const float tmp = w.T[i];
+      if (max_idx == cir) {  // the maximum was just overwritten: rescan the whole window, first maximum in buffer order
+        float bv = -1.0f;
+        int bj = 0x7fffffff;
+#pragma unroll 1
+        for (int j = lane; j < A; j += 32) {
+          int age = cir - j;
+          if (age < 0) age += A;
+          const int ip = i - age;
+          const float v = ip >= 0 ? w.T[ip] : w.mb[j];
+          if (v > bv) { bv = v; bj = j; }
+        }
+        const int vm = __reduce_max_sync(full, __float_as_int(bv));  // values are >= 0: integer order = float order
+        bj = (__float_as_int(bv) == vm) ? bj : 0x7fffffff;
+        max_idx = __reduce_min_sync(full, bj);
+        cur_max = __int_as_float(vm);
+      } else if (tmp >= cur_max) {
+        max_idx = cir;
+        cur_max = tmp;
+      }
+      if (++cir == A) cir = 0;
+      if (lane == 0) w.G[i] = cur_max;
+    }
+    __syncwarp();
+    // ---- phase 3 (:224-228): raw gain ----
+    bool any_lim = false;
+#pragma unroll 4
+    for (int i = lane; i < 1024; i += 32) {
+      const float mx = w.G[i];
+      const float g = mx > thr ? __fdiv_rn(thr, mx) : 1.0f;
+      any_lim |= g < 1.0f;
+      w.G[i] = g;
+    }
+    any_lim = __any_sync(full, any_lim);
+    __syncwarp();
+    // ---- phase 4 (:230-249): attack / release smoothing; at rest (gain 1 everywhere) it is the identity ----
+    float min_gain = 1.0f;
+    if (any_lim || psg != 1.0 || gm != 1.0f) {
+#pragma unroll 1
+      for (int i = 0; i < 1024; i++) {
+        const float gain = w.G[i];
+        if ((double)gain < psg) {
+          const float c = __fmul_rn(__fsub_rn(gain, __fmul_rn(0.1f, (float)psg)), 1.11111111f);
+          gm = gm > c ? c : gm;
+        } else {
+          gm = gain;
+        }
+        if ((double)gm < psg) {
+          psg = __dadd_rn(__dmul_rn((double)ac, __dsub_rn(psg, (double)gm)), (double)gm);
+          psg = psg > (double)gain ? psg : (double)gain;
+        } else {
+          psg = __dadd_rn(__dmul_rn((double)rc, __dsub_rn(psg, (double)gm)), (double)gm);
+        }
+        const float go = (float)psg;
+        if (lane == 0) w.G[i] = go;
+        if (go < min_gain) min_gain = go;
+      }
+      __syncwarp();
+    }
+    // ---- phase 5 (:251-276) + round16 (api.c:3676-3681): delayed input x gain, clamp, lanes = samples ----
+    i32 *out32 = p.out32 ? p.out32 + u * 1024 * ch : nullptr;
+    int16_t *pcm = p.pcm16 ? p.pcm16 + u * 1024 * ch : nullptr;
+    auto emit = [&](int i) {
+      const float g = w.G[i];
+      int idx = (di0 + i) % A;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        if (j >= ch) break;
+        float x;
+        if (i < A) x = dlg[idx * ch + j];
+        else x = __fmul_rn(__int2float_rn(in[(i - A) * ch + j]), j ? gt1 : gt0);
+        x = __fmul_rn(x, g);
+        long long q = (long long)x;
+        q = q > 2147483647LL ? 2147483647LL : (q < -2147483647LL ? -2147483647LL : q);
+        if (out32) out32[i * ch + j] = (i32)q;
+        if (pcm) pcm[i * ch + j] = (int16_t)round16((i32)q);
+      }
+    };
+#pragma unroll 1
+    for (int i = lane; i < 512; i += 32) emit(i);
+    __syncwarp();  // every read of the old delay line (i < A <= 512) is done before it is rewritten
+#pragma unroll 1
+    for (int i = 512 + lane; i < 1024; i += 32) emit(i);
+    __syncwarp();
+    // ---- state: the delay line and max_buf hold the last A samples of this frame ----
+#pragma unroll 1
+    for (int i = 1024 - A + lane; i < 1024; i += 32) {
+      const int idx = (di0 + i) % A;
+      for (int j = 0; j < ch; j++) dlg[idx * ch + j] = __fmul_rn(__int2float_rn(in[i * ch + j]), j ? gt1 : gt0);
+      mbg[(cir0 + i) % A] = w.T[i];
+    }
+    if (lane == 0) {
+      st[kPlGainMod] = __float_as_int(gm);
+      st[kPlMinGain] = __float_as_int(min_gain);
+      st[kPlPsg] = __double2loint(psg);
+      st[kPlPsg + 1] = __double2hiint(psg);
+      st[kPlCir] = cir;
+      st[kPlMaxIdx] = max_idx;
+      st[kPlDelayIdx] = (di0 + 1024) % A;
+      if (p.err) p.err[u] = 0;
+    }
+  }
+}
+
+cudaError_t launch_peak_limiter(const PeakLimArgs &args, int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  const size_t smem = sizeof(PlWarpS) * kPlWarps;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(peak_limiter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  long long need = (args.n_units + kPlWarps - 1) / kPlWarps;
+  long long grid = (long long)num_sms * 2;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  peak_limiter_kernel<<<(unsigned)grid, kPlWarps * 32, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace xb

@@ -1,6 +1,7 @@
 // xaac_b200_api.cu — the C-ABI (include/xaac_b200.h) over the sm_100a kernels.
 // No CPU fallback exists anywhere in this library: every entry point needs a CUDA device and reports
 // XAAC_B200_ERR_CUDA otherwise.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -954,6 +955,43 @@ int32_t xaac_b200_usac_fd_frm_dec_dev(xaac_b200_ctx *ctx, const int32_t *d_coef,
   a.n_units = n_units;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   LAUNCH("usac_fd_kernel", stream, xb::launch_usac_fd(a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_peak_limiter_state_init(int32_t *state, int32_t num_channels, int32_t sample_rate) {
+  // ixheaacd_peak_limiter_init (decoder/ixheaacd_peak_limiter.c:45-75): host-side, no device involved
+  if (!state || num_channels < 1 || num_channels > 2 || sample_rate < 1) return XAAC_B200_ERR_ARG;
+  const uint32_t attack = (uint32_t)(5.0f * (float)sample_rate / 1000);
+  if (attack < 1 || attack > (uint32_t)xb::kPlMaxAttack) return XAAC_B200_ERR_ARG;
+  memset(state, 0, sizeof(int32_t) * xb::kPlWords);
+  const float ac = (float)pow(0.1, 1.0 / (attack + 1));
+  const float rc = (float)pow(0.1, 1.0 / (50.0f * sample_rate / 1000 + 1));
+  const float one = 1.0f;
+  const double done = 1.0;
+  memcpy(state + xb::kPlAttackConst, &ac, 4);
+  memcpy(state + xb::kPlReleaseConst, &rc, 4);
+  memcpy(state + xb::kPlGainMod, &one, 4);
+  memcpy(state + xb::kPlMinGain, &one, 4);
+  memcpy(state + xb::kPlPsg, &done, 8);
+  state[xb::kPlAttack] = (int32_t)attack;
+  state[xb::kPlLimiterOn] = 1;
+  state[xb::kPlNumCh] = num_channels;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_peak_limiter_dev(xaac_b200_ctx *ctx, int32_t *d_state, const int32_t *d_samples,
+                                   const int8_t *d_qshift_adj, int32_t *d_out32, int16_t *d_pcm16, int32_t *d_err,
+                                   int64_t n_units, int32_t num_channels, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (n_units < 0 || num_channels < 1 || num_channels > 2) return bad_arg(ctx, "n_units / num_channels");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_state || !d_samples || !d_qshift_adj || (!d_out32 && !d_pcm16)) return bad_arg(ctx, "null buffer");
+  xb::PeakLimArgs a;
+  a.state = d_state; a.samples = d_samples; a.qshift_adj = d_qshift_adj; a.out32 = d_out32; a.pcm16 = d_pcm16; a.err = d_err;
+  a.n_units = n_units; a.ch = num_channels;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  LAUNCH("peak_limiter_kernel", stream, xb::launch_peak_limiter(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }

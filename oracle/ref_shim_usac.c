@@ -94,3 +94,71 @@ void ref_usac_fd_frm_dec_batch(int32_t *coef, int32_t *overlap, const int32_t *w
     err[u] = ref_usac_fd_frm_dec(coef + (size_t)u * 1024, overlap + (size_t)u * 1024, win_seq[u], win_shape[u],
                                  win_shape_prev[u], out + (size_t)u * 1024);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * AAC-LC output stage: ixheaacd_peak_limiter_init / ixheaacd_peak_limiter_process
+ * (decoder/ixheaacd_peak_limiter.c:45-75, 177-307) driven from the flat XO_PL_* record of oracle/src/xaac_oracle.h.
+ * ---------------------------------------------------------------------------------------------- */
+#include "ixheaacd_peak_limiter_struct_def.h"
+#include "ixheaac_constants.h"
+#include "ixheaac_basic_ops32.h"
+#include "ixheaac_basic_ops16.h"
+#include "src/xaac_oracle.h"
+WORD32 ixheaacd_peak_limiter_init(ia_peak_limiter_struct *, UWORD32, UWORD32, FLOAT32 *, UWORD32 *);
+VOID ixheaacd_peak_limiter_process(ia_peak_limiter_struct *, VOID *, UWORD32, UWORD8 *);
+
+static void pl_pack(int32_t *st, const ia_peak_limiter_struct *p) {
+  memset(st, 0, XO_PL_WORDS * 4);
+  memcpy(st + XO_PL_ATTACK_CONST, &p->attack_constant, 4);
+  memcpy(st + XO_PL_RELEASE_CONST, &p->release_constant, 4);
+  memcpy(st + XO_PL_GAIN_MOD, &p->gain_modified, 4);
+  memcpy(st + XO_PL_MIN_GAIN, &p->min_gain, 4);
+  memcpy(st + XO_PL_PSG, &p->pre_smoothed_gain, 8);
+  st[XO_PL_ATTACK] = (int32_t)p->attack_time_samples;
+  st[XO_PL_DELAY_IDX] = (int32_t)p->delayed_input_index;
+  st[XO_PL_MAX_IDX] = p->max_idx;
+  st[XO_PL_CIR] = p->cir_buf_pnt;
+  st[XO_PL_LIMITER_ON] = (int32_t)p->limiter_on;
+  st[XO_PL_NUM_CH] = (int32_t)p->num_channels;
+  memcpy(st + XO_PL_MAX_BUF, p->max_buf, 4 * p->attack_time_samples);
+  memcpy(st + XO_PL_DELAYED, p->delayed_input, 4 * p->attack_time_samples * p->num_channels);
+}
+static void pl_unpack(ia_peak_limiter_struct *p, const int32_t *st) {
+  memset(p, 0, sizeof(*p));
+  memcpy(&p->attack_constant, st + XO_PL_ATTACK_CONST, 4);
+  memcpy(&p->release_constant, st + XO_PL_RELEASE_CONST, 4);
+  memcpy(&p->gain_modified, st + XO_PL_GAIN_MOD, 4);
+  memcpy(&p->min_gain, st + XO_PL_MIN_GAIN, 4);
+  memcpy(&p->pre_smoothed_gain, st + XO_PL_PSG, 8);
+  p->attack_time_samples = (UWORD32)st[XO_PL_ATTACK];
+  p->delayed_input_index = (UWORD32)st[XO_PL_DELAY_IDX];
+  p->max_idx = st[XO_PL_MAX_IDX];
+  p->cir_buf_pnt = st[XO_PL_CIR];
+  p->limiter_on = (UWORD32)st[XO_PL_LIMITER_ON];
+  p->num_channels = (UWORD32)st[XO_PL_NUM_CH];
+  p->max_buf = p->buffer;
+  p->delayed_input = p->buffer + p->attack_time_samples * 4 + 32;
+  memcpy(p->max_buf, st + XO_PL_MAX_BUF, 4 * p->attack_time_samples);
+  memcpy(p->delayed_input, st + XO_PL_DELAYED, 4 * p->attack_time_samples * p->num_channels);
+}
+/* state of a freshly initialised limiter (ixheaacd_peak_limiter_init); returns delay_in_samples */
+int ref_peak_limiter_init(int32_t *st, int num_channels, int sample_rate) {
+  static __thread ia_peak_limiter_struct p;
+  UWORD32 delay = 0;
+  memset(&p, 0, sizeof(p));
+  ixheaacd_peak_limiter_init(&p, (UWORD32)num_channels, (UWORD32)sample_rate, p.buffer, &delay);
+  pl_pack(st, &p);
+  return (int)delay;
+}
+/* one frame: samples interleaved WORD32 [1024][ch] in place; pcm16 = round16 of the result (api.c:3676-3681) */
+void ref_peak_limiter_batch(int32_t *st, int32_t *samples, const int8_t *qshift_adj, int16_t *pcm16, int ch, int n) {
+  static __thread ia_peak_limiter_struct p;
+  for (int u = 0; u < n; u++) {
+    int32_t *s = st + (size_t)u * XO_PL_WORDS, *x = samples + (size_t)u * 1024 * ch;
+    pl_unpack(&p, s);
+    ixheaacd_peak_limiter_process(&p, x, 1024, (UWORD8 *)(qshift_adj + (size_t)u * ch));
+    pl_pack(s, &p);
+    if (pcm16)
+      for (int i = 0; i < 1024 * ch; i++) pcm16[(size_t)u * 1024 * ch + i] = ixheaac_round16(x[i]);
+  }
+}

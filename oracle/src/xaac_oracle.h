@@ -277,4 +277,25 @@ int xo_usac_fd_frm_dec(const uint8_t *urom, int32_t *coef, int32_t *ov, int win_
 void xo_usac_fd_frm_dec_batch(const uint8_t *urom, int32_t *coef, int32_t *ov, const int32_t *win_seq,
                               const int32_t *win_shape, const int32_t *win_shape_prev, int32_t *out, int32_t *err, int n);
 
+
+/* ---- AAC-LC output stage: peak limiter (peaklim.c) -----------------------------------------------------------------
+ * Per-stream state record = ia_peak_limiter_struct (decoder/ixheaacd_peak_limiter_struct_def.h:29-48) as 32-bit words */
+#define XO_PL_ATTACK_CONST 0   /* float  attack_constant */
+#define XO_PL_RELEASE_CONST 1  /* float  release_constant */
+#define XO_PL_GAIN_MOD 2       /* float  gain_modified */
+#define XO_PL_MIN_GAIN 3       /* float  min_gain (out) */
+#define XO_PL_PSG 4            /* double pre_smoothed_gain (2 words) */
+#define XO_PL_ATTACK 6         /* attack_time_samples (<= XO_PL_MAX_ATTACK) */
+#define XO_PL_DELAY_IDX 7      /* delayed_input_index */
+#define XO_PL_MAX_IDX 8        /* max_idx */
+#define XO_PL_CIR 9            /* cir_buf_pnt */
+#define XO_PL_LIMITER_ON 10
+#define XO_PL_NUM_CH 11        /* 1 or 2 */
+#define XO_PL_MAX_BUF 12       /* float[XO_PL_MAX_ATTACK] max_buf */
+#define XO_PL_MAX_ATTACK 512
+#define XO_PL_DELAYED 524      /* float[2 * XO_PL_MAX_ATTACK] delayed_input, [index][channel] */
+#define XO_PL_WORDS 1548
+int xo_peak_limiter(int32_t *st, int32_t *samples, int frame_len, const int8_t *qshift_adj, int16_t *pcm16);
+void xo_peak_limiter_batch(int32_t *st, int32_t *samples, const int8_t *qshift_adj, int16_t *pcm16, int32_t *err, int ch, int n);
+
 #endif

@@ -199,6 +199,18 @@ class Oracle:
                                           P(np.ascontiguousarray(win_shape_prev, np.int32)), P(out), P(err), n)
         return out, o, err
 
+    def peak_limiter_batch(self, st, samples, qshift_adj, ch):
+        """st [n,1548] int32 (XO_PL_*), samples int32 [n,1024,ch], qshift_adj int8 [n,ch].
+        Returns (st', samples', pcm16, err)."""
+        s = np.ascontiguousarray(st, np.int32).copy()
+        x = np.ascontiguousarray(samples, np.int32).copy()
+        q = np.ascontiguousarray(qshift_adj, np.int8)
+        n = x.shape[0]
+        pcm = np.zeros(x.shape, np.int16)
+        err = np.zeros(n, np.int32)
+        self.lib.xo_peak_limiter_batch(P(s), P(x), P(q), P(pcm), P(err), int(ch), n)
+        return s, x, pcm, err
+
     def imdct_out_to_pcm16(self, samples, qshift_adj, mode):
         x = np.ascontiguousarray(samples, np.int32)
         q = np.ascontiguousarray(qshift_adj, np.int8)
@@ -269,6 +281,19 @@ class Ref:
                                            P(np.ascontiguousarray(win_shape, np.int32)),
                                            P(np.ascontiguousarray(win_shape_prev, np.int32)), P(out), P(err), n)
         return out, o, err
+
+    def peak_limiter_init(self, ch, sample_rate):
+        st = np.zeros(PL_WORDS, np.int32)
+        delay = self.lib.ref_peak_limiter_init(P(st), int(ch), int(sample_rate))
+        return st, delay
+
+    def peak_limiter_batch(self, st, samples, qshift_adj, ch):
+        s = np.ascontiguousarray(st, np.int32).copy()
+        x = np.ascontiguousarray(samples, np.int32).copy()
+        q = np.ascontiguousarray(qshift_adj, np.int8)
+        pcm = np.zeros(x.shape, np.int16)
+        self.lib.ref_peak_limiter_batch(P(s), P(x), P(q), P(pcm), int(ch), x.shape[0])
+        return s, x, pcm
 
     def rom_imdct(self, nbytes=7500):
         fn = self.lib.ref_rom_imdct_tables
@@ -556,6 +581,50 @@ def synth_sbr_lp_units(n, seed, golden):
             side[u, 3] = rng.integers(0, 4)
             side[u, 4] = rng.integers(0, 2)
     return side, st, tin
+
+
+PL_WORDS = 1548
+
+
+def peak_limiter_reset_state(ch, sample_rate):
+    """state of ixheaacd_peak_limiter_init restated (decoder/ixheaacd_peak_limiter.c:45-75): attack = 5 ms, release = 50 ms"""
+    st = np.zeros(PL_WORDS, np.int32)
+    attack = int(np.float32(5.0) * np.float32(sample_rate) / np.float32(1000))
+    f = st.view(np.float32)
+    f[0] = np.float32(0.1 ** (1.0 / (attack + 1)))
+    f[1] = np.float32(0.1 ** (1.0 / (float(np.float32(50.0) * np.float32(sample_rate) / np.float32(1000)) + 1)))
+    f[2] = 1.0
+    f[3] = 1.0
+    st[4:6] = np.array([1.0], np.float64).view(np.int32)
+    st[6] = attack
+    st[10] = 1
+    st[11] = ch
+    return st
+
+
+def synth_peaklim_units(n, ch, seed, loud_fraction=0.5):
+    """WORD32 IMDCT-domain samples [n,1024,ch] + qshift_adj [n,ch]: quiet units (limiter at rest) and loud ones whose
+    scaled peaks exceed 2^31 (limiter engages), bursts and silence"""
+    rng = np.random.default_rng(seed)
+    x = np.zeros((n, 1024, ch), np.int32)
+    q = rng.integers(1, 3, (n, ch)).astype(np.int8)
+    for u in range(n):
+        loud = rng.random() < loud_fraction
+        amp = 2.0 ** (rng.uniform(29.0, 30.9) if loud else rng.uniform(10, 28))
+        kind = u % 4
+        tt = np.arange(1024)
+        if kind == 0:
+            s = np.sin(2 * np.pi * rng.uniform(0.001, 0.3) * tt + rng.uniform(0, 6))[:, None] * np.ones((1, ch))
+        elif kind == 1:
+            s = rng.standard_normal((1024, ch)) / 3
+        elif kind == 2:
+            s = np.zeros((1024, ch))
+            p = rng.integers(0, 900)
+            s[p:p + 100] = rng.standard_normal((100, ch))
+        else:
+            s = rng.uniform(-1, 1, (1024, ch))
+        x[u] = np.clip(s * amp, -2 ** 31, 2 ** 31 - 1).astype(np.int64).astype(np.int32)
+    return x, q
 
 
 def usac_seq_walk(n_units, n_frames, seed):
