@@ -40,6 +40,8 @@ CHAIN_KERNEL_BYTES = {
     # fused low-power stage (sbr_lp_kernel.cu): 2048 PCM16 in + 4096 PCM16 out + 2 x 5536 channel state (analysis ring 644,
     # synthesis ring 2564, envelope state 464, overlap rows 1536, LPC rows 256, scale factors / misc / bw 72) + 1480 side info
     "sbr_dec_lp_kernel": 18696,
+    # per channel unit (a stream = 2 units): 4096 WORD32 in + 2048 PCM16 out + 2 x 1.35 KB limiter state (220-sample window)
+    "peak_limiter_kernel": 8850,
 }
 USAC_FD_BYTES_PER_UNIT = 16384  # 4096 coefficients + 4096 overlap in + 4096 overlap out + 4096 WORD32 out
 WORKLOADS = {
@@ -49,6 +51,8 @@ WORKLOADS = {
     "aac_lc_stereo_imdct_ola": (1, 65536, "AAC-LC stereo 44.1 kHz batch=65536 frames, IMDCT+OLA only"),
     "heaacv1_stereo_chain": (2, 65536, "HE-AACv1 stereo 48 kHz batch=65536: IMDCT + 64-band QMF analysis/synthesis + LPP "
                                        "HF-gen + env_calc (fixed-point path of the reference, -esbr:0: low-power SBR)"),
+    "aac_lc_stereo_output": (1, 65536, "AAC-LC stereo 44.1 kHz batch=65536 frames with the reference's default flags: IMDCT+OLA "
+                                       "-> peak limiter -> PCM16"),
     "usac_fd_imdct": (4, 131072, "xHE-AAC/USAC stereo 32 kHz batch=131072: the fixed-point FD core transform of the chain "
                                  "(ixheaacd_fd_frm_dec: IMDCT 1024/128 + windowing + overlap); the float eSBR stage is not "
                                  "built yet"),
@@ -419,6 +423,61 @@ def cpu_arm_chain_lp(n_units, threads, seed, reps=1, min_seconds=0.0):
     return n_units * done / dt, "reference"
 
 
+def cpu_arm_lc_output(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time ixheaacd_imdct_process x 2 channels + ixheaacd_peak_limiter_process + round16 per stereo frame on host threads.
+    Returns (units_per_s, kind) with units = channels."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    if ref is None:
+        raise SystemExit("bench.py: the AAC-LC output CPU baseline needs oracle/_ref/libxaac_ref.so (make ref)")
+    P = oracle_util.P
+    n_units -= n_units & 1
+    nf = n_units // 2
+    rng = np.random.default_rng(seed)
+    s = rng.integers(12, 30, size=(n_units, 1))
+    spec0 = ((rng.random((n_units, 1024)) * 2 - 1) * (2.0 ** s)).astype(np.int64).astype(np.int32)
+    walk = sequence_walk(n_units, reps + 1, seed)
+    ovl = np.zeros((n_units, 512), np.int32)
+    pshape = np.zeros(n_units, np.int32)
+    pseq = np.zeros(n_units, np.int32)
+    out = np.zeros((n_units, 1024), np.int32)
+    adj = np.zeros(n_units, np.int32)
+    st = np.tile(ref.peak_limiter_init(2, 44100)[0], (nf, 1))
+    inter = np.zeros((nf, 1024, 2), np.int32)
+    pcm = np.zeros((nf, 1024, 2), np.int16)
+    bounds = np.linspace(0, nf, threads + 1).astype(int) * 2
+
+    def work(t, step, spec):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b <= a:
+            return
+        ws = np.ascontiguousarray(walk[step, a:b, 0], np.int32)
+        wh = np.ascontiguousarray(walk[step, a:b, 1], np.int32)
+        ref.lib.ref_imdct_process_batch(P(spec[a:b]), P(ovl[a:b]), P(pshape[a:b]), P(pseq[a:b]), P(ws), P(wh), P(out[a:b]),
+                                        P(adj[a:b]), b - a)
+        fa, fb = a // 2, b // 2
+        inter[fa:fb] = out[a:b].reshape(fb - fa, 2, 1024).transpose(0, 2, 1)
+        q = np.ascontiguousarray(adj[a:b].astype(np.int8).reshape(fb - fa, 2))
+        ref.lib.ref_peak_limiter_batch(P(st[fa:fb]), P(inter[fa:fb]), P(q), P(pcm[fa:fb]), 2, fb - fa)
+
+    def one_pass(step):
+        spec = spec0.copy()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t, step, spec)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    one_pass(0)
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass(1 + done % reps)
+        done += 1
+    return n_units * done / dt, "reference"
+
+
 def usac_walk(n_units, n_steps, seed):
     """ics[step][unit] = (window_sequence, window_shape) of a legal USAC FD walk, both channels of a frame alike:
     ~85 % ONLY_LONG, the rest start / short / stop / stop-start runs"""
@@ -512,6 +571,10 @@ STAGES = {
                                     stage="IMDCT + window/OLA (fixed-point WORD32, bit-exact)",
                                     ref_stage="ixheaacd_imdct_process", cpu=cpu_arm, cpu_units_per_core=4096,
                                     realtime_fps=43.066, h2d=4096 + 2, d2h=4096 + 1),
+    "aac_lc_stereo_output": dict(kernel=None, top_kernel="imdct_ola_kernel", bytes_per_unit=None,
+                                 stage="IMDCT + window/OLA (interleaved WORD32) -> peak limiter -> round16 (bit-exact)",
+                                 ref_stage="ixheaacd_imdct_process x 2 + ixheaacd_peak_limiter_process + round16",
+                                 cpu=cpu_arm_lc_output, cpu_units_per_core=2048, realtime_fps=43.066, h2d=4096 + 2, d2h=2048),
     "usac_fd_imdct": dict(kernel="usac_fd_kernel", bytes_per_unit=USAC_FD_BYTES_PER_UNIT,
                           stage="USAC FD core transform: IMDCT 1024 / 8 x 128 (saturating radix-4 FFT) + windowing + overlap "
                                 "(fixed-point WORD32, bit-exact)",
@@ -667,6 +730,59 @@ class ChainWork:
         self.state.close()
 
 
+class LcOutputWork:
+    """AAC-LC stereo frames with the reference's default flags: units 2k / 2k+1 = L / R of stream k; IMDCT writes the
+    interleaved WORD32 time buffer (ch_fac = 2), the limiter (one unit per stream) turns it into PCM16."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        self.spec = make_spec_torch(n_units, seed, dev)
+        # a quarter of the streams is loud enough to clip after the qshift scaling: the limiter engages there
+        loud = (torch.arange(n_units, device=dev) // 2) % int(os.environ.get("XAAC_LC_LOUD_EVERY", "4")) == 0
+        self.spec[loud] = self.spec[loud] << 3
+        self.walk = torch.from_numpy(sequence_walk(n_units, steps_total, seed)).to(dev)
+        self.nw = steps_total
+        self.state = xb.ImdctBatch(n_units, device=dev)
+        self.lim = xb.PeakLimiterBatch(n_units // 2, 2, 44100, device=dev)
+        self.w32 = torch.empty((n_units // 2, 1024, 2), dtype=torch.int32, device=dev)
+        self.adj = torch.empty((n_units,), dtype=torch.int8, device=dev)
+        self.pcm = torch.empty((n_units // 2, 1024, 2), dtype=torch.int16, device=dev)
+        self.err = torch.zeros((n_units // 2,), dtype=torch.int32, device=dev)
+
+    def step(self, i, stream):
+        xb, ctx = self.xb, self.ctx
+        xb.imdct_process(ctx, self.state, self.spec, self.walk[i % self.nw], self.w32, self.adj, ch_fac=2, stream=stream)
+        xb.peak_limiter_process(ctx, self.lim, self.w32, self.adj.view(self.n // 2, 2), self.pcm, err=self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0
+
+    def host_setup(self):
+        import torch
+        self.h_spec = torch.empty((self.n, 1024), dtype=torch.int32).pin_memory()
+        self.h_spec.copy_(self.spec)
+        self.h_pcm = torch.empty((self.n // 2, 1024, 2), dtype=torch.int16).pin_memory()
+        self.h_walk = self.walk.cpu().pin_memory()
+        self.d_spec = torch.empty_like(self.spec)
+        self.d_ics = torch.empty((self.n, 2), dtype=torch.uint8, device=self.spec.device)
+
+    def host_step(self, i):
+        import torch
+        s = torch.cuda.current_stream()
+        self.d_spec.copy_(self.h_spec, non_blocking=True)
+        self.d_ics.copy_(self.h_walk[i % self.nw], non_blocking=True)
+        self.xb.imdct_process(self.ctx, self.state, self.d_spec, self.d_ics, self.w32, self.adj, ch_fac=2, stream=s)
+        self.xb.peak_limiter_process(self.ctx, self.lim, self.w32, self.adj.view(self.n // 2, 2), self.pcm, err=self.err, stream=s)
+        self.h_pcm.copy_(self.pcm, non_blocking=True)
+        s.synchronize()
+
+    def host_close(self):
+        pass
+
+
 class UsacFdWork:
     def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
         import torch
@@ -757,7 +873,8 @@ class ChainLpWork:
 
 
 WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv2_chain": ChainWork,
-        "heaacv1_stereo_chain": ChainLpWork, "usac_fd_imdct": UsacFdWork}
+        "heaacv1_stereo_chain": ChainLpWork, "usac_fd_imdct": UsacFdWork,
+        "aac_lc_stereo_output": LcOutputWork}
 
 
 def main():

@@ -68,32 +68,76 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
       w.T[i] = m;
     }
     __syncwarp();
-    // ---- phase 2 (:207-222): window maximum with the reference's index bookkeeping; uniform over the warp ----
+    // ---- phase 2 (:207-222): window maximum with the reference's (max_idx, cir_buf_pnt) bookkeeping, 32 samples at a
+    // time (lane = sample).  Inside a chunk the reference's serial walk has two kinds of events: (a) a sample >= the
+    // running maximum moves max_idx to its own buffer position — found for all lanes at once with a prefix maximum;
+    // (b) the write pointer reaches max_idx, i.e. the maximum leaves the window — the window is rescanned (warp argmax,
+    // first maximum in buffer order).  After an (a) event max_idx is a position written in this chunk, which the pointer
+    // cannot reach again before the chunk ends (attack window >= 32 samples), so (b) can only precede the first (a). ----
     float cur_max = w.mb[max_idx];
+    if (A < 32) {  // shorter windows than a chunk (sample rates below 6.4 kHz): not produced by any supported stream
+      if (lane == 0 && p.err) p.err[u] = (i32)0x80000000;
+      continue;
+    }
 #pragma unroll 1
-    for (int i = 0; i < 1024; i++) {
-      const float tmp = w.T[i];
-      if (max_idx == cir) {  // the maximum was just overwritten: rescan the whole window, first maximum in buffer order
-        float bv = -1.0f;
-        int bj = 0x7fffffff;
+    for (int i0 = 0; i0 < 1024; i0 += 32) {
+      const float tv = w.T[i0 + lane];
+      int pos = cir + lane;
+      if (pos >= A) pos -= A;
+      int lane_start = 0;
+      float mres = 0.f;
 #pragma unroll 1
-        for (int j = lane; j < A; j += 32) {
-          int age = cir - j;
-          if (age < 0) age += A;
-          const int ip = i - age;
-          const float v = ip >= 0 ? w.T[ip] : w.mb[j];
-          if (v > bv) { bv = v; bj = j; }
+      while (true) {
+        int lb = max_idx - cir;
+        if (lb < 0) lb += A;
+        const float tt = lane >= lane_start ? tv : -1.0f;
+        float incl = tt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float o = __shfl_up_sync(full, incl, d);
+          if (lane >= d) incl = fmaxf(incl, o);
         }
-        const int vm = __reduce_max_sync(full, __float_as_int(bv));  // values are >= 0: integer order = float order
-        bj = (__float_as_int(bv) == vm) ? bj : 0x7fffffff;
-        max_idx = __reduce_min_sync(full, bj);
-        cur_max = __int_as_float(vm);
-      } else if (tmp >= cur_max) {
-        max_idx = cir;
-        cur_max = tmp;
+        float excl = __shfl_up_sync(full, incl, 1);
+        if (lane == 0) excl = -1.0f;
+        excl = fmaxf(excl, cur_max);
+        const unsigned aev = __ballot_sync(full, lane >= lane_start && tv >= excl);
+        const int first_a = aev ? __ffs(aev) - 1 : 32;
+        if (lb >= lane_start && lb < 32 && lb <= first_a) {
+          if (lane >= lane_start && lane < lb) mres = cur_max;
+          // the maximum was just overwritten at sample i0 + lb: rescan the window, first maximum in buffer order
+          const int i = i0 + lb;
+          int cirb = cir + lb;
+          if (cirb >= A) cirb -= A;
+          float bv = -1.0f;
+          int bj = 0x7fffffff;
+#pragma unroll 1
+          for (int j = lane; j < A; j += 32) {
+            int age = cirb - j;
+            if (age < 0) age += A;
+            const int ip = i - age;
+            const float v = ip >= 0 ? w.T[ip] : w.mb[j];
+            if (v > bv) { bv = v; bj = j; }
+          }
+          const int vm = __reduce_max_sync(full, __float_as_int(bv));  // values are >= 0: integer order = float order
+          bj = (__float_as_int(bv) == vm) ? bj : 0x7fffffff;
+          max_idx = __reduce_min_sync(full, bj);
+          cur_max = __int_as_float(vm);
+          if (lane == lb) mres = cur_max;
+          lane_start = lb + 1;
+          if (lane_start >= 32) break;
+        } else {
+          if (lane >= lane_start) mres = fmaxf(incl, cur_max);
+          if (aev) {
+            const int last_a = 31 - __clz(aev);
+            max_idx = __shfl_sync(full, pos, last_a);
+            cur_max = fmaxf(__shfl_sync(full, incl, 31), cur_max);
+          }
+          break;
+        }
       }
-      if (++cir == A) cir = 0;
-      if (lane == 0) w.G[i] = cur_max;
+      w.G[i0 + lane] = mres;
+      cir += 32;
+      if (cir >= A) cir -= A;
     }
     __syncwarp();
     // ---- phase 3 (:224-228): raw gain ----
@@ -134,9 +178,8 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
     // ---- phase 5 (:251-276) + round16 (api.c:3676-3681): delayed input x gain, clamp, lanes = samples ----
     i32 *out32 = p.out32 ? p.out32 + u * 1024 * ch : nullptr;
     int16_t *pcm = p.pcm16 ? p.pcm16 + u * 1024 * ch : nullptr;
-    auto emit = [&](int i) {
+    auto emit = [&](int i, int idx) {
       const float g = w.G[i];
-      int idx = (di0 + i) % A;
 #pragma unroll
       for (int j = 0; j < 2; j++) {
         if (j >= ch) break;
@@ -150,11 +193,20 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
         if (pcm) pcm[i * ch + j] = (int16_t)round16((i32)q);
       }
     };
+    int ridx = (di0 + lane) % A;
 #pragma unroll 1
-    for (int i = lane; i < 512; i += 32) emit(i);
+    for (int i = lane; i < 512; i += 32) {
+      emit(i, ridx);
+      ridx += 32;
+      if (ridx >= A) ridx -= A;
+    }
     __syncwarp();  // every read of the old delay line (i < A <= 512) is done before it is rewritten
 #pragma unroll 1
-    for (int i = 512 + lane; i < 1024; i += 32) emit(i);
+    for (int i = 512 + lane; i < 1024; i += 32) {
+      emit(i, ridx);
+      ridx += 32;
+      if (ridx >= A) ridx -= A;
+    }
     __syncwarp();
     // ---- state: the delay line and max_buf hold the last A samples of this frame ----
 #pragma unroll 1
