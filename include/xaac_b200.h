@@ -442,6 +442,29 @@ int32_t xaac_b200_set_usac_rom(xaac_b200_ctx *ctx, const void *tables, size_t by
 int32_t xaac_b200_usac_fd_frm_dec_dev(xaac_b200_ctx *ctx, const int32_t *d_coef, int32_t *d_overlap, uint8_t *d_wstate,
                                       const uint8_t *d_ics, int32_t *d_out, int64_t n_units, void *stream);
 
+/* ---- eSBR 64-band QMF synthesis bank (first piece of SURVEY.md 8a-E, the float eSBR path) ----------------------------
+ * Batched per-slot core of ixheaacd_esbr_synthesis_filt_block (decoder/ixheaacd_sbr_dec.c:447, lines 583-654:
+ * stereo_config_idx <= 0, 64 synthesis channels, 32 time slots): float -> WORD32 (x 64), ixheaacd_esbr_inv_modulation
+ * (decoder/ixheaacd_qmf_dec.c:733; link-time leaves ixheaacd_esbr_cos_sin_mod, ixheaacd_esbr_radix4bfly,
+ * ixheaacd_esbr_postradixcompute2, decoder/generic/ixheaacd_qmf_dec_generic.c), ixheaacd_shiftrountine_with_rnd_hq,
+ * ixheaacd_esbr_qmfsyn64_winadd, WORD32 -> float.  Integer arithmetic inside, hence bit-exact float output.  The
+ * regrouping, PS and DRC branches of the stage function stay with the caller.
+ * ROM blob (XAAC_EROM_BYTES), members of ia_qmf_dec_tables_struct (decoder/ixheaacd_sbr_rom.h:96-105) concatenated:
+ *   esbr_qmf_c[1280], esbr_w_32[60], esbr_sin_cos_twiddle_l64[64], esbr_alt_sin_twiddle_l64[32] (WORD32). */
+#define XAAC_EROM_QMF_C 0
+#define XAAC_EROM_W32 5120
+#define XAAC_EROM_SINCOS_L64 5360
+#define XAAC_EROM_ALTSIN_L64 5616
+#define XAAC_EROM_BYTES 5744
+int32_t xaac_b200_set_esbr_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes);
+/*   d_qmf    [n][32][128] float: per slot qmf_buf_real[i][0..63] | qmf_buf_imag[i][0..63]
+ *   d_states [n][1280] WORD32 ia_sbr_qmf_filter_bank_struct.filter_states_32, in/out
+ *   d_pos    [n][2] WORD32 {ixheaacd_drc_offset, filter_pos_syn_32 - esbr_qmf_c}, in/out
+ *   d_out    [n][2048] float time samples (ptr_sbr_dec->time_sample_buf)
+ *   d_err    [n] or NULL: 0 / 0x80000000 (ring positions the reference cannot produce) */
+int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32_t *d_states, int32_t *d_pos, float *d_out,
+                                   int32_t *d_err, int64_t n_units, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@ from . import _lib
 
 
 class Context:
-    def __init__(self, device=0, imdct_rom=None, qmf_rom=None, env_rom=None, misc_rom=None, ps_rom=None, usac_rom=None):
+    def __init__(self, device=0, imdct_rom=None, qmf_rom=None, env_rom=None, misc_rom=None, ps_rom=None, usac_rom=None, esbr_rom=None):
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         rc = self._lib.xaac_b200_create(ctypes.byref(self._h), int(device))
@@ -22,6 +22,7 @@ class Context:
                          misc_rom if misc_rom is not None else _lib.rom_blob("misc_rom.bin"))
         self.set_ps_rom(ps_rom if ps_rom is not None else _lib.rom_blob("ps_rom.bin"))
         self.set_usac_rom(usac_rom if usac_rom is not None else _lib.rom_blob("usac_rom.bin"))
+        self.set_esbr_rom(esbr_rom if esbr_rom is not None else _lib.rom_blob("esbr_rom.bin"))
 
     # -- plumbing ---------------------------------------------------------------------------------
     @property
@@ -60,6 +61,12 @@ class Context:
         """blob: the host's USAC FD tables concatenated in the XAAC_UROM_* order (15880 bytes)."""
         buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
         self.check(self._lib.xaac_b200_set_usac_rom(self._h, buf, len(blob)), "xaac_b200_set_usac_rom")
+
+    def set_esbr_rom(self, blob):
+        """blob: esbr_qmf_c | esbr_w_32 | esbr_sin_cos_twiddle_l64 | esbr_alt_sin_twiddle_l64 of the host's
+        ia_qmf_dec_tables_struct (5744 bytes)."""
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        self.check(self._lib.xaac_b200_set_esbr_rom(self._h, buf, len(blob)), "xaac_b200_set_esbr_rom")
 
     @property
     def num_sms(self):

@@ -271,6 +271,23 @@ struct PeakLimArgs {
 };
 cudaError_t launch_peak_limiter(const PeakLimArgs &args, int num_sms, cudaStream_t stream);
 
+// ---- eSBR 64-band synthesis bank (per-slot core of ixheaacd_esbr_synthesis_filt_block) --------------------------------
+// ROM blob: esbr_qmf_c[1280] | esbr_w_32[60] | esbr_sin_cos_twiddle_l64[64] | esbr_alt_sin_twiddle_l64[32] (WORD32)
+constexpr int kEsRomQmfC = 0, kEsRomW32 = 5120, kEsRomSinCos = 5360, kEsRomAlt = 5616, kEsRomBytes = 5744;
+struct EsbrSynthArgs {
+  const float *qmf;     // [n][32][128] per slot re[64] | im[64] (qmf_buf_real[i][k], qmf_buf_imag[i][k])
+  int32_t *states;      // [n][1280] filter_states_32, in/out
+  int32_t *pos;         // [n][2] {ixheaacd_drc_offset, filter_pos_syn_32 - esbr_qmf_c}, in/out
+  float *out;           // [n][2048] time samples
+  int32_t *err;         // [n] or null
+  const uint8_t *rom;   // device image built by esbr_synth_build_tables()
+  long long n_units;
+  int periodic;
+};
+size_t esbr_synth_table_bytes();
+int esbr_synth_build_tables(const uint8_t *erom, uint8_t *out);
+cudaError_t launch_esbr_synth(const EsbrSynthArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

@@ -27,6 +27,8 @@ struct xaac_b200_ctx {
   bool have_env_rom = false;
   uint8_t *d_rom_ps = nullptr;    // leading part of ia_ps_tables_struct
   uint8_t *d_rom_usac = nullptr;  // USAC FD tables (XAAC_UROM_*)
+  uint8_t *d_rom_esbr = nullptr;  // table image of esbr_synth_kernel
+  int esbr_periodic = 0;
   bool have_ps_rom = false;
   int ps_rot_nosat = 0;           // no fractional-delay phase factor equals -32768 (16x16 rotations cannot saturate)
   char err[256] = {0};
@@ -175,6 +177,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   if (ctx->d_rom_misc) cudaFree(ctx->d_rom_misc);
   if (ctx->d_rom_ps) cudaFree(ctx->d_rom_ps);
   if (ctx->d_rom_usac) cudaFree(ctx->d_rom_usac);
+  if (ctx->d_rom_esbr) cudaFree(ctx->d_rom_esbr);
   delete ctx;
 }
 
@@ -992,6 +995,40 @@ int32_t xaac_b200_peak_limiter_dev(xaac_b200_ctx *ctx, int32_t *d_state, const i
   a.n_units = n_units; a.ch = num_channels;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   LAUNCH("peak_limiter_kernel", stream, xb::launch_peak_limiter(a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_set_esbr_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
+  if (!ctx || !tables) return bad_arg(ctx, "null");
+  if (bytes < (size_t)xb::kEsRomBytes) return bad_arg(ctx, "eSBR ROM blob shorter than 5744 bytes");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  const size_t n = xb::esbr_synth_table_bytes();
+  uint8_t *img = (uint8_t *)calloc(1, n + 64);
+  if (!img) return XAAC_B200_FATAL;
+  ctx->esbr_periodic = xb::esbr_synth_build_tables((const uint8_t *)tables, img);
+  cudaError_t e = ctx->d_rom_esbr ? cudaSuccess : cudaMalloc((void **)&ctx->d_rom_esbr, n);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_rom_esbr, img, n, cudaMemcpyHostToDevice);
+  free(img);
+  if (e != cudaSuccess) return fail(ctx, e, "cudaMemcpy(esbr rom)");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32_t *d_states, int32_t *d_pos, float *d_out,
+                                   int32_t *d_err, int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->d_rom_esbr) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_qmf || !d_states || !d_pos || !d_out) return bad_arg(ctx, "null buffer");
+  xb::EsbrSynthArgs a;
+  a.qmf = d_qmf; a.states = d_states; a.pos = d_pos; a.out = d_out; a.err = d_err; a.rom = ctx->d_rom_esbr;
+  a.n_units = n_units; a.periodic = ctx->esbr_periodic;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }

@@ -1,0 +1,39 @@
+"""Host-side mirror of the reference's eSBR 64-band synthesis bank, batched.
+
+Reference: the per-slot core of ixheaacd_esbr_synthesis_filt_block(ia_sbr_dec_struct *, ..., FLOAT32 **qmf_buf_real,
+FLOAT32 **qmf_buf_imag, ...) (decoder/ixheaacd_sbr_dec.c:447, lines 583-654).  Unit = one output channel of one frame:
+
+  EsbrSynthBatch.states <- str_synthesis_qmf_bank.filter_states_32                       int32 [n, 1280]
+  EsbrSynthBatch.pos    <- {ixheaacd_drc_offset, filter_pos_syn_32 - esbr_qmf_c}        int32 [n, 2]
+  qmf                   <- qmf_buf_real[i][k] | qmf_buf_imag[i][k]                       float32 [n, 32, 128]
+  out                   <- time_sample_buf                                               float32 [n, 2048]
+"""
+import ctypes
+
+import torch
+
+from .imdct import _chk, _ptr
+
+
+class EsbrSynthBatch:
+    def __init__(self, n_units, device="cuda:0"):
+        self.n = int(n_units)
+        self.states = torch.zeros((self.n, 1280), dtype=torch.int32, device=device)
+        self.pos = torch.zeros((self.n, 2), dtype=torch.int32, device=device)
+
+
+def esbr_synthesis_filt(ctx, state, qmf, out=None, err=None, stream=None):
+    """Batched drop-in for the synthesis core of ixheaacd_esbr_synthesis_filt_block.  Returns (out, err)."""
+    n = state.n
+    _chk(qmf, torch.float32, (n, 32, 128), "qmf", "cuda")
+    if out is None:
+        out = torch.empty((n, 2048), dtype=torch.float32, device=qmf.device)
+    _chk(out, torch.float32, (n, 2048), "out", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=qmf.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(qmf.device)
+    rc = ctx._lib.xaac_b200_esbr_synth64_dev(ctx.handle, _ptr(qmf), _ptr(state.states), _ptr(state.pos), _ptr(out), _ptr(err),
+                                            n, ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_synth64_dev")
+    return out, err

@@ -507,3 +507,60 @@ void ref_chain_lp_step(void *hv, int a, int b, int32_t *spec, const uint8_t *ics
     for (int k = 0; k < 2048; k++) o[2 * k] = tbuf[k];
   }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * eSBR 64-band synthesis bank: the per-slot core of ixheaacd_esbr_synthesis_filt_block (decoder/ixheaacd_sbr_dec.c:
+ * 583-654, stereo_config_idx <= 0, 64 channels) driven leaf by leaf in the reference's own order:
+ * float -> WORD32 (x 64), ixheaacd_esbr_inv_modulation, ixheaacd_shiftrountine_with_rnd_hq, ixheaacd_esbr_qmfsyn64_winadd,
+ * WORD32 -> float (/ 65536).  qmf [32][128] (re 64 | im 64), fs [1280] in/out, pos {drc_offset, filter_pos_syn_32 offset}.
+ * ---------------------------------------------------------------------------------------------- */
+VOID ixheaacd_esbr_inv_modulation(WORD32 *, ia_sbr_qmf_filter_bank_struct *, ia_qmf_dec_tables_struct *, WORD32);
+VOID ixheaacd_shiftrountine_with_rnd_hq(WORD32 *, WORD32 *, WORD32 *, WORD32, WORD32);
+VOID ixheaacd_esbr_qmfsyn64_winadd(WORD32 *, WORD32 *, WORD32 *, WORD32 *, WORD32);
+
+const void *ref_rom_esbr_tables(int *bytes) {
+  static int32_t blob[1280 + 60 + 64 + 32];
+  const ia_qmf_dec_tables_struct *q = &ixheaacd_aac_qmf_dec_tables;
+  memcpy(blob, q->esbr_qmf_c, 1280 * 4);
+  memcpy(blob + 1280, q->esbr_w_32, 60 * 4);
+  memcpy(blob + 1340, q->esbr_sin_cos_twiddle_l64, 64 * 4);
+  memcpy(blob + 1404, q->esbr_alt_sin_twiddle_l64, 32 * 4);
+  if (bytes) *bytes = (int)sizeof(blob);
+  return blob;
+}
+
+void ref_esbr_synth64(const float *qmf, int32_t *fs, int32_t *pos, float *out) {
+  ia_qmf_dec_tables_struct *qt = (ia_qmf_dec_tables_struct *)&ixheaacd_aac_qmf_dec_tables;
+  ia_sbr_qmf_filter_bank_struct bank;
+  memset(&bank, 0, sizeof(bank));
+  bank.no_channels = 64;
+  bank.esbr_cos_twiddle = (WORD32 *)qt->esbr_sin_cos_twiddle_l64;
+  bank.esbr_alt_sin_twiddle = (WORD32 *)qt->esbr_alt_sin_twiddle_l64;
+  WORD32 *f1 = fs, *f2 = fs + 64, sixty4 = 64;
+  WORD32 off = pos[0];
+  WORD32 *filter_l = (WORD32 *)qt->esbr_qmf_c + pos[1];
+  for (int i = 0; i < 32; i++) {
+    WORD32 buf[128], time_out[64];
+    for (int k = 0; k < 64; k++) {
+      buf[k] = (WORD32)(qmf[128 * i + k] * 64);
+      buf[k + 64] = (WORD32)(qmf[128 * i + 64 + k] * 64);
+    }
+    ixheaacd_esbr_inv_modulation(buf, &bank, qt, 64);
+    ixheaacd_shiftrountine_with_rnd_hq(buf, buf + 64, &fs[off], 64, 6);
+    ixheaacd_esbr_qmfsyn64_winadd(f1, f2, filter_l, time_out, 1);
+    for (int k = 0; k < 64; k++) out[64 * i + k] = (FLOAT32)time_out[k] / (1 << 16);
+    f1 += sixty4;
+    f2 -= sixty4;
+    sixty4 = -sixty4;
+    off -= 128;
+    if (off < 0) off += 1280;
+    filter_l += 64;
+    if (filter_l == (WORD32 *)qt->esbr_qmf_c + 640) filter_l = (WORD32 *)qt->esbr_qmf_c;
+  }
+  pos[0] = off;
+  pos[1] = (int32_t)(filter_l - (WORD32 *)qt->esbr_qmf_c);
+}
+void ref_esbr_synth64_batch(const float *qmf, int32_t *fs, int32_t *pos, float *out, int n) {
+  for (int u = 0; u < n; u++)
+    ref_esbr_synth64(qmf + (size_t)u * 4096, fs + (size_t)u * 1280, pos + 2 * u, out + (size_t)u * 2048);
+}

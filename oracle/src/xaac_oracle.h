@@ -298,4 +298,15 @@ void xo_usac_fd_frm_dec_batch(const uint8_t *urom, int32_t *coef, int32_t *ov, c
 int xo_peak_limiter(int32_t *st, int32_t *samples, int frame_len, const int8_t *qshift_adj, int16_t *pcm16);
 void xo_peak_limiter_batch(int32_t *st, int32_t *samples, const int8_t *qshift_adj, int16_t *pcm16, int32_t *err, int ch, int n);
 
+
+/* ---- eSBR 64-band synthesis bank (esbr_qmf.c) ------------------------------------------------------------------------
+ * ROM blob (XO_EROM2_BYTES): members of ia_qmf_dec_tables_struct concatenated by ref_rom_esbr_tables() */
+#define XO_EROM2_QMF_C 0          /* WORD32[1280] esbr_qmf_c */
+#define XO_EROM2_W32 5120         /* WORD32[60]   esbr_w_32 */
+#define XO_EROM2_SINCOS_L64 5360  /* WORD32[64]   esbr_sin_cos_twiddle_l64 */
+#define XO_EROM2_ALTSIN_L64 5616  /* WORD32[32]   esbr_alt_sin_twiddle_l64 */
+#define XO_EROM2_BYTES 5744
+void xo_esbr_synth64(const uint8_t *erom, const float *qmf, int32_t *fs, int32_t *off_io, int32_t *fpos_io, float *out);
+void xo_esbr_synth64_batch(const uint8_t *erom, const float *qmf, int32_t *fs, int32_t *pos, float *out, int n);
+
 #endif

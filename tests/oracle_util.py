@@ -199,6 +199,21 @@ class Oracle:
                                           P(np.ascontiguousarray(win_shape_prev, np.int32)), P(out), P(err), n)
         return out, o, err
 
+    @property
+    def esrom(self):
+        if not hasattr(self, "_esrom"):
+            self._esrom = rom("esbr_rom.bin")
+        return self._esrom
+
+    def esbr_synth_batch(self, qmf, fs, pos):
+        """qmf float32 [n,32,128], fs int32 [n,1280], pos int32 [n,2].  Returns (out float32 [n,2048], fs', pos')."""
+        q = np.ascontiguousarray(qmf, np.float32)
+        f = np.ascontiguousarray(fs, np.int32).copy()
+        p = np.ascontiguousarray(pos, np.int32).copy()
+        out = np.zeros((q.shape[0], 2048), np.float32)
+        self.lib.xo_esbr_synth64_batch(P(self.esrom), P(q), P(f), P(p), P(out), q.shape[0])
+        return out, f, p
+
     def peak_limiter_batch(self, st, samples, qshift_adj, ch):
         """st [n,1548] int32 (XO_PL_*), samples int32 [n,1024,ch], qshift_adj int8 [n,ch].
         Returns (st', samples', pcm16, err)."""
@@ -281,6 +296,14 @@ class Ref:
                                            P(np.ascontiguousarray(win_shape, np.int32)),
                                            P(np.ascontiguousarray(win_shape_prev, np.int32)), P(out), P(err), n)
         return out, o, err
+
+    def esbr_synth_batch(self, qmf, fs, pos):
+        q = np.ascontiguousarray(qmf, np.float32)
+        f = np.ascontiguousarray(fs, np.int32).copy()
+        p = np.ascontiguousarray(pos, np.int32).copy()
+        out = np.zeros((q.shape[0], 2048), np.float32)
+        self.lib.ref_esbr_synth64_batch(P(q), P(f), P(p), P(out), q.shape[0])
+        return out, f, p
 
     def peak_limiter_init(self, ch, sample_rate):
         st = np.zeros(PL_WORDS, np.int32)
@@ -660,3 +683,23 @@ def synth_usac_units(n, seed):
         coef[3] = 1 << 20
         ov[0] = 0
     return coef, ov
+
+
+def synth_esbr_units(n, seed):
+    """float QMF matrices [n,32,128] (re 64 | im 64 per slot) with per-unit magnitude 2^-6 .. 2^22 (the float eSBR path works
+    on PCM-scaled floats), filter states [n,1280] and lock-step (drc_offset, filter_pos) pairs; a few corner units"""
+    rng = np.random.default_rng(seed)
+    mag = 2.0 ** rng.uniform(-6, 22, (n, 1, 1))
+    qmf = ((rng.random((n, 32, 128)) * 2 - 1) * mag).astype(np.float32)
+    usb = rng.integers(20, 65, n)
+    for u in range(n):
+        qmf[u, :, usb[u]:64] = 0
+        qmf[u, :, 64 + usb[u]:] = 0
+    fs = ((rng.random((n, 1280)) * 2 - 1) * 2.0 ** rng.integers(8, 30, (n, 1))).astype(np.int64).astype(np.int32)
+    ph = rng.integers(0, 5, n)
+    pos = np.stack([(256 * ph) % 1280, (128 * ((5 - ph) % 5)) % 640], 1).astype(np.int32)
+    if n > 3:
+        qmf[0] = 0
+        qmf[1] = 3.0e7
+        fs[0] = 0
+    return qmf, fs, pos
