@@ -43,6 +43,7 @@ CHAIN_KERNEL_BYTES = {
     # per channel unit (a stream = 2 units): 4096 WORD32 in + 2048 PCM16 out + 2 x 1.35 KB limiter state (220-sample window)
     "peak_limiter_kernel": 8850,
 }
+ESBR_SYNTH_BYTES_PER_UNIT = 34816  # 16384 float matrix + 5120 + 5120 WORD32 state + 8192 float out
 USAC_FD_BYTES_PER_UNIT = 16384  # 4096 coefficients + 4096 overlap in + 4096 overlap out + 4096 WORD32 out
 WORKLOADS = {
     # name -> (BASELINE.json config index, stereo frames per GPU, description)
@@ -56,6 +57,8 @@ WORKLOADS = {
     "usac_fd_imdct": (4, 131072, "xHE-AAC/USAC stereo 32 kHz batch=131072: the fixed-point FD core transform of the chain "
                                  "(ixheaacd_fd_frm_dec: IMDCT 1024/128 + windowing + overlap); the float eSBR stage is not "
                                  "built yet"),
+    "esbr_synth64": (4, 65536, "xHE-AAC/USAC eSBR stereo 32 kHz: the 64-band eSBR QMF synthesis bank of the chain (per-slot core of "
+                               "ixheaacd_esbr_synthesis_filt_block), batch=65536 stereo frames (131072 output channels)"),
     "qmf_synth_hq": (3, 65536, "stand-alone fixed-point HQ 64-band QMF synthesis stage of the HE-AAC chain, "
                                "batch=65536 stereo frames (131072 output channels)"),
 }
@@ -478,6 +481,44 @@ def cpu_arm_lc_output(n_units, threads, seed, reps=1, min_seconds=0.0):
     return n_units * done / dt, "reference"
 
 
+def cpu_arm_esbr_synth(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time the reference's eSBR synthesis leaves per unit on host threads (ref_esbr_synth64, oracle/ref_shim.c)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    P = oracle_util.P
+    qmf, fs, pos = oracle_util.synth_esbr_units(n_units, seed)
+    fs[:] = 0
+    pos[:] = 0
+    out = np.zeros((n_units, 2048), np.float32)
+    bounds = np.linspace(0, n_units, threads + 1).astype(int)
+    if ref is not None:
+        kind, fn, pre = "reference", ref.lib.ref_esbr_synth64_batch, []
+    else:
+        orc = oracle_util.Oracle()
+        kind, fn, pre = "port", orc.lib.xo_esbr_synth64_batch, [P(orc.esrom)]
+
+    def work(t):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            fn(*pre, P(qmf[a:b]), P(fs[a:b]), P(pos[a:b]), P(out[a:b]), b - a)
+
+    def one_pass():
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    one_pass()
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass()
+        done += 1
+    return n_units * done / dt, kind
+
+
 def usac_walk(n_units, n_steps, seed):
     """ics[step][unit] = (window_sequence, window_shape) of a legal USAC FD walk, both channels of a frame alike:
     ~85 % ONLY_LONG, the rest start / short / stop / stop-start runs"""
@@ -580,6 +621,12 @@ STAGES = {
                                 "(fixed-point WORD32, bit-exact)",
                           ref_stage="ixheaacd_fd_frm_dec", cpu=cpu_arm_usac, cpu_units_per_core=2048, realtime_fps=31.25,
                           h2d=4096 + 2, d2h=4096),
+    "esbr_synth64": dict(kernel="esbr_synth_kernel", bytes_per_unit=ESBR_SYNTH_BYTES_PER_UNIT,
+                         stage="eSBR 64-band QMF synthesis: float -> WORD32, inverse modulation (2 x 32-point FFT, 32-bit "
+                               "twiddles), 10-tap window with WORD64 accumulation, -> float (bit-exact)",
+                         ref_stage="ixheaacd_esbr_inv_modulation + ixheaacd_shiftrountine_with_rnd_hq + "
+                                   "ixheaacd_esbr_qmfsyn64_winadd x 32 slots", cpu=cpu_arm_esbr_synth,
+                         cpu_units_per_core=1024, realtime_fps=15.625, h2d=16384, d2h=8192),
     "qmf_synth_hq": dict(kernel="qmf_synth_hq_kernel", bytes_per_unit=SYNTH_BYTES_PER_UNIT,
                          stage="complex 64-band QMF synthesis (fixed-point, bit-exact)",
                          ref_stage="ixheaacd_cplx_synt_qmffilt", cpu=cpu_arm_synth, cpu_units_per_core=1024,
@@ -730,6 +777,42 @@ class ChainWork:
         self.state.close()
 
 
+class EsbrSynthWork:
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        mag = torch.exp2(torch.rand((n_units, 1, 1), generator=g, device=dev) * 20 - 4)
+        self.qmf = (torch.rand((n_units, 32, 128), generator=g, device=dev) * 2 - 1) * mag
+        self.state = xb.EsbrSynthBatch(n_units, device=dev)
+        self.out = torch.empty((n_units, 2048), dtype=torch.float32, device=dev)
+        self.err = torch.zeros((n_units,), dtype=torch.int32, device=dev)
+
+    def step(self, i, stream):
+        self.xb.esbr_synthesis_filt(self.ctx, self.state, self.qmf, self.out, self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0
+
+    def host_setup(self):
+        import torch
+        self.h_qmf = torch.empty((self.n, 32, 128), dtype=torch.float32).pin_memory()
+        self.h_qmf.copy_(self.qmf)
+        self.h_out = torch.empty((self.n, 2048), dtype=torch.float32).pin_memory()
+        self.d_qmf = torch.empty_like(self.qmf)
+
+    def host_step(self, i):
+        import torch
+        self.d_qmf.copy_(self.h_qmf, non_blocking=True)
+        self.xb.esbr_synthesis_filt(self.ctx, self.state, self.d_qmf, self.out, self.err)
+        self.h_out.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
+
+
 class LcOutputWork:
     """AAC-LC stereo frames with the reference's default flags: units 2k / 2k+1 = L / R of stream k; IMDCT writes the
     interleaved WORD32 time buffer (ch_fac = 2), the limiter (one unit per stream) turns it into PCM16."""
@@ -874,7 +957,7 @@ class ChainLpWork:
 
 WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv2_chain": ChainWork,
         "heaacv1_stereo_chain": ChainLpWork, "usac_fd_imdct": UsacFdWork,
-        "aac_lc_stereo_output": LcOutputWork}
+        "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork}
 
 
 def main():

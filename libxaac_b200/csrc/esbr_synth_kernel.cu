@@ -199,6 +199,15 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
       continue;
     }
     const int b0 = off0 >> 7;
+    {  // pull this warp's next unit towards L2 while this one is processed
+      const long long un = u + warps_total;
+      if (un < p.n_units) {
+        const char *q0 = reinterpret_cast<const char *>(p.qmf + un * 4096);
+        for (int o = lane * 128; o < 16384; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + o));
+        const char *q1 = reinterpret_cast<const char *>(p.states + un * 1280);
+        for (int o = lane * 128; o < 5120; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + o));
+      }
+    }
     // matrix rows: float -> WORD32 (sbr_dec.c:584-587), coalesced 512-byte row loads
     const float4 *src = reinterpret_cast<const float4 *>(p.qmf + u * 4096);
 #pragma unroll 4
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
     __syncwarp();
     es_cos_sin_mod(tab, rows + ES * lane);
     __syncwarp();
-    // 10-tap window (generic:1544-1575): lane -> outputs 2 * lane, 2 * lane + 1 of every slot
+    // 10-tap window (generic:1544-1575): lane -> outputs lane and lane + 32 of every slot (stride-1 rows: conflict-free)
     float *out = p.out + u * 2048;
     const int f0s = fpos0 >> 6;
     const bool lock = p.periodic && (off0 & 255) == 0 && (fpos0 & 127) == 0 && ((b0 + f0s) % 10 == 0);
@@ -231,10 +240,10 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
       i32 c0[10], c1[10];
 #pragma unroll
       for (int a = 0; a < 10; a++) {
-        c0[a] = tab.qmf_c[64 * a + 2 * lane];
-        c1[a] = tab.qmf_c[64 * a + 2 * lane + 1];
+        c0[a] = tab.qmf_c[64 * a + lane];
+        c1[a] = tab.qmf_c[64 * a + 32 + lane];
       }
-      const i32 *hp = rows + 2 * lane;
+      const i32 *hp = rows + lane;
 #pragma unroll 1
       for (int i = 0; i < 32; i++) {
         unsigned long long acc0 = 0, acc1 = 0;
@@ -242,11 +251,11 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
         for (int a = 0; a < 10; a++) {
           const i32 *q = hp + ES * (i - a) + 64 * (a & 1);
           acc0 += (unsigned long long)((long long)q[0] * c0[a]);
-          acc1 += (unsigned long long)((long long)q[1] * c1[a]);
+          acc1 += (unsigned long long)((long long)q[32] * c1[a]);
         }
         const i32 o0 = (i32)((long long)acc0 >> 31), o1 = (i32)((long long)acc1 >> 31);
-        *reinterpret_cast<float2 *>(out + 64 * i + 2 * lane) =
-            make_float2(__fmul_rn(__int2float_rn(o0), 1.0f / 65536.0f), __fmul_rn(__int2float_rn(o1), 1.0f / 65536.0f));
+        out[64 * i + lane] = __fmul_rn(__int2float_rn(o0), 1.0f / 65536.0f);
+        out[64 * i + 32 + lane] = __fmul_rn(__int2float_rn(o1), 1.0f / 65536.0f);
       }
     } else {
       int fpos = fpos0;
@@ -259,14 +268,14 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
         for (int b = 0; b < 10; b++) {
           int a = ab + b;
           if (a >= 10) a -= 10;
-          const i32 *q = rows + ES * (i - a) + 64 * ((i + b) & 1) + 2 * lane;
-          const i32 *c = tab.qmf_c + fpos + 64 * b + 2 * lane;
+          const i32 *q = rows + ES * (i - a) + 64 * ((i + b) & 1) + lane;
+          const i32 *c = tab.qmf_c + fpos + 64 * b + lane;
           acc0 += (unsigned long long)((long long)q[0] * c[0]);
-          acc1 += (unsigned long long)((long long)q[1] * c[1]);
+          acc1 += (unsigned long long)((long long)q[32] * c[32]);
         }
         const i32 o0 = (i32)((long long)acc0 >> 31), o1 = (i32)((long long)acc1 >> 31);
-        *reinterpret_cast<float2 *>(out + 64 * i + 2 * lane) =
-            make_float2(__fmul_rn(__int2float_rn(o0), 1.0f / 65536.0f), __fmul_rn(__int2float_rn(o1), 1.0f / 65536.0f));
+        out[64 * i + lane] = __fmul_rn(__int2float_rn(o0), 1.0f / 65536.0f);
+        out[64 * i + 32 + lane] = __fmul_rn(__int2float_rn(o1), 1.0f / 65536.0f);
         fpos += 64;
         if (fpos == 640) fpos = 0;
       }
