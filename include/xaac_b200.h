@@ -450,12 +450,17 @@ int32_t xaac_b200_usac_fd_frm_dec_dev(xaac_b200_ctx *ctx, const int32_t *d_coef,
  * ixheaacd_esbr_qmfsyn64_winadd, WORD32 -> float.  Integer arithmetic inside, hence bit-exact float output.  The
  * regrouping, PS and DRC branches of the stage function stay with the caller.
  * ROM blob (XAAC_EROM_BYTES), members of ia_qmf_dec_tables_struct (decoder/ixheaacd_sbr_rom.h:96-105) concatenated:
- *   esbr_qmf_c[1280], esbr_w_32[60], esbr_sin_cos_twiddle_l64[64], esbr_alt_sin_twiddle_l64[32] (WORD32). */
+ *   esbr_qmf_c[1280], esbr_w_32[60], esbr_sin_cos_twiddle_l64[64], esbr_alt_sin_twiddle_l64[32], esbr_w_16[24],
+ *   esbr_sin_cos_twiddle_l32[32], esbr_alt_sin_twiddle_l32[16], esbr_t_cos_sin_l32[64] (WORD32). */
 #define XAAC_EROM_QMF_C 0
 #define XAAC_EROM_W32 5120
 #define XAAC_EROM_SINCOS_L64 5360
 #define XAAC_EROM_ALTSIN_L64 5616
-#define XAAC_EROM_BYTES 5744
+#define XAAC_EROM_W16 5744         /* esbr_w_16[24] */
+#define XAAC_EROM_SINCOS_L32 5840  /* esbr_sin_cos_twiddle_l32[32] */
+#define XAAC_EROM_ALTSIN_L32 5968  /* esbr_alt_sin_twiddle_l32[16] */
+#define XAAC_EROM_TCOS_L32 6032    /* esbr_t_cos_sin_l32[64] */
+#define XAAC_EROM_BYTES 6288
 int32_t xaac_b200_set_esbr_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes);
 /*   d_qmf    [n][32][128] float: per slot qmf_buf_real[i][0..63] | qmf_buf_imag[i][0..63]
  *   d_states [n][1280] WORD32 ia_sbr_qmf_filter_bank_struct.filter_states_32, in/out
@@ -464,6 +469,17 @@ int32_t xaac_b200_set_esbr_rom(xaac_b200_ctx *ctx, const void *tables, size_t by
  *   d_err    [n] or NULL: 0 / 0x80000000 (ring positions the reference cannot produce) */
 int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32_t *d_states, int32_t *d_pos, float *d_out,
                                    int32_t *d_err, int64_t n_units, void *stream);
+
+/* eSBR 32-band QMF analysis bank: batched ixheaacd_esbr_analysis_filt_block(ia_sbr_dec_struct *, ia_sbr_tables_struct *,
+ * WORD32 op_delay) (decoder/ixheaacd_sbr_dec.c:185-295) for 32 analysis channels and 32 time slots, with its leaves
+ * ixheaacd_esbr_qmfanal32_winadd (decoder/ixheaacd_qmf_dec.c:537), ixheaacd_esbr_fwd_modulation, ixheaacd_esbr_cos_sin_mod,
+ * ixheaacd_esbr_radix4bfly, ixheaacd_esbr_postradixcompute4 (decoder/generic/ixheaacd_qmf_dec_generic.c).  Bit-exact floats.
+ *   d_time_in [n][1024] float  ptr_sbr_dec->time_sample_buf (core coder output x 2^-15, ixheaacd_ext_ch_ele.c:1040-1046)
+ *   d_states  [n][320] WORD32  str_codec_qmf_bank.anal_filter_states_32, in/out
+ *   d_pos     [n][2] WORD32    {state_new_samples_pos_low_32 - anal_filter_states_32, filter_pos_32 - esbr_qmf_c}, in/out
+ *   d_qmf     [n][32][128] float: qmf_buf_real[op_delay + i][0..31] at +0, qmf_buf_imag[..][0..31] at +64 of slot row i */
+int32_t xaac_b200_esbr_anal32_dev(xaac_b200_ctx *ctx, const float *d_time_in, int32_t *d_states, int32_t *d_pos, float *d_qmf,
+                                  int32_t *d_err, int64_t n_units, void *stream);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,10 @@ struct EsTab {
   i32 w32[60];
   i32 sincos[64];
   i32 alt[32];
+  i32 w16[24];
+  i32 sincos32[32];
+  i32 alt32[16];
+  i32 tcos32[64];
 };
 struct EsWarpS {
   i32 rows[(9 + 32) * ES];  // rows 0..8: old state blocks (age 9..1), row 9 + s: slot s
@@ -301,6 +305,259 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
   }
 }
 
+
+// =====================================================================================================================
+// eSBR 32-band analysis bank: ixheaacd_esbr_analysis_filt_block (decoder/ixheaacd_sbr_dec.c:185-295) for 32 channels and
+// 32 time slots: float -> WORD32 (x 2^15), ixheaacd_esbr_qmfanal32_winadd (decoder/ixheaacd_qmf_dec.c:537-640),
+// ixheaacd_esbr_fwd_modulation (generic:1463-1506) = >> 4, fold, ixheaacd_esbr_cos_sin_mod (M = 16, esbr_w_16,
+// ixheaacd_esbr_postradixcompute4), t_cos rotation, WORD32 -> float (x 1/256).
+// Window: lane = output, the time-invariant form of the ring bookkeeping (lock step) on a flat WORD32 history; modulation:
+// lane = slot, in place in the slot's row; rotation + conversion + coalesced store: lane = band.
+// Algorithmic HBM bytes per unit: 4096 (float in) + 1280 + 1280 (WORD32 ring in / out) + 8192 (32 x 32 complex float out).
+// =====================================================================================================================
+constexpr int kEaWarps = 12;
+constexpr int EA = 97;  // row stride: 96 words used (s1 at 0..31, window output at 0..63, s2 at 64..95)
+struct EaWarpS {
+  i32 T[1312];       // T[j] = sample at time j - 288 relative to the frame start (lock-step path); ring in the literal path
+  i32 rows[32 * EA];
+};
+struct EaBlockS {
+  EsTab tab;
+  EaWarpS w[kEaWarps];
+};
+
+// ixheaacd_esbr_cos_sin_mod for 32 channels (M = 16) on one slot row: s1 = sb[0..31], s2 = sb[64..95], in place
+XB_DEV void ea_cos_sin_mod(const EsTab &t, i32 *sb) {
+  i32 *s1 = sb, *s2 = sb + 64;
+#pragma unroll 1
+  for (int n = 0; n < 16; n += 2) {
+    const i32 wim0 = t.sincos32[2 * n], wre0 = t.sincos32[2 * n + 1], wim1 = t.sincos32[2 * n + 2], wre1 = t.sincos32[2 * n + 3];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      i32 *s = h ? s2 : s1;
+      const i32 a = s[n], b = s[31 - n], a1 = s[n + 1], b1 = s[30 - n];
+      if (!h) {
+        s[n] = padd(a, wre0, b, wim0);
+        s[n + 1] = psub(b, wre0, a, wim0);
+        s[31 - n] = psub(a1, wre1, b1, wim1);
+        s[30 - n] = padd(b1, wre1, a1, wim1);
+      } else {
+        s[n] = psub(b, wim0, a, wre0);
+        s[n + 1] = padd(a, wim0, b, wre0);
+        s[31 - n] = padd(b1, wim1, a1, wre1);
+        s[30 - n] = psub(a1, wim1, b1, wre1);
+      }
+    }
+  }
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    i32 *x = sb + 64 * h;
+    es_radix4(t.w16, x, 1, 4);
+    // generic:1059-1161 — final radix-4 (no twiddles) with digit-reversed scatter (dig_rev_table4_16 = {0, 16}), via registers
+    i32 v[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = x[i];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const int c = 16 * k + 8 * half, o = 4 * k + 2 * half;
+        const i32 xh0 = add_sat(v[c], v[c + 4]), xh1 = add_sat(v[c + 1], v[c + 5]);
+        const i32 xl0 = sub_sat(v[c], v[c + 4]), xl1 = sub_sat(v[c + 1], v[c + 5]);
+        const i32 zh0 = add_sat(v[c + 2], v[c + 6]), zh1 = add_sat(v[c + 3], v[c + 7]);
+        const i32 zl0 = sub_sat(v[c + 2], v[c + 6]), zl1 = sub_sat(v[c + 3], v[c + 7]);
+        x[o] = add_sat(xh0, zh0);
+        x[o + 1] = add_sat(xh1, zh1);
+        x[8 + o] = add_sat(xl0, zl1);
+        x[8 + o + 1] = sub_sat(xl1, zl0);
+        x[16 + o] = sub_sat(xh0, zh0);
+        x[16 + o + 1] = sub_sat(xh1, zh1);
+        x[24 + o] = sub_sat(xl0, zl1);
+        x[24 + o + 1] = add_sat(xl1, zl0);
+      }
+    }
+  }
+  {  // post-twiddle (generic:1365-1460), N = 32, H = 8, in place
+    const i32 f10 = s1[0], f11 = s1[1], f20 = s2[0], f21 = s2[1];
+    i32 re1 = s1[31], im1 = s1[30], re2 = s2[31], im2 = s2[30];
+    s1[0] = f10 >> 1;
+    s1[31] = neg_sat(f11 >> 1);
+    s2[31] = neg_sat(f20 >> 1);
+    s2[0] = f21 >> 1;
+#pragma unroll 1
+    for (int u = 0; u < 8; u++) {
+      const i32 wim = t.alt32[2 * u], wre = t.alt32[2 * u + 1];
+      i32 nre1 = 0, nim1 = 0, nre2 = 0, nim2 = 0;
+      if (u + 1 < 8) {
+        nre1 = s1[29 - 2 * u]; nim1 = s1[28 - 2 * u];
+        nre2 = s2[29 - 2 * u]; nim2 = s2[28 - 2 * u];
+      }
+      s1[30 - 2 * u] = padd(re1, wre, im1, wim);
+      s1[1 + 2 * u] = psub(im1, wre, re1, wim);
+      s2[1 + 2 * u] = neg_sat(padd(re2, wre, im2, wim));
+      s2[30 - 2 * u] = psub(re2, wim, im2, wre);
+      if (u + 1 < 8) {
+        i32 fim = s1[2 + 2 * u], fre = s1[3 + 2 * u];
+        s1[2 + 2 * u] = padd(fre, wim, fim, wre);
+        s1[29 - 2 * u] = psub(fim, wim, fre, wre);
+        fim = s2[2 + 2 * u];
+        fre = s2[3 + 2 * u];
+        s2[29 - 2 * u] = neg_sat(padd(fre, wim, fim, wre));
+        s2[2 + 2 * u] = psub(fre, wre, fim, wim);
+      }
+      re1 = nre1; im1 = nim1; re2 = nre2; im2 = nim2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EaBlockS &sm = *reinterpret_cast<EaBlockS *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    const i32 *src = reinterpret_cast<const i32 *>(p.rom);
+    i32 *dst = reinterpret_cast<i32 *>(&sm.tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(EsTab) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const EsTab &tab = sm.tab;
+  EaWarpS &w = sm.w[warp];
+  const long long warps_total = (long long)gridDim.x * kEaWarps;
+  const i32 tc = tab.tcos32[2 * lane], ts = tab.tcos32[2 * lane + 1];
+  for (long long u = (long long)blockIdx.x * kEaWarps + warp; u < p.n_units; u += warps_total) {
+    __syncwarp();
+    const float *tin = p.time_in + u * 1024;
+    i32 *ring = p.states + u * 320;
+    int pos = p.pos[2 * u], f1 = p.pos[2 * u + 1], f2 = f1 + 64;
+    if ((pos & 31) != 0 || pos < 0 || pos > 288 || (f1 & 63) != 0 || f1 < 0 || f1 > 576) {
+      if (lane == 0 && p.err) p.err[u] = (i32)0x80000000;
+      continue;
+    }
+    const int P0 = pos >> 5, F0 = f1 >> 6;
+    const bool lock = p.periodic && (pos & 63) == 0 && (f1 & 127) == 0 && pos <= 256 && f1 <= 512 && ((P0 + F0) % 10 == 0);
+    if (lock) {
+      // flat history: 288 old samples from the ring (block q holds slot P0 - q mod 10, newest sample first), 1024 new ones
+#pragma unroll 1
+      for (int j = lane; j < 288; j += 32) {
+        int q = P0 + 9 - (j >> 5);
+        if (q >= 10) q -= 10;
+        w.T[j] = ring[32 * q + 31 - (j & 31)];
+      }
+#pragma unroll 4
+      for (int j = lane; j < 1024; j += 32) w.T[288 + j] = f2i_x86(__fmul_rn(__ldg(tin + j), 32768.0f));
+      i32 ca[5], cb[5];
+#pragma unroll
+      for (int m = 0; m < 5; m++) {
+        ca[m] = tab.qmf_c[128 * m + 2 * lane];
+        cb[m] = tab.qmf_c[64 + 128 * m + 2 * lane];
+      }
+      __syncwarp();
+      const i32 *ta = w.T + 288 + 31 - lane, *tb = w.T + 288 - 1 - lane;
+#pragma unroll 2
+      for (int slot = 0; slot < 32; slot++) {
+        unsigned long long a = 0, b = 0;
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+          a += (unsigned long long)((long long)ta[32 * slot - 64 * m] * ca[m]);
+          b += (unsigned long long)((long long)tb[32 * slot - 64 * m] * cb[m]);
+        }
+        w.rows[EA * slot + lane] = (i32)((long long)a >> 31);
+        w.rows[EA * slot + 32 + lane] = (i32)((long long)b >> 31);
+      }
+      // ring after 32 slots
+#pragma unroll 1
+      for (int pp = lane; pp < 320; pp += 32) {
+        const int q = pp >> 5;
+        int d = (31 - (P0 - q)) % 10;
+        if (d < 0) d += 10;
+        ring[pp] = w.T[288 + 32 * (31 - d) + 31 - (pp & 31)];
+      }
+      const int Pf = (P0 + 8) % 10;
+      pos = 32 * Pf;
+      f1 = 64 * ((10 - Pf) % 10);
+    } else {
+      // literal ring emulation (sbr_dec.c:244-276) for (position, phase) pairs the reference never produces itself
+      i32 *rg = w.T;
+      for (int j = lane; j < 320; j += 32) rg[j] = ring[j];
+      __syncwarp();
+#pragma unroll 1
+      for (int slot = 0; slot < 32; slot++) {
+        rg[pos + 31 - lane] = f2i_x86(__fmul_rn(__ldg(tin + 32 * slot + lane), 32768.0f));
+        __syncwarp();
+        const i32 *fp1 = rg + ((slot & 1) ? 32 : 0), *fp2 = rg + ((slot & 1) ? 0 : 32);
+        unsigned long long a = 0, b = 0;
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          a += (unsigned long long)((long long)fp1[lane + 64 * j] * tab.qmf_c[f1 + 2 * (lane + 64 * j)]);
+          b += (unsigned long long)((long long)fp2[lane + 64 * j] * tab.qmf_c[f2 + 2 * (lane + 64 * j)]);
+        }
+        __syncwarp();
+        pos -= 32;
+        if (pos < 0) pos = 288;
+        {
+          const int n1 = f2 + 64, n2 = f1 + 64;
+          f1 = n1;
+          f2 = n2;
+          if (f2 > 640) {
+            f1 = 0;
+            f2 = 64;
+          }
+        }
+        w.rows[EA * slot + lane] = (i32)((long long)a >> 31);
+        w.rows[EA * slot + 32 + lane] = (i32)((long long)b >> 31);
+      }
+      for (int j = lane; j < 320; j += 32) ring[j] = rg[j];
+    }
+    __syncwarp();
+    {  // lane = slot: fold (generic:1475-1482) in place, then the modulation
+      i32 *sb = w.rows + EA * lane;
+#pragma unroll 1
+      for (int k = 0; k < 16; k++) {
+        const i32 a0 = sb[k] >> 4, a1 = sb[63 - k] >> 4, b0 = sb[31 - k] >> 4, b1 = sb[32 + k] >> 4;
+        sb[k] = sub_sat(a0, a1);
+        sb[64 + k] = add_sat(a0, a1);
+        sb[31 - k] = sub_sat(b0, b1);
+        sb[64 + 31 - k] = add_sat(b0, b1);
+      }
+      ea_cos_sin_mod(tab, sb);
+    }
+    __syncwarp();
+    // lane = band: t_cos rotation (generic:1490-1505), WORD32 -> float (x 1/256), coalesced rows of the output matrix
+    float *out = p.qmf + u * p.out_stride;
+#pragma unroll 2
+    for (int s = 0; s < 32; s++) {
+      const i32 re = w.rows[EA * s + lane], im = w.rows[EA * s + 64 + lane];
+      const i32 r2 = (i32)(((long long)re * tc + (long long)im * ts) >> 31);
+      const long long x = (long long)im * tc, y = (long long)re * ts;
+      long long d = (long long)((unsigned long long)x - (unsigned long long)y);
+      if (((x ^ y) & (x ^ d)) < 0) d = x < 0 ? (long long)0x8000000000000000ULL : 0x7fffffffffffffffLL;
+      out[128 * s + lane] = __fmul_rn(__int2float_rn(r2), 1.0f / 256.0f);
+      out[128 * s + 64 + lane] = __fmul_rn(__int2float_rn((i32)(d >> 31)), 1.0f / 256.0f);
+    }
+    if (lane == 0) {
+      p.pos[2 * u] = pos;
+      p.pos[2 * u + 1] = f1;
+      if (p.err) p.err[u] = 0;
+    }
+  }
+}
+
+cudaError_t launch_esbr_anal(const EsbrAnalArgs &args, int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  const size_t smem = sizeof(EaBlockS);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(esbr_anal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  long long need = (args.n_units + kEaWarps - 1) / kEaWarps;
+  long long grid = num_sms;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  esbr_anal_kernel<<<(unsigned)grid, kEaWarps * 32, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
 size_t esbr_synth_table_bytes() { return sizeof(EsTab); }
 // returns 1 if esbr_qmf_c is periodic with period 640 (the lock-step window form needs it), 0 otherwise
 int esbr_synth_build_tables(const uint8_t *erom, uint8_t *out) {
@@ -310,6 +567,10 @@ int esbr_synth_build_tables(const uint8_t *erom, uint8_t *out) {
   memcpy(t->w32, erom + kEsRomW32, sizeof(t->w32));
   memcpy(t->sincos, erom + kEsRomSinCos, sizeof(t->sincos));
   memcpy(t->alt, erom + kEsRomAlt, sizeof(t->alt));
+  memcpy(t->w16, erom + kEsRomW16, sizeof(t->w16));
+  memcpy(t->sincos32, erom + kEsRomSinCos32, sizeof(t->sincos32));
+  memcpy(t->alt32, erom + kEsRomAlt32, sizeof(t->alt32));
+  memcpy(t->tcos32, erom + kEsRomTCos32, sizeof(t->tcos32));
   int periodic = 1;
   for (int i = 0; i < 640; i++)
     if (c[i] != c[i + 640]) periodic = 0;

@@ -272,8 +272,10 @@ struct PeakLimArgs {
 cudaError_t launch_peak_limiter(const PeakLimArgs &args, int num_sms, cudaStream_t stream);
 
 // ---- eSBR 64-band synthesis bank (per-slot core of ixheaacd_esbr_synthesis_filt_block) --------------------------------
-// ROM blob: esbr_qmf_c[1280] | esbr_w_32[60] | esbr_sin_cos_twiddle_l64[64] | esbr_alt_sin_twiddle_l64[32] (WORD32)
-constexpr int kEsRomQmfC = 0, kEsRomW32 = 5120, kEsRomSinCos = 5360, kEsRomAlt = 5616, kEsRomBytes = 5744;
+// ROM blob: esbr_qmf_c[1280] | esbr_w_32[60] | esbr_sin_cos_twiddle_l64[64] | esbr_alt_sin_twiddle_l64[32] | esbr_w_16[24] |
+// esbr_sin_cos_twiddle_l32[32] | esbr_alt_sin_twiddle_l32[16] | esbr_t_cos_sin_l32[64] (WORD32)
+constexpr int kEsRomQmfC = 0, kEsRomW32 = 5120, kEsRomSinCos = 5360, kEsRomAlt = 5616, kEsRomW16 = 5744, kEsRomSinCos32 = 5840,
+              kEsRomAlt32 = 5968, kEsRomTCos32 = 6032, kEsRomBytes = 6288;
 struct EsbrSynthArgs {
   const float *qmf;     // [n][32][128] per slot re[64] | im[64] (qmf_buf_real[i][k], qmf_buf_imag[i][k])
   int32_t *states;      // [n][1280] filter_states_32, in/out
@@ -287,6 +289,18 @@ struct EsbrSynthArgs {
 size_t esbr_synth_table_bytes();
 int esbr_synth_build_tables(const uint8_t *erom, uint8_t *out);
 cudaError_t launch_esbr_synth(const EsbrSynthArgs &args, int num_sms, cudaStream_t stream);
+struct EsbrAnalArgs {
+  const float *time_in;  // [n][1024] core-coder samples (ptr_sbr_dec->time_sample_buf)
+  int32_t *states;       // [n][320] anal_filter_states_32, in/out
+  int32_t *pos;          // [n][2] {state_new_samples_pos_low_32 - anal_filter_states_32, filter_pos_32 - esbr_qmf_c}, in/out
+  float *qmf;            // unit u writes slot s at qmf + u * out_stride + 128 * s: re at +0..31, im at +64..95
+  int32_t *err;          // [n] or null
+  const uint8_t *rom;
+  long long n_units;
+  long long out_stride = 4096;
+  int periodic;
+};
+cudaError_t launch_esbr_anal(const EsbrAnalArgs &args, int num_sms, cudaStream_t stream);
 
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);

@@ -1001,7 +1001,7 @@ int32_t xaac_b200_peak_limiter_dev(xaac_b200_ctx *ctx, int32_t *d_state, const i
 
 int32_t xaac_b200_set_esbr_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
   if (!ctx || !tables) return bad_arg(ctx, "null");
-  if (bytes < (size_t)xb::kEsRomBytes) return bad_arg(ctx, "eSBR ROM blob shorter than 5744 bytes");
+  if (bytes < (size_t)xb::kEsRomBytes) return bad_arg(ctx, "eSBR ROM blob shorter than 6288 bytes");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   const size_t n = xb::esbr_synth_table_bytes();
   uint8_t *img = (uint8_t *)calloc(1, n + 64);
@@ -1029,6 +1029,25 @@ int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32
   a.n_units = n_units; a.periodic = ctx->esbr_periodic;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_esbr_anal32_dev(xaac_b200_ctx *ctx, const float *d_time_in, int32_t *d_states, int32_t *d_pos, float *d_qmf,
+                                  int32_t *d_err, int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->d_rom_esbr) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_time_in || !d_states || !d_pos || !d_qmf) return bad_arg(ctx, "null buffer");
+  xb::EsbrAnalArgs a;
+  a.time_in = d_time_in; a.states = d_states; a.pos = d_pos; a.qmf = d_qmf; a.err = d_err; a.rom = ctx->d_rom_esbr;
+  a.n_units = n_units; a.periodic = ctx->esbr_periodic;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  LAUNCH("esbr_anal_kernel", stream, xb::launch_esbr_anal(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }

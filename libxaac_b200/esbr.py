@@ -37,3 +37,31 @@ def esbr_synthesis_filt(ctx, state, qmf, out=None, err=None, stream=None):
                                             n, ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_esbr_synth64_dev")
     return out, err
+
+
+class EsbrAnalBatch:
+    """State of the eSBR 32-band analysis bank: str_codec_qmf_bank.anal_filter_states_32 int32 [n, 320] and
+    {state_new_samples_pos_low_32 offset, filter_pos_32 offset} int32 [n, 2]."""
+
+    def __init__(self, n_units, device="cuda:0"):
+        self.n = int(n_units)
+        self.states = torch.zeros((self.n, 320), dtype=torch.int32, device=device)
+        self.pos = torch.zeros((self.n, 2), dtype=torch.int32, device=device)
+
+
+def esbr_analysis_filt_block(ctx, state, time_in, qmf=None, err=None, stream=None):
+    """Batched drop-in for ixheaacd_esbr_analysis_filt_block (32 channels, 32 slots).  time_in float32 [n, 1024]; returns
+    (qmf float32 [n, 32, 128] with re at +0..31 and im at +64..95 of every slot row, err)."""
+    n = state.n
+    _chk(time_in, torch.float32, (n, 1024), "time_in", "cuda")
+    if qmf is None:
+        qmf = torch.zeros((n, 32, 128), dtype=torch.float32, device=time_in.device)
+    _chk(qmf, torch.float32, (n, 32, 128), "qmf", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=time_in.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(time_in.device)
+    rc = ctx._lib.xaac_b200_esbr_anal32_dev(ctx.handle, _ptr(time_in), _ptr(state.states), _ptr(state.pos), _ptr(qmf), _ptr(err),
+                                           n, ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_anal32_dev")
+    return qmf, err

@@ -519,12 +519,16 @@ VOID ixheaacd_shiftrountine_with_rnd_hq(WORD32 *, WORD32 *, WORD32 *, WORD32, WO
 VOID ixheaacd_esbr_qmfsyn64_winadd(WORD32 *, WORD32 *, WORD32 *, WORD32 *, WORD32);
 
 const void *ref_rom_esbr_tables(int *bytes) {
-  static int32_t blob[1280 + 60 + 64 + 32];
+  static int32_t blob[1280 + 60 + 64 + 32 + 24 + 32 + 16 + 64];
   const ia_qmf_dec_tables_struct *q = &ixheaacd_aac_qmf_dec_tables;
   memcpy(blob, q->esbr_qmf_c, 1280 * 4);
   memcpy(blob + 1280, q->esbr_w_32, 60 * 4);
   memcpy(blob + 1340, q->esbr_sin_cos_twiddle_l64, 64 * 4);
   memcpy(blob + 1404, q->esbr_alt_sin_twiddle_l64, 32 * 4);
+  memcpy(blob + 1436, q->esbr_w_16, 24 * 4);
+  memcpy(blob + 1460, q->esbr_sin_cos_twiddle_l32, 32 * 4);
+  memcpy(blob + 1492, q->esbr_alt_sin_twiddle_l32, 16 * 4);
+  memcpy(blob + 1508, q->esbr_t_cos_sin_l32, 64 * 4);
   if (bytes) *bytes = (int)sizeof(blob);
   return blob;
 }
@@ -563,4 +567,39 @@ void ref_esbr_synth64(const float *qmf, int32_t *fs, int32_t *pos, float *out) {
 void ref_esbr_synth64_batch(const float *qmf, int32_t *fs, int32_t *pos, float *out, int n) {
   for (int u = 0; u < n; u++)
     ref_esbr_synth64(qmf + (size_t)u * 4096, fs + (size_t)u * 1280, pos + 2 * u, out + (size_t)u * 2048);
+}
+
+
+/* eSBR 32-band analysis bank: ixheaacd_esbr_analysis_filt_block (decoder/ixheaacd_sbr_dec.c:185-295) itself, on a minimal
+ * ia_sbr_dec_struct: time_in [1024] float, states [320] in/out, pos {state_new_samples_pos_low_32 offset, filter_pos_32
+ * offset} in/out, qmf [32][128] float out (re at +0..31, im at +64..95). */
+VOID ixheaacd_esbr_analysis_filt_block(ia_sbr_dec_struct *, ia_sbr_tables_struct *, WORD32);
+void ref_esbr_anal32(const float *time_in, int32_t *states, int32_t *pos, float *qmf) {
+  static __thread ia_sbr_dec_struct d;
+  ia_qmf_dec_tables_struct *qt = (ia_qmf_dec_tables_struct *)&ixheaacd_aac_qmf_dec_tables;
+  ia_sbr_tables_struct tabs;
+  memset(&tabs, 0, sizeof(tabs));
+  memset(&d, 0, sizeof(d));
+  tabs.qmf_dec_tables_ptr = qt;
+  ia_sbr_qmf_filter_bank_struct *b = &d.str_codec_qmf_bank;
+  b->no_channels = 32;
+  b->num_time_slots = 32;
+  b->lsb = 0;
+  b->anal_filter_states_32 = states;
+  b->state_new_samples_pos_low_32 = states + pos[0];
+  b->analy_win_coeff_32 = qt->esbr_qmf_c;
+  b->filter_pos_32 = (WORD32 *)qt->esbr_qmf_c + pos[1];
+  b->esbr_cos_twiddle = (WORD32 *)qt->esbr_sin_cos_twiddle_l32;
+  b->esbr_alt_sin_twiddle = (WORD32 *)qt->esbr_alt_sin_twiddle_l32;
+  b->esbr_t_cos = (WORD32 *)qt->esbr_t_cos_sin_l32;
+  d.time_sample_buf = (FLOAT32 *)time_in;
+  ixheaacd_esbr_analysis_filt_block(&d, &tabs, 0);
+  for (int i = 0; i < 32; i++)
+    for (int k = 0; k < 32; k++) { qmf[128 * i + k] = d.qmf_buf_real[i][k]; qmf[128 * i + 64 + k] = d.qmf_buf_imag[i][k]; }
+  pos[0] = (int32_t)(b->state_new_samples_pos_low_32 - states);
+  pos[1] = (int32_t)(b->filter_pos_32 - (WORD32 *)qt->esbr_qmf_c);
+}
+void ref_esbr_anal32_batch(const float *time_in, int32_t *states, int32_t *pos, float *qmf, int n) {
+  for (int u = 0; u < n; u++)
+    ref_esbr_anal32(time_in + (size_t)u * 1024, states + (size_t)u * 320, pos + 2 * u, qmf + (size_t)u * 4096);
 }

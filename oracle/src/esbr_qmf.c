@@ -71,10 +71,31 @@ static void post_radix2_32e(i32 *y, const i32 *x) {
   }
 }
 
-/* generic:1163-1461 for no_channels = 64 (M = 32): sb[0..63] and sb[64..127] in place */
-static void esbr_cos_sin_mod64(const uint8_t *erom, i32 *sb) {
-  const int M = 32, N = 64, H = 16;
-  const i32 *tw = E32(XO_EROM2_SINCOS_L64), *alt = E32(XO_EROM2_ALTSIN_L64), *w = E32(XO_EROM2_W32);
+/* generic:1059-1161 with dig_rev_table4_16 = {0, 16}: final radix-4 (no twiddles) of the 16-point FFT */
+static void post_radix4_16e(i32 *y, const i32 *x) {
+  i32 *y0 = y, *y1 = y + 8, *y2 = y + 16, *y3 = y + 24;
+  for (int k = 0; k < 2; k++) {
+    const int h2 = (16 * k) >> 2;
+    for (int half = 0; half < 2; half++) {
+      const i32 *c = x + 16 * k + 8 * half;
+      const int o = h2 + 2 * half;
+      i32 xh0 = ox_add_sat(c[0], c[4]), xh1 = ox_add_sat(c[1], c[5]);
+      i32 xl0 = ox_sub_sat(c[0], c[4]), xl1 = ox_sub_sat(c[1], c[5]);
+      i32 zh0 = ox_add_sat(c[2], c[6]), zh1 = ox_add_sat(c[3], c[7]);
+      i32 zl0 = ox_sub_sat(c[2], c[6]), zl1 = ox_sub_sat(c[3], c[7]);
+      y0[o] = ox_add_sat(xh0, zh0); y0[o + 1] = ox_add_sat(xh1, zh1);
+      y1[o] = ox_add_sat(xl0, zl1); y1[o + 1] = ox_sub_sat(xl1, zl0);
+      y2[o] = ox_sub_sat(xh0, zh0); y2[o + 1] = ox_sub_sat(xh1, zh1);
+      y3[o] = ox_sub_sat(xl0, zl1); y3[o + 1] = ox_add_sat(xl1, zl0);
+    }
+  }
+}
+
+/* generic:1163-1461 for no_channels = 64 (M = 32, synthesis) or 32 (M = 16, analysis): sb[0..2M-1] and sb[64..64+2M-1] */
+static void esbr_cos_sin_mod(const uint8_t *erom, i32 *sb, int no_channels) {
+  const int M = no_channels >> 1, N = 2 * M, H = M >> 1;
+  const i32 *tw = E32(no_channels == 64 ? XO_EROM2_SINCOS_L64 : XO_EROM2_SINCOS_L32);
+  const i32 *alt = E32(no_channels == 64 ? XO_EROM2_ALTSIN_L64 : XO_EROM2_ALTSIN_L32);
   i32 t[128];
   i32 *s1 = sb, *s2 = sb + 64, *t1 = t, *t2 = t + 64;
   for (int n = 0; n < M; n++) { /* :1200-1295 */
@@ -94,14 +115,19 @@ static void esbr_cos_sin_mod64(const uint8_t *erom, i32 *sb) {
       t2[N - 2 - 2 * j] = psub(c, wim, d, wre);
     }
   }
-  for (int h = 0; h < 2; h++) { /* :1297-1303 */
-    radix4_stage32(w, t + 64 * h, 1, 8);
-    radix4_stage32(w + 48, t + 64 * h, 4, 2);
-    post_radix2_32e(sb + 64 * h, t + 64 * h);
+  for (int h = 0; h < 2; h++) { /* :1297-1314 */
+    if (M == 32) {
+      radix4_stage32(E32(XO_EROM2_W32), t + 64 * h, 1, 8);
+      radix4_stage32(E32(XO_EROM2_W32) + 48, t + 64 * h, 4, 2);
+      post_radix2_32e(sb + 64 * h, t + 64 * h);
+    } else {
+      radix4_stage32(E32(XO_EROM2_W16), t + 64 * h, 1, 4);
+      post_radix4_16e(sb + 64 * h, t + 64 * h);
+    }
   }
   i32 f1[64], f2[64]; /* post-twiddle :1365-1460, restated out of place */
-  memcpy(f1, s1, sizeof(f1));
-  memcpy(f2, s2, sizeof(f2));
+  memcpy(f1, s1, sizeof(i32) * N);
+  memcpy(f2, s2, sizeof(i32) * N);
   s1[0] = f1[0] >> 1;
   s1[N - 1] = ox_neg_sat(f1[1] >> 1);
   s2[N - 1] = ox_neg_sat(f2[0] >> 1);
@@ -126,6 +152,7 @@ static void esbr_cos_sin_mod64(const uint8_t *erom, i32 *sb) {
     }
   }
 }
+static void esbr_cos_sin_mod64(const uint8_t *erom, i32 *sb) { esbr_cos_sin_mod(erom, sb, 64); }
 
 /* The per-slot core of ixheaacd_esbr_synthesis_filt_block for 32 time slots.
  *   qmf   [32][128] float: re[64] | im[64] per slot (qmf_buf_real[i][k], qmf_buf_imag[i][k])
@@ -168,4 +195,59 @@ void xo_esbr_synth64(const uint8_t *erom, const float *qmf, i32 *fs, i32 *off_io
 void xo_esbr_synth64_batch(const uint8_t *erom, const float *qmf, i32 *fs, i32 *pos, float *out, int n) {
   for (int u = 0; u < n; u++)
     xo_esbr_synth64(erom, qmf + (size_t)u * 4096, fs + (size_t)u * 1280, pos + 2 * u, pos + 2 * u + 1, out + (size_t)u * 2048);
+}
+
+/* ixheaacd_esbr_analysis_filt_block (decoder/ixheaacd_sbr_dec.c:185-295) for 32 analysis channels and 32 time slots:
+ * float core samples -> WORD32 (x 2^15), ixheaacd_esbr_qmfanal32_winadd (decoder/ixheaacd_qmf_dec.c:537-640, WORD64
+ * accumulation), ixheaacd_esbr_fwd_modulation (generic:1463-1506: >> 4, fold, cos_sin_mod M = 16, t_cos rotation),
+ * WORD32 -> float (x 1/256).
+ *   time_in [1024] float; states [320] WORD32 anal_filter_states_32 (in/out); *pos = state_new_samples_pos_low_32 -
+ *   anal_filter_states_32, *fpos = filter_pos_32 - esbr_qmf_c (in/out); qmf [32][128] float: re at +0..31, im at +64..95 */
+void xo_esbr_anal32(const uint8_t *erom, const float *time_in, i32 *states, i32 *pos_io, i32 *fpos_io, float *qmf) {
+  const i32 *qc = E32(XO_EROM2_QMF_C), *tcos = E32(XO_EROM2_TCOS_L32);
+  int pos = *pos_io, f1 = *fpos_io, f2 = f1 + 64;
+  for (int i = 0; i < 32; i++) {
+    i32 buf[64], sb[128];
+    for (int z = 0; z < 32; z++) states[pos + 31 - z] = (i32)(time_in[32 * i + z] * (1 << 15));
+    const i32 *fp1 = states + ((i & 1) ? 32 : 0), *fp2 = states + ((i & 1) ? 0 : 32);
+    for (int n = 0; n < 32; n++) {
+      uint64_t a = 0, b = 0;
+      for (int j = 0; j < 5; j++) {
+        a += (uint64_t)((i64)fp1[n + 64 * j] * qc[f1 + 2 * (n + 64 * j)]);
+        b += (uint64_t)((i64)fp2[n + 64 * j] * qc[f2 + 2 * (n + 64 * j)]);
+      }
+      buf[n] = (i32)((i64)a >> 31);
+      buf[n + 32] = (i32)((i64)b >> 31);
+    }
+    pos -= 32;
+    if (pos < 0) pos = 288;
+    {
+      const int n1 = f2 + 64, n2 = f1 + 64;
+      f1 = n1;
+      f2 = n2;
+      if (f2 > 640) { f1 = 0; f2 = 64; }
+    }
+    memset(sb, 0, sizeof(sb));
+    for (int k = 0; k < 32; k++) { /* generic:1475-1482 */
+      const i32 t1 = ox_shr32(buf[k], 4), t2 = ox_shr32(buf[63 - k], 4);
+      sb[k] = ox_sub_sat(t1, t2);
+      sb[64 + k] = ox_add_sat(t1, t2);
+    }
+    esbr_cos_sin_mod(erom, sb, 32);
+    for (int k = 0; k < 32; k++) { /* generic:1490-1505, usb - lsb = 32 */
+      const i32 ch = tcos[2 * k], sh = tcos[2 * k + 1], re = sb[k], im = sb[64 + k];
+      const i32 r2 = (i32)(((i64)re * ch + (i64)im * sh) >> 31);
+      const i64 x = (i64)im * ch, y = (i64)re * sh;
+      i64 d;
+      if (__builtin_sub_overflow(x, y, &d)) d = x < 0 ? INT64_MIN : INT64_MAX;
+      qmf[128 * i + k] = (float)r2 * (1.0f / 256.0f);
+      qmf[128 * i + 64 + k] = (float)(i32)(d >> 31) * (1.0f / 256.0f);
+    }
+  }
+  *pos_io = pos;
+  *fpos_io = f1;
+}
+void xo_esbr_anal32_batch(const uint8_t *erom, const float *time_in, i32 *states, i32 *pos, float *qmf, int n) {
+  for (int u = 0; u < n; u++)
+    xo_esbr_anal32(erom, time_in + (size_t)u * 1024, states + (size_t)u * 320, pos + 2 * u, pos + 2 * u + 1, qmf + (size_t)u * 4096);
 }

@@ -305,8 +305,14 @@ void xo_peak_limiter_batch(int32_t *st, int32_t *samples, const int8_t *qshift_a
 #define XO_EROM2_W32 5120         /* WORD32[60]   esbr_w_32 */
 #define XO_EROM2_SINCOS_L64 5360  /* WORD32[64]   esbr_sin_cos_twiddle_l64 */
 #define XO_EROM2_ALTSIN_L64 5616  /* WORD32[32]   esbr_alt_sin_twiddle_l64 */
-#define XO_EROM2_BYTES 5744
+#define XO_EROM2_W16 5744         /* WORD32[24]   esbr_w_16 */
+#define XO_EROM2_SINCOS_L32 5840  /* WORD32[32]   esbr_sin_cos_twiddle_l32 */
+#define XO_EROM2_ALTSIN_L32 5968  /* WORD32[16]   esbr_alt_sin_twiddle_l32 */
+#define XO_EROM2_TCOS_L32 6032    /* WORD32[64]   esbr_t_cos_sin_l32 */
+#define XO_EROM2_BYTES 6288
 void xo_esbr_synth64(const uint8_t *erom, const float *qmf, int32_t *fs, int32_t *off_io, int32_t *fpos_io, float *out);
 void xo_esbr_synth64_batch(const uint8_t *erom, const float *qmf, int32_t *fs, int32_t *pos, float *out, int n);
+void xo_esbr_anal32(const uint8_t *erom, const float *time_in, int32_t *states, int32_t *pos_io, int32_t *fpos_io, float *qmf);
+void xo_esbr_anal32_batch(const uint8_t *erom, const float *time_in, int32_t *states, int32_t *pos, float *qmf, int n);
 
 #endif

@@ -214,6 +214,15 @@ class Oracle:
         self.lib.xo_esbr_synth64_batch(P(self.esrom), P(q), P(f), P(p), P(out), q.shape[0])
         return out, f, p
 
+    def esbr_anal_batch(self, time_in, states, pos):
+        """time_in float32 [n,1024], states int32 [n,320], pos int32 [n,2].  Returns (qmf float32 [n,32,128], states', pos')."""
+        t = np.ascontiguousarray(time_in, np.float32)
+        f = np.ascontiguousarray(states, np.int32).copy()
+        p = np.ascontiguousarray(pos, np.int32).copy()
+        q = np.zeros((t.shape[0], 32, 128), np.float32)
+        self.lib.xo_esbr_anal32_batch(P(self.esrom), P(t), P(f), P(p), P(q), t.shape[0])
+        return q, f, p
+
     def peak_limiter_batch(self, st, samples, qshift_adj, ch):
         """st [n,1548] int32 (XO_PL_*), samples int32 [n,1024,ch], qshift_adj int8 [n,ch].
         Returns (st', samples', pcm16, err)."""
@@ -304,6 +313,14 @@ class Ref:
         out = np.zeros((q.shape[0], 2048), np.float32)
         self.lib.ref_esbr_synth64_batch(P(q), P(f), P(p), P(out), q.shape[0])
         return out, f, p
+
+    def esbr_anal_batch(self, time_in, states, pos):
+        t = np.ascontiguousarray(time_in, np.float32)
+        f = np.ascontiguousarray(states, np.int32).copy()
+        p = np.ascontiguousarray(pos, np.int32).copy()
+        q = np.zeros((t.shape[0], 32, 128), np.float32)
+        self.lib.ref_esbr_anal32_batch(P(t), P(f), P(p), P(q), t.shape[0])
+        return q, f, p
 
     def peak_limiter_init(self, ch, sample_rate):
         st = np.zeros(PL_WORDS, np.int32)
@@ -703,3 +720,28 @@ def synth_esbr_units(n, seed):
         qmf[1] = 3.0e7
         fs[0] = 0
     return qmf, fs, pos
+
+
+def synth_esbr_anal_units(n, seed):
+    """float core samples [n,1024] in the float eSBR path's scale (+-1.0 = full scale after the 2^-15 hand-over), ring
+    states [n,320] and lock-step (position, coefficient phase) pairs"""
+    rng = np.random.default_rng(seed)
+    amp = 2.0 ** rng.uniform(-14, 0.5, (n, 1))
+    x = np.zeros((n, 1024), np.float32)
+    t = np.arange(1024)
+    for u in range(n):
+        k = u % 3
+        if k == 0:
+            s = np.sin(2 * np.pi * rng.uniform(0.001, 0.45) * t + rng.uniform(0, 6))
+        elif k == 1:
+            s = rng.standard_normal(1024) / 3
+        else:
+            s = rng.uniform(-1, 1, 1024)
+        x[u] = (s * amp[u]).astype(np.float32)
+    st = ((rng.random((n, 320)) * 2 - 1) * 2.0 ** rng.integers(2, 16, (n, 1))).astype(np.int64).astype(np.int32)
+    ph = rng.integers(0, 5, n)
+    pos = np.stack([(64 * ph) % 320, (128 * ((5 - ph) % 5)) % 640], 1).astype(np.int32)
+    if n > 2:
+        x[0] = 0
+        st[0] = 0
+    return x, st, pos

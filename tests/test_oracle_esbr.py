@@ -30,3 +30,36 @@ def test_esbr_synth_stream_state_carry(oracle, ref):
         o2, fs2, pos2 = ref.esbr_synth_batch(qmf, fs2, pos2)
         assert np.array_equal(o1.view(np.int32), o2.view(np.int32)) and np.array_equal(fs1, fs2) and np.array_equal(pos1, pos2)
     assert set(map(tuple, pos1.tolist())) <= {(0, 0), (256, 512), (512, 384), (768, 256), (1024, 128)}
+
+
+def test_esbr_anal_matches_reference(oracle, ref):
+    """ixheaacd_esbr_analysis_filt_block itself (32 channels, 32 slots) on a minimal ia_sbr_dec_struct"""
+    n = 200
+    x, st, pos = oracle_util.synth_esbr_anal_units(n, 3)
+    q1, s1, p1 = oracle.esbr_anal_batch(x, st, pos)
+    q2, s2, p2 = ref.esbr_anal_batch(x, st, pos)
+    assert np.array_equal(p1, p2) and np.array_equal(s1, s2)
+    for u in range(n):
+        assert np.array_equal(q1[u].view(np.int32), q2[u].view(np.int32)), f"unit {u}: {np.argwhere(q1[u] != q2[u])[:4].tolist()}"
+    assert np.abs(q2).max() > 0.01
+
+
+def test_esbr_anal_synth_stream(oracle, ref):
+    """analysis -> synthesis over 6 frames with both states carried (the low band passes straight through)"""
+    n = 8
+    x0, st, pos = oracle_util.synth_esbr_anal_units(n, 4)
+    st[:] = 0
+    pos[:] = 0
+    st2, pos2 = st.copy(), pos.copy()
+    fs = np.zeros((n, 1280), np.int32)
+    sp = np.zeros((n, 2), np.int32)
+    fs2, sp2 = fs.copy(), sp.copy()
+    for f in range(6):
+        x, _, _ = oracle_util.synth_esbr_anal_units(n, 30 + f)
+        q1, st, pos = oracle.esbr_anal_batch(x, st, pos)
+        q2, st2, pos2 = ref.esbr_anal_batch(x, st2, pos2)
+        assert np.array_equal(q1.view(np.int32), q2.view(np.int32)), f"frame {f}"
+        o1, fs, sp = oracle.esbr_synth_batch(q1, fs, sp)
+        o2, fs2, sp2 = ref.esbr_synth_batch(q2, fs2, sp2)
+        assert np.array_equal(o1.view(np.int32), o2.view(np.int32)), f"frame {f}"
+    assert np.array_equal(st, st2) and np.array_equal(fs, fs2)

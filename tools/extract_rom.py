@@ -48,9 +48,10 @@ EXTRA = [("ref_rom_qmf_tables", 3464, "qmf_rom.bin"), ("ref_rom_env_tables", 240
          # USAC frequency-domain core transform: FFT twiddles, pre / post twiddles (512, 64), sine / KBD windows (1024, 128)
          # concatenated by ref_rom_usac_tables (oracle/ref_shim_usac.c; layout XAAC_UROM_* in include/xaac_b200.h)
          ("ref_rom_usac_tables", 15880, "usac_rom.bin"),
-         # eSBR 64-band synthesis bank: esbr_qmf_c[1280], esbr_w_32[60], esbr_sin_cos_twiddle_l64[64], esbr_alt_sin_twiddle_l64[32]
+         # eSBR banks: esbr_qmf_c[1280], esbr_w_32[60], esbr_sin_cos_twiddle_l64[64], esbr_alt_sin_twiddle_l64[32], esbr_w_16[24],
+         # esbr_sin_cos_twiddle_l32[32], esbr_alt_sin_twiddle_l32[16], esbr_t_cos_sin_l32[64]
          # of ia_qmf_dec_tables_struct (decoder/ixheaacd_sbr_rom.h:96-105), concatenated by ref_rom_esbr_tables
-         ("ref_rom_esbr_tables", 5744, "esbr_rom.bin")]
+         ("ref_rom_esbr_tables", 6288, "esbr_rom.bin")]
 
 if __name__ == "__main__":
     main()
