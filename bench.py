@@ -43,6 +43,7 @@ CHAIN_KERNEL_BYTES = {
     # per channel unit (a stream = 2 units): 4096 WORD32 in + 2048 PCM16 out + 2 x 1.35 KB limiter state (220-sample window)
     "peak_limiter_kernel": 8850,
 }
+ESBR_ANAL_BYTES_PER_UNIT = 14848   # 4096 float in + 1280 + 1280 WORD32 ring + 8192 (32 x 32 complex float out)
 ESBR_SYNTH_BYTES_PER_UNIT = 34816  # 16384 float matrix + 5120 + 5120 WORD32 state + 8192 float out
 USAC_FD_BYTES_PER_UNIT = 16384  # 4096 coefficients + 4096 overlap in + 4096 overlap out + 4096 WORD32 out
 WORKLOADS = {
@@ -57,6 +58,8 @@ WORKLOADS = {
     "usac_fd_imdct": (4, 131072, "xHE-AAC/USAC stereo 32 kHz batch=131072: the fixed-point FD core transform of the chain "
                                  "(ixheaacd_fd_frm_dec: IMDCT 1024/128 + windowing + overlap); the float eSBR stage is not "
                                  "built yet"),
+    "esbr_anal32": (4, 65536, "xHE-AAC/USAC eSBR stereo 32 kHz: the 32-band eSBR QMF analysis bank of the chain "
+                              "(ixheaacd_esbr_analysis_filt_block), batch=65536 stereo frames (131072 core channels)"),
     "esbr_synth64": (4, 65536, "xHE-AAC/USAC eSBR stereo 32 kHz: the 64-band eSBR QMF synthesis bank of the chain (per-slot core of "
                                "ixheaacd_esbr_synthesis_filt_block), batch=65536 stereo frames (131072 output channels)"),
     "qmf_synth_hq": (3, 65536, "stand-alone fixed-point HQ 64-band QMF synthesis stage of the HE-AAC chain, "
@@ -481,6 +484,44 @@ def cpu_arm_lc_output(n_units, threads, seed, reps=1, min_seconds=0.0):
     return n_units * done / dt, "reference"
 
 
+def cpu_arm_esbr_anal(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time ixheaacd_esbr_analysis_filt_block per unit on host threads (ref_esbr_anal32, oracle/ref_shim.c)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    P = oracle_util.P
+    x, st, pos = oracle_util.synth_esbr_anal_units(n_units, seed)
+    st[:] = 0
+    pos[:] = 0
+    qmf = np.zeros((n_units, 32, 128), np.float32)
+    bounds = np.linspace(0, n_units, threads + 1).astype(int)
+    if ref is not None:
+        kind, fn, pre = "reference", ref.lib.ref_esbr_anal32_batch, []
+    else:
+        orc = oracle_util.Oracle()
+        kind, fn, pre = "port", orc.lib.xo_esbr_anal32_batch, [P(orc.esrom)]
+
+    def work(t):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            fn(*pre, P(x[a:b]), P(st[a:b]), P(pos[a:b]), P(qmf[a:b]), b - a)
+
+    def one_pass():
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for z in th:
+            z.start()
+        for z in th:
+            z.join()
+        return time.perf_counter() - t0
+
+    one_pass()
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass()
+        done += 1
+    return n_units * done / dt, kind
+
+
 def cpu_arm_esbr_synth(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time the reference's eSBR synthesis leaves per unit on host threads (ref_esbr_synth64, oracle/ref_shim.c)."""
     from tests import oracle_util
@@ -621,6 +662,11 @@ STAGES = {
                                 "(fixed-point WORD32, bit-exact)",
                           ref_stage="ixheaacd_fd_frm_dec", cpu=cpu_arm_usac, cpu_units_per_core=2048, realtime_fps=31.25,
                           h2d=4096 + 2, d2h=4096),
+    "esbr_anal32": dict(kernel="esbr_anal_kernel", bytes_per_unit=ESBR_ANAL_BYTES_PER_UNIT,
+                        stage="eSBR 32-band QMF analysis: float -> WORD32, 5-tap window with WORD64 accumulation, forward "
+                              "modulation (2 x 16-point FFT, 32-bit twiddles), t_cos rotation, -> float (bit-exact)",
+                        ref_stage="ixheaacd_esbr_analysis_filt_block", cpu=cpu_arm_esbr_anal, cpu_units_per_core=2048,
+                        realtime_fps=15.625, h2d=4096, d2h=8192),
     "esbr_synth64": dict(kernel="esbr_synth_kernel", bytes_per_unit=ESBR_SYNTH_BYTES_PER_UNIT,
                          stage="eSBR 64-band QMF synthesis: float -> WORD32, inverse modulation (2 x 32-point FFT, 32-bit "
                                "twiddles), 10-tap window with WORD64 accumulation, -> float (bit-exact)",
@@ -775,6 +821,42 @@ class ChainWork:
         self.h_imdct.close()
         self.h_state.close()
         self.state.close()
+
+
+class EsbrAnalWork:
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        amp = torch.exp2(torch.rand((n_units, 1), generator=g, device=dev) * 12 - 12)
+        self.x = (torch.rand((n_units, 1024), generator=g, device=dev) * 2 - 1) * amp
+        self.state = xb.EsbrAnalBatch(n_units, device=dev)
+        self.qmf = torch.zeros((n_units, 32, 128), dtype=torch.float32, device=dev)
+        self.err = torch.zeros((n_units,), dtype=torch.int32, device=dev)
+
+    def step(self, i, stream):
+        self.xb.esbr_analysis_filt_block(self.ctx, self.state, self.x, self.qmf, self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0
+
+    def host_setup(self):
+        import torch
+        self.h_x = torch.empty((self.n, 1024), dtype=torch.float32).pin_memory()
+        self.h_x.copy_(self.x)
+        self.h_q = torch.empty((self.n, 32, 128), dtype=torch.float32).pin_memory()
+        self.d_x = torch.empty_like(self.x)
+
+    def host_step(self, i):
+        import torch
+        self.d_x.copy_(self.h_x, non_blocking=True)
+        self.xb.esbr_analysis_filt_block(self.ctx, self.state, self.d_x, self.qmf, self.err)
+        self.h_q.copy_(self.qmf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
 
 
 class EsbrSynthWork:
@@ -957,7 +1039,8 @@ class ChainLpWork:
 
 WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv2_chain": ChainWork,
         "heaacv1_stereo_chain": ChainLpWork, "usac_fd_imdct": UsacFdWork,
-        "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork}
+        "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork,
+        "esbr_anal32": EsbrAnalWork}
 
 
 def main():

@@ -433,6 +433,12 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
       if (lane == 0 && p.err) p.err[u] = (i32)0x80000000;
       continue;
     }
+    if (u + warps_total < p.n_units) {  // pull the next unit's input and ring into L2 while this one computes
+      const char *q0 = reinterpret_cast<const char *>(tin + warps_total * 1024);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + lane * 128));
+      const char *q1 = reinterpret_cast<const char *>(ring + warps_total * 320);
+      if (lane < 10) asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + lane * 128));
+    }
     const int P0 = pos >> 5, F0 = f1 >> 6;
     const bool lock = p.periodic && (pos & 63) == 0 && (f1 & 127) == 0 && pos <= 256 && f1 <= 512 && ((P0 + F0) % 10 == 0);
     if (lock) {
@@ -443,8 +449,13 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
         if (q >= 10) q -= 10;
         w.T[j] = ring[32 * q + 31 - (j & 31)];
       }
-#pragma unroll 4
-      for (int j = lane; j < 1024; j += 32) w.T[288 + j] = f2i_x86(__fmul_rn(__ldg(tin + j), 32768.0f));
+      {
+        float v[32];  // all 32 loads in flight before the first conversion
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = __ldg(tin + 32 * j + lane);
+#pragma unroll
+        for (int j = 0; j < 32; j++) w.T[288 + 32 * j + lane] = f2i_x86(__fmul_rn(v[j], 32768.0f));
+      }
       i32 ca[5], cb[5];
 #pragma unroll
       for (int m = 0; m < 5; m++) {
