@@ -481,6 +481,41 @@ int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32
 int32_t xaac_b200_esbr_anal32_dev(xaac_b200_ctx *ctx, const float *d_time_in, int32_t *d_states, int32_t *d_pos, float *d_qmf,
                                   int32_t *d_err, int64_t n_units, void *stream);
 
+/* eSBR float HF generator: batched ixheaacd_generate_hf (decoder/ixheaacd_sbrdec_lpfuncs.c:981-1359) with
+ * ixheaacd_esbr_calc_co_variance (:781) and ixheaacd_esbr_chirp_fac_calc (:832), for the 2:1 system (is_usf_4 == 0) without
+ * pre-processing, LD-MPS and error concealment (units asking for those get err = -2 and are left to the reference).
+ * Float results are bit-identical to the reference build's (one IEEE rounding per operation, same order).
+ * QMF buffers are [n][XAAC_EHF_ROWS][64] floats and are the reference's own arrays from their FIRST row, i.e. row r is row
+ * r - SBR_HF_ADJ_OFFSET of the pointers ixheaacd_sbr_dec passes (decoder/ixheaacd_sbr_dec.c:921-929):
+ *   d_src_re/im  ptr_sbr_dec->qmf_buf_real / qmf_buf_imag                  (read: bands < f_master_tbl[0])
+ *   d_pv_re/im   ptr_sbr_dec->ph_vocod_qmf_real / ph_vocod_qmf_imag, or both NULL (no harmonic transposer)
+ *   d_dst_re/im  ptr_sbr_dec->sbr_qmf_out_real / sbr_qmf_out_imag, in/out: exactly the cells the reference writes
+ *   d_par        [n][XAAC_EHF_PAR_WORDS] WORD32, word offsets below
+ *   d_bw_prev    [n][6] float  ptr_frame_data->bw_array_prev, in/out
+ *   d_patch_out  [n][8] WORD32 {patch_param.num_patches, patch_param.start_subband[0..6]} or NULL
+ *   d_err        [n] or NULL: 0, -1 (the reference's own failure returns) or -2 (outside the supported subset) */
+#define XAAC_EHF_ROWS 40
+#define XAAC_EHF_NUM_MF 0         /* pstr_freq_band_data->num_mf_bands */
+#define XAAC_EHF_NUM_IF 1         /* pstr_freq_band_data->num_nf_bands */
+#define XAAC_EHF_SB_START 2       /* pstr_freq_band_data->sub_band_start */
+#define XAAC_EHF_BORDER_FIRST 3   /* str_frame_info_details.border_vec[0] */
+#define XAAC_EHF_BORDER_LAST 4    /* str_frame_info_details.border_vec[num_env] */
+#define XAAC_EHF_HBE_FLAG 5       /* ptr_header_data->hbe_flag */
+#define XAAC_EHF_PATCHING_MODE 6  /* ptr_frame_data->sbr_patching_mode */
+#define XAAC_EHF_FS 7             /* ptr_header_data->out_sampling_freq */
+#define XAAC_EHF_PRE_PROC 8       /* ptr_header_data->pre_proc_flag (must be 0) */
+#define XAAC_EHF_USF4 9           /* ptr_header_data->is_usf_4 (must be 0) */
+#define XAAC_EHF_MPS_SBR 10       /* ptr_frame_data->mps_sbr_flag */
+#define XAAC_EHF_COV_COUNT 11     /* ptr_frame_data->cov_count */
+#define XAAC_EHF_INVF 16          /* ptr_frame_data->sbr_invf_mode[0..4] */
+#define XAAC_EHF_INVF_PREV 21     /* ptr_frame_data->sbr_invf_mode_prev[0..4] */
+#define XAAC_EHF_INVF_TBL 26      /* pstr_freq_band_data->freq_band_tbl_noise[1..5] */
+#define XAAC_EHF_FMASTER 32       /* pstr_freq_band_data->f_master_tbl[0..56] */
+#define XAAC_EHF_PAR_WORDS 96
+int32_t xaac_b200_esbr_generate_hf_dev(xaac_b200_ctx *ctx, const float *d_src_re, const float *d_src_im, const float *d_pv_re,
+                                       const float *d_pv_im, float *d_dst_re, float *d_dst_im, const int32_t *d_par,
+                                       float *d_bw_prev, int32_t *d_patch_out, int32_t *d_err, int64_t n_units, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

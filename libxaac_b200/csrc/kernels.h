@@ -302,6 +302,22 @@ struct EsbrAnalArgs {
 };
 cudaError_t launch_esbr_anal(const EsbrAnalArgs &args, int num_sms, cudaStream_t stream);
 
+// eSBR float HF generator (ixheaacd_generate_hf): par[] word offsets = XAAC_EHF_* of include/xaac_b200.h
+constexpr int kEhfNumMf = 0, kEhfNumIf = 1, kEhfSbStart = 2, kEhfBorderFirst = 3, kEhfBorderLast = 4, kEhfHbeFlag = 5,
+              kEhfPatchingMode = 6, kEhfFs = 7, kEhfPreProc = 8, kEhfUsf4 = 9, kEhfMpsSbr = 10, kEhfCovCount = 11,
+              kEhfInvf = 16, kEhfInvfPrev = 21, kEhfInvfTbl = 26, kEhfFmaster = 32, kEhfParWords = 96;
+struct EsbrHfgenArgs {
+  const float *src_re, *src_im;  // [n][40][64] low-band QMF (qmf_buf_real / imag from their first row)
+  const float *pv_re, *pv_im;    // [n][40][64] phase-vocoder QMF (ph_vocod_qmf_real / imag) or null
+  float *dst_re, *dst_im;        // [n][40][64] sbr_qmf_out_real / imag, in/out (only the cells the reference writes)
+  const int32_t *par;            // [n][96]
+  float *bw_prev;                // [n][6] bw_array_prev, in/out
+  int32_t *patch_out;            // [n][8] {num_patches, start_subband[7]} or null
+  int32_t *err;                  // [n] or null
+  long long n_units;
+};
+cudaError_t launch_esbr_hfgen(const EsbrHfgenArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

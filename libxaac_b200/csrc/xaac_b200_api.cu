@@ -1052,6 +1052,23 @@ int32_t xaac_b200_esbr_anal32_dev(xaac_b200_ctx *ctx, const float *d_time_in, in
   return XAAC_B200_OK;
 }
 
+int32_t xaac_b200_esbr_generate_hf_dev(xaac_b200_ctx *ctx, const float *d_src_re, const float *d_src_im, const float *d_pv_re,
+                                       const float *d_pv_im, float *d_dst_re, float *d_dst_im, const int32_t *d_par,
+                                       float *d_bw_prev, int32_t *d_patch_out, int32_t *d_err, int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_src_re || !d_src_im || !d_dst_re || !d_dst_im || !d_par || !d_bw_prev) return bad_arg(ctx, "null buffer");
+  if ((d_pv_re == nullptr) != (d_pv_im == nullptr)) return bad_arg(ctx, "pv_re / pv_im must both be given or both be null");
+  xb::EsbrHfgenArgs a;
+  a.src_re = d_src_re; a.src_im = d_src_im; a.pv_re = d_pv_re; a.pv_im = d_pv_im; a.dst_re = d_dst_re; a.dst_im = d_dst_im;
+  a.par = d_par; a.bw_prev = d_bw_prev; a.patch_out = d_patch_out; a.err = d_err; a.n_units = n_units;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  LAUNCH("esbr_hfgen_kernel", stream, xb::launch_esbr_hfgen(a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
 int32_t xaac_b200_kernel_timing(xaac_b200_ctx *ctx, int32_t enable) {
   if (!ctx) return XAAC_B200_ERR_ARG;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");

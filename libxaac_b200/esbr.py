@@ -65,3 +65,38 @@ def esbr_analysis_filt_block(ctx, state, time_in, qmf=None, err=None, stream=Non
                                            n, ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_esbr_anal32_dev")
     return qmf, err
+
+
+EHF_ROWS, EHF_PAR_WORDS = 40, 96
+
+
+def esbr_generate_hf(ctx, src_re, src_im, dst_re, dst_im, par, bw_prev, pv_re=None, pv_im=None, patch_out=None, err=None,
+                     stream=None):
+    """Batched drop-in for ixheaacd_generate_hf (decoder/ixheaacd_sbrdec_lpfuncs.c:981), 2:1 system without
+    pre-processing.  QMF buffers float32 [n, 40, 64] = the reference's arrays from their first row (row r = row r - 2 of the
+    pointers the reference passes); dst_* and bw_prev [n, 6] are updated in place; par int32 [n, 96] (XAAC_EHF_* words).
+    Returns (patch_out int32 [n, 8] = {num_patches, start_subband[7]}, err int32 [n])."""
+    n = par.shape[0]
+    dev = par.device
+    for t, nm in ((src_re, "src_re"), (src_im, "src_im"), (dst_re, "dst_re"), (dst_im, "dst_im")):
+        _chk(t, torch.float32, (n, EHF_ROWS, 64), nm, "cuda")
+    if (pv_re is None) != (pv_im is None):
+        raise ValueError("pv_re and pv_im must both be given or both be None")
+    if pv_re is not None:
+        _chk(pv_re, torch.float32, (n, EHF_ROWS, 64), "pv_re", "cuda")
+        _chk(pv_im, torch.float32, (n, EHF_ROWS, 64), "pv_im", "cuda")
+    _chk(par, torch.int32, (n, EHF_PAR_WORDS), "par", "cuda")
+    _chk(bw_prev, torch.float32, (n, 6), "bw_prev", "cuda")
+    if patch_out is None:
+        patch_out = torch.zeros((n, 8), dtype=torch.int32, device=dev)
+    _chk(patch_out, torch.int32, (n, 8), "patch_out", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=dev)
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    rc = ctx._lib.xaac_b200_esbr_generate_hf_dev(ctx.handle, _ptr(src_re), _ptr(src_im), _ptr(pv_re) if pv_re is not None else None,
+                                                 _ptr(pv_im) if pv_im is not None else None, _ptr(dst_re), _ptr(dst_im),
+                                                 _ptr(par), _ptr(bw_prev), _ptr(patch_out), _ptr(err), n,
+                                                 ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_generate_hf_dev")
+    return patch_out, err

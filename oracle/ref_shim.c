@@ -603,3 +603,59 @@ void ref_esbr_anal32_batch(const float *time_in, int32_t *states, int32_t *pos, 
   for (int u = 0; u < n; u++)
     ref_esbr_anal32(time_in + (size_t)u * 1024, states + (size_t)u * 320, pos + 2 * u, qmf + (size_t)u * 4096);
 }
+
+/* ---- eSBR float HF generator: the unmodified ixheaacd_generate_hf (decoder/ixheaacd_sbrdec_lpfuncs.c:981) on flat
+ * records in the XO_EHF_* layout (oracle/src/xaac_oracle.h).  Buffers are [40][64]; the reference gets them + 2 rows. */
+WORD32 ixheaacd_generate_hf(FLOAT32 ptr_src_buf_real[][64], FLOAT32 ptr_src_buf_imag[][64],
+                            FLOAT32 ptr_ph_vocod_buf_real[][64], FLOAT32 ptr_ph_vocod_buf_imag[][64],
+                            FLOAT32 ptr_dst_buf_real[][64], FLOAT32 ptr_dst_buf_imag[][64],
+                            ia_sbr_frame_info_data_struct *ptr_frame_data, ia_sbr_header_data_struct *ptr_header_data,
+                            WORD32 ldmps_present, WORD32 time_slots, WORD32 ec_flag);
+int ref_esbr_generate_hf(const float *src_re, const float *src_im, const float *pv_re, const float *pv_im, float *dst_re,
+                         float *dst_im, const int32_t *par, float *bw_prev, int32_t *patch_out) {
+  static __thread ia_sbr_frame_info_data_struct fd;
+  static __thread ia_sbr_header_data_struct hd;
+  static __thread ia_freq_band_data_struct fb;
+  memset(&fd, 0, sizeof(fd));
+  memset(&hd, 0, sizeof(hd));
+  memset(&fb, 0, sizeof(fb));
+  hd.pstr_freq_band_data = &fb;
+  fb.num_mf_bands = (WORD16)par[XO_EHF_NUM_MF];
+  fb.num_nf_bands = (WORD16)par[XO_EHF_NUM_IF];
+  fb.sub_band_start = (WORD16)par[XO_EHF_SB_START];
+  for (int i = 0; i < 5; i++) fb.freq_band_tbl_noise[1 + i] = (WORD16)par[XO_EHF_INVF_TBL + i];
+  for (int i = 0; i < 57; i++) fb.f_master_tbl[i] = (WORD16)par[XO_EHF_FMASTER + i];
+  fd.str_frame_info_details.num_env = 1;
+  fd.str_frame_info_details.border_vec[0] = (WORD16)par[XO_EHF_BORDER_FIRST];
+  fd.str_frame_info_details.border_vec[1] = (WORD16)par[XO_EHF_BORDER_LAST];
+  hd.hbe_flag = par[XO_EHF_HBE_FLAG];
+  fd.sbr_patching_mode = par[XO_EHF_PATCHING_MODE];
+  hd.out_sampling_freq = par[XO_EHF_FS];
+  hd.pre_proc_flag = par[XO_EHF_PRE_PROC];
+  hd.is_usf_4 = par[XO_EHF_USF4];
+  fd.mps_sbr_flag = par[XO_EHF_MPS_SBR];
+  fd.cov_count = par[XO_EHF_COV_COUNT];
+  for (int i = 0; i < 5; i++) {
+    fd.sbr_invf_mode[i] = par[XO_EHF_INVF + i];
+    fd.sbr_invf_mode_prev[i] = par[XO_EHF_INVF_PREV + i];
+  }
+  for (int i = 0; i < 6; i++) fd.bw_array_prev[i] = bw_prev[i];
+  typedef FLOAT32(*rows_t)[64];
+  WORD32 e = ixheaacd_generate_hf((rows_t)(src_re + 128), (rows_t)(src_im + 128), pv_re ? (rows_t)(pv_re + 128) : NULL,
+                                  pv_im ? (rows_t)(pv_im + 128) : NULL, (rows_t)(dst_re + 128), (rows_t)(dst_im + 128),
+                                  &fd, &hd, 0, 32, 0);
+  if (e) return e;
+  patch_out[0] = fd.patch_param.num_patches;
+  for (int i = 0; i < 7; i++) patch_out[1 + i] = fd.patch_param.start_subband[i];
+  for (int i = 0; i < 6; i++) bw_prev[i] = fd.bw_array_prev[i];
+  return 0;
+}
+void ref_esbr_generate_hf_batch(const float *src_re, const float *src_im, const float *pv_re, const float *pv_im,
+                                float *dst_re, float *dst_im, const int32_t *par, float *bw_prev, int32_t *patch_out,
+                                int32_t *err, int n) {
+  const size_t B = (size_t)XO_EHF_ROWS * 64;
+  for (int u = 0; u < n; u++)
+    err[u] = ref_esbr_generate_hf(src_re + u * B, src_im + u * B, pv_re ? pv_re + u * B : 0, pv_im ? pv_im + u * B : 0,
+                                  dst_re + u * B, dst_im + u * B, par + (size_t)u * XO_EHF_PAR_WORDS, bw_prev + 6 * u,
+                                  patch_out + 8 * u);
+}

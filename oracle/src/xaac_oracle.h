@@ -315,4 +315,33 @@ void xo_esbr_synth64_batch(const uint8_t *erom, const float *qmf, int32_t *fs, i
 void xo_esbr_anal32(const uint8_t *erom, const float *time_in, int32_t *states, int32_t *pos_io, int32_t *fpos_io, float *qmf);
 void xo_esbr_anal32_batch(const uint8_t *erom, const float *time_in, int32_t *states, int32_t *pos, float *qmf, int n);
 
+/* ---- eSBR float HF generator (esbr_hfgen.c): ixheaacd_generate_hf ------------------------------------------------------
+ * QMF buffers are [XO_EHF_ROWS][64] floats; row r is row r - 2 of the pointers the reference passes
+ * (qmf_buf_real + SBR_HF_ADJ_OFFSET etc.), i.e. the reference's own arrays from their first row. par[] words: */
+#define XO_EHF_ROWS 40
+#define XO_EHF_NUM_MF 0        /* pstr_freq_band_data->num_mf_bands */
+#define XO_EHF_NUM_IF 1        /* pstr_freq_band_data->num_nf_bands */
+#define XO_EHF_SB_START 2      /* pstr_freq_band_data->sub_band_start */
+#define XO_EHF_BORDER_FIRST 3  /* str_frame_info_details.border_vec[0] */
+#define XO_EHF_BORDER_LAST 4   /* border_vec[num_env] */
+#define XO_EHF_HBE_FLAG 5
+#define XO_EHF_PATCHING_MODE 6 /* sbr_patching_mode */
+#define XO_EHF_FS 7            /* out_sampling_freq */
+#define XO_EHF_PRE_PROC 8      /* pre_proc_flag: not restated (libm log10 / pow); the kernel refuses it */
+#define XO_EHF_USF4 9          /* is_usf_4: refused (76-row covariance) */
+#define XO_EHF_MPS_SBR 10      /* mps_sbr_flag */
+#define XO_EHF_COV_COUNT 11
+#define XO_EHF_INVF 16         /* sbr_invf_mode[5] */
+#define XO_EHF_INVF_PREV 21    /* sbr_invf_mode_prev[5] */
+#define XO_EHF_INVF_TBL 26     /* freq_band_tbl_noise[1..5] */
+#define XO_EHF_FMASTER 32      /* f_master_tbl[57] */
+#define XO_EHF_PAR_WORDS 96
+/* returns 0 / -1 like the reference, -2 for a configuration outside the restated subset.  pv_* may be NULL (no HBE).
+ * patch_out[0] = num_patches, [1..7] = start_subband[]; bw_prev[6] in/out (bw_array_prev) */
+int xo_esbr_generate_hf(const float *src_re, const float *src_im, const float *pv_re, const float *pv_im, float *dst_re,
+                        float *dst_im, const int32_t *par, float *bw_prev, int32_t *patch_out);
+void xo_esbr_generate_hf_batch(const float *src_re, const float *src_im, const float *pv_re, const float *pv_im,
+                               float *dst_re, float *dst_im, const int32_t *par, float *bw_prev, int32_t *patch_out,
+                               int32_t *err, int n);
+
 #endif

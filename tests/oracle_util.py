@@ -745,3 +745,97 @@ def synth_esbr_anal_units(n, seed):
         x[0] = 0
         st[0] = 0
     return x, st, pos
+
+
+# ---- eSBR float HF generator (ixheaacd_generate_hf) ---------------------------------------------------------------------
+EHF_ROWS, EHF_PAR_WORDS = 40, 96
+EHF = dict(NUM_MF=0, NUM_IF=1, SB_START=2, BORDER_FIRST=3, BORDER_LAST=4, HBE_FLAG=5, PATCHING_MODE=6, FS=7, PRE_PROC=8,
+           USF4=9, MPS_SBR=10, COV_COUNT=11, INVF=16, INVF_PREV=21, INVF_TBL=26, FMASTER=32)
+
+
+def synth_esbr_hfgen_units(n, seed, hbe=True):
+    """Random but well-formed eSBR HF-generator units: master / noise band tables, inverse-filtering modes, frame borders,
+    low-band QMF history (noise, tones, silent bands) and, for HBE units, a phase-vocoder buffer.  Every 16th unit carries
+    a malformed noise table (the reference returns -1)."""
+    rng = np.random.default_rng(seed)
+    par = np.zeros((n, EHF_PAR_WORDS), np.int32)
+    src = np.zeros((2, n, EHF_ROWS, 64), np.float32)
+    pv = np.zeros((2, n, EHF_ROWS, 64), np.float32)
+    dst = (rng.standard_normal((2, n, EHF_ROWS, 64)) * 3).astype(np.float32)   # in/out: untouched cells must survive
+    bw_prev = np.zeros((n, 6), np.float32)
+    t = np.arange(EHF_ROWS)[:, None]
+    for u in range(n):
+        lsb = int(rng.integers(6, 33))
+        fm = [lsb]
+        while fm[-1] < 64 and len(fm) < 57:
+            w = int(rng.integers(1, 5)) if fm[-1] < 40 else int(rng.integers(2, 7))
+            if fm[-1] + w > 64 or (len(fm) > 6 and rng.random() < 0.04):
+                break
+            fm.append(fm[-1] + w)
+        if len(fm) < 3:
+            fm = [lsb, min(lsb + 4, 63), 64]
+        num_mf = len(fm) - 1
+        usb = fm[-1]
+        xi = int(rng.integers(0, min(4, num_mf)))
+        sb_start = fm[xi]
+        num_if = int(rng.integers(1, 6))
+        cuts = sorted(set(rng.choice(np.arange(sb_start + 1, usb + 1), size=min(num_if - 1, max(usb - sb_start - 1, 0)),
+                                     replace=False).tolist())) if usb - sb_start > 1 else []
+        cuts = [c for c in cuts if c < usb][: num_if - 1] + [usb]
+        num_if = len(cuts)
+        tbl = cuts + [usb] * (5 - len(cuts))
+        if u % 16 == 15:
+            tbl = [sb_start] * 5
+        p = par[u]
+        p[EHF["NUM_MF"]], p[EHF["NUM_IF"]], p[EHF["SB_START"]] = num_mf, num_if, sb_start
+        p[EHF["BORDER_FIRST"]] = int(rng.integers(0, 4))
+        p[EHF["BORDER_LAST"]] = int(rng.integers(14, 20))
+        p[EHF["HBE_FLAG"]] = int(hbe and rng.random() < 0.5)
+        p[EHF["PATCHING_MODE"]] = int(rng.random() < 0.5)
+        p[EHF["FS"]] = int(rng.choice([24000, 32000, 44100, 48000, 64000, 88200]))
+        if rng.random() < 0.15:
+            p[EHF["MPS_SBR"]] = 1
+            p[EHF["COV_COUNT"]] = int(rng.integers(0, 40))
+        p[EHF["INVF"]:EHF["INVF"] + 5] = rng.integers(0, 4, 5)
+        p[EHF["INVF_PREV"]:EHF["INVF_PREV"] + 5] = rng.integers(0, 4, 5)
+        p[EHF["INVF_TBL"]:EHF["INVF_TBL"] + 5] = tbl
+        p[EHF["FMASTER"]:EHF["FMASTER"] + len(fm)] = fm
+        bw_prev[u] = rng.choice([0.0, 0.6, 0.75, 0.9, 0.98, 0.3, 0.01], 6).astype(np.float32)
+        amp = 2.0 ** rng.uniform(-10, 10)
+        for buf in (src, pv):
+            kind = rng.integers(0, 4, 64)
+            for b in range(64):
+                if kind[b] == 0:      # noise
+                    buf[0, u, :, b] = rng.standard_normal(EHF_ROWS) * amp
+                    buf[1, u, :, b] = rng.standard_normal(EHF_ROWS) * amp
+                elif kind[b] == 1:    # tone (nearly singular covariance, large alpha)
+                    w, ph = rng.uniform(0, np.pi), rng.uniform(0, 6)
+                    buf[0, u, :, b] = np.cos(w * t[:, 0] + ph) * amp
+                    buf[1, u, :, b] = np.sin(w * t[:, 0] + ph) * amp
+                elif kind[b] == 2:    # tone + weak noise
+                    w, ph = rng.uniform(0, np.pi), rng.uniform(0, 6)
+                    buf[0, u, :, b] = (np.cos(w * t[:, 0] + ph) + 1e-3 * rng.standard_normal(EHF_ROWS)) * amp
+                    buf[1, u, :, b] = (np.sin(w * t[:, 0] + ph) + 1e-3 * rng.standard_normal(EHF_ROWS)) * amp
+                # kind 3: silent band
+    return dict(par=par, src_re=src[0], src_im=src[1], pv_re=pv[0], pv_im=pv[1], dst_re=dst[0], dst_im=dst[1],
+                bw_prev=bw_prev)
+
+
+def _esbr_hfgen_batch(fn, d, with_pv=True):
+    n = d["par"].shape[0]
+    dr, di = d["dst_re"].copy(), d["dst_im"].copy()
+    bw = d["bw_prev"].copy()
+    patch = np.zeros((n, 8), np.int32)
+    err = np.zeros(n, np.int32)
+    c = lambda a: np.ascontiguousarray(a)
+    fn(P(c(d["src_re"])), P(c(d["src_im"])), P(c(d["pv_re"])) if with_pv else None, P(c(d["pv_im"])) if with_pv else None,
+       P(dr), P(di), P(c(d["par"])), P(bw), P(patch), P(err), n)
+    return dr, di, bw, patch, err
+
+
+def oracle_esbr_hfgen_batch(orc, d, with_pv=True):
+    return _esbr_hfgen_batch(orc.lib.xo_esbr_generate_hf_batch, d, with_pv)
+
+
+def ref_esbr_hfgen_batch(ref, d, with_pv=True):
+    return _esbr_hfgen_batch(ref.lib.ref_esbr_generate_hf_batch, d, with_pv)

@@ -1,0 +1,81 @@
+"""GPU parity: esbr_hfgen_kernel (xaac_b200_esbr_generate_hf_dev) against the oracle / the compiled ixheaacd_generate_hf on
+the same seeded units — float results compared bit for bit (no tolerance), incl. cells the stage must leave untouched,
+the patch table, the chirp-factor state and the error returns."""
+import numpy as np
+import pytest
+import torch
+
+from tests import oracle_util
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(ctx, d, with_pv=True):
+    import libxaac_b200 as xb
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dr, di, bw = t(d["dst_re"]), t(d["dst_im"]), t(d["bw_prev"])
+    patch, err = xb.esbr_generate_hf(ctx, t(d["src_re"]), t(d["src_im"]), dr, di, t(d["par"]), bw,
+                                     pv_re=t(d["pv_re"]) if with_pv else None, pv_im=t(d["pv_im"]) if with_pv else None)
+    torch.cuda.synchronize()
+    return dr.cpu().numpy(), di.cpu().numpy(), bw.cpu().numpy(), patch.cpu().numpy(), err.cpu().numpy()
+
+
+def _same(a, b, what):
+    dr1, di1, bw1, pt1, e1 = a
+    dr2, di2, bw2, pt2, e2 = b
+    assert np.array_equal(e1, e2), f"{what}: err differs at {np.argwhere(e1 != e2).ravel()[:8]}"
+    ok = np.flatnonzero(e2 == 0)
+    assert np.array_equal(pt1[ok], pt2[ok]), f"{what}: patch tables"
+    assert np.array_equal(bw1[ok].view(np.int32), bw2[ok].view(np.int32)), f"{what}: bw_array_prev"
+    for x, y, nm in ((dr1, dr2, "re"), (di1, di2, "im")):
+        bad = np.argwhere(x[ok].view(np.int32) != y[ok].view(np.int32))
+        assert len(bad) == 0, f"{what}: {nm} differs in {len(bad)} cells, first (unit,row,band) {ok[bad[0][0]]},{bad[0][1:]}"
+    return len(ok)
+
+
+@pytest.mark.parametrize("with_pv", [True, False])
+def test_generate_hf_vs_oracle(ctx, oracle, with_pv):
+    d = oracle_util.synth_esbr_hfgen_units(1500, 21 + with_pv, hbe=with_pv)
+    good = _same(_run(ctx, d, with_pv), oracle_util.oracle_esbr_hfgen_batch(oracle, d, with_pv), f"pv={with_pv}")
+    assert good > 1000
+
+
+def test_generate_hf_vs_reference(ctx, ref):
+    d = oracle_util.synth_esbr_hfgen_units(600, 5)
+    _same(_run(ctx, d), oracle_util.ref_esbr_hfgen_batch(ref, d), "compiled reference")
+
+
+def test_generate_hf_stream_state(ctx, oracle):
+    """six frames with bw_array_prev carried on the device"""
+    import libxaac_b200 as xb
+    n = 64
+    d = oracle_util.synth_esbr_hfgen_units(n, 40)
+    d["par"][15::16, oracle_util.EHF["INVF_TBL"]:oracle_util.EHF["INVF_TBL"] + 5] = 64   # no failing units in the stream
+    bw_g = torch.from_numpy(d["bw_prev"]).cuda()
+    bw_o = d["bw_prev"].copy()
+    for f in range(6):
+        e = oracle_util.synth_esbr_hfgen_units(n, 50 + f)
+        for k in ("src_re", "src_im", "pv_re", "pv_im", "dst_re", "dst_im"):
+            d[k] = e[k]
+        d["par"][:, oracle_util.EHF["INVF_PREV"]:oracle_util.EHF["INVF_PREV"] + 5] = d["par"][:, oracle_util.EHF["INVF"]:oracle_util.EHF["INVF"] + 5]
+        d["par"][:, oracle_util.EHF["INVF"]:oracle_util.EHF["INVF"] + 5] = e["par"][:, oracle_util.EHF["INVF"]:oracle_util.EHF["INVF"] + 5]
+        d["bw_prev"] = bw_o
+        o = oracle_util.oracle_esbr_hfgen_batch(oracle, d)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        dr, di = t(d["dst_re"]), t(d["dst_im"])
+        patch, err = xb.esbr_generate_hf(ctx, t(d["src_re"]), t(d["src_im"]), dr, di, t(d["par"]), bw_g, pv_re=t(d["pv_re"]),
+                                         pv_im=t(d["pv_im"]))
+        torch.cuda.synchronize()
+        _same((dr.cpu().numpy(), di.cpu().numpy(), bw_g.cpu().numpy(), patch.cpu().numpy(), err.cpu().numpy()), o, f"frame {f}")
+        bw_o = o[2]
+
+
+def test_generate_hf_refuses_unsupported(ctx):
+    import libxaac_b200 as xb
+    d = oracle_util.synth_esbr_hfgen_units(8, 3)
+    d["par"][0, oracle_util.EHF["PRE_PROC"]] = 1
+    d["par"][1, oracle_util.EHF["USF4"]] = 1
+    d["par"][2, oracle_util.EHF["FS"]] = 0
+    out = _run(ctx, d)
+    assert list(out[4][:3]) == [-2, -2, -2]
+    assert np.array_equal(out[0][:3].view(np.int32), d["dst_re"][:3].view(np.int32))

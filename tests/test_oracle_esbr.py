@@ -63,3 +63,32 @@ def test_esbr_anal_synth_stream(oracle, ref):
         o2, fs2, sp2 = ref.esbr_synth_batch(q2, fs2, sp2)
         assert np.array_equal(o1.view(np.int32), o2.view(np.int32)), f"frame {f}"
     assert np.array_equal(st, st2) and np.array_equal(fs, fs2)
+
+
+def _same_hfgen(a, b, what):
+    dr1, di1, bw1, pt1, e1 = a
+    dr2, di2, bw2, pt2, e2 = b
+    assert np.array_equal(e1, e2), f"{what}: err differs at {np.argwhere(e1 != e2).ravel()[:8]}: {e1[e1 != e2][:8]} vs {e2[e1 != e2][:8]}"
+    ok = e2 == 0
+    for u in np.flatnonzero(ok):
+        assert np.array_equal(pt1[u], pt2[u]), f"{what}: unit {u} patches {pt1[u]} vs {pt2[u]}"
+        assert np.array_equal(bw1[u].view(np.int32), bw2[u].view(np.int32)), f"{what}: unit {u} bw"
+        for x, y, nm in ((dr1, dr2, "re"), (di1, di2, "im")):
+            if not np.array_equal(x[u].view(np.int32), y[u].view(np.int32)):
+                w = np.argwhere(x[u].view(np.int32) != y[u].view(np.int32))
+                raise AssertionError(f"{what}: unit {u} {nm} differs at {w[:6].tolist()} ({len(w)} cells)")
+    return int(ok.sum())
+
+
+def test_esbr_generate_hf_matches_reference(oracle, ref):
+    """ixheaacd_generate_hf itself (2:1 system, no pre-processing) — float results bit for bit, incl. untouched cells,
+    patch table, chirp-factor state and the -1 returns"""
+    d = oracle_util.synth_esbr_hfgen_units(400, 11)
+    a = oracle_util.oracle_esbr_hfgen_batch(oracle, d)
+    b = oracle_util.ref_esbr_hfgen_batch(ref, d)
+    good = _same_hfgen(a, b, "hbe buffers")
+    assert good > 300 and (b[4] == -1).sum() > 10
+    assert np.abs(b[0] - d["dst_re"]).max() > 0
+    d2 = oracle_util.synth_esbr_hfgen_units(200, 12, hbe=False)
+    _same_hfgen(oracle_util.oracle_esbr_hfgen_batch(oracle, d2, with_pv=False),
+                oracle_util.ref_esbr_hfgen_batch(ref, d2, with_pv=False), "no hbe")
