@@ -60,6 +60,9 @@ WORKLOADS = {
                                  "built yet"),
     "esbr_anal32": (4, 65536, "xHE-AAC/USAC eSBR stereo 32 kHz: the 32-band eSBR QMF analysis bank of the chain "
                               "(ixheaacd_esbr_analysis_filt_block), batch=65536 stereo frames (131072 core channels)"),
+    "esbr_generate_hf": (4, 65536, "xHE-AAC/USAC eSBR stereo: the float HF generator of the chain (ixheaacd_generate_hf: 38-slot "
+                                   "covariance, 2nd-order complex prediction, patching, HBE high band), batch=65536 stereo "
+                                   "frames (131072 core channels)"),
     "esbr_synth64": (4, 65536, "xHE-AAC/USAC eSBR stereo 32 kHz: the 64-band eSBR QMF synthesis bank of the chain (per-slot core of "
                                "ixheaacd_esbr_synthesis_filt_block), batch=65536 stereo frames (131072 output channels)"),
     "qmf_synth_hq": (3, 65536, "stand-alone fixed-point HQ 64-band QMF synthesis stage of the HE-AAC chain, "
@@ -522,6 +525,61 @@ def cpu_arm_esbr_anal(n_units, threads, seed, reps=1, min_seconds=0.0):
     return n_units * done / dt, kind
 
 
+def esbr_hfgen_bytes(par):
+    """Algorithmic HBM bytes per unit of ixheaacd_generate_hf from its parameters: covariance input (40 rows x the bands
+    it covers), patch / HBE filter input (slots + 2 rows x the high band; counted once although the HBE branch reads its
+    buffer twice), output (slots x [sub_band_start, 64)), 8 bytes per complex cell, + the 384-byte parameter record."""
+    from tests.oracle_util import EHF
+    num_mf = par[:, EHF["NUM_MF"]]
+    lsb = par[:, EHF["FMASTER"]]
+    usb = par[np.arange(len(par)), EHF["FMASTER"] + num_mf]
+    sbs = par[:, EHF["SB_START"]]
+    slots = 2 * (par[:, EHF["BORDER_LAST"]] - par[:, EHF["BORDER_FIRST"]])
+    lpc = (par[:, EHF["PATCHING_MODE"]] != 0) | (par[:, EHF["HBE_FLAG"]] == 0)
+    hb = usb - sbs
+    cells = np.where(lpc, 40 * (lsb - 1) + (slots + 2) * hb, 40 * hb) + slots * (64 - sbs)
+    return 8.0 * cells + 384
+
+
+def cpu_arm_esbr_hfgen(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time ixheaacd_generate_hf per unit on host threads (ref_esbr_generate_hf_batch, oracle/ref_shim.c)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    P = oracle_util.P
+    d = oracle_util.synth_esbr_hfgen_units(n_units, seed)
+    d["par"][15::16, oracle_util.EHF["INVF_TBL"]:oracle_util.EHF["INVF_TBL"] + 5] = 64
+    dr, di, bw = d["dst_re"].copy(), d["dst_im"].copy(), d["bw_prev"].copy()
+    patch = np.zeros((n_units, 8), np.int32)
+    err = np.zeros(n_units, np.int32)
+    bounds = np.linspace(0, n_units, threads + 1).astype(int)
+    if ref is not None:
+        kind, fn = "reference", ref.lib.ref_esbr_generate_hf_batch
+    else:
+        kind, fn = "port", oracle_util.Oracle().lib.xo_esbr_generate_hf_batch
+
+    def work(t):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            fn(P(d["src_re"][a:b]), P(d["src_im"][a:b]), P(d["pv_re"][a:b]), P(d["pv_im"][a:b]), P(dr[a:b]), P(di[a:b]),
+               P(d["par"][a:b]), P(bw[a:b]), P(patch[a:b]), P(err[a:b]), b - a)
+
+    def one_pass():
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for z in th:
+            z.start()
+        for z in th:
+            z.join()
+        return time.perf_counter() - t0
+
+    one_pass()
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass()
+        done += 1
+    return n_units * done / dt, kind
+
+
 def cpu_arm_esbr_synth(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time the reference's eSBR synthesis leaves per unit on host threads (ref_esbr_synth64, oracle/ref_shim.c)."""
     from tests import oracle_util
@@ -667,6 +725,11 @@ STAGES = {
                               "modulation (2 x 16-point FFT, 32-bit twiddles), t_cos rotation, -> float (bit-exact)",
                         ref_stage="ixheaacd_esbr_analysis_filt_block", cpu=cpu_arm_esbr_anal, cpu_units_per_core=2048,
                         realtime_fps=15.625, h2d=4096, d2h=8192),
+    "esbr_generate_hf": dict(kernel="esbr_hfgen_kernel", bytes_per_unit=None,
+                             stage="eSBR float HF generator: chirp factors, 38-slot complex covariance per low band, alpha "
+                                   "solve, patch walk + 2nd-order prediction filter, HBE high band (bit-exact floats)",
+                             ref_stage="ixheaacd_generate_hf", cpu=cpu_arm_esbr_hfgen, cpu_units_per_core=1024,
+                             realtime_fps=15.625, h2d=4 * 10240 + 384, d2h=2 * 10240, dtype="f32"),
     "esbr_synth64": dict(kernel="esbr_synth_kernel", bytes_per_unit=ESBR_SYNTH_BYTES_PER_UNIT,
                          stage="eSBR 64-band QMF synthesis: float -> WORD32, inverse modulation (2 x 32-point FFT, 32-bit "
                                "twiddles), 10-tap window with WORD64 accumulation, -> float (bit-exact)",
@@ -699,7 +762,7 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": "decoded_stereo_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (sample_units / 2) / fps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "vs_baseline": None, "dtype": stg.get("dtype", "int32"), "data": "synthetic",
         "config": {"workload": args.workload, "baseline_config": desc, "stage": stg["ref_stage"],
                    "step": f"bounded sample: {sample_units // 2} stereo frames per step on host cores"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
@@ -853,6 +916,60 @@ class EsbrAnalWork:
         self.d_x.copy_(self.h_x, non_blocking=True)
         self.xb.esbr_analysis_filt_block(self.ctx, self.state, self.d_x, self.qmf, self.err)
         self.h_q.copy_(self.qmf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
+
+
+class EsbrHfgenWork:
+    """131 072 units tiled from 1024 distinct seeded ones (tables, borders, modes, QMF history); the destination and the
+    chirp-factor state are carried on the device from step to step."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        from tests import oracle_util
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        base = min(1024, n_units)
+        d = oracle_util.synth_esbr_hfgen_units(base, seed)
+        d["par"][15::16, oracle_util.EHF["INVF_TBL"]:oracle_util.EHF["INVF_TBL"] + 5] = 64
+        # keep the units the stage accepts (random tables also produce the reference's own -1 returns, e.g. a 7th patch)
+        t0 = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in d.items()}
+        _, e0 = xb.esbr_generate_hf(ctx, t0["src_re"], t0["src_im"], t0["dst_re"].clone(), t0["dst_im"].clone(), t0["par"],
+                                    t0["bw_prev"].clone(), pv_re=t0["pv_re"], pv_im=t0["pv_im"])
+        keep = np.flatnonzero(e0.cpu().numpy() == 0)
+        d = {k: v[keep] for k, v in d.items()}
+        base = len(keep)
+        reps = (n_units + base - 1) // base
+        tile = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev).repeat((reps,) + (1,) * (a.ndim - 1))[:n_units].contiguous()
+        self.t = {k: tile(v) for k, v in d.items()}
+        self.patch = torch.zeros((n_units, 8), dtype=torch.int32, device=dev)
+        self.err = torch.zeros((n_units,), dtype=torch.int32, device=dev)
+        self.bytes_per_unit = float(esbr_hfgen_bytes(d["par"]).mean())
+
+    def step(self, i, stream):
+        t = self.t
+        self.xb.esbr_generate_hf(self.ctx, t["src_re"], t["src_im"], t["dst_re"], t["dst_im"], t["par"], t["bw_prev"],
+                                 pv_re=t["pv_re"], pv_im=t["pv_im"], patch_out=self.patch, err=self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0
+
+    def host_setup(self):
+        import torch
+        keys = ("src_re", "src_im", "pv_re", "pv_im", "par")
+        self.h_in = {k: torch.empty(self.t[k].shape, dtype=self.t[k].dtype).pin_memory() for k in keys}
+        for k in keys:
+            self.h_in[k].copy_(self.t[k])
+        self.h_out = [torch.empty(self.t[k].shape, dtype=torch.float32).pin_memory() for k in ("dst_re", "dst_im")]
+
+    def host_step(self, i):
+        import torch
+        for k, h in self.h_in.items():
+            self.t[k].copy_(h, non_blocking=True)
+        self.step(i, None)
+        self.h_out[0].copy_(self.t["dst_re"], non_blocking=True)
+        self.h_out[1].copy_(self.t["dst_im"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     def host_close(self):
@@ -1040,7 +1157,7 @@ class ChainLpWork:
 WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv2_chain": ChainWork,
         "heaacv1_stereo_chain": ChainLpWork, "usac_fd_imdct": UsacFdWork,
         "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork,
-        "esbr_anal32": EsbrAnalWork}
+        "esbr_anal32": EsbrAnalWork, "esbr_generate_hf": EsbrHfgenWork}
 
 
 def main():
@@ -1118,6 +1235,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = world * frames * K / (total_ms_max * 1e-3)
+    if getattr(work, "bytes_per_unit", None):
+        stg = dict(stg, bytes_per_unit=work.bytes_per_unit)
     kernel_ms = float(np.mean(step_ms))  # single-kernel workloads: one launch per step, step time == launch duration
     if hasattr(work, "check"):
         work.check()
@@ -1170,7 +1289,7 @@ def main():
         line = {
             "metric": "decoded_stereo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "vs_baseline": None, "dtype": stg.get("dtype", "int32"), "data": "synthetic",
             "config": {"workload": args.workload, "baseline_config": desc, "stereo_frames_per_gpu": frames,
                        "units_per_gpu": n_units, "stage": stg["stage"],
                        "l2_policy": "per-step working set > 1 GiB >> 126 MB L2 (no flush needed)",

@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(kEhWarps * 32) esbr_hfgen_kernel(EsbrHfgenArgs
     const float *pre = p.pv_re ? p.pv_re + u * kEhUnit : nullptr, *pim = p.pv_im ? p.pv_im + u * kEhUnit : nullptr;
     float *dre = p.dst_re + u * kEhUnit, *dim = p.dst_im + u * kEhUnit;
     float *bw_prev = p.bw_prev + 6 * u;
-
     if (lane < 8) {  // lpfuncs.c:832
       float bw = 0.0f;
       if (lane < num_if) {
@@ -309,7 +308,13 @@ __global__ void __launch_bounds__(kEhWarps * 32) esbr_hfgen_kernel(EsbrHfgenArgs
 
 cudaError_t launch_esbr_hfgen(const EsbrHfgenArgs &args, int num_sms, cudaStream_t stream) {
   long long need = (args.n_units + kEhWarps - 1) / kEhWarps;
-  long long grid = (long long)num_sms * 8;
+  static int occ = 0;  // persistent grid: exactly the CTAs that are resident, so "unit + warps_total" is the next one in flight
+  if (!occ) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, esbr_hfgen_kernel, kEhWarps * 32, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+  }
+  long long grid = (long long)num_sms * occ;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   esbr_hfgen_kernel<<<(unsigned)grid, kEhWarps * 32, 0, stream>>>(args);
