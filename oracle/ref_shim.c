@@ -659,3 +659,79 @@ void ref_esbr_generate_hf_batch(const float *src_re, const float *src_im, const 
                                   dst_re + u * B, dst_im + u * B, par + (size_t)u * XO_EHF_PAR_WORDS, bw_prev + 6 * u,
                                   patch_out + 8 * u);
 }
+
+/* ---- eSBR float envelope adjuster: the unmodified ixheaacd_sbr_env_calc (decoder/ixheaacd_esbr_envcal.c:71), ORIG_SBR
+ * branch, on flat records in the XO_EEC_* layout.  re / im are [40][64]; the reference gets them + 2 rows. */
+WORD32 ixheaacd_sbr_env_calc(ia_sbr_frame_info_data_struct *frame_data, FLOAT32 input_real[][64], FLOAT32 input_imag[][64],
+                             FLOAT32 input_real1[][64], FLOAT32 input_imag1[][64], WORD32 x_over_qmf[MAX_NUM_PATCHES],
+                             FLOAT32 *scratch_buff, FLOAT32 *env_out, WORD32 ldmps_present, WORD32 ec_flag);
+extern const FLOAT32 ixheaac_random_phase[512][2];
+void ref_rom_esbr_random_phase(float *out) { memcpy(out, ixheaac_random_phase, 1024 * sizeof(float)); }
+int ref_esbr_env_calc(float *re, float *im, int32_t *ipar, const float *fpar, float *state) {
+  static __thread ia_sbr_frame_info_data_struct fd;
+  static __thread ia_sbr_header_data_struct hd;
+  static __thread ia_freq_band_data_struct fb;
+  static __thread FLOAT32 scratch[1024], low_re[40][64], low_im[40][64];
+  WORD32 x_over[MAX_NUM_PATCHES] = {0};
+  memset(&fd, 0, sizeof(fd));
+  memset(&hd, 0, sizeof(hd));
+  memset(&fb, 0, sizeof(fb));
+  fd.pstr_sbr_header = &hd;
+  hd.pstr_freq_band_data = &fb;
+  fb.sub_band_start = (WORD16)ipar[XO_EEC_SB_START];
+  fb.sub_band_end = (WORD16)ipar[XO_EEC_SB_END];
+  fb.num_sf_bands[0] = (WORD16)ipar[XO_EEC_NUM_SF_LO];
+  fb.num_sf_bands[1] = (WORD16)ipar[XO_EEC_NUM_SF_HI];
+  fb.num_nf_bands = (WORD16)ipar[XO_EEC_NUM_NF];
+  fb.freq_band_table[0] = fb.freq_band_tbl_lo;
+  fb.freq_band_table[1] = fb.freq_band_tbl_hi;
+  for (int i = 0; i < 6; i++) fb.freq_band_tbl_noise[i] = (WORD16)ipar[XO_EEC_TBL_NOISE + i];
+  for (int i = 0; i < 29; i++) fb.freq_band_tbl_lo[i] = (WORD16)ipar[XO_EEC_TBL_LO + i];
+  for (int i = 0; i < 57; i++) fb.freq_band_tbl_hi[i] = (WORD16)ipar[XO_EEC_TBL_HI + i];
+  hd.is_usf_4 = ipar[XO_EEC_USF4];
+  hd.smoothing_mode = (WORD16)ipar[XO_EEC_SMOOTHING_MODE];
+  hd.interpol_freq = (WORD16)ipar[XO_EEC_INTERPOL_FREQ];
+  hd.limiter_bands = (WORD16)ipar[XO_EEC_LIMITER_BANDS];
+  hd.limiter_gains = (WORD16)ipar[XO_EEC_LIMITER_GAINS];
+  hd.esbr_start_up = ipar[XO_EEC_START_UP];
+  hd.esbr_start_up_pvc = ipar[XO_EEC_START_UP];
+  ia_frame_info_struct *fi = &fd.str_frame_info_details;
+  fi->num_env = (WORD16)ipar[XO_EEC_NUM_ENV];
+  fi->transient_env = (WORD16)ipar[XO_EEC_TRANS_ENV];
+  fi->num_noise_env = (WORD16)ipar[XO_EEC_NUM_NOISE_ENV];
+  for (int i = 0; i < 9; i++) fi->border_vec[i] = (WORD16)ipar[XO_EEC_BORDER + i];
+  for (int i = 0; i < 8; i++) fi->freq_res[i] = (WORD16)ipar[XO_EEC_FREQ_RES + i];
+  for (int i = 0; i < 3; i++) fi->noise_border_vec[i] = (WORD16)ipar[XO_EEC_NOISE_BORDER + i];
+  for (int i = 0; i < 8; i++) fd.inter_temp_shape_mode[i] = ipar[XO_EEC_INTER_TES + i];
+  for (int i = 0; i < 4; i++) fd.gate_mode[i] = ipar[XO_EEC_GATE_MODE + i];
+  for (int i = 0; i < 52; i++) fd.lim_table[i / 13][i % 13] = ipar[XO_EEC_LIM_TABLE + i];
+  for (int i = 0; i < 56; i++) fd.add_harmonics[i] = ipar[XO_EEC_ADD_HARM + i];
+  memcpy(fd.harm_flag_prev, ipar + XO_EEC_HARM_PREV, 64);
+  fd.env_short_flag_prev = ipar[XO_EEC_SHORT_PREV];
+  fd.harm_index = ipar[XO_EEC_HARM_INDEX];
+  fd.phase_index = ipar[XO_EEC_PHASE_INDEX];
+  fd.reset_flag = ipar[XO_EEC_RESET];
+  fd.sbr_mode = ipar[XO_EEC_SBR_MODE];
+  fd.prev_sbr_mode = ipar[XO_EEC_SBR_MODE];
+  fd.sbr_patching_mode = fd.prev_sbr_patching_mode = 0;
+  memcpy(fd.flt_env_sf_arr, fpar + XO_EEC_SFB_NRG, 448 * sizeof(float));
+  memcpy(fd.flt_noise_floor, fpar + XO_EEC_NOISE_FLOOR, 10 * sizeof(float));
+  memcpy(fd.e_gain, state, 320 * sizeof(float));
+  memcpy(fd.noise_buf, state + 320, 320 * sizeof(float));
+  typedef FLOAT32(*rows_t)[64];
+  WORD32 e = ixheaacd_sbr_env_calc(&fd, (rows_t)(re + 128), (rows_t)(im + 128), low_re + 2, low_im + 2, x_over, scratch, NULL, 0, 0);
+  if (e) return e;
+  memcpy(ipar + XO_EEC_HARM_PREV, fd.harm_flag_prev, 64);
+  ipar[XO_EEC_SHORT_PREV] = fd.env_short_flag_prev;
+  ipar[XO_EEC_HARM_INDEX] = fd.harm_index;
+  ipar[XO_EEC_PHASE_INDEX] = fd.phase_index;
+  ipar[XO_EEC_START_UP] = hd.esbr_start_up;
+  memcpy(state, fd.e_gain, 320 * sizeof(float));
+  memcpy(state + 320, fd.noise_buf, 320 * sizeof(float));
+  return 0;
+}
+void ref_esbr_env_calc_batch(float *re, float *im, int32_t *ipar, const float *fpar, float *state, int32_t *err, int n) {
+  for (int u = 0; u < n; u++)
+    err[u] = ref_esbr_env_calc(re + (size_t)u * 2560, im + (size_t)u * 2560, ipar + (size_t)u * XO_EEC_IPAR_WORDS,
+                               fpar + (size_t)u * XO_EEC_FPAR_WORDS, state + (size_t)u * XO_EEC_STATE_WORDS);
+}

@@ -344,4 +344,48 @@ void xo_esbr_generate_hf_batch(const float *src_re, const float *src_im, const f
                                float *dst_re, float *dst_im, const int32_t *par, float *bw_prev, int32_t *patch_out,
                                int32_t *err, int n);
 
+/* ---- eSBR float envelope adjuster (esbr_envcalc.c): ixheaacd_sbr_env_calc, ORIG_SBR branch ----------------------------
+ * ipar[] words (in/out where noted), fpar[] floats, state[] floats; QMF rows as for the HF generator (row r = row r - 2). */
+#define XO_EEC_SB_START 0
+#define XO_EEC_SB_END 1
+#define XO_EEC_NUM_ENV 2
+#define XO_EEC_TRANS_ENV 3
+#define XO_EEC_SHORT_PREV 4   /* env_short_flag_prev, in/out */
+#define XO_EEC_NUM_NOISE_ENV 5
+#define XO_EEC_NUM_SF_LO 6
+#define XO_EEC_NUM_SF_HI 7
+#define XO_EEC_NUM_NF 8
+#define XO_EEC_SMOOTHING_MODE 9
+#define XO_EEC_INTERPOL_FREQ 10
+#define XO_EEC_LIMITER_BANDS 11
+#define XO_EEC_LIMITER_GAINS 12
+#define XO_EEC_HARM_INDEX 13  /* in/out */
+#define XO_EEC_PHASE_INDEX 14 /* in/out */
+#define XO_EEC_START_UP 15    /* pstr_sbr_header->esbr_start_up, in/out */
+#define XO_EEC_RESET 16       /* reset_flag: must be 0 (limiter tables are rebuilt by the host) */
+#define XO_EEC_SBR_MODE 17    /* must be ORIG_SBR (1) */
+#define XO_EEC_USF4 18        /* must be 0 */
+#define XO_EEC_PATCHING_CHANGED 19 /* sbr_patching_mode != prev_sbr_patching_mode: must be 0 */
+#define XO_EEC_BORDER 24      /* border_vec[9] */
+#define XO_EEC_FREQ_RES 33    /* freq_res[8] */
+#define XO_EEC_NOISE_BORDER 41 /* noise_border_vec[3] */
+#define XO_EEC_INTER_TES 44   /* inter_temp_shape_mode[8]: must be 0 (gamma = 0) */
+#define XO_EEC_GATE_MODE 52   /* gate_mode[4] */
+#define XO_EEC_LIM_TABLE 56   /* lim_table[4][13] */
+#define XO_EEC_TBL_NOISE 108  /* freq_band_tbl_noise[6] */
+#define XO_EEC_TBL_LO 116     /* freq_band_tbl_lo[29] */
+#define XO_EEC_TBL_HI 148     /* freq_band_tbl_hi[57] */
+#define XO_EEC_ADD_HARM 208   /* add_harmonics[56] */
+#define XO_EEC_HARM_PREV 264  /* harm_flag_prev[64] as bytes (16 words), in/out */
+#define XO_EEC_IPAR_WORDS 288
+#define XO_EEC_SFB_NRG 0      /* flt_env_sf_arr[448] */
+#define XO_EEC_NOISE_FLOOR 448 /* flt_noise_floor[10] */
+#define XO_EEC_FPAR_WORDS 464
+#define XO_EEC_STATE_WORDS 640 /* e_gain[5][64] | noise_buf[5][64], in/out */
+#define XO_EEC_NUM_ROWS_MAX 38     /* slots 0..37 of the 40-row buffers */
+#define XO_EEC_RPHASE_WORDS 1024 /* ROM: ixheaac_random_phase[512][2] */
+int xo_esbr_env_calc(const float *rphase, float *re, float *im, int32_t *ipar, const float *fpar, float *state);
+void xo_esbr_env_calc_batch(const float *rphase, float *re, float *im, int32_t *ipar, const float *fpar, float *state,
+                            int32_t *err, int n);
+
 #endif

@@ -839,3 +839,117 @@ def oracle_esbr_hfgen_batch(orc, d, with_pv=True):
 
 def ref_esbr_hfgen_batch(ref, d, with_pv=True):
     return _esbr_hfgen_batch(ref.lib.ref_esbr_generate_hf_batch, d, with_pv)
+
+
+# ---- eSBR float envelope adjuster (ixheaacd_sbr_env_calc, ORIG_SBR) ------------------------------------------------------
+EEC_IPAR_WORDS, EEC_FPAR_WORDS, EEC_STATE_WORDS = 288, 464, 640
+EEC = dict(SB_START=0, SB_END=1, NUM_ENV=2, TRANS_ENV=3, SHORT_PREV=4, NUM_NOISE_ENV=5, NUM_SF_LO=6, NUM_SF_HI=7, NUM_NF=8,
+           SMOOTHING_MODE=9, INTERPOL_FREQ=10, LIMITER_BANDS=11, LIMITER_GAINS=12, HARM_INDEX=13, PHASE_INDEX=14, START_UP=15,
+           RESET=16, SBR_MODE=17, USF4=18, PATCHING_CHANGED=19, BORDER=24, FREQ_RES=33, NOISE_BORDER=41, INTER_TES=44,
+           GATE_MODE=52, LIM_TABLE=56, TBL_NOISE=108, TBL_LO=116, TBL_HI=148, ADD_HARM=208, HARM_PREV=264,
+           SFB_NRG=0, NOISE_FLOOR=448)
+
+
+def esbr_random_phase(ref=None):
+    """ixheaac_random_phase[512][2] (common/ixheaac_esbr_rom.c:437) — from the compiled reference when present, else the
+    committed blob libxaac_b200/rom/esbr_random_phase.bin"""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libxaac_b200", "rom", "esbr_random_phase.bin")
+    if ref is not None:
+        out = np.zeros(1024, np.float32)
+        ref.lib.ref_rom_esbr_random_phase(P(out))
+        return out
+    return np.fromfile(path, np.float32)
+
+
+def synth_esbr_envcalc_units(n, seed):
+    """Well-formed eSBR envelope-adjuster units: nested hi / lo / noise band tables, 1..5 envelopes with mixed resolution,
+    transient / short flags, limiter tables cut from the lo table, sinusoids, smoothing history; every 32nd unit carries an
+    invalid noise-envelope count (the reference returns IA_FATAL_ERROR after processing)."""
+    rng = np.random.default_rng(seed)
+    ipar = np.zeros((n, EEC_IPAR_WORDS), np.int32)
+    fpar = np.zeros((n, EEC_FPAR_WORDS), np.float32)
+    state = (2.0 ** rng.uniform(-6, 6, (n, EEC_STATE_WORDS))).astype(np.float32)
+    re = np.zeros((n, 40, 64), np.float32)
+    im = np.zeros((n, 40, 64), np.float32)
+    for u in range(n):
+        p = ipar[u]
+        sbs = int(rng.integers(6, 33))
+        hi = [sbs]
+        while hi[-1] < 64 and len(hi) < 49:
+            w = int(rng.integers(1, 4)) if hi[-1] < 40 else int(rng.integers(2, 6))
+            if hi[-1] + w > 64 or (len(hi) > 4 and rng.random() < 0.05):
+                break
+            hi.append(hi[-1] + w)
+        if len(hi) < 3:
+            hi = [sbs, sbs + 2, sbs + 4]
+        num_hi = len(hi) - 1
+        lo = hi[::2] if num_hi % 2 == 0 else [hi[0]] + hi[1::2]
+        num_lo = len(lo) - 1
+        sbe = hi[-1]
+        num_nf = int(rng.integers(1, min(5, num_lo) + 1))
+        inner = sorted(rng.choice(lo[1:-1], size=num_nf - 1, replace=False).tolist()) if num_nf > 1 else []
+        tn = [lo[0]] + inner + [sbe]
+        tn = tn + [sbe] * (6 - len(tn))
+        num_env = int(rng.integers(1, 6))
+        b0, bl = int(rng.integers(0, 3)), int(rng.integers(14, 20))
+        cuts = sorted(rng.choice(np.arange(b0 + 1, bl), size=num_env - 1, replace=False).tolist()) if num_env > 1 else []
+        border = [b0] + cuts + [bl]
+        if rng.random() < 0.05 and num_env > 1:
+            border[1] = border[0]            # an empty envelope
+        nne = 1 if num_env == 1 else 2
+        nb = [b0, bl, 0] if nne == 1 else [b0, border[int(rng.integers(1, num_env))], bl]
+        p[EEC["SB_START"]], p[EEC["SB_END"]], p[EEC["NUM_ENV"]] = sbs, sbe, num_env
+        p[EEC["TRANS_ENV"]] = int(rng.integers(-1, num_env + 1))
+        p[EEC["SHORT_PREV"]] = int(rng.choice([0, -1]))
+        p[EEC["NUM_NOISE_ENV"]] = nne if u % 32 != 31 else 3
+        p[EEC["NUM_SF_LO"]], p[EEC["NUM_SF_HI"]], p[EEC["NUM_NF"]] = num_lo, num_hi, num_nf
+        p[EEC["SMOOTHING_MODE"]] = int(rng.random() < 0.4)
+        p[EEC["INTERPOL_FREQ"]] = int(rng.random() < 0.6)
+        p[EEC["LIMITER_BANDS"]] = int(rng.integers(0, 4))
+        p[EEC["LIMITER_GAINS"]] = int(rng.integers(0, 4))
+        p[EEC["HARM_INDEX"]] = int(rng.integers(0, 4))
+        p[EEC["PHASE_INDEX"]] = int(rng.integers(0, 512))
+        p[EEC["START_UP"]] = int(rng.random() < 0.15)
+        p[EEC["SBR_MODE"]] = 1
+        p[EEC["BORDER"]:EEC["BORDER"] + len(border)] = border
+        p[EEC["FREQ_RES"]:EEC["FREQ_RES"] + num_env] = rng.integers(0, 2, num_env)
+        p[EEC["NOISE_BORDER"]:EEC["NOISE_BORDER"] + 3] = nb
+        for r in range(4):
+            g = 1 if r == 0 else int(rng.integers(1, min(12, num_lo) + 1))
+            ins = sorted(rng.choice(lo[1:-1], size=g - 1, replace=False).tolist()) if g > 1 else []
+            lt = [0] + [x - sbs for x in ins] + [sbe - sbs]
+            p[EEC["GATE_MODE"] + r] = g
+            p[EEC["LIM_TABLE"] + 13 * r:EEC["LIM_TABLE"] + 13 * r + len(lt)] = lt
+        p[EEC["TBL_NOISE"]:EEC["TBL_NOISE"] + 6] = tn
+        p[EEC["TBL_LO"]:EEC["TBL_LO"] + len(lo)] = lo
+        p[EEC["TBL_HI"]:EEC["TBL_HI"] + len(hi)] = hi
+        p[EEC["ADD_HARM"]:EEC["ADD_HARM"] + num_hi] = rng.random(num_hi) < 0.12
+        hp = (rng.random(64) < 0.2).astype(np.int8)
+        p[EEC["HARM_PREV"]:EEC["HARM_PREV"] + 16] = hp.view(np.int32)
+        fpar[u, :448] = 2.0 ** rng.uniform(-4, 26, 448)
+        fpar[u, 448:458] = 2.0 ** rng.uniform(-8, 8, 10)
+        if rng.random() < 0.1:
+            fpar[u, 448 + int(rng.integers(0, 10))] = 0.0
+        amp = 2.0 ** rng.uniform(-6, 12)
+        re[u] = rng.standard_normal((40, 64)) * amp
+        im[u] = rng.standard_normal((40, 64)) * amp
+        if rng.random() < 0.1:
+            re[u, :, sbs:sbs + 3] = 0
+            im[u, :, sbs:sbs + 3] = 0
+    return dict(re=re, im=im, ipar=ipar, fpar=fpar, state=state)
+
+
+def _esbr_envcalc_batch(fn, d, pre=()):
+    n = d["ipar"].shape[0]
+    re, im, ipar, state = d["re"].copy(), d["im"].copy(), d["ipar"].copy(), d["state"].copy()
+    err = np.zeros(n, np.int32)
+    fn(*pre, P(re), P(im), P(ipar), P(np.ascontiguousarray(d["fpar"])), P(state), P(err), n)
+    return re, im, ipar, state, err
+
+
+def oracle_esbr_envcalc_batch(orc, d, rphase):
+    return _esbr_envcalc_batch(orc.lib.xo_esbr_env_calc_batch, d, (P(rphase),))
+
+
+def ref_esbr_envcalc_batch(ref, d):
+    return _esbr_envcalc_batch(ref.lib.ref_esbr_env_calc_batch, d)

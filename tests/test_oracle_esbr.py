@@ -92,3 +92,28 @@ def test_esbr_generate_hf_matches_reference(oracle, ref):
     d2 = oracle_util.synth_esbr_hfgen_units(200, 12, hbe=False)
     _same_hfgen(oracle_util.oracle_esbr_hfgen_batch(oracle, d2, with_pv=False),
                 oracle_util.ref_esbr_hfgen_batch(ref, d2, with_pv=False), "no hbe")
+
+
+def same_envcalc(a, b, what):
+    re1, im1, ip1, st1, e1 = a
+    re2, im2, ip2, st2, e2 = b
+    assert np.array_equal(e1, e2), f"{what}: err differs at {np.argwhere(e1 != e2).ravel()[:8]}: {e1[e1 != e2][:8]} vs {e2[e1 != e2][:8]}"
+    ok = np.flatnonzero(e2 == 0)
+    for u in ok:
+        assert np.array_equal(ip1[u], ip2[u]), f"{what}: unit {u} ipar words {np.argwhere(ip1[u] != ip2[u]).ravel()[:8]}"
+        for x, y, nm in ((re1, re2, "re"), (im1, im2, "im"), (st1, st2, "state")):
+            if not np.array_equal(x[u].view(np.int32), y[u].view(np.int32)):
+                w = np.argwhere(x[u].view(np.int32) != y[u].view(np.int32))
+                raise AssertionError(f"{what}: unit {u} {nm} differs at {w[:6].tolist()} ({len(w)} cells)")
+    return len(ok)
+
+
+def test_esbr_env_calc_matches_reference(oracle, ref):
+    """ixheaacd_sbr_env_calc itself (ORIG_SBR, 2:1, no reset) — adjusted QMF cells, smoothing history, harmonic flags, phase
+    and harmonic indices bit for bit"""
+    rp = oracle_util.esbr_random_phase(ref)
+    d = oracle_util.synth_esbr_envcalc_units(400, 17)
+    b = oracle_util.ref_esbr_envcalc_batch(ref, d)
+    good = same_envcalc(oracle_util.oracle_esbr_envcalc_batch(oracle, d, rp), b, "env calc")
+    assert good > 350 and (b[4] != 0).sum() >= 12
+    assert np.abs(b[0] - d["re"]).max() > 0
