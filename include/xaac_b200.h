@@ -516,6 +516,57 @@ int32_t xaac_b200_esbr_generate_hf_dev(xaac_b200_ctx *ctx, const float *d_src_re
                                        const float *d_pv_im, float *d_dst_re, float *d_dst_im, const int32_t *d_par,
                                        float *d_bw_prev, int32_t *d_patch_out, int32_t *d_err, int64_t n_units, void *stream);
 
+/* eSBR float envelope adjuster: batched ixheaacd_sbr_env_calc (decoder/ixheaacd_esbr_envcal.c:71-908), the ORIG_SBR branch
+ * (:611-860) and epilogue, for the 2:1 system.  Not covered (err = -2, unit left to the reference): reset_flag / a change
+ * of sbr_patching_mode (ixheaacd_createlimiterbands is control plane — the host passes lim_table / gate_mode), PVC,
+ * LD-MPS, inter-TES (inter_temp_shape_mode != 0), error concealment.  Results are bit-identical to the reference build.
+ *   d_re / d_im  [n][XAAC_EHF_ROWS][64] float  sbr_qmf_out_real / sbr_qmf_out_imag from their first row (the destination
+ *                of xaac_b200_esbr_generate_hf_dev), adjusted in place
+ *   d_ipar       [n][XAAC_EEC_IPAR_WORDS] WORD32, word offsets below; the words marked in/out are updated
+ *   d_fpar       [n][XAAC_EEC_FPAR_WORDS] float: flt_env_sf_arr[448] | flt_noise_floor[10]
+ *   d_state      [n][640] float: frame_data->e_gain[5][64] | noise_buf[5][64], in/out
+ *   d_err        [n] or NULL: 0, -1 / 0x80000000 (the reference's own failure returns), -2 (unsupported subset) */
+#define XAAC_EEC_SB_START 0         /* pstr_freq_band_data->sub_band_start */
+#define XAAC_EEC_SB_END 1           /* pstr_freq_band_data->sub_band_end */
+#define XAAC_EEC_NUM_ENV 2          /* str_frame_info_details.num_env */
+#define XAAC_EEC_TRANS_ENV 3        /* str_frame_info_details.transient_env */
+#define XAAC_EEC_SHORT_PREV 4       /* env_short_flag_prev (in/out) */
+#define XAAC_EEC_NUM_NOISE_ENV 5    /* str_frame_info_details.num_noise_env */
+#define XAAC_EEC_NUM_SF_LO 6        /* num_sf_bands[LOW] */
+#define XAAC_EEC_NUM_SF_HI 7        /* num_sf_bands[HIGH] */
+#define XAAC_EEC_NUM_NF 8           /* num_nf_bands */
+#define XAAC_EEC_SMOOTHING_MODE 9   /* pstr_sbr_header->smoothing_mode */
+#define XAAC_EEC_INTERPOL_FREQ 10   /* pstr_sbr_header->interpol_freq */
+#define XAAC_EEC_LIMITER_BANDS 11   /* pstr_sbr_header->limiter_bands */
+#define XAAC_EEC_LIMITER_GAINS 12   /* pstr_sbr_header->limiter_gains */
+#define XAAC_EEC_HARM_INDEX 13      /* harm_index (in/out) */
+#define XAAC_EEC_PHASE_INDEX 14     /* phase_index (in/out) */
+#define XAAC_EEC_START_UP 15        /* pstr_sbr_header->esbr_start_up (in/out) */
+#define XAAC_EEC_RESET 16           /* reset_flag (must be 0) */
+#define XAAC_EEC_SBR_MODE 17        /* sbr_mode (must be ORIG_SBR = 1) */
+#define XAAC_EEC_USF4 18            /* is_usf_4 (must be 0) */
+#define XAAC_EEC_PATCHING_CHANGED 19 /* sbr_patching_mode != prev_sbr_patching_mode (must be 0) */
+#define XAAC_EEC_BORDER 24          /* border_vec[9] */
+#define XAAC_EEC_FREQ_RES 33        /* freq_res[8] */
+#define XAAC_EEC_NOISE_BORDER 41    /* noise_border_vec[3] */
+#define XAAC_EEC_INTER_TES 44       /* inter_temp_shape_mode[8] (must be 0) */
+#define XAAC_EEC_GATE_MODE 52       /* gate_mode[4] */
+#define XAAC_EEC_LIM_TABLE 56       /* lim_table[4][13] */
+#define XAAC_EEC_TBL_NOISE 108      /* freq_band_tbl_noise[6] */
+#define XAAC_EEC_TBL_LO 116         /* freq_band_tbl_lo[29] */
+#define XAAC_EEC_TBL_HI 148         /* freq_band_tbl_hi[57] */
+#define XAAC_EEC_ADD_HARM 208       /* add_harmonics[56] */
+#define XAAC_EEC_HARM_PREV 264      /* harm_flag_prev[64], one byte each (in/out) */
+#define XAAC_EEC_IPAR_WORDS 288
+#define XAAC_EEC_SFB_NRG 0
+#define XAAC_EEC_NOISE_FLOOR 448
+#define XAAC_EEC_FPAR_WORDS 464
+#define XAAC_EEC_STATE_WORDS 640
+/* random_phase = ixheaac_random_phase[512][2] (common/ixheaac_esbr_rom.c:437), 4096 bytes */
+int32_t xaac_b200_set_esbr_envcalc_rom(xaac_b200_ctx *ctx, const void *random_phase, size_t bytes);
+int32_t xaac_b200_esbr_env_calc_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im, int32_t *d_ipar, const float *d_fpar,
+                                    float *d_state, int32_t *d_err, int64_t n_units, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ class Context:
         self.set_ps_rom(ps_rom if ps_rom is not None else _lib.rom_blob("ps_rom.bin"))
         self.set_usac_rom(usac_rom if usac_rom is not None else _lib.rom_blob("usac_rom.bin"))
         self.set_esbr_rom(esbr_rom if esbr_rom is not None else _lib.rom_blob("esbr_rom.bin"))
+        self.set_esbr_envcalc_rom(_lib.rom_blob("esbr_random_phase.bin"))
 
     # -- plumbing ---------------------------------------------------------------------------------
     @property
@@ -67,6 +68,11 @@ class Context:
         ia_qmf_dec_tables_struct (5744 bytes)."""
         buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
         self.check(self._lib.xaac_b200_set_esbr_rom(self._h, buf, len(blob)), "xaac_b200_set_esbr_rom")
+
+    def set_esbr_envcalc_rom(self, blob):
+        """blob: ixheaac_random_phase[512][2] (4096 bytes)."""
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        self.check(self._lib.xaac_b200_set_esbr_envcalc_rom(self._h, buf, len(blob)), "xaac_b200_set_esbr_envcalc_rom")
 
     @property
     def num_sms(self):

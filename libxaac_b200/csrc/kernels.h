@@ -318,6 +318,25 @@ struct EsbrHfgenArgs {
 };
 cudaError_t launch_esbr_hfgen(const EsbrHfgenArgs &args, int num_sms, cudaStream_t stream);
 
+// eSBR float envelope adjuster (ixheaacd_sbr_env_calc, ORIG_SBR): word offsets = XAAC_EEC_* of include/xaac_b200.h
+constexpr int kEecSbStart = 0, kEecSbEnd = 1, kEecNumEnv = 2, kEecTransEnv = 3, kEecShortPrev = 4, kEecNumNoiseEnv = 5,
+              kEecNumSfLo = 6, kEecNumSfHi = 7, kEecNumNf = 8, kEecSmoothingMode = 9, kEecInterpolFreq = 10,
+              kEecLimiterBands = 11, kEecLimiterGains = 12, kEecHarmIndex = 13, kEecPhaseIndex = 14, kEecStartUp = 15,
+              kEecReset = 16, kEecSbrMode = 17, kEecUsf4 = 18, kEecPatchingChanged = 19, kEecBorder = 24, kEecFreqRes = 33,
+              kEecNoiseBorder = 41, kEecInterTes = 44, kEecGateMode = 52, kEecLimTable = 56, kEecTblNoise = 108,
+              kEecTblLo = 116, kEecTblHi = 148, kEecAddHarm = 208, kEecHarmPrev = 264, kEecIparWords = 288,
+              kEecSfbNrg = 0, kEecNoiseFloor = 448, kEecFparWords = 464, kEecStateWords = 640, kEecRphaseBytes = 4096;
+struct EsbrEnvcalcArgs {
+  float *re, *im;       // [n][40][64] sbr_qmf_out_real / imag from their first row, in/out
+  int32_t *ipar;        // [n][288], in/out words: env_short_flag_prev, harm_index, phase_index, esbr_start_up, harm_flag_prev
+  const float *fpar;    // [n][464] flt_env_sf_arr | flt_noise_floor
+  float *state;         // [n][640] e_gain[5][64] | noise_buf[5][64], in/out
+  const float *rphase;  // ixheaac_random_phase[512][2]
+  int32_t *err;         // [n] or null
+  long long n_units;
+};
+cudaError_t launch_esbr_envcalc(const EsbrEnvcalcArgs &args, int num_sms, cudaStream_t stream);
+
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
 

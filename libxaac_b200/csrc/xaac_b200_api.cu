@@ -28,6 +28,7 @@ struct xaac_b200_ctx {
   uint8_t *d_rom_ps = nullptr;    // leading part of ia_ps_tables_struct
   uint8_t *d_rom_usac = nullptr;  // USAC FD tables (XAAC_UROM_*)
   uint8_t *d_rom_esbr = nullptr;  // table image of esbr_synth_kernel
+  float *d_rom_rphase = nullptr;  // ixheaac_random_phase[512][2]
   int esbr_periodic = 0;
   bool have_ps_rom = false;
   int ps_rot_nosat = 0;           // no fractional-delay phase factor equals -32768 (16x16 rotations cannot saturate)
@@ -178,6 +179,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   if (ctx->d_rom_ps) cudaFree(ctx->d_rom_ps);
   if (ctx->d_rom_usac) cudaFree(ctx->d_rom_usac);
   if (ctx->d_rom_esbr) cudaFree(ctx->d_rom_esbr);
+  if (ctx->d_rom_rphase) cudaFree(ctx->d_rom_rphase);
   delete ctx;
 }
 
@@ -1065,6 +1067,35 @@ int32_t xaac_b200_esbr_generate_hf_dev(xaac_b200_ctx *ctx, const float *d_src_re
   a.par = d_par; a.bw_prev = d_bw_prev; a.patch_out = d_patch_out; a.err = d_err; a.n_units = n_units;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   LAUNCH("esbr_hfgen_kernel", stream, xb::launch_esbr_hfgen(a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_set_esbr_envcalc_rom(xaac_b200_ctx *ctx, const void *random_phase, size_t bytes) {
+  if (!ctx || !random_phase) return bad_arg(ctx, "null");
+  if (bytes < (size_t)xb::kEecRphaseBytes) return bad_arg(ctx, "ixheaac_random_phase blob shorter than 4096 bytes");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaError_t e = ctx->d_rom_rphase ? cudaSuccess : cudaMalloc((void **)&ctx->d_rom_rphase, xb::kEecRphaseBytes);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_rom_rphase, random_phase, xb::kEecRphaseBytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(ctx, e, "cudaMemcpy(esbr random phase)");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_esbr_env_calc_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im, int32_t *d_ipar, const float *d_fpar,
+                                    float *d_state, int32_t *d_err, int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->d_rom_rphase) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_envcalc_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_re || !d_im || !d_ipar || !d_fpar || !d_state) return bad_arg(ctx, "null buffer");
+  xb::EsbrEnvcalcArgs a;
+  a.re = d_re; a.im = d_im; a.ipar = d_ipar; a.fpar = d_fpar; a.state = d_state; a.rphase = ctx->d_rom_rphase; a.err = d_err;
+  a.n_units = n_units;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  LAUNCH("esbr_envcalc_kernel", stream, xb::launch_esbr_envcalc(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return XAAC_B200_OK;
 }

@@ -100,3 +100,29 @@ def esbr_generate_hf(ctx, src_re, src_im, dst_re, dst_im, par, bw_prev, pv_re=No
                                                  ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_esbr_generate_hf_dev")
     return patch_out, err
+
+
+EEC_IPAR_WORDS, EEC_FPAR_WORDS, EEC_STATE_WORDS = 288, 464, 640
+
+
+def esbr_env_calc(ctx, re, im, ipar, fpar, state, err=None, stream=None):
+    """Batched drop-in for ixheaacd_sbr_env_calc (decoder/ixheaacd_esbr_envcal.c:71), ORIG_SBR branch of the 2:1 system.
+    re / im float32 [n, 40, 64] (sbr_qmf_out_real / imag from their first row) are adjusted in place; ipar int32 [n, 288]
+    (XAAC_EEC_* words; env_short_flag_prev, harm_index, phase_index, esbr_start_up and harm_flag_prev are updated in
+    place), fpar float32 [n, 464] (envelope scale factors | noise floor), state float32 [n, 640] (e_gain | noise_buf,
+    updated in place).  Returns err int32 [n]."""
+    n = ipar.shape[0]
+    dev = ipar.device
+    _chk(re, torch.float32, (n, EHF_ROWS, 64), "re", "cuda")
+    _chk(im, torch.float32, (n, EHF_ROWS, 64), "im", "cuda")
+    _chk(ipar, torch.int32, (n, EEC_IPAR_WORDS), "ipar", "cuda")
+    _chk(fpar, torch.float32, (n, EEC_FPAR_WORDS), "fpar", "cuda")
+    _chk(state, torch.float32, (n, EEC_STATE_WORDS), "state", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=dev)
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    rc = ctx._lib.xaac_b200_esbr_env_calc_dev(ctx.handle, _ptr(re), _ptr(im), _ptr(ipar), _ptr(fpar), _ptr(state), _ptr(err), n,
+                                              ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_env_calc_dev")
+    return err
