@@ -825,7 +825,7 @@ def _esbr_hfgen_batch(fn, d, with_pv=True):
     n = d["par"].shape[0]
     dr, di = d["dst_re"].copy(), d["dst_im"].copy()
     bw = d["bw_prev"].copy()
-    patch = np.zeros((n, 8), np.int32)
+    patch = d["patch_in"].copy() if "patch_in" in d else np.zeros((n, 8), np.int32)
     err = np.zeros(n, np.int32)
     c = lambda a: np.ascontiguousarray(a)
     fn(P(c(d["src_re"])), P(c(d["src_im"])), P(c(d["pv_re"])) if with_pv else None, P(c(d["pv_im"])) if with_pv else None,

@@ -64,3 +64,10 @@ def test_env_calc_refuses_unsupported(ctx):
     assert list(out[4][:4]) == [-2, -2, -2, -2]
     assert np.array_equal(out[0][:4].view(np.int32), d["re"][:4].view(np.int32))
     assert np.array_equal(out[3][:4].view(np.int32), d["state"][:4].view(np.int32))
+
+
+def test_env_calc_golden(ctx):
+    """records tapped from real USAC decodes of the unmodified reference, incl. 8 consecutive calls"""
+    from tests.test_oracle_esbr import check_envcalc_golden, golden_envcalc_units, load_esbr_golden
+    g = load_esbr_golden("esbr_envcalc_tapped.npz")
+    check_envcalc_golden(_run(ctx, golden_envcalc_units(g)), g, "kernel vs tapped decode")

@@ -15,7 +15,8 @@ def _run(ctx, d, with_pv=True):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     dr, di, bw = t(d["dst_re"]), t(d["dst_im"]), t(d["bw_prev"])
     patch, err = xb.esbr_generate_hf(ctx, t(d["src_re"]), t(d["src_im"]), dr, di, t(d["par"]), bw,
-                                     pv_re=t(d["pv_re"]) if with_pv else None, pv_im=t(d["pv_im"]) if with_pv else None)
+                                     pv_re=t(d["pv_re"]) if with_pv else None, pv_im=t(d["pv_im"]) if with_pv else None,
+                                     patch_out=t(d["patch_in"]) if "patch_in" in d else None)
     torch.cuda.synchronize()
     return dr.cpu().numpy(), di.cpu().numpy(), bw.cpu().numpy(), patch.cpu().numpy(), err.cpu().numpy()
 
@@ -79,3 +80,10 @@ def test_generate_hf_refuses_unsupported(ctx):
     out = _run(ctx, d)
     assert list(out[4][:3]) == [-2, -2, -2]
     assert np.array_equal(out[0][:3].view(np.int32), d["dst_re"][:3].view(np.int32))
+
+
+def test_generate_hf_golden(ctx):
+    """records tapped from real USAC decodes of the unmodified reference (default patching + harmonic transposer)"""
+    from tests.test_oracle_esbr import check_hfgen_golden, golden_hfgen_units, load_esbr_golden
+    g = load_esbr_golden("esbr_hfgen_tapped.npz")
+    check_hfgen_golden(_run(ctx, golden_hfgen_units(g)), g, "kernel vs tapped decode")

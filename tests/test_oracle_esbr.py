@@ -117,3 +117,51 @@ def test_esbr_env_calc_matches_reference(oracle, ref):
     good = same_envcalc(oracle_util.oracle_esbr_envcalc_batch(oracle, d, rp), b, "env calc")
     assert good > 350 and (b[4] != 0).sum() >= 12
     assert np.abs(b[0] - d["re"]).max() > 0
+
+
+def load_esbr_golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
+def golden_hfgen_units(g):
+    return dict(par=g["par"], src_re=g["src_re"], src_im=g["src_im"], pv_re=g["pv_re"], pv_im=g["pv_im"],
+                dst_re=g["dst_in_re"], dst_im=g["dst_in_im"], bw_prev=g["bw_in"], patch_in=g["patch_in"])
+
+
+def check_hfgen_golden(out, g, what):
+    dr, di, bw, patch, err = out
+    assert np.array_equal(err, g["ret"]), f"{what}: return values"
+    assert np.array_equal(patch, g["patch"]), f"{what}: patch table"
+    assert np.array_equal(bw.view(np.int32), g["bw_out"].view(np.int32)), f"{what}: bw_array_prev"
+    for x, y, nm in ((dr, g["dst_out_re"], "re"), (di, g["dst_out_im"], "im")):
+        bad = np.argwhere(x.view(np.int32) != y.view(np.int32))
+        assert len(bad) == 0, f"{what}: {nm} differs in {len(bad)} cells, first {bad[0].tolist()}"
+
+
+def golden_envcalc_units(g):
+    return dict(re=g["re_in"], im=g["im_in"], ipar=g["ipar_in"], fpar=g["fpar"], state=g["state_in"])
+
+
+def check_envcalc_golden(out, g, what):
+    re, im, ipar, state, err = out
+    assert np.array_equal(err, g["ret"]), f"{what}: return values"
+    assert np.array_equal(ipar, g["ipar_out"]), f"{what}: ipar words {np.argwhere(ipar != g['ipar_out'])[:6].tolist()}"
+    for x, y, nm in ((re, g["re_out"], "re"), (im, g["im_out"], "im"), (state, g["state_out"], "state")):
+        bad = np.argwhere(x.view(np.int32) != y.view(np.int32))
+        assert len(bad) == 0, f"{what}: {nm} differs in {len(bad)} cells, first {bad[0].tolist()}"
+
+
+def test_esbr_generate_hf_golden(oracle):
+    """records tapped from real USAC decodes (default patching and harmonic transposer), tools/make_golden.py esbr"""
+    g = load_esbr_golden("esbr_hfgen_tapped.npz")
+    assert (g["has_pv"] != 0).sum() >= 4 and (g["has_pv"] == 0).sum() >= 4
+    check_hfgen_golden(oracle_util.oracle_esbr_hfgen_batch(oracle, golden_hfgen_units(g)), g, "oracle vs tapped decode")
+    assert np.abs(g["dst_out_re"] - g["dst_in_re"]).max() > 0
+
+
+def test_esbr_env_calc_golden(oracle):
+    g = load_esbr_golden("esbr_envcalc_tapped.npz")
+    rp = oracle_util.esbr_random_phase()
+    check_envcalc_golden(oracle_util.oracle_esbr_envcalc_batch(oracle, golden_envcalc_units(g), rp), g, "oracle vs tapped decode")
+    assert len(set(g["ipar_in"][:, oracle_util.EEC["NUM_ENV"]].tolist())) >= 3

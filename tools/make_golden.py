@@ -345,9 +345,72 @@ def make_usac_fd_golden(tmp):
     print(f"wrote {path}: {len(keep)} records, {os.path.getsize(path)} bytes")
 
 
+def make_esbr_golden(tmp):
+    """USAC (xHE-AAC, aot 42, ccfl 1024) stereo 32 kHz with eSBR, once with the default patching and once with the harmonic
+    transposer (-harmonic_sbr:1): every ixheaacd_generate_hf / ixheaacd_sbr_env_calc call of the real decodes is tapped
+    (oracle/ref_taps_esbr.c) in the flat XO_EHF_* / XO_EEC_* layouts.  A selection of records within the supported subset
+    is kept (plus the counts of everything seen)."""
+    fs, ch, br = 32000, 2, 64000
+    ehf_words = 4 + 96 + 6 + 6 + 8 + 8 + 8 * 2560
+    eec_words = 3 + 288 + 288 + 464 + 640 + 640 + 4 * 2560
+    ehf_sel, eec_sel, stats = [], [], []
+    for tag, extra, seed in (("plain", [], 21), ("hbe", ["-harmonic_sbr:1"], 22)):
+        wav = os.path.join(tmp, f"in_esbr_{tag}.wav")
+        write_wav(wav, synth(fs, 6.0, ch, seed), fs)
+        mp4 = os.path.join(tmp, f"esbr_{tag}.mp4")
+        run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{mp4}", "-aot:42", f"-br:{br}", "-ccfl_idx:3"] + extra)
+        meta = os.path.join(tmp, f"esbr_{tag}.txt")
+        tap = os.path.join(tmp, f"esbr_{tag}.tap")
+        decode_tap(mp4, os.path.join(tmp, "o.wav"), tap, [f"-imeta:{meta}", "-mp4:1"], stages="ehf,eec")
+        a = np.fromfile(tap + ".ehf", dtype=np.int32)
+        b = np.fromfile(tap + ".eec", dtype=np.int32)
+        assert a.size and a.size % ehf_words == 0 and b.size and b.size % eec_words == 0, (a.size, b.size)
+        a, b = a.reshape(-1, ehf_words), b.reshape(-1, eec_words)
+        assert (a[:, 0] == 0x31464845).all() and (b[:, 0] == 0x31434545).all()
+        par = a[:, 4:100]
+        ok_a = (a[:, 1] == 0) & (a[:, 3] == 0) & (par[:, 8] == 0) & (par[:, 9] == 0)
+        ip = b[:, 3:291]
+        ok_b = (b[:, 1] == 0) & (b[:, 2] == 0) & (ip[:, 16] == 0) & (ip[:, 17] == 1) & (ip[:, 18] == 0) & (ip[:, 19] == 0) \
+            & (ip[:, 44:52] == 0).all(1)
+        stats.append(f"{tag}: generate_hf {len(a)} calls ({int(ok_a.sum())} in subset; hbe_flag {int((par[:, 5] != 0).sum())}, "
+                     f"patching {int((par[:, 6] != 0).sum())}, pre_proc {int((par[:, 8] != 0).sum())}, has_pv {int((a[:, 2] != 0).sum())}); "
+                     f"env_calc {len(b)} calls ({int(ok_b.sum())} in subset; reset {int((ip[:, 16] != 0).sum())}, "
+                     f"patching changed {int((ip[:, 19] != 0).sum())}, inter-TES {int((ip[:, 44:52] != 0).any(1).sum())}, "
+                     f"num_env {np.bincount(ip[:, 2], minlength=6).tolist()})")
+        ia = np.flatnonzero(ok_a)
+        ib = np.flatnonzero(ok_b)
+        ehf_sel.append(a[ia[len(ia) // 5:: max(1, len(ia) // 6)][:6]])
+        # a run of 8 consecutive calls (4 frames x 2 channels) for the state carry + a spread of others
+        run0 = next((i for i in range(20, len(b) - 8) if ok_b[i:i + 8].all()), None)
+        keep = set(ib[len(ib) // 7:: max(1, len(ib) // 5)][:5].tolist())
+        if run0 is not None and tag == "plain":
+            keep.update(range(run0, run0 + 8))
+        eec_sel.append(b[sorted(keep)])
+    for s_ in stats:
+        print(s_)
+    a, b = np.concatenate(ehf_sel), np.concatenate(eec_sel)
+    f32 = lambda x: np.ascontiguousarray(x).view(np.float32)
+    q = a[:, 128:].reshape(len(a), 8, 40, 64)
+    path = os.path.join(GOLD, "esbr_hfgen_tapped.npz")
+    np.savez_compressed(path, ret=a[:, 1].copy(), has_pv=a[:, 2].copy(), par=a[:, 4:100].copy(), bw_in=f32(a[:, 100:106]),
+                        bw_out=f32(a[:, 106:112]), patch=a[:, 112:120].copy(), patch_in=a[:, 120:128].copy(), src_re=f32(q[:, 0]), src_im=f32(q[:, 1]),
+                        pv_re=f32(q[:, 2]), pv_im=f32(q[:, 3]), dst_in_re=f32(q[:, 4]), dst_in_im=f32(q[:, 5]),
+                        dst_out_re=f32(q[:, 6]), dst_out_im=f32(q[:, 7]), stats=np.array(stats))
+    print(f"wrote {path}: {len(a)} records, {os.path.getsize(path)} bytes")
+    o = 3
+    ipi, ipo = b[:, o:o + 288], b[:, o + 288:o + 576]
+    fp_ = f32(b[:, o + 576:o + 1040])
+    sti, sto = f32(b[:, o + 1040:o + 1680]), f32(b[:, o + 1680:o + 2320])
+    q = b[:, o + 2320:].reshape(len(b), 4, 40, 64)
+    path = os.path.join(GOLD, "esbr_envcalc_tapped.npz")
+    np.savez_compressed(path, ret=b[:, 1].copy(), ipar_in=ipi.copy(), ipar_out=ipo.copy(), fpar=fp_, state_in=sti, state_out=sto,
+                        re_in=f32(q[:, 0]), im_in=f32(q[:, 1]), re_out=f32(q[:, 2]), im_out=f32(q[:, 3]), stats=np.array(stats))
+    print(f"wrote {path}: {len(b)} records, {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
@@ -359,6 +422,8 @@ def main():
             make_sbrdec_golden(tmp)
         if "usac_fd" in which:
             make_usac_fd_golden(tmp)
+        if "esbr" in which:
+            make_esbr_golden(tmp)
         if "sbrdec_lp" in which:
             make_sbrdec_lp_golden(tmp)
 
