@@ -63,6 +63,9 @@ WORKLOADS = {
     "esbr_generate_hf": (4, 65536, "xHE-AAC/USAC eSBR stereo: the float HF generator of the chain (ixheaacd_generate_hf: 38-slot "
                                    "covariance, 2nd-order complex prediction, patching, HBE high band), batch=65536 stereo "
                                    "frames (131072 core channels)"),
+    "esbr_env_calc": (4, 65536, "xHE-AAC/USAC eSBR stereo: the float envelope adjuster of the chain (ixheaacd_sbr_env_calc, ORIG_SBR: "
+                                "energies, gains in double, limiter, smoothing, noise, sinusoids), batch=65536 stereo frames "
+                                "(131072 core channels)"),
     "esbr_synth64": (4, 65536, "xHE-AAC/USAC eSBR stereo 32 kHz: the 64-band eSBR QMF synthesis bank of the chain (per-slot core of "
                                "ixheaacd_esbr_synthesis_filt_block), batch=65536 stereo frames (131072 output channels)"),
     "qmf_synth_hq": (3, 65536, "stand-alone fixed-point HQ 64-band QMF synthesis stage of the HE-AAC chain, "
@@ -580,6 +583,54 @@ def cpu_arm_esbr_hfgen(n_units, threads, seed, reps=1, min_seconds=0.0):
     return n_units * done / dt, kind
 
 
+def esbr_envcalc_bytes(ipar):
+    """Algorithmic HBM bytes per unit of ixheaacd_sbr_env_calc: the adjusted cells read and written once (8 bytes per complex
+    cell each way), the smoothing history in and out (5120), the parameter records (1152 + 1856)."""
+    from tests.oracle_util import EEC
+    nsub = ipar[:, EEC["SB_END"]] - ipar[:, EEC["SB_START"]]
+    last = ipar[np.arange(len(ipar)), EEC["BORDER"] + ipar[:, EEC["NUM_ENV"]]]
+    slots = 2 * (last - ipar[:, EEC["BORDER"]])
+    return 16.0 * slots * nsub + 5120 + 1152 + 1856
+
+
+def cpu_arm_esbr_envcalc(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time ixheaacd_sbr_env_calc per unit on host threads (ref_esbr_env_calc_batch, oracle/ref_shim.c)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    P = oracle_util.P
+    d = oracle_util.synth_esbr_envcalc_units(n_units, seed)
+    E = oracle_util.EEC
+    d["ipar"][:, E["NUM_NOISE_ENV"]] = np.where(d["ipar"][:, E["NUM_ENV"]] == 1, 1, 2)
+    re, im, ipar, state = d["re"].copy(), d["im"].copy(), d["ipar"].copy(), d["state"].copy()
+    err = np.zeros(n_units, np.int32)
+    bounds = np.linspace(0, n_units, threads + 1).astype(int)
+    if ref is not None:
+        kind, fn, pre = "reference", ref.lib.ref_esbr_env_calc_batch, []
+    else:
+        kind, fn, pre = "port", oracle_util.Oracle().lib.xo_esbr_env_calc_batch, [P(oracle_util.esbr_random_phase())]
+
+    def work(t):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            fn(*pre, P(re[a:b]), P(im[a:b]), P(ipar[a:b]), P(d["fpar"][a:b]), P(state[a:b]), P(err[a:b]), b - a)
+
+    def one_pass():
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for z in th:
+            z.start()
+        for z in th:
+            z.join()
+        return time.perf_counter() - t0
+
+    one_pass()
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass()
+        done += 1
+    return n_units * done / dt, kind
+
+
 def cpu_arm_esbr_synth(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time the reference's eSBR synthesis leaves per unit on host threads (ref_esbr_synth64, oracle/ref_shim.c)."""
     from tests import oracle_util
@@ -730,6 +781,11 @@ STAGES = {
                                    "solve, patch walk + 2nd-order prediction filter, HBE high band (bit-exact floats)",
                              ref_stage="ixheaacd_generate_hf", cpu=cpu_arm_esbr_hfgen, cpu_units_per_core=1024,
                              realtime_fps=15.625, h2d=4 * 10240 + 384, d2h=2 * 10240, dtype="f32"),
+    "esbr_env_calc": dict(kernel="esbr_envcalc_kernel", bytes_per_unit=None,
+                          stage="eSBR float envelope adjuster: per-envelope energies, gains / noise / sinusoid levels (double), "
+                                "limiter + boost, 5-tap smoothing, noise and sinusoid insertion (bit-exact floats)",
+                          ref_stage="ixheaacd_sbr_env_calc", cpu=cpu_arm_esbr_envcalc, cpu_units_per_core=1024,
+                          realtime_fps=15.625, h2d=2 * 10240 + 1152 + 1856, d2h=2 * 10240, dtype="f32/f64"),
     "esbr_synth64": dict(kernel="esbr_synth_kernel", bytes_per_unit=ESBR_SYNTH_BYTES_PER_UNIT,
                          stage="eSBR 64-band QMF synthesis: float -> WORD32, inverse modulation (2 x 32-point FFT, 32-bit "
                                "twiddles), 10-tap window with WORD64 accumulation, -> float (bit-exact)",
@@ -976,6 +1032,53 @@ class EsbrHfgenWork:
         pass
 
 
+class EsbrEnvcalcWork:
+    """131 072 units tiled from 1024 distinct seeded ones; the QMF cells are adjusted in place step after step (the adjuster
+    normalises the band energies to the transmitted envelope, so the values stay bounded), history and indices carried."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        from tests import oracle_util
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        base = min(1024, n_units)
+        d = oracle_util.synth_esbr_envcalc_units(base, seed)
+        E = oracle_util.EEC
+        d["ipar"][:, E["NUM_NOISE_ENV"]] = np.where(d["ipar"][:, E["NUM_ENV"]] == 1, 1, 2)
+        reps = (n_units + base - 1) // base
+        tile = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev).repeat((reps,) + (1,) * (a.ndim - 1))[:n_units].contiguous()
+        self.t = {k: tile(v) for k, v in d.items()}
+        self.err = torch.zeros((n_units,), dtype=torch.int32, device=dev)
+        self.bytes_per_unit = float(esbr_envcalc_bytes(d["ipar"]).mean())
+
+    def step(self, i, stream):
+        t = self.t
+        self.xb.esbr_env_calc(self.ctx, t["re"], t["im"], t["ipar"], t["fpar"], t["state"], err=self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0
+
+    def host_setup(self):
+        import torch
+        keys = ("re", "im", "ipar", "fpar")
+        self.h_in = {k: torch.empty(self.t[k].shape, dtype=self.t[k].dtype).pin_memory() for k in keys}
+        for k in keys:
+            self.h_in[k].copy_(self.t[k])
+        self.h_out = [torch.empty(self.t[k].shape, dtype=torch.float32).pin_memory() for k in ("re", "im")]
+
+    def host_step(self, i):
+        import torch
+        t = self.t
+        for k, h in self.h_in.items():
+            t[k].copy_(h, non_blocking=True)
+        self.xb.esbr_env_calc(self.ctx, t["re"], t["im"], t["ipar"], t["fpar"], t["state"], err=self.err)
+        self.h_out[0].copy_(t["re"], non_blocking=True)
+        self.h_out[1].copy_(t["im"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
+
+
 class EsbrSynthWork:
     def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
         import torch
@@ -1157,7 +1260,8 @@ class ChainLpWork:
 WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv2_chain": ChainWork,
         "heaacv1_stereo_chain": ChainLpWork, "usac_fd_imdct": UsacFdWork,
         "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork,
-        "esbr_anal32": EsbrAnalWork, "esbr_generate_hf": EsbrHfgenWork}
+        "esbr_anal32": EsbrAnalWork, "esbr_generate_hf": EsbrHfgenWork,
+        "esbr_env_calc": EsbrEnvcalcWork}
 
 
 def main():

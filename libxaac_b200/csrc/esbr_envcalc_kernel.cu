@@ -39,7 +39,7 @@ __device__ __constant__ float kEcFir4[5] = {0.03183050093751f, 0.11516383427084f
                                             0.33333333333333f};
 __device__ __constant__ float kEcLimGains[4] = {0.70795f, 1.0f, 1.41254f, 1e10f};
 
-__global__ void __launch_bounds__(kEcWarps * 32) esbr_envcalc_kernel(EsbrEnvcalcArgs p) {
+__global__ void __launch_bounds__(kEcWarps * 32, 3) esbr_envcalc_kernel(EsbrEnvcalcArgs p) {
   __shared__ EcWarpS sm[kEcWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   EcWarpS &w = sm[warp];
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kEcWarps * 32) esbr_envcalc_kernel(EsbrEnvcalc
       }
     __syncwarp();
 
-    int kk = 0, next = -1, m = 0;
+    int kk = 0, next = -1, m = 0, map_res = -1, C = 0;
     for (int i = 0; i < num_env && !err; i++) {
       if (kk > 2) {
         err = (int)0x80000000;
@@ -127,10 +127,11 @@ __global__ void __launch_bounds__(kEcWarps * 32) esbr_envcalc_kernel(EsbrEnvcalc
       const i32 *tbl = ip + (res ? kEecTblHi : kEecTblLo);
       const int num_sf = res ? num_sf_hi : num_sf_lo;
 
-      // ---- map: c -> absolute band / scale-factor band / noise band
-      int C = 0;
-      {
+      // ---- map: c -> absolute band / scale-factor band / noise band (depends on the resolution only: kept across envelopes)
+      if (res != map_res) {
         int o = 0;
+        C = 0;
+        map_res = res;
         for (int j = 0; j < num_sf; j++) {
           const int li = tbl[j], ui = tbl[j + 1];
           if (li < 0 || ui > 64 || ui < li || C + (ui - li) > 64) {
