@@ -1430,9 +1430,10 @@ def main():
                     continue
                 w2 = WORK[name](xb, ctx, 131072, 8, seed, dev)
                 ms, _, _ = timed(w2, 5, 3)
-                ach = STAGES[name]["bytes_per_unit"] * 131072 / (float(np.mean(ms)) * 1e-3) / 1e9
+                bpu = getattr(w2, "bytes_per_unit", None) or STAGES[name]["bytes_per_unit"]
+                ach = bpu * 131072 / (float(np.mean(ms)) * 1e-3) / 1e9
                 extra[name] = {"kernel": STAGES[name]["kernel"], "launch_ms": float(np.mean(ms)),
-                               "units_per_launch": 131072, "bytes_per_unit": STAGES[name]["bytes_per_unit"],
+                               "units_per_launch": 131072, "bytes_per_unit": bpu,
                                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                "stereo_frames_per_sec": 65536 / (float(np.mean(ms)) * 1e-3)}
                 del w2

@@ -470,6 +470,13 @@ int32_t xaac_b200_set_esbr_rom(xaac_b200_ctx *ctx, const void *tables, size_t by
 int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32_t *d_states, int32_t *d_pos, float *d_out,
                                    int32_t *d_err, int64_t n_units, void *stream);
 
+/* The same bank with ixheaacd_samples_sat (decoder/ixheaacd_decode_main.c:82-104, pcmsize 16) fused into its store: clamp to
+ * [-32768, 32767], C cast (truncation towards zero), channel-interleaved.  Unit u is channel u % ch_fac of stream u / ch_fac;
+ * its sample i goes to d_pcm16[(stream * 2048 + i) * ch_fac + channel].  d_out may be NULL (PCM only). */
+int32_t xaac_b200_esbr_synth64_pcm16_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32_t *d_states, int32_t *d_pos,
+                                         float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units,
+                                         void *stream);
+
 /* eSBR 32-band QMF analysis bank: batched ixheaacd_esbr_analysis_filt_block(ia_sbr_dec_struct *, ia_sbr_tables_struct *,
  * WORD32 op_delay) (decoder/ixheaacd_sbr_dec.c:185-295) for 32 analysis channels and 32 time slots, with its leaves
  * ixheaacd_esbr_qmfanal32_winadd (decoder/ixheaacd_qmf_dec.c:537), ixheaacd_esbr_fwd_modulation, ixheaacd_esbr_cos_sin_mod,
@@ -480,6 +487,16 @@ int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32
  *   d_qmf     [n][32][128] float: qmf_buf_real[op_delay + i][0..31] at +0, qmf_buf_imag[..][0..31] at +64 of slot row i */
 int32_t xaac_b200_esbr_anal32_dev(xaac_b200_ctx *ctx, const float *d_time_in, int32_t *d_states, int32_t *d_pos, float *d_qmf,
                                   int32_t *d_err, int64_t n_units, void *stream);
+
+/* The same bank with the core -> eSBR hand-overs fused into its load:
+ *   _core_dev:  d_core [n][1024] WORD32 = usac_data->output_data_ptr[ch] (the output of xaac_b200_usac_fd_frm_dec_dev);
+ *               time_sample_vector = (FLOAT32)x * 2^-15 (decoder/ixheaacd_ext_ch_ele.c:1040-1046)
+ *   _pcm16_dev: d_pcm16 = the legacy core decoder's interleaved WORD16 time_data; unit u is channel u % ch_fac of stream
+ *               u / ch_fac and reads (FLOAT32)time_data[ch_fac * i + channel] (decoder/ixheaacd_api.c:3384-3437) */
+int32_t xaac_b200_esbr_anal32_core_dev(xaac_b200_ctx *ctx, const int32_t *d_core, int32_t *d_states, int32_t *d_pos,
+                                       float *d_qmf, int32_t *d_err, int64_t n_units, void *stream);
+int32_t xaac_b200_esbr_anal32_pcm16_dev(xaac_b200_ctx *ctx, const int16_t *d_pcm16, int32_t ch_fac, int32_t *d_states,
+                                        int32_t *d_pos, float *d_qmf, int32_t *d_err, int64_t n_units, void *stream);
 
 /* eSBR float HF generator: batched ixheaacd_generate_hf (decoder/ixheaacd_sbrdec_lpfuncs.c:981-1359) with
  * ixheaacd_esbr_calc_co_variance (:781) and ixheaacd_esbr_chirp_fac_calc (:832), for the 2:1 system (is_usf_4 == 0) without

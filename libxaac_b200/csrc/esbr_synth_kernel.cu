@@ -237,7 +237,17 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
     es_cos_sin_mod(tab, rows + ES * lane);
     __syncwarp();
     // 10-tap window (generic:1544-1575): lane -> outputs lane and lane + 32 of every slot (stride-1 rows: conflict-free)
-    float *out = p.out + u * 2048;
+    float *out = p.out ? p.out + u * 2048 : nullptr;
+    int16_t *pcm = p.pcm16 ? p.pcm16 + ((u / p.pcm_ch_fac) * 2048) * p.pcm_ch_fac + (u % p.pcm_ch_fac) : nullptr;
+    const int pstep = p.pcm_ch_fac;
+    auto emit = [&](int idx, i32 o) {  // WORD32 -> float (sbr_dec.c:650); optional ixheaacd_samples_sat (decode_main.c:82-104)
+      const float f = __fmul_rn(__int2float_rn(o), 1.0f / 65536.0f);
+      if (out) out[idx] = f;
+      if (pcm) {
+        const float c = f > 32767.0f ? 32767.0f : (f < -32768.0f ? -32768.0f : f);
+        pcm[idx * pstep] = (int16_t)__float2int_rz(c);
+      }
+    };
     const int f0s = fpos0 >> 6;
     const bool lock = p.periodic && (off0 & 255) == 0 && (fpos0 & 127) == 0 && ((b0 + f0s) % 10 == 0);
     if (lock) {
@@ -258,8 +268,8 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
           acc1 += (unsigned long long)((long long)q[32] * c1[a]);
         }
         const i32 o0 = (i32)((long long)acc0 >> 31), o1 = (i32)((long long)acc1 >> 31);
-        out[64 * i + lane] = __fmul_rn(__int2float_rn(o0), 1.0f / 65536.0f);
-        out[64 * i + 32 + lane] = __fmul_rn(__int2float_rn(o1), 1.0f / 65536.0f);
+        emit(64 * i + lane, o0);
+        emit(64 * i + 32 + lane, o1);
       }
     } else {
       int fpos = fpos0;
@@ -278,8 +288,8 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
           acc1 += (unsigned long long)((long long)q[32] * c[32]);
         }
         const i32 o0 = (i32)((long long)acc0 >> 31), o1 = (i32)((long long)acc1 >> 31);
-        out[64 * i + lane] = __fmul_rn(__int2float_rn(o0), 1.0f / 65536.0f);
-        out[64 * i + 32 + lane] = __fmul_rn(__int2float_rn(o1), 1.0f / 65536.0f);
+        emit(64 * i + lane, o0);
+        emit(64 * i + 32 + lane, o1);
         fpos += 64;
         if (fpos == 640) fpos = 0;
       }
@@ -426,7 +436,15 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
   const i32 tc = tab.tcos32[2 * lane], ts = tab.tcos32[2 * lane + 1];
   for (long long u = (long long)blockIdx.x * kEaWarps + warp; u < p.n_units; u += warps_total) {
     __syncwarp();
-    const float *tin = p.time_in + u * 1024;
+    const float *tin = p.time_in ? p.time_in + u * 1024 : nullptr;
+    const i32 *cin = p.core_in ? p.core_in + u * 1024 : nullptr;
+    const int16_t *pin = p.pcm_in ? p.pcm_in + ((u / p.pcm_ch_fac) * 1024) * p.pcm_ch_fac + (u % p.pcm_ch_fac) : nullptr;
+    const int pstep = p.pcm_ch_fac;
+    auto sample = [&](int j) -> float {  // the core-coder sample as the float the reference hands to the bank
+      if (tin) return __ldg(tin + j);
+      if (cin) return __fmul_rn(__int2float_rn(__ldg(cin + j)), 0.000030517578125f);
+      return __int2float_rn((int)__ldg(pin + j * pstep));
+    };
     i32 *ring = p.states + u * 320;
     int pos = p.pos[2 * u], f1 = p.pos[2 * u + 1], f2 = f1 + 64;
     if ((pos & 31) != 0 || pos < 0 || pos > 288 || (f1 & 63) != 0 || f1 < 0 || f1 > 576) {
@@ -434,8 +452,11 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
       continue;
     }
     if (u + warps_total < p.n_units) {  // pull the next unit's input and ring into L2 while this one computes
-      const char *q0 = reinterpret_cast<const char *>(tin + warps_total * 1024);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + lane * 128));
+      if (tin || cin) {
+        const char *q0 = tin ? reinterpret_cast<const char *>(tin + warps_total * 1024)
+                             : reinterpret_cast<const char *>(cin + warps_total * 1024);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + lane * 128));
+      }
       const char *q1 = reinterpret_cast<const char *>(ring + warps_total * 320);
       if (lane < 10) asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + lane * 128));
     }
@@ -452,7 +473,7 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
       {
         float v[32];  // all 32 loads in flight before the first conversion
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = __ldg(tin + 32 * j + lane);
+        for (int j = 0; j < 32; j++) v[j] = sample(32 * j + lane);
 #pragma unroll
         for (int j = 0; j < 32; j++) w.T[288 + 32 * j + lane] = f2i_x86(__fmul_rn(v[j], 32768.0f));
       }
@@ -493,7 +514,7 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
       __syncwarp();
 #pragma unroll 1
       for (int slot = 0; slot < 32; slot++) {
-        rg[pos + 31 - lane] = f2i_x86(__fmul_rn(__ldg(tin + 32 * slot + lane), 32768.0f));
+        rg[pos + 31 - lane] = f2i_x86(__fmul_rn(sample(32 * slot + lane), 32768.0f));
         __syncwarp();
         const i32 *fp1 = rg + ((slot & 1) ? 32 : 0), *fp2 = rg + ((slot & 1) ? 0 : 32);
         unsigned long long a = 0, b = 0;

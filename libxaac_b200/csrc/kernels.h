@@ -280,17 +280,22 @@ struct EsbrSynthArgs {
   const float *qmf;     // [n][32][128] per slot re[64] | im[64] (qmf_buf_real[i][k], qmf_buf_imag[i][k])
   int32_t *states;      // [n][1280] filter_states_32, in/out
   int32_t *pos;         // [n][2] {ixheaacd_drc_offset, filter_pos_syn_32 - esbr_qmf_c}, in/out
-  float *out;           // [n][2048] time samples
+  float *out;           // [n][2048] time samples, or null when only PCM is wanted
   int32_t *err;         // [n] or null
   const uint8_t *rom;   // device image built by esbr_synth_build_tables()
   long long n_units;
   int periodic;
+  int16_t *pcm16 = nullptr;  // optional fused ixheaacd_samples_sat: unit u = stream u / pcm_ch_fac, channel u % pcm_ch_fac;
+  int pcm_ch_fac = 1;        // sample i of the unit goes to pcm16[(stream * 2048 + i) * pcm_ch_fac + channel]
 };
 size_t esbr_synth_table_bytes();
 int esbr_synth_build_tables(const uint8_t *erom, uint8_t *out);
 cudaError_t launch_esbr_synth(const EsbrSynthArgs &args, int num_sms, cudaStream_t stream);
 struct EsbrAnalArgs {
-  const float *time_in;  // [n][1024] core-coder samples (ptr_sbr_dec->time_sample_buf)
+  const float *time_in;  // [n][1024] core-coder samples (ptr_sbr_dec->time_sample_buf); or one of the fused hand-overs:
+  const int32_t *core_in = nullptr;  // [n][1024] WORD32 USAC core output, x 2^-15 (ixheaacd_ext_ch_ele.c:1040-1046)
+  const int16_t *pcm_in = nullptr;   // legacy core PCM16, interleaved: unit u = stream u / pcm_ch_fac, channel u % pcm_ch_fac
+  int pcm_ch_fac = 1;                //   (FLOAT32)time_data[ch_fac * i + ch], ixheaacd_api.c:3384-3437
   int32_t *states;       // [n][320] anal_filter_states_32, in/out
   int32_t *pos;          // [n][2] {state_new_samples_pos_low_32 - anal_filter_states_32, filter_pos_32 - esbr_qmf_c}, in/out
   float *qmf;            // unit u writes slot s at qmf + u * out_stride + 128 * s: re at +0..31, im at +64..95

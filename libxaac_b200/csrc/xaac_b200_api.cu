@@ -1016,8 +1016,22 @@ int32_t xaac_b200_set_esbr_rom(xaac_b200_ctx *ctx, const void *tables, size_t by
   return XAAC_B200_OK;
 }
 
+static int32_t esbr_synth_common(xaac_b200_ctx *ctx, const float *d_qmf, int32_t *d_states, int32_t *d_pos, float *d_out,
+                                 int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream);
 int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32_t *d_states, int32_t *d_pos, float *d_out,
                                    int32_t *d_err, int64_t n_units, void *stream) {
+  if (ctx && n_units > 0 && !d_out) return bad_arg(ctx, "null buffer");
+  return esbr_synth_common(ctx, d_qmf, d_states, d_pos, d_out, nullptr, 1, d_err, n_units, stream);
+}
+int32_t xaac_b200_esbr_synth64_pcm16_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32_t *d_states, int32_t *d_pos,
+                                         float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units,
+                                         void *stream) {
+  if (ctx && n_units > 0 && !d_pcm16) return bad_arg(ctx, "null buffer");
+  if (ctx && (ch_fac < 1 || ch_fac > 8 || n_units % ch_fac != 0)) return bad_arg(ctx, "ch_fac must be 1..8 and divide n_units");
+  return esbr_synth_common(ctx, d_qmf, d_states, d_pos, d_out, d_pcm16, ch_fac, d_err, n_units, stream);
+}
+static int32_t esbr_synth_common(xaac_b200_ctx *ctx, const float *d_qmf, int32_t *d_states, int32_t *d_pos, float *d_out,
+                                 int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream) {
   if (!ctx) return XAAC_B200_ERR_ARG;
   if (!ctx->d_rom_esbr) {
     snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_rom has not been called");
@@ -1025,9 +1039,10 @@ int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32
   }
   if (n_units < 0) return bad_arg(ctx, "n_units");
   if (n_units == 0) return XAAC_B200_OK;
-  if (!d_qmf || !d_states || !d_pos || !d_out) return bad_arg(ctx, "null buffer");
+  if (!d_qmf || !d_states || !d_pos || (!d_out && !d_pcm16)) return bad_arg(ctx, "null buffer");
   xb::EsbrSynthArgs a;
   a.qmf = d_qmf; a.states = d_states; a.pos = d_pos; a.out = d_out; a.err = d_err; a.rom = ctx->d_rom_esbr;
+  a.pcm16 = d_pcm16; a.pcm_ch_fac = ch_fac;
   a.n_units = n_units; a.periodic = ctx->esbr_periodic;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(a, ctx->num_sms, (cudaStream_t)stream));
@@ -1035,8 +1050,28 @@ int32_t xaac_b200_esbr_synth64_dev(xaac_b200_ctx *ctx, const float *d_qmf, int32
   return XAAC_B200_OK;
 }
 
+static int32_t esbr_anal_common(xaac_b200_ctx *ctx, const float *d_time_in, const int32_t *d_core, const int16_t *d_pcm,
+                                int32_t ch_fac, int32_t *d_states, int32_t *d_pos, float *d_qmf, int32_t *d_err,
+                                int64_t n_units, void *stream);
 int32_t xaac_b200_esbr_anal32_dev(xaac_b200_ctx *ctx, const float *d_time_in, int32_t *d_states, int32_t *d_pos, float *d_qmf,
                                   int32_t *d_err, int64_t n_units, void *stream) {
+  if (ctx && n_units > 0 && !d_time_in) return bad_arg(ctx, "null buffer");
+  return esbr_anal_common(ctx, d_time_in, nullptr, nullptr, 1, d_states, d_pos, d_qmf, d_err, n_units, stream);
+}
+int32_t xaac_b200_esbr_anal32_core_dev(xaac_b200_ctx *ctx, const int32_t *d_core, int32_t *d_states, int32_t *d_pos,
+                                       float *d_qmf, int32_t *d_err, int64_t n_units, void *stream) {
+  if (ctx && n_units > 0 && !d_core) return bad_arg(ctx, "null buffer");
+  return esbr_anal_common(ctx, nullptr, d_core, nullptr, 1, d_states, d_pos, d_qmf, d_err, n_units, stream);
+}
+int32_t xaac_b200_esbr_anal32_pcm16_dev(xaac_b200_ctx *ctx, const int16_t *d_pcm16, int32_t ch_fac, int32_t *d_states,
+                                        int32_t *d_pos, float *d_qmf, int32_t *d_err, int64_t n_units, void *stream) {
+  if (ctx && n_units > 0 && !d_pcm16) return bad_arg(ctx, "null buffer");
+  if (ctx && (ch_fac < 1 || ch_fac > 8 || n_units % ch_fac != 0)) return bad_arg(ctx, "ch_fac must be 1..8 and divide n_units");
+  return esbr_anal_common(ctx, nullptr, nullptr, d_pcm16, ch_fac, d_states, d_pos, d_qmf, d_err, n_units, stream);
+}
+static int32_t esbr_anal_common(xaac_b200_ctx *ctx, const float *d_time_in, const int32_t *d_core, const int16_t *d_pcm,
+                                int32_t ch_fac, int32_t *d_states, int32_t *d_pos, float *d_qmf, int32_t *d_err,
+                                int64_t n_units, void *stream) {
   if (!ctx) return XAAC_B200_ERR_ARG;
   if (!ctx->d_rom_esbr) {
     snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_rom has not been called");
@@ -1044,8 +1079,9 @@ int32_t xaac_b200_esbr_anal32_dev(xaac_b200_ctx *ctx, const float *d_time_in, in
   }
   if (n_units < 0) return bad_arg(ctx, "n_units");
   if (n_units == 0) return XAAC_B200_OK;
-  if (!d_time_in || !d_states || !d_pos || !d_qmf) return bad_arg(ctx, "null buffer");
+  if ((!d_time_in && !d_core && !d_pcm) || !d_states || !d_pos || !d_qmf) return bad_arg(ctx, "null buffer");
   xb::EsbrAnalArgs a;
+  a.core_in = d_core; a.pcm_in = d_pcm; a.pcm_ch_fac = ch_fac;
   a.time_in = d_time_in; a.states = d_states; a.pos = d_pos; a.qmf = d_qmf; a.err = d_err; a.rom = ctx->d_rom_esbr;
   a.n_units = n_units; a.periodic = ctx->esbr_periodic;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");

@@ -22,20 +22,30 @@ class EsbrSynthBatch:
         self.pos = torch.zeros((self.n, 2), dtype=torch.int32, device=device)
 
 
-def esbr_synthesis_filt(ctx, state, qmf, out=None, err=None, stream=None):
-    """Batched drop-in for the synthesis core of ixheaacd_esbr_synthesis_filt_block.  Returns (out, err)."""
+def esbr_synthesis_filt(ctx, state, qmf, out=None, err=None, stream=None, pcm16=None, ch_fac=1, want_float=True):
+    """Batched drop-in for the synthesis core of ixheaacd_esbr_synthesis_filt_block.  Returns (out, err).
+    With pcm16 (int16 [n / ch_fac, 2048, ch_fac]) the store also applies ixheaacd_samples_sat (clamp + truncation,
+    channel-interleaved; unit u = channel u % ch_fac of stream u // ch_fac); want_float=False skips the float output."""
     n = state.n
     _chk(qmf, torch.float32, (n, 32, 128), "qmf", "cuda")
-    if out is None:
+    if out is None and want_float:
         out = torch.empty((n, 2048), dtype=torch.float32, device=qmf.device)
-    _chk(out, torch.float32, (n, 2048), "out", "cuda")
+    if out is not None:
+        _chk(out, torch.float32, (n, 2048), "out", "cuda")
     if err is None:
         err = torch.empty((n,), dtype=torch.int32, device=qmf.device)
     if stream is None:
         stream = torch.cuda.current_stream(qmf.device)
-    rc = ctx._lib.xaac_b200_esbr_synth64_dev(ctx.handle, _ptr(qmf), _ptr(state.states), _ptr(state.pos), _ptr(out), _ptr(err),
-                                            n, ctypes.c_void_p(stream.cuda_stream))
-    ctx.check(rc, "xaac_b200_esbr_synth64_dev")
+    if pcm16 is None:
+        rc = ctx._lib.xaac_b200_esbr_synth64_dev(ctx.handle, _ptr(qmf), _ptr(state.states), _ptr(state.pos), _ptr(out), _ptr(err),
+                                                n, ctypes.c_void_p(stream.cuda_stream))
+        ctx.check(rc, "xaac_b200_esbr_synth64_dev")
+    else:
+        _chk(pcm16, torch.int16, (n // ch_fac, 2048, ch_fac), "pcm16", "cuda")
+        rc = ctx._lib.xaac_b200_esbr_synth64_pcm16_dev(ctx.handle, _ptr(qmf), _ptr(state.states), _ptr(state.pos),
+                                                      _ptr(out) if out is not None else None, _ptr(pcm16), int(ch_fac),
+                                                      _ptr(err), n, ctypes.c_void_p(stream.cuda_stream))
+        ctx.check(rc, "xaac_b200_esbr_synth64_pcm16_dev")
     return out, err
 
 
@@ -49,11 +59,18 @@ class EsbrAnalBatch:
         self.pos = torch.zeros((self.n, 2), dtype=torch.int32, device=device)
 
 
-def esbr_analysis_filt_block(ctx, state, time_in, qmf=None, err=None, stream=None):
+def esbr_analysis_filt_block(ctx, state, time_in, qmf=None, err=None, stream=None, ch_fac=1):
     """Batched drop-in for ixheaacd_esbr_analysis_filt_block (32 channels, 32 slots).  time_in float32 [n, 1024]; returns
-    (qmf float32 [n, 32, 128] with re at +0..31 and im at +64..95 of every slot row, err)."""
+    (qmf float32 [n, 32, 128] with re at +0..31 and im at +64..95 of every slot row, err).
+    time_in may also be the core decoder's own output, the hand-over conversion then happens in the kernel's load:
+    int32 [n, 1024] (USAC core, x 2^-15) or int16 [n / ch_fac, 1024, ch_fac] (legacy interleaved PCM)."""
     n = state.n
-    _chk(time_in, torch.float32, (n, 1024), "time_in", "cuda")
+    if time_in.dtype == torch.int32:
+        _chk(time_in, torch.int32, (n, 1024), "time_in", "cuda")
+    elif time_in.dtype == torch.int16:
+        _chk(time_in, torch.int16, (n // ch_fac, 1024, ch_fac), "time_in", "cuda")
+    else:
+        _chk(time_in, torch.float32, (n, 1024), "time_in", "cuda")
     if qmf is None:
         qmf = torch.zeros((n, 32, 128), dtype=torch.float32, device=time_in.device)
     _chk(qmf, torch.float32, (n, 32, 128), "qmf", "cuda")
@@ -61,9 +78,14 @@ def esbr_analysis_filt_block(ctx, state, time_in, qmf=None, err=None, stream=Non
         err = torch.empty((n,), dtype=torch.int32, device=time_in.device)
     if stream is None:
         stream = torch.cuda.current_stream(time_in.device)
-    rc = ctx._lib.xaac_b200_esbr_anal32_dev(ctx.handle, _ptr(time_in), _ptr(state.states), _ptr(state.pos), _ptr(qmf), _ptr(err),
-                                           n, ctypes.c_void_p(stream.cuda_stream))
-    ctx.check(rc, "xaac_b200_esbr_anal32_dev")
+    tail = (_ptr(state.states), _ptr(state.pos), _ptr(qmf), _ptr(err), n, ctypes.c_void_p(stream.cuda_stream))
+    if time_in.dtype == torch.int32:
+        ctx.check(ctx._lib.xaac_b200_esbr_anal32_core_dev(ctx.handle, _ptr(time_in), *tail), "xaac_b200_esbr_anal32_core_dev")
+    elif time_in.dtype == torch.int16:
+        ctx.check(ctx._lib.xaac_b200_esbr_anal32_pcm16_dev(ctx.handle, _ptr(time_in), int(ch_fac), *tail),
+                  "xaac_b200_esbr_anal32_pcm16_dev")
+    else:
+        ctx.check(ctx._lib.xaac_b200_esbr_anal32_dev(ctx.handle, _ptr(time_in), *tail), "xaac_b200_esbr_anal32_dev")
     return qmf, err
 
 

@@ -735,3 +735,14 @@ void ref_esbr_env_calc_batch(float *re, float *im, int32_t *ipar, const float *f
     err[u] = ref_esbr_env_calc(re + (size_t)u * 2560, im + (size_t)u * 2560, ipar + (size_t)u * XO_EEC_IPAR_WORDS,
                                fpar + (size_t)u * XO_EEC_FPAR_WORDS, state + (size_t)u * XO_EEC_STATE_WORDS);
 }
+
+
+/* ---- ixheaacd_samples_sat (decoder/ixheaacd_decode_main.c:82): float[ch][4096] -> interleaved PCM16 */
+VOID ixheaacd_samples_sat(WORD8 *outbuffer, WORD32 num_samples_out, WORD32 pcmsize, FLOAT32 (*out_samples)[4096],
+                          WORD32 *out_bytes, WORD32 num_channel_out);
+void ref_samples_sat16(const float *in /* [nch][n] */, int nch, int n, int16_t *pcm) {
+  static __thread FLOAT32 buf[8][4096];
+  WORD32 bytes = 0;
+  for (int c = 0; c < nch; c++) memcpy(buf[c], in + (size_t)c * n, n * sizeof(float));
+  ixheaacd_samples_sat((WORD8 *)pcm, n, 16, buf, &bytes, nch);
+}

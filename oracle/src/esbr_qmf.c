@@ -251,3 +251,25 @@ void xo_esbr_anal32_batch(const uint8_t *erom, const float *time_in, i32 *states
   for (int u = 0; u < n; u++)
     xo_esbr_anal32(erom, time_in + (size_t)u * 1024, states + (size_t)u * 320, pos + 2 * u, pos + 2 * u + 1, qmf + (size_t)u * 4096);
 }
+
+
+/* ---- hand-overs around the eSBR stage ----------------------------------------------------------------- */
+/* USAC core -> eSBR: time_sample_vector = (FLOAT32)output_data_ptr * (FLOAT32)ONE_BY_TWO_POW_15 (ixheaacd_ext_ch_ele.c:1040) */
+void xo_esbr_core_to_float(const int32_t *core, float *out, int n) {
+  for (int k = 0; k < n; k++) out[k] = (float)((float)core[k] * (float)(0.000030517578125));
+}
+/* legacy core -> eSBR: (FLOAT32)time_data[ch_fac * i + ch], no scaling (ixheaacd_api.c:3384-3437) */
+void xo_esbr_pcm16_to_float(const int16_t *pcm, int ch_fac, int ch, float *out, int n) {
+  for (int i = 0; i < n; i++) out[i] = (float)pcm[ch_fac * i + ch];
+}
+/* ixheaacd_samples_sat, pcmsize 16 (ixheaacd_decode_main.c:82-104): clamp, then the C cast (truncation), interleaved */
+void xo_samples_sat16(const float *in, int ch_fac, int ch, int16_t *pcm, int n) {
+  for (int i = 0; i < n; i++) {
+    float v = in[i];
+    if (v > 32767.0f)
+      v = 32767.0f;
+    else if (v < -32768.0f)
+      v = -32768.0f;
+    pcm[ch_fac * i + ch] = (int16_t)v;
+  }
+}

@@ -315,6 +315,11 @@ void xo_esbr_synth64_batch(const uint8_t *erom, const float *qmf, int32_t *fs, i
 void xo_esbr_anal32(const uint8_t *erom, const float *time_in, int32_t *states, int32_t *pos_io, int32_t *fpos_io, float *qmf);
 void xo_esbr_anal32_batch(const uint8_t *erom, const float *time_in, int32_t *states, int32_t *pos, float *qmf, int n);
 
+/* eSBR hand-overs, esbr_qmf.c */
+void xo_esbr_core_to_float(const int32_t *core, float *out, int n);                  /* ixheaacd_ext_ch_ele.c:1040-1046 */
+void xo_esbr_pcm16_to_float(const int16_t *pcm, int ch_fac, int ch, float *out, int n); /* ixheaacd_api.c:3384-3437 */
+void xo_samples_sat16(const float *in, int ch_fac, int ch, int16_t *pcm, int n);      /* ixheaacd_decode_main.c:82-104 */
+
 /* ---- eSBR float HF generator (esbr_hfgen.c): ixheaacd_generate_hf ------------------------------------------------------
  * QMF buffers are [XO_EHF_ROWS][64] floats; row r is row r - 2 of the pointers the reference passes
  * (qmf_buf_real + SBR_HF_ADJ_OFFSET etc.), i.e. the reference's own arrays from their first row. par[] words: */

@@ -111,3 +111,56 @@ def test_analysis_synthesis_stream(ctx, oracle):
         eo, fs, sp = oracle.esbr_synth_batch(eq, fs, sp)
         assert np.array_equal(out.cpu().numpy().view(np.int32), eo.view(np.int32)), f"frame {f}"
     assert np.array_equal(a.states.cpu().numpy(), st) and np.array_equal(s.states.cpu().numpy(), fs)
+
+
+def test_fused_handovers(ctx, oracle):
+    """SURVEY 8a-F around the eSBR stage: USAC core WORD32 x 2^-15 and legacy interleaved PCM16 hand-overs fused into the
+    analysis bank's load, ixheaacd_samples_sat fused into the synthesis bank's store — against oracle glue + oracle banks"""
+    import torch
+    import libxaac_b200 as xb
+    P = oracle_util.P
+    rng = np.random.default_rng(12)
+    n = 96
+    _, st, pos = oracle_util.synth_esbr_anal_units(n, 21)
+    # USAC core output
+    core = (rng.standard_normal((n, 1024)) * 2.0 ** rng.integers(4, 28, (n, 1))).clip(-2**31, 2**31 - 1).astype(np.int64).astype(np.int32)
+    core[0, :4] = [2**31 - 1, -2**31, 16777217, -33554435]
+    xf = np.zeros((n, 1024), np.float32)
+    oracle.lib.xo_esbr_core_to_float(P(core), P(xf), n * 1024)
+    want = oracle.esbr_anal_batch(xf, st, pos)
+    ea = xb.EsbrAnalBatch(n)
+    ea.states.copy_(torch.from_numpy(st)); ea.pos.copy_(torch.from_numpy(pos))
+    q, err = xb.esbr_analysis_filt_block(ctx, ea, torch.from_numpy(core).cuda())
+    torch.cuda.synchronize()
+    assert int(err.abs().max()) == 0
+    assert np.array_equal(q.cpu().numpy().view(np.int32), want[0].view(np.int32))
+    assert np.array_equal(ea.states.cpu().numpy(), want[1])
+    # legacy stereo PCM16, interleaved
+    pcm = rng.integers(-32768, 32768, (n // 2, 1024, 2)).astype(np.int16)
+    for u in range(n):
+        oracle.lib.xo_esbr_pcm16_to_float(P(np.ascontiguousarray(pcm[u // 2])), 2, u % 2, P(xf[u]), 1024)
+    want = oracle.esbr_anal_batch(xf, st, pos)
+    ea.states.copy_(torch.from_numpy(st)); ea.pos.copy_(torch.from_numpy(pos))
+    q, err = xb.esbr_analysis_filt_block(ctx, ea, torch.from_numpy(pcm).cuda(), ch_fac=2)
+    torch.cuda.synchronize()
+    assert np.array_equal(q.cpu().numpy().view(np.int32), want[0].view(np.int32))
+    # synthesis + samples_sat (amplitudes around and beyond full scale)
+    qmf, fs, sp = oracle_util.synth_esbr_units(n, 31)
+    qmf *= (2.0 ** rng.uniform(-2, 13, (n, 1, 1))).astype(np.float32)
+    o, fs2, sp2 = oracle.esbr_synth_batch(qmf, fs, sp)
+    wpcm = np.zeros((n // 2, 2048, 2), np.int16)
+    for u in range(n):
+        oracle.lib.xo_samples_sat16(P(np.ascontiguousarray(o[u])), 2, u % 2, P(wpcm[u // 2]), 2048)
+    es = xb.EsbrSynthBatch(n)
+    es.states.copy_(torch.from_numpy(fs)); es.pos.copy_(torch.from_numpy(sp))
+    gp = torch.zeros((n // 2, 2048, 2), dtype=torch.int16, device="cuda")
+    out, err = xb.esbr_synthesis_filt(ctx, es, torch.from_numpy(qmf).cuda(), pcm16=gp, ch_fac=2)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.int32), o.view(np.int32))
+    assert np.array_equal(gp.cpu().numpy(), wpcm)
+    assert np.abs(wpcm.astype(np.int32)).max() > 30000   # the bank saturates in WORD32 first: |out| < 32768 always
+    es.states.copy_(torch.from_numpy(fs)); es.pos.copy_(torch.from_numpy(sp))
+    gp.zero_()
+    out, err = xb.esbr_synthesis_filt(ctx, es, torch.from_numpy(qmf).cuda(), pcm16=gp, ch_fac=2, want_float=False)
+    torch.cuda.synchronize()
+    assert out is None and np.array_equal(gp.cpu().numpy(), wpcm) and np.array_equal(es.states.cpu().numpy(), fs2)

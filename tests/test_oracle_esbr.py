@@ -165,3 +165,19 @@ def test_esbr_env_calc_golden(oracle):
     rp = oracle_util.esbr_random_phase()
     check_envcalc_golden(oracle_util.oracle_esbr_envcalc_batch(oracle, golden_envcalc_units(g), rp), g, "oracle vs tapped decode")
     assert len(set(g["ipar_in"][:, oracle_util.EEC["NUM_ENV"]].tolist())) >= 3
+
+
+def test_samples_sat_matches_reference(oracle, ref):
+    """float -> PCM16 hand-over (clamp, truncation towards zero, interleave) against ixheaacd_samples_sat itself"""
+    rng = np.random.default_rng(3)
+    n, nch = 2048, 2
+    x = (rng.standard_normal((nch, n)) * 20000).astype(np.float32)
+    x[0, :8] = [32767.0, 32767.5, 32768.0, -32768.0, -32768.5, -32769.0, 0.99, -0.99]
+    x[1, :4] = [1e9, -1e9, 0.0, -0.0]
+    want = np.zeros((n, nch), np.int16)
+    ref.lib.ref_samples_sat16(oracle_util.P(x), nch, n, oracle_util.P(want))
+    got = np.zeros((n, nch), np.int16)
+    for c in range(nch):
+        oracle.lib.xo_samples_sat16(oracle_util.P(np.ascontiguousarray(x[c])), nch, c, oracle_util.P(got), n)
+    assert np.array_equal(got, want)
+    assert list(want[:8, 0]) == [32767, 32767, 32767, -32768, -32768, -32768, 0, 0]
