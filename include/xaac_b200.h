@@ -584,6 +584,33 @@ int32_t xaac_b200_set_esbr_envcalc_rom(xaac_b200_ctx *ctx, const void *random_ph
 int32_t xaac_b200_esbr_env_calc_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im, int32_t *d_ipar, const float *d_fpar,
                                     float *d_state, int32_t *d_err, int64_t n_units, void *stream);
 
+/* Whole float eSBR stage: the eSBR branch of ixheaacd_sbr_dec (decoder/ixheaacd_sbr_dec.c:812-1006) for one USAC channel
+ * per unit with apply_processing = 1, hbe_flag = 0, no PS / MPS / DRC, stereo_config_idx <= 0, 2:1, 16 time slots:
+ *   history shift (memmove of op_delay + SBR_HF_ADJ_OFFSET = 8 rows of qmf_buf_* and sbr_qmf_out_*), 32-band analysis,
+ *   ixheaacd_generate_hf, ixheaacd_sbr_env_calc, ixheaacd_esbr_synthesis_regrp, 64-band synthesis, optional ixheaacd_samples_sat.
+ * Four kernel launches; the shifts, the regrouping and both hand-overs are fused into the banks' loads / stores.
+ * The per-stream state stays in HBM between calls (caller-owned device buffers, all in/out): */
+typedef struct xaac_b200_esbr_state_view {
+  float *qmf_re, *qmf_im;   /* [n][40][64] ptr_sbr_dec->qmf_buf_real / qmf_buf_imag, rows 0..39 */
+  float *out_re, *out_im;   /* [n][40][64] ptr_sbr_dec->sbr_qmf_out_real / sbr_qmf_out_imag, rows 0..39 */
+  int32_t *anal_states;     /* [n][320]  str_codec_qmf_bank.anal_filter_states_32 */
+  int32_t *anal_pos;        /* [n][2]    as for xaac_b200_esbr_anal32_dev */
+  int32_t *synth_states;    /* [n][1280] str_synthesis_qmf_bank.filter_states_32 */
+  int32_t *synth_pos;       /* [n][2]    as for xaac_b200_esbr_synth64_dev */
+  float *bw_prev;           /* [n][6]    ptr_frame_data->bw_array_prev */
+  int32_t *patch;           /* [n][8]    {patch_param.num_patches, start_subband[7]} */
+  float *ec_state;          /* [n][640]  e_gain | noise_buf */
+} xaac_b200_esbr_state_view;
+/*   d_time_in  [n][1024] float core samples, or NULL and d_core_in [n][1024] WORD32 (USAC core output, x 2^-15 in the load)
+ *   d_hf_par   [n][XAAC_EHF_PAR_WORDS]; d_ec_ipar [n][XAAC_EEC_IPAR_WORDS] (in/out words updated); d_ec_fpar [n][XAAC_EEC_FPAR_WORDS]
+ *   d_rg_par   [n][4] WORD32 {pstr_freq_band_data->qmf_sb_prev, sub_band_start, 2 * border_vec[0], 0}
+ *   d_out      [n][2048] float time samples or NULL; d_pcm16 interleaved PCM16 or NULL (ch_fac as for _synth64_pcm16_dev)
+ *   d_err      [4][n] or NULL: per unit the err word of the analysis, HF generator, envelope adjuster and synthesis kernels */
+int32_t xaac_b200_esbr_dec_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view *st, const float *d_time_in,
+                               const int32_t *d_core_in, const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar,
+                               const int32_t *d_rg_par, float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err,
+                               int64_t n_units, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ SIGNATURES = {
     "xaac_b200_esbr_synth64_pcm16_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "xaac_b200_esbr_anal32_core_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "xaac_b200_esbr_anal32_pcm16_dev": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "xaac_b200_esbr_dec_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "xaac_b200_esbr_generate_hf_dev": (_i32, [_vp] * 11 + [_i64, _vp]),
     "xaac_b200_set_esbr_envcalc_rom": (_i32, [_vp, _vp, _sz]),
     "xaac_b200_esbr_env_calc_dev": (_i32, [_vp] * 7 + [_i64, _vp]),

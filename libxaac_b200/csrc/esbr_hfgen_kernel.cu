@@ -120,6 +120,20 @@ __global__ void __launch_bounds__(kEhWarps * 32) esbr_hfgen_kernel(EsbrHfgenArgs
     const float *pre = p.pv_re ? p.pv_re + u * kEhUnit : nullptr, *pim = p.pv_im ? p.pv_im + u * kEhUnit : nullptr;
     float *dre = p.dst_re + u * kEhUnit, *dim = p.dst_im + u * kEhUnit;
     float *bw_prev = p.bw_prev + 6 * u;
+    if (p.shift_rows) {  // the stage's memmove of the 8 history rows (op_delay + SBR_HF_ADJ_OFFSET)
+      float vr[16], vi[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        vr[q] = dre[2048 + 32 * q + lane];
+        vi[q] = dim[2048 + 32 * q + lane];
+      }
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        dre[32 * q + lane] = vr[q];
+        dim[32 * q + lane] = vi[q];
+      }
+      __syncwarp();
+    }
     if (lane < 8) {  // lpfuncs.c:832
       float bw = 0.0f;
       if (lane < num_if) {

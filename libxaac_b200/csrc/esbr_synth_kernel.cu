@@ -206,22 +206,43 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
     {  // pull this warp's next unit towards L2 while this one is processed
       const long long un = u + warps_total;
       if (un < p.n_units) {
-        const char *q0 = reinterpret_cast<const char *>(p.qmf + un * 4096);
-        for (int o = lane * 128; o < 16384; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + o));
+        if (p.qmf) {
+          const char *q0 = reinterpret_cast<const char *>(p.qmf + un * 4096);
+          for (int o = lane * 128; o < 16384; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + o));
+        }
         const char *q1 = reinterpret_cast<const char *>(p.states + un * 1280);
         for (int o = lane * 128; o < 5120; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + o));
       }
     }
     // matrix rows: float -> WORD32 (sbr_dec.c:584-587), coalesced 512-byte row loads
-    const float4 *src = reinterpret_cast<const float4 *>(p.qmf + u * 4096);
+    if (!p.rg_par) {
+      const float4 *src = reinterpret_cast<const float4 *>(p.qmf + u * 4096);
 #pragma unroll 4
-    for (int s = 0; s < 32; s++) {
-      const float4 v = __ldg(src + 32 * s + lane);
-      i32 *r = rows + ES * s + 4 * lane;
-      r[0] = f2i_x86(__fmul_rn(v.x, 64.f));
-      r[1] = f2i_x86(__fmul_rn(v.y, 64.f));
-      r[2] = f2i_x86(__fmul_rn(v.z, 64.f));
-      r[3] = f2i_x86(__fmul_rn(v.w, 64.f));
+      for (int s = 0; s < 32; s++) {
+        const float4 v = __ldg(src + 32 * s + lane);
+        i32 *r = rows + ES * s + 4 * lane;
+        r[0] = f2i_x86(__fmul_rn(v.x, 64.f));
+        r[1] = f2i_x86(__fmul_rn(v.y, 64.f));
+        r[2] = f2i_x86(__fmul_rn(v.z, 64.f));
+        r[3] = f2i_x86(__fmul_rn(v.w, 64.f));
+      }
+    } else {  // stage mode: ixheaacd_esbr_synthesis_regrp in the load — low band from qmf_buf, high band from sbr_qmf_out
+      const int xo_first = p.rg_par[4 * u], xo_rest = p.rg_par[4 * u + 1], stop = p.rg_par[4 * u + 2];
+      const float *lo = (lane < 16 ? p.rg_low_re : p.rg_low_im) + u * 2560 + 128 + 4 * (lane & 15);
+      const float *hi = (lane < 16 ? p.rg_high_re : p.rg_high_im) + u * 2560 + 128 + 4 * (lane & 15);
+      const int k0 = 4 * (lane & 15);
+#pragma unroll 4
+      for (int s = 0; s < 32; s++) {
+        const int xo = s < stop ? xo_first : xo_rest;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (k0 < xo) a = *reinterpret_cast<const float4 *>(lo + 64 * s);
+        if (k0 + 3 >= xo) b = *reinterpret_cast<const float4 *>(hi + 64 * s);
+        i32 *r = rows + ES * s + 4 * lane;
+        r[0] = f2i_x86(__fmul_rn(k0 < xo ? a.x : b.x, 64.f));
+        r[1] = f2i_x86(__fmul_rn(k0 + 1 < xo ? a.y : b.y, 64.f));
+        r[2] = f2i_x86(__fmul_rn(k0 + 2 < xo ? a.z : b.z, 64.f));
+        r[3] = f2i_x86(__fmul_rn(k0 + 3 < xo ? a.w : b.w, 64.f));
+      }
     }
     {  // old ring blocks: the block of age a0 (1..9) goes to history row 9 - a0
       const i32 *ss = p.states + u * 1280;
@@ -555,6 +576,38 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
     }
     __syncwarp();
     // lane = band: t_cos rotation (generic:1490-1505), WORD32 -> float (x 1/256), coalesced rows of the output matrix
+    if (p.stage_re) {
+      float *sre = p.stage_re + u * 2560, *sim = p.stage_im + u * 2560;
+      {  // history rows: 32..39 -> 0..7, all 64 bands
+        float vr[16], vi[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          vr[q] = sre[2048 + 32 * q + lane];
+          vi[q] = sim[2048 + 32 * q + lane];
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          sre[32 * q + lane] = vr[q];
+          sim[32 * q + lane] = vi[q];
+        }
+      }
+#pragma unroll 2
+      for (int s = 0; s < 32; s++) {
+        const i32 re = w.rows[EA * s + lane], im = w.rows[EA * s + 64 + lane];
+        const i32 r2 = (i32)(((long long)re * tc + (long long)im * ts) >> 31);
+        const long long x = (long long)im * tc, y = (long long)re * ts;
+        long long d = (long long)((unsigned long long)x - (unsigned long long)y);
+        if (((x ^ y) & (x ^ d)) < 0) d = x < 0 ? (long long)0x8000000000000000ULL : 0x7fffffffffffffffLL;
+        sre[64 * (8 + s) + lane] = __fmul_rn(__int2float_rn(r2), 1.0f / 256.0f);
+        sim[64 * (8 + s) + lane] = __fmul_rn(__int2float_rn((i32)(d >> 31)), 1.0f / 256.0f);
+      }
+      if (lane == 0) {
+        p.pos[2 * u] = pos;
+        p.pos[2 * u + 1] = f1;
+        if (p.err) p.err[u] = 0;
+      }
+      continue;
+    }
     float *out = p.qmf + u * p.out_stride;
 #pragma unroll 2
     for (int s = 0; s < 32; s++) {

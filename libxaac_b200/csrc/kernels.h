@@ -285,6 +285,11 @@ struct EsbrSynthArgs {
   const uint8_t *rom;   // device image built by esbr_synth_build_tables()
   long long n_units;
   int periodic;
+  // stage mode (ixheaacd_esbr_synthesis_regrp fused into the load, sbr_dec.c:297-397, stereo_config_idx <= 0): slot s reads row
+  // 2 + s, band k from rg_low_* (qmf_buf) when k < x_over(s), else from rg_high_* (sbr_qmf_out); rg_par[u] = {x_over of the
+  // slots before stop_border (qmf_sb_prev), x_over of the others (sub_band_start), stop_border (2 * border_vec[0]), 0}
+  const float *rg_low_re = nullptr, *rg_low_im = nullptr, *rg_high_re = nullptr, *rg_high_im = nullptr;  // [n][40][64]
+  const int32_t *rg_par = nullptr;                                                                       // [n][4]
   int16_t *pcm16 = nullptr;  // optional fused ixheaacd_samples_sat: unit u = stream u / pcm_ch_fac, channel u % pcm_ch_fac;
   int pcm_ch_fac = 1;        // sample i of the unit goes to pcm16[(stream * 2048 + i) * pcm_ch_fac + channel]
 };
@@ -296,6 +301,9 @@ struct EsbrAnalArgs {
   const int32_t *core_in = nullptr;  // [n][1024] WORD32 USAC core output, x 2^-15 (ixheaacd_ext_ch_ele.c:1040-1046)
   const int16_t *pcm_in = nullptr;   // legacy core PCM16, interleaved: unit u = stream u / pcm_ch_fac, channel u % pcm_ch_fac
   int pcm_ch_fac = 1;                //   (FLOAT32)time_data[ch_fac * i + ch], ixheaacd_api.c:3384-3437
+  // stage mode: the unit's qmf_buf_real / imag arrays [n][40][64]; rows 32..39 move to rows 0..7 first (the memmove at the
+  // top of ixheaacd_sbr_dec's eSBR branch, sbr_dec.c:836-846, op_delay 6 + SBR_HF_ADJ_OFFSET 2), slot s goes to row 8 + s
+  float *stage_re = nullptr, *stage_im = nullptr;
   int32_t *states;       // [n][320] anal_filter_states_32, in/out
   int32_t *pos;          // [n][2] {state_new_samples_pos_low_32 - anal_filter_states_32, filter_pos_32 - esbr_qmf_c}, in/out
   float *qmf;            // unit u writes slot s at qmf + u * out_stride + 128 * s: re at +0..31, im at +64..95
@@ -320,6 +328,7 @@ struct EsbrHfgenArgs {
   int32_t *patch_out;            // [n][8] {num_patches, start_subband[7]} or null
   int32_t *err;                  // [n] or null
   long long n_units;
+  int shift_rows = 0;            // stage mode: rows 32..39 of dst move to rows 0..7 first (sbr_dec.c:848-856)
 };
 cudaError_t launch_esbr_hfgen(const EsbrHfgenArgs &args, int num_sms, cudaStream_t stream);
 

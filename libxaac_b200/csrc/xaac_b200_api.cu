@@ -1136,6 +1136,60 @@ int32_t xaac_b200_esbr_env_calc_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im
   return XAAC_B200_OK;
 }
 
+// Whole eSBR stage (eSBR branch of ixheaacd_sbr_dec for USAC mono / stereo channels without harmonic transposer, PS, MPS):
+// analysis bank (+ history shift, + core hand-over) -> HF generator (+ history shift) -> envelope adjuster -> synthesis bank
+// (+ regrouping, + optional PCM16 hand-over).  Four launches on one stream.
+int32_t xaac_b200_esbr_dec_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view *st, const float *d_time_in,
+                               const int32_t *d_core_in, const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar,
+                               const int32_t *d_rg_par, float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err,
+                               int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->d_rom_esbr || !ctx->d_rom_rphase) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_rom / xaac_b200_set_esbr_envcalc_rom have not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!st || !st->qmf_re || !st->qmf_im || !st->out_re || !st->out_im || !st->anal_states || !st->anal_pos ||
+      !st->synth_states || !st->synth_pos || !st->bw_prev || !st->patch || !st->ec_state)
+    return bad_arg(ctx, "state view with null members");
+  if ((!d_time_in && !d_core_in) || !d_hf_par || !d_ec_ipar || !d_ec_fpar || !d_rg_par || (!d_out && !d_pcm16))
+    return bad_arg(ctx, "null buffer");
+  if (d_pcm16 && (ch_fac < 1 || ch_fac > 8 || n_units % ch_fac != 0)) return bad_arg(ctx, "ch_fac must be 1..8 and divide n_units");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    xb::EsbrAnalArgs a;
+    a.time_in = d_time_in; a.core_in = d_time_in ? nullptr : d_core_in; a.states = st->anal_states; a.pos = st->anal_pos;
+    a.qmf = nullptr; a.stage_re = st->qmf_re; a.stage_im = st->qmf_im; a.err = d_err; a.rom = ctx->d_rom_esbr;
+    a.n_units = n_units; a.periodic = ctx->esbr_periodic;
+    LAUNCH("esbr_anal_kernel", stream, xb::launch_esbr_anal(a, ctx->num_sms, s));
+  }
+  {
+    xb::EsbrHfgenArgs a;
+    a.src_re = st->qmf_re; a.src_im = st->qmf_im; a.pv_re = nullptr; a.pv_im = nullptr; a.dst_re = st->out_re; a.dst_im = st->out_im;
+    a.par = d_hf_par; a.bw_prev = st->bw_prev; a.patch_out = st->patch; a.err = d_err ? d_err + n_units : nullptr;
+    a.n_units = n_units; a.shift_rows = 1;
+    LAUNCH("esbr_hfgen_kernel", stream, xb::launch_esbr_hfgen(a, ctx->num_sms, s));
+  }
+  {
+    xb::EsbrEnvcalcArgs a;
+    a.re = st->out_re; a.im = st->out_im; a.ipar = d_ec_ipar; a.fpar = d_ec_fpar; a.state = st->ec_state;
+    a.rphase = ctx->d_rom_rphase; a.err = d_err ? d_err + 2 * n_units : nullptr; a.n_units = n_units;
+    LAUNCH("esbr_envcalc_kernel", stream, xb::launch_esbr_envcalc(a, ctx->num_sms, s));
+  }
+  {
+    xb::EsbrSynthArgs a;
+    a.qmf = nullptr; a.states = st->synth_states; a.pos = st->synth_pos; a.out = d_out; a.err = d_err ? d_err + 3 * n_units : nullptr;
+    a.rom = ctx->d_rom_esbr; a.n_units = n_units; a.periodic = ctx->esbr_periodic;
+    a.rg_low_re = st->qmf_re; a.rg_low_im = st->qmf_im; a.rg_high_re = st->out_re; a.rg_high_im = st->out_im; a.rg_par = d_rg_par;
+    a.pcm16 = d_pcm16; a.pcm_ch_fac = d_pcm16 ? ch_fac : 1;
+    LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(a, ctx->num_sms, s));
+  }
+  ctx->launches += 4;
+  return XAAC_B200_OK;
+}
+
 int32_t xaac_b200_kernel_timing(xaac_b200_ctx *ctx, int32_t enable) {
   if (!ctx) return XAAC_B200_ERR_ARG;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");

@@ -148,3 +148,56 @@ def esbr_env_calc(ctx, re, im, ipar, fpar, state, err=None, stream=None):
                                               ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_esbr_env_calc_dev")
     return err
+
+
+class _EsbrStateView(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("qmf_re", "qmf_im", "out_re", "out_im", "anal_states", "anal_pos", "synth_states",
+                                               "synth_pos", "bw_prev", "patch", "ec_state")]
+
+
+class EsbrDecBatch:
+    """Per-channel state of the float eSBR stage, resident in HBM (xaac_b200_esbr_state_view): QMF history arrays, both bank
+    states, chirp factors, patch table, envelope-adjuster smoothing history."""
+    SHAPES = dict(qmf_re=((40, 64), torch.float32), qmf_im=((40, 64), torch.float32), out_re=((40, 64), torch.float32),
+                  out_im=((40, 64), torch.float32), anal_states=((320,), torch.int32), anal_pos=((2,), torch.int32),
+                  synth_states=((1280,), torch.int32), synth_pos=((2,), torch.int32), bw_prev=((6,), torch.float32),
+                  patch=((8,), torch.int32), ec_state=((640,), torch.float32))
+
+    def __init__(self, n_units, device="cuda:0"):
+        self.n = int(n_units)
+        for k, (shp, dt) in self.SHAPES.items():
+            setattr(self, k, torch.zeros((self.n,) + shp, dtype=dt, device=device))
+
+    def view(self):
+        return _EsbrStateView(**{k: ctypes.c_void_p(getattr(self, k).data_ptr()) for k in self.SHAPES})
+
+
+def esbr_dec(ctx, state, core, hf_par, ec_ipar, ec_fpar, rg_par, out=None, pcm16=None, ch_fac=1, err=None, stream=None,
+             want_float=True):
+    """Batched drop-in for the eSBR branch of ixheaacd_sbr_dec (USAC channel, no harmonic transposer / PS / MPS): core float32
+    or int32 [n, 1024] -> float32 [n, 2048] and / or interleaved PCM16 [n / ch_fac, 2048, ch_fac].  Returns (out, err[4, n])."""
+    n = state.n
+    dev = hf_par.device
+    _chk(core, core.dtype if core.dtype in (torch.float32, torch.int32) else torch.float32, (n, 1024), "core", "cuda")
+    _chk(hf_par, torch.int32, (n, EHF_PAR_WORDS), "hf_par", "cuda")
+    _chk(ec_ipar, torch.int32, (n, EEC_IPAR_WORDS), "ec_ipar", "cuda")
+    _chk(ec_fpar, torch.float32, (n, EEC_FPAR_WORDS), "ec_fpar", "cuda")
+    _chk(rg_par, torch.int32, (n, 4), "rg_par", "cuda")
+    if out is None and want_float:
+        out = torch.empty((n, 2048), dtype=torch.float32, device=dev)
+    if out is not None:
+        _chk(out, torch.float32, (n, 2048), "out", "cuda")
+    if pcm16 is not None:
+        _chk(pcm16, torch.int16, (n // ch_fac, 2048, ch_fac), "pcm16", "cuda")
+    if err is None:
+        err = torch.empty((4, n), dtype=torch.int32, device=dev)
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    v = state.view()
+    rc = ctx._lib.xaac_b200_esbr_dec_dev(ctx.handle, ctypes.byref(v), _ptr(core) if core.dtype == torch.float32 else None,
+                                         _ptr(core) if core.dtype == torch.int32 else None, _ptr(hf_par), _ptr(ec_ipar),
+                                         _ptr(ec_fpar), _ptr(rg_par), _ptr(out) if out is not None else None,
+                                         _ptr(pcm16) if pcm16 is not None else None, int(ch_fac), _ptr(err), n,
+                                         ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_dec_dev")
+    return out, err

@@ -190,6 +190,10 @@ WORD32 __real_ixheaacd_sbr_dec(ia_sbr_dec_struct *, WORD16 *, ia_sbr_header_data
                                ixheaacd_misc_tables *, WORD, ia_pvc_data_struct *, FLAG, WORD32[][64], WORD32, WORD32,
                                VOID *, WORD32, WORD32);
 
+void esbr_stage_tap_pre(ia_sbr_dec_struct *d, ia_sbr_header_data_struct *h, ia_sbr_frame_info_data_struct *f,
+                        ia_ps_dec_struct *ps, ia_sbr_tables_struct *t, int apply, int low_pow, int aot, int ldmps, int drc_on);
+void esbr_stage_tap_post(ia_sbr_dec_struct *d, ia_sbr_frame_info_data_struct *f, ia_sbr_tables_struct *t, int ret);
+
 WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *d, WORD16 *time, ia_sbr_header_data_struct *h,
                                ia_sbr_frame_info_data_struct *f, ia_sbr_prev_frame_data_struct *pv, ia_ps_dec_struct *ps,
                                ia_sbr_qmf_filter_bank_struct *bank_r, ia_sbr_scale_fact_struct *sf_r, FLAG apply,
@@ -212,8 +216,10 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *d, WORD16 *time, ia_sbr_header
     for (int i = 0; i < 1024; i++) tin[i] = time[ch_fac * i];
     fwrite(&magic, 4, 1, fp);
   }
+  esbr_stage_tap_pre(d, h, f, ps, t, apply, low_pow, aot, ldmps, drc_on);
   WORD32 ret = __real_ixheaacd_sbr_dec(d, time, h, f, pv, ps, bank_r, sf_r, apply, low_pow, work, t, ct, ch_fac, pvc,
                                        drc_on, drc, aot, ldmps, self, mps, ec);
+  esbr_stage_tap_post(d, f, t, ret);
   if (rec) {
     int32_t hdr[7] = {apply, ch_fac, aot, ps_present, ret, low_pow, 0};
     fwrite(hdr, 4, 7, fp);

@@ -15,6 +15,10 @@
 #include <stdint.h>
 #define REF_SHIM_HEADERS_ONLY
 #include "ref_headers.h"
+#include "ixheaacd_env_calc.h"
+#include "ixheaac_sbr_const.h"
+#include "ixheaacd_pvc_dec.h"
+#include "ixheaacd_sbr_dec.h"
 #include "src/xaac_oracle.h"
 
 static FILE *open_tap(const char *stage, const char *ext) {
@@ -30,6 +34,13 @@ static int tap_max(void) {
   const char *m = getenv("XAAC_TAP_MAX");
   return m ? atoi(m) : 1000000;
 }
+
+/* last packed records of the inner stages, for the whole-stage tap below */
+static int32_t g_ehf_par[XO_EHF_PAR_WORDS], g_ehf_patch_in[8];
+static float g_ehf_bw_in[6];
+static int g_ehf_called, g_eec_called;
+static int32_t g_eec_ipar_in[XO_EEC_IPAR_WORDS], g_eec_ipar_out[XO_EEC_IPAR_WORDS];
+static float g_eec_fpar[XO_EEC_FPAR_WORDS], g_eec_state_in[640];
 
 WORD32 __real_ixheaacd_generate_hf(FLOAT32 a[][64], FLOAT32 b[][64], FLOAT32 c[][64], FLOAT32 d[][64], FLOAT32 e[][64],
                                    FLOAT32 f[][64], ia_sbr_frame_info_data_struct *fd, ia_sbr_header_data_struct *hd,
@@ -48,7 +59,7 @@ WORD32 __wrap_ixheaacd_generate_hf(FLOAT32 src_re[][64], FLOAT32 src_im[][64], F
   int32_t head[4], par[XO_EHF_PAR_WORDS], patch[8], patch_in[8];
   float bw_in[6];
   const int has_pv = hd->hbe_flag && pv_re && pv_im;
-  if (rec) {
+  {
     ia_freq_band_data_struct *fb = hd->pstr_freq_band_data;
     memset(par, 0, sizeof(par));
     par[XO_EHF_NUM_MF] = fb->num_mf_bands;
@@ -74,6 +85,10 @@ WORD32 __wrap_ixheaacd_generate_hf(FLOAT32 src_re[][64], FLOAT32 src_im[][64], F
     for (int i = 0; i < 7; i++) patch_in[1 + i] = fd->patch_param.start_subband[i];
     memcpy(din[0], dst_re - 2, sizeof(din[0]));
     memcpy(din[1], dst_im - 2, sizeof(din[1]));
+    memcpy(g_ehf_par, par, sizeof(par));
+    memcpy(g_ehf_patch_in, patch_in, sizeof(patch_in));
+    memcpy(g_ehf_bw_in, bw_in, sizeof(bw_in));
+    g_ehf_called++;
   }
   WORD32 ret = __real_ixheaacd_generate_hf(src_re, src_im, pv_re, pv_im, dst_re, dst_im, fd, hd, ldmps, time_slots, ec_flag);
   if (rec) {
@@ -156,7 +171,7 @@ WORD32 __wrap_ixheaacd_sbr_env_calc(ia_sbr_frame_info_data_struct *fd, FLOAT32 r
   const int rec = fp && count < tap_max();
   static int32_t ip_in[XO_EEC_IPAR_WORDS], ip_out[XO_EEC_IPAR_WORDS];
   static float fpar[XO_EEC_FPAR_WORDS], st_in[640], qin[2][2560];
-  if (rec) {
+  {
     eec_pack(ip_in, fd);
     memset(fpar, 0, sizeof(fpar));
     memcpy(fpar + XO_EEC_SFB_NRG, fd->flt_env_sf_arr, 448 * 4);
@@ -165,11 +180,16 @@ WORD32 __wrap_ixheaacd_sbr_env_calc(ia_sbr_frame_info_data_struct *fd, FLOAT32 r
     memcpy(st_in + 320, fd->noise_buf, 320 * 4);
     memcpy(qin[0], re - 2, sizeof(qin[0]));
     memcpy(qin[1], im - 2, sizeof(qin[1]));
+    memcpy(g_eec_ipar_in, ip_in, sizeof(ip_in));
+    memcpy(g_eec_fpar, fpar, sizeof(fpar));
+    memcpy(g_eec_state_in, st_in, sizeof(st_in));
+    g_eec_called++;
   }
   WORD32 ret = __real_ixheaacd_sbr_env_calc(fd, re, im, re1, im1, x_over_qmf, scratch, env_out, ldmps, ec_flag);
+  eec_pack(ip_out, fd);
+  memcpy(g_eec_ipar_out, ip_out, sizeof(ip_out));
   if (rec) {
     int32_t head[3] = {0x31434545, ret, ldmps};
-    eec_pack(ip_out, fd);
     fwrite(head, 4, 3, fp);
     fwrite(ip_in, 4, XO_EEC_IPAR_WORDS, fp);
     fwrite(ip_out, 4, XO_EEC_IPAR_WORDS, fp);
@@ -185,4 +205,92 @@ WORD32 __wrap_ixheaacd_sbr_env_calc(ia_sbr_frame_info_data_struct *fd, FLOAT32 r
     count++;
   }
   return ret;
+}
+
+
+/* ---- whole eSBR stage: hooks called from __wrap_ixheaacd_sbr_dec (oracle/ref_taps.c) around the real call -----------------
+ * <tap>.esd record: int32 'ESD1', int32 head[15] = {ret, apply, hbe_flag, ps, stereo_config_idx, mps_sbr_flag, sbr_mode,
+ *   qmf_sb_prev (at entry), sub_band_start, border_vec[0], sbr_ratio_idx, usac_flag, channel id, generate_hf calls, env_calc calls},
+ *   float time_in[1024], state_in {float qmf_re[2560], qmf_im[2560], out_re[2560], out_im[2560], int32 anal[320], apos[2],
+ *   synth[1280], spos[2], float bw[6], int32 patch[8], float ec_state[640]}, int32 hf_par[96], ec_ipar_in[288], float ec_fpar[464],
+ *   float time_out[2048], state_out {same members}, int32 ec_ipar_out[288] */
+typedef struct {
+  float q[4][2560];
+  int32_t anal[320], apos[2], synth[1280], spos[2];
+  float bw[6];
+  int32_t patch[8];
+  float ec[640];
+} esd_state_t;
+static void esd_state(esd_state_t *s, ia_sbr_dec_struct *d, ia_sbr_frame_info_data_struct *f, ia_sbr_tables_struct *t) {
+  ia_sbr_qmf_filter_bank_struct *a = &d->str_codec_qmf_bank, *y = &d->str_synthesis_qmf_bank;
+  WORD32 *c = (WORD32 *)t->qmf_dec_tables_ptr->esbr_qmf_c;
+  memcpy(s->q[0], d->qmf_buf_real, sizeof(s->q[0]));
+  memcpy(s->q[1], d->qmf_buf_imag, sizeof(s->q[1]));
+  memcpy(s->q[2], d->sbr_qmf_out_real, sizeof(s->q[2]));
+  memcpy(s->q[3], d->sbr_qmf_out_imag, sizeof(s->q[3]));
+  memcpy(s->anal, a->anal_filter_states_32, sizeof(s->anal));
+  s->apos[0] = (int32_t)(a->state_new_samples_pos_low_32 - a->anal_filter_states_32);
+  s->apos[1] = (int32_t)(a->filter_pos_32 - c);
+  memcpy(s->synth, y->filter_states_32, sizeof(s->synth));
+  s->spos[0] = y->ixheaacd_drc_offset;
+  s->spos[1] = (int32_t)(y->filter_pos_syn_32 - y->p_filter_32);
+  memcpy(s->bw, f->bw_array_prev, sizeof(s->bw));
+  s->patch[0] = f->patch_param.num_patches;
+  for (int i = 0; i < 7; i++) s->patch[1 + i] = f->patch_param.start_subband[i];
+  memcpy(s->ec, f->e_gain, 320 * 4);
+  memcpy(s->ec + 320, f->noise_buf, 320 * 4);
+}
+static FILE *esd_fp;
+static int esd_count, esd_rec;
+static int32_t esd_head[16];
+static float esd_tin[1024];
+static esd_state_t esd_in, esd_out;
+void esbr_stage_tap_pre(ia_sbr_dec_struct *d, ia_sbr_header_data_struct *h, ia_sbr_frame_info_data_struct *f,
+                        ia_ps_dec_struct *ps, ia_sbr_tables_struct *t, int apply, int low_pow, int aot, int ldmps, int drc_on) {
+  static int tried = 0;
+  static void *chan[8];
+  if (!tried) {
+    tried = 1;
+    esd_fp = open_tap("esd", "esd");
+  }
+  esd_rec = esd_fp && esd_count < tap_max() && h->enh_sbr && h->usac_flag && !low_pow && !ldmps && !drc_on &&
+            h->num_time_slots == 16 && d->str_codec_qmf_bank.no_channels == 32 && d->str_synthesis_qmf_bank.no_channels == 64;
+  if (!esd_rec) return;
+  int ch = 0;
+  while (ch < 7 && chan[ch] && chan[ch] != (void *)d) ch++;
+  chan[ch] = d;
+  g_ehf_called = g_eec_called = 0;
+  esd_head[0] = 0x31445345;
+  esd_head[2] = apply;
+  esd_head[3] = h->hbe_flag;
+  esd_head[4] = (h->channel_mode == PS_STEREO) || h->enh_sbr_ps;
+  esd_head[5] = f->stereo_config_idx;
+  esd_head[6] = f->mps_sbr_flag;
+  esd_head[7] = f->sbr_mode;
+  esd_head[8] = h->pstr_freq_band_data->qmf_sb_prev;
+  esd_head[9] = h->pstr_freq_band_data->sub_band_start;
+  esd_head[10] = f->str_frame_info_details.border_vec[0];
+  esd_head[11] = h->sbr_ratio_idx;
+  esd_head[12] = h->usac_flag;
+  esd_head[13] = ch;
+  memcpy(esd_tin, d->time_sample_buf, sizeof(esd_tin));
+  esd_state(&esd_in, d, f, t);
+}
+void esbr_stage_tap_post(ia_sbr_dec_struct *d, ia_sbr_frame_info_data_struct *f, ia_sbr_tables_struct *t, int ret) {
+  if (!esd_rec) return;
+  esd_head[1] = ret;
+  esd_head[14] = g_ehf_called;
+  esd_head[15] = g_eec_called;
+  esd_state(&esd_out, d, f, t);
+  fwrite(esd_head, 4, 16, esd_fp);
+  fwrite(esd_tin, 4, 1024, esd_fp);
+  fwrite(&esd_in, sizeof(esd_in), 1, esd_fp);
+  fwrite(g_ehf_par, 4, XO_EHF_PAR_WORDS, esd_fp);
+  fwrite(g_eec_ipar_in, 4, XO_EEC_IPAR_WORDS, esd_fp);
+  fwrite(g_eec_fpar, 4, XO_EEC_FPAR_WORDS, esd_fp);
+  fwrite(d->time_sample_buf, 4, 2048, esd_fp);
+  fwrite(&esd_out, sizeof(esd_out), 1, esd_fp);
+  fwrite(g_eec_ipar_out, 4, XO_EEC_IPAR_WORDS, esd_fp);
+  fflush(esd_fp);
+  esd_count++;
 }

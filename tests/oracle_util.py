@@ -953,3 +953,34 @@ def oracle_esbr_envcalc_batch(orc, d, rphase):
 
 def ref_esbr_envcalc_batch(ref, d):
     return _esbr_envcalc_batch(ref.lib.ref_esbr_env_calc_batch, d)
+
+
+# ---- whole float eSBR stage (eSBR branch of ixheaacd_sbr_dec): composition of the oracle pieces --------------------------
+ESD_KEYS = ("qmf_re", "qmf_im", "out_re", "out_im", "anal_states", "anal_pos", "synth_states", "synth_pos", "bw_prev", "patch",
+            "ec_state")
+
+
+def oracle_esbr_stage(orc, rphase, st, time_in, hf_par, ec_ipar, ec_fpar, rg_par):
+    """One frame of n channels.  st: dict of ESD_KEYS arrays (copied, not modified).  Follows decoder/ixheaacd_sbr_dec.c:
+    836-856 (history shift), :877 (analysis into rows 8..39), :921 (generate_hf), :953 (sbr_env_calc), :297-397 (regrouping),
+    :583-654 (synthesis).  Returns (time_out [n,2048], st', ec_ipar', err [4,n])."""
+    n = time_in.shape[0]
+    s = {k: np.ascontiguousarray(v).copy() for k, v in st.items()}
+    for k in ("qmf_re", "qmf_im", "out_re", "out_im"):
+        s[k][:, 0:8] = s[k][:, 32:40]
+    q, s["anal_states"], s["anal_pos"] = orc.esbr_anal_batch(time_in, s["anal_states"], s["anal_pos"])
+    s["qmf_re"][:, 8:40, 0:32] = q[:, :, 0:32]
+    s["qmf_im"][:, 8:40, 0:32] = q[:, :, 64:96]
+    d = dict(par=hf_par, src_re=s["qmf_re"], src_im=s["qmf_im"], pv_re=s["qmf_re"], pv_im=s["qmf_im"], dst_re=s["out_re"],
+             dst_im=s["out_im"], bw_prev=s["bw_prev"], patch_in=s["patch"])
+    s["out_re"], s["out_im"], s["bw_prev"], s["patch"], e1 = oracle_esbr_hfgen_batch(orc, d, with_pv=False)
+    d = dict(re=s["out_re"], im=s["out_im"], ipar=ec_ipar, fpar=ec_fpar, state=s["ec_state"])
+    s["out_re"], s["out_im"], ipar2, s["ec_state"], e2 = oracle_esbr_envcalc_batch(orc, d, rphase)
+    m = np.zeros((n, 32, 128), np.float32)
+    k = np.arange(64)[None, :]
+    for u in range(n):
+        xo = np.where(np.arange(32) < rg_par[u, 2], rg_par[u, 0], rg_par[u, 1])[:, None]
+        m[u, :, :64] = np.where(k < xo, s["qmf_re"][u, 2:34], s["out_re"][u, 2:34])
+        m[u, :, 64:] = np.where(k < xo, s["qmf_im"][u, 2:34], s["out_im"][u, 2:34])
+    out, s["synth_states"], s["synth_pos"] = orc.esbr_synth_batch(m, s["synth_states"], s["synth_pos"])
+    return out, s, ipar2, np.stack([np.zeros(n, np.int32), e1, e2, np.zeros(n, np.int32)])

@@ -181,3 +181,33 @@ def test_samples_sat_matches_reference(oracle, ref):
         oracle.lib.xo_samples_sat16(oracle_util.P(np.ascontiguousarray(x[c])), nch, c, oracle_util.P(got), n)
     assert np.array_equal(got, want)
     assert list(want[:8, 0]) == [32767, 32767, 32767, -32768, -32768, -32768, 0, 0]
+
+
+def esbr_stage_golden_frames(g):
+    """yields per frame (records 2f, 2f+1 = channels 0, 1) the inputs and expected outputs of the tapped stage calls"""
+    head = g["head"]
+    assert (head[0::2, 12] == 0).all() and (head[1::2, 12] == 1).all()
+    for f in range(len(head) // 2):
+        r = slice(2 * f, 2 * f + 2)
+        rg = np.stack([head[r, 7], head[r, 8], 2 * head[r, 9], 0 * head[r, 9]], 1).astype(np.int32)
+        yield f, r, rg
+
+
+def test_esbr_stage_golden(oracle):
+    """the composed oracle stage against 8 consecutive frames x 2 channels tapped around ixheaacd_sbr_dec in a real USAC
+    decode: time output, both bank states, chirp factors, patch table, smoothing history, in/out parameter words per
+    frame, the QMF history arrays after the last frame"""
+    g = load_esbr_golden("esbr_stage_tapped.npz")
+    rp = oracle_util.esbr_random_phase()
+    st = {k: g["in0_" + k] for k in oracle_util.ESD_KEYS}
+    for f, r, rg in esbr_stage_golden_frames(g):
+        out, st, ipar2, err = oracle_util.oracle_esbr_stage(oracle, rp, st, g["time_in"][r], g["hf_par"][r], g["ec_ipar_in"][r],
+                                                            g["ec_fpar"][r], rg)
+        assert not err.any(), f"frame {f}: {err}"
+        assert np.array_equal(out.view(np.int32), g["time_out"][r].view(np.int32)), f"frame {f}: time output"
+        assert np.array_equal(ipar2, g["ec_ipar_out"][r]), f"frame {f}: in/out parameter words"
+        for k in ("anal_states", "anal_pos", "synth_states", "synth_pos", "bw_prev", "patch", "ec_state"):
+            assert np.array_equal(st[k].view(np.int32), g["out_" + k][r].view(np.int32)), f"frame {f}: {k}"
+    for k in ("qmf_re", "qmf_im", "out_re", "out_im"):
+        assert np.array_equal(st[k].view(np.int32), g["out_" + k].view(np.int32)), k
+    assert np.abs(g["time_out"]).max() > 100

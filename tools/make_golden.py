@@ -408,9 +408,65 @@ def make_esbr_golden(tmp):
     print(f"wrote {path}: {len(b)} records, {os.path.getsize(path)} bytes")
 
 
+def make_esbr_stage_golden(tmp):
+    """Whole float eSBR stage (ixheaacd_sbr_dec, eSBR branch) of a real USAC stereo decode: 8 consecutive frames of both
+    channels, tapped around the unmodified stage call (oracle/ref_taps_esbr.c: esbr_stage_tap_pre / _post)."""
+    fs, ch, br = 32000, 2, 64000
+    wav = os.path.join(tmp, "in_esd.wav")
+    write_wav(wav, synth(fs, 6.0, ch, 21), fs)
+    mp4 = os.path.join(tmp, "esd.mp4")
+    run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{mp4}", "-aot:42", f"-br:{br}", "-ccfl_idx:3"])
+    tap = os.path.join(tmp, "esd.tap")
+    decode_tap(mp4, os.path.join(tmp, "o.wav"), tap, [f"-imeta:{os.path.join(tmp, 'esd.txt')}", "-mp4:1"], stages="esd")
+    S = 4 * 2560 + 320 + 2 + 1280 + 2 + 6 + 8 + 640
+    W = 16 + 1024 + S + 96 + 288 + 464 + 2048 + S + 288
+    raw = np.fromfile(tap + ".esd", dtype=np.int32)
+    assert raw.size and raw.size % W == 0, raw.size
+    r = raw.reshape(-1, W)
+    assert (r[:, 0] == 0x31445345).all()
+    h = r[:, 1:16]
+    ok = (h[:, 0] == 0) & (h[:, 1] == 1) & (h[:, 2] == 0) & (h[:, 3] == 0) & (h[:, 4] <= 0) & (h[:, 5] == 0) & (h[:, 6] == 1) \
+        & (h[:, 13] == 1) & (h[:, 14] == 1)
+    print(f"eSBR stage: {len(r)} calls tapped, {int(ok.sum())} in the supported subset; qmf_sb_prev {sorted(set(h[:, 7].tolist()))}, "
+          f"sub_band_start {sorted(set(h[:, 8].tolist()))}, border0 {sorted(set(h[:, 9].tolist()))}")
+    n_rec = 16
+    r0 = next(i for i in range(20, len(r) - n_rec) if ok[i:i + n_rec].all() and h[i, 12] == 0)
+    sel = r[r0:r0 + n_rec]
+    f32 = lambda x: np.ascontiguousarray(x).view(np.float32)
+    o = 16
+    tin = f32(sel[:, o:o + 1024]); o += 1024
+    st_in = sel[:, o:o + S]; o += S
+    hf_par = sel[:, o:o + 96]; o += 96
+    ipar_in = sel[:, o:o + 288]; o += 288
+    fpar = f32(sel[:, o:o + 464]); o += 464
+    tout = f32(sel[:, o:o + 2048]); o += 2048
+    st_out = sel[:, o:o + S]; o += S
+    ipar_out = sel[:, o:o + 288]
+
+    def split(st):
+        q = f32(st[:, :10240]).reshape(-1, 4, 40, 64)
+        p = 10240
+        d = dict(qmf_re=q[:, 0], qmf_im=q[:, 1], out_re=q[:, 2], out_im=q[:, 3])
+        for k, n_, fl in (("anal_states", 320, 0), ("anal_pos", 2, 0), ("synth_states", 1280, 0), ("synth_pos", 2, 0),
+                          ("bw_prev", 6, 1), ("patch", 8, 0), ("ec_state", 640, 1)):
+            d[k] = f32(st[:, p:p + n_]) if fl else st[:, p:p + n_].copy()
+            p += n_
+        return d
+    si, so = split(st_in), split(st_out)
+    out = dict(head=sel[:, 1:16].copy(), time_in=tin, hf_par=hf_par.copy(), ec_ipar_in=ipar_in.copy(), ec_fpar=fpar,
+               time_out=tout, ec_ipar_out=ipar_out.copy())
+    for k, v in si.items():     # full state before the first frame of each channel
+        out["in0_" + k] = v[:2].copy()
+    for k, v in so.items():     # small states after every frame, the QMF arrays after the last frame of each channel
+        out["out_" + k] = v[-2:].copy() if k in ("qmf_re", "qmf_im", "out_re", "out_im") else v.copy()
+    path = os.path.join(GOLD, "esbr_stage_tapped.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {n_rec} records, {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr", "esbr_stage"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
@@ -424,6 +480,8 @@ def main():
             make_usac_fd_golden(tmp)
         if "esbr" in which:
             make_esbr_golden(tmp)
+        if "esbr_stage" in which:
+            make_esbr_stage_golden(tmp)
         if "sbrdec_lp" in which:
             make_sbrdec_lp_golden(tmp)
 
