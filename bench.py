@@ -63,6 +63,9 @@ WORKLOADS = {
     "esbr_generate_hf": (4, 65536, "xHE-AAC/USAC eSBR stereo: the float HF generator of the chain (ixheaacd_generate_hf: 38-slot "
                                    "covariance, 2nd-order complex prediction, patching, HBE high band), batch=65536 stereo "
                                    "frames (131072 core channels)"),
+    "xheaac_stereo_chain": (4, 65536, "xHE-AAC/USAC stereo 32 kHz with eSBR (default patching, no harmonic transposer / PS) batch=65536: "
+                                      "FD core IMDCT -> float eSBR stage (QMF analysis, HF generator, envelope adjuster, QMF "
+                                      "synthesis) -> stereo PCM16, per channel"),
     "esbr_env_calc": (4, 65536, "xHE-AAC/USAC eSBR stereo: the float envelope adjuster of the chain (ixheaacd_sbr_env_calc, ORIG_SBR: "
                                 "energies, gains in double, limiter, smoothing, noise, sinusoids), batch=65536 stereo frames "
                                 "(131072 core channels)"),
@@ -529,9 +532,10 @@ def cpu_arm_esbr_anal(n_units, threads, seed, reps=1, min_seconds=0.0):
 
 
 def esbr_hfgen_bytes(par):
-    """Algorithmic HBM bytes per unit of ixheaacd_generate_hf from its parameters: covariance input (40 rows x the bands
-    it covers), patch / HBE filter input (slots + 2 rows x the high band; counted once although the HBE branch reads its
-    buffer twice), output (slots x [sub_band_start, 64)), 8 bytes per complex cell, + the 384-byte parameter record."""
+    """Algorithmic HBM bytes per unit of ixheaacd_generate_hf from its parameters: every source cell once (40 rows x the low
+    band below f_master_tbl[0] for the covariance / patch branch — the patches re-read cells the covariance already
+    touched — or 40 rows x the high band of the phase-vocoder buffer for the HBE branch), every output cell once (slots x
+    [sub_band_start, 64)), 8 bytes per complex cell, + the 384-byte parameter record."""
     from tests.oracle_util import EHF
     num_mf = par[:, EHF["NUM_MF"]]
     lsb = par[:, EHF["FMASTER"]]
@@ -539,8 +543,7 @@ def esbr_hfgen_bytes(par):
     sbs = par[:, EHF["SB_START"]]
     slots = 2 * (par[:, EHF["BORDER_LAST"]] - par[:, EHF["BORDER_FIRST"]])
     lpc = (par[:, EHF["PATCHING_MODE"]] != 0) | (par[:, EHF["HBE_FLAG"]] == 0)
-    hb = usb - sbs
-    cells = np.where(lpc, 40 * (lsb - 1) + (slots + 2) * hb, 40 * hb) + slots * (64 - sbs)
+    cells = np.where(lpc, 40 * (lsb - 1), 40 * (usb - sbs)) + slots * (64 - sbs)
     return 8.0 * cells + 384
 
 
@@ -629,6 +632,74 @@ def cpu_arm_esbr_envcalc(n_units, threads, seed, reps=1, min_seconds=0.0):
         dt += one_pass()
         done += 1
     return n_units * done / dt, kind
+
+
+def load_esbr_stage_golden():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "esbr_stage_tapped.npz"))
+    return {k: g[k] for k in g.files}
+
+
+def esbr_stage_params(g, n_units, f):
+    """parameter records of frame f (0..7) of the tapped stream for n_units channel units (unit u = channel u % 2)"""
+    j = (np.arange(n_units) % 2) + 2 * (f % 8)
+    h = g["head"][j]
+    rg = np.stack([h[:, 7], h[:, 8], 2 * h[:, 9], 0 * h[:, 9]], 1).astype(np.int32)
+    return (np.ascontiguousarray(g["hf_par"][j]), np.ascontiguousarray(g["ec_ipar_in"][j]), np.ascontiguousarray(g["ec_fpar"][j]),
+            np.ascontiguousarray(rg))
+
+
+def cpu_arm_xheaac_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time the reference's own xHE-AAC chain per channel unit on host threads (ref_xheaac_chain_batch, oracle/ref_shim.c)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    if ref is None:
+        raise SystemExit("bench.py: the xHE-AAC chain CPU baseline needs oracle/_ref/libxaac_ref.so (make ref)")
+    P = oracle_util.P
+    n_units -= n_units & 1
+    g = load_esbr_stage_golden()
+    rng = np.random.default_rng(seed)
+    sc = rng.integers(10, 20, size=(n_units, 1))
+    coef0 = ((rng.random((n_units, 1024)) * 2 - 1) * (2.0 ** sc)).astype(np.int64).astype(np.int32)
+    walk = usac_walk(n_units, reps + 1, seed)
+    ov = np.zeros((n_units, 1024), np.int32)
+    prev = np.zeros(n_units, np.int32)
+    ch = np.arange(n_units) % 2
+    q4 = np.ascontiguousarray(np.stack([g["in0_" + k][ch] for k in ("qmf_re", "qmf_im", "out_re", "out_im")], 1))
+    st = {k: np.ascontiguousarray(g["in0_" + k][ch]) for k in ("anal_states", "anal_pos", "synth_states", "synth_pos", "bw_prev",
+                                                                "patch", "ec_state")}
+    params = [esbr_stage_params(g, n_units, f) for f in range(8)]
+    pcm = np.zeros((n_units // 2, 2048, 2), np.int16)
+    err = np.zeros(n_units, np.int32)
+    bounds = (np.linspace(0, n_units // 2, threads + 1).astype(int)) * 2
+
+    def work(t, coef, seq, shape, pr):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            ref.lib.ref_xheaac_chain_batch(P(coef), P(ov), P(seq), P(shape), P(prev), P(q4), P(st["anal_states"]), P(st["anal_pos"]),
+                                           P(st["synth_states"]), P(st["synth_pos"]), P(st["bw_prev"]), P(st["patch"]),
+                                           P(st["ec_state"]), P(pr[0]), P(pr[1]), P(pr[2]), P(pr[3]), P(pcm), P(err), a, b)
+
+    def one_pass(step):
+        coef = coef0.copy()
+        seq = np.ascontiguousarray(walk[step, :, 0], np.int32)
+        shape = np.ascontiguousarray(walk[step, :, 1], np.int32)
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t, coef, seq, shape, params[step % 8])) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        dt = time.perf_counter() - t0
+        prev[:] = shape
+        assert not err.any(), "reference xHE-AAC chain returned an error"
+        return dt
+
+    one_pass(0)
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass(1 + done % reps)
+        done += 1
+    return n_units * done / dt, "reference"
 
 
 def cpu_arm_esbr_synth(n_units, threads, seed, reps=1, min_seconds=0.0):
@@ -781,6 +852,12 @@ STAGES = {
                                    "solve, patch walk + 2nd-order prediction filter, HBE high band (bit-exact floats)",
                              ref_stage="ixheaacd_generate_hf", cpu=cpu_arm_esbr_hfgen, cpu_units_per_core=1024,
                              realtime_fps=15.625, h2d=4 * 10240 + 384, d2h=2 * 10240, dtype="f32"),
+    "xheaac_stereo_chain": dict(kernel=None, top_kernel="esbr_synth_kernel", bytes_per_unit=None,
+                                stage="USAC FD core transform -> (x 2^-15 in the load) eSBR analysis bank -> HF generator -> envelope "
+                                      "adjuster -> (regrouping in the load) eSBR synthesis bank -> (samples_sat in the store) PCM16",
+                                ref_stage="ixheaacd_fd_frm_dec -> eSBR branch of ixheaacd_sbr_dec -> ixheaacd_samples_sat",
+                                cpu=cpu_arm_xheaac_chain, cpu_units_per_core=256, cpu_reps=6, realtime_fps=15.625,
+                                h2d=4096 + 2 + 384 + 1152 + 1856 + 16, d2h=4096, dtype="int32 + f32/f64"),
     "esbr_env_calc": dict(kernel="esbr_envcalc_kernel", bytes_per_unit=None,
                           stage="eSBR float envelope adjuster: per-envelope energies, gains / noise / sinusoid levels (double), "
                                 "limiter + boost, 5-tap smoothing, noise and sinusoid insertion (bit-exact floats)",
@@ -1079,6 +1156,80 @@ class EsbrEnvcalcWork:
         pass
 
 
+class XheaacChainWork:
+    """Stereo xHE-AAC frames: unit = one core channel (units 2k / 2k+1 = L / R of stream k): USAC FD core transform -> float
+    eSBR stage -> interleaved stereo PCM16, 5 launches per step.  eSBR parameters and initial state are tiled from a tapped
+    real stream (8 consecutive frames); core spectra are seeded noise with a window-sequence walk."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        g = load_esbr_stage_golden()
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        sc = torch.randint(10, 20, (n_units, 1), generator=gen, device=dev).to(torch.float32)
+        self.coef = ((torch.rand((n_units, 1024), generator=gen, device=dev) * 2 - 1) * torch.exp2(sc)).to(torch.int32)
+        self.walk = torch.from_numpy(usac_walk(n_units, steps_total, seed)).to(dev)
+        self.nw = steps_total
+        self.core_state = xb.UsacFdBatch(n_units, device=dev)
+        self.core = torch.empty((n_units, 1024), dtype=torch.int32, device=dev)
+        self.state = xb.EsbrDecBatch(n_units, device=dev)
+        ch = np.arange(n_units) % 2
+        for k in xb.EsbrDecBatch.SHAPES:
+            getattr(self.state, k).copy_(torch.from_numpy(np.ascontiguousarray(g["in0_" + k][ch])))
+        self.params = [[torch.from_numpy(a).to(dev) for a in esbr_stage_params(g, n_units, f)] for f in range(8)]
+        self.pcm = torch.zeros((n_units // 2, 2048, 2), dtype=torch.int16, device=dev)
+        self.err = torch.zeros((4, n_units), dtype=torch.int32, device=dev)
+        hf = np.concatenate([esbr_stage_params(g, 2, f)[0] for f in range(8)])
+        ec = np.concatenate([esbr_stage_params(g, 2, f)[1] for f in range(8)])
+        CHAIN_KERNEL_BYTES.update({
+            "usac_fd_kernel": USAC_FD_BYTES_PER_UNIT,
+            # stage mode: 4096 core in + 2 x 1280 ring + 2 x 8 rows x 256 B history r/w + 32 rows x 32 bands x 8 B written
+            "esbr_anal_kernel": 4096 + 2560 + 8192 + 8192,
+            "esbr_hfgen_kernel": float(esbr_hfgen_bytes(hf).mean()) + 8192,      # + the history rows of sbr_qmf_out r/w
+            "esbr_envcalc_kernel": float(esbr_envcalc_bytes(ec).mean()),
+            # stage mode: 32 rows x 64 bands x 8 B regrouped in + 2 x 5120 state + 4096 PCM16 out
+            "esbr_synth_kernel": 16384 + 10240 + 4096,
+        })
+
+    def step(self, i, stream):
+        xb = self.xb
+        xb.usac_fd_frm_dec(self.ctx, self.core_state, self.coef, self.walk[i % self.nw], self.core, stream=stream)
+        hf, ip, fp, rg = self.params[i % 8]
+        xb.esbr_dec(self.ctx, self.state, self.core, hf, ip, fp, rg, pcm16=self.pcm, ch_fac=2, err=self.err, stream=stream,
+                    want_float=False)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0
+
+    def host_setup(self):
+        import torch
+        self.h_coef = torch.empty((self.n, 1024), dtype=torch.int32).pin_memory()
+        self.h_coef.copy_(self.coef)
+        self.h_walk = self.walk.cpu().pin_memory()
+        self.h_params = [[a.cpu().pin_memory() for a in p] for p in self.params]
+        self.h_pcm = torch.empty((self.n // 2, 2048, 2), dtype=torch.int16).pin_memory()
+        self.d_coef = torch.empty_like(self.coef)
+        self.d_ics = torch.empty((self.n, 2), dtype=torch.uint8, device=self.coef.device)
+        self.d_params = [torch.empty_like(a) for a in self.params[0]]
+
+    def host_step(self, i):
+        import torch
+        xb = self.xb
+        self.d_coef.copy_(self.h_coef, non_blocking=True)
+        self.d_ics.copy_(self.h_walk[i % self.nw], non_blocking=True)
+        for d, h in zip(self.d_params, self.h_params[i % 8]):
+            d.copy_(h, non_blocking=True)
+        xb.usac_fd_frm_dec(self.ctx, self.core_state, self.d_coef, self.d_ics, self.core)
+        hf, ip, fp, rg = self.d_params
+        xb.esbr_dec(self.ctx, self.state, self.core, hf, ip, fp, rg, pcm16=self.pcm, ch_fac=2, err=self.err, want_float=False)
+        self.h_pcm.copy_(self.pcm, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
+
+
 class EsbrSynthWork:
     def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
         import torch
@@ -1261,7 +1412,7 @@ WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv
         "heaacv1_stereo_chain": ChainLpWork, "usac_fd_imdct": UsacFdWork,
         "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork,
         "esbr_anal32": EsbrAnalWork, "esbr_generate_hf": EsbrHfgenWork,
-        "esbr_env_calc": EsbrEnvcalcWork}
+        "esbr_env_calc": EsbrEnvcalcWork, "xheaac_stereo_chain": XheaacChainWork}
 
 
 def main():

@@ -746,3 +746,50 @@ void ref_samples_sat16(const float *in /* [nch][n] */, int nch, int n, int16_t *
   for (int c = 0; c < nch; c++) memcpy(buf[c], in + (size_t)c * n, n * sizeof(float));
   ixheaacd_samples_sat((WORD8 *)pcm, n, 16, buf, &bytes, nch);
 }
+
+/* ---- xHE-AAC chain of one channel unit on the reference's own functions (bench.py --workload xheaac_stereo_chain, CPU arm):
+ * ixheaacd_fd_frm_dec -> x 2^-15 (ext_ch_ele.c:1040) -> the eSBR branch of ixheaacd_sbr_dec spelled out with its leaf
+ * functions (history memmoves, ixheaacd_esbr_analysis_filt_block, ixheaacd_generate_hf, ixheaacd_sbr_env_calc,
+ * regrouping as ixheaacd_esbr_synthesis_regrp, synthesis core) -> ixheaacd_samples_sat.  The analysis output is copied into
+ * the stage arrays (the reference writes them in place: 8 KB of extra copy per unit in this arm). */
+int ref_usac_fd_frm_dec(int32_t *coef, int32_t *overlap, int win_seq, int win_shape, int win_shape_prev, int32_t *out);
+void ref_xheaac_chain_batch(int32_t *coef, int32_t *overlap, const int32_t *win_seq, const int32_t *win_shape,
+                            const int32_t *win_shape_prev, float *q4 /* [n][4][2560] */, int32_t *anal, int32_t *apos,
+                            int32_t *synth, int32_t *spos, float *bw, int32_t *patch, float *ec, const int32_t *hf_par,
+                            int32_t *ec_ipar, const float *ec_fpar, const int32_t *rg, int16_t *pcm /* [n/2][2048][2] */,
+                            int32_t *err, int a, int b) {
+  static __thread int32_t core[1024];
+  static __thread float tin[1024], qa[32 * 128], m[32 * 128], tout[2048];
+  for (int u = a; u < b; u++) {
+    float *q = q4 + (size_t)u * 4 * 2560;
+    int e = ref_usac_fd_frm_dec(coef + (size_t)u * 1024, overlap + (size_t)u * 1024, win_seq[u], win_shape[u],
+                                win_shape_prev[u], core);
+    for (int k = 0; k < 1024; k++) tin[k] = (FLOAT32)((FLOAT32)core[k] * (FLOAT32)(0.000030517578125));
+    for (int z = 0; z < 4; z++) memmove(q + 2560 * z, q + 2560 * z + 32 * 64, 8 * 64 * sizeof(float));
+    ref_esbr_anal32(tin, anal + (size_t)u * 320, apos + 2 * u, qa);
+    for (int s = 0; s < 32; s++) {
+      memcpy(q + 64 * (8 + s), qa + 128 * s, 32 * sizeof(float));
+      memcpy(q + 2560 + 64 * (8 + s), qa + 128 * s + 64, 32 * sizeof(float));
+    }
+    e |= ref_esbr_generate_hf(q, q + 2560, NULL, NULL, q + 5120, q + 7680, hf_par + (size_t)u * XO_EHF_PAR_WORDS, bw + 6 * u,
+                              patch + 8 * u);
+    e |= ref_esbr_env_calc(q + 5120, q + 7680, ec_ipar + (size_t)u * XO_EEC_IPAR_WORDS, ec_fpar + (size_t)u * XO_EEC_FPAR_WORDS,
+                           ec + (size_t)u * 640);
+    const int32_t *r = rg + 4 * u;
+    for (int s = 0; s < 32; s++) {
+      const int xo = s < r[2] ? r[0] : r[1];
+      for (int k = 0; k < 64; k++) {
+        m[128 * s + k] = k < xo ? q[64 * (2 + s) + k] : q[5120 + 64 * (2 + s) + k];
+        m[128 * s + 64 + k] = k < xo ? q[2560 + 64 * (2 + s) + k] : q[7680 + 64 * (2 + s) + k];
+      }
+    }
+    ref_esbr_synth64(m, synth + (size_t)u * 1280, spos + 2 * u, tout);
+    int16_t *o = pcm + (size_t)(u / 2) * 4096 + (u & 1);
+    for (int i = 0; i < 2048; i++) {
+      float v = tout[i];
+      if (v > 32767.0f) v = 32767.0f; else if (v < -32768.0f) v = -32768.0f;
+      o[2 * i] = (int16_t)v;
+    }
+    err[u] = e;
+  }
+}
