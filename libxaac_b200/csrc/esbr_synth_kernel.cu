@@ -56,7 +56,15 @@ XB_DEV i32 psub(i32 a, i32 w1, i32 b, i32 w2) {  // ixheaac_sub64_sat(a w1, b w2
   return (i32)(d >> 32);
 }
 
+// SAT = false: the unit's magnitude bound proves that no add / sub / negate of the transform can saturate (see the kernel),
+// so they run as plain wrapping instructions (1 SASS instruction instead of 5) with identical results
+template <bool SAT> XB_DEV i32 tadd(i32 a, i32 b) { return SAT ? add_sat(a, b) : wadd(a, b); }
+template <bool SAT> XB_DEV i32 tsub(i32 a, i32 b) { return SAT ? sub_sat(a, b) : wsub(a, b); }
+template <bool SAT> XB_DEV i32 tneg(i32 a) { return SAT ? neg_sat(a) : wneg(a); }
+template <bool SAT> XB_DEV i32 tpsub(i32 a, i32 w1, i32 b, i32 w2) { return SAT ? psub(a, w1, b, w2) : psubw(a, w1, b, w2); }
+
 // generic:880-973, in place on interleaved complex x (one lane)
+template <bool SAT>
 XB_DEV void es_radix4(const i32 *w, i32 *x, int groups, int span) {
 #pragma unroll 1
   for (int g = 0; g < groups; g++) {
@@ -66,13 +74,13 @@ XB_DEV void es_radix4(const i32 *w, i32 *x, int groups, int span) {
       const i32 *tw = w + 6 * i;
       const i32 si1 = tw[0], co1 = tw[1], si2 = tw[2], co2 = tw[3], si3 = tw[4], co3 = tw[5];
       const i32 a0 = e0[0], a1 = e0[1], b0 = e1[0], b1 = e1[1], c0 = e2[0], c1 = e2[1], d0 = e3[0], d1 = e3[1];
-      const i32 xh0 = add_sat(a0, c0), xl0 = sub_sat(a0, c0), xh20 = add_sat(b0, d0), xl20 = sub_sat(b0, d0);
-      const i32 xh1 = add_sat(a1, c1), xl1 = sub_sat(a1, c1), xh21 = add_sat(b1, d1), xl21 = sub_sat(b1, d1);
-      const i32 xt0 = sub_sat(xh0, xh20), yt0 = sub_sat(xh1, xh21);
-      const i32 xt1 = add_sat(xl0, xl21), xt2 = sub_sat(xl0, xl21);
-      const i32 yt2 = add_sat(xl1, xl20), yt1 = sub_sat(xl1, xl20);
-      e0[0] = add_sat(xh0, xh20);
-      e0[1] = add_sat(xh1, xh21);
+      const i32 xh0 = tadd<SAT>(a0, c0), xl0 = tsub<SAT>(a0, c0), xh20 = tadd<SAT>(b0, d0), xl20 = tsub<SAT>(b0, d0);
+      const i32 xh1 = tadd<SAT>(a1, c1), xl1 = tsub<SAT>(a1, c1), xh21 = tadd<SAT>(b1, d1), xl21 = tsub<SAT>(b1, d1);
+      const i32 xt0 = tsub<SAT>(xh0, xh20), yt0 = tsub<SAT>(xh1, xh21);
+      const i32 xt1 = tadd<SAT>(xl0, xl21), xt2 = tsub<SAT>(xl0, xl21);
+      const i32 yt2 = tadd<SAT>(xl1, xl20), yt1 = tsub<SAT>(xl1, xl20);
+      e0[0] = tadd<SAT>(xh0, xh20);
+      e0[1] = tadd<SAT>(xh1, xh21);
       e3[0] = lsl(padd(yt2, si3, xt2, co3), 1);
       e3[1] = lsl(psubw(yt2, co3, xt2, si3), 1);
       e2[0] = lsl(padd(yt0, si2, xt0, co2), 1);
@@ -84,6 +92,7 @@ XB_DEV void es_radix4(const i32 *w, i32 *x, int groups, int span) {
 }
 
 // ixheaacd_esbr_cos_sin_mod for 64 channels on one slot row sb[0..63] | sb[64..127], in place (one lane)
+template <bool SAT>
 XB_DEV void es_cos_sin_mod(const EsTab &t, i32 *sb) {
   i32 *s1 = sb, *s2 = sb + 64;
   // pre-twiddle (generic:1200-1295), two steps at a time: steps n (even) and n + 1 read and write the same four words
@@ -96,22 +105,22 @@ XB_DEV void es_cos_sin_mod(const EsTab &t, i32 *sb) {
       const i32 a = s[n], b = s[63 - n], a1 = s[n + 1], b1 = s[62 - n];
       if (!h) {
         s[n] = padd(a, wre0, b, wim0);
-        s[n + 1] = psub(b, wre0, a, wim0);
-        s[63 - n] = psub(a1, wre1, b1, wim1);
+        s[n + 1] = tpsub<SAT>(b, wre0, a, wim0);
+        s[63 - n] = tpsub<SAT>(a1, wre1, b1, wim1);
         s[62 - n] = padd(b1, wre1, a1, wim1);
       } else {
-        s[n] = psub(b, wim0, a, wre0);
+        s[n] = tpsub<SAT>(b, wim0, a, wre0);
         s[n + 1] = padd(a, wim0, b, wre0);
         s[63 - n] = padd(b1, wim1, a1, wre1);
-        s[62 - n] = psub(a1, wim1, b1, wre1);
+        s[62 - n] = tpsub<SAT>(a1, wim1, b1, wre1);
       }
     }
   }
 #pragma unroll 1
   for (int h = 0; h < 2; h++) {
     i32 *x = sb + 64 * h;
-    es_radix4(t.w32, x, 1, 8);
-    es_radix4(t.w32 + 48, x, 4, 2);
+    es_radix4<SAT>(t.w32, x, 1, 8);
+    es_radix4<SAT>(t.w32 + 48, x, 4, 2);
     // generic:975-1057 — final radix-2 with digit-reversed scatter, through registers (dig_rev_table2_32 = {0,64,16,80})
     i32 v[64];
 #pragma unroll
@@ -123,14 +132,14 @@ XB_DEV void es_cos_sin_mod(const EsTab &t, i32 *sb) {
       for (int half = 0; half < 2; half++) {
         const int c = (blk >> 1) * 32 + (blk & 1) * 8 + 16 * half;
         const int q = h2 + 2 * half;
-        x[q] = add_sat(v[c], v[c + 2]);
-        x[q + 1] = add_sat(v[c + 1], v[c + 3]);
-        x[32 + q] = sub_sat(v[c], v[c + 2]);
-        x[32 + q + 1] = sub_sat(v[c + 1], v[c + 3]);
-        x[8 + q] = add_sat(v[c + 4], v[c + 6]);
-        x[8 + q + 1] = add_sat(v[c + 5], v[c + 7]);
-        x[40 + q] = sub_sat(v[c + 4], v[c + 6]);
-        x[40 + q + 1] = sub_sat(v[c + 5], v[c + 7]);
+        x[q] = tadd<SAT>(v[c], v[c + 2]);
+        x[q + 1] = tadd<SAT>(v[c + 1], v[c + 3]);
+        x[32 + q] = tsub<SAT>(v[c], v[c + 2]);
+        x[32 + q + 1] = tsub<SAT>(v[c + 1], v[c + 3]);
+        x[8 + q] = tadd<SAT>(v[c + 4], v[c + 6]);
+        x[8 + q + 1] = tadd<SAT>(v[c + 5], v[c + 7]);
+        x[40 + q] = tsub<SAT>(v[c + 4], v[c + 6]);
+        x[40 + q + 1] = tsub<SAT>(v[c + 5], v[c + 7]);
       }
     }
   }
@@ -139,8 +148,8 @@ XB_DEV void es_cos_sin_mod(const EsTab &t, i32 *sb) {
     const i32 f10 = s1[0], f11 = s1[1], f20 = s2[0], f21 = s2[1];
     i32 re1 = s1[63], im1 = s1[62], re2 = s2[63], im2 = s2[62];
     s1[0] = f10 >> 1;
-    s1[63] = neg_sat(f11 >> 1);
-    s2[63] = neg_sat(f20 >> 1);
+    s1[63] = tneg<SAT>(f11 >> 1);
+    s2[63] = tneg<SAT>(f20 >> 1);
     s2[0] = f21 >> 1;
 #pragma unroll 1
     for (int u = 0; u < 16; u++) {
@@ -151,17 +160,17 @@ XB_DEV void es_cos_sin_mod(const EsTab &t, i32 *sb) {
         nre2 = s2[61 - 2 * u]; nim2 = s2[60 - 2 * u];
       }
       s1[62 - 2 * u] = padd(re1, wre, im1, wim);
-      s1[1 + 2 * u] = psub(im1, wre, re1, wim);
-      s2[1 + 2 * u] = neg_sat(padd(re2, wre, im2, wim));
-      s2[62 - 2 * u] = psub(re2, wim, im2, wre);
+      s1[1 + 2 * u] = tpsub<SAT>(im1, wre, re1, wim);
+      s2[1 + 2 * u] = tneg<SAT>(padd(re2, wre, im2, wim));
+      s2[62 - 2 * u] = tpsub<SAT>(re2, wim, im2, wre);
       if (u + 1 < 16) {
         i32 fim = s1[2 + 2 * u], fre = s1[3 + 2 * u];
         s1[2 + 2 * u] = padd(fre, wim, fim, wre);
-        s1[61 - 2 * u] = psub(fim, wim, fre, wre);
+        s1[61 - 2 * u] = tpsub<SAT>(fim, wim, fre, wre);
         fim = s2[2 + 2 * u];
         fre = s2[3 + 2 * u];
-        s2[61 - 2 * u] = neg_sat(padd(fre, wim, fim, wre));
-        s2[2 + 2 * u] = psub(fre, wre, fim, wim);
+        s2[61 - 2 * u] = tneg<SAT>(padd(fre, wim, fim, wre));
+        s2[2 + 2 * u] = tpsub<SAT>(fre, wre, fim, wim);
       }
       re1 = nre1; im1 = nim1; re2 = nre2; im2 = nim2;
     }
@@ -170,10 +179,10 @@ XB_DEV void es_cos_sin_mod(const EsTab &t, i32 *sb) {
 #pragma unroll 1
   for (int j = 0; j < 32; j++) {
     const i32 r1 = sb[j], i1 = sb[64 + j], r2 = sb[63 - j], i2 = sb[127 - j];
-    sb[127 - j] = shl32_sat(add_sat(i1, r1), 6);
-    sb[63 - j] = shl32_sat(sub_sat(i2, r2), 6);
-    sb[j] = shl32_sat(sub_sat(i1, r1), 6);
-    sb[64 + j] = shl32_sat(add_sat(i2, r2), 6);
+    sb[127 - j] = shl32_sat(tadd<SAT>(i1, r1), 6);
+    sb[63 - j] = shl32_sat(tsub<SAT>(i2, r2), 6);
+    sb[j] = shl32_sat(tsub<SAT>(i1, r1), 6);
+    sb[64 + j] = shl32_sat(tadd<SAT>(i2, r2), 6);
   }
 }
 
@@ -215,6 +224,7 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
       }
     }
     // matrix rows: float -> WORD32 (sbr_dec.c:584-587), coalesced 512-byte row loads
+    u32 mx = 0;  // OR of |v| (|v| - 1 for negative v) over the unit: the magnitude bound of the transform input
     if (!p.rg_par) {
       const float4 *src = reinterpret_cast<const float4 *>(p.qmf + u * 4096);
 #pragma unroll 4
@@ -225,6 +235,7 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
         r[1] = f2i_x86(__fmul_rn(v.y, 64.f));
         r[2] = f2i_x86(__fmul_rn(v.z, 64.f));
         r[3] = f2i_x86(__fmul_rn(v.w, 64.f));
+        mx |= (u32)(r[0] ^ (r[0] >> 31)) | (u32)(r[1] ^ (r[1] >> 31)) | (u32)(r[2] ^ (r[2] >> 31)) | (u32)(r[3] ^ (r[3] >> 31));
       }
     } else {  // stage mode: ixheaacd_esbr_synthesis_regrp in the load — low band from qmf_buf, high band from sbr_qmf_out
       const int xo_first = p.rg_par[4 * u], xo_rest = p.rg_par[4 * u + 1], stop = p.rg_par[4 * u + 2];
@@ -242,6 +253,7 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
         r[1] = f2i_x86(__fmul_rn(k0 + 1 < xo ? a.y : b.y, 64.f));
         r[2] = f2i_x86(__fmul_rn(k0 + 2 < xo ? a.z : b.z, 64.f));
         r[3] = f2i_x86(__fmul_rn(k0 + 3 < xo ? a.w : b.w, 64.f));
+        mx |= (u32)(r[0] ^ (r[0] >> 31)) | (u32)(r[1] ^ (r[1] >> 31)) | (u32)(r[2] ^ (r[2] >> 31)) | (u32)(r[3] ^ (r[3] >> 31));
       }
     }
     {  // old ring blocks: the block of age a0 (1..9) goes to history row 9 - a0
@@ -255,7 +267,14 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
       }
     }
     __syncwarp();
-    es_cos_sin_mod(tab, rows + ES * lane);
+    // The transform grows magnitudes by at most 8 x 8 x 2 = 128 (two radix-4 stages whose twiddled outputs are
+    // lsl((a w1 + b w2) >> 32, 1) <= 8 x input, one radix-2 stage; pre- and post-twiddles do not grow) and the state
+    // conversion adds two outputs: with every |v| <= 2^22 nothing reaches 2^31, no saturating operation can saturate and
+    // the wrapping variant computes the same words.
+    if (__reduce_or_sync(0xffffffffu, mx) < (1u << 22))
+      es_cos_sin_mod<false>(tab, rows + ES * lane);
+    else
+      es_cos_sin_mod<true>(tab, rows + ES * lane);
     __syncwarp();
     // 10-tap window (generic:1544-1575): lane -> outputs lane and lane + 32 of every slot (stride-1 rows: conflict-free)
     float *out = p.out ? p.out + u * 2048 : nullptr;
@@ -383,7 +402,7 @@ XB_DEV void ea_cos_sin_mod(const EsTab &t, i32 *sb) {
 #pragma unroll 1
   for (int h = 0; h < 2; h++) {
     i32 *x = sb + 64 * h;
-    es_radix4(t.w16, x, 1, 4);
+    es_radix4<true>(t.w16, x, 1, 4);
     // generic:1059-1161 — final radix-4 (no twiddles) with digit-reversed scatter (dig_rev_table4_16 = {0, 16}), via registers
     i32 v[32];
 #pragma unroll
