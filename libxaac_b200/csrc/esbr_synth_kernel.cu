@@ -377,6 +377,7 @@ struct EaBlockS {
 };
 
 // ixheaacd_esbr_cos_sin_mod for 32 channels (M = 16) on one slot row: s1 = sb[0..31], s2 = sb[64..95], in place
+template <bool SAT>
 XB_DEV void ea_cos_sin_mod(const EsTab &t, i32 *sb) {
   i32 *s1 = sb, *s2 = sb + 64;
 #pragma unroll 1
@@ -388,21 +389,21 @@ XB_DEV void ea_cos_sin_mod(const EsTab &t, i32 *sb) {
       const i32 a = s[n], b = s[31 - n], a1 = s[n + 1], b1 = s[30 - n];
       if (!h) {
         s[n] = padd(a, wre0, b, wim0);
-        s[n + 1] = psub(b, wre0, a, wim0);
-        s[31 - n] = psub(a1, wre1, b1, wim1);
+        s[n + 1] = tpsub<SAT>(b, wre0, a, wim0);
+        s[31 - n] = tpsub<SAT>(a1, wre1, b1, wim1);
         s[30 - n] = padd(b1, wre1, a1, wim1);
       } else {
-        s[n] = psub(b, wim0, a, wre0);
+        s[n] = tpsub<SAT>(b, wim0, a, wre0);
         s[n + 1] = padd(a, wim0, b, wre0);
         s[31 - n] = padd(b1, wim1, a1, wre1);
-        s[30 - n] = psub(a1, wim1, b1, wre1);
+        s[30 - n] = tpsub<SAT>(a1, wim1, b1, wre1);
       }
     }
   }
 #pragma unroll 1
   for (int h = 0; h < 2; h++) {
     i32 *x = sb + 64 * h;
-    es_radix4<true>(t.w16, x, 1, 4);
+    es_radix4<SAT>(t.w16, x, 1, 4);
     // generic:1059-1161 — final radix-4 (no twiddles) with digit-reversed scatter (dig_rev_table4_16 = {0, 16}), via registers
     i32 v[32];
 #pragma unroll
@@ -412,18 +413,18 @@ XB_DEV void ea_cos_sin_mod(const EsTab &t, i32 *sb) {
 #pragma unroll
       for (int half = 0; half < 2; half++) {
         const int c = 16 * k + 8 * half, o = 4 * k + 2 * half;
-        const i32 xh0 = add_sat(v[c], v[c + 4]), xh1 = add_sat(v[c + 1], v[c + 5]);
-        const i32 xl0 = sub_sat(v[c], v[c + 4]), xl1 = sub_sat(v[c + 1], v[c + 5]);
-        const i32 zh0 = add_sat(v[c + 2], v[c + 6]), zh1 = add_sat(v[c + 3], v[c + 7]);
-        const i32 zl0 = sub_sat(v[c + 2], v[c + 6]), zl1 = sub_sat(v[c + 3], v[c + 7]);
-        x[o] = add_sat(xh0, zh0);
-        x[o + 1] = add_sat(xh1, zh1);
-        x[8 + o] = add_sat(xl0, zl1);
-        x[8 + o + 1] = sub_sat(xl1, zl0);
-        x[16 + o] = sub_sat(xh0, zh0);
-        x[16 + o + 1] = sub_sat(xh1, zh1);
-        x[24 + o] = sub_sat(xl0, zl1);
-        x[24 + o + 1] = add_sat(xl1, zl0);
+        const i32 xh0 = tadd<SAT>(v[c], v[c + 4]), xh1 = tadd<SAT>(v[c + 1], v[c + 5]);
+        const i32 xl0 = tsub<SAT>(v[c], v[c + 4]), xl1 = tsub<SAT>(v[c + 1], v[c + 5]);
+        const i32 zh0 = tadd<SAT>(v[c + 2], v[c + 6]), zh1 = tadd<SAT>(v[c + 3], v[c + 7]);
+        const i32 zl0 = tsub<SAT>(v[c + 2], v[c + 6]), zl1 = tsub<SAT>(v[c + 3], v[c + 7]);
+        x[o] = tadd<SAT>(xh0, zh0);
+        x[o + 1] = tadd<SAT>(xh1, zh1);
+        x[8 + o] = tadd<SAT>(xl0, zl1);
+        x[8 + o + 1] = tsub<SAT>(xl1, zl0);
+        x[16 + o] = tsub<SAT>(xh0, zh0);
+        x[16 + o + 1] = tsub<SAT>(xh1, zh1);
+        x[24 + o] = tsub<SAT>(xl0, zl1);
+        x[24 + o + 1] = tadd<SAT>(xl1, zl0);
       }
     }
   }
@@ -431,8 +432,8 @@ XB_DEV void ea_cos_sin_mod(const EsTab &t, i32 *sb) {
     const i32 f10 = s1[0], f11 = s1[1], f20 = s2[0], f21 = s2[1];
     i32 re1 = s1[31], im1 = s1[30], re2 = s2[31], im2 = s2[30];
     s1[0] = f10 >> 1;
-    s1[31] = neg_sat(f11 >> 1);
-    s2[31] = neg_sat(f20 >> 1);
+    s1[31] = tneg<SAT>(f11 >> 1);
+    s2[31] = tneg<SAT>(f20 >> 1);
     s2[0] = f21 >> 1;
 #pragma unroll 1
     for (int u = 0; u < 8; u++) {
@@ -443,17 +444,17 @@ XB_DEV void ea_cos_sin_mod(const EsTab &t, i32 *sb) {
         nre2 = s2[29 - 2 * u]; nim2 = s2[28 - 2 * u];
       }
       s1[30 - 2 * u] = padd(re1, wre, im1, wim);
-      s1[1 + 2 * u] = psub(im1, wre, re1, wim);
-      s2[1 + 2 * u] = neg_sat(padd(re2, wre, im2, wim));
-      s2[30 - 2 * u] = psub(re2, wim, im2, wre);
+      s1[1 + 2 * u] = tpsub<SAT>(im1, wre, re1, wim);
+      s2[1 + 2 * u] = tneg<SAT>(padd(re2, wre, im2, wim));
+      s2[30 - 2 * u] = tpsub<SAT>(re2, wim, im2, wre);
       if (u + 1 < 8) {
         i32 fim = s1[2 + 2 * u], fre = s1[3 + 2 * u];
         s1[2 + 2 * u] = padd(fre, wim, fim, wre);
-        s1[29 - 2 * u] = psub(fim, wim, fre, wre);
+        s1[29 - 2 * u] = tpsub<SAT>(fim, wim, fre, wre);
         fim = s2[2 + 2 * u];
         fre = s2[3 + 2 * u];
-        s2[29 - 2 * u] = neg_sat(padd(fre, wim, fim, wre));
-        s2[2 + 2 * u] = psub(fre, wre, fim, wim);
+        s2[29 - 2 * u] = tneg<SAT>(padd(fre, wim, fim, wre));
+        s2[2 + 2 * u] = tpsub<SAT>(fre, wre, fim, wim);
       }
       re1 = nre1; im1 = nim1; re2 = nre2; im2 = nim2;
     }
@@ -583,15 +584,22 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
     __syncwarp();
     {  // lane = slot: fold (generic:1475-1482) in place, then the modulation
       i32 *sb = w.rows + EA * lane;
+      u32 mx = 0;
 #pragma unroll 1
       for (int k = 0; k < 16; k++) {
         const i32 a0 = sb[k] >> 4, a1 = sb[63 - k] >> 4, b0 = sb[31 - k] >> 4, b1 = sb[32 + k] >> 4;
-        sb[k] = sub_sat(a0, a1);
-        sb[64 + k] = add_sat(a0, a1);
-        sb[31 - k] = sub_sat(b0, b1);
-        sb[64 + 31 - k] = add_sat(b0, b1);
+        const i32 v0 = sub_sat(a0, a1), v1 = add_sat(a0, a1), v2 = sub_sat(b0, b1), v3 = add_sat(b0, b1);
+        sb[k] = v0;
+        sb[64 + k] = v1;
+        sb[31 - k] = v2;
+        sb[64 + 31 - k] = v3;
+        mx |= (u32)(v0 ^ (v0 >> 31)) | (u32)(v1 ^ (v1 >> 31)) | (u32)(v2 ^ (v2 >> 31)) | (u32)(v3 ^ (v3 >> 31));
       }
-      ea_cos_sin_mod(tab, sb);
+      // growth of the 16-point transform: <= 8 (radix-4 with twiddles) x 4 (plain radix-4) = 32; below 2^25 nothing saturates
+      if (__reduce_or_sync(0xffffffffu, mx) < (1u << 25))
+        ea_cos_sin_mod<false>(tab, sb);
+      else
+        ea_cos_sin_mod<true>(tab, sb);
     }
     __syncwarp();
     // lane = band: t_cos rotation (generic:1490-1505), WORD32 -> float (x 1/256), coalesced rows of the output matrix

@@ -34,44 +34,54 @@ XB_DEV i32 mul_sat31(i32 a, i32 b) {
   return ((a & b) == (i32)0x80000000 && a == b) ? 0x7fffffff : r;
 }
 XB_DEV i32 mul_sh1(i32 a, i32 b) { return (i32)(((long long)a * (long long)b) >> 31); }  // vec_baisc_ops.h:28
-XB_DEV i32 sh1(i32 a) { return add_sat(a, a); }                                            // ixheaac_shl32_sat(a, 1)
+// SAT = false: the stage's input bound proves that no product, add, subtract or doubling of the stage can leave 32 bits
+// (bounds at fft_batch), so they run as plain wrapping instructions (1 SASS instruction instead of 5) and give the same words
+template <bool SAT> XB_DEV i32 fadd(i32 a, i32 b) { return SAT ? add_sat(a, b) : wadd(a, b); }
+template <bool SAT> XB_DEV i32 fsub(i32 a, i32 b) { return SAT ? sub_sat(a, b) : wsub(a, b); }
+template <bool SAT> XB_DEV i32 fsh1(i32 a) { return SAT ? add_sat(a, a) : (i32)((u32)a << 1); }  // ixheaac_shl32_sat(a, 1)
+template <bool SAT> XB_DEV i32 fmul31(i32 a, i32 b) { return SAT ? mul_sat31(a, b) : mul_sh1(a, b); }
+XB_DEV i32 amax(i32 m, i32 v) { return max(m, max(v, ~v)); }  // running bound: |v| <= amax + 1
 
-XB_DEV void rot_a(i32 &xr, i32 &xi, i32 wh, i32 wl) {
-  const i32 t = add_sat(mul_sat31(xr, wl), mul_sat31(xi, wh));
-  xi = add_sat(wneg(mul_sat31(xr, wh)), mul_sat31(xi, wl));
+template <bool SAT> XB_DEV void rot_a(i32 &xr, i32 &xi, i32 wh, i32 wl) {
+  const i32 t = fadd<SAT>(fmul31<SAT>(xr, wl), fmul31<SAT>(xi, wh));
+  xi = fadd<SAT>(wneg(fmul31<SAT>(xr, wh)), fmul31<SAT>(xi, wl));
   xr = t;
 }
-XB_DEV void rot_b(i32 &xr, i32 &xi, i32 wh, i32 wl) {
-  const i32 t = sub_sat(mul_sat31(xr, wh), mul_sat31(xi, wl));
-  xi = add_sat(mul_sat31(xr, wl), mul_sat31(xi, wh));
+template <bool SAT> XB_DEV void rot_b(i32 &xr, i32 &xi, i32 wh, i32 wl) {
+  const i32 t = fsub<SAT>(fmul31<SAT>(xr, wh), fmul31<SAT>(xi, wl));
+  xi = fadd<SAT>(fmul31<SAT>(xr, wl), fmul31<SAT>(xi, wh));
   xr = t;
 }
-XB_DEV void rot_c(i32 &xr, i32 &xi, i32 wh, i32 wl) {
-  const i32 t = wneg(add_sat(mul_sat31(xr, wl), mul_sat31(xi, wh)));
-  xi = add_sat(wneg(mul_sat31(xr, wh)), mul_sat31(xi, wl));
+template <bool SAT> XB_DEV void rot_c(i32 &xr, i32 &xi, i32 wh, i32 wl) {
+  const i32 t = wneg(fadd<SAT>(fmul31<SAT>(xr, wl), fmul31<SAT>(xi, wh)));
+  xi = fadd<SAT>(wneg(fmul31<SAT>(xr, wh)), fmul31<SAT>(xi, wl));
   xr = t;
 }
 
 // fft.c:1995-2012 (alt: :2390-2407).  Legs in, the reference's store order out: o0 = x0, o1 = x2, o2 = x1, o3 = (x3i, x3r).
+template <bool SAT>
 XB_DEV void bfly4(int2 x0, int2 x1, int2 x2, int2 x3, bool alt, int2 &o0, int2 &o1, int2 &o2, int2 &o3) {
-  i32 x0r = add_sat(x0.x, x2.x), x0i = add_sat(x0.y, x2.y);
-  i32 x2r = sub_sat(x0r, sh1(x2.x)), x2i = sub_sat(x0i, sh1(x2.y));
-  i32 x1r = add_sat(x1.x, x3.x);
-  i32 x1i = alt ? sub_sat(x1.y, x3.y) : add_sat(x1.y, x3.y);
-  i32 x3r = sub_sat(x1r, sh1(x3.x));
-  i32 x3i = alt ? add_sat(x1i, sh1(x3.y)) : sub_sat(x1i, sh1(x3.y));
-  x0r = add_sat(x0r, x1r);
-  x0i = add_sat(x0i, x1i);
-  x1r = sub_sat(x0r, sh1(x1r));
-  x1i = sub_sat(x0i, sh1(x1i));
-  x2r = sub_sat(x2r, x3i);
-  x2i = add_sat(x2i, x3r);
-  x3i = add_sat(x2r, sh1(x3i));
-  x3r = sub_sat(x2i, sh1(x3r));
+  i32 x0r = fadd<SAT>(x0.x, x2.x), x0i = fadd<SAT>(x0.y, x2.y);
+  i32 x2r = fsub<SAT>(x0r, fsh1<SAT>(x2.x)), x2i = fsub<SAT>(x0i, fsh1<SAT>(x2.y));
+  i32 x1r = fadd<SAT>(x1.x, x3.x);
+  i32 x1i = alt ? fsub<SAT>(x1.y, x3.y) : fadd<SAT>(x1.y, x3.y);
+  i32 x3r = fsub<SAT>(x1r, fsh1<SAT>(x3.x));
+  i32 x3i = alt ? fadd<SAT>(x1i, fsh1<SAT>(x3.y)) : fsub<SAT>(x1i, fsh1<SAT>(x3.y));
+  x0r = fadd<SAT>(x0r, x1r);
+  x0i = fadd<SAT>(x0i, x1i);
+  x1r = fsub<SAT>(x0r, fsh1<SAT>(x1r));
+  x1i = fsub<SAT>(x0i, fsh1<SAT>(x1i));
+  x2r = fsub<SAT>(x2r, x3i);
+  x2i = fadd<SAT>(x2i, x3r);
+  x3i = fadd<SAT>(x2r, fsh1<SAT>(x3i));
+  x3r = fsub<SAT>(x2i, fsh1<SAT>(x3r));
   o0 = make_int2(x0r, x0i);
   o1 = make_int2(x2r, x2i);
   o2 = make_int2(x1r, x1i);
   o3 = make_int2(x3i, x3r);
+}
+XB_DEV i32 amax4(i32 m, int2 a, int2 b, int2 c, int2 d) {
+  return amax(amax(amax(amax(amax(amax(amax(amax(m, a.x), a.y), b.x), b.y), c.x), c.y), d.x), d.y);
 }
 
 XB_DEV unsigned dig_rev16(unsigned v) {  // fft.c:39-46 without the final shift
@@ -89,10 +99,18 @@ XB_DEV void st2(i32 *buf, int a, int2 v) { *reinterpret_cast<int2 *>(buf + PA(a)
 
 // ixheaacd_complex_fft_p2_dec, fft_mode = 1, as a batch of `nblk` transforms of `np` points (nblk * np = 512):
 // px (interleaved re, im; already divided by 1 << shift) -> y.  Both buffers are padded (PA).
-XB_DEV void fft_batch(const i32 *tw, const i32 *px, i32 *y, int np, int lane) {
+// Every stage exists twice: with the reference's saturating operations, and with wrapping ones for inputs whose bound B
+// (|x| <= B, tracked exactly from stage to stage) proves that the exact value of every intermediate fits 32 bits.  With
+// rotated legs bounded by 2B the largest intermediates of a butterfly are x0 + x2 + x1 + x3 <= 7B and the doubled terms
+// shl(x1r, 1), shl(x3i, 1) <= 8B: B < 2^28 for the middle stages, B < 2^29 for the first one (no rotation: 4B), B < 2^30 for
+// the final radix-2 stage (only the rotation can saturate: 2B).  Products of such values with a twiddle fit too, and the one
+// saturating product INT_MIN x INT_MIN needs a data word of INT_MIN.
+template <bool SAT>
+XB_DEV i32 fft_first(const i32 *px, i32 *y, int np, int lane) {
   const bool p512 = np == 512;
   const int lg_q = p512 ? 7 : 4;  // log2(butterflies per block)
   const int dr_shift = p512 ? 6 : 9;
+  i32 m = 0;
   // ---- first radix-4 stage with digit reversal (fft.c:1969-2020) ----
 #pragma unroll 1
   for (int t = 0; t < 4; t++) {
@@ -106,75 +124,98 @@ XB_DEV void fft_batch(const i32 *tw, const i32 *px, i32 *y, int np, int lane) {
     ld2(px, base + h2 + (np >> 1), b);
     ld2(px, base + h2 + np, c);
     ld2(px, base + h2 + np + (np >> 1), d);
-    bfly4(a, b, c, d, false, o0, o1, o2, o3);
+    bfly4<SAT>(a, b, c, d, false, o0, o1, o2, o3);
+    m = amax4(m, o0, o1, o2, o3);
     st2(y, base + 2 * i, o0);
     st2(y, base + 2 * i + 2, o1);
     st2(y, base + 2 * i + 4, o2);
     st2(y, base + 2 * i + 6, o3);
   }
+  return m;
+}
+// ---- one middle radix-4 stage (fft.c:2025-2422) ----
+template <bool SAT>
+XB_DEV i32 fft_mid(const i32 *tw, i32 *y, int np, int lane, int del, int lg_del, int nodespacing) {
+  const int lg_q = np == 512 ? 7 : 4;
+  i32 m = 0;
+#pragma unroll 1
+  for (int t = 0; t < 4; t++) {
+    const int q = lane + 32 * t;
+    const int blk = q >> lg_q, rem = q & ((1 << lg_q) - 1);
+    const int jj = rem & (del - 1), g = rem >> lg_del;
+    const int j = jj * nodespacing;
+    const int a0 = blk * 2 * np + 2 * jj + 8 * del * g;
+    int2 x0, x1, x2, x3, o0, o1, o2, o3;
+    ld2(y, a0, x0);
+    ld2(y, a0 + 2 * del, x1);
+    ld2(y, a0 + 4 * del, x2);
+    ld2(y, a0 + 6 * del, x3);
+    bool alt = false;
+    if (jj > 0) {
+      const i32 w1h = __ldg(tw + 2 * j), w1l = __ldg(tw + 2 * j + 1);
+      rot_a<SAT>(x1.x, x1.y, w1h, w1l);
+      if (j <= 85) {
+        rot_a<SAT>(x2.x, x2.y, __ldg(tw + 4 * j), __ldg(tw + 4 * j + 1));
+        rot_a<SAT>(x3.x, x3.y, __ldg(tw + 6 * j), __ldg(tw + 6 * j + 1));
+      } else if (j <= 128) {
+        rot_a<SAT>(x2.x, x2.y, __ldg(tw + 4 * j), __ldg(tw + 4 * j + 1));
+        rot_b<SAT>(x3.x, x3.y, __ldg(tw + 6 * j - 512), __ldg(tw + 6 * j - 511));
+      } else if (j <= 170) {
+        rot_b<SAT>(x2.x, x2.y, __ldg(tw + 4 * j - 512), __ldg(tw + 4 * j - 511));
+        rot_b<SAT>(x3.x, x3.y, __ldg(tw + 6 * j - 512), __ldg(tw + 6 * j - 511));
+      } else {
+        rot_b<SAT>(x2.x, x2.y, __ldg(tw + 4 * j - 512), __ldg(tw + 4 * j - 511));
+        rot_c<SAT>(x3.x, x3.y, __ldg(tw + 6 * j - 1024), __ldg(tw + 6 * j - 1023));
+        alt = true;
+      }
+    }
+    bfly4<SAT>(x0, x1, x2, x3, alt, o0, o1, o2, o3);
+    m = amax4(m, o0, o1, o2, o3);
+    st2(y, a0, o0);
+    st2(y, a0 + 2 * del, o1);
+    st2(y, a0 + 4 * del, o2);
+    st2(y, a0 + 6 * del, o3);
+  }
+  return m;
+}
+// ---- final radix-2 stage of the 512-point transform (fft.c:2423-2481): del = 256, twiddle step 4 words ----
+template <bool SAT>
+XB_DEV void fft_last(const i32 *tw, i32 *y, int lane) {
+#pragma unroll 1
+  for (int t = 0; t < 8; t++) {
+    const int q = lane + 32 * t;  // 0..255: first half rot_a (q < 128), second half rot_b
+    const int tt = q & 127;
+    int2 x0, x1;
+    ld2(y, 2 * q, x0);
+    ld2(y, 2 * q + 512, x1);
+    const i32 wh = __ldg(tw + 4 * tt), wl = __ldg(tw + 4 * tt + 1);
+    if (q < 128) rot_a<SAT>(x1.x, x1.y, wh, wl);
+    else rot_b<SAT>(x1.x, x1.y, wh, wl);
+    st2(y, 2 * q + 512, make_int2(wsub(x0.x / 2, x1.x / 2), wsub(x0.y / 2, x1.y / 2)));
+    st2(y, 2 * q, make_int2(wadd(x0.x / 2, x1.x / 2), wadd(x0.y / 2, x1.y / 2)));
+  }
+}
+// in_bound: amax over the words of px (warp-uniform)
+XB_DEV void fft_batch(const i32 *tw, const i32 *px, i32 *y, int np, int lane, i32 in_bound) {
+  const bool p512 = np == 512;
+  i32 m = in_bound < (1 << 29) - 2 ? fft_first<false>(px, y, np, lane) : fft_first<true>(px, y, np, lane);
+  m = __reduce_max_sync(0xffffffffu, m);
   __syncwarp();
-  // ---- middle radix-4 stages (fft.c:2025-2422) ----
   const int n_mid = p512 ? 3 : 2;
   int del = 4, lg_del = 2, nodespacing = 64;
 #pragma unroll 1
   for (int st = 0; st < n_mid; st++) {
-#pragma unroll 1
-    for (int t = 0; t < 4; t++) {
-      const int q = lane + 32 * t;
-      const int blk = q >> lg_q, rem = q & ((1 << lg_q) - 1);
-      const int jj = rem & (del - 1), g = rem >> lg_del;
-      const int j = jj * nodespacing;
-      const int a0 = blk * 2 * np + 2 * jj + 8 * del * g;
-      int2 x0, x1, x2, x3, o0, o1, o2, o3;
-      ld2(y, a0, x0);
-      ld2(y, a0 + 2 * del, x1);
-      ld2(y, a0 + 4 * del, x2);
-      ld2(y, a0 + 6 * del, x3);
-      bool alt = false;
-      if (jj > 0) {
-        const i32 w1h = __ldg(tw + 2 * j), w1l = __ldg(tw + 2 * j + 1);
-        rot_a(x1.x, x1.y, w1h, w1l);
-        if (j <= 85) {
-          rot_a(x2.x, x2.y, __ldg(tw + 4 * j), __ldg(tw + 4 * j + 1));
-          rot_a(x3.x, x3.y, __ldg(tw + 6 * j), __ldg(tw + 6 * j + 1));
-        } else if (j <= 128) {
-          rot_a(x2.x, x2.y, __ldg(tw + 4 * j), __ldg(tw + 4 * j + 1));
-          rot_b(x3.x, x3.y, __ldg(tw + 6 * j - 512), __ldg(tw + 6 * j - 511));
-        } else if (j <= 170) {
-          rot_b(x2.x, x2.y, __ldg(tw + 4 * j - 512), __ldg(tw + 4 * j - 511));
-          rot_b(x3.x, x3.y, __ldg(tw + 6 * j - 512), __ldg(tw + 6 * j - 511));
-        } else {
-          rot_b(x2.x, x2.y, __ldg(tw + 4 * j - 512), __ldg(tw + 4 * j - 511));
-          rot_c(x3.x, x3.y, __ldg(tw + 6 * j - 1024), __ldg(tw + 6 * j - 1023));
-          alt = true;
-        }
-      }
-      bfly4(x0, x1, x2, x3, alt, o0, o1, o2, o3);
-      st2(y, a0, o0);
-      st2(y, a0 + 2 * del, o1);
-      st2(y, a0 + 4 * del, o2);
-      st2(y, a0 + 6 * del, o3);
-    }
+    m = m < (1 << 28) - 2 ? fft_mid<false>(tw, y, np, lane, del, lg_del, nodespacing)
+                          : fft_mid<true>(tw, y, np, lane, del, lg_del, nodespacing);
+    m = __reduce_max_sync(0xffffffffu, m);
     __syncwarp();
     nodespacing >>= 2;
     del <<= 2;
     lg_del += 2;
   }
-  // ---- final radix-2 stage of the 512-point transform (fft.c:2423-2481): del = 256, twiddle step 4 words ----
   if (p512) {
-#pragma unroll 1
-    for (int t = 0; t < 8; t++) {
-      const int q = lane + 32 * t;  // 0..255: first half rot_a (q < 128), second half rot_b
-      const int tt = q & 127;
-      int2 x0, x1;
-      ld2(y, 2 * q, x0);
-      ld2(y, 2 * q + 512, x1);
-      const i32 wh = __ldg(tw + 4 * tt), wl = __ldg(tw + 4 * tt + 1);
-      if (q < 128) rot_a(x1.x, x1.y, wh, wl);
-      else rot_b(x1.x, x1.y, wh, wl);
-      st2(y, 2 * q + 512, make_int2(wsub(x0.x / 2, x1.x / 2), wsub(x0.y / 2, x1.y / 2)));
-      st2(y, 2 * q, make_int2(wadd(x0.x / 2, x1.x / 2), wadd(x0.y / 2, x1.y / 2)));
-    }
+    if (m < (1 << 30) - 2) fft_last<false>(tw, y, lane);
+    else fft_last<true>(tw, y, lane);
     __syncwarp();
   }
 }
@@ -201,6 +242,7 @@ XB_DEV int imdct_batch(const uint8_t *rom, i32 *A, i32 *B, int nblk, int pre_sh,
   const int shift = (lg & 1) ? (lg + 3) / 2 : (lg + 4) / 2;
   const int div = 1 << shift;
   // pre-twiddle (imdct.c:111-127) in place, pairs (i, nl-1-i): complex i at words 2i, 2i+1 of its block
+  i32 bound = 0;
 #pragma unroll 2
   for (int q = lane; q < 256; q += 32) {
     const int ppb = nl >> 1;  // pairs per block
@@ -215,11 +257,14 @@ XB_DEV int imdct_batch(const uint8_t *rom, i32 *A, i32 *B, int nblk, int pre_sh,
     const i32 m1 = wsub(mul32(hi.y, c1), mul32(lo.x, s1));
     const i32 r2 = wsub(mul32(neg_sat(hi.x), c2), mul32(lo.y, s2));
     const i32 m2 = wsub(mul32(lo.y, c2), mul32(hi.x, s2));
-    st2(A, base + 2 * i, make_int2(r1 / div, m1 / div));   // fft.c:1443-1446: C division
-    st2(A, base + 2 * i2, make_int2(r2 / div, m2 / div));
+    const int2 v1 = make_int2(r1 / div, m1 / div), v2 = make_int2(r2 / div, m2 / div);  // fft.c:1443-1446: C division
+    bound = amax(amax(amax(amax(bound, v1.x), v1.y), v2.x), v2.y);
+    st2(A, base + 2 * i, v1);
+    st2(A, base + 2 * i2, v2);
   }
+  bound = __reduce_max_sync(0xffffffffu, bound);
   __syncwarp();
-  fft_batch(tw, A, B, nl, lane);
+  fft_batch(tw, A, B, nl, lane, bound);
   // post-twiddle (imdct.c:129-147): B (r, im interleaved) -> A
 #pragma unroll 2
   for (int q = lane; q < 512; q += 32) {
