@@ -12,7 +12,7 @@
 // lane = TIME SLOT for the modulation: the 32 slots of a unit are 32 independent 2 x 32-point transforms, each run
 // serially by one lane in place in its own 128-word row of shared memory (row stride 129 words: conflict-free); the
 // digit-reversed radix-2 pass goes through registers.  The slot's row then receives its 128 WORD32 state samples, so
-// the rows double as the window history; the 9 older blocks of the state ring sit in the 9 rows before row 0.
+// the rows double as the window history; the 9 older blocks of the state ring stay in registers (a lane only needs its own taps).
 // lane = output sample pair for the 10-tap window, in the time-invariant form the reference's ring / coefficient
 // bookkeeping collapses to when both are in lock step (see sbr_lp_kernel.cu); other states take the literal form.
 // Algorithmic HBM bytes per unit: 16 384 (float matrix) + 5120 + 5120 (WORD32 state in / out) + 8192 (float out) = 34 816.
@@ -24,7 +24,7 @@
 
 namespace xb {
 
-constexpr int kEsWarps = 10;
+constexpr int kEsWarps = 13;
 constexpr int ES = 129;  // row stride in words
 
 struct EsTab {
@@ -38,7 +38,7 @@ struct EsTab {
   i32 tcos32[64];
 };
 struct EsWarpS {
-  i32 rows[(9 + 32) * ES];  // rows 0..8: old state blocks (age 9..1), row 9 + s: slot s
+  i32 rows[32 * ES];  // row s: slot s (matrix row, then its 128 state samples); the 9 older state blocks stay in registers
 };
 struct EsBlockS {
   EsTab tab;
@@ -201,8 +201,7 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
   }
   __syncthreads();
   const EsTab &tab = sm.tab;
-  i32 *hist = sm.w[warp].rows;
-  i32 *rows = hist + 9 * ES;
+  i32 *rows = sm.w[warp].rows;
   const long long warps_total = (long long)gridDim.x * kEsWarps;
   for (long long u = (long long)blockIdx.x * kEsWarps + warp; u < p.n_units; u += warps_total) {
     __syncwarp();
@@ -256,15 +255,16 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
         mx |= (u32)(r[0] ^ (r[0] >> 31)) | (u32)(r[1] ^ (r[1] >> 31)) | (u32)(r[2] ^ (r[2] >> 31)) | (u32)(r[3] ^ (r[3] >> 31));
       }
     }
-    {  // old ring blocks: the block of age a0 (1..9) goes to history row 9 - a0
-      const i32 *ss = p.states + u * 1280;
-#pragma unroll 1
-      for (int i = lane; i < 1280; i += 32) {
-        const int b = i >> 7;
-        int a0 = b - b0;
-        if (a0 < 0) a0 += 10;
-        if (a0 != 0) hist[ES * (9 - a0) + (i & 127)] = ss[i];
-      }
+    // old ring blocks: the block of age a0 (1..9) is ring block (b0 + a0) mod 10; a lane only ever needs words lane,
+    // lane + 32, lane + 64, lane + 96 of each (its own window taps), so the history lives in registers
+    const i32 *ss = p.states + u * 1280;
+    i32 hr[9][4];
+#pragma unroll
+    for (int a0 = 1; a0 <= 9; a0++) {
+      int b = b0 + a0;
+      if (b >= 10) b -= 10;
+#pragma unroll
+      for (int j = 0; j < 4; j++) hr[a0 - 1][j] = __ldg(ss + 128 * b + 32 * j + lane);
     }
     __syncwarp();
     // The transform grows magnitudes by at most 8 x 8 x 2 = 128 (two radix-4 stages whose twiddled outputs are
@@ -298,8 +298,29 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
         c1[a] = tab.qmf_c[64 * a + 32 + lane];
       }
       const i32 *hp = rows + lane;
+#pragma unroll
+      for (int i = 0; i < 9; i++) {  // slots whose window still reaches into the old state (registers)
+        unsigned long long acc0 = 0, acc1 = 0;
+#pragma unroll
+        for (int a = 0; a < 10; a++) {
+          i32 q0, q1;
+          if (a <= i) {
+            const i32 *q = hp + ES * (i - a) + 64 * (a & 1);
+            q0 = q[0];
+            q1 = q[32];
+          } else {
+            q0 = hr[a - i - 1][2 * (a & 1)];
+            q1 = hr[a - i - 1][2 * (a & 1) + 1];
+          }
+          acc0 += (unsigned long long)((long long)q0 * c0[a]);
+          acc1 += (unsigned long long)((long long)q1 * c1[a]);
+        }
+        const i32 o0 = (i32)((long long)acc0 >> 31), o1 = (i32)((long long)acc1 >> 31);
+        emit(64 * i + lane, o0);
+        emit(64 * i + 32 + lane, o1);
+      }
 #pragma unroll 1
-      for (int i = 0; i < 32; i++) {
+      for (int i = 9; i < 32; i++) {
         unsigned long long acc0 = 0, acc1 = 0;
 #pragma unroll
         for (int a = 0; a < 10; a++) {
@@ -322,7 +343,9 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
         for (int b = 0; b < 10; b++) {
           int a = ab + b;
           if (a >= 10) a -= 10;
-          const i32 *q = rows + ES * (i - a) + 64 * ((i + b) & 1) + lane;
+          int hb = b0 + a - i;  // ring block of the old state when the tap is older than this frame
+          if (hb >= 10) hb -= 10;
+          const i32 *q = (i >= a ? rows + ES * (i - a) : ss + 128 * hb) + 64 * ((i + b) & 1) + lane;
           const i32 *c = tab.qmf_c + fpos + 64 * b + lane;
           acc0 += (unsigned long long)((long long)q[0] * c[0]);
           acc1 += (unsigned long long)((long long)q[32] * c[32]);
