@@ -291,6 +291,12 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
   for (long long u = (long long)blockIdx.x * kUfWarps + warp; u < p.n_units; u += warps_total) {
     __syncwarp();
     const int win_seq = p.ics[2 * u], win_shape = p.ics[2 * u + 1], shape_prev = p.wstate[u];
+    if (u + warps_total < p.n_units) {  // pull this warp's next unit (coefficients + overlap, 8 KB) towards L2
+      const char *q0 = reinterpret_cast<const char *>(p.coef + (u + warps_total) * 1024);
+      const char *q1 = reinterpret_cast<const char *>(p.overlap + (u + warps_total) * 1024);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + lane * 128));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + lane * 128));
+    }
     {
       const int4 *src = reinterpret_cast<const int4 *>(p.coef + u * 1024);
 #pragma unroll 4
