@@ -24,6 +24,7 @@ namespace xb {
 
 constexpr int kUfWarps = 8;
 constexpr int kUfBuf = 1280;  // 1024 words + 8 pad words per 32
+constexpr int kURomPad = 15888;  // kURomBytes rounded up to 16
 
 XB_DEV int PA(int a) { return a + ((a >> 5) << 3); }  // padded address of word a
 
@@ -152,20 +153,20 @@ XB_DEV i32 fft_mid(const i32 *tw, i32 *y, int np, int lane, int del, int lg_del,
     ld2(y, a0 + 6 * del, x3);
     bool alt = false;
     if (jj > 0) {
-      const i32 w1h = __ldg(tw + 2 * j), w1l = __ldg(tw + 2 * j + 1);
+      const i32 w1h = (*(tw + 2 * j)), w1l = (*(tw + 2 * j + 1));
       rot_a<SAT>(x1.x, x1.y, w1h, w1l);
       if (j <= 85) {
-        rot_a<SAT>(x2.x, x2.y, __ldg(tw + 4 * j), __ldg(tw + 4 * j + 1));
-        rot_a<SAT>(x3.x, x3.y, __ldg(tw + 6 * j), __ldg(tw + 6 * j + 1));
+        rot_a<SAT>(x2.x, x2.y, (*(tw + 4 * j)), (*(tw + 4 * j + 1)));
+        rot_a<SAT>(x3.x, x3.y, (*(tw + 6 * j)), (*(tw + 6 * j + 1)));
       } else if (j <= 128) {
-        rot_a<SAT>(x2.x, x2.y, __ldg(tw + 4 * j), __ldg(tw + 4 * j + 1));
-        rot_b<SAT>(x3.x, x3.y, __ldg(tw + 6 * j - 512), __ldg(tw + 6 * j - 511));
+        rot_a<SAT>(x2.x, x2.y, (*(tw + 4 * j)), (*(tw + 4 * j + 1)));
+        rot_b<SAT>(x3.x, x3.y, (*(tw + 6 * j - 512)), (*(tw + 6 * j - 511)));
       } else if (j <= 170) {
-        rot_b<SAT>(x2.x, x2.y, __ldg(tw + 4 * j - 512), __ldg(tw + 4 * j - 511));
-        rot_b<SAT>(x3.x, x3.y, __ldg(tw + 6 * j - 512), __ldg(tw + 6 * j - 511));
+        rot_b<SAT>(x2.x, x2.y, (*(tw + 4 * j - 512)), (*(tw + 4 * j - 511)));
+        rot_b<SAT>(x3.x, x3.y, (*(tw + 6 * j - 512)), (*(tw + 6 * j - 511)));
       } else {
-        rot_b<SAT>(x2.x, x2.y, __ldg(tw + 4 * j - 512), __ldg(tw + 4 * j - 511));
-        rot_c<SAT>(x3.x, x3.y, __ldg(tw + 6 * j - 1024), __ldg(tw + 6 * j - 1023));
+        rot_b<SAT>(x2.x, x2.y, (*(tw + 4 * j - 512)), (*(tw + 4 * j - 511)));
+        rot_c<SAT>(x3.x, x3.y, (*(tw + 6 * j - 1024)), (*(tw + 6 * j - 1023)));
         alt = true;
       }
     }
@@ -188,7 +189,7 @@ XB_DEV void fft_last(const i32 *tw, i32 *y, int lane) {
     int2 x0, x1;
     ld2(y, 2 * q, x0);
     ld2(y, 2 * q + 512, x1);
-    const i32 wh = __ldg(tw + 4 * tt), wl = __ldg(tw + 4 * tt + 1);
+    const i32 wh = (*(tw + 4 * tt)), wl = (*(tw + 4 * tt + 1));
     if (q < 128) rot_a<SAT>(x1.x, x1.y, wh, wl);
     else rot_b<SAT>(x1.x, x1.y, wh, wl);
     st2(y, 2 * q + 512, make_int2(wsub(x0.x / 2, x1.x / 2), wsub(x0.y / 2, x1.y / 2)));
@@ -252,7 +253,7 @@ XB_DEV int imdct_batch(const uint8_t *rom, i32 *A, i32 *B, int nblk, int pre_sh,
     ld2(A, base + 2 * i, lo);       // x[2i], x[2i+1]
     ld2(A, base + 2 * i2, hi);      // x[2 i2], x[2 i2 + 1] = x[2nl-1-2i]
     lo.x = lsl(lo.x, pre_sh); lo.y = lsl(lo.y, pre_sh); hi.x = lsl(hi.x, pre_sh); hi.y = lsl(hi.y, pre_sh);
-    const i32 c1 = __ldg(cs + i), s1 = __ldg(sn + i), c2 = __ldg(cs + i2), s2 = __ldg(sn + i2);
+    const i32 c1 = (*(cs + i)), s1 = (*(sn + i)), c2 = (*(cs + i2)), s2 = (*(sn + i2));
     const i32 r1 = wsub(mul32(neg_sat(lo.x), c1), mul32(hi.y, s1));
     const i32 m1 = wsub(mul32(hi.y, c1), mul32(lo.x, s1));
     const i32 r2 = wsub(mul32(neg_sat(hi.x), c2), mul32(lo.y, s2));
@@ -271,7 +272,7 @@ XB_DEV int imdct_batch(const uint8_t *rom, i32 *A, i32 *B, int nblk, int pre_sh,
     const int blk = q / nl, i = q % nl;
     int2 v;
     ld2(B, blk * N + 2 * i, v);
-    const i32 c = __ldg(cs + i), s = __ldg(sn + i);
+    const i32 c = (*(cs + i)), s = (*(sn + i));
     A[PA(blk * N + 2 * i)] = wneg(wsub(mul32(v.x, c), mul32(v.y, s)));
     A[PA(blk * N + 2 * nl - 1 - 2 * i)] = wneg(wadd(mul32(v.y, c), mul32(v.x, s)));
   }
@@ -283,7 +284,15 @@ XB_DEV int imdct_batch(const uint8_t *rom, i32 *A, i32 *B, int nblk, int pre_sh,
 
 __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  i32 *smem = reinterpret_cast<i32 *>(smem_raw);
+  // the tables (15.9 KB: FFT twiddles, pre / post twiddles, windows) first, then the per-warp buffers
+  const uint8_t *rom = smem_raw;
+  {
+    const i32 *src = reinterpret_cast<const i32 *>(p.rom);
+    i32 *dst = reinterpret_cast<i32 *>(smem_raw);
+    for (int i = threadIdx.x; i < kURomBytes / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  i32 *smem = reinterpret_cast<i32 *>(smem_raw + kURomPad);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   i32 *A = smem + warp * 2 * kUfBuf, *B = A + kUfBuf;
   const long long warps_total = (long long)gridDim.x * kUfWarps;
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
     int max_shift = max_headroom(A, lane);
     int shiftp = (int)(int8_t)(max_shift + 6);
     const bool is_short = win_seq == 2;
-    shiftp = (int)(int8_t)(shiftp - imdct_batch(p.rom, A, B, is_short ? 8 : 1, max_shift, lane));
+    shiftp = (int)(int8_t)(shiftp - imdct_batch(rom, A, B, is_short ? 8 : 1, max_shift, lane));
     max_shift = max_headroom(A, lane);
     // imdct.c:93-99 with max_shift - 1: a count of -1 clears the block in the reference build (PSLLD, see oracle)
     const int nsh = max_shift - 1;
@@ -321,12 +330,12 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
     if (!is_short) {
       int output_q;
       if (win_seq == 0 || win_seq == 1) {  // ixheaacd_windowing_long1 (basic_ops.c:77-123)
-        const i32 *win = reinterpret_cast<const i32 *>(p.rom + (shape_prev ? kURomKbd1024 : kURomSine1024));
+        const i32 *win = reinterpret_cast<const i32 *>(rom + (shape_prev ? kURomKbd1024 : kURomSine1024));
         const bool gt = shiftp > so;
         const int sh = gt ? shiftp - so : so - shiftp;
 #pragma unroll 2
         for (int i = lane; i < 512; i += 32) {
-          const i32 wf = __ldg(win + i), wr = __ldg(win + 1023 - i), a = IN(512 + i), o1 = ov[i], o2 = ov[1023 - i];
+          const i32 wf = (*(win + i)), wr = (*(win + 1023 - i)), a = IN(512 + i), o1 = ov[i], o2 = ov[1023 - i];
           i32 d1, d2;
           if (gt) {
             d1 = add_sat(mul_sh1(a, wf) >> sh, mul_sh1(o1, wr));
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
         }
         output_q = gt ? so : shiftp;
       } else {  // ixheaacd_windowing_long3 (basic_ops.c:298-372), n_flat = 448, n_trans = 128
-        const i32 *wsh = reinterpret_cast<const i32 *>(p.rom + (shape_prev ? kURomKbd128 : kURomSine128));
+        const i32 *wsh = reinterpret_cast<const i32 *>(rom + (shape_prev ? kURomKbd128 : kURomSine128));
         const bool gt = shiftp > so;
         const int sh = gt ? shiftp - so : so - shiftp;
 #pragma unroll 2
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
           if (i < 448) d = gt ? ov[i] : (ov[i] >> sh);
           else if (i < 576) {
             const i32 a = i < 512 ? IN(512 + i) : neg_sat(IN(512 + 1023 - i));
-            const i32 wf = __ldg(wsh + i - 448), wr = __ldg(wsh + 127 - (i - 448));
+            const i32 wf = (*(wsh + i - 448)), wr = (*(wsh + 127 - (i - 448)));
             d = gt ? add_sat(mul_sh1(a, wf) >> sh, mul_sh1(ov[i], wr)) : add_sat(mul_sh1(a, wf), mul_sh1(ov[i], wr) >> sh);
           } else {
             const i32 a = neg_sat(IN(512 + 1023 - i));
@@ -376,8 +385,8 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
       }
     } else {
       // EIGHT_SHORT (imdct.c:336-475): the 2048-word work buffer is out (low half) | ov (high half) in HBM / L2
-      const i32 *wsh = reinterpret_cast<const i32 *>(p.rom + (win_shape ? kURomKbd128 : kURomSine128));
-      const i32 *wpv = reinterpret_cast<const i32 *>(p.rom + (shape_prev ? kURomKbd128 : kURomSine128));
+      const i32 *wsh = reinterpret_cast<const i32 *>(rom + (win_shape ? kURomKbd128 : kURomSine128));
+      const i32 *wpv = reinterpret_cast<const i32 *>(rom + (shape_prev ? kURomKbd128 : kURomSine128));
       auto BUF = [&](int i) -> i32 * { return i < 1024 ? out + i : ov + (i - 1024); };
       for (int i = lane; i < 1024; i += 32) {
         out[i] = ov[i];
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
       {  // ixheaacd_windowing_short2 (basic_ops.c:429-478): src1 = in + 64, fp = buf + 448
         const int sh = so_gt ? so - shiftp : shiftp - so;
         for (int i = lane; i < 64; i += 32) {
-          const i32 wf = __ldg(wpv + i), wr = __ldg(wpv + 127 - i), a = IN(64 + i);
+          const i32 wf = (*(wpv + i)), wr = (*(wpv + 127 - i)), a = IN(64 + i);
           i32 *f1 = BUF(448 + i), *f2 = BUF(448 + 127 - i);
           if (so_gt) {
             *f1 = add_sat(mul_sh1(a, wf), mul_sh1(*f1, wr) >> sh);
@@ -406,7 +415,7 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
       {  // ixheaacd_windowing_short3 (basic_ops.c:480-521): src1 = in, fp = buf + 576
         const int sh = so_gt ? so - shiftp : shiftp - so;
         for (int i = lane; i < 64; i += 32) {
-          const i32 wr = __ldg(wsh + 127 - i), wf = __ldg(wsh + i), a = neg_sat(IN(63 - i));
+          const i32 wr = (*(wsh + 127 - i)), wf = (*(wsh + i)), a = neg_sat(IN(63 - i));
           i32 *f1 = BUF(576 + i), *f2 = BUF(576 + 127 - i);
           if (so_gt) {
             *f1 = add_sat(mul_sh1(a, wr), *f1 >> sh);
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
         const int fp0 = 448 + 128 * k, s0 = 128 * k;
         const bool flag = k < 7;
         for (int i = lane; i < 64; i += 32) {
-          const i32 wf = __ldg(wsh + i), wr = __ldg(wsh + 127 - i), a = IN(s0 + 64 + i);
+          const i32 wf = (*(wsh + i)), wr = (*(wsh + 127 - i)), a = IN(s0 + 64 + i);
           i32 *f1 = BUF(fp0 + i), *f2 = BUF(fp0 + 127 - i);
           if (big) {
             *f1 = add_sat(mul_sh1(a, wf) >> sh4, *f1);
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
           const int t = i - 64;
           const i32 a = neg_sat(IN(s0 + 127 - i));
           i32 *pa = BUF(fp0 + i + 64), *pb = BUF(fp0 + 384 - 64 - i - 1);
-          const i32 va = flag ? mul_sh1(a, __ldg(wsh + 127 - t)) : a, vb = flag ? mul_sh1(a, __ldg(wsh + t)) : a;
+          const i32 va = flag ? mul_sh1(a, (*(wsh + 127 - t))) : a, vb = flag ? mul_sh1(a, (*(wsh + t))) : a;
           if (big) {
             *pa = add_sat(va >> sh4, *pa >> (so - oq));
             *pb = add_sat(vb >> sh4, *pb >> (so - oq));
@@ -466,7 +475,7 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
   }
 }
 
-size_t usac_fd_smem_bytes() { return (size_t)kUfWarps * 2 * kUfBuf * 4; }
+size_t usac_fd_smem_bytes() { return (size_t)kURomPad + (size_t)kUfWarps * 2 * kUfBuf * 4; }
 
 // nothing in the kernel depends on table values beyond their layout; kept as the install-time hook
 int usac_fd_check_tables(const uint8_t *urom) { return urom ? 0 : -1; }
