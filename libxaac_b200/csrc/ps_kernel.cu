@@ -430,21 +430,18 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       __syncwarp();
       // bins 8..13 are QMF bands 3..8: fetch from the owning lane
       const u32 tq = __shfl_sync(full, tA, (lane >= 8 && lane < 14) ? lane - 5 : 0);
+      // group sum of this lane's bin (bins 14..19), selected branch-free before the lanes split up
+      u32 vsel = gsum[0];
+#pragma unroll
+      for (int g = 1; g < 6; g++) vsel = (lane - 14 == g) ? gsum[g] : vsel;
       if (lane < 20) {
         const int bin = lane;
-        i32 pwr;
+        i32 pwr = bin < 14 ? (i32)tq : (i32)min(vsel, 0x7fffffffu);
         if (bin < 8) {  // hybrid sub-subbands: bins 0 / 1 pair (0, 5) / (4, 1), bins 2..7 one sub-subband each
           const int s1 = bin == 0 ? 0 : (bin == 1 ? 4 : (int)borders[bin + 2]), s2 = bin == 0 ? 5 : 1;
           pwr = add_sat(pw(lre[s1]), pw(lim[s1]));
           const i32 p2 = add_sat(add_sat(pwr, pw(lre[s2])), pw(lim[s2]));
           if (bin < 2) pwr = p2;
-        }
-        else if (bin < 14) pwr = (i32)tq;
-        else {
-          u32 v = gsum[0];
-#pragma unroll
-          for (int g = 1; g < 6; g++) if (bin - 14 == g) v = gsum[g];
-          pwr = (i32)min(v, 0x7fffffffu);
         }
         i32 pv = shl32(pwr, 1);
         if (pv < 0) pv = 0;
