@@ -200,7 +200,23 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
     __syncwarp();
     {
       const i32 *src = reinterpret_cast<const i32 *>(p.ps_state + u * kPsDspWords);
-      for (int i = lane; i < kPsDspWords / 2; i += 32) reinterpret_cast<i32 *>(st)[i] = src[i];
+      // 649 8-byte words (the unit stride 5192 B is 8-byte aligned): all of a lane's 21 loads in flight before the stores
+      static_assert(kPsDspWords % 4 == 0, "PS state blob must be a whole number of 8-byte words");
+      const int2 *src2 = reinterpret_cast<const int2 *>(src);
+      int2 v[21];
+#pragma unroll
+      for (int q = 0; q < 21; q++) {
+        const int i = lane + 32 * q;
+        v[q] = i < kPsDspWords / 4 ? src2[i] : make_int2(0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < 21; q++) {
+        const int i = lane + 32 * q;
+        if (i < kPsDspWords / 4) {
+          reinterpret_cast<i32 *>(st)[2 * i] = v[q].x;
+          reinterpret_cast<i32 *>(st)[2 * i + 1] = v[q].y;
+        }
+      }
       w.hyb[lane] = 0;
       w.hyb[32 + lane] = 0;
     }
@@ -573,7 +589,8 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       if (lane < 12) {
         const int s_ = lane >> 2, c = lane & 3, o = s_ == 0 ? 0 : 6 + 2 * (s_ - 1), cnt = s_ == 0 ? 6 : 2;
         fold = w.hyb[16 * c + o];
-        for (int q = 1; q < cnt; q++) fold = add_sat(fold, w.hyb[16 * c + o + q]);
+#pragma unroll
+        for (int q = 1; q < 6; q++) fold = add_sat(fold, q < cnt ? w.hyb[16 * c + o + q] : 0);  // add_sat(x, 0) = x
       }
       {
         const int src = 4 * min(lane, 2);
