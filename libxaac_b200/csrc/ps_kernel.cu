@@ -33,6 +33,7 @@ struct PsWarpS {
   i32 hyb[64];              // left_re[16] | left_im[16] | right_re[16] | right_im[16]
   i32 xs[3][2][44];         // hybrid filter input history: 12 delayed + 32 new samples of QMF bands 0..2 (re, im)
   i32 hybL[32][21];         // hybrid analysis of all 32 slots: [slot][re 0..9 | im 10..19] (odd row stride: no conflicts)
+  u32 pwt[32][21];          // power per parameter bin of all 32 slots: [slot][bin 0..19] (odd row stride)
   int16_t tr[24];           // transient ratio per bin (+ tr[20] = 0)
 };
 
@@ -354,13 +355,46 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
     i32 H11r = H11[2 * gi], H12r = H11[2 * gi + 1], H21r = H21[2 * gi], H22r = H21[2 * gi + 1];
     i32 D11r = d11[2 * gi], D12r = d11[2 * gi + 1], D21r = d21[2 * gi], D22r = d21[2 * gi + 1];
     const int b20 = borders[20], b21 = borders[21], b22 = borders[22];
-    // power terms of the wide parameter bins 14..19 = stereo groups 16..21 (ps_dec.c:535-556): group of band k
-    int gshA = -1, gshB = -1, grpA = -1, grpB = -1;
-    for (int g = 16; g < 22; g++) {
-      if (lane >= borders[g] && lane < borders[g + 1]) { grpA = g - 16; gshA = rom[kPsRomGroupShift + g - 16]; }
-      if (lane + 32 >= borders[g] && lane + 32 < borders[g + 1]) { grpB = g - 16; gshB = rom[kPsRomGroupShift + g - 16]; }
-    }
     const int shA_ov = pre(lane, 0), shA_lb = pre(lane, 6), shB_ov = pre(lane + 32, 0), shB_lb = pre(lane + 32, 6);
+
+    // ---- power per parameter bin of all 32 slots (ps_dec.c:482-556): it does not depend on the slot-serial peak state, so
+    //      lane = slot sums its own row serially instead of six warp reductions per slot.  All terms are >= 0, so the
+    //      reference's running add32_sat equals min(MAX_32, exact sum); the exact group sums stay below 2^32 after the
+    //      group shifts.  Bands below the first PS border slot still use the previous frame's usb.
+    {
+      const int s_ = lane;
+      const i32 *row = mat + 128 * s_;
+      const int border0 = prm[kPsPrmBorder];
+      const int usb_eff = s_ >= border0 ? usb : ps_usb;
+      auto tpow = [&](int k) {
+        const int sh = k < lsb ? (s_ < 6 ? ov_lb_shift : lb_shift) : (k < usb ? hb_shift : 0);
+        const i32 r = blockshift(row[k], sh), i = blockshift(row[64 + k], sh);
+        return min((u32)pw(r) + (u32)pw(i), 0x7fffffffu);
+      };
+#pragma unroll
+      for (int k = 3; k < 9; k++) w.pwt[s_][5 + k] = tpow(k);  // bins 8..13 = QMF bands 3..8
+#pragma unroll 1
+      for (int g = 0; g < 6; g++) {
+        const int k0 = borders[16 + g], k1 = min((int)borders[17 + g], 64), gsh = rom[kPsRomGroupShift + g];
+        u32 acc = 0;
+#pragma unroll 2
+        for (int k = k0; k < k1; k++) {
+          const u32 t = tpow(k);
+          if (k < usb_eff) acc += t >> gsh;
+        }
+        w.pwt[s_][14 + g] = min(acc, 0x7fffffffu);
+      }
+      // bins 0..7: hybrid sub-subbands — bins 0 / 1 pair (0, 5) / (4, 1), bins 2..7 one sub-subband each
+      const i32 *hre = w.hybL[s_], *him = w.hybL[s_] + 10;
+#pragma unroll
+      for (int bin = 0; bin < 8; bin++) {
+        const int s1 = bin == 0 ? 0 : (bin == 1 ? 4 : (int)borders[bin + 2]), s2 = bin == 0 ? 5 : 1;
+        i32 pwr = add_sat(pw(hre[s1]), pw(him[s1]));
+        if (bin < 2) pwr = add_sat(add_sat(pwr, pw(hre[s2])), pw(him[s2]));
+        w.pwt[s_][bin] = (u32)pwr;
+      }
+    }
+    __syncwarp();
 
     // the left row of the next slot is fetched one slot ahead (its latency was the top stall of the slot loop)
     i32 nAr = mat[lane], nAi = mat[64 + lane], nBr = mat[32 + lane], nBi = mat[96 + lane];
@@ -434,31 +468,10 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       const i32 *lre = w.hyb, *lim = w.hyb + 16;
       i32 *rre = w.hyb + 32, *rim = w.hyb + 48;
 
-      // ---- power per parameter bin (ps_dec.c:482-556).  All terms are >= 0, so the reference's running add32_sat
-      //      equals min(MAX_32, exact sum); the exact group sums stay below 2^32 after the group shifts ----
-      const u32 tA = min((u32)pw(lAr) + (u32)pw(lAi), 0x7fffffffu), tB = min((u32)pw(lBr) + (u32)pw(lBi), 0x7fffffffu);
-      u32 gsum[6];
-#pragma unroll
-      for (int g = 0; g < 6; g++) {
-        const u32 v = ((grpA == g && lane < ps_usb) ? (tA >> gshA) : 0u) + ((grpB == g && lane + 32 < ps_usb) ? (tB >> gshB) : 0u);
-        gsum[g] = __reduce_add_sync(full, v);
-      }
-      __syncwarp();
-      // bins 8..13 are QMF bands 3..8: fetch from the owning lane
-      const u32 tq = __shfl_sync(full, tA, (lane >= 8 && lane < 14) ? lane - 5 : 0);
-      // group sum of this lane's bin (bins 14..19), selected branch-free before the lanes split up
-      u32 vsel = gsum[0];
-#pragma unroll
-      for (int g = 1; g < 6; g++) vsel = (lane - 14 == g) ? gsum[g] : vsel;
+      // ---- transient detection per parameter bin (ps_dec.c:482-620); the powers come from the pre-pass ----
       if (lane < 20) {
         const int bin = lane;
-        i32 pwr = bin < 14 ? (i32)tq : (i32)min(vsel, 0x7fffffffu);
-        if (bin < 8) {  // hybrid sub-subbands: bins 0 / 1 pair (0, 5) / (4, 1), bins 2..7 one sub-subband each
-          const int s1 = bin == 0 ? 0 : (bin == 1 ? 4 : (int)borders[bin + 2]), s2 = bin == 0 ? 5 : 1;
-          pwr = add_sat(pw(lre[s1]), pw(lim[s1]));
-          const i32 p2 = add_sat(add_sat(pwr, pw(lre[s2])), pw(lim[s2]));
-          if (bin < 2) pwr = p2;
-        }
+        const i32 pwr = (i32)w.pwt[slot][bin];
         i32 pv = shl32(pwr, 1);
         if (pv < 0) pv = 0;
         i32 pk = lsl(mul32x16(peak[bin], 0x620a), 1);
