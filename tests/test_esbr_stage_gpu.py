@@ -77,3 +77,32 @@ def test_stage_batch_vs_oracle(ctx, oracle):
         assert np.array_equal(ip_g.cpu().numpy(), ipar), f"frame {f}: parameter words"
         for k in oracle_util.ESD_KEYS:
             assert np.array_equal(getattr(s, k).cpu().numpy().view(np.int32), st[k].view(np.int32)), f"frame {f}: {k}"
+
+
+def test_stage_full_batch_tiling(ctx):
+    """BASELINE batch size (131 072 channel units = 65 536 stereo frames): the two tapped channels tiled over the whole batch,
+    two frames with the state carried — every copy must reproduce the tapped records bit for bit (persistent grid-stride
+    tiling, state addressing and the interleaved PCM16 store at full size)"""
+    import libxaac_b200 as xb
+    g = load_esbr_golden("esbr_stage_tapped.npz")
+    n = 131072
+    rep = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda().repeat((n // 2,) + (1,) * (a.ndim - 1)).contiguous()
+    s = xb.EsbrDecBatch(n)
+    for k in oracle_util.ESD_KEYS:
+        getattr(s, k).copy_(rep(g["in0_" + k]))
+    pcm = torch.zeros((n // 2, 2048, 2), dtype=torch.int16, device="cuda")
+    for f, r, rg in esbr_stage_golden_frames(g):
+        if f >= 2:
+            break
+        ipar = rep(g["ec_ipar_in"][r])
+        out, err = xb.esbr_dec(ctx, s, rep(g["time_in"][r]), rep(g["hf_par"][r]), ipar, rep(g["ec_fpar"][r]), rep(rg), pcm16=pcm, ch_fac=2)
+        torch.cuda.synchronize()
+        assert int(err.abs().max()) == 0
+        want = torch.from_numpy(np.ascontiguousarray(g["time_out"][r])).cuda()
+        assert torch.equal(out.view(torch.int32).view(n // 2, 2, 2048), want.view(torch.int32).unsqueeze(0).expand(n // 2, 2, 2048)), f"frame {f}"
+        assert torch.equal(pcm, pcm[:1].expand_as(pcm))
+        assert torch.equal(ipar, torch.from_numpy(np.ascontiguousarray(g["ec_ipar_out"][r])).cuda().repeat(n // 2, 1))
+        for k in ("anal_states", "synth_states", "ec_state", "bw_prev"):
+            w = torch.from_numpy(np.ascontiguousarray(g["out_" + k][r])).cuda()
+            t = getattr(s, k)
+            assert torch.equal(t.view(torch.int32).view(n // 2, 2, -1), w.view(torch.int32).unsqueeze(0).expand(n // 2, 2, w.shape[-1])), f"frame {f}: {k}"
