@@ -79,3 +79,23 @@ def test_golden_tapped_real_decode(ctx):
     out, ov, ws = run_gpu(ctx, g["coef"], g["ov_in"], h[:, 1], h[:, 2], h[:, 3])
     assert np.array_equal(out, g["out"]) and np.array_equal(ov, g["ov_out"])
     assert np.array_equal(ws, h[:, 2].astype(np.uint8))
+
+
+def test_full_batch_tiling_property(ctx):
+    """BASELINE batch size (262 144 channel units = 131 072 stereo frames): the tapped records tiled over the whole batch —
+    every copy must reproduce its record bit for bit (grid-stride tiling, all window sequences side by side)"""
+    import os
+    import torch
+    import libxaac_b200 as xb
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "usac_fd_tapped.npz"))
+    h = g["hdr"]
+    m = len(h)
+    n = 262144
+    reps = (n + m - 1) // m
+    tile = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda().repeat((reps,) + (1,) * (a.ndim - 1))[:n].contiguous()
+    st = xb.UsacFdBatch(n)
+    st.overlap.copy_(tile(g["ov_in"]))
+    st.wstate.copy_(tile(h[:, 3].astype(np.uint8)))
+    out = xb.usac_fd_frm_dec(ctx, st, tile(g["coef"]), tile(np.stack([h[:, 1], h[:, 2]], 1).astype(np.uint8)))
+    torch.cuda.synchronize()
+    assert torch.equal(out, tile(g["out"])) and torch.equal(st.overlap, tile(g["ov_out"]))
