@@ -154,9 +154,15 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
     // ---- phase 4 (:230-249): attack / release smoothing; at rest (gain 1 everywhere) it is the identity ----
     float min_gain = 1.0f;
     if (any_lim || psg != 1.0 || gm != 1.0f) {
+      // 32 samples per chunk: one coalesced load, the values reach the (warp-uniform) recursion through shuffles that do not
+      // depend on it, the results are collected in the owning lane and stored once — no shared-memory latency on the chain
 #pragma unroll 1
-      for (int i = 0; i < 1024; i++) {
-        const float gain = w.G[i];
+      for (int cb = 0; cb < 1024; cb += 32) {
+       const float gv = w.G[cb + lane];
+       float gout = 0.0f;
+#pragma unroll
+       for (int q = 0; q < 32; q++) {
+        const float gain = __shfl_sync(full, gv, q);
         if ((double)gain < psg) {
           const float c = __fmul_rn(__fsub_rn(gain, __fmul_rn(0.1f, (float)psg)), 1.11111111f);
           gm = gm > c ? c : gm;
@@ -170,8 +176,10 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
           psg = __dadd_rn(__dmul_rn((double)rc, __dsub_rn(psg, (double)gm)), (double)gm);
         }
         const float go = (float)psg;
-        if (lane == 0) w.G[i] = go;
+        gout = lane == q ? go : gout;
         if (go < min_gain) min_gain = go;
+       }
+       w.G[cb + lane] = gout;
       }
       __syncwarp();
     }
