@@ -231,6 +231,14 @@ qmf_anal_hq_kernel(QmfAnalArgs p) {
   __syncthreads();
   const int warps_total = gridDim.x * kAnaWarps;
   for (long long u = (long long)blockIdx.x * kAnaWarps + warp; u < p.n_units; u += warps_total) {
+    if (u + warps_total < p.n_units) {  // pull this warp's next unit (2 KB of PCM, 640 B of ring) towards L2
+      const long long un = u + warps_total;
+      const int16_t *q0 = p.pcm + (p.pcm_unit_stride ? un * p.pcm_unit_stride
+                                                       : ((p.ch_fac == 1) ? un * 1024 : (un / p.ch_fac) * (1024LL * p.ch_fac)));
+      const int lines = 16 * (p.pcm_unit_stride ? 1 : p.ch_fac);
+      if (lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(q0) + lane * 128));
+      if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.states + un * 320) + lane * 128));
+    }
     if (p.exact)
       anal_unit<true>(p, sm, sm.w_[warp], u, lane);
     else
