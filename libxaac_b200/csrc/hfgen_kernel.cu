@@ -22,7 +22,8 @@
 
 namespace xb {
 
-constexpr int kHfWarps = 8;
+constexpr int kHfWarps = 7;
+constexpr int kHfColWords = 38 * 2 * 32;  // per warp: the low-band column set of one pass (38 rows x re, im x 32 bands)
 
 // ops32.h:134 — second operand contributes only its high half (not commutative)
 XB_DEV i32 hm(i32 a, i32 b) { return __mulhi(a, (i32)((u32)b & 0xffff0000u)); }
@@ -51,7 +52,11 @@ XB_DEV i32 fix_div(i32 op1, i32 op2) {
 __global__ void __launch_bounds__(kHfWarps * 32)
 hf_generator_hq_kernel(HfGenArgs p) {
   __shared__ int16_t s_prm[kHfWarps][80];
+  extern __shared__ __align__(16) i32 s_col[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the covariance pass leaves every row of its band here; the patch passes (one per patch that maps the band) read it back
+  // instead of going to L2 again
+  i32 *colr = s_col + warp * kHfColWords + lane, *coli = colr + 38 * 32;
   const unsigned full = 0xffffffffu;
   const int warps_total = gridDim.x * kHfWarps;
   // ISO/IEC 14496-3 newBw table, Q31 (sbrdec_lpfuncs.c:85-89): rows = previous mode, columns = current mode
@@ -129,6 +134,8 @@ hf_generator_hq_kernel(HfGenArgs p) {
         for (int q = 0; q < 4; q++) { pr[q] = mat[128 * q + lb]; pi[q] = mat[128 * q + 64 + lb]; }
 #pragma unroll 4
         for (int m = 0; m < L; m++) {
+          colr[32 * m] = pr[m & 3];
+          coli[32 * m] = pi[m & 3];
           const i32 r0 = pr[m & 3] >> 3, i0 = pi[m & 3] >> 3;
           if (m + 4 < L) { pr[m & 3] = mat[128 * (m + 4) + lb]; pi[m & 3] = mat[128 * (m + 4) + 64 + lb]; }
           i32 A = wadd(hm(r0, r1), hm(i0, i1)), B = wsub(hm(i0, r1), hm(r0, i1));
@@ -198,19 +205,14 @@ hf_generator_hq_kernel(HfGenArgs p) {
         bw = mult16_shl_sat(bw, bw);
         const i32 a1r = mult16_shl_sat(bw, ar1), a1i = mult16_shl_sat(bw, ai1);
         // rows relative to the reference scratch: row 0,1 = LPC states, row t+2 = matrix row t
-        auto rowr = [&](int t) { return t < 2 ? lpc[128 * t + lb] : mat[128 * (t - 2) + lb]; };
-        auto rowi = [&](int t) { return t < 2 ? lpc[128 * t + 64 + lb] : mat[128 * (t - 2) + 64 + lb]; };
+        auto srcr = [&](int t) { return t < L ? colr[32 * t] : mat[128 * t + lb]; };  // matrix row t of band lb
+        auto srci = [&](int t) { return t < L ? coli[32 * t] : mat[128 * t + 64 + lb]; };
+        auto rowr = [&](int t) { return t < 2 ? lpc[128 * t + lb] : srcr(t - 2); };
+        auto rowi = [&](int t) { return t < 2 ? lpc[128 * t + 64 + lb] : srci(t - 2); };
         i32 p2r = rowr(start_idx), p2i = rowi(start_idx), p1r = rowr(start_idx + 1), p1i = rowi(start_idx + 1);
-        // the source column is prefetched two slots ahead (these reads hit L2: the covariance pass has just streamed them)
-        i32 nr0 = start_idx < stop_idx ? mat[128 * start_idx + lb] : 0, ni0 = start_idx < stop_idx ? mat[128 * start_idx + 64 + lb] : 0;
-        i32 nr1 = start_idx + 1 < stop_idx ? mat[128 * (start_idx + 1) + lb] : 0;
-        i32 ni1 = start_idx + 1 < stop_idx ? mat[128 * (start_idx + 1) + 64 + lb] : 0;
 #pragma unroll 2
         for (int t = start_idx; t < stop_idx; t++) {
-          const i32 cr = nr0, ci = ni0;  // scratch row t + 2
-          nr0 = nr1;
-          ni0 = ni1;
-          if (t + 2 < stop_idx) { nr1 = mat[128 * (t + 2) + lb]; ni1 = mat[128 * (t + 2) + 64 + lb]; }
+          const i32 cr = srcr(t), ci = srci(t);  // scratch row t + 2
           i32 outr, outi;
           if (bw > 0) {
             i32 acc = wsub(wadd(wsub(mul32x16(p1r, a0r), mul32x16(p1i, a0i)), mul32x16(p2r, a1r)), mul32x16(p2i, a1i));
@@ -236,7 +238,14 @@ cudaError_t launch_hf_generator_hq(const HfGenArgs &args, int num_sms, cudaStrea
   long long grid = (long long)num_sms * 8;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  hf_generator_hq_kernel<<<(unsigned)grid, kHfWarps * 32, 0, stream>>>(args);
+  const size_t smem = (size_t)kHfWarps * kHfColWords * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hf_generator_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  hf_generator_hq_kernel<<<(unsigned)grid, kHfWarps * 32, smem, stream>>>(args);
   return cudaGetLastError();
 }
 
