@@ -160,7 +160,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
         for (int c = lane; c < sb_end - max_qmf; c += 32) {
           const int k = max_qmf + c;
           i32 max_val = 1;
-#pragma unroll 1
+#pragma unroll 4
           for (int l = start; l < end; l++) {
             max_val = max(max_val, abs_nrm(mat[128 * l + k]));
             max_val = max(max_val, abs_nrm(mat[128 * l + 64 + k]));
@@ -168,7 +168,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
           const int pre = pnorm32(max_val) - 4;
           int shift = 16 - pre;
           i32 accu = 0;
-#pragma unroll 1
+#pragma unroll 2
           for (int l = start; l < end; l++) {
             const i32 a = mat[128 * l + k], b = mat[128 * l + 64 + k];
             const i32 ta = sext16(shift > 0 ? (a >> shift) : lsl(a, -shift));
