@@ -204,7 +204,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
             while (ftab[j + 1] <= k) j++;
             li = ftab[j];
             ui = ftab[j + 1];
-#pragma unroll 1
+#pragma unroll 4
             for (int l = start; l < end; l++) orv |= abs_nrm(mat[128 * l + k]) | abs_nrm(mat[128 * l + 64 + k]);
             w.line[k - first_li] = orv;
           }
@@ -220,7 +220,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
           if (act) {
             const int s = min(16 - pre, 31);
             i32 line = 0;
-#pragma unroll 1
+#pragma unroll 2
             for (int l = start; l < end; l++) {
               const i32 ta = sext16(shr32_dir(mat[128 * l + k], s));
               line = add_sat(line, ta * ta);
