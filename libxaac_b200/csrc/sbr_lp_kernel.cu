@@ -1165,15 +1165,26 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
     }
     // ---------------- load ----------------
     {
+      // all of a lane's loads of the three records are issued before the first store (12 + 4 + 5 independent requests)
       const i32 *src = reinterpret_cast<const i32 *>(p.side + u * kSideWords);
-#pragma unroll 1
-      for (int i = lane; i < 370; i += 32) reinterpret_cast<i32 *>(w.side)[i] = __ldg(src + i);  // words 0..739
       const i32 *ss = reinterpret_cast<const i32 *>(p.env + u * kEnvStWords);
-#pragma unroll 1
-      for (int i = lane; i < kEnvStWords / 2; i += 32) reinterpret_cast<i32 *>(w.st)[i] = ss[i];
       const i32 *rs = reinterpret_cast<const i32 *>(p.anal_states + u * 320);
-#pragma unroll 1
-      for (int i = lane; i < 160; i += 32) reinterpret_cast<i32 *>(w.ring)[i] = rs[i];
+      constexpr int nA = (370 + 31) / 32, nB = (kEnvStWords / 2 + 31) / 32, nC = 5;
+      i32 va[nA], vb[nB], vc[nC];
+#pragma unroll
+      for (int q = 0; q < nA; q++) va[q] = lane + 32 * q < 370 ? __ldg(src + lane + 32 * q) : 0;  // words 0..739
+#pragma unroll
+      for (int q = 0; q < nB; q++) vb[q] = lane + 32 * q < kEnvStWords / 2 ? ss[lane + 32 * q] : 0;
+#pragma unroll
+      for (int q = 0; q < nC; q++) vc[q] = rs[lane + 32 * q];
+#pragma unroll
+      for (int q = 0; q < nA; q++)
+        if (lane + 32 * q < 370) reinterpret_cast<i32 *>(w.side)[lane + 32 * q] = va[q];
+#pragma unroll
+      for (int q = 0; q < nB; q++)
+        if (lane + 32 * q < kEnvStWords / 2) reinterpret_cast<i32 *>(w.st)[lane + 32 * q] = vb[q];
+#pragma unroll
+      for (int q = 0; q < nC; q++) reinterpret_cast<i32 *>(w.ring)[lane + 32 * q] = vc[q];
       if (lane < 8) w.sf[lane] = p.sf[u * 8 + lane];
       if (lane < 16) w.misc[lane] = p.misc[u * 16 + lane];
       const i32 *ov = p.ov + u * 768;
