@@ -1188,10 +1188,18 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
       if (lane < 8) w.sf[lane] = p.sf[u * 8 + lane];
       if (lane < 16) w.misc[lane] = p.misc[u * 16 + lane];
       const i32 *ov = p.ov + u * 768;
-#pragma unroll 1
-      for (int l = 0; l < 6; l++) {
-        m[LS * l + lane] = ov[64 * l + lane];
-        m[LS * l + 32 + lane] = ov[64 * l + 32 + lane];
+      {
+        i32 vo[12];
+#pragma unroll
+        for (int l = 0; l < 6; l++) {
+          vo[2 * l] = ov[64 * l + lane];
+          vo[2 * l + 1] = ov[64 * l + 32 + lane];
+        }
+#pragma unroll
+        for (int l = 0; l < 6; l++) {
+          m[LS * l + lane] = vo[2 * l];
+          m[LS * l + 32 + lane] = vo[2 * l + 1];
+        }
       }
       const i32 *lpc = p.lpc + u * 256;
       x[lane] = lpc[lane];
@@ -1270,8 +1278,11 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
         if (p.in_ch == 1 && ((reinterpret_cast<uintptr_t>(pcm) & 3) == 0)) {
           const i32 *src = reinterpret_cast<const i32 *>(pcm);
           i32 *dst = reinterpret_cast<i32 *>(T + 288);
-#pragma unroll 4
-          for (int j = lane; j < 512; j += 32) dst[j] = __ldg(src + j);
+          i32 vp[16];  // the whole frame's PCM: 16 requests in flight
+#pragma unroll
+          for (int q = 0; q < 16; q++) vp[q] = __ldg(src + lane + 32 * q);
+#pragma unroll
+          for (int q = 0; q < 16; q++) dst[lane + 32 * q] = vp[q];
         } else {
 #pragma unroll 4
           for (int j = lane; j < 1024; j += 32) T[288 + j] = pcm[(long long)p.in_ch * j];
@@ -1461,12 +1472,15 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
       }
       {
         const i32 *ss = reinterpret_cast<const i32 *>(p.syn_states + u * 1280);
-#pragma unroll 1
-        for (int i = lane; i < 640; i += 32) {
-          const int b = i >> 6;
+        i32 vs[20];  // the synthesis ring (2.5 KB): 20 requests in flight, then the scatter into the history rows
+#pragma unroll
+        for (int q = 0; q < 20; q++) vs[q] = ss[lane + 32 * q];
+#pragma unroll
+        for (int q = 0; q < 20; q++) {
+          const int i = lane + 32 * q, b = i >> 6;
           int a0 = b - b0;
           if (a0 < 0) a0 += 10;
-          if (a0 != 0) hist[LS * (9 - a0) + (i & 63)] = ss[i];
+          if (a0 != 0) hist[LS * (9 - a0) + (i & 63)] = vs[q];
         }
       }
     }
