@@ -71,11 +71,20 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
     }
     {
       const i32 *src = reinterpret_cast<const i32 *>(p.params + u * p.prm_stride);
-#pragma unroll 1
-      for (int i = lane; i < kEnvPrmWords / 2; i += 32) reinterpret_cast<i32 *>(w.prm)[i] = __ldg(src + i);
+      // all of a lane's loads of both records in flight before the first store (11 + 4 requests)
       const i32 *ss = reinterpret_cast<const i32 *>(p.state + u * kEnvStWords);
-#pragma unroll 1
-      for (int i = lane; i < kEnvStWords / 2; i += 32) reinterpret_cast<i32 *>(w.st)[i] = ss[i];
+      constexpr int nA = (kEnvPrmWords / 2 + 31) / 32, nB = (kEnvStWords / 2 + 31) / 32;
+      i32 va[nA], vb[nB];
+#pragma unroll
+      for (int q = 0; q < nA; q++) va[q] = lane + 32 * q < kEnvPrmWords / 2 ? __ldg(src + lane + 32 * q) : 0;
+#pragma unroll
+      for (int q = 0; q < nB; q++) vb[q] = lane + 32 * q < kEnvStWords / 2 ? ss[lane + 32 * q] : 0;
+#pragma unroll
+      for (int q = 0; q < nA; q++)
+        if (lane + 32 * q < kEnvPrmWords / 2) reinterpret_cast<i32 *>(w.prm)[lane + 32 * q] = va[q];
+#pragma unroll
+      for (int q = 0; q < nB; q++)
+        if (lane + 32 * q < kEnvStWords / 2) reinterpret_cast<i32 *>(w.st)[lane + 32 * q] = vb[q];
 #pragma unroll 1
       for (int i = lane; i < 2 * kMaxB; i += 32) w.est[i] = w.gain[i] = w.noise[i] = w.sine[i] = w.orig[i] = 0;
 #pragma unroll 1

@@ -48,7 +48,13 @@ __global__ void __launch_bounds__(kEcWarps * 32, 3) esbr_envcalc_kernel(EsbrEnvc
   for (long long u = (long long)blockIdx.x * kEcWarps + warp; u < p.n_units; u += warps_total) {
     __syncwarp();
     i32 *g_ipar = p.ipar + u * kEecIparWords;
-    for (int i = lane; i < kEecIparWords; i += 32) w.ipar[i] = g_ipar[i];
+    {
+      i32 vi[kEecIparWords / 32];  // 9 requests in flight
+#pragma unroll
+      for (int q = 0; q < kEecIparWords / 32; q++) vi[q] = g_ipar[lane + 32 * q];
+#pragma unroll
+      for (int q = 0; q < kEecIparWords / 32; q++) w.ipar[lane + 32 * q] = vi[q];
+    }
     __syncwarp();
     const i32 *ip = w.ipar;
     const int sbs = ip[kEecSbStart], sbe = ip[kEecSbEnd], nsub = sbe - sbs;
