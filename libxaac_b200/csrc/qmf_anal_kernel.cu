@@ -69,14 +69,24 @@ __device__ __forceinline__ void anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm
   const int fh = r8 >> 2, fi = r8 & 3;  // FFT: half, butterfly position
   __syncwarp();
 
+  // the PCM of the next group of four slots is fetched while this group is processed
+  int16_t nv[4];
+#pragma unroll
+  for (int s = 0; s < 4; s++) nv[s] = pcm[(long long)p.ch_fac * (32 * s + lane)];
 #pragma unroll 1
   for (int g = 0; g < 8; g++) {
     i32 s1v[4], s2v[4];  // fold outputs of the four slots of this group: S1[lane], S2[lane]
+    int16_t cv[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      cv[s] = nv[s];
+      if (g < 7) nv[s] = pcm[(long long)p.ch_fac * (32 * (4 * (g + 1) + s) + lane)];
+    }
 #pragma unroll
     for (int s = 0; s < 4; s++) {
       const int slot = 4 * g + s;
       // new samples, reversed, into the ring (generic:670-672)
-      ws.ring[pos + 31 - lane] = pcm[(long long)p.ch_fac * (32 * slot + lane)];
+      ws.ring[pos + 31 - lane] = cv[s];
       __syncwarp();
       // 5-tap window (generic:528-588): lane n -> out[n] (fp1, filter_1) and out[32+n] (fp2, filter_2)
       const int16_t *fp1 = ws.ring + ((slot & 1) ? 32 : 0), *fp2 = ws.ring + ((slot & 1) ? 0 : 32);
