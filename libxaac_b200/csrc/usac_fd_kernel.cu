@@ -308,11 +308,11 @@ __global__ void __launch_bounds__(kUfWarps * 32) usac_fd_kernel(UsacFdArgs p) {
     }
     {
       const int4 *src = reinterpret_cast<const int4 *>(p.coef + u * 1024);
-#pragma unroll 4
-      for (int i = lane; i < 256; i += 32) {
-        const int4 v = __ldg(src + i);
-        *reinterpret_cast<int4 *>(A + PA(4 * i)) = v;
-      }
+      int4 v[8];  // the unit's 4 KB of coefficients: 8 x 16-byte requests per lane in flight
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] = __ldg(src + lane + 32 * q);
+#pragma unroll
+      for (int q = 0; q < 8; q++) *reinterpret_cast<int4 *>(A + PA(4 * (lane + 32 * q))) = v[q];
     }
     __syncwarp();
     i32 *ov = p.overlap + u * 1024, *out = p.out + u * 1024;
