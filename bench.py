@@ -1514,7 +1514,7 @@ def main():
                                   "achieved": None if b is None else b * n_units / (per * 1e-3) / 1e9}
 
     # ---- end-to-end arm: host buffers through the C-ABI ---------------------------------------------------
-    Ke = args.e2e_steps or min(K, 10)
+    Ke = args.e2e_steps or min(K, 20)
     work.host_setup()
     work.host_step(0)  # warm-up (staging allocation, first-touch of the pinned buffers)
     work.host_step(1)
