@@ -26,7 +26,15 @@ __global__ void __launch_bounds__(kGlueWarps * 32) sbr_pre_kernel(SbrStageArgs p
     const i32 *ov = p.ov + u * 768;
     int16_t *sf = p.sf + u * 8, *misc = p.misc + u * 16;
     const int16_t *env = p.side + u * kSideWords + kSideEnv;
-    for (int i = lane; i < 768; i += 32) m[i] = ov[i];
+    {  // 3 KB copy: all six 16-byte requests of a lane in flight (the compiler cannot order m[] stores past ov[] loads itself)
+      const int4 *src = reinterpret_cast<const int4 *>(ov);
+      int4 *dst = reinterpret_cast<int4 *>(m);
+      int4 v[6];
+#pragma unroll
+      for (int q = 0; q < 6; q++) v[q] = __ldg(src + lane + 32 * q);
+#pragma unroll
+      for (int q = 0; q < 6; q++) dst[lane + 32 * q] = v[q];
+    }
     __syncwarp();
     if (p.side[u * kSideWords + kSideApply]) {
       const int old_lsb = misc[kMiscMaxQmfPrev], new_lsb = env[kEnvMaxQmfSubband];
