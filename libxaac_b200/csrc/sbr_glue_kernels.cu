@@ -162,14 +162,33 @@ __global__ void __launch_bounds__(kGlueWarps * 32) sbr_post_kernel(SbrStageArgs 
     }
     const int usb = misc[kMiscCodecUsb];
     i32 *lpc = p.lpc + u * 256;
-    for (int i = 0; i < 2; i++)
-      if (lane < usb) {
-        lpc[128 * i + lane] = m[128 * (30 + i) + lane];
-        lpc[128 * i + 64 + lane] = m[128 * (30 + i) + 64 + lane];
-      }
-    // sbr_dec.c:1284-1290 copies 64 * op_delay = 384 words: slots 32..34 in the complex layout
+    // sbr_dec.c:1284-1290 copies 64 * op_delay = 384 words: slots 32..34 in the complex layout.  All loads of both copies
+    // are issued before the first store (the compiler cannot move m[] loads past lpc[] / ov[] stores itself).
     i32 *ov = p.ov + u * 768;
-    for (int i = lane; i < 384; i += 32) ov[i] = m[32 * 128 + i];
+    {
+      i32 vl[4] = {0, 0, 0, 0};
+      if (lane < usb) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          vl[2 * i] = m[128 * (30 + i) + lane];
+          vl[2 * i + 1] = m[128 * (30 + i) + 64 + lane];
+        }
+      }
+      const int4 *src = reinterpret_cast<const int4 *>(m + 32 * 128);
+      int4 vo[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) vo[q] = src[lane + 32 * q];
+      if (lane < usb) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          lpc[128 * i + lane] = vl[2 * i];
+          lpc[128 * i + 64 + lane] = vl[2 * i + 1];
+        }
+      }
+      int4 *dst = reinterpret_cast<int4 *>(ov);
+#pragma unroll
+      for (int q = 0; q < 3; q++) dst[lane + 32 * q] = vo[q];
+    }
     __syncwarp();
     if (lane == 0) {
       synp[0] = sf[kSfOvLb];
