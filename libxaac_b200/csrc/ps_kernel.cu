@@ -398,10 +398,11 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
 
     // the left row of the next slot is fetched one slot ahead (its latency was the top stall of the slot loop)
     i32 nAr = mat[lane], nAi = mat[64 + lane], nBr = mat[32 + lane], nBi = mat[96 + lane];
+    int next_border = prm[kPsPrmBorder];  // border of envelope `env`, kept in a register (prm lives in global memory)
 #pragma unroll 1
     for (int slot = 0; slot < 32; slot++) {
       // ---- ixheaacd_init_rot_env at PS envelope borders (ps_dec.c:714-854): lane = stereo group ----
-      if (env < 7 && slot == prm[kPsPrmBorder + env]) {
+      if (env < 7 && slot == next_border) {
         if (env == 0) {
           const int usb_prev = ps_usb;
           ps_usb = usb;
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
           hv11 = h11; hv12 = h12; hv21 = h21; hv22 = h22;
         }
         env++;
+        next_border = env < 7 ? prm[kPsPrmBorder + env] : -1;
         __syncwarp();
       }
 
