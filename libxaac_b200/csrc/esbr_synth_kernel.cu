@@ -528,11 +528,16 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
     const bool lock = p.periodic && (pos & 63) == 0 && (f1 & 127) == 0 && pos <= 256 && f1 <= 512 && ((P0 + F0) % 10 == 0);
     if (lock) {
       // flat history: 288 old samples from the ring (block q holds slot P0 - q mod 10, newest sample first), 1024 new ones
-#pragma unroll 1
-      for (int j = lane; j < 288; j += 32) {
-        int q = P0 + 9 - (j >> 5);
-        if (q >= 10) q -= 10;
-        w.T[j] = ring[32 * q + 31 - (j & 31)];
+      {
+        i32 vh[9];  // the nine old blocks: all requests in flight
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          int q = P0 + 9 - r;
+          if (q >= 10) q -= 10;
+          vh[r] = ring[32 * q + 31 - lane];
+        }
+#pragma unroll
+        for (int r = 0; r < 9; r++) w.T[32 * r + lane] = vh[r];
       }
       {
         float v[32];  // all 32 loads in flight before the first conversion
