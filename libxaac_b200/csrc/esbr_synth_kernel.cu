@@ -683,12 +683,12 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
 }
 
 cudaError_t launch_esbr_anal(const EsbrAnalArgs &args, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+  static xb::PerDeviceOnce configured;
   const size_t smem = sizeof(EaBlockS);
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(esbr_anal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.done();
   }
   long long need = (args.n_units + kEaWarps - 1) / kEaWarps;
   long long grid = num_sms;
@@ -718,12 +718,12 @@ int esbr_synth_build_tables(const uint8_t *erom, uint8_t *out) {
 }
 
 cudaError_t launch_esbr_synth(const EsbrSynthArgs &args, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+  static xb::PerDeviceOnce configured;
   const size_t smem = sizeof(EsBlockS);
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(esbr_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.done();
   }
   long long need = (args.n_units + kEsWarps - 1) / kEsWarps;
   long long grid = num_sms;

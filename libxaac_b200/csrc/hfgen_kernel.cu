@@ -239,11 +239,11 @@ cudaError_t launch_hf_generator_hq(const HfGenArgs &args, int num_sms, cudaStrea
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   const size_t smem = (size_t)kHfWarps * kHfColWords * 4;
-  static bool configured = false;
-  if (!configured) {
+  static xb::PerDeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(hf_generator_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.done();
   }
   hf_generator_hq_kernel<<<(unsigned)grid, kHfWarps * 32, smem, stream>>>(args);
   return cudaGetLastError();

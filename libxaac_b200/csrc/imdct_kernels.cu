@@ -611,12 +611,12 @@ imdct_ola_kernel(ImdctArgs p) {
 size_t imdct_smem_bytes() { return sizeof(BlockSmem); }
 
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+  static xb::PerDeviceOnce configured;
   size_t smem = sizeof(BlockSmem);
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(imdct_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.done();
   }
   int blocks_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (blocks_per_sm < 1) blocks_per_sm = 1;

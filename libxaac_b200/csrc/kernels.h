@@ -1,9 +1,22 @@
 // kernels.h — internal launch interface between the C-ABI (xaac_b200_api.cu) and the kernels.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace xb {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: every launcher keeps one of these and opts
+// its kernel in once per device the calling thread is on (a process may hold contexts on several GPUs).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  int dev = 0;
+  bool needed() {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return ((mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0;
+  }
+  void done() { mask.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
 
 // Byte offsets inside the IMDCT ROM blob: the leading 7500 bytes of the reference's
 // ia_aac_dec_imdct_tables_struct (decoder/ixheaacd_aac_rom.h:112-121), which the host passes in

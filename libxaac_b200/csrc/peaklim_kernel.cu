@@ -237,12 +237,12 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
 }
 
 cudaError_t launch_peak_limiter(const PeakLimArgs &args, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+  static xb::PerDeviceOnce configured;
   const size_t smem = sizeof(PlWarpS) * kPlWarps;
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(peak_limiter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.done();
   }
   long long need = (args.n_units + kPlWarps - 1) / kPlWarps;
   long long grid = (long long)num_sms * 2;

@@ -315,12 +315,12 @@ int qmf_anal_build_tables(const uint8_t *qrom, uint8_t *out) {
 }
 
 cudaError_t launch_qmf_anal_hq(const QmfAnalArgs &args, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+  static xb::PerDeviceOnce configured;
   size_t smem = sizeof(AnaBlockSmem);
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(qmf_anal_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.done();
   }
   int blocks_per_sm = 4;
   long long need = (args.n_units + kAnaWarps - 1) / kAnaWarps;

@@ -461,13 +461,13 @@ int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
 }
 
 cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+  static xb::PerDeviceOnce configured;
   size_t smem = sizeof(SynBlockSmem);
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e =
         cudaFuncSetAttribute(qmf_synth_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.done();
   }
   int blocks_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (blocks_per_sm < 1) blocks_per_sm = 1;

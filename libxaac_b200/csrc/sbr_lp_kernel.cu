@@ -1621,12 +1621,12 @@ int sbr_lp_build_tables(const uint8_t *qrom, uint8_t *out) {
 }
 
 cudaError_t launch_sbr_dec_lp(const SbrLpArgs &args, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+  static xb::PerDeviceOnce configured;
   const size_t smem = sizeof(LpBlockS);
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(sbr_dec_lp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.done();
   }
   long long need = (args.n_units + kLpWarps - 1) / kLpWarps;
   long long grid = num_sms;

@@ -481,12 +481,12 @@ size_t usac_fd_smem_bytes() { return (size_t)kURomPad + (size_t)kUfWarps * 2 * k
 int usac_fd_check_tables(const uint8_t *urom) { return urom ? 0 : -1; }
 
 cudaError_t launch_usac_fd(const UsacFdArgs &args, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+  static xb::PerDeviceOnce configured;
   const size_t smem = usac_fd_smem_bytes();
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(usac_fd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.done();
   }
   long long need = (args.n_units + kUfWarps - 1) / kUfWarps;
   long long grid = (long long)num_sms * 2;

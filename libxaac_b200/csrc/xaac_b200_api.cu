@@ -96,6 +96,20 @@ void tick(xaac_b200_ctx *ctx, cudaStream_t st, const char *name, bool start) {
   }
 }
 
+// a launch failed between the start and the stop tick: drop the start event
+void tick_abort(xaac_b200_ctx *ctx) {
+  if (!ctx->timing || ctx->n_ticks >= xaac_b200_ctx::kMaxTicks) return;
+  cudaEventDestroy(ctx->tick_ev[ctx->n_ticks][0]);
+}
+
+// error exit of a *_host pipeline: earlier chunks may still have D2H copies into the caller's buffers in flight
+int32_t drain(xaac_b200_ctx *ctx, int32_t rc) {
+  if (rc != XAAC_B200_OK && ctx)
+    for (int i = 0; i < xaac_b200_ctx::kPipe; i++)
+      if (ctx->streams[i]) cudaStreamSynchronize(ctx->streams[i]);
+  return rc;
+}
+
 int32_t fail(xaac_b200_ctx *ctx, cudaError_t e, const char *what) {
   if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
   return XAAC_B200_ERR_CUDA;
@@ -107,9 +121,14 @@ int32_t bad_arg(xaac_b200_ctx *ctx, const char *what) {
 // kernel launch with optional per-kernel CUDA-event timing (xaac_b200_kernel_timing)
 #define LAUNCH(name, strm, call)                                   \
   do {                                                             \
+    cudaError_t e__ = cudaSetDevice(ctx->device);                  \
+    if (e__ != cudaSuccess) return fail(ctx, e__, "cudaSetDevice"); \
     tick(ctx, (cudaStream_t)(strm), name, true);                   \
-    cudaError_t e__ = (call);                                      \
-    if (e__ != cudaSuccess) return fail(ctx, e__, "launch " name); \
+    e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                      \
+      tick_abort(ctx);                                             \
+      return fail(ctx, e__, "launch " name);                       \
+    }                                                              \
     tick(ctx, (cudaStream_t)(strm), name, false);                  \
   } while (0)
 #define CK(call, what)                              \
@@ -257,6 +276,7 @@ int32_t xaac_b200_imdct_state_create(xaac_b200_ctx *ctx, int64_t n_units, xaac_b
     return fail(ctx, e, "imdct_state_create");
   }
   *out = st;
+  CK(cudaStreamSynchronize(0), "state init sync");  // order legacy-stream memsets / pageable copies before the non-blocking pipeline streams
   return XAAC_B200_OK;
 }
 
@@ -274,6 +294,7 @@ int32_t xaac_b200_imdct_state_upload(xaac_b200_ctx *ctx, xaac_b200_imdct_state *
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   CK(cudaMemcpy(st->d_overlap, overlap, (size_t)st->n_units * 2048, cudaMemcpyHostToDevice), "H2D overlap");
   CK(cudaMemcpy(st->d_wstate, wstate, (size_t)st->n_units * 2, cudaMemcpyHostToDevice), "H2D wstate");
+  CK(cudaStreamSynchronize(0), "state init sync");  // order legacy-stream memsets / pageable copies before the non-blocking pipeline streams
   return XAAC_B200_OK;
 }
 
@@ -289,7 +310,7 @@ int32_t xaac_b200_imdct_state_download(xaac_b200_ctx *ctx, xaac_b200_imdct_state
 // Host-buffer entry point: chunks the batch and runs H2D / kernel / D2H of successive chunks on kPipe
 // streams so PCIe and the SMs overlap. Pinned host memory makes the copies truly asynchronous.
 // The overlap/window state never leaves HBM.
-int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, const int32_t *spec,
+static int32_t xaac_b200_imdct_process_host_impl(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, const int32_t *spec,
                                      const uint8_t *ics, int32_t *out, int8_t *qshift_adj, int32_t ch_fac) {
   if (!ctx || !state) return XAAC_B200_ERR_ARG;
   const int64_t n_units = state->n_units;
@@ -437,6 +458,7 @@ int32_t xaac_b200_qmf_synth_state_create(xaac_b200_ctx *ctx, int64_t n_units, xa
     return fail(ctx, e, "qmf_synth_state_create");
   }
   *out = st;
+  CK(cudaStreamSynchronize(0), "state init sync");  // order legacy-stream memsets / pageable copies before the non-blocking pipeline streams
   return XAAC_B200_OK;
 }
 
@@ -454,6 +476,7 @@ int32_t xaac_b200_qmf_synth_state_upload(xaac_b200_ctx *ctx, xaac_b200_qmf_synth
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   CK(cudaMemcpy(st->d_states, filter_states, (size_t)st->n_units * 2560, cudaMemcpyHostToDevice), "H2D states");
   CK(cudaMemcpy(st->d_pos, pos, (size_t)st->n_units * 4, cudaMemcpyHostToDevice), "H2D pos");
+  CK(cudaStreamSynchronize(0), "state init sync");  // order legacy-stream memsets / pageable copies before the non-blocking pipeline streams
   return XAAC_B200_OK;
 }
 
@@ -466,7 +489,7 @@ int32_t xaac_b200_qmf_synth_state_download(xaac_b200_ctx *ctx, xaac_b200_qmf_syn
   return XAAC_B200_OK;
 }
 
-int32_t xaac_b200_qmf_synth_hq_host(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *state, const int32_t *matrix,
+static int32_t xaac_b200_qmf_synth_hq_host_impl(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *state, const int32_t *matrix,
                                     const int16_t *params, int16_t *pcm, int32_t ch_fac) {
   if (!ctx || !state) return XAAC_B200_ERR_ARG;
   const int64_t n_units = state->n_units;
@@ -676,6 +699,7 @@ int32_t xaac_b200_sbr_state_create(xaac_b200_ctx *ctx, int64_t n_units, int32_t 
     return fail(ctx, e, "cudaMalloc(sbr state)");
   }
   *out = s;
+  CK(cudaStreamSynchronize(0), "state init sync");  // order legacy-stream memsets / pageable copies before the non-blocking pipeline streams
   return XAAC_B200_OK;
 }
 
@@ -701,6 +725,7 @@ static int32_t sbr_state_copy(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, int16_
     if (!s->with_ps) return bad_arg(ctx, "state was created without PS");
     CK(run(ps, n_ps, ps_blob, 2 * (size_t)xb::kPsStWords), "ps state copy");
   }
+  CK(cudaStreamSynchronize(0), "state copy sync");  // order against the non-blocking pipeline streams
   return XAAC_B200_OK;
 }
 
@@ -825,7 +850,7 @@ int32_t xaac_b200_sbr_dec_lp_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, con
 }
 
 // HE-AAC frame from host buffers: IMDCT (mono or one core channel per unit) -> WORD32->PCM16 hand-over -> SBR stage.
-int32_t xaac_b200_heaac_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *ist, xaac_b200_sbr_state *s,
+static int32_t xaac_b200_heaac_frame_host_impl(xaac_b200_ctx *ctx, xaac_b200_imdct_state *ist, xaac_b200_sbr_state *s,
                                    const int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *pcm,
                                    int32_t *err) {
   int32_t rc = sbr_check(ctx, s);
@@ -873,7 +898,7 @@ int32_t xaac_b200_heaac_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *is
 }
 
 // Stereo HE-AACv1 (low-power SBR) frames from host buffers: unit = one channel; IMDCT -> hand-over -> fused LP stage.
-int32_t xaac_b200_heaac_lp_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *ist, xaac_b200_sbr_state *s,
+static int32_t xaac_b200_heaac_lp_frame_host_impl(xaac_b200_ctx *ctx, xaac_b200_imdct_state *ist, xaac_b200_sbr_state *s,
                                       const int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *pcm,
                                       int32_t out_ch, int32_t *err) {
   if (!ctx || !s) return XAAC_B200_ERR_ARG;
@@ -887,7 +912,8 @@ int32_t xaac_b200_heaac_lp_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state 
   if (out_ch < 1 || out_ch > 8 || (s->n_units % out_ch) != 0) return bad_arg(ctx, "out_ch must divide the number of units");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   const int64_t n_units = s->n_units;
-  int64_t chunk = 4096;  // multiple of every out_ch <= 8
+  int64_t chunk = 4096;
+  chunk -= chunk % out_ch;  // a chunk holds whole frames: the kernel derives frame / channel from the chunk-local index
   if (chunk > n_units) chunk = n_units;
   // per-unit staging: spec 4096 | WORD32 out 4096 | side 2464 | pcm16 in 2048 | pcm out 4096 | err 4 | ics 2 | adj 1 (+1)
   const size_t o_spec = 0, o_w32 = 4096, o_side = 8192, o_p16 = 8192 + 2464, o_pcm = o_p16 + 2048, o_err = o_pcm + 4096,
@@ -1230,6 +1256,29 @@ int32_t xaac_b200_kernel_times(xaac_b200_ctx *ctx, char *buf, size_t buf_bytes) 
     o += (size_t)w;
   }
   return XAAC_B200_OK;
+}
+
+// *_host entry points: on any error the pipeline streams are drained before returning
+int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, const int32_t *spec,
+                                     const uint8_t *ics, int32_t *out, int8_t *qshift_adj, int32_t ch_fac) {
+  return drain(ctx, xaac_b200_imdct_process_host_impl(ctx, state, spec, ics, out, qshift_adj, ch_fac));
+}
+
+int32_t xaac_b200_qmf_synth_hq_host(xaac_b200_ctx *ctx, xaac_b200_qmf_synth_state *state, const int32_t *matrix,
+                                    const int16_t *params, int16_t *pcm, int32_t ch_fac) {
+  return drain(ctx, xaac_b200_qmf_synth_hq_host_impl(ctx, state, matrix, params, pcm, ch_fac));
+}
+
+int32_t xaac_b200_heaac_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *ist, xaac_b200_sbr_state *s,
+                                   const int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *pcm,
+                                   int32_t *err) {
+  return drain(ctx, xaac_b200_heaac_frame_host_impl(ctx, ist, s, spec, ics, side, pcm, err));
+}
+
+int32_t xaac_b200_heaac_lp_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *ist, xaac_b200_sbr_state *s,
+                                      const int32_t *spec, const uint8_t *ics, const int16_t *side, int16_t *pcm,
+                                      int32_t out_ch, int32_t *err) {
+  return drain(ctx, xaac_b200_heaac_lp_frame_host_impl(ctx, ist, s, spec, ics, side, pcm, out_ch, err));
 }
 
 }  // extern "C"

@@ -30,10 +30,14 @@ def esbr_synthesis_filt(ctx, state, qmf, out=None, err=None, stream=None, pcm16=
     _chk(qmf, torch.float32, (n, 32, 128), "qmf", "cuda")
     if out is None and want_float:
         out = torch.empty((n, 2048), dtype=torch.float32, device=qmf.device)
+    if out is None and pcm16 is None:
+        raise ValueError("esbr_synthesis_filt: neither float output (want_float / out) nor pcm16 requested")
     if out is not None:
         _chk(out, torch.float32, (n, 2048), "out", "cuda")
     if err is None:
         err = torch.empty((n,), dtype=torch.int32, device=qmf.device)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(qmf.device)
     if pcm16 is None:
@@ -76,6 +80,8 @@ def esbr_analysis_filt_block(ctx, state, time_in, qmf=None, err=None, stream=Non
     _chk(qmf, torch.float32, (n, 32, 128), "qmf", "cuda")
     if err is None:
         err = torch.empty((n,), dtype=torch.int32, device=time_in.device)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(time_in.device)
     tail = (_ptr(state.states), _ptr(state.pos), _ptr(qmf), _ptr(err), n, ctypes.c_void_p(stream.cuda_stream))
@@ -114,6 +120,8 @@ def esbr_generate_hf(ctx, src_re, src_im, dst_re, dst_im, par, bw_prev, pv_re=No
     _chk(patch_out, torch.int32, (n, 8), "patch_out", "cuda")
     if err is None:
         err = torch.empty((n,), dtype=torch.int32, device=dev)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(dev)
     rc = ctx._lib.xaac_b200_esbr_generate_hf_dev(ctx.handle, _ptr(src_re), _ptr(src_im), _ptr(pv_re) if pv_re is not None else None,
@@ -142,6 +150,8 @@ def esbr_env_calc(ctx, re, im, ipar, fpar, state, err=None, stream=None):
     _chk(state, torch.float32, (n, EEC_STATE_WORDS), "state", "cuda")
     if err is None:
         err = torch.empty((n,), dtype=torch.int32, device=dev)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(dev)
     rc = ctx._lib.xaac_b200_esbr_env_calc_dev(ctx.handle, _ptr(re), _ptr(im), _ptr(ipar), _ptr(fpar), _ptr(state), _ptr(err), n,
@@ -191,6 +201,8 @@ def esbr_dec(ctx, state, core, hf_par, ec_ipar, ec_fpar, rg_par, out=None, pcm16
         _chk(pcm16, torch.int16, (n // ch_fac, 2048, ch_fac), "pcm16", "cuda")
     if err is None:
         err = torch.empty((4, n), dtype=torch.int32, device=dev)
+    else:
+        _chk(err, torch.int32, (4, n), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(dev)
     v = state.view()

@@ -46,6 +46,8 @@ def peak_limiter_process(ctx, state, samples, qshift_adj, pcm16=None, out32=None
         pcm16 = torch.empty((n, 1024, ch), dtype=torch.int16, device=samples.device)
     if err is None:
         err = torch.empty((n,), dtype=torch.int32, device=samples.device)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(samples.device)
     rc = ctx._lib.xaac_b200_peak_limiter_dev(ctx.handle, _ptr(state.state), _ptr(samples), _ptr(qshift_adj),

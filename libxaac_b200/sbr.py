@@ -51,6 +51,8 @@ def calc_sbrenvelope(ctx, params, sf, state, matrix, err=None, stream=None):
     _chk(matrix, torch.int32, (n, 38, 128), "matrix", "cuda")
     if err is None:
         err = torch.empty((n,), dtype=torch.int32, device=matrix.device)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(matrix.device)
     rc = ctx._lib.xaac_b200_calc_sbrenvelope_hq_dev(ctx.handle, _ptr(params), _ptr(sf), _ptr(state), _ptr(matrix),
@@ -120,6 +122,8 @@ def sbr_dec(ctx, state, side, time_in, time_out=None, err=None, stream=None):
     _chk(time_out, torch.int16, shape, "time_out", "cuda")
     if err is None:
         err = torch.empty((n,), dtype=torch.int32, device=side.device)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(side.device)
     rc = ctx._lib.xaac_b200_sbr_dec_hq_dev(ctx.handle, state.handle, _ptr(side), _ptr(time_in), _ptr(time_out), _ptr(err),
@@ -142,6 +146,8 @@ def sbr_dec_lp(ctx, state, side, time_in, time_out=None, out_ch=1, err=None, str
     _chk(time_out, torch.int16, shape, "time_out", "cuda")
     if err is None:
         err = torch.empty((n,), dtype=torch.int32, device=side.device)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(side.device)
     rc = ctx._lib.xaac_b200_sbr_dec_lp_dev(ctx.handle, state.handle, _ptr(side), _ptr(time_in), _ptr(time_out), int(out_ch),
@@ -159,6 +165,8 @@ def heaac_frame_host(ctx, imdct_state, sbr_state, spec_coeff, ics, side, pcm, er
     _chk(ics, torch.uint8, (n, 2), "ics", "cpu")
     _chk(side, torch.int16, (n, SIDE_WORDS), "side", "cpu")
     _chk(pcm, torch.int16, (n, 2048, 2) if sbr_state.with_ps else (n, 2048), "pcm", "cpu")
+    if err is not None:
+        _chk(err, torch.int32, (n,), "err", "cpu")
     rc = ctx._lib.xaac_b200_heaac_frame_host(ctx.handle, imdct_state._h, sbr_state.handle, _ptr(spec_coeff), _ptr(ics),
                                             _ptr(side), _ptr(pcm), None if err is None else _ptr(err))
     ctx.check(rc, "xaac_b200_heaac_frame_host")
@@ -174,6 +182,8 @@ def heaac_lp_frame_host(ctx, imdct_state, sbr_state, spec_coeff, ics, side, pcm,
     _chk(ics, torch.uint8, (n, 2), "ics", "cpu")
     _chk(side, torch.int16, (n, SIDE_WORDS), "side", "cpu")
     _chk(pcm, torch.int16, (n // out_ch, 2048, out_ch), "pcm", "cpu")
+    if err is not None:
+        _chk(err, torch.int32, (n,), "err", "cpu")
     rc = ctx._lib.xaac_b200_heaac_lp_frame_host(ctx.handle, imdct_state._h, sbr_state.handle, _ptr(spec_coeff), _ptr(ics),
                                                _ptr(side), _ptr(pcm), int(out_ch), None if err is None else _ptr(err))
     ctx.check(rc, "xaac_b200_heaac_lp_frame_host")
