@@ -393,4 +393,52 @@ int xo_esbr_env_calc(const float *rphase, float *re, float *im, int32_t *ipar, c
 void xo_esbr_env_calc_batch(const float *rphase, float *re, float *im, int32_t *ipar, const float *fpar, float *state,
                             int32_t *err, int n);
 
+/* ---- eSBR QMF harmonic transposer (esbr_hbe.c): ixheaacd_qmf_hbe_apply (decoder/ixheaacd_hbe_trans.c:224-296) --------
+ * 2:1 system, 32 QMF columns per call (no_bins = 32, qmf_voc_columns = 16), synth_size 4, 8, 12, 16 (FFT banks) and 20
+ * (direct-form banks; for this size the reference's FFT pointers stay NULL, so it re-initialises the instance on every
+ * call, hbe_trans.c:240-248, 162-167: synth_buf / analy_buf start from zero each frame — restated as such).  ROM blob = the reference's global float tables concatenated by ref_rom_hbe_tables(), word offsets: */
+#define XO_HROM_WIN 0          /* ixheaac_sub_samp_qmf_window_coeff[1560] (common/ixheaac_esbr_rom.c) */
+#define XO_HROM_SYNCOS 1560    /* ixheaac_synth_cos_table_kl_4[16] | _8[32] | _12[48] | _16[64] */
+#define XO_HROM_ANACS 1720     /* ixheaac_analy_cos_sin_table_kl_8[32] | _16[64] | _24[96] | _32[128] */
+#define XO_HROM_COSTRANS 2040  /* ixheaac_cos_table_trans_qmf[7][64] */
+#define XO_HROM_FFTTW 2488     /* ixheaac_twiddle_table_fft_float[514] (+2 pad) */
+#define XO_HROM_TW24 3004      /* ixheaac_twidle_tbl_24[32] */
+#define XO_HROM_TW48 3036      /* ixheaac_twidle_tbl_48[64] */
+#define XO_HROM_PVCOS 3100     /* ixheaac_phase_vocoder_cos_table[64] */
+#define XO_HROM_PVSIN 3164     /* ixheaac_phase_vocoder_sin_table[64] */
+#define XO_HROM_INTERP 3228    /* ixheaac_hbe_post_anal_proc_interp_coeff[4][2] */
+#define XO_HROM_SELCASE 3236   /* ixheaac_sel_case[5][8] */
+#define XO_HROM_XP2 3276       /* ixheaac_hbe_x_prod_cos_table_trans_2[512] */
+#define XO_HROM_XP3 3788       /* ..._trans_3[512] */
+#define XO_HROM_XP4 4300       /* ..._trans_4[512] */
+#define XO_HROM_XP41 4812      /* ..._trans_4_1[512] */
+#define XO_HROM_SYN20 5324     /* ixheaac_synth_cos_table_kl_20[800] (direct-form bank, synth_size 20) */
+#define XO_HROM_ANA40 6124     /* ixheaac_analy_cos_sin_table_kl_40[3200] */
+#define XO_HROM_WORDS 9324
+/* cfg[] words (ia_esbr_hbe_txposer_struct members set by ixheaacd_qmf_hbe_data_reinit, + the call's pitch_in_bins) */
+#define XO_HBE_SYNTH_SIZE 0
+#define XO_HBE_K_START 1
+#define XO_HBE_START_BAND 2
+#define XO_HBE_END_BAND 3
+#define XO_HBE_MAX_STRETCH 4
+#define XO_HBE_PITCH 5
+#define XO_HBE_USF4 6          /* upsamp_4_flag: must be 0 */
+#define XO_HBE_REINIT 7        /* informational (taps): the instance's FFT pointers were NULL at entry, i.e. the reference
+                                * re-initialised it inside the call (always the case for synth_size 20) */
+#define XO_HBE_XOVER 8         /* x_over_qmf[6] */
+#define XO_HBE_CFG_WORDS 16
+/* state[] floats, in/out: what the transposer carries from one call to the next */
+#define XO_HBE_ST_TAIL 0       /* [32]  ptr_input_buf[no_bins * synth_size ..+ synth_size) (the next call's first samples) */
+#define XO_HBE_ST_SYNTH 32     /* [384] synth_buf[0..18 * synth_size) */
+#define XO_HBE_ST_ANAL 416     /* [384] analy_buf[0..18 * synth_size) */
+#define XO_HBE_ST_QIN 800      /* [12][128] qmf_in_buf rows 16..27 (the next call's rows 0..11) */
+#define XO_HBE_ST_QOUT 2336    /* [10][128] qmf_out_buf rows 32..41 (the next call's rows 0..9; rows above are zero) */
+#define XO_HBE_ST_WORDS 3616
+/* qmf_re / qmf_im: [32][64] the frame's new QMF slots; pv_re / pv_im: [32][64], bands start_band..end_band-1 written.
+ * Returns 0, the reference's error codes, or -2 (outside the restated subset). */
+int xo_esbr_hbe_apply(const float *rom, const int32_t *cfg, float *state, const float *qmf_re, const float *qmf_im,
+                      float *pv_re, float *pv_im);
+void xo_esbr_hbe_apply_batch(const float *rom, const int32_t *cfg, float *state, const float *qmf_re, const float *qmf_im,
+                             float *pv_re, float *pv_im, int32_t *err, int n);
+
 #endif

@@ -984,3 +984,110 @@ def oracle_esbr_stage(orc, rphase, st, time_in, hf_par, ec_ipar, ec_fpar, rg_par
         m[u, :, 64:] = np.where(k < xo, s["qmf_im"][u, 2:34], s["out_im"][u, 2:34])
     out, s["synth_states"], s["synth_pos"] = orc.esbr_synth_batch(m, s["synth_states"], s["synth_pos"])
     return out, s, ipar2, np.stack([np.zeros(n, np.int32), e1, e2, np.zeros(n, np.int32)])
+
+
+# ---- eSBR QMF harmonic transposer (ixheaacd_qmf_hbe_apply) ---------------------------------------------------------------
+HBE_CFG_WORDS, HBE_ST_WORDS = 16, 3616
+HBE_ST_TAIL, HBE_ST_SYNTH, HBE_ST_ANAL, HBE_ST_QIN, HBE_ST_QOUT = 0, 32, 416, 800, 2336
+
+
+def hbe_rom():
+    return np.fromfile(os.path.join(ROM_DIR, "hbe_rom.bin"), dtype=np.float32)
+
+
+def oracle_hbe_batch(orc, cfg, state, qre, qim, pv_re=None, pv_im=None):
+    """Returns (pv_re, pv_im, state_out, err); pv_* start from the given arrays (only bands start..end-1 are written)."""
+    n = len(cfg)
+    st = np.ascontiguousarray(state, np.float32).copy()
+    pr = np.zeros((n, 32, 64), np.float32) if pv_re is None else np.ascontiguousarray(pv_re, np.float32).copy()
+    pi = np.zeros((n, 32, 64), np.float32) if pv_im is None else np.ascontiguousarray(pv_im, np.float32).copy()
+    err = np.zeros(n, np.int32)
+    r = hbe_rom()
+    orc.lib.xo_esbr_hbe_apply_batch(P(r), P(np.ascontiguousarray(cfg, np.int32)), P(st), P(np.ascontiguousarray(qre, np.float32)),
+                                    P(np.ascontiguousarray(qim, np.float32)), P(pr), P(pi), P(err), n)
+    return pr, pi, st, err
+
+
+def ref_hbe_batch(ref, cfg, state, qre, qim, tbl=None, pv_re=None, pv_im=None):
+    """The compiled ixheaacd_qmf_hbe_apply; tbl int16 [n,128] = {num_lo, num_hi, lo[0..num_lo], hi[0..num_hi]} (needed for
+    synth_size 20, where the reference re-initialises from the frequency tables inside the call)."""
+    n = len(cfg)
+    st = np.ascontiguousarray(state, np.float32).copy()
+    pr = np.zeros((n, 32, 64), np.float32) if pv_re is None else np.ascontiguousarray(pv_re, np.float32).copy()
+    pi = np.zeros((n, 32, 64), np.float32) if pv_im is None else np.ascontiguousarray(pv_im, np.float32).copy()
+    err = np.zeros(n, np.int32)
+    t = None if tbl is None else np.ascontiguousarray(tbl, np.int16)
+    ref.lib.ref_esbr_hbe_apply_batch(P(np.ascontiguousarray(cfg, np.int32)), P(st), P(np.ascontiguousarray(qre, np.float32)),
+                                     P(np.ascontiguousarray(qim, np.float32)), P(pr), P(pi), None if t is None else P(t), P(err), n)
+    return pr, pi, st, err
+
+
+def hbe_tables(rng, kx, top):
+    """A plausible pair of SBR frequency-band tables starting at QMF band kx and ending at `top`: HIGH with steps 1..3,
+    LOW = every other HIGH border (as ixheaacd_calc_frq_bnd_tbls derives it)."""
+    hi = [kx]
+    while hi[-1] < top:
+        hi.append(min(top, hi[-1] + int(rng.integers(1, 4))))
+    lo = hi[::2] if (len(hi) - 1) % 2 == 0 else [hi[0]] + hi[1::2]
+    t = np.zeros(128, np.int16)
+    t[0], t[1] = len(lo) - 1, len(hi) - 1
+    t[2:2 + len(lo)] = lo
+    t[2 + len(lo):2 + len(lo) + len(hi)] = hi
+    return t
+
+
+def ref_hbe_reinit(ref, tbl):
+    """ixheaacd_qmf_hbe_data_reinit on a table row of hbe_tables(): returns (ret, cfg[16])."""
+    cfg = np.zeros(HBE_CFG_WORDS, np.int32)
+    nlo, nhi = int(tbl[0]), int(tbl[1])
+    lo = np.ascontiguousarray(tbl[2:2 + nlo + 1])
+    hi = np.ascontiguousarray(tbl[2 + nlo + 1:2 + nlo + 1 + nhi + 1])
+    ret = ref.lib.ref_esbr_hbe_reinit(P(lo), nlo, P(hi), nhi, P(cfg))
+    return ret, cfg
+
+
+def synth_hbe_units(n, seed, ref, pitch_mode="mixed", sizes=(4, 8, 12, 16, 20)):
+    """n transposer units over a spread of configurations derived by the reference's own re-initialisation from random
+    frequency tables (so synth_size 20 is drivable through the shim too), with random state and QMF input.
+    pitch_mode: "zero" (plain products), "pitch" (cross products, pitch_in_bins >= 12) or "mixed"."""
+    rng = np.random.default_rng(seed)
+    cfg = np.zeros((n, HBE_CFG_WORDS), np.int32)
+    tbl = np.zeros((n, 128), np.int16)
+    for u in range(n):
+        while True:
+            s = sizes[u % len(sizes)]
+            lo_kx = {4: 1, 8: 4, 12: 12, 16: 20, 20: 28}[s]
+            kx = int(rng.integers(lo_kx, lo_kx + 8 if s != 4 else 4))
+            if s == 20:
+                kx = int(rng.integers(28, 36))
+            top = int(rng.integers(min(63, kx + 6), 65))
+            t = hbe_tables(rng, kx, top)
+            ret, c = ref_hbe_reinit(ref, t)
+            if ret == 0 and c[0] == s and c[4] >= 2 and c[1] >= 0 and c[1] + s <= 32 and not (c[4] >= 4 and c[10] <= 1):
+                break
+        if pitch_mode == "pitch" or (pitch_mode == "mixed" and u % 3 == 1):
+            c[5] = int(rng.integers(12, 128))
+        elif pitch_mode == "mixed" and u % 3 == 2:
+            c[5] = int(rng.integers(0, 12))
+        cfg[u], tbl[u] = c, t
+    amp = 10.0 ** rng.uniform(-2, 3.5, size=(n, 1, 1))
+    qre = (rng.standard_normal((n, 32, 64)) * amp).astype(np.float32)
+    qim = (rng.standard_normal((n, 32, 64)) * amp).astype(np.float32)
+    qre[::7, 5:9] = 0
+    qim[::7, 5:9] = 0
+    state = np.zeros((n, HBE_ST_WORDS), np.float32)
+    a2 = amp[:, 0]
+    state[:, :HBE_ST_QIN] = (rng.standard_normal((n, HBE_ST_QIN)) * a2).astype(np.float32)
+    for u in range(n):  # qmf_in history is only ever non-zero inside the analysis bank's band range
+        s, k = int(cfg[u, 0]), int(cfg[u, 1])
+        q = np.zeros((12, 128), np.float32)
+        q[:, 4 * k:4 * k + 4 * s] = rng.standard_normal((12, 4 * s)) * a2[u]
+        state[u, HBE_ST_QIN:HBE_ST_QOUT] = q.ravel()
+        o = np.zeros((10, 128), np.float32)
+        o[:9, 2 * cfg[u, 2]:2 * cfg[u, 3]] = rng.standard_normal((9, 2 * (cfg[u, 3] - cfg[u, 2]))) * a2[u]
+        state[u, HBE_ST_QOUT:] = o.ravel()
+        state[u, HBE_ST_TAIL + s:HBE_ST_SYNTH] = 0          # words past the instance's sizes are not part of the state
+        state[u, HBE_ST_SYNTH + 18 * s:HBE_ST_ANAL] = 0
+        state[u, HBE_ST_ANAL + 18 * s:HBE_ST_QIN] = 0
+    state[::5] = 0
+    return cfg, tbl, state, qre, qim

@@ -51,7 +51,10 @@ EXTRA = [("ref_rom_qmf_tables", 3464, "qmf_rom.bin"), ("ref_rom_env_tables", 240
          # eSBR banks: esbr_qmf_c[1280], esbr_w_32[60], esbr_sin_cos_twiddle_l64[64], esbr_alt_sin_twiddle_l64[32], esbr_w_16[24],
          # esbr_sin_cos_twiddle_l32[32], esbr_alt_sin_twiddle_l32[16], esbr_t_cos_sin_l32[64]
          # of ia_qmf_dec_tables_struct (decoder/ixheaacd_sbr_rom.h:96-105), concatenated by ref_rom_esbr_tables
-         ("ref_rom_esbr_tables", 6288, "esbr_rom.bin")]
+         ("ref_rom_esbr_tables", 6288, "esbr_rom.bin"),
+         # QMF harmonic transposer: the reference's global float tables (common/ixheaac_esbr_rom.c) concatenated by
+         # ref_rom_hbe_tables (oracle/ref_shim_hbe.c; layout XAAC_HROM_* in include/xaac_b200.h)
+         ("ref_rom_hbe_tables", 9324 * 4, "hbe_rom.bin")]
 
 if __name__ == "__main__":
     main()

@@ -464,9 +464,57 @@ def make_esbr_stage_golden(tmp):
     print(f"wrote {path}: {n_rec} records, {os.path.getsize(path)} bytes")
 
 
+HBE_WORDS = 2 + 16 + 3616 + 4 * 2048 + 3616
+
+
+def read_hbe_records(path):
+    a = np.fromfile(path, dtype=np.int32)
+    assert a.size and a.size % HBE_WORDS == 0, a.size
+    a = a.reshape(-1, HBE_WORDS)
+    assert (a[:, 0] == 0x31454248).all()
+    return a
+
+
+def make_hbe_golden(tmp):
+    """QMF harmonic transposer ixheaacd_qmf_hbe_apply of real USAC decodes (-harmonic_sbr:1, stereo 32 kHz): every call is
+    tapped (oracle/ref_shim_hbe.c) in the flat XO_HBE_* layout.  Kept: 8 consecutive calls (4 frames x 2 channels) for the
+    state carry plus a spread over the pitch values the encoder signals."""
+    fs, ch, br = 32000, 2, 64000
+    wav = os.path.join(tmp, "in_hbe.wav")
+    write_wav(wav, synth(fs, 6.0, ch, 22), fs)
+    mp4 = os.path.join(tmp, "hbe.mp4")
+    run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{mp4}", "-aot:42", f"-br:{br}", "-ccfl_idx:3", "-harmonic_sbr:1"])
+    tap = os.path.join(tmp, "hbe.tap")
+    decode_tap(mp4, os.path.join(tmp, "o.wav"), tap, [f"-imeta:{os.path.join(tmp, 'hbe.txt')}", "-mp4:1"], stages="hbe")
+    a = read_hbe_records(tap + ".hbe")
+    cfg = a[:, 2:18]
+    ok = a[:, 1] == 0
+    pitches = sorted(set(cfg[:, 5].tolist()))
+    stats = (f"qmf_hbe_apply: {len(a)} calls, {int(ok.sum())} ok; synth_size {sorted(set(cfg[:, 0].tolist()))}, k_start "
+             f"{sorted(set(cfg[:, 1].tolist()))}, bands {sorted(set(map(tuple, cfg[:, 2:4].tolist())))}, max_stretch "
+             f"{sorted(set(cfg[:, 4].tolist()))}, pitch_in_bins {pitches}, reinit inside the call {int(cfg[:, 7].sum())}")
+    print(stats)
+    run0 = next(i for i in range(40, len(a) - 8) if ok[i:i + 8].all())
+    keep = set(range(run0, run0 + 8))
+    for pv in pitches:
+        idx = np.flatnonzero(ok & (cfg[:, 5] == pv))
+        keep.update(idx[len(idx) // 2: len(idx) // 2 + 2].tolist())
+    sel = a[sorted(keep)]
+    f32 = lambda x: np.ascontiguousarray(x).view(np.float32)
+    o = 18
+    st_in = f32(sel[:, o:o + 3616]); o += 3616
+    q = f32(sel[:, o:o + 4 * 2048]).reshape(len(sel), 4, 32, 64); o += 4 * 2048
+    st_out = f32(sel[:, o:o + 3616])
+    path = os.path.join(GOLD, "esbr_hbe_tapped.npz")
+    np.savez_compressed(path, ret=sel[:, 1].copy(), cfg=sel[:, 2:18].copy(), state_in=st_in, state_out=st_out, qmf_re=q[:, 0],
+                        qmf_im=q[:, 1], pv_re=q[:, 2], pv_im=q[:, 3], run=np.array([sorted(keep).index(run0), 8]),
+                        stats=np.array([stats]))
+    print(f"wrote {path}: {len(sel)} records, {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr", "esbr_stage"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr", "esbr_stage", "hbe"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
@@ -484,6 +532,8 @@ def main():
             make_esbr_stage_golden(tmp)
         if "sbrdec_lp" in which:
             make_sbrdec_lp_golden(tmp)
+        if "hbe" in which:
+            make_hbe_golden(tmp)
 
 
 if __name__ == "__main__":
