@@ -16,7 +16,10 @@ lib: $(LIB)
 
 build/%.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p build
-	$(NVCC) $(NVFLAGS) -c $< -o $@
+	$(NVCC) $(NVFLAGS) $(FLAGS_$*) -c $< -o $@
+
+# float code written as plain expressions in the reference's evaluation order: no FMA contraction (the reference build has none)
+FLAGS_esbr_hbe_kernel := -fmad=false
 
 $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)

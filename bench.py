@@ -63,9 +63,15 @@ WORKLOADS = {
     "esbr_generate_hf": (4, 65536, "xHE-AAC/USAC eSBR stereo: the float HF generator of the chain (ixheaacd_generate_hf: 38-slot "
                                    "covariance, 2nd-order complex prediction, patching, HBE high band), batch=65536 stereo "
                                    "frames (131072 core channels)"),
-    "xheaac_stereo_chain": (4, 65536, "xHE-AAC/USAC stereo 32 kHz with eSBR (default patching, no harmonic transposer / PS) batch=65536: "
-                                      "FD core IMDCT -> float eSBR stage (QMF analysis, HF generator, envelope adjuster, QMF "
-                                      "synthesis) -> stereo PCM16, per channel"),
+    "xheaac_stereo_chain": (4, 131072, "xHE-AAC/USAC eSBR stereo 32 kHz batch=131072 stereo frames (262144 core channels): FD core IMDCT -> "
+                                       "float eSBR stage with the QMF harmonic transposer (HBE: real synthesis bank, complex analysis "
+                                       "bank, stretch-2 products + pitch cross products as the reference encoder signals them), HF "
+                                       "generator, envelope adjuster, polyphase QMF synthesis -> stereo PCM16"),
+    "esbr_hbe": (4, 65536, "xHE-AAC/USAC eSBR stereo: the QMF harmonic transposer of the chain (ixheaacd_qmf_hbe_apply), "
+                           "batch=65536 stereo frames (131072 core channels)"),
+    "xheaac_plain_stereo_chain": (4, 65536, "xHE-AAC/USAC stereo 32 kHz with eSBR, default (LPP) patching instead of the harmonic "
+                                            "transposer, batch=65536: FD core IMDCT -> float eSBR stage (QMF analysis, HF generator, "
+                                            "envelope adjuster, QMF synthesis) -> stereo PCM16, per channel"),
     "esbr_env_calc": (4, 65536, "xHE-AAC/USAC eSBR stereo: the float envelope adjuster of the chain (ixheaacd_sbr_env_calc, ORIG_SBR: "
                                 "energies, gains in double, limiter, smoothing, noise, sinusoids), batch=65536 stereo frames "
                                 "(131072 core channels)"),
@@ -639,6 +645,23 @@ def load_esbr_stage_golden():
     return {k: g[k] for k in g.files}
 
 
+def load_esbr_hbe_stage_golden():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "esbr_hbe_stage_tapped.npz"))
+    return {k: g[k] for k in g.files}
+
+
+HBE_FRAMES = 6  # consecutive frames in tests/golden/esbr_hbe_stage_tapped.npz
+
+
+def esbr_hbe_stage_params(g, n_units, f):
+    """(hbe_cfg, hf_par, ec_ipar, ec_fpar, rg_par) of frame f (0..5) of the tapped -harmonic_sbr:1 stream, unit u = channel u % 2"""
+    j = (np.arange(n_units) % 2) + 2 * (f % HBE_FRAMES)
+    h = g["head"][j]
+    rg = np.stack([h[:, 7], h[:, 8], 2 * h[:, 9], 0 * h[:, 9]], 1).astype(np.int32)
+    return (np.ascontiguousarray(g["hbe_cfg"][j]), np.ascontiguousarray(g["hf_par"][j]), np.ascontiguousarray(g["ec_ipar_in"][j]),
+            np.ascontiguousarray(g["ec_fpar"][j]), np.ascontiguousarray(rg))
+
+
 def esbr_stage_params(g, n_units, f):
     """parameter records of frame f (0..7) of the tapped stream for n_units channel units (unit u = channel u % 2)"""
     j = (np.arange(n_units) % 2) + 2 * (f % 8)
@@ -646,6 +669,120 @@ def esbr_stage_params(g, n_units, f):
     rg = np.stack([h[:, 7], h[:, 8], 2 * h[:, 9], 0 * h[:, 9]], 1).astype(np.int32)
     return (np.ascontiguousarray(g["hf_par"][j]), np.ascontiguousarray(g["ec_ipar_in"][j]), np.ascontiguousarray(g["ec_fpar"][j]),
             np.ascontiguousarray(rg))
+
+
+def esbr_hbe_bytes(cfg):
+    """Algorithmic HBM bytes per unit of ixheaacd_qmf_hbe_apply: the synthesis bank's input cells (32 columns x synth_size bands
+    x 8 B), the written phase-vocoder cells (32 rows x (end - start) bands x 8 B) and the instance state read and written once
+    (tail + both bank histories 38 x synth_size words, 12 analysis rows x 4 synth_size words, 10 carry rows x 2 (end - start))."""
+    s, nb = cfg[:, 0].astype(np.int64), (cfg[:, 3] - cfg[:, 2]).astype(np.int64)
+    state = 4 * (37 * s + 12 * 4 * s + 10 * 2 * nb)
+    return 32 * s * 8 + 32 * nb * 8 + 2 * state
+
+
+def cpu_arm_esbr_hbe(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time ixheaacd_qmf_hbe_apply per unit on host threads (ref_esbr_hbe_apply_batch, oracle/ref_shim_hbe.c)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    if ref is None:
+        raise SystemExit("bench.py: the harmonic-transposer CPU baseline needs oracle/_ref/libxaac_ref.so (make ref)")
+    P = oracle_util.P
+    g = np.load(os.path.join(ROOT, "tests", "golden", "esbr_hbe_tapped.npz"))
+    k = len(g["cfg"])
+    idx = np.arange(n_units) % k
+    cfg = np.ascontiguousarray(g["cfg"][idx])
+    state = np.ascontiguousarray(g["state_in"][idx])
+    qre, qim = np.ascontiguousarray(g["qmf_re"][idx]), np.ascontiguousarray(g["qmf_im"][idx])
+    pr, pi = np.zeros_like(qre), np.zeros_like(qim)
+    tbl = np.zeros((n_units, 128), np.int16)
+    tbl[:, :6] = [1, 1, cfg[0, 2], cfg[0, 3], cfg[0, 2], cfg[0, 3]]
+    err = np.zeros(n_units, np.int32)
+    bounds = np.linspace(0, n_units, threads + 1).astype(int)
+
+    def work(t):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            ref.lib.ref_esbr_hbe_apply_batch(P(cfg[a:]), P(state[a:]), P(qre[a:]), P(qim[a:]), P(pr[a:]), P(pi[a:]), P(tbl[a:]),
+                                             P(err[a:]), b - a)
+
+    def one_pass():
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    one_pass()
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass()
+        done += 1
+    assert not err.any()
+    return n_units * done / dt, "reference"
+
+
+def cpu_arm_xheaac_hbe_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time the reference's own xHE-AAC chain WITH the harmonic transposer per channel unit on host threads
+    (ref_xheaac_hbe_chain_batch, oracle/ref_shim_hbe.c: ixheaacd_fd_frm_dec -> ixheaacd_esbr_analysis_filt_block ->
+    ixheaacd_qmf_hbe_apply -> ixheaacd_generate_hf -> ixheaacd_sbr_env_calc -> synthesis -> ixheaacd_samples_sat)."""
+    from tests import oracle_util
+    ref = oracle_util.Ref.try_load()
+    if ref is None:
+        raise SystemExit("bench.py: the xHE-AAC chain CPU baseline needs oracle/_ref/libxaac_ref.so (make ref)")
+    P = oracle_util.P
+    n_units -= n_units & 1
+    g = load_esbr_hbe_stage_golden()
+    rng = np.random.default_rng(seed)
+    sc = rng.integers(10, 20, size=(n_units, 1))
+    coef0 = ((rng.random((n_units, 1024)) * 2 - 1) * (2.0 ** sc)).astype(np.int64).astype(np.int32)
+    walk = usac_walk(n_units, reps + 1, seed)
+    ov = np.zeros((n_units, 1024), np.int32)
+    prev = np.zeros(n_units, np.int32)
+    ch = np.arange(n_units) % 2
+    q6 = np.ascontiguousarray(np.concatenate([g["in0_" + k][ch].reshape(n_units, -1) for k in
+                                              ("qmf_re", "qmf_im", "out_re", "out_im", "pv_re", "pv_im")], 1))
+    st = {k: np.ascontiguousarray(g["in0_" + k][ch]) for k in ("anal_states", "anal_pos", "synth_states", "synth_pos", "bw_prev",
+                                                                "patch", "ec_state", "hbe_state")}
+    params = [esbr_hbe_stage_params(g, n_units, f) for f in range(HBE_FRAMES)]
+    # frequency tables that make the reference's in-call re-initialisation (bank size 20) reproduce the tapped configuration
+    c0 = g["hbe_cfg"][0]
+    tbl = np.zeros(128, np.int16)
+    tbl[:6] = [1, 1, c0[2], c0[3], c0[2], c0[3]]
+    pcm = np.zeros((n_units // 2, 2048, 2), np.int16)
+    err = np.zeros(n_units, np.int32)
+    bounds = (np.linspace(0, n_units // 2, threads + 1).astype(int)) * 2
+
+    def work(t, coef, seq, shape, pr):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b > a:
+            ref.lib.ref_xheaac_hbe_chain_batch(P(coef), P(ov), P(seq), P(shape), P(prev), P(q6), P(st["anal_states"]),
+                                               P(st["anal_pos"]), P(st["synth_states"]), P(st["synth_pos"]), P(st["bw_prev"]),
+                                               P(st["patch"]), P(st["ec_state"]), P(st["hbe_state"]), P(pr[0]), P(tbl), P(pr[1]),
+                                               P(pr[2]), P(pr[3]), P(pr[4]), P(pcm), P(err), a, b)
+
+    def one_pass(step):
+        coef = coef0.copy()
+        seq = np.ascontiguousarray(walk[step, :, 0], np.int32)
+        shape = np.ascontiguousarray(walk[step, :, 1], np.int32)
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t, coef, seq, shape, params[step % HBE_FRAMES])) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        dt = time.perf_counter() - t0
+        prev[:] = shape
+        assert not err.any(), f"reference xHE-AAC (HBE) chain returned an error: {sorted(set(err.tolist()))}"
+        return dt
+
+    one_pass(0)
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass(1 + done % reps)
+        done += 1
+    return n_units * done / dt, "reference"
 
 
 def cpu_arm_xheaac_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
@@ -853,6 +990,19 @@ STAGES = {
                              ref_stage="ixheaacd_generate_hf", cpu=cpu_arm_esbr_hfgen, cpu_units_per_core=1024,
                              realtime_fps=15.625, h2d=4 * 10240 + 384, d2h=2 * 10240, dtype="f32"),
     "xheaac_stereo_chain": dict(kernel=None, top_kernel="esbr_synth_kernel", bytes_per_unit=None,
+                                stage="USAC FD core transform -> (x 2^-15 in the load) eSBR analysis bank (32-slot codec delay) -> QMF "
+                                      "harmonic transposer -> HF generator -> envelope adjuster -> (regrouping in the load) eSBR "
+                                      "synthesis bank -> (samples_sat in the store) PCM16",
+                                ref_stage="ixheaacd_fd_frm_dec -> eSBR branch of ixheaacd_sbr_dec with hbe_flag = 1 (ixheaacd_qmf_hbe_apply "
+                                          "included) -> ixheaacd_samples_sat",
+                                cpu=cpu_arm_xheaac_hbe_chain, cpu_units_per_core=128, cpu_reps=6, realtime_fps=15.625,
+                                h2d=4096 + 2 + 64 + 384 + 1152 + 1856 + 16, d2h=4096, dtype="int32 + f32/f64"),
+    "esbr_hbe": dict(kernel="esbr_hbe_kernel", bytes_per_unit=None,
+                     stage="QMF harmonic transposer: critically sampled real synthesis bank, 2x complex analysis bank, stretch-2/3/4 "
+                           "products with pitch cross products, phase rotation (bit-exact floats)",
+                     ref_stage="ixheaacd_qmf_hbe_apply", cpu=cpu_arm_esbr_hbe, cpu_units_per_core=512,
+                     realtime_fps=15.625, h2d=2 * 8192 + 64, d2h=2 * 8192, dtype="f32/f64"),
+    "xheaac_plain_stereo_chain": dict(kernel=None, top_kernel="esbr_synth_kernel", bytes_per_unit=None,
                                 stage="USAC FD core transform -> (x 2^-15 in the load) eSBR analysis bank -> HF generator -> envelope "
                                       "adjuster -> (regrouping in the load) eSBR synthesis bank -> (samples_sat in the store) PCM16",
                                 ref_stage="ixheaacd_fd_frm_dec -> eSBR branch of ixheaacd_sbr_dec -> ixheaacd_samples_sat",
@@ -1230,6 +1380,129 @@ class XheaacChainWork:
         pass
 
 
+class XheaacHbeChainWork(XheaacChainWork):
+    """BASELINE configs[4]: as XheaacChainWork with the harmonic transposer (hbe_flag = 1), 6 launches per step; parameters and
+    initial state tiled from 6 consecutive frames of a tapped -harmonic_sbr:1 stream (bank size 20, stretch 2, pitch 24 / 96)."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        g = load_esbr_hbe_stage_golden()
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        sc = torch.randint(10, 20, (n_units, 1), generator=gen, device=dev).to(torch.float32)
+        self.coef = ((torch.rand((n_units, 1024), generator=gen, device=dev) * 2 - 1) * torch.exp2(sc)).to(torch.int32)
+        self.walk = torch.from_numpy(usac_walk(n_units, steps_total, seed)).to(dev)
+        self.nw = steps_total
+        self.core_state = xb.UsacFdBatch(n_units, device=dev)
+        self.core = torch.empty((n_units, 1024), dtype=torch.int32, device=dev)
+        self.state = xb.EsbrDecHbeBatch(n_units, device=dev)
+        for k in xb.EsbrDecHbeBatch.SHAPES:
+            v = torch.from_numpy(np.ascontiguousarray(g["in0_" + k])).to(dev)
+            getattr(self.state, k).view((n_units // 2, 2) + tuple(v.shape[1:])).copy_(v.unsqueeze(0).expand((n_units // 2,) + tuple(v.shape)))
+        self.params = [[torch.from_numpy(a).to(dev) for a in esbr_hbe_stage_params(g, n_units, f)] for f in range(HBE_FRAMES)]
+        self.pcm = torch.zeros((n_units // 2, 2048, 2), dtype=torch.int16, device=dev)
+        self.err = torch.zeros((5, n_units), dtype=torch.int32, device=dev)
+        hf = np.concatenate([esbr_hbe_stage_params(g, 2, f)[1] for f in range(HBE_FRAMES)])
+        ec = np.concatenate([esbr_hbe_stage_params(g, 2, f)[2] for f in range(HBE_FRAMES)])
+        CHAIN_KERNEL_BYTES.update({
+            "usac_fd_kernel": USAC_FD_BYTES_PER_UNIT,
+            # stage mode with the 32-slot delay: 4096 core in + 2 x 1280 ring + 2 x 40 rows x 256 B history r/w (low 32 bands count:
+            # 2 x 40 x 128 B x 2) + 32 rows x 32 bands x 8 B written
+            "esbr_anal_kernel": 4096 + 2560 + 2 * 40 * 128 * 2 + 8192,
+            "esbr_hbe_kernel": float(esbr_hbe_bytes(g["hbe_cfg"]).mean()) + 2 * 8 * 512,   # + ph_vocod history rows r/w
+            "esbr_hfgen_kernel": float(esbr_hfgen_bytes(hf).mean()) + 8192,
+            "esbr_envcalc_kernel": float(esbr_envcalc_bytes(ec).mean()),
+            "esbr_synth_kernel": 16384 + 10240 + 4096,
+        })
+
+    def step(self, i, stream):
+        xb = self.xb
+        xb.usac_fd_frm_dec(self.ctx, self.core_state, self.coef, self.walk[i % self.nw], self.core, stream=stream)
+        hc, hf, ip, fp, rg = self.params[i % HBE_FRAMES]
+        xb.esbr_dec_hbe(self.ctx, self.state, self.core, hc, hf, ip, fp, rg, pcm16=self.pcm, ch_fac=2, err=self.err, stream=stream,
+                        want_float=False)
+
+    def host_setup(self):
+        import torch
+        self.h_coef = torch.empty((self.n, 1024), dtype=torch.int32).pin_memory()
+        self.h_coef.copy_(self.coef)
+        self.h_walk = self.walk.cpu().pin_memory()
+        self.h_params = [[a.cpu().pin_memory() for a in p] for p in self.params]
+        self.h_pcm = torch.empty((self.n // 2, 2048, 2), dtype=torch.int16).pin_memory()
+        self.d_coef = torch.empty_like(self.coef)
+        self.d_ics = torch.empty((self.n, 2), dtype=torch.uint8, device=self.coef.device)
+        self.d_params = [torch.empty_like(a) for a in self.params[0]]
+
+    def host_step(self, i):
+        import torch
+        xb = self.xb
+        self.d_coef.copy_(self.h_coef, non_blocking=True)
+        self.d_ics.copy_(self.h_walk[i % self.nw], non_blocking=True)
+        for d, h in zip(self.d_params, self.h_params[i % HBE_FRAMES]):
+            d.copy_(h, non_blocking=True)
+        xb.usac_fd_frm_dec(self.ctx, self.core_state, self.d_coef, self.d_ics, self.core)
+        hc, hf, ip, fp, rg = self.d_params
+        xb.esbr_dec_hbe(self.ctx, self.state, self.core, hc, hf, ip, fp, rg, pcm16=self.pcm, ch_fac=2, err=self.err, want_float=False)
+        self.h_pcm.copy_(self.pcm, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+
+class EsbrHbeWork:
+    """The harmonic transposer on its own: 16 tapped calls tiled over the batch, state carried from step to step."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        g = np.load(os.path.join(ROOT, "tests", "golden", "esbr_hbe_tapped.npz"))
+        k = len(g["cfg"])
+        idx = torch.arange(n_units, device=dev) % k
+        self.cfg = torch.from_numpy(g["cfg"]).to(dev)[idx].contiguous()
+        self.hb = xb.EsbrHbeBatch(n_units, device=dev)
+        self.hb.state.copy_(torch.from_numpy(g["state_in"]).to(dev)[idx])
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        amp = torch.exp2(torch.rand((n_units, 1, 1), generator=gen, device=dev) * 8 + 2)
+        self.qre = (torch.randn((n_units, 32, 64), generator=gen, device=dev) * amp)
+        self.qim = (torch.randn((n_units, 32, 64), generator=gen, device=dev) * amp)
+        self.qre[:, :, 32:] = 0   # the 32-band analysis bank leaves the upper half empty
+        self.qim[:, :, 32:] = 0
+        self.pr = torch.zeros((n_units, 32, 64), dtype=torch.float32, device=dev)
+        self.pi = torch.zeros_like(self.pr)
+        self.err = torch.zeros((n_units,), dtype=torch.int32, device=dev)
+        self.bytes_per_unit = float(esbr_hbe_bytes(g["cfg"]).mean())
+
+    def step(self, i, stream):
+        self.xb.esbr_qmf_hbe_apply(self.ctx, self.hb, self.qre, self.qim, self.pr, self.pi, self.cfg, err=self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0
+
+    def host_setup(self):
+        import torch
+        self.h_qre = torch.empty((self.n, 32, 64), dtype=torch.float32).pin_memory()
+        self.h_qim = torch.empty((self.n, 32, 64), dtype=torch.float32).pin_memory()
+        self.h_qre.copy_(self.qre)
+        self.h_qim.copy_(self.qim)
+        self.h_cfg = self.cfg.cpu().pin_memory()
+        self.h_pr = torch.empty((self.n, 32, 64), dtype=torch.float32).pin_memory()
+        self.h_pi = torch.empty((self.n, 32, 64), dtype=torch.float32).pin_memory()
+        self.d_qre, self.d_qim, self.d_cfg = torch.empty_like(self.qre), torch.empty_like(self.qim), torch.empty_like(self.cfg)
+
+    def host_step(self, i):
+        import torch
+        self.d_qre.copy_(self.h_qre, non_blocking=True)
+        self.d_qim.copy_(self.h_qim, non_blocking=True)
+        self.d_cfg.copy_(self.h_cfg, non_blocking=True)
+        self.xb.esbr_qmf_hbe_apply(self.ctx, self.hb, self.d_qre, self.d_qim, self.pr, self.pi, self.d_cfg, err=self.err)
+        self.h_pr.copy_(self.pr, non_blocking=True)
+        self.h_pi.copy_(self.pi, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
+
+
 class EsbrSynthWork:
     def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
         import torch
@@ -1412,7 +1685,8 @@ WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv
         "heaacv1_stereo_chain": ChainLpWork, "usac_fd_imdct": UsacFdWork,
         "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork,
         "esbr_anal32": EsbrAnalWork, "esbr_generate_hf": EsbrHfgenWork,
-        "esbr_env_calc": EsbrEnvcalcWork, "xheaac_stereo_chain": XheaacChainWork}
+        "esbr_env_calc": EsbrEnvcalcWork, "xheaac_stereo_chain": XheaacHbeChainWork, "esbr_hbe": EsbrHbeWork,
+        "xheaac_plain_stereo_chain": XheaacChainWork}
 
 
 def main():

@@ -584,6 +584,59 @@ int32_t xaac_b200_set_esbr_envcalc_rom(xaac_b200_ctx *ctx, const void *random_ph
 int32_t xaac_b200_esbr_env_calc_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im, int32_t *d_ipar, const float *d_fpar,
                                     float *d_state, int32_t *d_err, int64_t n_units, void *stream);
 
+/* QMF harmonic transposer: batched ixheaacd_qmf_hbe_apply (decoder/ixheaacd_hbe_trans.c:224-296) with
+ * ixheaacd_real_synth_filt / ixheaacd_complex_anal_filt (decoder/ixheaacd_esbr_polyphase.c:157, 48),
+ * ixheaacd_hbe_post_anal_process + prod2/3/4 + xprod2/3/4 (hbe_trans.c:298-1606) and the FFTs of common/ixheaac_esbr_fft.c,
+ * for the 2:1 system (32 QMF columns per call): bank sizes 4 / 8 / 12 / 16 (FFT banks) and 20 (direct form; for this size the
+ * reference's FFT pointers stay NULL and it re-initialises the instance inside every call, hbe_trans.c:240-248 — the bank
+ * histories then start from zero each frame, reproduced).  Float results are bit-identical to the reference build's.
+ * ROM blob = the reference's global float tables (common/ixheaac_esbr_rom.c) concatenated, float-word offsets: */
+#define XAAC_HROM_WIN 0          /* ixheaac_sub_samp_qmf_window_coeff[1560] */
+#define XAAC_HROM_SYNCOS 1560    /* ixheaac_synth_cos_table_kl_4[16] | _8[32] | _12[48] | _16[64] */
+#define XAAC_HROM_ANACS 1720     /* ixheaac_analy_cos_sin_table_kl_8[32] | _16[64] | _24[96] | _32[128] */
+#define XAAC_HROM_COSTRANS 2040  /* ixheaac_cos_table_trans_qmf[7][64] */
+#define XAAC_HROM_FFTTW 2488     /* ixheaac_twiddle_table_fft_float[514] (+ 2 words of padding) */
+#define XAAC_HROM_TW24 3004      /* ixheaac_twidle_tbl_24[32] */
+#define XAAC_HROM_TW48 3036      /* ixheaac_twidle_tbl_48[64] */
+#define XAAC_HROM_PVCOS 3100     /* ixheaac_phase_vocoder_cos_table[64] */
+#define XAAC_HROM_PVSIN 3164     /* ixheaac_phase_vocoder_sin_table[64] */
+#define XAAC_HROM_INTERP 3228    /* ixheaac_hbe_post_anal_proc_interp_coeff[4][2] */
+#define XAAC_HROM_SELCASE 3236   /* ixheaac_sel_case[5][8] */
+#define XAAC_HROM_XP2 3276       /* ixheaac_hbe_x_prod_cos_table_trans_2[512] */
+#define XAAC_HROM_XP3 3788       /* ixheaac_hbe_x_prod_cos_table_trans_3[512] */
+#define XAAC_HROM_XP4 4300       /* ixheaac_hbe_x_prod_cos_table_trans_4[512] */
+#define XAAC_HROM_XP41 4812      /* ixheaac_hbe_x_prod_cos_table_trans_4_1[512] */
+#define XAAC_HROM_SYN20 5324     /* ixheaac_synth_cos_table_kl_20[800] */
+#define XAAC_HROM_ANA40 6124     /* ixheaac_analy_cos_sin_table_kl_40[3200] */
+#define XAAC_HROM_WORDS 9324
+int32_t xaac_b200_set_hbe_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes);
+/* d_cfg [n][XAAC_HBE_CFG_WORDS] WORD32: the members of ia_esbr_hbe_txposer_struct that ixheaacd_qmf_hbe_data_reinit
+ * (hbe_trans.c:103-222, control plane, stays on the host) derives from the frequency tables, plus the call's pitch_in_bins */
+#define XAAC_HBE_SYNTH_SIZE 0
+#define XAAC_HBE_K_START 1
+#define XAAC_HBE_START_BAND 2
+#define XAAC_HBE_END_BAND 3
+#define XAAC_HBE_MAX_STRETCH 4
+#define XAAC_HBE_PITCH 5         /* ptr_frame_data->pitch_in_bins: < 12 plain products, >= 12 cross products */
+#define XAAC_HBE_USF4 6          /* upsamp_4_flag (must be 0) */
+#define XAAC_HBE_XOVER 8         /* x_over_qmf[6] */
+#define XAAC_HBE_CFG_WORDS 16
+/* d_state [n][XAAC_HBE_ST_WORDS] float, in/out: what the instance carries between calls, in the reference's own order */
+#define XAAC_HBE_ST_TAIL 0       /* [32]      ptr_input_buf[no_bins * synth_size ..+ synth_size) */
+#define XAAC_HBE_ST_SYNTH 32     /* [384]     synth_buf[0 .. 18 * synth_size) */
+#define XAAC_HBE_ST_ANAL 416     /* [384]     analy_buf[0 .. 18 * synth_size) */
+#define XAAC_HBE_ST_QIN 800      /* [12][128] qmf_in_buf rows 16..27 (the next call's rows 0..11); only columns
+                                  *           4 k_start .. 4 (k_start + synth_size) - 1 are ever non-zero / touched */
+#define XAAC_HBE_ST_QOUT 2336    /* [10][128] qmf_out_buf rows 32..41 (the next call's rows 0..9; the rows above are zero) */
+#define XAAC_HBE_ST_WORDS 3616
+/*   d_qmf_re / d_qmf_im [n][32][64] the frame's 32 new QMF slots (qmf_buf_real/imag + op_delay + SBR_HF_ADJ_OFFSET +
+ *                        ESBR_HBE_DELAY_OFFSET, decoder/ixheaacd_sbr_dec.c:899-904)
+ *   d_pv_re / d_pv_im   [n][32][64] ph_vocod_qmf_real/imag + op_delay + SBR_HF_ADJ_OFFSET; bands start_band..end_band-1 written
+ *   d_err [n] or NULL: 0, -1 / 0x80000000 (the reference's own failure returns), -2 (outside the supported subset) */
+int32_t xaac_b200_esbr_hbe_apply_dev(xaac_b200_ctx *ctx, const float *d_qmf_re, const float *d_qmf_im, float *d_pv_re,
+                                     float *d_pv_im, const int32_t *d_cfg, float *d_state, int32_t *d_err, int64_t n_units,
+                                     void *stream);
+
 /* Whole float eSBR stage: the eSBR branch of ixheaacd_sbr_dec (decoder/ixheaacd_sbr_dec.c:812-1006) for one USAC channel
  * per unit with apply_processing = 1, hbe_flag = 0, no PS / MPS / DRC, stereo_config_idx <= 0, 2:1, 16 time slots:
  *   history shift (memmove of op_delay + SBR_HF_ADJ_OFFSET = 8 rows of qmf_buf_* and sbr_qmf_out_*), 32-band analysis,
@@ -610,6 +663,21 @@ int32_t xaac_b200_esbr_dec_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_vi
                                const int32_t *d_core_in, const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar,
                                const int32_t *d_rg_par, float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err,
                                int64_t n_units, void *stream);
+
+/* The same stage with the harmonic transposer (ptr_header_data->hbe_flag = 1, sbr_patching_mode = 0 frames use it in the HF
+ * generator): the core QMF is delayed by ESBR_HBE_DELAY_OFFSET = 32 slots, so base.qmf_re / qmf_im are [n][72][64] (rows 32..71
+ * move to rows 0..39 every frame, the analysis bank writes rows 40..71, decoder/ixheaacd_sbr_dec.c:821-846), and the
+ * transposer (xaac_b200_esbr_hbe_apply_dev, fused history shift of its output rows) runs between the analysis bank and the HF
+ * generator.  Five launches.  d_hf_par must carry XAAC_EHF_HBE_FLAG = 1; d_err is [5][n] (row 4 = the transposer). */
+typedef struct xaac_b200_esbr_hbe_state_view {
+  xaac_b200_esbr_state_view base;
+  float *pv_re, *pv_im;     /* [n][40][64] ptr_sbr_dec->ph_vocod_qmf_real / ph_vocod_qmf_imag, rows 0..39 */
+  float *hbe_state;         /* [n][XAAC_HBE_ST_WORDS] */
+} xaac_b200_esbr_hbe_state_view;
+int32_t xaac_b200_esbr_dec_hbe_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const float *d_time_in,
+                                   const int32_t *d_core_in, const int32_t *d_hbe_cfg, const int32_t *d_hf_par,
+                                   int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par, float *d_out,
+                                   int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream);
 
 #ifdef __cplusplus
 }

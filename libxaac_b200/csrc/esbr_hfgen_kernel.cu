@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kEhWarps * 32) esbr_hfgen_kernel(EsbrHfgenArgs
       if (lane == 0 && p.err) p.err[u] = err;
       continue;
     }
-    const float *sre = p.src_re + u * kEhUnit, *sim = p.src_im + u * kEhUnit;
+    const float *sre = p.src_re + u * p.src_stride, *sim = p.src_im + u * p.src_stride;
     const float *pre = p.pv_re ? p.pv_re + u * kEhUnit : nullptr, *pim = p.pv_im ? p.pv_im + u * kEhUnit : nullptr;
     float *dre = p.dst_re + u * kEhUnit, *dim = p.dst_im + u * kEhUnit;
     float *bw_prev = p.bw_prev + 6 * u;

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kEsWarps * 32, 1) esbr_synth_kernel(EsbrSynthA
       }
     } else {  // stage mode: ixheaacd_esbr_synthesis_regrp in the load — low band from qmf_buf, high band from sbr_qmf_out
       const int xo_first = p.rg_par[4 * u], xo_rest = p.rg_par[4 * u + 1], stop = p.rg_par[4 * u + 2];
-      const float *lo = (lane < 16 ? p.rg_low_re : p.rg_low_im) + u * 2560 + 128 + 4 * (lane & 15);
+      const float *lo = (lane < 16 ? p.rg_low_re : p.rg_low_im) + u * p.rg_low_stride + 128 + 4 * (lane & 15);
       const float *hi = (lane < 16 ? p.rg_high_re : p.rg_high_im) + u * 2560 + 128 + 4 * (lane & 15);
       const int k0 = 4 * (lane & 15);
 #pragma unroll 4
@@ -632,19 +632,22 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
     __syncwarp();
     // lane = band: t_cos rotation (generic:1490-1505), WORD32 -> float (x 1/256), coalesced rows of the output matrix
     if (p.stage_re) {
-      float *sre = p.stage_re + u * 2560, *sim = p.stage_im + u * 2560;
-      {  // history rows: 32..39 -> 0..7, all 64 bands
+      const int hist = p.stage_hist_rows;
+      float *sre = p.stage_re + u * (long long)(32 + hist) * 64, *sim = p.stage_im + u * (long long)(32 + hist) * 64;
+      for (int r0 = 0; r0 < hist; r0 += 8) {  // history rows: 32.. -> 0.. (forward copy, 8 rows at a time), all 64 bands
         float vr[16], vi[16];
 #pragma unroll
         for (int q = 0; q < 16; q++) {
-          vr[q] = sre[2048 + 32 * q + lane];
-          vi[q] = sim[2048 + 32 * q + lane];
+          vr[q] = sre[64 * (32 + r0) + 32 * q + lane];
+          vi[q] = sim[64 * (32 + r0) + 32 * q + lane];
         }
+        __syncwarp();
 #pragma unroll
         for (int q = 0; q < 16; q++) {
-          sre[32 * q + lane] = vr[q];
-          sim[32 * q + lane] = vi[q];
+          sre[64 * r0 + 32 * q + lane] = vr[q];
+          sim[64 * r0 + 32 * q + lane] = vi[q];
         }
+        __syncwarp();
       }
 #pragma unroll 2
       for (int s = 0; s < 32; s++) {
@@ -653,8 +656,8 @@ __global__ void __launch_bounds__(kEaWarps * 32, 1) esbr_anal_kernel(EsbrAnalArg
         const long long x = (long long)im * tc, y = (long long)re * ts;
         long long d = (long long)((unsigned long long)x - (unsigned long long)y);
         if (((x ^ y) & (x ^ d)) < 0) d = x < 0 ? (long long)0x8000000000000000ULL : 0x7fffffffffffffffLL;
-        sre[64 * (8 + s) + lane] = __fmul_rn(__int2float_rn(r2), 1.0f / 256.0f);
-        sim[64 * (8 + s) + lane] = __fmul_rn(__int2float_rn((i32)(d >> 31)), 1.0f / 256.0f);
+        sre[64 * (hist + s) + lane] = __fmul_rn(__int2float_rn(r2), 1.0f / 256.0f);
+        sim[64 * (hist + s) + lane] = __fmul_rn(__int2float_rn((i32)(d >> 31)), 1.0f / 256.0f);
       }
       if (lane == 0) {
         p.pos[2 * u] = pos;

@@ -303,6 +303,7 @@ struct EsbrSynthArgs {
   // slots before stop_border (qmf_sb_prev), x_over of the others (sub_band_start), stop_border (2 * border_vec[0]), 0}
   const float *rg_low_re = nullptr, *rg_low_im = nullptr, *rg_high_re = nullptr, *rg_high_im = nullptr;  // [n][40][64]
   const int32_t *rg_par = nullptr;                                                                       // [n][4]
+  long long rg_low_stride = 2560;  // floats per unit of rg_low_* (72 x 64 with the harmonic transposer)
   int16_t *pcm16 = nullptr;  // optional fused ixheaacd_samples_sat: unit u = stream u / pcm_ch_fac, channel u % pcm_ch_fac;
   int pcm_ch_fac = 1;        // sample i of the unit goes to pcm16[(stream * 2048 + i) * pcm_ch_fac + channel]
 };
@@ -317,6 +318,9 @@ struct EsbrAnalArgs {
   // stage mode: the unit's qmf_buf_real / imag arrays [n][40][64]; rows 32..39 move to rows 0..7 first (the memmove at the
   // top of ixheaacd_sbr_dec's eSBR branch, sbr_dec.c:836-846, op_delay 6 + SBR_HF_ADJ_OFFSET 2), slot s goes to row 8 + s
   float *stage_re = nullptr, *stage_im = nullptr;
+  // with the harmonic transposer the arrays are [n][72][64]: the core QMF is delayed by ESBR_HBE_DELAY_OFFSET = 32 slots
+  // (codec_x_delay, sbr_dec.c:821-823), rows 32..71 move to 0..39 and slot s goes to row 40 + s
+  int stage_hist_rows = 8;           // 8 or 40
   int32_t *states;       // [n][320] anal_filter_states_32, in/out
   int32_t *pos;          // [n][2] {state_new_samples_pos_low_32 - anal_filter_states_32, filter_pos_32 - esbr_qmf_c}, in/out
   float *qmf;            // unit u writes slot s at qmf + u * out_stride + 128 * s: re at +0..31, im at +64..95
@@ -342,6 +346,7 @@ struct EsbrHfgenArgs {
   int32_t *err;                  // [n] or null
   long long n_units;
   int shift_rows = 0;            // stage mode: rows 32..39 of dst move to rows 0..7 first (sbr_dec.c:848-856)
+  long long src_stride = 2560;   // floats per unit of src_* (72 x 64 with the harmonic transposer's delayed core QMF)
 };
 cudaError_t launch_esbr_hfgen(const EsbrHfgenArgs &args, int num_sms, cudaStream_t stream);
 
@@ -366,5 +371,28 @@ cudaError_t launch_esbr_envcalc(const EsbrEnvcalcArgs &args, int num_sms, cudaSt
 
 size_t imdct_smem_bytes();
 cudaError_t launch_imdct(const ImdctArgs &args, int num_sms, cudaStream_t stream);
+
+// QMF harmonic transposer (ixheaacd_qmf_hbe_apply): ROM word offsets = XAAC_HROM_*, cfg words = XAAC_HBE_*, state words =
+// XAAC_HBE_ST_* of include/xaac_b200.h
+constexpr int kHromWin = 0, kHromSynCos = 1560, kHromAnaCs = 1720, kHromCosTrans = 2040, kHromFftTw = 2488, kHromTw24 = 3004,
+              kHromTw48 = 3036, kHromPvCos = 3100, kHromPvSin = 3164, kHromInterp = 3228, kHromSelCase = 3236, kHromXp2 = 3276,
+              kHromXp3 = 3788, kHromXp4 = 4300, kHromXp41 = 4812, kHromSyn20 = 5324, kHromAna40 = 6124, kHromWords = 9324;
+constexpr int kHbeSynthSize = 0, kHbeKStart = 1, kHbeStartBand = 2, kHbeEndBand = 3, kHbeMaxStretch = 4, kHbePitch = 5,
+              kHbeUsf4 = 6, kHbeXover = 8, kHbeCfgWords = 16;
+constexpr int kHbeStTail = 0, kHbeStSynth = 32, kHbeStAnal = 416, kHbeStQin = 800, kHbeStQout = 2336, kHbeStWords = 3616;
+struct EsbrHbeArgs {
+  const float *qmf_re, *qmf_im;  // first of the 32 new QMF rows of unit 0; unit u at + u * in_stride floats, rows of 64
+  float *pv_re, *pv_im;          // first of the 32 output rows of unit 0; unit u at + u * out_stride floats
+  long long in_stride, out_stride;
+  const int32_t *cfg;            // [n][16]
+  float *state;                  // [n][3616] in/out
+  int32_t *err;                  // [n] or null
+  const float *rom;              // device copy of the XAAC_HROM_* blob
+  long long n_units;
+  // stage mode: pv_* point at row 8 of [n][40][64] arrays (ph_vocod_qmf_real / imag); rows 32..39 move to rows 0..7 first
+  // (sbr_dec.c:858-867)
+  int shift_rows = 0;
+};
+cudaError_t launch_esbr_hbe(const EsbrHbeArgs &args, int num_sms, cudaStream_t stream);
 
 }  // namespace xb

@@ -29,6 +29,7 @@ struct xaac_b200_ctx {
   uint8_t *d_rom_usac = nullptr;  // USAC FD tables (XAAC_UROM_*)
   uint8_t *d_rom_esbr = nullptr;  // table image of esbr_synth_kernel
   float *d_rom_rphase = nullptr;  // ixheaac_random_phase[512][2]
+  float *d_rom_hbe = nullptr;     // XAAC_HROM_* blob of the harmonic transposer
   int esbr_periodic = 0;
   bool have_ps_rom = false;
   int ps_rot_nosat = 0;           // no fractional-delay phase factor equals -32768 (16x16 rotations cannot saturate)
@@ -199,6 +200,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   if (ctx->d_rom_usac) cudaFree(ctx->d_rom_usac);
   if (ctx->d_rom_esbr) cudaFree(ctx->d_rom_esbr);
   if (ctx->d_rom_rphase) cudaFree(ctx->d_rom_rphase);
+  if (ctx->d_rom_hbe) cudaFree(ctx->d_rom_hbe);
   delete ctx;
 }
 
@@ -1162,16 +1164,51 @@ int32_t xaac_b200_esbr_env_calc_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im
   return XAAC_B200_OK;
 }
 
+int32_t xaac_b200_set_hbe_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
+  if (!ctx || !tables) return bad_arg(ctx, "null");
+  if (bytes < (size_t)xb::kHromWords * 4) return bad_arg(ctx, "harmonic-transposer ROM blob shorter than 37296 bytes");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaError_t e = ctx->d_rom_hbe ? cudaSuccess : cudaMalloc((void **)&ctx->d_rom_hbe, (size_t)xb::kHromWords * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_rom_hbe, tables, (size_t)xb::kHromWords * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(ctx, e, "cudaMemcpy(hbe rom)");
+  return XAAC_B200_OK;
+}
+
+static int32_t hbe_launch(xaac_b200_ctx *ctx, const float *d_qmf_re, const float *d_qmf_im, int64_t in_stride, float *d_pv_re,
+                          float *d_pv_im, int64_t out_stride, const int32_t *d_cfg, float *d_state, int32_t *d_err,
+                          int64_t n_units, void *stream) {
+  xb::EsbrHbeArgs a;
+  a.qmf_re = d_qmf_re; a.qmf_im = d_qmf_im; a.pv_re = d_pv_re; a.pv_im = d_pv_im; a.in_stride = in_stride; a.out_stride = out_stride;
+  a.cfg = d_cfg; a.state = d_state; a.err = d_err; a.rom = ctx->d_rom_hbe; a.n_units = n_units;
+  LAUNCH("esbr_hbe_kernel", stream, xb::launch_esbr_hbe(a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_esbr_hbe_apply_dev(xaac_b200_ctx *ctx, const float *d_qmf_re, const float *d_qmf_im, float *d_pv_re,
+                                     float *d_pv_im, const int32_t *d_cfg, float *d_state, int32_t *d_err, int64_t n_units,
+                                     void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->d_rom_hbe) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_hbe_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_qmf_re || !d_qmf_im || !d_pv_re || !d_pv_im || !d_cfg || !d_state) return bad_arg(ctx, "null buffer");
+  return hbe_launch(ctx, d_qmf_re, d_qmf_im, 2048, d_pv_re, d_pv_im, 2048, d_cfg, d_state, d_err, n_units, stream);
+}
+
 // Whole eSBR stage (eSBR branch of ixheaacd_sbr_dec for USAC mono / stereo channels without harmonic transposer, PS, MPS):
 // analysis bank (+ history shift, + core hand-over) -> HF generator (+ history shift) -> envelope adjuster -> synthesis bank
 // (+ regrouping, + optional PCM16 hand-over).  Four launches on one stream.
-int32_t xaac_b200_esbr_dec_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view *st, const float *d_time_in,
-                               const int32_t *d_core_in, const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar,
-                               const int32_t *d_rg_par, float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err,
-                               int64_t n_units, void *stream) {
-  if (!ctx) return XAAC_B200_ERR_ARG;
-  if (!ctx->d_rom_esbr || !ctx->d_rom_rphase) {
-    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_rom / xaac_b200_set_esbr_envcalc_rom have not been called");
+static int32_t esbr_dec_impl(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view *st, float *pv_re, float *pv_im,
+                             float *hbe_state, const int32_t *d_hbe_cfg, const float *d_time_in, const int32_t *d_core_in,
+                             const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par,
+                             float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream) {
+  const bool hbe = pv_re != nullptr;
+  if (!ctx->d_rom_esbr || !ctx->d_rom_rphase || (hbe && !ctx->d_rom_hbe)) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_rom / _set_esbr_envcalc_rom / _set_hbe_rom have not been called");
     return XAAC_B200_ERR_NO_ROM;
   }
   if (n_units < 0) return bad_arg(ctx, "n_units");
@@ -1184,18 +1221,28 @@ int32_t xaac_b200_esbr_dec_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_vi
   if (d_pcm16 && (ch_fac < 1 || ch_fac > 8 || n_units % ch_fac != 0)) return bad_arg(ctx, "ch_fac must be 1..8 and divide n_units");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
+  const long long low_stride = hbe ? 72 * 64 : 40 * 64;
   {
     xb::EsbrAnalArgs a;
     a.time_in = d_time_in; a.core_in = d_time_in ? nullptr : d_core_in; a.states = st->anal_states; a.pos = st->anal_pos;
     a.qmf = nullptr; a.stage_re = st->qmf_re; a.stage_im = st->qmf_im; a.err = d_err; a.rom = ctx->d_rom_esbr;
-    a.n_units = n_units; a.periodic = ctx->esbr_periodic;
+    a.n_units = n_units; a.periodic = ctx->esbr_periodic; a.stage_hist_rows = hbe ? 40 : 8;
     LAUNCH("esbr_anal_kernel", stream, xb::launch_esbr_anal(a, ctx->num_sms, s));
+  }
+  if (hbe) {  // sbr_dec.c:896-907: the frame's new slots (rows 40..71) -> ph_vocod_qmf rows 8..39
+    xb::EsbrHbeArgs a;
+    a.qmf_re = st->qmf_re + 40 * 64; a.qmf_im = st->qmf_im + 40 * 64; a.in_stride = low_stride;
+    a.pv_re = pv_re + 8 * 64; a.pv_im = pv_im + 8 * 64; a.out_stride = 40 * 64;
+    a.cfg = d_hbe_cfg; a.state = hbe_state; a.err = d_err ? d_err + 4 * n_units : nullptr; a.rom = ctx->d_rom_hbe;
+    a.n_units = n_units; a.shift_rows = 1;
+    LAUNCH("esbr_hbe_kernel", stream, xb::launch_esbr_hbe(a, ctx->num_sms, s));
+    ctx->launches++;
   }
   {
     xb::EsbrHfgenArgs a;
-    a.src_re = st->qmf_re; a.src_im = st->qmf_im; a.pv_re = nullptr; a.pv_im = nullptr; a.dst_re = st->out_re; a.dst_im = st->out_im;
+    a.src_re = st->qmf_re; a.src_im = st->qmf_im; a.pv_re = pv_re; a.pv_im = pv_im; a.dst_re = st->out_re; a.dst_im = st->out_im;
     a.par = d_hf_par; a.bw_prev = st->bw_prev; a.patch_out = st->patch; a.err = d_err ? d_err + n_units : nullptr;
-    a.n_units = n_units; a.shift_rows = 1;
+    a.n_units = n_units; a.shift_rows = 1; a.src_stride = low_stride;
     LAUNCH("esbr_hfgen_kernel", stream, xb::launch_esbr_hfgen(a, ctx->num_sms, s));
   }
   {
@@ -1209,11 +1256,32 @@ int32_t xaac_b200_esbr_dec_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_vi
     a.qmf = nullptr; a.states = st->synth_states; a.pos = st->synth_pos; a.out = d_out; a.err = d_err ? d_err + 3 * n_units : nullptr;
     a.rom = ctx->d_rom_esbr; a.n_units = n_units; a.periodic = ctx->esbr_periodic;
     a.rg_low_re = st->qmf_re; a.rg_low_im = st->qmf_im; a.rg_high_re = st->out_re; a.rg_high_im = st->out_im; a.rg_par = d_rg_par;
+    a.rg_low_stride = low_stride;
     a.pcm16 = d_pcm16; a.pcm_ch_fac = d_pcm16 ? ch_fac : 1;
     LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(a, ctx->num_sms, s));
   }
   ctx->launches += 4;
   return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_esbr_dec_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view *st, const float *d_time_in,
+                               const int32_t *d_core_in, const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar,
+                               const int32_t *d_rg_par, float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err,
+                               int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  return esbr_dec_impl(ctx, st, nullptr, nullptr, nullptr, nullptr, d_time_in, d_core_in, d_hf_par, d_ec_ipar, d_ec_fpar, d_rg_par,
+                       d_out, d_pcm16, ch_fac, d_err, n_units, stream);
+}
+
+// The same stage with the harmonic transposer (hbe_flag = 1): five launches.
+int32_t xaac_b200_esbr_dec_hbe_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const float *d_time_in,
+                                   const int32_t *d_core_in, const int32_t *d_hbe_cfg, const int32_t *d_hf_par,
+                                   int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par, float *d_out,
+                                   int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!st || !st->pv_re || !st->pv_im || !st->hbe_state || !d_hbe_cfg) return bad_arg(ctx, "harmonic-transposer state / cfg missing");
+  return esbr_dec_impl(ctx, &st->base, st->pv_re, st->pv_im, st->hbe_state, d_hbe_cfg, d_time_in, d_core_in, d_hf_par, d_ec_ipar,
+                       d_ec_fpar, d_rg_par, d_out, d_pcm16, ch_fac, d_err, n_units, stream);
 }
 
 int32_t xaac_b200_kernel_timing(xaac_b200_ctx *ctx, int32_t enable) {

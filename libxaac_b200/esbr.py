@@ -213,3 +213,88 @@ def esbr_dec(ctx, state, core, hf_par, ec_ipar, ec_fpar, rg_par, out=None, pcm16
                                          ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_esbr_dec_dev")
     return out, err
+
+
+HBE_CFG_WORDS, HBE_ST_WORDS = 16, 3616
+
+
+class EsbrHbeBatch:
+    """State of n harmonic-transposer instances (ia_esbr_hbe_txposer_struct): float32 [n, 3616] in the XAAC_HBE_ST_* layout."""
+
+    def __init__(self, n_units, device="cuda:0"):
+        self.n = int(n_units)
+        self.state = torch.zeros((self.n, HBE_ST_WORDS), dtype=torch.float32, device=device)
+
+
+def esbr_qmf_hbe_apply(ctx, hbe, qmf_re, qmf_im, pv_re, pv_im, cfg, err=None, stream=None):
+    """Batched drop-in for ixheaacd_qmf_hbe_apply (decoder/ixheaacd_hbe_trans.c:224): qmf_re / qmf_im float32 [n, 32, 64] are
+    the frame's new QMF slots, pv_re / pv_im float32 [n, 32, 64] receive bands start_band..end_band-1 of the phase-vocoder
+    output, cfg int32 [n, 16] (XAAC_HBE_* words), hbe.state is updated in place.  Returns err int32 [n]."""
+    n = hbe.n
+    for t, nm in ((qmf_re, "qmf_re"), (qmf_im, "qmf_im"), (pv_re, "pv_re"), (pv_im, "pv_im")):
+        _chk(t, torch.float32, (n, 32, 64), nm, "cuda")
+    _chk(cfg, torch.int32, (n, HBE_CFG_WORDS), "cfg", "cuda")
+    _chk(hbe.state, torch.float32, (n, HBE_ST_WORDS), "state", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=cfg.device)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
+    if stream is None:
+        stream = torch.cuda.current_stream(cfg.device)
+    rc = ctx._lib.xaac_b200_esbr_hbe_apply_dev(ctx.handle, _ptr(qmf_re), _ptr(qmf_im), _ptr(pv_re), _ptr(pv_im), _ptr(cfg),
+                                               _ptr(hbe.state), _ptr(err), n, ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_hbe_apply_dev")
+    return err
+
+
+class _EsbrHbeStateView(ctypes.Structure):
+    _fields_ = [("base", _EsbrStateView), ("pv_re", ctypes.c_void_p), ("pv_im", ctypes.c_void_p), ("hbe_state", ctypes.c_void_p)]
+
+
+class EsbrDecHbeBatch(EsbrDecBatch):
+    """State of the eSBR stage with the harmonic transposer (xaac_b200_esbr_hbe_state_view): the core QMF arrays carry the
+    transposer's 32-slot delay (72 rows), plus the phase-vocoder arrays and the transposer instances."""
+    SHAPES = dict(EsbrDecBatch.SHAPES, qmf_re=((72, 64), torch.float32), qmf_im=((72, 64), torch.float32),
+                  pv_re=((40, 64), torch.float32), pv_im=((40, 64), torch.float32), hbe_state=((HBE_ST_WORDS,), torch.float32))
+
+    def view(self):
+        base = _EsbrStateView(**{k: ctypes.c_void_p(getattr(self, k).data_ptr()) for k in EsbrDecBatch.SHAPES})
+        return _EsbrHbeStateView(base, ctypes.c_void_p(self.pv_re.data_ptr()), ctypes.c_void_p(self.pv_im.data_ptr()),
+                                 ctypes.c_void_p(self.hbe_state.data_ptr()))
+
+
+def esbr_dec_hbe(ctx, state, core, hbe_cfg, hf_par, ec_ipar, ec_fpar, rg_par, out=None, pcm16=None, ch_fac=1, err=None,
+                 stream=None, want_float=True):
+    """Batched drop-in for the eSBR branch of ixheaacd_sbr_dec with hbe_flag = 1 (USAC channel, harmonic transposer between
+    the analysis bank and the HF generator).  Arguments as esbr_dec plus hbe_cfg int32 [n, 16]; state is an EsbrDecHbeBatch.
+    Returns (out, err[5, n])."""
+    n = state.n
+    dev = hf_par.device
+    _chk(core, core.dtype if core.dtype in (torch.float32, torch.int32) else torch.float32, (n, 1024), "core", "cuda")
+    _chk(hbe_cfg, torch.int32, (n, HBE_CFG_WORDS), "hbe_cfg", "cuda")
+    _chk(hf_par, torch.int32, (n, EHF_PAR_WORDS), "hf_par", "cuda")
+    _chk(ec_ipar, torch.int32, (n, EEC_IPAR_WORDS), "ec_ipar", "cuda")
+    _chk(ec_fpar, torch.float32, (n, EEC_FPAR_WORDS), "ec_fpar", "cuda")
+    _chk(rg_par, torch.int32, (n, 4), "rg_par", "cuda")
+    if out is None and want_float:
+        out = torch.empty((n, 2048), dtype=torch.float32, device=dev)
+    if out is None and pcm16 is None:
+        raise ValueError("esbr_dec_hbe: neither float output nor pcm16 requested")
+    if out is not None:
+        _chk(out, torch.float32, (n, 2048), "out", "cuda")
+    if pcm16 is not None:
+        _chk(pcm16, torch.int16, (n // ch_fac, 2048, ch_fac), "pcm16", "cuda")
+    if err is None:
+        err = torch.empty((5, n), dtype=torch.int32, device=dev)
+    else:
+        _chk(err, torch.int32, (5, n), "err", "cuda")
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    v = state.view()
+    rc = ctx._lib.xaac_b200_esbr_dec_hbe_dev(ctx.handle, ctypes.byref(v), _ptr(core) if core.dtype == torch.float32 else None,
+                                             _ptr(core) if core.dtype == torch.int32 else None, _ptr(hbe_cfg), _ptr(hf_par),
+                                             _ptr(ec_ipar), _ptr(ec_fpar), _ptr(rg_par), _ptr(out) if out is not None else None,
+                                             _ptr(pcm16) if pcm16 is not None else None, int(ch_fac), _ptr(err), n,
+                                             ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_dec_hbe_dev")
+    return out, err

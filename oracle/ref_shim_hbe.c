@@ -61,7 +61,7 @@ const void *ref_rom_hbe_tables(int *bytes) {
 }
 
 /* ---- flat <-> ia_esbr_hbe_txposer_struct ---- */
-static void hbe_cfg_pack(int32_t *cfg, const ia_esbr_hbe_txposer_struct *t, int pitch) {
+void hbe_cfg_pack(int32_t *cfg, const ia_esbr_hbe_txposer_struct *t, int pitch) {
   memset(cfg, 0, 4 * XO_HBE_CFG_WORDS);
   cfg[XO_HBE_SYNTH_SIZE] = t->synth_size;
   cfg[XO_HBE_K_START] = t->k_start;
@@ -73,7 +73,7 @@ static void hbe_cfg_pack(int32_t *cfg, const ia_esbr_hbe_txposer_struct *t, int 
   for (int i = 0; i < 6; i++) cfg[XO_HBE_XOVER + i] = t->x_over_qmf[i];
 }
 /* returns 0 when the instance satisfies the invariants the flat state relies on */
-static int hbe_state_pack(float *st, const ia_esbr_hbe_txposer_struct *t) {
+int hbe_state_pack(float *st, const ia_esbr_hbe_txposer_struct *t) {
   const int S = t->synth_size;
   int bad = 0;
   memset(st, 0, 4 * XO_HBE_ST_WORDS);
@@ -110,9 +110,9 @@ static const FLOAT32 *prot(int len) { /* = the file-static ixheaacd_map_prot_fil
  * (synth_size 20); they must reproduce cfg (use ref_esbr_hbe_reinit to derive cfg from them). */
 int ref_esbr_hbe_apply_tbl(const int32_t *cfg, float *state, const float *qmf_re, const float *qmf_im, float *pv_re,
                            float *pv_im, const int16_t *tbl) {
-  static ia_esbr_hbe_txposer_struct t;
-  static double pers[16384]; /* 128 KB >= MAX_HBE_PERSISTENT_SIZE for the 2:1 system */
-  static ia_sbr_header_data_struct hd;
+  static __thread ia_esbr_hbe_txposer_struct t;
+  static __thread double pers[16384]; /* 128 KB >= MAX_HBE_PERSISTENT_SIZE for the 2:1 system */
+  static __thread ia_sbr_header_data_struct hd;
   WORD32 used = 0;
   memset(pers, 0, sizeof(pers));
   ixheaacd_esbr_hbe_data_init(&t, 1024, 0, 2048, pers, &used);
@@ -164,8 +164,8 @@ int ref_esbr_hbe_apply_tbl(const int32_t *cfg, float *state, const float *qmf_re
   t.analy_wind_coeff = (FLOAT32 *)prot(2 * S);
   hbe_state_unpack(&t, state);
   memset(&hd, 0, sizeof(hd));
-  static ia_freq_band_data_struct fb;
-  static WORD16 lo[64], hi[64];
+  static __thread ia_freq_band_data_struct fb;
+  static __thread WORD16 lo[64], hi[64];
   if (tbl) {
     memset(&fb, 0, sizeof(fb));
     fb.num_sf_bands[0] = tbl[0];
@@ -178,7 +178,7 @@ int ref_esbr_hbe_apply_tbl(const int32_t *cfg, float *state, const float *qmf_re
   } else if (S == 20) {
     return -2;
   }
-  static FLOAT32 in_re[32][64], in_im[32][64], o_re[32][64], o_im[32][64];
+  static __thread FLOAT32 in_re[32][64], in_im[32][64], o_re[32][64], o_im[32][64];
   memcpy(in_re, qmf_re, sizeof(in_re));
   memcpy(in_im, qmf_im, sizeof(in_im));
   memcpy(o_re, pv_re, sizeof(o_re));
@@ -206,6 +206,72 @@ void ref_esbr_hbe_apply_batch(const int32_t *cfg, float *state, const float *qmf
   }
 }
 
+#ifndef XAAC_REF_TAPS
+/* ---- CPU baseline of bench.py --workload xheaac_stereo_chain (BASELINE configs[4]): one stereo xHE-AAC frame per pair of
+ * units through the reference's own functions, harmonic transposer included: ixheaacd_fd_frm_dec -> x 2^-15 -> the eSBR branch
+ * of ixheaacd_sbr_dec with hbe_flag = 1 spelled out with its leaf functions (history memmoves incl. the 32-slot codec delay,
+ * ixheaacd_esbr_analysis_filt_block, ixheaacd_qmf_hbe_apply, ixheaacd_generate_hf, ixheaacd_sbr_env_calc, regrouping, synthesis
+ * core) -> ixheaacd_samples_sat.  q6 = [n] x {qmf_re[72*64], qmf_im[72*64], out_re[2560], out_im[2560], pv_re[2560], pv_im[2560]}.
+ * The transposer instance is rebuilt from the flat state on every call (about 130 KB of memset / memcpy per unit in this arm
+ * that the real decoder does not pay: a few per cent of the unit's time). */
+int ref_usac_fd_frm_dec(int32_t *coef, int32_t *overlap, int win_seq, int win_shape, int win_shape_prev, int32_t *out);
+void ref_esbr_anal32(const float *time_in, int32_t *states, int32_t *pos, float *qmf);
+int ref_esbr_generate_hf(const float *src_re, const float *src_im, const float *pv_re, const float *pv_im, float *dst_re,
+                         float *dst_im, const int32_t *par, float *bw_prev, int32_t *patch_out);
+int ref_esbr_env_calc(float *re, float *im, int32_t *ipar, const float *fpar, float *state);
+void ref_esbr_synth64(const float *qmf, int32_t *fs, int32_t *pos, float *out);
+#define Q6_WORDS (2 * 4608 + 4 * 2560)
+void ref_xheaac_hbe_chain_batch(int32_t *coef, int32_t *overlap, const int32_t *win_seq, const int32_t *win_shape,
+                                const int32_t *win_shape_prev, float *q6, int32_t *anal, int32_t *apos, int32_t *synth,
+                                int32_t *spos, float *bw, int32_t *patch, float *ec, float *hbe_state, const int32_t *hbe_cfg,
+                                const int16_t *hbe_tbl, const int32_t *hf_par, int32_t *ec_ipar, const float *ec_fpar,
+                                const int32_t *rg, int16_t *pcm /* [n/2][2048][2] */, int32_t *err, int a, int b) {
+  static __thread int32_t core[1024];
+  static __thread float tin[1024], qa[32 * 128], m[32 * 128], tout[2048], lre[2560], lim[2560];
+  for (int u = a; u < b; u++) {
+    float *q = q6 + (size_t)u * Q6_WORDS;
+    float *qre = q, *qim = q + 4608, *ore = q + 9216, *oim = ore + 2560, *pre = oim + 2560, *pim = pre + 2560;
+    int e = ref_usac_fd_frm_dec(coef + (size_t)u * 1024, overlap + (size_t)u * 1024, win_seq[u], win_shape[u],
+                                win_shape_prev[u], core);
+    for (int k = 0; k < 1024; k++) tin[k] = (FLOAT32)((FLOAT32)core[k] * (FLOAT32)(0.000030517578125));
+    memmove(qre, qre + 32 * 64, 40 * 64 * sizeof(float));
+    memmove(qim, qim + 32 * 64, 40 * 64 * sizeof(float));
+    memmove(ore, ore + 32 * 64, 8 * 64 * sizeof(float));
+    memmove(oim, oim + 32 * 64, 8 * 64 * sizeof(float));
+    memmove(pre, pre + 32 * 64, 8 * 64 * sizeof(float));
+    memmove(pim, pim + 32 * 64, 8 * 64 * sizeof(float));
+    ref_esbr_anal32(tin, anal + (size_t)u * 320, apos + 2 * u, qa);
+    for (int s = 0; s < 32; s++) {
+      memcpy(qre + 64 * (40 + s), qa + 128 * s, 32 * sizeof(float));
+      memcpy(qim + 64 * (40 + s), qa + 128 * s + 64, 32 * sizeof(float));
+    }
+    e |= ref_esbr_hbe_apply_tbl(hbe_cfg + (size_t)u * XO_HBE_CFG_WORDS, hbe_state + (size_t)u * XO_HBE_ST_WORDS, qre + 40 * 64,
+                                qim + 40 * 64, pre + 8 * 64, pim + 8 * 64, hbe_tbl);
+    memcpy(lre, qre, sizeof(lre));
+    memcpy(lim, qim, sizeof(lim));
+    e |= ref_esbr_generate_hf(lre, lim, pre, pim, ore, oim, hf_par + (size_t)u * XO_EHF_PAR_WORDS, bw + 6 * u, patch + 8 * u);
+    e |= ref_esbr_env_calc(ore, oim, ec_ipar + (size_t)u * XO_EEC_IPAR_WORDS, ec_fpar + (size_t)u * XO_EEC_FPAR_WORDS,
+                           ec + (size_t)u * 640);
+    const int32_t *r = rg + 4 * u;
+    for (int s = 0; s < 32; s++) {
+      const int xo = s < r[2] ? r[0] : r[1];
+      for (int k = 0; k < 64; k++) {
+        m[128 * s + k] = k < xo ? qre[64 * (2 + s) + k] : ore[64 * (2 + s) + k];
+        m[128 * s + 64 + k] = k < xo ? qim[64 * (2 + s) + k] : oim[64 * (2 + s) + k];
+      }
+    }
+    ref_esbr_synth64(m, synth + (size_t)u * 1280, spos + 2 * u, tout);
+    int16_t *o = pcm + (size_t)(u / 2) * 4096 + (u & 1);
+    for (int i = 0; i < 2048; i++) {
+      float v = tout[i];
+      if (v > 32767.0f) v = 32767.0f; else if (v < -32768.0f) v = -32768.0f;
+      o[2 * i] = (int16_t)v;
+    }
+    err[u] = e;
+  }
+}
+#endif
+
 /* ixheaacd_qmf_hbe_data_reinit (hbe_trans.c:103-222) on flat frequency tables, for test-side construction of cfg[] */
 int ref_esbr_hbe_reinit(const int16_t *tbl_lo, int num_lo, const int16_t *tbl_hi, int num_hi, int32_t *cfg) {
   static ia_esbr_hbe_txposer_struct t;
@@ -224,6 +290,8 @@ int ref_esbr_hbe_reinit(const int16_t *tbl_lo, int num_lo, const int16_t *tbl_hi
 
 #ifdef XAAC_REF_TAPS
 /* ---- tap (linked into xaacdec_tap only) ---- */
+int32_t g_hbe_cfg[XO_HBE_CFG_WORDS];
+int g_hbe_called;
 WORD32 __real_ixheaacd_qmf_hbe_apply(ia_esbr_hbe_txposer_struct *t, FLOAT32 a[][64], FLOAT32 b[][64], WORD32 num_columns,
                                      FLOAT32 c[][64], FLOAT32 d[][64], WORD32 pitch_in_bins, ia_sbr_header_data_struct *hd);
 WORD32 __wrap_ixheaacd_qmf_hbe_apply(ia_esbr_hbe_txposer_struct *t, FLOAT32 qre[][64], FLOAT32 qim[][64], WORD32 num_columns,
@@ -260,6 +328,8 @@ WORD32 __wrap_ixheaacd_qmf_hbe_apply(ia_esbr_hbe_txposer_struct *t, FLOAT32 qre[
     fprintf(stderr, "hbe call: S %d k_start %d bands %d..%d stretch %d xo %d %d %d %d pitch %d fft_null %d ret %d\n", t->synth_size,
             t->k_start, t->start_band, t->end_band, t->max_stretch, t->x_over_qmf[0], t->x_over_qmf[1], t->x_over_qmf[2],
             t->x_over_qmf[3], pitch_in_bins, fft_null, ret);
+  hbe_cfg_pack(g_hbe_cfg, t, pitch_in_bins); /* for the whole-stage tap (ref_taps_esbr.c) */
+  g_hbe_called++;
   if (rec) {
     const int S = t->synth_size;
     int bad = S < 1 || S > 20;

@@ -245,6 +245,9 @@ static int esd_count, esd_rec;
 static int32_t esd_head[16];
 static float esd_tin[1024];
 static esd_state_t esd_in, esd_out;
+static int esh_rec;
+static void esh_pre(ia_sbr_dec_struct *d, ia_sbr_header_data_struct *h, ia_sbr_frame_info_data_struct *f, ia_sbr_tables_struct *t,
+                    int eligible);
 void esbr_stage_tap_pre(ia_sbr_dec_struct *d, ia_sbr_header_data_struct *h, ia_sbr_frame_info_data_struct *f,
                         ia_ps_dec_struct *ps, ia_sbr_tables_struct *t, int apply, int low_pow, int aot, int ldmps, int drc_on) {
   static int tried = 0;
@@ -253,9 +256,11 @@ void esbr_stage_tap_pre(ia_sbr_dec_struct *d, ia_sbr_header_data_struct *h, ia_s
     tried = 1;
     esd_fp = open_tap("esd", "esd");
   }
-  esd_rec = esd_fp && esd_count < tap_max() && h->enh_sbr && h->usac_flag && !low_pow && !ldmps && !drc_on &&
-            h->num_time_slots == 16 && d->str_codec_qmf_bank.no_channels == 32 && d->str_synthesis_qmf_bank.no_channels == 64;
-  if (!esd_rec) return;
+  const int eligible = h->enh_sbr && h->usac_flag && !low_pow && !ldmps && !drc_on && h->num_time_slots == 16 &&
+                       d->str_codec_qmf_bank.no_channels == 32 && d->str_synthesis_qmf_bank.no_channels == 64;
+  esd_rec = esd_fp && esd_count < tap_max() && eligible;
+  esh_pre(d, h, f, t, eligible);
+  if (!esd_rec && !esh_rec) return;
   int ch = 0;
   while (ch < 7 && chan[ch] && chan[ch] != (void *)d) ch++;
   chan[ch] = d;
@@ -276,7 +281,81 @@ void esbr_stage_tap_pre(ia_sbr_dec_struct *d, ia_sbr_header_data_struct *h, ia_s
   memcpy(esd_tin, d->time_sample_buf, sizeof(esd_tin));
   esd_state(&esd_in, d, f, t);
 }
+/* ---- the same stage with the harmonic transposer (hbe_flag): <tap>.esh record
+ *   int32 'ESH1', head[15] as above, float time_in[1024], esh_state_t state_in, int32 hf_par[96], ec_ipar_in[288], float ec_fpar[464],
+ *   int32 hbe_cfg[16], float time_out[2048], esh_state_t state_out, int32 ec_ipar_out[288] */
+typedef struct {
+  float qre[72 * 64], qim[72 * 64], ore[2560], oim[2560], pre[2560], pim[2560];
+  int32_t anal[320], apos[2], synth[1280], spos[2];
+  float bw[6];
+  int32_t patch[8];
+  float ec[640];
+  float hbe[XO_HBE_ST_WORDS];
+} esh_state_t;
+extern int32_t g_hbe_cfg[XO_HBE_CFG_WORDS];
+extern int g_hbe_called;
+int hbe_state_pack(float *st, const ia_esbr_hbe_txposer_struct *t);
+static int esh_state(esh_state_t *s, ia_sbr_dec_struct *d, ia_sbr_frame_info_data_struct *f, ia_sbr_tables_struct *t) {
+  static esd_state_t tmp;
+  esd_state(&tmp, d, f, t);
+  memcpy(s->qre, d->qmf_buf_real, sizeof(s->qre));
+  memcpy(s->qim, d->qmf_buf_imag, sizeof(s->qim));
+  memcpy(s->ore, tmp.q[2], sizeof(s->ore));
+  memcpy(s->oim, tmp.q[3], sizeof(s->oim));
+  memcpy(s->pre, d->ph_vocod_qmf_real, sizeof(s->pre));
+  memcpy(s->pim, d->ph_vocod_qmf_imag, sizeof(s->pim));
+  memcpy(s->anal, tmp.anal, sizeof(s->anal));
+  memcpy(s->apos, tmp.apos, sizeof(s->apos));
+  memcpy(s->synth, tmp.synth, sizeof(s->synth));
+  memcpy(s->spos, tmp.spos, sizeof(s->spos));
+  memcpy(s->bw, tmp.bw, sizeof(s->bw));
+  memcpy(s->patch, tmp.patch, sizeof(s->patch));
+  memcpy(s->ec, tmp.ec, sizeof(s->ec));
+  return d->p_hbe_txposer ? hbe_state_pack(s->hbe, d->p_hbe_txposer) : -1;
+}
+static FILE *esh_fp;
+static int esh_count, esh_bad;
+static esh_state_t esh_in, esh_out;
+static void esh_pre(ia_sbr_dec_struct *d, ia_sbr_header_data_struct *h, ia_sbr_frame_info_data_struct *f, ia_sbr_tables_struct *t,
+                    int eligible) {
+  static int tried = 0;
+  if (!tried) {
+    tried = 1;
+    esh_fp = open_tap("esh", "esh");
+  }
+  esh_rec = esh_fp && esh_count < tap_max() && eligible && h->hbe_flag;
+  if (!esh_rec) return;
+  g_hbe_called = 0;
+  esh_bad = esh_state(&esh_in, d, f, t);
+}
+static void esh_post(ia_sbr_dec_struct *d, ia_sbr_frame_info_data_struct *f, ia_sbr_tables_struct *t) {
+  if (!esh_rec) return;
+  esh_bad |= esh_state(&esh_out, d, f, t);
+  int32_t head[16];
+  memcpy(head, esd_head, sizeof(head));
+  head[0] = 0x31485345;
+  if (esh_bad || g_hbe_called != 1) head[1] = -101;
+  fwrite(head, 4, 16, esh_fp);
+  fwrite(esd_tin, 4, 1024, esh_fp);
+  fwrite(&esh_in, sizeof(esh_in), 1, esh_fp);
+  fwrite(g_ehf_par, 4, XO_EHF_PAR_WORDS, esh_fp);
+  fwrite(g_eec_ipar_in, 4, XO_EEC_IPAR_WORDS, esh_fp);
+  fwrite(g_eec_fpar, 4, XO_EEC_FPAR_WORDS, esh_fp);
+  fwrite(g_hbe_cfg, 4, XO_HBE_CFG_WORDS, esh_fp);
+  fwrite(d->time_sample_buf, 4, 2048, esh_fp);
+  fwrite(&esh_out, sizeof(esh_out), 1, esh_fp);
+  fwrite(g_eec_ipar_out, 4, XO_EEC_IPAR_WORDS, esh_fp);
+  fflush(esh_fp);
+  esh_count++;
+}
+
 void esbr_stage_tap_post(ia_sbr_dec_struct *d, ia_sbr_frame_info_data_struct *f, ia_sbr_tables_struct *t, int ret) {
+  if (esh_rec) {
+    esd_head[1] = ret;
+    esd_head[14] = g_ehf_called;
+    esd_head[15] = g_eec_called;
+    esh_post(d, f, t);
+  }
   if (!esd_rec) return;
   esd_head[1] = ret;
   esd_head[14] = g_ehf_called;

@@ -1091,3 +1091,39 @@ def synth_hbe_units(n, seed, ref, pitch_mode="mixed", sizes=(4, 8, 12, 16, 20)):
         state[u, HBE_ST_ANAL + 18 * s:HBE_ST_QIN] = 0
     state[::5] = 0
     return cfg, tbl, state, qre, qim
+
+
+ESH_KEYS = ESD_KEYS + ("pv_re", "pv_im", "hbe_state")
+
+
+def oracle_esbr_hbe_stage(orc, rphase, st, time_in, hbe_cfg, hf_par, ec_ipar, ec_fpar, rg_par):
+    """The eSBR stage with the harmonic transposer (hbe_flag = 1): as oracle_esbr_stage, but the core QMF arrays have 72 rows
+    (delayed by ESBR_HBE_DELAY_OFFSET = 32 slots: rows 32..71 -> 0..39, analysis into rows 40..71, decoder/ixheaacd_sbr_dec.c:
+    821-846, 877-880), the transposer turns the new slots into ph_vocod_qmf rows 8..39 (:896-907) and the HF generator reads them.
+    Returns (time_out, st', ec_ipar', err [5, n])."""
+    n = time_in.shape[0]
+    s = {k: np.ascontiguousarray(v).copy() for k, v in st.items()}
+    for k in ("qmf_re", "qmf_im"):
+        s[k][:, 0:40] = s[k][:, 32:72].copy()
+    for k in ("out_re", "out_im", "pv_re", "pv_im"):
+        s[k][:, 0:8] = s[k][:, 32:40]
+    q, s["anal_states"], s["anal_pos"] = orc.esbr_anal_batch(time_in, s["anal_states"], s["anal_pos"])
+    s["qmf_re"][:, 40:72, 0:32] = q[:, :, 0:32]
+    s["qmf_im"][:, 40:72, 0:32] = q[:, :, 64:96]
+    pr, pi, s["hbe_state"], e4 = oracle_hbe_batch(orc, hbe_cfg, s["hbe_state"], s["qmf_re"][:, 40:72], s["qmf_im"][:, 40:72],
+                                                  s["pv_re"][:, 8:40], s["pv_im"][:, 8:40])
+    s["pv_re"][:, 8:40], s["pv_im"][:, 8:40] = pr, pi
+    d = dict(par=hf_par, src_re=np.ascontiguousarray(s["qmf_re"][:, :40]), src_im=np.ascontiguousarray(s["qmf_im"][:, :40]),
+             pv_re=s["pv_re"], pv_im=s["pv_im"], dst_re=s["out_re"], dst_im=s["out_im"], bw_prev=s["bw_prev"], patch_in=s["patch"])
+    s["out_re"], s["out_im"], s["bw_prev"], s["patch"], e1 = oracle_esbr_hfgen_batch(orc, d, with_pv=True)
+    d = dict(re=s["out_re"], im=s["out_im"], ipar=ec_ipar, fpar=ec_fpar, state=s["ec_state"])
+    s["out_re"], s["out_im"], ipar2, s["ec_state"], e2 = oracle_esbr_envcalc_batch(orc, d, rphase)
+    m = np.zeros((n, 32, 128), np.float32)
+    k = np.arange(64)[None, :]
+    for u in range(n):
+        xo = np.where(np.arange(32) < rg_par[u, 2], rg_par[u, 0], rg_par[u, 1])[:, None]
+        m[u, :, :64] = np.where(k < xo, s["qmf_re"][u, 2:34], s["out_re"][u, 2:34])
+        m[u, :, 64:] = np.where(k < xo, s["qmf_im"][u, 2:34], s["out_im"][u, 2:34])
+    out, s["synth_states"], s["synth_pos"] = orc.esbr_synth_batch(m, s["synth_states"], s["synth_pos"])
+    z = np.zeros(n, np.int32)
+    return out, s, ipar2, np.stack([z, e1, e2, z, e4])

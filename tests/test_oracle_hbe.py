@@ -76,3 +76,23 @@ def test_hbe_oracle_streams_match_reference(oracle, ref):
         assert (e1 == 0).all() and (e2 == 0).all()
         m = band_mask(cfg)
         assert np.array_equal(bits(p1)[m], bits(p2)[m]) and np.array_equal(bits(i1)[m], bits(i2)[m]) and np.array_equal(bits(s1), bits(s2))
+
+
+def test_esbr_stage_with_hbe_golden(oracle):
+    """the composed oracle stage (analysis bank -> harmonic transposer -> HF generator -> envelope adjuster -> regrouping ->
+    synthesis bank) against 6 consecutive frames x 2 channels tapped around ixheaacd_sbr_dec in a real -harmonic_sbr:1 decode"""
+    from tests.test_oracle_esbr import esbr_stage_golden_frames
+    g = np.load(os.path.join(os.path.dirname(GOLD), "esbr_hbe_stage_tapped.npz"))
+    rp = oracle_util.esbr_random_phase()
+    st = {k: g["in0_" + k] for k in oracle_util.ESH_KEYS}
+    for f, r, rg in esbr_stage_golden_frames(g):
+        out, st, ipar2, err = oracle_util.oracle_esbr_hbe_stage(oracle, rp, st, g["time_in"][r], g["hbe_cfg"][r], g["hf_par"][r],
+                                                                g["ec_ipar_in"][r], g["ec_fpar"][r], rg)
+        assert not err.any(), f"frame {f}: {err}"
+        assert np.array_equal(bits(out), bits(g["time_out"][r])), f"frame {f}: time output"
+        assert np.array_equal(ipar2, g["ec_ipar_out"][r]), f"frame {f}: in/out parameter words"
+        for k in ("anal_states", "anal_pos", "synth_states", "synth_pos", "bw_prev", "patch", "ec_state", "hbe_state"):
+            assert np.array_equal(st[k].view(np.int32), g["out_" + k][r].view(np.int32)), f"frame {f}: {k}"
+    for k in ("qmf_re", "qmf_im", "out_re", "out_im", "pv_re", "pv_im"):
+        assert np.array_equal(st[k].view(np.int32), g["out_" + k].view(np.int32)), k
+    assert np.abs(g["time_out"]).max() > 100

@@ -512,9 +512,80 @@ def make_hbe_golden(tmp):
     print(f"wrote {path}: {len(sel)} records, {os.path.getsize(path)} bytes")
 
 
+def make_esbr_hbe_stage_golden(tmp):
+    """Whole float eSBR stage WITH the harmonic transposer (hbe_flag = 1) of a real USAC stereo decode (-harmonic_sbr:1):
+    6 consecutive frames of both channels tapped around the unmodified ixheaacd_sbr_dec (oracle/ref_taps_esbr.c, '.esh')."""
+    fs, ch, br = 32000, 2, 64000
+    wav = os.path.join(tmp, "in_esh.wav")
+    write_wav(wav, synth(fs, 6.0, ch, 22), fs)
+    mp4 = os.path.join(tmp, "esh.mp4")
+    run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{mp4}", "-aot:42", f"-br:{br}", "-ccfl_idx:3", "-harmonic_sbr:1"])
+    tap = os.path.join(tmp, "esh.tap")
+    decode_tap(mp4, os.path.join(tmp, "o.wav"), tap, [f"-imeta:{os.path.join(tmp, 'esh.txt')}", "-mp4:1"], stages="esh")
+    S = 2 * 4608 + 4 * 2560 + 320 + 2 + 1280 + 2 + 6 + 8 + 640 + 3616
+    W = 16 + 1024 + S + 96 + 288 + 464 + 16 + 2048 + S + 288
+    raw = np.fromfile(tap + ".esh", dtype=np.int32)
+    assert raw.size and raw.size % W == 0, raw.size
+    r = raw.reshape(-1, W)
+    assert (r[:, 0] == 0x31485345).all()
+    h = r[:, 1:16]
+    ok = (h[:, 0] == 0) & (h[:, 1] == 1) & (h[:, 2] == 1) & (h[:, 3] == 0) & (h[:, 4] <= 0) & (h[:, 5] == 0) & (h[:, 6] == 1) \
+        & (h[:, 13] == 1) & (h[:, 14] == 1)
+    o = 16 + 1024 + S
+    hfp = r[:, o:o + 96]
+    ipi = r[:, o + 96:o + 96 + 288]
+    # a change of sbr_patching_mode / a reset frame makes ixheaacd_sbr_env_calc rebuild its limiter tables (control plane: the
+    # host recomputes them before the call, see INTEGRATION.md); the tap records the tables as they were BEFORE the call
+    ok &= (ipi[:, 16] == 0) & (ipi[:, 19] == 0)
+    cfg = r[:, o + 96 + 288 + 464:o + 96 + 288 + 464 + 16]
+    print(f"eSBR+HBE stage: {len(r)} calls tapped, {int(ok.sum())} in the supported subset; patching mode {sorted(set(hfp[:, 6].tolist()))}, "
+          f"pitch {sorted(set(cfg[:, 5].tolist()))}, qmf_sb_prev {sorted(set(h[:, 7].tolist()))}, sub_band_start {sorted(set(h[:, 8].tolist()))}")
+    n_rec = 12
+    # a run that contains both plain (pitch 0) and cross-product frames if there is one
+    cands = [i for i in range(20, len(r) - n_rec) if ok[i:i + n_rec].all() and h[i, 12] == 0]
+    r0 = next((i for i in cands if len(set(cfg[i:i + n_rec, 5].tolist())) > 1), cands[0])
+    sel = r[r0:r0 + n_rec]
+    f32 = lambda x: np.ascontiguousarray(x).view(np.float32)
+    o = 16
+    tin = f32(sel[:, o:o + 1024]); o += 1024
+    st_in = sel[:, o:o + S]; o += S
+    hf_par = sel[:, o:o + 96]; o += 96
+    ipar_in = sel[:, o:o + 288]; o += 288
+    fpar = f32(sel[:, o:o + 464]); o += 464
+    hcfg = sel[:, o:o + 16]; o += 16
+    tout = f32(sel[:, o:o + 2048]); o += 2048
+    st_out = sel[:, o:o + S]; o += S
+    ipar_out = sel[:, o:o + 288]
+
+    def split(st):
+        d = {}
+        p = 0
+        for k, shp, fl in (("qmf_re", (72, 64), 1), ("qmf_im", (72, 64), 1), ("out_re", (40, 64), 1), ("out_im", (40, 64), 1),
+                           ("pv_re", (40, 64), 1), ("pv_im", (40, 64), 1), ("anal_states", (320,), 0), ("anal_pos", (2,), 0),
+                           ("synth_states", (1280,), 0), ("synth_pos", (2,), 0), ("bw_prev", (6,), 1), ("patch", (8,), 0),
+                           ("ec_state", (640,), 1), ("hbe_state", (3616,), 1)):
+            n_ = int(np.prod(shp))
+            a = st[:, p:p + n_]
+            d[k] = (f32(a) if fl else a.copy()).reshape((len(st),) + shp)
+            p += n_
+        assert p == S
+        return d
+    si, so = split(st_in), split(st_out)
+    out = dict(head=sel[:, 1:16].copy(), time_in=tin, hf_par=hf_par.copy(), ec_ipar_in=ipar_in.copy(), ec_fpar=fpar,
+               hbe_cfg=hcfg.copy(), time_out=tout, ec_ipar_out=ipar_out.copy())
+    big = ("qmf_re", "qmf_im", "out_re", "out_im", "pv_re", "pv_im")
+    for k, v in si.items():
+        out["in0_" + k] = v[:2].copy()
+    for k, v in so.items():
+        out["out_" + k] = v[-2:].copy() if k in big else v.copy()
+    path = os.path.join(GOLD, "esbr_hbe_stage_tapped.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {n_rec} records, {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr", "esbr_stage", "hbe"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr", "esbr_stage", "hbe", "hbe_stage"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
@@ -534,6 +605,8 @@ def main():
             make_sbrdec_lp_golden(tmp)
         if "hbe" in which:
             make_hbe_golden(tmp)
+        if "hbe_stage" in which:
+            make_esbr_hbe_stage_golden(tmp)
 
 
 if __name__ == "__main__":
