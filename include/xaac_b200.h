@@ -277,6 +277,8 @@ int32_t xaac_b200_set_ps_rom(xaac_b200_ctx *ctx, const void *ps_tables, size_t b
 #define XAAC_SIDE_PS_PRM 744   /* [488] XAAC_PS_PRM_*: ia_ps_dec_struct.iid_quant, num_env, border_position[7],
                                   iid_par_table[7][34], icc_par_table[7][34] after ixheaacd_decode_ps_data */
 #define XAAC_SIDE_WORDS 1232
+#define XAAC_ENV_PRM_WORDS 656
+#define XAAC_ENV_ST_WORDS 232
 #define XAAC_PS_PRM_IID_QUANT 0
 #define XAAC_PS_PRM_NUM_ENV 1
 #define XAAC_PS_PRM_BORDER 2
@@ -290,6 +292,12 @@ int32_t xaac_b200_set_ps_rom(xaac_b200_ctx *ctx, const void *ps_tables, size_t b
 #define XAAC_SBR_ST_SF 324          /* [8]    str_sbr_scale_fact (XAAC_SF_*) */
 #define XAAC_SBR_ST_MISC 332        /* [16]   0 prev max_qmf_subband_aac, 1 prev end_position, 2..11 prev sbr_invf_mode,
                                               12 codec bank usb, 13 synthesis bank lsb, 14 synthesis bank usb */
+#define XAAC_SBR_MISC_MAX_QMF_PREV 0 /* words of XAAC_SBR_ST_MISC */
+#define XAAC_SBR_MISC_END_POS_PREV 1
+#define XAAC_SBR_MISC_INVF_PREV 2    /* [10] */
+#define XAAC_SBR_MISC_CODEC_USB 12
+#define XAAC_SBR_MISC_SYN_LSB 13
+#define XAAC_SBR_MISC_SYN_USB 14
 #define XAAC_SBR_ST_ENV 348         /* [232]  str_sbr_calc_env (XAAC_ENV_ST_*) */
 #define XAAC_SBR_ST_SYN_STATES 580  /* [1280] str_synthesis_qmf_bank.filter_states */
 #define XAAC_SBR_ST_BW_PREV 1860    /* WORD32[6]      str_hf_generator.bw_array_prev */
@@ -307,6 +315,13 @@ int32_t xaac_b200_set_ps_rom(xaac_b200_ctx *ctx, const void *ps_tables, size_t b
 #define XAAC_PS_ST_HVEC 2032
 #define XAAC_PS_ST_IDX 2320         /* [12] delay_buf_idx_ser[3], delay_buf_idx, delay_buf_idx_long, delay_buffer_scale,
                                             usb, -, right bank lsb, right bank usb */
+#define XAAC_PS_IDX_SER 0            /* words of XAAC_PS_ST_IDX: [3] delay_buf_idx_ser */
+#define XAAC_PS_IDX_DELAY 3
+#define XAAC_PS_IDX_DELAY_LONG 4
+#define XAAC_PS_IDX_SCALE 5
+#define XAAC_PS_IDX_USB 6
+#define XAAC_PS_IDX_LSB_R 8
+#define XAAC_PS_IDX_USB_R 9
 #define XAAC_PS_ST_PEAK 2332        /* WORD32[3][20] */
 #define XAAC_PS_ST_HYB 2452         /* WORD32[3][2][12] */
 #define XAAC_PS_ST_SYN_STATES_R 2596
@@ -678,6 +693,14 @@ int32_t xaac_b200_esbr_dec_hbe_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_
                                    const int32_t *d_core_in, const int32_t *d_hbe_cfg, const int32_t *d_hf_par,
                                    int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par, float *d_out,
                                    int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream);
+
+/* ---- raw device-memory helpers for C hosts that do not link the CUDA runtime themselves (the reference-side drop-in glue,
+ * libxaac_b200/dropin/ixheaacd_b200_glue.c): allocation and synchronous copies on the context's device ---- */
+int32_t xaac_b200_dev_alloc(xaac_b200_ctx *ctx, size_t bytes, void **d_ptr);
+int32_t xaac_b200_dev_free(xaac_b200_ctx *ctx, void *d_ptr);
+int32_t xaac_b200_h2d(xaac_b200_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int32_t xaac_b200_d2h(xaac_b200_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int32_t xaac_b200_dev_memset(xaac_b200_ctx *ctx, void *d_ptr, int32_t value, size_t bytes);
 
 #ifdef __cplusplus
 }

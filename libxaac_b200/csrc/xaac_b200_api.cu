@@ -1326,6 +1326,38 @@ int32_t xaac_b200_kernel_times(xaac_b200_ctx *ctx, char *buf, size_t buf_bytes) 
   return XAAC_B200_OK;
 }
 
+int32_t xaac_b200_dev_alloc(xaac_b200_ctx *ctx, size_t bytes, void **d_ptr) {
+  if (!ctx || !d_ptr) return bad_arg(ctx, "dev_alloc");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaMalloc(d_ptr, bytes ? bytes : 1), "cudaMalloc");
+  return XAAC_B200_OK;
+}
+int32_t xaac_b200_dev_free(xaac_b200_ctx *ctx, void *d_ptr) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (d_ptr) CK(cudaFree(d_ptr), "cudaFree");
+  return XAAC_B200_OK;
+}
+int32_t xaac_b200_h2d(xaac_b200_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+  if (!ctx || !d_dst || !h_src) return bad_arg(ctx, "h2d");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy H2D");
+  return XAAC_B200_OK;
+}
+int32_t xaac_b200_d2h(xaac_b200_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+  if (!ctx || !h_dst || !d_src) return bad_arg(ctx, "d2h");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy D2H");
+  return XAAC_B200_OK;
+}
+int32_t xaac_b200_dev_memset(xaac_b200_ctx *ctx, void *d_ptr, int32_t value, size_t bytes) {
+  if (!ctx || !d_ptr) return bad_arg(ctx, "dev_memset");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CK(cudaMemset(d_ptr, value, bytes), "cudaMemset");
+  CK(cudaStreamSynchronize(0), "sync");
+  return XAAC_B200_OK;
+}
+
 // *_host entry points: on any error the pipeline streams are drained before returning
 int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, const int32_t *spec,
                                      const uint8_t *ics, int32_t *out, int8_t *qshift_adj, int32_t ch_fac) {

@@ -1,0 +1,96 @@
+"""GPU: the drop-in boundary is real.  libxaac_b200/dropin/_build/xaacdec_b200 (make dropin) is the reference's OWN testbench
+and decoder library, unmodified, linked with the link-time stage overrides of libxaac_b200/dropin/ixheaacd_b200_glue.c
+(ld --wrap=ixheaacd_imdct_process / ixheaacd_sbr_dec / ixheaacd_fd_frm_dec) against libxaac_b200.so: the reference's bitstream
+parser calls the B200 kernels.  Whole files of >= 3000 frames made by the reference encoder are decoded by it and by the plain
+reference decoder (oracle/_ref/xaacdec); the WAV files must be byte-identical and, for the encoder's default settings, not one
+stage call may fall back to the reference's own code."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+B200 = os.path.join(ROOT, "libxaac_b200", "dropin", "_build", "xaacdec_b200")
+
+
+def _need():
+    for p in (B200, os.path.join(REFDIR, "xaacdec"), os.path.join(REFDIR, "xaacenc")):
+        if not os.path.exists(p):
+            pytest.skip(f"{os.path.relpath(p, ROOT)} not built (make ref && make dropin; needs /root/reference at build time)")
+
+
+def _synth_wav(path, fs, seconds, ch, seed):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_golden as mg
+    mg.write_wav(path, mg.synth(fs, seconds, ch, seed), fs)
+
+
+def _run(cmd, env=None):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert r.returncode == 0, (cmd, r.stdout.decode(errors="replace")[-1500:], r.stderr.decode(errors="replace")[-1500:])
+    return r.stderr.decode(errors="replace")
+
+
+CASES = [
+    # name, encoder args, sample rate, channels, seconds (>= 3000 frames), decoder args, expected GPU stage counters
+    ("aac_lc_stereo", ["-aot:2", "-adts:1", "-br:128000"], 44100, 2, 71.0, [], dict(imdct=6000)),
+    ("heaac_v1_mono", ["-aot:5", "-adts:1", "-br:32000"], 44100, 1, 141.0, ["-esbr:0"], dict(imdct=3000, hq=3000)),
+    ("heaac_v1_stereo", ["-aot:5", "-adts:1", "-br:48000"], 48000, 2, 130.0, ["-esbr:0"], dict(imdct=6000, lp=6000)),
+    ("heaac_v2", ["-aot:29", "-adts:1", "-br:32000"], 44100, 2, 141.0, ["-esbr:0"], dict(imdct=3000, ps=3000)),
+]
+
+
+@pytest.mark.parametrize("name,enc,fs,ch,secs,dec,want", CASES, ids=[c[0] for c in CASES])
+def test_whole_file_through_reference_parser(tmp_path, name, enc, fs, ch, secs, dec, want):
+    _need()
+    wav = str(tmp_path / "in.wav")
+    _synth_wav(wav, fs, secs, ch, 100 + len(name))
+    bits = str(tmp_path / (name + ".aac"))
+    _run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{bits}"] + enc)
+    ref_wav, our_wav = str(tmp_path / "ref.wav"), str(tmp_path / "b200.wav")
+    _run([os.path.join(REFDIR, "xaacdec"), f"-ifile:{bits}", f"-ofile:{ref_wav}"] + dec)
+    log = _run([B200, f"-ifile:{bits}", f"-ofile:{our_wav}"] + dec, env=dict(os.environ, IXHEAACD_B200_STATS="1"))
+    m = re.search(r"imdct_process: (\d+) on the GPU, (\d+) by the reference; sbr_dec: (\d+) HQ \+ (\d+) HQ/PS \+ (\d+) LP on the GPU, "
+                  r"(\d+) by the reference; fd_frm_dec: (\d+) on the GPU, (\d+) by the reference", log)
+    assert m, log[-800:]
+    imdct, imdct_ref, hq, ps, lp, sbr_ref, fd, fd_ref = map(int, m.groups())
+    a, b = open(ref_wav, "rb").read(), open(our_wav, "rb").read()
+    assert len(a) == len(b) and len(a) > 44 + 2 * ch * 1024 * 2900
+    if a != b:
+        x, y = np.frombuffer(a[44:], np.int16), np.frombuffer(b[44:], np.int16)
+        bad = np.flatnonzero(x != y)
+        raise AssertionError(f"{name}: {bad.size} of {x.size} samples differ, first at sample {bad[0]} (frame {bad[0] // (ch * 1024)}), "
+                             f"max |diff| {np.abs(x.astype(int) - y.astype(int)).max()}")
+    assert imdct_ref == 0 and sbr_ref == 0 and fd_ref == 0, f"{name}: stage calls fell back to the reference: {m.group(0)}"
+    assert imdct >= want.get("imdct", 0) and hq >= want.get("hq", 0) and ps >= want.get("ps", 0) and lp >= want.get("lp", 0), m.group(0)
+    if "hq" not in want:
+        assert hq == 0
+    if "lp" not in want:
+        assert lp == 0
+    if "ps" not in want:
+        assert ps == 0
+
+
+def test_usac_core_through_reference_parser(tmp_path):
+    """xHE-AAC (USAC, aot 42, ccfl 1024): the FD core transform of every frame runs on the GPU behind ixheaacd_fd_frm_dec; the
+    float eSBR branch of ixheaacd_sbr_dec is still the reference's own code in this binding (counted)."""
+    _need()
+    wav = str(tmp_path / "in.wav")
+    _synth_wav(wav, 32000, 100.0, 2, 77)
+    bits = str(tmp_path / "usac.mp4")
+    _run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{bits}", "-aot:42", "-br:64000", "-ccfl_idx:3"])
+    meta = str(tmp_path / "usac.txt")
+    ref_wav, our_wav = str(tmp_path / "ref.wav"), str(tmp_path / "b200.wav")
+    _run([os.path.join(REFDIR, "xaacdec"), f"-ifile:{bits}", f"-ofile:{ref_wav}", f"-imeta:{meta}", "-mp4:1"])
+    log = _run([B200, f"-ifile:{bits}", f"-ofile:{our_wav}", f"-imeta:{meta}", "-mp4:1"], env=dict(os.environ, IXHEAACD_B200_STATS="1"))
+    m = re.search(r"fd_frm_dec: (\d+) on the GPU, (\d+) by the reference", log)
+    assert m, log[-800:]
+    fd, fd_ref = map(int, m.groups())
+    a, b = open(ref_wav, "rb").read(), open(our_wav, "rb").read()
+    assert a == b, "USAC decode differs"
+    assert fd >= 2 * 1500 and fd_ref == 0, m.group(0)
