@@ -701,6 +701,13 @@ int32_t xaac_b200_dev_free(xaac_b200_ctx *ctx, void *d_ptr);
 int32_t xaac_b200_h2d(xaac_b200_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int32_t xaac_b200_d2h(xaac_b200_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 int32_t xaac_b200_dev_memset(xaac_b200_ctx *ctx, void *d_ptr, int32_t value, size_t bytes);
+/* Peer buffers for multi-GPU hosts (one process per GPU): a buffer from xaac_b200_dev_alloc is exported as a 64-byte CUDA IPC
+ * handle; another process imports it on ITS device with peer access enabled, and may then pass the pointer to any _dev entry
+ * point: the kernels load / store the peer GPU's HBM over NVLink directly (e.g. pre-parsed per-frame buffers that live on one
+ * rank are consumed in place instead of being scattered first). */
+int32_t xaac_b200_ipc_export(xaac_b200_ctx *ctx, void *d_ptr, void *handle64);
+int32_t xaac_b200_ipc_import(xaac_b200_ctx *ctx, const void *handle64, void **d_ptr);
+int32_t xaac_b200_ipc_close(xaac_b200_ctx *ctx, void *d_ptr);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,9 @@ SIGNATURES = {
     "xaac_b200_h2d": (_i32, [_vp, _vp, _vp, _sz]),
     "xaac_b200_d2h": (_i32, [_vp, _vp, _vp, _sz]),
     "xaac_b200_dev_memset": (_i32, [_vp, _vp, _i32, _sz]),
+    "xaac_b200_ipc_export": (_i32, [_vp, _vp, _vp]),
+    "xaac_b200_ipc_import": (_i32, [_vp, _vp, _vp]),
+    "xaac_b200_ipc_close": (_i32, [_vp, _vp]),
     "xaac_b200_set_hbe_rom": (_i32, [_vp, _vp, _sz]),
     "xaac_b200_esbr_hbe_apply_dev": (_i32, [_vp] * 8 + [_i64, _vp]),
     "xaac_b200_esbr_dec_hbe_dev": (_i32, [_vp] * 11 + [_i32, _vp, _i64, _vp]),

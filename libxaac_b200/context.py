@@ -106,6 +106,27 @@ class Context:
     def sync(self):
         self.check(self._lib.xaac_b200_sync(self._h), "xaac_b200_sync")
 
+    # ---- raw device buffers and peer (CUDA IPC) buffers: the multi-GPU I/O path, one process per GPU ----
+    def dev_tensor(self, nbytes, dtype, shape):
+        """A device buffer from xaac_b200_dev_alloc (a cudaMalloc base pointer, hence exportable) viewed as a torch tensor."""
+        p = ctypes.c_void_p()
+        self.check(self._lib.xaac_b200_dev_alloc(self._h, int(nbytes), ctypes.byref(p)), "xaac_b200_dev_alloc")
+        return _RawBuffer(self, p.value, int(nbytes), owned=True).as_tensor(dtype, shape)
+
+    def ipc_export(self, tensor):
+        """64-byte CUDA IPC handle of a tensor made by dev_tensor()."""
+        h = (ctypes.c_char * 64)()
+        self.check(self._lib.xaac_b200_ipc_export(self._h, ctypes.c_void_p(tensor.data_ptr()), h), "xaac_b200_ipc_export")
+        return bytes(h)
+
+    def ipc_import(self, handle, nbytes, dtype, shape):
+        """Map another rank's exported buffer on this context's device (peer access over NVLink) and view it as a tensor; the
+        _dev entry points accept it like any device pointer."""
+        p = ctypes.c_void_p()
+        hb = (ctypes.c_char * 64).from_buffer_copy(handle)
+        self.check(self._lib.xaac_b200_ipc_import(self._h, hb, ctypes.byref(p)), "xaac_b200_ipc_import")
+        return _RawBuffer(self, p.value, int(nbytes), owned=False).as_tensor(dtype, shape)
+
     def close(self):
         if self._h:
             self._lib.xaac_b200_destroy(self._h)
@@ -116,3 +137,29 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class _RawBuffer:
+    """Holder that exposes a raw device pointer through __cuda_array_interface__ (torch.as_tensor aliases it)."""
+
+    def __init__(self, ctx, ptr, nbytes, owned):
+        self.ctx, self.ptr, self.nbytes, self.owned = ctx, ptr, nbytes, owned
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2, "strides": None}
+
+    def as_tensor(self, dtype, shape):
+        import torch
+        t = torch.as_tensor(self, device="cuda")
+        t = t.view(dtype).view(shape)
+        t._xaac_holder = self  # keeps the mapping alive as long as the tensor
+        return t
+
+    def __del__(self):
+        try:
+            if self.ptr and self.ctx._h:
+                if self.owned:
+                    self.ctx._lib.xaac_b200_dev_free(self.ctx._h, ctypes.c_void_p(self.ptr))
+                else:
+                    self.ctx._lib.xaac_b200_ipc_close(self.ctx._h, ctypes.c_void_p(self.ptr))
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+        self.ptr = None

@@ -1358,6 +1358,30 @@ int32_t xaac_b200_dev_memset(xaac_b200_ctx *ctx, void *d_ptr, int32_t value, siz
   return XAAC_B200_OK;
 }
 
+int32_t xaac_b200_ipc_export(xaac_b200_ctx *ctx, void *d_ptr, void *handle64) {
+  if (!ctx || !d_ptr || !handle64) return bad_arg(ctx, "ipc_export");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, d_ptr), "cudaIpcGetMemHandle");
+  memcpy(handle64, &h, 64);
+  return XAAC_B200_OK;
+}
+int32_t xaac_b200_ipc_import(xaac_b200_ctx *ctx, const void *handle64, void **d_ptr) {
+  if (!ctx || !d_ptr || !handle64) return bad_arg(ctx, "ipc_import");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");  // the mapping (and the lazily enabled peer access) is for THIS device
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+  return XAAC_B200_OK;
+}
+int32_t xaac_b200_ipc_close(xaac_b200_ctx *ctx, void *d_ptr) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (d_ptr) CK(cudaIpcCloseMemHandle(d_ptr), "cudaIpcCloseMemHandle");
+  return XAAC_B200_OK;
+}
+
 // *_host entry points: on any error the pipeline streams are drained before returning
 int32_t xaac_b200_imdct_process_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *state, const int32_t *spec,
                                      const uint8_t *ics, int32_t *out, int8_t *qshift_adj, int32_t ch_fac) {
