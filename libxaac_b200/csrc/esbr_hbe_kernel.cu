@@ -31,7 +31,7 @@ namespace xb {
 #define XB_DEV __device__ __forceinline__
 #define XB_NOINL __device__ __noinline__
 
-constexpr int kHbWarps = 6;
+constexpr int kHbWarps = 8;
 // CTA-shared tables (float words)
 constexpr int kHtWin = 0;         // ixheaac_sub_samp_qmf_window_coeff[1560]
 constexpr int kHtSyn20 = 1560;    // ixheaac_synth_cos_table_kl_20, rows 0..30 x 20
@@ -39,12 +39,15 @@ constexpr int kHtCosTrans = 2360; // ixheaac_cos_table_trans_qmf[7][64]
 constexpr int kHtAna40 = 2808;    // ixheaac_analy_cos_sin_table_kl_40 as 40 rows of stride 82 (two rows 20 apart: distinct banks)
 constexpr int kHtWords = 2808 + 40 * 82;
 // per-warp regions (float words)
-constexpr int kHbE = 2016;   // time signal (<= 51 S - 1 words); phase C: NORM2 [28][72]
-constexpr int kHbR1 = 2688;  // A: V [41][<=41] + LOC [20][33] | B: U [80][17] | C: NORM4 [28][72] + OUTC [42][16]
+constexpr int kHbE = 1024;   // time signal (<= 51 S - 1 words); phase C: NORM4 [26][37] (<= 18 bands)
+constexpr int kHbR1 = 2688;  // A: V [41][<=41] + LOC [20][33] | B: U [80][17] | C: NORM2 [26][73] + OUTC [42][17]
 constexpr int kHbQW = 82;    // row stride of the analysis matrix (<= 80 words used)
 constexpr int kHbQ = 28 * kHbQW;
 constexpr int kHbWarpWords = kHbE + kHbR1 + kHbQ;
-constexpr int kNW = 72;      // row stride of the normalised matrices (<= 36 bands)
+constexpr int kNW = 73;      // row stride of the stretch-2 normalised matrix (<= 36 bands; odd: lane = column walks rows)
+constexpr int kN4W = 37;     // row stride of the stretch-4 normalised matrix (<= 18 bands)
+constexpr int kNRows = 26;   // rows 0..25 of the normalised matrices are the ones the products read
+constexpr int kOW = 17;      // row stride of the 8-band output chunk (16 words used)
 
 struct cf { float r, i; };
 
@@ -286,29 +289,44 @@ struct QinView {
 
 struct XAdd { float r0, i0, r1, i1; bool on; };  // cross-product contributions to rows 2 col + 5 and 2 col + 6
 
-// hbe_trans.c:1105-1243 (inside ixheaacd_hbe_post_anal_xprod2)
-XB_DEV XAdd xprod2(const QinView &Q, int b, int col, float p, const float *cs_theta) {
+// hbe_trans.c:1105-1243 (inside ixheaacd_hbe_post_anal_xprod2).  N2 = the stretch-2 normalised matrix (bands nlo..nhi, rows
+// 1..25): a normalised cell the search needs is the same expression the matrix already holds (x * mag2(x)), so it is read back
+// instead of being recomputed when it lies inside the matrix.
+XB_DEV XAdd xprod2(const QinView &Q, const float *N2, int nlo, int nhi, int b, int col, float p, const float *cs_theta) {
   XAdd a = {0, 0, 0, 0, false};
   double temp_fac = (2.0 * b + 1 - (double)p) * 0.5;
   const int n1 = ((int)(temp_fac)) << 1, n2 = ((int)(temp_fac + (double)p)) << 1;
   const int zr = col + 6;
-  float mag_zero = Q.at(zr, 2 * b) * Q.at(zr, 2 * b) + Q.at(zr, 2 * b + 1) * Q.at(zr, 2 * b + 1);
-  float m1 = Q.at(zr, n1) * Q.at(zr, n1) + Q.at(zr, n1 + 1) * Q.at(zr, n1 + 1);
-  float m2 = Q.at(zr, n2) * Q.at(zr, n2) + Q.at(zr, n2 + 1) * Q.at(zr, n2 + 1);
+  const float z0 = Q.at(zr, 2 * b), z1 = Q.at(zr, 2 * b + 1);
+  const float a0 = Q.at(zr, n1), a1 = Q.at(zr, n1 + 1), b0 = Q.at(zr, n2), b1 = Q.at(zr, n2 + 1);
+  float mag_zero = z0 * z0 + z1 * z1;
+  float m1 = a0 * a0 + a1 * a1;
+  float m2 = b0 * b0 + b1 * b1;
   float t = m1 < m2 ? m1 : m2;
   float max_mag = 0;
   int max_n1 = 0, max_n2 = 0;
   if (t > 0) { max_mag = t; max_n1 = n1; max_n2 = n2; }
   if (!(max_mag > mag_zero && max_n1 >= 0 && max_n2 < 128)) return a;
-  float zr_ = Q.at(zr, max_n1), zi_ = Q.at(zr, max_n1 + 1), vyr[2], vyi[2];
-  float m = mag2(zr_, zi_);
-  zr_ *= m; zi_ *= m;
+  float zr_, zi_, vyr[2], vyi[2];
+  const int ba = max_n1 >> 1, bb = max_n2 >> 1;
+  if (ba >= nlo && ba <= nhi) {
+    zr_ = N2[zr * kNW + 2 * (ba - nlo)];
+    zi_ = N2[zr * kNW + 2 * (ba - nlo) + 1];
+  } else {
+    const float m = mag2(a0, a1);
+    zr_ = a0 * m; zi_ = a1 * m;
+  }
 #pragma unroll
   for (int k = 0; k < 2; k++) {
-    float tr = Q.at(zr - 1 + k, max_n2), ti = Q.at(zr - 1 + k, max_n2 + 1);
-    m = mag2(tr, ti);
-    vyr[k] = tr * m;
-    vyi[k] = ti * m;
+    if (bb >= nlo && bb <= nhi) {
+      vyr[k] = N2[(zr - 1 + k) * kNW + 2 * (bb - nlo)];
+      vyi[k] = N2[(zr - 1 + k) * kNW + 2 * (bb - nlo) + 1];
+    } else {
+      float tr = Q.at(zr - 1 + k, max_n2), ti = Q.at(zr - 1 + k, max_n2 + 1);
+      const float m = mag2(tr, ti);
+      vyr[k] = tr * m;
+      vyi[k] = ti * m;
+    }
   }
   float tr = vyr[0] * zr_ - vyi[0] * zi_, ti = vyr[0] * zi_ + vyi[0] * zr_;
   const float c0 = __ldg(cs_theta), c1 = __ldg(cs_theta + 1);
@@ -547,7 +565,7 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
     else if (ms >= 4 && xo2 <= 1) err = (int)0x80000000;  // hbe_trans.c:1572
     else if (ms >= 2 && (xo1 < xo0 || min(xo1, 63) - xo0 + 1 > 36)) err = -2;
     else if (ms >= 3 && xo2 < xo1) err = -2;
-    else if (ms >= 4 && (xo3 < xo2 || (((xo3 - 1) >> 1) + 1) - max(0, (xo2 >> 1) - 1) + 1 > 36)) err = -2;
+    else if (ms >= 4 && (xo3 < xo2 || min(63, ((xo3 - 1) >> 1) + 1) - max(0, (xo2 >> 1) - 1) + 1 > 18)) err = -2;
     if (err) {
       if (p.err && lane == 0) p.err[u] = err;
       continue;
@@ -597,11 +615,14 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
       float *v = V + (lane + 9) * VS;
       if (S == 20) {  // polyphase.c:203-229; rows 0..9 of the table only produce values the later rows overwrite
         const float *pt = tabs + kHtSyn20 + 10 * 20;
+        float loc[20];
+#pragma unroll
+        for (int k = 0; k < 20; k++) loc[k] = LOC[k * 33 + lane];
 #pragma unroll 1
         for (int l = 10; l <= 30; l++) {
           float accu = 0.0f;
 #pragma unroll
-          for (int k = 0; k < 20; k++) accu += LOC[k * 33 + lane] * pt[k];
+          for (int k = 0; k < 20; k++) accu += loc[k] * pt[k];
           pt += 20;
           if (l <= 20) { v[l] = accu; v[20 - l] = accu; }
           else if (l < 30) { v[l] = accu; v[60 - l] = -accu; }
@@ -722,12 +743,13 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
     const QinView Q = {QM, lo, nq};
     const float pf = (float)((double)pitch * 0.08333333333333);  // hbe_trans.c:1557, 2:1 system
     const bool xp = !(pf < 1.0f);
-    float *N2 = E, *N4 = R1, *OUTC = R1 + 28 * kNW;
+    float *N2 = R1, *N4 = E, *OUTC = R1 + kNRows * kNW;
+    static_assert(kNRows * kNW + 42 * kOW <= kHbR1 && kNRows * kN4W <= kHbE, "phase C buffers");
     const int n4lo = max(0, (xo2 >> 1) - 1), n4hi = min(63, ((xo3 - 1) >> 1) + 1);
     if (ms >= 2) {
       const int nb = min(xo1, 63) - xo0 + 1;
-      for (int e = lane; e < 28 * nb; e += 32) {
-        const int r = e / nb, b = e - r * nb;
+      for (int e = lane; e < 25 * nb; e += 32) {  // rows 1..25 are the ones the products read
+        const int r = 1 + e / nb, b = e - (r - 1) * nb;
         const float xr = Q.at(r, 2 * (xo0 + b)), xi = Q.at(r, 2 * (xo0 + b) + 1);
         const float m = mag2(xr, xi);
         N2[r * kNW + 2 * b] = xr * m;
@@ -736,12 +758,12 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
     }
     if (ms >= 4) {
       const int nb = n4hi - n4lo + 1;
-      for (int e = lane; e < 28 * nb; e += 32) {
+      for (int e = lane; e < kNRows * nb; e += 32) {
         const int r = e / nb, b = e - r * nb;
         const float xr = Q.at(r, 2 * (n4lo + b)), xi = Q.at(r, 2 * (n4lo + b) + 1);
         const float m = mag4(xr, xi);
-        N4[r * kNW + 2 * b] = xr * m;
-        N4[r * kNW + 2 * b + 1] = xi * m;
+        N4[r * kN4W + 2 * b] = xr * m;
+        N4[r * kN4W + 2 * b + 1] = xi * m;
       }
     }
     __syncwarp();
@@ -749,7 +771,7 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
     for (int b0 = sb; b0 < eb; b0 += 8) {
       for (int e = lane; e < 42 * 16; e += 32) {
         const int r = e >> 4, c = e & 15, band = b0 + (c >> 1);
-        OUTC[e] = (r < 10 && band < eb) ? st[kHbeStQout + r * 128 + 2 * band + (c & 1)] : 0.0f;
+        OUTC[r * kOW + c] = (r < 10 && band < eb) ? st[kHbeStQout + r * 128 + 2 * band + (c & 1)] : 0.0f;
       }
       __syncwarp();
 #pragma unroll 1
@@ -768,7 +790,7 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
         if (T == 2) {
           xzr = N2[(6 + ci) * kNW + 2 * (b - xo0)];
           xzi = N2[(6 + ci) * kNW + 2 * (b - xo0) + 1];
-          if (xp) xa = xprod2(Q, b, ci, pf, rom + kHromXp2 + (pitch << 1));
+          if (xp) xa = xprod2(Q, N2, xo0, min(xo1, 63), b, ci, pf, rom + kHromXp2 + (pitch << 1));
         } else if (T == 3) {
           prod3_vectors(QM, lo, nq, rom, b, ci, vx, vc, two);
           if (!two) {
@@ -786,7 +808,7 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
         } else if (T == 4) {
           const int inp = b >> 1;
           ip = (b & 1) ? (inp + 1) : (inp - 1);
-          float xr = N4[(6 + ci) * kNW + 2 * (inp - n4lo)], xi = N4[(6 + ci) * kNW + 2 * (inp - n4lo) + 1];
+          float xr = N4[(6 + ci) * kN4W + 2 * (inp - n4lo)], xi = N4[(6 + ci) * kN4W + 2 * (inp - n4lo) + 1];
           const float tr = xr, ti = xi;
           float t = xr * xr - xi * xi;
           xi = xr * xi + xi * xr;
@@ -816,11 +838,11 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
                 cim = ai * 0.23570225f;
               }
             } else {
-              const float a = N4[(ci + 2 * k) * kNW + 2 * (ip - n4lo)], bi = N4[(ci + 2 * k) * kNW + 2 * (ip - n4lo) + 1];
+              const float a = N4[(ci + 2 * k) * kN4W + 2 * (ip - n4lo)], bi = N4[(ci + 2 * k) * kN4W + 2 * (ip - n4lo) + 1];
               cr = (a * xzr - bi * xzi) * 0.6666667f;
               cim = (a * xzi + bi * xzr) * 0.6666667f;
             }
-            float *cell = OUTC + (T - 1 + 2 * ci + k) * 16 + 2 * bb;
+            float *cell = OUTC + (T - 1 + 2 * ci + k) * kOW + 2 * bb;
             float o0 = cell[0] + cr, o1 = cell[1] + cim;
             if (xa.on && k == kx0) { o0 += xa.r0; o1 += xa.i0; }
             if (xa.on && k == kx0 + 1) { o0 += xa.r1; o1 += xa.i1; }
@@ -834,7 +856,7 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
       for (int e = lane; e < 32 * 8; e += 32) {
         const int r = e >> 3, c = e & 7, band = b0 + c;
         if (band < eb) {
-          const float a = OUTC[r * 16 + 2 * c], cc = OUTC[r * 16 + 2 * c + 1];
+          const float a = OUTC[r * kOW + 2 * c], cc = OUTC[r * kOW + 2 * c + 1];
           const float pc = __ldg(rom + kHromPvCos + band), ps = __ldg(rom + kHromPvSin + band);
           pvr[r * 64 + band] = a * pc - cc * ps;
           pvi[r * 64 + band] = a * ps + cc * pc;
@@ -842,7 +864,7 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
       }
       for (int e = lane; e < 10 * 16; e += 32) {
         const int r = e >> 4, c = e & 15, band = b0 + (c >> 1);
-        if (band < eb) st[kHbeStQout + r * 128 + 2 * band + (c & 1)] = OUTC[(32 + r) * 16 + c];
+        if (band < eb) st[kHbeStQout + r * 128 + 2 * band + (c & 1)] = OUTC[(32 + r) * kOW + c];
       }
       __syncwarp();
     }

@@ -70,7 +70,9 @@ struct xaac_b200_sbr_state {
   int32_t *bw_prev = nullptr, *lpc = nullptr, *ov = nullptr;
   // PS state (host blob XAAC_PS_ST_*)
   int16_t *ps = nullptr, *syn_states_r = nullptr, *syn_pos_r = nullptr, *sf_r = nullptr;
-  // scratch
+  // stage scratch, sized by the units in flight (scratch_cap), not by the batch: a whole-batch _dev call needs n_units of it, the
+  // chunked host pipeline kPipe chunks (ensure_sbr_scratch)
+  int64_t scratch_cap = 0;
   int32_t *matrix = nullptr, *right = nullptr, *err = nullptr;
   int16_t *usb = nullptr, *hf_prm = nullptr, *synp = nullptr, *synp_r = nullptr, *ps_done = nullptr;
 };
@@ -684,17 +686,6 @@ int32_t xaac_b200_sbr_state_create(xaac_b200_ctx *ctx, int64_t n_units, int32_t 
   if (s->with_ps)
     for (int i = 0; i < n_ps; i++) alloc0(ps[i].dev, ps[i].bytes * (size_t)n_units);
   alloc0((void **)&s->err, (size_t)n_units * 4);
-  if (!s->lp_only) {
-    alloc0((void **)&s->matrix, (size_t)n_units * xb::kSbrMatWords * 4);
-    alloc0((void **)&s->usb, (size_t)n_units * 2);
-    alloc0((void **)&s->hf_prm, (size_t)n_units * 160);
-    alloc0((void **)&s->synp, (size_t)n_units * 16);
-  }
-  if (s->with_ps) {
-    alloc0((void **)&s->right, (size_t)n_units * 4096 * 4);
-    alloc0((void **)&s->synp_r, (size_t)n_units * 16);
-    alloc0((void **)&s->ps_done, (size_t)n_units * 2);
-  }
   if (!ok) {
     cudaError_t e = cudaGetLastError();
     xaac_b200_sbr_state_destroy(ctx, s);
@@ -741,14 +732,45 @@ int32_t xaac_b200_sbr_state_download(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s,
 
 extern "C" int32_t xaac_b200_imdct_out_to_pcm16_dev(xaac_b200_ctx *, const int32_t *, const int8_t *, int16_t *, int64_t,
                                                     int32_t, void *);
-// One frame for units [u0, u0 + n) of the state; d_side / d_time_in / d_time_out / d_err point at the chunk's first unit.
+// (re)allocate the stage scratch of an HQ state for `units` units in flight (synchronises the device when it grows)
+static int32_t ensure_sbr_scratch(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, int64_t units) {
+  if (s->lp_only || units <= s->scratch_cap) return XAAC_B200_OK;
+  CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  void **old[] = {(void **)&s->matrix, (void **)&s->right, (void **)&s->usb, (void **)&s->hf_prm, (void **)&s->synp,
+                  (void **)&s->synp_r, (void **)&s->ps_done};
+  for (void **q : old) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
+  }
+  s->scratch_cap = 0;
+  bool ok = true;
+  auto alloc0 = [&](void **q, size_t bytes) {
+    if (!ok) return;
+    if (cudaMalloc(q, bytes) != cudaSuccess || cudaMemset(*q, 0, bytes) != cudaSuccess) ok = false;
+  };
+  alloc0((void **)&s->matrix, (size_t)units * xb::kSbrMatWords * 4);
+  alloc0((void **)&s->usb, (size_t)units * 2);
+  alloc0((void **)&s->hf_prm, (size_t)units * 160);
+  alloc0((void **)&s->synp, (size_t)units * 16);
+  if (s->with_ps) {
+    alloc0((void **)&s->right, (size_t)units * 4096 * 4);
+    alloc0((void **)&s->synp_r, (size_t)units * 16);
+    alloc0((void **)&s->ps_done, (size_t)units * 2);
+  }
+  if (!ok) return fail(ctx, cudaGetLastError(), "cudaMalloc(sbr stage scratch)");
+  CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  s->scratch_cap = units;
+  return XAAC_B200_OK;
+}
+// One frame for units [u0, u0 + n) of the state, using scratch slots [su0, su0 + n); d_side / d_time_in / d_time_out / d_err
+// point at the chunk's first unit.
 static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long long u0, long long n, const int16_t *d_side,
-                             const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, cudaStream_t st) {
+                             const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, cudaStream_t st, long long su0) {
   int32_t *err = d_err ? d_err : s->err + u0;
   xb::SbrStageArgs g;
-  g.side = d_side; g.matrix = s->matrix + u0 * xb::kSbrMatWords; g.ov = s->ov + u0 * 768; g.lpc = s->lpc + u0 * 256;
-  g.sf = s->sf + u0 * 8; g.misc = s->misc + u0 * 16; g.usb = s->usb + u0; g.hf_prm = s->hf_prm + u0 * 80;
-  g.synp = s->synp + u0 * 8; g.err = err; g.n_units = n;
+  g.side = d_side; g.matrix = s->matrix + su0 * xb::kSbrMatWords; g.ov = s->ov + u0 * 768; g.lpc = s->lpc + u0 * 256;
+  g.sf = s->sf + u0 * 8; g.misc = s->misc + u0 * 16; g.usb = s->usb + su0; g.hf_prm = s->hf_prm + su0 * 80;
+  g.synp = s->synp + su0 * 8; g.err = err; g.n_units = n;
   LAUNCH("sbr_pre_kernel", st, xb::launch_sbr_pre(g, ctx->num_sms, st));
   {
     xb::QmfAnalArgs a;
@@ -780,8 +802,8 @@ static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long lo
   y.mat_stride = xb::kSbrMatWords;
   if (s->with_ps) {
     xb::PsArgs a;
-    a.side = d_side; a.matrix = g.matrix; a.right = s->right + u0 * 4096; a.ps_state = s->ps + u0 * xb::kPsDspWords;
-    a.sf = g.sf; a.sf_r = s->sf_r + u0 * 8; a.synp = g.synp; a.synp_r = s->synp_r + u0 * 8; a.ps_done = s->ps_done + u0;
+    a.side = d_side; a.matrix = g.matrix; a.right = s->right + su0 * 4096; a.ps_state = s->ps + u0 * xb::kPsDspWords;
+    a.sf = g.sf; a.sf_r = s->sf_r + u0 * 8; a.synp = g.synp; a.synp_r = s->synp_r + su0 * 8; a.ps_done = s->ps_done + su0;
     a.err = err; a.ps_rom = ctx->d_rom_ps; a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n; a.rot_nosat = ctx->ps_rot_nosat;
     LAUNCH("ps_frame_kernel", st, xb::launch_ps_frame(a, ctx->num_sms, st));
     y.ch_fac = 2;
@@ -816,7 +838,9 @@ int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, con
   if (rc != XAAC_B200_OK) return rc;
   if (!d_side || !d_time_in || !d_time_out) return bad_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-  return sbr_dec_range(ctx, s, 0, s->n_units, d_side, d_time_in, d_time_out, d_err, (cudaStream_t)stream);
+  rc = ensure_sbr_scratch(ctx, s, s->n_units);
+  if (rc != XAAC_B200_OK) return rc;
+  return sbr_dec_range(ctx, s, 0, s->n_units, d_side, d_time_in, d_time_out, d_err, (cudaStream_t)stream, 0);
 }
 
 // One low-power frame for units [u0, u0 + n) of the state.
@@ -870,6 +894,9 @@ static int32_t xaac_b200_heaac_frame_host_impl(xaac_b200_ctx *ctx, xaac_b200_imd
                o_err = o_pcm + 2 * out_words, o_ics = o_err + 4, o_adj = o_ics + 2, per_unit = o_adj + 2;
   rc = ensure_stage(ctx, per_unit * (size_t)chunk);
   if (rc != XAAC_B200_OK) return rc;
+  // stage scratch for the chunks in flight only (one slot range per pipeline stream), not for the whole batch
+  rc = ensure_sbr_scratch(ctx, s, (int64_t)xaac_b200_ctx::kPipe * chunk);
+  if (rc != XAAC_B200_OK) return rc;
   int slot = 0;
   for (int64_t u0 = 0; u0 < n_units; u0 += chunk, slot = (slot + 1) % xaac_b200_ctx::kPipe) {
     const int64_t n = (n_units - u0 < chunk) ? (n_units - u0) : chunk;
@@ -890,7 +917,7 @@ static int32_t xaac_b200_heaac_frame_host_impl(xaac_b200_ctx *ctx, xaac_b200_imd
     if (rc != XAAC_B200_OK) return rc;
     rc = xaac_b200_imdct_out_to_pcm16_dev(ctx, d_w32, d_adj, d_p16, n, 0, st);
     if (rc != XAAC_B200_OK) return rc;
-    rc = sbr_dec_range(ctx, s, u0, n, d_side, d_p16, d_pcm, d_err, st);
+    rc = sbr_dec_range(ctx, s, u0, n, d_side, d_p16, d_pcm, d_err, st, (long long)slot * chunk);
     if (rc != XAAC_B200_OK) return rc;
     CK(cudaMemcpyAsync(pcm + u0 * out_words, d_pcm, (size_t)n * out_words * 2, cudaMemcpyDeviceToHost, st), "D2H pcm");
     if (err) CK(cudaMemcpyAsync(err + u0, d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H err");
