@@ -670,16 +670,19 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
     const int lo = 4 * ks, nq = 4 * S;
     {
       const float *win = tabs + kHtWin + win_off(A);
-      for (int col = 0; col < 16; col++)
-        for (int i = lane; i < 2 * A; i += 32) {
+      for (int i = lane; i < 2 * A; i += 32) {  // lane = window phase: its five taps stay in registers for all 16 columns
+        float wj[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) wj[j] = win[i + 2 * A * j];
+        const float *ep = E + e0 + A - i;
+#pragma unroll 4
+        for (int col = 0; col < 16; col++) {
           float accu = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 5; j++) {
-            const int idx = i + 2 * A * j;
-            accu = accu + E[e0 + (col + 1) * A - idx] * win[idx];
-          }
+          for (int j = 0; j < 5; j++) accu = accu + ep[col * A - 2 * A * j] * wj[j];
           U[i * 17 + col] = accu;
         }
+      }
       for (int e = lane; e < 12 * nq; e += 32) {  // rows 0..11 = the previous call's rows 16..27
         const int r = e / nq, c = e - r * nq;
         QM[r * kHbQW + c] = st[kHbeStQin + r * 128 + lo + c];
@@ -697,23 +700,30 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
       const float u0 = U[col], u40 = U[40 * 17 + col];
       float *row = QM + (col + 12) * kHbQW;
 #pragma unroll 1
-      for (int kk = 0; kk < 10; kk++) {
-        const int k = half * 20 + 2 * kk;
-        const float *t0 = tabs + kHtAna40 + k * 82, *t1 = t0 + 82;
-        float ar0 = u40, ai0 = -u0, ar1 = u40, ai1 = u0;
+      for (int kk = 0; kk < 5; kk++) {  // four bins per pass share the sample loads
+        const int k = half * 20 + 4 * kk;
+        const float *t0 = tabs + kHtAna40 + k * 82;
+        float ar[4], ai[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          ar[q] = u40;
+          ai[q] = (q & 1) ? u0 : -u0;  // k is even
+        }
 #pragma unroll 3
         for (int l = 1; l < 40; l++) {
           const float ul = U[l * 17 + col], um = U[(80 - l) * 17 + col];
-          const float2 w0 = *reinterpret_cast<const float2 *>(t0 + 2 * l), w1 = *reinterpret_cast<const float2 *>(t1 + 2 * l);
-          ar0 = ar0 + ul * w0.x;
-          ai0 = ai0 + um * w0.y;
-          ar1 = ar1 + ul * w1.x;
-          ai1 = ai1 + um * w1.y;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const float2 w = *reinterpret_cast<const float2 *>(t0 + 82 * q + 2 * l);
+            ar[q] = ar[q] + ul * w.x;
+            ai[q] = ai[q] + um * w.y;
+          }
         }
-        row[2 * k] = ar0;
-        row[2 * k + 1] = ai0;
-        row[2 * k + 2] = ar1;
-        row[2 * k + 3] = ai1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          row[2 * (k + q)] = ar[q];
+          row[2 * (k + q) + 1] = ai[q];
+        }
       }
     } else if (lane < 16) {
       float u_in[256], u_out[256];
@@ -774,6 +784,45 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
         OUTC[r * kOW + c] = (r < 10 && band < eb) ? st[kHbeStQout + r * 128 + 2 * band + (c & 1)] : 0.0f;
       }
       __syncwarp();
+      // bands of this chunk that are neither stretch-3 nor stretch-4 (the common case: max_stretch = 2): the four bands a lane
+      // owns walk the taps together, one lock step per tap instead of four
+      const bool only2 = !((ms >= 3 && b0 + 8 > xo1 && b0 < xo2) || (ms >= 4 && b0 + 8 > xo2 && b0 < xo3));
+      if (only2) {
+        float xr4[4], xi4[4];
+        XAdd xa4[4];
+        bool act[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int b = b0 + 2 * q + bp;
+          act[q] = b < eb && ms >= 2 && b >= xo0 && b < xo1;
+          xa4[q] = XAdd{0, 0, 0, 0, false};
+          xr4[q] = xi4[q] = 0;
+          if (act[q]) {
+            xr4[q] = N2[(6 + ci) * kNW + 2 * (b - xo0)];
+            xi4[q] = N2[(6 + ci) * kNW + 2 * (b - xo0) + 1];
+            if (xp) xa4[q] = xprod2(Q, N2, xo0, min(xo1, 63), b, ci, pf, rom + kHromXp2 + (pitch << 1));
+          }
+        }
+#pragma unroll 1
+        for (int k = 9; k >= 0; k--) {
+          const float *nrow = N2 + (1 + ci + k) * kNW + 2 * (b0 + bp - xo0);
+          float *orow = OUTC + (1 + 2 * ci + k) * kOW + 2 * bp;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (act[q]) {
+              const float tr = nrow[4 * q], ti = nrow[4 * q + 1];
+              const float cr = (tr * xr4[q] - ti * xi4[q]) * 0.3333333f;
+              const float cim = (tr * xi4[q] + ti * xr4[q]) * 0.3333333f;
+              float o0 = orow[4 * q] + cr, o1 = orow[4 * q + 1] + cim;
+              if (xa4[q].on && k == 4) { o0 += xa4[q].r0; o1 += xa4[q].i0; }
+              if (xa4[q].on && k == 5) { o0 += xa4[q].r1; o1 += xa4[q].i1; }
+              orow[4 * q] = o0;
+              orow[4 * q + 1] = o1;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
 #pragma unroll 1
       for (int q = 0; q < 4; q++) {
         const int bb = 2 * q + bp, b = b0 + bb;
@@ -851,6 +900,7 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
           }
           __syncwarp();
         }
+      }
       }
       // ---- phase D: rotation (hbe_trans.c:280-294), carry rows ----
       for (int e = lane; e < 32 * 8; e += 32) {
