@@ -83,11 +83,26 @@ WORKLOADS = {
 
 
 def ncu_traffic():
-    """per-unit DRAM bytes of each kernel measured by ncu (profiles/r1_traffic.json); bench.py does not run ncu"""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
-        return {}
-    return {k: v for k, v in json.load(open(p)).items() if isinstance(v, dict)}
+    """per-unit DRAM bytes of each kernel measured by ncu (profiles/r2_traffic.json, tools/update_traffic.py); bench.py does not run
+    ncu.  An entry whose kernel source has changed since the capture (source_sha256) is flagged stale instead of silently reused."""
+    if getattr(ncu_traffic, "_cache", None) is not None:
+        return ncu_traffic._cache
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    out = {}
+    if os.path.exists(p):
+        import hashlib
+        for k, v in json.load(open(p)).items():
+            if not isinstance(v, dict):
+                continue
+            v = dict(v)
+            src, h = v.get("kernel_source"), v.get("source_sha256")
+            if src and h and os.path.exists(os.path.join(ROOT, src)):
+                if hashlib.sha256(open(os.path.join(ROOT, src), "rb").read()).hexdigest()[:16] != h:
+                    v["stale"] = True
+                    sys.stderr.write(f"[bench] warning: {src} changed since the ncu capture of {k}: its DRAM traffic figure is stale\n")
+            out[k] = v
+    ncu_traffic._cache = out
+    return out
 
 
 def peaks():
@@ -2111,7 +2126,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": stg["kernel"], "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (ncu_traffic().get(stg["kernel"], {}).get("bytes_per_unit", 0) * n_units) or None,
-                         "traffic_source": ncu_traffic().get(stg["kernel"], {}).get("source"), "peak_source": peak_src,
+                         "traffic_source": ncu_traffic().get(stg["kernel"], {}).get("source"),
+                         "traffic_stale": bool(ncu_traffic().get(stg["kernel"], {}).get("stale", False)), "peak_source": peak_src,
                          "bytes_per_unit": stg["bytes_per_unit"], "units_per_launch": n_units,
                          "launch_ms": kernel_ms},
         }
@@ -2146,6 +2162,37 @@ def main():
                 del w2
                 torch.cuda.empty_cache()
             line["stage_rooflines"] = extra
+            # the other BASELINE configs at their own batch sizes, device-resident and through host buffers (short runs), so that the
+            # driver-run line carries them too and not only the builder's own captures
+            other = {}
+            for name in ("aac_lc_stereo_imdct_ola", "heaacv1_stereo_chain", "xheaac_stereo_chain"):
+                if name == args.workload:
+                    continue
+                ci, fr, _ = WORKLOADS[name]
+                upf2 = STAGES[name].get("units_per_frame", 2)
+                w2 = WORK[name](xb, ctx, upf2 * fr, 8, 0xAAC0 + ci, dev)
+                ms, tot, nl = timed(w2, 5, 3)
+                if hasattr(w2, "check"):
+                    w2.check()
+                w2.host_setup()
+                for s_ in range(2):
+                    w2.host_step(s_)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                for s_ in range(3):
+                    w2.host_step(2 + s_)
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+                other[name] = {"baseline_config_index": ci, "stereo_frames": fr, "value": fr * 5 / (tot * 1e-3), "unit": "frames/s",
+                               "ms_per_step": tot / 5, "steps": 5, "warmup": 3, "gpu_launches": int(nl),
+                               "e2e": {"value": fr * 3 / dt, "unit": "frames/s", "steps": 3,
+                                       "h2d_bytes_per_step": upf2 * fr * STAGES[name]["h2d"],
+                                       "d2h_bytes_per_step": upf2 * fr * STAGES[name]["d2h"]},
+                               "realtime_x_per_stream": (fr * 5 / (tot * 1e-3)) / fr / STAGES[name]["realtime_fps"]}
+                w2.host_close()
+                del w2
+                torch.cuda.empty_cache()
+            line["other_configs"] = other
         if not args.no_cpu_baseline and world == 1:
             cores = host_threads()
             stg = STAGES[args.workload]
