@@ -30,6 +30,8 @@
 #include "ixheaacd_info.h"
 #include "ixheaacd_main.h"
 #include "ixheaacd_windows.h"
+#include "ixheaacd_sbrqmftrans.h"
+#include "ixheaac_esbr_rom.h"
 
 /* ---- the reference's own implementations (ld --wrap) ---- */
 VOID __real_ixheaacd_imdct_process(ia_aac_dec_overlap_info *, WORD32 *, ia_ics_info_struct *, VOID *, const WORD16, WORD32 *,
@@ -40,6 +42,9 @@ WORD32 __real_ixheaacd_sbr_dec(ia_sbr_dec_struct *, WORD16 *, ia_sbr_header_data
                                WORD, ia_pvc_data_struct *, FLAG, WORD32[][64], WORD32, WORD32, VOID *, WORD32, WORD32);
 WORD32 __real_ixheaacd_fd_frm_dec(ia_usac_data_struct *usac_data, WORD32 i_ch);
 
+extern const FLOAT32 ixheaac_twiddle_table_fft_float[514];
+extern const FLOAT32 ixheaac_twidle_tbl_48[64];
+extern const FLOAT32 ixheaac_twidle_tbl_24[32];
 extern const WORD32 ixheaacd_twiddle_table_fft_32x32[514];
 extern const WORD32 ixheaacd_pre_post_twid_cos_512[512];
 extern const WORD32 ixheaacd_pre_post_twid_sin_512[512];
@@ -57,15 +62,21 @@ static struct {
   int8_t *d_adj;
   int16_t *d_side, *d_tin, *d_pcm;
   xaac_b200_sbr_state *st_hq, *st_ps, *st_lp;
-  long n_imdct, n_imdct_ref, n_sbr_hq, n_sbr_ps, n_sbr_lp, n_sbr_ref, n_fd, n_fd_ref;
+  /* float eSBR stage, one unit */
+  int have_esbr_rom;
+  float *e_q[6], *e_bw, *e_ec, *e_hbe, *e_fpar, *e_tin, *e_out;
+  int32_t *e_anal, *e_apos, *e_synth, *e_spos, *e_patch, *e_hbecfg, *e_hfpar, *e_ipar, *e_rg, *e_err;
+  long n_imdct, n_imdct_ref, n_sbr_hq, n_sbr_ps, n_sbr_lp, n_sbr_ref, n_fd, n_fd_ref, n_esbr, n_esbr_hbe, n_esbr_ref;
 } G;
 
 static void b200_report(void) {
   if (G.stats)
     fprintf(stderr,
             "[ixheaacd_b200] imdct_process: %ld on the GPU, %ld by the reference; sbr_dec: %ld HQ + %ld HQ/PS + %ld LP on the GPU, "
-            "%ld by the reference; fd_frm_dec: %ld on the GPU, %ld by the reference\n",
-            G.n_imdct, G.n_imdct_ref, G.n_sbr_hq, G.n_sbr_ps, G.n_sbr_lp, G.n_sbr_ref, G.n_fd, G.n_fd_ref);
+            "%ld by the reference; fd_frm_dec: %ld on the GPU, %ld by the reference; eSBR sbr_dec: %ld + %ld with HBE on the GPU, "
+            "%ld by the reference\n",
+            G.n_imdct, G.n_imdct_ref, G.n_sbr_hq, G.n_sbr_ps, G.n_sbr_lp, G.n_sbr_ref, G.n_fd, G.n_fd_ref, G.n_esbr, G.n_esbr_hbe,
+            G.n_esbr_ref);
   if (G.ctx) xaac_b200_destroy(G.ctx);
   G.ctx = NULL;
 }
@@ -204,6 +215,291 @@ static void unpack_ps_state_into(const int16_t *p, ia_ps_dec_struct *ps, ia_sbr_
   unpack_sf(p + XAAC_PS_ST_SF_R, sf_r);
 }
 
+/* ================================ ixheaacd_sbr_dec (float eSBR branch, USAC channels) ================================ */
+/* The eSBR branch of ixheaacd_sbr_dec (decoder/ixheaacd_sbr_dec.c:812-1006) for a USAC channel, with or without the harmonic
+ * transposer: xaac_b200_esbr_dec_dev / xaac_b200_esbr_dec_hbe_dev.  Frames on which ixheaacd_sbr_env_calc rebuilds its limiter
+ * tables (reset_flag, a change of sbr_patching_mode: ixheaacd_createlimiterbands needs THIS frame's patch table, which the HF
+ * generator of the same call produces) and everything outside the kernels' subset stay with the reference's code. */
+static void esbr_rom_once(xaac_b200_ctx *c, ia_sbr_tables_struct *t) {
+  if (G.have_esbr_rom) return;
+  ia_qmf_dec_tables_struct *q = t->qmf_dec_tables_ptr;
+  static int32_t er[XAAC_EROM_BYTES / 4];
+  memcpy((char *)er + XAAC_EROM_QMF_C, q->esbr_qmf_c, 1280 * 4);
+  memcpy((char *)er + XAAC_EROM_W32, q->esbr_w_32, 60 * 4);
+  memcpy((char *)er + XAAC_EROM_SINCOS_L64, q->esbr_sin_cos_twiddle_l64, 64 * 4);
+  memcpy((char *)er + XAAC_EROM_ALTSIN_L64, q->esbr_alt_sin_twiddle_l64, 32 * 4);
+  memcpy((char *)er + XAAC_EROM_W16, q->esbr_w_16, 24 * 4);
+  memcpy((char *)er + XAAC_EROM_SINCOS_L32, q->esbr_sin_cos_twiddle_l32, 32 * 4);
+  memcpy((char *)er + XAAC_EROM_ALTSIN_L32, q->esbr_alt_sin_twiddle_l32, 16 * 4);
+  memcpy((char *)er + XAAC_EROM_TCOS_L32, q->esbr_t_cos_sin_l32, 64 * 4);
+  B200(xaac_b200_set_esbr_rom(c, er, sizeof(er)), "set_esbr_rom");
+  B200(xaac_b200_set_esbr_envcalc_rom(c, ixheaac_random_phase, 4096), "set_esbr_envcalc_rom");
+  static float hr[XAAC_HROM_WORDS];
+  memcpy(hr + XAAC_HROM_WIN, ixheaac_sub_samp_qmf_window_coeff, 1560 * 4);
+  memcpy(hr + XAAC_HROM_SYNCOS, ixheaac_synth_cos_table_kl_4, 16 * 4);
+  memcpy(hr + XAAC_HROM_SYNCOS + 16, ixheaac_synth_cos_table_kl_8, 32 * 4);
+  memcpy(hr + XAAC_HROM_SYNCOS + 48, ixheaac_synth_cos_table_kl_12, 48 * 4);
+  memcpy(hr + XAAC_HROM_SYNCOS + 96, ixheaac_synth_cos_table_kl_16, 64 * 4);
+  memcpy(hr + XAAC_HROM_ANACS, ixheaac_analy_cos_sin_table_kl_8, 32 * 4);
+  memcpy(hr + XAAC_HROM_ANACS + 32, ixheaac_analy_cos_sin_table_kl_16, 64 * 4);
+  memcpy(hr + XAAC_HROM_ANACS + 96, ixheaac_analy_cos_sin_table_kl_24, 96 * 4);
+  memcpy(hr + XAAC_HROM_ANACS + 192, ixheaac_analy_cos_sin_table_kl_32, 128 * 4);
+  memcpy(hr + XAAC_HROM_COSTRANS, ixheaac_cos_table_trans_qmf, 448 * 4);
+  memcpy(hr + XAAC_HROM_FFTTW, ixheaac_twiddle_table_fft_float, 514 * 4);
+  memcpy(hr + XAAC_HROM_TW24, ixheaac_twidle_tbl_24, 32 * 4);
+  memcpy(hr + XAAC_HROM_TW48, ixheaac_twidle_tbl_48, 64 * 4);
+  memcpy(hr + XAAC_HROM_PVCOS, ixheaac_phase_vocoder_cos_table, 64 * 4);
+  memcpy(hr + XAAC_HROM_PVSIN, ixheaac_phase_vocoder_sin_table, 64 * 4);
+  memcpy(hr + XAAC_HROM_INTERP, ixheaac_hbe_post_anal_proc_interp_coeff, 8 * 4);
+  memcpy(hr + XAAC_HROM_SELCASE, ixheaac_sel_case, 40 * 4);
+  memcpy(hr + XAAC_HROM_XP2, ixheaac_hbe_x_prod_cos_table_trans_2, 512 * 4);
+  memcpy(hr + XAAC_HROM_XP3, ixheaac_hbe_x_prod_cos_table_trans_3, 512 * 4);
+  memcpy(hr + XAAC_HROM_XP4, ixheaac_hbe_x_prod_cos_table_trans_4, 512 * 4);
+  memcpy(hr + XAAC_HROM_XP41, ixheaac_hbe_x_prod_cos_table_trans_4_1, 512 * 4);
+  memcpy(hr + XAAC_HROM_SYN20, ixheaac_synth_cos_table_kl_20, 800 * 4);
+  memcpy(hr + XAAC_HROM_ANA40, ixheaac_analy_cos_sin_table_kl_40, 3200 * 4);
+  B200(xaac_b200_set_hbe_rom(c, hr, sizeof(hr)), "set_hbe_rom");
+  for (int i = 0; i < 6; i++) B200(xaac_b200_dev_alloc(c, 72 * 64 * 4, (void **)&G.e_q[i]), "alloc");
+  B200(xaac_b200_dev_alloc(c, 32, (void **)&G.e_bw), "alloc");
+  B200(xaac_b200_dev_alloc(c, 640 * 4, (void **)&G.e_ec), "alloc");
+  B200(xaac_b200_dev_alloc(c, XAAC_HBE_ST_WORDS * 4, (void **)&G.e_hbe), "alloc");
+  B200(xaac_b200_dev_alloc(c, XAAC_EEC_FPAR_WORDS * 4, (void **)&G.e_fpar), "alloc");
+  B200(xaac_b200_dev_alloc(c, 4096, (void **)&G.e_tin), "alloc");
+  B200(xaac_b200_dev_alloc(c, 8192, (void **)&G.e_out), "alloc");
+  B200(xaac_b200_dev_alloc(c, 320 * 4, (void **)&G.e_anal), "alloc");
+  B200(xaac_b200_dev_alloc(c, 16, (void **)&G.e_apos), "alloc");
+  B200(xaac_b200_dev_alloc(c, 1280 * 4, (void **)&G.e_synth), "alloc");
+  B200(xaac_b200_dev_alloc(c, 16, (void **)&G.e_spos), "alloc");
+  B200(xaac_b200_dev_alloc(c, 32, (void **)&G.e_patch), "alloc");
+  B200(xaac_b200_dev_alloc(c, XAAC_HBE_CFG_WORDS * 4, (void **)&G.e_hbecfg), "alloc");
+  B200(xaac_b200_dev_alloc(c, XAAC_EHF_PAR_WORDS * 4, (void **)&G.e_hfpar), "alloc");
+  B200(xaac_b200_dev_alloc(c, XAAC_EEC_IPAR_WORDS * 4, (void **)&G.e_ipar), "alloc");
+  B200(xaac_b200_dev_alloc(c, 16, (void **)&G.e_rg), "alloc");
+  B200(xaac_b200_dev_alloc(c, 32, (void **)&G.e_err), "alloc");
+  G.have_esbr_rom = 1;
+}
+
+static void esbr_pack_hf_par(int32_t *par, const ia_sbr_frame_info_data_struct *fd, const ia_sbr_header_data_struct *hd) {
+  const ia_freq_band_data_struct *fb = hd->pstr_freq_band_data;
+  memset(par, 0, 4 * XAAC_EHF_PAR_WORDS);
+  par[XAAC_EHF_NUM_MF] = fb->num_mf_bands;
+  par[XAAC_EHF_NUM_IF] = fb->num_nf_bands;
+  par[XAAC_EHF_SB_START] = fb->sub_band_start;
+  par[XAAC_EHF_BORDER_FIRST] = fd->str_frame_info_details.border_vec[0];
+  par[XAAC_EHF_BORDER_LAST] = fd->str_frame_info_details.border_vec[fd->str_frame_info_details.num_env];
+  par[XAAC_EHF_HBE_FLAG] = hd->hbe_flag;
+  par[XAAC_EHF_PATCHING_MODE] = fd->sbr_patching_mode;
+  par[XAAC_EHF_FS] = hd->out_sampling_freq;
+  par[XAAC_EHF_PRE_PROC] = hd->pre_proc_flag;
+  par[XAAC_EHF_USF4] = hd->is_usf_4;
+  par[XAAC_EHF_MPS_SBR] = fd->mps_sbr_flag;
+  par[XAAC_EHF_COV_COUNT] = fd->cov_count;
+  for (int i = 0; i < 5; i++) {
+    par[XAAC_EHF_INVF + i] = fd->sbr_invf_mode[i];
+    par[XAAC_EHF_INVF_PREV + i] = fd->sbr_invf_mode_prev[i];
+    par[XAAC_EHF_INVF_TBL + i] = fb->freq_band_tbl_noise[1 + i];
+  }
+  for (int i = 0; i < 57; i++) par[XAAC_EHF_FMASTER + i] = fb->f_master_tbl[i];
+}
+static void esbr_pack_ec_ipar(int32_t *ip, const ia_sbr_frame_info_data_struct *fd, const ia_sbr_header_data_struct *hd) {
+  const ia_freq_band_data_struct *fb = hd->pstr_freq_band_data;
+  const ia_frame_info_struct *fi = &fd->str_frame_info_details;
+  memset(ip, 0, 4 * XAAC_EEC_IPAR_WORDS);
+  ip[XAAC_EEC_SB_START] = fb->sub_band_start;
+  ip[XAAC_EEC_SB_END] = fb->sub_band_end;
+  ip[XAAC_EEC_NUM_ENV] = fi->num_env;
+  ip[XAAC_EEC_TRANS_ENV] = fi->transient_env;
+  ip[XAAC_EEC_SHORT_PREV] = fd->env_short_flag_prev;
+  ip[XAAC_EEC_NUM_NOISE_ENV] = fi->num_noise_env;
+  ip[XAAC_EEC_NUM_SF_LO] = fb->num_sf_bands[0];
+  ip[XAAC_EEC_NUM_SF_HI] = fb->num_sf_bands[1];
+  ip[XAAC_EEC_NUM_NF] = fb->num_nf_bands;
+  ip[XAAC_EEC_SMOOTHING_MODE] = hd->smoothing_mode;
+  ip[XAAC_EEC_INTERPOL_FREQ] = hd->interpol_freq;
+  ip[XAAC_EEC_LIMITER_BANDS] = hd->limiter_bands;
+  ip[XAAC_EEC_LIMITER_GAINS] = hd->limiter_gains;
+  ip[XAAC_EEC_HARM_INDEX] = fd->harm_index;
+  ip[XAAC_EEC_PHASE_INDEX] = fd->phase_index;
+  ip[XAAC_EEC_START_UP] = hd->esbr_start_up;
+  ip[XAAC_EEC_RESET] = fd->reset_flag;
+  ip[XAAC_EEC_SBR_MODE] = fd->sbr_mode;
+  ip[XAAC_EEC_USF4] = hd->is_usf_4;
+  ip[XAAC_EEC_PATCHING_CHANGED] = fd->sbr_patching_mode != fd->prev_sbr_patching_mode;
+  for (int i = 0; i < 9; i++) ip[XAAC_EEC_BORDER + i] = fi->border_vec[i];
+  for (int i = 0; i < 8; i++) ip[XAAC_EEC_FREQ_RES + i] = fi->freq_res[i];
+  for (int i = 0; i < 3; i++) ip[XAAC_EEC_NOISE_BORDER + i] = fi->noise_border_vec[i];
+  for (int i = 0; i < 8; i++) ip[XAAC_EEC_INTER_TES + i] = fd->inter_temp_shape_mode[i];
+  for (int i = 0; i < 4; i++) ip[XAAC_EEC_GATE_MODE + i] = fd->gate_mode[i];
+  for (int i = 0; i < 52; i++) ip[XAAC_EEC_LIM_TABLE + i] = fd->lim_table[i / 13][i % 13];
+  for (int i = 0; i < 6; i++) ip[XAAC_EEC_TBL_NOISE + i] = fb->freq_band_tbl_noise[i];
+  for (int i = 0; i < 29; i++) ip[XAAC_EEC_TBL_LO + i] = fb->freq_band_tbl_lo[i];
+  for (int i = 0; i < 57; i++) ip[XAAC_EEC_TBL_HI + i] = fb->freq_band_tbl_hi[i];
+  for (int i = 0; i < 56; i++) ip[XAAC_EEC_ADD_HARM + i] = fd->add_harmonics[i];
+  memcpy(ip + XAAC_EEC_HARM_PREV, fd->harm_flag_prev, 64);
+}
+
+static WORD32 esbr_dec_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_header_data_struct *hd,
+                            ia_sbr_frame_info_data_struct *fd, ia_sbr_tables_struct *t, ia_pvc_data_struct *pvc, int *done) {
+  *done = 0;
+  esbr_rom_once(c, t);
+  const int hbe = hd->hbe_flag != 0;
+  ia_esbr_hbe_txposer_struct *tx = d->p_hbe_txposer;
+  ia_sbr_qmf_filter_bank_struct *a = &d->str_codec_qmf_bank, *y = &d->str_synthesis_qmf_bank;
+  WORD32 *qc = (WORD32 *)t->qmf_dec_tables_ptr->esbr_qmf_c;
+  const int rows = hbe ? 72 : 40;
+  static int32_t hf_par[XAAC_EHF_PAR_WORDS], ipar[XAAC_EEC_IPAR_WORDS], hcfg[XAAC_HBE_CFG_WORDS], rg[4], apos[2], spos[2], patch[8],
+      err[5];
+  static float fpar[XAAC_EEC_FPAR_WORDS], ec[640], hst[XAAC_HBE_ST_WORDS], bw[6];
+  if (hbe) {
+    if (!tx) return 0;
+    if (tx->ixheaacd_cmplx_anal_fft == NULL) { /* hbe_trans.c:240-248: the reference re-initialises inside the call */
+      WORD32 e = ixheaacd_qmf_hbe_data_reinit(tx, hd->pstr_freq_band_data->freq_band_table, hd->pstr_freq_band_data->num_sf_bands,
+                                              hd->is_usf_4);
+      if (e) return 0; /* let the reference report it */
+    }
+    const int S = tx->synth_size;
+    if (S < 1 || S > 20 || tx->no_bins != 32) return 0;
+    memset(hcfg, 0, sizeof(hcfg));
+    hcfg[XAAC_HBE_SYNTH_SIZE] = S;
+    hcfg[XAAC_HBE_K_START] = tx->k_start;
+    hcfg[XAAC_HBE_START_BAND] = tx->start_band;
+    hcfg[XAAC_HBE_END_BAND] = tx->end_band;
+    hcfg[XAAC_HBE_MAX_STRETCH] = tx->max_stretch;
+    hcfg[XAAC_HBE_PITCH] = fd->pitch_in_bins;
+    hcfg[XAAC_HBE_USF4] = tx->upsamp_4_flag;
+    for (int i = 0; i < 6; i++) hcfg[XAAC_HBE_XOVER + i] = tx->x_over_qmf[i];
+    memset(hst, 0, sizeof(hst));
+    memcpy(hst + XAAC_HBE_ST_TAIL, tx->ptr_input_buf + tx->no_bins * S, S * 4);
+    memcpy(hst + XAAC_HBE_ST_SYNTH, tx->synth_buf, 18 * S * 4);
+    memcpy(hst + XAAC_HBE_ST_ANAL, tx->analy_buf, 18 * S * 4);
+    for (int r = 0; r < 12; r++) memcpy(hst + XAAC_HBE_ST_QIN + 128 * r, tx->qmf_in_buf[16 + r], 512);
+    for (int r = 0; r < 10; r++) memcpy(hst + XAAC_HBE_ST_QOUT + 128 * r, tx->qmf_out_buf[32 + r], 512);
+  }
+  esbr_pack_hf_par(hf_par, fd, hd);
+  esbr_pack_ec_ipar(ipar, fd, hd);
+  memset(fpar, 0, sizeof(fpar));
+  memcpy(fpar + XAAC_EEC_SFB_NRG, fd->flt_env_sf_arr, 448 * 4);
+  memcpy(fpar + XAAC_EEC_NOISE_FLOOR, fd->flt_noise_floor, 10 * 4);
+  memcpy(ec, fd->e_gain, 320 * 4);
+  memcpy(ec + 320, fd->noise_buf, 320 * 4);
+  memcpy(bw, fd->bw_array_prev, sizeof(bw));
+  patch[0] = fd->patch_param.num_patches;
+  for (int i = 0; i < 7; i++) patch[1 + i] = fd->patch_param.start_subband[i];
+  rg[0] = hd->pstr_freq_band_data->qmf_sb_prev;
+  rg[1] = hd->pstr_freq_band_data->sub_band_start;
+  rg[2] = 2 * fd->str_frame_info_details.border_vec[0];
+  rg[3] = 0;
+  apos[0] = (int32_t)(a->state_new_samples_pos_low_32 - a->anal_filter_states_32);
+  apos[1] = (int32_t)(a->filter_pos_32 - qc);
+  spos[0] = y->ixheaacd_drc_offset;
+  spos[1] = (int32_t)(y->filter_pos_syn_32 - y->p_filter_32);
+  if (apos[0] < 0 || apos[0] >= 320 || apos[1] < 0 || apos[1] > 640 || spos[1] < 0 || spos[1] > 640) return 0;
+  float *src[6] = {&d->qmf_buf_real[0][0], &d->qmf_buf_imag[0][0], &d->sbr_qmf_out_real[0][0], &d->sbr_qmf_out_imag[0][0],
+                   &d->ph_vocod_qmf_real[0][0], &d->ph_vocod_qmf_imag[0][0]};
+  for (int i = 0; i < (hbe ? 6 : 4); i++)
+    B200(xaac_b200_h2d(c, G.e_q[i], src[i], (size_t)(i < 2 ? rows : 40) * 64 * 4), "h2d qmf");
+  B200(xaac_b200_h2d(c, G.e_anal, a->anal_filter_states_32, 320 * 4), "h2d");
+  B200(xaac_b200_h2d(c, G.e_apos, apos, 8), "h2d");
+  B200(xaac_b200_h2d(c, G.e_synth, y->filter_states_32, 1280 * 4), "h2d");
+  B200(xaac_b200_h2d(c, G.e_spos, spos, 8), "h2d");
+  B200(xaac_b200_h2d(c, G.e_bw, bw, 24), "h2d");
+  B200(xaac_b200_h2d(c, G.e_patch, patch, 32), "h2d");
+  B200(xaac_b200_h2d(c, G.e_ec, ec, sizeof(ec)), "h2d");
+  B200(xaac_b200_h2d(c, G.e_hfpar, hf_par, sizeof(hf_par)), "h2d");
+  B200(xaac_b200_h2d(c, G.e_ipar, ipar, sizeof(ipar)), "h2d");
+  B200(xaac_b200_h2d(c, G.e_fpar, fpar, sizeof(fpar)), "h2d");
+  B200(xaac_b200_h2d(c, G.e_rg, rg, 16), "h2d");
+  B200(xaac_b200_h2d(c, G.e_tin, d->time_sample_buf, 4096), "h2d");
+  xaac_b200_esbr_hbe_state_view v;
+  memset(&v, 0, sizeof(v));
+  v.base.qmf_re = G.e_q[0]; v.base.qmf_im = G.e_q[1]; v.base.out_re = G.e_q[2]; v.base.out_im = G.e_q[3];
+  v.base.anal_states = G.e_anal; v.base.anal_pos = G.e_apos; v.base.synth_states = G.e_synth; v.base.synth_pos = G.e_spos;
+  v.base.bw_prev = G.e_bw; v.base.patch = G.e_patch; v.base.ec_state = G.e_ec;
+  v.pv_re = G.e_q[4]; v.pv_im = G.e_q[5]; v.hbe_state = G.e_hbe;
+  memset(err, 0, sizeof(err));
+  B200(xaac_b200_h2d(c, G.e_err, err, sizeof(err)), "h2d");
+  if (hbe) {
+    B200(xaac_b200_h2d(c, G.e_hbe, hst, sizeof(hst)), "h2d");
+    B200(xaac_b200_h2d(c, G.e_hbecfg, hcfg, sizeof(hcfg)), "h2d");
+    B200(xaac_b200_esbr_dec_hbe_dev(c, &v, G.e_tin, NULL, G.e_hbecfg, G.e_hfpar, G.e_ipar, G.e_fpar, G.e_rg, G.e_out, NULL, 1,
+                                    G.e_err, 1, NULL), "esbr_dec_hbe_dev");
+  } else {
+    B200(xaac_b200_esbr_dec_dev(c, &v.base, G.e_tin, NULL, G.e_hfpar, G.e_ipar, G.e_fpar, G.e_rg, G.e_out, NULL, 1, G.e_err, 1, NULL),
+         "esbr_dec_dev");
+  }
+  B200(xaac_b200_d2h(c, err, G.e_err, sizeof(err)), "d2h err");
+  for (int i = 0; i < 5; i++)
+    if (err[i] == -2) return 0; /* outside the kernels' subset: nothing on the host has been touched yet */
+  *done = 1;
+  for (int i = 0; i < 5; i++)
+    if (err[i] != 0) return err[i]; /* the reference's own failure codes */
+  /* ---- results and state back into the reference's structs ---- */
+  for (int i = 0; i < (hbe ? 6 : 4); i++)
+    B200(xaac_b200_d2h(c, src[i], G.e_q[i], (size_t)(i < 2 ? rows : 40) * 64 * 4), "d2h qmf");
+  B200(xaac_b200_d2h(c, a->anal_filter_states_32, G.e_anal, 320 * 4), "d2h");
+  B200(xaac_b200_d2h(c, apos, G.e_apos, 8), "d2h");
+  B200(xaac_b200_d2h(c, y->filter_states_32, G.e_synth, 1280 * 4), "d2h");
+  B200(xaac_b200_d2h(c, spos, G.e_spos, 8), "d2h");
+  B200(xaac_b200_d2h(c, bw, G.e_bw, 24), "d2h");
+  B200(xaac_b200_d2h(c, patch, G.e_patch, 32), "d2h");
+  B200(xaac_b200_d2h(c, ec, G.e_ec, sizeof(ec)), "d2h");
+  static int32_t ipar_in[XAAC_EEC_IPAR_WORDS];
+  memcpy(ipar_in, ipar, sizeof(ipar));
+  B200(xaac_b200_d2h(c, ipar, G.e_ipar, sizeof(ipar)), "d2h");
+  B200(xaac_b200_d2h(c, d->time_sample_buf, G.e_out, 8192), "d2h out");
+  a->usb = a->no_channels; /* sbr_dec.c:238 */
+  a->state_new_samples_pos_low_32 = a->anal_filter_states_32 + apos[0];
+  a->filter_pos_32 = qc + apos[1];
+  y->esbr_cos_twiddle = (WORD32 *)t->qmf_dec_tables_ptr->esbr_sin_cos_twiddle_l64; /* sbr_dec.c:567-580 */
+  y->esbr_alt_sin_twiddle = (WORD32 *)t->qmf_dec_tables_ptr->esbr_alt_sin_twiddle_l64;
+  y->p_filter_32 = qc;
+  y->filter_pos_syn_32 = qc + spos[1];
+  y->ixheaacd_drc_offset = spos[0];
+  memcpy(fd->bw_array_prev, bw, sizeof(bw));
+  fd->patch_param.num_patches = patch[0];
+  for (int i = 0; i < 7; i++) fd->patch_param.start_subband[i] = patch[1 + i];
+  memcpy(fd->e_gain, ec, 320 * 4);
+  memcpy(fd->noise_buf, ec + 320, 320 * 4);
+  /* ixheaacd_sbr_env_calc's epilogue (esbr_envcal.c:861-908) */
+  const int sbs = hd->pstr_freq_band_data->sub_band_start;
+  memcpy(fd->harm_flag_varlen_prev, fd->harm_flag_prev, 64);
+  memcpy(fd->harm_flag_prev, ipar + XAAC_EEC_HARM_PREV, 64);
+  for (int i = 0; i < 64; i++) fd->harm_flag_varlen[i] = i >= sbs ? fd->harm_flag_prev[i] : 0;
+  fd->env_short_flag_prev = ipar[XAAC_EEC_SHORT_PREV];
+  memcpy(&fd->str_frame_info_prev, &fd->str_frame_info_details, sizeof(ia_frame_info_struct));
+  if (fd->str_frame_info_details.num_env == 1) fd->var_len_id_prev = 0;
+  else if (fd->str_frame_info_details.num_env == 2) fd->var_len_id_prev = 1;
+  {
+    const int nnf = hd->pstr_freq_band_data->num_nf_bands;
+    for (int i = 0; i < nnf; i++)
+      fd->prev_noise_level[i] = fd->flt_noise_floor[(fd->str_frame_info_details.num_noise_env - 1) * nnf + i];
+  }
+  fd->harm_index = ipar[XAAC_EEC_HARM_INDEX];
+  fd->phase_index = ipar[XAAC_EEC_PHASE_INDEX];
+  hd->esbr_start_up = ipar[XAAC_EEC_START_UP];
+  /* the rest of the stage's bookkeeping (sbr_dec.c:931-1003) */
+  pvc->pvc_rate = hd->upsamp_fac;
+  pvc->prev_pvc_flg = 0;
+  pvc->prev_first_bnd_idx = hd->pstr_freq_band_data->sub_band_start;
+  pvc->prev_pvc_rate = pvc->pvc_rate;
+  fd->pstr_sbr_header = hd;
+  d->band_count = hd->pstr_freq_band_data->sub_band_end;
+  fd->reset_flag = 0;
+  fd->prev_sbr_mode = fd->sbr_mode;
+  if (hbe) {
+    const int S = tx->synth_size;
+    B200(xaac_b200_d2h(c, hst, G.e_hbe, sizeof(hst)), "d2h hbe");
+    memcpy(tx->ptr_input_buf + tx->no_bins * S, hst + XAAC_HBE_ST_TAIL, S * 4);
+    memcpy(tx->synth_buf, hst + XAAC_HBE_ST_SYNTH, 18 * S * 4);
+    memcpy(tx->analy_buf, hst + XAAC_HBE_ST_ANAL, 18 * S * 4);
+    for (int r = 0; r < 12; r++) memcpy(tx->qmf_in_buf[16 + r], hst + XAAC_HBE_ST_QIN + 128 * r, 512);
+    for (int r = 0; r < 10; r++) memcpy(tx->qmf_out_buf[32 + r], hst + XAAC_HBE_ST_QOUT + 128 * r, 512);
+    for (int r = 42; r < 64; r++) memset(tx->qmf_out_buf[r], 0, 512);
+  }
+  (void)ipar_in;
+  return 0;
+}
+
 WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *ptr_sbr_dec, WORD16 *ptr_time_data, ia_sbr_header_data_struct *ptr_header_data,
                                ia_sbr_frame_info_data_struct *ptr_frame_data, ia_sbr_prev_frame_data_struct *ptr_frame_data_prev,
                                ia_ps_dec_struct *ptr_ps_dec, ia_sbr_qmf_filter_bank_struct *ptr_qmf_synth_bank_r,
@@ -213,6 +509,32 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *ptr_sbr_dec, WORD16 *ptr_time_
                                FLAG drc_on, WORD32 drc_sbr_factors[][64], WORD32 audio_object_type, WORD32 ldmps_present,
                                VOID *self, WORD32 heaac_mps_present, WORD32 ec_flag) {
   xaac_b200_ctx *c = b200_ctx();
+  if (c && ptr_header_data->enh_sbr && ptr_header_data->usac_flag && audio_object_type != AOT_ER_AAC_ELD &&
+      audio_object_type != AOT_ER_AAC_LD) {
+    /* float eSBR branch of a USAC channel */
+    int tes = 0;
+    for (int i = 0; i < 8; i++) tes |= ptr_frame_data->inter_temp_shape_mode[i];
+    const int ok = apply_processing && !low_pow_flag && !ldmps_present && !drc_on && !heaac_mps_present && !ec_flag &&
+                   ptr_header_data->num_time_slots == 16 && ptr_sbr_dec->str_codec_qmf_bank.no_channels == 32 &&
+                   ptr_sbr_dec->str_synthesis_qmf_bank.no_channels == 64 && ptr_header_data->channel_mode != PS_STEREO &&
+                   !ptr_header_data->enh_sbr_ps && ptr_frame_data->stereo_config_idx <= 0 && !ptr_frame_data->mps_sbr_flag &&
+                   ptr_frame_data->sbr_mode == ORIG_SBR && !ptr_header_data->is_usf_4 && !ptr_header_data->pre_proc_flag && !tes &&
+                   !ptr_frame_data->reset_flag && ptr_frame_data->sbr_patching_mode == ptr_frame_data->prev_sbr_patching_mode &&
+                   (ptr_frame_data->str_frame_info_details.num_noise_env == 1 || ptr_frame_data->str_frame_info_details.num_noise_env == 2);
+    if (ok) {
+      int done = 0;
+      WORD32 r = esbr_dec_b200(c, ptr_sbr_dec, ptr_header_data, ptr_frame_data, sbr_tables_ptr, ptr_pvc_data_str, &done);
+      if (done) {
+        if (ptr_header_data->hbe_flag) G.n_esbr_hbe++; else G.n_esbr++;
+        return r;
+      }
+    }
+    G.n_esbr_ref++;
+    return __real_ixheaacd_sbr_dec(ptr_sbr_dec, ptr_time_data, ptr_header_data, ptr_frame_data, ptr_frame_data_prev, ptr_ps_dec,
+                                   ptr_qmf_synth_bank_r, ptr_sbr_sf_r, apply_processing, low_pow_flag, ptr_work_buf_core,
+                                   sbr_tables_ptr, pstr_common_tables, ch_fac, ptr_pvc_data_str, drc_on, drc_sbr_factors,
+                                   audio_object_type, ldmps_present, self, heaac_mps_present, ec_flag);
+  }
   /* the low-power branch never runs PS (the caller may still hand over the PS instance of the element) */
   const int ps_present = !low_pow_flag && ptr_ps_dec != NULL && ptr_qmf_synth_bank_r != NULL && ptr_sbr_sf_r != NULL;
   const int eligible = c && !ptr_header_data->enh_sbr && ptr_header_data->num_time_slots == 16 && ptr_header_data->time_step == 2 &&
