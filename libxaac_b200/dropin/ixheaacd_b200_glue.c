@@ -375,6 +375,16 @@ static WORD32 esbr_dec_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_heade
     for (int r = 0; r < 12; r++) memcpy(hst + XAAC_HBE_ST_QIN + 128 * r, tx->qmf_in_buf[16 + r], 512);
     for (int r = 0; r < 10; r++) memcpy(hst + XAAC_HBE_ST_QOUT + 128 * r, tx->qmf_out_buf[32 + r], 512);
   }
+  if (hbe && !hd->usac_flag) {
+    /* sbr_dec.c:868-874 (legacy streams): after the history shift the reference clears (64 - qmf_sb_prev) BYTES — not floats —
+     * from band qmf_sb_prev of rows 2..7; those are rows 34..39 before the shift, which the kernel performs */
+    const int q = hd->pstr_freq_band_data->qmf_sb_prev;
+    if (q >= 0 && q < 64)
+      for (int i = 2; i < 8; i++) {
+        memset(&d->qmf_buf_real[32 + i][q], 0, (size_t)(64 - q));
+        memset(&d->qmf_buf_imag[32 + i][q], 0, (size_t)(64 - q));
+      }
+  }
   esbr_pack_hf_par(hf_par, fd, hd);
   esbr_pack_ec_ipar(ipar, fd, hd);
   memset(fpar, 0, sizeof(fpar));
@@ -509,12 +519,13 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *ptr_sbr_dec, WORD16 *ptr_time_
                                FLAG drc_on, WORD32 drc_sbr_factors[][64], WORD32 audio_object_type, WORD32 ldmps_present,
                                VOID *self, WORD32 heaac_mps_present, WORD32 ec_flag) {
   xaac_b200_ctx *c = b200_ctx();
-  if (c && ptr_header_data->enh_sbr && ptr_header_data->usac_flag && audio_object_type != AOT_ER_AAC_ELD &&
-      audio_object_type != AOT_ER_AAC_LD) {
-    /* float eSBR branch of a USAC channel */
+  if (c && ptr_header_data->enh_sbr && audio_object_type != AOT_ER_AAC_ELD && audio_object_type != AOT_ER_AAC_LD) {
+    /* float eSBR branch: a USAC channel, or a legacy HE-AAC channel decoded in the reference's default (eSBR) mode, where the
+     * harmonic transposer is forced on (decoder/ixheaacd_sbrdecoder.c:400-403) */
     int tes = 0;
     for (int i = 0; i < 8; i++) tes |= ptr_frame_data->inter_temp_shape_mode[i];
-    const int ok = apply_processing && !low_pow_flag && !ldmps_present && !drc_on && !heaac_mps_present && !ec_flag &&
+    const int ok = apply_processing && (!low_pow_flag || !ptr_header_data->usac_flag) && !ldmps_present && !drc_on &&
+                   !heaac_mps_present && !ec_flag && (ptr_header_data->usac_flag || ptr_header_data->hbe_flag) &&
                    ptr_header_data->num_time_slots == 16 && ptr_sbr_dec->str_codec_qmf_bank.no_channels == 32 &&
                    ptr_sbr_dec->str_synthesis_qmf_bank.no_channels == 64 && ptr_header_data->channel_mode != PS_STEREO &&
                    !ptr_header_data->enh_sbr_ps && ptr_frame_data->stereo_config_idx <= 0 && !ptr_frame_data->mps_sbr_flag &&

@@ -107,3 +107,28 @@ def test_usac_through_reference_parser(tmp_path, name, extra):
         assert es_hbe >= 2 * 1400 and es_ref <= 0.06 * (es + es_hbe + es_ref), m.group(0)
     else:
         assert es >= 2 * 1500 and es_hbe == 0 and es_ref <= 4, m.group(0)
+
+
+@pytest.mark.parametrize("name,enc,fs,ch,secs", [("heaac_v1_stereo_default_mode", ["-aot:5", "-adts:1", "-br:48000"], 48000, 2, 70.0),
+                                                 ("heaac_v1_mono_default_mode", ["-aot:5", "-adts:1", "-br:32000"], 44100, 1, 70.0)])
+def test_legacy_heaac_in_default_esbr_mode(tmp_path, name, enc, fs, ch, secs):
+    """HE-AACv1 decoded with the reference's DEFAULT flags (no -esbr:0): the float eSBR branch with the harmonic transposer
+    forced on (decoder/ixheaacd_sbrdecoder.c:400-403) — IMDCT and the eSBR + HBE stage on the GPU behind the reference parser, the
+    PCM16 <-> float hand-overs stay the reference's (ixheaacd_api.c:3384-3437, ixheaacd_samples_sat)."""
+    _need()
+    wav = str(tmp_path / "in.wav")
+    _synth_wav(wav, fs, secs, ch, 5 + len(name))
+    bits = str(tmp_path / (name + ".aac"))
+    _run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{bits}"] + enc)
+    ref_wav, our_wav = str(tmp_path / "ref.wav"), str(tmp_path / "b200.wav")
+    _run([os.path.join(REFDIR, "xaacdec"), f"-ifile:{bits}", f"-ofile:{ref_wav}"])
+    log = _run([B200, f"-ifile:{bits}", f"-ofile:{our_wav}"], env=dict(os.environ, IXHEAACD_B200_STATS="1"))
+    m = re.search(r"imdct_process: (\d+) on the GPU, (\d+) by the reference.*eSBR sbr_dec: (\d+) \+ (\d+) with HBE on the GPU, (\d+) by the reference", log)
+    assert m, log[-800:]
+    imdct, imdct_ref, es, es_hbe, es_ref = map(int, m.groups())
+    a, b = open(ref_wav, "rb").read(), open(our_wav, "rb").read()
+    assert len(a) == len(b) and len(a) > 100000
+    x, y = np.frombuffer(a[44:], np.int16).astype(np.int32), np.frombuffer(b[44:], np.int16).astype(np.int32)
+    bad = np.flatnonzero(x != y)
+    assert bad.size == 0, f"{name}: {bad.size} of {x.size} samples differ, first at {bad[0]}, max |diff| {np.abs(x - y).max()}; {m.group(0)}"
+    assert imdct_ref == 0 and es_hbe >= ch * 1400 and es_ref <= ch * 3, m.group(0)
