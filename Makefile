@@ -20,6 +20,7 @@ build/%.o: $(CSRC)/%.cu $(HDR)
 
 # float code written as plain expressions in the reference's evaluation order: no FMA contraction (the reference build has none)
 FLAGS_esbr_hbe_kernel := -fmad=false
+FLAGS_esbr_ps_kernel  := -fmad=false
 
 $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
@@ -40,7 +41,7 @@ DROPIN_WRAPS := -Wl,--wrap=ixheaacd_imdct_process -Wl,--wrap=ixheaacd_sbr_dec -W
 DROPIN_FLAGS := -std=gnu99 -D_X86_ -DX86_64 -D_X86_64_ -DLOUDNESS_LEVELING_SUPPORT -O2 -fwrapv -w \
                 -UARM_PROFILE_HW -UARM_PROFILE_BOARD -DDRC_ENABLE -DMULTICHANNEL_ENABLE -DECLIPSE -DWIN32
 dropin: $(DROPIN_OUT)/xaacdec_b200
-$(DROPIN_OUT)/xaacdec_b200: $(LIB) $(DROPIN)/ixheaacd_b200_glue.c $(DROPIN)/ixheaacd_b200_pack.h $(DROPIN)/ixheaacd_b200_ref_headers.h include/xaac_b200.h oracle/_ref/libxaacdec.a
+$(DROPIN_OUT)/xaacdec_b200: $(LIB) $(DROPIN)/ixheaacd_b200_glue.c $(DROPIN)/ixheaacd_b200_pack.h $(DROPIN)/ixheaacd_b200_pack_ps_flt.h $(DROPIN)/ixheaacd_b200_ref_headers.h include/xaac_b200.h oracle/_ref/libxaacdec.a
 	@mkdir -p $(DROPIN_OUT)
 	gcc $(DROPIN_FLAGS) -I$(REF)/common -I$(REF)/decoder -I$(REF)/decoder/drc_src -I$(REF)/test/decoder -I$(DROPIN) -Iinclude \
 	    -o $@ $(wildcard $(REF)/test/decoder/*.c) $(DROPIN)/ixheaacd_b200_glue.c $(DROPIN_WRAPS) oracle/_ref/libxaacdec.a \

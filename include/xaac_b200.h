@@ -694,6 +694,71 @@ int32_t xaac_b200_esbr_dec_hbe_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_
                                    int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par, float *d_out,
                                    int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream);
 
+/* ---- float parametric stereo of the eSBR branch: ixheaacd_esbr_apply_ps (decoder/ixheaacd_ps_dec_flt.c:381-505) in the 20-band
+ * configuration the bitstream parser always selects (use_34_st_bands = 0, use_pca_rot_flg = 0, ixheaacd_sbrdec_lpfuncs.c:636-637),
+ * ps_mode = 0: hybrid analysis, transient detection, all-pass decorrelation, rotation, hybrid synthesis, fused with the
+ * regrouping (ixheaacd_esbr_synthesis_regrp) and the six look-ahead slots of decoder/ixheaacd_sbr_dec.c:481-517.
+ * ROM blob (float / int32 words), built from ia_ps_tables_struct (decoder/ixheaacd_sbr_rom.h:158-239): */
+#define XAAC_FPSROM_P8 0         /* p8_13_20[13] */
+#define XAAC_FPSROM_P2 16        /* p2_13_20[13] */
+#define XAAC_FPSROM_COS2 32      /* cos_mod_2channel[2][13] */
+#define XAAC_FPSROM_CS8 64       /* cos_sin_mod_8channel[8][26] */
+#define XAAC_FPSROM_QF_RE 272    /* qmf_fract_delay_phase_factor_re[64] */
+#define XAAC_FPSROM_QF_IM 336    /* qmf_fract_delay_phase_factor_im[64] */
+#define XAAC_FPSROM_SUB_RE 400   /* frac_delay_phase_fac_qmf_sub_re_20[12] */
+#define XAAC_FPSROM_SUB_IM 416   /* frac_delay_phase_fac_qmf_sub_im_20[12] */
+#define XAAC_FPSROM_QSER_RE 432  /* qmf_ser_fract_delay_phase_factor_re[64][3] */
+#define XAAC_FPSROM_QSER_IM 624  /* qmf_ser_fract_delay_phase_factor_im[64][3] */
+#define XAAC_FPSROM_SSER_RE 816  /* frac_delay_phase_fac_ser_qmf_sub_re_20[12][3] */
+#define XAAC_FPSROM_SSER_IM 856  /* frac_delay_phase_fac_ser_qmf_sub_im_20[12][3] */
+#define XAAC_FPSROM_DECAY 896    /* all_pass_link_decay_ser[3] */
+#define XAAC_FPSROM_QDELN 900    /* int32 qmf_delay_idx_tbl[64] */
+#define XAAC_FPSROM_GRB 964      /* int32 group_borders_20_tbl[23] */
+#define XAAC_FPSROM_BGM 988      /* int32 bin_group_map_20[22] (bit 12 = NEGATE_IPD_MASK) */
+#define XAAC_FPSROM_DSER 1012    /* int32 delay_sample_ser[3] (rev_link_delay_ser) */
+#define XAAC_FPSROM_WORDS 1016
+int32_t xaac_b200_set_fps_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes);
+/* d_side [n][XAAC_FPS_SIDE_WORDS]: int32 words num_env, border_position[0..5], usb (sub_band_end); then six sets of
+ * [8][20] floats h11r h12r h21r h22r h11i h12i h21i h22i: set 0 = h*_prev of the instance, set 1 + e = the h*_vec of envelope e
+ * (ps_dec_flt.c:920-1020; double-precision libm on the host — see libxaac_b200/dropin/ixheaacd_b200_pack_ps_flt.h).
+ * Supported: border_position[0] = 0, border_position[num_env] = 32, strictly increasing; anything else -> err -2. */
+#define XAAC_FPS_SIDE_NUM_ENV 0
+#define XAAC_FPS_SIDE_BORDER 1
+#define XAAC_FPS_SIDE_USB 7
+#define XAAC_FPS_SIDE_H 16
+#define XAAC_FPS_SIDE_WORDS 1024
+/* d_state [n][XAAC_FPS_ST_WORDS] in/out (float words unless noted), members of ia_ps_dec_struct: */
+#define XAAC_FPS_ST_HYB 0        /* hyb_qmf_buf_re_34[5][12] | _im (bands 0..2 are also hyb_qmf_buf_*_20) */
+#define XAAC_FPS_ST_SUBDEL 120   /* sub_qmf_delay_buf_re[2][0..11] | _im */
+#define XAAC_FPS_ST_SERSUB 168   /* ser_sub_qmf_dealy_buf_re[3][5][0..11] | _im */
+#define XAAC_FPS_ST_QDEL 528     /* qmf_delay_buf_re[14][64] | _im */
+#define XAAC_FPS_ST_SERQ 2320    /* ser_qmf_delay_buf_re[3][5][64] | _im */
+#define XAAC_FPS_ST_BINS 4240    /* peak_decay_fast_bin[20] | prev_nrg_bin[20] | prev_peak_diff_bin[20] */
+#define XAAC_FPS_ST_IDX 4300     /* int32 delay_buf_idx, delay_buf_idx_ser[3], delay_qmf_delay_buf_idx[64] */
+#define XAAC_FPS_ST_WORDS 4368
+/* The mono channel is read exactly as the synthesis bank's stage mode reads it: slot s, band k = row 2 + s of d_low_* when
+ * k < x_over(s), else of d_high_* (d_rg_par as in xaac_b200_esbr_dec_dev); rows 34..39, bands 0..4 of d_low_* are the look-ahead.
+ * low_rows = 40 or 72 (rows per unit of d_low_*).  d_left / d_right [n][32][128]: per slot re[64] | im[64]. */
+int32_t xaac_b200_esbr_ps_apply_dev(xaac_b200_ctx *ctx, const float *d_low_re, const float *d_low_im, int32_t low_rows,
+                                    const float *d_high_re, const float *d_high_im, const int32_t *d_rg_par,
+                                    const float *d_side, float *d_state, float *d_left, float *d_right, int32_t *d_err,
+                                    int64_t n_units, void *stream);
+/* Whole stage for a mono + PS element (channel_mode == PS_STEREO or enh_sbr_ps, decoder/ixheaacd_sbr_dec.c:976-1001): the stage
+ * of xaac_b200_esbr_dec_dev / _dec_hbe_dev (st->pv_re = NULL selects the former) up to the envelope adjuster, the PS kernel,
+ * then the synthesis bank twice — the left matrix through the element's own bank, the right one through the second channel's.
+ * d_err is [6][n] (row 4 = transposer, row 5 = PS). */
+typedef struct xaac_b200_esbr_ps_view {
+  float *ps_state;          /* [n][XAAC_FPS_ST_WORDS] */
+  float *left, *right;      /* [n][32][128] scratch */
+  int32_t *synth_states_r;  /* [n][1280] pstr_sbr_channel[1]->str_sbr_dec.str_synthesis_qmf_bank.filter_states_32 */
+  int32_t *synth_pos_r;     /* [n][2] */
+} xaac_b200_esbr_ps_view;
+int32_t xaac_b200_esbr_dec_ps_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const xaac_b200_esbr_ps_view *ps,
+                                  const float *d_time_in, const int32_t *d_core_in, const int32_t *d_hbe_cfg,
+                                  const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par,
+                                  const float *d_ps_side, float *d_out_l, float *d_out_r, int32_t *d_err, int64_t n_units,
+                                  void *stream);
+
 /* ---- raw device-memory helpers for C hosts that do not link the CUDA runtime themselves (the reference-side drop-in glue,
  * libxaac_b200/dropin/ixheaacd_b200_glue.c): allocation and synchronous copies on the context's device ---- */
 int32_t xaac_b200_dev_alloc(xaac_b200_ctx *ctx, size_t bytes, void **d_ptr);

@@ -25,6 +25,7 @@ class Context:
         self.set_esbr_rom(esbr_rom if esbr_rom is not None else _lib.rom_blob("esbr_rom.bin"))
         self.set_esbr_envcalc_rom(_lib.rom_blob("esbr_random_phase.bin"))
         self.set_hbe_rom(_lib.rom_blob("hbe_rom.bin"))
+        self.set_fps_rom(_lib.rom_blob("fps_rom.bin"))
 
     # -- plumbing ---------------------------------------------------------------------------------
     @property
@@ -74,6 +75,11 @@ class Context:
         """The harmonic transposer's float tables (XAAC_HROM_* layout, 37296 bytes)."""
         buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
         self.check(self._lib.xaac_b200_set_hbe_rom(self._h, buf, len(blob)), "xaac_b200_set_hbe_rom")
+
+    def set_fps_rom(self, blob):
+        """The float parametric stereo's tables (XAAC_FPSROM_* layout, 4064 bytes)."""
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        self.check(self._lib.xaac_b200_set_fps_rom(self._h, buf, len(blob)), "xaac_b200_set_fps_rom")
 
     def set_esbr_envcalc_rom(self, blob):
         """blob: ixheaac_random_phase[512][2] (4096 bytes)."""

@@ -395,4 +395,29 @@ struct EsbrHbeArgs {
 };
 cudaError_t launch_esbr_hbe(const EsbrHbeArgs &args, int num_sms, cudaStream_t stream);
 
+// eSBR float parametric stereo (ixheaacd_esbr_apply_ps, 20-band configuration): ROM word offsets = XAAC_FPSROM_*, side words =
+// XAAC_FPS_SIDE_*, state words = XAAC_FPS_ST_* of include/xaac_b200.h
+constexpr int kFpsRomP8 = 0, kFpsRomP2 = 16, kFpsRomCos2 = 32, kFpsRomCs8 = 64, kFpsRomQfRe = 272, kFpsRomQfIm = 336,
+              kFpsRomSubRe = 400, kFpsRomSubIm = 416, kFpsRomQSerRe = 432, kFpsRomQSerIm = 624, kFpsRomSSerRe = 816,
+              kFpsRomSSerIm = 856, kFpsRomDecay = 896, kFpsRomQdelN = 900, kFpsRomGrb = 964, kFpsRomBgm = 988,
+              kFpsRomDser = 1012, kFpsRomWords = 1016;
+constexpr int kFpsSideNumEnv = 0, kFpsSideBorder = 1, kFpsSideUsb = 7, kFpsSideH = 16, kFpsSideWords = 1024;
+constexpr int kFpsStHyb = 0, kFpsStSubDel = 120, kFpsStSerSub = 168, kFpsStQDel = 528, kFpsStSerQ = 2320, kFpsStBins = 4240,
+              kFpsStIdx = 4300, kFpsStWords = 4368;
+struct EsbrPsArgs {
+  // the mono channel before regrouping, exactly what the synthesis bank's stage mode reads (EsbrSynthArgs::rg_*): slot s, band k
+  // comes from row 2 + s of low_* when k < x_over(s), else of high_*; rows 34..39 of low_* (bands 0..4) are the look-ahead
+  const float *low_re, *low_im;    // [n][>= 40][64], unit stride low_stride
+  const float *high_re, *high_im;  // [n][40][64]
+  const int32_t *rg_par;           // [n][4]
+  long long low_stride = 2560;
+  const float *side;               // [n][1024]: num_env, border_position[0..5], usb (int32 words) | previous + per-envelope h11..h22
+  float *state;                    // [n][4368] in/out
+  float *left, *right;             // [n][32][128] per slot re[64] | im[64]: the synthesis bank kernel's input layout
+  int32_t *err;                    // [n] or null
+  const float *rom;                // device copy of the XAAC_FPSROM_* blob
+  long long n_units;
+};
+cudaError_t launch_esbr_ps(const EsbrPsArgs &args, int num_sms, cudaStream_t stream);
+
 }  // namespace xb

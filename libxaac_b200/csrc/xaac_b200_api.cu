@@ -30,6 +30,7 @@ struct xaac_b200_ctx {
   uint8_t *d_rom_esbr = nullptr;  // table image of esbr_synth_kernel
   float *d_rom_rphase = nullptr;  // ixheaac_random_phase[512][2]
   float *d_rom_hbe = nullptr;     // XAAC_HROM_* blob of the harmonic transposer
+  float *d_rom_fps = nullptr;     // XAAC_FPSROM_* blob of the float parametric stereo
   int esbr_periodic = 0;
   bool have_ps_rom = false;
   int ps_rot_nosat = 0;           // no fractional-delay phase factor equals -32768 (16x16 rotations cannot saturate)
@@ -203,6 +204,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   if (ctx->d_rom_esbr) cudaFree(ctx->d_rom_esbr);
   if (ctx->d_rom_rphase) cudaFree(ctx->d_rom_rphase);
   if (ctx->d_rom_hbe) cudaFree(ctx->d_rom_hbe);
+  if (ctx->d_rom_fps) cudaFree(ctx->d_rom_fps);
   delete ctx;
 }
 
@@ -1226,16 +1228,53 @@ int32_t xaac_b200_esbr_hbe_apply_dev(xaac_b200_ctx *ctx, const float *d_qmf_re, 
   return hbe_launch(ctx, d_qmf_re, d_qmf_im, 2048, d_pv_re, d_pv_im, 2048, d_cfg, d_state, d_err, n_units, stream);
 }
 
+int32_t xaac_b200_set_fps_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
+  if (!ctx || !tables) return bad_arg(ctx, "null");
+  if (bytes < (size_t)xb::kFpsRomWords * 4) return bad_arg(ctx, "float-PS ROM blob shorter than 4064 bytes");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaError_t e = ctx->d_rom_fps ? cudaSuccess : cudaMalloc((void **)&ctx->d_rom_fps, (size_t)xb::kFpsRomWords * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_rom_fps, tables, (size_t)xb::kFpsRomWords * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(ctx, e, "cudaMemcpy(fps rom)");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_esbr_ps_apply_dev(xaac_b200_ctx *ctx, const float *d_low_re, const float *d_low_im, int32_t low_rows,
+                                    const float *d_high_re, const float *d_high_im, const int32_t *d_rg_par,
+                                    const float *d_side, float *d_state, float *d_left, float *d_right, int32_t *d_err,
+                                    int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->d_rom_fps) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_fps_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (low_rows != 40 && low_rows != 72) return bad_arg(ctx, "low_rows must be 40 or 72");
+  if (!d_low_re || !d_low_im || !d_high_re || !d_high_im || !d_rg_par || !d_side || !d_state || !d_left || !d_right)
+    return bad_arg(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  xb::EsbrPsArgs a;
+  a.low_re = d_low_re; a.low_im = d_low_im; a.high_re = d_high_re; a.high_im = d_high_im; a.rg_par = d_rg_par;
+  a.low_stride = (long long)low_rows * 64; a.side = d_side; a.state = d_state; a.left = d_left; a.right = d_right; a.err = d_err;
+  a.rom = ctx->d_rom_fps; a.n_units = n_units;
+  LAUNCH("esbr_ps_kernel", stream, xb::launch_esbr_ps(a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
 // Whole eSBR stage (eSBR branch of ixheaacd_sbr_dec for USAC mono / stereo channels without harmonic transposer, PS, MPS):
 // analysis bank (+ history shift, + core hand-over) -> HF generator (+ history shift) -> envelope adjuster -> synthesis bank
 // (+ regrouping, + optional PCM16 hand-over).  Four launches on one stream.
 static int32_t esbr_dec_impl(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view *st, float *pv_re, float *pv_im,
                              float *hbe_state, const int32_t *d_hbe_cfg, const float *d_time_in, const int32_t *d_core_in,
                              const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par,
-                             float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream) {
+                             float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream,
+                             const xaac_b200_esbr_ps_view *ps = nullptr, const float *d_ps_side = nullptr,
+                             float *d_out_r = nullptr) {
   const bool hbe = pv_re != nullptr;
-  if (!ctx->d_rom_esbr || !ctx->d_rom_rphase || (hbe && !ctx->d_rom_hbe)) {
-    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_rom / _set_esbr_envcalc_rom / _set_hbe_rom have not been called");
+  if (!ctx->d_rom_esbr || !ctx->d_rom_rphase || (hbe && !ctx->d_rom_hbe) || (ps && !ctx->d_rom_fps)) {
+    snprintf(ctx->err, sizeof(ctx->err),
+             "xaac_b200_set_esbr_rom / _set_esbr_envcalc_rom / _set_hbe_rom / _set_fps_rom have not been called");
     return XAAC_B200_ERR_NO_ROM;
   }
   if (n_units < 0) return bad_arg(ctx, "n_units");
@@ -1278,6 +1317,25 @@ static int32_t esbr_dec_impl(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view
     a.rphase = ctx->d_rom_rphase; a.err = d_err ? d_err + 2 * n_units : nullptr; a.n_units = n_units;
     LAUNCH("esbr_envcalc_kernel", stream, xb::launch_esbr_envcalc(a, ctx->num_sms, s));
   }
+  if (ps) {  // sbr_dec.c:976-1001: regrouping + PS, then both channels' synthesis banks
+    if (!ps->ps_state || !ps->left || !ps->right || !ps->synth_states_r || !ps->synth_pos_r || !d_ps_side || !d_out || !d_out_r)
+      return bad_arg(ctx, "PS view with null members");
+    xb::EsbrPsArgs a;
+    a.low_re = st->qmf_re; a.low_im = st->qmf_im; a.high_re = st->out_re; a.high_im = st->out_im; a.rg_par = d_rg_par;
+    a.low_stride = low_stride; a.side = d_ps_side; a.state = ps->ps_state; a.left = ps->left; a.right = ps->right;
+    a.err = d_err ? d_err + 5 * n_units : nullptr; a.rom = ctx->d_rom_fps; a.n_units = n_units;
+    LAUNCH("esbr_ps_kernel", stream, xb::launch_esbr_ps(a, ctx->num_sms, s));
+    for (int ch = 0; ch < 2; ch++) {
+      xb::EsbrSynthArgs y;
+      y.qmf = ch ? ps->right : ps->left; y.states = ch ? ps->synth_states_r : st->synth_states;
+      y.pos = ch ? ps->synth_pos_r : st->synth_pos; y.out = ch ? d_out_r : d_out;
+      y.err = (d_err && !ch) ? d_err + 3 * n_units : nullptr;
+      y.rom = ctx->d_rom_esbr; y.n_units = n_units; y.periodic = ctx->esbr_periodic;
+      LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(y, ctx->num_sms, s));
+    }
+    ctx->launches += 6;
+    return XAAC_B200_OK;
+  }
   {
     xb::EsbrSynthArgs a;
     a.qmf = nullptr; a.states = st->synth_states; a.pos = st->synth_pos; a.out = d_out; a.err = d_err ? d_err + 3 * n_units : nullptr;
@@ -1309,6 +1367,21 @@ int32_t xaac_b200_esbr_dec_hbe_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_
   if (!st || !st->pv_re || !st->pv_im || !st->hbe_state || !d_hbe_cfg) return bad_arg(ctx, "harmonic-transposer state / cfg missing");
   return esbr_dec_impl(ctx, &st->base, st->pv_re, st->pv_im, st->hbe_state, d_hbe_cfg, d_time_in, d_core_in, d_hf_par, d_ec_ipar,
                        d_ec_fpar, d_rg_par, d_out, d_pcm16, ch_fac, d_err, n_units, stream);
+}
+
+// Mono + PS element: the stage above up to the envelope adjuster, the PS kernel, two synthesis banks.
+int32_t xaac_b200_esbr_dec_ps_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const xaac_b200_esbr_ps_view *ps,
+                                  const float *d_time_in, const int32_t *d_core_in, const int32_t *d_hbe_cfg,
+                                  const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par,
+                                  const float *d_ps_side, float *d_out_l, float *d_out_r, int32_t *d_err, int64_t n_units,
+                                  void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!st || !ps) return bad_arg(ctx, "state views missing");
+  const bool hbe = st->pv_re != nullptr;
+  if (hbe && (!st->pv_im || !st->hbe_state || !d_hbe_cfg)) return bad_arg(ctx, "harmonic-transposer state / cfg missing");
+  return esbr_dec_impl(ctx, &st->base, hbe ? st->pv_re : nullptr, hbe ? st->pv_im : nullptr, hbe ? st->hbe_state : nullptr,
+                       d_hbe_cfg, d_time_in, d_core_in, d_hf_par, d_ec_ipar, d_ec_fpar, d_rg_par, d_out_l, nullptr, 1, d_err,
+                       n_units, stream, ps, d_ps_side, d_out_r);
 }
 
 int32_t xaac_b200_kernel_timing(xaac_b200_ctx *ctx, int32_t enable) {

@@ -23,6 +23,7 @@
 #include <string.h>
 #include <stdint.h>
 #include "ixheaacd_b200_pack.h"
+#include "ixheaacd_b200_pack_ps_flt.h"
 #include "ixheaacd_interface.h"
 #include "ixheaacd_tns_usac.h"
 #include "ixheaacd_acelp_info.h"
@@ -66,6 +67,9 @@ static struct {
   int have_esbr_rom;
   float *e_q[6], *e_bw, *e_ec, *e_hbe, *e_fpar, *e_tin, *e_out;
   int32_t *e_anal, *e_apos, *e_synth, *e_spos, *e_patch, *e_hbecfg, *e_hfpar, *e_ipar, *e_rg, *e_err;
+  float *e_ps_state, *e_ps_left, *e_ps_right, *e_ps_side, *e_out_r; /* mono + PS element: float parametric stereo */
+  int32_t *e_synth_r, *e_spos_r;
+  long n_esbr_ps;
   long n_imdct, n_imdct_ref, n_sbr_hq, n_sbr_ps, n_sbr_lp, n_sbr_ref, n_fd, n_fd_ref, n_esbr, n_esbr_hbe, n_esbr_ref;
 } G;
 
@@ -73,10 +77,10 @@ static void b200_report(void) {
   if (G.stats)
     fprintf(stderr,
             "[ixheaacd_b200] imdct_process: %ld on the GPU, %ld by the reference; sbr_dec: %ld HQ + %ld HQ/PS + %ld LP on the GPU, "
-            "%ld by the reference; fd_frm_dec: %ld on the GPU, %ld by the reference; eSBR sbr_dec: %ld + %ld with HBE on the GPU, "
-            "%ld by the reference\n",
+            "%ld by the reference; fd_frm_dec: %ld on the GPU, %ld by the reference; eSBR sbr_dec: %ld + %ld with HBE + %ld with PS "
+            "on the GPU, %ld by the reference\n",
             G.n_imdct, G.n_imdct_ref, G.n_sbr_hq, G.n_sbr_ps, G.n_sbr_lp, G.n_sbr_ref, G.n_fd, G.n_fd_ref, G.n_esbr, G.n_esbr_hbe,
-            G.n_esbr_ref);
+            G.n_esbr_ps, G.n_esbr_ref);
   if (G.ctx) xaac_b200_destroy(G.ctx);
   G.ctx = NULL;
 }
@@ -276,6 +280,16 @@ static void esbr_rom_once(xaac_b200_ctx *c, ia_sbr_tables_struct *t) {
   B200(xaac_b200_dev_alloc(c, XAAC_EEC_IPAR_WORDS * 4, (void **)&G.e_ipar), "alloc");
   B200(xaac_b200_dev_alloc(c, 16, (void **)&G.e_rg), "alloc");
   B200(xaac_b200_dev_alloc(c, 32, (void **)&G.e_err), "alloc");
+  static float pr[XAAC_FPSROM_WORDS];
+  b200_fps_pack_rom(pr, t->ps_tables_ptr, t->ps_tables_ptr->rev_link_delay_ser);
+  B200(xaac_b200_set_fps_rom(c, pr, sizeof(pr)), "set_fps_rom");
+  B200(xaac_b200_dev_alloc(c, XAAC_FPS_ST_WORDS * 4, (void **)&G.e_ps_state), "alloc");
+  B200(xaac_b200_dev_alloc(c, 4096 * 4, (void **)&G.e_ps_left), "alloc");
+  B200(xaac_b200_dev_alloc(c, 4096 * 4, (void **)&G.e_ps_right), "alloc");
+  B200(xaac_b200_dev_alloc(c, XAAC_FPS_SIDE_WORDS * 4, (void **)&G.e_ps_side), "alloc");
+  B200(xaac_b200_dev_alloc(c, 8192, (void **)&G.e_out_r), "alloc");
+  B200(xaac_b200_dev_alloc(c, 1280 * 4, (void **)&G.e_synth_r), "alloc");
+  B200(xaac_b200_dev_alloc(c, 16, (void **)&G.e_spos_r), "alloc");
   G.have_esbr_rom = 1;
 }
 
@@ -339,17 +353,33 @@ static void esbr_pack_ec_ipar(int32_t *ip, const ia_sbr_frame_info_data_struct *
 }
 
 static WORD32 esbr_dec_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_header_data_struct *hd,
-                            ia_sbr_frame_info_data_struct *fd, ia_sbr_tables_struct *t, ia_pvc_data_struct *pvc, int *done) {
+                            ia_sbr_frame_info_data_struct *fd, ia_sbr_tables_struct *t, ia_pvc_data_struct *pvc,
+                            ia_ps_dec_struct *ps, VOID *self, int *done) {
   *done = 0;
   esbr_rom_once(c, t);
+  /* mono + PS element (sbr_dec.c:976-1001): the right channel leaves through the second channel's synthesis bank */
+  ia_sbr_qmf_filter_bank_struct *yr = NULL;
+  static float ps_side[XAAC_FPS_SIDE_WORDS], ps_st[XAAC_FPS_ST_WORDS];
+  static b200_fps_commit_rec ps_cm;
+  int32_t spos_r[2] = {0, 0};
+  if (ps) {
+    if (!self) return 0;
+    yr = &((ia_handle_sbr_dec_inst_struct)self)->pstr_sbr_channel[1]->str_sbr_dec.str_synthesis_qmf_bank;
+    if (yr->no_channels != 64) return 0;
+    if (b200_fps_side(ps_side, &ps_cm, ps, t->ps_tables_ptr, hd->pstr_freq_band_data->sub_band_end) != 0) return 0;
+    b200_fps_pack_state(ps_st, ps);
+    spos_r[0] = yr->ixheaacd_drc_offset;
+    spos_r[1] = (int32_t)(yr->filter_pos_syn_32 - yr->p_filter_32);
+    if (spos_r[1] < 0 || spos_r[1] > 640) return 0;
+  }
   const int hbe = hd->hbe_flag != 0;
   ia_esbr_hbe_txposer_struct *tx = d->p_hbe_txposer;
   ia_sbr_qmf_filter_bank_struct *a = &d->str_codec_qmf_bank, *y = &d->str_synthesis_qmf_bank;
   WORD32 *qc = (WORD32 *)t->qmf_dec_tables_ptr->esbr_qmf_c;
   const int rows = hbe ? 72 : 40;
-  static int32_t hf_par[XAAC_EHF_PAR_WORDS], ipar[XAAC_EEC_IPAR_WORDS], hcfg[XAAC_HBE_CFG_WORDS], rg[4], apos[2], spos[2], patch[8],
-      err[5];
+  static int32_t hf_par[XAAC_EHF_PAR_WORDS], ipar[XAAC_EEC_IPAR_WORDS], hcfg[XAAC_HBE_CFG_WORDS], rg[4], apos[2], spos[2], patch[8];
   static float fpar[XAAC_EEC_FPAR_WORDS], ec[640], hst[XAAC_HBE_ST_WORDS], bw[6];
+  int32_t err[6];
   if (hbe) {
     if (!tx) return 0;
     if (tx->ixheaacd_cmplx_anal_fft == NULL) { /* hbe_trans.c:240-248: the reference re-initialises inside the call */
@@ -431,6 +461,19 @@ static WORD32 esbr_dec_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_heade
   if (hbe) {
     B200(xaac_b200_h2d(c, G.e_hbe, hst, sizeof(hst)), "h2d");
     B200(xaac_b200_h2d(c, G.e_hbecfg, hcfg, sizeof(hcfg)), "h2d");
+  }
+  if (ps) {
+    xaac_b200_esbr_ps_view pv;
+    pv.ps_state = G.e_ps_state; pv.left = G.e_ps_left; pv.right = G.e_ps_right; pv.synth_states_r = G.e_synth_r;
+    pv.synth_pos_r = G.e_spos_r;
+    B200(xaac_b200_h2d(c, G.e_ps_state, ps_st, sizeof(ps_st)), "h2d ps");
+    B200(xaac_b200_h2d(c, G.e_ps_side, ps_side, sizeof(ps_side)), "h2d ps");
+    B200(xaac_b200_h2d(c, G.e_synth_r, yr->filter_states_32, 1280 * 4), "h2d ps");
+    B200(xaac_b200_h2d(c, G.e_spos_r, spos_r, 8), "h2d ps");
+    if (!hbe) { v.pv_re = NULL; v.pv_im = NULL; v.hbe_state = NULL; }
+    B200(xaac_b200_esbr_dec_ps_dev(c, &v, &pv, G.e_tin, NULL, hbe ? G.e_hbecfg : NULL, G.e_hfpar, G.e_ipar, G.e_fpar, G.e_rg,
+                                   G.e_ps_side, G.e_out, G.e_out_r, G.e_err, 1, NULL), "esbr_dec_ps_dev");
+  } else if (hbe) {
     B200(xaac_b200_esbr_dec_hbe_dev(c, &v, G.e_tin, NULL, G.e_hbecfg, G.e_hfpar, G.e_ipar, G.e_fpar, G.e_rg, G.e_out, NULL, 1,
                                     G.e_err, 1, NULL), "esbr_dec_hbe_dev");
   } else {
@@ -438,10 +481,10 @@ static WORD32 esbr_dec_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_heade
          "esbr_dec_dev");
   }
   B200(xaac_b200_d2h(c, err, G.e_err, sizeof(err)), "d2h err");
-  for (int i = 0; i < 5; i++)
+  for (int i = 0; i < 6; i++)
     if (err[i] == -2) return 0; /* outside the kernels' subset: nothing on the host has been touched yet */
   *done = 1;
-  for (int i = 0; i < 5; i++)
+  for (int i = 0; i < 6; i++)
     if (err[i] != 0) return err[i]; /* the reference's own failure codes */
   /* ---- results and state back into the reference's structs ---- */
   for (int i = 0; i < (hbe ? 6 : 4); i++)
@@ -456,7 +499,23 @@ static WORD32 esbr_dec_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_heade
   static int32_t ipar_in[XAAC_EEC_IPAR_WORDS];
   memcpy(ipar_in, ipar, sizeof(ipar));
   B200(xaac_b200_d2h(c, ipar, G.e_ipar, sizeof(ipar)), "d2h");
-  B200(xaac_b200_d2h(c, d->time_sample_buf, G.e_out, 8192), "d2h out");
+  if (ps) {
+    B200(xaac_b200_d2h(c, ps->time_sample_buf[0], G.e_out, 8192), "d2h out");
+    B200(xaac_b200_d2h(c, ps->time_sample_buf[1], G.e_out_r, 8192), "d2h out");
+    B200(xaac_b200_d2h(c, ps_st, G.e_ps_state, sizeof(ps_st)), "d2h ps");
+    b200_fps_unpack_state(ps_st, ps);
+    b200_fps_commit(ps, &ps_cm, t->ps_tables_ptr);
+    B200(xaac_b200_d2h(c, yr->filter_states_32, G.e_synth_r, 1280 * 4), "d2h ps");
+    B200(xaac_b200_d2h(c, spos_r, G.e_spos_r, 8), "d2h ps");
+    yr->esbr_cos_twiddle = (WORD32 *)t->qmf_dec_tables_ptr->esbr_sin_cos_twiddle_l64; /* sbr_dec.c:567-580, second call */
+    yr->esbr_alt_sin_twiddle = (WORD32 *)t->qmf_dec_tables_ptr->esbr_alt_sin_twiddle_l64;
+    yr->p_filter_32 = qc;
+    yr->filter_pos_syn_32 = qc + spos_r[1];
+    yr->ixheaacd_drc_offset = spos_r[0];
+    ((ia_sbr_frame_info_data_struct *)((ia_handle_sbr_dec_inst_struct)self)->frame_buffer[1])->reset_flag = 0; /* sbr_dec.c:659 */
+  } else {
+    B200(xaac_b200_d2h(c, d->time_sample_buf, G.e_out, 8192), "d2h out");
+  }
   a->usb = a->no_channels; /* sbr_dec.c:238 */
   a->state_new_samples_pos_low_32 = a->anal_filter_states_32 + apos[0];
   a->filter_pos_32 = qc + apos[1];
@@ -524,19 +583,21 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *ptr_sbr_dec, WORD16 *ptr_time_
      * harmonic transposer is forced on (decoder/ixheaacd_sbrdecoder.c:400-403) */
     int tes = 0;
     for (int i = 0; i < 8; i++) tes |= ptr_frame_data->inter_temp_shape_mode[i];
+    const int with_ps = ptr_header_data->channel_mode == PS_STEREO || ptr_header_data->enh_sbr_ps;
     const int ok = apply_processing && (!low_pow_flag || !ptr_header_data->usac_flag) && !ldmps_present && !drc_on &&
                    !heaac_mps_present && !ec_flag && (ptr_header_data->usac_flag || ptr_header_data->hbe_flag) &&
                    ptr_header_data->num_time_slots == 16 && ptr_sbr_dec->str_codec_qmf_bank.no_channels == 32 &&
-                   ptr_sbr_dec->str_synthesis_qmf_bank.no_channels == 64 && ptr_header_data->channel_mode != PS_STEREO &&
-                   !ptr_header_data->enh_sbr_ps && ptr_frame_data->stereo_config_idx <= 0 && !ptr_frame_data->mps_sbr_flag &&
+                   ptr_sbr_dec->str_synthesis_qmf_bank.no_channels == 64 && (!with_ps || (ptr_ps_dec != NULL && self != NULL)) &&
+                   ptr_frame_data->stereo_config_idx <= 0 && !ptr_frame_data->mps_sbr_flag &&
                    ptr_frame_data->sbr_mode == ORIG_SBR && !ptr_header_data->is_usf_4 && !ptr_header_data->pre_proc_flag && !tes &&
                    !ptr_frame_data->reset_flag && ptr_frame_data->sbr_patching_mode == ptr_frame_data->prev_sbr_patching_mode &&
                    (ptr_frame_data->str_frame_info_details.num_noise_env == 1 || ptr_frame_data->str_frame_info_details.num_noise_env == 2);
     if (ok) {
       int done = 0;
-      WORD32 r = esbr_dec_b200(c, ptr_sbr_dec, ptr_header_data, ptr_frame_data, sbr_tables_ptr, ptr_pvc_data_str, &done);
+      WORD32 r = esbr_dec_b200(c, ptr_sbr_dec, ptr_header_data, ptr_frame_data, sbr_tables_ptr, ptr_pvc_data_str,
+                               with_ps ? ptr_ps_dec : NULL, self, &done);
       if (done) {
-        if (ptr_header_data->hbe_flag) G.n_esbr_hbe++; else G.n_esbr++;
+        if (with_ps) G.n_esbr_ps++; else if (ptr_header_data->hbe_flag) G.n_esbr_hbe++; else G.n_esbr++;
         return r;
       }
     }

@@ -298,3 +298,108 @@ def esbr_dec_hbe(ctx, state, core, hbe_cfg, hf_par, ec_ipar, ec_fpar, rg_par, ou
                                              ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_esbr_dec_hbe_dev")
     return out, err
+
+
+# ---- float parametric stereo (ixheaacd_esbr_apply_ps, decoder/ixheaacd_ps_dec_flt.c:381-505) ----
+FPS_SIDE_WORDS, FPS_ST_WORDS = 1024, 4368
+
+
+def esbr_apply_ps(ctx, low_re, low_im, high_re, high_im, rg_par, side, state, left=None, right=None, err=None, stream=None):
+    """Batched drop-in for ixheaacd_esbr_apply_ps in the 20-band configuration, fused with the regrouping and the look-ahead
+    slots of decoder/ixheaacd_sbr_dec.c:481-517.  low_re / low_im float32 [n, 40 | 72, 64] (qmf_buf_real / imag), high_re /
+    high_im float32 [n, 40, 64] (sbr_qmf_out_real / imag), rg_par int32 [n, 4], side float32 [n, 1024] (XAAC_FPS_SIDE_*), state
+    float32 [n, 4368] (XAAC_FPS_ST_*, updated in place).  Returns (left, right, err): float32 [n, 32, 128] per slot
+    re[64] | im[64], err int32 [n] (0, or -2 for borders outside the supported subset)."""
+    n = int(state.shape[0])
+    rows = int(low_re.shape[1])
+    for t, nm in ((low_re, "low_re"), (low_im, "low_im")):
+        _chk(t, torch.float32, (n, rows, 64), nm, "cuda")
+    for t, nm in ((high_re, "high_re"), (high_im, "high_im")):
+        _chk(t, torch.float32, (n, 40, 64), nm, "cuda")
+    _chk(rg_par, torch.int32, (n, 4), "rg_par", "cuda")
+    _chk(side, torch.float32, (n, FPS_SIDE_WORDS), "side", "cuda")
+    _chk(state, torch.float32, (n, FPS_ST_WORDS), "state", "cuda")
+    dev = state.device
+    if left is None:
+        left = torch.empty((n, 32, 128), dtype=torch.float32, device=dev)
+    if right is None:
+        right = torch.empty((n, 32, 128), dtype=torch.float32, device=dev)
+    _chk(left, torch.float32, (n, 32, 128), "left", "cuda")
+    _chk(right, torch.float32, (n, 32, 128), "right", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=dev)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    rc = ctx._lib.xaac_b200_esbr_ps_apply_dev(ctx.handle, _ptr(low_re), _ptr(low_im), rows, _ptr(high_re), _ptr(high_im),
+                                              _ptr(rg_par), _ptr(side), _ptr(state), _ptr(left), _ptr(right), _ptr(err), n,
+                                              ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_ps_apply_dev")
+    return left, right, err
+
+
+class _EsbrPsView(ctypes.Structure):
+    _fields_ = [("ps_state", ctypes.c_void_p), ("left", ctypes.c_void_p), ("right", ctypes.c_void_p),
+                ("synth_states_r", ctypes.c_void_p), ("synth_pos_r", ctypes.c_void_p)]
+
+
+class EsbrDecPsBatch(EsbrDecHbeBatch):
+    """State of the eSBR stage of a mono + PS element: the harmonic-transposer stage's state (hbe=False drops the transposer
+    and its 32-slot delay) plus the PS instance, the second channel's synthesis bank and the two QMF matrices in flight."""
+
+    def __init__(self, n_units, device="cuda:0", hbe=True):
+        self.hbe = bool(hbe)
+        self.SHAPES = dict(EsbrDecHbeBatch.SHAPES if hbe else EsbrDecBatch.SHAPES, ps_state=((FPS_ST_WORDS,), torch.float32),
+                           left=((32, 128), torch.float32), right=((32, 128), torch.float32),
+                           synth_states_r=((1280,), torch.int32), synth_pos_r=((2,), torch.int32))
+        EsbrDecBatch.__init__(self, n_units, device)
+
+    def view(self):
+        base = _EsbrStateView(**{k: ctypes.c_void_p(getattr(self, k).data_ptr()) for k in EsbrDecBatch.SHAPES})
+        pv = [ctypes.c_void_p(getattr(self, k).data_ptr()) if self.hbe else None for k in ("pv_re", "pv_im", "hbe_state")]
+        return _EsbrHbeStateView(base, *pv)
+
+    def ps_view(self):
+        return _EsbrPsView(*[ctypes.c_void_p(getattr(self, k).data_ptr())
+                             for k in ("ps_state", "left", "right", "synth_states_r", "synth_pos_r")])
+
+
+def esbr_dec_ps(ctx, state, core, hbe_cfg, hf_par, ec_ipar, ec_fpar, rg_par, ps_side, out_l=None, out_r=None, err=None,
+                stream=None):
+    """Batched drop-in for the eSBR branch of ixheaacd_sbr_dec for a mono + PS element (channel_mode == PS_STEREO or
+    enh_sbr_ps, decoder/ixheaacd_sbr_dec.c:976-1001).  Arguments as esbr_dec_hbe (hbe_cfg = None without the transposer) plus
+    ps_side float32 [n, 1024]; state is an EsbrDecPsBatch.  Returns (out_l, out_r, err[6, n]) with float32 [n, 2048] outputs."""
+    n = state.n
+    dev = hf_par.device
+    _chk(core, core.dtype if core.dtype in (torch.float32, torch.int32) else torch.float32, (n, 1024), "core", "cuda")
+    if state.hbe:
+        _chk(hbe_cfg, torch.int32, (n, HBE_CFG_WORDS), "hbe_cfg", "cuda")
+    _chk(hf_par, torch.int32, (n, EHF_PAR_WORDS), "hf_par", "cuda")
+    _chk(ec_ipar, torch.int32, (n, EEC_IPAR_WORDS), "ec_ipar", "cuda")
+    _chk(ec_fpar, torch.float32, (n, EEC_FPAR_WORDS), "ec_fpar", "cuda")
+    _chk(rg_par, torch.int32, (n, 4), "rg_par", "cuda")
+    _chk(ps_side, torch.float32, (n, FPS_SIDE_WORDS), "ps_side", "cuda")
+    if out_l is None:
+        out_l = torch.empty((n, 2048), dtype=torch.float32, device=dev)
+    if out_r is None:
+        out_r = torch.empty((n, 2048), dtype=torch.float32, device=dev)
+    _chk(out_l, torch.float32, (n, 2048), "out_l", "cuda")
+    _chk(out_r, torch.float32, (n, 2048), "out_r", "cuda")
+    if err is None:
+        err = torch.empty((6, n), dtype=torch.int32, device=dev)
+        if not state.hbe:
+            err[4].zero_()
+    else:
+        _chk(err, torch.int32, (6, n), "err", "cuda")
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    v, pv = state.view(), state.ps_view()
+    rc = ctx._lib.xaac_b200_esbr_dec_ps_dev(ctx.handle, ctypes.byref(v), ctypes.byref(pv),
+                                            _ptr(core) if core.dtype == torch.float32 else None,
+                                            _ptr(core) if core.dtype == torch.int32 else None,
+                                            _ptr(hbe_cfg) if state.hbe else None, _ptr(hf_par), _ptr(ec_ipar), _ptr(ec_fpar),
+                                            _ptr(rg_par), _ptr(ps_side), _ptr(out_l), _ptr(out_r), _ptr(err), n,
+                                            ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_dec_ps_dev")
+    return out_l, out_r, err

@@ -1127,3 +1127,67 @@ def oracle_esbr_hbe_stage(orc, rphase, st, time_in, hbe_cfg, hf_par, ec_ipar, ec
     out, s["synth_states"], s["synth_pos"] = orc.esbr_synth_batch(m, s["synth_states"], s["synth_pos"])
     z = np.zeros(n, np.int32)
     return out, s, ipar2, np.stack([z, e1, e2, z, e4])
+
+
+# ---- float parametric stereo (ixheaacd_esbr_apply_ps) ----
+FPS_PAR_WORDS, FPS_HST_WORDS, FPS_SIDE_WORDS, FPS_ST_WORDS = 386, 228, 1024, 4368
+
+
+def fps_rom():
+    return np.fromfile(os.path.join(ROOT, "libxaac_b200", "rom", "fps_rom.bin"), np.float32)
+
+
+def fps_fresh_state(n):
+    """The instance right after ixheaacd_create_ps_esbr_dec (ps_dec_flt.c:297-379): everything zero, h11 / h12 real parts one."""
+    st = np.zeros((n, FPS_ST_WORDS), np.float32)
+    hst = np.zeros((n, FPS_HST_WORDS), np.float32)
+    hst[:, 0:40] = 1.0
+    return st, hst
+
+
+def synth_fps_frame(n, rng, good_borders=True):
+    """One frame of inputs for n independent mono + PS channels: the low-band QMF arrays (left slot i = row 2 + i, rows 34..39
+    the look-ahead) and the frame's PS parameters in the shim's par layout."""
+    gain = (10.0 ** rng.uniform(0.0, 3.5, (n, 1, 1))).astype(np.float32)
+    tilt = np.exp(-np.arange(64) / rng.uniform(6, 40, (n, 1, 1))).astype(np.float32)
+    low_re = (rng.standard_normal((n, 40, 64)).astype(np.float32) * gain * tilt).astype(np.float32)
+    low_im = (rng.standard_normal((n, 40, 64)).astype(np.float32) * gain * tilt).astype(np.float32)
+    par = np.zeros((n, FPS_PAR_WORDS), np.int32)
+    for u in range(n):
+        ne = int(rng.integers(1, 6))
+        inner = np.sort(rng.choice(np.arange(1, 32), ne - 1, replace=False)) if ne > 1 else np.zeros(0, np.int64)
+        b = np.concatenate([[0], inner, [32]])
+        if not good_borders:
+            b[-1] = 30
+        par[u, 0] = ne
+        par[u, 1:1 + len(b)] = b
+        usb = int(rng.integers(24, 65))
+        par[u, 7] = usb
+        fine = int(rng.integers(0, 2))
+        par[u, 8] = fine
+        par[u, 9] = int(rng.integers(0, 3))
+        lim = 15 if fine else 7
+        par[u, 16:116] = rng.integers(-lim, lim + 1, 100)
+        par[u, 116:216] = rng.integers(0, 8, 100)
+        if rng.random() < 0.75:
+            par[u, 216:301] = rng.integers(0, 8, 85)
+            par[u, 301:386] = rng.integers(0, 8, 85)
+        low_re[u, :, usb:] = 0
+        low_im[u, :, usb:] = 0
+    return low_re, low_im, par
+
+
+def ref_fps_batch(ref, low_re, low_im, par, state, hst):
+    """The compiled ixheaacd_esbr_apply_ps through oracle/ref_shim_fps.c.  Returns dict(side, commit, left, right, state, hst, rc):
+    side / commit are what the drop-in's host code (b200_fps_side) derives from the same parameters before the call."""
+    n = len(par)
+    st = np.ascontiguousarray(state, np.float32).copy()
+    h = np.ascontiguousarray(hst, np.float32).copy()
+    side = np.zeros((n, FPS_SIDE_WORDS), np.float32)
+    commit = np.zeros((n, FPS_HST_WORDS), np.float32)
+    left = np.zeros((n, 32, 128), np.float32)
+    right = np.zeros((n, 32, 128), np.float32)
+    ref.lib.ref_fps_apply_batch.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 9
+    rc = ref.lib.ref_fps_apply_batch(n, P(np.ascontiguousarray(low_re, np.float32)), P(np.ascontiguousarray(low_im, np.float32)),
+                                     P(np.ascontiguousarray(par, np.int32)), P(st), P(h), P(side), P(commit), P(left), P(right))
+    return dict(side=side, commit=commit, left=left, right=right, state=st, hst=h, rc=rc)

@@ -92,7 +92,7 @@ def test_usac_through_reference_parser(tmp_path, name, extra):
     ref_wav, our_wav = str(tmp_path / "ref.wav"), str(tmp_path / "b200.wav")
     _run([os.path.join(REFDIR, "xaacdec"), f"-ifile:{bits}", f"-ofile:{ref_wav}", f"-imeta:{meta}", "-mp4:1"])
     log = _run([B200, f"-ifile:{bits}", f"-ofile:{our_wav}", f"-imeta:{meta}", "-mp4:1"], env=dict(os.environ, IXHEAACD_B200_STATS="1"))
-    m = re.search(r"fd_frm_dec: (\d+) on the GPU, (\d+) by the reference; eSBR sbr_dec: (\d+) \+ (\d+) with HBE on the GPU, (\d+) by the reference", log)
+    m = re.search(r"fd_frm_dec: (\d+) on the GPU, (\d+) by the reference; eSBR sbr_dec: (\d+) \+ (\d+) with HBE \+ \d+ with PS on the GPU, (\d+) by the reference", log)
     assert m, log[-800:]
     fd, fd_ref, es, es_hbe, es_ref = map(int, m.groups())
     a, b = open(ref_wav, "rb").read(), open(our_wav, "rb").read()
@@ -123,7 +123,7 @@ def test_legacy_heaac_in_default_esbr_mode(tmp_path, name, enc, fs, ch, secs):
     ref_wav, our_wav = str(tmp_path / "ref.wav"), str(tmp_path / "b200.wav")
     _run([os.path.join(REFDIR, "xaacdec"), f"-ifile:{bits}", f"-ofile:{ref_wav}"])
     log = _run([B200, f"-ifile:{bits}", f"-ofile:{our_wav}"], env=dict(os.environ, IXHEAACD_B200_STATS="1"))
-    m = re.search(r"imdct_process: (\d+) on the GPU, (\d+) by the reference.*eSBR sbr_dec: (\d+) \+ (\d+) with HBE on the GPU, (\d+) by the reference", log)
+    m = re.search(r"imdct_process: (\d+) on the GPU, (\d+) by the reference.*eSBR sbr_dec: (\d+) \+ (\d+) with HBE \+ \d+ with PS on the GPU, (\d+) by the reference", log)
     assert m, log[-800:]
     imdct, imdct_ref, es, es_hbe, es_ref = map(int, m.groups())
     a, b = open(ref_wav, "rb").read(), open(our_wav, "rb").read()
@@ -132,3 +132,30 @@ def test_legacy_heaac_in_default_esbr_mode(tmp_path, name, enc, fs, ch, secs):
     bad = np.flatnonzero(x != y)
     assert bad.size == 0, f"{name}: {bad.size} of {x.size} samples differ, first at {bad[0]}, max |diff| {np.abs(x - y).max()}; {m.group(0)}"
     assert imdct_ref == 0 and es_hbe >= ch * 1400 and es_ref <= ch * 3, m.group(0)
+
+
+def test_heaac_v2_in_default_esbr_mode(tmp_path):
+    """HE-AACv2 (mono core + SBR + PS) decoded with the reference's DEFAULT flags: the float eSBR branch with the harmonic
+    transposer forced on AND the float parametric stereo (ixheaacd_esbr_apply_ps) — analysis bank, transposer, HF generator,
+    envelope adjuster, PS kernel and both synthesis banks on the GPU behind the reference parser; the mixing matrices are
+    prepared by the glue with the C library the reference itself calls."""
+    _need()
+    name, fs, secs = "heaac_v2_default_mode", 44100, 70.0
+    wav = str(tmp_path / "in.wav")
+    _synth_wav(wav, fs, secs, 2, 31)
+    bits = str(tmp_path / (name + ".aac"))
+    _run([os.path.join(REFDIR, "xaacenc"), f"-ifile:{wav}", f"-ofile:{bits}", "-aot:29", "-adts:1", "-br:32000"])
+    ref_wav, our_wav = str(tmp_path / "ref.wav"), str(tmp_path / "b200.wav")
+    _run([os.path.join(REFDIR, "xaacdec"), f"-ifile:{bits}", f"-ofile:{ref_wav}"])
+    log = _run([B200, f"-ifile:{bits}", f"-ofile:{our_wav}"], env=dict(os.environ, IXHEAACD_B200_STATS="1"))
+    m = re.search(r"imdct_process: (\d+) on the GPU, (\d+) by the reference.*eSBR sbr_dec: (\d+) \+ (\d+) with HBE \+ (\d+) with PS on the GPU, "
+                  r"(\d+) by the reference", log)
+    assert m, log[-800:]
+    imdct, imdct_ref, es, es_hbe, es_ps, es_ref = map(int, m.groups())
+    a, b = open(ref_wav, "rb").read(), open(our_wav, "rb").read()
+    assert len(a) == len(b) and len(a) > 100000
+    x, y = np.frombuffer(a[44:], np.int16).astype(np.int32), np.frombuffer(b[44:], np.int16).astype(np.int32)
+    bad = np.flatnonzero(x != y)
+    assert bad.size == 0, f"{name}: {bad.size} of {x.size} samples differ, first at {bad[0]}, max |diff| {np.abs(x - y).max()}; {m.group(0)}"
+    assert imdct_ref == 0 and es_ps >= 1400 and es_ref <= 6, m.group(0)
+    assert np.abs(x[0::2] - x[1::2]).max() > 100  # a real stereo image came out of the mono core

@@ -54,7 +54,9 @@ EXTRA = [("ref_rom_qmf_tables", 3464, "qmf_rom.bin"), ("ref_rom_env_tables", 240
          ("ref_rom_esbr_tables", 6288, "esbr_rom.bin"),
          # QMF harmonic transposer: the reference's global float tables (common/ixheaac_esbr_rom.c) concatenated by
          # ref_rom_hbe_tables (oracle/ref_shim_hbe.c; layout XAAC_HROM_* in include/xaac_b200.h)
-         ("ref_rom_hbe_tables", 9324 * 4, "hbe_rom.bin")]
+         ("ref_rom_hbe_tables", 9324 * 4, "hbe_rom.bin"),
+         # ref_rom_fps_tables (oracle/ref_shim_fps.c; layout XAAC_FPSROM_*)
+         ("ref_rom_fps_tables", 1016 * 4, "fps_rom.bin")]
 
 if __name__ == "__main__":
     main()

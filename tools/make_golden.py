@@ -583,9 +583,39 @@ def make_esbr_hbe_stage_golden(tmp):
     print(f"wrote {path}: {n_rec} records, {os.path.getsize(path)} bytes")
 
 
+def make_fps_golden(tmp):
+    """Float parametric stereo ixheaacd_esbr_apply_ps: outputs of the COMPILED reference function (oracle/ref_shim_fps.c) for 4
+    seeded channels over 3 consecutive frames (state carried), inputs quantised to int16 x 2^k so they store compactly.  Also
+    holds the side records / smoothing history the drop-in's host code derives (checked against the reference by
+    tests/test_ps_flt_host.py where oracle/_ref is present)."""
+    sys.path.insert(0, ROOT)
+    from tests import oracle_util as ou
+    ref = ou.Ref.try_load()
+    rng = np.random.default_rng(20261017)
+    n, frames = 4, 3
+    st, hst = ou.fps_fresh_state(n)
+    rec = {k: [] for k in ("low_re_i16", "low_im_i16", "par", "side", "left", "right", "state_out", "hst_out")}
+    shift = np.array([-4, 0, -8, -2], np.int32)
+    for f in range(frames):
+        lr, li, par = ou.synth_fps_frame(n, rng)
+        qr = np.clip(np.round(lr / np.abs(lr).max((1, 2), keepdims=True) * 30000), -32768, 32767).astype(np.int16)
+        qi = np.clip(np.round(li / np.abs(li).max((1, 2), keepdims=True) * 30000), -32768, 32767).astype(np.int16)
+        lr = np.ldexp(qr.astype(np.float32), shift[:, None, None]).astype(np.float32)
+        li = np.ldexp(qi.astype(np.float32), shift[:, None, None]).astype(np.float32)
+        r = ou.ref_fps_batch(ref, lr, li, par, st, hst)
+        assert r["rc"] == 0
+        for k, v in (("low_re_i16", qr), ("low_im_i16", qi), ("par", par), ("side", r["side"]), ("left", r["left"]),
+                     ("right", r["right"]), ("state_out", r["state"]), ("hst_out", r["hst"])):
+            rec[k].append(v)
+        st, hst = r["state"], r["hst"]
+    path = os.path.join(GOLD, "esbr_ps_ref.npz")
+    np.savez_compressed(path, shift=shift, **{k: np.stack(v) for k, v in rec.items()})
+    print(f"wrote {path}: {frames} frames x {n} channels, {os.path.getsize(path)} bytes")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr", "esbr_stage", "hbe", "hbe_stage"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr", "esbr_stage", "hbe", "hbe_stage", "fps"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
@@ -607,6 +637,8 @@ def main():
             make_hbe_golden(tmp)
         if "hbe_stage" in which:
             make_esbr_hbe_stage_golden(tmp)
+        if "fps" in which:
+            make_fps_golden(tmp)
 
 
 if __name__ == "__main__":
