@@ -67,6 +67,10 @@ WORKLOADS = {
                                        "float eSBR stage with the QMF harmonic transposer (HBE: real synthesis bank, complex analysis "
                                        "bank, stretch-2 products + pitch cross products as the reference encoder signals them), HF "
                                        "generator, envelope adjuster, polyphase QMF synthesis -> stereo PCM16"),
+    "heaacv2_esbr_chain": (3, 65536, "HE-AACv2 (mono core + SBR + PS) decoded with the reference's DEFAULT flags, batch=65536 stereo "
+                                     "frames: the float eSBR stage of the mono + PS element (harmonic transposer forced on for "
+                                     "legacy streams) with the float parametric stereo -> float stereo output; the AAC-LC core "
+                                     "IMDCT of the chain is not part of this workload (aac_lc_stereo_imdct_ola measures it)"),
     "esbr_hbe": (4, 65536, "xHE-AAC/USAC eSBR stereo: the QMF harmonic transposer of the chain (ixheaacd_qmf_hbe_apply), "
                            "batch=65536 stereo frames (131072 core channels)"),
     "xheaac_plain_stereo_chain": (4, 65536, "xHE-AAC/USAC stereo 32 kHz with eSBR, default (LPP) patching instead of the harmonic "
@@ -800,6 +804,60 @@ def cpu_arm_xheaac_hbe_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
     return n_units * done / dt, "reference"
 
 
+def cpu_arm_heaacv2_esbr_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time the reference's eSBR stage of mono + PS elements (harmonic transposer + float PS, two synthesis banks) per element on
+    host threads (ref_heaacv2_esbr_chain_batch, oracle/ref_shim_fps.c).  n_units counts elements (stream-frames) and, like the
+    other chain arm with units_per_frame = 1, the return value is 2 x elements/s."""
+    from tests import oracle_util as ou
+    ref = ou.Ref.try_load()
+    if ref is None:
+        raise SystemExit("bench.py: the HE-AACv2 eSBR chain CPU baseline needs oracle/_ref/libxaac_ref.so (make ref)")
+    n = max(threads, n_units)
+    g = load_esbr_hbe_stage_golden()
+    pg = np.load(os.path.join(ROOT, "tests", "golden", "esbr_ps_ref.npz"))
+    st = ou.heaacv2_esbr_units(g, n)
+    q6 = np.ascontiguousarray(np.concatenate([st[k].reshape(n, -1) for k in ou.ESP_KEYS[:6]], 1))
+    c0 = g["hbe_cfg"][0]
+    tbl = np.zeros(128, np.int16)
+    tbl[:6] = [1, 1, c0[2], c0[3], c0[2], c0[3]]
+    rng = np.random.default_rng(seed)
+    time_in = (rng.standard_normal((n, 1024)) * 4000).astype(np.float32)
+    frames = []
+    for f in range(HBE_FRAMES):
+        hc, hf, ip, fp, rg = esbr_hbe_stage_params(g, n, f)
+        par = np.ascontiguousarray(pg["par"][f % 3][np.arange(n) % 4]).copy()
+        par[:, 7] = ip[:, 1]
+        frames.append((hc, hf, ip, fp, rg, par))
+    bounds = np.linspace(0, n, threads + 1).astype(int)
+
+    def one_pass(step):
+        hc, hf, ip, fp, rg, par = frames[step % HBE_FRAMES]
+        ipar = ip.copy()
+        errs = [None] * threads
+
+        def work(t):
+            a, b = int(bounds[t]), int(bounds[t + 1])
+            if b > a:
+                errs[t] = ou.ref_heaacv2_esbr_chain(ref, st, time_in, hc, tbl, hf, ipar, fp, rg, par, a, b, q6=q6)[2][a:b]
+
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        dt = time.perf_counter() - t0
+        assert not any(e is not None and e.any() for e in errs), "reference HE-AACv2 eSBR chain returned an error"
+        return dt
+
+    one_pass(0)
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass(1 + done)
+        done += 1
+    return 2.0 * n * done / dt, "reference"
+
+
 def cpu_arm_xheaac_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time the reference's own xHE-AAC chain per channel unit on host threads (ref_xheaac_chain_batch, oracle/ref_shim.c)."""
     from tests import oracle_util
@@ -1012,6 +1070,16 @@ STAGES = {
                                           "included) -> ixheaacd_samples_sat",
                                 cpu=cpu_arm_xheaac_hbe_chain, cpu_units_per_core=128, cpu_reps=6, realtime_fps=15.625,
                                 h2d=4096 + 2 + 64 + 384 + 1152 + 1856 + 16, d2h=4096, dtype="int32 + f32/f64"),
+    "heaacv2_esbr_chain": dict(kernel=None, top_kernel="esbr_ps_kernel", bytes_per_unit=None, units_per_frame=1,
+                               stage="eSBR analysis bank (32-slot codec delay) -> QMF harmonic transposer -> HF generator -> envelope "
+                                     "adjuster -> (regrouping + look-ahead in the load) float parametric stereo: hybrid analysis, "
+                                     "transient detector, all-pass decorrelator, rotation, hybrid synthesis -> eSBR synthesis bank "
+                                     "x 2 (left through the element's bank, right through the second channel's)",
+                               ref_stage="eSBR branch of ixheaacd_sbr_dec for a mono + PS element with hbe_flag = 1: "
+                                         "ixheaacd_esbr_analysis_filt_block -> ixheaacd_qmf_hbe_apply -> ixheaacd_generate_hf -> "
+                                         "ixheaacd_sbr_env_calc -> ixheaacd_esbr_apply_ps -> 2 x synthesis",
+                               cpu=cpu_arm_heaacv2_esbr_chain, cpu_units_per_core=64, cpu_reps=6, realtime_fps=21.533,
+                               h2d=4096 + 64 + 384 + 1152 + 1856 + 16 + 4096, d2h=2 * 8192, dtype="f32/f64"),
     "esbr_hbe": dict(kernel="esbr_hbe_kernel", bytes_per_unit=None,
                      stage="QMF harmonic transposer: critically sampled real synthesis bank, 2x complex analysis bank, stretch-2/3/4 "
                            "products with pitch cross products, phase rotation (bit-exact floats)",
@@ -1461,6 +1529,79 @@ class XheaacHbeChainWork(XheaacChainWork):
         xb.esbr_dec_hbe(self.ctx, self.state, self.core, hc, hf, ip, fp, rg, pcm16=self.pcm, ch_fac=2, err=self.err, want_float=False)
         self.h_pcm.copy_(self.pcm, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+
+
+class Heaacv2EsbrChainWork:
+    """Mono + PS elements (unit = one element = one stereo stream-frame): the float eSBR stage with the harmonic transposer and the
+    float parametric stereo, 7 launches per step.  eSBR parameters and initial state are tiled from the tapped -harmonic_sbr:1
+    stream, PS side records from the golden records of the compiled reference (tests/golden/esbr_ps_ref.npz); the PS state and
+    the second synthesis bank start fresh and stay resident."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        g = load_esbr_hbe_stage_golden()
+        pg = np.load(os.path.join(ROOT, "tests", "golden", "esbr_ps_ref.npz"))
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        self.time_in = torch.randn((n_units, 1024), generator=gen, device=dev) * 4000.0
+        self.state = xb.EsbrDecPsBatch(n_units, device=dev)
+        for k in xb.EsbrDecHbeBatch.SHAPES:
+            v = torch.from_numpy(np.ascontiguousarray(g["in0_" + k])).to(dev)
+            getattr(self.state, k).view((n_units // 2, 2) + tuple(v.shape[1:])).copy_(v.unsqueeze(0).expand((n_units // 2,) + tuple(v.shape)))
+        self.params = []
+        for f in range(HBE_FRAMES):
+            hc, hf, ip, fp, rg = esbr_hbe_stage_params(g, n_units, f)
+            side = np.ascontiguousarray(pg["side"][f % 3][np.arange(n_units) % 4]).copy()
+            side.view(np.int32)[:, 7] = ip[:, 1]  # usb = sub_band_end of the element
+            self.params.append([torch.from_numpy(a).to(dev) for a in (hc, hf, ip, fp, rg, side)])
+        self.out_l = torch.empty((n_units, 2048), dtype=torch.float32, device=dev)
+        self.out_r = torch.empty((n_units, 2048), dtype=torch.float32, device=dev)
+        self.err = torch.zeros((6, n_units), dtype=torch.int32, device=dev)
+        hf = np.concatenate([esbr_hbe_stage_params(g, 2, f)[1] for f in range(HBE_FRAMES)])
+        ec = np.concatenate([esbr_hbe_stage_params(g, 2, f)[2] for f in range(HBE_FRAMES)])
+        CHAIN_KERNEL_BYTES.update({
+            "esbr_anal_kernel": 4096 + 2560 + 2 * 40 * 128 * 2 + 8192,
+            "esbr_hbe_kernel": float(esbr_hbe_bytes(g["hbe_cfg"]).mean()) + 2 * 8 * 512,
+            "esbr_hfgen_kernel": float(esbr_hfgen_bytes(hf).mean()) + 8192,
+            "esbr_envcalc_kernel": float(esbr_envcalc_bytes(ec).mean()),
+            # 32 slots x 64 bands x 8 B regrouped in + 6 x 5 look-ahead cells + 4096 side + 2 x 17472 state + 2 x 16384 matrices out
+            "esbr_ps_kernel": 16384 + 240 + 4096 + 2 * 17472 + 2 * 16384,
+            # plain mode, per launch (two per step): 16384 matrix in + 2 x 5120 state + 8192 float out
+            "esbr_synth_kernel": 16384 + 10240 + 8192,
+        })
+
+    def step(self, i, stream):
+        hc, hf, ip, fp, rg, side = self.params[i % HBE_FRAMES]
+        self.xb.esbr_dec_ps(self.ctx, self.state, self.time_in, hc, hf, ip, fp, rg, side, out_l=self.out_l, out_r=self.out_r,
+                            err=self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0
+
+    def host_setup(self):
+        import torch
+        self.h_time = torch.empty((self.n, 1024), dtype=torch.float32).pin_memory()
+        self.h_time.copy_(self.time_in)
+        self.h_params = [[a.cpu().pin_memory() for a in p] for p in self.params]
+        self.h_l = torch.empty((self.n, 2048), dtype=torch.float32).pin_memory()
+        self.h_r = torch.empty((self.n, 2048), dtype=torch.float32).pin_memory()
+        self.d_time = torch.empty_like(self.time_in)
+        self.d_params = [torch.empty_like(a) for a in self.params[0]]
+
+    def host_step(self, i):
+        import torch
+        self.d_time.copy_(self.h_time, non_blocking=True)
+        for d, h in zip(self.d_params, self.h_params[i % HBE_FRAMES]):
+            d.copy_(h, non_blocking=True)
+        hc, hf, ip, fp, rg, side = self.d_params
+        self.xb.esbr_dec_ps(self.ctx, self.state, self.d_time, hc, hf, ip, fp, rg, side, out_l=self.out_l, out_r=self.out_r, err=self.err)
+        self.h_l.copy_(self.out_l, non_blocking=True)
+        self.h_r.copy_(self.out_r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
 
 
 class EsbrHbeWork:
@@ -1950,7 +2091,7 @@ WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv
         "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork,
         "esbr_anal32": EsbrAnalWork, "esbr_generate_hf": EsbrHfgenWork,
         "esbr_env_calc": EsbrEnvcalcWork, "xheaac_stereo_chain": XheaacHbeChainWork, "esbr_hbe": EsbrHbeWork,
-        "xheaac_plain_stereo_chain": XheaacChainWork}
+        "xheaac_plain_stereo_chain": XheaacChainWork, "heaacv2_esbr_chain": Heaacv2EsbrChainWork}
 
 
 def main():

@@ -1191,3 +1191,57 @@ def ref_fps_batch(ref, low_re, low_im, par, state, hst):
     rc = ref.lib.ref_fps_apply_batch(n, P(np.ascontiguousarray(low_re, np.float32)), P(np.ascontiguousarray(low_im, np.float32)),
                                      P(np.ascontiguousarray(par, np.int32)), P(st), P(h), P(side), P(commit), P(left), P(right))
     return dict(side=side, commit=commit, left=left, right=right, state=st, hst=h, rc=rc)
+
+
+def ref_fps_side_batch(ref, par, hst):
+    """The drop-in's host-side preparation alone (b200_fps_side + b200_fps_commit through oracle/ref_shim_fps.c): returns
+    (side [n, 1024], hst advanced by the frame)."""
+    n = len(par)
+    h = np.ascontiguousarray(hst, np.float32).copy()
+    side = np.zeros((n, FPS_SIDE_WORDS), np.float32)
+    ref.lib.ref_fps_side_batch.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 3
+    rc = ref.lib.ref_fps_side_batch(n, P(np.ascontiguousarray(par, np.int32)), P(h), P(side))
+    assert rc == 0
+    return side, h
+
+
+ESP_KEYS = ("qmf_re", "qmf_im", "out_re", "out_im", "pv_re", "pv_im", "anal_states", "anal_pos", "synth_states", "synth_pos",
+            "bw_prev", "patch", "ec_state", "hbe_state")
+
+
+def heaacv2_esbr_units(g, n):
+    """Initial state of n mono + PS elements for the HE-AACv2 default-mode stage: the eSBR part tiled from the channels of the
+    tapped -harmonic_sbr:1 stream (tests/golden/esbr_hbe_stage_tapped.npz), PS instance and second synthesis bank fresh."""
+    ch = np.arange(n) % 2
+    st = {k: np.ascontiguousarray(g["in0_" + k][ch]).copy() for k in ESP_KEYS}
+    st["ps_state"], st["ps_hst"] = fps_fresh_state(n)
+    st["synth_states_r"] = np.zeros((n, 1280), np.int32)
+    st["synth_pos_r"] = np.zeros((n, 2), np.int32)
+    return st
+
+
+def ref_heaacv2_esbr_chain(ref, st, time_in, hbe_cfg, hbe_tbl, hf_par, ec_ipar, ec_fpar, rg, ps_par, a=0, b=None, q6=None):
+    """ref_heaacv2_esbr_chain_batch (oracle/ref_shim_fps.c) on the state dict of heaacv2_esbr_units, updated in place; ec_ipar is
+    in/out.  Returns (out_l, out_r, err)."""
+    n = len(time_in)
+    b = n if b is None else b
+    own = q6 is None
+    if own:
+        q6 = np.ascontiguousarray(np.concatenate([st[k].reshape(n, -1) for k in ESP_KEYS[:6]], 1))
+    out_l = np.zeros((n, 2048), np.float32)
+    out_r = np.zeros((n, 2048), np.float32)
+    err = np.zeros(n, np.int32)
+    ref.lib.ref_heaacv2_esbr_chain_batch(P(np.ascontiguousarray(time_in, np.float32)), P(q6), P(st["anal_states"]), P(st["anal_pos"]),
+                                         P(st["synth_states"]), P(st["synth_pos"]), P(st["bw_prev"]), P(st["patch"]), P(st["ec_state"]),
+                                         P(st["hbe_state"]), P(np.ascontiguousarray(hbe_cfg, np.int32)), P(hbe_tbl),
+                                         P(np.ascontiguousarray(hf_par, np.int32)), P(ec_ipar), P(np.ascontiguousarray(ec_fpar, np.float32)),
+                                         P(np.ascontiguousarray(rg, np.int32)), P(np.ascontiguousarray(ps_par, np.int32)),
+                                         P(st["ps_state"]), P(st["ps_hst"]), P(st["synth_states_r"]), P(st["synth_pos_r"]),
+                                         P(out_l), P(out_r), P(err), int(a), int(b))
+    if own:
+        o = 0
+        for k in ESP_KEYS[:6]:
+            w = st[k][0].size
+            st[k][...] = q6[:, o:o + w].reshape(st[k].shape)
+            o += w
+    return out_l, out_r, err

@@ -103,3 +103,53 @@ def test_ps_kernel_refuses_unsupported_borders(ctx):
     left, right, st_out, err = run_gpu(ctx, lr, li, side, st)
     assert err[0] == -2 and err[1] == -2 and (err[2:] == 0).all()
     assert np.array_equal(bits(st_out[:2]), bits(st[:2]))
+
+
+def _stage_frame(g, f, n, rng):
+    """records of frame f of the tapped -harmonic_sbr:1 stream tiled over n mono + PS elements, plus random PS parameters"""
+    r = (np.arange(n) % 2) + 2 * (f % 6)
+    h = g["head"][r]
+    rg = np.stack([h[:, 7], h[:, 8], 2 * h[:, 9], 0 * h[:, 9]], 1).astype(np.int32)
+    gain = np.ldexp(1.0, -((np.arange(n) // 2) % 3)).astype(np.float32)[:, None]
+    time_in = (g["time_in"][r] * gain).astype(np.float32)
+    _, _, par = ou.synth_fps_frame(n, rng)
+    ipar = np.ascontiguousarray(g["ec_ipar_in"][r]).copy()
+    par[:, 7] = ipar[:, 1]  # usb = sub_band_end
+    return time_in, g["hbe_cfg"][r], g["hf_par"][r], ipar, g["ec_fpar"][r], rg, par
+
+
+def test_mono_ps_stage_matches_reference_chain(ctx, ref):
+    """xaac_b200_esbr_dec_ps_dev (analysis -> transposer -> HF generator -> envelope adjuster -> PS -> two synthesis banks, state
+    resident) against the same chain assembled from the compiled reference's stage functions, 4 frames, bit for bit"""
+    import torch
+    import libxaac_b200 as xb
+    g = np.load(os.path.join(os.path.dirname(GOLD), "esbr_hbe_stage_tapped.npz"))
+    rng = np.random.default_rng(21)
+    n = 96
+    st = ou.heaacv2_esbr_units(g, n)
+    c0 = g["hbe_cfg"][0]
+    tbl = np.zeros(128, np.int16)
+    tbl[:6] = [1, 1, c0[2], c0[3], c0[2], c0[3]]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    s = xb.EsbrDecPsBatch(n)
+    for k in ou.ESP_KEYS:
+        getattr(s, k).copy_(t(st[k]))
+    s.ps_state.copy_(t(st["ps_state"]))
+    hst = st["ps_hst"].copy()
+    for f in range(4):
+        time_in, hc, hf, ipar, fp, rg, par = _stage_frame(g, f, n, rng)
+        side, hst = ou.ref_fps_side_batch(ref, par, hst)
+        ipar_ref = ipar.copy()
+        wl, wr, err = ou.ref_heaacv2_esbr_chain(ref, st, time_in, hc, tbl, hf, ipar_ref, fp, rg, par)
+        assert not err.any(), err
+        d_ipar = t(ipar)
+        ol, orr, e = xb.esbr_dec_ps(ctx, s, t(time_in), t(hc), t(hf), d_ipar, t(fp), t(rg), t(side))
+        torch.cuda.synchronize()
+        assert int(e.abs().max()) == 0, e.cpu().numpy()
+        assert np.array_equal(bits(ol.cpu().numpy()), bits(wl)), f"frame {f}: left"
+        assert np.array_equal(bits(orr.cpu().numpy()), bits(wr)), f"frame {f}: right"
+        assert np.array_equal(d_ipar.cpu().numpy(), ipar_ref), f"frame {f}: in/out parameter words"
+        for k in ("anal_states", "synth_states", "synth_pos", "ec_state", "bw_prev", "hbe_state", "ps_state", "synth_states_r", "synth_pos_r"):
+            assert np.array_equal(getattr(s, k).cpu().numpy().view(np.int32), st[k].view(np.int32)), f"frame {f}: {k}"
+        assert np.array_equal(bits(hst), bits(st["ps_hst"])), f"frame {f}: smoothing history"
+    assert np.abs(wr).max() > 100 and np.abs(wl - wr).max() > 10
