@@ -27,7 +27,11 @@ constexpr int kPowStride = 21;
 constexpr int kPowWords = 32 * kPowStride;
 constexpr int kPStride = 65;
 constexpr int kPWords = 32 * kPStride;
-constexpr int kPsWarpWords = kWWords + kHyWords + kPowWords + kPWords;
+constexpr int kRingWords = 28 * 32;       // one lane's delay line + serial all-pass states: 28 floats, [slot][lane]
+constexpr int kHsWords = 6 * 160;          // the frame's mixing matrices: previous + up to 5 envelopes, [set][8][20]
+constexpr int kPsWarpWords = kWWords + kHyWords + kPowWords + kPWords + kRingWords + kHsWords;
+// ring slots of one lane, all-pass (sub)bands: delay line re 0..1, im 2..3; link m of length {3, 4, 5}: re at 4 + {0, 3, 7},
+// im at 16 + {0, 3, 7}.  Plain-delay bands (QMF bands >= 23): re 0..13, im 14..27.
 
 struct Left {
   const float *lre, *lim, *hre, *him;
@@ -36,7 +40,8 @@ struct Left {
   __device__ __forceinline__ void at(int s, int k, float &re, float &im) const {
     const int xo = s < stop ? xo_first : xo_rest;
     const int o = (2 + s) * 64 + k;
-    if (k < xo) { re = lre[o]; im = lim[o]; } else { re = hre[o]; im = him[o]; }
+    const float *pr = k < xo ? lre : hre, *pi = k < xo ? lim : him;  // a select, not a branch: the loads of a batch overlap
+    re = __ldg(pr + o); im = __ldg(pi + o);
   }
   // slots 32..37 (bands 0..4) always come from the low-band array (sbr_dec.c:485-506)
   __device__ __forceinline__ void ahead(int s, int k, float &re, float &im) const {
@@ -52,8 +57,8 @@ struct Mix {  // one bin's interpolated matrix
   float r11, r12, r21, r22, i11, i12, i21, i22;
   float d11r, d12r, d21r, d22r, d11i, d12i, d21i, d22i;
   // ps_dec_flt.c:1030-1075: start from the previous envelope's matrix, step = (target - start) / L
-  __device__ __forceinline__ void start(const float *side, int env, int bin, bool neg, int L) {
-    const float *a = side + kFpsSideH + env * 160 + bin;        // previous (set env), target (set env + 1)
+  __device__ __forceinline__ void start(const float *hs, int env, int bin, bool neg, int L) {
+    const float *a = hs + env * 160 + bin;                      // previous (set env), target (set env + 1)
     const float *b = a + 160;
     const float sg = neg ? -1.0f : 1.0f;
     r11 = a[0]; r12 = a[20]; r21 = a[40]; r22 = a[60];
@@ -75,20 +80,9 @@ struct Mix {  // one bin's interpolated matrix
   }
 };
 
-// One decorrelator recursion in time for one (sub)band (ps_dec_flt.c:655-712 / 736-803) fused with its rotation
-// (ps_dec_flt.c:1077-1100 / 1150-1186).  D: [rows][stride] delay line pair, S: [3][5][stride] all-pass states.
-struct Lane {
-  float *d_re, *d_im;     // column of the delay buffer (row stride ds)
-  float *s_re, *s_im;     // column of the serial all-pass buffers (row stride ds, link stride 5 * ds)
-  int ds;
-  float fr, fi, sr[3], si[3], c[3];  // fractional-delay phase factors, decay_scale_factor * all_pass_link_decay_ser[m]
-  bool plain;             // QMF bands >= NUM_OF_ALL_PASS_CHNLS: pure delay
-  int qidx, qnum;
-};
-
 }  // namespace
 
-__global__ void __launch_bounds__(kPsWarps * 32) esbr_ps_kernel(const EsbrPsArgs p) {
+__global__ void __launch_bounds__(kPsWarps * 32, 2) esbr_ps_kernel(const EsbrPsArgs p) {
   extern __shared__ float smem[];
   float *rom = smem;  // kFpsRomWords
   for (int i = threadIdx.x; i < kFpsRomWords; i += blockDim.x) rom[i] = p.rom[i];
@@ -99,7 +93,9 @@ __global__ void __launch_bounds__(kPsWarps * 32) esbr_ps_kernel(const EsbrPsArgs
   float *HL_re = W + kWWords, *HL_im = HL_re + 32 * kHyStride, *HR_re = HL_im + 32 * kHyStride, *HR_im = HR_re + 32 * kHyStride;
   float *POW = HR_im + 32 * kHyStride;
   float *PT = POW + kPowWords;
-  const int *grb = irom + kFpsRomGrb, *bgm = irom + kFpsRomBgm, *dser = irom + kFpsRomDser, *qdeln = irom + kFpsRomQdelN;
+  float *RING = PT + kPWords + lane;
+  float *HS = PT + kPWords + kRingWords;
+  const int *grb = irom + kFpsRomGrb, *bgm = irom + kFpsRomBgm, *qdeln = irom + kFpsRomQdelN;
 
   for (long long u = (long long)blockIdx.x * kPsWarps + warp; u < p.n_units; u += (long long)gridDim.x * kPsWarps) {
     const float *side = p.side + u * kFpsSideWords;
@@ -124,11 +120,16 @@ __global__ void __launch_bounds__(kPsWarps * 32) esbr_ps_kernel(const EsbrPsArgs
     L.xo_first = p.rg_par[4 * u]; L.xo_rest = p.rg_par[4 * u + 1]; L.stop = p.rg_par[4 * u + 2];
     float *out_l = p.left + u * 4096, *out_r = p.right + u * 4096;
 
+    {  // the mixing matrices of the frame -> shared memory (every band lane of a bin interpolates them again)
+      const int cnt = (num_env + 1) * 160;
+#pragma unroll 6
+      for (int i = lane; i < cnt; i += 32) HS[i] = __ldg(side + kFpsSideH + i);
+    }
     // ps_dec_flt.c:419-431: bands above usb forget their decorrelator history
     for (int sb = lane; sb < 64; sb += 32)
       if (sb >= usb) {
         for (int m = 0; m < 3; m++)
-          for (int k = 0; k < dser[m]; k++) {
+          for (int k = 0; k < 3 + m; k++) {
             st[kFpsStSerQ + (m * 5 + k) * 64 + sb] = 0.f;
             st[kFpsStSerQ + 960 + (m * 5 + k) * 64 + sb] = 0.f;
           }
@@ -192,12 +193,13 @@ __global__ void __launch_bounds__(kPsWarps * 32) esbr_ps_kernel(const EsbrPsArgs
       r[2] += r[5]; i[2] += i[5]; r[5] = 0.f; i[5] = 0.f;
     }
     // ---- |x|^2 of the QMF bands 3..63, lane = band
-    for (int k = 0; k < 32; k++)
-      for (int sb = lane; sb < 64; sb += 32) {
-        float re, im;
-        L.at(k, sb, re, im);
-        PT[k * kPStride + sb] = re * re + im * im;
-      }
+    for (int k0 = 0; k0 < 32; k0 += 4) {
+      float re[8], im[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) L.at(k0 + (j >> 1), lane + 32 * (j & 1), re[j], im[j]);
+#pragma unroll
+      for (int j = 0; j < 8; j++) PT[(k0 + (j >> 1)) * kPStride + lane + 32 * (j & 1)] = re[j] * re[j] + im[j] * im[j];
+    }
     __syncwarp();
     // ---- band powers per parameter bin, lane = slot (ps_dec_flt.c:610-636)
     {
@@ -234,7 +236,10 @@ __global__ void __launch_bounds__(kPsWarps * 32) esbr_ps_kernel(const EsbrPsArgs
     const int l_delay0 = ist[0];
     const int ser0[3] = {ist[1], ist[2], ist[3]};
     int l_delay_end = l_delay0, ser_end[3] = {ser0[0], ser0[1], ser0[2]};
-    // ---- decorrelator + rotation: pass 0 = the 10 sub-subband groups, passes 1, 2 = QMF bands 3..34 and 35..63
+    constexpr int d0 = 3, d1 = 4, d2 = 5;  // delay_sample_ser (checked against the ROM by xaac_b200_set_fps_rom)
+    // ---- decorrelator (ps_dec_flt.c:655-712 / 736-803) fused with the rotation (ps_dec_flt.c:1077-1100 / 1150-1186), one
+    // (sub)band per lane, serial over the slots: pass 0 = the 10 sub-subband groups, passes 1, 2 = QMF bands 3..34 and 35..63.
+    // The lane's delay line and all-pass states live in shared memory for the pass (28 floats), the pass's 32 input bands too.
     for (int pass = 0; pass < 3; pass++) {
       int sb, gr;
       bool active;
@@ -244,74 +249,101 @@ __global__ void __launch_bounds__(kPsWarps * 32) esbr_ps_kernel(const EsbrPsArgs
         sb = (pass == 1 ? 3 : 35) + lane; active = sb < 64;
         gr = 10;
         if (active) while (sb >= grb[gr + 1]) gr++;
+        __syncwarp();
+        const int sbl = active ? sb : 63;
+        for (int k0 = 0; k0 < 32; k0 += 8) {  // input tile [slot][re 32 | im 32], coalesced rows, 8 rows in flight
+          float re[8], im[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) L.at(k0 + j, sbl, re[j], im[j]);
+#pragma unroll
+          for (int j = 0; j < 8; j++) { PT[(k0 + j) * 64 + lane] = re[j]; PT[(k0 + j) * 64 + 32 + lane] = im[j]; }
+        }
       }
+      const bool plain = pass != 0 && sb >= 23;
+      const int ds = pass == 0 ? 12 : 64;
+      float *g_d = st + (pass == 0 ? kFpsStSubDel : kFpsStQDel) + sb, *g_s = st + (pass == 0 ? kFpsStSerSub : kFpsStSerQ) + sb;
+      const int d_im = pass == 0 ? 24 : 896, s_im = pass == 0 ? 180 : 960;
+      const int qnum = plain ? qdeln[sb] : 1;
+      int qidx = plain ? ist[4 + sb] : 0;
+      float fr = 0.f, fi = 0.f, sr[3] = {0.f, 0.f, 0.f}, si[3] = {0.f, 0.f, 0.f}, c[3] = {0.f, 0.f, 0.f};
       if (active) {
+        {  // all 28 words of the lane's state in flight at once (link lengths 3, 4, 5: checked by xaac_b200_set_fps_rom)
+          float v[28];
+          if (plain) {
+#pragma unroll
+            for (int r = 0; r < 14; r++) {
+              v[r] = r < qnum ? g_d[r * ds] : 0.f;
+              v[14 + r] = r < qnum ? g_d[d_im + r * ds] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 2; r++) { v[r] = g_d[r * ds]; v[2 + r] = g_d[d_im + r * ds]; }
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+#pragma unroll
+              for (int r = 0; r < 3 + m; r++) {
+                v[4 + (m == 0 ? 0 : m == 1 ? 3 : 7) + r] = g_s[(m * 5 + r) * ds];
+                v[16 + (m == 0 ? 0 : m == 1 ? 3 : 7) + r] = g_s[s_im + (m * 5 + r) * ds];
+              }
+          }
+#pragma unroll
+          for (int r = 0; r < 28; r++) RING[32 * r] = v[r];
+        }
+        if (!plain) {
+          float dsf = 1.0f;
+          if (pass == 0) {
+            fr = rom[kFpsRomSubRe + sb]; fi = rom[kFpsRomSubIm + sb];
+          } else {
+            fr = rom[kFpsRomQfRe + sb]; fi = rom[kFpsRomQfIm + sb];
+            dsf = (sb <= 3) ? 1.0f : 1.0f + 3.0f * 0.05f - 0.05f * (float)sb;  // ps_dec_flt.c:738-744, decay_cutoff = 3
+            dsf = dsf > 0.0f ? dsf : 0.0f;
+          }
+          for (int m = 0; m < 3; m++) {
+            sr[m] = rom[(pass == 0 ? kFpsRomSSerRe : kFpsRomQSerRe) + sb * 3 + m];
+            si[m] = rom[(pass == 0 ? kFpsRomSSerIm : kFpsRomQSerIm) + sb * 3 + m];
+            c[m] = dsf * rom[kFpsRomDecay + m];
+          }
+        }
         const int bin = bgm[gr] & 0xfff;
         const bool neg = (bgm[gr] & 0x1000) != 0;
-        Lane a;
-        if (pass == 0) {
-          a.ds = 12;
-          a.d_re = st + kFpsStSubDel + sb; a.d_im = a.d_re + 24;
-          a.s_re = st + kFpsStSerSub + sb; a.s_im = a.s_re + 180;
-          a.fr = rom[kFpsRomSubRe + sb]; a.fi = rom[kFpsRomSubIm + sb];
-          for (int m = 0; m < 3; m++) {
-            a.sr[m] = rom[kFpsRomSSerRe + sb * 3 + m]; a.si[m] = rom[kFpsRomSSerIm + sb * 3 + m];
-            a.c[m] = 1.0f * rom[kFpsRomDecay + m];
-          }
-          a.plain = false; a.qidx = 0; a.qnum = 1;
-        } else {
-          a.ds = 64;
-          a.d_re = st + kFpsStQDel + sb; a.d_im = a.d_re + 896;
-          a.s_re = st + kFpsStSerQ + sb; a.s_im = a.s_re + 960;
-          a.fr = rom[kFpsRomQfRe + sb]; a.fi = rom[kFpsRomQfIm + sb];
-          // ps_dec_flt.c:738-744 with decay_cutoff = 3
-          float dsf = (sb <= 3) ? 1.0f : 1.0f + 3.0f * 0.05f - 0.05f * (float)sb;
-          dsf = dsf > 0.0f ? dsf : 0.0f;
-          for (int m = 0; m < 3; m++) {
-            a.sr[m] = rom[kFpsRomQSerRe + sb * 3 + m]; a.si[m] = rom[kFpsRomQSerIm + sb * 3 + m];
-            a.c[m] = dsf * rom[kFpsRomDecay + m];
-          }
-          a.plain = sb >= 23;
-          a.qidx = ist[4 + sb]; a.qnum = qdeln[sb];
-        }
-        int ld = l_delay0, sd[3] = {ser0[0], ser0[1], ser0[2]};
-        const int d0 = dser[0], d1 = dser[1], d2 = dser[2];
+        int ld = l_delay0, sd0 = ser0[0], sd1 = ser0[1], sd2 = ser0[2];
         Mix H;
         for (int env = 0; env < num_env; env++) {
           const int k0 = iside[kFpsSideBorder + env], k1 = iside[kFpsSideBorder + env + 1];
-          H.start(side, env, bin, neg, k1 - k0);
+          H.start(HS, env, bin, neg, k1 - k0);
           for (int k = k0; k < k1; k++) {
             float lr, li;
-            if (pass == 0) { lr = HL_re[k * kHyStride + sb]; li = HL_im[k * kHyStride + sb]; } else L.at(k, sb, lr, li);
+            if (pass == 0) { lr = HL_re[k * kHyStride + sb]; li = HL_im[k * kHyStride + sb]; }
+            else { lr = PT[k * 64 + lane]; li = PT[k * 64 + 32 + lane]; }
             float r0, i0;
-            if (a.plain) {
-              r0 = a.d_re[a.qidx * a.ds]; i0 = a.d_im[a.qidx * a.ds];
-              a.d_re[a.qidx * a.ds] = lr; a.d_im[a.qidx * a.ds] = li;
-              if (++a.qidx >= a.qnum) a.qidx = 0;
+            if (plain) {
+              r0 = RING[32 * qidx]; i0 = RING[32 * (14 + qidx)];
+              RING[32 * qidx] = lr; RING[32 * (14 + qidx)] = li;
+              if (++qidx >= qnum) qidx = 0;
             } else {
-              const float x0 = a.d_re[ld * a.ds], y0 = a.d_im[ld * a.ds];
-              a.d_re[ld * a.ds] = lr; a.d_im[ld * a.ds] = li;
-              r0 = x0 * a.fr - y0 * a.fi;
-              i0 = x0 * a.fi + y0 * a.fr;
+              const float x0 = RING[32 * ld], y0 = RING[32 * (2 + ld)];
+              RING[32 * ld] = lr; RING[32 * (2 + ld)] = li;
+              r0 = x0 * fr - y0 * fi;
+              i0 = x0 * fi + y0 * fr;
 #pragma unroll
               for (int m = 0; m < 3; m++) {
-                const int o = (m * 5 + sd[m]) * a.ds;
-                const float x = a.s_re[o], y = a.s_im[o];
-                float re = x * a.sr[m] - y * a.si[m];
-                float im = x * a.si[m] + y * a.sr[m];
-                re += (-a.c[m]) * r0;
-                im += (-a.c[m]) * i0;
-                a.s_re[o] = r0 + a.c[m] * re;
-                a.s_im[o] = i0 + a.c[m] * im;
+                const int o = 32 * (4 + (m == 0 ? 0 : m == 1 ? 3 : 7) + (m == 0 ? sd0 : m == 1 ? sd1 : sd2));
+                const float x = RING[o], y = RING[o + 32 * 12];
+                float re = x * sr[m] - y * si[m];
+                float im = x * si[m] + y * sr[m];
+                re += (-c[m]) * r0;
+                im += (-c[m]) * i0;
+                RING[o] = r0 + c[m] * re;
+                RING[o + 32 * 12] = i0 + c[m] * im;
                 r0 = re; i0 = im;
               }
             }
             const float tr = POW[k * kPowStride + bin];
             float rr = tr * r0, ri = tr * i0;
             if (++ld >= 2) ld = 0;
-            if (++sd[0] >= d0) sd[0] = 0;
-            if (++sd[1] >= d1) sd[1] = 0;
-            if (++sd[2] >= d2) sd[2] = 0;
+            if (++sd0 >= d0) sd0 = 0;
+            if (++sd1 >= d1) sd1 = 0;
+            if (++sd2 >= d2) sd2 = 0;
             H.step();
             H.apply(lr, li, rr, ri);
             if (pass == 0) {
@@ -323,8 +355,20 @@ __global__ void __launch_bounds__(kPsWarps * 32) esbr_ps_kernel(const EsbrPsArgs
             }
           }
         }
-        if (pass != 0 && a.plain) ist[4 + sb] = a.qidx;
-        l_delay_end = ld; ser_end[0] = sd[0]; ser_end[1] = sd[1]; ser_end[2] = sd[2];
+        if (plain) {
+          ist[4 + sb] = qidx;
+          for (int r = 0; r < qnum; r++) { g_d[r * ds] = RING[32 * r]; g_d[d_im + r * ds] = RING[32 * (14 + r)]; }
+        } else {
+          for (int r = 0; r < 2; r++) { g_d[r * ds] = RING[32 * r]; g_d[d_im + r * ds] = RING[32 * (2 + r)]; }
+#pragma unroll
+          for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int r = 0; r < 3 + m; r++) {
+              g_s[(m * 5 + r) * ds] = RING[32 * (4 + (m == 0 ? 0 : m == 1 ? 3 : 7) + r)];
+              g_s[s_im + (m * 5 + r) * ds] = RING[32 * (16 + (m == 0 ? 0 : m == 1 ? 3 : 7) + r)];
+            }
+        }
+        l_delay_end = ld; ser_end[0] = sd0; ser_end[1] = sd1; ser_end[2] = sd2;
       }
       if (pass == 0) {  // sub-subbands 4 and 5 were folded into 3 and 2; the right matrix keeps zeros there
         HR_re[lane * kHyStride + 4] = 0.f; HR_im[lane * kHyStride + 4] = 0.f;

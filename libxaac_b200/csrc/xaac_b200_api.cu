@@ -1231,6 +1231,13 @@ int32_t xaac_b200_esbr_hbe_apply_dev(xaac_b200_ctx *ctx, const float *d_qmf_re, 
 int32_t xaac_b200_set_fps_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
   if (!ctx || !tables) return bad_arg(ctx, "null");
   if (bytes < (size_t)xb::kFpsRomWords * 4) return bad_arg(ctx, "float-PS ROM blob shorter than 4064 bytes");
+  {
+    const int32_t *w = (const int32_t *)tables;  // the kernel unrolls the serial all-pass links with these lengths
+    if (w[xb::kFpsRomDser] != 3 || w[xb::kFpsRomDser + 1] != 4 || w[xb::kFpsRomDser + 2] != 5)
+      return bad_arg(ctx, "float-PS ROM: delay_sample_ser is not {3, 4, 5}");
+    for (int i = 0; i < 64; i++)
+      if (w[xb::kFpsRomQdelN + i] < 1 || w[xb::kFpsRomQdelN + i] > 14) return bad_arg(ctx, "float-PS ROM: qmf_delay_idx_tbl out of 1..14");
+  }
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   cudaError_t e = ctx->d_rom_fps ? cudaSuccess : cudaMalloc((void **)&ctx->d_rom_fps, (size_t)xb::kFpsRomWords * 4);
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_rom_fps, tables, (size_t)xb::kFpsRomWords * 4, cudaMemcpyHostToDevice);
