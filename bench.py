@@ -2306,7 +2306,7 @@ def main():
             # the other BASELINE configs at their own batch sizes, device-resident and through host buffers (short runs), so that the
             # driver-run line carries them too and not only the builder's own captures
             other = {}
-            for name in ("aac_lc_stereo_imdct_ola", "heaacv1_stereo_chain", "xheaac_stereo_chain"):
+            for name in ("aac_lc_stereo_imdct_ola", "heaacv1_stereo_chain", "xheaac_stereo_chain", "heaacv2_esbr_chain"):
                 if name == args.workload:
                     continue
                 ci, fr, _ = WORKLOADS[name]
