@@ -574,10 +574,14 @@ int32_t xaac_b200_esbr_generate_hf_dev(xaac_b200_ctx *ctx, const float *d_src_re
 #define XAAC_EEC_HARM_INDEX 13      /* harm_index (in/out) */
 #define XAAC_EEC_PHASE_INDEX 14     /* phase_index (in/out) */
 #define XAAC_EEC_START_UP 15        /* pstr_sbr_header->esbr_start_up (in/out) */
-#define XAAC_EEC_RESET 16           /* reset_flag (must be 0) */
+#define XAAC_EEC_RESET 16           /* reset_flag: esbr_start_up = 1, phase_index = 0 (esbr_envcal.c:169-172); needs LIM_REBUILT */
 #define XAAC_EEC_SBR_MODE 17        /* sbr_mode (must be ORIG_SBR = 1) */
 #define XAAC_EEC_USF4 18            /* is_usf_4 (must be 0) */
-#define XAAC_EEC_PATCHING_CHANGED 19 /* sbr_patching_mode != prev_sbr_patching_mode (must be 0) */
+#define XAAC_EEC_PATCHING_CHANGED 19 /* sbr_patching_mode != prev_sbr_patching_mode; needs LIM_REBUILT */
+#define XAAC_EEC_LIM_REBUILT 20     /* 1 = the host has run ixheaacd_createlimiterbands (esbr_envcal.c:173-188, control plane) for this
+                                     * reset / patching-change frame and LIM_TABLE / GATE_MODE carry the result; without it such a
+                                     * frame returns -2.  With LPP patching the patch table comes from the HF generator of the same
+                                     * frame: call xaac_b200_esbr_dec_front_dev, read `patch`, rebuild, call _back_dev */
 #define XAAC_EEC_BORDER 24          /* border_vec[9] */
 #define XAAC_EEC_FREQ_RES 33        /* freq_res[8] */
 #define XAAC_EEC_NOISE_BORDER 41    /* noise_border_vec[3] */
@@ -758,6 +762,33 @@ int32_t xaac_b200_esbr_dec_ps_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_s
                                   const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par,
                                   const float *d_ps_side, float *d_out_l, float *d_out_r, int32_t *d_err, int64_t n_units,
                                   void *stream);
+
+/* The stage in two halves.  On reset frames and on frames where sbr_patching_mode changes, ixheaacd_sbr_env_calc first rebuilds
+ * its limiter tables from the patch table that ixheaacd_generate_hf of the SAME frame has just produced
+ * (ixheaacd_createlimiterbands, decoder/ixheaacd_esbr_envcal.c:169-190, 910-1012: a shell sort and a handful of double-precision
+ * log() calls per stream — control plane).  A host that has such units in the batch calls
+ *   _front_dev  (analysis bank, [transposer], HF generator; d_err rows 0, 1, 4),
+ *   reads st->base.patch of those units, runs ixheaacd_createlimiterbands, stores the tables at XAAC_EEC_LIM_TABLE / _GATE_MODE of
+ *   their d_ec_ipar records and sets XAAC_EEC_LIM_REBUILT,
+ *   _back_dev   (envelope adjuster, [PS], synthesis bank(s); d_err rows 2, 3, 5).
+ * st->pv_re = NULL selects the stage without the transposer, ps = NULL the stage without PS (then d_out_r / d_ps_side are unused
+ * and d_pcm16 is allowed).  Calling both halves back to back equals xaac_b200_esbr_dec_dev / _dec_hbe_dev / _dec_ps_dev. */
+int32_t xaac_b200_esbr_dec_front_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const float *d_time_in,
+                                     const int32_t *d_core_in, const int32_t *d_hbe_cfg, const int32_t *d_hf_par, int32_t *d_err,
+                                     int64_t n_units, void *stream);
+int32_t xaac_b200_esbr_dec_back_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const xaac_b200_esbr_ps_view *ps,
+                                    int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par, const float *d_ps_side,
+                                    float *d_out, float *d_out_r, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err,
+                                    int64_t n_units, void *stream);
+
+/* apply_processing = 0 (frames before the first SBR header of a stream): the stage only upsamples — history shifts, analysis bank,
+ * sbr_qmf_out cleared, synthesis bank over the regrouped core bands (d_rg_par = {x, sub_band_start, 0, 0}); with ps the right
+ * channel is the same matrix through the second channel's bank (decoder/ixheaacd_sbr_dec.c:518-525, 836-878, 964-1003).  The
+ * transposer, HF generator, envelope adjuster and PS instances are not touched. */
+int32_t xaac_b200_esbr_dec_bypass_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const xaac_b200_esbr_ps_view *ps,
+                                      const float *d_time_in, const int32_t *d_core_in, const int32_t *d_rg_par, float *d_out,
+                                      float *d_out_r, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units,
+                                      void *stream);
 
 /* ---- raw device-memory helpers for C hosts that do not link the CUDA runtime themselves (the reference-side drop-in glue,
  * libxaac_b200/dropin/ixheaacd_b200_glue.c): allocation and synchronous copies on the context's device ---- */

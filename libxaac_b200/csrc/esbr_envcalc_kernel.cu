@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(kEcWarps * 32, 3) esbr_envcalc_kernel(EsbrEnvc
     const unsigned char *harm_prev = reinterpret_cast<const unsigned char *>(ip + kEecHarmPrev);
     int harm_index = ip[kEecHarmIndex], phase_index = ip[kEecPhaseIndex], start_up = ip[kEecStartUp];
     int err = 0;
-    if (ip[kEecReset] || ip[kEecSbrMode] != 1 || ip[kEecUsf4] || ip[kEecPatchingChanged]) err = -2;
+    if (ip[kEecSbrMode] != 1 || ip[kEecUsf4]) err = -2;
+    // envcal.c:169-190: on these frames the reference rebuilds its limiter tables from the patch table first; the host does
+    // that (ixheaacd_createlimiterbands, control plane) and says so, otherwise the frame is refused
+    if ((ip[kEecReset] || ip[kEecPatchingChanged]) && !ip[kEecLimRebuilt]) err = -2;
+    if (ip[kEecReset]) { start_up = 1; phase_index = 0; }
     if (sbs < 0 || sbe > 64 || nsub < 0 || num_env < 1 || num_env > 8 || num_nf < 1 || num_nf > 5 || (lb & ~3) || (lg & ~3)) err = -2;
     const int num_sf_lo = ip[kEecNumSfLo], num_sf_hi = ip[kEecNumSfHi];
     const int gate = err ? 0 : ip[kEecGateMode + lb];

@@ -354,7 +354,7 @@ cudaError_t launch_esbr_hfgen(const EsbrHfgenArgs &args, int num_sms, cudaStream
 constexpr int kEecSbStart = 0, kEecSbEnd = 1, kEecNumEnv = 2, kEecTransEnv = 3, kEecShortPrev = 4, kEecNumNoiseEnv = 5,
               kEecNumSfLo = 6, kEecNumSfHi = 7, kEecNumNf = 8, kEecSmoothingMode = 9, kEecInterpolFreq = 10,
               kEecLimiterBands = 11, kEecLimiterGains = 12, kEecHarmIndex = 13, kEecPhaseIndex = 14, kEecStartUp = 15,
-              kEecReset = 16, kEecSbrMode = 17, kEecUsf4 = 18, kEecPatchingChanged = 19, kEecBorder = 24, kEecFreqRes = 33,
+              kEecReset = 16, kEecSbrMode = 17, kEecUsf4 = 18, kEecPatchingChanged = 19, kEecLimRebuilt = 20, kEecBorder = 24, kEecFreqRes = 33,
               kEecNoiseBorder = 41, kEecInterTes = 44, kEecGateMode = 52, kEecLimTable = 56, kEecTblNoise = 108,
               kEecTblLo = 116, kEecTblHi = 148, kEecAddHarm = 208, kEecHarmPrev = 264, kEecIparWords = 288,
               kEecSfbNrg = 0, kEecNoiseFloor = 448, kEecFparWords = 464, kEecStateWords = 640, kEecRphaseBytes = 4096;

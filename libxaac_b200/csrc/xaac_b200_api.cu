@@ -1277,7 +1277,9 @@ static int32_t esbr_dec_impl(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view
                              const int32_t *d_hf_par, int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par,
                              float *d_out, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units, void *stream,
                              const xaac_b200_esbr_ps_view *ps = nullptr, const float *d_ps_side = nullptr,
-                             float *d_out_r = nullptr) {
+                             float *d_out_r = nullptr, int phases = 3) {
+  // phases: 1 = front (analysis bank, transposer, HF generator), 2 = back (envelope adjuster, PS, synthesis), 3 = both
+  const bool front = (phases & 1) != 0, back = (phases & 2) != 0;
   const bool hbe = pv_re != nullptr;
   if (!ctx->d_rom_esbr || !ctx->d_rom_rphase || (hbe && !ctx->d_rom_hbe) || (ps && !ctx->d_rom_fps)) {
     snprintf(ctx->err, sizeof(ctx->err),
@@ -1289,20 +1291,20 @@ static int32_t esbr_dec_impl(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view
   if (!st || !st->qmf_re || !st->qmf_im || !st->out_re || !st->out_im || !st->anal_states || !st->anal_pos ||
       !st->synth_states || !st->synth_pos || !st->bw_prev || !st->patch || !st->ec_state)
     return bad_arg(ctx, "state view with null members");
-  if ((!d_time_in && !d_core_in) || !d_hf_par || !d_ec_ipar || !d_ec_fpar || !d_rg_par || (!d_out && !d_pcm16))
-    return bad_arg(ctx, "null buffer");
-  if (d_pcm16 && (ch_fac < 1 || ch_fac > 8 || n_units % ch_fac != 0)) return bad_arg(ctx, "ch_fac must be 1..8 and divide n_units");
+  if (front && ((!d_time_in && !d_core_in) || !d_hf_par)) return bad_arg(ctx, "null buffer");
+  if (back && (!d_ec_ipar || !d_ec_fpar || !d_rg_par || (!d_out && !d_pcm16))) return bad_arg(ctx, "null buffer");
+  if (back && d_pcm16 && (ch_fac < 1 || ch_fac > 8 || n_units % ch_fac != 0)) return bad_arg(ctx, "ch_fac must be 1..8 and divide n_units");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   cudaStream_t s = (cudaStream_t)stream;
   const long long low_stride = hbe ? 72 * 64 : 40 * 64;
-  {
+  if (front) {
     xb::EsbrAnalArgs a;
     a.time_in = d_time_in; a.core_in = d_time_in ? nullptr : d_core_in; a.states = st->anal_states; a.pos = st->anal_pos;
     a.qmf = nullptr; a.stage_re = st->qmf_re; a.stage_im = st->qmf_im; a.err = d_err; a.rom = ctx->d_rom_esbr;
     a.n_units = n_units; a.periodic = ctx->esbr_periodic; a.stage_hist_rows = hbe ? 40 : 8;
     LAUNCH("esbr_anal_kernel", stream, xb::launch_esbr_anal(a, ctx->num_sms, s));
   }
-  if (hbe) {  // sbr_dec.c:896-907: the frame's new slots (rows 40..71) -> ph_vocod_qmf rows 8..39
+  if (front && hbe) {  // sbr_dec.c:896-907: the frame's new slots (rows 40..71) -> ph_vocod_qmf rows 8..39
     xb::EsbrHbeArgs a;
     a.qmf_re = st->qmf_re + 40 * 64; a.qmf_im = st->qmf_im + 40 * 64; a.in_stride = low_stride;
     a.pv_re = pv_re + 8 * 64; a.pv_im = pv_im + 8 * 64; a.out_stride = 40 * 64;
@@ -1311,13 +1313,15 @@ static int32_t esbr_dec_impl(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view
     LAUNCH("esbr_hbe_kernel", stream, xb::launch_esbr_hbe(a, ctx->num_sms, s));
     ctx->launches++;
   }
-  {
+  if (front) {
     xb::EsbrHfgenArgs a;
     a.src_re = st->qmf_re; a.src_im = st->qmf_im; a.pv_re = pv_re; a.pv_im = pv_im; a.dst_re = st->out_re; a.dst_im = st->out_im;
     a.par = d_hf_par; a.bw_prev = st->bw_prev; a.patch_out = st->patch; a.err = d_err ? d_err + n_units : nullptr;
     a.n_units = n_units; a.shift_rows = 1; a.src_stride = low_stride;
     LAUNCH("esbr_hfgen_kernel", stream, xb::launch_esbr_hfgen(a, ctx->num_sms, s));
+    ctx->launches += 2;
   }
+  if (!back) return XAAC_B200_OK;
   {
     xb::EsbrEnvcalcArgs a;
     a.re = st->out_re; a.im = st->out_im; a.ipar = d_ec_ipar; a.fpar = d_ec_fpar; a.state = st->ec_state;
@@ -1340,7 +1344,7 @@ static int32_t esbr_dec_impl(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view
       y.rom = ctx->d_rom_esbr; y.n_units = n_units; y.periodic = ctx->esbr_periodic;
       LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(y, ctx->num_sms, s));
     }
-    ctx->launches += 6;
+    ctx->launches += 4;
     return XAAC_B200_OK;
   }
   {
@@ -1352,7 +1356,7 @@ static int32_t esbr_dec_impl(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view
     a.pcm16 = d_pcm16; a.pcm_ch_fac = d_pcm16 ? ch_fac : 1;
     LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(a, ctx->num_sms, s));
   }
-  ctx->launches += 4;
+  ctx->launches += 2;
   return XAAC_B200_OK;
 }
 
@@ -1389,6 +1393,85 @@ int32_t xaac_b200_esbr_dec_ps_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_s
   return esbr_dec_impl(ctx, &st->base, hbe ? st->pv_re : nullptr, hbe ? st->pv_im : nullptr, hbe ? st->hbe_state : nullptr,
                        d_hbe_cfg, d_time_in, d_core_in, d_hf_par, d_ec_ipar, d_ec_fpar, d_rg_par, d_out_l, nullptr, 1, d_err,
                        n_units, stream, ps, d_ps_side, d_out_r);
+}
+
+// The stage in two halves, for frames on which the host has to look at the HF generator's patch table before the envelope
+// adjuster runs (reset frames and frames where sbr_patching_mode changes: ixheaacd_createlimiterbands, esbr_envcal.c:169-190).
+int32_t xaac_b200_esbr_dec_front_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const float *d_time_in,
+                                     const int32_t *d_core_in, const int32_t *d_hbe_cfg, const int32_t *d_hf_par, int32_t *d_err,
+                                     int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!st) return bad_arg(ctx, "state view missing");
+  const bool hbe = st->pv_re != nullptr;
+  if (hbe && (!st->pv_im || !st->hbe_state || !d_hbe_cfg)) return bad_arg(ctx, "harmonic-transposer state / cfg missing");
+  return esbr_dec_impl(ctx, &st->base, hbe ? st->pv_re : nullptr, hbe ? st->pv_im : nullptr, hbe ? st->hbe_state : nullptr,
+                       d_hbe_cfg, d_time_in, d_core_in, d_hf_par, nullptr, nullptr, nullptr, nullptr, nullptr, 1, d_err, n_units,
+                       stream, nullptr, nullptr, nullptr, 1);
+}
+
+int32_t xaac_b200_esbr_dec_back_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const xaac_b200_esbr_ps_view *ps,
+                                    int32_t *d_ec_ipar, const float *d_ec_fpar, const int32_t *d_rg_par, const float *d_ps_side,
+                                    float *d_out, float *d_out_r, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err,
+                                    int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!st) return bad_arg(ctx, "state view missing");
+  if (ps && d_pcm16) return bad_arg(ctx, "the mono + PS stage has float outputs only");
+  const bool hbe = st->pv_re != nullptr;
+  return esbr_dec_impl(ctx, &st->base, hbe ? st->pv_re : nullptr, hbe ? st->pv_im : nullptr, hbe ? st->hbe_state : nullptr, nullptr,
+                       nullptr, nullptr, nullptr, d_ec_ipar, d_ec_fpar, d_rg_par, d_out, d_pcm16, ch_fac, d_err, n_units, stream, ps,
+                       d_ps_side, d_out_r, 2);
+}
+
+// apply_processing = 0 (the first frames of a stream, before the SBR header has been seen): the stage only upsamples — history
+// shifts, analysis bank, sbr_qmf_out cleared, synthesis bank(s) over the regrouped core bands (sbr_dec.c:836-878, 964-1003).
+int32_t xaac_b200_esbr_dec_bypass_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_hbe_state_view *st, const xaac_b200_esbr_ps_view *ps,
+                                      const float *d_time_in, const int32_t *d_core_in, const int32_t *d_rg_par, float *d_out,
+                                      float *d_out_r, int16_t *d_pcm16, int32_t ch_fac, int32_t *d_err, int64_t n_units,
+                                      void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->d_rom_esbr) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!st || !st->base.qmf_re || !st->base.qmf_im || !st->base.out_re || !st->base.out_im || !st->base.anal_states ||
+      !st->base.anal_pos || !st->base.synth_states || !st->base.synth_pos)
+    return bad_arg(ctx, "state view with null members");
+  if ((!d_time_in && !d_core_in) || !d_rg_par || (!d_out && !d_pcm16)) return bad_arg(ctx, "null buffer");
+  if (ps && (!ps->synth_states_r || !ps->synth_pos_r || !d_out_r || !d_out || d_pcm16)) return bad_arg(ctx, "PS view / outputs");
+  if (d_pcm16 && (ch_fac < 1 || ch_fac > 8 || n_units % ch_fac != 0)) return bad_arg(ctx, "ch_fac must be 1..8 and divide n_units");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool hbe = st->pv_re != nullptr;
+  const long long low_stride = hbe ? 72 * 64 : 40 * 64;
+  {
+    xb::EsbrAnalArgs a;
+    a.time_in = d_time_in; a.core_in = d_time_in ? nullptr : d_core_in; a.states = st->base.anal_states; a.pos = st->base.anal_pos;
+    a.qmf = nullptr; a.stage_re = st->base.qmf_re; a.stage_im = st->base.qmf_im; a.err = d_err; a.rom = ctx->d_rom_esbr;
+    a.n_units = n_units; a.periodic = ctx->esbr_periodic; a.stage_hist_rows = hbe ? 40 : 8;
+    LAUNCH("esbr_anal_kernel", stream, xb::launch_esbr_anal(a, ctx->num_sms, s));
+  }
+  if (hbe) {  // sbr_dec.c:858-867: the phase-vocoder arrays still move their last 8 rows to the front
+    if (!st->pv_im) return bad_arg(ctx, "pv_im");
+    CK(cudaMemcpy2DAsync(st->pv_re, 2560 * 4, st->pv_re + 32 * 64, 2560 * 4, 8 * 64 * 4, (size_t)n_units, cudaMemcpyDeviceToDevice, s), "shift");
+    CK(cudaMemcpy2DAsync(st->pv_im, 2560 * 4, st->pv_im + 32 * 64, 2560 * 4, 8 * 64 * 4, (size_t)n_units, cudaMemcpyDeviceToDevice, s), "shift");
+  }
+  // sbr_dec.c:964-969 clears all of sbr_qmf_out (the shift of its history rows before that is moot)
+  CK(cudaMemsetAsync(st->base.out_re, 0, (size_t)n_units * 2560 * 4, s), "memset");
+  CK(cudaMemsetAsync(st->base.out_im, 0, (size_t)n_units * 2560 * 4, s), "memset");
+  for (int ch = 0; ch < (ps ? 2 : 1); ch++) {
+    xb::EsbrSynthArgs a;
+    a.qmf = nullptr; a.states = ch ? ps->synth_states_r : st->base.synth_states; a.pos = ch ? ps->synth_pos_r : st->base.synth_pos;
+    a.out = ch ? d_out_r : d_out; a.err = (d_err && !ch) ? d_err + 3 * n_units : nullptr;
+    a.rom = ctx->d_rom_esbr; a.n_units = n_units; a.periodic = ctx->esbr_periodic;
+    a.rg_low_re = st->base.qmf_re; a.rg_low_im = st->base.qmf_im; a.rg_high_re = st->base.out_re; a.rg_high_im = st->base.out_im;
+    a.rg_par = d_rg_par; a.rg_low_stride = low_stride;
+    a.pcm16 = ch ? nullptr : d_pcm16; a.pcm_ch_fac = d_pcm16 ? ch_fac : 1;
+    LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(a, ctx->num_sms, s));
+  }
+  ctx->launches += ps ? 3 : 2;
+  return XAAC_B200_OK;
 }
 
 int32_t xaac_b200_kernel_timing(xaac_b200_ctx *ctx, int32_t enable) {

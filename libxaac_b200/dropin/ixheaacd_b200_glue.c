@@ -69,7 +69,8 @@ static struct {
   int32_t *e_anal, *e_apos, *e_synth, *e_spos, *e_patch, *e_hbecfg, *e_hfpar, *e_ipar, *e_rg, *e_err;
   float *e_ps_state, *e_ps_left, *e_ps_right, *e_ps_side, *e_out_r; /* mono + PS element: float parametric stereo */
   int32_t *e_synth_r, *e_spos_r;
-  long n_esbr_ps;
+  long n_esbr_ps, n_esbr_rebuilt, n_esbr_bypass;
+  int32_t last_err[6];
   long n_imdct, n_imdct_ref, n_sbr_hq, n_sbr_ps, n_sbr_lp, n_sbr_ref, n_fd, n_fd_ref, n_esbr, n_esbr_hbe, n_esbr_ref;
 } G;
 
@@ -78,9 +79,9 @@ static void b200_report(void) {
     fprintf(stderr,
             "[ixheaacd_b200] imdct_process: %ld on the GPU, %ld by the reference; sbr_dec: %ld HQ + %ld HQ/PS + %ld LP on the GPU, "
             "%ld by the reference; fd_frm_dec: %ld on the GPU, %ld by the reference; eSBR sbr_dec: %ld + %ld with HBE + %ld with PS "
-            "on the GPU, %ld by the reference\n",
+            "on the GPU (%ld with the limiter tables rebuilt between the stage halves) + %ld pass-through, %ld by the reference\n",
             G.n_imdct, G.n_imdct_ref, G.n_sbr_hq, G.n_sbr_ps, G.n_sbr_lp, G.n_sbr_ref, G.n_fd, G.n_fd_ref, G.n_esbr, G.n_esbr_hbe,
-            G.n_esbr_ps, G.n_esbr_ref);
+            G.n_esbr_ps, G.n_esbr_rebuilt, G.n_esbr_bypass, G.n_esbr_ref);
   if (G.ctx) xaac_b200_destroy(G.ctx);
   G.ctx = NULL;
 }
@@ -98,7 +99,7 @@ static xaac_b200_ctx *b200_ctx(void) {
     const char *e = getenv("IXHEAACD_B200_DISABLE"), *s = getenv("IXHEAACD_B200_STATS"), *d = getenv("IXHEAACD_B200_DEVICE");
     G.tried = 1;
     G.disabled = e && *e && *e != '0';
-    G.stats = s && *s && *s != '0';
+    G.stats = s && *s && *s != '0' ? atoi(s) : 0;
     atexit(b200_report);
     if (!G.disabled) {
       if (xaac_b200_create(&G.ctx, d ? atoi(d) : 0) != XAAC_B200_OK) {
@@ -462,25 +463,47 @@ static WORD32 esbr_dec_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_heade
     B200(xaac_b200_h2d(c, G.e_hbe, hst, sizeof(hst)), "h2d");
     B200(xaac_b200_h2d(c, G.e_hbecfg, hcfg, sizeof(hcfg)), "h2d");
   }
+  /* the stage in its two halves (include/xaac_b200.h): between them the host does what only the host can do on reset frames and on
+   * frames where sbr_patching_mode changes — rebuild the limiter tables (ixheaacd_createlimiterbands, esbr_envcal.c:169-190) from the
+   * patch table the HF generator of this very frame has produced */
+  xaac_b200_esbr_ps_view pv;
+  memset(&pv, 0, sizeof(pv));
   if (ps) {
-    xaac_b200_esbr_ps_view pv;
     pv.ps_state = G.e_ps_state; pv.left = G.e_ps_left; pv.right = G.e_ps_right; pv.synth_states_r = G.e_synth_r;
     pv.synth_pos_r = G.e_spos_r;
     B200(xaac_b200_h2d(c, G.e_ps_state, ps_st, sizeof(ps_st)), "h2d ps");
     B200(xaac_b200_h2d(c, G.e_ps_side, ps_side, sizeof(ps_side)), "h2d ps");
     B200(xaac_b200_h2d(c, G.e_synth_r, yr->filter_states_32, 1280 * 4), "h2d ps");
     B200(xaac_b200_h2d(c, G.e_spos_r, spos_r, 8), "h2d ps");
-    if (!hbe) { v.pv_re = NULL; v.pv_im = NULL; v.hbe_state = NULL; }
-    B200(xaac_b200_esbr_dec_ps_dev(c, &v, &pv, G.e_tin, NULL, hbe ? G.e_hbecfg : NULL, G.e_hfpar, G.e_ipar, G.e_fpar, G.e_rg,
-                                   G.e_ps_side, G.e_out, G.e_out_r, G.e_err, 1, NULL), "esbr_dec_ps_dev");
-  } else if (hbe) {
-    B200(xaac_b200_esbr_dec_hbe_dev(c, &v, G.e_tin, NULL, G.e_hbecfg, G.e_hfpar, G.e_ipar, G.e_fpar, G.e_rg, G.e_out, NULL, 1,
-                                    G.e_err, 1, NULL), "esbr_dec_hbe_dev");
-  } else {
-    B200(xaac_b200_esbr_dec_dev(c, &v.base, G.e_tin, NULL, G.e_hfpar, G.e_ipar, G.e_fpar, G.e_rg, G.e_out, NULL, 1, G.e_err, 1, NULL),
-         "esbr_dec_dev");
   }
+  if (!hbe) { v.pv_re = NULL; v.pv_im = NULL; v.hbe_state = NULL; }
+  B200(xaac_b200_esbr_dec_front_dev(c, &v, G.e_tin, NULL, hbe ? G.e_hbecfg : NULL, G.e_hfpar, G.e_err, 1, NULL), "esbr_dec_front_dev");
+  if (fd->reset_flag || fd->sbr_patching_mode != fd->prev_sbr_patching_mode) {
+    B200(xaac_b200_d2h(c, err, G.e_err, sizeof(err)), "d2h err");
+    memcpy(G.last_err, err, sizeof(err));
+    for (int i = 0; i < 6; i++)
+      if (err[i] == -2) return 0;
+    for (int i = 0; i < 6; i++)
+      if (err[i] != 0) { *done = 1; return err[i]; }
+    B200(xaac_b200_d2h(c, patch, G.e_patch, 32), "d2h patch");
+    fd->patch_param.num_patches = patch[0]; /* what ixheaacd_generate_hf leaves there (the reference recomputes the same on a fallback) */
+    for (int i = 0; i < 7; i++) fd->patch_param.start_subband[i] = patch[1 + i];
+    if (ixheaacd_createlimiterbands(fd->lim_table, fd->gate_mode, hd->pstr_freq_band_data->freq_band_tbl_lo,
+                                    hd->pstr_freq_band_data->num_sf_bands[LOW], hbe ? tx->x_over_qmf : NULL, fd->sbr_patching_mode,
+                                    hd->is_usf_4, &fd->patch_param, 0)) {
+      *done = 1;
+      return IA_FATAL_ERROR;
+    }
+    for (int i = 0; i < 4; i++) ipar[XAAC_EEC_GATE_MODE + i] = fd->gate_mode[i];
+    for (int i = 0; i < 52; i++) ipar[XAAC_EEC_LIM_TABLE + i] = fd->lim_table[i / 13][i % 13];
+    ipar[XAAC_EEC_LIM_REBUILT] = 1;
+    B200(xaac_b200_h2d(c, G.e_ipar, ipar, sizeof(ipar)), "h2d");
+    G.n_esbr_rebuilt++;
+  }
+  B200(xaac_b200_esbr_dec_back_dev(c, &v, ps ? &pv : NULL, G.e_ipar, G.e_fpar, G.e_rg, ps ? G.e_ps_side : NULL, G.e_out,
+                                   ps ? G.e_out_r : NULL, NULL, 1, G.e_err, 1, NULL), "esbr_dec_back_dev");
   B200(xaac_b200_d2h(c, err, G.e_err, sizeof(err)), "d2h err");
+  memcpy(G.last_err, err, sizeof(err));
   for (int i = 0; i < 6; i++)
     if (err[i] == -2) return 0; /* outside the kernels' subset: nothing on the host has been touched yet */
   *done = 1;
@@ -555,6 +578,7 @@ static WORD32 esbr_dec_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_heade
   d->band_count = hd->pstr_freq_band_data->sub_band_end;
   fd->reset_flag = 0;
   fd->prev_sbr_mode = fd->sbr_mode;
+  fd->prev_sbr_patching_mode = fd->sbr_patching_mode; /* esbr_envcal.c:189 */
   if (hbe) {
     const int S = tx->synth_size;
     B200(xaac_b200_d2h(c, hst, G.e_hbe, sizeof(hst)), "d2h hbe");
@@ -566,6 +590,110 @@ static WORD32 esbr_dec_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_heade
     for (int r = 42; r < 64; r++) memset(tx->qmf_out_buf[r], 0, 512);
   }
   (void)ipar_in;
+  return 0;
+}
+
+/* apply_processing = 0: the frames before the first SBR header of a stream only pass through the banks (sbr_dec.c:836-878, 964-1003) */
+static WORD32 esbr_bypass_b200(xaac_b200_ctx *c, ia_sbr_dec_struct *d, ia_sbr_header_data_struct *hd,
+                               ia_sbr_frame_info_data_struct *fd, ia_sbr_tables_struct *t, ia_ps_dec_struct *ps, VOID *self,
+                               int *done) {
+  *done = 0;
+  esbr_rom_once(c, t);
+  const int hbe = hd->hbe_flag != 0;
+  const int rows = hbe ? 72 : 40;
+  ia_sbr_qmf_filter_bank_struct *a = &d->str_codec_qmf_bank, *y = &d->str_synthesis_qmf_bank, *yr = NULL;
+  WORD32 *qc = (WORD32 *)t->qmf_dec_tables_ptr->esbr_qmf_c;
+  int32_t rg[4], apos[2], spos[2], spos_r[2] = {0, 0}, err[6];
+  if (ps) {
+    if (!self) return 0;
+    yr = &((ia_handle_sbr_dec_inst_struct)self)->pstr_sbr_channel[1]->str_sbr_dec.str_synthesis_qmf_bank;
+    if (yr->no_channels != 64) return 0;
+    spos_r[0] = yr->ixheaacd_drc_offset;
+    spos_r[1] = (int32_t)(yr->filter_pos_syn_32 - yr->p_filter_32);
+    if (spos_r[1] < 0 || spos_r[1] > 640) return 0;
+  }
+  apos[0] = (int32_t)(a->state_new_samples_pos_low_32 - a->anal_filter_states_32);
+  apos[1] = (int32_t)(a->filter_pos_32 - qc);
+  spos[0] = y->ixheaacd_drc_offset;
+  spos[1] = (int32_t)(y->filter_pos_syn_32 - y->p_filter_32);
+  if (apos[0] < 0 || apos[0] >= 320 || apos[1] < 0 || apos[1] > 640 || spos[1] < 0 || spos[1] > 640) return 0;
+  if (hbe && !hd->usac_flag) { /* sbr_dec.c:868-874, see esbr_dec_b200 */
+    const int q = hd->pstr_freq_band_data->qmf_sb_prev;
+    if (q >= 0 && q < 64)
+      for (int i = 2; i < 8; i++) {
+        memset(&d->qmf_buf_real[32 + i][q], 0, (size_t)(64 - q));
+        memset(&d->qmf_buf_imag[32 + i][q], 0, (size_t)(64 - q));
+      }
+  }
+  rg[0] = 0; rg[1] = hd->pstr_freq_band_data->sub_band_start; rg[2] = 0; rg[3] = 0; /* sbr_dec.c:305-318, 380: stop_border 0 */
+  float *src[6] = {&d->qmf_buf_real[0][0], &d->qmf_buf_imag[0][0], &d->sbr_qmf_out_real[0][0], &d->sbr_qmf_out_imag[0][0],
+                   &d->ph_vocod_qmf_real[0][0], &d->ph_vocod_qmf_imag[0][0]};
+  for (int i = 0; i < (hbe ? 6 : 2); i++)
+    if (i < 2 || i > 3) B200(xaac_b200_h2d(c, G.e_q[i], src[i], (size_t)(i < 2 ? rows : 40) * 64 * 4), "h2d qmf");
+  B200(xaac_b200_h2d(c, G.e_anal, a->anal_filter_states_32, 320 * 4), "h2d");
+  B200(xaac_b200_h2d(c, G.e_apos, apos, 8), "h2d");
+  B200(xaac_b200_h2d(c, G.e_synth, y->filter_states_32, 1280 * 4), "h2d");
+  B200(xaac_b200_h2d(c, G.e_spos, spos, 8), "h2d");
+  B200(xaac_b200_h2d(c, G.e_rg, rg, 16), "h2d");
+  B200(xaac_b200_h2d(c, G.e_tin, d->time_sample_buf, 4096), "h2d");
+  memset(err, 0, sizeof(err));
+  B200(xaac_b200_h2d(c, G.e_err, err, sizeof(err)), "h2d");
+  xaac_b200_esbr_hbe_state_view v;
+  xaac_b200_esbr_ps_view pv;
+  memset(&v, 0, sizeof(v));
+  memset(&pv, 0, sizeof(pv));
+  v.base.qmf_re = G.e_q[0]; v.base.qmf_im = G.e_q[1]; v.base.out_re = G.e_q[2]; v.base.out_im = G.e_q[3];
+  v.base.anal_states = G.e_anal; v.base.anal_pos = G.e_apos; v.base.synth_states = G.e_synth; v.base.synth_pos = G.e_spos;
+  if (hbe) { v.pv_re = G.e_q[4]; v.pv_im = G.e_q[5]; v.hbe_state = G.e_hbe; }
+  if (ps) {
+    pv.synth_states_r = G.e_synth_r; pv.synth_pos_r = G.e_spos_r;
+    B200(xaac_b200_h2d(c, G.e_synth_r, yr->filter_states_32, 1280 * 4), "h2d ps");
+    B200(xaac_b200_h2d(c, G.e_spos_r, spos_r, 8), "h2d ps");
+  }
+  B200(xaac_b200_esbr_dec_bypass_dev(c, &v, ps ? &pv : NULL, G.e_tin, NULL, G.e_rg, G.e_out, ps ? G.e_out_r : NULL, NULL, 1, G.e_err, 1,
+                                     NULL), "esbr_dec_bypass_dev");
+  B200(xaac_b200_d2h(c, err, G.e_err, sizeof(err)), "d2h err");
+  memcpy(G.last_err, err, sizeof(err));
+  for (int i = 0; i < 6; i++)
+    if (err[i] == -2) return 0;
+  *done = 1;
+  for (int i = 0; i < 6; i++)
+    if (err[i] != 0) return err[i];
+  for (int i = 0; i < (hbe ? 6 : 2); i++)
+    if (i < 2 || i > 3) B200(xaac_b200_d2h(c, src[i], G.e_q[i], (size_t)(i < 2 ? rows : 40) * 64 * 4), "d2h qmf");
+  for (int i = 0; i < 64; i++) { /* sbr_dec.c:964-969 */
+    memset(d->sbr_qmf_out_real[i], 0, 64 * sizeof(FLOAT32));
+    memset(d->sbr_qmf_out_imag[i], 0, 64 * sizeof(FLOAT32));
+  }
+  B200(xaac_b200_d2h(c, a->anal_filter_states_32, G.e_anal, 320 * 4), "d2h");
+  B200(xaac_b200_d2h(c, apos, G.e_apos, 8), "d2h");
+  B200(xaac_b200_d2h(c, y->filter_states_32, G.e_synth, 1280 * 4), "d2h");
+  B200(xaac_b200_d2h(c, spos, G.e_spos, 8), "d2h");
+  a->usb = a->no_channels;
+  a->state_new_samples_pos_low_32 = a->anal_filter_states_32 + apos[0];
+  a->filter_pos_32 = qc + apos[1];
+  y->esbr_cos_twiddle = (WORD32 *)t->qmf_dec_tables_ptr->esbr_sin_cos_twiddle_l64;
+  y->esbr_alt_sin_twiddle = (WORD32 *)t->qmf_dec_tables_ptr->esbr_alt_sin_twiddle_l64;
+  y->p_filter_32 = qc;
+  y->filter_pos_syn_32 = qc + spos[1];
+  y->ixheaacd_drc_offset = spos[0];
+  if (ps) {
+    B200(xaac_b200_d2h(c, ps->time_sample_buf[0], G.e_out, 8192), "d2h out");
+    B200(xaac_b200_d2h(c, ps->time_sample_buf[1], G.e_out_r, 8192), "d2h out");
+    B200(xaac_b200_d2h(c, yr->filter_states_32, G.e_synth_r, 1280 * 4), "d2h ps");
+    B200(xaac_b200_d2h(c, spos_r, G.e_spos_r, 8), "d2h ps");
+    yr->esbr_cos_twiddle = (WORD32 *)t->qmf_dec_tables_ptr->esbr_sin_cos_twiddle_l64;
+    yr->esbr_alt_sin_twiddle = (WORD32 *)t->qmf_dec_tables_ptr->esbr_alt_sin_twiddle_l64;
+    yr->p_filter_32 = qc;
+    yr->filter_pos_syn_32 = qc + spos_r[1];
+    yr->ixheaacd_drc_offset = spos_r[0];
+    ((ia_sbr_frame_info_data_struct *)((ia_handle_sbr_dec_inst_struct)self)->frame_buffer[1])->reset_flag = 0;
+  } else {
+    B200(xaac_b200_d2h(c, d->time_sample_buf, G.e_out, 8192), "d2h out");
+  }
+  d->band_count = hd->pstr_freq_band_data->sub_band_end;
+  fd->reset_flag = 0;
+  fd->prev_sbr_mode = fd->sbr_mode;
   return 0;
 }
 
@@ -584,24 +712,35 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *ptr_sbr_dec, WORD16 *ptr_time_
     int tes = 0;
     for (int i = 0; i < 8; i++) tes |= ptr_frame_data->inter_temp_shape_mode[i];
     const int with_ps = ptr_header_data->channel_mode == PS_STEREO || ptr_header_data->enh_sbr_ps;
-    const int ok = apply_processing && (!low_pow_flag || !ptr_header_data->usac_flag) && !ldmps_present && !drc_on &&
+    const int ok = (!low_pow_flag || !ptr_header_data->usac_flag) && !ldmps_present && !drc_on &&
                    !heaac_mps_present && !ec_flag && (ptr_header_data->usac_flag || ptr_header_data->hbe_flag) &&
                    ptr_header_data->num_time_slots == 16 && ptr_sbr_dec->str_codec_qmf_bank.no_channels == 32 &&
                    ptr_sbr_dec->str_synthesis_qmf_bank.no_channels == 64 && (!with_ps || (ptr_ps_dec != NULL && self != NULL)) &&
-                   ptr_frame_data->stereo_config_idx <= 0 && !ptr_frame_data->mps_sbr_flag &&
-                   ptr_frame_data->sbr_mode == ORIG_SBR && !ptr_header_data->is_usf_4 && !ptr_header_data->pre_proc_flag && !tes &&
-                   !ptr_frame_data->reset_flag && ptr_frame_data->sbr_patching_mode == ptr_frame_data->prev_sbr_patching_mode &&
-                   (ptr_frame_data->str_frame_info_details.num_noise_env == 1 || ptr_frame_data->str_frame_info_details.num_noise_env == 2);
+                   ptr_frame_data->stereo_config_idx <= 0 && !ptr_frame_data->mps_sbr_flag && !ptr_header_data->is_usf_4 &&
+                   (!apply_processing ||
+                    (ptr_frame_data->sbr_mode == ORIG_SBR && !ptr_header_data->pre_proc_flag && !tes &&
+                     (ptr_frame_data->str_frame_info_details.num_noise_env == 1 ||
+                      ptr_frame_data->str_frame_info_details.num_noise_env == 2)));
     if (ok) {
       int done = 0;
-      WORD32 r = esbr_dec_b200(c, ptr_sbr_dec, ptr_header_data, ptr_frame_data, sbr_tables_ptr, ptr_pvc_data_str,
-                               with_ps ? ptr_ps_dec : NULL, self, &done);
+      WORD32 r = apply_processing
+                     ? esbr_dec_b200(c, ptr_sbr_dec, ptr_header_data, ptr_frame_data, sbr_tables_ptr, ptr_pvc_data_str,
+                                     with_ps ? ptr_ps_dec : NULL, self, &done)
+                     : esbr_bypass_b200(c, ptr_sbr_dec, ptr_header_data, ptr_frame_data, sbr_tables_ptr, with_ps ? ptr_ps_dec : NULL,
+                                        self, &done);
       if (done) {
-        if (with_ps) G.n_esbr_ps++; else if (ptr_header_data->hbe_flag) G.n_esbr_hbe++; else G.n_esbr++;
+        if (!apply_processing) G.n_esbr_bypass++; else if (with_ps) G.n_esbr_ps++; else if (ptr_header_data->hbe_flag) G.n_esbr_hbe++; else G.n_esbr++;
         return r;
       }
     }
     G.n_esbr_ref++;
+    if (G.stats > 1)
+      fprintf(stderr, "[ixheaacd_b200] eSBR frame left to the reference: eligible %d (apply %d low_pow %d usac %d hbe %d slots %d ps %d "
+              "sbr_mode %d usf4 %d pre_proc %d tes %d noise_env %d reset %d) err %d %d %d %d %d %d\n", ok, (int)apply_processing,
+              (int)low_pow_flag, (int)ptr_header_data->usac_flag, (int)ptr_header_data->hbe_flag, (int)ptr_header_data->num_time_slots,
+              with_ps, (int)ptr_frame_data->sbr_mode, (int)ptr_header_data->is_usf_4, (int)ptr_header_data->pre_proc_flag, tes,
+              (int)ptr_frame_data->str_frame_info_details.num_noise_env, (int)ptr_frame_data->reset_flag, G.last_err[0], G.last_err[1],
+              G.last_err[2], G.last_err[3], G.last_err[4], G.last_err[5]);
     return __real_ixheaacd_sbr_dec(ptr_sbr_dec, ptr_time_data, ptr_header_data, ptr_frame_data, ptr_frame_data_prev, ptr_ps_dec,
                                    ptr_qmf_synth_bank_r, ptr_sbr_sf_r, apply_processing, low_pow_flag, ptr_work_buf_core,
                                    sbr_tables_ptr, pstr_common_tables, ch_fac, ptr_pvc_data_str, drc_on, drc_sbr_factors,

@@ -39,7 +39,10 @@ int xo_esbr_env_calc(const float *rphase, float *re, float *im, int32_t *ipar, c
   float nrg_tone[64], noise_level[64], nrg_est[64], nrg_ref[64], nrg_gain[64], tmpf[64];
   int kk = 0, next = -1, m = 0;
 
-  if (ipar[XO_EEC_RESET] || ipar[XO_EEC_SBR_MODE] != 1 || ipar[XO_EEC_USF4] || ipar[XO_EEC_PATCHING_CHANGED]) return -2;
+  if (ipar[XO_EEC_SBR_MODE] != 1 || ipar[XO_EEC_USF4]) return -2;
+  /* envcal.c:169-190: the limiter tables of these frames are rebuilt first (ixheaacd_createlimiterbands, host side) */
+  if ((ipar[XO_EEC_RESET] || ipar[XO_EEC_PATCHING_CHANGED]) && !ipar[XO_EEC_LIM_REBUILT]) return -2;
+  if (ipar[XO_EEC_RESET]) { start_up = 1; phase_index = 0; }
   if (sbs < 0 || sbe > 64 || nsub < 0 || num_env < 1 || num_env > 8 || num_nf < 1 || num_nf > 5 || (lb & ~3) || (lg & ~3)) return -2;
   if (num_sf[0] < 0 || num_sf[0] > 28 || num_sf[1] < 0 || num_sf[1] > 56 || gate_mode[lb] < 0 || gate_mode[lb] > 12) return -2;
   if ((unsigned)harm_index > 3u || (unsigned)phase_index > 511u) return -2;

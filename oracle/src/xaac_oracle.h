@@ -367,10 +367,11 @@ void xo_esbr_generate_hf_batch(const float *src_re, const float *src_im, const f
 #define XO_EEC_HARM_INDEX 13  /* in/out */
 #define XO_EEC_PHASE_INDEX 14 /* in/out */
 #define XO_EEC_START_UP 15    /* pstr_sbr_header->esbr_start_up, in/out */
-#define XO_EEC_RESET 16       /* reset_flag: must be 0 (limiter tables are rebuilt by the host) */
+#define XO_EEC_RESET 16       /* reset_flag (needs XO_EEC_LIM_REBUILT: the limiter tables are rebuilt by the host) */
 #define XO_EEC_SBR_MODE 17    /* must be ORIG_SBR (1) */
 #define XO_EEC_USF4 18        /* must be 0 */
-#define XO_EEC_PATCHING_CHANGED 19 /* sbr_patching_mode != prev_sbr_patching_mode: must be 0 */
+#define XO_EEC_PATCHING_CHANGED 19 /* sbr_patching_mode != prev_sbr_patching_mode */
+#define XO_EEC_LIM_REBUILT 20 /* the host has rebuilt lim_table / gate_mode for this reset / patching-change frame */
 #define XO_EEC_BORDER 24      /* border_vec[9] */
 #define XO_EEC_FREQ_RES 33    /* freq_res[8] */
 #define XO_EEC_NOISE_BORDER 41 /* noise_border_vec[3] */

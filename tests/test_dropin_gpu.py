@@ -80,8 +80,8 @@ def test_whole_file_through_reference_parser(tmp_path, name, enc, fs, ch, secs, 
 def test_usac_through_reference_parser(tmp_path, name, extra):
     """xHE-AAC (USAC, aot 42, ccfl 1024, stereo 32 kHz): the FD core transform of every frame runs on the GPU behind
     ixheaacd_fd_frm_dec and the float eSBR branch behind ixheaacd_sbr_dec — xaac_b200_esbr_dec_dev, or xaac_b200_esbr_dec_hbe_dev
-    when the stream carries the harmonic transposer.  Only the frames on which ixheaacd_sbr_env_calc rebuilds its limiter tables
-    (the reset frame at the start, a change of sbr_patching_mode) stay with the reference.  The float path is graded at +-1 LSB
+    when the stream carries the harmonic transposer.  On reset frames and on frames where sbr_patching_mode changes the glue runs the
+    stage in its two halves and rebuilds the limiter tables (ixheaacd_createlimiterbands) in between, so they stay on the GPU too.  The float path is graded at +-1 LSB
     (SURVEY 8c); the decode is expected to be byte-identical."""
     _need()
     wav = str(tmp_path / "in.wav")
@@ -92,7 +92,7 @@ def test_usac_through_reference_parser(tmp_path, name, extra):
     ref_wav, our_wav = str(tmp_path / "ref.wav"), str(tmp_path / "b200.wav")
     _run([os.path.join(REFDIR, "xaacdec"), f"-ifile:{bits}", f"-ofile:{ref_wav}", f"-imeta:{meta}", "-mp4:1"])
     log = _run([B200, f"-ifile:{bits}", f"-ofile:{our_wav}", f"-imeta:{meta}", "-mp4:1"], env=dict(os.environ, IXHEAACD_B200_STATS="1"))
-    m = re.search(r"fd_frm_dec: (\d+) on the GPU, (\d+) by the reference; eSBR sbr_dec: (\d+) \+ (\d+) with HBE \+ \d+ with PS on the GPU, (\d+) by the reference", log)
+    m = re.search(r"fd_frm_dec: (\d+) on the GPU, (\d+) by the reference; eSBR sbr_dec: (\d+) \+ (\d+) with HBE \+ \d+ with PS on the GPU[^,]*, (\d+) by the reference", log)
     assert m, log[-800:]
     fd, fd_ref, es, es_hbe, es_ref = map(int, m.groups())
     a, b = open(ref_wav, "rb").read(), open(our_wav, "rb").read()
@@ -103,10 +103,12 @@ def test_usac_through_reference_parser(tmp_path, name, extra):
                                                        f"max |diff| {np.abs(x - y).max()}")
     assert bad.size == 0, f"{name}: within +-1 LSB but not identical: {bad.size} samples"
     assert fd >= 2 * 1500 and fd_ref == 0, m.group(0)
+    # the one frame left to the reference is the stream's first, where sbr_mode is still UNKNOWN_SBR and ixheaacd_sbr_env_calc skips its
+    # per-envelope estimates (it then works on whatever its scratch buffer holds)
     if extra:
-        assert es_hbe >= 2 * 1400 and es_ref <= 0.06 * (es + es_hbe + es_ref), m.group(0)
+        assert es_hbe >= 2 * 1500 and es_ref <= 1, m.group(0)
     else:
-        assert es >= 2 * 1500 and es_hbe == 0 and es_ref <= 4, m.group(0)
+        assert es >= 2 * 1500 and es_hbe == 0 and es_ref <= 1, m.group(0)
 
 
 @pytest.mark.parametrize("name,enc,fs,ch,secs", [("heaac_v1_stereo_default_mode", ["-aot:5", "-adts:1", "-br:48000"], 48000, 2, 70.0),
@@ -123,7 +125,7 @@ def test_legacy_heaac_in_default_esbr_mode(tmp_path, name, enc, fs, ch, secs):
     ref_wav, our_wav = str(tmp_path / "ref.wav"), str(tmp_path / "b200.wav")
     _run([os.path.join(REFDIR, "xaacdec"), f"-ifile:{bits}", f"-ofile:{ref_wav}"])
     log = _run([B200, f"-ifile:{bits}", f"-ofile:{our_wav}"], env=dict(os.environ, IXHEAACD_B200_STATS="1"))
-    m = re.search(r"imdct_process: (\d+) on the GPU, (\d+) by the reference.*eSBR sbr_dec: (\d+) \+ (\d+) with HBE \+ \d+ with PS on the GPU, (\d+) by the reference", log)
+    m = re.search(r"imdct_process: (\d+) on the GPU, (\d+) by the reference.*eSBR sbr_dec: (\d+) \+ (\d+) with HBE \+ \d+ with PS on the GPU[^,]*, (\d+) by the reference", log)
     assert m, log[-800:]
     imdct, imdct_ref, es, es_hbe, es_ref = map(int, m.groups())
     a, b = open(ref_wav, "rb").read(), open(our_wav, "rb").read()
@@ -131,7 +133,7 @@ def test_legacy_heaac_in_default_esbr_mode(tmp_path, name, enc, fs, ch, secs):
     x, y = np.frombuffer(a[44:], np.int16).astype(np.int32), np.frombuffer(b[44:], np.int16).astype(np.int32)
     bad = np.flatnonzero(x != y)
     assert bad.size == 0, f"{name}: {bad.size} of {x.size} samples differ, first at {bad[0]}, max |diff| {np.abs(x - y).max()}; {m.group(0)}"
-    assert imdct_ref == 0 and es_hbe >= ch * 1400 and es_ref <= ch * 3, m.group(0)
+    assert imdct_ref == 0 and es_hbe >= ch * 1400 and es_ref == 0, m.group(0)  # not one stage call falls back
 
 
 def test_heaac_v2_in_default_esbr_mode(tmp_path):
@@ -148,7 +150,7 @@ def test_heaac_v2_in_default_esbr_mode(tmp_path):
     ref_wav, our_wav = str(tmp_path / "ref.wav"), str(tmp_path / "b200.wav")
     _run([os.path.join(REFDIR, "xaacdec"), f"-ifile:{bits}", f"-ofile:{ref_wav}"])
     log = _run([B200, f"-ifile:{bits}", f"-ofile:{our_wav}"], env=dict(os.environ, IXHEAACD_B200_STATS="1"))
-    m = re.search(r"imdct_process: (\d+) on the GPU, (\d+) by the reference.*eSBR sbr_dec: (\d+) \+ (\d+) with HBE \+ (\d+) with PS on the GPU, "
+    m = re.search(r"imdct_process: (\d+) on the GPU, (\d+) by the reference.*eSBR sbr_dec: (\d+) \+ (\d+) with HBE \+ (\d+) with PS on the GPU[^,]*, "
                   r"(\d+) by the reference", log)
     assert m, log[-800:]
     imdct, imdct_ref, es, es_hbe, es_ps, es_ref = map(int, m.groups())
@@ -157,5 +159,5 @@ def test_heaac_v2_in_default_esbr_mode(tmp_path):
     x, y = np.frombuffer(a[44:], np.int16).astype(np.int32), np.frombuffer(b[44:], np.int16).astype(np.int32)
     bad = np.flatnonzero(x != y)
     assert bad.size == 0, f"{name}: {bad.size} of {x.size} samples differ, first at {bad[0]}, max |diff| {np.abs(x - y).max()}; {m.group(0)}"
-    assert imdct_ref == 0 and es_ps >= 1400 and es_ref <= 6, m.group(0)
+    assert imdct_ref == 0 and es_ps >= 1400 and es_ref == 0, m.group(0)  # not one stage call falls back
     assert np.abs(x[0::2] - x[1::2]).max() > 100  # a real stereo image came out of the mono core
