@@ -403,3 +403,83 @@ def esbr_dec_ps(ctx, state, core, hbe_cfg, hf_par, ec_ipar, ec_fpar, rg_par, ps_
                                             ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_esbr_dec_ps_dev")
     return out_l, out_r, err
+
+
+# ---- the stage in two halves / pass-through (include/xaac_b200.h: xaac_b200_esbr_dec_front_dev / _back_dev / _bypass_dev) ----
+def _hbe_view(state):
+    """xaac_b200_esbr_hbe_state_view of an EsbrDecBatch / EsbrDecHbeBatch / EsbrDecPsBatch (pv_* NULL without the transposer)"""
+    if isinstance(state, EsbrDecPsBatch):
+        return state.view()
+    if isinstance(state, EsbrDecHbeBatch):
+        return state.view()
+    return _EsbrHbeStateView(state.view(), None, None, None)
+
+
+def esbr_dec_front(ctx, state, core, hbe_cfg, hf_par, err, stream=None):
+    """First half of the eSBR stage: analysis bank, harmonic transposer (when the state carries one), HF generator.  err int32
+    [6, n]: rows 0, 1, 4 are written.  Afterwards state.patch holds the patch table of the frame — what a host needs to rebuild
+    the limiter tables (ixheaacd_createlimiterbands) on reset frames and on frames where sbr_patching_mode changes."""
+    n = state.n
+    dev = hf_par.device
+    _chk(hf_par, torch.int32, (n, EHF_PAR_WORDS), "hf_par", "cuda")
+    _chk(err, torch.int32, (6, n), "err", "cuda")
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    v = _hbe_view(state)
+    rc = ctx._lib.xaac_b200_esbr_dec_front_dev(ctx.handle, ctypes.byref(v), _ptr(core) if core.dtype == torch.float32 else None,
+                                               _ptr(core) if core.dtype == torch.int32 else None,
+                                               _ptr(hbe_cfg) if hbe_cfg is not None else None, _ptr(hf_par), _ptr(err), n,
+                                               ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_dec_front_dev")
+    return err
+
+
+def esbr_dec_back(ctx, state, ec_ipar, ec_fpar, rg_par, err, ps_side=None, out=None, out_r=None, pcm16=None, ch_fac=1, stream=None):
+    """Second half: envelope adjuster, PS (state is an EsbrDecPsBatch and ps_side is given), synthesis bank(s).  err rows 2, 3, 5."""
+    n = state.n
+    dev = ec_ipar.device
+    _chk(ec_ipar, torch.int32, (n, EEC_IPAR_WORDS), "ec_ipar", "cuda")
+    _chk(ec_fpar, torch.float32, (n, EEC_FPAR_WORDS), "ec_fpar", "cuda")
+    _chk(rg_par, torch.int32, (n, 4), "rg_par", "cuda")
+    _chk(err, torch.int32, (6, n), "err", "cuda")
+    with_ps = ps_side is not None
+    if out is None and pcm16 is None:
+        out = torch.empty((n, 2048), dtype=torch.float32, device=dev)
+    if with_ps and out_r is None:
+        out_r = torch.empty((n, 2048), dtype=torch.float32, device=dev)
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    v = _hbe_view(state)
+    pv = state.ps_view() if with_ps else None
+    rc = ctx._lib.xaac_b200_esbr_dec_back_dev(ctx.handle, ctypes.byref(v), ctypes.byref(pv) if with_ps else None, _ptr(ec_ipar),
+                                              _ptr(ec_fpar), _ptr(rg_par), _ptr(ps_side) if with_ps else None,
+                                              _ptr(out) if out is not None else None, _ptr(out_r) if with_ps else None,
+                                              _ptr(pcm16) if pcm16 is not None else None, int(ch_fac), _ptr(err), n,
+                                              ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_dec_back_dev")
+    return out, out_r, err
+
+
+def esbr_dec_bypass(ctx, state, core, rg_par, err, out=None, out_r=None, stream=None):
+    """apply_processing = 0: analysis bank, sbr_qmf_out cleared, synthesis bank(s) over the regrouped core bands (rg_par =
+    {x, sub_band_start, 0, 0}); with an EsbrDecPsBatch the same matrix also leaves through the second channel's bank."""
+    n = state.n
+    dev = rg_par.device
+    _chk(rg_par, torch.int32, (n, 4), "rg_par", "cuda")
+    _chk(err, torch.int32, (6, n), "err", "cuda")
+    with_ps = isinstance(state, EsbrDecPsBatch)
+    if out is None:
+        out = torch.empty((n, 2048), dtype=torch.float32, device=dev)
+    if with_ps and out_r is None:
+        out_r = torch.empty((n, 2048), dtype=torch.float32, device=dev)
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    v = _hbe_view(state)
+    pv = state.ps_view() if with_ps else None
+    rc = ctx._lib.xaac_b200_esbr_dec_bypass_dev(ctx.handle, ctypes.byref(v), ctypes.byref(pv) if with_ps else None,
+                                                _ptr(core) if core.dtype == torch.float32 else None,
+                                                _ptr(core) if core.dtype == torch.int32 else None, _ptr(rg_par), _ptr(out),
+                                                _ptr(out_r) if with_ps else None, None, 1, _ptr(err), n,
+                                                ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_esbr_dec_bypass_dev")
+    return out, out_r, err

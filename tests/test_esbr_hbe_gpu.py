@@ -181,3 +181,39 @@ def test_stage_with_hbe_full_batch_tiling(ctx):
             w = torch.from_numpy(np.ascontiguousarray(g["out_" + k][r])).cuda()
             tt = getattr(s, k)
             assert torch.equal(tt.view(torch.int32).view(n // 2, 2, -1), w.view(torch.int32).unsqueeze(0).expand(n // 2, 2, w.shape[-1])), f"frame {f}: {k}"
+
+
+def test_stage_in_two_halves_equals_the_single_call(ctx):
+    """xaac_b200_esbr_dec_front_dev + _back_dev (the split a host uses to rebuild the limiter tables between the HF generator and
+    the envelope adjuster) against the tapped stream, bit for bit; and a frame flagged as 'patching mode changed' is refused
+    without XAAC_EEC_LIM_REBUILT and accepted with it"""
+    import torch
+    import libxaac_b200 as xb
+    from tests.test_oracle_esbr import esbr_stage_golden_frames
+    g = np.load(os.path.join(os.path.dirname(GOLD), "esbr_hbe_stage_tapped.npz"))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    s = xb.EsbrDecHbeBatch(2)
+    for k in oracle_util.ESH_KEYS:
+        getattr(s, k).copy_(t(g["in0_" + k]))
+    for f, r, rg in esbr_stage_golden_frames(g):
+        ip = np.ascontiguousarray(g["ec_ipar_in"][r]).copy()
+        err = torch.zeros((6, 2), dtype=torch.int32, device="cuda")
+        xb.esbr_dec_front(ctx, s, t(g["time_in"][r]), t(g["hbe_cfg"][r]), t(g["hf_par"][r]), err)
+        if f == 2:  # what the drop-in does on such a frame: same tables, flagged as rebuilt
+            probe = ip.copy()
+            probe[:, 19] = 1
+            saved = {k: getattr(s, k).clone() for k in ("synth_states", "synth_pos", "ec_state")}
+            _, _, e2 = xb.esbr_dec_back(ctx, s, t(probe), t(g["ec_fpar"][r]), t(rg), err.clone())
+            torch.cuda.synchronize()
+            assert (e2.cpu().numpy()[2] == -2).all()
+            for k, v in saved.items():
+                getattr(s, k).copy_(v)
+            ip[:, 19] = 1
+            ip[:, 20] = 1
+        ipar = t(ip)
+        out, _, err = xb.esbr_dec_back(ctx, s, ipar, t(g["ec_fpar"][r]), t(rg), err)
+        torch.cuda.synchronize()
+        assert int(err.abs().max()) == 0, f"frame {f}: {err.cpu().numpy()}"
+        assert np.array_equal(bits(out.cpu().numpy()), bits(g["time_out"][r])), f"frame {f}: time output"
+        for k in ("anal_states", "synth_states", "bw_prev", "patch", "ec_state", "hbe_state"):
+            assert np.array_equal(getattr(s, k).cpu().numpy().view(np.int32), g["out_" + k][r].view(np.int32)), f"frame {f}: {k}"
