@@ -585,7 +585,7 @@ int32_t xaac_b200_esbr_generate_hf_dev(xaac_b200_ctx *ctx, const float *d_src_re
 #define XAAC_EEC_BORDER 24          /* border_vec[9] */
 #define XAAC_EEC_FREQ_RES 33        /* freq_res[8] */
 #define XAAC_EEC_NOISE_BORDER 41    /* noise_border_vec[3] */
-#define XAAC_EEC_INTER_TES 44       /* inter_temp_shape_mode[8] (must be 0) */
+#define XAAC_EEC_INTER_TES 44       /* inter_temp_shape_mode[8], 0..3; an envelope with a non-zero mode needs the low band */
 #define XAAC_EEC_GATE_MODE 52       /* gate_mode[4] */
 #define XAAC_EEC_LIM_TABLE 56       /* lim_table[4][13] */
 #define XAAC_EEC_TBL_NOISE 108      /* freq_band_tbl_noise[6] */
@@ -602,6 +602,13 @@ int32_t xaac_b200_esbr_generate_hf_dev(xaac_b200_ctx *ctx, const float *d_src_re
 int32_t xaac_b200_set_esbr_envcalc_rom(xaac_b200_ctx *ctx, const void *random_phase, size_t bytes);
 int32_t xaac_b200_esbr_env_calc_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im, int32_t *d_ipar, const float *d_fpar,
                                     float *d_state, int32_t *d_err, int64_t n_units, void *stream);
+/* The same with the low band at hand, for envelopes that use inter-TES (XAAC_EEC_INTER_TES + env != 0: ixheaacd_apply_inter_tes,
+ * decoder/ixheaacd_esbr_envcal.c:1021-1096, called at :824-836): d_low_re / d_low_im [n][low_rows][64] = qmf_buf_real / imag from
+ * their first row (low_rows 40, or 72 with the harmonic transposer's delayed core QMF).  Without them (NULL, or the entry above)
+ * a frame with an inter-TES envelope returns -2.  The whole-stage entries always pass the low band. */
+int32_t xaac_b200_esbr_env_calc_tes_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im, const float *d_low_re, const float *d_low_im,
+                                        int32_t low_rows, int32_t *d_ipar, const float *d_fpar, float *d_state, int32_t *d_err,
+                                        int64_t n_units, void *stream);
 
 /* QMF harmonic transposer: batched ixheaacd_qmf_hbe_apply (decoder/ixheaacd_hbe_trans.c:224-296) with
  * ixheaacd_real_synth_filt / ixheaacd_complex_anal_filt (decoder/ixheaacd_esbr_polyphase.c:157, 48),

@@ -66,6 +66,7 @@ SIGNATURES = {
     "xaac_b200_esbr_generate_hf_dev": (_i32, [_vp] * 11 + [_i64, _vp]),
     "xaac_b200_set_esbr_envcalc_rom": (_i32, [_vp, _vp, _sz]),
     "xaac_b200_esbr_env_calc_dev": (_i32, [_vp] * 7 + [_i64, _vp]),
+    "xaac_b200_esbr_env_calc_tes_dev": (_i32, [_vp] * 5 + [_i32] + [_vp] * 4 + [_i64, _vp]),
     "xaac_b200_dev_alloc": (_i32, [_vp, _sz, _vp]),
     "xaac_b200_dev_free": (_i32, [_vp, _vp]),
     "xaac_b200_h2d": (_i32, [_vp, _vp, _vp, _sz]),

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kEcWarps * 32, 3) esbr_envcalc_kernel(EsbrEnvc
     if ((unsigned)harm_index > 3u || (unsigned)phase_index > 511u) err = -2;
     if (!err) {
       for (int i = 0; i < num_env; i++)
-        if (ip[kEecInterTes + i] || border[i] < 0 || 2 * border[i + 1] > 38) err = -2;
+        if ((unsigned)ip[kEecInterTes + i] > 3u || (ip[kEecInterTes + i] && !p.low_re) || border[i] < 0 || 2 * border[i + 1] > 38)
+          err = -2;
       const i32 *lim = ip + kEecLimTable + 13 * lb;
       for (int c = 0; c <= gate; c++)
         if (lim[c] < 0 || lim[c] > 64) err = -2;
@@ -284,9 +285,13 @@ __global__ void __launch_bounds__(kEcWarps * 32, 3) esbr_envcalc_kernel(EsbrEnvc
         }
       }
       start_up = 0;
+      // inter-TES (envcal.c:824-836, 1021-1096) rescales the envelope's slots between the gain / noise pass and the sinusoids, so
+      // an envelope that uses it (gamma > 0) adds its sinusoids in a pass of its own; otherwise both happen in one visit of a cell
+      const int tes_mode = ip[kEecInterTes + i];
+      const int harm_index0 = harm_index;
       for (int l = l0; l < l1; l++) {
-        const float hp0 = (harm_index == 0) ? 1.0f : (harm_index == 2) ? -1.0f : 0.0f;
-        const float hp1 = (harm_index == 1) ? 1.0f : (harm_index == 3) ? -1.0f : 0.0f;
+        const float hp0 = tes_mode ? 0.0f : (harm_index == 0) ? 1.0f : (harm_index == 2) ? -1.0f : 0.0f;
+        const float hp1 = tes_mode ? 0.0f : (harm_index == 1) ? 1.0f : (harm_index == 3) ? -1.0f : 0.0f;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           if (act[h]) {
@@ -309,8 +314,10 @@ __global__ void __launch_bounds__(kEcWarps * 32, 3) esbr_envcalc_kernel(EsbrEnvc
             float *pr = CROW(re, l) + sbs + k, *pi = CROW(im, l) + sbs + k;
             float vr = __fadd_rn(__fmul_rn(*pr, sb_gain), __fmul_rn(sb_noise, __ldg(p.rphase + 2 * ph)));
             float vi = __fadd_rn(__fmul_rn(*pi, sb_gain), __fmul_rn(sb_noise, __ldg(p.rphase + 2 * ph + 1)));
-            vr = __fadd_rn(vr, __fmul_rn(tk[h], hp0));
-            vi = __fadd_rn(vi, __fmul_rn(__fmul_rn(tk[h], finv[h]), hp1));
+            if (!tes_mode) {
+              vr = __fadd_rn(vr, __fmul_rn(tk[h], hp0));
+              vi = __fadd_rn(vi, __fmul_rn(__fmul_rn(tk[h], finv[h]), hp1));
+            }
             *pr = vr;
             *pi = vi;
           }
@@ -327,6 +334,81 @@ __global__ void __launch_bounds__(kEcWarps * 32, 3) esbr_envcalc_kernel(EsbrEnvc
         harm_index = (harm_index + 1) & 3;
       }
       __syncwarp();
+      if (tes_mode) {
+        const float gamma = tes_mode == 1 ? 1.0f : tes_mode == 2 ? 2.0f : 4.0f;  // ixheaac_q_gamma_table
+        const int ns = l1 - l0;
+        const float *lr0 = p.low_re + u * p.low_stride, *li0 = p.low_im + u * p.low_stride;
+        // the low bands of the envelope's slots are copied next to the high bands first (envcal.c:1039-1044)
+        for (int l = l0; l < l1; l++)
+          for (int j = lane; j < sbs; j += 32) {
+            CROW(re, l)[j] = CROW(lr0, l)[j];
+            CROW(im, l)[j] = CROW(li0, l)[j];
+          }
+        __syncwarp();
+        // per-slot powers, lane = slot (two rounds when the envelope has more than 32 slots), sums in band order
+        float pl[2] = {0.f, 0.f}, ph[2] = {0.f, 0.f}, g[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int sI = lane + 32 * h;
+          if (sI < ns) {
+            const float *rr = CROW(re, l0 + sI), *ii = CROW(im, l0 + sI);
+            float a = 0.0f, b = 0.0f;
+            for (int j = 0; j < sbs; j++) {
+              a = __fadd_rn(a, __fmul_rn(rr[j], rr[j]));
+              a = __fadd_rn(a, __fmul_rn(ii[j], ii[j]));
+            }
+            for (int j = sbs; j < sbe; j++) {
+              b = __fadd_rn(b, __fmul_rn(rr[j], rr[j]));
+              b = __fadd_rn(b, __fmul_rn(ii[j], ii[j]));
+            }
+            pl[h] = a;
+            ph[h] = b;
+          }
+        }
+        float tot_lo = 0.0f, tot_hi = 0.0f;
+        for (int sI = 0; sI < ns; sI++) {  // totals in slot order (every lane keeps a copy)
+          tot_lo = __fadd_rn(tot_lo, __shfl_sync(0xffffffffu, sI < 32 ? pl[0] : pl[1], sI & 31));
+          tot_hi = __fadd_rn(tot_hi, __shfl_sync(0xffffffffu, sI < 32 ? ph[0] : ph[1], sI & 31));
+        }
+        const float den = __fadd_rn(tot_lo, 1.0e-6f);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          float q = (float)sqrt((double)__fdiv_rn(__fmul_rn(pl[h], (float)ns), den));
+          q = __fadd_rn(1.0f, __fmul_rn(gamma, __fsub_rn(q, 1.0f)));
+          if (q < 0.2f) q = 0.2f;
+          g[h] = q;
+          ph[h] = __fmul_rn(ph[h], __fmul_rn(q, q));
+        }
+        float tot_after = 1.0e-6f;
+        for (int sI = 0; sI < ns; sI++)
+          tot_after = __fadd_rn(tot_after, __shfl_sync(0xffffffffu, sI < 32 ? ph[0] : ph[1], sI & 31));
+        const float gain_adj = (float)sqrt((double)__fdiv_rn(tot_hi, tot_after));
+        for (int sI = 0; sI < ns; sI++) {
+          const float gs = __fmul_rn(__shfl_sync(0xffffffffu, sI < 32 ? g[0] : g[1], sI & 31), gain_adj);
+          float *rr = CROW(re, l0 + sI), *ii = CROW(im, l0 + sI);
+          for (int j = sbs + lane; j < sbe; j += 32) {
+            rr[j] = __fmul_rn(rr[j], gs);
+            ii[j] = __fmul_rn(ii[j], gs);
+          }
+        }
+        __syncwarp();
+        // the sinusoids of the envelope (envcal.c:838-858)
+        int hx = harm_index0;
+        for (int l = l0; l < l1; l++) {
+          const float hp0 = (hx == 0) ? 1.0f : (hx == 2) ? -1.0f : 0.0f;
+          const float hp1 = (hx == 1) ? 1.0f : (hx == 3) ? -1.0f : 0.0f;
+#pragma unroll
+          for (int h = 0; h < 2; h++)
+            if (act[h]) {
+              const int k = lane + 32 * h;
+              float *pr = CROW(re, l) + sbs + k, *pi = CROW(im, l) + sbs + k;
+              *pr = __fadd_rn(*pr, __fmul_rn(tk[h], hp0));
+              *pi = __fadd_rn(*pi, __fmul_rn(__fmul_rn(tk[h], finv[h]), hp1));
+            }
+          hx = (hx + 1) & 3;
+        }
+        __syncwarp();
+      }
     }
     if (err) {
       if (lane == 0 && p.err) p.err[u] = err;

@@ -366,6 +366,10 @@ struct EsbrEnvcalcArgs {
   const float *rphase;  // ixheaac_random_phase[512][2]
   int32_t *err;         // [n] or null
   long long n_units;
+  // inter-TES (envelopes with inter_temp_shape_mode != 0): the low band, qmf_buf_real / imag from their first row; unit stride in
+  // floats (2560, or 4608 with the harmonic transposer's delayed core QMF).  Null: such frames return -2.
+  const float *low_re = nullptr, *low_im = nullptr;
+  long long low_stride = 2560;
 };
 cudaError_t launch_esbr_envcalc(const EsbrEnvcalcArgs &args, int num_sms, cudaStream_t stream);
 

@@ -43,6 +43,7 @@ struct xaac_b200_ctx {
   cudaEvent_t tick_ev[kMaxTicks][2];
   // staging for the *_host entry points: kPipe chunks in flight, one stream each
   static constexpr int kPipe = 3;
+  int64_t host_chunk = 4096;  // units per pipeline chunk of xaac_b200_heaac_frame_host (XAAC_B200_HOST_CHUNK overrides, tuning only)
   cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
   void *stage[kPipe] = {nullptr, nullptr, nullptr};
   size_t stage_bytes = 0;
@@ -170,6 +171,10 @@ int32_t xaac_b200_create(xaac_b200_ctx **out, int32_t device) {
   xaac_b200_ctx *ctx = new (std::nothrow) xaac_b200_ctx();
   if (!ctx) return XAAC_B200_FATAL;
   ctx->device = device;
+  if (const char *hc = getenv("XAAC_B200_HOST_CHUNK")) {
+    const long v = atol(hc);
+    if (v >= 256 && v <= (1 << 20)) ctx->host_chunk = v;
+  }
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
       cudaMalloc((void **)&ctx->d_rom_imdct, xb::kRomImdctBytes + 64) != cudaSuccess) {
@@ -888,7 +893,7 @@ static int32_t xaac_b200_heaac_frame_host_impl(xaac_b200_ctx *ctx, xaac_b200_imd
   if (!spec || !ics || !side || !pcm) return bad_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   const int64_t n_units = s->n_units;
-  int64_t chunk = 4096;
+  int64_t chunk = ctx->host_chunk;
   if (chunk > n_units) chunk = n_units;
   const size_t out_words = s->with_ps ? 4096 : 2048;
   // per-unit staging: spec 4096 | WORD32 out 4096 | side 2464 | pcm16 in 2048 | pcm out 2*out_words | err 4 | ics 2 | adj 1 (+1)
@@ -1176,7 +1181,14 @@ int32_t xaac_b200_set_esbr_envcalc_rom(xaac_b200_ctx *ctx, const void *random_ph
 
 int32_t xaac_b200_esbr_env_calc_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im, int32_t *d_ipar, const float *d_fpar,
                                     float *d_state, int32_t *d_err, int64_t n_units, void *stream) {
+  return xaac_b200_esbr_env_calc_tes_dev(ctx, d_re, d_im, nullptr, nullptr, 40, d_ipar, d_fpar, d_state, d_err, n_units, stream);
+}
+
+int32_t xaac_b200_esbr_env_calc_tes_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im, const float *d_low_re, const float *d_low_im,
+                                        int32_t low_rows, int32_t *d_ipar, const float *d_fpar, float *d_state, int32_t *d_err,
+                                        int64_t n_units, void *stream) {
   if (!ctx) return XAAC_B200_ERR_ARG;
+  if ((d_low_re == nullptr) != (d_low_im == nullptr) || (low_rows != 40 && low_rows != 72)) return bad_arg(ctx, "low-band arrays");
   if (!ctx->d_rom_rphase) {
     snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_esbr_envcalc_rom has not been called");
     return XAAC_B200_ERR_NO_ROM;
@@ -1186,7 +1198,7 @@ int32_t xaac_b200_esbr_env_calc_dev(xaac_b200_ctx *ctx, float *d_re, float *d_im
   if (!d_re || !d_im || !d_ipar || !d_fpar || !d_state) return bad_arg(ctx, "null buffer");
   xb::EsbrEnvcalcArgs a;
   a.re = d_re; a.im = d_im; a.ipar = d_ipar; a.fpar = d_fpar; a.state = d_state; a.rphase = ctx->d_rom_rphase; a.err = d_err;
-  a.n_units = n_units;
+  a.n_units = n_units; a.low_re = d_low_re; a.low_im = d_low_im; a.low_stride = (long long)low_rows * 64;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   LAUNCH("esbr_envcalc_kernel", stream, xb::launch_esbr_envcalc(a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
@@ -1326,6 +1338,7 @@ static int32_t esbr_dec_impl(xaac_b200_ctx *ctx, const xaac_b200_esbr_state_view
     xb::EsbrEnvcalcArgs a;
     a.re = st->out_re; a.im = st->out_im; a.ipar = d_ec_ipar; a.fpar = d_ec_fpar; a.state = st->ec_state;
     a.rphase = ctx->d_rom_rphase; a.err = d_err ? d_err + 2 * n_units : nullptr; a.n_units = n_units;
+    a.low_re = st->qmf_re; a.low_im = st->qmf_im; a.low_stride = low_stride;  // inter-TES reads the low band
     LAUNCH("esbr_envcalc_kernel", stream, xb::launch_esbr_envcalc(a, ctx->num_sms, s));
   }
   if (ps) {  // sbr_dec.c:976-1001: regrouping + PS, then both channels' synthesis banks

@@ -69,7 +69,7 @@ static struct {
   int32_t *e_anal, *e_apos, *e_synth, *e_spos, *e_patch, *e_hbecfg, *e_hfpar, *e_ipar, *e_rg, *e_err;
   float *e_ps_state, *e_ps_left, *e_ps_right, *e_ps_side, *e_out_r; /* mono + PS element: float parametric stereo */
   int32_t *e_synth_r, *e_spos_r;
-  long n_esbr_ps, n_esbr_rebuilt, n_esbr_bypass;
+  long n_esbr_ps, n_esbr_rebuilt, n_esbr_bypass, n_esbr_tes;
   int32_t last_err[6];
   long n_imdct, n_imdct_ref, n_sbr_hq, n_sbr_ps, n_sbr_lp, n_sbr_ref, n_fd, n_fd_ref, n_esbr, n_esbr_hbe, n_esbr_ref;
 } G;
@@ -79,9 +79,9 @@ static void b200_report(void) {
     fprintf(stderr,
             "[ixheaacd_b200] imdct_process: %ld on the GPU, %ld by the reference; sbr_dec: %ld HQ + %ld HQ/PS + %ld LP on the GPU, "
             "%ld by the reference; fd_frm_dec: %ld on the GPU, %ld by the reference; eSBR sbr_dec: %ld + %ld with HBE + %ld with PS "
-            "on the GPU (%ld with the limiter tables rebuilt between the stage halves) + %ld pass-through, %ld by the reference\n",
+            "on the GPU (%ld with the limiter tables rebuilt between the stage halves; %ld with inter-TES) + %ld pass-through, %ld by the reference\n",
             G.n_imdct, G.n_imdct_ref, G.n_sbr_hq, G.n_sbr_ps, G.n_sbr_lp, G.n_sbr_ref, G.n_fd, G.n_fd_ref, G.n_esbr, G.n_esbr_hbe,
-            G.n_esbr_ps, G.n_esbr_rebuilt, G.n_esbr_bypass, G.n_esbr_ref);
+            G.n_esbr_ps, G.n_esbr_rebuilt, G.n_esbr_tes, G.n_esbr_bypass, G.n_esbr_ref);
   if (G.ctx) xaac_b200_destroy(G.ctx);
   G.ctx = NULL;
 }
@@ -718,7 +718,7 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *ptr_sbr_dec, WORD16 *ptr_time_
                    ptr_sbr_dec->str_synthesis_qmf_bank.no_channels == 64 && (!with_ps || (ptr_ps_dec != NULL && self != NULL)) &&
                    ptr_frame_data->stereo_config_idx <= 0 && !ptr_frame_data->mps_sbr_flag && !ptr_header_data->is_usf_4 &&
                    (!apply_processing ||
-                    (ptr_frame_data->sbr_mode == ORIG_SBR && !ptr_header_data->pre_proc_flag && !tes &&
+                    (ptr_frame_data->sbr_mode == ORIG_SBR && !ptr_header_data->pre_proc_flag &&
                      (ptr_frame_data->str_frame_info_details.num_noise_env == 1 ||
                       ptr_frame_data->str_frame_info_details.num_noise_env == 2)));
     if (ok) {
@@ -729,6 +729,7 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *ptr_sbr_dec, WORD16 *ptr_time_
                      : esbr_bypass_b200(c, ptr_sbr_dec, ptr_header_data, ptr_frame_data, sbr_tables_ptr, with_ps ? ptr_ps_dec : NULL,
                                         self, &done);
       if (done) {
+        if (apply_processing && tes) G.n_esbr_tes++;
         if (!apply_processing) G.n_esbr_bypass++; else if (with_ps) G.n_esbr_ps++; else if (ptr_header_data->hbe_flag) G.n_esbr_hbe++; else G.n_esbr++;
         return r;
       }

@@ -135,12 +135,13 @@ def esbr_generate_hf(ctx, src_re, src_im, dst_re, dst_im, par, bw_prev, pv_re=No
 EEC_IPAR_WORDS, EEC_FPAR_WORDS, EEC_STATE_WORDS = 288, 464, 640
 
 
-def esbr_env_calc(ctx, re, im, ipar, fpar, state, err=None, stream=None):
+def esbr_env_calc(ctx, re, im, ipar, fpar, state, err=None, stream=None, low_re=None, low_im=None):
     """Batched drop-in for ixheaacd_sbr_env_calc (decoder/ixheaacd_esbr_envcal.c:71), ORIG_SBR branch of the 2:1 system.
     re / im float32 [n, 40, 64] (sbr_qmf_out_real / imag from their first row) are adjusted in place; ipar int32 [n, 288]
     (XAAC_EEC_* words; env_short_flag_prev, harm_index, phase_index, esbr_start_up and harm_flag_prev are updated in
     place), fpar float32 [n, 464] (envelope scale factors | noise floor), state float32 [n, 640] (e_gain | noise_buf,
-    updated in place).  Returns err int32 [n]."""
+    updated in place).  low_re / low_im float32 [n, 40 | 72, 64] (qmf_buf_real / imag from their first row) are needed when an
+    envelope uses inter-TES (ixheaacd_apply_inter_tes); without them such a frame returns -2.  Returns err int32 [n]."""
     n = ipar.shape[0]
     dev = ipar.device
     _chk(re, torch.float32, (n, EHF_ROWS, 64), "re", "cuda")
@@ -154,6 +155,14 @@ def esbr_env_calc(ctx, re, im, ipar, fpar, state, err=None, stream=None):
         _chk(err, torch.int32, (n,), "err", "cuda")
     if stream is None:
         stream = torch.cuda.current_stream(dev)
+    if low_re is not None:
+        rows = int(low_re.shape[1])
+        _chk(low_re, torch.float32, (n, rows, 64), "low_re", "cuda")
+        _chk(low_im, torch.float32, (n, rows, 64), "low_im", "cuda")
+        rc = ctx._lib.xaac_b200_esbr_env_calc_tes_dev(ctx.handle, _ptr(re), _ptr(im), _ptr(low_re), _ptr(low_im), rows, _ptr(ipar),
+                                                      _ptr(fpar), _ptr(state), _ptr(err), n, ctypes.c_void_p(stream.cuda_stream))
+        ctx.check(rc, "xaac_b200_esbr_env_calc_tes_dev")
+        return err
     rc = ctx._lib.xaac_b200_esbr_env_calc_dev(ctx.handle, _ptr(re), _ptr(im), _ptr(ipar), _ptr(fpar), _ptr(state), _ptr(err), n,
                                               ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_esbr_env_calc_dev")

@@ -667,6 +667,7 @@ WORD32 ixheaacd_sbr_env_calc(ia_sbr_frame_info_data_struct *frame_data, FLOAT32 
                              FLOAT32 *scratch_buff, FLOAT32 *env_out, WORD32 ldmps_present, WORD32 ec_flag);
 extern const FLOAT32 ixheaac_random_phase[512][2];
 void ref_rom_esbr_random_phase(float *out) { memcpy(out, ixheaac_random_phase, 1024 * sizeof(float)); }
+static __thread const float *g_ec_low_re, *g_ec_low_im; /* set by ref_esbr_env_calc_tes: the low band inter-TES reads */
 int ref_esbr_env_calc(float *re, float *im, int32_t *ipar, const float *fpar, float *state) {
   static __thread ia_sbr_frame_info_data_struct fd;
   static __thread ia_sbr_header_data_struct hd;
@@ -719,6 +720,10 @@ int ref_esbr_env_calc(float *re, float *im, int32_t *ipar, const float *fpar, fl
   memcpy(fd.e_gain, state, 320 * sizeof(float));
   memcpy(fd.noise_buf, state + 320, 320 * sizeof(float));
   typedef FLOAT32(*rows_t)[64];
+  if (g_ec_low_re) {
+    memcpy(low_re, g_ec_low_re, sizeof(low_re));
+    memcpy(low_im, g_ec_low_im, sizeof(low_im));
+  }
   WORD32 e = ixheaacd_sbr_env_calc(&fd, (rows_t)(re + 128), (rows_t)(im + 128), low_re + 2, low_im + 2, x_over, scratch, NULL, 0, 0);
   if (e) return e;
   memcpy(ipar + XO_EEC_HARM_PREV, fd.harm_flag_prev, 64);
@@ -729,6 +734,17 @@ int ref_esbr_env_calc(float *re, float *im, int32_t *ipar, const float *fpar, fl
   memcpy(state, fd.e_gain, 320 * sizeof(float));
   memcpy(state + 320, fd.noise_buf, 320 * sizeof(float));
   return 0;
+}
+/* with the low band (qmf_buf_real / imag rows 0..39) for envelopes that use inter-TES */
+void ref_esbr_env_calc_tes_batch(float *re, float *im, const float *low_re, const float *low_im, int32_t *ipar, const float *fpar,
+                                 float *state, int32_t *err, int n) {
+  for (int u = 0; u < n; u++) {
+    g_ec_low_re = low_re + (size_t)u * 2560;
+    g_ec_low_im = low_im + (size_t)u * 2560;
+    err[u] = ref_esbr_env_calc(re + (size_t)u * 2560, im + (size_t)u * 2560, ipar + (size_t)u * XO_EEC_IPAR_WORDS,
+                               fpar + (size_t)u * XO_EEC_FPAR_WORDS, state + (size_t)u * XO_EEC_STATE_WORDS);
+  }
+  g_ec_low_re = g_ec_low_im = NULL;
 }
 void ref_esbr_env_calc_batch(float *re, float *im, int32_t *ipar, const float *fpar, float *state, int32_t *err, int n) {
   for (int u = 0; u < n; u++)

@@ -1245,3 +1245,25 @@ def ref_heaacv2_esbr_chain(ref, st, time_in, hbe_cfg, hbe_tbl, hf_par, ec_ipar, 
             st[k][...] = q6[:, o:o + w].reshape(st[k].shape)
             o += w
     return out_l, out_r, err
+
+
+def synth_esbr_envcalc_tes_units(n, seed):
+    """synth_esbr_envcalc_units with inter-TES modes 0..3 on the envelopes and a low band (qmf_buf rows) for them to read"""
+    d = synth_esbr_envcalc_units(n, seed)
+    rng = np.random.default_rng(seed + 1000)
+    for u in range(n):
+        ne = int(d["ipar"][u, EEC["NUM_ENV"]])
+        d["ipar"][u, 44:44 + ne] = rng.integers(0, 4, ne)
+    amp = (2.0 ** rng.uniform(-6, 12, (n, 1, 1))).astype(np.float32)
+    d["low_re"] = (rng.standard_normal((n, 40, 64)).astype(np.float32) * amp).astype(np.float32)
+    d["low_im"] = (rng.standard_normal((n, 40, 64)).astype(np.float32) * amp).astype(np.float32)
+    return d
+
+
+def ref_esbr_envcalc_tes_batch(ref, d):
+    n = d["ipar"].shape[0]
+    re, im, ipar, state = d["re"].copy(), d["im"].copy(), d["ipar"].copy(), d["state"].copy()
+    err = np.zeros(n, np.int32)
+    ref.lib.ref_esbr_env_calc_tes_batch(P(re), P(im), P(np.ascontiguousarray(d["low_re"])), P(np.ascontiguousarray(d["low_im"])),
+                                        P(ipar), P(np.ascontiguousarray(d["fpar"])), P(state), P(err), n)
+    return re, im, ipar, state, err

@@ -105,7 +105,7 @@ def test_usac_through_reference_parser(tmp_path, name, extra):
     assert fd >= 2 * 1500 and fd_ref == 0, m.group(0)
     # the one frame left to the reference is the stream's first, where sbr_mode is still UNKNOWN_SBR and ixheaacd_sbr_env_calc skips its
     # per-envelope estimates (it then works on whatever its scratch buffer holds)
-    if extra:
+    if extra == ["-harmonic_sbr:1"]:
         assert es_hbe >= 2 * 1500 and es_ref <= 1, m.group(0)
     else:
         assert es >= 2 * 1500 and es_hbe == 0 and es_ref <= 1, m.group(0)

@@ -71,3 +71,21 @@ def test_env_calc_golden(ctx):
     from tests.test_oracle_esbr import check_envcalc_golden, golden_envcalc_units, load_esbr_golden
     g = load_esbr_golden("esbr_envcalc_tapped.npz")
     check_envcalc_golden(_run(ctx, golden_envcalc_units(g)), g, "kernel vs tapped decode")
+
+
+def test_env_calc_inter_tes_vs_reference(ctx, ref):
+    """envelopes with inter-TES (gamma 1 / 2 / 4 mixed with 0): ixheaacd_apply_inter_tes between the gain pass and the sinusoids,
+    against the compiled ixheaacd_sbr_env_calc fed with the same low band; all cells of both arrays compared (the low bands of
+    the TES envelopes' slots are copied next to the high bands)"""
+    import libxaac_b200 as xb
+    d = oracle_util.synth_esbr_envcalc_tes_units(800, 17)
+    want = oracle_util.ref_esbr_envcalc_tes_batch(ref, d)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    re, im, ipar, state = t(d["re"]), t(d["im"]), t(d["ipar"]), t(d["state"])
+    err = xb.esbr_env_calc(ctx, re, im, ipar, t(d["fpar"]), state, low_re=t(d["low_re"]), low_im=t(d["low_im"]))
+    torch.cuda.synchronize()
+    got = (re.cpu().numpy(), im.cpu().numpy(), ipar.cpu().numpy(), state.cpu().numpy(), err.cpu().numpy())
+    good = same_envcalc(got, want, "compiled reference, inter-TES")
+    assert good > 600
+    used = (d["ipar"][:, 44:52] != 0).any(1) & (want[4] == 0)
+    assert used.sum() > 300
