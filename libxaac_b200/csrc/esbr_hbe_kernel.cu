@@ -600,10 +600,20 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
     const int VS = 2 * S + 1;
     {
       const float *ct = tabs + kHtCosTrans + ks * 32;
-      for (int e = lane; e < 32 * S; e += 32) {
-        const int col = e / S, k = e - col * S;
-        const float re = __ldg(qre + col * 64 + ks + k), im = __ldg(qim + col * 64 + ks + k);
-        LOC[k * 33 + col] = ct[(k << 1) + 0] * re + ct[(k << 1) + 1] * im;
+      for (int e4 = lane; e4 < 32 * S; e4 += 128) {  // four requests per array in flight (the loads head a dependent chain)
+        float re[4], im[4];
+        int kq[4], cq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = min(e4 + 32 * q, 32 * S - 1);
+          cq[q] = e / S;
+          kq[q] = e - cq[q] * S;
+          re[q] = __ldg(qre + cq[q] * 64 + ks + kq[q]);
+          im[q] = __ldg(qim + cq[q] * 64 + ks + kq[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (e4 + 32 * q < 32 * S) LOC[kq[q] * 33 + cq[q]] = ct[(kq[q] << 1) + 0] * re[q] + ct[(kq[q] << 1) + 1] * im[q];
       }
       for (int e = lane; e < 9 * 2 * S; e += 32) {  // columns -1..-9 = synth_buf[0..18 S)
         const int m = e / (2 * S), pos = e - m * 2 * S;
@@ -683,9 +693,19 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
           U[i * 17 + col] = accu;
         }
       }
-      for (int e = lane; e < 12 * nq; e += 32) {  // rows 0..11 = the previous call's rows 16..27
-        const int r = e / nq, c = e - r * nq;
-        QM[r * kHbQW + c] = st[kHbeStQin + r * 128 + lo + c];
+      for (int e4 = lane; e4 < 12 * nq; e4 += 128) {  // rows 0..11 = the previous call's rows 16..27
+        float v[4];
+        int rq[4], cq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = min(e4 + 32 * q, 12 * nq - 1);
+          rq[q] = e / nq;
+          cq[q] = e - rq[q] * nq;
+          v[q] = st[kHbeStQin + rq[q] * 128 + lo + cq[q]];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (e4 + 32 * q < 12 * nq) QM[rq[q] * kHbQW + cq[q]] = v[q];
       }
     }
     __syncwarp();
@@ -779,10 +799,21 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
     __syncwarp();
     const int ci = lane & 15, bp = lane >> 4;
     for (int b0 = sb; b0 < eb; b0 += 8) {
-      for (int e = lane; e < 42 * 16; e += 32) {
-        const int r = e >> 4, c = e & 15, band = b0 + (c >> 1);
-        OUTC[r * kOW + c] = (r < 10 && band < eb) ? st[kHbeStQout + r * 128 + 2 * band + (c & 1)] : 0.0f;
+      // the chunk is planar: column = 8 * (0 re | 1 im) + band - b0, so that a half-warp's two band parities fall on odd / even banks
+      {
+        float v[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {  // carry rows 0..9
+          const int e = lane + 32 * q, r = e >> 4, c = e & 15, band = b0 + (c & 7);
+          v[q] = band < eb ? st[kHbeStQout + r * 128 + 2 * band + (c >> 3)] : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+          const int e = lane + 32 * q;
+          OUTC[(e >> 4) * kOW + (e & 15)] = v[q];
+        }
       }
+      for (int e = 160 + lane; e < 42 * 16; e += 32) OUTC[(e >> 4) * kOW + (e & 15)] = 0.0f;
       __syncwarp();
       // bands of this chunk that are neither stretch-3 nor stretch-4 (the common case: max_stretch = 2): the four bands a lane
       // owns walk the taps together, one lock step per tap instead of four
@@ -806,18 +837,18 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
 #pragma unroll 1
         for (int k = 9; k >= 0; k--) {
           const float *nrow = N2 + (1 + ci + k) * kNW + 2 * (b0 + bp - xo0);
-          float *orow = OUTC + (1 + 2 * ci + k) * kOW + 2 * bp;
+          float *orow = OUTC + (1 + 2 * ci + k) * kOW + bp;
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             if (act[q]) {
               const float tr = nrow[4 * q], ti = nrow[4 * q + 1];
               const float cr = (tr * xr4[q] - ti * xi4[q]) * 0.3333333f;
               const float cim = (tr * xi4[q] + ti * xr4[q]) * 0.3333333f;
-              float o0 = orow[4 * q] + cr, o1 = orow[4 * q + 1] + cim;
+              float o0 = orow[2 * q] + cr, o1 = orow[8 + 2 * q] + cim;
               if (xa4[q].on && k == 4) { o0 += xa4[q].r0; o1 += xa4[q].i0; }
               if (xa4[q].on && k == 5) { o0 += xa4[q].r1; o1 += xa4[q].i1; }
-              orow[4 * q] = o0;
-              orow[4 * q + 1] = o1;
+              orow[2 * q] = o0;
+              orow[8 + 2 * q] = o1;
             }
           }
           __syncwarp();
@@ -891,12 +922,12 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
               cr = (a * xzr - bi * xzi) * 0.6666667f;
               cim = (a * xzi + bi * xzr) * 0.6666667f;
             }
-            float *cell = OUTC + (T - 1 + 2 * ci + k) * kOW + 2 * bb;
-            float o0 = cell[0] + cr, o1 = cell[1] + cim;
+            float *cell = OUTC + (T - 1 + 2 * ci + k) * kOW + bb;
+            float o0 = cell[0] + cr, o1 = cell[8] + cim;
             if (xa.on && k == kx0) { o0 += xa.r0; o1 += xa.i0; }
             if (xa.on && k == kx0 + 1) { o0 += xa.r1; o1 += xa.i1; }
             cell[0] = o0;
-            cell[1] = o1;
+            cell[8] = o1;
           }
           __syncwarp();
         }
@@ -906,15 +937,15 @@ __global__ void __launch_bounds__(kHbWarps * 32) esbr_hbe_kernel(EsbrHbeArgs p) 
       for (int e = lane; e < 32 * 8; e += 32) {
         const int r = e >> 3, c = e & 7, band = b0 + c;
         if (band < eb) {
-          const float a = OUTC[r * kOW + 2 * c], cc = OUTC[r * kOW + 2 * c + 1];
+          const float a = OUTC[r * kOW + c], cc = OUTC[r * kOW + 8 + c];
           const float pc = __ldg(rom + kHromPvCos + band), ps = __ldg(rom + kHromPvSin + band);
           pvr[r * 64 + band] = a * pc - cc * ps;
           pvi[r * 64 + band] = a * ps + cc * pc;
         }
       }
       for (int e = lane; e < 10 * 16; e += 32) {
-        const int r = e >> 4, c = e & 15, band = b0 + (c >> 1);
-        if (band < eb) st[kHbeStQout + r * 128 + 2 * band + (c & 1)] = OUTC[(32 + r) * kOW + c];
+        const int r = e >> 4, c = e & 15, band = b0 + (c & 7);
+        if (band < eb) st[kHbeStQout + r * 128 + 2 * band + (c >> 3)] = OUTC[(32 + r) * kOW + c];
       }
       __syncwarp();
     }
