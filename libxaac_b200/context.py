@@ -26,6 +26,7 @@ class Context:
         self.set_esbr_envcalc_rom(_lib.rom_blob("esbr_random_phase.bin"))
         self.set_hbe_rom(_lib.rom_blob("hbe_rom.bin"))
         self.set_fps_rom(_lib.rom_blob("fps_rom.bin"))
+        self.set_block_rom(_lib.rom_blob("block_rom.bin"))
 
     # -- plumbing ---------------------------------------------------------------------------------
     @property
@@ -80,6 +81,11 @@ class Context:
         """The float parametric stereo's tables (XAAC_FPSROM_* layout, 4064 bytes)."""
         buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
         self.check(self._lib.xaac_b200_set_fps_rom(self._h, buf, len(blob)), "xaac_b200_set_fps_rom")
+
+    def set_block_rom(self, blob):
+        """The leading 620 bytes of ia_aac_dec_block_tables_struct (scale tables, TNS coefficient tables) for the spectral stage."""
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        self.check(self._lib.xaac_b200_set_block_rom(self._h, buf, len(blob)), "xaac_b200_set_block_rom")
 
     def set_esbr_envcalc_rom(self, blob):
         """blob: ixheaac_random_phase[512][2] (4096 bytes)."""

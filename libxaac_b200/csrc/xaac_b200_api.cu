@@ -31,6 +31,7 @@ struct xaac_b200_ctx {
   float *d_rom_rphase = nullptr;  // ixheaac_random_phase[512][2]
   float *d_rom_hbe = nullptr;     // XAAC_HROM_* blob of the harmonic transposer
   float *d_rom_fps = nullptr;     // XAAC_FPSROM_* blob of the float parametric stereo
+  int32_t *d_rom_block = nullptr; // leading 620 bytes of ia_aac_dec_block_tables_struct (spectral stage)
   int esbr_periodic = 0;
   bool have_ps_rom = false;
   int ps_rot_nosat = 0;           // no fractional-delay phase factor equals -32768 (16x16 rotations cannot saturate)
@@ -210,6 +211,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
   if (ctx->d_rom_rphase) cudaFree(ctx->d_rom_rphase);
   if (ctx->d_rom_hbe) cudaFree(ctx->d_rom_hbe);
   if (ctx->d_rom_fps) cudaFree(ctx->d_rom_fps);
+  if (ctx->d_rom_block) cudaFree(ctx->d_rom_block);
   delete ctx;
 }
 
@@ -1484,6 +1486,34 @@ int32_t xaac_b200_esbr_dec_bypass_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_h
     LAUNCH("esbr_synth_kernel", stream, xb::launch_esbr_synth(a, ctx->num_sms, s));
   }
   ctx->launches += ps ? 3 : 2;
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_set_block_rom(xaac_b200_ctx *ctx, const void *block_tables, size_t bytes) {
+  if (!ctx || !block_tables) return bad_arg(ctx, "null");
+  if (bytes < (size_t)xb::kBromBytes) return bad_arg(ctx, "block-tables ROM shorter than 620 bytes");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaError_t e = ctx->d_rom_block ? cudaSuccess : cudaMalloc((void **)&ctx->d_rom_block, 640);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_rom_block, block_tables, xb::kBromBytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(ctx, e, "cudaMemcpy(block rom)");
+  return XAAC_B200_OK;
+}
+
+int32_t xaac_b200_aac_spectral_dev(xaac_b200_ctx *ctx, int32_t *d_spec, const uint8_t *d_side, int32_t *d_err, int64_t n_units,
+                                   void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->d_rom_block) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_block_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_spec || !d_side || !d_err) return bad_arg(ctx, "null buffer (d_err carries the per-element verdict between the two kernels)");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  xb::AacSpectralArgs a;
+  a.spec = d_spec; a.side = d_side; a.err = d_err; a.rom = ctx->d_rom_block; a.n_units = n_units;
+  LAUNCH("aac_spectral_kernels", stream, xb::launch_aac_spectral(a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches += 2;
   return XAAC_B200_OK;
 }
 

@@ -1267,3 +1267,93 @@ def ref_esbr_envcalc_tes_batch(ref, d):
     ref.lib.ref_esbr_env_calc_tes_batch(P(re), P(im), P(np.ascontiguousarray(d["low_re"])), P(np.ascontiguousarray(d["low_im"])),
                                         P(ipar), P(np.ascontiguousarray(d["fpar"])), P(state), P(err), n)
     return re, im, ipar, state, err
+
+
+# ---- AAC pre-IMDCT spectral stage (ixheaacd_channel_pair_process) ----
+SPS_BYTES, SPS_CH, SPS_CH_BYTES = 3456, 544, 1456
+SFB_LONG_44 = [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 48, 56, 64, 72, 80, 88, 96, 108, 120, 132, 144, 160, 176, 196, 216, 240, 264,
+               292, 320, 352, 384, 416, 448, 480, 512, 544, 576, 608, 640, 672, 704, 736, 768, 800, 832, 864, 896, 928, 1024]
+SFB_SHORT_44 = [0, 4, 8, 12, 16, 20, 28, 36, 44, 56, 68, 80, 96, 112, 128]
+
+
+def synth_sps_units(n, seed, tns=True, stereo_tools=True, pns=False):
+    """Elements for the AAC-LC spectral stage at 44.1 kHz: single channels and pairs, long / start / stop / eight-short sequences
+    with random grouping, random M/S masks and intensity bands, up to three TNS filters per window (orders up to 12 / 7, both
+    directions and resolutions), spectra of mixed magnitude up to full scale."""
+    rng = np.random.default_rng(seed)
+    rec = np.zeros((n, SPS_BYTES), np.uint8)
+    spec = np.zeros((n, 2, 1024), np.int32)
+    for u in range(n):
+        r = rec[u]
+        hdr = r[:32].view(np.int32)
+        num_ch = 2 if rng.random() < 0.8 else 1
+        common = int(num_ch == 2 and rng.random() < 0.8)
+        hdr[0], hdr[1] = num_ch, common
+        ws0 = int(rng.choice([0, 0, 1, 2, 2, 3]))
+        groups0 = None
+        for c in range(num_ch):
+            b = r[SPS_CH + c * SPS_CH_BYTES: SPS_CH + (c + 1) * SPS_CH_BYTES]
+            w = b[:32].view(np.int32)
+            ws = ws0 if (common or c == 0) else int(rng.choice([0, 1, 2, 3]))
+            short = ws == 2
+            tbl = SFB_SHORT_44 if short else SFB_LONG_44
+            nsfb = len(tbl) - 1
+            if common and c == 1:
+                max_sfb, glens = int(r[SPS_CH:][:32].view(np.int32)[1]), groups0
+            else:
+                max_sfb = int(rng.integers(1, nsfb + 1))
+                if short:
+                    cuts = sorted(rng.choice(np.arange(1, 8), int(rng.integers(0, 5)), replace=False).tolist())
+                    edges = [0] + cuts + [8]
+                    glens = [edges[i + 1] - edges[i] for i in range(len(edges) - 1)]
+                else:
+                    glens = [1]
+                groups0 = glens
+            w[0], w[1], w[2], w[3], w[4], w[5] = ws, max_sfb, len(glens), int(pns and rng.random() < 0.5), 14 if short else 42, 4
+            b[32:32 + len(glens)] = np.array(glens, np.uint8)
+            cbk = rng.integers(1, 12, 128).astype(np.int8)
+            if stereo_tools and c == 1:
+                m = rng.random(128) < 0.25
+                cbk[m] = rng.choice([14, 15], int(m.sum()))
+            b[40:168] = cbk.view(np.uint8)
+            b[168:424].view(np.int16)[:] = rng.integers(-40, 60, 128)
+            ti = b[424:424 + 924]
+            if tns and rng.random() < 0.7:
+                ti[:4].view(np.int32)[0] = 1
+                for win in range(8 if short else 1):
+                    nf = int(rng.integers(0, 2 if short else 4))
+                    ti[4 + win] = nf
+                    top = nsfb
+                    for f in range(nf):
+                        fb = ti[12 + (win * 3 + f) * 38: 12 + (win * 3 + f + 1) * 38]
+                        length = int(rng.integers(0, top + 1))
+                        fb[:4].view(np.int16)[:] = [max(top - length, 0), top]
+                        top = max(top - length, 0)
+                        order = int(rng.integers(0, (7 if short else 12) + 1))
+                        res = int(rng.integers(0, 2))
+                        fb[4] = np.uint8(255 if rng.random() < 0.5 else 1)   # direction -1 / 1
+                        fb[5], fb[6] = res, order
+                        lim = 8 if res else 4
+                        fb[7:7 + order] = rng.integers(-lim, lim, order).astype(np.int8).view(np.uint8)
+            b[1348:1348 + 2 * len(tbl)].view(np.int16)[:] = tbl
+            mag = int(rng.choice([8, 14, 20, 26, 30, 31]))
+            x = rng.integers(-(1 << mag), 1 << mag, 1024, dtype=np.int64)
+            if rng.random() < 0.3:
+                x[rng.random(1024) < 0.02] = rng.choice([-(1 << 31), (1 << 31) - 1])
+            if short:
+                for wdw in range(8):
+                    x[128 * wdw + tbl[max_sfb]:128 * (wdw + 1)] = 0
+            else:
+                x[tbl[max_sfb]:] = 0
+            spec[u, c] = np.clip(x, -(1 << 31), (1 << 31) - 1).astype(np.int32)
+        if stereo_tools:
+            r[32:544] = (rng.random(512) < 0.4).astype(np.uint8)
+    return spec, rec
+
+
+def ref_channel_pair_process(ref, spec, rec):
+    s = np.ascontiguousarray(spec, np.int32).copy()
+    err = np.zeros(len(rec), np.int32)
+    ref.lib.ref_channel_pair_process_batch.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    ref.lib.ref_channel_pair_process_batch(len(rec), P(s), P(np.ascontiguousarray(rec, np.uint8)), P(err))
+    return s, err

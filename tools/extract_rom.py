@@ -56,7 +56,9 @@ EXTRA = [("ref_rom_qmf_tables", 3464, "qmf_rom.bin"), ("ref_rom_env_tables", 240
          # ref_rom_hbe_tables (oracle/ref_shim_hbe.c; layout XAAC_HROM_* in include/xaac_b200.h)
          ("ref_rom_hbe_tables", 9324 * 4, "hbe_rom.bin"),
          # ref_rom_fps_tables (oracle/ref_shim_fps.c; layout XAAC_FPSROM_*)
-         ("ref_rom_fps_tables", 1016 * 4, "fps_rom.bin")]
+         ("ref_rom_fps_tables", 1016 * 4, "fps_rom.bin"),
+         # leading part of ia_aac_dec_block_tables_struct (decoder/ixheaacd_aac_rom.h:25-31) through scale_mant_tab
+         ("ref_rom_block_tables", 620, "block_rom.bin")]
 
 if __name__ == "__main__":
     main()
