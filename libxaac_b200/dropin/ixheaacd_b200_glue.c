@@ -24,6 +24,8 @@
 #include <stdint.h>
 #include "ixheaacd_b200_pack.h"
 #include "ixheaacd_b200_pack_ps_flt.h"
+#include "ixheaacd_b200_pack_spec.h"
+#include "ixheaacd_audioobjtypes.h"
 #include "ixheaacd_interface.h"
 #include "ixheaacd_tns_usac.h"
 #include "ixheaacd_acelp_info.h"
@@ -42,6 +44,8 @@ WORD32 __real_ixheaacd_sbr_dec(ia_sbr_dec_struct *, WORD16 *, ia_sbr_header_data
                                ia_sbr_scale_fact_struct *, FLAG, FLAG, WORD32 *, ia_sbr_tables_struct *, ixheaacd_misc_tables *,
                                WORD, ia_pvc_data_struct *, FLAG, WORD32[][64], WORD32, WORD32, VOID *, WORD32, WORD32);
 WORD32 __real_ixheaacd_fd_frm_dec(ia_usac_data_struct *usac_data, WORD32 i_ch);
+IA_ERRORCODE __real_ixheaacd_channel_pair_process(ia_aac_dec_channel_info_struct *[], WORD32, ia_aac_dec_tables_struct *, WORD32, WORD32,
+                                                  WORD32, WORD32, WORD32 *, WORD32 *, void *);
 
 extern const FLOAT32 ixheaac_twiddle_table_fft_float[514];
 extern const FLOAT32 ixheaac_twidle_tbl_48[64];
@@ -70,6 +74,11 @@ static struct {
   float *e_ps_state, *e_ps_left, *e_ps_right, *e_ps_side, *e_out_r; /* mono + PS element: float parametric stereo */
   int32_t *e_synth_r, *e_spos_r;
   long n_esbr_ps, n_esbr_rebuilt, n_esbr_bypass, n_esbr_tes;
+  /* pre-IMDCT spectral stage */
+  int have_block_rom;
+  uint8_t *d_sps;
+  int32_t *d_sps_spec;
+  long n_cpp, n_cpp_ref, n_cpp_ms, n_cpp_tns;
   int32_t last_err[6];
   long n_imdct, n_imdct_ref, n_sbr_hq, n_sbr_ps, n_sbr_lp, n_sbr_ref, n_fd, n_fd_ref, n_esbr, n_esbr_hbe, n_esbr_ref;
 } G;
@@ -82,6 +91,9 @@ static void b200_report(void) {
             "on the GPU (%ld with the limiter tables rebuilt between the stage halves; %ld with inter-TES) + %ld pass-through, %ld by the reference\n",
             G.n_imdct, G.n_imdct_ref, G.n_sbr_hq, G.n_sbr_ps, G.n_sbr_lp, G.n_sbr_ref, G.n_fd, G.n_fd_ref, G.n_esbr, G.n_esbr_hbe,
             G.n_esbr_ps, G.n_esbr_rebuilt, G.n_esbr_tes, G.n_esbr_bypass, G.n_esbr_ref);
+  if (G.stats)
+    fprintf(stderr, "[ixheaacd_b200] channel_pair_process: %ld on the GPU (%ld with M/S or intensity bands, %ld with TNS), %ld by the "
+            "reference\n", G.n_cpp, G.n_cpp_ms, G.n_cpp_tns, G.n_cpp_ref);
   if (G.ctx) xaac_b200_destroy(G.ctx);
   G.ctx = NULL;
 }
@@ -801,6 +813,52 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *ptr_sbr_dec, WORD16 *ptr_time_
   }
   if (low_pow_flag) G.n_sbr_lp++; else if (ps_present && side[XAAC_SIDE_PS]) G.n_sbr_ps++; else G.n_sbr_hq++;
   return err;
+}
+
+/* ================================ ixheaacd_channel_pair_process ================================ */
+IA_ERRORCODE __wrap_ixheaacd_channel_pair_process(ia_aac_dec_channel_info_struct *ptr_aac_dec_channel_info[CHANNELS], WORD32 num_ch,
+                                                  ia_aac_dec_tables_struct *ptr_aac_tables, WORD32 total_channels,
+                                                  WORD32 object_type, WORD32 aac_spect_data_resil_flag,
+                                                  WORD32 aac_sf_data_resil_flag, WORD32 *in_data, WORD32 *out_data, void *self_ptr) {
+  xaac_b200_ctx *c = b200_ctx();
+  static uint8_t rec[XAAC_SPS_BYTES];
+  const int eligible = c && (object_type == AOT_AAC_LC || object_type == AOT_SBR || object_type == AOT_PS) && total_channels <= 2 &&
+                       num_ch >= 1 && num_ch <= 2 && !aac_spect_data_resil_flag && !aac_sf_data_resil_flag;
+  if (eligible && b200_sps_pack(rec, ptr_aac_dec_channel_info, num_ch, ptr_aac_tables) == 0) {
+    int32_t err = 0;
+    if (!G.have_block_rom) {
+      B200(xaac_b200_set_block_rom(c, ptr_aac_tables->pstr_block_tables, 620), "set_block_rom");
+      B200(xaac_b200_dev_alloc(c, XAAC_SPS_BYTES, (void **)&G.d_sps), "alloc");
+      B200(xaac_b200_dev_alloc(c, 8192, (void **)&G.d_sps_spec), "alloc");
+      G.have_block_rom = 1;
+    }
+    B200(xaac_b200_h2d(c, G.d_sps, rec, sizeof(rec)), "h2d sps");
+    for (int ch = 0; ch < num_ch; ch++)
+      B200(xaac_b200_h2d(c, G.d_sps_spec + 1024 * ch, ptr_aac_dec_channel_info[ch]->ptr_spec_coeff, 4096), "h2d spec");
+    B200(xaac_b200_aac_spectral_dev(c, G.d_sps_spec, G.d_sps, G.d_err, 1, NULL), "aac_spectral_dev");
+    B200(xaac_b200_d2h(c, &err, G.d_err, 4), "d2h err");
+    if (err == 0) {
+      for (int ch = 0; ch < num_ch; ch++)
+        B200(xaac_b200_d2h(c, ptr_aac_dec_channel_info[ch]->ptr_spec_coeff, G.d_sps_spec + 1024 * ch, 4096), "d2h spec");
+      /* ixheaacd_pns_process still counts the frames of the first channel (pns_js_thumb.c:196-198) */
+      ptr_aac_dec_channel_info[0]->pstr_pns_rand_vec_data->pns_frame_number++;
+      G.n_cpp++;
+      {
+        int any_ms = 0, any_tns = 0;
+        if (num_ch == 2) {
+          for (int i = 0; i < 512 && !any_ms; i++) any_ms = ptr_aac_dec_channel_info[0]->common_window && rec[XAAC_SPS_MS_USED + i];
+          for (int i = 0; i < 128 && !any_ms; i++) any_ms = ptr_aac_dec_channel_info[1]->ptr_code_book[i] >= 14;
+        }
+        for (int ch = 0; ch < num_ch; ch++) any_tns |= ptr_aac_dec_channel_info[ch]->str_tns_info.tns_data_present != 0;
+        G.n_cpp_ms += any_ms;
+        G.n_cpp_tns += any_tns;
+      }
+      return IA_NO_ERROR;
+    }
+  }
+  G.n_cpp_ref++;
+  return __real_ixheaacd_channel_pair_process(ptr_aac_dec_channel_info, num_ch, ptr_aac_tables, total_channels, object_type,
+                                              aac_spect_data_resil_flag, aac_sf_data_resil_flag, in_data, out_data, self_ptr);
 }
 
 /* ================================ ixheaacd_fd_frm_dec ================================ */

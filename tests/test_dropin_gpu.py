@@ -1,6 +1,6 @@
 """GPU: the drop-in boundary is real.  libxaac_b200/dropin/_build/xaacdec_b200 (make dropin) is the reference's OWN testbench
 and decoder library, unmodified, linked with the link-time stage overrides of libxaac_b200/dropin/ixheaacd_b200_glue.c
-(ld --wrap=ixheaacd_imdct_process / ixheaacd_sbr_dec / ixheaacd_fd_frm_dec) against libxaac_b200.so: the reference's bitstream
+(ld --wrap=ixheaacd_imdct_process / ixheaacd_sbr_dec / ixheaacd_fd_frm_dec / ixheaacd_channel_pair_process) against libxaac_b200.so: the reference's bitstream
 parser calls the B200 kernels.  Whole files of >= 3000 frames made by the reference encoder are decoded by it and by the plain
 reference decoder (oracle/_ref/xaacdec); the WAV files must be byte-identical and, for the encoder's default settings, not one
 stage call may fall back to the reference's own code."""
@@ -74,6 +74,13 @@ def test_whole_file_through_reference_parser(tmp_path, name, enc, fs, ch, secs, 
         assert lp == 0
     if "ps" not in want:
         assert ps == 0
+    # the pre-IMDCT spectral stage (ixheaacd_channel_pair_process: M/S, intensity, TNS) of every element ran on the GPU as well
+    m2 = re.search(r"channel_pair_process: (\d+) on the GPU \((\d+) with M/S or intensity bands, (\d+) with TNS\), (\d+) by the reference", log)
+    assert m2, log[-600:]
+    cpp, cpp_ms, cpp_tns, cpp_ref = map(int, m2.groups())
+    assert cpp >= 3000 and cpp_ref == 0 and cpp_tns >= 50, m2.group(0)
+    if name in ("aac_lc_stereo", "heaac_v1_stereo"):
+        assert cpp_ms >= 2000, m2.group(0)
 
 
 @pytest.mark.parametrize("name,extra", [("usac", []), ("usac_hbe", ["-harmonic_sbr:1"])])

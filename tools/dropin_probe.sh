@@ -8,7 +8,7 @@ R='oracle/_ref'; B='libxaac_b200/dropin/_build/xaacdec_b200'
 os.makedirs('/tmp/dp',exist_ok=True)
 def run(cmd,env=None):
     r=subprocess.run(cmd,stdout=subprocess.PIPE,stderr=subprocess.PIPE,env=env); return r.stderr.decode(errors='replace')
-cases=[('usact',32000,2,20.0,['-aot:42','-br:64000','-ccfl_idx:3','-inter_tes_enc:1'],True),('usacp',32000,2,20.0,['-aot:42','-br:64000','-ccfl_idx:3','-pvc_enc:1'],True),('usac',32000,2,20.0,['-aot:42','-br:64000','-ccfl_idx:3'],True),('usach',32000,2,20.0,['-aot:42','-br:64000','-ccfl_idx:3','-harmonic_sbr:1'],True),
+cases=[('lc',44100,2,12.0,['-aot:2','-adts:1','-br:128000'],False),('lcm',44100,1,12.0,['-aot:2','-adts:1','-br:64000'],False),('usac',32000,2,20.0,['-aot:42','-br:64000','-ccfl_idx:3'],True),('usach',32000,2,20.0,['-aot:42','-br:64000','-ccfl_idx:3','-harmonic_sbr:1'],True),
        ('v1s',48000,2,12.0,['-aot:5','-adts:1','-br:48000'],False),('v2',44100,2,12.0,['-aot:29','-adts:1','-br:32000'],False)]
 for name,fs,ch,secs,enc,mp4 in cases:
     wav=f'/tmp/dp/{name}.wav'; mg.write_wav(wav,mg.synth(fs,secs,ch,7),fs)
