@@ -802,20 +802,22 @@ int32_t xaac_b200_esbr_dec_bypass_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_h
  * decoder/ixheaacd_stereo.c:54-116), intensity stereo (ixheaacd_intensity_stereo_process, :129-236) and TNS
  * (ixheaacd_aac_tns_process, decoder/ixheaacd_pns_js_thumb.c:248-514, with ixheaacd_tns_decode_coef,
  * ixheaacd_tns_parcor_lpc_convert_dec, ixheaacd_calc_max_spectral_line_dec, ixheaacd_tns_ar_filter_dec) on the dequantised,
- * scale-factor-applied spectrum, in place.  Elements that use PNS (generator state across frames and channels), LTP or the
- * error-resilient syntaxes are refused with -2 and left untouched.
+ * scale-factor-applied spectrum, in place, and perceptual noise substitution (ixheaacd_map_ms_mask_pns, channel.c:703-726;
+ * ixheaacd_pns_process / ixheaacd_gen_rand_vec, pns_js_thumb.c:74-200; ixheaacd_sqrt, decoder/ixheaacd_basic_funcs.c:155-196).
+ * Elements that use LTP or the error-resilient syntaxes are not covered; malformed side info is refused with -2, element untouched.
  * ROM: the leading 620 bytes of ia_aac_dec_block_tables_struct (decoder/ixheaacd_aac_rom.h:25-43: pow table, scale_table,
  * tns_max_bands_tbl, tns_coeff3_16, tns_coeff4_16, scale_mant_tab), passed as the reference passes pstr_block_tables.
  * d_side [n][XAAC_SPS_BYTES] per element — the reference's own plain-data members, byte for byte: */
 #define XAAC_SPS_NUM_CH 0            /* int32 word 0: channels of the element (1, 2) */
 #define XAAC_SPS_COMMON_WINDOW 1     /* int32 word 1: ptr_aac_dec_channel_info[LEFT]->common_window */
+#define XAAC_SPS_CORRELATED 16       /* byte offset: pstr_pns_corr_info->correlated[16] of LEFT as the parser left it */
 #define XAAC_SPS_MS_USED 32          /* byte offset: pstr_stereo_info->ms_used[8][64] */
 #define XAAC_SPS_CH 544              /* byte offset of channel 0's block; channel 1 follows at + XAAC_SPS_CH_BYTES */
-#define XAAC_SPS_CH_BYTES 1456
+#define XAAC_SPS_CH_BYTES 1584
 #define XAAC_SPS_CH_WINDOW_SEQUENCE 0 /* int32 words of a channel block: str_ics_info.window_sequence, */
 #define XAAC_SPS_CH_MAX_SFB 1         /*   .max_sfb, */
 #define XAAC_SPS_CH_NUM_WINDOW_GROUPS 2 /* .num_window_groups, */
-#define XAAC_SPS_CH_PNS_ACTIVE 3      /*   str_pns_info.pns_active (must be 0), */
+#define XAAC_SPS_CH_PNS_ACTIVE 3      /*   str_pns_info.pns_active, */
 #define XAAC_SPS_CH_TNS_MAX_BANDS 4   /*   tns_max_bands_tbl[sampling_rate_index][window_sequence is short], */
 #define XAAC_SPS_CH_SR_INDEX 5        /*   str_ics_info.sampling_rate_index (informational) */
 #define XAAC_SPS_CH_GROUP_LEN 32     /* byte offsets inside a channel block: str_ics_info.window_group_length[8] */
@@ -823,12 +825,15 @@ int32_t xaac_b200_esbr_dec_bypass_dev(xaac_b200_ctx *ctx, const xaac_b200_esbr_h
 #define XAAC_SPS_CH_SCALE_FACTOR 168 /*   ptr_scale_factor[128] (WORD16) */
 #define XAAC_SPS_CH_TNS 424          /*   ia_tns_info_aac_struct str_tns_info, 924 bytes as laid out by the x86-64 ABI */
 #define XAAC_SPS_CH_SFB_INDEX 1348   /*   str_aac_sfb_info[window_sequence].sfb_index[0..51] (WORD16) */
-#define XAAC_SPS_BYTES 3456
+#define XAAC_SPS_CH_PNS_USED 1456    /*   str_pns_info.pns_used[128] */
+#define XAAC_SPS_BYTES 3712
 int32_t xaac_b200_set_block_rom(xaac_b200_ctx *ctx, const void *block_tables, size_t bytes);
 /* d_spec [n][2][1024] WORD32 (ptr_spec_coeff of LEFT, RIGHT; the second half is not touched for single-channel elements), in/out;
- * d_err [n]: 0, or -2 for an element outside the subset.  Two launches. */
-int32_t xaac_b200_aac_spectral_dev(xaac_b200_ctx *ctx, int32_t *d_spec, const uint8_t *d_side, int32_t *d_err, int64_t n_units,
-                                   void *stream);
+ * d_pns_seed [n] in/out: pstr_pns_rand_vec_data->current_seed of the stream the element belongs to (the generator runs on from
+ * frame to frame); NULL when no element uses PNS (one that does then gets -2); d_err [n]: 0, or -2.  Three launches (two without
+ * d_pns_seed).  pns_frame_number (a plain frame counter) stays with the host. */
+int32_t xaac_b200_aac_spectral_dev(xaac_b200_ctx *ctx, int32_t *d_spec, const uint8_t *d_side, int32_t *d_pns_seed, int32_t *d_err,
+                                   int64_t n_units, void *stream);
 
 /* ---- raw device-memory helpers for C hosts that do not link the CUDA runtime themselves (the reference-side drop-in glue,
  * libxaac_b200/dropin/ixheaacd_b200_glue.c): allocation and synchronous copies on the context's device ---- */

@@ -5,10 +5,12 @@
 //   ixheaacd_aac_tns_process            decoder/ixheaacd_pns_js_thumb.c:248-514 with the selector leaves
 //     ixheaacd_tns_decode_coef (:202), ixheaacd_tns_parcor_lpc_convert_dec (decoder/ixheaacd_aac_tns.c:147),
 //     ixheaacd_calc_max_spectral_line_dec (:422), ixheaacd_tns_ar_filter_dec (:371)
-// Elements with perceptual noise substitution (its generator state runs across frames and channels) are refused (-2): the
-// reference encoder never emits them.  Two kernels: the stereo tools with a warp per element (rows of an sfb are coalesced
-// 128-byte requests), then TNS with a THREAD per channel — the all-pole filter is a recursion over up to 1024 spectral lines
-// whose saturating accumulation fixes the order of every add, so the parallelism is across the batch.
+//   ixheaacd_map_ms_mask_pns (channel.c:703-726), ixheaacd_pns_process / ixheaacd_gen_rand_vec (pns_js_thumb.c:74-200) with
+//     ixheaacd_sqrt / ixheaacd_one_by_sqrt_calc (decoder/ixheaacd_basic_funcs.c:155-196), ixheaac_div32_pos_normb
+// Three kernels: the stereo tools with a warp per element (rows of an sfb are coalesced 128-byte requests); perceptual noise
+// substitution with a THREAD per element (one linear-congruential generator runs through all noise bands of both channels, and
+// on into the next frame); TNS with a thread per channel — the all-pole filter is a recursion over up to 1024 spectral lines
+// whose saturating accumulation fixes the order of every add.  For the serial parts the parallelism is across the batch.
 // Record layout: XAAC_SPS_* of include/xaac_b200.h (the reference's own structs, byte for byte, where they are plain data).
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -31,6 +33,7 @@ struct ChanView {
   XB_DEV int scale_factor(int i) const { return reinterpret_cast<const int16_t *>(b + kSpsChScaleFactor)[i]; }
   XB_DEV const unsigned char *tns() const { return b + kSpsChTns; }
   XB_DEV int sfb_index(int i) const { return reinterpret_cast<const int16_t *>(b + kSpsChSfbIndex)[i]; }
+  XB_DEV int pns_used(int i) const { return b[kSpsChPnsUsed + i]; }
 };
 
 // Everything ixheaacd_aac_tns_process decides from the side information alone about one filter (no spectral data involved).
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(256) aac_stereo_tools_kernel(const AacSpectral
     for (int c = 0; c < 2 && !bad; c++) {
       if (c >= num_ch) break;
       const int ws = ch[c].window_sequence(), ms = ch[c].max_sfb(), ng = ch[c].num_window_groups();
-      if (ws < 0 || ws > 3 || ms < 0 || ms > (ws == 2 ? 15 : 51) || ng < 1 || ng > 8 || ch[c].pns_active()) bad = 1;
+      if (ws < 0 || ws > 3 || ms < 0 || ms > (ws == 2 ? 15 : 51) || ng < 1 || ng > 8 || (ch[c].pns_active() && !p.pns_seed)) bad = 1;
       int tot = 0;
       for (int g = 0; g < ng && !bad; g++) {
         const int gl = ch[c].group_len(g);
@@ -118,6 +121,8 @@ __global__ void __launch_bounds__(256) aac_stereo_tools_kernel(const AacSpectral
     int32_t *l_spec = p.spec + u * 2048, *r_spec = l_spec + 1024;
     const unsigned char *ms_used = rec + kSpsMsUsed;
     // ---- ixheaacd_ms_stereo_process: groups / lengths / max_sfb of LEFT, band widths of RIGHT's window sequence
+    // ixheaacd_map_ms_mask_pns first takes the bands that are noise in BOTH channels out of the mask (channel.c:703-726)
+    const bool map_pns = common_window && (ch[0].pns_active() || ch[1].pns_active());
     if (common_window) {
       const int max_sfb = ch[0].max_sfb();
       int w = 0;
@@ -126,6 +131,7 @@ __global__ void __launch_bounds__(256) aac_stereo_tools_kernel(const AacSpectral
           const int base = w << 7;
           for (int sfb = 0; sfb < max_sfb; sfb++) {
             if (!ms_used[g * 64 + sfb]) continue;
+            if (map_pns && ch[0].pns_used((g << 4) + sfb) && ch[1].pns_used((g << 4) + sfb)) continue;
             const int k0 = ch[1].sfb_index(sfb), k1 = ch[1].sfb_index(sfb + 1);
             for (int k = k0 + lane; k < k1 && base + k < 1024; k += 32) {
               const i32 a = l_spec[base + k], b = r_spec[base + k];
@@ -149,7 +155,11 @@ __global__ void __launch_bounds__(256) aac_stereo_tools_kernel(const AacSpectral
             const int sfb_factor = ch[1].scale_factor(16 * g + sfb);
             int scf_exp = sfb_factor >> 2;
             i32 scale = __ldg(p.rom + kBromScaleTable + (sfb_factor & 3));
-            if (!((ms_used[g * 64 + sfb] ? 1 : 0) ^ (cb & 1))) scale = wneg(scale);
+            int msu = ms_used[g * 64 + sfb] ? 1 : 0;
+            if (msu && map_pns && g < ch[0].num_window_groups() && sfb < ch[0].max_sfb() && ch[0].pns_used((g << 4) + sfb) &&
+                ch[1].pns_used((g << 4) + sfb))
+              msu = 0;
+            if (!(msu ^ (cb & 1))) scale = wneg(scale);
             scf_exp = -(scf_exp + 2);
             const int k0 = ch[1].sfb_index(sfb), k1 = ch[1].sfb_index(sfb + 1);
             for (int k = k0 + lane; k < k1 && base + k < 1024; k += 32) {
@@ -169,7 +179,123 @@ __global__ void __launch_bounds__(256) aac_stereo_tools_kernel(const AacSpectral
   }
 }
 
-// ---- kernel 2: TNS, a thread per channel ----
+// ---- kernel 2: perceptual noise substitution, a thread per element ----
+namespace {
+XB_DEV i32 mult32_shl_sat(i32 a, i32 b) {
+  if (a == (i32)0x80000000 && b == (i32)0x80000000) return 0x7fffffff;
+  return lsl(__mulhi(a, b), 1);
+}
+XB_DEV i32 mult32x16_shl(i32 a, i32 b16) { return lsl(mul32x16(a, b16), 1); }
+XB_DEV i32 shl32_dir_sat_limit_(i32 a, int b) { return b < 0 ? shr32(a, min(-b, 31)) : shl32_sat(a, b); }
+XB_DEV i32 shr32_dir_sat_limit_(i32 a, int b) { return b < 0 ? shl32_sat(a, -b) : shr32(a, min(b, 31)); }
+// decoder/ixheaacd_basic_funcs.c:155-181
+XB_DEV i32 one_by_sqrt_calc(i32 op) {
+  i32 a = add_sat((i32)0x900ebee0, mult32x16_shl(op, 0x39d9));
+  // ixheaac_mult32x16h_in32_shl_sat(op, a): its saturation test compares the 32-bit b with (WORD16)0x8000
+  i32 iy = add_sat(0x573b645a, (op == (i32)0x80000000 && a == -32768) ? 0x7fffffff : mult32x16_shl(op, a >> 16));
+  iy = shl32_dir_sat_limit_(iy, 1);
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    a = mult32_shl_sat(op, iy);
+    a = sub_sat(0x40000000, shl32_dir_sat_limit_(mult32_shl_sat(a, iy), 1));
+    iy = add_sat(iy, mult32_shl_sat(a, iy));
+  }
+  return iy;
+}
+XB_DEV i32 fix_sqrt(i32 op) {  // ixheaacd_sqrt, :183-196
+  if (op == 0) return 0;
+  int shift = (int16_t)(norm32(op) & ~1);
+  op = shl32_dir_sat_limit_(op, shift);
+  shift = shr32_dir_sat_limit_(shift, 1);
+  op = mult32_shl_sat(one_by_sqrt_calc(op), op);
+  return shr32_dir_sat_limit_(op, sat16(shift - 1));
+}
+XB_DEV i32 div32_pos_normb(i32 a, i32 b) {  // common/ixheaac_basic_ops.h:74-99
+  if (a == b) return 0x7fffffff;
+  u32 nr = (u32)a, dr = (u32)b, q = 0;
+  for (int i = 0; i < 32; i++) {
+    q <<= 1;
+    if (nr >= dr) { nr -= dr; q += 1; }
+    nr <<= 1;
+  }
+  return (i32)q;
+}
+// ixheaacd_gen_rand_vec (pns_js_thumb.c:74-112): `count` = sfb_width + 1 lines
+XB_DEV void gen_rand_vec(i32 scale, int shift, i32 *spec, int count, i32 &seed) {
+  i32 nrg = 0;
+  for (int i = 0; i < count; i++) {
+    seed = (i32)(1664525u * (u32)seed + 1013904223u);
+    const i32 v = seed >> 3;
+    spec[i] = v;
+    nrg = add_sat(nrg, mult32_shl_sat(v, v));
+  }
+  int nrg_scale = norm32(nrg);
+  if (nrg_scale > 0) {
+    nrg_scale &= ~1;
+    nrg = shl32_sat(nrg, nrg_scale);
+    shift = shift - (nrg_scale >> 1);
+  }
+  nrg = fix_sqrt(nrg);
+  scale = div32_pos_normb(scale, nrg);
+  if (shift < -31) shift = -31;
+  for (int i = 0; i < count; i++) spec[i] = shr32_dir_sat_limit_(mult32_shl_sat(spec[i], scale), shift);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128) aac_pns_kernel(const AacSpectralArgs p) {
+  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= p.n_units || !p.pns_seed || p.err[u] != 0) return;
+  const unsigned char *rec = p.side + u * kSpsBytes;
+  const int num_ch = reinterpret_cast<const int *>(rec)[kSpsNumCh], common_window = reinterpret_cast<const int *>(rec)[kSpsCommonWindow];
+  const ChanView ch[2] = {{rec + kSpsCh}, {rec + kSpsCh + kSpsChBytes}};
+  const bool any = ch[0].pns_active() || (num_ch > 1 && ch[1].pns_active());
+  if (!any) return;
+  // correlation flags: what the parser left plus every band of LEFT's mask (ixheaacd_map_ms_mask_pns / ixheaacd_set_corr_info)
+  unsigned corr[4];
+  for (int i = 0; i < 4; i++) corr[i] = reinterpret_cast<const unsigned *>(rec + kSpsCorrelated)[i];
+  if (num_ch > 1 && common_window)
+    for (int g = 0; g < ch[0].num_window_groups(); g++)
+      for (int sfb = 0; sfb < ch[0].max_sfb(); sfb++)
+        if (rec[kSpsMsUsed + g * 64 + sfb]) {
+          const int band = (g << 4) + sfb;
+          corr[band >> 5] |= 1u << (band & 31);
+        }
+  i32 seed = p.pns_seed[u];
+  i32 rv[128];  // random_vector: written by the first channel, consumed (and advanced) by the second
+  for (int i = 0; i < 128; i++) rv[i] = 0;
+  for (int c = 0; c < num_ch; c++) {
+    if (!ch[c].pns_active()) continue;
+    i32 *spec = p.spec + u * 2048 + c * 1024;
+    int w = 0;
+    for (int g = 0; g < ch[c].num_window_groups(); g++)
+      for (int gl = 0; gl < ch[c].group_len(g); gl++, w++) {
+        const int base = w << 7;
+        for (int sfb = 0; sfb < ch[c].max_sfb(); sfb++) {
+          const int band = (g << 4) + sfb;
+          if (!ch[c].pns_used(band)) continue;
+          const int sf = ch[c].scale_factor(band);
+          const i32 scale_mant = __ldg(p.rom + kBromScaleMant + (sf & 3));
+          const int scale_exp = (31 - (sf >> 2)) - 4;
+          const int k0 = ch[c].sfb_index(sfb), cnt = ch[c].sfb_index(sfb + 1) - k0;
+          if (cnt <= 0 || base + k0 + cnt > 1024) continue;
+          i32 *ps = spec + base + k0;
+          if ((corr[band >> 5] >> (band & 31)) & 1) {
+            if (c == 0) {
+              rv[band] = seed;
+              gen_rand_vec(scale_mant, scale_exp, ps, cnt, seed);
+            } else {
+              gen_rand_vec(scale_mant, scale_exp, ps, cnt, rv[band]);
+            }
+          } else {
+            gen_rand_vec(scale_mant, scale_exp, ps, cnt, seed);
+          }
+        }
+      }
+  }
+  p.pns_seed[u] = seed;
+}
+
+// ---- kernel 3: TNS, a thread per channel ----
 namespace {
 XB_DEV i32 mult16x16_shl_sat(i32 a, i32 b) {
   const i32 pr = a * b;
@@ -294,6 +420,11 @@ cudaError_t launch_aac_spectral(const AacSpectralArgs &args, int num_sms, cudaSt
   aac_stereo_tools_kernel<<<(unsigned)grid, 256, 0, stream>>>(args);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (args.pns_seed) {
+    aac_pns_kernel<<<(unsigned)((args.n_units + 127) / 128), 128, 0, stream>>>(args);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   const long long threads = 2 * args.n_units;
   aac_tns_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(args);
   return cudaGetLastError();

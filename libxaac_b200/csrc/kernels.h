@@ -427,13 +427,16 @@ cudaError_t launch_esbr_ps(const EsbrPsArgs &args, int num_sms, cudaStream_t str
 // AAC pre-IMDCT spectral stage (ixheaacd_channel_pair_process for AAC-LC): record byte offsets = XAAC_SPS_* of include/xaac_b200.h,
 // ROM = the leading 620 bytes of ia_aac_dec_block_tables_struct (decoder/ixheaacd_aac_rom.h:25-43)
 constexpr int kSpsNumCh = 0, kSpsCommonWindow = 1;                       // int32 words of the header
-constexpr int kSpsMsUsed = 32, kSpsCh = 544, kSpsChBytes = 1456, kSpsBytes = 544 + 2 * 1456;
-constexpr int kSpsChGroupLen = 32, kSpsChCodeBook = 40, kSpsChScaleFactor = 168, kSpsChTns = 424, kSpsChSfbIndex = 1348;
-constexpr int kBromBytes = 620, kBromScaleTable = 129 /* int32 index */, kBromTnsCoeff3 = 278, kBromTnsCoeff4 = 286 /* int16 index */;
+constexpr int kSpsCorrelated = 16, kSpsMsUsed = 32, kSpsCh = 544, kSpsChBytes = 1584, kSpsBytes = 544 + 2 * 1584;
+constexpr int kSpsChGroupLen = 32, kSpsChCodeBook = 40, kSpsChScaleFactor = 168, kSpsChTns = 424, kSpsChSfbIndex = 1348,
+              kSpsChPnsUsed = 1456;
+constexpr int kBromBytes = 620, kBromScaleTable = 129 /* int32 index */, kBromTnsCoeff3 = 278, kBromTnsCoeff4 = 286 /* int16 index */,
+              kBromScaleMant = 151 /* int32 index */;
 struct AacSpectralArgs {
   int32_t *spec;              // [n][2][1024] ptr_spec_coeff of the element's channels (second unused for a single channel), in/out
   const unsigned char *side;  // [n][kSpsBytes]
-  int32_t *err;               // [n] or null: 0, -2 (outside the supported subset: nothing touched)
+  int32_t *err;               // [n]: 0, -2 (outside the supported subset: nothing touched)
+  int32_t *pns_seed;          // [n] pstr_pns_rand_vec_data->current_seed, in/out; null: elements that use PNS get -2
   const int32_t *rom;
   long long n_units;
 };

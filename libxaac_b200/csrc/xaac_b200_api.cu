@@ -1499,8 +1499,8 @@ int32_t xaac_b200_set_block_rom(xaac_b200_ctx *ctx, const void *block_tables, si
   return XAAC_B200_OK;
 }
 
-int32_t xaac_b200_aac_spectral_dev(xaac_b200_ctx *ctx, int32_t *d_spec, const uint8_t *d_side, int32_t *d_err, int64_t n_units,
-                                   void *stream) {
+int32_t xaac_b200_aac_spectral_dev(xaac_b200_ctx *ctx, int32_t *d_spec, const uint8_t *d_side, int32_t *d_pns_seed, int32_t *d_err,
+                                   int64_t n_units, void *stream) {
   if (!ctx) return XAAC_B200_ERR_ARG;
   if (!ctx->d_rom_block) {
     snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_block_rom has not been called");
@@ -1511,9 +1511,9 @@ int32_t xaac_b200_aac_spectral_dev(xaac_b200_ctx *ctx, int32_t *d_spec, const ui
   if (!d_spec || !d_side || !d_err) return bad_arg(ctx, "null buffer (d_err carries the per-element verdict between the two kernels)");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   xb::AacSpectralArgs a;
-  a.spec = d_spec; a.side = d_side; a.err = d_err; a.rom = ctx->d_rom_block; a.n_units = n_units;
+  a.spec = d_spec; a.side = d_side; a.err = d_err; a.pns_seed = d_pns_seed; a.rom = ctx->d_rom_block; a.n_units = n_units;
   LAUNCH("aac_spectral_kernels", stream, xb::launch_aac_spectral(a, ctx->num_sms, (cudaStream_t)stream));
-  ctx->launches += 2;
+  ctx->launches += d_pns_seed ? 3 : 2;
   return XAAC_B200_OK;
 }
 

@@ -77,8 +77,8 @@ static struct {
   /* pre-IMDCT spectral stage */
   int have_block_rom;
   uint8_t *d_sps;
-  int32_t *d_sps_spec;
-  long n_cpp, n_cpp_ref, n_cpp_ms, n_cpp_tns;
+  int32_t *d_sps_spec, *d_sps_seed;
+  long n_cpp, n_cpp_ref, n_cpp_ms, n_cpp_tns, n_cpp_pns;
   int32_t last_err[6];
   long n_imdct, n_imdct_ref, n_sbr_hq, n_sbr_ps, n_sbr_lp, n_sbr_ref, n_fd, n_fd_ref, n_esbr, n_esbr_hbe, n_esbr_ref;
 } G;
@@ -92,8 +92,8 @@ static void b200_report(void) {
             G.n_imdct, G.n_imdct_ref, G.n_sbr_hq, G.n_sbr_ps, G.n_sbr_lp, G.n_sbr_ref, G.n_fd, G.n_fd_ref, G.n_esbr, G.n_esbr_hbe,
             G.n_esbr_ps, G.n_esbr_rebuilt, G.n_esbr_tes, G.n_esbr_bypass, G.n_esbr_ref);
   if (G.stats)
-    fprintf(stderr, "[ixheaacd_b200] channel_pair_process: %ld on the GPU (%ld with M/S or intensity bands, %ld with TNS), %ld by the "
-            "reference\n", G.n_cpp, G.n_cpp_ms, G.n_cpp_tns, G.n_cpp_ref);
+    fprintf(stderr, "[ixheaacd_b200] channel_pair_process: %ld on the GPU (%ld with M/S or intensity bands, %ld with TNS, %ld with PNS), %ld by the "
+            "reference\n", G.n_cpp, G.n_cpp_ms, G.n_cpp_tns, G.n_cpp_pns, G.n_cpp_ref);
   if (G.ctx) xaac_b200_destroy(G.ctx);
   G.ctx = NULL;
 }
@@ -830,18 +830,32 @@ IA_ERRORCODE __wrap_ixheaacd_channel_pair_process(ia_aac_dec_channel_info_struct
       B200(xaac_b200_set_block_rom(c, ptr_aac_tables->pstr_block_tables, 620), "set_block_rom");
       B200(xaac_b200_dev_alloc(c, XAAC_SPS_BYTES, (void **)&G.d_sps), "alloc");
       B200(xaac_b200_dev_alloc(c, 8192, (void **)&G.d_sps_spec), "alloc");
+      B200(xaac_b200_dev_alloc(c, 16, (void **)&G.d_sps_seed), "alloc");
       G.have_block_rom = 1;
     }
     B200(xaac_b200_h2d(c, G.d_sps, rec, sizeof(rec)), "h2d sps");
     for (int ch = 0; ch < num_ch; ch++)
       B200(xaac_b200_h2d(c, G.d_sps_spec + 1024 * ch, ptr_aac_dec_channel_info[ch]->ptr_spec_coeff, 4096), "h2d spec");
-    B200(xaac_b200_aac_spectral_dev(c, G.d_sps_spec, G.d_sps, G.d_err, 1, NULL), "aac_spectral_dev");
+    int any_pns = 0;
+    for (int ch = 0; ch < num_ch; ch++) any_pns |= ptr_aac_dec_channel_info[ch]->str_pns_info.pns_active != 0;
+    ia_pns_rand_vec_struct *rnd = ptr_aac_dec_channel_info[0]->pstr_pns_rand_vec_data;
+    int32_t seed = rnd->current_seed;
+    if (any_pns) B200(xaac_b200_h2d(c, G.d_sps_seed, &seed, 4), "h2d seed");
+    B200(xaac_b200_aac_spectral_dev(c, G.d_sps_spec, G.d_sps, any_pns ? G.d_sps_seed : NULL, G.d_err, 1, NULL), "aac_spectral_dev");
     B200(xaac_b200_d2h(c, &err, G.d_err, 4), "d2h err");
     if (err == 0) {
       for (int ch = 0; ch < num_ch; ch++)
         B200(xaac_b200_d2h(c, ptr_aac_dec_channel_info[ch]->ptr_spec_coeff, G.d_sps_spec + 1024 * ch, 4096), "d2h spec");
       /* ixheaacd_pns_process still counts the frames of the first channel (pns_js_thumb.c:196-198) */
-      ptr_aac_dec_channel_info[0]->pstr_pns_rand_vec_data->pns_frame_number++;
+      rnd->pns_frame_number++;
+      if (any_pns) {
+        B200(xaac_b200_d2h(c, &seed, G.d_sps_seed, 4), "d2h seed");
+        rnd->current_seed = seed;
+        /* what else the reference leaves in the structs: the mask / correlation flags as ixheaacd_map_ms_mask_pns rewrites them
+         * (its own code, run after the fact on the untouched side info); random_vector is scratch of the call */
+        if (num_ch > 1 && ptr_aac_dec_channel_info[0]->common_window) ixheaacd_map_ms_mask_pns(ptr_aac_dec_channel_info);
+        G.n_cpp_pns++;
+      }
       G.n_cpp++;
       {
         int any_ms = 0, any_tns = 0;

@@ -18,12 +18,13 @@ static int b200_sps_pack(uint8_t *rec, ia_aac_dec_channel_info_struct *ci[], int
   hdr[XAAC_SPS_NUM_CH] = num_ch;
   hdr[XAAC_SPS_COMMON_WINDOW] = ci[0]->common_window;
   if (ci[0]->pstr_stereo_info) memcpy(rec + XAAC_SPS_MS_USED, ci[0]->pstr_stereo_info->ms_used, 512);
+  if (ci[0]->pstr_pns_corr_info) memcpy(rec + XAAC_SPS_CORRELATED, ci[0]->pstr_pns_corr_info->correlated, 16);
   for (int c = 0; c < num_ch; c++) {
     uint8_t *b = rec + XAAC_SPS_CH + c * XAAC_SPS_CH_BYTES;
     int32_t *w = (int32_t *)b;
     const ia_ics_info_struct *ics = &ci[c]->str_ics_info;
     const int ws = ics->window_sequence;
-    if (ics->frame_length != 1024 || ws < 0 || ws > 3 || ci[c]->str_pns_info.pns_active) return -1;
+    if (ics->frame_length != 1024 || ws < 0 || ws > 3) return -1;
     w[XAAC_SPS_CH_WINDOW_SEQUENCE] = ws;
     w[XAAC_SPS_CH_MAX_SFB] = ics->max_sfb;
     w[XAAC_SPS_CH_NUM_WINDOW_GROUPS] = ics->num_window_groups;
@@ -35,6 +36,7 @@ static int b200_sps_pack(uint8_t *rec, ia_aac_dec_channel_info_struct *ci[], int
     memcpy(b + XAAC_SPS_CH_CODE_BOOK, ci[c]->ptr_code_book, 128);
     memcpy(b + XAAC_SPS_CH_SCALE_FACTOR, ci[c]->ptr_scale_factor, 256);
     memcpy(b + XAAC_SPS_CH_TNS, &ci[c]->str_tns_info, 924);
+    memcpy(b + XAAC_SPS_CH_PNS_USED, ci[c]->str_pns_info.pns_used, 128);
     {
       const WORD16 *idx = t->str_aac_sfb_info[ws].sfb_index;
       const int n = ws == 2 ? 16 : 52; /* sfb_short_table[16] / sfb_long_table[52] (decoder/ixheaacd_aac_rom.h:184-185) */

@@ -24,8 +24,9 @@ const void *ref_rom_block_tables(int *bytes) {
   return &ixheaacd_aac_block_tables;
 }
 
-/* spec [n][2][1024] in/out; rec [n][XAAC_SPS_BYTES]; err [n] = the function's return value */
-void ref_channel_pair_process_batch(int64_t n, int32_t *spec, const uint8_t *rec, int32_t *err) {
+/* spec [n][2][1024] in/out; rec [n][XAAC_SPS_BYTES]; seed [n] in/out (current_seed of the PNS generator); err [n] = the function's
+ * return value */
+void ref_channel_pair_process_batch(int64_t n, int32_t *spec, const uint8_t *rec, int32_t *seed, int32_t *err) {
   static ia_aac_dec_channel_info_struct ci[2];
   static ia_stereo_info_struct stereo;
   static ia_pns_correlation_info_struct corr;
@@ -45,6 +46,8 @@ void ref_channel_pair_process_batch(int64_t n, int32_t *spec, const uint8_t *rec
     memset(&rnd, 0, sizeof(rnd));
     tabs.pstr_block_tables = (ia_aac_dec_block_tables_struct *)&ixheaacd_aac_block_tables;
     memcpy(stereo.ms_used, r + XAAC_SPS_MS_USED, 512);
+    memcpy(corr.correlated, r + XAAC_SPS_CORRELATED, 16);
+    rnd.current_seed = seed[u];
     for (int c = 0; c < 2; c++) {
       const uint8_t *b = r + XAAC_SPS_CH + c * XAAC_SPS_CH_BYTES;
       const int32_t *w = (const int32_t *)b;
@@ -59,6 +62,8 @@ void ref_channel_pair_process_batch(int64_t n, int32_t *spec, const uint8_t *rec
       memcpy(cb[c], b + XAAC_SPS_CH_CODE_BOOK, 128);
       memcpy(sf[c], b + XAAC_SPS_CH_SCALE_FACTOR, 256);
       memcpy(&ci[c].str_tns_info, b + XAAC_SPS_CH_TNS, 924);
+      memcpy(ci[c].str_pns_info.pns_used, b + XAAC_SPS_CH_PNS_USED, 128);
+      ci[c].str_pns_info.pns_active = (UWORD16)w[XAAC_SPS_CH_PNS_ACTIVE];
       ci[c].ptr_code_book = cb[c];
       ci[c].ptr_scale_factor = sf[c];
       ci[c].ptr_spec_coeff = spec + u * 2048 + c * 1024;
@@ -77,5 +82,6 @@ void ref_channel_pair_process_batch(int64_t n, int32_t *spec, const uint8_t *rec
     }
     memcpy(tabs.sfb_long_table, sfb_idx[0], sizeof(tabs.sfb_long_table));
     err[u] = ixheaacd_channel_pair_process(pci, num_ch, &tabs, num_ch, 2 /* AOT_AAC_LC */, 0, 0, NULL, NULL, NULL);
+    seed[u] = rnd.current_seed;
   }
 }

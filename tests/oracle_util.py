@@ -1270,7 +1270,7 @@ def ref_esbr_envcalc_tes_batch(ref, d):
 
 
 # ---- AAC pre-IMDCT spectral stage (ixheaacd_channel_pair_process) ----
-SPS_BYTES, SPS_CH, SPS_CH_BYTES = 3456, 544, 1456
+SPS_BYTES, SPS_CH, SPS_CH_BYTES = 3712, 544, 1584
 SFB_LONG_44 = [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 48, 56, 64, 72, 80, 88, 96, 108, 120, 132, 144, 160, 176, 196, 216, 240, 264,
                292, 320, 352, 384, 416, 448, 480, 512, 544, 576, 608, 640, 672, 704, 736, 768, 800, 832, 864, 896, 928, 1024]
 SFB_SHORT_44 = [0, 4, 8, 12, 16, 20, 28, 36, 44, 56, 68, 80, 96, 112, 128]
@@ -1309,12 +1309,17 @@ def synth_sps_units(n, seed, tns=True, stereo_tools=True, pns=False):
                 else:
                     glens = [1]
                 groups0 = glens
-            w[0], w[1], w[2], w[3], w[4], w[5] = ws, max_sfb, len(glens), int(pns and rng.random() < 0.5), 14 if short else 42, 4
+            pa = int(pns and rng.random() < 0.6)
+            w[0], w[1], w[2], w[3], w[4], w[5] = ws, max_sfb, len(glens), pa, 14 if short else 42, 4
             b[32:32 + len(glens)] = np.array(glens, np.uint8)
             cbk = rng.integers(1, 12, 128).astype(np.int8)
             if stereo_tools and c == 1:
                 m = rng.random(128) < 0.25
                 cbk[m] = rng.choice([14, 15], int(m.sum()))
+            if pa:
+                m = rng.random(128) < 0.3
+                cbk[m] = 13
+                b[1456:1584] = m.astype(np.uint8)
             b[40:168] = cbk.view(np.uint8)
             b[168:424].view(np.int16)[:] = rng.integers(-40, 60, 128)
             ti = b[424:424 + 924]
@@ -1348,12 +1353,15 @@ def synth_sps_units(n, seed, tns=True, stereo_tools=True, pns=False):
             spec[u, c] = np.clip(x, -(1 << 31), (1 << 31) - 1).astype(np.int32)
         if stereo_tools:
             r[32:544] = (rng.random(512) < 0.4).astype(np.uint8)
+        if pns and rng.random() < 0.3:
+            r[16:32] = rng.integers(0, 256, 16).astype(np.uint8)   # correlation flags the parser may have left
     return spec, rec
 
 
-def ref_channel_pair_process(ref, spec, rec):
+def ref_channel_pair_process(ref, spec, rec, seed=None):
     s = np.ascontiguousarray(spec, np.int32).copy()
     err = np.zeros(len(rec), np.int32)
-    ref.lib.ref_channel_pair_process_batch.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-    ref.lib.ref_channel_pair_process_batch(len(rec), P(s), P(np.ascontiguousarray(rec, np.uint8)), P(err))
-    return s, err
+    sd = np.zeros(len(rec), np.int32) if seed is None else np.ascontiguousarray(seed, np.int32).copy()
+    ref.lib.ref_channel_pair_process_batch.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 4
+    ref.lib.ref_channel_pair_process_batch(len(rec), P(s), P(np.ascontiguousarray(rec, np.uint8)), P(sd), P(err))
+    return (s, err) if seed is None else (s, err, sd)

@@ -52,7 +52,27 @@ def test_whole_stage(ctx, ref):
     check(run_gpu(ctx, spec, rec), ou.ref_channel_pair_process(ref, spec, rec), rec, "M/S + intensity + TNS")
 
 
-def test_pns_elements_are_refused_untouched(ctx):
+def test_pns_with_generator_state(ctx, ref):
+    """perceptual noise substitution: the generator state (current_seed) enters and leaves per element, correlated bands reuse the
+    first channel's seeds, noise bands common to both channels drop out of the M/S mask; three consecutive frames carry the seed"""
+    import torch
+    import libxaac_b200 as xb
+    n = 2500
+    seed = np.random.default_rng(1).integers(-2**31, 2**31, n).astype(np.int32)
+    d_seed = torch.from_numpy(seed.copy()).cuda()
+    for f in range(3):
+        spec, rec = ou.synth_sps_units(n, 20 + f, pns=True)
+        wout, werr, wseed = ou.ref_channel_pair_process(ref, spec, rec, seed)
+        s = torch.from_numpy(spec.copy()).cuda()
+        err = xb.aac_channel_pair_process(ctx, s, torch.from_numpy(rec).cuda(), pns_seed=d_seed)
+        torch.cuda.synchronize()
+        check((s.cpu().numpy(), err.cpu().numpy()), (wout, werr), rec, f"PNS frame {f}")
+        assert np.array_equal(d_seed.cpu().numpy(), wseed), f"frame {f}: generator state"
+        assert (wseed != seed).mean() > 0.4
+        seed = wseed
+
+
+def test_pns_elements_are_refused_without_generator_state(ctx):
     spec, rec = ou.synth_sps_units(64, 6, pns=True)
     out, err = run_gpu(ctx, spec, rec)
     pns = np.array([any(rec[u][ou.SPS_CH + c * ou.SPS_CH_BYTES:][:32].view(np.int32)[3] for c in range(int(rec[u][:4].view(np.int32)[0])))

@@ -75,7 +75,7 @@ def test_whole_file_through_reference_parser(tmp_path, name, enc, fs, ch, secs, 
     if "ps" not in want:
         assert ps == 0
     # the pre-IMDCT spectral stage (ixheaacd_channel_pair_process: M/S, intensity, TNS) of every element ran on the GPU as well
-    m2 = re.search(r"channel_pair_process: (\d+) on the GPU \((\d+) with M/S or intensity bands, (\d+) with TNS\), (\d+) by the reference", log)
+    m2 = re.search(r"channel_pair_process: (\d+) on the GPU \((\d+) with M/S or intensity bands, (\d+) with TNS, \d+ with PNS\), (\d+) by the reference", log)
     assert m2, log[-600:]
     cpp, cpp_ms, cpp_tns, cpp_ref = map(int, m2.groups())
     assert cpp >= 3000 and cpp_ref == 0 and cpp_tns >= 50, m2.group(0)
