@@ -71,6 +71,9 @@ WORKLOADS = {
                                      "frames: the float eSBR stage of the mono + PS element (harmonic transposer forced on for "
                                      "legacy streams) with the float parametric stereo -> float stereo output; the AAC-LC core "
                                      "IMDCT of the chain is not part of this workload (aac_lc_stereo_imdct_ola measures it)"),
+    "aac_lc_spectral": (1, 65536, "AAC-LC stereo 44.1 kHz batch=65536 frames: the pre-IMDCT spectral stage of the chain "
+                                  "(ixheaacd_channel_pair_process: M/S and intensity stereo, perceptual noise substitution, TNS) on "
+                                  "channel pairs, in place"),
     "esbr_hbe": (4, 65536, "xHE-AAC/USAC eSBR stereo: the QMF harmonic transposer of the chain (ixheaacd_qmf_hbe_apply), "
                            "batch=65536 stereo frames (131072 core channels)"),
     "xheaac_plain_stereo_chain": (4, 65536, "xHE-AAC/USAC stereo 32 kHz with eSBR, default (LPP) patching instead of the harmonic "
@@ -804,6 +807,57 @@ def cpu_arm_xheaac_hbe_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
     return n_units * done / dt, "reference"
 
 
+def spectral_units(n, seed):
+    """records for the spectral-stage workload: 2048 distinct seeded elements tiled over the batch — M/S masks on every pair,
+    intensity bands on a quarter of the right channels' bands, TNS on about 12 % and PNS on about 25 % of the channels"""
+    from tests import oracle_util as ou
+    k = min(n, 2048)
+    spec, rec = ou.synth_sps_units(k, seed, pns=True, tns_prob=0.12, pns_prob=0.25)
+    idx = np.arange(n) % k
+    return spec[idx], rec[idx]
+
+
+def cpu_arm_aac_spectral(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time ixheaacd_channel_pair_process per element on host threads (ref_channel_pair_process_batch, oracle/ref_shim_sps.c).
+    n_units counts elements (stream-frames); like the other arms with units_per_frame = 1 the return value is 2 x elements/s."""
+    from tests import oracle_util as ou
+    ref = ou.Ref.try_load()
+    if ref is None:
+        raise SystemExit("bench.py: the spectral-stage CPU baseline needs oracle/_ref/libxaac_ref.so (make ref)")
+    P = ou.P
+    n = max(threads, n_units)
+    spec0, rec = spectral_units(n, seed)
+    rec = np.ascontiguousarray(rec)
+    seeds = np.arange(n, dtype=np.int32)
+    err = np.zeros(n, np.int32)
+    bounds = np.linspace(0, n, threads + 1).astype(int)
+    ref.lib.ref_channel_pair_process_batch.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 4
+
+    def one_pass():
+        spec = spec0.copy()
+
+        def work(t):
+            a, b = int(bounds[t]), int(bounds[t + 1])
+            if b > a:
+                ref.lib.ref_channel_pair_process_batch(b - a, P(spec[a:]), P(rec[a:]), P(seeds[a:]), P(err[a:]))
+
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    one_pass()
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass()
+        done += 1
+    assert not err.any()
+    return 2.0 * n * done / dt, "reference"
+
+
 def cpu_arm_heaacv2_esbr_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time the reference's eSBR stage of mono + PS elements (harmonic transposer + float PS, two synthesis banks) per element on
     host threads (ref_heaacv2_esbr_chain_batch, oracle/ref_shim_fps.c).  n_units counts elements (stream-frames) and, like the
@@ -1080,6 +1134,12 @@ STAGES = {
                                          "ixheaacd_sbr_env_calc -> ixheaacd_esbr_apply_ps -> 2 x synthesis",
                                cpu=cpu_arm_heaacv2_esbr_chain, cpu_units_per_core=64, cpu_reps=6, realtime_fps=21.533,
                                h2d=4096 + 64 + 384 + 1152 + 1856 + 16 + 4096, d2h=2 * 8192, dtype="f32/f64"),
+    "aac_lc_spectral": dict(kernel="aac_spectral_kernels", bytes_per_unit=2 * 2 * 4096 + 3712 + 8, units_per_frame=1,
+                            stage="M/S + intensity stereo (warp per element), PNS (thread per element: one generator through both "
+                                  "channels), TNS (thread per channel: all-pole recursion with saturating accumulation) — three "
+                                  "launches timed as one unit",
+                            ref_stage="ixheaacd_channel_pair_process", cpu=cpu_arm_aac_spectral, cpu_units_per_core=4096,
+                            realtime_fps=43.066, h2d=2 * 4096 + 3712 + 4, d2h=2 * 4096 + 4, dtype="int32"),
     "esbr_hbe": dict(kernel="esbr_hbe_kernel", bytes_per_unit=None,
                      stage="QMF harmonic transposer: critically sampled real synthesis bank, 2x complex analysis bank, stretch-2/3/4 "
                            "products with pitch cross products, phase rotation (bit-exact floats)",
@@ -1529,6 +1589,47 @@ class XheaacHbeChainWork(XheaacChainWork):
         xb.esbr_dec_hbe(self.ctx, self.state, self.core, hc, hf, ip, fp, rg, pcm16=self.pcm, ch_fac=2, err=self.err, want_float=False)
         self.h_pcm.copy_(self.pcm, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+
+
+class SpectralWork:
+    """AAC-LC channel pairs through the pre-IMDCT spectral stage, in place, the PNS generator state resident."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        spec, rec = spectral_units(n_units, seed)
+        self.spec0 = torch.from_numpy(np.ascontiguousarray(spec)).to(dev)
+        self.spec = self.spec0.clone()
+        self.rec = torch.from_numpy(np.ascontiguousarray(rec)).to(dev)
+        self.seed = torch.arange(n_units, dtype=torch.int32, device=dev)
+        self.err = torch.zeros((n_units,), dtype=torch.int32, device=dev)
+
+    def step(self, i, stream):
+        self.xb.aac_channel_pair_process(self.ctx, self.spec, self.rec, pns_seed=self.seed, err=self.err, stream=stream)
+
+    def check(self):
+        assert int(self.err.abs().max().item()) == 0
+
+    def host_setup(self):
+        import torch
+        self.h_spec = torch.empty((self.n, 2, 1024), dtype=torch.int32).pin_memory()
+        self.h_spec.copy_(self.spec0)
+        self.h_rec = self.rec.cpu().pin_memory()
+        self.h_seed = self.seed.cpu().pin_memory()
+        self.h_out = torch.empty((self.n, 2, 1024), dtype=torch.int32).pin_memory()
+
+    def host_step(self, i):
+        import torch
+        self.spec.copy_(self.h_spec, non_blocking=True)
+        self.rec.copy_(self.h_rec, non_blocking=True)
+        self.seed.copy_(self.h_seed, non_blocking=True)
+        self.xb.aac_channel_pair_process(self.ctx, self.spec, self.rec, pns_seed=self.seed, err=self.err)
+        self.h_out.copy_(self.spec, non_blocking=True)
+        self.h_seed.copy_(self.seed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
 
 
 class Heaacv2EsbrChainWork:
@@ -2091,7 +2192,7 @@ WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv
         "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork,
         "esbr_anal32": EsbrAnalWork, "esbr_generate_hf": EsbrHfgenWork,
         "esbr_env_calc": EsbrEnvcalcWork, "xheaac_stereo_chain": XheaacHbeChainWork, "esbr_hbe": EsbrHbeWork,
-        "xheaac_plain_stereo_chain": XheaacChainWork, "heaacv2_esbr_chain": Heaacv2EsbrChainWork}
+        "xheaac_plain_stereo_chain": XheaacChainWork, "heaacv2_esbr_chain": Heaacv2EsbrChainWork, "aac_lc_spectral": SpectralWork}
 
 
 def main():

@@ -27,14 +27,14 @@ const void *ref_rom_block_tables(int *bytes) {
 /* spec [n][2][1024] in/out; rec [n][XAAC_SPS_BYTES]; seed [n] in/out (current_seed of the PNS generator); err [n] = the function's
  * return value */
 void ref_channel_pair_process_batch(int64_t n, int32_t *spec, const uint8_t *rec, int32_t *seed, int32_t *err) {
-  static ia_aac_dec_channel_info_struct ci[2];
-  static ia_stereo_info_struct stereo;
-  static ia_pns_correlation_info_struct corr;
-  static ia_pns_rand_vec_struct rnd;
-  static ia_aac_dec_tables_struct tabs;
-  static WORD32 scratch[2][1024];
-  static WORD16 sfb_idx[4][52], sf[2][128];
-  static WORD8 sfb_w[4][52], cb[2][128];
+  static __thread ia_aac_dec_channel_info_struct ci[2];
+  static __thread ia_stereo_info_struct stereo;
+  static __thread ia_pns_correlation_info_struct corr;
+  static __thread ia_pns_rand_vec_struct rnd;
+  static __thread ia_aac_dec_tables_struct tabs;
+  static __thread WORD32 scratch[2][1024];
+  static __thread WORD16 sfb_idx[4][52], sf[2][128];
+  static __thread WORD8 sfb_w[4][52], cb[2][128];
   ia_aac_dec_channel_info_struct *pci[2] = {&ci[0], &ci[1]};
   for (int64_t u = 0; u < n; u++) {
     const uint8_t *r = rec + u * XAAC_SPS_BYTES;

@@ -1276,7 +1276,7 @@ SFB_LONG_44 = [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 48, 56, 64, 72, 80, 88, 
 SFB_SHORT_44 = [0, 4, 8, 12, 16, 20, 28, 36, 44, 56, 68, 80, 96, 112, 128]
 
 
-def synth_sps_units(n, seed, tns=True, stereo_tools=True, pns=False):
+def synth_sps_units(n, seed, tns=True, stereo_tools=True, pns=False, tns_prob=0.7, pns_prob=0.6):
     """Elements for the AAC-LC spectral stage at 44.1 kHz: single channels and pairs, long / start / stop / eight-short sequences
     with random grouping, random M/S masks and intensity bands, up to three TNS filters per window (orders up to 12 / 7, both
     directions and resolutions), spectra of mixed magnitude up to full scale."""
@@ -1309,7 +1309,7 @@ def synth_sps_units(n, seed, tns=True, stereo_tools=True, pns=False):
                 else:
                     glens = [1]
                 groups0 = glens
-            pa = int(pns and rng.random() < 0.6)
+            pa = int(pns and rng.random() < pns_prob)
             w[0], w[1], w[2], w[3], w[4], w[5] = ws, max_sfb, len(glens), pa, 14 if short else 42, 4
             b[32:32 + len(glens)] = np.array(glens, np.uint8)
             cbk = rng.integers(1, 12, 128).astype(np.int8)
@@ -1323,7 +1323,7 @@ def synth_sps_units(n, seed, tns=True, stereo_tools=True, pns=False):
             b[40:168] = cbk.view(np.uint8)
             b[168:424].view(np.int16)[:] = rng.integers(-40, 60, 128)
             ti = b[424:424 + 924]
-            if tns and rng.random() < 0.7:
+            if tns and rng.random() < tns_prob:
                 ti[:4].view(np.int32)[0] = 1
                 for win in range(8 if short else 1):
                     nf = int(rng.integers(0, 2 if short else 4))

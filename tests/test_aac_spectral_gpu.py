@@ -79,3 +79,17 @@ def test_pns_elements_are_refused_without_generator_state(ctx):
                     for u in range(64)])
     assert pns.sum() > 10 and (err[pns] == -2).all() and (err[~pns] == 0).all()
     assert np.array_equal(out[pns], spec[pns])
+
+
+def test_golden_records(ctx):
+    """records of the compiled reference function committed under tests/golden (no oracle/_ref needed)"""
+    import os
+    import torch
+    import libxaac_b200 as xb
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "aac_spectral_ref.npz"))
+    s = torch.from_numpy(g["spec_in"].copy()).cuda()
+    seed = torch.from_numpy(g["seed_in"].copy()).cuda()
+    err = xb.aac_channel_pair_process(ctx, s, torch.from_numpy(g["rec"]).cuda(), pns_seed=seed)
+    torch.cuda.synchronize()
+    assert int(err.abs().max()) == 0
+    assert np.array_equal(s.cpu().numpy(), g["spec_out"]) and np.array_equal(seed.cpu().numpy(), g["seed_out"])

@@ -613,9 +613,25 @@ def make_fps_golden(tmp):
     print(f"wrote {path}: {frames} frames x {n} channels, {os.path.getsize(path)} bytes")
 
 
+def make_sps_golden(tmp):
+    """AAC pre-IMDCT spectral stage ixheaacd_channel_pair_process (AAC-LC): outputs of the COMPILED reference function
+    (oracle/ref_shim_sps.c) for 20 seeded elements covering M/S, intensity, PNS (with generator state) and TNS."""
+    sys.path.insert(0, ROOT)
+    from tests import oracle_util as ou
+    ref = ou.Ref.try_load()
+    spec, rec = ou.synth_sps_units(20, 20261018, pns=True)
+    seed = (np.arange(20, dtype=np.int64) * 2654435761 % (1 << 32)).astype(np.uint32).view(np.int32)
+    out, err, seed_out = ou.ref_channel_pair_process(ref, spec, rec, seed)
+    assert (err == 0).all()
+    path = os.path.join(GOLD, "aac_spectral_ref.npz")
+    np.savez_compressed(path, spec_in=spec, rec=rec, seed_in=seed, spec_out=out, seed_out=seed_out)
+    print(f"wrote {path}: 20 elements, {os.path.getsize(path)} bytes; changed cells {int((out != spec).sum())}, "
+          f"seeds advanced {int((seed_out != seed).sum())}")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr", "esbr_stage", "hbe", "hbe_stage", "fps"]
+    which = sys.argv[1:] or ["imdct", "hfgen", "envcalc", "sbrdec", "sbrdec_lp", "usac_fd", "esbr", "esbr_stage", "hbe", "hbe_stage", "fps", "sps"]
     with tempfile.TemporaryDirectory() as tmp:
         if "imdct" in which:
             make_imdct_golden(tmp)
@@ -639,6 +655,8 @@ def main():
             make_esbr_hbe_stage_golden(tmp)
         if "fps" in which:
             make_fps_golden(tmp)
+        if "sps" in which:
+            make_sps_golden(tmp)
 
 
 if __name__ == "__main__":
