@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxaac_b200.so")
+# XAAC_B200_LIB: another build of the same library (kernel A/B measurements); default is the in-tree one
+LIB_PATH = os.environ.get("XAAC_B200_LIB") or os.path.join(_HERE, "libxaac_b200.so")
 ROM_DIR = os.path.join(_HERE, "rom")
 
 FATAL = -0x80000000

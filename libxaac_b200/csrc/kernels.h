@@ -82,9 +82,12 @@ struct QmfSynthArgs {
   long long mat_stride = 4096;      // words between the matrices of consecutive units (4864 inside the SBR stage)
   long long pcm_unit_stride = 0;    // != 0: unit u writes at pcm + u * pcm_unit_stride with sample stride ch_fac
   const int16_t *gate = nullptr;    // optional: unit u is skipped when gate[u] == 0
+  const void *twiddles = nullptr;   // HOST pointer: image built by qmf_synth_build_twiddles(), passed to the kernel by value
 };
 
 size_t qmf_synth_table_bytes();
+size_t qmf_synth_twiddle_bytes();
+void qmf_synth_build_twiddles(const uint8_t *qrom, void *out);
 int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out);  // returns fast_bits (>0) or -1
 cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStream_t stream);
 

@@ -23,10 +23,14 @@
 // The saturating adds of the reference's window-add can never saturate with the standard prototype filter
 // (sum of |coefficients| over the 10 taps <= 57308 < 65535, verified when the ROM is installed), so the taps are
 // accumulated with wrapping multiply-adds, which is bit-identical.
+#include <cstddef>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 #include "fixmath.cuh"
 #include "kernels.h"
+#include "qmf_synth_core.cuh"
 
 namespace xb {
 
@@ -385,7 +389,188 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
   }
 }
 
-size_t qmf_synth_table_bytes() { return offsetof(SynBlockSmem, w); }
+
+// =====================================================================================================================
+// Variant (opt-in, XAAC_B200_SYNTH_TMA=1): lane = slot modulation in registers, matrix rows staged by 1-D bulk copies (TMA), linear-time window.
+// See qmf_synth_core.cuh for the arithmetic and the layout; this part is the data movement.
+//
+// Per warp in shared memory: 41 rows x 132 words (9 rows of history + the 32 rows of the frame; the frame rows arrive by
+// one 512-byte cp.async.bulk per lane, complete on the warp's mbarrier, and are overwritten in place by the folded
+// filter-state samples) + the per-band block-shift table of the unit (2 variants x 64 bands x (mul, shr)).
+// 8 warps per SM (22.7 KB each, 255 registers): a half FFT of a slot (32 complex words) lives in registers.
+// =====================================================================================================================
+using namespace syn;
+
+constexpr int kSyn2Warps = 8;  // 2 per scheduler: 255 registers, no spills (10 warps at 168 registers measured slower)
+constexpr size_t kSynV2CoefOffset = offsetof(SynBlockSmem, w);  // qmf_c as 640 32-bit words follows the v1 tables
+
+struct Syn2Warp {
+  i32 rows[kRows * kRowW];  // row -9 .. row 31
+  int2 sh[2][64];           // [0]: slots < split (overlap scale), [1]: the others; per band (mul, shr)
+};
+struct Syn2Smem {
+  Syn2Warp w[kSyn2Warps];
+  unsigned long long bar[kSyn2Warps];
+};
+
+XB_DEV u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+XB_DEV void mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+XB_DEV void mbar_arrive_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+XB_DEV void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+XB_DEV void bulk_prefetch_l2(const void *src, u32 bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+XB_DEV void mbar_wait(u32 bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "XB_SYN_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra XB_SYN_DONE;\n"
+      "bra XB_SYN_WAIT;\n"
+      "XB_SYN_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+XB_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kSyn2Warps * 32, 1)
+qmf_synth_hq_tma_kernel(const __grid_constant__ QmfSynthArgs p, const __grid_constant__ SynTw tw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Syn2Smem &sm = *reinterpret_cast<Syn2Smem *>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  Syn2Warp &W = sm.w[warp];
+  const u32 bar = smem_u32(&sm.bar[warp]);
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+
+  const long long warps_total = (long long)gridDim.x * kSyn2Warps;
+  i32 *const row = W.rows + (kHist + lane) * kRowW;                 // phase A: this lane's slot
+  int4 *const rows4 = reinterpret_cast<int4 *>(W.rows);             // phase B: row -9 first
+  const u32 row_s = smem_u32(row);
+  const i32 *c32 = reinterpret_cast<const i32 *>(p.rom + kSynV2CoefOffset);
+
+  auto next_unit = [&](long long u) {
+    while (u < p.n_units && p.gate && p.gate[u] == 0) u += warps_total;
+    return u;
+  };
+  auto issue = [&](long long u) {  // one 512-byte row per lane
+    if (lane == 0) mbar_arrive_expect_tx(bar, 32 * 512);
+    bulk_g2s(row_s, p.matrix + u * p.mat_stride + 128 * lane, 512, bar);
+  };
+
+  long long u = next_unit((long long)blockIdx.x * kSyn2Warps + warp);
+  if (u < p.n_units) issue(u);
+  u32 parity = 0;
+
+  while (u < p.n_units) {
+    const long long un = next_unit(u + warps_total);
+    if (un < p.n_units) bulk_prefetch_l2(p.matrix + un * p.mat_stride + 128 * lane, 512);
+    const int16_t *prm = p.params + u * 8;
+    const int ov_lb_scale = prm[0], lb_scale = prm[1], hb_scale = prm[2], st_syn = prm[3];
+    const int lsb = prm[4], usb = prm[5], split = prm[6];
+    const int off0 = p.pos[2 * u], fpos0 = p.pos[2 * u + 1];
+    const int Bw0 = off0 >> 7, fp0 = fpos0 >> 6;
+    // qmf_dec.c:914-926, :1055
+    const int ov_lb_shift = (st_syn - ov_lb_scale) - 8, lb_shift = (st_syn - lb_scale) - 8;
+    const int hb_shift = (st_syn - hb_scale) - 8;
+    const FoldK fk = fold_consts(-(st_syn - 3) + 1);
+
+    // ---- while the rows are in flight: history, block-shift table, window coefficients ----
+    i32 *st32 = reinterpret_cast<i32 *>(p.states + u * 1280);
+    {
+      i32 wv[20];
+#pragma unroll
+      for (int t = 0; t < 20; t++) wv[t] = st32[32 * t + lane];
+#pragma unroll
+      for (int B = 0; B < 10; B++) history_store(rows4, lane, B, Bw0, wv[2 * B], wv[2 * B + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int band = lane + 32 * k;
+      W.sh[0][band] = shift_entry(band < lsb ? ov_lb_shift : (band < usb ? hb_shift : 0));
+      W.sh[1][band] = shift_entry(band < lsb ? lb_shift : (band < usb ? hb_shift : 0));
+    }
+    WinCoef wc;
+    window_coefs(wc, c32, lane, Bw0, fp0);
+    int16_t *pcm = p.pcm + (p.pcm_unit_stride ? u * p.pcm_unit_stride
+                                               : ((p.ch_fac == 1) ? u * 2048 : (u / p.ch_fac) * (2048LL * p.ch_fac) + (u % p.ch_fac)));
+    __syncwarp();
+    mbar_wait(bar, parity);
+    parity ^= 1;
+
+    // ---- phase A: lane = slot ----
+    {
+      // block shift (env_calc.c:1099) of the lane's row in place + magnitude bounds of the shifted values
+      i32 mx = 0, mn = 0;
+      shift_row(row, W.sh[lane < split ? 0 : 1], mx, mn);
+      // Below 2^fast_bits no add of the modulation can saturate and wrapping adds are bit-identical; if any lane of the
+      // warp left the bound (never on decoder data) the unit runs with the reference's saturating adds.
+      const i32 lim = (i32)(1u << p.fast_bits);
+      const bool bad = (mx >= lim) || (mn < -lim);
+      if (__any_sync(0xffffffffu, bad))
+        slot_modulate<true>(row, tw, fk, 0);
+      else
+        slot_modulate<false>(row, tw, fk, p.zero);
+    }
+    __syncwarp();
+
+    // ---- phase B: lane = output pair ----
+    if (Bw0 & 1)
+      window_unit<1>(rows4, lane, wc, pcm, p.ch_fac);
+    else
+      window_unit<0>(rows4, lane, wc, pcm, p.ch_fac);
+
+    // ---- filter state (the last 10 blocks) back to the ring, ring / coefficient positions ----
+    {
+      int B = Bw0 + 8;  // ring block of slot 22: (Bw0 - 22) mod 10
+      if (B >= 10) B -= 10;
+#pragma unroll
+      for (int r = 22; r < 32; r++) {
+        i32 w0, w1;
+        state_words(rows4, lane, r, w0, w1);
+        st32[32 * (2 * B) + lane] = w0;
+        st32[32 * (2 * B + 1) + lane] = w1;
+        B = B ? B - 1 : 9;
+      }
+    }
+    if (lane == 0) {
+      int off = off0, fpos = fpos0;
+      if (off0 >= 0 && off0 < 1280 && fpos0 >= 0 && fpos0 < 640 && (fpos0 & 63) == 0) {  // 32 steps, closed form
+        off += 1024;
+        if (off >= 1280) off -= 1280;
+        fpos += 128;
+        if (fpos >= 640) fpos -= 640;
+      } else {
+        for (int s = 0; s < 32; s++) {
+          off -= 128;
+          if (off < 0) off += 1280;
+          fpos += 64;
+          if (fpos == 640) fpos = 0;
+        }
+      }
+      p.pos[2 * u] = (int16_t)off;
+      p.pos[2 * u + 1] = (int16_t)fpos;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    u = un;
+    if (u < p.n_units) issue(u);
+  }
+}
+
+size_t qmf_synth_table_bytes() { return offsetof(SynBlockSmem, w) + 640 * 4; }
 
 // Host-side construction of the block-shared table image from the reference-layout QMF ROM blob
 // (leading bytes of ia_qmf_dec_tables_struct). Returns false if the prototype violates the no-saturation bound.
@@ -420,6 +605,12 @@ int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
     }
   for (int i = 0; i < 32; i++)
     if (t->postmap[i] < 0) return -1;
+  // the register-resident modulation (version 2) has the digit reversal compiled in and needs the 640-periodic qmf_c
+  for (int i = 0; i < 32; i++)
+    if (t->postmap[i] != (syn::post_src(i) | (i >= 16 ? 256 : 0))) return -1;
+  for (int i = 0; i < 640; i++)
+    if (c[i] != c[i + 640]) return -1;
+  memcpy(out + kSynV2CoefOffset, c, 640 * 4);
   // no-saturation bound of the window-add accumulation (see file header)
   for (int fpos = 0; fpos < 640; fpos += 64)
     for (int k = 0; k < 64; k++) {
@@ -460,7 +651,7 @@ int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
   return fast_bits;
 }
 
-cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStream_t stream) {
+static cudaError_t launch_qmf_synth_hq_pairs(const QmfSynthArgs &args, int num_sms, cudaStream_t stream) {
   static xb::PerDeviceOnce configured;
   size_t smem = sizeof(SynBlockSmem);
   if (configured.needed()) {
@@ -477,6 +668,45 @@ cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStrea
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   qmf_synth_hq_kernel<<<(unsigned)grid, kSynWarps * 32, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
+
+void qmf_synth_build_twiddles(const uint8_t *qrom, void *out) {
+  SynTw *t = reinterpret_cast<SynTw *>(out);
+  const int16_t *w32 = reinterpret_cast<const int16_t *>(qrom + kQRomW32);
+  const int16_t *sc = reinterpret_cast<const int16_t *>(qrom + kQRomSinCosL64);
+  const int16_t *al = reinterpret_cast<const int16_t *>(qrom + kQRomAltSinL64);
+  auto hi = [](int16_t v) { return (int32_t)((uint32_t)(uint16_t)v << 16); };
+  for (int n = 0; n < 32; n++) t->pre[n] = make_int2(hi(sc[2 * n]), hi(sc[2 * n + 1]));
+  for (int n = 0; n < 16; n++) t->alt[n] = make_int2(hi(al[2 * n]), hi(al[2 * n + 1]));
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 3; j++) t->w1[3 * i + j] = make_int2(hi(w32[6 * i + 2 * j]), hi(w32[6 * i + 2 * j + 1]));
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 3; j++)
+      t->w2[3 * i + j] = make_int2(hi(w32[48 + 6 * i + 2 * j]), hi(w32[48 + 6 * i + 2 * j + 1]));
+}
+size_t qmf_synth_twiddle_bytes() { return sizeof(SynTw); }
+
+cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStream_t stream) {
+  // Default: the slot-pair kernel above (1.69 ms per 131 072 units).  XAAC_B200_SYNTH_TMA=1 selects the bulk-copy-staged
+  // lane = slot variant (bit-identical, 2.09 ms: 2 warps per scheduler cannot hide its dependent chains — profiles/r2_synth_tma.md).
+  static const bool use_tma = getenv("XAAC_B200_SYNTH_TMA") != nullptr;
+  if (!use_tma) return launch_qmf_synth_hq_pairs(args, num_sms, stream);
+  // the rows are staged by 16-byte-granular bulk copies
+  if (!args.twiddles || ((uintptr_t)args.matrix & 15) != 0 || (args.mat_stride & 3) != 0) return cudaErrorInvalidValue;
+  static xb::PerDeviceOnce configured;
+  const size_t smem = sizeof(Syn2Smem);
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(qmf_synth_hq_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured.done();
+  }
+  long long need = (args.n_units + kSyn2Warps - 1) / kSyn2Warps;
+  long long grid = num_sms;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  qmf_synth_hq_tma_kernel<<<(unsigned)grid, kSyn2Warps * 32, smem, stream>>>(args, *reinterpret_cast<const SynTw *>(args.twiddles));
   return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@ struct xaac_b200_ctx {
   uint8_t *d_rom_qmf_syn = nullptr;  // table image of qmf_synth_hq_kernel
   bool have_qmf_rom = false;
   int qmf_fast_bits = 0;
+  alignas(16) uint8_t qmf_syn_tw[1024] = {0};  // twiddle image of qmf_synth_hq_kernel (kernel parameter, by value)
   uint8_t *d_rom_qmf_ana = nullptr;  // table image of qmf_anal_hq_kernel
   int qmf_anal_exact = 0;
   uint8_t *d_rom_lp = nullptr;       // table image of sbr_dec_lp_kernel (null: tables unsupported by the LP kernel)
@@ -421,6 +422,8 @@ int32_t xaac_b200_set_qmf_rom(xaac_b200_ctx *ctx, const void *tables, size_t byt
       ctx->d_rom_lp = nullptr;
     }
   }
+  if (xb::qmf_synth_twiddle_bytes() > sizeof(ctx->qmf_syn_tw)) return XAAC_B200_FATAL;
+  xb::qmf_synth_build_twiddles((const uint8_t *)tables, ctx->qmf_syn_tw);
   ctx->have_qmf_rom = true;
   ctx->qmf_fast_bits = fast_bits;
   return XAAC_B200_OK;
@@ -445,6 +448,7 @@ int32_t xaac_b200_qmf_synth_hq_dev(xaac_b200_ctx *ctx, const int32_t *d_matrix, 
   a.params = d_params;
   a.pcm = d_pcm;
   a.rom = ctx->d_rom_qmf_syn;
+  a.twiddles = ctx->qmf_syn_tw;
   a.fast_bits = ctx->qmf_fast_bits;
   a.zero = 0;
   a.n_units = n_units;
@@ -807,7 +811,7 @@ static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long lo
   ctx->launches += 6;
   xb::QmfSynthArgs y;
   y.matrix = g.matrix; y.states = s->syn_states + u0 * 1280; y.pos = s->syn_pos + u0 * 2; y.params = g.synp;
-  y.pcm = d_time_out; y.rom = ctx->d_rom_qmf_syn; y.n_units = n; y.fast_bits = ctx->qmf_fast_bits; y.zero = 0;
+  y.pcm = d_time_out; y.rom = ctx->d_rom_qmf_syn; y.twiddles = ctx->qmf_syn_tw; y.n_units = n; y.fast_bits = ctx->qmf_fast_bits; y.zero = 0;
   y.mat_stride = xb::kSbrMatWords;
   if (s->with_ps) {
     xb::PsArgs a;

@@ -125,3 +125,18 @@ def test_full_batch_properties(ctx, oracle):
     z = xb.cplx_synt_qmffilt(ctx, st0, torch.zeros((256, 32, 128), dtype=torch.int32, device="cuda"),
                              xb.synth_params(-8, -8, -8, 32, 64).expand(256, 8).contiguous().cuda())
     assert int(z.abs().max()) == 0 and int(st0.filter_states.abs().max()) == 0
+
+
+def test_tma_staged_variant_is_bit_identical():
+    """The opt-in bulk-copy-staged lane = slot kernel (XAAC_B200_SYNTH_TMA=1, read once per process) must pass this same
+    module; its arithmetic is also checked on the CPU by tests/test_synth_sim.py."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("XAAC_B200_SYNTH_TMA"):
+        pytest.skip("already running the variant")
+    env = dict(os.environ, XAAC_B200_SYNTH_TMA="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "not tma_staged_variant"], env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
