@@ -42,6 +42,10 @@ CHAIN_KERNEL_BYTES = {
     "sbr_dec_lp_kernel": 18696,
     # per channel unit (a stream = 2 units): 4096 WORD32 in + 2048 PCM16 out + 2 x 1.35 KB limiter state (220-sample window)
     "peak_limiter_kernel": 8850,
+    # streams whose attack / release recursion is active finish in two follow-up kernels; their traffic is scratch (raw and
+    # smoothed gains, 4 KB per stream each way) on top of the stage's algorithmic bytes, so no roofline figure is attached
+    "peak_limiter_smooth_kernel": None,
+    "peak_limiter_finish_kernel": None,
 }
 ESBR_ANAL_BYTES_PER_UNIT = 14848   # 4096 float in + 1280 + 1280 WORD32 ring + 8192 (32 x 32 complex float out)
 ESBR_SYNTH_BYTES_PER_UNIT = 34816  # 16384 float matrix + 5120 + 5120 WORD32 state + 8192 float out

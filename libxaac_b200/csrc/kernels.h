@@ -284,8 +284,13 @@ struct PeakLimArgs {
   int32_t *err;              // [n] or null
   long long n_units;
   int ch;
+  // deferred smoothing (set by launch_peak_limiter from the scratch block; null: everything inside the main kernel)
+  float *gbuf = nullptr;     // [n][1024] raw, then smoothed gains of the deferred streams
+  int *list = nullptr;       // [n] queued stream indices
+  int *count = nullptr;      // queue length
 };
-cudaError_t launch_peak_limiter(const PeakLimArgs &args, int num_sms, cudaStream_t stream);
+size_t peak_limiter_scratch_bytes(long long n_units);
+cudaError_t launch_peak_limiter(const PeakLimArgs &args, void *scratch, int which, int num_sms, cudaStream_t stream);
 
 // ---- eSBR 64-band synthesis bank (per-slot core of ixheaacd_esbr_synthesis_filt_block) --------------------------------
 // ROM blob: esbr_qmf_c[1280] | esbr_w_32[60] | esbr_sin_cos_twiddle_l64[64] | esbr_alt_sin_twiddle_l64[32] | esbr_w_16[24] |

@@ -13,6 +13,11 @@
 // rest and no sample of the frame exceeds the threshold (every real frame that does not clip); (5) delayed, limited
 // output, lanes = samples.  All float / double arithmetic uses the round-to-nearest intrinsics in the reference's
 // operation order (the reference build is x86-64 SSE2 without FMA), so results are bit-identical.
+// Phase (4) is one dependent chain per STREAM.  Run inside this kernel it keeps a whole warp busy with one lane's worth of
+// work (25 k of the kernel's 29 k warp instructions per stream), so streams that need it are DEFERRED when the caller
+// provides scratch memory: this kernel stores their raw gains and queues them, peak_limiter_smooth_kernel runs the
+// recursion with lane = stream (32 streams per warp, gains transposed through shared memory), and
+// peak_limiter_finish_kernel emits their output (phase 5).  Streams at rest finish here as before.
 // Algorithmic HBM bytes per stream (stereo): 8192 (WORD32 in) + 4096 (PCM16 out) + 2 x ~3 KB state.
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -21,13 +26,76 @@
 
 namespace xb {
 
-constexpr int kPlWarps = 8;
+constexpr int kPlWarps = 7;   // 71.7 KB of shared memory per block: three blocks per SM
+constexpr int kPlSmoothWarps = 4;
+constexpr int kPlFinishWarps = 8;
 
 struct PlWarpS {
   float T[1024];   // channel maximum per sample
   float G[1024];   // window maximum, then raw gain, then smoothed gain per sample
   float mb[kPlMaxAttack];  // max_buf at frame start
 };
+
+// phase 5 (:251-276) + round16 (api.c:3676-3681): delayed input x smoothed gain G[i], clamp, lanes = samples; then the
+// delay line takes the last A samples of this frame
+XB_DEV void pl_emit_frame(const PeakLimArgs &p, long long u, i32 *st, const float *G, int lane, int ch, int A, int di0,
+                          float gt0, float gt1) {
+  const i32 *in = p.samples + u * 1024 * ch;
+  float *dlg = reinterpret_cast<float *>(st + kPlDelayed);
+  i32 *out32 = p.out32 ? p.out32 + u * 1024 * ch : nullptr;
+  int16_t *pcm = p.pcm16 ? p.pcm16 + u * 1024 * ch : nullptr;
+  auto lim = [](float x, float g) {
+    const long long q = (long long)__fmul_rn(x, g);
+    return (i32)(q > 2147483647LL ? 2147483647LL : (q < -2147483647LL ? -2147483647LL : q));
+  };
+  auto emit = [&](int i, int idx) {
+    const float g = G[i];
+    if (ch == 2) {  // both channels of a sample as one 8-byte request each way
+      float x0, x1;
+      if (i < A) {
+        const float2 d = *reinterpret_cast<const float2 *>(dlg + 2 * idx);
+        x0 = d.x, x1 = d.y;
+      } else {
+        const int2 v = *reinterpret_cast<const int2 *>(in + 2 * (i - A));
+        x0 = __fmul_rn(__int2float_rn(v.x), gt0), x1 = __fmul_rn(__int2float_rn(v.y), gt1);
+      }
+      const i32 q0 = lim(x0, g), q1 = lim(x1, g);
+      if (out32) *reinterpret_cast<int2 *>(out32 + 2 * i) = make_int2(q0, q1);
+      if (pcm) *reinterpret_cast<i32 *>(pcm + 2 * i) = (round16(q0) & 0xffff) | (i32)((u32)round16(q1) << 16);
+    } else {
+      const float x = i < A ? dlg[idx] : __fmul_rn(__int2float_rn(in[i - A]), gt0);
+      const i32 q = lim(x, g);
+      if (out32) out32[i] = q;
+      if (pcm) pcm[i] = (int16_t)round16(q);
+    }
+  };
+  // samples 0 .. A-1 come out of the delay line, the others out of this frame; several requests in flight per lane
+#pragma unroll 4
+  for (int i = lane; i < A; i += 32) emit(i, (di0 + i) % A);
+#pragma unroll 4
+  for (int i = A + lane; i < 1024; i += 32) emit(i, 0);
+  __syncwarp();  // every read of the old delay line is done before it is rewritten
+#pragma unroll 1
+  for (int i = 1024 - A + lane; i < 1024; i += 32) {
+    const int idx = (di0 + i) % A;
+    for (int j = 0; j < ch; j++) dlg[idx * ch + j] = __fmul_rn(__int2float_rn(in[i * ch + j]), j ? gt1 : gt0);
+  }
+}
+
+// one step of the attack / release recursion (:230-249); returns the smoothed gain.  Branch-free: the two arms of the
+// reference's second if differ only in the smoothing constant (and the attack arm's final max), so lanes that run
+// different streams do not diverge.
+XB_DEV float pl_smooth_step(float gain, float &gm, double &psg, const double ac, const double rc) {
+  const double gd = (double)gain;
+  const float c = __fmul_rn(__fsub_rn(gain, __fmul_rn(0.1f, (float)psg)), 1.11111111f);
+  gm = gd < psg ? (gm > c ? c : gm) : gain;
+  const double gmd = (double)gm;
+  const bool attack = gmd < psg;
+  double np = __dadd_rn(__dmul_rn(attack ? ac : rc, __dsub_rn(psg, gmd)), gmd);
+  if (attack) np = np > gd ? np : gd;
+  psg = np;
+  return (float)np;
+}
 
 __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -47,7 +115,7 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
       continue;
     }
     const i32 *in = p.samples + u * 1024 * ch;
-    float *mbg = reinterpret_cast<float *>(st + kPlMaxBuf), *dlg = reinterpret_cast<float *>(st + kPlDelayed);
+    float *mbg = reinterpret_cast<float *>(st + kPlMaxBuf);
     const float ac = __int_as_float(st[kPlAttackConst]), rc = __int_as_float(st[kPlReleaseConst]);
     float gm = __int_as_float(st[kPlGainMod]);
     double psg = __hiloint2double(st[kPlPsg + 1], st[kPlPsg]);
@@ -153,7 +221,9 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
     __syncwarp();
     // ---- phase 4 (:230-249): attack / release smoothing; at rest (gain 1 everywhere) it is the identity ----
     float min_gain = 1.0f;
-    if (any_lim || psg != 1.0 || gm != 1.0f) {
+    const bool active = any_lim || psg != 1.0 || gm != 1.0f;
+    const bool defer = active && p.gbuf != nullptr;
+    if (active && !defer) {
       // 32 samples per chunk: one coalesced load, the values reach the (warp-uniform) recursion through shuffles that do not
       // depend on it, the results are collected in the owning lane and stored once — no shared-memory latency on the chain
 #pragma unroll 1
@@ -162,20 +232,7 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
        float gout = 0.0f;
 #pragma unroll
        for (int q = 0; q < 32; q++) {
-        const float gain = __shfl_sync(full, gv, q);
-        if ((double)gain < psg) {
-          const float c = __fmul_rn(__fsub_rn(gain, __fmul_rn(0.1f, (float)psg)), 1.11111111f);
-          gm = gm > c ? c : gm;
-        } else {
-          gm = gain;
-        }
-        if ((double)gm < psg) {
-          psg = __dadd_rn(__dmul_rn((double)ac, __dsub_rn(psg, (double)gm)), (double)gm);
-          psg = psg > (double)gain ? psg : (double)gain;
-        } else {
-          psg = __dadd_rn(__dmul_rn((double)rc, __dsub_rn(psg, (double)gm)), (double)gm);
-        }
-        const float go = (float)psg;
+        const float go = pl_smooth_step(__shfl_sync(full, gv, q), gm, psg, (double)ac, (double)rc);
         gout = lane == q ? go : gout;
         if (go < min_gain) min_gain = go;
        }
@@ -183,46 +240,20 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
       }
       __syncwarp();
     }
-    // ---- phase 5 (:251-276) + round16 (api.c:3676-3681): delayed input x gain, clamp, lanes = samples ----
-    i32 *out32 = p.out32 ? p.out32 + u * 1024 * ch : nullptr;
-    int16_t *pcm = p.pcm16 ? p.pcm16 + u * 1024 * ch : nullptr;
-    auto emit = [&](int i, int idx) {
-      const float g = w.G[i];
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        if (j >= ch) break;
-        float x;
-        if (i < A) x = dlg[idx * ch + j];
-        else x = __fmul_rn(__int2float_rn(in[(i - A) * ch + j]), j ? gt1 : gt0);
-        x = __fmul_rn(x, g);
-        long long q = (long long)x;
-        q = q > 2147483647LL ? 2147483647LL : (q < -2147483647LL ? -2147483647LL : q);
-        if (out32) out32[i * ch + j] = (i32)q;
-        if (pcm) pcm[i * ch + j] = (int16_t)round16((i32)q);
+    // ---- max_buf holds the channel maxima of the last A samples of this frame ----
+#pragma unroll 1
+    for (int i = 1024 - A + lane; i < 1024; i += 32) mbg[(cir0 + i) % A] = w.T[i];
+    if (defer) {  // raw gains to scratch, recursion and output in the two follow-up kernels
+#pragma unroll 4
+      for (int i = lane; i < 1024; i += 32) p.gbuf[u * 1024 + i] = w.G[i];
+      if (lane == 0) {
+        st[kPlCir] = cir;
+        st[kPlMaxIdx] = max_idx;
+        p.list[atomicAdd(p.count, 1)] = (int)u;
       }
-    };
-    int ridx = (di0 + lane) % A;
-#pragma unroll 1
-    for (int i = lane; i < 512; i += 32) {
-      emit(i, ridx);
-      ridx += 32;
-      if (ridx >= A) ridx -= A;
+      continue;
     }
-    __syncwarp();  // every read of the old delay line (i < A <= 512) is done before it is rewritten
-#pragma unroll 1
-    for (int i = 512 + lane; i < 1024; i += 32) {
-      emit(i, ridx);
-      ridx += 32;
-      if (ridx >= A) ridx -= A;
-    }
-    __syncwarp();
-    // ---- state: the delay line and max_buf hold the last A samples of this frame ----
-#pragma unroll 1
-    for (int i = 1024 - A + lane; i < 1024; i += 32) {
-      const int idx = (di0 + i) % A;
-      for (int j = 0; j < ch; j++) dlg[idx * ch + j] = __fmul_rn(__int2float_rn(in[i * ch + j]), j ? gt1 : gt0);
-      mbg[(cir0 + i) % A] = w.T[i];
-    }
+    pl_emit_frame(p, u, st, w.G, lane, ch, A, di0, gt0, gt1);
     if (lane == 0) {
       st[kPlGainMod] = __float_as_int(gm);
       st[kPlMinGain] = __float_as_int(min_gain);
@@ -236,7 +267,120 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
   }
 }
 
-cudaError_t launch_peak_limiter(const PeakLimArgs &args, int num_sms, cudaStream_t stream) {
+// Attack / release recursion of the deferred streams, lane = stream: a warp takes 32 queued streams, moves their raw gains
+// through a 32 x 32 shared-memory tile (coalesced rows in, lane-private rows out: stride 33, no bank conflicts) and walks the
+// 1024 samples once.  Results replace the raw gains in the scratch buffer; gain_modified, pre_smoothed_gain and min_gain go
+// to the state records.
+__global__ void __launch_bounds__(kPlSmoothWarps * 32) peak_limiter_smooth_kernel(PeakLimArgs p) {
+  __shared__ float tile[kPlSmoothWarps][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  const int n = *p.count;
+  const int groups = (n + 31) >> 5;
+  for (int g = blockIdx.x * kPlSmoothWarps + warp; g < groups; g += gridDim.x * kPlSmoothWarps) {
+    const int k = 32 * g + lane;
+    const bool mine = k < n;
+    const long long u = mine ? p.list[k] : -1;
+    i32 *st = mine ? p.state + u * kPlWords : nullptr;
+    float gm = 1.f, min_gain = 1.f;
+    double ac = 0.0, rc = 0.0, psg = 1.0;
+    if (mine) {
+      ac = (double)__int_as_float(st[kPlAttackConst]);
+      rc = (double)__int_as_float(st[kPlReleaseConst]);
+      gm = __int_as_float(st[kPlGainMod]);
+      psg = __hiloint2double(st[kPlPsg + 1], st[kPlPsg]);
+    }
+    float (*t)[33] = tile[warp];
+    // lane s of the shuffle = stream s of the group; its 128-byte row of the chunk is one coalesced request.  The next
+    // chunk's 32 rows are requested before the recursion of the current one starts.
+    float nx[32];
+#pragma unroll
+    for (int s = 0; s < 32; s++) {
+      const long long us = __shfl_sync(full, u, s);
+      nx[s] = us >= 0 ? p.gbuf[us * 1024 + lane] : 1.0f;
+    }
+#pragma unroll 1
+    for (int cb = 0; cb < 1024; cb += 32) {
+#pragma unroll
+      for (int s = 0; s < 32; s++) t[s][lane] = nx[s];
+      __syncwarp();
+      if (cb + 32 < 1024) {
+#pragma unroll
+        for (int s = 0; s < 32; s++) {
+          const long long us = __shfl_sync(full, u, s);
+          nx[s] = us >= 0 ? p.gbuf[us * 1024 + cb + 32 + lane] : 1.0f;
+        }
+      }
+      if (mine) {
+#pragma unroll 4
+        for (int q = 0; q < 32; q++) {
+          const float go = pl_smooth_step(t[lane][q], gm, psg, ac, rc);
+          t[lane][q] = go;
+          if (go < min_gain) min_gain = go;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < 32; s++) {
+        const long long us = __shfl_sync(full, u, s);
+        if (us >= 0) p.gbuf[us * 1024 + cb + lane] = t[s][lane];
+      }
+      __syncwarp();
+    }
+    if (mine) {
+      st[kPlGainMod] = __float_as_int(gm);
+      st[kPlMinGain] = __float_as_int(min_gain);
+      st[kPlPsg] = __double2loint(psg);
+      st[kPlPsg + 1] = __double2hiint(psg);
+    }
+  }
+}
+
+// Output of the deferred streams (phase 5) from the smoothed gains in scratch, one warp per stream.
+__global__ void __launch_bounds__(kPlFinishWarps * 32) peak_limiter_finish_kernel(PeakLimArgs p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = *p.count;
+  for (int k = blockIdx.x * kPlFinishWarps + warp; k < n; k += gridDim.x * kPlFinishWarps) {
+    const long long u = p.list[k];
+    i32 *st = p.state + u * kPlWords;
+    const int ch = p.ch, A = st[kPlAttack], di0 = st[kPlDelayIdx];
+    const float gt0 = (float)(1 << p.qshift_adj[u * ch]), gt1 = ch > 1 ? (float)(1 << p.qshift_adj[u * ch + 1]) : 0.f;
+    pl_emit_frame(p, u, st, p.gbuf + u * 1024, lane, ch, A, di0, gt0, gt1);
+    if (lane == 0) {
+      st[kPlDelayIdx] = (di0 + 1024) % A;
+      if (p.err) p.err[u] = 0;
+    }
+  }
+}
+
+size_t peak_limiter_scratch_bytes(long long n_units) { return (size_t)n_units * (4096 + 4) + 48; }
+
+// scratch (peak_limiter_scratch_bytes, 16-byte aligned) or null: with scratch, streams whose smoothing recursion is active are
+// finished by the two follow-up kernels.  which = 0 / 1 / 2 launches the main, the smoothing or the finishing kernel.
+cudaError_t launch_peak_limiter(const PeakLimArgs &args_in, void *scratch, int which, int num_sms, cudaStream_t stream) {
+  PeakLimArgs args = args_in;
+  if (scratch) {
+    args.count = reinterpret_cast<int *>(scratch);
+    args.list = args.count + 4;
+    args.gbuf = reinterpret_cast<float *>(args.list + args.n_units + (4 - (args.n_units & 3)) % 4);
+  }
+  if (which == 1) {
+    long long need = ((args.n_units + 31) / 32 + kPlSmoothWarps - 1) / kPlSmoothWarps;
+    long long grid = (long long)num_sms * 4;
+    if (grid > need) grid = need;
+    peak_limiter_smooth_kernel<<<(unsigned)(grid < 1 ? 1 : grid), kPlSmoothWarps * 32, 0, stream>>>(args);
+    return cudaGetLastError();
+  }
+  long long need = (args.n_units + kPlWarps - 1) / kPlWarps;
+  long long grid = (long long)num_sms * 3;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  if (which == 2) {  // no shared memory: 64 warps per SM
+    long long g2 = (long long)num_sms * 8, need2 = (args.n_units + kPlFinishWarps - 1) / kPlFinishWarps;
+    if (g2 > need2) g2 = need2;
+    peak_limiter_finish_kernel<<<(unsigned)(g2 < 1 ? 1 : g2), kPlFinishWarps * 32, 0, stream>>>(args);
+    return cudaGetLastError();
+  }
   static xb::PerDeviceOnce configured;
   const size_t smem = sizeof(PlWarpS) * kPlWarps;
   if (configured.needed()) {
@@ -244,10 +388,10 @@ cudaError_t launch_peak_limiter(const PeakLimArgs &args, int num_sms, cudaStream
     if (e != cudaSuccess) return e;
     configured.done();
   }
-  long long need = (args.n_units + kPlWarps - 1) / kPlWarps;
-  long long grid = (long long)num_sms * 2;
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
+  if (scratch) {
+    cudaError_t e = cudaMemsetAsync(args.count, 0, 16, stream);
+    if (e != cudaSuccess) return e;
+  }
   peak_limiter_kernel<<<(unsigned)grid, kPlWarps * 32, smem, stream>>>(args);
   return cudaGetLastError();
 }

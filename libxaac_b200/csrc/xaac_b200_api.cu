@@ -19,7 +19,8 @@ struct xaac_b200_ctx {
   uint8_t *d_rom_qmf_syn = nullptr;  // table image of qmf_synth_hq_kernel
   bool have_qmf_rom = false;
   int qmf_fast_bits = 0;
-  alignas(16) uint8_t qmf_syn_tw[1024] = {0};  // twiddle image of qmf_synth_hq_kernel (kernel parameter, by value)
+  alignas(16) uint8_t qmf_syn_tw[1024] = {0};
+  cudaMemPool_t pool = nullptr;   // stream-ordered scratch of the stages that need some (kept across calls: no release threshold)  // twiddle image of qmf_synth_hq_kernel (kernel parameter, by value)
   uint8_t *d_rom_qmf_ana = nullptr;  // table image of qmf_anal_hq_kernel
   int qmf_anal_exact = 0;
   uint8_t *d_rom_lp = nullptr;       // table image of sbr_dec_lp_kernel (null: tables unsupported by the LP kernel)
@@ -201,6 +202,7 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
     if (ctx->stage[i]) cudaFree(ctx->stage[i]);
   }
   if (ctx->d_rom_imdct) cudaFree(ctx->d_rom_imdct);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->d_rom_qmf_syn) cudaFree(ctx->d_rom_qmf_syn);
   if (ctx->d_rom_qmf_ana) cudaFree(ctx->d_rom_qmf_ana);
   if (ctx->d_rom_lp) cudaFree(ctx->d_rom_lp);
@@ -1064,8 +1066,30 @@ int32_t xaac_b200_peak_limiter_dev(xaac_b200_ctx *ctx, int32_t *d_state, const i
   a.state = d_state; a.samples = d_samples; a.qshift_adj = d_qshift_adj; a.out32 = d_out32; a.pcm16 = d_pcm16; a.err = d_err;
   a.n_units = n_units; a.ch = num_channels;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-  LAUNCH("peak_limiter_kernel", stream, xb::launch_peak_limiter(a, ctx->num_sms, (cudaStream_t)stream));
+  // Streams whose attack / release recursion is active are finished by two follow-up kernels (recursion with lane = stream);
+  // their raw gains travel through a stream-ordered scratch block (4 KB per stream).
+  void *scratch = nullptr;
+  if (n_units >= 64) {
+    if (!ctx->pool) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = ctx->device;
+      CK(cudaMemPoolCreate(&ctx->pool, &props), "cudaMemPoolCreate");
+      unsigned long long keep = ~0ull;
+      CK(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep), "cudaMemPoolSetAttribute");
+    }
+    CK(cudaMallocFromPoolAsync(&scratch, xb::peak_limiter_scratch_bytes(n_units), ctx->pool, (cudaStream_t)stream),
+       "cudaMallocFromPoolAsync");
+  }
+  LAUNCH("peak_limiter_kernel", stream, xb::launch_peak_limiter(a, scratch, 0, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
+  if (scratch) {
+    LAUNCH("peak_limiter_smooth_kernel", stream, xb::launch_peak_limiter(a, scratch, 1, ctx->num_sms, (cudaStream_t)stream));
+    LAUNCH("peak_limiter_finish_kernel", stream, xb::launch_peak_limiter(a, scratch, 2, ctx->num_sms, (cudaStream_t)stream));
+    ctx->launches += 2;
+    CK(cudaFreeAsync(scratch, (cudaStream_t)stream), "cudaFreeAsync");
+  }
   return XAAC_B200_OK;
 }
 

@@ -1,10 +1,17 @@
-for v in "" ls5x2 ls10 w8 w5x2; do
-  if [ -n "$v" ]; then export XAAC_B200_LIB=$PWD/build/var/libxaac_b200_$v.so; fi
-  timeout 300 python bench.py --workload qmf_synth_hq --steps 10 --warmup 3 --no-cpu-baseline --no-extra-stages 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('variant [$v]', d['ms_per_step'], d['roofline']['frac'])"
-done
-export XAAC_B200_LIB=$PWD/build/var/libxaac_b200_ls5x2.so
-timeout 300 python -m pytest tests/test_qmf_synth_gpu.py -x -q -m gpu 2>&1 | tail -3
-bash tools/ncu_quick.sh qmf_synth_hq_kernel gpurun_out/synth_v2_quick_c.csv -- python bench.py --workload qmf_synth_hq --steps 3 --warmup 3 --no-cpu-baseline --no-extra-stages > /dev/null 2>&1
-grep '^"0"' gpurun_out/synth_v2_quick_c.csv | awk -F'","' '{print $(NF-2), $(NF)}' | grep -v "launch__\|barrier_per\|lg_thr\|mio\|branch"
+timeout 900 python -m pytest tests/test_peaklim_gpu.py -x -q -m gpu 2>&1 | tail -2
+timeout 300 python bench.py --workload aac_lc_stereo_output --steps 10 --warmup 3 --no-cpu-baseline --no-extra-stages > gpurun_out/lcout_split_d.json 2> gpurun_out/lcout_split_d.err
+python - <<'P'
+import json
+d=json.loads(open("gpurun_out/lcout_split_d.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d.get("e2e",{}).get("value"))
+for k,v in d.get("kernels",{}).items(): print(k, round(v["launch_ms"],4), v.get("frac"))
+P
+
+python - <<'P'
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/peaklim_quick_d.csv")) if len(r)>10 and r[0].isdigit()]
+by={}
+for r in rows: by.setdefault((r[0],r[4].split("(")[0]),{})[r[-3]]=r[-1]
+for k,v in by.items():
+    print(k, {m.replace("smsp__average_warps_issue_stalled_","st_").replace("_per_issue_active.ratio",""):x for m,x in v.items() if not m.startswith("launch")})
+P
