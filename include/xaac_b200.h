@@ -835,6 +835,57 @@ int32_t xaac_b200_set_block_rom(xaac_b200_ctx *ctx, const void *block_tables, si
 int32_t xaac_b200_aac_spectral_dev(xaac_b200_ctx *ctx, int32_t *d_spec, const uint8_t *d_side, int32_t *d_pns_seed, int32_t *d_err,
                                    int64_t n_units, void *stream);
 
+/* ---- SBR side-info dequantisation --------------------------------------------------------------------
+ * Batched drop-in for ixheaacd_dec_sbrdata(hdr_ch0, hdr_ch1, frame_ch0, prev_ch0, frame_ch1, prev_ch1, common_tables, ldmps_present,
+ * audio_object_type, ec_flag) (decoder/ixheaacd_env_dec.c:628; called from ixheaacd_applysbr, decoder/ixheaacd_sbrdecoder.c:711 and
+ * :1263) on the fixed-point path: usac_flag = enh_sbr = 0 (xaacdec -esbr:0), ldmps_present = 0, ec_flag = 0, not AOT_ER_AAC_ELD.
+ * Covers ixheaacd_dec_envelope (:727: timing check, ixheaacd_lean_sbrconcealment, ixheaacd_wrong_timing_compensate, coupling-mode
+ * change, ixheaacd_process_del_cod_env_data, ixheaacd_check_env_data with its one retry, ixheaacd_dequant_env_data),
+ * ixheaacd_calc_noise_floor (:396) and ixheaacd_sbr_env_dequant_coup_fix (:516).  The FLOAT32 shadow arrays of the frame data
+ * (flt_env_sf_arr / flt_noise_floor, consumed by the eSBR branch only) are not produced.
+ * One record per element, WORD16 words: header, then one block per channel; every field is the reference field of that name.
+ * Fields marked io are rewritten in place. */
+#define XAAC_SD_NUM_CH 0          /* 1: ptr_sbr_data_ch_1 == NULL, 2: channel pair */
+#define XAAC_SD_SHARED_HDR 1      /* 1: ptr_header_data_ch_0 == ptr_header_data_ch_1 (one err_flag / err_flag_prev for both) */
+#define XAAC_SD_ERR 2             /* out: what the function returned: 0, 1 = IA_FATAL_ERROR, 2 = -1 (ixheaacd_wrong_timing_compensate) */
+#define XAAC_SD_CH 8              /* first channel block */
+#define XAAC_SD_CH_WORDS 648
+#define XAAC_SD_WORDS (XAAC_SD_CH + 2 * XAAC_SD_CH_WORDS) /* 1304 words = 2608 bytes */
+/* channel block */
+#define XAAC_SDC_NUM_SF_LO 0      /* pstr_freq_band_data->num_sf_bands[LOW] */
+#define XAAC_SDC_NUM_SF_HI 1      /*                      num_sf_bands[HIGH] */
+#define XAAC_SDC_NUM_NF 2         /*                      num_nf_bands */
+#define XAAC_SDC_NUM_TIME_SLOTS 3 /* header num_time_slots */
+#define XAAC_SDC_ERR_FLAG 4       /* io header err_flag */
+#define XAAC_SDC_ERR_FLAG_PREV 5  /* io header err_flag_prev */
+#define XAAC_SDC_HDR_AMP_RES 6    /* header amp_res */
+#define XAAC_SDC_NUM_NOISE_SFAC 7 /* out (channel 0 of a coupled pair): num_noise_sfac */
+#define XAAC_SDC_NUM_ENV 8        /* io str_frame_info_details.num_env */
+#define XAAC_SDC_NUM_NOISE_ENV 9  /* io                       .num_noise_env */
+#define XAAC_SDC_TRANSIENT_ENV 10 /* io                       .transient_env */
+#define XAAC_SDC_AMP_RES 11       /* io amp_res */
+#define XAAC_SDC_COUPLING 12      /* io coupling_mode */
+#define XAAC_SDC_NUM_ENV_SFAC 13  /* io num_env_sfac */
+#define XAAC_SDC_MAX_QMF_SB 14    /* io max_qmf_subband_aac */
+#define XAAC_SDC_FREQ_RES 16      /* io freq_res[8] */
+#define XAAC_SDC_BORDER 24        /* io border_vec[9] */
+#define XAAC_SDC_NOISE_BORDER 33  /* io noise_border_vec[3] */
+#define XAAC_SDC_DIR 36           /* io del_cod_dir_arr[8] */
+#define XAAC_SDC_DIR_NOISE 44     /* io del_cod_dir_noise_arr[2] */
+#define XAAC_SDC_INVF 46          /* io sbr_invf_mode[10] */
+#define XAAC_SDC_ADD_HARM 56      /* io add_harmonics[56] */
+#define XAAC_SDC_ENV 112          /* io int_env_sf_arr[448]: Huffman-decoded deltas in, (mantissa | exponent) words out */
+#define XAAC_SDC_NOISE 560        /* io int_noise_floor[10] */
+#define XAAC_SDC_PREV_NRG 570     /* io prev sfb_nrg_prev[56] */
+#define XAAC_SDC_PREV_NOISE 626   /* io prev prev_noise_level[5] */
+#define XAAC_SDC_PREV_AMP_RES 631 /* prev amp_res */
+#define XAAC_SDC_PREV_END_POS 632 /* prev end_position */
+#define XAAC_SDC_PREV_MAX_QMF 633 /* prev max_qmf_subband_aac */
+#define XAAC_SDC_PREV_COUPLING 634 /* prev coupling_mode */
+#define XAAC_SDC_PREV_INVF 635    /* prev sbr_invf_mode[10] */
+/* d_records [n][XAAC_SD_WORDS] in/out.  Needs xaac_b200_set_env_rom (the misc tables: log_dual_is_table, inv_table).  One launch. */
+int32_t xaac_b200_dec_sbrdata_dev(xaac_b200_ctx *ctx, int16_t *d_records, int64_t n_elements, void *stream);
+
 /* ---- raw device-memory helpers for C hosts that do not link the CUDA runtime themselves (the reference-side drop-in glue,
  * libxaac_b200/dropin/ixheaacd_b200_glue.c): allocation and synchronous copies on the context's device ---- */
 int32_t xaac_b200_dev_alloc(xaac_b200_ctx *ctx, size_t bytes, void **d_ptr);

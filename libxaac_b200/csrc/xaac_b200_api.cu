@@ -1093,6 +1093,20 @@ int32_t xaac_b200_peak_limiter_dev(xaac_b200_ctx *ctx, int32_t *d_state, const i
   return XAAC_B200_OK;
 }
 
+int32_t xaac_b200_dec_sbrdata_dev(xaac_b200_ctx *ctx, int16_t *d_records, int64_t n_elements, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (!ctx->have_env_rom || !ctx->d_rom_misc) {
+    snprintf(ctx->err, sizeof(ctx->err), "xaac_b200_set_env_rom has not been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (n_elements < 0) return bad_arg(ctx, "n_elements");
+  if (n_elements == 0) return XAAC_B200_OK;
+  if (!d_records || ((uintptr_t)d_records & 15) != 0) return bad_arg(ctx, "records: null or not 16-byte aligned");
+  LAUNCH("sbr_sideinfo_kernel", stream, xb::launch_sbr_sideinfo(d_records, n_elements, ctx->d_rom_misc, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
 int32_t xaac_b200_set_esbr_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
   if (!ctx || !tables) return bad_arg(ctx, "null");
   if (bytes < (size_t)xb::kEsRomBytes) return bad_arg(ctx, "eSBR ROM blob shorter than 6288 bytes");

@@ -376,6 +376,12 @@ class Ref:
         self.lib.ref_cos_sin_mod(P(sb), int(no_channels))
         return sb
 
+    def dec_sbrdata_batch(self, records):
+        """XAAC_SD_* records through the compiled ixheaacd_dec_sbrdata (oracle/ref_shim_sd.c); returns the rewritten records"""
+        r = np.ascontiguousarray(records, np.int16).copy()
+        self.lib.ref_dec_sbrdata_batch(ctypes.c_int64(r.shape[0]), P(r))
+        return r
+
     def synth(self, matrix, filter_states, pos, params, ch_fac=1):
         """single unit through ixheaacd_cplx_synt_qmffilt"""
         m = np.ascontiguousarray(matrix, np.int32).copy()
@@ -1365,3 +1371,94 @@ def ref_channel_pair_process(ref, spec, rec, seed=None):
     ref.lib.ref_channel_pair_process_batch.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 4
     ref.lib.ref_channel_pair_process_batch(len(rec), P(s), P(np.ascontiguousarray(rec, np.uint8)), P(sd), P(err))
     return (s, err) if seed is None else (s, err, sd)
+
+
+# ---- SBR side-info dequantisation (ixheaacd_dec_sbrdata) ---------------------------------------------------------------
+SD_WORDS, SD_CH, SD_CH_WORDS = 1304, 8, 648
+SDC = dict(NUM_SF_LO=0, NUM_SF_HI=1, NUM_NF=2, NUM_TIME_SLOTS=3, ERR_FLAG=4, ERR_FLAG_PREV=5, HDR_AMP_RES=6, NUM_NOISE_SFAC=7,
+           NUM_ENV=8, NUM_NOISE_ENV=9, TRANSIENT_ENV=10, AMP_RES=11, COUPLING=12, NUM_ENV_SFAC=13, MAX_QMF_SB=14, FREQ_RES=16,
+           BORDER=24, NOISE_BORDER=33, DIR=36, DIR_NOISE=44, INVF=46, ADD_HARM=56, ENV=112, NOISE=560, PREV_NRG=570,
+           PREV_NOISE=626, PREV_AMP_RES=631, PREV_END_POS=632, PREV_MAX_QMF=633, PREV_COUPLING=634, PREV_INVF=635)
+
+
+def synth_sbrdata_records(n, seed):
+    """Seeded XAAC_SD_* records (include/xaac_b200.h) as the SBR payload parser leaves them before ixheaacd_dec_sbrdata: valid
+    frame grids and band counts, delta-coded envelope / noise indices in both directions and resolutions, mono elements, plain
+    and coupled pairs with own or shared headers; a fraction of the elements has a timing mismatch against the previous frame
+    (concealment / timing compensation / coupling-mode change), raised error flags, or values that fail the range check (retry
+    through the concealment)."""
+    rng = np.random.default_rng(seed)
+    rec = np.zeros((n, SD_WORDS), np.int16)
+    for u in range(n):
+        two = rng.random() < 0.6
+        shared = two and rng.random() < 0.5
+        coupled = two and rng.random() < 0.5
+        rec[u, 0] = 2 if two else 1
+        rec[u, 1] = 1 if shared else 0
+        nlo = int(rng.integers(3, 25))
+        kind = rng.random()
+        nhi = 2 * nlo - int(rng.integers(0, 2)) if kind < 0.6 else int(rng.integers(nlo, min(3 * nlo, 56) + 1))
+        nhi = max(min(nhi, 56), nlo)
+        nnf = int(rng.integers(1, 6))
+        hamp = int(rng.integers(0, 2))
+        mismatch = rng.random()
+        for c in range(2 if two else 1):
+            b = rec[u, SD_CH + c * SD_CH_WORDS: SD_CH + (c + 1) * SD_CH_WORDS]
+            b[SDC["NUM_SF_LO"]], b[SDC["NUM_SF_HI"]], b[SDC["NUM_NF"]], b[SDC["NUM_TIME_SLOTS"]] = nlo, nhi, nnf, 16
+            b[SDC["HDR_AMP_RES"]] = hamp
+            if rng.random() < 0.08:
+                b[SDC["ERR_FLAG"]] = 1
+            if rng.random() < 0.08:
+                b[SDC["ERR_FLAG_PREV"]] = 1
+            nenv = int(rng.integers(1, 6))
+            cuts = np.sort(rng.choice(np.arange(1, 16), nenv - 1, replace=False)) if nenv > 1 else np.array([], int)
+            start = int(rng.integers(0, 3))
+            border = np.concatenate([[start], np.maximum(cuts, start + 1), [16]])
+            border = np.maximum.accumulate(border)
+            b[SDC["NUM_ENV"]] = nenv
+            b[SDC["BORDER"]: SDC["BORDER"] + nenv + 1] = border
+            nne = 2 if (nenv > 1 and rng.random() < 0.6) else 1
+            b[SDC["NUM_NOISE_ENV"]] = nne
+            b[SDC["NOISE_BORDER"]] = start
+            b[SDC["NOISE_BORDER"] + 1] = border[nenv // 2] if nne == 2 else 16
+            b[SDC["NOISE_BORDER"] + 2] = 16 if nne == 2 else 0
+            b[SDC["TRANSIENT_ENV"]] = int(rng.integers(-1, nenv))
+            amp = int(rng.integers(0, 2))
+            b[SDC["AMP_RES"]] = amp
+            b[SDC["COUPLING"]] = (1 if c == 0 else 2) if coupled else 0
+            fres = rng.integers(0, 2, 8)
+            b[SDC["FREQ_RES"]: SDC["FREQ_RES"] + 8] = fres
+            dirs = rng.integers(0, 2, 8)
+            b[SDC["DIR"]: SDC["DIR"] + 8] = dirs
+            b[SDC["DIR_NOISE"]: SDC["DIR_NOISE"] + 2] = rng.integers(0, 2, 2)
+            b[SDC["INVF"]: SDC["INVF"] + 10] = rng.integers(0, 4, 10)
+            b[SDC["ADD_HARM"]: SDC["ADD_HARM"] + 56] = rng.integers(0, 2, 56)
+            b[SDC["MAX_QMF_SB"]] = int(rng.integers(8, 33))
+            off = 0
+            big = rng.random() < 0.06
+            for i in range(nenv):
+                nsb = nhi if fres[i] else nlo
+                if dirs[i] == 0:
+                    d = rng.integers(-5, 6, nsb)
+                    d[0] = rng.integers(0, 45 >> amp)
+                else:
+                    d = rng.integers(-3, 4, nsb)
+                if big and i == nenv - 1:
+                    d[int(rng.integers(0, nsb))] += 90
+                b[SDC["ENV"] + off: SDC["ENV"] + off + nsb] = d
+                off += nsb
+            b[SDC["NUM_ENV_SFAC"]] = off
+            nf = rng.integers(-3, 4, 10)
+            nf[0] = rng.integers(0, 30)
+            nf[nnf] = rng.integers(0, 30)
+            b[SDC["NOISE"]: SDC["NOISE"] + 10] = nf
+            b[SDC["NUM_NOISE_SFAC"]] = int(rng.integers(0, 11))
+            b[SDC["PREV_NRG"]: SDC["PREV_NRG"] + 56] = rng.integers(-2, 60 >> amp, 56)
+            b[SDC["PREV_NOISE"]: SDC["PREV_NOISE"] + 5] = rng.integers(0, 31, 5)
+            b[SDC["PREV_AMP_RES"]] = int(rng.integers(0, 2))
+            b[SDC["PREV_END_POS"]] = 16 + start + (0 if mismatch > 0.25 else int(rng.integers(-1, 3)))
+            b[SDC["PREV_MAX_QMF"]] = int(rng.integers(8, 33))
+            # a mono element has no second channel to take energies from: its previous coupling mode is always off
+            b[SDC["PREV_COUPLING"]] = b[SDC["COUPLING"]] if (rng.random() < 0.8 or not two) else int(rng.integers(0, 3))
+            b[SDC["PREV_INVF"]: SDC["PREV_INVF"] + 10] = rng.integers(0, 4, 10)
+    return rec
