@@ -38,11 +38,11 @@ REF        ?= /root/reference
 DROPIN     := libxaac_b200/dropin
 DROPIN_OUT := $(DROPIN)/_build
 DROPIN_WRAPS := -Wl,--wrap=ixheaacd_imdct_process -Wl,--wrap=ixheaacd_sbr_dec -Wl,--wrap=ixheaacd_fd_frm_dec \
-                -Wl,--wrap=ixheaacd_channel_pair_process
+                -Wl,--wrap=ixheaacd_channel_pair_process -Wl,--wrap=ixheaacd_dec_sbrdata
 DROPIN_FLAGS := -std=gnu99 -D_X86_ -DX86_64 -D_X86_64_ -DLOUDNESS_LEVELING_SUPPORT -O2 -fwrapv -w \
                 -UARM_PROFILE_HW -UARM_PROFILE_BOARD -DDRC_ENABLE -DMULTICHANNEL_ENABLE -DECLIPSE -DWIN32
 dropin: $(DROPIN_OUT)/xaacdec_b200
-$(DROPIN_OUT)/xaacdec_b200: $(LIB) $(DROPIN)/ixheaacd_b200_glue.c $(DROPIN)/ixheaacd_b200_pack.h $(DROPIN)/ixheaacd_b200_pack_ps_flt.h $(DROPIN)/ixheaacd_b200_pack_spec.h $(DROPIN)/ixheaacd_b200_ref_headers.h include/xaac_b200.h oracle/_ref/libxaacdec.a
+$(DROPIN_OUT)/xaacdec_b200: $(LIB) $(DROPIN)/ixheaacd_b200_glue.c $(DROPIN)/ixheaacd_b200_pack.h $(DROPIN)/ixheaacd_b200_pack_ps_flt.h $(DROPIN)/ixheaacd_b200_pack_spec.h $(DROPIN)/ixheaacd_b200_pack_sd.h $(DROPIN)/ixheaacd_b200_ref_headers.h include/xaac_b200.h oracle/_ref/libxaacdec.a
 	@mkdir -p $(DROPIN_OUT)
 	gcc $(DROPIN_FLAGS) -I$(REF)/common -I$(REF)/decoder -I$(REF)/decoder/drc_src -I$(REF)/test/decoder -I$(DROPIN) -Iinclude \
 	    -o $@ $(wildcard $(REF)/test/decoder/*.c) $(DROPIN)/ixheaacd_b200_glue.c $(DROPIN_WRAPS) oracle/_ref/libxaacdec.a \

@@ -25,6 +25,7 @@
 #include "ixheaacd_b200_pack.h"
 #include "ixheaacd_b200_pack_ps_flt.h"
 #include "ixheaacd_b200_pack_spec.h"
+#include "ixheaacd_b200_pack_sd.h"
 #include "ixheaacd_audioobjtypes.h"
 #include "ixheaacd_interface.h"
 #include "ixheaacd_tns_usac.h"
@@ -79,6 +80,10 @@ static struct {
   uint8_t *d_sps;
   int32_t *d_sps_spec, *d_sps_seed;
   long n_cpp, n_cpp_ref, n_cpp_ms, n_cpp_tns, n_cpp_pns;
+  /* SBR side-info dequantisation */
+  int16_t *d_sd;
+  int have_sd_rom;
+  long n_sd, n_sd_ref, n_sd_coupled, n_sd_concealed;
   int32_t last_err[6];
   long n_imdct, n_imdct_ref, n_sbr_hq, n_sbr_ps, n_sbr_lp, n_sbr_ref, n_fd, n_fd_ref, n_esbr, n_esbr_hbe, n_esbr_ref;
 } G;
@@ -94,6 +99,9 @@ static void b200_report(void) {
   if (G.stats)
     fprintf(stderr, "[ixheaacd_b200] channel_pair_process: %ld on the GPU (%ld with M/S or intensity bands, %ld with TNS, %ld with PNS), %ld by the "
             "reference\n", G.n_cpp, G.n_cpp_ms, G.n_cpp_tns, G.n_cpp_pns, G.n_cpp_ref);
+  if (G.stats)
+    fprintf(stderr, "[ixheaacd_b200] dec_sbrdata: %ld on the GPU (%ld coupled pairs, %ld with a concealed channel), %ld by the reference\n",
+            G.n_sd, G.n_sd_coupled, G.n_sd_concealed, G.n_sd_ref);
   if (G.ctx) xaac_b200_destroy(G.ctx);
   G.ctx = NULL;
 }
@@ -873,6 +881,45 @@ IA_ERRORCODE __wrap_ixheaacd_channel_pair_process(ia_aac_dec_channel_info_struct
   G.n_cpp_ref++;
   return __real_ixheaacd_channel_pair_process(ptr_aac_dec_channel_info, num_ch, ptr_aac_tables, total_channels, object_type,
                                               aac_spect_data_resil_flag, aac_sf_data_resil_flag, in_data, out_data, self_ptr);
+}
+
+/* ================================ ixheaacd_dec_sbrdata ================================ */
+IA_ERRORCODE __real_ixheaacd_dec_sbrdata(ia_sbr_header_data_struct *, ia_sbr_header_data_struct *, ia_sbr_frame_info_data_struct *,
+                                         ia_sbr_prev_frame_data_struct *, ia_sbr_frame_info_data_struct *,
+                                         ia_sbr_prev_frame_data_struct *, ixheaacd_misc_tables *, WORD32, WORD32, WORD32);
+/* decoder/ixheaacd_env_dec.c:628 (called from ixheaacd_applysbr, decoder/ixheaacd_sbrdecoder.c:711, :1263): the fixed-point path
+ * (xaacdec -esbr:0) runs on the GPU; USAC / enh_sbr frames keep the reference's float dequantisation (libm pow). */
+IA_ERRORCODE __wrap_ixheaacd_dec_sbrdata(ia_sbr_header_data_struct *ptr_header_data_ch_0, ia_sbr_header_data_struct *ptr_header_data_ch_1,
+                                         ia_sbr_frame_info_data_struct *ptr_sbr_data_ch_0,
+                                         ia_sbr_prev_frame_data_struct *ptr_prev_data_ch_0,
+                                         ia_sbr_frame_info_data_struct *ptr_sbr_data_ch_1,
+                                         ia_sbr_prev_frame_data_struct *ptr_prev_data_ch_1, ixheaacd_misc_tables *ptr_common_tables,
+                                         WORD32 ldmps_present, WORD32 audio_object_type, WORD32 ec_flag) {
+  xaac_b200_ctx *c = b200_ctx();
+  static int16_t rec[XAAC_SD_WORDS];
+  if (c && !G.have_sd_rom) { /* the first call comes before the first ixheaacd_sbr_dec: the misc tables go to the device here */
+    B200(xaac_b200_set_env_rom(c, &ixheaacd_aac_dec_env_calc_tables, 2404, ptr_common_tables, 2470), "set_env_rom");
+    G.have_sd_rom = 1;
+  }
+  if (c &&
+      b200_sd_pack(rec, ptr_header_data_ch_0, ptr_header_data_ch_1, ptr_sbr_data_ch_0, ptr_prev_data_ch_0, ptr_sbr_data_ch_1,
+                   ptr_prev_data_ch_1, ldmps_present, audio_object_type, ec_flag) == 0) {
+    const int was_err = ptr_header_data_ch_0->err_flag || (ptr_sbr_data_ch_1 && ptr_header_data_ch_1->err_flag);
+    if (!G.d_sd) B200(xaac_b200_dev_alloc(c, sizeof(rec), (void **)&G.d_sd), "alloc");
+    B200(xaac_b200_h2d(c, G.d_sd, rec, sizeof(rec)), "h2d sbrdata");
+    B200(xaac_b200_dec_sbrdata_dev(c, G.d_sd, 1, NULL), "dec_sbrdata_dev");
+    B200(xaac_b200_d2h(c, rec, G.d_sd, sizeof(rec)), "d2h sbrdata");
+    b200_sd_unpack(rec, ptr_header_data_ch_0, ptr_header_data_ch_1, ptr_sbr_data_ch_0, ptr_prev_data_ch_0, ptr_sbr_data_ch_1,
+                   ptr_prev_data_ch_1);
+    G.n_sd++;
+    G.n_sd_coupled += ptr_sbr_data_ch_1 && ptr_sbr_data_ch_0->coupling_mode;
+    G.n_sd_concealed += !was_err && (ptr_header_data_ch_0->err_flag || (ptr_sbr_data_ch_1 && ptr_header_data_ch_1->err_flag));
+    return rec[XAAC_SD_ERR] == 0 ? IA_NO_ERROR : (rec[XAAC_SD_ERR] == 2 ? (IA_ERRORCODE)-1 : (IA_ERRORCODE)IA_FATAL_ERROR);
+  }
+  G.n_sd_ref++;
+  return __real_ixheaacd_dec_sbrdata(ptr_header_data_ch_0, ptr_header_data_ch_1, ptr_sbr_data_ch_0, ptr_prev_data_ch_0,
+                                     ptr_sbr_data_ch_1, ptr_prev_data_ch_1, ptr_common_tables, ldmps_present, audio_object_type,
+                                     ec_flag);
 }
 
 /* ================================ ixheaacd_fd_frm_dec ================================ */

@@ -81,6 +81,12 @@ def test_whole_file_through_reference_parser(tmp_path, name, enc, fs, ch, secs, 
     assert cpp >= 3000 and cpp_ref == 0 and cpp_tns >= 50, m2.group(0)
     if name in ("aac_lc_stereo", "heaac_v1_stereo"):
         assert cpp_ms >= 2000, m2.group(0)
+    # ... and so did the SBR side-info dequantisation (ixheaacd_dec_sbrdata) of every SBR frame
+    m3 = re.search(r"dec_sbrdata: (\d+) on the GPU \((\d+) coupled pairs, (\d+) with a concealed channel\), (\d+) by the reference", log)
+    assert m3, log[-600:]
+    sd, sd_coupled, sd_conc, sd_ref = map(int, m3.groups())
+    if name != "aac_lc_stereo":
+        assert sd >= 2900 and sd_ref == 0, m3.group(0)
 
 
 @pytest.mark.parametrize("name,extra", [("usac", []), ("usac_hbe", ["-harmonic_sbr:1"])])

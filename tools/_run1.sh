@@ -1,2 +1,1 @@
-timeout 900 python -m pytest tests/test_sbr_sideinfo_gpu.py -x -q -m gpu > gpurun_out/sd_test.log 2>&1
-head -60 gpurun_out/sd_test.log
+timeout 1500 python -m pytest tests/test_dropin_gpu.py -x -q -m gpu 2>&1 | tail -12
