@@ -75,6 +75,8 @@ WORKLOADS = {
                                      "frames: the float eSBR stage of the mono + PS element (harmonic transposer forced on for "
                                      "legacy streams) with the float parametric stereo -> float stereo output; the AAC-LC core "
                                      "IMDCT of the chain is not part of this workload (aac_lc_stereo_imdct_ola measures it)"),
+    "sbr_sideinfo": (3, 131072, "HE-AAC (SBR) batch=131072 elements: SBR side-info dequantisation of the chain (ixheaacd_dec_sbrdata, "
+                                "fixed-point path): envelope / noise-floor delta decoding, concealment, dequantisation, coupling"),
     "aac_lc_spectral": (1, 65536, "AAC-LC stereo 44.1 kHz batch=65536 frames: the pre-IMDCT spectral stage of the chain "
                                   "(ixheaacd_channel_pair_process: M/S and intensity stereo, perceptual noise substitution, TNS) on "
                                   "channel pairs, in place"),
@@ -862,6 +864,52 @@ def cpu_arm_aac_spectral(n_units, threads, seed, reps=1, min_seconds=0.0):
     return 2.0 * n * done / dt, "reference"
 
 
+def sideinfo_records(n, seed):
+    """seeded XAAC_SD_* records (tests/oracle_util.synth_sbrdata_records): 4096 distinct elements tiled over the batch"""
+    from tests import oracle_util as ou
+    k = min(n, 4096)
+    rec = ou.synth_sbrdata_records(k, seed)
+    return rec[np.arange(n) % k]
+
+
+def cpu_arm_sbr_sideinfo(n_units, threads, seed, reps=1, min_seconds=0.0):
+    """Time ixheaacd_dec_sbrdata per element on host threads (ref_dec_sbrdata_batch, oracle/ref_shim_sd.c: record -> reference
+    structs -> the compiled function -> record; the struct rebuild is part of the measured time and stated in `sample`).
+    n_units counts elements; like the other arms with units_per_frame = 1 the return value is 2 x elements/s."""
+    from tests import oracle_util as ou
+    ref = ou.Ref.try_load()
+    if ref is None:
+        raise SystemExit("bench.py: the side-info CPU baseline needs oracle/_ref/libxaac_ref.so (make ref)")
+    P = ou.P
+    n = max(threads, n_units)
+    rec0 = np.ascontiguousarray(sideinfo_records(n, seed))
+    bounds = np.linspace(0, n, threads + 1).astype(int)
+    ref.lib.ref_dec_sbrdata_batch.argtypes = [ctypes.c_int64, ctypes.c_void_p]
+
+    def one_pass():
+        rec = rec0.copy()
+
+        def work(t):
+            a, b = int(bounds[t]), int(bounds[t + 1])
+            if b > a:
+                ref.lib.ref_dec_sbrdata_batch(b - a, P(rec[a:]))
+
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    one_pass()
+    dt, done = 0.0, 0
+    while done < reps or dt < min_seconds:
+        dt += one_pass()
+        done += 1
+    return 2.0 * n * done / dt, "reference"
+
+
 def cpu_arm_heaacv2_esbr_chain(n_units, threads, seed, reps=1, min_seconds=0.0):
     """Time the reference's eSBR stage of mono + PS elements (harmonic transposer + float PS, two synthesis banks) per element on
     host threads (ref_heaacv2_esbr_chain_batch, oracle/ref_shim_fps.c).  n_units counts elements (stream-frames) and, like the
@@ -1144,6 +1192,12 @@ STAGES = {
                                   "launches timed as one unit",
                             ref_stage="ixheaacd_channel_pair_process", cpu=cpu_arm_aac_spectral, cpu_units_per_core=4096,
                             realtime_fps=43.066, h2d=2 * 4096 + 3712 + 4, d2h=2 * 4096 + 4, dtype="int32"),
+    "sbr_sideinfo": dict(kernel="sbr_sideinfo_kernel", bytes_per_unit=2 * 2608, units_per_frame=1,
+                         stage="warp per element: frequency-direction delta decoding as a warp prefix sum, time direction and "
+                               "low -> high resolution mapping per band, concealment / timing compensation / range-check retry, "
+                               "(mantissa | exponent) dequantisation, noise floor, coupled-pair conversion (bit-exact)",
+                         ref_stage="ixheaacd_dec_sbrdata", cpu=cpu_arm_sbr_sideinfo, cpu_units_per_core=8192,
+                         realtime_fps=21.533, h2d=2608, d2h=2608, dtype="int16"),
     "esbr_hbe": dict(kernel="esbr_hbe_kernel", bytes_per_unit=None,
                      stage="QMF harmonic transposer: critically sampled real synthesis bank, 2x complex analysis bank, stretch-2/3/4 "
                            "products with pitch cross products, phase rotation (bit-exact floats)",
@@ -1630,6 +1684,37 @@ class SpectralWork:
         self.xb.aac_channel_pair_process(self.ctx, self.spec, self.rec, pns_seed=self.seed, err=self.err)
         self.h_out.copy_(self.spec, non_blocking=True)
         self.h_seed.copy_(self.seed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def host_close(self):
+        pass
+
+
+class SideinfoWork:
+    """SBR elements through the side-info dequantisation; every step starts from the same parsed records (the stage rewrites
+    them in place), restored by a device copy outside the kernel's own time but inside the step."""
+
+    def __init__(self, xb, ctx, n_units, steps_total, seed, dev):
+        import torch
+        self.xb, self.ctx, self.n = xb, ctx, n_units
+        self.rec0 = torch.from_numpy(np.ascontiguousarray(sideinfo_records(n_units, seed))).to(dev)
+        self.rec = self.rec0.clone()
+
+    def step(self, i, stream):
+        self.xb.dec_sbrdata(self.ctx, self.rec, stream=stream)
+
+    def check(self):
+        assert int((self.rec[:, 2] != 0).sum().item()) < self.n // 4
+
+    def host_setup(self):
+        self.h_rec = self.rec0.cpu().pin_memory()
+        self.h_out = self.h_rec.clone().pin_memory()
+
+    def host_step(self, i):
+        import torch
+        self.rec.copy_(self.h_rec, non_blocking=True)
+        self.xb.dec_sbrdata(self.ctx, self.rec)
+        self.h_out.copy_(self.rec, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     def host_close(self):
@@ -2196,7 +2281,7 @@ WORK = {"aac_lc_stereo_imdct_ola": ImdctWork, "qmf_synth_hq": SynthWork, "heaacv
         "aac_lc_stereo_output": LcOutputWork, "esbr_synth64": EsbrSynthWork,
         "esbr_anal32": EsbrAnalWork, "esbr_generate_hf": EsbrHfgenWork,
         "esbr_env_calc": EsbrEnvcalcWork, "xheaac_stereo_chain": XheaacHbeChainWork, "esbr_hbe": EsbrHbeWork,
-        "xheaac_plain_stereo_chain": XheaacChainWork, "heaacv2_esbr_chain": Heaacv2EsbrChainWork, "aac_lc_spectral": SpectralWork}
+        "xheaac_plain_stereo_chain": XheaacChainWork, "heaacv2_esbr_chain": Heaacv2EsbrChainWork, "aac_lc_spectral": SpectralWork, "sbr_sideinfo": SideinfoWork}
 
 
 def main():
