@@ -38,7 +38,7 @@ REF        ?= /root/reference
 DROPIN     := libxaac_b200/dropin
 DROPIN_OUT := $(DROPIN)/_build
 DROPIN_WRAPS := -Wl,--wrap=ixheaacd_imdct_process -Wl,--wrap=ixheaacd_sbr_dec -Wl,--wrap=ixheaacd_fd_frm_dec \
-                -Wl,--wrap=ixheaacd_channel_pair_process -Wl,--wrap=ixheaacd_dec_sbrdata
+                -Wl,--wrap=ixheaacd_channel_pair_process -Wl,--wrap=ixheaacd_dec_sbrdata -Wl,--wrap=ixheaacd_decode_ps_data
 DROPIN_FLAGS := -std=gnu99 -D_X86_ -DX86_64 -D_X86_64_ -DLOUDNESS_LEVELING_SUPPORT -O2 -fwrapv -w \
                 -UARM_PROFILE_HW -UARM_PROFILE_BOARD -DDRC_ENABLE -DMULTICHANNEL_ENABLE -DECLIPSE -DWIN32
 dropin: $(DROPIN_OUT)/xaacdec_b200

@@ -886,6 +886,31 @@ int32_t xaac_b200_aac_spectral_dev(xaac_b200_ctx *ctx, int32_t *d_spec, const ui
 /* d_records [n][XAAC_SD_WORDS] in/out.  Needs xaac_b200_set_env_rom (the misc tables: log_dual_is_table, inv_table).  One launch. */
 int32_t xaac_b200_dec_sbrdata_dev(xaac_b200_ctx *ctx, int16_t *d_records, int64_t n_elements, void *stream);
 
+/* PS side info: batched drop-in for ixheaacd_decode_ps_data(ia_ps_dec_struct *, frame_size) (decoder/ixheaacd_ps_bitdec.c:98; called
+ * from ixheaacd_applysbr, decoder/ixheaacd_sbrdecoder.c:723): time / frequency delta decoding of the IID and ICC indices with their
+ * clamps, 10 -> 20 band expansion, the "no data" and variable-border envelope fix-ups, ixheaacd_map_34_params_to_20
+ * (decoder/ixheaacd_sbrdec_lpfuncs.c:561).  One record per PS instance, WORD16 words, every field the ia_ps_dec_struct member of
+ * that name (decoder/ixheaacd_ps_dec.h:137-159). */
+#define XAAC_PSD_DATA_PRESENT 0   /* io ps_data_present (cleared) */
+#define XAAC_PSD_ENABLE_IID 1
+#define XAAC_PSD_ENABLE_ICC 2
+#define XAAC_PSD_IID_MODE 3       /* 0 / 1 / 2: 10 / 20 / 34 bands */
+#define XAAC_PSD_ICC_MODE 4
+#define XAAC_PSD_IID_QUANT 5
+#define XAAC_PSD_FRAME_CLASS 6
+#define XAAC_PSD_NUM_ENV 7        /* io */
+#define XAAC_PSD_FRAME_SIZE 8     /* 1024 or 960 (the function's second argument) */
+#define XAAC_PSD_BORDER 9         /* io border_position[7] */
+#define XAAC_PSD_IID_DT 16        /* iid_dt[5] */
+#define XAAC_PSD_ICC_DT 21        /* icc_dt[5] */
+#define XAAC_PSD_IID_TABLE 32     /* io iid_par_table[7][34] */
+#define XAAC_PSD_ICC_TABLE 270    /* io icc_par_table[7][34] */
+#define XAAC_PSD_IID_PREV 508     /* io iid_par_prev[34] */
+#define XAAC_PSD_ICC_PREV 542     /* io icc_par_prev[34] */
+#define XAAC_PSD_WORDS 576        /* 1152 bytes */
+/* d_records [n][XAAC_PSD_WORDS] in/out, 16-byte aligned.  One launch; needs no tables. */
+int32_t xaac_b200_decode_ps_data_dev(xaac_b200_ctx *ctx, int16_t *d_records, int64_t n_units, void *stream);
+
 /* ---- raw device-memory helpers for C hosts that do not link the CUDA runtime themselves (the reference-side drop-in glue,
  * libxaac_b200/dropin/ixheaacd_b200_glue.c): allocation and synchronous copies on the context's device ---- */
 int32_t xaac_b200_dev_alloc(xaac_b200_ctx *ctx, size_t bytes, void **d_ptr);

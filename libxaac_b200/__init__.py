@@ -29,13 +29,14 @@ from .output import PeakLimiterBatch, peak_limiter_process, peak_limiter_reset_s
 from .esbr import (EsbrAnalBatch, EsbrDecBatch, EsbrDecHbeBatch, EsbrHbeBatch, EsbrSynthBatch, esbr_analysis_filt_block, esbr_dec,  # noqa: F401
                    esbr_dec_hbe, esbr_dec_ps, esbr_apply_ps, EsbrDecPsBatch, esbr_dec_front, esbr_dec_back, esbr_dec_bypass, esbr_env_calc, esbr_generate_hf, esbr_qmf_hbe_apply, esbr_synthesis_filt)
 from .spectral import aac_channel_pair_process  # noqa: F401
-from .sideinfo import SD_WORDS, dec_sbrdata  # noqa: F401
+from .sideinfo import PSD_WORDS, SD_WORDS, dec_sbrdata, decode_ps_data  # noqa: F401
 from .usac import STOP_START_SEQUENCE, UsacFdBatch, usac_fd_frm_dec  # noqa: F401
 from .sbr import SbrState, calc_sbrenvelope, heaac_frame_host, heaac_lp_frame_host, hf_generator, sbr_dec, sbr_dec_lp  # noqa: F401
 
 __all__ = [
     "aac_channel_pair_process",
     "dec_sbrdata",
+    "decode_ps_data",
     "hf_generator",
     "calc_sbrenvelope",
     "SbrState",

@@ -83,6 +83,7 @@ SIGNATURES = {
     "xaac_b200_set_block_rom": (_i32, [_vp, _vp, _sz]),
     "xaac_b200_aac_spectral_dev": (_i32, [_vp] * 5 + [_i64, _vp]),
     "xaac_b200_dec_sbrdata_dev": (_i32, [_vp, _vp, _i64, _vp]),
+    "xaac_b200_decode_ps_data_dev": (_i32, [_vp, _vp, _i64, _vp]),
     "xaac_b200_esbr_ps_apply_dev": (_i32, [_vp] * 3 + [_i32] + [_vp] * 8 + [_i64, _vp]),
     "xaac_b200_esbr_dec_ps_dev": (_i32, [_vp] * 14 + [_i64, _vp]),
     "xaac_b200_esbr_dec_front_dev": (_i32, [_vp] * 7 + [_i64, _vp]),

@@ -294,6 +294,7 @@ cudaError_t launch_peak_limiter(const PeakLimArgs &args, void *scratch, int whic
 
 // ---- SBR side-info dequantisation (sbr_sideinfo_kernel.cu): records [n][XAAC_SD_WORDS], in/out ----
 cudaError_t launch_sbr_sideinfo(int16_t *records, long long n, const uint8_t *misc_rom, int num_sms, cudaStream_t stream);
+cudaError_t launch_ps_sideinfo(int16_t *records, long long n, int num_sms, cudaStream_t stream);  // [n][XAAC_PSD_WORDS]
 
 // ---- eSBR 64-band synthesis bank (per-slot core of ixheaacd_esbr_synthesis_filt_block) --------------------------------
 // ROM blob: esbr_qmf_c[1280] | esbr_w_32[60] | esbr_sin_cos_twiddle_l64[64] | esbr_alt_sin_twiddle_l64[32] | esbr_w_16[24] |

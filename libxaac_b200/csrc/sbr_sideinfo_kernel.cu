@@ -425,6 +425,155 @@ __global__ void __launch_bounds__(kSdWarps * 32) sbr_sideinfo_kernel(int16_t *re
   }
 }
 
+// ---- PS side info: ixheaacd_decode_ps_data (decoder/ixheaacd_ps_bitdec.c:98-282) -------------------------------------------------
+// One warp per PS instance, the record (1152 bytes) in shared memory.  The delta chains are clamped after every step, so they are
+// sequential by contract; the IID and ICC chains are independent of each other and run side by side on two lanes, the copies and
+// the 34 -> 20 band mapping on all lanes.
+XB_DEV i32 ps_clamp(i32 v, i32 lo, i32 hi) { return v < lo ? lo : (v > hi ? hi : v); }
+XB_DEV i32 ps_div2(i32 op) { return s16(op < 0 ? -((-op) >> 1) : (op >> 1)); }
+XB_DEV i32 ps_div3(i32 op) {  // ixheaacd_divideby3 (ps_bitdec.c:77)
+  const bool sign = op < 0;
+  if (sign) op = -op;
+  const i32 t = s16((s16(op << 2) * 0x2aab) >> 15);
+  const i32 r = t >> 2;
+  return s16(sign ? -r : r);
+}
+// one parameter set (IID or ICC) of one envelope: delta decoding + clamps + 10 -> 20 expansion (ps_bitdec.c:126-196)
+XB_DEV void ps_decode_set(int16_t *tab, const int16_t *prev, bool enable, bool dt, int mode, i32 lo, i32 hi) {
+  const int nb = mode == 0 ? 10 : (mode == 1 ? 20 : 34), step = mode ? 1 : 2;
+  if (enable) {
+    if (dt) {
+      for (int i = 0; i < nb; i++) tab[i] = (int16_t)ps_clamp(s16(prev[step * i] + tab[i]), lo, hi);
+    } else {
+      tab[0] = (int16_t)ps_clamp(tab[0], lo, hi);
+      for (int i = 1; i < nb; i++) tab[i] = (int16_t)ps_clamp(s16(tab[i - 1] + tab[i]), lo, hi);
+    }
+  } else {
+    for (int i = 0; i < nb; i++) tab[i] = 0;
+  }
+  if (step == 2)
+    for (int i = 2 * nb - 1; i != 0; i--) tab[i] = tab[i >> 1];
+}
+// ixheaacd_map_34_params_to_20 (sbrdec_lpfuncs.c:561): in place, every output reads inputs at or above its own index
+XB_DEV void ps_map_34_to_20(int16_t *p) {
+  p[0] = (int16_t)ps_div3(p[0] + p[0] + p[1]);
+  p[1] = (int16_t)ps_div3(p[1] + p[2] + p[2]);
+  p[2] = (int16_t)ps_div3(p[3] + p[3] + p[4]);
+  p[3] = (int16_t)ps_div3(p[4] + p[5] + p[5]);
+  p[4] = (int16_t)ps_div2(p[6] + p[7]);
+  p[5] = (int16_t)ps_div2(p[8] + p[9]);
+  p[6] = p[10];
+  p[7] = p[11];
+  p[8] = (int16_t)ps_div2(p[12] + p[13]);
+  p[9] = (int16_t)ps_div2(p[14] + p[15]);
+  p[10] = p[16];
+  p[11] = p[17];
+  p[12] = p[18];
+  p[13] = p[19];
+  p[14] = (int16_t)ps_div2(p[20] + p[21]);
+  p[15] = (int16_t)ps_div2(p[22] + p[23]);
+  p[16] = (int16_t)ps_div2(p[24] + p[25]);
+  p[17] = (int16_t)ps_div2(p[26] + p[27]);
+  p[18] = (int16_t)ps_div2(ps_div2(p[28] + p[29] + p[30] + p[31]));
+  p[19] = (int16_t)ps_div2(p[32] + p[33]);
+}
+
+constexpr int kPsdWarps = 8;
+__global__ void __launch_bounds__(kPsdWarps * 32) ps_sideinfo_kernel(int16_t *records, long long n) {
+  __shared__ __align__(16) int16_t ws[kPsdWarps][XAAC_PSD_WORDS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int16_t *r = ws[warp];
+  const long long warps_total = (long long)gridDim.x * kPsdWarps;
+  for (long long u = (long long)blockIdx.x * kPsdWarps + warp; u < n; u += warps_total) {
+    int4 *g = reinterpret_cast<int4 *>(records + u * XAAC_PSD_WORDS);
+    int4 *s4 = reinterpret_cast<int4 *>(r);
+    __syncwarp();
+    for (int i = lane; i < XAAC_PSD_WORDS / 8; i += 32) s4[i] = g[i];
+    __syncwarp();
+    const int iid_mode = min(max((int)r[XAAC_PSD_IID_MODE], 0), 2), icc_mode = min(max((int)r[XAAC_PSD_ICC_MODE], 0), 2);
+    const int max_cols = r[XAAC_PSD_FRAME_SIZE] == 960 ? 30 : 32;
+    int num_env = r[XAAC_PSD_DATA_PRESENT] ? min(max((int)r[XAAC_PSD_NUM_ENV], 0), 5) : 0;
+    if (lane < 2) {  // lane 0: IID, lane 1: ICC
+      int16_t *tab = r + (lane ? XAAC_PSD_ICC_TABLE : XAAC_PSD_IID_TABLE);
+      const int16_t *prev0 = r + (lane ? XAAC_PSD_ICC_PREV : XAAC_PSD_IID_PREV);
+      const bool enable = r[lane ? XAAC_PSD_ENABLE_ICC : XAAC_PSD_ENABLE_IID] != 0;
+      const int mode = lane ? icc_mode : iid_mode;
+      const i32 lv = r[XAAC_PSD_IID_QUANT] ? 15 : 7;
+      for (int e = 0; e < num_env; e++)
+        ps_decode_set(tab + 34 * e, e ? tab + 34 * (e - 1) : prev0, enable, r[(lane ? XAAC_PSD_ICC_DT : XAAC_PSD_IID_DT) + e] != 0, mode,
+                      lane ? 0 : -lv, lane ? 7 : lv);
+    }
+    __syncwarp();
+    if (num_env == 0) {  // no PS data in this frame: one envelope holding the previous parameters (ps_bitdec.c:199-215)
+      num_env = 1;
+      for (int i = lane; i < 68; i += 32) {
+        const int set = i >= 34, b = set ? i - 34 : i;
+        const bool en = r[set ? XAAC_PSD_ENABLE_ICC : XAAC_PSD_ENABLE_IID] != 0;
+        r[(set ? XAAC_PSD_ICC_TABLE : XAAC_PSD_IID_TABLE) + b] = en ? r[(set ? XAAC_PSD_ICC_PREV : XAAC_PSD_IID_PREV) + b] : (int16_t)0;
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < 68; i += 32) {  // the last envelope becomes the previous one (:217-223)
+      const int set = i >= 34, b = set ? i - 34 : i;
+      r[(set ? XAAC_PSD_ICC_PREV : XAAC_PSD_IID_PREV) + b] = r[(set ? XAAC_PSD_ICC_TABLE : XAAC_PSD_IID_TABLE) + 34 * (num_env - 1) + b];
+    }
+    __syncwarp();
+    int16_t *bp = r + XAAC_PSD_BORDER;
+    if (r[XAAC_PSD_FRAME_CLASS] == 0) {  // fixed borders (:227-247)
+      if (lane == 0) {
+        const int shift = num_env == 2 ? 1 : (num_env == 4 ? 2 : 0);
+        bp[0] = 0;
+        for (int e = 1; e < num_env; e++) bp[e] = (int16_t)((e * max_cols) >> shift);
+        bp[num_env] = (int16_t)max_cols;
+      }
+    } else {  // variable borders (:248-277)
+      const bool extend = bp[num_env] < max_cols;
+      __syncwarp();
+      if (extend) {
+        num_env++;
+        for (int i = lane; i < 68; i += 32) {
+          const int set = i >= 34, b = set ? i - 34 : i;
+          int16_t *t = r + (set ? XAAC_PSD_ICC_TABLE : XAAC_PSD_IID_TABLE);
+          t[34 * (num_env - 1) + b] = t[34 * (num_env - 2) + b];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        bp[0] = 0;
+        if (extend) bp[num_env] = (int16_t)max_cols;
+        for (int e = 1; e < num_env; e++) {
+          int thr = max_cols - (num_env - e);
+          if (bp[e] > thr) {
+            bp[e] = (int16_t)thr;
+          } else {
+            thr = bp[e - 1] + 1;
+            if (bp[e] < thr) bp[e] = (int16_t)thr;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // 34 -> 20 bands, envelope per lane (:279-285)
+    if (lane < num_env && iid_mode == 2) ps_map_34_to_20(r + XAAC_PSD_IID_TABLE + 34 * lane);
+    if (lane >= 8 && lane - 8 < num_env && icc_mode == 2) ps_map_34_to_20(r + XAAC_PSD_ICC_TABLE + 34 * (lane - 8));
+    if (lane == 31) {
+      r[XAAC_PSD_NUM_ENV] = (int16_t)num_env;
+      r[XAAC_PSD_DATA_PRESENT] = 0;
+    }
+    __syncwarp();
+    for (int i = lane; i < XAAC_PSD_WORDS / 8; i += 32) g[i] = s4[i];
+  }
+}
+
+cudaError_t launch_ps_sideinfo(int16_t *records, long long n, int num_sms, cudaStream_t stream) {
+  long long need = (n + kPsdWarps - 1) / kPsdWarps;
+  long long grid = (long long)num_sms * 8;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  ps_sideinfo_kernel<<<(unsigned)grid, kPsdWarps * 32, 0, stream>>>(records, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sbr_sideinfo(int16_t *records, long long n, const uint8_t *misc_rom, int num_sms, cudaStream_t stream) {
   long long need = (n + kSdWarps - 1) / kSdWarps;
   long long grid = (long long)num_sms * 8;

@@ -1107,6 +1107,16 @@ int32_t xaac_b200_dec_sbrdata_dev(xaac_b200_ctx *ctx, int16_t *d_records, int64_
   return XAAC_B200_OK;
 }
 
+int32_t xaac_b200_decode_ps_data_dev(xaac_b200_ctx *ctx, int16_t *d_records, int64_t n_units, void *stream) {
+  if (!ctx) return XAAC_B200_ERR_ARG;
+  if (n_units < 0) return bad_arg(ctx, "n_units");
+  if (n_units == 0) return XAAC_B200_OK;
+  if (!d_records || ((uintptr_t)d_records & 15) != 0) return bad_arg(ctx, "records: null or not 16-byte aligned");
+  LAUNCH("ps_sideinfo_kernel", stream, xb::launch_ps_sideinfo(d_records, n_units, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return XAAC_B200_OK;
+}
+
 int32_t xaac_b200_set_esbr_rom(xaac_b200_ctx *ctx, const void *tables, size_t bytes) {
   if (!ctx || !tables) return bad_arg(ctx, "null");
   if (bytes < (size_t)xb::kEsRomBytes) return bad_arg(ctx, "eSBR ROM blob shorter than 6288 bytes");

@@ -84,6 +84,8 @@ static struct {
   int16_t *d_sd;
   int have_sd_rom;
   long n_sd, n_sd_ref, n_sd_coupled, n_sd_concealed;
+  int16_t *d_psd;
+  long n_psd;
   int32_t last_err[6];
   long n_imdct, n_imdct_ref, n_sbr_hq, n_sbr_ps, n_sbr_lp, n_sbr_ref, n_fd, n_fd_ref, n_esbr, n_esbr_hbe, n_esbr_ref;
 } G;
@@ -102,6 +104,7 @@ static void b200_report(void) {
   if (G.stats)
     fprintf(stderr, "[ixheaacd_b200] dec_sbrdata: %ld on the GPU (%ld coupled pairs, %ld with a concealed channel), %ld by the reference\n",
             G.n_sd, G.n_sd_coupled, G.n_sd_concealed, G.n_sd_ref);
+  if (G.stats) fprintf(stderr, "[ixheaacd_b200] decode_ps_data: %ld on the GPU\n", G.n_psd);
   if (G.ctx) xaac_b200_destroy(G.ctx);
   G.ctx = NULL;
 }
@@ -920,6 +923,25 @@ IA_ERRORCODE __wrap_ixheaacd_dec_sbrdata(ia_sbr_header_data_struct *ptr_header_d
   return __real_ixheaacd_dec_sbrdata(ptr_header_data_ch_0, ptr_header_data_ch_1, ptr_sbr_data_ch_0, ptr_prev_data_ch_0,
                                      ptr_sbr_data_ch_1, ptr_prev_data_ch_1, ptr_common_tables, ldmps_present, audio_object_type,
                                      ec_flag);
+}
+
+/* ================================ ixheaacd_decode_ps_data ================================ */
+VOID __real_ixheaacd_decode_ps_data(ia_ps_dec_struct *ptr_ps_dec, WORD32 frame_size);
+/* decoder/ixheaacd_ps_bitdec.c:98 (called from ixheaacd_applysbr, decoder/ixheaacd_sbrdecoder.c:723) */
+VOID __wrap_ixheaacd_decode_ps_data(ia_ps_dec_struct *ptr_ps_dec, WORD32 frame_size) {
+  xaac_b200_ctx *c = b200_ctx();
+  static int16_t rec[XAAC_PSD_WORDS];
+  if (!c) {
+    __real_ixheaacd_decode_ps_data(ptr_ps_dec, frame_size);
+    return;
+  }
+  b200_psd_pack(rec, ptr_ps_dec, frame_size);
+  if (!G.d_psd) B200(xaac_b200_dev_alloc(c, sizeof(rec), (void **)&G.d_psd), "alloc");
+  B200(xaac_b200_h2d(c, G.d_psd, rec, sizeof(rec)), "h2d psdata");
+  B200(xaac_b200_decode_ps_data_dev(c, G.d_psd, 1, NULL), "decode_ps_data_dev");
+  B200(xaac_b200_d2h(c, rec, G.d_psd, sizeof(rec)), "d2h psdata");
+  b200_psd_unpack(rec, ptr_ps_dec);
+  G.n_psd++;
 }
 
 /* ================================ ixheaacd_fd_frm_dec ================================ */

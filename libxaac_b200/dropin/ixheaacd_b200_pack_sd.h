@@ -97,4 +97,36 @@ static void b200_sd_unpack(const int16_t *rec, ia_sbr_header_data_struct *h0, ia
   }
   b200_sd_unpack_ch(rec + XAAC_SD_CH, h0, f0, p0);
 }
+/* ---- ixheaacd_decode_ps_data (decoder/ixheaacd_ps_bitdec.c:98): ia_ps_dec_struct <-> XAAC_PSD_* record ---- */
+static void b200_psd_pack(int16_t *r, const ia_ps_dec_struct *ps, WORD32 frame_size) {
+  int i;
+  memset(r, 0, XAAC_PSD_WORDS * 2);
+  r[XAAC_PSD_DATA_PRESENT] = (int16_t)ps->ps_data_present;
+  r[XAAC_PSD_ENABLE_IID] = (int16_t)ps->enable_iid;
+  r[XAAC_PSD_ENABLE_ICC] = (int16_t)ps->enable_icc;
+  r[XAAC_PSD_IID_MODE] = ps->iid_mode;
+  r[XAAC_PSD_ICC_MODE] = ps->icc_mode;
+  r[XAAC_PSD_IID_QUANT] = (int16_t)ps->iid_quant;
+  r[XAAC_PSD_FRAME_CLASS] = (int16_t)ps->frame_class;
+  r[XAAC_PSD_NUM_ENV] = ps->num_env;
+  r[XAAC_PSD_FRAME_SIZE] = (int16_t)frame_size;
+  memcpy(r + XAAC_PSD_BORDER, ps->border_position, 7 * 2);
+  for (i = 0; i < 5; i++) {
+    r[XAAC_PSD_IID_DT + i] = (int16_t)ps->iid_dt[i];
+    r[XAAC_PSD_ICC_DT + i] = (int16_t)ps->icc_dt[i];
+  }
+  memcpy(r + XAAC_PSD_IID_TABLE, ps->iid_par_table, 7 * 34 * 2);
+  memcpy(r + XAAC_PSD_ICC_TABLE, ps->icc_par_table, 7 * 34 * 2);
+  memcpy(r + XAAC_PSD_IID_PREV, ps->iid_par_prev, 34 * 2);
+  memcpy(r + XAAC_PSD_ICC_PREV, ps->icc_par_prev, 34 * 2);
+}
+static void b200_psd_unpack(const int16_t *r, ia_ps_dec_struct *ps) {
+  ps->ps_data_present = r[XAAC_PSD_DATA_PRESENT];
+  ps->num_env = r[XAAC_PSD_NUM_ENV];
+  memcpy(ps->border_position, r + XAAC_PSD_BORDER, 7 * 2);
+  memcpy(ps->iid_par_table, r + XAAC_PSD_IID_TABLE, 7 * 34 * 2);
+  memcpy(ps->icc_par_table, r + XAAC_PSD_ICC_TABLE, 7 * 34 * 2);
+  memcpy(ps->iid_par_prev, r + XAAC_PSD_IID_PREV, 34 * 2);
+  memcpy(ps->icc_par_prev, r + XAAC_PSD_ICC_PREV, 34 * 2);
+}
 #endif

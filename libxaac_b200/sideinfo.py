@@ -21,3 +21,18 @@ def dec_sbrdata(ctx, records, stream=None):
     rc = ctx._lib.xaac_b200_dec_sbrdata_dev(ctx.handle, _ptr(records), n, ctypes.c_void_p(stream.cuda_stream))
     ctx.check(rc, "xaac_b200_dec_sbrdata_dev")
     return records
+
+
+PSD_WORDS = 576  # XAAC_PSD_WORDS
+
+
+def decode_ps_data(ctx, records, stream=None):
+    """Batched drop-in for ixheaacd_decode_ps_data (decoder/ixheaacd_ps_bitdec.c:98).  records int16 [n, 576] (XAAC_PSD_* layout),
+    rewritten in place: IID / ICC indices delta-decoded and clamped, envelope borders fixed up, 34-band sets mapped to 20."""
+    n = int(records.shape[0])
+    _chk(records, torch.int16, (n, PSD_WORDS), "records", "cuda")
+    if stream is None:
+        stream = torch.cuda.current_stream(records.device)
+    rc = ctx._lib.xaac_b200_decode_ps_data_dev(ctx.handle, _ptr(records), n, ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_decode_ps_data_dev")
+    return records

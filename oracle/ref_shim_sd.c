@@ -83,3 +83,27 @@ void ref_dec_sbrdata_batch(int64_t n, int16_t *rec) {
     r[XAAC_SD_ERR] = rc == 0 ? 0 : (rc == (IA_ERRORCODE)-1 ? 2 : 1);
   }
 }
+
+/* ixheaacd_decode_ps_data (decoder/ixheaacd_ps_bitdec.c:98) on XAAC_PSD_* records, in place */
+VOID ixheaacd_decode_ps_data(ia_ps_dec_struct *ptr_ps_dec, WORD32 frame_size);
+void ref_decode_ps_data_batch(int64_t n, int16_t *rec) {
+  static __thread ia_ps_dec_struct ps;
+  for (int64_t u = 0; u < n; u++) {
+    int16_t *r = rec + u * XAAC_PSD_WORDS;
+    memset(&ps, 0, sizeof(ps));
+    b200_psd_unpack(r, &ps);
+    ps.enable_iid = r[XAAC_PSD_ENABLE_IID];
+    ps.enable_icc = r[XAAC_PSD_ENABLE_ICC];
+    ps.iid_mode = r[XAAC_PSD_IID_MODE];
+    ps.icc_mode = r[XAAC_PSD_ICC_MODE];
+    ps.iid_quant = r[XAAC_PSD_IID_QUANT];
+    ps.frame_class = r[XAAC_PSD_FRAME_CLASS];
+    for (int i = 0; i < 5; i++) {
+      ps.iid_dt[i] = r[XAAC_PSD_IID_DT + i];
+      ps.icc_dt[i] = r[XAAC_PSD_ICC_DT + i];
+    }
+    const int frame_size = r[XAAC_PSD_FRAME_SIZE];
+    ixheaacd_decode_ps_data(&ps, frame_size);
+    b200_psd_pack(r, &ps, frame_size);
+  }
+}

@@ -382,6 +382,12 @@ class Ref:
         self.lib.ref_dec_sbrdata_batch(ctypes.c_int64(r.shape[0]), P(r))
         return r
 
+    def decode_ps_data_batch(self, records):
+        """XAAC_PSD_* records through the compiled ixheaacd_decode_ps_data (oracle/ref_shim_sd.c)"""
+        r = np.ascontiguousarray(records, np.int16).copy()
+        self.lib.ref_decode_ps_data_batch(ctypes.c_int64(r.shape[0]), P(r))
+        return r
+
     def synth(self, matrix, filter_states, pos, params, ch_fac=1):
         """single unit through ixheaacd_cplx_synt_qmffilt"""
         m = np.ascontiguousarray(matrix, np.int32).copy()
@@ -1461,4 +1467,46 @@ def synth_sbrdata_records(n, seed):
             # a mono element has no second channel to take energies from: its previous coupling mode is always off
             b[SDC["PREV_COUPLING"]] = b[SDC["COUPLING"]] if (rng.random() < 0.8 or not two) else int(rng.integers(0, 3))
             b[SDC["PREV_INVF"]: SDC["PREV_INVF"] + 10] = rng.integers(0, 4, 10)
+    return rec
+
+
+PSD_WORDS = 576
+PSD = dict(DATA_PRESENT=0, ENABLE_IID=1, ENABLE_ICC=2, IID_MODE=3, ICC_MODE=4, IID_QUANT=5, FRAME_CLASS=6, NUM_ENV=7, FRAME_SIZE=8,
+           BORDER=9, IID_DT=16, ICC_DT=21, IID_TABLE=32, ICC_TABLE=270, IID_PREV=508, ICC_PREV=542)
+
+
+def synth_psdata_records(n, seed):
+    """Seeded XAAC_PSD_* records as ixheaacd_read_ps_data leaves them: 10 / 20 / 34-band IID and ICC sets, coarse and fine IID
+    quantisation, time- and frequency-direction deltas (with values that hit the clamps), fixed and variable envelope borders
+    (some short of the frame end, some out of order), frames without PS data, 960-sample frames."""
+    rng = np.random.default_rng(seed)
+    rec = np.zeros((n, PSD_WORDS), np.int16)
+    for u in range(n):
+        r = rec[u]
+        r[PSD["DATA_PRESENT"]] = rng.random() < 0.85
+        r[PSD["ENABLE_IID"]] = rng.random() < 0.85
+        r[PSD["ENABLE_ICC"]] = rng.random() < 0.85
+        r[PSD["IID_MODE"]] = rng.integers(0, 3)
+        r[PSD["ICC_MODE"]] = rng.integers(0, 3)
+        r[PSD["IID_QUANT"]] = rng.integers(0, 2)
+        fc = int(rng.random() < 0.4)
+        r[PSD["FRAME_CLASS"]] = fc
+        cols = 30 if rng.random() < 0.1 else 32
+        r[PSD["FRAME_SIZE"]] = 960 if cols == 30 else 1024
+        ne = int(rng.choice([0, 1, 2, 4])) if fc == 0 else int(rng.integers(1, 5))
+        r[PSD["NUM_ENV"]] = ne
+        if fc:
+            b = np.sort(rng.integers(1, cols + 1, ne))
+            if rng.random() < 0.2 and ne > 1:
+                b = rng.permutation(b)
+            r[PSD["BORDER"] + 1: PSD["BORDER"] + 1 + ne] = b
+            r[PSD["BORDER"]] = rng.integers(0, 3)
+        else:
+            r[PSD["BORDER"]: PSD["BORDER"] + 7] = rng.integers(0, 33, 7)
+        r[PSD["IID_DT"]: PSD["IID_DT"] + 5] = rng.integers(0, 2, 5)
+        r[PSD["ICC_DT"]: PSD["ICC_DT"] + 5] = rng.integers(0, 2, 5)
+        r[PSD["IID_TABLE"]: PSD["IID_TABLE"] + 238] = rng.integers(-6, 7, 238)
+        r[PSD["ICC_TABLE"]: PSD["ICC_TABLE"] + 238] = rng.integers(-3, 4, 238)
+        r[PSD["IID_PREV"]: PSD["IID_PREV"] + 34] = rng.integers(-15, 16, 34)
+        r[PSD["ICC_PREV"]: PSD["ICC_PREV"] + 34] = rng.integers(0, 8, 34)
     return rec

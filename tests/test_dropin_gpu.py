@@ -87,6 +87,10 @@ def test_whole_file_through_reference_parser(tmp_path, name, enc, fs, ch, secs, 
     sd, sd_coupled, sd_conc, sd_ref = map(int, m3.groups())
     if name != "aac_lc_stereo":
         assert sd >= 2900 and sd_ref == 0, m3.group(0)
+    m4 = re.search(r"decode_ps_data: (\d+) on the GPU", log)
+    assert m4, log[-600:]
+    if name == "heaac_v2":
+        assert int(m4.group(1)) >= 2900, m4.group(0)
 
 
 @pytest.mark.parametrize("name,extra", [("usac", []), ("usac_hbe", ["-harmonic_sbr:1"])])

@@ -65,3 +65,49 @@ def test_frames_carry_state(ctx, ref):
         for s in carry:
             nxt[:, s] = out_r[:, s]
         cur_g, cur_r = nxt.copy(), nxt.copy()
+
+
+# ---- PS side info: ixheaacd_decode_ps_data ----------------------------------------------------------------------------
+def run_gpu_ps(ctx, rec):
+    import torch
+    import libxaac_b200 as xb
+    d = torch.from_numpy(rec.copy()).cuda()
+    xb.decode_ps_data(ctx, d)
+    torch.cuda.synchronize()
+    return d.cpu().numpy()
+
+
+def explain_ps(got, exp):
+    bad = np.argwhere(got != exp)
+    u, w = bad[0]
+    names = {v: k for k, v in oracle_util.PSD.items()}
+    field = max(o for o in names if o <= w)
+    return (f"{len(np.unique(bad[:, 0]))} records differ; first: record {u} word {w} ({names[field]}+{w - field}) gpu={got[u, w]} "
+            f"ref={exp[u, w]}")
+
+
+@pytest.mark.parametrize("seed,n", [(31, 100), (32, 20000)])
+def test_ps_records_vs_compiled_reference(ctx, ref, seed, n):
+    rec = oracle_util.synth_psdata_records(n, seed)
+    exp = ref.decode_ps_data_batch(rec)
+    got = run_gpu_ps(ctx, rec)
+    assert np.array_equal(got, exp), explain_ps(got, exp)
+
+
+def test_ps_golden_records(ctx):
+    g = np.load(GOLDEN)
+    got = run_gpu_ps(ctx, g["ps_records_in"])
+    assert np.array_equal(got, g["ps_records_out"]), explain_ps(got, g["ps_records_out"])
+
+
+def test_ps_frames_carry_state(ctx, ref):
+    """iid_par_prev / icc_par_prev carried over 6 frames"""
+    n = 400
+    cur = oracle_util.synth_psdata_records(n, 41)
+    P = oracle_util.PSD
+    for f in range(6):
+        out_g, out_r = run_gpu_ps(ctx, cur), ref.decode_ps_data_batch(cur)
+        assert np.array_equal(out_g, out_r), f"frame {f}: " + explain_ps(out_g, out_r)
+        nxt = oracle_util.synth_psdata_records(n, 42 + f)
+        nxt[:, P["IID_PREV"]: P["IID_PREV"] + 68] = out_r[:, P["IID_PREV"]: P["IID_PREV"] + 68]
+        cur = nxt
