@@ -267,72 +267,51 @@ __global__ void __launch_bounds__(kPlWarps * 32) peak_limiter_kernel(PeakLimArgs
   }
 }
 
-// Attack / release recursion of the deferred streams, lane = stream: a warp takes 32 queued streams, moves their raw gains
-// through a 32 x 32 shared-memory tile (coalesced rows in, lane-private rows out: stride 33, no bank conflicts) and walks the
-// 1024 samples once.  Results replace the raw gains in the scratch buffer; gain_modified, pre_smoothed_gain and min_gain go
-// to the state records.
+// Attack / release recursion of the deferred streams, lane = stream: a warp takes 32 queued streams.  Each lane reads its own
+// stream's gains 32 at a time as eight 16-byte requests (every request of the warp touches 32 different 128-byte lines, each one
+// used in full — no transposition through shared memory, no shuffles), runs the recursion over them in registers with the next
+// 32 already requested, and writes the smoothed gains back in place.  gain_modified, pre_smoothed_gain and min_gain go to the
+// state records.
 __global__ void __launch_bounds__(kPlSmoothWarps * 32) peak_limiter_smooth_kernel(PeakLimArgs p) {
-  __shared__ float tile[kPlSmoothWarps][32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned full = 0xffffffffu;
   const int n = *p.count;
   const int groups = (n + 31) >> 5;
   for (int g = blockIdx.x * kPlSmoothWarps + warp; g < groups; g += gridDim.x * kPlSmoothWarps) {
     const int k = 32 * g + lane;
-    const bool mine = k < n;
-    const long long u = mine ? p.list[k] : -1;
-    i32 *st = mine ? p.state + u * kPlWords : nullptr;
-    float gm = 1.f, min_gain = 1.f;
-    double ac = 0.0, rc = 0.0, psg = 1.0;
-    if (mine) {
-      ac = (double)__int_as_float(st[kPlAttackConst]);
-      rc = (double)__int_as_float(st[kPlReleaseConst]);
-      gm = __int_as_float(st[kPlGainMod]);
-      psg = __hiloint2double(st[kPlPsg + 1], st[kPlPsg]);
-    }
-    float (*t)[33] = tile[warp];
-    // lane s of the shuffle = stream s of the group; its 128-byte row of the chunk is one coalesced request.  The next
-    // chunk's 32 rows are requested before the recursion of the current one starts.
-    float nx[32];
+    if (k >= n) continue;
+    const long long u = p.list[k];
+    i32 *st = p.state + u * kPlWords;
+    const double ac = (double)__int_as_float(st[kPlAttackConst]), rc = (double)__int_as_float(st[kPlReleaseConst]);
+    float gm = __int_as_float(st[kPlGainMod]), min_gain = 1.f;
+    double psg = __hiloint2double(st[kPlPsg + 1], st[kPlPsg]);
+    float4 *gp = reinterpret_cast<float4 *>(p.gbuf + u * 1024);
+    float4 nx[8];
 #pragma unroll
-    for (int s = 0; s < 32; s++) {
-      const long long us = __shfl_sync(full, u, s);
-      nx[s] = us >= 0 ? p.gbuf[us * 1024 + lane] : 1.0f;
-    }
+    for (int q = 0; q < 8; q++) nx[q] = gp[q];
 #pragma unroll 1
-    for (int cb = 0; cb < 1024; cb += 32) {
+    for (int cb = 0; cb < 256; cb += 8) {
+      float4 cur[8];
 #pragma unroll
-      for (int s = 0; s < 32; s++) t[s][lane] = nx[s];
-      __syncwarp();
-      if (cb + 32 < 1024) {
+      for (int q = 0; q < 8; q++) cur[q] = nx[q];
+      if (cb + 8 < 256) {
 #pragma unroll
-        for (int s = 0; s < 32; s++) {
-          const long long us = __shfl_sync(full, u, s);
-          nx[s] = us >= 0 ? p.gbuf[us * 1024 + cb + 32 + lane] : 1.0f;
-        }
+        for (int q = 0; q < 8; q++) nx[q] = gp[cb + 8 + q];
       }
-      if (mine) {
-#pragma unroll 4
-        for (int q = 0; q < 32; q++) {
-          const float go = pl_smooth_step(t[lane][q], gm, psg, ac, rc);
-          t[lane][q] = go;
-          if (go < min_gain) min_gain = go;
-        }
-      }
-      __syncwarp();
 #pragma unroll
-      for (int s = 0; s < 32; s++) {
-        const long long us = __shfl_sync(full, u, s);
-        if (us >= 0) p.gbuf[us * 1024 + cb + lane] = t[s][lane];
+      for (int q = 0; q < 8; q++) {
+        float go;
+        go = pl_smooth_step(cur[q].x, gm, psg, ac, rc); cur[q].x = go; min_gain = go < min_gain ? go : min_gain;
+        go = pl_smooth_step(cur[q].y, gm, psg, ac, rc); cur[q].y = go; min_gain = go < min_gain ? go : min_gain;
+        go = pl_smooth_step(cur[q].z, gm, psg, ac, rc); cur[q].z = go; min_gain = go < min_gain ? go : min_gain;
+        go = pl_smooth_step(cur[q].w, gm, psg, ac, rc); cur[q].w = go; min_gain = go < min_gain ? go : min_gain;
       }
-      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; q++) gp[cb + q] = cur[q];
     }
-    if (mine) {
-      st[kPlGainMod] = __float_as_int(gm);
-      st[kPlMinGain] = __float_as_int(min_gain);
-      st[kPlPsg] = __double2loint(psg);
-      st[kPlPsg + 1] = __double2hiint(psg);
-    }
+    st[kPlGainMod] = __float_as_int(gm);
+    st[kPlMinGain] = __float_as_int(min_gain);
+    st[kPlPsg] = __double2loint(psg);
+    st[kPlPsg + 1] = __double2hiint(psg);
   }
 }
 
