@@ -1251,7 +1251,9 @@ def run_reference_arm(args, rank, world):
                    "step": f"bounded sample: {sample_units // 2} stereo frames per step on host cores"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
                          "sample": f"{sample_units} {unit_name} per pass, at least {max(1, args.steps)} passes and 10 s "
-                                   f"of timed CPU work (+1 warm-up pass), {cores} threads, private state per unit"},
+                                   f"of timed CPU work (+1 warm-up pass), {cores} threads, private state per unit; the flat-record -> reference-struct "
+                                   f"refresh of oracle/ref_shim*.c (a few KB of copies per frame: < 1 % of a frame's time for the DSP stages, "
+                                   f"a comparable share for sbr_sideinfo, whose function runs ~1 us per element) is inside the timed region"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
@@ -2470,6 +2472,14 @@ def main():
             line["roofline"]["note"] = ("per-launch duration from CUDA events around every launch of a second pass of "
                                         "the same steps" + ("; two launches per step (left, right)"
                                                             if top == "qmf_synth_hq_kernel" else ""))
+            # the kernel that takes the largest share of the step, with its own roofline figures (the `kernel` above is the
+            # one BASELINE.json's metric names, which need not be the dominant one)
+            dom = max(kernel_table, key=lambda k_: kernel_table[k_]["share_of_step"])
+            dv = kernel_table[dom]
+            line["roofline"]["dominant_kernel"] = {
+                "kernel": dom, "share_of_step": dv["share_of_step"], "launch_ms": dv["launch_ms"], "achieved": dv["achieved"],
+                "frac": dv["frac"], "bytes_per_unit": dv["bytes_per_unit"],
+                "traffic": (ncu_traffic().get(dom, {}).get("bytes_per_unit", 0) * n_units) or None}
         if sharded is not None:
             line["sharded_io"] = sharded
         if args.workload == "aac_lc_stereo_imdct_ola":
