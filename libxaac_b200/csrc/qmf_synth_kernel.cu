@@ -110,8 +110,8 @@ struct SynLane {       // per-lane constants of the modulation stages
 // Modulation of one slot pair: block-shifted inputs v[8] (a,b,c,d per slot; odd lanes hold them swapped, which turns
 // the reference's alternating front/back pre-twiddle steps into one branch-free formula) -> fo[8] folded state samples
 // (sign-extended WORD16 values) of the slot this lane serves (lanes 0-15: first slot, 16-31: second).
-template <bool SAT>
-XB_DEV void modulate_pair(const i32 *v, int2 *T, const SynBlockSmem &sm, const SynLane &L, int lane, i32 clamp_lo,
+template <bool SAT, class SM>
+XB_DEV void modulate_pair(const i32 *v, int2 *T, const SM &sm, const SynLane &L, int lane, i32 clamp_lo,
                           i32 clamp_hi, i32 fold_mul, i32 z, i32 *fo) {
   const int2 ptw = sm.pre_tw[lane];
   // ---- pre-twiddle (generic:290-367) ----
@@ -197,6 +197,27 @@ XB_DEV void modulate_pair(const i32 *v, int2 *T, const SynBlockSmem &sm, const S
   fo[7] = R(A_<SAT>(G2[0], G1[0]));  // st[127-2u]
 }
 
+// per-lane constants of the modulation stages (lanes 0-15 serve the first slot of a pair, 16-31 the second)
+XB_DEV void syn_lane_setup(SynLane &L, int lane, const i32 *postmap) {
+  const int fs_slot = lane >> 4;
+  L.r16 = lane & 15;
+  const int h1 = L.r16 >> 3, i1 = L.r16 & 7, g2 = (L.r16 >> 1) & 3, i2 = L.r16 & 1;
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    L.s1idx[m] = fs_slot * kTSlot + h1 * kTHalf + tsw(i1 + 8 * m);          // legs at i1 + 8m
+    L.s2idx[m] = fs_slot * kTSlot + h1 * kTHalf + tsw(8 * g2 + i2 + 2 * m);  // legs at 8 g2 + i2 + 2m
+  }
+  const i32 pm_f = postmap[L.r16], pm_b = postmap[31 - L.r16];
+  L.pf_a = fs_slot * kTSlot + tsw(pm_f & 255);
+  L.pf_b = fs_slot * kTSlot + tsw((pm_f & 255) + 1);
+  L.pb_a = fs_slot * kTSlot + tsw(pm_b & 255);
+  L.pb_b = fs_slot * kTSlot + tsw((pm_b & 255) + 1);
+  L.pf_sgn = ((pm_f >> 8) & 1) ? -1 : 1;
+  L.pb_sgn = ((pm_b >> 8) & 1) ? -1 : 1;
+  // pre-twiddle: step n = lane; even n -> complex n/2, odd n -> complex 31-(n-1)/2
+  L.pre_e = tsw((lane & 1) ? 31 - (lane >> 1) : (lane >> 1));
+}
+
 __global__ void __launch_bounds__(kSynWarps * 32, 2)
 qmf_synth_hq_kernel(QmfSynthArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -217,24 +238,7 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
   // lane roles in the FFT / post stages: lanes 0-15 serve the first slot of a pair, 16-31 the second
   SynLane L;
   const int fs_slot = lane >> 4;
-  L.r16 = lane & 15;
-  {
-    const int h1 = L.r16 >> 3, i1 = L.r16 & 7, g2 = (L.r16 >> 1) & 3, i2 = L.r16 & 1;
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-      L.s1idx[m] = fs_slot * kTSlot + h1 * kTHalf + tsw(i1 + 8 * m);          // legs at i1 + 8m
-      L.s2idx[m] = fs_slot * kTSlot + h1 * kTHalf + tsw(8 * g2 + i2 + 2 * m);  // legs at 8 g2 + i2 + 2m
-    }
-    const i32 pm_f = sm.postmap[L.r16], pm_b = sm.postmap[31 - L.r16];
-    L.pf_a = fs_slot * kTSlot + tsw(pm_f & 255);
-    L.pf_b = fs_slot * kTSlot + tsw((pm_f & 255) + 1);
-    L.pb_a = fs_slot * kTSlot + tsw(pm_b & 255);
-    L.pb_b = fs_slot * kTSlot + tsw((pm_b & 255) + 1);
-    L.pf_sgn = ((pm_f >> 8) & 1) ? -1 : 1;
-    L.pb_sgn = ((pm_b >> 8) & 1) ? -1 : 1;
-    // pre-twiddle: step n = lane; even n -> complex n/2, odd n -> complex 31-(n-1)/2
-    L.pre_e = tsw((lane & 1) ? 31 - (lane >> 1) : (lane >> 1));
-  }
+  syn_lane_setup(L, lane, sm.postmap);
   // band read first / second by this lane (odd lanes swapped, see modulate_pair)
   const int bandA = (lane & 1) ? 63 - lane : lane;
   const int bandB = 63 - bandA;
@@ -391,6 +395,239 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
 
 
 // =====================================================================================================================
+// Slot-pair modulation (as above) + linear-time window, four slots per pass.
+//
+// The modulation is the slot-pair code of qmf_synth_hq_kernel.  What changes is the filter state: instead of the reference's ring
+// in a tap-major transposed layout with a rotating coefficient pointer (one window pass per slot: 5 LDS.128 + 10 LDS.64 + 20 IMAD,
+// two warp syncs), the folded blocks go to a ring of 16 ROWS in time order (row = slot & 15, 128 words: output pair k' owns words
+// 4k'..4k'+3 = both 64-sample halves) and the window runs once per FOUR slots: the 13 rows s0-9 .. s0+3 are read once (13 LDS.128)
+// for all 80 taps, and the coefficient of a block depends on its age only (see qmf_synth_core.cuh), so a tap is
+// row[s - a][half(a)] * w_a with w_a read once per pass.  Shared memory per warp: 8 KB rows + 1.25 KB FFT workspace; one block of
+// 23 warps per SM (88 registers).
+// =====================================================================================================================
+constexpr int kG4Warps = 23;
+constexpr size_t kSynV2CoefOffset = offsetof(SynBlockSmem, w);  // qmf_c as 640 32-bit words follows the slot-pair kernel's tables
+
+struct SynG4Warp {
+  i32 rows[16 * 128];
+  int2 T[2 * kTSlot];
+};
+struct SynG4Block {
+  int2 pre_tw[32];
+  int2 alt_tw[16];
+  int2 w1[24];
+  int2 w2[6];
+  i32 postmap[32];
+  int2 cw[20 * 32];  // cw[32 b + k'] = (qmf_c[64 (b mod 10) + 2k'], qmf_c[.. + 1]), sign-extended: tap of age a at block kappa + a
+  SynG4Warp w[kG4Warps];
+};
+constexpr size_t kSynTablesOffset = offsetof(SynBlockSmem, pre_tw);   // pre_tw .. postmap inside the table image
+constexpr size_t kSynTablesBytes = offsetof(SynBlockSmem, w) - offsetof(SynBlockSmem, pre_tw);
+static_assert(kSynTablesBytes == offsetof(SynG4Block, cw), "table block layouts must match");
+
+// window of slots s0 .. s0+3 (s0 = 4 g, GPH = g & 3 fixes the ring rows at compile time) for output pair `lane`
+template <int P, int GPH>
+XB_DEV void window_ring4(const i32 *rows, const int2 *cwk, int lane, i32 (&o)[4][2]) {
+  i32 acc[4][2];
+#pragma unroll
+  for (int t = 0; t < 4; t++) acc[t][0] = acc[t][1] = 0x4000;
+#pragma unroll
+  for (int r = -9; r < 4; r++) {
+    const int4 x = *reinterpret_cast<const int4 *>(rows + ((4 * GPH + r) & 15) * 128 + 4 * lane);
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int a = t - r;
+      if (a < 0 || a > 9) continue;
+      const int2 w = cwk[32 * a];
+      const bool h = ((P + a) & 1) != 0;
+      acc[t][0] += (h ? x.z : x.x) * w.x;
+      acc[t][1] += (h ? x.w : x.y) * w.y;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    o[t][0] = max(-0x40000000, min(0x3fffffff, acc[t][0])) >> 15;
+    o[t][1] = max(-0x40000000, min(0x3fffffff, acc[t][1])) >> 15;
+  }
+}
+template <int P>
+XB_DEV void window_ring4_dispatch(int gph, const i32 *rows, const int2 *cwk, int lane, i32 (&o)[4][2]) {
+  switch (gph) {
+    case 0: window_ring4<P, 0>(rows, cwk, lane, o); break;
+    case 1: window_ring4<P, 1>(rows, cwk, lane, o); break;
+    case 2: window_ring4<P, 2>(rows, cwk, lane, o); break;
+    default: window_ring4<P, 3>(rows, cwk, lane, o); break;
+  }
+}
+
+__global__ void __launch_bounds__(kG4Warps * 32, 1)
+qmf_synth_hq_g4_kernel(QmfSynthArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SynG4Block &sm = *reinterpret_cast<SynG4Block *>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  {
+    const i32 *src = reinterpret_cast<const i32 *>(p.rom + kSynTablesOffset);
+    i32 *dst = reinterpret_cast<i32 *>(&sm);
+    for (int i = threadIdx.x; i < (int)(kSynTablesBytes / 4); i += blockDim.x) dst[i] = src[i];
+    const i32 *c32 = reinterpret_cast<const i32 *>(p.rom + kSynV2CoefOffset);
+    for (int i = threadIdx.x; i < 20 * 32; i += blockDim.x) {
+      const i32 v = c32[32 * ((i >> 5) % 10) + (i & 31)];
+      sm.cw[i] = make_int2((i32)(int16_t)v, v >> 16);
+    }
+  }
+  __syncthreads();
+  i32 *rows = sm.w[warp].rows;
+  int2 *T = sm.w[warp].T;
+  const int warps_total = gridDim.x * kG4Warps;
+  SynLane L;
+  const int fs_slot = lane >> 4;
+  syn_lane_setup(L, lane, sm.postmap);
+  const int bandA = (lane & 1) ? 63 - lane : lane;
+  const int bandB = 63 - bandA;
+
+  for (long long u = (long long)blockIdx.x * kG4Warps + warp; u < p.n_units; u += warps_total) {
+    if (p.gate && p.gate[u] == 0) continue;
+    const i32 *mat = p.matrix + u * p.mat_stride;
+    const int16_t *prm = p.params + u * 8;
+    const int ov_lb_scale = prm[0], lb_scale = prm[1], hb_scale = prm[2], st_syn = prm[3];
+    const int lsb = prm[4], usb = prm[5], split = prm[6];
+    const int off0 = p.pos[2 * u], fpos0 = p.pos[2 * u + 1];
+    const int Bw0 = off0 >> 7;
+    int kappa = (fpos0 >> 6) + Bw0;
+    if (kappa >= 10) kappa -= 10;
+    const int2 *cwk = sm.cw + 32 * kappa + lane;
+    int ov_lb_shift = (st_syn - ov_lb_scale) - 8, lb_shift = (st_syn - lb_scale) - 8;
+    int hb_shift = (st_syn - hb_scale) - 8;
+    const int out_shift = -(st_syn - 3) + 1;
+    auto enc = [](int sh, i32 &mul, int &shr) {
+      sh = max(-31, min(31, sh));
+      mul = sh > 0 ? (i32)(1u << sh) : 1;
+      shr = sh < 0 ? -sh : 0;
+    };
+    i32 mulA_ov, mulA_lb, mulB_ov, mulB_lb;
+    int shrA_ov, shrA_lb, shrB_ov, shrB_lb;
+    enc(bandA < lsb ? ov_lb_shift : (bandA < usb ? hb_shift : 0), mulA_ov, shrA_ov);
+    enc(bandA < lsb ? lb_shift : (bandA < usb ? hb_shift : 0), mulA_lb, shrA_lb);
+    enc(bandB < lsb ? ov_lb_shift : (bandB < usb ? hb_shift : 0), mulB_ov, shrB_ov);
+    enc(bandB < lsb ? lb_shift : (bandB < usb ? hb_shift : 0), mulB_lb, shrB_lb);
+    const i32 clamp_lo = (i32)0x80000000 >> out_shift;
+    const i32 clamp_hi = (i32)(0x7fff7fffu >> out_shift);
+    const i32 fold_mul = (i32)(1u << out_shift);
+
+    // ---- history: ring block B of filter_states (reference layout) has age a = (B - Bw0) mod 10 -> row (-a) & 15 ----
+    i32 *st32 = reinterpret_cast<i32 *>(p.states + u * 1280);
+    {
+      i32 wv[20];
+#pragma unroll
+      for (int t = 0; t < 20; t++) wv[t] = st32[32 * t + lane];
+#pragma unroll
+      for (int B = 0; B < 10; B++) {
+        int a = B - Bw0;
+        if (a < 0) a += 10;
+        if (a != 0)
+          *reinterpret_cast<int4 *>(rows + ((16 - a) & 15) * 128 + 4 * lane) =
+              make_int4((i32)(int16_t)wv[2 * B], wv[2 * B] >> 16, (i32)(int16_t)wv[2 * B + 1], wv[2 * B + 1] >> 16);
+      }
+    }
+    __syncwarp();
+
+    i32 nx[8];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const i32 *m = mat + 128 * s;
+      nx[4 * s + 0] = __ldg(m + bandA);
+      nx[4 * s + 1] = __ldg(m + bandB);
+      nx[4 * s + 2] = __ldg(m + 64 + bandA);
+      nx[4 * s + 3] = __ldg(m + 64 + bandB);
+    }
+    int16_t *pcm = p.pcm + (p.pcm_unit_stride ? u * p.pcm_unit_stride
+                                               : ((p.ch_fac == 1) ? u * 2048 : (u / p.ch_fac) * (2048LL * p.ch_fac) + (u % p.ch_fac)));
+
+#pragma unroll 1
+    for (int pr = 0; pr < 16; pr++) {
+      i32 v[8];
+      u32 mag = 0;
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const bool ov = (2 * pr + s) < split;
+        const i32 mA = ov ? mulA_ov : mulA_lb, mB = ov ? mulB_ov : mulB_lb;
+        const int rA = ov ? shrA_ov : shrA_lb, rB = ov ? shrB_ov : shrB_lb;
+        v[4 * s + 0] = (i32)((u32)nx[4 * s + 0] * (u32)mA) >> rA;
+        v[4 * s + 1] = (i32)((u32)nx[4 * s + 1] * (u32)mB) >> rB;
+        v[4 * s + 2] = (i32)((u32)nx[4 * s + 2] * (u32)mA) >> rA;
+        v[4 * s + 3] = (i32)((u32)nx[4 * s + 3] * (u32)mB) >> rB;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) mag |= (u32)(v[j] ^ (v[j] >> 31));
+      if (pr < 15) {
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const i32 *m = mat + 128 * (2 * pr + 2 + s);
+          nx[4 * s + 0] = __ldg(m + bandA);
+          nx[4 * s + 1] = __ldg(m + bandB);
+          nx[4 * s + 2] = __ldg(m + 64 + bandA);
+          nx[4 * s + 3] = __ldg(m + 64 + bandB);
+        }
+      }
+      mag = __reduce_or_sync(0xffffffffu, mag);
+      i32 fo[8];
+      if ((mag >> p.fast_bits) == 0)
+        modulate_pair<false>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, p.zero, fo);
+      else
+        modulate_pair<true>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, 0, fo);
+      // ---- the fold of this lane's slot into its row: pairs r16 and 31 - r16, both halves ----
+      {
+        i32 *row = rows + ((2 * pr + fs_slot) & 15) * 128;
+        *reinterpret_cast<int4 *>(row + 4 * L.r16) = make_int4(fo[0], fo[1], fo[4], fo[5]);
+        *reinterpret_cast<int4 *>(row + 4 * (31 - L.r16)) = make_int4(fo[2], fo[3], fo[6], fo[7]);
+      }
+      if (pr & 1) {  // ---- four new rows are complete: window of slots 2 pr - 2 .. 2 pr + 1 ----
+        __syncwarp();
+        const int s0 = 2 * pr - 2;
+        i32 o[4][2];
+        if (Bw0 & 1)
+          window_ring4_dispatch<1>((s0 >> 2) & 3, rows, cwk, lane, o);
+        else
+          window_ring4_dispatch<0>((s0 >> 2) & 3, rows, cwk, lane, o);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int slot = s0 + t;
+          if (p.ch_fac == 1) {
+            *reinterpret_cast<i32 *>(pcm + 64 * slot + 2 * lane) = (o[t][0] & 0xffff) | (i32)((u32)o[t][1] << 16);
+          } else {
+            pcm[p.ch_fac * (64 * slot + 2 * lane)] = (int16_t)o[t][0];
+            pcm[p.ch_fac * (64 * slot + 2 * lane + 1)] = (int16_t)o[t][1];
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- the last ten blocks back to the reference's ring: slot r sits at ring block (Bw0 - r) mod 10 ----
+    {
+      int B = Bw0 + 8;  // slot 22
+      if (B >= 10) B -= 10;
+#pragma unroll
+      for (int r = 22; r < 32; r++) {
+        const int4 x = *reinterpret_cast<const int4 *>(rows + (r & 15) * 128 + 4 * lane);
+        st32[32 * (2 * B) + lane] = (i32)(((u32)x.x & 0xffffu) | ((u32)x.y << 16));
+        st32[32 * (2 * B + 1) + lane] = (i32)(((u32)x.z & 0xffffu) | ((u32)x.w << 16));
+        B = B ? B - 1 : 9;
+      }
+      if (lane == 0) {
+        int off = off0 + 1024, fpos = fpos0 + 128;  // 32 steps of -128 mod 1280 / +64 mod 640
+        if (off >= 1280) off -= 1280;
+        if (fpos >= 640) fpos -= 640;
+        p.pos[2 * u] = (int16_t)off;
+        p.pos[2 * u + 1] = (int16_t)fpos;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// =====================================================================================================================
 // Variant (opt-in, XAAC_B200_SYNTH_TMA=1): lane = slot modulation in registers, matrix rows staged by 1-D bulk copies (TMA), linear-time window.
 // See qmf_synth_core.cuh for the arithmetic and the layout; this part is the data movement.
 //
@@ -402,7 +639,6 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
 using namespace syn;
 
 constexpr int kSyn2Warps = 8;  // 2 per scheduler: 255 registers, no spills (10 warps at 168 registers measured slower)
-constexpr size_t kSynV2CoefOffset = offsetof(SynBlockSmem, w);  // qmf_c as 640 32-bit words follows the v1 tables
 
 struct Syn2Warp {
   i32 rows[kRows * kRowW];  // row -9 .. row 31
@@ -692,6 +928,22 @@ cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStrea
   // Default: the slot-pair kernel above (1.69 ms per 131 072 units).  XAAC_B200_SYNTH_TMA=1 selects the bulk-copy-staged
   // lane = slot variant (bit-identical, 2.09 ms: 2 warps per scheduler cannot hide its dependent chains — profiles/r2_synth_tma.md).
   static const bool use_tma = getenv("XAAC_B200_SYNTH_TMA") != nullptr;
+  static const bool use_ring = getenv("XAAC_B200_SYNTH_RING") != nullptr;  // the original per-slot ring window
+  if (!use_tma && !use_ring) {
+    static xb::PerDeviceOnce configured_g4;
+    const size_t smem4 = sizeof(SynG4Block);
+    if (configured_g4.needed()) {
+      cudaError_t e = cudaFuncSetAttribute(qmf_synth_hq_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+      if (e != cudaSuccess) return e;
+      configured_g4.done();
+    }
+    long long need4 = (args.n_units + kG4Warps - 1) / kG4Warps;
+    long long grid4 = num_sms;
+    if (grid4 > need4) grid4 = need4;
+    if (grid4 < 1) grid4 = 1;
+    qmf_synth_hq_g4_kernel<<<(unsigned)grid4, kG4Warps * 32, smem4, stream>>>(args);
+    return cudaGetLastError();
+  }
   if (!use_tma) return launch_qmf_synth_hq_pairs(args, num_sms, stream);
   // the rows are staged by 16-byte-granular bulk copies
   if (!args.twiddles || ((uintptr_t)args.matrix & 15) != 0 || (args.mat_stride & 3) != 0) return cudaErrorInvalidValue;

@@ -1,13 +1,10 @@
-timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 900 python bench.py > gpurun_out/r2_bench_default_final2.json 2> gpurun_out/r2_bench_default_final2.err; tail -2 gpurun_out/r2_bench_default_final2.err
-timeout 600 python bench.py --impl reference > gpurun_out/r2_bench_default_ref_final2.json 2>/dev/null
-timeout 600 python bench.py --workload aac_lc_stereo_output --no-extra-stages > gpurun_out/r2_bench_lcout_final2.json 2>/dev/null
-timeout 600 python bench.py --workload sbr_sideinfo --no-extra-stages > gpurun_out/r2_bench_sideinfo_final2.json 2>/dev/null
-python - <<'P'
-import json
-for f in ("r2_bench_default_final2","r2_bench_default_ref_final2","r2_bench_lcout_final2","r2_bench_sideinfo_final2"):
-    try:
-        d=json.loads(open("gpurun_out/%s.json"%f).read().strip().splitlines()[-1])
-        print(f, "value %.4g ms %.4g e2e %.4g"%(d["value"], d["ms_per_step"], d["e2e"]["value"]), "roof", (d.get("roofline") or {}).get("frac"), "dom", ((d.get("roofline") or {}).get("dominant_kernel") or {}).get("kernel"), "cpu", (d.get("cpu_baseline") or {}).get("value"))
-    except Exception as e: print(f,"ERR",e)
-P
+timeout 900 python -m pytest tests/test_qmf_synth_gpu.py tests/test_chain_gpu.py tests/test_sbrdec_gpu.py -x -q -m gpu 2>&1 | tail -4
+for v in "" RING; do
+  if [ -n "$v" ]; then export XAAC_B200_SYNTH_RING=1; fi
+  timeout 300 python bench.py --workload qmf_synth_hq --steps 20 --warmup 5 --no-cpu-baseline --no-extra-stages 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('variant [$v]', d['ms_per_step'], d['roofline']['frac'])"
+done
+unset XAAC_B200_SYNTH_RING
+bash tools/ncu_quick.sh qmf_synth_hq gpurun_out/r2_synth_g4_quick_a.csv -- python bench.py --workload qmf_synth_hq --steps 3 --warmup 3 --no-cpu-baseline --no-extra-stages > /dev/null 2>&1
+grep '^"0"' gpurun_out/r2_synth_g4_quick_a.csv | awk -F'","' '{print $(NF-2), $(NF)}' | grep -v "launch__\|barrier_per\|lg_thr\|mio\|branch"
