@@ -15,14 +15,17 @@
 //   HBM matrix[32][128] WORD32 --LDG.32 coalesced, register double-buffered one slot pair ahead-->
 //     block shift -> pre-twiddle -> smem T (two slots at a time so that the 2 x 16 radix-4 butterflies of a stage
 //     fill all 32 lanes) -> radix-4, radix-4 -> radix-2 + post-twiddle + fold fused in registers
-//     -> filter state (smem, tap-major transposed, one sign-extended sample per word so a tap is one IMAD)
-//     -> window-add -> PCM16 pairs, STG.32 coalesced.
-//   HBM filter_states[1280] WORD16 is read once and written once per unit in the reference's own layout.
+//     -> ring of 16 rows in shared memory, one per slot (sign-extended samples, one per word so a tap is one IMAD; output
+//        pair k' owns words 4k'..4k'+3 of a row)
+//     -> every four slots: 10-tap window over the 13 rows they need, coefficients by block age -> PCM16 pairs, STG.32 coalesced.
+//   HBM filter_states[1280] WORD16 is read once and written once per unit in the reference's own (ring) layout.
 // Algorithmic HBM bytes per unit: 16384 + 2560 + 2560 + 4096 = 25600.
 //
 // The saturating adds of the reference's window-add can never saturate with the standard prototype filter
 // (sum of |coefficients| over the 10 taps <= 57308 < 65535, verified when the ROM is installed), so the taps are
 // accumulated with wrapping multiply-adds, which is bit-identical.
+//
+// The same file holds the opt-in bulk-copy (TMA) staged variant qmf_synth_hq_tma_kernel (XAAC_B200_SYNTH_TMA=1).
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
@@ -34,27 +37,19 @@
 
 namespace xb {
 
-constexpr int kSynWarps = 12;          // warps per block
-constexpr int kStStride = 44;          // words per output pair in the transposed filter state (40 used)
-constexpr int kStWords = 32 * kStStride;
-constexpr int kCoStride = 38;          // words per output pair in the transposed coefficient table (19 taps x 2)
 constexpr int kTHalf = 40;             // int2 per FFT half (32 used; +8 keeps the two halves on disjoint bank pairs)
 constexpr int kTSlot = 2 * kTHalf;
 
-struct SynWarpSmem {
-  i32 st[kStWords];      // filter state: [pair k'][class][block B][elem], sign-extended WORD16 samples
-  int2 T[2 * kTSlot];    // FFT workspace for two slots
-};
-
-struct SynBlockSmem {
-  i32 coef[32 * kCoStride];  // qmf_c[2k'+elem+64q], sign-extended
+// block-shared tables, pre-shifted on the host (qmf_synth_build_tables); the device image is this struct followed by qmf_c as
+// 640 32-bit words (two consecutive WORD16 coefficients per word)
+struct SynTables {
   int2 pre_tw[32];           // (wim<<16, wre<<16)  sbr_sin_cos_twiddle_l64
   int2 alt_tw[16];           // (wim<<16, wre<<16)  sbr_alt_sin_twiddle_l64
   int2 w1[24];               // radix-4 stage 1: position i -> (si,co) x 3, each << 16
   int2 w2[6];                // radix-4 stage 2: position i -> (si,co) x 3
   i32 postmap[32];           // F[p] = T[a] (+|-) T[a+1]: a | sign<<8
-  SynWarpSmem w[kSynWarps];
 };
+constexpr size_t kSynV2CoefOffset = sizeof(SynTables);
 
 // slot-local swizzle of the FFT workspace (see DESIGN.md §QMF synthesis): keeps stage-1 (stride 8), stage-2
 // (stride 2 inside groups of 8) and the pre-twiddle scatter conflict-free for 64-bit accesses.
@@ -218,195 +213,18 @@ XB_DEV void syn_lane_setup(SynLane &L, int lane, const i32 *postmap) {
   L.pre_e = tsw((lane & 1) ? 31 - (lane >> 1) : (lane >> 1));
 }
 
-__global__ void __launch_bounds__(kSynWarps * 32, 2)
-qmf_synth_hq_kernel(QmfSynthArgs p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SynBlockSmem &sm = *reinterpret_cast<SynBlockSmem *>(smem_raw);
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  {  // block-shared tables (already pre-shifted/transposed on the host, see xaac_b200_set_qmf_rom)
-    const i32 *src = reinterpret_cast<const i32 *>(p.rom);
-    i32 *dst = reinterpret_cast<i32 *>(&sm);
-    const int nwords = (int)(offsetof(SynBlockSmem, w) / 4);
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  i32 *st = sm.w[warp].st;
-  int2 *T = sm.w[warp].T;
-  const int warps_total = gridDim.x * kSynWarps;
-
-  // lane roles in the FFT / post stages: lanes 0-15 serve the first slot of a pair, 16-31 the second
-  SynLane L;
-  const int fs_slot = lane >> 4;
-  syn_lane_setup(L, lane, sm.postmap);
-  // band read first / second by this lane (odd lanes swapped, see modulate_pair)
-  const int bandA = (lane & 1) ? 63 - lane : lane;
-  const int bandB = 63 - bandA;
-
-  for (long long u = (long long)blockIdx.x * kSynWarps + warp; u < p.n_units; u += warps_total) {
-    if (p.gate && p.gate[u] == 0) continue;
-    const i32 *mat = p.matrix + u * p.mat_stride;
-    const int16_t *prm = p.params + u * 8;
-    const int ov_lb_scale = prm[0], lb_scale = prm[1], hb_scale = prm[2], st_syn = prm[3];
-    const int lsb = prm[4], usb = prm[5], split = prm[6];
-    int off = p.pos[2 * u], fpos = p.pos[2 * u + 1];
-    // qmf_dec.c:914-926, :1055
-    int ov_lb_shift = (st_syn - ov_lb_scale) - 8, lb_shift = (st_syn - lb_scale) - 8;
-    int hb_shift = (st_syn - hb_scale) - 8;
-    const int out_shift = -(st_syn - 3) + 1;
-    // per-lane block shift of its two bands: value * mul >> shr   (env_calc.c:1099-1157)
-    auto enc = [](int sh, i32 &mul, int &shr) {
-      sh = max(-31, min(31, sh));
-      mul = sh > 0 ? (i32)(1u << sh) : 1;
-      shr = sh < 0 ? -sh : 0;
-    };
-    i32 mulA_ov, mulA_lb, mulB_ov, mulB_lb;
-    int shrA_ov, shrA_lb, shrB_ov, shrB_lb;
-    enc(bandA < lsb ? ov_lb_shift : (bandA < usb ? hb_shift : 0), mulA_ov, shrA_ov);
-    enc(bandA < lsb ? lb_shift : (bandA < usb ? hb_shift : 0), mulA_lb, shrA_lb);
-    enc(bandB < lsb ? ov_lb_shift : (bandB < usb ? hb_shift : 0), mulB_ov, shrB_ov);
-    enc(bandB < lsb ? lb_shift : (bandB < usb ? hb_shift : 0), mulB_lb, shrB_lb);
-    // fold: round16(shl32_sat(x, out_shift)) == ((clamp(x) << s) + 0x8000) >> 16 with the clamp bounds below
-    const i32 clamp_lo = (i32)0x80000000 >> out_shift;
-    const i32 clamp_hi = (i32)(0x7fff7fffu >> out_shift);
-    const i32 fold_mul = (i32)(1u << out_shift);
-
-    // ---- filter state: HBM (reference layout, WORD16[1280]) -> smem (tap-major, <<16); lane = output pair ----
-    {
-      const i32 *src = reinterpret_cast<const i32 *>(p.states + u * 1280);
-      i32 wv[20];
-#pragma unroll
-      for (int t = 0; t < 20; t++) wv[t] = __ldg(src + 32 * t + lane);  // t = 2B + h: samples 128B + 64h + 2 lane (+1)
-#pragma unroll
-      for (int t = 0; t < 20; t++) {
-        const int B = t >> 1, h = t & 1;
-        *reinterpret_cast<int2 *>(st + lane * kStStride + ((h ^ (B & 1)) * 20) + 2 * B) =
-            make_int2((i32)(int16_t)wv[t], wv[t] >> 16);
-      }
-    }
-    __syncwarp();
-
-    // register prefetch of the first slot pair
-    i32 nx[8];
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-      const i32 *m = mat + 128 * s;
-      nx[4 * s + 0] = __ldg(m + bandA);
-      nx[4 * s + 1] = __ldg(m + bandB);
-      nx[4 * s + 2] = __ldg(m + 64 + bandA);
-      nx[4 * s + 3] = __ldg(m + 64 + bandB);
-    }
-    int16_t *pcm = p.pcm + (p.pcm_unit_stride ? u * p.pcm_unit_stride
-                                               : ((p.ch_fac == 1) ? u * 2048 : (u / p.ch_fac) * (2048LL * p.ch_fac) + (u % p.ch_fac)));
-
-#pragma unroll 1
-    for (int pr = 0; pr < 16; pr++) {
-      // ---- block shift (env_calc.c:1099) of the pair's inputs + magnitude classification ----
-      i32 v[8];
-      u32 mag = 0;
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const bool ov = (2 * pr + s) < split;
-        const i32 mA = ov ? mulA_ov : mulA_lb, mB = ov ? mulB_ov : mulB_lb;
-        const int rA = ov ? shrA_ov : shrA_lb, rB = ov ? shrB_ov : shrB_lb;
-        v[4 * s + 0] = (i32)((u32)nx[4 * s + 0] * (u32)mA) >> rA;
-        v[4 * s + 1] = (i32)((u32)nx[4 * s + 1] * (u32)mB) >> rB;
-        v[4 * s + 2] = (i32)((u32)nx[4 * s + 2] * (u32)mA) >> rA;
-        v[4 * s + 3] = (i32)((u32)nx[4 * s + 3] * (u32)mB) >> rB;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; j++) mag |= (u32)(v[j] ^ (v[j] >> 31));
-      if (pr < 15) {
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-          const i32 *m = mat + 128 * (2 * pr + 2 + s);
-          nx[4 * s + 0] = __ldg(m + bandA);
-          nx[4 * s + 1] = __ldg(m + bandB);
-          nx[4 * s + 2] = __ldg(m + 64 + bandA);
-          nx[4 * s + 3] = __ldg(m + 64 + bandB);
-        }
-      }
-      mag = __reduce_or_sync(0xffffffffu, mag);
-      i32 fo[8];
-      if ((mag >> p.fast_bits) == 0)
-        modulate_pair<false>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, p.zero, fo);
-      else
-        modulate_pair<true>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, 0, fo);
-
-      // ---- per slot: commit the fold into the ring, then the 10-tap window (generic:1508) ----
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const int Bw = off >> 7;
-        if (fs_slot == s) {
-          const int c0 = (Bw & 1) * 20 + 2 * Bw, c1 = ((Bw & 1) ^ 1) * 20 + 2 * Bw;
-          *reinterpret_cast<int2 *>(st + L.r16 * kStStride + c0) = make_int2(fo[0], fo[1]);
-          *reinterpret_cast<int2 *>(st + (31 - L.r16) * kStStride + c0) = make_int2(fo[2], fo[3]);
-          *reinterpret_cast<int2 *>(st + L.r16 * kStStride + c1) = make_int2(fo[4], fo[5]);
-          *reinterpret_cast<int2 *>(st + (31 - L.r16) * kStStride + c1) = make_int2(fo[6], fo[7]);
-        }
-        __syncwarp();
-        const int slot = 2 * pr + s;
-        const int4 *sv = reinterpret_cast<const int4 *>(st + lane * kStStride + (slot & 1) * 20);
-        const int2 *cv = reinterpret_cast<const int2 *>(sm.coef + lane * kCoStride + 2 * (fpos >> 6));
-        i32 acc0 = 0x4000, acc1 = 0x4000;
-#pragma unroll
-        for (int q = 0; q < 5; q++) {
-          int4 x = sv[q];
-          int2 ca = cv[2 * q], cb = cv[2 * q + 1];
-          acc0 += x.x * ca.x;
-          acc1 += x.y * ca.y;
-          acc0 += x.z * cb.x;
-          acc1 += x.w * cb.y;
-        }
-        // shl32_sat(acc, 1) >> 16  ==  clamp(acc, -2^30, 2^30-1) >> 15
-        i32 o0 = max(-0x40000000, min(0x3fffffff, acc0)) >> 15;
-        i32 o1 = max(-0x40000000, min(0x3fffffff, acc1)) >> 15;
-        if (p.ch_fac == 1) {
-          *reinterpret_cast<i32 *>(pcm + 64 * slot + 2 * lane) = (o0 & 0xffff) | (i32)((u32)o1 << 16);
-        } else {
-          pcm[p.ch_fac * (64 * slot + 2 * lane)] = (int16_t)o0;
-          pcm[p.ch_fac * (64 * slot + 2 * lane + 1)] = (int16_t)o1;
-        }
-        off -= 128;
-        if (off < 0) off += 1280;
-        fpos += 64;
-        if (fpos == 640) fpos = 0;
-        __syncwarp();
-      }
-    }
-
-    // ---- filter state back to HBM in the reference layout ----
-    {
-      i32 *dst = reinterpret_cast<i32 *>(p.states + u * 1280);
-#pragma unroll
-      for (int t = 0; t < 20; t++) {
-        const int B = t >> 1, h = t & 1;
-        int2 x = *reinterpret_cast<const int2 *>(st + lane * kStStride + ((h ^ (B & 1)) * 20) + 2 * B);
-        dst[32 * t + lane] = (i32)(((u32)x.x & 0xffffu) | ((u32)x.y << 16));
-      }
-      if (lane == 0) {
-        p.pos[2 * u] = (int16_t)off;
-        p.pos[2 * u + 1] = (int16_t)fpos;
-      }
-    }
-    __syncwarp();
-  }
-}
-
-
 // =====================================================================================================================
-// Slot-pair modulation (as above) + linear-time window, four slots per pass.
+// The kernel: slot-pair modulation (above) + linear-time window, four slots per pass.
 //
-// The modulation is the slot-pair code of qmf_synth_hq_kernel.  What changes is the filter state: instead of the reference's ring
-// in a tap-major transposed layout with a rotating coefficient pointer (one window pass per slot: 5 LDS.128 + 10 LDS.64 + 20 IMAD,
-// two warp syncs), the folded blocks go to a ring of 16 ROWS in time order (row = slot & 15, 128 words: output pair k' owns words
+// Filter state: instead of the reference's ring with a rotating coefficient pointer (round 1 kept it, tap-major transposed: one
+// window pass per slot = 5 LDS.128 + 10 LDS.64 + 20 IMAD and two warp syncs; 1.69 ms per 131 072 units) the folded blocks go to a
+// ring of 16 ROWS in time order (row = slot & 15, 128 words: output pair k' owns words
 // 4k'..4k'+3 = both 64-sample halves) and the window runs once per FOUR slots: the 13 rows s0-9 .. s0+3 are read once (13 LDS.128)
 // for all 80 taps, and the coefficient of a block depends on its age only (see qmf_synth_core.cuh), so a tap is
 // row[s - a][half(a)] * w_a with w_a read once per pass.  Shared memory per warp: 8 KB rows + 1.25 KB FFT workspace; one block of
 // 23 warps per SM (88 registers).
 // =====================================================================================================================
 constexpr int kG4Warps = 23;
-constexpr size_t kSynV2CoefOffset = offsetof(SynBlockSmem, w);  // qmf_c as 640 32-bit words follows the slot-pair kernel's tables
 
 struct SynG4Warp {
   i32 rows[16 * 128];
@@ -421,9 +239,7 @@ struct SynG4Block {
   int2 cw[20 * 32];  // cw[32 b + k'] = (qmf_c[64 (b mod 10) + 2k'], qmf_c[.. + 1]), sign-extended: tap of age a at block kappa + a
   SynG4Warp w[kG4Warps];
 };
-constexpr size_t kSynTablesOffset = offsetof(SynBlockSmem, pre_tw);   // pre_tw .. postmap inside the table image
-constexpr size_t kSynTablesBytes = offsetof(SynBlockSmem, w) - offsetof(SynBlockSmem, pre_tw);
-static_assert(kSynTablesBytes == offsetof(SynG4Block, cw), "table block layouts must match");
+static_assert(sizeof(SynTables) == offsetof(SynG4Block, cw), "the block starts with the table image");
 
 // window of slots s0 .. s0+3 (s0 = 4 g, GPH = g & 3 fixes the ring rows at compile time) for output pair `lane`
 template <int P, int GPH>
@@ -461,15 +277,15 @@ XB_DEV void window_ring4_dispatch(int gph, const i32 *rows, const int2 *cwk, int
 }
 
 __global__ void __launch_bounds__(kG4Warps * 32, 1)
-qmf_synth_hq_g4_kernel(QmfSynthArgs p) {
+qmf_synth_hq_kernel(QmfSynthArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SynG4Block &sm = *reinterpret_cast<SynG4Block *>(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   {
-    const i32 *src = reinterpret_cast<const i32 *>(p.rom + kSynTablesOffset);
+    const i32 *src = reinterpret_cast<const i32 *>(p.rom);
     i32 *dst = reinterpret_cast<i32 *>(&sm);
-    for (int i = threadIdx.x; i < (int)(kSynTablesBytes / 4); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(SynTables) / 4); i += blockDim.x) dst[i] = src[i];
     const i32 *c32 = reinterpret_cast<const i32 *>(p.rom + kSynV2CoefOffset);
     for (int i = threadIdx.x; i < 20 * 32; i += blockDim.x) {
       const i32 v = c32[32 * ((i >> 5) % 10) + (i & 31)];
@@ -511,6 +327,8 @@ qmf_synth_hq_g4_kernel(QmfSynthArgs p) {
     enc(bandA < lsb ? lb_shift : (bandA < usb ? hb_shift : 0), mulA_lb, shrA_lb);
     enc(bandB < lsb ? ov_lb_shift : (bandB < usb ? hb_shift : 0), mulB_ov, shrB_ov);
     enc(bandB < lsb ? lb_shift : (bandB < usb ? hb_shift : 0), mulB_lb, shrB_lb);
+    const bool noshift = __all_sync(0xffffffffu, (mulA_ov & mulA_lb & mulB_ov & mulB_lb) == 1 && (shrA_ov | shrA_lb | shrB_ov | shrB_lb) == 0);
+    const i32 fast_lim = (i32)(1u << p.fast_bits);
     const i32 clamp_lo = (i32)0x80000000 >> out_shift;
     const i32 clamp_hi = (i32)(0x7fff7fffu >> out_shift);
     const i32 fold_mul = (i32)(1u << out_shift);
@@ -547,19 +365,25 @@ qmf_synth_hq_g4_kernel(QmfSynthArgs p) {
 #pragma unroll 1
     for (int pr = 0; pr < 16; pr++) {
       i32 v[8];
-      u32 mag = 0;
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const bool ov = (2 * pr + s) < split;
-        const i32 mA = ov ? mulA_ov : mulA_lb, mB = ov ? mulB_ov : mulB_lb;
-        const int rA = ov ? shrA_ov : shrA_lb, rB = ov ? shrB_ov : shrB_lb;
-        v[4 * s + 0] = (i32)((u32)nx[4 * s + 0] * (u32)mA) >> rA;
-        v[4 * s + 1] = (i32)((u32)nx[4 * s + 1] * (u32)mB) >> rB;
-        v[4 * s + 2] = (i32)((u32)nx[4 * s + 2] * (u32)mA) >> rA;
-        v[4 * s + 3] = (i32)((u32)nx[4 * s + 3] * (u32)mB) >> rB;
+      for (int j = 0; j < 8; j++) v[j] = nx[j];
+      if (!noshift) {  // the left channel after PS arrives in the synthesis scale already: no block shifts at all
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const bool ov = (2 * pr + s) < split;
+          const i32 mA = ov ? mulA_ov : mulA_lb, mB = ov ? mulB_ov : mulB_lb;
+          const int rA = ov ? shrA_ov : shrA_lb, rB = ov ? shrB_ov : shrB_lb;
+          v[4 * s + 0] = (i32)((u32)v[4 * s + 0] * (u32)mA) >> rA;
+          v[4 * s + 1] = (i32)((u32)v[4 * s + 1] * (u32)mB) >> rB;
+          v[4 * s + 2] = (i32)((u32)v[4 * s + 2] * (u32)mA) >> rA;
+          v[4 * s + 3] = (i32)((u32)v[4 * s + 3] * (u32)mB) >> rB;
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 8; j++) mag |= (u32)(v[j] ^ (v[j] >> 31));
+      // all inputs inside [-2^fast_bits, 2^fast_bits): three-input min / max, one instruction per two values
+      i32 vmx = max(max(v[0], v[1]), max(v[2], v[3])), vmn = min(min(v[0], v[1]), min(v[2], v[3]));
+      vmx = max(vmx, max(max(v[4], v[5]), max(v[6], v[7])));
+      vmn = min(vmn, min(min(v[4], v[5]), min(v[6], v[7])));
+      const bool big = vmx >= fast_lim || vmn < -fast_lim;
       if (pr < 15) {
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -570,9 +394,8 @@ qmf_synth_hq_g4_kernel(QmfSynthArgs p) {
           nx[4 * s + 3] = __ldg(m + 64 + bandB);
         }
       }
-      mag = __reduce_or_sync(0xffffffffu, mag);
       i32 fo[8];
-      if ((mag >> p.fast_bits) == 0)
+      if (!__any_sync(0xffffffffu, big))
         modulate_pair<false>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, p.zero, fo);
       else
         modulate_pair<true>(v, T, sm, L, lane, clamp_lo, clamp_hi, fold_mul, 0, fo);
@@ -806,21 +629,18 @@ qmf_synth_hq_tma_kernel(const __grid_constant__ QmfSynthArgs p, const __grid_con
   }
 }
 
-size_t qmf_synth_table_bytes() { return offsetof(SynBlockSmem, w) + 640 * 4; }
+size_t qmf_synth_table_bytes() { return sizeof(SynTables) + 640 * 4; }
 
-// Host-side construction of the block-shared table image from the reference-layout QMF ROM blob
-// (leading bytes of ia_qmf_dec_tables_struct). Returns false if the prototype violates the no-saturation bound.
+// Host-side construction of the table image from the reference-layout QMF ROM blob (leading bytes of
+// ia_qmf_dec_tables_struct).  Returns fast_bits (> 0), or -1 if the tables are not the ones the kernels are built for.
 int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
-  SynBlockSmem *t = reinterpret_cast<SynBlockSmem *>(out);  // only the leading table part is written
+  SynTables *t = reinterpret_cast<SynTables *>(out);
   const int16_t *w32 = reinterpret_cast<const int16_t *>(qrom + kQRomW32);
   const int32_t *dr = reinterpret_cast<const int32_t *>(qrom + kQRomDigRev2_32);
   const int16_t *sc = reinterpret_cast<const int16_t *>(qrom + kQRomSinCosL64);
   const int16_t *al = reinterpret_cast<const int16_t *>(qrom + kQRomAltSinL64);
   const int16_t *c = reinterpret_cast<const int16_t *>(qrom + kQRomQmfC);
   auto hi = [](int16_t v) { return (int32_t)((uint32_t)(uint16_t)v << 16); };
-  for (int k = 0; k < 32; k++)
-    for (int q = 0; q < 19; q++)
-      for (int e = 0; e < 2; e++) t->coef[k * kCoStride + 2 * q + e] = (int32_t)c[2 * k + e + 64 * q];
   for (int n = 0; n < 32; n++) t->pre_tw[n] = make_int2(hi(sc[2 * n]), hi(sc[2 * n + 1]));
   for (int n = 0; n < 16; n++) t->alt_tw[n] = make_int2(hi(al[2 * n]), hi(al[2 * n + 1]));
   for (int i = 0; i < 8; i++)
@@ -841,7 +661,8 @@ int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
     }
   for (int i = 0; i < 32; i++)
     if (t->postmap[i] < 0) return -1;
-  // the register-resident modulation (version 2) has the digit reversal compiled in and needs the 640-periodic qmf_c
+  // the register-resident modulation of the TMA variant has the digit reversal compiled in; the linear-time window of both
+  // kernels needs the 640-periodic qmf_c (coefficient by block age, qmf_synth_core.cuh)
   for (int i = 0; i < 32; i++)
     if (t->postmap[i] != (syn::post_src(i) | (i >= 16 ? 256 : 0))) return -1;
   for (int i = 0; i < 640; i++)
@@ -887,27 +708,6 @@ int qmf_synth_build_tables(const uint8_t *qrom, uint8_t *out) {
   return fast_bits;
 }
 
-static cudaError_t launch_qmf_synth_hq_pairs(const QmfSynthArgs &args, int num_sms, cudaStream_t stream) {
-  static xb::PerDeviceOnce configured;
-  size_t smem = sizeof(SynBlockSmem);
-  if (configured.needed()) {
-    cudaError_t e =
-        cudaFuncSetAttribute(qmf_synth_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured.done();
-  }
-  int blocks_per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (blocks_per_sm < 1) blocks_per_sm = 1;
-  if (blocks_per_sm > 2) blocks_per_sm = 2;
-  long long need = (args.n_units + kSynWarps - 1) / kSynWarps;
-  long long grid = (long long)num_sms * blocks_per_sm;
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
-  qmf_synth_hq_kernel<<<(unsigned)grid, kSynWarps * 32, smem, stream>>>(args);
-  return cudaGetLastError();
-}
-
-
 void qmf_synth_build_twiddles(const uint8_t *qrom, void *out) {
   SynTw *t = reinterpret_cast<SynTw *>(out);
   const int16_t *w32 = reinterpret_cast<const int16_t *>(qrom + kQRomW32);
@@ -925,15 +725,14 @@ void qmf_synth_build_twiddles(const uint8_t *qrom, void *out) {
 size_t qmf_synth_twiddle_bytes() { return sizeof(SynTw); }
 
 cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStream_t stream) {
-  // Default: the slot-pair kernel above (1.69 ms per 131 072 units).  XAAC_B200_SYNTH_TMA=1 selects the bulk-copy-staged
-  // lane = slot variant (bit-identical, 2.09 ms: 2 warps per scheduler cannot hide its dependent chains — profiles/r2_synth_tma.md).
+  // XAAC_B200_SYNTH_TMA=1 selects the bulk-copy-staged lane = slot variant (bit-identical, 2.09 ms against 1.45 ms per 131 072
+  // units: 2 warps per scheduler cannot hide its dependent chains — profiles/r2_synth_tma.md)
   static const bool use_tma = getenv("XAAC_B200_SYNTH_TMA") != nullptr;
-  static const bool use_ring = getenv("XAAC_B200_SYNTH_RING") != nullptr;  // the original per-slot ring window
-  if (!use_tma && !use_ring) {
+  if (!use_tma) {
     static xb::PerDeviceOnce configured_g4;
     const size_t smem4 = sizeof(SynG4Block);
     if (configured_g4.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(qmf_synth_hq_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+      cudaError_t e = cudaFuncSetAttribute(qmf_synth_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
       if (e != cudaSuccess) return e;
       configured_g4.done();
     }
@@ -941,10 +740,9 @@ cudaError_t launch_qmf_synth_hq(const QmfSynthArgs &args, int num_sms, cudaStrea
     long long grid4 = num_sms;
     if (grid4 > need4) grid4 = need4;
     if (grid4 < 1) grid4 = 1;
-    qmf_synth_hq_g4_kernel<<<(unsigned)grid4, kG4Warps * 32, smem4, stream>>>(args);
+    qmf_synth_hq_kernel<<<(unsigned)grid4, kG4Warps * 32, smem4, stream>>>(args);
     return cudaGetLastError();
   }
-  if (!use_tma) return launch_qmf_synth_hq_pairs(args, num_sms, stream);
   // the rows are staged by 16-byte-granular bulk copies
   if (!args.twiddles || ((uintptr_t)args.matrix & 15) != 0 || (args.mat_stride & 3) != 0) return cudaErrorInvalidValue;
   static xb::PerDeviceOnce configured;
