@@ -100,6 +100,7 @@ struct SynLane {       // per-lane constants of the modulation stages
   i32 pf_sgn, pb_sgn;          // +1 / -1
   int pre_e;                   // pre-twiddle scatter slot
   int r16;
+  int2 ptw, w1a, w1b, w1c, w2a, w2b, w2c, altb, altf;  // the lane's twiddles, loop-invariant
 };
 
 // Modulation of one slot pair: block-shifted inputs v[8] (a,b,c,d per slot; odd lanes hold them swapped, which turns
@@ -108,7 +109,7 @@ struct SynLane {       // per-lane constants of the modulation stages
 template <bool SAT, class SM>
 XB_DEV void modulate_pair(const i32 *v, int2 *T, const SM &sm, const SynLane &L, int lane, i32 clamp_lo,
                           i32 clamp_hi, i32 fold_mul, i32 z, i32 *fo) {
-  const int2 ptw = sm.pre_tw[lane];
+  const int2 ptw = L.ptw;
   // ---- pre-twiddle (generic:290-367) ----
 #pragma unroll
   for (int s = 0; s < 2; s++) {
@@ -123,22 +124,19 @@ XB_DEV void modulate_pair(const i32 *v, int2 *T, const SM &sm, const SynLane &L,
   }
   __syncwarp();
   {  // ---- radix-4 stage 1 (span 8) ----
-    const int i1 = L.r16 & 7;
     int2 e0 = T[L.s1idx[0]], e1 = T[L.s1idx[1]], e2 = T[L.s1idx[2]], e3 = T[L.s1idx[3]];
-    radix4<SAT>(e0, e1, e2, e3, sm.w1[3 * i1], sm.w1[3 * i1 + 1], sm.w1[3 * i1 + 2], z);
+    radix4<SAT>(e0, e1, e2, e3, L.w1a, L.w1b, L.w1c, z);
     T[L.s1idx[0]] = e0; T[L.s1idx[1]] = e1; T[L.s1idx[2]] = e2; T[L.s1idx[3]] = e3;
   }
   __syncwarp();
   {  // ---- radix-4 stage 2 (4 groups, span 2) ----
-    const int i2 = L.r16 & 1;
     int2 e0 = T[L.s2idx[0]], e1 = T[L.s2idx[1]], e2 = T[L.s2idx[2]], e3 = T[L.s2idx[3]];
-    radix4<SAT>(e0, e1, e2, e3, sm.w2[3 * i2], sm.w2[3 * i2 + 1], sm.w2[3 * i2 + 2], z);
+    radix4<SAT>(e0, e1, e2, e3, L.w2a, L.w2b, L.w2c, z);
     T[L.s2idx[0]] = e0; T[L.s2idx[1]] = e1; T[L.s2idx[2]] = e2; T[L.s2idx[3]] = e3;
   }
   __syncwarp();
   // ---- radix-2 + digit reversal (generic:1934) + post-twiddle (generic:388-465) + fold (generic:1638) ----
-  const int2 alt_b = sm.alt_tw[L.r16];
-  const int2 alt_f = sm.alt_tw[L.r16 > 0 ? L.r16 - 1 : 0];
+  const int2 alt_b = L.altb, alt_f = L.altf;
   i32 G1[4], G2[4];  // [0]=G[2u] [1]=G[2u+1] [2]=G[62-2u] [3]=G[63-2u]
 #pragma unroll
   for (int h = 0; h < 2; h++) {
@@ -222,9 +220,10 @@ XB_DEV void syn_lane_setup(SynLane &L, int lane, const i32 *postmap) {
 // 4k'..4k'+3 = both 64-sample halves) and the window runs once per FOUR slots: the 13 rows s0-9 .. s0+3 are read once (13 LDS.128)
 // for all 80 taps, and the coefficient of a block depends on its age only (see qmf_synth_core.cuh), so a tap is
 // row[s - a][half(a)] * w_a with w_a read once per pass.  Shared memory per warp: 8 KB rows + 1.25 KB FFT workspace; one block of
-// 23 warps per SM (88 registers).
+// 16 warps per SM — four per scheduler, which leaves room for the lane's nine twiddle pairs in registers (a warp count that is
+// not a multiple of four costs 10 %: the schedulers run unevenly loaded).
 // =====================================================================================================================
-constexpr int kG4Warps = 23;
+constexpr int kG4Warps = 16;  // 4 per scheduler; measured: 12 -> 1.51 ms, 16 -> 1.37, 20 -> 1.38, 18 / 22 / 23 (uneven) -> 1.45-1.51
 
 struct SynG4Warp {
   i32 rows[16 * 128];
@@ -299,6 +298,13 @@ qmf_synth_hq_kernel(QmfSynthArgs p) {
   SynLane L;
   const int fs_slot = lane >> 4;
   syn_lane_setup(L, lane, sm.postmap);
+  {
+    const int i1 = L.r16 & 7, i2 = L.r16 & 1;
+    L.ptw = sm.pre_tw[lane];
+    L.w1a = sm.w1[3 * i1]; L.w1b = sm.w1[3 * i1 + 1]; L.w1c = sm.w1[3 * i1 + 2];
+    L.w2a = sm.w2[3 * i2]; L.w2b = sm.w2[3 * i2 + 1]; L.w2c = sm.w2[3 * i2 + 2];
+    L.altb = sm.alt_tw[L.r16]; L.altf = sm.alt_tw[L.r16 > 0 ? L.r16 - 1 : 0];
+  }
   const int bandA = (lane & 1) ? 63 - lane : lane;
   const int bandB = 63 - bandA;
 
