@@ -2460,6 +2460,7 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (ncu_traffic().get(stg["kernel"], {}).get("bytes_per_unit", 0) * n_units) or None,
                          "traffic_source": ncu_traffic().get(stg["kernel"], {}).get("source"),
+                         "traffic_standalone": (ncu_traffic().get(stg["kernel"], {}).get("standalone_bytes_per_unit", 0) * n_units) or None,
                          "traffic_stale": bool(ncu_traffic().get(stg["kernel"], {}).get("stale", False)), "peak_source": peak_src,
                          "bytes_per_unit": stg["bytes_per_unit"], "units_per_launch": n_units,
                          "launch_ms": kernel_ms},
