@@ -1055,6 +1055,17 @@ int32_t xaac_b200_peak_limiter_state_init(int32_t *state, int32_t num_channels, 
   return XAAC_B200_OK;
 }
 
+static int32_t peak_limiter_launches(xaac_b200_ctx *ctx, const xb::PeakLimArgs &a, void *scratch, void *stream) {
+  LAUNCH("peak_limiter_kernel", stream, xb::launch_peak_limiter(a, scratch, 0, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  if (scratch) {
+    LAUNCH("peak_limiter_smooth_kernel", stream, xb::launch_peak_limiter(a, scratch, 1, ctx->num_sms, (cudaStream_t)stream));
+    LAUNCH("peak_limiter_finish_kernel", stream, xb::launch_peak_limiter(a, scratch, 2, ctx->num_sms, (cudaStream_t)stream));
+    ctx->launches += 2;
+  }
+  return XAAC_B200_OK;
+}
+
 int32_t xaac_b200_peak_limiter_dev(xaac_b200_ctx *ctx, int32_t *d_state, const int32_t *d_samples,
                                    const int8_t *d_qshift_adj, int32_t *d_out32, int16_t *d_pcm16, int32_t *d_err,
                                    int64_t n_units, int32_t num_channels, void *stream) {
@@ -1082,15 +1093,11 @@ int32_t xaac_b200_peak_limiter_dev(xaac_b200_ctx *ctx, int32_t *d_state, const i
     CK(cudaMallocFromPoolAsync(&scratch, xb::peak_limiter_scratch_bytes(n_units), ctx->pool, (cudaStream_t)stream),
        "cudaMallocFromPoolAsync");
   }
-  LAUNCH("peak_limiter_kernel", stream, xb::launch_peak_limiter(a, scratch, 0, ctx->num_sms, (cudaStream_t)stream));
-  ctx->launches++;
-  if (scratch) {
-    LAUNCH("peak_limiter_smooth_kernel", stream, xb::launch_peak_limiter(a, scratch, 1, ctx->num_sms, (cudaStream_t)stream));
-    LAUNCH("peak_limiter_finish_kernel", stream, xb::launch_peak_limiter(a, scratch, 2, ctx->num_sms, (cudaStream_t)stream));
-    ctx->launches += 2;
-    CK(cudaFreeAsync(scratch, (cudaStream_t)stream), "cudaFreeAsync");
-  }
-  return XAAC_B200_OK;
+  const int32_t rc = peak_limiter_launches(ctx, a, scratch, stream);
+  // the scratch block goes back to the pool on every path (stream-ordered: after the kernels that were queued)
+  if (scratch && cudaFreeAsync(scratch, (cudaStream_t)stream) != cudaSuccess && rc == XAAC_B200_OK)
+    return fail(ctx, cudaGetLastError(), "cudaFreeAsync");
+  return rc;
 }
 
 int32_t xaac_b200_dec_sbrdata_dev(xaac_b200_ctx *ctx, int16_t *d_records, int64_t n_elements, void *stream) {
