@@ -22,7 +22,7 @@
 
 namespace xb {
 
-constexpr int kHfWarps = 7;
+constexpr int kHfWarps = 4;   // 38 KB of shared memory per block: five blocks = 20 warps per SM, four-warp blocks load the schedulers evenly (7-warp blocks: 1.26 -> 1.24 ms)
 constexpr int kHfColWords = 38 * 2 * 32;  // per warp: the low-band column set of one pass (38 rows x re, im x 32 bands)
 
 // ops32.h:134 — second operand contributes only its high half (not commutative)
@@ -235,7 +235,7 @@ hf_generator_hq_kernel(HfGenArgs p) {
 
 cudaError_t launch_hf_generator_hq(const HfGenArgs &args, int num_sms, cudaStream_t stream) {
   long long need = (args.n_units + kHfWarps - 1) / kHfWarps;
-  long long grid = (long long)num_sms * 8;
+  long long grid = (long long)num_sms * 5;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   const size_t smem = (size_t)kHfWarps * kHfColWords * 4;

@@ -26,7 +26,7 @@
 
 namespace xb {
 
-constexpr int kPlWarps = 7;   // 71.7 KB of shared memory per block: three blocks per SM
+constexpr int kPlWarps = 4;   // 41 KB of shared memory per block: five blocks = 20 warps per SM, evenly spread over the schedulers
 constexpr int kPlSmoothWarps = 4;
 constexpr int kPlFinishWarps = 8;
 
@@ -351,7 +351,7 @@ cudaError_t launch_peak_limiter(const PeakLimArgs &args_in, void *scratch, int w
     return cudaGetLastError();
   }
   long long need = (args.n_units + kPlWarps - 1) / kPlWarps;
-  long long grid = (long long)num_sms * 3;
+  long long grid = (long long)num_sms * 5;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   if (which == 2) {  // no shared memory: 64 warps per SM

@@ -1,12 +1,7 @@
-timeout 900 python bench.py > gpurun_out/r2_bench_default_final3.json 2> gpurun_out/r2_bench_default_final3.err; tail -2 gpurun_out/r2_bench_default_final3.err
-timeout 600 python bench.py --impl reference > gpurun_out/r2_bench_default_ref_final3.json 2>/dev/null
-python - <<'P'
-import json
-for f in ("r2_bench_default_final3","r2_bench_default_ref_final3"):
-    d=json.loads(open("gpurun_out/%s.json"%f).read().strip().splitlines()[-1])
-    print(f, "value %.4g ms %.4g e2e %.4g"%(d["value"], d["ms_per_step"], d["e2e"]["value"]), "roof", (d.get("roofline") or {}).get("frac"), "dom", ((d.get("roofline") or {}).get("dominant_kernel") or {}).get("kernel"))
-    if "other_configs" in d:
-        for k,v in d["other_configs"].items(): print("   ", k, "%.4g"%v["value"], "e2e %.4g"%v["e2e"]["value"])
-    if "stage_rooflines" in d:
-        for k,v in d["stage_rooflines"].items(): print("   stage", k, v["kernel"], round(v["frac"],3))
-P
+timeout 1500 python -m pytest tests/test_envcalc_gpu.py tests/test_hfgen_gpu.py tests/test_peaklim_gpu.py tests/test_sbrdec_gpu.py tests/test_chain_gpu.py tests/test_dropin_gpu.py -x -q -m gpu 2>&1 | tail -3
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-stages --e2e-steps 1 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernels']; print('chain', d['ms_per_step'], d['value'], 'envcalc', k['calc_sbrenvelope_hq_kernel']['launch_ms'], 'hfgen', k['hf_generator_hq_kernel']['launch_ms'])"
+timeout 300 python bench.py --workload aac_lc_stereo_output --steps 10 --warmup 3 --no-cpu-baseline --no-extra-stages --e2e-steps 1 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernels']; print('lcout', d['ms_per_step'], {n:round(x['launch_ms'],3) for n,x in k.items()})"
