@@ -1,6 +1,6 @@
-timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 600 python bench.py --workload aac_lc_stereo_output --no-extra-stages > gpurun_out/r2_bench_lcout_final3.json 2>/dev/null
-python -c "
-import json
-d=json.loads(open('gpurun_out/r2_bench_lcout_final3.json').read().strip().splitlines()[-1]); print('lcout', d['value'], d['ms_per_step'], d['e2e']['value'], d['cpu_baseline']['value'])"
+for v in "" u20 u12; do
+  if [ -n "$v" ]; then export XAAC_B200_LIB=$PWD/build/var/libxaac_b200_$v.so; fi
+  timeout 300 python bench.py --workload usac_fd_imdct --steps 10 --warmup 3 --no-cpu-baseline --no-extra-stages --e2e-steps 1 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('variant [$v]', d['ms_per_step'], d['roofline']['frac'])"
+done
