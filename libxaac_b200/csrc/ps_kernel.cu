@@ -34,7 +34,6 @@ struct PsWarpS {
   i32 xs[3][2][44];         // hybrid filter input history: 12 delayed + 32 new samples of QMF bands 0..2 (re, im)
   i32 hybL[32][21];         // hybrid analysis of all 32 slots: [slot][re 0..9 | im 10..19] (odd row stride: no conflicts)
   u32 pwt[32][21];          // power per parameter bin of all 32 slots: [slot][bin 0..19] (odd row stride)
-  int16_t tr[24];           // transient ratio per bin (+ tr[20] = 0)
 };
 
 XB_DEV i32 m16(i32 a, i32 b) { return a * b; }                                  // mult16x16in32
@@ -168,6 +167,7 @@ XB_DEV i32 blockshift(i32 v, int sh) {  // ixheaacd_adjust_scale_dec semantics (
   return sh > 0 ? lsl(v, sh) : (v >> -sh);
 }
 
+template <bool NOSAT>
 __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
   __shared__ PsWarpS ws[kPsWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -345,9 +345,10 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
     }
     const int trbin = hy ? rom[kPsRomHybToBin + sb] : rom[kPsRomDelayToBin + sb];
     const int rd0 = rom[kPsRomRevDelay], rd1 = rom[kPsRomRevDelay + 1], rd2 = rom[kPsRomRevDelay + 2];
-    const bool nosat = p.rot_nosat != 0;  // no fractional-delay factor is -32768: the 16x16 rotations cannot saturate
-    auto rotr = [&](i32 r, i32 i, i32 fr, i32 fi) { return sext16((nosat ? r * fr - i * fi : sub_sat(r * fr, i * fi)) >> 15); };
-    auto roti = [&](i32 r, i32 i, i32 fr, i32 fi) { return sext16((nosat ? r * fi + i * fr : add_sat(r * fi, i * fr)) >> 15); };
+    // NOSAT: no fractional-delay factor of the ROM is -32768, the 16x16 rotations cannot saturate (one kernel per case: the
+    // saturating forms cost 5 instructions per add and were 7 % of the kernel when selected at run time)
+    auto rotr = [&](i32 r, i32 i, i32 fr, i32 fi) { return sext16((NOSAT ? r * fr - i * fi : sub_sat(r * fr, i * fi)) >> 15); };
+    auto roti = [&](i32 r, i32 i, i32 fr, i32 fi) { return sext16((NOSAT ? r * fi + i * fr : add_sat(r * fi, i * fr)) >> 15); };
     // mixing matrices: lane g < 22 keeps h11/h12/h21/h22 of stereo group g (previous envelope target, interpolated
     // value, per-slot increment) in registers for the whole frame
     const int gi = lane < 22 ? lane : 0;
@@ -366,9 +367,20 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       const i32 *row = mat + 128 * s_;
       const int border0 = prm[kPsPrmBorder];
       const int usb_eff = s_ >= border0 ? usb : ps_usb;
+      // block shifts of this lane's slot as (mul, shr) pairs per band region: value * mul >> shr, branch-free
+      auto enc = [](int sh, i32 &mul, int &shr) {
+        sh = max(-31, min(31, sh));
+        mul = sh > 0 ? (i32)(1u << sh) : 1;
+        shr = sh < 0 ? -sh : 0;
+      };
+      i32 mul_lo, mul_hb;
+      int shr_lo, shr_hb;
+      enc(s_ < 6 ? ov_lb_shift : lb_shift, mul_lo, shr_lo);
+      enc(hb_shift, mul_hb, shr_hb);
       auto tpow = [&](int k) {
-        const int sh = k < lsb ? (s_ < 6 ? ov_lb_shift : lb_shift) : (k < usb ? hb_shift : 0);
-        const i32 r = blockshift(row[k], sh), i = blockshift(row[64 + k], sh);
+        const i32 mul = k < lsb ? mul_lo : (k < usb ? mul_hb : 1);
+        const int shr = k < lsb ? shr_lo : (k < usb ? shr_hb : 0);
+        const i32 r = (i32)((u32)row[k] * (u32)mul) >> shr, i = (i32)((u32)row[64 + k] * (u32)mul) >> shr;
         return min((u32)pw(r) + (u32)pw(i), 0x7fffffffu);
       };
 #pragma unroll
@@ -393,6 +405,34 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
         if (bin < 2) pwr = add_sat(add_sat(pwr, pw(hre[s2])), pw(him[s2]));
         w.pwt[s_][bin] = (u32)pwr;
       }
+    }
+    __syncwarp();
+
+    // ---- transient detection per parameter bin (ps_dec.c:482-620) for all 32 slots: a recursion over the slots per bin that
+    //      nothing else feeds, so it runs here with its state in registers (lane = bin) instead of once per slot through shared
+    //      memory; the transient ratio replaces the bin's power in pwt[slot][bin] (column 20 = 0: "no transient steering").
+    //      The division only runs when some bin of the slot is in a transient.
+    if (lane < 20) {
+      i32 pk = peak[lane], nrg = peak[20 + lane], pdk = peak[40 + lane];
+#pragma unroll 2
+      for (int slot = 0; slot < 32; slot++) {
+        const i32 pwr = (i32)w.pwt[slot][lane];
+        i32 pv = shl32(pwr, 1);
+        if (pv < 0) pv = 0;
+        pk = lsl(mul32x16(pk, 0x620a), 1);
+        if (pv > pk) pk = pv;
+        pdk = add_sat(lsl(mul32x16(pdk, 0x6000), 1), sub_sat(pk, pv) >> 2);
+        nrg = add_sat(lsl(mul32x16(nrg, 0x6000), 1), pv >> 2);
+        const i32 pd = add_sat(pdk, pdk >> 1);
+        i32 tr = 0x7fff;
+        if (pd > nrg) tr = sext16(divide16_pos_lo(nrg, pd));
+        w.pwt[slot][lane] = (u32)tr;
+      }
+      peak[lane] = pk;
+      peak[20 + lane] = nrg;
+      peak[40 + lane] = pdk;
+    } else if (lane == 20) {
+      for (int slot = 0; slot < 32; slot++) w.pwt[slot][20] = 0;
     }
     __syncwarp();
 
@@ -470,26 +510,6 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       const i32 *lre = w.hyb, *lim = w.hyb + 16;
       i32 *rre = w.hyb + 32, *rim = w.hyb + 48;
 
-      // ---- transient detection per parameter bin (ps_dec.c:482-620); the powers come from the pre-pass ----
-      if (lane < 20) {
-        const int bin = lane;
-        const i32 pwr = (i32)w.pwt[slot][bin];
-        i32 pv = shl32(pwr, 1);
-        if (pv < 0) pv = 0;
-        i32 pk = lsl(mul32x16(peak[bin], 0x620a), 1);
-        if (pv > pk) pk = pv;
-        peak[bin] = pk;
-        i32 pd = add_sat(lsl(mul32x16(peak[40 + bin], 0x6000), 1), sub_sat(pk, pv) >> 2);
-        peak[40 + bin] = pd;
-        const i32 nrg = add_sat(lsl(mul32x16(peak[20 + bin], 0x6000), 1), pv >> 2);
-        peak[20 + bin] = nrg;
-        pd = add_sat(pd, pd >> 1);
-        w.tr[bin] = pd <= nrg ? (int16_t)0x7fff : (int16_t)divide16_pos_lo(nrg, pd);
-      } else if (lane == 20) {
-        w.tr[20] = 0;
-      }
-      __syncwarp();
-
       // ---- all-pass decorrelators (ps_dec.c:236-448) ----
       i32 apr = 0, api = 0;  // decorrelated signal of QMF band sb (lanes 10..29)
       const i32 qin_r = __shfl_sync(full, lAr, sb), qin_i = __shfl_sync(full, lAi, sb);  // left input of QMF band sb
@@ -513,7 +533,7 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
           rin = rt;
           iin = it;
         }
-        const i32 t = w.tr[trbin];
+        const i32 t = (i32)w.pwt[slot][trbin];
         apr = shl32(rin * t, 1);
         api = shl32(iin * t, 1);
         if (hy) { rre[sb] = apr; rim[sb] = api; }
@@ -527,7 +547,7 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
         if (lane < 3 || lane >= 23) { rAr = 0; rAi = 0; }
         if (lane >= b20 && lane < min(us, b21)) {
           int16_t *d = st + kPsStLd + 24 * d_long + 2 * (lane - b20);
-          const i32 r = d[0], i = d[1], t = w.tr[18];
+          const i32 r = d[0], i = d[1], t = (i32)w.pwt[slot][18];
           d[0] = (int16_t)round16(lAr);
           d[1] = (int16_t)round16(lAi);
           rAr = shl32(r * t, 1);
@@ -536,14 +556,14 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
         const int kB = lane + 32;
         if (kB >= b20 && kB < min(us, b21)) {
           int16_t *d = st + kPsStLd + 24 * d_long + 2 * (kB - b20);
-          const i32 r = d[0], i = d[1], t = w.tr[18];
+          const i32 r = d[0], i = d[1], t = (i32)w.pwt[slot][18];
           d[0] = (int16_t)round16(lBr);
           d[1] = (int16_t)round16(lBi);
           rBr = shl32(r * t, 1);
           rBi = shl32(i * t, 1);
         } else if (kB >= b21 && kB < min(us, b22)) {
           int16_t *d = st + kPsStSd + 2 * (kB - b21);
-          const i32 r = d[0], i = d[1], t = w.tr[19];
+          const i32 r = d[0], i = d[1], t = (i32)w.pwt[slot][19];
           d[0] = (int16_t)round16(lBr);
           d[1] = (int16_t)round16(lBi);
           rBr = shl32(r * t, 1);
@@ -671,7 +691,10 @@ cudaError_t launch_ps_frame(const PsArgs &args, int num_sms, cudaStream_t stream
   long long grid = (long long)num_sms * 8;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  ps_frame_kernel<<<(unsigned)grid, kPsWarps * 32, 0, stream>>>(args);
+  if (args.rot_nosat)
+    ps_frame_kernel<true><<<(unsigned)grid, kPsWarps * 32, 0, stream>>>(args);
+  else
+    ps_frame_kernel<false><<<(unsigned)grid, kPsWarps * 32, 0, stream>>>(args);
   return cudaGetLastError();
 }
 
