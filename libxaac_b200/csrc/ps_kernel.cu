@@ -540,8 +540,24 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       }
       // right input of bands lane / lane + 32 before the rotation: all-pass output (bands 3..22, from lane band + 7),
       // plain delays (ps_dec.c:596-645) or zero at and above usb
-      i32 rAr = __shfl_sync(full, apr, min(lane + 7, 29)), rAi = __shfl_sync(full, api, min(lane + 7, 29));
-      i32 rBr = 0, rBi = 0;
+      i32 rAr = 0, rAi = 0, rBr = 0, rBi = 0;
+      if (as_built) {
+        // the as-built rotation zeroes both outputs of every QMF band below usb and the right input is zero above it, so the
+        // delayed samples are never looked at: only the delay lines move on
+        const int us = sext16(ps_usb), kB = lane + 32;
+        if (lane >= b20 && lane < min(us, b21)) {
+          int16_t *d = st + kPsStLd + 24 * d_long + 2 * (lane - b20);
+          d[0] = (int16_t)round16(lAr);
+          d[1] = (int16_t)round16(lAi);
+        }
+        if (kB >= b20 && kB < min(us, b22)) {
+          int16_t *d = kB < b21 ? st + kPsStLd + 24 * d_long + 2 * (kB - b20) : st + kPsStSd + 2 * (kB - b21);
+          d[0] = (int16_t)round16(lBr);
+          d[1] = (int16_t)round16(lBi);
+        }
+      } else {
+      rAr = __shfl_sync(full, apr, min(lane + 7, 29));
+      rAi = __shfl_sync(full, api, min(lane + 7, 29));
       {
         const int us = sext16(ps_usb);
         if (lane < 3 || lane >= 23) { rAr = 0; rAi = 0; }
@@ -571,6 +587,7 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
         }
         if (lane >= ps_usb) { rAr = 0; rAi = 0; }
         if (kB >= ps_usb) { rBr = 0; rBi = 0; }
+      }
       }
       d_long = sext16(d_long + 1);
       if (d_long >= 14) d_long = 0;
