@@ -356,7 +356,20 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
     i32 H11r = H11[2 * gi], H12r = H11[2 * gi + 1], H21r = H21[2 * gi], H22r = H21[2 * gi + 1];
     i32 D11r = d11[2 * gi], D12r = d11[2 * gi + 1], D21r = d21[2 * gi], D22r = d21[2 * gi + 1];
     const int b20 = borders[20], b21 = borders[21], b22 = borders[22];
-    const int shA_ov = pre(lane, 0), shA_lb = pre(lane, 6), shB_ov = pre(lane + 32, 0), shB_lb = pre(lane + 32, 6);
+    // pre-shifts of this lane's two bands as (mul, shr) pairs: value * mul >> shr, branch-free in the slot loop
+    i32 mA_ov, mA_lb, mB_ov, mB_lb;
+    int rA_ov, rA_lb, rB_ov, rB_lb;
+    {
+      auto enc = [](int sh, i32 &mul, int &shr) {
+        sh = max(-31, min(31, sh));
+        mul = sh > 0 ? (i32)(1u << sh) : 1;
+        shr = sh < 0 ? -sh : 0;
+      };
+      enc(pre(lane, 0), mA_ov, rA_ov);
+      enc(pre(lane, 6), mA_lb, rA_lb);
+      enc(pre(lane + 32, 0), mB_ov, rB_ov);
+      enc(pre(lane + 32, 6), mB_lb, rB_lb);
+    }
 
     // ---- power per parameter bin of all 32 slots (ps_dec.c:482-556): it does not depend on the slot-serial peak state, so
     //      lane = slot sums its own row serially instead of six warp reductions per slot.  All terms are >= 0, so the
@@ -493,11 +506,12 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       // ---- left row (pre-shifted), this slot's hybrid sub-subbands ----
       i32 lAr, lAi, lBr, lBi;  // bands lane and lane + 32 of the left input
       {
-        const int sA = slot < 6 ? shA_ov : shA_lb, sB = slot < 6 ? shB_ov : shB_lb;
-        lAr = blockshift(nAr, sA);
-        lAi = blockshift(nAi, sA);
-        lBr = blockshift(nBr, sB);
-        lBi = blockshift(nBi, sB);
+        const i32 mA = slot < 6 ? mA_ov : mA_lb, mB = slot < 6 ? mB_ov : mB_lb;
+        const int rA = slot < 6 ? rA_ov : rA_lb, rB = slot < 6 ? rB_ov : rB_lb;
+        lAr = (i32)((u32)nAr * (u32)mA) >> rA;
+        lAi = (i32)((u32)nAi * (u32)mA) >> rA;
+        lBr = (i32)((u32)nBr * (u32)mB) >> rB;
+        lBi = (i32)((u32)nBi * (u32)mB) >> rB;
         if (slot < 31) {
           const i32 *row = mat + 128 * (slot + 1);
           nAr = row[lane]; nAi = row[64 + lane]; nBr = row[32 + lane]; nBi = row[96 + lane];
