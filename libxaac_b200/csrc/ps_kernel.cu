@@ -20,6 +20,7 @@
 // Algorithmic HBM bytes per unit: 16 KB left rows in + 16 KB left out + 16 KB right out + 2 x 5.2 KB state + 1 KB
 // parameters ~= 59.5 KB.
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include "fixmath.cuh"
 #include "kernels.h"
@@ -452,6 +453,10 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
     // the left row of the next slot is fetched one slot ahead (its latency was the top stall of the slot loop)
     i32 nAr = mat[lane], nAi = mat[64 + lane], nBr = mat[32 + lane], nBi = mat[96 + lane];
     int next_border = prm[kPsPrmBorder];  // border of envelope `env`, kept in a register (prm lives in global memory)
+    // The slot loop exists twice, with the rotation variant as a compile-time constant: selected at run time inside one loop
+    // the compiler hoisted part of the other variant's arithmetic above the branch (40 wasted instructions per slot).
+    auto slot_loop = [&](auto ab_tag) {
+      constexpr bool AS_BUILT = decltype(ab_tag)::value;
 #pragma unroll 1
     for (int slot = 0; slot < 32; slot++) {
       // ---- ixheaacd_init_rot_env at PS envelope borders (ps_dec.c:714-854): lane = stereo group ----
@@ -555,7 +560,7 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       // right input of bands lane / lane + 32 before the rotation: all-pass output (bands 3..22, from lane band + 7),
       // plain delays (ps_dec.c:596-645) or zero at and above usb
       i32 rAr = 0, rAi = 0, rBr = 0, rBi = 0;
-      if (as_built) {
+      if (AS_BUILT) {
         // the as-built rotation zeroes both outputs of every QMF band below usb and the right input is zero above it, so the
         // delayed samples are never looked at: only the delay lines move on
         const int us = sext16(ps_usb), kB = lane + 32;
@@ -627,7 +632,7 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       // QMF bands 3..usb-1.  as_built: the reference's x86-64 gcc build reads its type-punned coefficient copy as
       // zero (see apply_rot in oracle/src/ps.c), so both outputs are 0 there.
       i32 oLAr = lAr, oLAi = lAi, oLBr = lBr, oLBi = lBi, oRAr = rAr, oRAi = rAi, oRBr = rBr, oRBi = rBi;
-      if (as_built) {
+      if (AS_BUILT) {
         if (lane >= 3 && lane < ps_usb) { oLAr = oLAi = oRAr = oRAi = 0; }
         if (lane + 32 < ps_usb) { oLBr = oLBi = oRBr = oRBi = 0; }
       } else {
@@ -683,6 +688,11 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       }
       __syncwarp();
     }
+    };
+    if (as_built)
+      slot_loop(std::true_type{});
+    else
+      slot_loop(std::false_type{});
     if (lane < 22) {  // mixing-matrix state back to shared memory
       h11v[2 * lane] = (int16_t)hv11; h11v[2 * lane + 1] = (int16_t)hv12; h21v[2 * lane] = (int16_t)hv21; h21v[2 * lane + 1] = (int16_t)hv22;
       H11[2 * lane] = (int16_t)H11r; H11[2 * lane + 1] = (int16_t)H12r; H21[2 * lane] = (int16_t)H21r; H21[2 * lane + 1] = (int16_t)H22r;
