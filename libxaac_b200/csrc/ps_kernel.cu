@@ -169,7 +169,7 @@ XB_DEV i32 blockshift(i32 v, int sh) {  // ixheaacd_adjust_scale_dec semantics (
 }
 
 template <bool NOSAT>
-__global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
+__global__ void __launch_bounds__(kPsWarps * 32, 4) ps_frame_kernel(PsArgs p) {
   __shared__ PsWarpS ws[kPsWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu;
@@ -391,25 +391,38 @@ __global__ void __launch_bounds__(kPsWarps * 32) ps_frame_kernel(PsArgs p) {
       int shr_lo, shr_hb;
       enc(s_ < 6 ? ov_lb_shift : lb_shift, mul_lo, shr_lo);
       enc(hb_shift, mul_hb, shr_hb);
-      auto tpow = [&](int k) {
-        const i32 mul = k < lsb ? mul_lo : (k < usb ? mul_hb : 1);
-        const int shr = k < lsb ? shr_lo : (k < usb ? shr_hb : 0);
-        const i32 r = (i32)((u32)row[k] * (u32)mul) >> shr, i = (i32)((u32)row[64 + k] * (u32)mul) >> shr;
-        return min((u32)pw(r) + (u32)pw(i), 0x7fffffffu);
-      };
+      // The lane walks its own row in 16-byte requests (four bands of one component each: 32 requests instead of 122 scalar
+      // ones that each touched one word of 32 different sectors — 18 % of the kernel's stall samples sat on them).  The band ->
+      // bin map is the standard one (QMF bands 3..8 = bins 8..13, then [9,11) [11,14) [14,18) [18,23) [23,35) [35,64), checked
+      // against borders_group when the ROM is installed), so every accumulator is a register.
+      const int4 *row4 = reinterpret_cast<const int4 *>(row);
+      i32 gsh[6];
 #pragma unroll
-      for (int k = 3; k < 9; k++) w.pwt[s_][5 + k] = tpow(k);  // bins 8..13 = QMF bands 3..8
-#pragma unroll 1
-      for (int g = 0; g < 6; g++) {
-        const int k0 = borders[16 + g], k1 = min((int)borders[17 + g], 64), gsh = rom[kPsRomGroupShift + g];
-        u32 acc = 0;
-#pragma unroll 2
-        for (int k = k0; k < k1; k++) {
-          const u32 t = tpow(k);
-          if (k < usb_eff) acc += t >> gsh;
+      for (int g = 0; g < 6; g++) gsh[g] = rom[kPsRomGroupShift + g];
+      u32 acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < 16; c++) {
+        const int4 vr = row4[c], vi = row4[16 + c];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int k = 4 * c + j;
+          if (k < 3) continue;
+          const i32 xr = j == 0 ? vr.x : (j == 1 ? vr.y : (j == 2 ? vr.z : vr.w));
+          const i32 xi = j == 0 ? vi.x : (j == 1 ? vi.y : (j == 2 ? vi.z : vi.w));
+          const i32 mul = k < lsb ? mul_lo : (k < usb ? mul_hb : 1);
+          const int shr = k < lsb ? shr_lo : (k < usb ? shr_hb : 0);
+          const i32 r = (i32)((u32)xr * (u32)mul) >> shr, i = (i32)((u32)xi * (u32)mul) >> shr;
+          const u32 t = min((u32)pw(r) + (u32)pw(i), 0x7fffffffu);
+          if (k < 9) {
+            w.pwt[s_][5 + k] = t;  // bins 8..13 = QMF bands 3..8
+          } else {
+            const int g = k < 11 ? 0 : (k < 14 ? 1 : (k < 18 ? 2 : (k < 23 ? 3 : (k < 35 ? 4 : 5))));
+            if (k < usb_eff) acc[g] += t >> gsh[g];
+          }
         }
-        w.pwt[s_][14 + g] = min(acc, 0x7fffffffu);
       }
+#pragma unroll
+      for (int g = 0; g < 6; g++) w.pwt[s_][14 + g] = min(acc[g], 0x7fffffffu);
       // bins 0..7: hybrid sub-subbands — bins 0 / 1 pair (0, 5) / (4, 1), bins 2..7 one sub-subband each
       const i32 *hre = w.hybL[s_], *him = w.hybL[s_] + 10;
 #pragma unroll

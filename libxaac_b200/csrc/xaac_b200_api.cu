@@ -632,6 +632,12 @@ int32_t xaac_b200_calc_sbrenvelope_hq_dev(xaac_b200_ctx *ctx, const int16_t *d_p
 int32_t xaac_b200_set_ps_rom(xaac_b200_ctx *ctx, const void *ps_tables, size_t bytes) {
   if (!ctx || !ps_tables) return bad_arg(ctx, "null");
   if (bytes < (size_t)xb::kPsRomBytes) return bad_arg(ctx, "PS ROM blob shorter than 1230 bytes");
+  {  // the PS kernel has the QMF band -> parameter bin map of borders_group[10..22] compiled in (power pre-pass)
+    static const int16_t kStdBorders[13] = {3, 4, 5, 6, 7, 8, 9, 11, 14, 18, 23, 35, 64};
+    const int16_t *t = (const int16_t *)ps_tables + xb::kPsRomBordersGroup + 10;
+    for (int i = 0; i < 13; i++)
+      if (t[i] != kStdBorders[i]) return bad_arg(ctx, "PS tables: unexpected borders_group");
+  }
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (!ctx->d_rom_ps) CK(cudaMalloc((void **)&ctx->d_rom_ps, xb::kPsRomBytes + 50), "cudaMalloc(ps rom)");
   CK(cudaMemcpy(ctx->d_rom_ps, ps_tables, xb::kPsRomBytes, cudaMemcpyHostToDevice), "H2D ps rom");
