@@ -25,6 +25,7 @@
 #include "fixmath.cuh"
 #include "kernels.h"
 #include "sbr_common.cuh"
+#include "sbr_glue_units.cuh"
 #include "env_common.cuh"
 
 namespace xb {
@@ -38,8 +39,11 @@ struct EnvWarpS {
   int8_t sine_mapped[kMaxB + 8];
 };
 
-__global__ void __launch_bounds__(kEnvWarps * 32)
-calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
+// POST: the whole-stage driver's variant — after a unit's envelope adjustment the same warp runs sbr_post_unit
+// (sbr_dec.c:1205-1245, :1284-1308: previous-frame data, LPC rows, overlap save, synthesis parameters) on the rows it
+// has just touched, instead of a separate sbr_post_kernel launch.
+template <bool POST>
+__device__ __forceinline__ void calc_sbrenvelope_hq_body(const EnvCalcArgs &p, const SbrStageArgs &g) {
   __shared__ EnvRomS rom;
   __shared__ EnvWarpS ws[kEnvWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -67,6 +71,7 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
     __syncwarp();
     if (p.gate && p.gate[u * p.gate_stride] == 0) {
       if (lane == 0 && p.err) p.err[u] = 0;
+      if (POST) sbr_post_unit(g, u, lane, false);
       continue;
     }
     {
@@ -508,7 +513,21 @@ calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
       for (int i = lane; i < kEnvStWords / 2; i += 32) ds[i] = reinterpret_cast<const i32 *>(w.st)[i];
       if (lane == 0 && p.err) p.err[u] = err ? (i32)0x80000000 : 0;
     }
+    if (POST) {
+      __syncwarp();
+      sbr_post_unit(g, u, lane, __shfl_sync(full, err, 0) != 0);
+    }
   }
+}
+
+__global__ void __launch_bounds__(kEnvWarps * 32)
+calc_sbrenvelope_hq_kernel(EnvCalcArgs p) {
+  calc_sbrenvelope_hq_body<false>(p, SbrStageArgs());
+}
+
+__global__ void __launch_bounds__(kEnvWarps * 32)
+calc_sbrenvelope_hq_post_kernel(EnvCalcArgs p, SbrStageArgs g) {
+  calc_sbrenvelope_hq_body<true>(p, g);
 }
 
 cudaError_t launch_calc_sbrenvelope_hq(const EnvCalcArgs &args, int num_sms, cudaStream_t stream) {
@@ -517,6 +536,15 @@ cudaError_t launch_calc_sbrenvelope_hq(const EnvCalcArgs &args, int num_sms, cud
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   calc_sbrenvelope_hq_kernel<<<(unsigned)grid, kEnvWarps * 32, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_calc_sbrenvelope_hq_post(const EnvCalcArgs &args, const SbrStageArgs &g, int num_sms, cudaStream_t stream) {
+  long long need = (args.n_units + kEnvWarps - 1) / kEnvWarps;
+  long long grid = (long long)num_sms * 4;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  calc_sbrenvelope_hq_post_kernel<<<(unsigned)grid, kEnvWarps * 32, 0, stream>>>(args, g);
   return cudaGetLastError();
 }
 

@@ -205,6 +205,10 @@ struct SbrStageArgs {
 cudaError_t launch_sbr_pre(const SbrStageArgs &a, int num_sms, cudaStream_t s);
 cudaError_t launch_sbr_scale(const SbrStageArgs &a, int num_sms, cudaStream_t s);
 cudaError_t launch_sbr_post(const SbrStageArgs &a, int num_sms, cudaStream_t s);
+// sbr_pre + analysis bank + sbr_scale of one unit by one warp (qmf_anal_kernel.cu); a.usb is not used
+cudaError_t launch_sbr_front_hq(const QmfAnalArgs &a, const SbrStageArgs &g, int num_sms, cudaStream_t s);
+// envelope adjuster + sbr_post of one unit by one warp (envcalc_kernel.cu); a.err receives the adjuster's return value
+cudaError_t launch_calc_sbrenvelope_hq_post(const EnvCalcArgs &a, const SbrStageArgs &g, int num_sms, cudaStream_t s);
 cudaError_t launch_pcm16_from_imdct(const int32_t *in, const int8_t *qshift_adj, int16_t *out, long long n_units, int mode,
                                     int num_sms, cudaStream_t s);
 

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include "fixmath.cuh"
 #include "kernels.h"
+#include "sbr_glue_units.cuh"
 
 namespace xb {
 
@@ -46,9 +47,12 @@ struct AnaBlockSmem {
 
 XB_DEV i32 mul32x16_shl(i32 a, i32 c16) { return lsl(__mulhi(a, (i32)((u32)c16 << 16)), 1); }  // ops40.h:23
 
-template <bool SAT>
-__device__ __forceinline__ void anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm, AnaWarpSmem &ws, long long u,
-                                          int lane) {
+// FRONT: the unit runs inside sbr_front_hq_kernel — usb comes from the caller (sbr_pre_unit of the same warp) and the
+// return value is this lane's OR of ixheaac_abs32_nrm over everything it stored for bands < usb (the headroom scan of
+// rows 6..37, ixheaacd_expsubbandsamples at sbr_dec.c:1050, collected on the fly).
+template <bool SAT, bool FRONT>
+__device__ __forceinline__ i32 anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm, AnaWarpSmem &ws, long long u,
+                                         int lane, int usb_in) {
   auto ADD = [](i32 a, i32 b) { return SAT ? add_sat(a, b) : wadd(a, b); };
   auto SUB = [](i32 a, i32 b) { return SAT ? sub_sat(a, b) : wsub(a, b); };
   auto NEG = [](i32 a) { return SAT ? neg_sat(a) : wneg(a); };
@@ -57,7 +61,8 @@ __device__ __forceinline__ void anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm
                                                      : ((p.ch_fac == 1) ? u * 1024 : (u / p.ch_fac) * (1024LL * p.ch_fac) + (u % p.ch_fac)));
   i32 *mat = p.matrix + u * p.mat_stride;
   int pos = p.pos[2 * u], f1 = p.pos[2 * u + 1], f2 = f1 + 64;
-  const int usb = p.usb[u];
+  const int usb = FRONT ? usb_in : p.usb[u];
+  i32 hr_mask = 0;
   {  // ring: HBM -> smem (same layout)
     const i32 *src = reinterpret_cast<const i32 *>(p.states + u * 320);
     i32 *dst = reinterpret_cast<i32 *>(ws.ring);
@@ -203,6 +208,7 @@ __device__ __forceinline__ void anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm
           i32 i2 = sub_sat(mul32x16_shl(im, cs.x), mul32x16_shl(re, cs.y));
           re = r2;
           im = i2;
+          if (FRONT) hr_mask |= abs_nrm(re) | abs_nrm(im);
         }
         ore[j] = re;
         oim[j] = im;
@@ -225,6 +231,7 @@ __device__ __forceinline__ void anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm
     }
   }
   __syncwarp();
+  return hr_mask;
 }
 
 __global__ void __launch_bounds__(kAnaWarps * 32)
@@ -250,9 +257,46 @@ qmf_anal_hq_kernel(QmfAnalArgs p) {
       if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.states + un * 320) + lane * 128));
     }
     if (p.exact)
-      anal_unit<true>(p, sm, sm.w_[warp], u, lane);
+      anal_unit<true, false>(p, sm, sm.w_[warp], u, lane, 0);
     else
-      anal_unit<false>(p, sm, sm.w_[warp], u, lane);
+      anal_unit<false, false>(p, sm, sm.w_[warp], u, lane, 0);
+  }
+}
+
+// The front of the fixed-point HQ SBR stage of one unit by one warp (ixheaacd_sbr_dec, decoder/ixheaacd_sbr_dec.c:749-774,
+// :790-826, :1050-1127): overlap rows + ixheaacd_rescale_x_overlap, the analysis bank, then the headroom scans / rescale /
+// clear of the low band and the HF generator's argument record.  Replaces the sbr_pre_kernel -> qmf_anal_hq_kernel ->
+// sbr_scale_kernel sequence: two launches less, the current rows' headroom is collected while they are produced, and
+// the rescale pass finds the rows it has just written in L2 (one DRAM write-back per row instead of write + read + write).
+__global__ void __launch_bounds__(kAnaWarps * 32, 4)
+sbr_front_hq_kernel(QmfAnalArgs p, SbrStageArgs g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AnaBlockSmem &sm = *reinterpret_cast<AnaBlockSmem *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    const i32 *src = reinterpret_cast<const i32 *>(p.rom);
+    i32 *dst = reinterpret_cast<i32 *>(&sm);
+    const int nwords = (int)(offsetof(AnaBlockSmem, w_) / 4);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int warps_total = gridDim.x * kAnaWarps;
+  for (long long u = (long long)blockIdx.x * kAnaWarps + warp; u < p.n_units; u += warps_total) {
+    if (u + warps_total < p.n_units) {  // pull this warp's next unit (PCM, ring, overlap rows, LPC rows) towards L2
+      const long long un = u + warps_total;
+      const int16_t *q0 = p.pcm + (p.pcm_unit_stride ? un * p.pcm_unit_stride
+                                                       : ((p.ch_fac == 1) ? un * 1024 : (un / p.ch_fac) * (1024LL * p.ch_fac)));
+      const int lines = 16 * (p.pcm_unit_stride ? 1 : p.ch_fac);
+      if (lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(q0) + lane * 128));
+      if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.states + un * 320) + lane * 128));
+      if (lane < 24) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(g.ov + un * 768) + lane * 128));
+      if (lane < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(g.lpc + un * 256) + lane * 128));
+    }
+    const int usb = sbr_pre_unit(g, u, lane);
+    const i32 mask = p.exact ? anal_unit<true, true>(p, sm, sm.w_[warp], u, lane, usb)
+                             : anal_unit<false, true>(p, sm, sm.w_[warp], u, lane, usb);
+    sbr_scale_unit(g, u, lane, usb, usb <= 32 ? mask : -1);
+    __syncwarp();
   }
 }
 
@@ -312,6 +356,23 @@ int qmf_anal_build_tables(const uint8_t *qrom, uint8_t *out) {
   double G = F * smax(al, 8) / 65536.0 + 2.0;                // post-twiddle
   if (F / 2.0 + 1.0 > G) G = F / 2.0 + 1.0;
   return (G * 1.0001 + 16.0 < 2147483647.0) ? 0 : 1;
+}
+
+cudaError_t launch_sbr_front_hq(const QmfAnalArgs &args, const SbrStageArgs &g, int num_sms, cudaStream_t stream) {
+  static xb::PerDeviceOnce configured;
+  size_t smem = sizeof(AnaBlockSmem);
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(sbr_front_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured.done();
+  }
+  int blocks_per_sm = 4;
+  long long need = (args.n_units + kAnaWarps - 1) / kAnaWarps;
+  long long grid = (long long)num_sms * blocks_per_sm;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  sbr_front_hq_kernel<<<(unsigned)grid, kAnaWarps * 32, smem, stream>>>(args, g);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_qmf_anal_hq(const QmfAnalArgs &args, int num_sms, cudaStream_t stream) {

@@ -36,6 +36,7 @@ struct xaac_b200_ctx {
   int32_t *d_rom_block = nullptr; // leading 620 bytes of ia_aac_dec_block_tables_struct (spectral stage)
   int esbr_periodic = 0;
   bool have_ps_rom = false;
+  int sbr_unfused = 0;            // XAAC_B200_SBR_UNFUSED=1: the HQ stage launches its glue kernels separately (A/B, tests)
   int ps_rot_nosat = 0;           // no fractional-delay phase factor equals -32768 (16x16 rotations cannot saturate)
   char err[256] = {0};
   // optional per-kernel timing (CUDA events on the launching stream around every kernel)
@@ -174,6 +175,7 @@ int32_t xaac_b200_create(xaac_b200_ctx **out, int32_t device) {
   xaac_b200_ctx *ctx = new (std::nothrow) xaac_b200_ctx();
   if (!ctx) return XAAC_B200_FATAL;
   ctx->device = device;
+  if (const char *uf = getenv("XAAC_B200_SBR_UNFUSED")) ctx->sbr_unfused = atoi(uf) != 0;
   if (const char *hc = getenv("XAAC_B200_HOST_CHUNK")) {
     const long v = atol(hc);
     if (v >= 256 && v <= (1 << 20)) ctx->host_chunk = v;
@@ -792,15 +794,20 @@ static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long lo
   g.side = d_side; g.matrix = s->matrix + su0 * xb::kSbrMatWords; g.ov = s->ov + u0 * 768; g.lpc = s->lpc + u0 * 256;
   g.sf = s->sf + u0 * 8; g.misc = s->misc + u0 * 16; g.usb = s->usb + su0; g.hf_prm = s->hf_prm + su0 * 80;
   g.synp = s->synp + su0 * 8; g.err = err; g.n_units = n;
-  LAUNCH("sbr_pre_kernel", st, xb::launch_sbr_pre(g, ctx->num_sms, st));
   {
     xb::QmfAnalArgs a;
     a.pcm = d_time_in; a.states = s->anal_states + u0 * 320; a.pos = s->anal_pos + u0 * 2; a.usb = g.usb;
     a.matrix = g.matrix + 6 * 128; a.rom = ctx->d_rom_qmf_ana; a.n_units = n; a.ch_fac = 1;
     a.exact = ctx->qmf_anal_exact; a.mat_stride = xb::kSbrMatWords;
-    LAUNCH("qmf_anal_hq_kernel", st, xb::launch_qmf_anal_hq(a, ctx->num_sms, st));
+    if (ctx->sbr_unfused) {
+      LAUNCH("sbr_pre_kernel", st, xb::launch_sbr_pre(g, ctx->num_sms, st));
+      LAUNCH("qmf_anal_hq_kernel", st, xb::launch_qmf_anal_hq(a, ctx->num_sms, st));
+      LAUNCH("sbr_scale_kernel", st, xb::launch_sbr_scale(g, ctx->num_sms, st));
+      ctx->launches += 2;
+    } else {  // the three of them per unit by one warp
+      LAUNCH("sbr_front_hq_kernel", st, xb::launch_sbr_front_hq(a, g, ctx->num_sms, st));
+    }
   }
-  LAUNCH("sbr_scale_kernel", st, xb::launch_sbr_scale(g, ctx->num_sms, st));
   {
     xb::HfGenArgs a;
     a.lpc = g.lpc; a.matrix = g.matrix; a.params = g.hf_prm; a.bw_prev = s->bw_prev + u0 * 6;
@@ -813,10 +820,15 @@ static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long lo
     a.params = d_side; a.prm_stride = xb::kSideWords; a.sf = g.sf; a.state = s->env + u0 * xb::kEnvStWords;
     a.matrix = g.matrix; a.err = err; a.env_rom = ctx->d_rom_env; a.misc_rom = ctx->d_rom_misc; a.n_units = n;
     a.gate = d_side + xb::kSideApply; a.gate_stride = xb::kSideWords; a.max_qmf_prev = g.misc;
-    LAUNCH("calc_sbrenvelope_hq_kernel", st, xb::launch_calc_sbrenvelope_hq(a, ctx->num_sms, st));
+    if (ctx->sbr_unfused) {
+      LAUNCH("calc_sbrenvelope_hq_kernel", st, xb::launch_calc_sbrenvelope_hq(a, ctx->num_sms, st));
+      LAUNCH("sbr_post_kernel", st, xb::launch_sbr_post(g, ctx->num_sms, st));
+      ctx->launches += 1;
+    } else {
+      LAUNCH("calc_sbrenvelope_hq_post_kernel", st, xb::launch_calc_sbrenvelope_hq_post(a, g, ctx->num_sms, st));
+    }
   }
-  LAUNCH("sbr_post_kernel", st, xb::launch_sbr_post(g, ctx->num_sms, st));
-  ctx->launches += 6;
+  ctx->launches += 3;
   xb::QmfSynthArgs y;
   y.matrix = g.matrix; y.states = s->syn_states + u0 * 1280; y.pos = s->syn_pos + u0 * 2; y.params = g.synp;
   y.pcm = d_time_out; y.rom = ctx->d_rom_qmf_syn; y.twiddles = ctx->qmf_syn_tw; y.n_units = n; y.fast_bits = ctx->qmf_fast_bits; y.zero = 0;
