@@ -35,6 +35,11 @@ CHAIN_KERNEL_BYTES = {
     "hf_generator_hq_kernel": 13824,      # hfgen_kernel.cu header
     "calc_sbrenvelope_hq_kernel": 19760,  # envcalc_kernel.cu header
     "sbr_post_kernel": 4672,              # 1536 overlap out + LPC rows 2 x 1024 + parameters
+    # the stage as the driver runs it (glue inside the heavy kernels; the three above only with XAAC_B200_SBR_UNFUSED=1):
+    # 4096 WORD32 core output + 2 x 640 ring + 3072 overlap slots in + 38 rows x 512 B matrix out (32 bands x 8 B + the cleared
+    # upper half) + 2 x 1024 LPC rows r/w + 160 HF generator record
+    "sbr_front_hq_kernel": 30112,
+    "calc_sbrenvelope_hq_post_kernel": 24432,  # envelope adjuster 19760 + previous-frame / overlap save 4672
     "ps_frame_kernel": 60928,             # ps_kernel.cu header
     "qmf_synth_hq_kernel": SYNTH_BYTES_PER_UNIT,
     # fused low-power stage (sbr_lp_kernel.cu): 2048 PCM16 in + 4096 PCM16 out + 2 x 5536 channel state (analysis ring 644,
@@ -1338,15 +1343,13 @@ class ChainWork:
         self.state.upload(np.tile(st0, (n_units, 1)), np.tile(ps0, (n_units, 1)))
         self.w32 = torch.empty((n_units, 1024), dtype=torch.int32, device=dev)
         self.adj = torch.empty((n_units,), dtype=torch.int8, device=dev)
-        self.p16 = torch.empty((n_units, 1024), dtype=torch.int16, device=dev)
         self.pcm = torch.empty((n_units, 2048, 2), dtype=torch.int16, device=dev)
         self.err = torch.zeros((n_units,), dtype=torch.int32, device=dev)
 
     def step(self, i, stream):
         xb, ctx = self.xb, self.ctx
         xb.imdct_process(ctx, self.imdct_state, self.spec, self.walk[i % self.nw], self.w32, self.adj, stream=stream)
-        xb.imdct_out_to_pcm16(ctx, self.w32, self.adj, 0, self.p16, stream=stream)
-        xb.sbr_dec(ctx, self.state, self.side[i % 11], self.p16, self.pcm, self.err, stream=stream)
+        xb.sbr_dec_w32(ctx, self.state, self.side[i % 11], self.w32, self.adj, self.pcm, self.err, stream=stream)
 
     def check(self):
         assert int(self.err.abs().max().item()) == 0, "the SBR stage reported an error for some unit"
@@ -2108,8 +2111,7 @@ def sharded_io_arm(xb, ctx, dev, rank, world, total_frames, K, seed, barrier):
     def compute(c):
         w = works[c]
         xb.imdct_process(ctx, w.imdct_state, w.spec, w.ics_in, w.w32, w.adj, stream=stream)
-        xb.imdct_out_to_pcm16(ctx, w.w32, w.adj, 0, w.p16, stream=stream)
-        xb.sbr_dec(ctx, w.state, w.side_in, w.p16, w.pcm, w.err, stream=stream)
+        xb.sbr_dec_w32(ctx, w.state, w.side_in, w.w32, w.adj, w.pcm, w.err, stream=stream)
 
     def gather(c):
         ops = []
@@ -2218,8 +2220,7 @@ def sharded_io_arm(xb, ctx, dev, rank, world, total_frames, K, seed, barrier):
                 w = works[c]
                 stream.wait_event(pulls[c])
                 xb.imdct_process(ctx, w.imdct_state, p_spec[a + lo:a + hi], w.ics_pull, w.w32, w.adj, stream=stream)
-                xb.imdct_out_to_pcm16(ctx, w.w32, w.adj, 0, w.p16, stream=stream)
-                xb.sbr_dec(ctx, w.state, w.side_pull, w.p16, w.pcm, w.err, stream=stream)
+                xb.sbr_dec_w32(ctx, w.state, w.side_pull, w.w32, w.adj, w.pcm, w.err, stream=stream)
                 ev = torch.cuda.Event()
                 ev.record(stream)
                 cs.wait_event(ev)

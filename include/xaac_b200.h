@@ -352,6 +352,13 @@ int32_t xaac_b200_sbr_state_download(xaac_b200_ctx *ctx, xaac_b200_sbr_state *st
  *              valid output nor a defined state, as in the reference, which aborts the frame */
 int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, const int16_t *d_side,
                                  const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, void *stream);
+/* The same stage fed with the core coder's WORD32 output: d_w32 [n][1024] and d_qshift_adj [n] as written by
+ * xaac_b200_imdct_process_dev.  The WORD32 -> WORD16 hand-over of ixheaacd_allocate_sbr_scr (decoder/ixheaacd_api.c:337-370,
+ * round16(shl32_sat(x, qshift_adj))) happens in the analysis bank's load, so the PCM16 copy of the core output never
+ * exists in HBM (one launch and 6 KB of traffic per unit less than xaac_b200_imdct_out_to_pcm16_dev + the call above). */
+int32_t xaac_b200_sbr_dec_hq_w32_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, const int16_t *d_side,
+                                     const int32_t *d_w32, const int8_t *d_qshift_adj, int16_t *d_time_out,
+                                     int32_t *d_err, void *stream);
 
 /* ---- low-power (real-valued) SBR stage: ixheaacd_sbr_dec with low_pow_flag = 1 --------------------------------
  * The path the reference runs for stereo HE-AACv1 in its fixed-point mode (decoder/ixheaacd_sbrdecoder.c:408-419:
@@ -373,8 +380,8 @@ int32_t xaac_b200_sbr_dec_lp_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state,
                                  void *stream);
 
 /* Host-buffer entry point for a whole HE-AAC (v1 mono / v2) frame per unit: IMDCT + window/OLA of the core channel
- * (xaac_b200_imdct_process_dev), the WORD32 -> PCM16 hand-over (xaac_b200_imdct_out_to_pcm16_dev, mode 0) and the SBR
- * stage, chunked and pipelined over internal streams (H2D, kernels, D2H overlap).  Both states stay resident in HBM.
+ * (xaac_b200_imdct_process_dev), the WORD32 -> PCM16 hand-over (inside the analysis bank's load, as in
+ * xaac_b200_sbr_dec_hq_w32_dev) and the SBR stage, chunked and pipelined over internal streams (H2D, kernels, D2H overlap).  Both states stay resident in HBM.
  *   spec [n][1024] WORD32, ics [n][2], side [n][1232] WORD16 (host, pinned recommended)
  *   pcm  [n][2048] PCM16, or [n][2048][2] for a PS state; err [n] WORD32 or NULL */
 int32_t xaac_b200_heaac_frame_host(xaac_b200_ctx *ctx, xaac_b200_imdct_state *imdct_state, xaac_b200_sbr_state *sbr_state,

@@ -50,6 +50,7 @@ SIGNATURES = {
     "xaac_b200_sbr_state_upload": (_i32, [_vp, _vp, _vp, _vp]),
     "xaac_b200_sbr_state_download": (_i32, [_vp, _vp, _vp, _vp]),
     "xaac_b200_sbr_dec_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "xaac_b200_sbr_dec_hq_w32_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xaac_b200_sbr_dec_lp_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "xaac_b200_heaac_frame_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xaac_b200_heaac_lp_frame_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),

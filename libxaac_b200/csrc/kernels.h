@@ -103,6 +103,10 @@ struct QmfAnalArgs {
   int exact;               // 1: use saturating adds in the modulation (only if the table bound check failed)
   long long mat_stride = 4096;      // words between the matrices of consecutive units
   long long pcm_unit_stride = 0;    // != 0: unit u reads at pcm + u * pcm_unit_stride with sample stride ch_fac
+  // != null: the core coder's WORD32 output [n_units][1024] + its qshift_adj [n_units]; the bank converts on load
+  // (round16(shl32_sat(x, qshift_adj)), ixheaacd_allocate_sbr_scr, decoder/ixheaacd_api.c:337-370); pcm is ignored, ch_fac = 1
+  const int32_t *w32 = nullptr;
+  const int8_t *qshift_adj = nullptr;
 };
 
 size_t qmf_anal_table_bytes();

@@ -50,7 +50,7 @@ XB_DEV i32 mul32x16_shl(i32 a, i32 c16) { return lsl(__mulhi(a, (i32)((u32)c16 <
 // FRONT: the unit runs inside sbr_front_hq_kernel — usb comes from the caller (sbr_pre_unit of the same warp) and the
 // return value is this lane's OR of ixheaac_abs32_nrm over everything it stored for bands < usb (the headroom scan of
 // rows 6..37, ixheaacd_expsubbandsamples at sbr_dec.c:1050, collected on the fly).
-template <bool SAT, bool FRONT>
+template <bool SAT, bool FRONT, bool W32>
 __device__ __forceinline__ i32 anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm, AnaWarpSmem &ws, long long u,
                                          int lane, int usb_in) {
   auto ADD = [](i32 a, i32 b) { return SAT ? add_sat(a, b) : wadd(a, b); };
@@ -75,17 +75,21 @@ __device__ __forceinline__ i32 anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm,
   __syncwarp();
 
   // the PCM of the next group of four slots is fetched while this group is processed
-  int16_t nv[4];
+  const i32 *w32 = W32 ? p.w32 + u * 1024 : nullptr;
+  const int qadj = W32 ? p.qshift_adj[u] : 0;
+  // raw loads only (the conversion of a WORD32 sample waits for its load, so it happens where the sample is consumed)
+  auto sample = [&](int i) -> i32 { return W32 ? __ldg(w32 + i) : (i32)pcm[(long long)p.ch_fac * i]; };
+  i32 nv[4];
 #pragma unroll
-  for (int s = 0; s < 4; s++) nv[s] = pcm[(long long)p.ch_fac * (32 * s + lane)];
+  for (int s = 0; s < 4; s++) nv[s] = sample(32 * s + lane);
 #pragma unroll 1
   for (int g = 0; g < 8; g++) {
     i32 s1v[4], s2v[4];  // fold outputs of the four slots of this group: S1[lane], S2[lane]
     int16_t cv[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-      cv[s] = nv[s];
-      if (g < 7) nv[s] = pcm[(long long)p.ch_fac * (32 * (4 * (g + 1) + s) + lane)];
+      cv[s] = W32 ? (int16_t)round16(shl32_sat(nv[s], qadj)) : (int16_t)nv[s];
+      if (g < 7) nv[s] = sample(32 * (4 * (g + 1) + s) + lane);
     }
 #pragma unroll
     for (int s = 0; s < 4; s++) {
@@ -234,6 +238,7 @@ __device__ __forceinline__ i32 anal_unit(const QmfAnalArgs &p, AnaBlockSmem &sm,
   return hr_mask;
 }
 
+template <bool W32>
 __global__ void __launch_bounds__(kAnaWarps * 32)
 qmf_anal_hq_kernel(QmfAnalArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -253,13 +258,14 @@ qmf_anal_hq_kernel(QmfAnalArgs p) {
       const int16_t *q0 = p.pcm + (p.pcm_unit_stride ? un * p.pcm_unit_stride
                                                        : ((p.ch_fac == 1) ? un * 1024 : (un / p.ch_fac) * (1024LL * p.ch_fac)));
       const int lines = 16 * (p.pcm_unit_stride ? 1 : p.ch_fac);
-      if (lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(q0) + lane * 128));
+      if (W32) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.w32 + un * 1024) + lane * 128));
+      else if (lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(q0) + lane * 128));
       if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.states + un * 320) + lane * 128));
     }
     if (p.exact)
-      anal_unit<true, false>(p, sm, sm.w_[warp], u, lane, 0);
+      anal_unit<true, false, W32>(p, sm, sm.w_[warp], u, lane, 0);
     else
-      anal_unit<false, false>(p, sm, sm.w_[warp], u, lane, 0);
+      anal_unit<false, false, W32>(p, sm, sm.w_[warp], u, lane, 0);
   }
 }
 
@@ -268,6 +274,7 @@ qmf_anal_hq_kernel(QmfAnalArgs p) {
 // clear of the low band and the HF generator's argument record.  Replaces the sbr_pre_kernel -> qmf_anal_hq_kernel ->
 // sbr_scale_kernel sequence: two launches less, the current rows' headroom is collected while they are produced, and
 // the rescale pass finds the rows it has just written in L2 (one DRAM write-back per row instead of write + read + write).
+template <bool W32>
 __global__ void __launch_bounds__(kAnaWarps * 32, 4)
 sbr_front_hq_kernel(QmfAnalArgs p, SbrStageArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -287,14 +294,15 @@ sbr_front_hq_kernel(QmfAnalArgs p, SbrStageArgs g) {
       const int16_t *q0 = p.pcm + (p.pcm_unit_stride ? un * p.pcm_unit_stride
                                                        : ((p.ch_fac == 1) ? un * 1024 : (un / p.ch_fac) * (1024LL * p.ch_fac)));
       const int lines = 16 * (p.pcm_unit_stride ? 1 : p.ch_fac);
-      if (lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(q0) + lane * 128));
+      if (W32) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.w32 + un * 1024) + lane * 128));
+      else if (lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(q0) + lane * 128));
       if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.states + un * 320) + lane * 128));
       if (lane < 24) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(g.ov + un * 768) + lane * 128));
       if (lane < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(g.lpc + un * 256) + lane * 128));
     }
     const int usb = sbr_pre_unit(g, u, lane);
-    const i32 mask = p.exact ? anal_unit<true, true>(p, sm, sm.w_[warp], u, lane, usb)
-                             : anal_unit<false, true>(p, sm, sm.w_[warp], u, lane, usb);
+    const i32 mask = p.exact ? anal_unit<true, true, W32>(p, sm, sm.w_[warp], u, lane, usb)
+                             : anal_unit<false, true, W32>(p, sm, sm.w_[warp], u, lane, usb);
     sbr_scale_unit(g, u, lane, usb, usb <= 32 ? mask : -1);
     __syncwarp();
   }
@@ -362,7 +370,9 @@ cudaError_t launch_sbr_front_hq(const QmfAnalArgs &args, const SbrStageArgs &g, 
   static xb::PerDeviceOnce configured;
   size_t smem = sizeof(AnaBlockSmem);
   if (configured.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(sbr_front_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sbr_front_hq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(sbr_front_hq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured.done();
   }
@@ -371,7 +381,10 @@ cudaError_t launch_sbr_front_hq(const QmfAnalArgs &args, const SbrStageArgs &g, 
   long long grid = (long long)num_sms * blocks_per_sm;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  sbr_front_hq_kernel<<<(unsigned)grid, kAnaWarps * 32, smem, stream>>>(args, g);
+  if (args.w32)
+    sbr_front_hq_kernel<true><<<(unsigned)grid, kAnaWarps * 32, smem, stream>>>(args, g);
+  else
+    sbr_front_hq_kernel<false><<<(unsigned)grid, kAnaWarps * 32, smem, stream>>>(args, g);
   return cudaGetLastError();
 }
 
@@ -379,7 +392,9 @@ cudaError_t launch_qmf_anal_hq(const QmfAnalArgs &args, int num_sms, cudaStream_
   static xb::PerDeviceOnce configured;
   size_t smem = sizeof(AnaBlockSmem);
   if (configured.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(qmf_anal_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qmf_anal_hq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(qmf_anal_hq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured.done();
   }
@@ -388,7 +403,10 @@ cudaError_t launch_qmf_anal_hq(const QmfAnalArgs &args, int num_sms, cudaStream_
   long long grid = (long long)num_sms * blocks_per_sm;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  qmf_anal_hq_kernel<<<(unsigned)grid, kAnaWarps * 32, smem, stream>>>(args);
+  if (args.w32)
+    qmf_anal_hq_kernel<true><<<(unsigned)grid, kAnaWarps * 32, smem, stream>>>(args);
+  else
+    qmf_anal_hq_kernel<false><<<(unsigned)grid, kAnaWarps * 32, smem, stream>>>(args);
   return cudaGetLastError();
 }
 

@@ -787,8 +787,10 @@ static int32_t ensure_sbr_scratch(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, in
 }
 // One frame for units [u0, u0 + n) of the state, using scratch slots [su0, su0 + n); d_side / d_time_in / d_time_out / d_err
 // point at the chunk's first unit.
+// d_w32 != null: the core coder's WORD32 output + qshift_adj of the chunk instead of d_time_in (converted on load).
 static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long long u0, long long n, const int16_t *d_side,
-                             const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, cudaStream_t st, long long su0) {
+                             const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, cudaStream_t st, long long su0,
+                             const int32_t *d_w32 = nullptr, const int8_t *d_adj = nullptr) {
   int32_t *err = d_err ? d_err : s->err + u0;
   xb::SbrStageArgs g;
   g.side = d_side; g.matrix = s->matrix + su0 * xb::kSbrMatWords; g.ov = s->ov + u0 * 768; g.lpc = s->lpc + u0 * 256;
@@ -798,7 +800,7 @@ static int32_t sbr_dec_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long lo
     xb::QmfAnalArgs a;
     a.pcm = d_time_in; a.states = s->anal_states + u0 * 320; a.pos = s->anal_pos + u0 * 2; a.usb = g.usb;
     a.matrix = g.matrix + 6 * 128; a.rom = ctx->d_rom_qmf_ana; a.n_units = n; a.ch_fac = 1;
-    a.exact = ctx->qmf_anal_exact; a.mat_stride = xb::kSbrMatWords;
+    a.exact = ctx->qmf_anal_exact; a.mat_stride = xb::kSbrMatWords; a.w32 = d_w32; a.qshift_adj = d_adj;
     if (ctx->sbr_unfused) {
       LAUNCH("sbr_pre_kernel", st, xb::launch_sbr_pre(g, ctx->num_sms, st));
       LAUNCH("qmf_anal_hq_kernel", st, xb::launch_qmf_anal_hq(a, ctx->num_sms, st));
@@ -876,6 +878,17 @@ int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, con
   return sbr_dec_range(ctx, s, 0, s->n_units, d_side, d_time_in, d_time_out, d_err, (cudaStream_t)stream, 0);
 }
 
+int32_t xaac_b200_sbr_dec_hq_w32_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side, const int32_t *d_w32,
+                                     const int8_t *d_qshift_adj, int16_t *d_time_out, int32_t *d_err, void *stream) {
+  int32_t rc = sbr_check(ctx, s);
+  if (rc != XAAC_B200_OK) return rc;
+  if (!d_side || !d_w32 || !d_qshift_adj || !d_time_out) return bad_arg(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  rc = ensure_sbr_scratch(ctx, s, s->n_units);
+  if (rc != XAAC_B200_OK) return rc;
+  return sbr_dec_range(ctx, s, 0, s->n_units, d_side, nullptr, d_time_out, d_err, (cudaStream_t)stream, 0, d_w32, d_qshift_adj);
+}
+
 // One low-power frame for units [u0, u0 + n) of the state.
 static int32_t sbr_dec_lp_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long long u0, long long n, const int16_t *d_side,
                                 const int16_t *d_time_in, int16_t *d_time_out, int32_t out_ch, int32_t *d_err,
@@ -936,7 +949,7 @@ static int32_t xaac_b200_heaac_frame_host_impl(xaac_b200_ctx *ctx, xaac_b200_imd
     cudaStream_t st = ctx->streams[slot];
     uint8_t *base = (uint8_t *)ctx->stage[slot];
     int32_t *d_spec = (int32_t *)(base + o_spec * chunk), *d_w32 = (int32_t *)(base + o_w32 * chunk);
-    int16_t *d_side = (int16_t *)(base + o_side * chunk), *d_p16 = (int16_t *)(base + o_p16 * chunk);
+    int16_t *d_side = (int16_t *)(base + o_side * chunk);
     int16_t *d_pcm = (int16_t *)(base + o_pcm * chunk);
     int32_t *d_err = (int32_t *)(base + o_err * chunk);
     uint8_t *d_ics = base + o_ics * chunk;
@@ -948,9 +961,8 @@ static int32_t xaac_b200_heaac_frame_host_impl(xaac_b200_ctx *ctx, xaac_b200_imd
     rc = xaac_b200_imdct_process_dev(ctx, d_spec, ist->d_overlap + u0 * 512, ist->d_wstate + u0 * 2, d_ics, d_w32, d_adj, n,
                                      1, st);
     if (rc != XAAC_B200_OK) return rc;
-    rc = xaac_b200_imdct_out_to_pcm16_dev(ctx, d_w32, d_adj, d_p16, n, 0, st);
-    if (rc != XAAC_B200_OK) return rc;
-    rc = sbr_dec_range(ctx, s, u0, n, d_side, d_p16, d_pcm, d_err, st, (long long)slot * chunk);
+    // the WORD32 -> PCM16 hand-over happens in the analysis bank's load
+    rc = sbr_dec_range(ctx, s, u0, n, d_side, nullptr, d_pcm, d_err, st, (long long)slot * chunk, d_w32, d_adj);
     if (rc != XAAC_B200_OK) return rc;
     CK(cudaMemcpyAsync(pcm + u0 * out_words, d_pcm, (size_t)n * out_words * 2, cudaMemcpyDeviceToHost, st), "D2H pcm");
     if (err) CK(cudaMemcpyAsync(err + u0, d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H err");

@@ -132,6 +132,30 @@ def sbr_dec(ctx, state, side, time_in, time_out=None, err=None, stream=None):
     return time_out, err
 
 
+def sbr_dec_w32(ctx, state, side, w32, qshift_adj, time_out=None, err=None, stream=None):
+    """sbr_dec fed with the core coder's WORD32 output (w32 int32 [n,1024], qshift_adj int8 [n], both as written by
+    imdct_process): the WORD32 -> WORD16 hand-over of ixheaacd_allocate_sbr_scr (decoder/ixheaacd_api.c:337-370) runs in
+    the analysis bank's load.  Same results as imdct_out_to_pcm16(mode 0) followed by sbr_dec."""
+    n = state.n_units
+    _chk(side, torch.int16, (n, SIDE_WORDS), "side", "cuda")
+    _chk(w32, torch.int32, (n, 1024), "w32", "cuda")
+    _chk(qshift_adj, torch.int8, (n,), "qshift_adj", "cuda")
+    shape = (n, 2048, 2) if state.with_ps else (n, 2048)
+    if time_out is None:
+        time_out = torch.zeros(shape, dtype=torch.int16, device=side.device)
+    _chk(time_out, torch.int16, shape, "time_out", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=side.device)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
+    if stream is None:
+        stream = torch.cuda.current_stream(side.device)
+    rc = ctx._lib.xaac_b200_sbr_dec_hq_w32_dev(ctx.handle, state.handle, _ptr(side), _ptr(w32), _ptr(qshift_adj),
+                                              _ptr(time_out), _ptr(err), ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_sbr_dec_hq_w32_dev")
+    return time_out, err
+
+
 def sbr_dec_lp(ctx, state, side, time_in, time_out=None, out_ch=1, err=None, stream=None):
     """Batched drop-in for ixheaacd_sbr_dec with low_pow_flag = 1 (the fixed-point path of stereo HE-AACv1,
     decoder/ixheaacd_sbr_dec.c:662; one fused kernel).  side int16 [n,1232]; time_in int16 [n,1024]; returns

@@ -123,3 +123,49 @@ def test_full_batch_tiling_property(ctx, oracle):
         got = o[0].cpu().numpy()
         assert np.array_equal(got[:, :, 0], ol) and np.array_equal(got[:, :, 1], orr), f"frame {f}: tile 0 vs oracle"
     state.close()
+
+
+def _run_stage(xb, c, g, n, frames, w32_path, seed=77):
+    """`frames` frames of n PS units on context c; returns the PCM of every frame and the final state blobs"""
+    import torch
+    rng = np.random.default_rng(seed)
+    sst = xb.SbrState(c, n, with_ps=True)
+    base = 1
+    sst.upload(np.tile(g["st_in"][base], (n, 1)), np.tile(g["ps_in"][base], (n, 1)))
+    outs = []
+    for f in range(frames):
+        s = rng.integers(8, 31, (n, 1))
+        w32 = ((rng.random((n, 1024)) * 2 - 1) * 2.0 ** s).astype(np.int64).clip(-2 ** 31, 2 ** 31 - 1).astype(np.int32)
+        w32[0, :4] = (2 ** 31 - 1, -2 ** 31, 0x7FFF8000, -1)  # the hand-over's saturation corners
+        adj = rng.integers(1, 3, n).astype(np.int8)
+        side = torch.from_numpy(np.ascontiguousarray(g["side"][base + (np.arange(n) + f) % 11])).cuda()
+        d_w32, d_adj = torch.from_numpy(w32).cuda(), torch.from_numpy(adj).cuda()
+        if w32_path:
+            pcm, err = xb.sbr_dec_w32(c, sst, side, d_w32, d_adj)
+        else:
+            pcm, err = xb.sbr_dec(c, sst, side, xb.imdct_out_to_pcm16(c, d_w32, d_adj, 0))
+        outs.append((pcm.cpu().numpy(), err.cpu().numpy()))
+    return outs, sst.download()
+
+
+def test_sbr_dec_w32_and_fused_glue_match_the_separate_kernels(ctx, monkeypatch):
+    """The stage as the driver normally runs it (overlap rows + analysis bank + rescale in one kernel, previous-frame /
+    overlap save inside the envelope kernel, WORD32 hand-over in the bank's load) against the same stage with every glue
+    kernel launched on its own (XAAC_B200_SBR_UNFUSED=1) behind the PCM16 hand-over kernel: PCM, err and state identical.
+    The separate kernels are the ones test_sbrdec_gpu.py pins on the tapped reference records."""
+    import libxaac_b200 as xb
+    g = np.load(GOLD)
+    n, frames = 1500, 4
+    monkeypatch.setenv("XAAC_B200_SBR_UNFUSED", "1")
+    c2 = xb.Context(0)
+    monkeypatch.delenv("XAAC_B200_SBR_UNFUSED")
+    try:
+        ref, (st_r, ps_r) = _run_stage(xb, c2, g, n, frames, w32_path=False)
+    finally:
+        c2.close()
+    for w32_path in (False, True):
+        got, (st_g, ps_g) = _run_stage(xb, ctx, g, n, frames, w32_path=w32_path)
+        for f in range(frames):
+            assert np.array_equal(got[f][1], ref[f][1]), f"frame {f}: err (w32_path={w32_path})"
+            assert np.array_equal(got[f][0], ref[f][0]), f"frame {f}: PCM (w32_path={w32_path})"
+        assert np.array_equal(st_g, st_r) and np.array_equal(ps_g, ps_r)

@@ -17,7 +17,8 @@ SRC = {"imdct_ola_kernel": "imdct_kernels.cu", "pcm16_from_imdct_kernel": "sbr_g
        "esbr_hbe_kernel": "esbr_hbe_kernel.cu", "esbr_hfgen_kernel": "esbr_hfgen_kernel.cu", "esbr_envcalc_kernel": "esbr_envcalc_kernel.cu",
        "esbr_synth_kernel": "esbr_synth_kernel.cu", "esbr_ps_kernel": "esbr_ps_kernel.cu", "sbr_dec_lp_kernel": "sbr_lp_kernel.cu", "peak_limiter_kernel": "peaklim_kernel.cu",
        "peak_limiter_smooth_kernel": "peaklim_kernel.cu", "peak_limiter_finish_kernel": "peaklim_kernel.cu",
-       "sbr_sideinfo_kernel": "sbr_sideinfo_kernel.cu", "ps_sideinfo_kernel": "sbr_sideinfo_kernel.cu"}
+       "sbr_sideinfo_kernel": "sbr_sideinfo_kernel.cu", "ps_sideinfo_kernel": "sbr_sideinfo_kernel.cu",
+       "sbr_front_hq_kernel": "qmf_anal_kernel.cu", "calc_sbrenvelope_hq_post_kernel": "envcalc_kernel.cu"}
 
 
 def sha(path):
