@@ -36,6 +36,12 @@ struct xaac_b200_ctx {
   int32_t *d_rom_block = nullptr; // leading 620 bytes of ia_aac_dec_block_tables_struct (spectral stage)
   int esbr_periodic = 0;
   bool have_ps_rom = false;
+  // XAAC_B200_DEV_CHUNK=N (experiment): the device-resident HQ stage runs in chunks of N units round-robin over dev_streams
+  // internal streams, every stream re-using its own scratch slots so that the stage's matrices stay L2-resident
+  long dev_chunk = 0;
+  int dev_streams = 4;
+  cudaStream_t dev_st[8] = {};
+  cudaEvent_t dev_fork = nullptr, dev_join[8] = {};
   int sbr_unfused = 0;            // XAAC_B200_SBR_UNFUSED=1: the HQ stage launches its glue kernels separately (A/B, tests)
   int ps_rot_nosat = 0;           // no fractional-delay phase factor equals -32768 (16x16 rotations cannot saturate)
   char err[256] = {0};
@@ -176,6 +182,8 @@ int32_t xaac_b200_create(xaac_b200_ctx **out, int32_t device) {
   if (!ctx) return XAAC_B200_FATAL;
   ctx->device = device;
   if (const char *uf = getenv("XAAC_B200_SBR_UNFUSED")) ctx->sbr_unfused = atoi(uf) != 0;
+  if (const char *dc = getenv("XAAC_B200_DEV_CHUNK")) ctx->dev_chunk = atol(dc);
+  if (const char *ds = getenv("XAAC_B200_DEV_STREAMS")) ctx->dev_streams = atoi(ds) < 1 ? 1 : (atoi(ds) > 8 ? 8 : atoi(ds));
   if (const char *hc = getenv("XAAC_B200_HOST_CHUNK")) {
     const long v = atol(hc);
     if (v >= 256 && v <= (1 << 20)) ctx->host_chunk = v;
@@ -867,15 +875,51 @@ static int32_t sbr_check(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s) {
   return XAAC_B200_OK;
 }
 
+// whole batch of a state on the caller's stream, or (XAAC_B200_DEV_CHUNK) chunked over internal streams forked from / joined to it
+static int32_t sbr_dec_all(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side, const int16_t *d_time_in,
+                           const int32_t *d_w32, const int8_t *d_adj, int16_t *d_time_out, int32_t *d_err, cudaStream_t stream) {
+  const long long n = s->n_units;
+  const long long chunk = ctx->dev_chunk;
+  if (chunk <= 0 || n <= chunk) {
+    int32_t rc = ensure_sbr_scratch(ctx, s, n);
+    if (rc != XAAC_B200_OK) return rc;
+    return sbr_dec_range(ctx, s, 0, n, d_side, d_time_in, d_time_out, d_err, stream, 0, d_w32, d_adj);
+  }
+  const int K = ctx->dev_streams;
+  if (!ctx->dev_fork) {
+    CK(cudaEventCreateWithFlags(&ctx->dev_fork, cudaEventDisableTiming), "cudaEventCreate");
+    for (int k = 0; k < 8; k++) {
+      CK(cudaStreamCreateWithFlags(&ctx->dev_st[k], cudaStreamNonBlocking), "cudaStreamCreate");
+      CK(cudaEventCreateWithFlags(&ctx->dev_join[k], cudaEventDisableTiming), "cudaEventCreate");
+    }
+  }
+  int32_t rc = ensure_sbr_scratch(ctx, s, (long long)K * chunk);
+  if (rc != XAAC_B200_OK) return rc;
+  CK(cudaEventRecord(ctx->dev_fork, stream), "cudaEventRecord");
+  for (int k = 0; k < K; k++) CK(cudaStreamWaitEvent(ctx->dev_st[k], ctx->dev_fork, 0), "cudaStreamWaitEvent");
+  const long long out_words = s->with_ps ? 4096 : 2048;
+  int k = 0;
+  for (long long u0 = 0; u0 < n; u0 += chunk, k = (k + 1) % K) {
+    const long long m = n - u0 < chunk ? n - u0 : chunk;
+    rc = sbr_dec_range(ctx, s, u0, m, d_side + u0 * xb::kSideWords, d_time_in ? d_time_in + u0 * 1024 : nullptr,
+                       d_time_out + u0 * out_words, d_err ? d_err + u0 : nullptr, ctx->dev_st[k], (long long)k * chunk,
+                       d_w32 ? d_w32 + u0 * 1024 : nullptr, d_adj ? d_adj + u0 : nullptr);
+    if (rc != XAAC_B200_OK) return rc;
+  }
+  for (int q = 0; q < K; q++) {
+    CK(cudaEventRecord(ctx->dev_join[q], ctx->dev_st[q]), "cudaEventRecord");
+    CK(cudaStreamWaitEvent(stream, ctx->dev_join[q], 0), "cudaStreamWaitEvent");
+  }
+  return XAAC_B200_OK;
+}
+
 int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side,
                                  const int16_t *d_time_in, int16_t *d_time_out, int32_t *d_err, void *stream) {
   int32_t rc = sbr_check(ctx, s);
   if (rc != XAAC_B200_OK) return rc;
   if (!d_side || !d_time_in || !d_time_out) return bad_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-  rc = ensure_sbr_scratch(ctx, s, s->n_units);
-  if (rc != XAAC_B200_OK) return rc;
-  return sbr_dec_range(ctx, s, 0, s->n_units, d_side, d_time_in, d_time_out, d_err, (cudaStream_t)stream, 0);
+  return sbr_dec_all(ctx, s, d_side, d_time_in, nullptr, nullptr, d_time_out, d_err, (cudaStream_t)stream);
 }
 
 int32_t xaac_b200_sbr_dec_hq_w32_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side, const int32_t *d_w32,
@@ -884,9 +928,7 @@ int32_t xaac_b200_sbr_dec_hq_w32_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s,
   if (rc != XAAC_B200_OK) return rc;
   if (!d_side || !d_w32 || !d_qshift_adj || !d_time_out) return bad_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-  rc = ensure_sbr_scratch(ctx, s, s->n_units);
-  if (rc != XAAC_B200_OK) return rc;
-  return sbr_dec_range(ctx, s, 0, s->n_units, d_side, nullptr, d_time_out, d_err, (cudaStream_t)stream, 0, d_w32, d_qshift_adj);
+  return sbr_dec_all(ctx, s, d_side, nullptr, d_w32, d_qshift_adj, d_time_out, d_err, (cudaStream_t)stream);
 }
 
 // One low-power frame for units [u0, u0 + n) of the state.
