@@ -521,9 +521,12 @@ int32_t xaac_b200_esbr_anal32_pcm16_dev(xaac_b200_ctx *ctx, const int16_t *d_pcm
                                         int32_t *d_pos, float *d_qmf, int32_t *d_err, int64_t n_units, void *stream);
 
 /* eSBR float HF generator: batched ixheaacd_generate_hf (decoder/ixheaacd_sbrdec_lpfuncs.c:981-1359) with
- * ixheaacd_esbr_calc_co_variance (:781) and ixheaacd_esbr_chirp_fac_calc (:832), for the 2:1 system (is_usf_4 == 0) without
- * pre-processing, LD-MPS and error concealment (units asking for those get err = -2 and are left to the reference).
- * Float results are bit-identical to the reference build's (one IEEE rounding per operation, same order).
+ * ixheaacd_esbr_calc_co_variance (:781), ixheaacd_esbr_chirp_fac_calc (:832) and ixheaacd_pre_processing (:928-979, with
+ * ixheaacd_polyfit / ixheaacd_gausssolve), for the 2:1 system (is_usf_4 == 0) without LD-MPS and error concealment (units
+ * asking for those get err = -2 and are left to the reference).
+ * Float results are bit-identical to the reference build's (one IEEE rounding per operation, same order); the one exception is
+ * a pre-processing gain, whose log10 / pow run in double on the device like the reference's libm calls and can round to the
+ * neighbouring float (1 ulp, ~1e-8 of the values; inside the +-1 LSB the float path is graded at).
  * QMF buffers are [n][XAAC_EHF_ROWS][64] floats and are the reference's own arrays from their FIRST row, i.e. row r is row
  * r - SBR_HF_ADJ_OFFSET of the pointers ixheaacd_sbr_dec passes (decoder/ixheaacd_sbr_dec.c:921-929):
  *   d_src_re/im  ptr_sbr_dec->qmf_buf_real / qmf_buf_imag                  (read: bands < f_master_tbl[0])
@@ -542,7 +545,7 @@ int32_t xaac_b200_esbr_anal32_pcm16_dev(xaac_b200_ctx *ctx, const int16_t *d_pcm
 #define XAAC_EHF_HBE_FLAG 5       /* ptr_header_data->hbe_flag */
 #define XAAC_EHF_PATCHING_MODE 6  /* ptr_frame_data->sbr_patching_mode */
 #define XAAC_EHF_FS 7             /* ptr_header_data->out_sampling_freq */
-#define XAAC_EHF_PRE_PROC 8       /* ptr_header_data->pre_proc_flag (must be 0) */
+#define XAAC_EHF_PRE_PROC 8       /* ptr_header_data->pre_proc_flag: 1 runs ixheaacd_pre_processing (lpfuncs.c:928-979) */
 #define XAAC_EHF_USF4 9           /* ptr_header_data->is_usf_4 (must be 0) */
 #define XAAC_EHF_MPS_SBR 10       /* ptr_frame_data->mps_sbr_flag */
 #define XAAC_EHF_COV_COUNT 11     /* ptr_frame_data->cov_count */

@@ -3,7 +3,8 @@
 // One warp owns one unit (one channel of one frame).  Replaces
 //   ixheaacd_generate_hf              decoder/ixheaacd_sbrdec_lpfuncs.c:981-1359
 //   ixheaacd_esbr_calc_co_variance    :781-830        ixheaacd_esbr_chirp_fac_calc   :832-849
-// for the 2:1 system (38-slot covariance) without pre-processing (libm log10 / pow), LD-MPS and error concealment.
+// and ixheaacd_pre_processing :928-979 (+ ixheaacd_polyfit, ixheaacd_gausssolve :851-926)
+// for the 2:1 system (38-slot covariance) without LD-MPS and error concealment.
 // Every float operation is an explicit round-to-nearest intrinsic in the reference's evaluation order — the reference
 // build has neither FMA contraction nor reassociation — so the float output is bit-identical, not just within 1 LSB.
 //
@@ -31,6 +32,7 @@ struct EhWarpS {
   float a[4][64];  // alpha_real[k][0], alpha_imag[k][0], alpha_real[k][1], alpha_imag[k][1]
   i32 par[kEhfParWords];
   float bw[8];
+  float gain[64];  // ixheaacd_pre_processing: gain per source band (1 without pre-processing); low-band level in dB on the way
 };
 
 struct Cov {
@@ -93,6 +95,128 @@ XB_DEV void solve_alpha(const Cov &c, float &ar0, float &ai0, float &ar1, float 
   if (m0 >= 16.0f || m1 >= 16.0f) ar0 = ai0 = ar1 = ai1 = 0.0f;
 }
 
+// ixheaacd_pre_processing + ixheaacd_polyfit + ixheaacd_gausssolve (decoder/ixheaacd_sbrdec_lpfuncs.c:851-979): the low band's
+// level in dB per band (lane = band, serial over the slots in the reference's order), a third-order least-squares fit of it
+// (one lane: the sums and the 4 x 4 elimination are serial by contract), gain[k] = 10^((mean - fit(k)) / 20).  log10 / pow run
+// in double like the reference's libm calls and are rounded to float afterwards: CUDA's double-precision log10 / pow are within
+// 1-2 ulp of the correctly rounded double, so the float differs from glibc's only when the double result lies within ~1e-16
+// relative of a float rounding boundary (probability ~1e-8 per value; the tests allow 1 float ulp on such a gain).
+__device__ __noinline__ void esbr_pre_processing(const float *sre, const float *sim, float *gain, int n, int start, int end,
+                                                 int lane) {
+  const unsigned full = 0xffffffffu;
+  const bool have = n != 0 && end != start;
+  for (int k = lane; k < 64; k += 32) {
+    float le = 0.0f;
+    if (have && k < n) {
+      float temp = 0.0f;
+#pragma unroll 4
+      for (int i = start; i < end; i++) {
+        const float r = __ldg(EROW(sre, i) + k), q = __ldg(EROW(sim, i) + k);
+        temp = __fadd_rn(temp, __fadd_rn(__fmul_rn(r, r), __fmul_rn(q, q)));
+      }
+      temp = __fdiv_rn(temp, (float)(end - start));
+      le = (float)(10.0 * log10((double)__fadd_rn(temp, 1.0f)));
+    }
+    gain[k] = le;  // low_env[k]
+  }
+  __syncwarp();
+  float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f, mean = 0.0f;
+  if (lane == 0) {
+    if (have) {
+      for (int k = 0; k < n; k++) mean = __fadd_rn(mean, gain[k]);
+      mean = __fdiv_rn(mean, (float)n);
+    }
+    float a[4][4], b[4], y[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      b[i] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) a[i][j] = 0.0f;
+    }
+    for (int k = 0; k < n; k++) {
+      float v[7];
+      v[0] = 1.0f;
+#pragma unroll
+      for (int i = 1; i <= 6; i++) v[i] = __fmul_rn((float)k, v[i - 1]);
+      const float yk = gain[k];
+#pragma unroll
+      for (int i = 0; i <= 3; i++) {
+        b[i] = __fadd_rn(b[i], __fmul_rn(v[3 - i], yk));
+#pragma unroll
+        for (int j = 0; j <= 3; j++) a[i][j] = __fadd_rn(a[i][j], v[6 - i - j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int imax = i;
+#pragma unroll
+      for (int k = i + 1; k < 4; k++) {
+        float ak = 0.0f, am = 0.0f;  // a[k][i], a[imax][i] with static indices
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          if (r == k) ak = a[r][i];
+          if (r == imax) am = a[r][i];
+        }
+        if (fabsf(ak) > fabsf(am)) imax = k;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (r == imax && r != i) {  // swap rows i and imax (columns >= i) and the right-hand sides
+          const float t = b[r];
+          b[r] = b[i];
+          b[i] = t;
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (j >= i) {
+              const float w = a[r][j];
+              a[r][j] = a[i][j];
+              a[i][j] = w;
+            }
+        }
+      }
+      const float v = a[i][i];
+      b[i] = __fdiv_rn(b[i], v);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (j >= i) a[i][j] = __fdiv_rn(a[i][j], v);
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (k > i) {
+          const float w = a[k][i];
+          b[k] = __fsub_rn(b[k], __fmul_rn(w, b[i]));
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (j > i) a[k][j] = __fsub_rn(a[k][j], __fmul_rn(w, a[i][j]));
+        }
+    }
+#pragma unroll
+    for (int i = 3; i >= 0; i--) {
+      y[i] = b[i];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (j > i) y[i] = __fsub_rn(y[i], __fmul_rn(a[i][j], y[j]));
+    }
+    p0 = y[0]; p1 = y[1]; p2 = y[2]; p3 = y[3];
+  }
+  p0 = __shfl_sync(full, p0, 0); p1 = __shfl_sync(full, p1, 0); p2 = __shfl_sync(full, p2, 0); p3 = __shfl_sync(full, p3, 0);
+  mean = __shfl_sync(full, mean, 0);
+  __syncwarp();
+  for (int k = lane; k < 64; k += 32) {
+    float g = 1.0f;
+    if (k < n) {
+      float x = (float)k, sl = p3;
+      sl = __fadd_rn(sl, __fmul_rn(p2, x));
+      x = __fmul_rn(x, x);
+      sl = __fadd_rn(sl, __fmul_rn(p1, x));
+      x = __fmul_rn(x, (float)k);
+      sl = __fadd_rn(sl, __fmul_rn(p0, x));
+      g = (float)pow(10.0, (double)__fdiv_rn(__fsub_rn(mean, sl), 20.0f));
+    }
+    gain[k] = g;
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kEhWarps * 32) esbr_hfgen_kernel(EsbrHfgenArgs p) {
   __shared__ EhWarpS sm[kEhWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -106,7 +230,7 @@ __global__ void __launch_bounds__(kEhWarps * 32) esbr_hfgen_kernel(EsbrHfgenArgs
     const int num_mf = par[kEhfNumMf], num_if = par[kEhfNumIf], sb_start = par[kEhfSbStart];
     const int hbe = par[kEhfHbeFlag], patching = par[kEhfPatchingMode], fs = par[kEhfFs];
     int err = 0;
-    if (par[kEhfPreProc] || par[kEhfUsf4] || num_mf < 1 || num_mf > 56 || num_if < 0 || num_if > 5 || fs <= 0) err = -2;
+    if (par[kEhfUsf4] || num_mf < 1 || num_mf > 56 || num_if < 0 || num_if > 5 || fs <= 0) err = -2;
     const int lsb = err ? 0 : fm[0], usb = err ? 0 : fm[num_mf], xover = sb_start - lsb;
     const int start = par[kEhfBorderFirst] * 2, end = 32 + (par[kEhfBorderLast] - 16) * 2, cov_len = 38;
     if (start < 0 || end > EHF_ROWS - 2 || lsb < 0 || usb > 64 || lsb > usb) err = -2;
@@ -154,6 +278,8 @@ __global__ void __launch_bounds__(kEhWarps * 32) esbr_hfgen_kernel(EsbrHfgenArgs
     __syncwarp();
 
     int patch = 0;
+    const bool pre_proc = par[kEhfPreProc] != 0;
+    if (pre_proc) esbr_pre_processing(sre, sim, w.gain, lsb, start, end, lane);  // lpfuncs.c:1052
     if (patching || !hbe) {
       int cov_count = lsb;
       if (par[kEhfMpsSbr]) cov_count = lsb < par[kEhfCovCount] ? lsb : par[kEhfCovCount];
@@ -231,6 +357,7 @@ __global__ void __launch_bounds__(kEhWarps * 32) esbr_hfgen_kernel(EsbrHfgenArgs
           const float a0r = __fmul_rn(bw, w.a[0][k]), a0i = __fmul_rn(bw, w.a[1][k]);
           bw = __fmul_rn(bw, bw);
           const float a1r = __fmul_rn(bw, w.a[2][k]), a1i = __fmul_rn(bw, w.a[3][k]);
+          const float gain = pre_proc ? w.gain[k] : 1.0f;
           if (bw > 0.0f) {
             float r2 = __ldg(EROW(sre, start - 2) + k), i2 = __ldg(EROW(sim, start - 2) + k);
             float r1 = __ldg(EROW(sre, start - 1) + k), i1 = __ldg(EROW(sim, start - 1) + k);
@@ -241,15 +368,17 @@ __global__ void __launch_bounds__(kEhWarps * 32) esbr_hfgen_kernel(EsbrHfgenArgs
                                          __fmul_rn(a1i, i2));
               const float ti = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0i, r1), __fmul_rn(a0r, i1)), __fmul_rn(a1i, r2)),
                                          __fmul_rn(a1r, i2));
-              EROW(dre, i)[k2] = __fadd_rn(r0, tr);
-              EROW(dim, i)[k2] = __fadd_rn(i0, ti);
+              // dst = src * gain; dst += (...) * gain (lpfuncs.c:1226-1243); gain = 1 without pre-processing (exact products)
+              EROW(dre, i)[k2] = __fadd_rn(__fmul_rn(r0, gain), __fmul_rn(tr, gain));
+              EROW(dim, i)[k2] = __fadd_rn(__fmul_rn(i0, gain), __fmul_rn(ti, gain));
               r2 = r1; i2 = i1; r1 = r0; i1 = i0;
             }
           } else {
 #pragma unroll 4
             for (int i = start; i < end; i++) {
-              EROW(dre, i)[k2] = __ldg(EROW(sre, i) + k);
-              EROW(dim, i)[k2] = __ldg(EROW(sim, i) + k);
+              const float r0 = __ldg(EROW(sre, i) + k), i0 = __ldg(EROW(sim, i) + k);
+              EROW(dre, i)[k2] = __fmul_rn(r0, gain);
+              EROW(dim, i)[k2] = __fmul_rn(i0, gain);
             }
           }
         }

@@ -741,7 +741,7 @@ WORD32 __wrap_ixheaacd_sbr_dec(ia_sbr_dec_struct *ptr_sbr_dec, WORD16 *ptr_time_
                    ptr_sbr_dec->str_synthesis_qmf_bank.no_channels == 64 && (!with_ps || (ptr_ps_dec != NULL && self != NULL)) &&
                    ptr_frame_data->stereo_config_idx <= 0 && !ptr_frame_data->mps_sbr_flag && !ptr_header_data->is_usf_4 &&
                    (!apply_processing ||
-                    (ptr_frame_data->sbr_mode == ORIG_SBR && !ptr_header_data->pre_proc_flag &&
+                    (ptr_frame_data->sbr_mode == ORIG_SBR &&
                      (ptr_frame_data->str_frame_info_details.num_noise_env == 1 ||
                       ptr_frame_data->str_frame_info_details.num_noise_env == 2)));
     if (ok) {

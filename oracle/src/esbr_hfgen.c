@@ -5,6 +5,7 @@
  * for the 2:1 system without pre-processing, LD-MPS or error concealment.  Every float operation is written out one
  * rounding at a time in the reference's evaluation order (the reference build has no FMA and no reassociation), so the
  * results are bit-identical; pinned against the compiled function itself (tests/test_oracle_esbr.py). */
+#include <math.h>
 #include <string.h>
 #include "xaac_oracle.h"
 
@@ -85,12 +86,110 @@ static int closest_entry_down(int goal, const int32_t *fm, int num_mf) { /* lpfu
   return fm[idx];
 }
 
+/* ixheaacd_gausssolve / ixheaacd_polyfit / ixheaacd_pre_processing (decoder/ixheaacd_sbrdec_lpfuncs.c:851-979): the spectral tilt of
+ * the low band (third-order fit of its per-band level in dB) becomes a gain per source band of the patches.  Every float
+ * operation is its own statement through a volatile so that no contraction can change a rounding; log10 / pow are libm's, in
+ * double, as in the reference. */
+static void pre_processing(const float *src_re, const float *src_im, float *gain, int n, int start, int end) {
+  float low_env[64] = {0};
+  volatile float mean = 0, t, u, v_;
+  if (n != 0 && end != start) {
+    for (int k = 0; k < n; k++) {
+      volatile float temp = 0;
+      for (int i = start; i < end; i++) {
+        t = ROW(src_re, i)[k] * ROW(src_re, i)[k];
+        u = ROW(src_im, i)[k] * ROW(src_im, i)[k];
+        t = t + u;
+        temp = temp + t;
+      }
+      temp = temp / (float)(end - start);
+      t = temp + 1.0f;
+      low_env[k] = (float)(10 * log10((double)t));
+      mean = mean + low_env[k];
+    }
+    mean = mean / (float)n;
+  }
+  float a[4][4], b[4], vv[7], p[4];
+  for (int i = 0; i < 4; i++) {
+    b[i] = 0.0f;
+    for (int j = 0; j < 4; j++) a[i][j] = 0.0f;
+  }
+  for (int k = 0; k < n; k++) {
+    vv[0] = 1.0f;
+    for (int i = 1; i <= 6; i++) {
+      t = (float)k * vv[i - 1];
+      vv[i] = t;
+    }
+    for (int i = 0; i <= 3; i++) {
+      t = vv[3 - i] * low_env[k];
+      u = b[i] + t;
+      b[i] = u;
+      for (int j = 0; j <= 3; j++) {
+        u = a[i][j] + vv[6 - i - j];
+        a[i][j] = u;
+      }
+    }
+  }
+  for (int i = 0; i < 4; i++) { /* :851 */
+    int imax = i;
+    for (int k = i + 1; k < 4; k++)
+      if (fabs(a[k][i]) > fabs(a[imax][i])) imax = k;
+    if (imax != i) {
+      float w = b[imax];
+      b[imax] = b[i];
+      b[i] = w;
+      for (int j = i; j < 4; j++) {
+        w = a[imax][j];
+        a[imax][j] = a[i][j];
+        a[i][j] = w;
+      }
+    }
+    v_ = a[i][i];
+    t = b[i] / v_;
+    b[i] = t;
+    for (int j = i; j < 4; j++) {
+      t = a[i][j] / v_;
+      a[i][j] = t;
+    }
+    for (int k = i + 1; k < 4; k++) {
+      v_ = a[k][i];
+      t = v_ * b[i];
+      u = b[k] - t;
+      b[k] = u;
+      for (int j = i + 1; j < 4; j++) {
+        t = v_ * a[i][j];
+        u = a[k][j] - t;
+        a[k][j] = u;
+      }
+    }
+  }
+  for (int i = 3; i >= 0; i--) {
+    p[i] = b[i];
+    for (int j = i + 1; j < 4; j++) {
+      t = a[i][j] * p[j];
+      u = p[i] - t;
+      p[i] = u;
+    }
+  }
+  for (int k = 0; k < n; k++) {
+    volatile float x = (float)k, sl = p[3];
+    t = p[2] * x; sl = sl + t;
+    x = x * x;
+    t = p[1] * x; sl = sl + t;
+    x = x * (float)k;
+    t = p[0] * x; sl = sl + t;
+    t = mean - sl;
+    u = t / 20.0f;
+    gain[k] = (float)pow(10, (double)u);
+  }
+}
+
 int xo_esbr_generate_hf(const float *src_re, const float *src_im, const float *pv_re, const float *pv_im, float *dst_re,
                         float *dst_im, const int32_t *par, float *bw_prev, int32_t *patch_out) {
   const int32_t *fm = par + XO_EHF_FMASTER, *invf_tbl = par + XO_EHF_INVF_TBL;
   const int num_mf = par[XO_EHF_NUM_MF], num_if = par[XO_EHF_NUM_IF], sb_start = par[XO_EHF_SB_START];
   const int hbe = par[XO_EHF_HBE_FLAG], patching = par[XO_EHF_PATCHING_MODE];
-  if (par[XO_EHF_PRE_PROC] || par[XO_EHF_USF4] || num_mf < 1 || num_mf > 56 || num_if < 0 || num_if > 5) return -2;
+  if (par[XO_EHF_USF4] || num_mf < 1 || num_mf > 56 || num_if < 0 || num_if > 5) return -2;
   const int lsb = fm[0], usb = fm[num_mf], xover = sb_start - fm[0];
   const int start = par[XO_EHF_BORDER_FIRST] * 2, end = 32 + (par[XO_EHF_BORDER_LAST] - 16) * 2, cov_len = 38;
   if (start < 0 || end > XO_EHF_ROWS - 2 || lsb < 0 || usb > 64 || lsb > usb) return -2;
@@ -99,6 +198,10 @@ int xo_esbr_generate_hf(const float *src_re, const float *src_im, const float *p
   if (par[XO_EHF_FS] <= 0) return -2;
   float bw_array[6] = {0};
   int patch = 0;
+  const int pre_proc = par[XO_EHF_PRE_PROC] != 0;
+  float gain_vector[64];
+  for (int k = 0; k < 64; k++) gain_vector[k] = 1.0f;
+  if (pre_proc) pre_processing(src_re, src_im, gain_vector, lsb, start, end); /* lpfuncs.c:1052 */
 
   for (int i = 0; i < num_if; i++) { /* lpfuncs.c:832 */
     volatile float a, b;
@@ -177,14 +280,17 @@ int xo_esbr_generate_hf(const float *src_re, const float *src_im, const float *p
         a1i = bw * ai[k][1];
         for (int i = start; i < end; i++) {
           volatile float t, u, dr, di;
-          dr = ROW(src_re, i)[k] * 1.0f;
-          di = ROW(src_im, i)[k] * 1.0f;
+          const float gain = gain_vector[k];
+          dr = ROW(src_re, i)[k] * gain;
+          di = ROW(src_im, i)[k] * gain;
           if (bw > 0.0f) {
             const float r1 = ROW(src_re, i - 1)[k], i1 = ROW(src_im, i - 1)[k];
             const float r2 = ROW(src_re, i - 2)[k], i2 = ROW(src_im, i - 2)[k];
             t = a0r * r1; u = a0i * i1; t = t - u; u = a1r * r2; t = t + u; u = a1i * i2; t = t - u;
+            t = t * gain;
             dr = dr + t;
             t = a0i * r1; u = a0r * i1; t = t + u; u = a1i * r2; t = t + u; u = a1r * i2; t = t + u;
+            t = t * gain;
             di = di + t;
           }
           ROW(dst_re, i)[k2] = dr;

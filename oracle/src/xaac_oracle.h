@@ -332,7 +332,7 @@ void xo_samples_sat16(const float *in, int ch_fac, int ch, int16_t *pcm, int n);
 #define XO_EHF_HBE_FLAG 5
 #define XO_EHF_PATCHING_MODE 6 /* sbr_patching_mode */
 #define XO_EHF_FS 7            /* out_sampling_freq */
-#define XO_EHF_PRE_PROC 8      /* pre_proc_flag: not restated (libm log10 / pow); the kernel refuses it */
+#define XO_EHF_PRE_PROC 8      /* pre_proc_flag: ixheaacd_pre_processing (libm log10 / pow in double) */
 #define XO_EHF_USF4 9          /* is_usf_4: refused (76-row covariance) */
 #define XO_EHF_MPS_SBR 10      /* mps_sbr_flag */
 #define XO_EHF_COV_COUNT 11

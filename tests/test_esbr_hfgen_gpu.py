@@ -1,6 +1,6 @@
 """GPU parity: esbr_hfgen_kernel (xaac_b200_esbr_generate_hf_dev) against the oracle / the compiled ixheaacd_generate_hf on
-the same seeded units — float results compared bit for bit (no tolerance), incl. cells the stage must leave untouched,
-the patch table, the chirp-factor state and the error returns."""
+the same seeded units — float results compared bit for bit (no tolerance; the pre-processing test states its own), incl. cells the
+stage must leave untouched, the patch table, the chirp-factor state and the error returns."""
 import numpy as np
 import pytest
 import torch
@@ -74,12 +74,40 @@ def test_generate_hf_stream_state(ctx, oracle):
 def test_generate_hf_refuses_unsupported(ctx):
     import libxaac_b200 as xb
     d = oracle_util.synth_esbr_hfgen_units(8, 3)
-    d["par"][0, oracle_util.EHF["PRE_PROC"]] = 1
     d["par"][1, oracle_util.EHF["USF4"]] = 1
     d["par"][2, oracle_util.EHF["FS"]] = 0
     out = _run(ctx, d)
-    assert list(out[4][:3]) == [-2, -2, -2]
-    assert np.array_equal(out[0][:3].view(np.int32), d["dst_re"][:3].view(np.int32))
+    assert list(out[4][1:3]) == [-2, -2]
+    assert np.array_equal(out[0][1:3].view(np.int32), d["dst_re"][1:3].view(np.int32))
+
+
+@pytest.mark.parametrize("with_pv", [True, False])
+def test_generate_hf_pre_processing(ctx, oracle, with_pv):
+    """pre_proc_flag = 1 (ixheaacd_pre_processing, decoder/ixheaacd_sbrdec_lpfuncs.c:928-979).  The oracle is pinned bit for bit on
+    the compiled function (tests/test_oracle_esbr.py).  The two libm calls (log10, pow: in double, rounded to float) are CUDA's on
+    the device: a gain may differ from glibc's by one float ulp when the double result sits on a float rounding boundary, so the
+    tolerance written here is 2 float ulps per output cell, on at most 0.1 % of the units; everything else bit for bit."""
+    d = oracle_util.synth_esbr_hfgen_units(1500, 61 + with_pv, hbe=with_pv)
+    d["par"][:, oracle_util.EHF["PRE_PROC"]] = 1
+    if with_pv:
+        d["par"][::2, oracle_util.EHF["PATCHING_MODE"]] = 1
+    got = _run(ctx, d, with_pv)
+    want = oracle_util.oracle_esbr_hfgen_batch(oracle, d, with_pv)
+    assert np.array_equal(got[4], want[4])
+    ok = np.flatnonzero(want[4] == 0)
+    assert len(ok) > 1000
+    assert np.array_equal(got[3][ok], want[3][ok]) and np.array_equal(got[2][ok].view(np.int32), want[2][ok].view(np.int32))
+    off_units = 0
+    for x, y in ((got[0], want[0]), (got[1], want[1])):
+        xi, yi = x[ok].view(np.int32).astype(np.int64), y[ok].view(np.int32).astype(np.int64)
+        diff = np.abs(xi - yi)
+        assert diff.max() <= 2, f"max ulp distance {diff.max()}"
+        off_units = max(off_units, int((diff.reshape(len(ok), -1).max(axis=1) > 0).sum()))
+    assert off_units <= max(1, len(ok) // 1000), f"{off_units} of {len(ok)} units are not bit-identical"
+    d0 = dict(d)
+    d0["par"] = d["par"].copy()
+    d0["par"][:, oracle_util.EHF["PRE_PROC"]] = 0
+    assert not np.array_equal(_run(ctx, d0, with_pv)[0].view(np.int32), got[0].view(np.int32)), "the gains changed nothing"
 
 
 def test_generate_hf_golden(ctx):

@@ -124,6 +124,25 @@ def load_esbr_golden(name):
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
 
 
+def test_esbr_generate_hf_pre_processing_matches_reference(oracle, ref):
+    """pre_proc_flag = 1: ixheaacd_pre_processing (decoder/ixheaacd_sbrdec_lpfuncs.c:928-979 — low-band level in dB, third-order
+    ixheaacd_polyfit with ixheaacd_gausssolve, gain = 10^((mean - slope) / 20)) scales every patch by the gain of its source band.
+    The restatement calls the same libm, so the floats are identical to the compiled function's."""
+    for hbe in (True, False):
+        d = oracle_util.synth_esbr_hfgen_units(300, 31 + hbe, hbe=hbe)
+        d["par"][:, oracle_util.EHF["PRE_PROC"]] = 1
+        if hbe:
+            d["par"][::2, oracle_util.EHF["PATCHING_MODE"]] = 1  # the gains only act in the LPP patch branch
+        a = oracle_util.oracle_esbr_hfgen_batch(oracle, d, with_pv=hbe)
+        b = oracle_util.ref_esbr_hfgen_batch(ref, d, with_pv=hbe)
+        good = _same_hfgen(a, b, f"pre-processing, hbe={hbe}")
+        d0 = dict(d)
+        d0["par"] = d["par"].copy()
+        d0["par"][:, oracle_util.EHF["PRE_PROC"]] = 0
+        a0 = oracle_util.oracle_esbr_hfgen_batch(oracle, d0, with_pv=hbe)
+        assert not np.array_equal(a[0].view(np.int32), a0[0].view(np.int32)), "the gains changed nothing"
+
+
 def golden_hfgen_units(g):
     return dict(par=g["par"], src_re=g["src_re"], src_im=g["src_im"], pv_re=g["pv_re"], pv_im=g["pv_im"],
                 dst_re=g["dst_in_re"], dst_im=g["dst_in_im"], bw_prev=g["bw_in"], patch_in=g["patch_in"])
