@@ -2005,8 +2005,7 @@ class ChainLpWork:
     def step(self, i, stream):
         xb, ctx = self.xb, self.ctx
         xb.imdct_process(ctx, self.imdct_state, self.spec, self.walk[i % self.nw], self.w32, self.adj, stream=stream)
-        xb.imdct_out_to_pcm16(ctx, self.w32, self.adj, 0, self.p16, stream=stream)
-        xb.sbr_dec_lp(ctx, self.state, self.side[i % 12], self.p16, self.pcm, 2, self.err, stream=stream)
+        xb.sbr_dec_lp_w32(ctx, self.state, self.side[i % 12], self.w32, self.adj, self.pcm, 2, self.err, stream=stream)
 
     def check(self):
         assert int(self.err.abs().max().item()) == 0, "the LP SBR stage reported an error for some unit"

@@ -379,6 +379,12 @@ int32_t xaac_b200_sbr_dec_lp_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state,
                                  const int16_t *d_time_in, int16_t *d_time_out, int32_t out_ch, int32_t *d_err,
                                  void *stream);
 
+/* The low-power stage fed with the core coder's WORD32 output (d_w32 [n][1024], d_qshift_adj [n] as written by
+ * xaac_b200_imdct_process_dev): the hand-over of ixheaacd_allocate_sbr_scr (decoder/ixheaacd_api.c:337-370) runs in the kernel's load. */
+int32_t xaac_b200_sbr_dec_lp_w32_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *state, const int16_t *d_side,
+                                     const int32_t *d_w32, const int8_t *d_qshift_adj, int16_t *d_time_out, int32_t out_ch,
+                                     int32_t *d_err, void *stream);
+
 /* Host-buffer entry point for a whole HE-AAC (v1 mono / v2) frame per unit: IMDCT + window/OLA of the core channel
  * (xaac_b200_imdct_process_dev), the WORD32 -> PCM16 hand-over (inside the analysis bank's load, as in
  * xaac_b200_sbr_dec_hq_w32_dev) and the SBR stage, chunked and pipelined over internal streams (H2D, kernels, D2H overlap).  Both states stay resident in HBM.

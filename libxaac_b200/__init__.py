@@ -31,7 +31,7 @@ from .esbr import (EsbrAnalBatch, EsbrDecBatch, EsbrDecHbeBatch, EsbrHbeBatch, E
 from .spectral import aac_channel_pair_process  # noqa: F401
 from .sideinfo import PSD_WORDS, SD_WORDS, dec_sbrdata, decode_ps_data  # noqa: F401
 from .usac import STOP_START_SEQUENCE, UsacFdBatch, usac_fd_frm_dec  # noqa: F401
-from .sbr import SbrState, calc_sbrenvelope, heaac_frame_host, heaac_lp_frame_host, hf_generator, sbr_dec, sbr_dec_lp, sbr_dec_w32  # noqa: F401
+from .sbr import SbrState, calc_sbrenvelope, heaac_frame_host, heaac_lp_frame_host, hf_generator, sbr_dec, sbr_dec_lp, sbr_dec_lp_w32, sbr_dec_w32  # noqa: F401
 
 __all__ = [
     "aac_channel_pair_process",
@@ -42,6 +42,7 @@ __all__ = [
     "SbrState",
     "sbr_dec",
     "sbr_dec_w32",
+    "sbr_dec_lp_w32",
     "sbr_dec_lp",
     "PeakLimiterBatch",
     "peak_limiter_process",

@@ -52,6 +52,7 @@ SIGNATURES = {
     "xaac_b200_sbr_dec_hq_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xaac_b200_sbr_dec_hq_w32_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xaac_b200_sbr_dec_lp_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "xaac_b200_sbr_dec_lp_w32_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "xaac_b200_heaac_frame_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xaac_b200_heaac_lp_frame_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "xaac_b200_peak_limiter_state_init": (_i32, [_vp, _i32, _i32]),

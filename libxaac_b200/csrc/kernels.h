@@ -248,6 +248,10 @@ struct SbrLpArgs {
   long long in_unit_stride = 1024;
   int in_ch = 1;
   int out_ch = 1;
+  // != null: the core coder's WORD32 output [n][1024] + qshift_adj [n] instead of time_in; converted on load
+  // (round16(shl32_sat(x, qshift_adj)), ixheaacd_allocate_sbr_scr, decoder/ixheaacd_api.c:337-370)
+  const int32_t *w32 = nullptr;
+  const int8_t *qshift_adj = nullptr;
 };
 size_t sbr_lp_table_bytes();
 int sbr_lp_build_tables(const uint8_t *qrom, uint8_t *out);  // 0 ok, -1 tables unsupported

@@ -1155,7 +1155,8 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
           for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
         };
         pf(p.side + un * kSideWords, 1480);
-        pf(p.time_in + un * p.in_unit_stride, p.in_ch == 1 ? 2048 : 0);
+        if (p.w32) pf(p.w32 + un * 1024, 4096);
+        else pf(p.time_in + un * p.in_unit_stride, p.in_ch == 1 ? 2048 : 0);
         pf(p.syn_states + un * 1280, 2560);
         pf(p.ov + un * 768, 1536);
         pf(p.anal_states + un * 320, 640);
@@ -1259,6 +1260,11 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
     // ---------------- analysis: 5-tap window per slot (generic:528-588), lanes = outputs ----------------
     {
       const int16_t *pcm = p.time_in + u * p.in_unit_stride;
+      const i32 *w32 = p.w32 ? p.w32 + u * 1024 : nullptr;
+      const int qadj = p.w32 ? p.qshift_adj[u] : 0;
+      auto samp = [&](int j) -> i32 {  // core-coder sample j of the frame as the WORD16 the reference's hand-over produces
+        return w32 ? round16(shl32_sat(__ldg(w32 + j), qadj)) : (i32)pcm[(long long)p.in_ch * j];
+      };
       int pos = p.anal_pos[2 * u], f1 = p.anal_pos[2 * u + 1], f2 = f1 + 64;
       // The reference keeps its 320-sample ring position and its coefficient phase in lock step (pos / 32 + filter_pos / 64
       // = 0 mod 10, both even, from reset on); then the window is the time-invariant FIR
@@ -1275,7 +1281,16 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
           if (q >= 10) q -= 10;
           T[j] = w.ring[32 * q + 31 - (j & 31)];
         }
-        if (p.in_ch == 1 && ((reinterpret_cast<uintptr_t>(pcm) & 3) == 0)) {
+        if (w32) {  // the whole frame's WORD32 samples, 2 x 16 requests in flight, converted on the way into the history
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            i32 vp[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) vp[q] = __ldg(w32 + 512 * h + lane + 32 * q);
+#pragma unroll
+            for (int q = 0; q < 16; q++) T[288 + 512 * h + lane + 32 * q] = (int16_t)round16(shl32_sat(vp[q], qadj));
+          }
+        } else if (p.in_ch == 1 && ((reinterpret_cast<uintptr_t>(pcm) & 3) == 0)) {
           const i32 *src = reinterpret_cast<const i32 *>(pcm);
           i32 *dst = reinterpret_cast<i32 *>(T + 288);
           i32 vp[16];  // the whole frame's PCM: 16 requests in flight
@@ -1285,7 +1300,7 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
           for (int q = 0; q < 16; q++) dst[lane + 32 * q] = vp[q];
         } else {
 #pragma unroll 4
-          for (int j = lane; j < 1024; j += 32) T[288 + j] = pcm[(long long)p.in_ch * j];
+          for (int j = lane; j < 1024; j += 32) T[288 + j] = (int16_t)samp(j);
         }
         i32 ca[5], cb[5];
 #pragma unroll
@@ -1318,11 +1333,11 @@ __global__ void __launch_bounds__(kLpWarps * 32, 1) sbr_dec_lp_kernel(SbrLpArgs 
         pos = 32 * Pf;
         f1 = 64 * ((10 - Pf) % 10);
       } else {
-        i32 nxt = pcm[(long long)p.in_ch * lane];
+        i32 nxt = samp(lane);
 #pragma unroll 1
         for (int slot = 0; slot < 32; slot++) {
           w.ring[pos + 31 - lane] = (int16_t)nxt;
-          if (slot < 31) nxt = pcm[(long long)p.in_ch * (32 * (slot + 1) + lane)];
+          if (slot < 31) nxt = samp(32 * (slot + 1) + lane);
           __syncwarp();
           const int16_t *fp1 = w.ring + ((slot & 1) ? 32 : 0), *fp2 = w.ring + ((slot & 1) ? 0 : 32);
           i32 a = 0, b = 0;

@@ -934,8 +934,9 @@ int32_t xaac_b200_sbr_dec_hq_w32_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s,
 // One low-power frame for units [u0, u0 + n) of the state.
 static int32_t sbr_dec_lp_range(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, long long u0, long long n, const int16_t *d_side,
                                 const int16_t *d_time_in, int16_t *d_time_out, int32_t out_ch, int32_t *d_err,
-                                cudaStream_t st) {
+                                cudaStream_t st, const int32_t *d_w32 = nullptr, const int8_t *d_adj = nullptr) {
   xb::SbrLpArgs a;
+  a.w32 = d_w32; a.qshift_adj = d_adj;
   a.side = d_side; a.time_in = d_time_in; a.time_out = d_time_out;
   a.anal_states = s->anal_states + u0 * 320; a.anal_pos = s->anal_pos + u0 * 2; a.syn_pos = s->syn_pos + u0 * 2;
   a.sf = s->sf + u0 * 8; a.misc = s->misc + u0 * 16; a.env = s->env + u0 * xb::kEnvStWords;
@@ -961,6 +962,22 @@ int32_t xaac_b200_sbr_dec_lp_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, con
   if (out_ch < 1 || (s->n_units % out_ch) != 0) return bad_arg(ctx, "out_ch must divide the number of units");
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   return sbr_dec_lp_range(ctx, s, 0, s->n_units, d_side, d_time_in, d_time_out, out_ch, d_err, (cudaStream_t)stream);
+}
+
+int32_t xaac_b200_sbr_dec_lp_w32_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side, const int32_t *d_w32,
+                                     const int8_t *d_qshift_adj, int16_t *d_time_out, int32_t out_ch, int32_t *d_err,
+                                     void *stream) {
+  if (!ctx || !s) return XAAC_B200_ERR_ARG;
+  if (!ctx->have_qmf_rom || !ctx->have_env_rom) {
+    snprintf(ctx->err, sizeof(ctx->err), "set_qmf_rom / set_env_rom have not both been called");
+    return XAAC_B200_ERR_NO_ROM;
+  }
+  if (!ctx->d_rom_lp) return bad_arg(ctx, "the installed QMF tables are not supported by the low-power kernel");
+  if (!d_side || !d_w32 || !d_qshift_adj || !d_time_out) return bad_arg(ctx, "null buffer");
+  if (out_ch < 1 || (s->n_units % out_ch) != 0) return bad_arg(ctx, "out_ch must divide the number of units");
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return sbr_dec_lp_range(ctx, s, 0, s->n_units, d_side, nullptr, d_time_out, out_ch, d_err, (cudaStream_t)stream, d_w32,
+                          d_qshift_adj);
 }
 
 // HE-AAC frame from host buffers: IMDCT (mono or one core channel per unit) -> WORD32->PCM16 hand-over -> SBR stage.
@@ -1042,7 +1059,7 @@ static int32_t xaac_b200_heaac_lp_frame_host_impl(xaac_b200_ctx *ctx, xaac_b200_
     cudaStream_t st = ctx->streams[slot];
     uint8_t *base = (uint8_t *)ctx->stage[slot];
     int32_t *d_spec = (int32_t *)(base + o_spec * chunk), *d_w32 = (int32_t *)(base + o_w32 * chunk);
-    int16_t *d_side = (int16_t *)(base + o_side * chunk), *d_p16 = (int16_t *)(base + o_p16 * chunk);
+    int16_t *d_side = (int16_t *)(base + o_side * chunk);
     int16_t *d_pcm = (int16_t *)(base + o_pcm * chunk);
     int32_t *d_err = (int32_t *)(base + o_err * chunk);
     uint8_t *d_ics = base + o_ics * chunk;
@@ -1054,9 +1071,8 @@ static int32_t xaac_b200_heaac_lp_frame_host_impl(xaac_b200_ctx *ctx, xaac_b200_
     rc = xaac_b200_imdct_process_dev(ctx, d_spec, ist->d_overlap + u0 * 512, ist->d_wstate + u0 * 2, d_ics, d_w32, d_adj, n,
                                      1, st);
     if (rc != XAAC_B200_OK) return rc;
-    rc = xaac_b200_imdct_out_to_pcm16_dev(ctx, d_w32, d_adj, d_p16, n, 0, st);
-    if (rc != XAAC_B200_OK) return rc;
-    rc = sbr_dec_lp_range(ctx, s, u0, n, d_side, d_p16, d_pcm, out_ch, d_err, st);
+    // the WORD32 -> PCM16 hand-over happens in the fused stage's load
+    rc = sbr_dec_lp_range(ctx, s, u0, n, d_side, nullptr, d_pcm, out_ch, d_err, st, d_w32, d_adj);
     if (rc != XAAC_B200_OK) return rc;
     CK(cudaMemcpyAsync(pcm + u0 * 2048, d_pcm, (size_t)n * 4096, cudaMemcpyDeviceToHost, st), "D2H pcm");
     if (err) CK(cudaMemcpyAsync(err + u0, d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H err");

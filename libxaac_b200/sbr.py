@@ -180,6 +180,29 @@ def sbr_dec_lp(ctx, state, side, time_in, time_out=None, out_ch=1, err=None, str
     return time_out, err
 
 
+def sbr_dec_lp_w32(ctx, state, side, w32, qshift_adj, time_out=None, out_ch=1, err=None, stream=None):
+    """sbr_dec_lp fed with the core coder's WORD32 output (w32 int32 [n,1024], qshift_adj int8 [n] as written by imdct_process);
+    same results as imdct_out_to_pcm16(mode 0) followed by sbr_dec_lp."""
+    n = state.n_units
+    _chk(side, torch.int16, (n, SIDE_WORDS), "side", "cuda")
+    _chk(w32, torch.int32, (n, 1024), "w32", "cuda")
+    _chk(qshift_adj, torch.int8, (n,), "qshift_adj", "cuda")
+    shape = (n, 2048) if out_ch == 1 else (n // out_ch, 2048, out_ch)
+    if time_out is None:
+        time_out = torch.zeros(shape, dtype=torch.int16, device=side.device)
+    _chk(time_out, torch.int16, shape, "time_out", "cuda")
+    if err is None:
+        err = torch.empty((n,), dtype=torch.int32, device=side.device)
+    else:
+        _chk(err, torch.int32, (n,), "err", "cuda")
+    if stream is None:
+        stream = torch.cuda.current_stream(side.device)
+    rc = ctx._lib.xaac_b200_sbr_dec_lp_w32_dev(ctx.handle, state.handle, _ptr(side), _ptr(w32), _ptr(qshift_adj), _ptr(time_out),
+                                              int(out_ch), _ptr(err), ctypes.c_void_p(stream.cuda_stream))
+    ctx.check(rc, "xaac_b200_sbr_dec_lp_w32_dev")
+    return time_out, err
+
+
 def heaac_frame_host(ctx, imdct_state, sbr_state, spec_coeff, ics, side, pcm, err=None):
     """One HE-AAC frame per unit from host buffers (IMDCT + hand-over + SBR stage, chunked / pipelined inside the
     library; both states stay in HBM).  spec_coeff int32 [n,1024], ics uint8 [n,2], side int16 [n,1232] and pcm int16

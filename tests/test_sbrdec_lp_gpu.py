@@ -203,3 +203,42 @@ def test_non_lockstep_ring_positions(ctx, oracle):
     for u in range(n):
         es, eo, ee = oracle.sbr_dec_lp(side[u], st[u], tin[u])
         check(u, st2[u], out[u], err[u], es, eo, ee, "non-lockstep")
+
+
+def test_sbr_dec_lp_w32_matches_handover_kernel(ctx):
+    """xaac_b200_sbr_dec_lp_w32_dev (the WORD32 -> WORD16 hand-over of ixheaacd_allocate_sbr_scr inside the stage's load) against
+    the separate hand-over kernel followed by xaac_b200_sbr_dec_lp_dev: PCM, err and state identical — lock-step units (vector load
+    path) and units in every other (position, phase) state (literal ring emulation), incl. the hand-over's saturation corners."""
+    import torch
+    import libxaac_b200 as xb
+    g = np.load(GOLD)
+    n = 600
+    side, st, _ = oracle_util.synth_sbr_lp_units(n, 23, g)
+    rng = np.random.default_rng(23)
+    half = n // 2
+    st[half:, 320] = 32 * rng.integers(0, 10, n - half)
+    st[half:, 321] = 64 * rng.integers(0, 10, n - half)
+    res = []
+    for w32_path in (False, True):
+        state = xb.SbrState(ctx, n, low_power=True)
+        state.upload(st, None)
+        frames = []
+        r2 = np.random.default_rng(5)
+        for f in range(3):
+            s = r2.integers(8, 31, (n, 1))
+            w32 = ((r2.random((n, 1024)) * 2 - 1) * 2.0 ** s).astype(np.int64).clip(-2 ** 31, 2 ** 31 - 1).astype(np.int32)
+            w32[0, :4] = (2 ** 31 - 1, -2 ** 31, 0x7FFF8000, -1)
+            adj = r2.integers(1, 3, n).astype(np.int8)
+            d_side = torch.from_numpy(np.ascontiguousarray(side)).cuda()
+            d_w32, d_adj = torch.from_numpy(w32).cuda(), torch.from_numpy(adj).cuda()
+            if w32_path:
+                out, err = xb.sbr_dec_lp_w32(ctx, state, d_side, d_w32, d_adj, out_ch=2)
+            else:
+                out, err = xb.sbr_dec_lp(ctx, state, d_side, xb.imdct_out_to_pcm16(ctx, d_w32, d_adj, 0), out_ch=2)
+            frames.append((out.cpu().numpy(), err.cpu().numpy()))
+        res.append((frames, state.download()[0]))
+        state.close()
+    for f in range(3):
+        assert np.array_equal(res[0][0][f][1], res[1][0][f][1]), f"frame {f}: err"
+        assert np.array_equal(res[0][0][f][0], res[1][0][f][0]), f"frame {f}: PCM"
+    assert np.array_equal(res[0][1], res[1][1])
