@@ -52,10 +52,13 @@ struct xaac_b200_ctx {
   const char *tick_name[kMaxTicks];
   cudaEvent_t tick_ev[kMaxTicks][2];
   // staging for the *_host entry points: kPipe chunks in flight, one stream each
-  static constexpr int kPipe = 3;
+#ifndef XB_PIPE
+#define XB_PIPE 3
+#endif
+  static constexpr int kPipe = XB_PIPE;
   int64_t host_chunk = 4096;  // units per pipeline chunk of xaac_b200_heaac_frame_host (XAAC_B200_HOST_CHUNK overrides, tuning only)
-  cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
-  void *stage[kPipe] = {nullptr, nullptr, nullptr};
+  cudaStream_t streams[kPipe] = {};
+  void *stage[kPipe] = {};
   size_t stage_bytes = 0;
 };
 
