@@ -23,7 +23,11 @@
 namespace xb {
 
 constexpr int kHfWarps = 4;   // 38 KB of shared memory per block: five blocks = 20 warps per SM, four-warp blocks load the schedulers evenly (7-warp blocks: 1.26 -> 1.24 ms)
-constexpr int kHfColWords = 38 * 2 * 32;  // per warp: the low-band column set of one pass (38 rows x re, im x 32 bands)
+constexpr int kHfColWords = 38 * 2 * 32;
+#ifndef HF_AHEAD
+#define HF_AHEAD 8
+#endif
+constexpr int kHfAhead = HF_AHEAD;  // rows of the covariance pass in flight per lane (power of two); 4: 1.231 ms, 8: 1.167 ms, 16: 1.740 ms (128 registers)  // per warp: the low-band column set of one pass (38 rows x re, im x 32 bands)
 
 // ops32.h:134 — second operand contributes only its high half (not commutative)
 XB_DEV i32 hm(i32 a, i32 b) { return __mulhi(a, (i32)((u32)b & 0xffff0000u)); }
@@ -127,17 +131,18 @@ hf_generator_hq_kernel(HfGenArgs p) {
           p12 = A;
           p12i = B;
         }
-        // rows are prefetched four ahead (register ring): each iteration's two loads are a coalesced 128-byte request per
+        // rows are prefetched kHfAhead ahead (register ring): each iteration's two loads are a coalesced 128-byte request per
         // component, and the arithmetic of row m overlaps the latency of rows m+1..m+4
-        i32 pr[4], pi[4];
+        i32 pr[kHfAhead], pi[kHfAhead];
 #pragma unroll
-        for (int q = 0; q < 4; q++) { pr[q] = mat[128 * q + lb]; pi[q] = mat[128 * q + 64 + lb]; }
-#pragma unroll 4
+        for (int q = 0; q < kHfAhead; q++) { pr[q] = mat[128 * q + lb]; pi[q] = mat[128 * q + 64 + lb]; }
+#pragma unroll kHfAhead
         for (int m = 0; m < L; m++) {
-          colr[32 * m] = pr[m & 3];
-          coli[32 * m] = pi[m & 3];
-          const i32 r0 = pr[m & 3] >> 3, i0 = pi[m & 3] >> 3;
-          if (m + 4 < L) { pr[m & 3] = mat[128 * (m + 4) + lb]; pi[m & 3] = mat[128 * (m + 4) + 64 + lb]; }
+          constexpr int K = kHfAhead - 1;
+          colr[32 * m] = pr[m & K];
+          coli[32 * m] = pi[m & K];
+          const i32 r0 = pr[m & K] >> 3, i0 = pi[m & K] >> 3;
+          if (m + kHfAhead < L) { pr[m & K] = mat[128 * (m + kHfAhead) + lb]; pi[m & K] = mat[128 * (m + kHfAhead) + 64 + lb]; }
           i32 A = wadd(hm(r0, r1), hm(i0, i1)), B = wsub(hm(i0, r1), hm(r0, i1));
           p01 = wadd(p01, A);
           p01i = wadd(p01i, B);
