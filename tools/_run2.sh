@@ -1,10 +1,8 @@
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_2gpu_final5.json 2> gpurun_out/r2_bench_2gpu_final5.err
-tail -3 gpurun_out/r2_bench_2gpu_final5.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_2gpu_final6.json 2> gpurun_out/r2_bench_2gpu_final6.err
 python - <<'P'
 import json
-d=json.loads([l for l in open("gpurun_out/r2_bench_2gpu_final5.json").read().strip().splitlines() if l.startswith("{")][-1])
+d=json.loads([l for l in open("gpurun_out/r2_bench_2gpu_final6.json").read().strip().splitlines() if l.startswith("{")][-1])
 print("n_gpus", d["n_gpus"], "value %.4g ms %.4g e2e %.4g"%(d["value"], d["ms_per_step"], d["e2e"]["value"]), "scaling", d["scaling"])
 s=d.get("sharded_io") or {}
-print({k:(v if not isinstance(v,dict) else {a:b for a,b in v.items() if not isinstance(b,(dict,list))}) for k,v in s.items()})
+print(s.get('ms_per_step_overlapped'), (s.get('peer_memory') or {}).get('ms_per_step'))
 P
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 1 --impl reference 2>/dev/null | tail -1 | cut -c1-200
