@@ -1140,12 +1140,13 @@ def host_threads():
 
 STAGES = {
     "heaacv2_chain": dict(kernel=None, bytes_per_unit=None, units_per_frame=1,
-                          stage="IMDCT+OLA -> PCM16 hand-over -> QMF analysis -> HF generation -> envelope adjustment -> "
-                                "PS hybrid/decorrelation/rotation -> 2 x QMF synthesis (fixed-point, bit-exact)",
+                          stage="IMDCT+OLA -> QMF analysis (WORD32 -> PCM16 hand-over in its load, block-FP bookkeeping in the same "
+                                "kernel) -> HF generation -> envelope adjustment -> PS hybrid/decorrelation/rotation -> "
+                                "2 x QMF synthesis (fixed-point, bit-exact; 7 launches)",
                           ref_stage="ixheaacd_imdct_process + ixheaacd_sbr_dec (HQ, PS)", cpu=cpu_arm_chain,
                           cpu_units_per_core=128, cpu_reps=12, realtime_fps=21.533, h2d=4096 + 2 + 2464, d2h=8192),
     "heaacv1_stereo_chain": dict(kernel=None, top_kernel="sbr_dec_lp_kernel", bytes_per_unit=None,
-                                 stage="per channel: IMDCT+OLA -> PCM16 hand-over -> fused low-power SBR stage (real QMF "
+                                 stage="per channel: IMDCT+OLA -> fused low-power SBR stage (WORD32 -> PCM16 hand-over in its load, real QMF "
                                        "analysis, LP HF generation, envelope adjustment + alias reduction, real QMF "
                                        "synthesis; fixed-point, bit-exact)",
                                  ref_stage="ixheaacd_imdct_process + ixheaacd_sbr_dec (low power)", cpu=cpu_arm_chain_lp,
