@@ -214,6 +214,11 @@ void xaac_b200_destroy(xaac_b200_ctx *ctx) {
     if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
     if (ctx->stage[i]) cudaFree(ctx->stage[i]);
   }
+  for (int k = 0; k < 8; k++) {  // streams / events of the opt-in chunked device path (XAAC_B200_DEV_CHUNK)
+    if (ctx->dev_st[k]) cudaStreamDestroy(ctx->dev_st[k]);
+    if (ctx->dev_join[k]) cudaEventDestroy(ctx->dev_join[k]);
+  }
+  if (ctx->dev_fork) cudaEventDestroy(ctx->dev_fork);
   if (ctx->d_rom_imdct) cudaFree(ctx->d_rom_imdct);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->d_rom_qmf_syn) cudaFree(ctx->d_rom_qmf_syn);
@@ -907,13 +912,13 @@ static int32_t sbr_dec_all(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int
     rc = sbr_dec_range(ctx, s, u0, m, d_side + u0 * xb::kSideWords, d_time_in ? d_time_in + u0 * 1024 : nullptr,
                        d_time_out + u0 * out_words, d_err ? d_err + u0 : nullptr, ctx->dev_st[k], (long long)k * chunk,
                        d_w32 ? d_w32 + u0 * 1024 : nullptr, d_adj ? d_adj + u0 : nullptr);
-    if (rc != XAAC_B200_OK) return rc;
+    if (rc != XAAC_B200_OK) break;  // the caller's stream still joins the chunks already queued
   }
   for (int q = 0; q < K; q++) {
     CK(cudaEventRecord(ctx->dev_join[q], ctx->dev_st[q]), "cudaEventRecord");
     CK(cudaStreamWaitEvent(stream, ctx->dev_join[q], 0), "cudaStreamWaitEvent");
   }
-  return XAAC_B200_OK;
+  return rc;
 }
 
 int32_t xaac_b200_sbr_dec_hq_dev(xaac_b200_ctx *ctx, xaac_b200_sbr_state *s, const int16_t *d_side,

@@ -169,3 +169,17 @@ def test_sbr_dec_w32_and_fused_glue_match_the_separate_kernels(ctx, monkeypatch)
             assert np.array_equal(got[f][1], ref[f][1]), f"frame {f}: err (w32_path={w32_path})"
             assert np.array_equal(got[f][0], ref[f][0]), f"frame {f}: PCM (w32_path={w32_path})"
         assert np.array_equal(st_g, st_r) and np.array_equal(ps_g, ps_r)
+    # the opt-in chunked form of the device-resident entry points (chunks of 400 units round-robin over 3 internal streams
+    # forked from / joined to the caller's stream, per-stream scratch slots): same results, ragged last chunk included
+    monkeypatch.setenv("XAAC_B200_DEV_CHUNK", "400")
+    monkeypatch.setenv("XAAC_B200_DEV_STREAMS", "3")
+    c3 = xb.Context(0)
+    monkeypatch.delenv("XAAC_B200_DEV_CHUNK")
+    monkeypatch.delenv("XAAC_B200_DEV_STREAMS")
+    try:
+        got, (st_g, ps_g) = _run_stage(xb, c3, g, n, frames, w32_path=True)
+    finally:
+        c3.close()
+    for f in range(frames):
+        assert np.array_equal(got[f][1], ref[f][1]) and np.array_equal(got[f][0], ref[f][0]), f"frame {f}: chunked device path"
+    assert np.array_equal(st_g, st_r) and np.array_equal(ps_g, ps_r)
